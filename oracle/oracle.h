@@ -1,0 +1,71 @@
+/*
+ * oracle/oracle.h -- C interface of the CPU oracle (TEST INFRASTRUCTURE).
+ * See oracle.c for the provenance of every function.
+ */
+#ifndef DMG_ORACLE_H
+#define DMG_ORACLE_H
+#include <stdint.h>
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct orc_tree orc_tree;
+typedef struct orc_tdm_model orc_tdm_model;
+typedef struct orc_otm_model orc_otm_model;
+typedef struct orc_dr_model orc_dr_model;
+
+orc_tree *orc_tree_create(int max_level, int64_t n_nodes, const int32_t *codes, const int32_t *node_ids,
+                          const uint8_t *is_leaf, int64_t n_items, const int32_t *leaf_ids,
+                          const int32_t *leaf_codes);
+void orc_tree_destroy(orc_tree *t);
+void orc_tdm_id_to_code(const orc_tree *t, int T, const int32_t *ids, int32_t *codes, uint8_t *masked);
+
+/* params = compact DIN vector [emb | W_att | W1 | b1 | W2 | b2]; NOT copied. */
+orc_tdm_model *orc_tdm_model_create(int64_t rows, int E, int T, const float *params);
+void orc_tdm_model_destroy(orc_tdm_model *m);
+orc_otm_model *orc_otm_model_create(int64_t rows, int E, int T, const double *params);
+void orc_otm_model_destroy(orc_otm_model *m);
+
+int orc_din_forward_f32_api(const orc_tdm_model *m, int64_t n, const int32_t *node, const int32_t *seq,
+                            const int32_t *mask_flat, int64_t n_mask, float *out);
+int orc_din_forward_f64_api(const orc_otm_model *m, int64_t n, const int32_t *node, const int32_t *seq,
+                            const int32_t *mask_flat, int64_t n_mask, double *out);
+
+int orc_tdm_recommend_raw(const orc_tree *t, const orc_tdm_model *m, const int32_t *seq_ids, int beam,
+                          int use_mask, const int32_t *consumed, int n_consumed, int32_t *out_items,
+                          float *out_logits, int cap);
+int orc_tdm_recommend(const orc_tree *t, const orc_tdm_model *m, const int32_t *seq_ids, int beam, int topk,
+                      int use_mask, const int32_t *consumed, int n_consumed, int widen_beam,
+                      int32_t *out_items, float *out_logits, double *out_prob);
+int orc_tdm_retrieve_batch(const orc_tree *t, const orc_tdm_model *m, int B, const int32_t *seq_ids, int beam,
+                           int topk, int use_mask, const int64_t *cons_off, const int32_t *cons, int widen_beam,
+                           int n_threads, int32_t *out_items, float *out_logits, int32_t *out_counts);
+
+int orc_otm_beam_search(const orc_otm_model *m, const int32_t *seq, int leaf_level, int beam, int use_mask,
+                        int32_t *out_ids, double *out_scores);
+int orc_otm_recommend(const orc_otm_model *m, const int32_t *seq_leaf_ids, int leaf_level, int beam, int topk,
+                      int use_mask, const int32_t *leaf_item, int32_t *out_items, double *out_scores,
+                      double *out_prob);
+int orc_otm_retrieve_batch(const orc_otm_model *m, int B, const int32_t *seq_leaf_ids, int leaf_level, int beam,
+                           int topk, int use_mask, const int32_t *leaf_item, int n_threads, int32_t *out_items,
+                           double *out_scores, int32_t *out_counts);
+
+orc_dr_model *orc_dr_model_create(int num_item, int K, int D, int T, int E, const double *layer_emb,
+                                  const double *const *layer_w, const double *const *layer_b,
+                                  const double *rr_emb, const double *rr_w, const double *rr_b,
+                                  const double *sm_w, const double *sm_b);
+void orc_dr_model_destroy(orc_dr_model *m);
+int orc_dr_beam_search(const orc_dr_model *m, const int32_t *seq, int beam, int32_t *out_paths, double *out_prob);
+int orc_dr_rerank(const orc_dr_model *m, const int32_t *seq, int n_cand, const int32_t *cand, double *out);
+int orc_dr_recommend(const orc_dr_model *m, const int32_t *seq, int beam, int topk, const int64_t *path_off,
+                     const int32_t *path_items, int32_t *out_ids, double *out_scores, double *out_prob);
+
+void orc_softmax_f32(int n, int dim, const float *in, float *out);
+void orc_softmax_grad_f32(int n, int dim, const float *y, const float *go, float *gi);
+float orc_expf_api(float x);
+double orc_exp_api(double x);
+
+#ifdef __cplusplus
+}
+#endif
+#endif
