@@ -1,0 +1,245 @@
+"""ctypes binding of libdismember_gpu.so -- the same symbols the JNI shim binds.
+
+There is no fallback: if the shared library is missing or no CUDA device is
+present, constructing an Engine raises.  Nothing here imports oracle/.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import re
+from typing import Optional
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libdismember_gpu.so")
+HEADER_PATH = os.path.join(os.path.dirname(_HERE), "include", "dismember_gpu.h")
+
+DMG_OK, DMG_ERR_INVALID_ARG, DMG_ERR_CUDA, DMG_ERR_INDEX, DMG_ERR_STATE, DMG_ERR_UNSUPPORTED, DMG_ERR_NOMEM = 0, -1, -2, -3, -4, -5, -6
+DMG_F32, DMG_F64 = 0, 1
+
+
+class DmgError(RuntimeError):
+    def __init__(self, code: int, msg: str):
+        super().__init__(f"[dmg {code}] {msg}")
+        self.code = code
+
+
+class DmgIndexError(DmgError, IndexError):
+    """ArrayIndexOutOfBoundsException of LookupTable.embeddingLookup."""
+
+
+class DmgArgumentError(DmgError, ValueError):
+    """IllegalArgumentException / require(...)"""
+
+
+def declared_symbols() -> list:
+    """Every DMG_API function declared in include/dismember_gpu.h."""
+    with open(HEADER_PATH) as f:
+        text = f.read()
+    return sorted(set(re.findall(r"DMG_API\s+[\w\s\*]+?\b(dmg_\w+)\s*\(", text)))
+
+
+_lib = None
+
+
+def load_library(build_if_missing: bool = True):
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        if not build_if_missing:
+            raise OSError(f"{LIB_PATH} not built (run python -m dismember_b200.build)")
+        from . import build as _build
+        _build.build()
+    L = C.CDLL(LIB_PATH)
+    vp, i32, i64, u64, dbl = C.c_void_p, C.c_int32, C.c_int64, C.c_uint64, C.c_double
+    sig = {
+        "dmg_create": [i32, C.POINTER(vp)],
+        "dmg_destroy": [vp],
+        "dmg_set_stream": [vp, vp],
+        "dmg_synchronize": [vp],
+        "dmg_set_profiling": [vp, i32],
+        "dmg_kernel_time": [vp, C.POINTER(dbl), C.POINTER(i64)],
+        "dmg_load_tree_tdm": [vp, i32, i64, vp, vp, vp, i64, vp, vp],
+        "dmg_load_tree_complete": [vp, i32, i64, vp, vp],
+        "dmg_load_din_weights": [vp, i32, i64, i32, i32, vp],
+        "dmg_init_din_weights": [vp, i32, i64, i32, i32, u64],
+        "dmg_download_din_weights": [vp, vp, i64],
+        "dmg_tdm_retrieve": [vp, i32, vp, i32, i32, i32, vp, vp, i32, vp, vp, vp],
+        "dmg_tdm_retrieve_dev": [vp, i32, vp, i32, i32, i32, vp, vp, vp],
+        "dmg_otm_beam_search": [vp, i32, vp, i32, i32, vp, vp, vp],
+        "dmg_otm_retrieve": [vp, i32, vp, i32, i32, i32, vp, vp, vp],
+        "dmg_score_pairs": [vp, i64, vp, vp, vp, i64, vp],
+        "dmg_dr_load": [vp, i32, i32, i32, i32, i32, vp, C.POINTER(vp), C.POINTER(vp), vp, vp, vp, vp, vp],
+        "dmg_dr_load_paths": [vp, vp, vp],
+        "dmg_dr_beam_search": [vp, i32, vp, i32, vp, vp, vp],
+        "dmg_dr_retrieve": [vp, i32, vp, i32, i32, vp, vp, vp],
+        "dmg_train_step": [vp, i64, vp, vp, vp, i64, vp, dbl, i32, vp],
+        "dmg_din_gradients": [vp, i64, vp, vp, vp, i64, vp, vp, vp, i64],
+        "dmg_tdm_sample_expand": [vp, i32, vp, vp, vp, i32, u64, vp, vp, vp, vp],
+        "dmg_jtm_item_weights": [vp, i32, vp, vp, vp, i32, i32, vp],
+    }
+    for name, args in sig.items():
+        fn = getattr(L, name)
+        fn.argtypes = args
+        fn.restype = i32
+    L.dmg_last_error.argtypes = [vp]
+    L.dmg_last_error.restype = C.c_char_p
+    L.dmg_version.argtypes = []
+    L.dmg_version.restype = C.c_char_p
+    L.dmg_launch_count.argtypes = [vp]
+    L.dmg_launch_count.restype = i64
+    _lib = L
+    return L
+
+
+def _p(a: Optional[np.ndarray]):
+    return None if a is None else a.ctypes.data_as(C.c_void_p)
+
+
+def _i32(a):
+    return np.ascontiguousarray(a, dtype=np.int32)
+
+
+class Engine:
+    """One dmg handle = one CUDA device + stream (not thread-safe, like a model clone)."""
+
+    def __init__(self, device: int = 0):
+        self.L = load_library()
+        h = C.c_void_p()
+        rc = self.L.dmg_create(device, C.byref(h))
+        if rc != DMG_OK:
+            raise DmgError(rc, (self.L.dmg_last_error(None) or b"").decode())
+        self.h = h
+        self.device = device
+        self.din_dtype = None
+        self.E = self.T = None
+        self.rows = None
+
+    # -- plumbing ---------------------------------------------------------------
+    def _check(self, rc: int):
+        if rc == DMG_OK:
+            return
+        msg = (self.L.dmg_last_error(self.h) or b"").decode()
+        if rc == DMG_ERR_INDEX:
+            raise DmgIndexError(rc, msg)
+        if rc == DMG_ERR_INVALID_ARG:
+            raise DmgArgumentError(rc, msg)
+        raise DmgError(rc, msg)
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.L.dmg_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def set_stream(self, cuda_stream: Optional[int]):
+        self._check(self.L.dmg_set_stream(self.h, C.c_void_p(cuda_stream) if cuda_stream else None))
+
+    def synchronize(self):
+        self._check(self.L.dmg_synchronize(self.h))
+
+    @property
+    def launch_count(self) -> int:
+        return int(self.L.dmg_launch_count(self.h))
+
+    def set_profiling(self, on: bool):
+        self._check(self.L.dmg_set_profiling(self.h, int(on)))
+
+    def kernel_time(self):
+        """-> (total ms of the beam-search kernel, launches) since the last call; synchronises."""
+        ms, n = C.c_double(), C.c_int64()
+        self._check(self.L.dmg_kernel_time(self.h, C.byref(ms), C.byref(n)))
+        return ms.value, n.value
+
+    # -- index structures -------------------------------------------------------
+    def load_tree_tdm(self, max_level, codes, node_ids, is_leaf, leaf_ids, leaf_codes):
+        codes, node_ids, leaf_ids, leaf_codes = _i32(codes), _i32(node_ids), _i32(leaf_ids), _i32(leaf_codes)
+        is_leaf = np.ascontiguousarray(is_leaf, np.uint8)
+        self._check(self.L.dmg_load_tree_tdm(self.h, int(max_level), len(codes), _p(codes), _p(node_ids), _p(is_leaf),
+                                             len(leaf_ids), _p(leaf_ids), _p(leaf_codes)))
+
+    def load_tree_complete(self, leaf_level, item_ids, leaf_ids):
+        item_ids, leaf_ids = _i32(item_ids), _i32(leaf_ids)
+        self._check(self.L.dmg_load_tree_complete(self.h, int(leaf_level), len(item_ids), _p(item_ids), _p(leaf_ids)))
+
+    # -- weights ----------------------------------------------------------------
+    def load_din_weights(self, params: np.ndarray, rows: int, E: int, T: int):
+        if params.dtype == np.float32:
+            dt = DMG_F32
+        elif params.dtype == np.float64:
+            dt = DMG_F64
+        else:
+            raise DmgArgumentError(DMG_ERR_INVALID_ARG, "DIN parameters must be float32 or float64")
+        params = np.ascontiguousarray(params).ravel()
+        n = rows * E + E * E + 2 * E * E + 2 * E + 1
+        if params.size != n:
+            raise DmgArgumentError(DMG_ERR_INVALID_ARG, f"compact DIN vector must hold {n} values, got {params.size}")
+        self._check(self.L.dmg_load_din_weights(self.h, dt, rows, E, T, _p(params)))
+        self.din_dtype, self.rows, self.E, self.T = params.dtype, rows, E, T
+
+    def init_din_weights(self, dtype, rows: int, E: int, T: int, seed: int):
+        dtype = np.dtype(dtype)
+        dt = DMG_F32 if dtype == np.float32 else DMG_F64
+        self._check(self.L.dmg_init_din_weights(self.h, dt, rows, E, T, seed))
+        self.din_dtype, self.rows, self.E, self.T = dtype, rows, E, T
+
+    def download_din_weights(self) -> np.ndarray:
+        n = self.rows * self.E + 3 * self.E * self.E + 2 * self.E + 1
+        out = np.empty(n, self.din_dtype)
+        self._check(self.L.dmg_download_din_weights(self.h, _p(out), n))
+        return out
+
+    # -- retrieval --------------------------------------------------------------
+    def tdm_retrieve(self, item_seq, beam, topk, use_mask=True, consumed_off=None, consumed=None, widen_beam=False):
+        seq = _i32(item_seq).reshape(-1, self.T)
+        B = len(seq)
+        items = np.empty((B, topk), np.int32)
+        logits = np.empty((B, topk), np.float32)
+        counts = np.empty(B, np.int32)
+        co = None if consumed_off is None else np.ascontiguousarray(consumed_off, np.int64)
+        cc = None if consumed is None else _i32(consumed)
+        self._check(self.L.dmg_tdm_retrieve(self.h, B, _p(seq), beam, topk, int(use_mask), _p(co), _p(cc),
+                                            int(widen_beam), _p(items), _p(logits), _p(counts)))
+        return items, logits, counts
+
+    def tdm_retrieve_dev(self, B, d_seq_ptr, beam, topk, use_mask, d_items_ptr, d_logits_ptr, d_counts_ptr):
+        """Device-pointer form (ints from tensor.data_ptr()); asynchronous on the handle's stream."""
+        vp = C.c_void_p
+        self._check(self.L.dmg_tdm_retrieve_dev(self.h, B, vp(d_seq_ptr), beam, topk, int(use_mask), vp(d_items_ptr),
+                                                vp(d_logits_ptr), vp(d_counts_ptr)))
+
+    def otm_beam_search(self, leaf_seq, beam, use_mask=True):
+        seq = _i32(leaf_seq).reshape(-1, self.T)
+        B = len(seq)
+        s = int(beam).bit_length() - 1
+        width = 2 * max(beam, 1 << s)
+        ids = np.empty((B, width), np.int32)
+        sc = np.empty((B, width), np.float64)
+        counts = np.empty(B, np.int32)
+        self._check(self.L.dmg_otm_beam_search(self.h, B, _p(seq), beam, int(use_mask), _p(ids), _p(sc), _p(counts)))
+        return ids, sc, counts
+
+    def otm_retrieve(self, leaf_seq, beam, topk, use_mask=True):
+        seq = _i32(leaf_seq).reshape(-1, self.T)
+        B = len(seq)
+        items = np.empty((B, topk), np.int32)
+        sc = np.empty((B, topk), np.float64)
+        counts = np.empty(B, np.int32)
+        self._check(self.L.dmg_otm_retrieve(self.h, B, _p(seq), beam, topk, int(use_mask), _p(items), _p(sc), _p(counts)))
+        return items, sc, counts
+
+    def score_pairs(self, node, seq, mask_flat=None):
+        node = _i32(node).ravel()
+        seq = _i32(seq).reshape(len(node), self.T)
+        out = np.empty(len(node), self.din_dtype)
+        m = None if mask_flat is None else _i32(mask_flat).ravel()
+        self._check(self.L.dmg_score_pairs(self.h, len(node), _p(node), _p(seq), _p(m), 0 if m is None else len(m), _p(out)))
+        return out

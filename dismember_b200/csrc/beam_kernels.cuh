@@ -1,0 +1,641 @@
+// beam_kernels.cuh -- K1/K2/K3: persistent CTA-per-user beam search with the fused DIN scorer.
+//
+// Replaces, for a whole batch of users in ONE launch:
+//   Recommender._recommend            tdm/src/main/scala/com/mass/tdm/model/Recommender.scala:40-107
+//   CandidateSearcher.batchBeamSearch otm/src/main/scala/com/mass/otm/model/CandidateSearcher.scala:15-56
+//   DIN.buildModel graph forward      tdm/.../model/DIN.scala:14-43 (EmbeddingShare, Attention, Mask,
+//                                     SoftMax, MatMul, Concat, Linear, ReLU of scalann/.../nn)
+//   final stable sort + take(topk)    Recommender.scala:37, TDM.scala:21, OTM.scala:17-21
+//
+// One CTA owns one user at a time and walks every tree level without leaving the SM: the
+// beam, candidate codes and scores live in shared memory, the user's T history rows are
+// staged once through the TMA bulk-copy engine (cp.async.bulk + mbarrier), candidate rows are
+// gathered with 16-byte cp.async into a double-buffered row tile while the previous tile is
+// being scored, and only topk results leave the chip.  Users are independent, so there is no
+// grid-wide synchronisation and no per-level kernel launch.
+//
+// "strict" arithmetic (dmg_math.cuh): every GEMM element is one sequential-k fma chain in
+// registers, so results are bit-identical to the CPU oracle.
+#pragma once
+#include "dmg_common.cuh"
+#include "dmg_math.cuh"
+
+namespace dmg {
+
+enum { MODE_TDM_TOPK = 0, MODE_OTM_DUMP = 1, MODE_OTM_TOPK = 2 };
+
+template <typename real> struct BeamParams {
+    const real *emb, *wattT, *w1T, *b1, *w2, *b2;
+    real scale;
+    int T, B;
+    const int32_t *hist;        // B x T embedding indices, -1 = padding (zero row)
+    const uint8_t *hist_mask;   // B x T, 1 = position listed in the Mask input
+    int beam;
+    const int32_t *beam_user;   // nullable: per-user beam (Recommender.scala:28-31)
+    int always_sort;            // OTM sorts every level after the first; TDM only when > beam
+    const uint32_t *exists;     // code-existence bitmap, nullptr = complete tree
+    int leaf_level;
+    int mode, topk;
+    const int32_t *leaf_item;   // [2^L] item id of a leaf slot, -1 = none
+    const int64_t *cons_off;    // nullable consumed-items CSR
+    const int32_t *cons;
+    int32_t *out_items;
+    real *out_scores;
+    int32_t *out_counts;
+    int out_stride;
+    int cap, capp;              // candidate capacity (>= 2*max beam) and its power of two
+};
+
+// ---- sort keys: (score desc, candidate position asc) == the reference's stable sort ------
+struct Key128 { uint64_t hi, lo; };
+__device__ __forceinline__ bool key_less(uint64_t a, uint64_t b) { return a < b; }
+__device__ __forceinline__ bool key_less(const Key128 &a, const Key128 &b)
+{
+    return a.hi < b.hi || (a.hi == b.hi && a.lo < b.lo);
+}
+template <typename real> struct KeyOf;
+template <> struct KeyOf<float> {
+    using type = uint64_t;
+    static __device__ __forceinline__ type make(float s, int pos)
+    {
+        return ((uint64_t)order_key(s) << 32) | (uint32_t)(0xFFFFFFFFu - (uint32_t)pos);
+    }
+    static __device__ __forceinline__ type lowest() { return 0; }
+    static __device__ __forceinline__ bool is_lowest(type k) { return k == 0; }
+    static __device__ __forceinline__ int pos(type k) { return (int)(0xFFFFFFFFu - (uint32_t)k); }
+};
+template <> struct KeyOf<double> {
+    using type = Key128;
+    static __device__ __forceinline__ type make(double s, int pos)
+    {
+        Key128 k; k.hi = order_key(s); k.lo = (uint64_t)(0xFFFFFFFFu - (uint32_t)pos); return k;
+    }
+    static __device__ __forceinline__ type lowest() { Key128 k; k.hi = 0; k.lo = 0; return k; }
+    static __device__ __forceinline__ bool is_lowest(const type &k) { return k.hi == 0 && k.lo == 0; }
+    static __device__ __forceinline__ int pos(const type &k) { return (int)(0xFFFFFFFFu - (uint32_t)k.lo); }
+};
+
+template <typename K> __device__ void bitonic_sort_desc(K *keys, int n)
+{
+    for (int k = 2; k <= n; k <<= 1) {
+        for (int j = k >> 1; j > 0; j >>= 1) {
+            for (int i = threadIdx.x; i < n; i += blockDim.x) {
+                int ixj = i ^ j;
+                if (ixj > i) {
+                    K a = keys[i], b = keys[ixj];
+                    bool sw = ((i & k) == 0) ? key_less(a, b) : key_less(b, a);
+                    if (sw) { keys[i] = b; keys[ixj] = a; }
+                }
+            }
+            __syncthreads();
+        }
+    }
+}
+
+// ---- vector smem access -------------------------------------------------------------------
+__device__ __forceinline__ void ld4(const float *p, float (&v)[4])
+{
+    float4 t = *reinterpret_cast<const float4 *>(p);
+    v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
+}
+__device__ __forceinline__ void ld4(const double *p, double (&v)[4])
+{
+    double2 a = *reinterpret_cast<const double2 *>(p), b = *reinterpret_cast<const double2 *>(p + 2);
+    v[0] = a.x; v[1] = a.y; v[2] = b.x; v[3] = b.y;
+}
+__device__ __forceinline__ void st4(float *p, const float (&v)[4])
+{
+    *reinterpret_cast<float4 *>(p) = make_float4(v[0], v[1], v[2], v[3]);
+}
+__device__ __forceinline__ void st4(double *p, const double (&v)[4])
+{
+    *reinterpret_cast<double2 *>(p) = make_double2(v[0], v[1]);
+    *reinterpret_cast<double2 *>(p + 2) = make_double2(v[2], v[3]);
+}
+
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void cp_async16(void *dst, const void *src)
+{
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(dst)), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+// TMA bulk copy (non-tensor form) global -> shared, completion on an mbarrier.
+__device__ __forceinline__ void mbar_init(uint64_t *bar, int count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity)
+{
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "WAIT_%=:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra DONE_%=;\n\t"
+        "bra WAIT_%=;\n\t"
+        "DONE_%=:\n\t}" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void tma_bulk_g2s(void *dst, const void *src, uint32_t bytes, uint64_t *bar)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+__device__ __forceinline__ bool code_exists(const uint32_t *bm, int64_t c)
+{
+    return bm == nullptr || ((__ldg(bm + (c >> 5)) >> (c & 31)) & 1u);
+}
+
+// Block-wide exclusive scan of one small int per thread (kThreads threads). Returns the
+// exclusive prefix; *total receives the block sum.  sWarp: >= 8 ints of shared scratch.
+__device__ __forceinline__ int block_exscan(int v, int *sWarp, int *total)
+{
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    int inc = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        int t = __shfl_up_sync(0xffffffffu, inc, o);
+        if (lane >= o) inc += t;
+    }
+    if (lane == 31) sWarp[w] = inc;
+    __syncthreads();
+    int base = 0, tot = 0;
+#pragma unroll
+    for (int i = 0; i < kThreads / 32; i++) {
+        int s = sWarp[i];
+        if (i < w) base += s;
+        tot += s;
+    }
+    __syncthreads();
+    *total = tot;
+    return base + inc - v;
+}
+
+// ---- compile-time geometry ----------------------------------------------------------------
+template <typename real, int E> struct Geo {
+    static constexpr int R = sizeof(real) == 4 ? 128 : 64;       // rows per tile
+    static constexpr int NBUF = sizeof(real) == 4 ? 2 : 1;       // row-tile buffers
+    static constexpr int VEC = 16 / sizeof(real);                // reals per 16 B
+    static constexpr int LD = E + VEC;                           // padded row stride
+    static constexpr int PLD = kMaxT + 1;                        // score/prob row stride
+    static constexpr int TX = E / 4;                             // GEMM: column threads (4 cols each)
+    static constexpr int TY = kThreads / TX;                     // GEMM: row threads
+    static constexpr int TM = R / TY;                            // GEMM: rows per thread
+    static constexpr int NP = kThreads / R;                      // attention: threads per row
+    static constexpr int MAXJ = (kMaxT + NP - 1) / NP;
+    static constexpr int KW = E / NP;                            // attention: k-range per thread
+    static_assert(E % 4 == 0 && TX * TY == kThreads && TM * TY == R && TM >= 1, "bad geometry");
+    static_assert(KW % 4 == 0 || KW == 2 || KW == 4, "bad attention split");
+
+    static size_t smem_bytes(int cap, int capp)
+    {
+        size_t reals = (size_t)E * E + 2 * (size_t)E * E + 2 * (size_t)E + 4 + (size_t)kMaxT * E +
+                       (size_t)NBUF * R * LD + (size_t)R * LD + (size_t)R * PLD + (size_t)cap;
+        size_t b = reals * sizeof(real);
+        b = (b + 15) & ~(size_t)15;
+        b += (size_t)capp * sizeof(typename KeyOf<real>::type);
+        b += (size_t)cap * 2 * sizeof(int32_t);
+        b += 64 * sizeof(int32_t);
+        b += 16;                                                 // mbarrier
+        return b;
+    }
+};
+
+// ---- the DIN scorer on one tile of R candidate rows -----------------------------------------
+// sX: gathered candidate rows [R][LD]; sK: history [T][E]; results -> sScore[0..nrows).
+template <typename real, int E>
+__device__ __forceinline__ void score_tile(const real *__restrict__ sX, real *__restrict__ sA, real *__restrict__ sP,
+                                           const real *__restrict__ sK, const int32_t *__restrict__ sMask,
+                                           const real *__restrict__ sWattT, const real *__restrict__ sW1T,
+                                           const real *__restrict__ sB1, const real *__restrict__ sW2,
+                                           real b2, real scale, int T, int nrows, real *__restrict__ sScoreOut)
+{
+    using G = Geo<real, E>;
+    const int tid = threadIdx.x;
+
+    // (1) attention scores: s[r][j] = scale * sum_k x[r][k] K[j][k]   (MatMul transB + Mask)
+    {
+        const int r = tid / G::NP, part = tid % G::NP;
+        if (r < nrows) {
+            real acc[G::MAXJ];
+#pragma unroll
+            for (int jj = 0; jj < G::MAXJ; jj++) acc[jj] = (real)0;
+            const real *xr = sX + r * G::LD;
+#pragma unroll 2
+            for (int k = 0; k < E; k += 4) {
+                real xv[4];
+                ld4(xr + k, xv);
+#pragma unroll
+                for (int jj = 0; jj < G::MAXJ; jj++) {
+                    const int j = part + jj * G::NP;
+                    if (j < T) {
+                        real kv[4];
+                        ld4(sK + j * E + k, kv);
+                        acc[jj] = fma_(xv[0], kv[0], acc[jj]);
+                        acc[jj] = fma_(xv[1], kv[1], acc[jj]);
+                        acc[jj] = fma_(xv[2], kv[2], acc[jj]);
+                        acc[jj] = fma_(xv[3], kv[3], acc[jj]);
+                    }
+                }
+            }
+#pragma unroll
+            for (int jj = 0; jj < G::MAXJ; jj++) {
+                const int j = part + jj * G::NP;
+                if (j < T) {
+                    real s = mul_(acc[jj], scale);
+                    if (sMask[j]) s = mask_value<real>::get();
+                    sP[r * G::PLD + j] = s;
+                }
+            }
+        }
+    }
+    __syncthreads();
+    // (2) softmax over T per row (SoftMax.scala:27-42)
+    if (tid < nrows) {
+        real *pr = sP + tid * G::PLD;
+        real mx = pr[0];
+        for (int j = 1; j < T; j++) { real v = pr[j]; mx = (v > mx || v != v) ? v : mx; }
+        real sum = (real)0;
+        for (int j = 0; j < T; j++) { real e = exp_(sub_(pr[j], mx)); pr[j] = e; sum = add_(sum, e); }
+        const real inv = inv_(sum);
+        for (int j = 0; j < T; j++) pr[j] = mul_(pr[j], inv);
+    }
+    __syncthreads();
+    // (3) a[r][k] = sum_j p[r][j] K[j][k]   (MatMul)
+    {
+        const int r = tid / G::NP, part = tid % G::NP;
+        if (r < nrows) {
+            real acc[G::KW];
+#pragma unroll
+            for (int kk = 0; kk < G::KW; kk++) acc[kk] = (real)0;
+            const real *pr = sP + r * G::PLD;
+            for (int j = 0; j < T; j++) {
+                const real pj = pr[j];
+                const real *kj = sK + j * E + part * G::KW;
+#pragma unroll
+                for (int kk = 0; kk < G::KW; kk += G::VEC) {
+                    if constexpr (G::VEC == 4) {
+                        real kv[4];
+                        ld4(kj + kk, kv);
+#pragma unroll
+                        for (int q = 0; q < 4; q++) acc[kk + q] = fma_(pj, kv[q], acc[kk + q]);
+                    } else {
+#pragma unroll
+                        for (int q = 0; q < G::VEC; q++) acc[kk + q] = fma_(pj, kj[kk + q], acc[kk + q]);
+                    }
+                }
+            }
+            real *ar = sA + r * G::LD + part * G::KW;
+#pragma unroll
+            for (int kk = 0; kk < G::KW; kk++) ar[kk] = acc[kk];
+        }
+    }
+    __syncthreads();
+    // (4) att = a . Watt^T   (Linear(E,E), no bias) ; (5) h = relu([x|att] . W1^T + b1)
+    const int ty = tid / G::TX, tx = tid % G::TX;
+    const int row0 = ty * G::TM;
+    const bool active = row0 < nrows;
+    real acc[G::TM][4];
+#pragma unroll
+    for (int i = 0; i < G::TM; i++)
+#pragma unroll
+        for (int c = 0; c < 4; c++) acc[i][c] = (real)0;
+    if (active) {
+#pragma unroll 2
+        for (int k = 0; k < E; k += 4) {
+            real bv[4][4];
+#pragma unroll
+            for (int kk = 0; kk < 4; kk++) ld4(sWattT + (k + kk) * E + tx * 4, bv[kk]);
+#pragma unroll
+            for (int i = 0; i < G::TM; i++) {
+                real av[4];
+                ld4(sA + (row0 + i) * G::LD + k, av);
+#pragma unroll
+                for (int kk = 0; kk < 4; kk++)
+#pragma unroll
+                    for (int c = 0; c < 4; c++) acc[i][c] = fma_(av[kk], bv[kk][c], acc[i][c]);
+            }
+        }
+    }
+    __syncthreads();                       // every read of a[] done before att overwrites it
+    if (active) {
+#pragma unroll
+        for (int i = 0; i < G::TM; i++) st4(sA + (row0 + i) * G::LD + tx * 4, acc[i]);
+    }
+    __syncthreads();
+#pragma unroll
+    for (int i = 0; i < G::TM; i++)
+#pragma unroll
+        for (int c = 0; c < 4; c++) acc[i][c] = (real)0;
+    if (active) {
+#pragma unroll 2
+        for (int k = 0; k < E; k += 4) {               // item half of the concat
+            real bv[4][4];
+#pragma unroll
+            for (int kk = 0; kk < 4; kk++) ld4(sW1T + (k + kk) * E + tx * 4, bv[kk]);
+#pragma unroll
+            for (int i = 0; i < G::TM; i++) {
+                real av[4];
+                ld4(sX + (row0 + i) * G::LD + k, av);
+#pragma unroll
+                for (int kk = 0; kk < 4; kk++)
+#pragma unroll
+                    for (int c = 0; c < 4; c++) acc[i][c] = fma_(av[kk], bv[kk][c], acc[i][c]);
+            }
+        }
+#pragma unroll 2
+        for (int k = 0; k < E; k += 4) {               // attention half
+            real bv[4][4];
+#pragma unroll
+            for (int kk = 0; kk < 4; kk++) ld4(sW1T + (E + k + kk) * E + tx * 4, bv[kk]);
+#pragma unroll
+            for (int i = 0; i < G::TM; i++) {
+                real av[4];
+                ld4(sA + (row0 + i) * G::LD + k, av);
+#pragma unroll
+                for (int kk = 0; kk < 4; kk++)
+#pragma unroll
+                    for (int c = 0; c < 4; c++) acc[i][c] = fma_(av[kk], bv[kk][c], acc[i][c]);
+            }
+        }
+        real b1v[4];
+        ld4(sB1 + tx * 4, b1v);
+#pragma unroll
+        for (int i = 0; i < G::TM; i++)
+#pragma unroll
+            for (int c = 0; c < 4; c++) acc[i][c] = relu_(add_(acc[i][c], b1v[c]));
+    }
+    __syncthreads();                       // every read of att[] done before h overwrites it
+    if (active) {
+#pragma unroll
+        for (int i = 0; i < G::TM; i++) st4(sA + (row0 + i) * G::LD + tx * 4, acc[i]);
+    }
+    __syncthreads();
+    // (6) logit = h . W2 + b2   (Linear(E,1)), sequential over the hidden units
+    if (tid < nrows) {
+        const real *hr = sA + tid * G::LD;
+        real l = (real)0;
+#pragma unroll 4
+        for (int o = 0; o < E; o += 4) {
+            real hv[4], wv[4];
+            ld4(hr + o, hv);
+            ld4(sW2 + o, wv);
+            l = fma_(hv[0], wv[0], l);
+            l = fma_(hv[1], wv[1], l);
+            l = fma_(hv[2], wv[2], l);
+            l = fma_(hv[3], wv[3], l);
+        }
+        sScoreOut[tid] = add_(l, b2);
+    }
+    __syncthreads();
+}
+
+template <typename real, int E>
+__device__ __forceinline__ void gather_tile(real *__restrict__ sXbuf, const real *__restrict__ emb,
+                                            const int32_t *__restrict__ codes, int nrows)
+{
+    using G = Geo<real, E>;
+    constexpr int VPR = E / G::VEC;        // 16-byte vectors per row
+    for (int idx = threadIdx.x; idx < nrows * VPR; idx += blockDim.x) {
+        const int r = idx / VPR, v = idx % VPR;
+        cp_async16(sXbuf + r * G::LD + v * G::VEC, emb + (size_t)codes[r] * E + v * G::VEC);
+    }
+}
+
+template <typename real, int E>
+__global__ void __launch_bounds__(kThreads, 1) beam_search_kernel(const BeamParams<real> p)
+{
+    using G = Geo<real, E>;
+    using KO = KeyOf<real>;
+    using KeyT = typename KO::type;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    real *sWattT = reinterpret_cast<real *>(smem_raw);
+    real *sW1T = sWattT + E * E;
+    real *sB1 = sW1T + 2 * E * E;
+    real *sW2 = sB1 + E;
+    real *sB2 = sW2 + E;                         // 4 reals
+    real *sK = sB2 + 4;
+    real *sX = sK + kMaxT * E;
+    real *sA = sX + G::NBUF * G::R * G::LD;
+    real *sP = sA + G::R * G::LD;
+    real *sScore = sP + G::R * G::PLD;
+    size_t off = ((size_t)((unsigned char *)(sScore + p.cap) - smem_raw) + 15) & ~(size_t)15;
+    KeyT *sKey = reinterpret_cast<KeyT *>(smem_raw + off);
+    int32_t *sCode0 = reinterpret_cast<int32_t *>(sKey + p.capp);
+    int32_t *sCode1 = sCode0 + p.cap;
+    int32_t *sMisc = sCode1 + p.cap;             // [0..15] history codes, [16..31] mask, [32..39] scan, [40..] scalars
+    uint64_t *sBar = reinterpret_cast<uint64_t *>(sMisc + 64);
+
+    const int tid = threadIdx.x;
+    const int T = p.T;
+
+    // weights -> shared, once per CTA
+    for (int i = tid; i < E * E; i += kThreads) sWattT[i] = p.wattT[i];
+    for (int i = tid; i < 2 * E * E; i += kThreads) sW1T[i] = p.w1T[i];
+    for (int i = tid; i < E; i += kThreads) { sB1[i] = p.b1[i]; sW2[i] = p.w2[i]; }
+    if (tid == 0) { sB2[0] = p.b2[0]; mbar_init(sBar, 1); }
+    __syncthreads();
+    const real b2 = sB2[0];
+    uint32_t bar_phase = 0;
+
+    for (int user = blockIdx.x; user < p.B; user += gridDim.x) {
+        // ---- K2: history tile --------------------------------------------------------------
+        if (tid < kMaxT) {
+            int c = -1, m = 0;
+            if (tid < T) { c = p.hist[(size_t)user * T + tid]; m = p.hist_mask[(size_t)user * T + tid]; }
+            sMisc[tid] = c;
+            sMisc[16 + tid] = m;
+        }
+        __syncthreads();
+        fence_proxy_async();
+        if (tid == 0) {
+            uint32_t bytes = 0;
+            for (int j = 0; j < T; j++) if (sMisc[j] >= 0) bytes += E * sizeof(real);
+            mbar_expect_tx(sBar, bytes);
+            for (int j = 0; j < T; j++)
+                if (sMisc[j] >= 0) tma_bulk_g2s(sK + j * E, p.emb + (size_t)sMisc[j] * E, E * sizeof(real), sBar);
+        }
+        for (int i = tid; i < T * E; i += kThreads)
+            if (sMisc[i / E] < 0) sK[i] = (real)0;             // paddingIdx -> zero row
+        mbar_wait(sBar, bar_phase);
+        bar_phase ^= 1;
+        __syncthreads();
+
+        // ---- initial beam: every existing code of level s, pred 0 --------------------------
+        const int beam = p.beam_user ? p.beam_user[user] : p.beam;
+        int s_level = 31 - __clz(beam);                          // floor(log2 beam)
+        int32_t *cur = sCode0, *nxt = sCode1;
+        int count = 0;
+        if (s_level <= p.leaf_level) {
+            const int64_t start = ((int64_t)1 << s_level) - 1;
+            const int n0 = 1 << s_level;
+            for (int base = 0; base < n0; base += kThreads) {
+                int i = base + tid;
+                int e = (i < n0 && code_exists(p.exists, start + i)) ? 1 : 0;
+                int tot;
+                int o = block_exscan(e, sMisc + 32, &tot);
+                if (e) cur[count + o] = (int32_t)(start + i);
+                count += tot;
+            }
+            for (int i = tid; i < count; i += kThreads) sScore[i] = (real)0;
+            __syncthreads();
+        }
+
+        // ---- level loop ---------------------------------------------------------------------
+        for (int level = s_level; level < p.leaf_level && count > 0; level++) {
+            int nb = count;
+            if (count > beam || (p.always_sort && level != s_level)) {
+                int n2 = 2;
+                while (n2 < count) n2 <<= 1;
+                for (int i = tid; i < n2; i += kThreads) sKey[i] = i < count ? KO::make(sScore[i], i) : KO::lowest();
+                __syncthreads();
+                bitonic_sort_desc(sKey, n2);
+                nb = count < beam ? count : beam;
+                for (int i = tid; i < nb; i += kThreads) nxt[i] = cur[KO::pos(sKey[i])];
+                __syncthreads();
+                int32_t *t = cur; cur = nxt; nxt = t;
+            }
+            // children 2c+1, 2c+2 that exist, order preserved (Recommender.scala:88-92)
+            int nc = 0;
+            if (p.exists == nullptr) {
+                for (int i = tid; i < nb; i += kThreads) { int32_t c = cur[i]; nxt[2 * i] = 2 * c + 1; nxt[2 * i + 1] = 2 * c + 2; }
+                nc = 2 * nb;
+                __syncthreads();
+            } else {
+                for (int base = 0; base < nb; base += kThreads) {
+                    int i = base + tid;
+                    int64_t c = i < nb ? cur[i] : 0;
+                    int e1 = (i < nb && code_exists(p.exists, 2 * c + 1)) ? 1 : 0;
+                    int e2 = (i < nb && code_exists(p.exists, 2 * c + 2)) ? 1 : 0;
+                    int tot;
+                    int o = block_exscan(e1 + e2, sMisc + 32, &tot);
+                    if (e1) nxt[nc + o] = (int32_t)(2 * c + 1);
+                    if (e2) nxt[nc + o + e1] = (int32_t)(2 * c + 2);
+                    nc += tot;
+                }
+                __syncthreads();
+            }
+            { int32_t *t = cur; cur = nxt; nxt = t; }
+            count = nc;
+            // score the candidates tile by tile, prefetching the next tile's rows
+            const int ntiles = (count + G::R - 1) / G::R;
+            if (ntiles > 0) {
+                gather_tile<real, E>(sX, p.emb, cur, count < G::R ? count : G::R);
+                cp_async_commit();
+            }
+            for (int t = 0; t < ntiles; t++) {
+                const int r0 = t * G::R;
+                const int nrows = count - r0 < G::R ? count - r0 : G::R;
+                real *buf = sX + (G::NBUF == 2 ? (t & 1) : 0) * G::R * G::LD;
+                if (G::NBUF == 2 && t + 1 < ntiles) {
+                    const int r1 = r0 + G::R;
+                    gather_tile<real, E>(sX + ((t + 1) & 1) * G::R * G::LD, p.emb, cur + r1,
+                                         count - r1 < G::R ? count - r1 : G::R);
+                    cp_async_commit();
+                    cp_async_wait<1>();
+                } else {
+                    cp_async_wait<0>();
+                }
+                __syncthreads();
+                score_tile<real, E>(buf, sA, sP, sK, sMisc + 16, sWattT, sW1T, sB1, sW2, b2, p.scale, T, nrows,
+                                    sScore + r0);
+                if (G::NBUF == 1 && t + 1 < ntiles) {
+                    const int r1 = r0 + G::R;
+                    gather_tile<real, E>(sX, p.emb, cur + r1, count - r1 < G::R ? count - r1 : G::R);
+                    cp_async_commit();
+                }
+            }
+        }
+
+        // ---- K3: results ----------------------------------------------------------------------
+        // TDM: candidates that did not reach the leaf level are dropped (they never become leaves).
+        const int64_t leaf_start = ((int64_t)1 << p.leaf_level) - 1;
+        const bool at_leaf = (s_level <= p.leaf_level);
+        if (p.mode == MODE_OTM_DUMP) {
+            for (int i = tid; i < p.out_stride; i += kThreads) {
+                p.out_items[(size_t)user * p.out_stride + i] = i < count ? cur[i] : -1;
+                p.out_scores[(size_t)user * p.out_stride + i] = i < count ? sScore[i] : (real)0;
+            }
+            if (tid == 0) p.out_counts[user] = count;
+        } else {
+            int n2 = 2;
+            while (n2 < count) n2 <<= 1;
+            const int64_t c0 = p.cons_off ? p.cons_off[user] : 0, c1 = p.cons_off ? p.cons_off[user + 1] : 0;
+            for (int i = tid; i < n2; i += kThreads) {
+                KeyT k = KO::lowest();
+                if (i < count && at_leaf) {
+                    int64_t slot = (int64_t)cur[i] - leaf_start;
+                    int32_t item = (slot >= 0 && slot < ((int64_t)1 << p.leaf_level)) ? __ldg(p.leaf_item + slot) : -1;
+                    bool keep = item >= 0;
+                    for (int64_t q = c0; q < c1 && keep; q++) keep = (__ldg(p.cons + q) != item);
+                    if (keep) k = KO::make(sScore[i], i);
+                }
+                sKey[i] = k;
+            }
+            __syncthreads();
+            if (count > 0) bitonic_sort_desc(sKey, n2);
+            for (int i = tid; i < p.topk; i += kThreads) {
+                int32_t item = -1;
+                real sc = (real)0;
+                if (i < count && !KO::is_lowest(sKey[i])) {
+                    int pos = KO::pos(sKey[i]);
+                    item = __ldg(p.leaf_item + ((int64_t)cur[pos] - leaf_start));
+                    sc = sScore[pos];
+                }
+                p.out_items[(size_t)user * p.out_stride + i] = item;
+                p.out_scores[(size_t)user * p.out_stride + i] = sc;
+            }
+            if (tid == 0) {
+                int valid = 0;
+                const int lim = count < p.topk ? count : p.topk;
+                while (valid < lim && !KO::is_lowest(sKey[valid])) valid++;
+                p.out_counts[user] = valid;
+            }
+        }
+        __syncthreads();
+    }
+}
+
+// ---- K2 (host-facing part): item ids -> codes + mask, validity ------------------------------
+// TDMTree.idToCode (tdm/src/main/scala/com/mass/tdm/tree/TDMTree.scala:35-56).
+__global__ void tdm_ids_to_codes_kernel(const int32_t *__restrict__ ids, int64_t n, const int32_t *__restrict__ id_code,
+                                        int32_t non_leaf_offset, int32_t max_code, int64_t table_rows, int use_mask,
+                                        int32_t *__restrict__ codes, uint8_t *__restrict__ mask, int32_t *__restrict__ err_flag)
+{
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const int32_t id = ids[i];
+    int32_t code;
+    uint8_t m = 0;
+    if (id == 0) { m = 1; code = -1; }
+    else if (id > 0 && id < non_leaf_offset && id_code[id] >= 0) code = id_code[id];
+    else {
+        int64_t tmp = (int64_t)id - non_leaf_offset;
+        if (tmp > max_code) { m = 1; code = -1; }
+        else code = (int32_t)tmp;
+    }
+    if (code < -1 || (int64_t)code >= table_rows) { atomicExch(err_flag, 1); code = -1; }
+    codes[i] = code;
+    mask[i] = use_mask ? m : 0;
+}
+
+// OTM / generic: sequence entries are already embedding indices; mask where == -1.
+__global__ void seq_to_codes_kernel(const int32_t *__restrict__ seq, int64_t n, int64_t table_rows, int use_mask,
+                                    int32_t *__restrict__ codes, uint8_t *__restrict__ mask, int32_t *__restrict__ err_flag)
+{
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    int32_t c = seq[i];
+    if (c < -1 || (int64_t)c >= table_rows) { atomicExch(err_flag, 1); c = -1; }
+    codes[i] = c;
+    mask[i] = (use_mask && c == -1) ? 1 : 0;
+}
+
+}  // namespace dmg

@@ -1,0 +1,590 @@
+// capi.cu -- the C ABI of include/dismember_gpu.h: handle lifecycle, index/weight upload and
+// the retrieval entry points (TDM/JTM, OTM, model.forward).  Deep Retrieval lives in dr.cu,
+// training / JTM in train.cu.
+#include <algorithm>
+#include <cmath>
+#include <mutex>
+
+#include "beam_kernels.cuh"
+#include "rows_kernels.cuh"
+
+using namespace dmg;
+
+static std::string g_create_error;
+
+DMG_API const char *dmg_version(void) { return "dismember-b200 0.1 (sm_100a)"; }
+
+DMG_API const char *dmg_last_error(dmg_handle_t h) { return h ? h->err.c_str() : g_create_error.c_str(); }
+
+DMG_API int32_t dmg_create(int32_t device, dmg_handle_t *out)
+{
+    if (!out) return DMG_ERR_INVALID_ARG;
+    *out = nullptr;
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || n == 0) {
+        g_create_error = std::string("no CUDA device: ") + cudaGetErrorString(e) +
+                         " (this engine has no CPU fallback)";
+        return DMG_ERR_CUDA;
+    }
+    if (device < 0 || device >= n) { g_create_error = "device ordinal out of range"; return DMG_ERR_INVALID_ARG; }
+    dmg_handle_t h = new dmg_handle_s();
+    h->device = device;
+    cudaDeviceProp prop;
+    if ((e = cudaSetDevice(device)) != cudaSuccess || (e = cudaGetDeviceProperties(&prop, device)) != cudaSuccess ||
+        (e = cudaStreamCreateWithFlags(&h->own_stream, cudaStreamNonBlocking)) != cudaSuccess ||
+        (e = cudaMalloc(&h->d_flags, 64 * sizeof(int32_t))) != cudaSuccess ||
+        (e = cudaMemset(h->d_flags, 0, 64 * sizeof(int32_t))) != cudaSuccess) {
+        g_create_error = std::string("dmg_create: ") + cudaGetErrorString(e);
+        delete h;
+        return DMG_ERR_CUDA;
+    }
+    if (prop.major < 10) {
+        g_create_error = "dmg_create: device is not sm_100 (Blackwell) -- kernels are built for sm_100a only";
+        cudaStreamDestroy(h->own_stream); cudaFree(h->d_flags); delete h;
+        return DMG_ERR_UNSUPPORTED;
+    }
+    h->stream = h->own_stream;
+    h->sm_count = prop.multiProcessorCount;
+    h->smem_optin = prop.sharedMemPerBlockOptin;
+    *out = h;
+    return DMG_OK;
+}
+
+static void free_tree(TreeDev &t)
+{
+    cudaFree(t.d_exists); cudaFree(t.d_leaf_item); cudaFree(t.d_id_code);
+    t = TreeDev();
+}
+static void free_din(DinDev &d)
+{
+    cudaFree(d.d_params); cudaFree(d.d_wattT); cudaFree(d.d_w1T); cudaFree(d.d_grad); cudaFree(d.d_m); cudaFree(d.d_v);
+    d = DinDev();
+}
+void dmg_free_dr(DrDev &d);     // dr.cu
+
+DMG_API int32_t dmg_destroy(dmg_handle_t h)
+{
+    if (!h) return DMG_ERR_INVALID_ARG;
+    cudaSetDevice(h->device);
+    cudaStreamSynchronize(h->stream);
+    free_tree(h->tree);
+    free_din(h->din);
+    dmg_free_dr(h->dr);
+    for (Scratch *s : {&h->s_in, &h->s_out, &h->s_work}) { cudaFree(s->d); cudaFreeHost(s->h); }
+    for (auto &ev : h->prof_events) { cudaEventDestroy(ev.first); cudaEventDestroy(ev.second); }
+    cudaFree(h->d_flags);
+    cudaStreamDestroy(h->own_stream);
+    delete h;
+    return DMG_OK;
+}
+
+DMG_API int32_t dmg_set_stream(dmg_handle_t h, void *cuda_stream)
+{
+    if (!h) return DMG_ERR_INVALID_ARG;
+    h->stream = cuda_stream ? (cudaStream_t)cuda_stream : h->own_stream;
+    return DMG_OK;
+}
+
+DMG_API int32_t dmg_synchronize(dmg_handle_t h)
+{
+    if (!h) return DMG_ERR_INVALID_ARG;
+    DMG_CUDA(h, cudaSetDevice(h->device));
+    DMG_CUDA(h, cudaStreamSynchronize(h->stream));
+    return DMG_OK;
+}
+
+DMG_API int64_t dmg_launch_count(dmg_handle_t h) { return h ? h->launches : 0; }
+
+DMG_API int32_t dmg_set_profiling(dmg_handle_t h, int32_t on)
+{
+    if (!h) return DMG_ERR_INVALID_ARG;
+    h->profiling = on != 0;
+    return DMG_OK;
+}
+
+DMG_API int32_t dmg_kernel_time(dmg_handle_t h, double *total_ms, int64_t *n_launches)
+{
+    if (!h || !total_ms || !n_launches) return DMG_ERR_INVALID_ARG;
+    DMG_CUDA(h, cudaSetDevice(h->device));
+    DMG_CUDA(h, cudaStreamSynchronize(h->stream));
+    double tot = 0.0;
+    for (auto &ev : h->prof_events) {
+        float ms = 0.f;
+        DMG_CUDA(h, cudaEventElapsedTime(&ms, ev.first, ev.second));
+        tot += ms;
+        cudaEventDestroy(ev.first); cudaEventDestroy(ev.second);
+    }
+    *total_ms = tot;
+    *n_launches = (int64_t)h->prof_events.size();
+    h->prof_events.clear();
+    return DMG_OK;
+}
+
+// ------------------------------------------------------------------------------------- trees
+DMG_API int32_t dmg_load_tree_tdm(dmg_handle_t h, int32_t max_level, int64_t n_nodes, const int32_t *codes,
+                                  const int32_t *node_ids, const uint8_t *is_leaf, int64_t n_items,
+                                  const int32_t *leaf_ids, const int32_t *leaf_codes)
+{
+    if (!h) return DMG_ERR_INVALID_ARG;
+    if (max_level < 0 || max_level > 29 || n_nodes <= 0 || n_items <= 0 || !codes || !node_ids || !is_leaf ||
+        !leaf_ids || !leaf_codes)
+        return fail(h, DMG_ERR_INVALID_ARG, "dmg_load_tree_tdm: bad arguments (max_level must be in [0,29])");
+    DMG_CUDA(h, cudaSetDevice(h->device));
+    const int64_t n_codes = ((int64_t)1 << (max_level + 1)) - 1;
+    const int64_t leaf_start = ((int64_t)1 << max_level) - 1, n_slots = (int64_t)1 << max_level;
+    std::vector<uint32_t> bm((size_t)((n_codes + 31) / 32), 0u);
+    std::vector<int32_t> leaf_item((size_t)n_slots, -1);
+    for (int64_t i = 0; i < n_nodes; i++) {
+        const int64_t c = codes[i];
+        if (c < 0 || c >= n_codes)
+            return fail(h, DMG_ERR_INVALID_ARG, "dmg_load_tree_tdm: node code %lld outside [0, 2^(max_level+1)-1)", (long long)c);
+        bm[(size_t)(c >> 5)] |= 1u << (c & 31);
+        if (is_leaf[i]) {
+            if (c < leaf_start)
+                return fail(h, DMG_ERR_UNSUPPORTED,
+                            "dmg_load_tree_tdm: leaf code %lld lies above max_level %d; every writer of the format "
+                            "(TreeBuilder.flattenLeaves, JTMTree.writeTree) sinks leaves to max_level", (long long)c, max_level);
+            leaf_item[(size_t)(c - leaf_start)] = node_ids[i];
+        } else if (c >= leaf_start) {
+            return fail(h, DMG_ERR_UNSUPPORTED, "dmg_load_tree_tdm: non-leaf node %lld at max_level", (long long)c);
+        }
+    }
+    int32_t mx_id = -1, mx_code = -1;
+    for (int64_t i = 0; i < n_items; i++) { mx_id = std::max(mx_id, leaf_ids[i]); mx_code = std::max(mx_code, leaf_codes[i]); }
+    if (mx_id < 0) return fail(h, DMG_ERR_INVALID_ARG, "dmg_load_tree_tdm: no non-negative leaf id");
+    const int32_t offset = mx_id + 1;                                  // DistTree.scala:35
+    std::vector<int32_t> id_code((size_t)offset, -1);
+    for (int64_t i = 0; i < n_items; i++)
+        if (leaf_ids[i] >= 0) id_code[(size_t)leaf_ids[i]] = leaf_codes[i];
+    free_tree(h->tree);
+    TreeDev &t = h->tree;
+    DMG_CUDA(h, cudaMalloc(&t.d_exists, bm.size() * sizeof(uint32_t)));
+    DMG_CUDA(h, cudaMalloc(&t.d_leaf_item, leaf_item.size() * sizeof(int32_t)));
+    DMG_CUDA(h, cudaMalloc(&t.d_id_code, id_code.size() * sizeof(int32_t)));
+    DMG_CUDA(h, cudaMemcpy(t.d_exists, bm.data(), bm.size() * sizeof(uint32_t), cudaMemcpyHostToDevice));
+    DMG_CUDA(h, cudaMemcpy(t.d_leaf_item, leaf_item.data(), leaf_item.size() * sizeof(int32_t), cudaMemcpyHostToDevice));
+    DMG_CUDA(h, cudaMemcpy(t.d_id_code, id_code.data(), id_code.size() * sizeof(int32_t), cudaMemcpyHostToDevice));
+    t.loaded = true; t.complete = false; t.max_level = max_level; t.n_codes = n_codes;
+    t.non_leaf_offset = offset; t.max_code = mx_code; t.n_items = n_items;
+    return DMG_OK;
+}
+
+DMG_API int32_t dmg_load_tree_complete(dmg_handle_t h, int32_t leaf_level, int64_t n_items, const int32_t *item_ids,
+                                       const int32_t *leaf_ids)
+{
+    if (!h) return DMG_ERR_INVALID_ARG;
+    if (leaf_level < 0 || leaf_level > 29 || n_items <= 0 || !item_ids || !leaf_ids)
+        return fail(h, DMG_ERR_INVALID_ARG, "dmg_load_tree_complete: bad arguments");
+    DMG_CUDA(h, cudaSetDevice(h->device));
+    const int64_t leaf_start = ((int64_t)1 << leaf_level) - 1, n_slots = (int64_t)1 << leaf_level;
+    std::vector<int32_t> leaf_item((size_t)n_slots, -1);
+    for (int64_t i = 0; i < n_items; i++) {
+        const int64_t s = (int64_t)leaf_ids[i] - leaf_start;
+        if (s < 0 || s >= n_slots)
+            return fail(h, DMG_ERR_INVALID_ARG, "dmg_load_tree_complete: leaf id %d not on level %d", leaf_ids[i], leaf_level);
+        leaf_item[(size_t)s] = item_ids[i];
+    }
+    free_tree(h->tree);
+    TreeDev &t = h->tree;
+    DMG_CUDA(h, cudaMalloc(&t.d_leaf_item, leaf_item.size() * sizeof(int32_t)));
+    DMG_CUDA(h, cudaMemcpy(t.d_leaf_item, leaf_item.data(), leaf_item.size() * sizeof(int32_t), cudaMemcpyHostToDevice));
+    t.loaded = true; t.complete = true; t.max_level = leaf_level; t.n_codes = ((int64_t)1 << (leaf_level + 1)) - 1;
+    t.n_items = n_items;
+    return DMG_OK;
+}
+
+// ----------------------------------------------------------------------------------- weights
+template <typename real> static int32_t make_transposes(dmg_handle_t h)
+{
+    DinDev &d = h->din;
+    const int E = d.E;
+    DMG_CUDA(h, cudaMalloc(&d.d_wattT, sizeof(real) * E * E));
+    DMG_CUDA(h, cudaMalloc(&d.d_w1T, sizeof(real) * 2 * E * E));
+    transpose_kernel<real><<<(E * E + 255) / 256, 256, 0, h->stream>>>(d.watt<real>(), (real *)d.d_wattT, E, E);
+    transpose_kernel<real><<<(2 * E * E + 255) / 256, 256, 0, h->stream>>>(d.w1<real>(), (real *)d.d_w1T, E, 2 * E);
+    h->launches += 2;
+    DMG_CUDA(h, cudaGetLastError());
+    DMG_CUDA(h, cudaStreamSynchronize(h->stream));
+    return DMG_OK;
+}
+
+int32_t dmg_refresh_transposes(dmg_handle_t h)       // used by train.cu after an optimiser step
+{
+    DinDev &d = h->din;
+    const int E = d.E;
+    if (d.dtype == DMG_F32) {
+        transpose_kernel<float><<<(E * E + 255) / 256, 256, 0, h->stream>>>(d.watt<float>(), (float *)d.d_wattT, E, E);
+        transpose_kernel<float><<<(2 * E * E + 255) / 256, 256, 0, h->stream>>>(d.w1<float>(), (float *)d.d_w1T, E, 2 * E);
+    } else {
+        transpose_kernel<double><<<(E * E + 255) / 256, 256, 0, h->stream>>>(d.watt<double>(), (double *)d.d_wattT, E, E);
+        transpose_kernel<double><<<(2 * E * E + 255) / 256, 256, 0, h->stream>>>(d.w1<double>(), (double *)d.d_w1T, E, 2 * E);
+    }
+    h->launches += 2;
+    DMG_CUDA(h, cudaGetLastError());
+    return DMG_OK;
+}
+
+static int32_t alloc_din(dmg_handle_t h, int32_t dtype, int64_t rows, int32_t E, int32_t T)
+{
+    if (dtype != DMG_F32 && dtype != DMG_F64) return fail(h, DMG_ERR_INVALID_ARG, "dtype must be DMG_F32 or DMG_F64");
+    if (rows <= 0 || E <= 0 || T <= 0) return fail(h, DMG_ERR_INVALID_ARG, "rows, E, T must be positive");
+    if (T > kMaxT) return fail(h, DMG_ERR_UNSUPPORTED, "seq_len %d > %d", T, kMaxT);
+    if (E % 4 != 0 || E > 256) return fail(h, DMG_ERR_UNSUPPORTED, "embed_size %d: must be a multiple of 4, <= 256", E);
+    DMG_CUDA(h, cudaSetDevice(h->device));
+    free_din(h->din);
+    DinDev &d = h->din;
+    d.dtype = dtype; d.rows = rows; d.E = E; d.T = T; d.esz = dtype == DMG_F32 ? 4 : 8;
+    d.n_params = rows * E + (int64_t)E * E + (int64_t)2 * E * E + 2 * (int64_t)E + 1;
+    DMG_CUDA(h, cudaMalloc(&d.d_params, (size_t)d.n_params * d.esz));
+    return DMG_OK;
+}
+
+DMG_API int32_t dmg_load_din_weights(dmg_handle_t h, int32_t dtype, int64_t rows, int32_t E, int32_t T, const void *params)
+{
+    if (!h || !params) return h ? fail(h, DMG_ERR_INVALID_ARG, "dmg_load_din_weights: null params") : DMG_ERR_INVALID_ARG;
+    DMG_TRY(alloc_din(h, dtype, rows, E, T));
+    DinDev &d = h->din;
+    DMG_CUDA(h, cudaMemcpy(d.d_params, params, (size_t)d.n_params * d.esz, cudaMemcpyHostToDevice));
+    DMG_TRY(dtype == DMG_F32 ? make_transposes<float>(h) : make_transposes<double>(h));
+    d.loaded = true;
+    return DMG_OK;
+}
+
+DMG_API int32_t dmg_init_din_weights(dmg_handle_t h, int32_t dtype, int64_t rows, int32_t E, int32_t T, uint64_t seed)
+{
+    if (!h) return DMG_ERR_INVALID_ARG;
+    DMG_TRY(alloc_din(h, dtype, rows, E, T));
+    DinDev &d = h->din;
+    const int64_t n_rand = rows * E + (int64_t)E * E + (int64_t)2 * E * E;       // emb, W_att, W1
+    const int grid = h->sm_count * 8;
+    DMG_CUDA(h, cudaMemsetAsync(d.d_params, 0, (size_t)d.n_params * d.esz, h->stream));
+    if (dtype == DMG_F32) {
+        randn_fill_kernel<float><<<grid, 256, 0, h->stream>>>((float *)d.d_params, n_rand, seed, 0.05);
+        randn_fill_kernel<float><<<1, 256, 0, h->stream>>>(d.w2<float>(), E, seed ^ 0x5bd1e995u, 0.05);
+    } else {
+        randn_fill_kernel<double><<<grid, 256, 0, h->stream>>>((double *)d.d_params, n_rand, seed, 0.05);
+        randn_fill_kernel<double><<<1, 256, 0, h->stream>>>(d.w2<double>(), E, seed ^ 0x5bd1e995u, 0.05);
+    }
+    h->launches += 2;
+    DMG_CUDA(h, cudaGetLastError());
+    DMG_TRY(dtype == DMG_F32 ? make_transposes<float>(h) : make_transposes<double>(h));
+    d.loaded = true;
+    return DMG_OK;
+}
+
+DMG_API int32_t dmg_download_din_weights(dmg_handle_t h, void *params, int64_t n)
+{
+    if (!h || !params) return DMG_ERR_INVALID_ARG;
+    if (!h->din.loaded) return fail(h, DMG_ERR_STATE, "no DIN weights loaded");
+    if (n != h->din.n_params) return fail(h, DMG_ERR_INVALID_ARG, "expected %lld elements", (long long)h->din.n_params);
+    DMG_CUDA(h, cudaSetDevice(h->device));
+    DMG_CUDA(h, cudaStreamSynchronize(h->stream));
+    DMG_CUDA(h, cudaMemcpy(params, h->din.d_params, (size_t)n * h->din.esz, cudaMemcpyDeviceToHost));
+    return DMG_OK;
+}
+
+// --------------------------------------------------------------------------------- retrieval
+template <typename real, int E>
+static int32_t launch_beam_E(dmg_handle_t h, const BeamParams<real> &p)
+{
+    using G = Geo<real, E>;
+    const size_t smem = G::smem_bytes(p.cap, p.capp);
+    if (smem > h->smem_optin)
+        return fail(h, DMG_ERR_UNSUPPORTED, "beam too large: needs %zu B of shared memory per CTA (limit %zu)", smem, h->smem_optin);
+    auto kern = beam_search_kernel<real, E>;
+    DMG_CUDA(h, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const int grid = std::min(p.B, h->sm_count);
+    cudaEvent_t e0 = nullptr, e1 = nullptr;
+    if (h->profiling) {
+        DMG_CUDA(h, cudaEventCreate(&e0));
+        DMG_CUDA(h, cudaEventCreate(&e1));
+        DMG_CUDA(h, cudaEventRecord(e0, h->stream));
+    }
+    kern<<<grid, kThreads, smem, h->stream>>>(p);
+    h->launches += 1;
+    DMG_CUDA(h, cudaGetLastError());
+    if (h->profiling) {
+        DMG_CUDA(h, cudaEventRecord(e1, h->stream));
+        h->prof_events.emplace_back(e0, e1);
+    }
+    return DMG_OK;
+}
+
+template <typename real> static int32_t launch_beam(dmg_handle_t h, const BeamParams<real> &p, int E)
+{
+    switch (E) {
+        case 16: return launch_beam_E<real, 16>(h, p);
+        case 32: return launch_beam_E<real, 32>(h, p);
+        case 64: return launch_beam_E<real, 64>(h, p);
+        default:
+            return fail(h, DMG_ERR_UNSUPPORTED, "beam search kernels are built for embed_size 16, 32 and 64 (got %d)", E);
+    }
+}
+
+template <typename real> static void fill_scorer(const DinDev &d, BeamParams<real> &p)
+{
+    p.emb = d.emb<real>(); p.wattT = (const real *)d.d_wattT; p.w1T = (const real *)d.d_w1T;
+    p.b1 = d.b1<real>(); p.w2 = d.w2<real>(); p.b2 = d.b2<real>();
+    p.scale = (real)(1.0 / std::sqrt((double)d.E));                      // Mask.scala:12
+    p.T = d.T;
+}
+
+static int pow2_ge(int n) { int p = 2; while (p < n) p <<= 1; return p; }
+static int lower_log2(int n) { int l = 0; while ((2 << l) <= n) l++; return l; }   // == floor(log(n)/log(2)) for n >= 1
+
+static int32_t check_flag(dmg_handle_t h, const char *what)
+{
+    int32_t flag = 0;
+    DMG_CUDA(h, cudaMemcpyAsync(&flag, h->d_flags, sizeof(int32_t), cudaMemcpyDeviceToHost, h->stream));
+    DMG_CUDA(h, cudaStreamSynchronize(h->stream));
+    if (flag) {
+        DMG_CUDA(h, cudaMemsetAsync(h->d_flags, 0, sizeof(int32_t), h->stream));
+        return fail(h, DMG_ERR_INDEX, "%s: embeddingLookup failed, index outside [0, %lld)", what, (long long)h->din.rows);
+    }
+    return DMG_OK;
+}
+
+// Enqueue K2 + K1 for a TDM batch whose inputs already sit on the device.
+static int32_t tdm_enqueue(dmg_handle_t h, int32_t B, const int32_t *d_seq, int32_t beam, int max_beam,
+                           const int32_t *d_beam_user, int32_t topk, int32_t use_mask, const int64_t *d_cons_off,
+                           const int32_t *d_cons, int32_t *d_items, float *d_logits, int32_t *d_counts)
+{
+    const DinDev &d = h->din;
+    const TreeDev &t = h->tree;
+    const int T = d.T;
+    DMG_TRY(ensure_dev(h, h->s_work, Carver::need({(size_t)B * T * 4, (size_t)B * T})));
+    Carver cw(h->s_work.d);
+    int32_t *d_codes = cw.take<int32_t>((size_t)B * T);
+    uint8_t *d_mask = cw.take<uint8_t>((size_t)B * T);
+    const int64_t n = (int64_t)B * T;
+    tdm_ids_to_codes_kernel<<<(unsigned)((n + 255) / 256), 256, 0, h->stream>>>(
+        d_seq, n, t.d_id_code, t.non_leaf_offset, t.max_code, d.rows, use_mask, d_codes, d_mask, h->d_flags);
+    h->launches += 1;
+    DMG_CUDA(h, cudaGetLastError());
+    BeamParams<float> p;
+    memset(&p, 0, sizeof(p));
+    fill_scorer(d, p);
+    p.B = B; p.hist = d_codes; p.hist_mask = d_mask; p.beam = beam; p.beam_user = d_beam_user;
+    p.always_sort = 0; p.exists = t.complete ? nullptr : t.d_exists; p.leaf_level = t.max_level;
+    p.mode = MODE_TDM_TOPK; p.topk = topk; p.leaf_item = t.d_leaf_item; p.cons_off = d_cons_off; p.cons = d_cons;
+    p.out_items = d_items; p.out_scores = d_logits; p.out_counts = d_counts; p.out_stride = topk;
+    p.cap = std::max(((2 * max_beam + 7) / 8) * 8, 8);
+    p.cap = std::max(p.cap, ((topk + 7) / 8) * 8);
+    p.capp = pow2_ge(p.cap);
+    return launch_beam<float>(h, p, d.E);
+}
+
+static int32_t tdm_precheck(dmg_handle_t h, int32_t B, int32_t beam, int32_t topk)
+{
+    if (!h) return DMG_ERR_INVALID_ARG;
+    if (!h->tree.loaded || !h->din.loaded) return fail(h, DMG_ERR_STATE, "tree and DIN weights must be loaded first");
+    if (h->tree.complete || !h->tree.d_id_code) return fail(h, DMG_ERR_STATE, "dmg_tdm_retrieve needs a tree loaded with dmg_load_tree_tdm");
+    if (h->din.dtype != DMG_F32) return fail(h, DMG_ERR_STATE, "TDM/JTM scorer is Module[Float]: load DMG_F32 weights");
+    if (B <= 0 || beam <= 0 || topk <= 0) return fail(h, DMG_ERR_INVALID_ARG, "B, beam and topk must be positive");  // require(candidateNum > 0)
+    if (h->din.rows < h->tree.n_codes)
+        return fail(h, DMG_ERR_INVALID_ARG, "node table has %lld rows, tree needs %lld", (long long)h->din.rows, (long long)h->tree.n_codes);
+    return DMG_OK;
+}
+
+DMG_API int32_t dmg_tdm_retrieve_dev(dmg_handle_t h, int32_t B, const int32_t *d_item_seq, int32_t beam, int32_t topk,
+                                     int32_t use_mask, int32_t *d_out_items, float *d_out_logits, int32_t *d_out_counts)
+{
+    DMG_TRY(tdm_precheck(h, B, beam, topk));
+    if (!d_item_seq || !d_out_items || !d_out_logits || !d_out_counts) return fail(h, DMG_ERR_INVALID_ARG, "null device pointer");
+    DMG_CUDA(h, cudaSetDevice(h->device));
+    return tdm_enqueue(h, B, d_item_seq, beam, beam, nullptr, topk, use_mask, nullptr, nullptr, d_out_items, d_out_logits, d_out_counts);
+}
+
+DMG_API int32_t dmg_tdm_retrieve(dmg_handle_t h, int32_t B, const int32_t *item_seq, int32_t beam, int32_t topk,
+                                 int32_t use_mask, const int64_t *consumed_off, const int32_t *consumed_items,
+                                 int32_t widen_beam, int32_t *out_items, float *out_logits, int32_t *out_counts)
+{
+    DMG_TRY(tdm_precheck(h, B, beam, topk));
+    if (!item_seq || !out_items || !out_logits || !out_counts) return fail(h, DMG_ERR_INVALID_ARG, "null host pointer");
+    if (consumed_off && !consumed_items && consumed_off[B] > 0) return fail(h, DMG_ERR_INVALID_ARG, "consumed_items is null");
+    DMG_CUDA(h, cudaSetDevice(h->device));
+    const int T = h->din.T;
+    const int64_t n_cons = consumed_off ? consumed_off[B] : 0;
+    const bool per_user = consumed_off && widen_beam;
+    // pinned staging: [seq | cons_off | cons | beam_user]
+    const size_t b_seq = (size_t)B * T * 4, b_off = consumed_off ? (size_t)(B + 1) * 8 : 0, b_cons = (size_t)n_cons * 4,
+                 b_beam = per_user ? (size_t)B * 4 : 0;
+    const size_t in_bytes = Carver::need({b_seq, b_off, b_cons, b_beam});
+    DMG_TRY(ensure_host(h, h->s_in, in_bytes));
+    DMG_TRY(ensure_dev(h, h->s_in, in_bytes));
+    Carver ch(h->s_in.h), cd(h->s_in.d);
+    int32_t *hs = ch.take<int32_t>((size_t)B * T), *ds = cd.take<int32_t>((size_t)B * T);
+    int64_t *ho = ch.take<int64_t>(consumed_off ? B + 1 : 0), *dof = cd.take<int64_t>(consumed_off ? B + 1 : 0);
+    int32_t *hc = ch.take<int32_t>((size_t)n_cons), *dc = cd.take<int32_t>((size_t)n_cons);
+    int32_t *hb = ch.take<int32_t>(per_user ? B : 0), *db = cd.take<int32_t>(per_user ? B : 0);
+    memcpy(hs, item_seq, b_seq);
+    int max_beam = beam;
+    if (consumed_off) {
+        memcpy(ho, consumed_off, b_off);
+        if (n_cons) memcpy(hc, consumed_items, b_cons);
+        if (per_user)
+            for (int u = 0; u < B; u++) {                                   // Recommender.scala:28-31
+                const int w = (int)((consumed_off[u + 1] - consumed_off[u] + topk) / 2);
+                hb[u] = std::max(w, beam);
+                max_beam = std::max(max_beam, hb[u]);
+            }
+    }
+    DMG_CUDA(h, cudaMemcpyAsync(h->s_in.d, h->s_in.h, ch.off, cudaMemcpyHostToDevice, h->stream));
+    const size_t out_bytes = Carver::need({(size_t)B * topk * 4, (size_t)B * topk * 4, (size_t)B * 4});
+    DMG_TRY(ensure_host(h, h->s_out, out_bytes));
+    DMG_TRY(ensure_dev(h, h->s_out, out_bytes));
+    Carver oh(h->s_out.h), od(h->s_out.d);
+    int32_t *h_items = oh.take<int32_t>((size_t)B * topk), *d_items = od.take<int32_t>((size_t)B * topk);
+    float *h_log = oh.take<float>((size_t)B * topk), *d_log = od.take<float>((size_t)B * topk);
+    int32_t *h_cnt = oh.take<int32_t>(B), *d_cnt = od.take<int32_t>(B);
+    DMG_TRY(tdm_enqueue(h, B, ds, beam, max_beam, per_user ? db : nullptr, topk, use_mask, consumed_off ? dof : nullptr,
+                        consumed_off ? dc : nullptr, d_items, d_log, d_cnt));
+    DMG_CUDA(h, cudaMemcpyAsync(h->s_out.h, h->s_out.d, od.off, cudaMemcpyDeviceToHost, h->stream));
+    DMG_TRY(check_flag(h, "dmg_tdm_retrieve"));
+    memcpy(out_items, h_items, (size_t)B * topk * 4);
+    memcpy(out_logits, h_log, (size_t)B * topk * 4);
+    memcpy(out_counts, h_cnt, (size_t)B * 4);
+    return DMG_OK;
+}
+
+// OTM: batchBeamSearch (dump) and recommend (topk) share one path.
+static int32_t otm_run(dmg_handle_t h, int32_t B, const int32_t *leaf_seq, int32_t beam, int32_t use_mask, int mode,
+                       int32_t topk, int32_t *out_ids, double *out_scores, int32_t *out_counts)
+{
+    if (!h) return DMG_ERR_INVALID_ARG;
+    if (!h->tree.loaded || !h->din.loaded) return fail(h, DMG_ERR_STATE, "tree and DIN weights must be loaded first");
+    if (!h->tree.complete) return fail(h, DMG_ERR_STATE, "OTM needs a complete tree (dmg_load_tree_complete)");
+    if (h->din.dtype != DMG_F64) return fail(h, DMG_ERR_STATE, "OTM scorer is DeepModel[Double]: load DMG_F64 weights");
+    if (B <= 0 || beam <= 0 || (mode == MODE_OTM_TOPK && topk <= 0) || !leaf_seq || !out_ids || !out_scores || !out_counts)
+        return fail(h, DMG_ERR_INVALID_ARG, "bad arguments");
+    if (h->din.rows < h->tree.n_codes)
+        return fail(h, DMG_ERR_INVALID_ARG, "node table has %lld rows, tree needs %lld", (long long)h->din.rows, (long long)h->tree.n_codes);
+    DMG_CUDA(h, cudaSetDevice(h->device));
+    const DinDev &d = h->din;
+    const TreeDev &t = h->tree;
+    const int T = d.T;
+    const int s = lower_log2(beam);
+    const int width = 2 * std::max(beam, 1 << s);                      // entries per user in dump mode
+    const int stride = mode == MODE_OTM_DUMP ? width : topk;
+    const size_t b_seq = (size_t)B * T * 4;
+    DMG_TRY(ensure_host(h, h->s_in, b_seq));
+    DMG_TRY(ensure_dev(h, h->s_in, b_seq));
+    memcpy(h->s_in.h, leaf_seq, b_seq);
+    DMG_CUDA(h, cudaMemcpyAsync(h->s_in.d, h->s_in.h, b_seq, cudaMemcpyHostToDevice, h->stream));
+    DMG_TRY(ensure_dev(h, h->s_work, Carver::need({(size_t)B * T * 4, (size_t)B * T})));
+    Carver cw(h->s_work.d);
+    int32_t *d_codes = cw.take<int32_t>((size_t)B * T);
+    uint8_t *d_mask = cw.take<uint8_t>((size_t)B * T);
+    const int64_t n = (int64_t)B * T;
+    seq_to_codes_kernel<<<(unsigned)((n + 255) / 256), 256, 0, h->stream>>>((const int32_t *)h->s_in.d, n, d.rows, use_mask,
+                                                                            d_codes, d_mask, h->d_flags);
+    h->launches += 1;
+    DMG_CUDA(h, cudaGetLastError());
+    const size_t out_bytes = Carver::need({(size_t)B * stride * 4, (size_t)B * stride * 8, (size_t)B * 4});
+    DMG_TRY(ensure_host(h, h->s_out, out_bytes));
+    DMG_TRY(ensure_dev(h, h->s_out, out_bytes));
+    Carver oh(h->s_out.h), od(h->s_out.d);
+    int32_t *h_ids = oh.take<int32_t>((size_t)B * stride), *d_ids = od.take<int32_t>((size_t)B * stride);
+    double *h_sc = oh.take<double>((size_t)B * stride), *d_sc = od.take<double>((size_t)B * stride);
+    int32_t *h_cnt = oh.take<int32_t>(B), *d_cnt = od.take<int32_t>(B);
+    BeamParams<double> p;
+    memset(&p, 0, sizeof(p));
+    fill_scorer(d, p);
+    p.B = B; p.hist = d_codes; p.hist_mask = d_mask; p.beam = beam; p.beam_user = nullptr;
+    p.always_sort = 1; p.exists = nullptr; p.leaf_level = t.max_level;
+    p.mode = mode; p.topk = topk; p.leaf_item = t.d_leaf_item;
+    p.out_items = d_ids; p.out_scores = d_sc; p.out_counts = d_cnt; p.out_stride = stride;
+    p.cap = std::max(((width + 7) / 8) * 8, 8);
+    p.cap = std::max(p.cap, ((std::max(topk, 1) + 7) / 8) * 8);
+    p.capp = pow2_ge(p.cap);
+    DMG_TRY(launch_beam<double>(h, p, d.E));
+    DMG_CUDA(h, cudaMemcpyAsync(h->s_out.h, h->s_out.d, od.off, cudaMemcpyDeviceToHost, h->stream));
+    DMG_TRY(check_flag(h, "dmg_otm"));
+    memcpy(out_ids, h_ids, (size_t)B * stride * 4);
+    memcpy(out_scores, h_sc, (size_t)B * stride * 8);
+    memcpy(out_counts, h_cnt, (size_t)B * 4);
+    return DMG_OK;
+}
+
+DMG_API int32_t dmg_otm_beam_search(dmg_handle_t h, int32_t B, const int32_t *leaf_seq, int32_t beam, int32_t use_mask,
+                                    int32_t *out_ids, double *out_scores, int32_t *out_counts)
+{
+    return otm_run(h, B, leaf_seq, beam, use_mask, MODE_OTM_DUMP, 0, out_ids, out_scores, out_counts);
+}
+
+DMG_API int32_t dmg_otm_retrieve(dmg_handle_t h, int32_t B, const int32_t *leaf_seq, int32_t beam, int32_t topk,
+                                 int32_t use_mask, int32_t *out_items, double *out_scores, int32_t *out_counts)
+{
+    return otm_run(h, B, leaf_seq, beam, use_mask, MODE_OTM_TOPK, topk, out_items, out_scores, out_counts);
+}
+
+// model.forward on n rows
+DMG_API int32_t dmg_score_pairs(dmg_handle_t h, int64_t n, const int32_t *node, const int32_t *seq, const int32_t *mask_flat,
+                                int64_t n_mask, void *out)
+{
+    if (!h) return DMG_ERR_INVALID_ARG;
+    if (!h->din.loaded) return fail(h, DMG_ERR_STATE, "DIN weights must be loaded first");
+    if (n < 0 || n_mask < 0 || (n > 0 && (!node || !seq || !out)) || (n_mask > 0 && !mask_flat))
+        return fail(h, DMG_ERR_INVALID_ARG, "bad arguments");
+    if (n == 0) return DMG_OK;
+    DMG_CUDA(h, cudaSetDevice(h->device));
+    const DinDev &d = h->din;
+    const int T = d.T, E = d.E;
+    const size_t b_node = (size_t)n * 4, b_seq = (size_t)n * T * 4, b_mask = (size_t)n_mask * 4;
+    const size_t in_bytes = Carver::need({b_node, b_seq, b_mask});
+    DMG_TRY(ensure_host(h, h->s_in, in_bytes));
+    DMG_TRY(ensure_dev(h, h->s_in, in_bytes));
+    Carver ch(h->s_in.h), cd(h->s_in.d);
+    int32_t *hn = ch.take<int32_t>((size_t)n), *dn = cd.take<int32_t>((size_t)n);
+    int32_t *hs = ch.take<int32_t>((size_t)n * T), *ds = cd.take<int32_t>((size_t)n * T);
+    int32_t *hm = ch.take<int32_t>((size_t)n_mask), *dm = cd.take<int32_t>((size_t)n_mask);
+    memcpy(hn, node, b_node); memcpy(hs, seq, b_seq);
+    if (n_mask) memcpy(hm, mask_flat, b_mask);
+    DMG_CUDA(h, cudaMemcpyAsync(h->s_in.d, h->s_in.h, ch.off, cudaMemcpyHostToDevice, h->stream));
+    DMG_TRY(ensure_dev(h, h->s_work, Carver::need({(size_t)n * T})));
+    uint8_t *d_mask = (uint8_t *)h->s_work.d;
+    DMG_CUDA(h, cudaMemsetAsync(d_mask, 0, (size_t)n * T, h->stream));
+    if (n_mask) {
+        mask_scatter_kernel<<<(unsigned)((n_mask + 255) / 256), 256, 0, h->stream>>>(dm, n_mask, n * T, d_mask, h->d_flags);
+        h->launches += 1;
+    }
+    check_index_kernel<<<(unsigned)((n + 255) / 256), 256, 0, h->stream>>>(dn, n, d.rows, h->d_flags);
+    check_index_kernel<<<(unsigned)((n * T + 255) / 256), 256, 0, h->stream>>>(ds, n * T, d.rows, h->d_flags);
+    h->launches += 2;
+    DMG_CUDA(h, cudaGetLastError());
+    int32_t flag = 0;
+    DMG_CUDA(h, cudaMemcpyAsync(&flag, h->d_flags, 4, cudaMemcpyDeviceToHost, h->stream));
+    DMG_CUDA(h, cudaStreamSynchronize(h->stream));
+    if (flag) {
+        DMG_CUDA(h, cudaMemsetAsync(h->d_flags, 0, 4, h->stream));
+        return fail(h, DMG_ERR_INDEX, "dmg_score_pairs: embeddingLookup failed, index outside [0, %lld) or bad mask position", (long long)d.rows);
+    }
+    const size_t out_bytes = (size_t)n * d.esz;
+    DMG_TRY(ensure_host(h, h->s_out, out_bytes));
+    DMG_TRY(ensure_dev(h, h->s_out, out_bytes));
+    const size_t smem = (size_t)kRowsRB * ((size_t)4 * E + (size_t)T * E + T + 1) * d.esz;
+    const int grid = (int)std::min<int64_t>((n + kRowsRB - 1) / kRowsRB, (int64_t)h->sm_count * 8);
+    if (d.dtype == DMG_F32) {
+        auto kern = din_rows_forward_kernel<float>;
+        DMG_CUDA(h, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        kern<<<grid, kRowsThreads, smem, h->stream>>>(d.emb<float>(), (const float *)d.d_wattT, (const float *)d.d_w1T,
+                                                      d.b1<float>(), d.w2<float>(), d.b2<float>(),
+                                                      (float)(1.0 / std::sqrt((double)E)), E, T, n, dn, ds, d_mask,
+                                                      (float *)h->s_out.d);
+    } else {
+        auto kern = din_rows_forward_kernel<double>;
+        DMG_CUDA(h, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        kern<<<grid, kRowsThreads, smem, h->stream>>>(d.emb<double>(), (const double *)d.d_wattT, (const double *)d.d_w1T,
+                                                      d.b1<double>(), d.w2<double>(), d.b2<double>(),
+                                                      1.0 / std::sqrt((double)E), E, T, n, dn, ds, d_mask,
+                                                      (double *)h->s_out.d);
+    }
+    h->launches += 1;
+    DMG_CUDA(h, cudaGetLastError());
+    DMG_CUDA(h, cudaMemcpyAsync(h->s_out.h, h->s_out.d, out_bytes, cudaMemcpyDeviceToHost, h->stream));
+    DMG_CUDA(h, cudaStreamSynchronize(h->stream));
+    memcpy(out, h->s_out.h, out_bytes);
+    return DMG_OK;
+}
+

@@ -1,0 +1,156 @@
+// dmg_common.cuh -- handle, error plumbing and small device helpers.
+#pragma once
+#include <cstdarg>
+#include <cstdint>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include <cuda_runtime.h>
+
+#include "../../include/dismember_gpu.h"
+
+namespace dmg {
+
+constexpr int kMaxT = 16;          // history length supported by the fused kernels (reference: 10)
+constexpr int kThreads = 256;      // CTA size of the beam-search / scorer kernels
+
+// ---- device-side index structures -------------------------------------------------------
+struct TreeDev {
+    bool loaded = false;
+    bool complete = false;         // OTM / synthetic complete tree: every code exists
+    int max_level = 0;             // leaf level L
+    int64_t n_codes = 0;           // 2^(L+1)-1
+    uint32_t *d_exists = nullptr;  // bitmap over codes (null when complete)
+    int32_t *d_leaf_item = nullptr;  // [2^L] item id held by leaf slot, -1 = empty
+    int32_t *d_id_code = nullptr;  // TDM: [non_leaf_offset] item id -> code, -1 = unknown
+    int32_t non_leaf_offset = 0;   // DistTree.scala:35
+    int32_t max_code = -1;         // DistTree.scala:36
+    int64_t n_items = 0;
+};
+
+struct DinDev {
+    bool loaded = false;
+    int dtype = DMG_F32;
+    int64_t rows = 0;
+    int E = 0, T = 0;
+    size_t esz = 4;
+    void *d_params = nullptr;      // compact vector [emb | Watt | W1 | b1 | W2 | b2]
+    void *d_wattT = nullptr;       // k-major copies  WattT[k][o], W1T[k][o]
+    void *d_w1T = nullptr;
+    int64_t n_params = 0;
+    // training state (allocated lazily)
+    void *d_grad = nullptr, *d_m = nullptr, *d_v = nullptr;
+    template <typename real> real *emb() const { return (real *)d_params; }
+    template <typename real> real *watt() const { return (real *)d_params + rows * E; }
+    template <typename real> real *w1() const { return watt<real>() + (int64_t)E * E; }
+    template <typename real> real *b1() const { return w1<real>() + (int64_t)2 * E * E; }
+    template <typename real> real *w2() const { return b1<real>() + E; }
+    template <typename real> real *b2() const { return w2<real>() + E; }
+};
+
+struct DrDev {
+    bool loaded = false, paths_loaded = false;
+    int num_item = 0, K = 0, D = 0, T = 0, E = 0;
+    double *d_layer_emb = nullptr;
+    std::vector<double *> d_layer_w, d_layer_b;     // device pointers per layer
+    std::vector<double *> d_layer_wT;               // in-major copies [in][K]
+    double *d_rr_emb = nullptr, *d_rr_w = nullptr, *d_rr_b = nullptr, *d_sm_w = nullptr, *d_sm_b = nullptr;
+    int64_t *d_path_off = nullptr;
+    int32_t *d_path_items = nullptr;
+    std::vector<int64_t> h_path_off;                // kept for output sizing
+};
+
+struct Scratch {                    // grow-only device / pinned buffers
+    void *d = nullptr; size_t d_bytes = 0;
+    void *h = nullptr; size_t h_bytes = 0;
+};
+
+}  // namespace dmg
+
+struct dmg_handle_s {
+    int device = 0;
+    cudaStream_t own_stream = nullptr;
+    cudaStream_t stream = nullptr;
+    int sm_count = 0;
+    size_t smem_optin = 0;
+    std::string err;
+    int64_t launches = 0;
+    dmg::TreeDev tree;
+    dmg::DinDev din;
+    dmg::DrDev dr;
+    dmg::Scratch s_in, s_out, s_work;
+    int32_t *d_flags = nullptr;     // [0] = index error flag, [1] = work counter
+    bool profiling = false;
+    std::vector<std::pair<cudaEvent_t, cudaEvent_t>> prof_events;
+};
+
+namespace dmg {
+
+inline int32_t fail(dmg_handle_t h, int32_t code, const char *fmt, ...)
+{
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof(buf), fmt, ap);
+    va_end(ap);
+    if (h) h->err = buf;
+    return code;
+}
+
+#define DMG_CUDA(h, expr)                                                                         \
+    do {                                                                                          \
+        cudaError_t e_ = (expr);                                                                  \
+        if (e_ != cudaSuccess)                                                                    \
+            return dmg::fail(h, DMG_ERR_CUDA, "%s failed: %s (%s:%d)", #expr,                    \
+                             cudaGetErrorString(e_), __FILE__, __LINE__);                         \
+    } while (0)
+
+#define DMG_TRY(expr)                                                                             \
+    do {                                                                                          \
+        int32_t rc_ = (expr);                                                                     \
+        if (rc_ != DMG_OK) return rc_;                                                            \
+    } while (0)
+
+inline int32_t ensure_dev(dmg_handle_t h, Scratch &s, size_t bytes)
+{
+    if (bytes <= s.d_bytes) return DMG_OK;
+    if (s.d) cudaFree(s.d);
+    s.d = nullptr; s.d_bytes = 0;
+    size_t want = bytes + bytes / 4 + 256;
+    DMG_CUDA(h, cudaMalloc(&s.d, want));
+    s.d_bytes = want;
+    return DMG_OK;
+}
+
+inline int32_t ensure_host(dmg_handle_t h, Scratch &s, size_t bytes)
+{
+    if (bytes <= s.h_bytes) return DMG_OK;
+    if (s.h) cudaFreeHost(s.h);
+    s.h = nullptr; s.h_bytes = 0;
+    size_t want = bytes + bytes / 4 + 256;
+    DMG_CUDA(h, cudaMallocHost(&s.h, want));
+    s.h_bytes = want;
+    return DMG_OK;
+}
+
+// Bump allocator over one scratch block (256 B aligned slices).
+struct Carver {
+    char *base; size_t off = 0;
+    explicit Carver(void *p) : base((char *)p) {}
+    template <typename T> T *take(size_t n)
+    {
+        T *p = (T *)(base + off);
+        off += (n * sizeof(T) + 255) & ~(size_t)255;
+        return p;
+    }
+    static size_t need(std::initializer_list<size_t> bytes)
+    {
+        size_t t = 0;
+        for (size_t b : bytes) t += (b + 255) & ~(size_t)255;
+        return t;
+    }
+};
+
+}  // namespace dmg

@@ -1,0 +1,203 @@
+/*
+ * dismember_gpu.h -- C ABI of the B200-native retrieval engine (libdismember_gpu.so).
+ *
+ * Drop-in boundary for ONE path of massquantity/dismember: level-synchronous
+ * beam search over the TDM/JTM/OTM binary tree and Deep Retrieval's K^D paths,
+ * the DIN scorer behind it, its training step and the JTM re-assignment scores.
+ * The reference has no FFI of its own on this path -- the seam is the Scala call
+ * `model.forward(features)` made once per tree level by the searchers and, one
+ * level up, recommend/_recommend/batchBeamSearch.  Every entry point below names
+ * the reference interface it replaces (paths relative to the reference root).
+ * The JNI shim (jni/com_mass_gpu_DismemberGPU.c) and the ctypes binding
+ * (dismember_b200/_capi.py) bind exactly these symbols; see INTEGRATION.md.
+ *
+ * Conventions
+ *  - every function returns int32 status: 0 = DMG_OK, <0 = error; the message
+ *    is available from dmg_last_error(h).  No exception crosses the boundary.
+ *  - plain pointers and sizes only.  Unless a name ends in _dev, pointers are
+ *    HOST memory owned by the caller; the library copies in/out and returns
+ *    after the results are complete.  *_dev variants take DEVICE pointers,
+ *    enqueue on the handle's stream and return without synchronising.
+ *  - a handle is bound to one CUDA device + one stream and is NOT thread-safe:
+ *    one handle per host thread, mirroring "one model clone per thread"
+ *    (tdm/src/main/scala/com/mass/tdm/optim/LocalOptimizer.scala:35-40).
+ *  - there is no CPU fallback: without a CUDA device dmg_create fails.
+ */
+#ifndef DISMEMBER_GPU_H
+#define DISMEMBER_GPU_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#if defined(_WIN32)
+#define DMG_API __declspec(dllexport)
+#else
+#define DMG_API __attribute__((visibility("default")))
+#endif
+
+typedef struct dmg_handle_s *dmg_handle_t;
+
+enum {
+    DMG_OK = 0,
+    DMG_ERR_INVALID_ARG = -1,  /* IllegalArgumentException / require(...) failures          */
+    DMG_ERR_CUDA = -2,         /* CUDA runtime error (message holds cudaGetErrorString)      */
+    DMG_ERR_INDEX = -3,        /* ArrayIndexOutOfBoundsException of LookupTable.scala:46-52  */
+    DMG_ERR_STATE = -4,        /* tree / weights not loaded yet                              */
+    DMG_ERR_UNSUPPORTED = -5,  /* shape outside what the kernels are built for               */
+    DMG_ERR_NOMEM = -6
+};
+
+enum { DMG_F32 = 0, DMG_F64 = 1 };
+
+/* ---- lifecycle ------------------------------------------------------------------------ */
+DMG_API int32_t dmg_create(int32_t device, dmg_handle_t *out);
+DMG_API int32_t dmg_destroy(dmg_handle_t h);
+DMG_API const char *dmg_last_error(dmg_handle_t h);      /* h may be NULL: last create error   */
+DMG_API const char *dmg_version(void);
+/* Use a caller-owned cudaStream_t (e.g. the framework's current stream) instead of the
+ * handle's own; pass NULL to go back.  Lets callers time with their own CUDA events. */
+DMG_API int32_t dmg_set_stream(dmg_handle_t h, void *cuda_stream);
+DMG_API int32_t dmg_synchronize(dmg_handle_t h);
+/* number of kernels this handle has launched so far (bench.py's gpu_launches). */
+DMG_API int64_t dmg_launch_count(dmg_handle_t h);
+/* Optional per-kernel timing of the dominant (beam-search) kernel: when on, every launch is
+ * bracketed by CUDA events on the launching stream.  dmg_kernel_time synchronises, returns
+ * the accumulated milliseconds and launch count since the last call, and resets both. */
+DMG_API int32_t dmg_set_profiling(dmg_handle_t h, int32_t on);
+DMG_API int32_t dmg_kernel_time(dmg_handle_t h, double *total_ms, int64_t *n_launches);
+
+/* ---- index structures ----------------------------------------------------------------- */
+/* TDM/JTM tree = the maps DistTree.loadData/loadItems build
+ * (tdm/src/main/scala/com/mass/tdm/tree/DistTree.scala:25-87): one entry per stored node
+ * (codes/node_ids/is_leaf = codeNodeMap) and the Part_* leaf (id, code) pairs (idCodeMap).
+ * nonLeafOffset = max(leaf id)+1 and maxCode = max(leaf code) are derived as in :35-36.
+ * All writers of the format put every leaf at max_level (TreeBuilder.flattenLeaves
+ * TreeBuilder.scala:133-140, JTMTree.writeTree JTMTree.scala:115-182); a tree with a leaf
+ * above max_level is rejected with DMG_ERR_UNSUPPORTED. */
+DMG_API int32_t dmg_load_tree_tdm(dmg_handle_t h, int32_t max_level, int64_t n_nodes,
+                                  const int32_t *codes, const int32_t *node_ids,
+                                  const uint8_t *is_leaf, int64_t n_items,
+                                  const int32_t *leaf_ids, const int32_t *leaf_codes);
+
+/* OTM: complete binary tree; itemIdMapping item -> leaf node id
+ * (otm/src/main/scala/com/mass/otm/model/OTM.scala:6-12, Serialization.loadMapping).
+ * leaf_level = upperLog2(n_items) (OTM.scala:12). */
+DMG_API int32_t dmg_load_tree_complete(dmg_handle_t h, int32_t leaf_level, int64_t n_items,
+                                       const int32_t *item_ids, const int32_t *leaf_ids);
+
+/* ---- DIN scorer weights --------------------------------------------------------------- */
+/* The compact parameter vector of Module.parameters()/adjustParameters()
+ * (scalann/.../nn/graphnn/Graph.scala:37-48, nn/abstractnn/AbstractModule.scala:163):
+ *   [ emb rows*E | W_att E*E | W1 E*2E | b1 E | W2 E | b2 1 ]  row-major [out,in],
+ * dtype DMG_F32 (tdm/jtm DIN.buildModel[Float]) or DMG_F64 (otm DIN.buildModel[Double]).
+ * rows = numIndex of EmbeddingShare (tdm DIN.scala:18: 2^(maxLevel+1)-1).  T = seq_len. */
+DMG_API int32_t dmg_load_din_weights(dmg_handle_t h, int32_t dtype, int64_t rows, int32_t E,
+                                     int32_t T, const void *params);
+/* Same, node table initialised on the device like EmbeddingShare/Linear do at construction
+ * (randn(0, 0.05), biases 0: EmbeddingShare.scala:21, Linear.scala:12-13), counter-based RNG. */
+DMG_API int32_t dmg_init_din_weights(dmg_handle_t h, int32_t dtype, int64_t rows, int32_t E,
+                                     int32_t T, uint64_t seed);
+/* Copy the compact vector back (Serialization.saveModel side).  n = element count. */
+DMG_API int32_t dmg_download_din_weights(dmg_handle_t h, void *params, int64_t n);
+
+/* ---- retrieval ------------------------------------------------------------------------ */
+/* Recommender.recommendItems / TDM.recommend over a batch of users
+ * (tdm/.../model/Recommender.scala:18-107, TDM.scala:17-22; batched caller
+ * tdm/.../evaluation/Evaluator.scala:51-66).
+ *   item_seq       B x T item ids, 0 = padding (TDMTree.idToCode, TDMTree.scala:35-56)
+ *   beam           candidateNum; consumed_off != NULL && widen_beam: per user
+ *                  max((|consumed|+topk)/2, beam) as in Recommender.scala:28-31
+ *   consumed_off   nullable, B+1 offsets into consumed_items (item ids to drop, :104)
+ *   out_items      B x topk item ids, -1 padded;  out_logits B x topk raw logits (apply
+ *                  TDM.sigmoid on the host);  out_counts B = number of valid entries.
+ * Ties are broken exactly like the reference's stable sorts (earlier candidate first). */
+DMG_API int32_t dmg_tdm_retrieve(dmg_handle_t h, int32_t B, const int32_t *item_seq, int32_t beam,
+                                 int32_t topk, int32_t use_mask, const int64_t *consumed_off,
+                                 const int32_t *consumed_items, int32_t widen_beam,
+                                 int32_t *out_items, float *out_logits, int32_t *out_counts);
+DMG_API int32_t dmg_tdm_retrieve_dev(dmg_handle_t h, int32_t B, const int32_t *d_item_seq,
+                                     int32_t beam, int32_t topk, int32_t use_mask,
+                                     int32_t *d_out_items, float *d_out_logits,
+                                     int32_t *d_out_counts);
+
+/* CandidateSearcher.batchBeamSearch (otm/.../model/CandidateSearcher.scala:15-56): per user
+ * the 2*beam candidates of the leaf level with their Double scores, in candidate order.
+ *   leaf_seq  B x T leaf node ids, -1 = padding.  out_ids/out_scores: B x 2*max(beam,2^s). */
+DMG_API int32_t dmg_otm_beam_search(dmg_handle_t h, int32_t B, const int32_t *leaf_seq,
+                                    int32_t beam, int32_t use_mask, int32_t *out_ids,
+                                    double *out_scores, int32_t *out_counts);
+/* OTM.recommend over a batch (otm/.../model/OTM.scala:14-23): leaf candidates that map back
+ * to an item, stable sort desc, topk.  out_scores = raw logits (sigmoid on the host). */
+DMG_API int32_t dmg_otm_retrieve(dmg_handle_t h, int32_t B, const int32_t *leaf_seq, int32_t beam,
+                                 int32_t topk, int32_t use_mask, int32_t *out_items,
+                                 double *out_scores, int32_t *out_counts);
+
+/* model.forward(Table(item, seq, mask)) on n independent rows -- the seam itself
+ * (Recommender.scala:94, otm CandidateSearcher.scala:41,77, OTMTree.scala:168,198,
+ * jtm TreeLearning.scala:168).  node[n], seq[n*T] = embedding indices, -1 = padding;
+ * mask_flat = flat positions row*T+j (nullable).  out: n logits of the loaded dtype. */
+DMG_API int32_t dmg_score_pairs(dmg_handle_t h, int64_t n, const int32_t *node, const int32_t *seq,
+                                const int32_t *mask_flat, int64_t n_mask, void *out);
+
+/* ---- Deep Retrieval ------------------------------------------------------------------- */
+/* LayerModel + RerankModel parameters (deep-retrieval/.../model/LayerModel.scala:22-39,
+ * RerankModel.scala:20-41), all Double, row-major [out,in]:
+ *   layer_emb (num_item + K*(D-1)) x E ; layer_w[d] K x (T+d)E ; layer_b[d] K ;
+ *   rr_emb num_item x E ; rr_w E x T*E ; rr_b E ; sm_w num_item x E ; sm_b num_item. */
+DMG_API int32_t dmg_dr_load(dmg_handle_t h, int32_t num_item, int32_t K, int32_t D, int32_t T,
+                            int32_t E, const double *layer_emb, const double *const *layer_w,
+                            const double *const *layer_b, const double *rr_emb, const double *rr_w,
+                            const double *rr_b, const double *sm_w, const double *sm_b);
+/* MappingOp.pathItemMapping as CSR over path keys sum_d c_d K^(D-1-d)
+ * (MappingOp.scala:17-28): path_off[K^D + 1], path_items[path_off[K^D]]. */
+DMG_API int32_t dmg_dr_load_paths(dmg_handle_t h, const int64_t *path_off, const int32_t *path_items);
+/* CandidateSearcher.beamSearch (dr CandidateSearcher.scala:22-60): seq = B x T item indices
+ * (-1 padding); out_paths B x beam x D, out_probs B x beam, out_counts B. */
+DMG_API int32_t dmg_dr_beam_search(dmg_handle_t h, int32_t B, const int32_t *seq, int32_t beam,
+                                   int32_t *out_paths, double *out_probs, int32_t *out_counts);
+/* DeepRetrieval.recommend (DeepRetrieval.scala:26-46): beam search -> path items -> rerank
+ * -> stable sort desc -> topk.  out_items = item indices (map with idItemMapping on host). */
+DMG_API int32_t dmg_dr_retrieve(dmg_handle_t h, int32_t B, const int32_t *seq, int32_t beam,
+                                int32_t topk, int32_t *out_items, double *out_scores,
+                                int32_t *out_counts);
+
+/* ---- training ------------------------------------------------------------------------- */
+/* One step of LocalOptimizer.optimize on an already expanded batch
+ * (tdm/.../optim/LocalOptimizer.scala:58-120,139-187; otm/.../optim/LocalOptimizer.scala:73-80):
+ * zeroGradParameters, DIN forward, BCECriterionWithLogits (mean), backward with scatter-add
+ * into the node table, dense Adam over the whole flat vector (scalann/.../optim/Adam.scala:19-73,
+ * beta 0.9/0.999, eps 1e-8).  rows x (node, seq[T], label); step_t = 1-based timestep.
+ * out_loss: one value of the loaded dtype. */
+DMG_API int32_t dmg_train_step(dmg_handle_t h, int64_t rows, const int32_t *node, const int32_t *seq,
+                               const int32_t *mask_flat, int64_t n_mask, const void *labels,
+                               double lr, int32_t step_t, void *out_loss);
+/* forward + backward only: gradient of the compact vector (testing / syncGradients). */
+DMG_API int32_t dmg_din_gradients(dmg_handle_t h, int64_t rows, const int32_t *node,
+                                  const int32_t *seq, const int32_t *mask_flat, int64_t n_mask,
+                                  const void *labels, void *out_loss, void *out_grad, int64_t n_grad);
+/* NegativeSampler.sample + MiniBatch.convert (tdm/.../utils/NegativeSampler.scala:76-158,
+ * tdm/.../dataset/MiniBatch.scala:49-88): per target item the ancestor positives and
+ * layer_neg[l] uniform negatives per level >= start_level, ascending code order per level.
+ * out arrays sized n_targets * layer_sum. */
+DMG_API int32_t dmg_tdm_sample_expand(dmg_handle_t h, int32_t n_targets, const int32_t *target_items,
+                                      const int32_t *item_seq, const int32_t *layer_neg,
+                                      int32_t start_level, uint64_t seed, int32_t *out_node,
+                                      int32_t *out_seq, float *out_label, int32_t *out_rows);
+
+/* ---- JTM tree learning ---------------------------------------------------------------- */
+/* TreeLearning.aggregateWeights (jtm/.../optim/TreeLearning.scala:152-174): for each item i
+ * with samples [sample_off[i], sample_off[i+1]) (histories sample_seq, T item ids each) and
+ * each of its n_child candidate children, weight = sum over the nodes on the child->parent
+ * path (exclusive) of the summed logits of the item's samples; -1e6 when an item has no
+ * sample (:160).  out_weights: n_items x n_child (float). */
+DMG_API int32_t dmg_jtm_item_weights(dmg_handle_t h, int32_t n_items, const int64_t *sample_off,
+                                     const int32_t *sample_seq, const int32_t *parent_code,
+                                     int32_t old_level, int32_t level, float *out_weights);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DISMEMBER_GPU_H */

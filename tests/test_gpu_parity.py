@@ -1,0 +1,254 @@
+"""Parity tests proper: the CUDA path, called through the C ABI, against the CPU oracle on the
+same inputs.  Bar: item ids identical (ties broken identically), scores BIT-identical -- the
+engine's strict arithmetic spec equals the oracle's (tolerance stated where it is not zero)."""
+import numpy as np
+import pytest
+
+from dismember_b200 import synth
+
+pytestmark = pytest.mark.gpu
+
+
+def bits(a):
+    a = np.ascontiguousarray(a)
+    return a.view(np.uint32 if a.dtype == np.float32 else np.uint64)
+
+
+def load_jtm(engine, f):
+    engine.load_tree_tdm(int(f["max_level"]), f["codes"], f["node_ids"], f["is_leaf"], f["leaf_ids"], f["leaf_codes"])
+    engine.load_din_weights(f["params"], 8191, int(f["E"]), int(f["T"]))
+
+
+def load_otm(engine, f):
+    n = len(f["items"])
+    leaf_level = int(np.ceil(np.log(n) / np.log(2)))
+    engine.load_tree_complete(leaf_level, f["items"], f["leaf_ids"])
+    engine.load_din_weights(f["params"], 8191, int(f["E"]), int(f["T"]))
+    return leaf_level
+
+
+# ------------------------------------------------------------------ fixtures of the reference
+@pytest.mark.parametrize("beam", [20, 200])
+def test_tdm_fixture_matches_golden_and_oracle(engine, jtm_fix, jtm_oracle, queries, golden_out, beam):
+    load_jtm(engine, jtm_fix)
+    items, logits, counts = engine.tdm_retrieve(queries["seqs"], beam, 10)
+    assert (items == golden_out[f"tdm_items_b{beam}"]).all()
+    assert (bits(logits) == bits(golden_out[f"tdm_logits_b{beam}"])).all()
+    assert (counts == golden_out[f"tdm_counts_b{beam}"]).all()
+    tree, model = jtm_oracle
+    oi, ol, oc = model.retrieve_batch(tree, queries["seqs"], beam, 10, n_threads=4)
+    assert (items == oi).all() and (bits(logits) == bits(ol)).all() and (counts == oc).all()
+
+
+def test_tdm_eval_variant_with_consumed(engine, jtm_fix, queries, golden_out):
+    load_jtm(engine, jtm_fix)
+    items, logits, counts = engine.tdm_retrieve(queries["seqs"], 20, 10, True, queries["cons_off"], queries["cons"], True)
+    assert (items == golden_out["tdm_eval_items"]).all()
+    assert (bits(logits) == bits(golden_out["tdm_eval_logits"])).all()
+    assert (counts == golden_out["tdm_eval_counts"]).all()
+
+
+@pytest.mark.parametrize("beam", [20, 200])
+def test_otm_fixture(engine, otm_fix, otm_oracle, queries, golden_out, beam):
+    load_otm(engine, otm_fix)
+    model, leaf_level, leaf_item, item_leaf = otm_oracle
+    seqs = np.array([[item_leaf.get(int(x), -1) for x in s] for s in queries["seqs"]], np.int32)
+    items, scores, counts = engine.otm_retrieve(seqs, beam, 10)
+    assert (items == golden_out[f"otm_items_b{beam}"]).all()
+    assert (bits(scores) == bits(golden_out[f"otm_scores_b{beam}"])).all()
+    ids, sc, cnt = engine.otm_beam_search(seqs[:32], beam)
+    for u in range(32):
+        oi, os_ = model.beam_search(seqs[u], leaf_level, beam)
+        assert cnt[u] == len(oi) and (ids[u, :cnt[u]] == oi).all() and (bits(sc[u, :cnt[u]]) == bits(os_)).all()
+
+
+@pytest.mark.parametrize("which", ["f32", "f64"])
+def test_score_pairs_is_model_forward(engine, orc, jtm_fix, otm_fix, which):
+    fix = jtm_fix if which == "f32" else otm_fix
+    engine.load_din_weights(fix["params"], 8191, 16, 10)
+    model = (orc.TdmModel if which == "f32" else orc.OtmModel)(fix["params"], 8191, 16, 10)
+    rng = np.random.default_rng(1)
+    n = 1000
+    node = rng.integers(0, 8191, n).astype(np.int32)
+    seq = rng.integers(0, 8191, (n, 10)).astype(np.int32)
+    seq[rng.random((n, 10)) < 0.3] = -1
+    seq[:7] = -1
+    mask = np.flatnonzero((seq == -1).ravel()).astype(np.int32)
+    got = engine.score_pairs(node, seq, mask)
+    want = model.forward(node, seq, mask)
+    assert (bits(got) == bits(want)).all()
+    # unmasked padding (useMask = false path): zero rows still enter the softmax
+    got = engine.score_pairs(node[:64], seq[:64], None)
+    assert (bits(got) == bits(model.forward(node[:64], seq[:64], None))).all()
+
+
+# ------------------------------------------------------------------ synthetic catalogues
+@pytest.mark.parametrize("E,n_items,beam", [(64, 20000, 200), (32, 5000, 50), (16, 1000, 200), (64, 300, 7)])
+def test_tdm_synthetic(engine, orc, E, n_items, beam):
+    tf = synth.tdm_tree(n_items, seed=E)
+    rows = (1 << (tf.max_level + 1)) - 1
+    params = synth.din_params(rows, E, seed=7)
+    engine.load_tree_tdm(tf.max_level, tf.codes, tf.node_ids, tf.is_leaf, tf.leaf_ids, tf.leaf_codes)
+    engine.load_din_weights(params, rows, E, 10)
+    seqs = synth.queries(96, 10, n_items, seed=11)
+    seqs[0] = 0                                               # all padding
+    items, logits, counts = engine.tdm_retrieve(seqs, beam, 10)
+    tree = orc.Tree.from_treefile(tf)
+    model = orc.TdmModel(params, rows, E, 10)
+    oi, ol, oc = model.retrieve_batch(tree, seqs, beam, 10, n_threads=8)
+    assert (counts == oc).all()
+    assert (items == oi).all()
+    assert (bits(logits) == bits(ol)).all()
+
+
+def test_otm_synthetic_e64(engine, orc):
+    items, leaves, leaf_level = synth.otm_mapping(3000, seed=5)
+    rows = (1 << (leaf_level + 1)) - 1
+    params = synth.din_params(rows, 64, seed=9, dtype=np.float64)
+    engine.load_tree_complete(leaf_level, items, leaves)
+    engine.load_din_weights(params, rows, 64, 10)
+    model = orc.OtmModel(params, rows, 64, 10)
+    leaf_item = np.full(1 << leaf_level, -1, np.int32)
+    leaf_item[leaves - ((1 << leaf_level) - 1)] = items
+    rng = np.random.default_rng(3)
+    seqs = leaves[rng.integers(0, len(leaves), (24, 10))].astype(np.int32)
+    seqs[rng.random(seqs.shape) < 0.2] = -1
+    got_i, got_s, got_c = engine.otm_retrieve(seqs, 100, 10)
+    oi, os_, oc = model.retrieve_batch(seqs, leaf_level, 100, 10, leaf_item, n_threads=8)
+    assert (got_c == oc).all() and (got_i == oi).all() and (bits(got_s) == bits(os_)).all()
+
+
+# ------------------------------------------------------------------ ties, edges, errors
+def test_ties_break_like_stable_sort(engine, orc, jtm_fix, jtm_oracle):
+    """A zero model makes every score equal: the result is decided by tie-breaking alone."""
+    f = jtm_fix
+    engine.load_tree_tdm(int(f["max_level"]), f["codes"], f["node_ids"], f["is_leaf"], f["leaf_ids"], f["leaf_codes"])
+    zero = np.zeros(131857, np.float32)
+    engine.load_din_weights(zero, 8191, 16, 10)
+    tree, _ = jtm_oracle
+    model = orc.TdmModel(zero, 8191, 16, 10)
+    seqs = np.zeros((3, 10), np.int32)
+    seqs[1, 5:] = [2126, 204, 3257, 3439, 996]
+    for beam in (5, 20, 200):
+        items, logits, counts = engine.tdm_retrieve(seqs, beam, 10)
+        oi, ol, oc = model.retrieve_batch(tree, seqs, beam, 10)
+        assert (items == oi).all() and (counts == oc).all() and (logits == 0).all()
+
+
+def test_beam_edges(engine, orc, jtm_fix, jtm_oracle):
+    load_jtm(engine, jtm_fix)
+    tree, model = jtm_oracle
+    seqs = np.zeros((2, 10), np.int32)
+    seqs[1] = [0, 0, 2126, 204, 3257, 3439, 996, 1681, 3438, 1882]
+    for beam, topk in [(1, 1), (2, 5), (3, 10), (4096, 10), (5000, 10), (9000, 3), (63, 200)]:
+        try:
+            items, logits, counts = engine.tdm_retrieve(seqs, beam, topk)
+        except Exception as e:                      # very wide beams may exceed shared memory: must be a clean error
+            assert "beam too large" in str(e)
+            continue
+        oi, ol, oc = model.retrieve_batch(tree, seqs, beam, topk)
+        assert (counts == oc).all() and (items == oi).all() and (bits(logits) == bits(ol)).all(), (beam, topk)
+
+
+def test_single_user_and_odd_batches(engine, jtm_fix, golden_out, queries):
+    load_jtm(engine, jtm_fix)
+    for B in (1, 3, 149, 256):
+        items, logits, counts = engine.tdm_retrieve(queries["seqs"][:B], 20, 10)
+        assert (items == golden_out["tdm_items_b20"][:B]).all()
+
+
+def test_invalid_index_raises(engine, jtm_fix):
+    from dismember_b200 import DmgIndexError, DmgArgumentError
+    load_jtm(engine, jtm_fix)
+    seqs = np.zeros((2, 10), np.int32)
+    seqs[0, 3] = -7                                  # idToCode yields a negative embedding index
+    with pytest.raises(DmgIndexError):
+        engine.tdm_retrieve(seqs, 20, 10)
+    # engine stays usable afterwards
+    seqs[0, 3] = 0
+    engine.tdm_retrieve(seqs, 20, 10)
+    with pytest.raises(DmgIndexError):
+        engine.score_pairs(np.array([9000], np.int32), np.zeros((1, 10), np.int32))
+    with pytest.raises(DmgArgumentError):
+        engine.tdm_retrieve(seqs, 0, 10)             # require(candidateNum > 0)
+
+
+def test_unknown_item_quirk(engine, jtm_fix, jtm_oracle):
+    """ids above nonLeafOffset address ancestors (id - offset); too-large ones are masked."""
+    load_jtm(engine, jtm_fix)
+    tree, model = jtm_oracle
+    off = int(jtm_fix["leaf_ids"].max()) + 1
+    seqs = np.zeros((3, 10), np.int32)
+    seqs[0, -3:] = [off + 5, off + 100, off + 8189]          # ancestor pseudo-ids
+    seqs[1, -2:] = [off + 8190, off + 100000]                # > maxCode -> masked
+    items, logits, counts = engine.tdm_retrieve(seqs, 20, 10)
+    oi, ol, oc = model.retrieve_batch(tree, seqs, 20, 10)
+    assert (items == oi).all() and (bits(logits) == bits(ol)).all()
+    # an id below nonLeafOffset that is not a leaf becomes a negative index: the reference throws
+    from dismember_b200 import DmgIndexError
+    known = set(jtm_fix["leaf_ids"].tolist())
+    missing = next(i for i in range(1, off - 1) if i not in known)
+    seqs[2, -1] = missing
+    with pytest.raises(DmgIndexError):
+        engine.tdm_retrieve(seqs, 20, 10)
+    with pytest.raises(IndexError):
+        model.retrieve_batch(tree, seqs, 20, 10)
+
+
+# ------------------------------------------------------------------ host mirrors read like the Scala specs
+def test_tdm_recommend_api(jtm_fix, golden_out):
+    """TdmModelTrainSpec.scala:85-96: recommend(sequence, topk = 3, candidateNum = 20) has length 3 and is
+    identical after the model is loaded again."""
+    from dismember_b200.formats.tree_file import TreeFile
+    from dismember_b200.tdm import TDM
+    f = jtm_fix
+    tf = TreeFile(int(f["max_level"]), f["codes"], f["node_ids"], f["is_leaf"], f["prob"], f["leaf_ids"], f["leaf_codes"])
+    sequence = [0, 0, 2126, 204, 3257, 3439, 996, 1681, 3438, 1882]
+    m1 = TDM().set_tree(tf).set_parameters(f["params"], 16, 10)
+    rec1 = m1.recommend(sequence, topk=3, candidate_num=20)
+    assert len(rec1) == 3
+    assert [r[0] for r in rec1] == golden_out["tdm_items_b20"][0, :3].tolist()
+    assert all(0.0 < r[1] < 1.0 for r in rec1)
+    params_back = m1.engine.download_din_weights()
+    m2 = TDM().set_tree(tf).set_parameters(params_back, 16, 10)
+    assert m2.recommend(sequence, topk=3, candidate_num=20) == rec1
+    m1.engine.close(); m2.engine.close()
+
+
+def test_otm_recommend_api(otm_fix, golden_out):
+    from dismember_b200.otm import OTM
+    f = otm_fix
+    m = OTM().set_mapping(f["items"], f["leaf_ids"]).set_parameters(f["params"], 16, 10)
+    rec = m.recommend([0, 0, 2126, 204, 3257, 3439, 996, 1681, 3438, 1882], topk=3, beam_size=20)
+    assert len(rec) == 3 and [r[0] for r in rec] == golden_out["otm_items_b20"][0, :3].tolist()
+    m.engine.close()
+
+
+# ------------------------------------------------------------------ BASELINE-size properties
+def test_full_size_properties(engine):
+    """1M-item catalogue (BASELINE configs[1]): size-independent properties instead of an oracle run:
+    determinism, sortedness, leaf range, beam monotonicity of the best score."""
+    n_items = 1_000_000
+    tf = synth.tdm_tree(n_items, seed=1)
+    rows = (1 << (tf.max_level + 1)) - 1
+    engine.load_tree_tdm(tf.max_level, tf.codes, tf.node_ids, tf.is_leaf, tf.leaf_ids, tf.leaf_codes)
+    engine.init_din_weights(np.float32, rows, 64, 10, seed=2)
+    seqs = synth.queries(1024, 10, n_items, seed=4)
+    a = engine.tdm_retrieve(seqs, 200, 10)
+    b = engine.tdm_retrieve(seqs, 200, 10)
+    assert all((x == y).all() for x, y in zip(a, b))                       # idempotent / deterministic
+    items, logits, counts = a
+    assert (counts == 10).all() and items.min() >= 1 and items.max() <= n_items
+    assert (np.diff(logits, axis=1) <= 0).all()                            # sorted descending
+    assert all(len(set(r.tolist())) == 10 for r in items[:64])             # no duplicates
+    # a user's result does not depend on who else is in the batch
+    c = engine.tdm_retrieve(seqs[100:164], 200, 10)
+    assert (c[0] == items[100:164]).all() and (bits(c[1]) == bits(logits[100:164])).all()
+    # the retrieved logits equal model.forward on (leaf code, history)
+    item_code = np.zeros(n_items + 1, np.int64)
+    item_code[tf.leaf_ids] = tf.leaf_codes
+    u = 5
+    hist = np.where(seqs[u] > 0, item_code[np.maximum(seqs[u], 0)], -1).astype(np.int32)
+    node = item_code[items[u]].astype(np.int32)
+    fw = engine.score_pairs(node, np.tile(hist, (10, 1)), np.flatnonzero(np.tile(hist == -1, 10)).astype(np.int32))
+    assert (bits(fw) == bits(logits[u])).all()

@@ -1,0 +1,89 @@
+"""Pin the oracle's numerics on everything the reference's own tests pin, plus independent
+float64 restatements in numpy.  (scalann/src/test/scala/SoftMaxTest.scala)"""
+import numpy as np
+import pytest
+
+
+def test_softmax_known_answer(orc):
+    # SoftMaxTest.scala:8-27 (values from PyTorch), tolerance 1e-4 as in the Scala test
+    x = np.array([[5, 2, 0.8], [0.3, 0.4, 1.0]], np.float32)
+    want = np.array([[0.9392, 0.0468, 0.0141], [0.2428, 0.2683, 0.4889]], np.float32)
+    got = orc.softmax_f32(x)
+    assert np.abs(got - want).max() < 1e-4
+    go = np.array([[0.5, 0.1, 0.6], [0.1, 0.9, 0.6]], np.float32)
+    want_g = np.array([[0.0162, -0.0179, 0.0017], [-0.1115, 0.0915, 0.0200]], np.float32)
+    assert np.abs(orc.softmax_grad_f32(got, go) - want_g).max() < 1e-4
+
+
+def test_exp_accuracy(orc):
+    L = orc.lib()
+    xs = np.concatenate([np.linspace(-104, 88.7, 20001), -np.logspace(-6, 2, 500), [0.0, -0.0, 1.0, -1.0]])
+    got = np.array([L.orc_expf_api(float(np.float32(x))) for x in xs], np.float64)
+    ref = np.exp(xs.astype(np.float32).astype(np.float64))
+    normal = ref > 1e-37
+    rel = np.abs(got[normal] - ref[normal]) / ref[normal]
+    assert rel.max() < 2.5e-7                       # <= ~2 ulp of fp32
+    assert L.orc_expf_api(0.0) == 1.0 and L.orc_expf_api(-3.4e38) == 0.0
+    xs = np.concatenate([np.linspace(-745, 709, 20001), [0.0, 1.0, -1.0]])
+    got = np.array([L.orc_exp_api(float(x)) for x in xs])
+    ref = np.exp(xs)
+    normal = ref > 1e-300
+    assert (np.abs(got[normal] - ref[normal]) / ref[normal]).max() < 4.5e-16
+    assert L.orc_exp_api(0.0) == 1.0
+
+
+def _din_numpy(params, rows, E, T, node, seq, masked):
+    """independent float64 restatement (different code path: dense numpy ops)"""
+    p = np.asarray(params, np.float64)
+    o = 0
+    emb = p[o:o + rows * E].reshape(rows, E); o += rows * E
+    watt = p[o:o + E * E].reshape(E, E); o += E * E
+    w1 = p[o:o + 2 * E * E].reshape(E, 2 * E); o += 2 * E * E
+    b1 = p[o:o + E]; o += E
+    w2 = p[o:o + E]; o += E
+    b2 = p[o]
+    q = np.where(node[:, None] >= 0, emb[np.maximum(node, 0)], 0.0)
+    K = np.where(seq[:, :, None] >= 0, emb[np.maximum(seq, 0)], 0.0)
+    s = np.einsum("ne,nte->nt", q, K) / np.sqrt(E)
+    s = np.where(masked, -3.4028234663852886e38, s)
+    s = s - s.max(1, keepdims=True)
+    pr = np.exp(s)
+    pr /= pr.sum(1, keepdims=True)
+    a = np.einsum("nt,nte->ne", pr, K)
+    att = a @ watt.T
+    h = np.maximum(np.concatenate([q, att], 1) @ w1.T + b1, 0.0)
+    return h @ w2 + b2
+
+
+@pytest.mark.parametrize("dtype", [np.float32, np.float64])
+def test_din_forward_matches_numpy(orc, jtm_fix, otm_fix, dtype):
+    rng = np.random.default_rng(0)
+    fix = jtm_fix if dtype == np.float32 else otm_fix
+    model = (orc.TdmModel if dtype == np.float32 else orc.OtmModel)(fix["params"], 8191, 16, 10)
+    n = 300
+    node = rng.integers(0, 8191, n).astype(np.int32)
+    seq = rng.integers(0, 8191, (n, 10)).astype(np.int32)
+    seq[rng.random((n, 10)) < 0.3] = -1
+    seq[:5] = -1                                    # fully padded histories
+    masked = seq == -1
+    got = model.forward(node, seq, np.flatnonzero(masked.ravel()).astype(np.int32))
+    want = _din_numpy(fix["params"], 8191, 16, 10, node, seq, masked)
+    tol = 2e-5 if dtype == np.float32 else 1e-12
+    assert np.abs(got - want).max() < tol * max(1.0, np.abs(want).max())
+
+
+def test_din_forward_rejects_bad_index(orc, jtm_fix):
+    model = orc.TdmModel(jtm_fix["params"], 8191, 16, 10)
+    node = np.array([8191], np.int32)
+    seq = np.full((1, 10), -1, np.int32)
+    with pytest.raises(IndexError):
+        model.forward(node, seq)
+
+
+def test_sort_is_stable_total_order(orc, jtm_oracle):
+    # all-equal scores: a zero model keeps the first `beam` candidates in code order
+    tree, _ = jtm_oracle
+    zero = np.zeros(131857, np.float32)
+    m = orc.TdmModel(zero, 8191, 16, 10)
+    items, logits = m.recommend_raw(tree, np.zeros(10, np.int32), 20)
+    assert (logits == 0).all() and len(items) > 0
