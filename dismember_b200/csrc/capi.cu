@@ -12,6 +12,17 @@ using namespace dmg;
 
 static std::string g_create_error;
 
+// Stream-ordered upload: a blocking cudaMemcpy from pageable memory may return before the DMA
+// lands and is NOT ordered with the handle's non-blocking stream, so every upload goes through
+// the stream the kernels run on and is waited for (the caller may free `src` on return).
+static int32_t h2d(dmg_handle_t h, void *dst, const void *src, size_t bytes)
+{
+    if (bytes == 0) return DMG_OK;
+    DMG_CUDA(h, cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, h->stream));
+    DMG_CUDA(h, cudaStreamSynchronize(h->stream));
+    return DMG_OK;
+}
+
 DMG_API const char *dmg_version(void) { return "dismember-b200 0.1 (sm_100a)"; }
 
 DMG_API const char *dmg_last_error(dmg_handle_t h) { return h ? h->err.c_str() : g_create_error.c_str(); }
@@ -162,9 +173,9 @@ DMG_API int32_t dmg_load_tree_tdm(dmg_handle_t h, int32_t max_level, int64_t n_n
     DMG_CUDA(h, cudaMalloc(&t.d_exists, bm.size() * sizeof(uint32_t)));
     DMG_CUDA(h, cudaMalloc(&t.d_leaf_item, leaf_item.size() * sizeof(int32_t)));
     DMG_CUDA(h, cudaMalloc(&t.d_id_code, id_code.size() * sizeof(int32_t)));
-    DMG_CUDA(h, cudaMemcpy(t.d_exists, bm.data(), bm.size() * sizeof(uint32_t), cudaMemcpyHostToDevice));
-    DMG_CUDA(h, cudaMemcpy(t.d_leaf_item, leaf_item.data(), leaf_item.size() * sizeof(int32_t), cudaMemcpyHostToDevice));
-    DMG_CUDA(h, cudaMemcpy(t.d_id_code, id_code.data(), id_code.size() * sizeof(int32_t), cudaMemcpyHostToDevice));
+    DMG_TRY(h2d(h, t.d_exists, bm.data(), bm.size() * sizeof(uint32_t)));
+    DMG_TRY(h2d(h, t.d_leaf_item, leaf_item.data(), leaf_item.size() * sizeof(int32_t)));
+    DMG_TRY(h2d(h, t.d_id_code, id_code.data(), id_code.size() * sizeof(int32_t)));
     t.loaded = true; t.complete = false; t.max_level = max_level; t.n_codes = n_codes;
     t.non_leaf_offset = offset; t.max_code = mx_code; t.n_items = n_items;
     return DMG_OK;
@@ -188,7 +199,7 @@ DMG_API int32_t dmg_load_tree_complete(dmg_handle_t h, int32_t leaf_level, int64
     free_tree(h->tree);
     TreeDev &t = h->tree;
     DMG_CUDA(h, cudaMalloc(&t.d_leaf_item, leaf_item.size() * sizeof(int32_t)));
-    DMG_CUDA(h, cudaMemcpy(t.d_leaf_item, leaf_item.data(), leaf_item.size() * sizeof(int32_t), cudaMemcpyHostToDevice));
+    DMG_TRY(h2d(h, t.d_leaf_item, leaf_item.data(), leaf_item.size() * sizeof(int32_t)));
     t.loaded = true; t.complete = true; t.max_level = leaf_level; t.n_codes = ((int64_t)1 << (leaf_level + 1)) - 1;
     t.n_items = n_items;
     return DMG_OK;
@@ -245,7 +256,7 @@ DMG_API int32_t dmg_load_din_weights(dmg_handle_t h, int32_t dtype, int64_t rows
     if (!h || !params) return h ? fail(h, DMG_ERR_INVALID_ARG, "dmg_load_din_weights: null params") : DMG_ERR_INVALID_ARG;
     DMG_TRY(alloc_din(h, dtype, rows, E, T));
     DinDev &d = h->din;
-    DMG_CUDA(h, cudaMemcpy(d.d_params, params, (size_t)d.n_params * d.esz, cudaMemcpyHostToDevice));
+    DMG_TRY(h2d(h, d.d_params, params, (size_t)d.n_params * d.esz));
     DMG_TRY(dtype == DMG_F32 ? make_transposes<float>(h) : make_transposes<double>(h));
     d.loaded = true;
     return DMG_OK;
