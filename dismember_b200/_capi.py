@@ -243,3 +243,40 @@ class Engine:
         m = None if mask_flat is None else _i32(mask_flat).ravel()
         self._check(self.L.dmg_score_pairs(self.h, len(node), _p(node), _p(seq), _p(m), 0 if m is None else len(m), _p(out)))
         return out
+
+    # -- Deep Retrieval ------------------------------------------------------------
+    def dr_load(self, num_item, K, D, T, E, layer_emb, layer_w, layer_b, rr_emb, rr_w, rr_b, sm_w, sm_b):
+        c = lambda a: np.ascontiguousarray(a, np.float64)
+        layer_w = [c(w) for w in layer_w]
+        layer_b = [c(b) for b in layer_b]
+        wp = (C.c_void_p * D)(*[w.ctypes.data for w in layer_w])
+        bp = (C.c_void_p * D)(*[b.ctypes.data for b in layer_b])
+        arrs = [c(layer_emb), c(rr_emb), c(rr_w), c(rr_b), c(sm_w), c(sm_b)]
+        self._check(self.L.dmg_dr_load(self.h, num_item, K, D, T, E, _p(arrs[0]), wp, bp, _p(arrs[1]), _p(arrs[2]),
+                                       _p(arrs[3]), _p(arrs[4]), _p(arrs[5])))
+        self.dr_shape = (num_item, K, D, T, E)
+
+    def dr_load_paths(self, path_off, path_items):
+        po = np.ascontiguousarray(path_off, np.int64)
+        pi = _i32(path_items)
+        self._check(self.L.dmg_dr_load_paths(self.h, _p(po), _p(pi)))
+
+    def dr_beam_search(self, seq, beam):
+        _, K, D, T, E = self.dr_shape
+        seq = _i32(seq).reshape(-1, T)
+        B = len(seq)
+        paths = np.empty((B, beam, D), np.int32)
+        probs = np.empty((B, beam), np.float64)
+        counts = np.empty(B, np.int32)
+        self._check(self.L.dmg_dr_beam_search(self.h, B, _p(seq), beam, _p(paths), _p(probs), _p(counts)))
+        return paths, probs, counts
+
+    def dr_retrieve(self, seq, beam, topk):
+        _, K, D, T, E = self.dr_shape
+        seq = _i32(seq).reshape(-1, T)
+        B = len(seq)
+        items = np.empty((B, topk), np.int32)
+        sc = np.empty((B, topk), np.float64)
+        counts = np.empty(B, np.int32)
+        self._check(self.L.dmg_dr_retrieve(self.h, B, _p(seq), beam, topk, _p(items), _p(sc), _p(counts)))
+        return items, sc, counts

@@ -19,6 +19,7 @@
 #pragma once
 #include "dmg_common.cuh"
 #include "dmg_math.cuh"
+#include "device_utils.cuh"
 
 namespace dmg {
 
@@ -45,138 +46,6 @@ template <typename real> struct BeamParams {
     int out_stride;
     int cap, capp;              // candidate capacity (>= 2*max beam) and its power of two
 };
-
-// ---- sort keys: (score desc, candidate position asc) == the reference's stable sort ------
-struct Key128 { uint64_t hi, lo; };
-__device__ __forceinline__ bool key_less(uint64_t a, uint64_t b) { return a < b; }
-__device__ __forceinline__ bool key_less(const Key128 &a, const Key128 &b)
-{
-    return a.hi < b.hi || (a.hi == b.hi && a.lo < b.lo);
-}
-template <typename real> struct KeyOf;
-template <> struct KeyOf<float> {
-    using type = uint64_t;
-    static __device__ __forceinline__ type make(float s, int pos)
-    {
-        return ((uint64_t)order_key(s) << 32) | (uint32_t)(0xFFFFFFFFu - (uint32_t)pos);
-    }
-    static __device__ __forceinline__ type lowest() { return 0; }
-    static __device__ __forceinline__ bool is_lowest(type k) { return k == 0; }
-    static __device__ __forceinline__ int pos(type k) { return (int)(0xFFFFFFFFu - (uint32_t)k); }
-};
-template <> struct KeyOf<double> {
-    using type = Key128;
-    static __device__ __forceinline__ type make(double s, int pos)
-    {
-        Key128 k; k.hi = order_key(s); k.lo = (uint64_t)(0xFFFFFFFFu - (uint32_t)pos); return k;
-    }
-    static __device__ __forceinline__ type lowest() { Key128 k; k.hi = 0; k.lo = 0; return k; }
-    static __device__ __forceinline__ bool is_lowest(const type &k) { return k.hi == 0 && k.lo == 0; }
-    static __device__ __forceinline__ int pos(const type &k) { return (int)(0xFFFFFFFFu - (uint32_t)k.lo); }
-};
-
-template <typename K> __device__ void bitonic_sort_desc(K *keys, int n)
-{
-    for (int k = 2; k <= n; k <<= 1) {
-        for (int j = k >> 1; j > 0; j >>= 1) {
-            for (int i = threadIdx.x; i < n; i += blockDim.x) {
-                int ixj = i ^ j;
-                if (ixj > i) {
-                    K a = keys[i], b = keys[ixj];
-                    bool sw = ((i & k) == 0) ? key_less(a, b) : key_less(b, a);
-                    if (sw) { keys[i] = b; keys[ixj] = a; }
-                }
-            }
-            __syncthreads();
-        }
-    }
-}
-
-// ---- vector smem access -------------------------------------------------------------------
-__device__ __forceinline__ void ld4(const float *p, float (&v)[4])
-{
-    float4 t = *reinterpret_cast<const float4 *>(p);
-    v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
-}
-__device__ __forceinline__ void ld4(const double *p, double (&v)[4])
-{
-    double2 a = *reinterpret_cast<const double2 *>(p), b = *reinterpret_cast<const double2 *>(p + 2);
-    v[0] = a.x; v[1] = a.y; v[2] = b.x; v[3] = b.y;
-}
-__device__ __forceinline__ void st4(float *p, const float (&v)[4])
-{
-    *reinterpret_cast<float4 *>(p) = make_float4(v[0], v[1], v[2], v[3]);
-}
-__device__ __forceinline__ void st4(double *p, const double (&v)[4])
-{
-    *reinterpret_cast<double2 *>(p) = make_double2(v[0], v[1]);
-    *reinterpret_cast<double2 *>(p + 2) = make_double2(v[2], v[3]);
-}
-
-__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ void cp_async16(void *dst, const void *src)
-{
-    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(dst)), "l"(src) : "memory");
-}
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
-template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
-
-// TMA bulk copy (non-tensor form) global -> shared, completion on an mbarrier.
-__device__ __forceinline__ void mbar_init(uint64_t *bar, int count)
-{
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-}
-__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes)
-{
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity)
-{
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "WAIT_%=:\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
-        "@p bra DONE_%=;\n\t"
-        "bra WAIT_%=;\n\t"
-        "DONE_%=:\n\t}" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
-}
-__device__ __forceinline__ void tma_bulk_g2s(void *dst, const void *src, uint32_t bytes, uint64_t *bar)
-{
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                 ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
-}
-__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
-
-__device__ __forceinline__ bool code_exists(const uint32_t *bm, int64_t c)
-{
-    return bm == nullptr || ((__ldg(bm + (c >> 5)) >> (c & 31)) & 1u);
-}
-
-// Block-wide exclusive scan of one small int per thread (kThreads threads). Returns the
-// exclusive prefix; *total receives the block sum.  sWarp: >= 8 ints of shared scratch.
-__device__ __forceinline__ int block_exscan(int v, int *sWarp, int *total)
-{
-    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-    int inc = v;
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-        int t = __shfl_up_sync(0xffffffffu, inc, o);
-        if (lane >= o) inc += t;
-    }
-    if (lane == 31) sWarp[w] = inc;
-    __syncthreads();
-    int base = 0, tot = 0;
-#pragma unroll
-    for (int i = 0; i < kThreads / 32; i++) {
-        int s = sWarp[i];
-        if (i < w) base += s;
-        tot += s;
-    }
-    __syncthreads();
-    *total = tot;
-    return base + inc - v;
-}
 
 // ---- compile-time geometry ----------------------------------------------------------------
 template <typename real, int E> struct Geo {
@@ -605,7 +474,7 @@ __global__ void __launch_bounds__(kThreads, 1) beam_search_kernel(const BeamPara
 
 // ---- K2 (host-facing part): item ids -> codes + mask, validity ------------------------------
 // TDMTree.idToCode (tdm/src/main/scala/com/mass/tdm/tree/TDMTree.scala:35-56).
-__global__ void tdm_ids_to_codes_kernel(const int32_t *__restrict__ ids, int64_t n, const int32_t *__restrict__ id_code,
+static __global__ void tdm_ids_to_codes_kernel(const int32_t *__restrict__ ids, int64_t n, const int32_t *__restrict__ id_code,
                                         int32_t non_leaf_offset, int32_t max_code, int64_t table_rows, int use_mask,
                                         int32_t *__restrict__ codes, uint8_t *__restrict__ mask, int32_t *__restrict__ err_flag)
 {
@@ -627,7 +496,7 @@ __global__ void tdm_ids_to_codes_kernel(const int32_t *__restrict__ ids, int64_t
 }
 
 // OTM / generic: sequence entries are already embedding indices; mask where == -1.
-__global__ void seq_to_codes_kernel(const int32_t *__restrict__ seq, int64_t n, int64_t table_rows, int use_mask,
+static __global__ void seq_to_codes_kernel(const int32_t *__restrict__ seq, int64_t n, int64_t table_rows, int use_mask,
                                     int32_t *__restrict__ codes, uint8_t *__restrict__ mask, int32_t *__restrict__ err_flag)
 {
     int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;

@@ -94,7 +94,7 @@ __global__ void __launch_bounds__(kRowsThreads) din_rows_forward_kernel(
 }
 
 // mask tensor (flat positions row*T+j, Recommender.scala:141-147) -> dense n x T bytes
-__global__ void mask_scatter_kernel(const int32_t *__restrict__ flat, int64_t n_mask, int64_t limit,
+static __global__ void mask_scatter_kernel(const int32_t *__restrict__ flat, int64_t n_mask, int64_t limit,
                                     uint8_t *__restrict__ mask, int32_t *__restrict__ err_flag)
 {
     int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -105,7 +105,7 @@ __global__ void mask_scatter_kernel(const int32_t *__restrict__ flat, int64_t n_
 }
 
 // index validation for model.forward inputs: [-1, rows)
-__global__ void check_index_kernel(const int32_t *__restrict__ idx, int64_t n, int64_t rows, int32_t *__restrict__ err_flag)
+static __global__ void check_index_kernel(const int32_t *__restrict__ idx, int64_t n, int64_t rows, int32_t *__restrict__ err_flag)
 {
     int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;

@@ -252,3 +252,71 @@ def test_full_size_properties(engine):
     node = item_code[items[u]].astype(np.int32)
     fw = engine.score_pairs(node, np.tile(hist, (10, 1)), np.flatnonzero(np.tile(hist == -1, 10)).astype(np.int32))
     assert (bits(fw) == bits(logits[u])).all()
+
+
+# ------------------------------------------------------------------ Deep Retrieval
+def _dr_models(orc, f):
+    D = int(f["D"])
+    args = (int(f["num_item"]), int(f["K"]), D, int(f["T"]), int(f["E"]), f["layer_emb"],
+            [f[f"layer_w{d}"] for d in range(D)], [f[f"layer_b{d}"] for d in range(D)],
+            f["rr_emb"], f["rr_w"], f["rr_b"], f["sm_w"], f["sm_b"])
+    return args, orc.DrModel(*args)
+
+
+@pytest.mark.parametrize("beam", [20, 50, 1, 300])
+def test_dr_beam_search_fixture(engine, orc, dr_fix, queries, golden_out, beam):
+    args, model = _dr_models(orc, dr_fix)
+    engine.dr_load(*args)
+    item_id = {int(a): int(b) for a, b in zip(dr_fix["map_items"], dr_fix["map_ids"])}
+    seqs = np.array([[item_id.get(int(x), -1) for x in s] for s in queries["seqs"][:48]], np.int32)
+    seqs[1] = -1
+    paths, probs, counts = engine.dr_beam_search(seqs, beam)
+    for u in range(len(seqs)):
+        op, opr = model.beam_search(seqs[u], beam)
+        assert counts[u] == len(op)
+        assert (paths[u, :counts[u]] == op).all(), (u, beam)
+        assert (bits(probs[u, :counts[u]]) == bits(opr)).all()
+    if beam in (20, 50):
+        assert (paths[0] == golden_out[f"dr_paths_b{beam}"][0]).all()
+
+
+def test_dr_retrieve_fixture(engine, orc, dr_fix, queries):
+    from dismember_b200.dr import build_path_csr
+    args, model = _dr_models(orc, dr_fix)
+    engine.dr_load(*args)
+    off, flat = build_path_csr(dr_fix["map_ids"], dr_fix["map_paths"], int(dr_fix["K"]))
+    engine.dr_load_paths(off, flat)
+    item_id = {int(a): int(b) for a, b in zip(dr_fix["map_items"], dr_fix["map_ids"])}
+    seqs = np.array([[item_id.get(int(x), -1) for x in s] for s in queries["seqs"][:32]], np.int32)
+    for beam, topk in [(50, 10), (300, 20)]:
+        items, scores, counts = engine.dr_retrieve(seqs, beam, topk)
+        for u in range(len(seqs)):
+            oi, os_, _ = model.recommend(seqs[u], topk, beam, off, flat)
+            assert counts[u] == len(oi) and (items[u, :counts[u]] == oi).all()
+            assert (bits(scores[u, :counts[u]]) == bits(os_)).all()
+
+
+def test_dr_synthetic_wide(engine, orc):
+    """K=64, D=3, E=32 with many ties-free random weights and a dense path->items map."""
+    rng = np.random.default_rng(12)
+    num_item, K, D, T, E = 500, 64, 3, 10, 32
+    layer_emb = rng.normal(0, 0.3, (num_item + K * (D - 1), E))
+    layer_w = [rng.normal(0, 0.3, (K, (T + d) * E)) for d in range(D)]
+    layer_b = [rng.normal(0, 0.1, K) for d in range(D)]
+    rr_emb = rng.normal(0, 0.3, (num_item, E)); rr_w = rng.normal(0, 0.2, (E, T * E)); rr_b = rng.normal(0, 0.1, E)
+    sm_w = rng.normal(0, 0.3, (num_item, E)); sm_b = rng.normal(0, 0.1, num_item)
+    args = (num_item, K, D, T, E, layer_emb, layer_w, layer_b, rr_emb, rr_w, rr_b, sm_w, sm_b)
+    model = orc.DrModel(*args)
+    engine.dr_load(*args)
+    from dismember_b200.dr import build_path_csr
+    paths = rng.integers(0, 4, (num_item, 3, D))            # few distinct paths -> long item lists
+    off, flat = build_path_csr(np.arange(num_item), paths, K)
+    engine.dr_load_paths(off, flat)
+    seqs = rng.integers(-1, num_item, (20, T)).astype(np.int32)
+    p, pr, c = engine.dr_beam_search(seqs, 100)
+    items, scores, counts = engine.dr_retrieve(seqs, 100, 25)
+    for u in range(len(seqs)):
+        op, opr = model.beam_search(seqs[u], 100)
+        assert (p[u, :c[u]] == op).all() and (bits(pr[u, :c[u]]) == bits(opr)).all()
+        oi, os_, _ = model.recommend(seqs[u], 25, 100, off, flat)
+        assert counts[u] == len(oi) and (items[u, :counts[u]] == oi).all() and (bits(scores[u, :counts[u]]) == bits(os_)).all()
