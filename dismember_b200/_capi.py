@@ -78,8 +78,8 @@ def load_library(build_if_missing: bool = True):
         "dmg_dr_retrieve": [vp, i32, vp, i32, i32, vp, vp, vp],
         "dmg_train_step": [vp, i64, vp, vp, vp, i64, vp, dbl, i32, vp],
         "dmg_din_gradients": [vp, i64, vp, vp, vp, i64, vp, vp, vp, i64],
-        "dmg_tdm_sample_expand": [vp, i32, vp, vp, vp, i32, u64, vp, vp, vp, vp],
-        "dmg_jtm_item_weights": [vp, i32, vp, vp, vp, i32, i32, vp],
+        "dmg_tdm_sample_expand": [vp, i32, vp, vp, vp, i32, u64, vp, vp, vp, C.POINTER(i32)],
+        "dmg_jtm_item_weights": [vp, i32, vp, vp, vp, i32, i32, i32, i32, i32, vp],
     }
     for name, args in sig.items():
         fn = getattr(L, name)
@@ -280,3 +280,52 @@ class Engine:
         counts = np.empty(B, np.int32)
         self._check(self.L.dmg_dr_retrieve(self.h, B, _p(seq), beam, topk, _p(items), _p(sc), _p(counts)))
         return items, sc, counts
+
+    # -- training / JTM ---------------------------------------------------------------
+    def din_gradients(self, node, seq, mask_flat, labels):
+        node = _i32(node).ravel()
+        seq = _i32(seq).reshape(len(node), self.T)
+        labels = np.ascontiguousarray(labels, self.din_dtype).ravel()
+        m = None if mask_flat is None else _i32(mask_flat).ravel()
+        n = self.rows * self.E + 3 * self.E * self.E + 2 * self.E + 1
+        grad = np.empty(n, self.din_dtype)
+        loss = np.zeros(1, self.din_dtype)
+        self._check(self.L.dmg_din_gradients(self.h, len(node), _p(node), _p(seq), _p(m), 0 if m is None else len(m),
+                                             _p(labels), _p(loss), _p(grad), n))
+        return grad, loss[0]
+
+    def train_step(self, node, seq, mask_flat, labels, lr, step_t):
+        node = _i32(node).ravel()
+        seq = _i32(seq).reshape(len(node), self.T)
+        labels = np.ascontiguousarray(labels, self.din_dtype).ravel()
+        m = None if mask_flat is None else _i32(mask_flat).ravel()
+        loss = np.zeros(1, self.din_dtype)
+        self._check(self.L.dmg_train_step(self.h, len(node), _p(node), _p(seq), _p(m), 0 if m is None else len(m),
+                                          _p(labels), float(lr), int(step_t), _p(loss)))
+        return loss[0]
+
+    def tdm_sample_expand(self, target_items, item_seq, layer_neg, start_level, seed):
+        tg = _i32(target_items).ravel()
+        seq = _i32(item_seq).reshape(len(tg), self.T)
+        neg = _i32(layer_neg).ravel()
+        layer_sum = int(sum(1 + int(x) for x in neg[start_level:]))
+        rows = len(tg) * layer_sum
+        node = np.empty(rows, np.int32)
+        oseq = np.empty((rows, self.T), np.int32)
+        lab = np.empty(rows, np.float32)
+        n = C.c_int32()
+        self._check(self.L.dmg_tdm_sample_expand(self.h, len(tg), _p(tg), _p(seq), _p(neg), start_level, seed, _p(node),
+                                                 _p(oseq), _p(lab), C.byref(n)))
+        assert n.value == rows
+        return node, oseq, lab
+
+    def jtm_item_weights(self, sample_off, sample_seq, parent_code, old_level, level, hierarchical=False, min_level=0,
+                         use_mask=True):
+        off = np.ascontiguousarray(sample_off, np.int64)
+        n_items = len(off) - 1
+        seq = _i32(sample_seq).reshape(-1, self.T)
+        par = _i32(parent_code).ravel()
+        out = np.empty((n_items, 1 << (level - old_level)), np.float32)
+        self._check(self.L.dmg_jtm_item_weights(self.h, n_items, _p(off), _p(seq), _p(par), old_level, level,
+                                                int(hierarchical), int(min_level), int(use_mask), _p(out)))
+        return out

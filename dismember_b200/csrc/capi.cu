@@ -356,6 +356,17 @@ static int32_t check_flag(dmg_handle_t h, const char *what)
     return DMG_OK;
 }
 
+// K2 on its own (used by the sampler in train.cu): TDMTree.idToCode on device-resident ids.
+int32_t dmg_tdm_ids_to_codes(dmg_handle_t h, const int32_t *d_ids, int64_t n, int use_mask, int32_t *d_codes, uint8_t *d_mask)
+{
+    const TreeDev &t = h->tree;
+    tdm_ids_to_codes_kernel<<<(unsigned)((n + 255) / 256), 256, 0, h->stream>>>(d_ids, n, t.d_id_code, t.non_leaf_offset, t.max_code,
+                                                                              h->din.rows, use_mask, d_codes, d_mask, h->d_flags);
+    h->launches += 1;
+    DMG_CUDA(h, cudaGetLastError());
+    return DMG_OK;
+}
+
 // Enqueue K2 + K1 for a TDM batch whose inputs already sit on the device.
 static int32_t tdm_enqueue(dmg_handle_t h, int32_t B, const int32_t *d_seq, int32_t beam, int max_beam,
                            const int32_t *d_beam_user, int32_t topk, int32_t use_mask, const int64_t *d_cons_off,

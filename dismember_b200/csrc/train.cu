@@ -1,7 +1,674 @@
-// train.cu -- training / JTM entry points (placeholder until the kernels land).
-#include "dmg_common.cuh"
+// train.cu -- training path (K4-K7) and JTM item->node weights (K9).
+//
+//   K5 din_train_kernel      forward + BCECriterionWithLogits + backward of the DIN graph on an
+//                            expanded batch      (StaticGraph.scala:23-116, BCECriterionWithLogits.scala:28-91,
+//                            Linear.scala:58-114, ReLU.scala:46-88, Concat.scala:45-80, MatMul.scala:46-70,
+//                            SoftMax.scala:46-65, Mask.scala:35-56)
+//   K6 embedding scatter-add atomicAdd into the dense node-table gradient (LookupTable.scala:56-88)
+//   K7 adam_dense_kernel     dense Adam over the whole flat vector, zeroGradParameters fused
+//                            (Adam.scala:19-73, AbstractModule.scala:43-50)
+//   K4 tdm_sample_kernel     ancestor positives + per-level uniform negatives (NegativeSampler.scala:76-158,
+//                            MiniBatch.scala:49-88)
+//   K9 jtm kernels           TreeLearning.aggregateWeights (jtm/.../optim/TreeLearning.scala:152-174)
+// Floating-point accumulation order differs from a single JVM thread (atomics), so training parity
+// is tolerance-based (1e-5 relative, tests/test_gpu_train.py); Adam itself is elementwise and exact.
+#include <algorithm>
+#include <cmath>
+
+#include "device_utils.cuh"
+#include "rows_kernels.cuh"
+
 using namespace dmg;
-DMG_API int32_t dmg_train_step(dmg_handle_t h, int64_t, const int32_t *, const int32_t *, const int32_t *, int64_t, const void *, double, int32_t, void *) { return fail(h, DMG_ERR_UNSUPPORTED, "not built yet"); }
-DMG_API int32_t dmg_din_gradients(dmg_handle_t h, int64_t, const int32_t *, const int32_t *, const int32_t *, int64_t, const void *, void *, void *, int64_t) { return fail(h, DMG_ERR_UNSUPPORTED, "not built yet"); }
-DMG_API int32_t dmg_tdm_sample_expand(dmg_handle_t h, int32_t, const int32_t *, const int32_t *, const int32_t *, int32_t, uint64_t, int32_t *, int32_t *, float *, int32_t *) { return fail(h, DMG_ERR_UNSUPPORTED, "not built yet"); }
-DMG_API int32_t dmg_jtm_item_weights(dmg_handle_t h, int32_t, const int64_t *, const int32_t *, const int32_t *, int32_t, int32_t, float *) { return fail(h, DMG_ERR_UNSUPPORTED, "not built yet"); }
+
+int32_t dmg_refresh_transposes(dmg_handle_t h);     // capi.cu
+int32_t dmg_tdm_ids_to_codes(dmg_handle_t h, const int32_t *d_ids, int64_t n, int use_mask, int32_t *d_codes, uint8_t *d_mask);  // capi.cu
+
+namespace {
+
+constexpr int kTrThreads = 128;
+constexpr int kTrRB = 8;
+
+__device__ __forceinline__ float log1pexp_(float e) { return logf(1.0f + e); }
+__device__ __forceinline__ double log1pexp_(double e) { return log(1.0 + e); }
+__device__ __forceinline__ float sqrt_(float x) { return __fsqrt_rn(x); }
+__device__ __forceinline__ double sqrt_(double x) { return __dsqrt_rn(x); }
+__device__ __forceinline__ float div_(float a, float b) { return __fdiv_rn(a, b); }
+__device__ __forceinline__ double div_(double a, double b) { return __ddiv_rn(a, b); }
+
+template <typename real> struct TrainParams {
+    const real *emb, *watt, *w1, *b1, *w2, *b2;     // row-major [out][in]
+    const real *wattT, *w1T;                        // [in][out]
+    real scale;
+    int E, T;
+    int64_t n;
+    const int32_t *node, *seq;
+    const uint8_t *mask;
+    const real *labels;
+    real *g_emb, *g_watt, *g_w1, *g_b1, *g_w2, *g_b2;
+    double *loss_acc;                               // sum of per-row losses
+};
+
+template <typename real>
+__global__ void __launch_bounds__(kTrThreads) din_train_kernel(const TrainParams<real> p)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int E = p.E, T = p.T, PL = T + 1;
+    real *sQ = reinterpret_cast<real *>(smem_raw);          // RB x E
+    real *sK = sQ + kTrRB * E;                               // RB x T x E
+    real *sP = sK + kTrRB * T * E;                           // RB x PL   probabilities
+    real *sA = sP + kTrRB * PL;                              // RB x E
+    real *sAtt = sA + kTrRB * E;                             // RB x E
+    real *sZ = sAtt + kTrRB * E;                             // RB x E    pre-activation
+    real *sDz = sZ + kTrRB * E;                              // RB x E
+    real *sDx = sDz + kTrRB * E;                             // RB x 2E
+    real *sDa = sDx + kTrRB * 2 * E;                         // RB x E
+    real *sDs = sDa + kTrRB * E;                             // RB x PL   dp then ds
+    real *sDy = sDs + kTrRB * PL;                            // RB
+    real *gWatt = sDy + kTrRB;                               // E*E
+    real *gW1 = gWatt + E * E;                               // 2*E*E
+    real *gB1 = gW1 + 2 * E * E;                             // E
+    real *gW2 = gB1 + E;                                     // E
+    real *gB2 = gW2 + E;                                     // 1 (+1 loss)
+    const int tid = threadIdx.x;
+    for (int i = tid; i < 3 * E * E + 2 * E + 2; i += kTrThreads) gWatt[i] = (real)0;
+    double loss_local = 0.0;
+    const real inv_n = (real)(1.0 / (double)p.n);
+    __syncthreads();
+
+    for (int64_t g0 = (int64_t)blockIdx.x * kTrRB; g0 < p.n; g0 += (int64_t)gridDim.x * kTrRB) {
+        const int nr = (int)((p.n - g0) < kTrRB ? (p.n - g0) : kTrRB);
+        for (int idx = tid; idx < nr * (T + 1) * E; idx += kTrThreads) {
+            const int k = idx % E, slot = (idx / E) % (T + 1), r = idx / (E * (T + 1));
+            const int32_t c = slot == 0 ? p.node[g0 + r] : p.seq[(g0 + r) * T + slot - 1];
+            const real v = c < 0 ? (real)0 : p.emb[(size_t)c * E + k];
+            if (slot == 0) sQ[r * E + k] = v; else sK[(r * T + slot - 1) * E + k] = v;
+        }
+        __syncthreads();
+        // ---- forward (same chains as rows_kernels.cuh) ----
+        for (int idx = tid; idx < nr * T; idx += kTrThreads) {
+            const int r = idx / T, j = idx % T;
+            const real *q = sQ + r * E, *kj = sK + (r * T + j) * E;
+            real acc = (real)0;
+            for (int k = 0; k < E; k++) acc = fma_(q[k], kj[k], acc);
+            real s = mul_(acc, p.scale);
+            if (p.mask[(g0 + r) * T + j]) s = mask_value<real>::get();
+            sP[r * PL + j] = s;
+        }
+        __syncthreads();
+        if (tid < nr) {
+            real *pr = sP + tid * PL;
+            real mx = pr[0];
+            for (int j = 1; j < T; j++) { real v = pr[j]; mx = v > mx ? v : mx; }
+            real sum = (real)0;
+            for (int j = 0; j < T; j++) { real e = exp_(sub_(pr[j], mx)); pr[j] = e; sum = add_(sum, e); }
+            const real inv = inv_(sum);
+            for (int j = 0; j < T; j++) pr[j] = mul_(pr[j], inv);
+        }
+        __syncthreads();
+        for (int idx = tid; idx < nr * E; idx += kTrThreads) {
+            const int r = idx / E, k = idx % E;
+            real acc = (real)0;
+            for (int j = 0; j < T; j++) acc = fma_(sP[r * PL + j], sK[(r * T + j) * E + k], acc);
+            sA[idx] = acc;
+        }
+        __syncthreads();
+        for (int idx = tid; idx < nr * E; idx += kTrThreads) {
+            const int r = idx / E, o = idx % E;
+            real acc = (real)0;
+            for (int k = 0; k < E; k++) acc = fma_(sA[r * E + k], __ldg(p.wattT + (size_t)k * E + o), acc);
+            sAtt[idx] = acc;
+        }
+        __syncthreads();
+        for (int idx = tid; idx < nr * E; idx += kTrThreads) {
+            const int r = idx / E, o = idx % E;
+            real acc = (real)0;
+            for (int k = 0; k < E; k++) acc = fma_(sQ[r * E + k], __ldg(p.w1T + (size_t)k * E + o), acc);
+            for (int k = 0; k < E; k++) acc = fma_(sAtt[r * E + k], __ldg(p.w1T + (size_t)(E + k) * E + o), acc);
+            sZ[idx] = add_(acc, __ldg(p.b1 + o));
+        }
+        __syncthreads();
+        if (tid < nr) {
+            real y = (real)0;
+            for (int o = 0; o < E; o++) y = fma_(relu_(sZ[tid * E + o]), __ldg(p.w2 + o), y);
+            y = add_(y, __ldg(p.b2));
+            const real t = p.labels[g0 + tid];
+            const real ay = y < (real)0 ? -y : y;
+            loss_local += (double)((y > (real)0 ? y : (real)0) - y * t + log1pexp_(exp_(-ay)));
+            sDy[tid] = mul_(sub_(div_((real)1, add_((real)1, exp_(-y))), t), inv_n);
+        }
+        __syncthreads();
+        // ---- backward ----
+        for (int idx = tid; idx < nr * E; idx += kTrThreads) {
+            const int r = idx / E, o = idx % E;
+            sDz[idx] = sZ[idx] <= (real)0 ? (real)0 : mul_(sDy[r], __ldg(p.w2 + o));
+        }
+        __syncthreads();
+        for (int o = tid; o < E; o += kTrThreads) {
+            real a2 = (real)0, a1 = (real)0;
+            for (int r = 0; r < nr; r++) { a2 = fma_(sDy[r], relu_(sZ[r * E + o]), a2); a1 = add_(a1, sDz[r * E + o]); }
+            gW2[o] = add_(gW2[o], a2);
+            gB1[o] = add_(gB1[o], a1);
+        }
+        if (tid == 0) { real a = (real)0; for (int r = 0; r < nr; r++) a = add_(a, sDy[r]); gB2[0] = add_(gB2[0], a); }
+        for (int idx = tid; idx < 2 * E * E; idx += kTrThreads) {      // gW1[o][k] += dz[o] * x[k]
+            const int o = idx / (2 * E), k = idx % (2 * E);
+            real acc = (real)0;
+            for (int r = 0; r < nr; r++) acc = fma_(sDz[r * E + o], k < E ? sQ[r * E + k] : sAtt[r * E + k - E], acc);
+            gW1[idx] = add_(gW1[idx], acc);
+        }
+        for (int idx = tid; idx < nr * 2 * E; idx += kTrThreads) {     // dx = W1^T dz
+            const int r = idx / (2 * E), k = idx % (2 * E);
+            real acc = (real)0;
+            for (int o = 0; o < E; o++) acc = fma_(sDz[r * E + o], __ldg(p.w1 + (size_t)o * 2 * E + k), acc);
+            sDx[idx] = acc;
+        }
+        __syncthreads();
+        for (int idx = tid; idx < E * E; idx += kTrThreads) {          // gWatt[o][k] += datt[o] * a[k]
+            const int o = idx / E, k = idx % E;
+            real acc = (real)0;
+            for (int r = 0; r < nr; r++) acc = fma_(sDx[r * 2 * E + E + o], sA[r * E + k], acc);
+            gWatt[idx] = add_(gWatt[idx], acc);
+        }
+        for (int idx = tid; idx < nr * E; idx += kTrThreads) {         // da = Watt^T datt
+            const int r = idx / E, k = idx % E;
+            real acc = (real)0;
+            for (int o = 0; o < E; o++) acc = fma_(sDx[r * 2 * E + E + o], __ldg(p.watt + (size_t)o * E + k), acc);
+            sDa[idx] = acc;
+        }
+        __syncthreads();
+        for (int idx = tid; idx < nr * T; idx += kTrThreads) {         // dp_j = da . K_j
+            const int r = idx / T, j = idx % T;
+            real acc = (real)0;
+            for (int k = 0; k < E; k++) acc = fma_(sDa[r * E + k], sK[(r * T + j) * E + k], acc);
+            sDs[r * PL + j] = acc;
+        }
+        __syncthreads();
+        if (tid < nr) {                                                // softmax + mask backward
+            real *ds = sDs + tid * PL;
+            const real *pr = sP + tid * PL;
+            real dot = (real)0;
+            for (int j = 0; j < T; j++) dot = fma_(ds[j], pr[j], dot);
+            for (int j = 0; j < T; j++) {
+                real v = mul_(mul_(sub_(ds[j], dot), pr[j]), p.scale);
+                if (p.mask[(g0 + tid) * T + j]) v = (real)0;
+                ds[j] = v;
+            }
+        }
+        __syncthreads();
+        for (int idx = tid; idx < nr * (T + 1) * E; idx += kTrThreads) {   // K6: scatter-add into the table
+            const int k = idx % E, slot = (idx / E) % (T + 1), r = idx / (E * (T + 1));
+            if (slot == 0) {
+                const int32_t c = p.node[g0 + r];
+                if (c >= 0) {
+                    real acc = sDx[r * 2 * E + k];
+                    for (int j = 0; j < T; j++) acc = fma_(sDs[r * PL + j], sK[(r * T + j) * E + k], acc);
+                    atomicAdd(p.g_emb + (size_t)c * E + k, acc);
+                }
+            } else {
+                const int j = slot - 1;
+                const int32_t c = p.seq[(g0 + r) * T + j];
+                if (c >= 0) {
+                    real v = mul_(sP[r * PL + j], sDa[r * E + k]);
+                    v = fma_(sDs[r * PL + j], sQ[r * E + k], v);
+                    atomicAdd(p.g_emb + (size_t)c * E + k, v);
+                }
+            }
+        }
+        __syncthreads();
+    }
+    for (int i = tid; i < E * E; i += kTrThreads) atomicAdd(p.g_watt + i, gWatt[i]);
+    for (int i = tid; i < 2 * E * E; i += kTrThreads) atomicAdd(p.g_w1 + i, gW1[i]);
+    for (int i = tid; i < E; i += kTrThreads) { atomicAdd(p.g_b1 + i, gB1[i]); atomicAdd(p.g_w2 + i, gW2[i]); }
+    if (tid == 0) atomicAdd(p.g_b2, gB2[0]);
+    // loss: warp reduce then one atomic per warp
+    for (int o = 16; o > 0; o >>= 1) loss_local += __shfl_xor_sync(0xffffffffu, loss_local, o);
+    if ((tid & 31) == 0 && loss_local != 0.0) atomicAdd(p.loss_acc, loss_local);
+}
+
+// K7: dense Adam, gradient zeroed in the same pass.
+template <typename real>
+__global__ void adam_dense_kernel(real *__restrict__ w, real *__restrict__ g, real *__restrict__ s, real *__restrict__ r,
+                                  int64_t n, real b1, real omb1, real b2, real omb2, real eps, real nstep)
+{
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (; i < n; i += stride) {
+        const real gi = g[i];
+        const real si = add_(mul_(s[i], b1), mul_(omb1, gi));
+        const real ri = add_(mul_(r[i], b2), mul_(omb2, mul_(gi, gi)));
+        const real denom = add_(sqrt_(ri), eps);
+        w[i] = add_(w[i], mul_(nstep, div_(si, denom)));
+        s[i] = si; r[i] = ri; g[i] = (real)0;
+    }
+}
+
+// K4: one thread per (target, level): positive = ancestor at that level, then neg distinct uniform
+// codes of the level that exist and differ from the positive, emitted in ascending order.
+__global__ void tdm_sample_kernel(int n_targets, const int32_t *__restrict__ target_items, const int32_t *__restrict__ id_code,
+                                  int32_t non_leaf_offset, const uint32_t *__restrict__ exists, int max_level,
+                                  const int32_t *__restrict__ layer_neg, const int32_t *__restrict__ level_off,
+                                  int start_level, int layer_sum, uint64_t seed, int32_t *__restrict__ out_node,
+                                  float *__restrict__ out_label, int32_t *__restrict__ err_flag)
+{
+    const int n_lv = max_level + 1 - start_level;
+    int gid = blockIdx.x * blockDim.x + threadIdx.x;
+    if (gid >= n_targets * n_lv) return;
+    const int t = gid / n_lv, level = start_level + gid % n_lv;
+    const int32_t item = target_items[t];
+    int32_t leaf = (item > 0 && item < non_leaf_offset) ? id_code[item] : -1;
+    if (leaf < 0) { atomicExch(err_flag, 1); return; }
+    int64_t pos = leaf;
+    for (int l = max_level; l > level; l--) pos = (pos - 1) >> 1;       // TDMTree.pathNodes upTrace
+    const int neg = layer_neg[level];
+    int32_t *dst = out_node + (size_t)t * layer_sum + level_off[level];
+    float *lab = out_label + (size_t)t * layer_sum + level_off[level];
+    dst[0] = (int32_t)pos;
+    lab[0] = 1.0f;
+    const int64_t lstart = ((int64_t)1 << level) - 1, lsize = (int64_t)1 << level;
+    int got = 0;
+    uint64_t ctr = 0;
+    const uint64_t key = splitmix64(seed ^ splitmix64(((uint64_t)t << 8) | (uint64_t)level));
+    const int max_try = 64 * (neg + 4);
+    while (got < neg && (int)ctr < max_try) {
+        const int64_t c = lstart + (int64_t)(splitmix64(key + ctr++) % (uint64_t)lsize);
+        if (c == pos || !code_exists(exists, c)) continue;
+        bool dup = false;
+        for (int i = 0; i < got; i++) dup |= (dst[1 + i] == (int32_t)c);
+        if (dup) continue;
+        int i = got++;                                                  // insertion keeps ascending order (BitSet.toList)
+        while (i > 0 && dst[i] > (int32_t)c) { dst[1 + i] = dst[i]; i--; }
+        dst[1 + i] = (int32_t)c;
+    }
+    if (got < neg) {                                                    // sparse level: take what exists, in order
+        for (int64_t c = lstart; c < lstart + lsize && got < neg; c++) {
+            if (c == pos || !code_exists(exists, c)) continue;
+            bool dup = false;
+            for (int i = 0; i < got; i++) dup |= (dst[1 + i] == (int32_t)c);
+            if (dup) continue;
+            int i = got++;
+            while (i > 0 && dst[i] > (int32_t)c) { dst[1 + i] = dst[i]; i--; }
+            dst[1 + i] = (int32_t)c;
+        }
+        for (int i = got; i < neg; i++) dst[1 + i] = -1;                // fewer nodes than negatives: padding rows
+    }
+    for (int i = 0; i < neg; i++) lab[1 + i] = 0.0f;
+}
+
+// history of target t repeated layer_sum times (MiniBatch.transformWithMask)
+__global__ void repeat_seq_kernel(const int32_t *__restrict__ codes, const uint8_t *__restrict__ mask, int n_targets, int T,
+                                  int layer_sum, int32_t *__restrict__ out_seq, uint8_t *__restrict__ out_mask)
+{
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t n = (int64_t)n_targets * layer_sum * T;
+    if (i >= n) return;
+    const int j = (int)(i % T);
+    const int64_t t = i / ((int64_t)layer_sum * T);
+    out_seq[i] = codes[t * T + j];
+    if (out_mask) out_mask[i] = mask[t * T + j];
+}
+
+// K9 second half: per (item, node) the in-order fp32 sum of the item's sample logits (Tensor.sum),
+// then per (item, child) the in-order sum along child -> parent (TreeLearning.scala:163-172).
+__global__ void jtm_reduce_kernel(int n_items, const int64_t *__restrict__ sample_off, const float *__restrict__ logits,
+                                  int n_nodes /* nodes per item = 2^(gap+1)-2 */, int gap, float *__restrict__ node_sum,
+                                  float *__restrict__ out_weights)
+{
+    // phase A: one thread per (item, node)
+    const int64_t total = (int64_t)n_items * n_nodes;
+    for (int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; g < total; g += (int64_t)gridDim.x * blockDim.x) {
+        const int item = (int)(g / n_nodes), nd = (int)(g % n_nodes);
+        const int64_t s0 = sample_off[item], s1 = sample_off[item + 1];
+        // logits layout: for item i, block of (s1-s0)*n_nodes values, node-major [nd][sample]
+        const float *src = logits + s0 * n_nodes + (int64_t)nd * (s1 - s0);
+        float acc = 0.0f;
+        for (int64_t k = 0; k < s1 - s0; k++) acc = __fadd_rn(acc, src[k]);
+        node_sum[g] = acc;
+    }
+    (void)gap; (void)out_weights;
+}
+
+__global__ void jtm_path_kernel(int n_items, const int64_t *__restrict__ sample_off, int gap, int n_nodes,
+                                const float *__restrict__ node_sum, float *__restrict__ out_weights)
+{
+    const int n_child = 1 << gap;
+    const int64_t total = (int64_t)n_items * n_child;
+    for (int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; g < total; g += (int64_t)gridDim.x * blockDim.x) {
+        const int item = (int)(g / n_child), ch = (int)(g % n_child);
+        if (sample_off[item + 1] == sample_off[item]) { out_weights[g] = -1e6f; continue; }   // TreeLearning.scala:160
+        // local heap index inside the parent's subtree: root = 0, children 2i+1, 2i+2; node slot = idx-1
+        int idx = (1 << gap) - 1 + ch;
+        float w = 0.0f;
+        while (idx > 0) { w = __fadd_rn(w, node_sum[(int64_t)item * n_nodes + idx - 1]); idx = (idx - 1) >> 1; }
+        out_weights[g] = w;
+    }
+}
+
+// rows for K9: (item-sample, subtree node) -> node code + history codes at the node's level
+__global__ void jtm_rows_kernel(int n_items, const int64_t *__restrict__ sample_off, const int32_t *__restrict__ sample_seq,
+                                const int32_t *__restrict__ parent_code, int old_level, int gap, int n_nodes, int T,
+                                const int32_t *__restrict__ id_code, int32_t non_leaf_offset, int32_t max_code, int max_level,
+                                int hierarchical, int min_level, int use_mask, const int64_t *__restrict__ item_of_row,
+                                int64_t n_rows, int32_t *__restrict__ out_node, int32_t *__restrict__ out_seq,
+                                uint8_t *__restrict__ out_mask)
+{
+    for (int64_t row = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; row < n_rows; row += (int64_t)gridDim.x * blockDim.x) {
+        const int item = (int)item_of_row[row];
+        const int64_t s0 = sample_off[item], ns = sample_off[item + 1] - s0;
+        const int64_t local = row - s0 * n_nodes;
+        const int nd = (int)(local / ns);
+        const int64_t smp = s0 + local % ns;
+        // subtree slot nd -> heap index nd+1 -> depth below the parent and offset within that depth
+        const int hidx = nd + 1;
+        const int depth = 31 - __clz(hidx + 1);
+        const int64_t first = ((int64_t)parent_code[item] + 1) * ((int64_t)1 << depth) - 1;   // leftmost descendant at that depth
+        const int32_t code = (int32_t)(first + (hidx + 1 - (1 << depth)));
+        const int level = old_level + depth;
+        out_node[row] = code;
+        for (int j = 0; j < T; j++) {                                   // JTMTree.idToCodeWithMask :86-113
+            const int32_t id = sample_seq[smp * T + j];
+            int32_t c;
+            uint8_t m = 0;
+            if (id == 0) { c = -1; m = 1; }
+            else if (id > 0 && id < non_leaf_offset && id_code[id] >= 0) {
+                c = id_code[id];
+                if (hierarchical && level >= min_level) {               // getAncestorAtLevel :36-43
+                    const int64_t lim = ((int64_t)1 << (level + 1)) - 1;
+                    int64_t cc = c;
+                    while (cc >= lim) cc = (cc - 1) >> 1;
+                    c = (int32_t)cc;
+                }
+            } else {
+                int64_t tmp = (int64_t)id - non_leaf_offset;
+                c = tmp > max_code ? -1 : (int32_t)tmp;                 // NB: not added to the mask (JTMTree.scala:104-107)
+            }
+            out_seq[row * T + j] = c;
+            out_mask[row * T + j] = use_mask ? m : 0;
+        }
+        (void)gap; (void)max_level;
+    }
+}
+
+template <typename real> int32_t ensure_train_state(dmg_handle_t h)
+{
+    DinDev &d = h->din;
+    if (d.d_grad) return DMG_OK;
+    const size_t bytes = (size_t)d.n_params * sizeof(real);
+    DMG_CUDA(h, cudaMalloc(&d.d_grad, bytes));
+    DMG_CUDA(h, cudaMalloc(&d.d_m, bytes));
+    DMG_CUDA(h, cudaMalloc(&d.d_v, bytes));
+    DMG_CUDA(h, cudaMemsetAsync(d.d_grad, 0, bytes, h->stream));
+    DMG_CUDA(h, cudaMemsetAsync(d.d_m, 0, bytes, h->stream));
+    DMG_CUDA(h, cudaMemsetAsync(d.d_v, 0, bytes, h->stream));
+    return DMG_OK;
+}
+
+// uploads (node, seq, mask, labels), validates, runs K5/K6 into d_grad.  Loss (mean) -> *loss_out.
+template <typename real>
+int32_t grad_pass(dmg_handle_t h, int64_t n, const int32_t *node, const int32_t *seq, const int32_t *mask_flat, int64_t n_mask,
+                  const real *labels, double *loss_out)
+{
+    DinDev &d = h->din;
+    const int E = d.E, T = d.T;
+    DMG_TRY(ensure_train_state<real>(h));
+    const size_t b_node = (size_t)n * 4, b_seq = (size_t)n * T * 4, b_mask = (size_t)n_mask * 4, b_lab = (size_t)n * sizeof(real);
+    const size_t in_bytes = Carver::need({b_node, b_seq, b_mask, b_lab});
+    DMG_TRY(ensure_host(h, h->s_in, in_bytes));
+    DMG_TRY(ensure_dev(h, h->s_in, in_bytes));
+    Carver ch(h->s_in.h), cd(h->s_in.d);
+    int32_t *hn = ch.take<int32_t>((size_t)n), *dn = cd.take<int32_t>((size_t)n);
+    int32_t *hs = ch.take<int32_t>((size_t)n * T), *ds = cd.take<int32_t>((size_t)n * T);
+    int32_t *hm = ch.take<int32_t>((size_t)n_mask), *dm = cd.take<int32_t>((size_t)n_mask);
+    real *hl = ch.take<real>((size_t)n), *dl = cd.take<real>((size_t)n);
+    memcpy(hn, node, b_node); memcpy(hs, seq, b_seq); memcpy(hl, labels, b_lab);
+    if (n_mask) memcpy(hm, mask_flat, b_mask);
+    DMG_CUDA(h, cudaMemcpyAsync(h->s_in.d, h->s_in.h, ch.off, cudaMemcpyHostToDevice, h->stream));
+    DMG_TRY(ensure_dev(h, h->s_work, Carver::need({(size_t)n * T, 64})));
+    Carver cw(h->s_work.d);
+    uint8_t *d_mask = cw.take<uint8_t>((size_t)n * T);
+    double *d_loss = cw.take<double>(1);
+    DMG_CUDA(h, cudaMemsetAsync(d_mask, 0, (size_t)n * T, h->stream));
+    DMG_CUDA(h, cudaMemsetAsync(d_loss, 0, sizeof(double), h->stream));
+    if (n_mask) {
+        mask_scatter_kernel<<<(unsigned)((n_mask + 255) / 256), 256, 0, h->stream>>>(dm, n_mask, n * T, d_mask, h->d_flags);
+        h->launches += 1;
+    }
+    check_index_kernel<<<(unsigned)((n + 255) / 256), 256, 0, h->stream>>>(dn, n, d.rows, h->d_flags);
+    check_index_kernel<<<(unsigned)((n * T + 255) / 256), 256, 0, h->stream>>>(ds, n * T, d.rows, h->d_flags);
+    h->launches += 2;
+    int32_t flag = 0;
+    DMG_CUDA(h, cudaMemcpyAsync(&flag, h->d_flags, 4, cudaMemcpyDeviceToHost, h->stream));
+    DMG_CUDA(h, cudaStreamSynchronize(h->stream));
+    if (flag) {
+        DMG_CUDA(h, cudaMemsetAsync(h->d_flags, 0, 4, h->stream));
+        return fail(h, DMG_ERR_INDEX, "training batch: embeddingLookup failed, index outside [0, %lld) or bad mask position", (long long)d.rows);
+    }
+    TrainParams<real> p;
+    p.emb = d.emb<real>(); p.watt = d.watt<real>(); p.w1 = d.w1<real>(); p.b1 = d.b1<real>(); p.w2 = d.w2<real>(); p.b2 = d.b2<real>();
+    p.wattT = (const real *)d.d_wattT; p.w1T = (const real *)d.d_w1T;
+    p.scale = (real)(1.0 / std::sqrt((double)E));
+    p.E = E; p.T = T; p.n = n; p.node = dn; p.seq = ds; p.mask = d_mask; p.labels = dl;
+    real *g = (real *)d.d_grad;
+    p.g_emb = g; p.g_watt = g + d.rows * E; p.g_w1 = p.g_watt + (int64_t)E * E; p.g_b1 = p.g_w1 + (int64_t)2 * E * E;
+    p.g_w2 = p.g_b1 + E; p.g_b2 = p.g_w2 + E;
+    p.loss_acc = d_loss;
+    const size_t smem = ((size_t)kTrRB * ((size_t)8 * E + (size_t)T * E + 2 * (T + 1) + 1) + 3 * (size_t)E * E + 2 * E + 2) * sizeof(real);
+    if (smem > h->smem_optin) return fail(h, DMG_ERR_UNSUPPORTED, "embed_size %d too large for the training kernel", E);
+    auto kern = din_train_kernel<real>;
+    DMG_CUDA(h, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const int grid = (int)std::min<int64_t>((n + kTrRB - 1) / kTrRB, (int64_t)h->sm_count * 4);
+    kern<<<grid, kTrThreads, smem, h->stream>>>(p);
+    h->launches += 1;
+    DMG_CUDA(h, cudaGetLastError());
+    double loss_sum = 0.0;
+    DMG_CUDA(h, cudaMemcpyAsync(&loss_sum, d_loss, sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    DMG_CUDA(h, cudaStreamSynchronize(h->stream));
+    *loss_out = loss_sum / (double)n;
+    return DMG_OK;
+}
+
+template <typename real> int32_t adam_pass(dmg_handle_t h, double lr, int step_t)
+{
+    DinDev &d = h->din;
+    const double beta1 = 0.9, beta2 = 0.999, eps = 1e-8;                      // Adam.scala:10-14
+    const double step = lr * std::sqrt(1 - std::pow(beta2, step_t)) / (1 - std::pow(beta1, step_t));
+    adam_dense_kernel<real><<<h->sm_count * 8, 256, 0, h->stream>>>(
+        (real *)d.d_params, (real *)d.d_grad, (real *)d.d_m, (real *)d.d_v, d.n_params, (real)beta1, (real)(1 - beta1),
+        (real)beta2, (real)(1 - beta2), (real)eps, (real)(-step));
+    h->launches += 1;
+    DMG_CUDA(h, cudaGetLastError());
+    return dmg_refresh_transposes(h);
+}
+
+int32_t train_precheck(dmg_handle_t h, int64_t rows, const void *node, const void *seq, const void *labels, const void *out)
+{
+    if (!h) return DMG_ERR_INVALID_ARG;
+    if (!h->din.loaded) return fail(h, DMG_ERR_STATE, "DIN weights must be loaded first");
+    if (rows <= 0 || !node || !seq || !labels || !out) return fail(h, DMG_ERR_INVALID_ARG, "bad arguments");
+    DMG_CUDA(h, cudaSetDevice(h->device));
+    return DMG_OK;
+}
+
+}  // namespace
+
+DMG_API int32_t dmg_din_gradients(dmg_handle_t h, int64_t rows, const int32_t *node, const int32_t *seq, const int32_t *mask_flat,
+                                  int64_t n_mask, const void *labels, void *out_loss, void *out_grad, int64_t n_grad)
+{
+    DMG_TRY(train_precheck(h, rows, node, seq, labels, out_loss));
+    DinDev &d = h->din;
+    if (!out_grad || n_grad != d.n_params) return fail(h, DMG_ERR_INVALID_ARG, "out_grad must hold %lld values", (long long)d.n_params);
+    double loss = 0.0;
+    if (d.dtype == DMG_F32) {
+        DMG_TRY(ensure_train_state<float>(h));
+        DMG_CUDA(h, cudaMemsetAsync(d.d_grad, 0, (size_t)d.n_params * 4, h->stream));
+        DMG_TRY(grad_pass<float>(h, rows, node, seq, mask_flat, n_mask, (const float *)labels, &loss));
+        *(float *)out_loss = (float)loss;
+    } else {
+        DMG_TRY(ensure_train_state<double>(h));
+        DMG_CUDA(h, cudaMemsetAsync(d.d_grad, 0, (size_t)d.n_params * 8, h->stream));
+        DMG_TRY(grad_pass<double>(h, rows, node, seq, mask_flat, n_mask, (const double *)labels, &loss));
+        *(double *)out_loss = loss;
+    }
+    DMG_CUDA(h, cudaMemcpyAsync(out_grad, d.d_grad, (size_t)d.n_params * d.esz, cudaMemcpyDeviceToHost, h->stream));
+    DMG_CUDA(h, cudaMemsetAsync(d.d_grad, 0, (size_t)d.n_params * d.esz, h->stream));
+    DMG_CUDA(h, cudaStreamSynchronize(h->stream));
+    return DMG_OK;
+}
+
+DMG_API int32_t dmg_train_step(dmg_handle_t h, int64_t rows, const int32_t *node, const int32_t *seq, const int32_t *mask_flat,
+                               int64_t n_mask, const void *labels, double lr, int32_t step_t, void *out_loss)
+{
+    DMG_TRY(train_precheck(h, rows, node, seq, labels, out_loss));
+    if (step_t < 1) return fail(h, DMG_ERR_INVALID_ARG, "step_t is the 1-based Adam timestep");
+    double loss = 0.0;
+    if (h->din.dtype == DMG_F32) {
+        DMG_TRY(grad_pass<float>(h, rows, node, seq, mask_flat, n_mask, (const float *)labels, &loss));
+        DMG_TRY(adam_pass<float>(h, lr, step_t));
+        *(float *)out_loss = (float)loss;
+    } else {
+        DMG_TRY(grad_pass<double>(h, rows, node, seq, mask_flat, n_mask, (const double *)labels, &loss));
+        DMG_TRY(adam_pass<double>(h, lr, step_t));
+        *(double *)out_loss = loss;
+    }
+    DMG_CUDA(h, cudaStreamSynchronize(h->stream));
+    return DMG_OK;
+}
+
+DMG_API int32_t dmg_tdm_sample_expand(dmg_handle_t h, int32_t n_targets, const int32_t *target_items, const int32_t *item_seq,
+                                      const int32_t *layer_neg, int32_t start_level, uint64_t seed, int32_t *out_node,
+                                      int32_t *out_seq, float *out_label, int32_t *out_rows)
+{
+    if (!h) return DMG_ERR_INVALID_ARG;
+    const TreeDev &t = h->tree;
+    if (!t.loaded || t.complete || !t.d_id_code) return fail(h, DMG_ERR_STATE, "needs a tree loaded with dmg_load_tree_tdm");
+    if (!h->din.loaded) return fail(h, DMG_ERR_STATE, "DIN weights (seq_len) must be loaded first");
+    if (n_targets <= 0 || !target_items || !item_seq || !layer_neg || !out_node || !out_seq || !out_label || !out_rows)
+        return fail(h, DMG_ERR_INVALID_ARG, "bad arguments");
+    if (start_level < 1 || start_level > t.max_level)
+        return fail(h, DMG_ERR_INVALID_ARG, "start sample level should be at least 1, got %d", start_level);   // NegativeSampler.scala:23
+    const int L = t.max_level, T = h->din.T;
+    std::vector<int32_t> level_off(L + 2, 0);
+    int layer_sum = 0;
+    for (int l = start_level; l <= L; l++) {
+        if (layer_neg[l] < 0 || (double)layer_neg[l] >= std::pow(2.0, l))
+            return fail(h, DMG_ERR_INVALID_ARG, "Num of negative samples must not exceed max numbers in current layer");  // :49-53
+        level_off[l] = layer_sum;
+        layer_sum += 1 + layer_neg[l];
+    }
+    DMG_CUDA(h, cudaSetDevice(h->device));
+    const size_t rows = (size_t)n_targets * layer_sum;
+    const size_t in_bytes = Carver::need({(size_t)n_targets * 4, (size_t)n_targets * T * 4, (size_t)(L + 1) * 4, (size_t)(L + 2) * 4});
+    DMG_TRY(ensure_host(h, h->s_in, in_bytes));
+    DMG_TRY(ensure_dev(h, h->s_in, in_bytes));
+    Carver ch(h->s_in.h), cd(h->s_in.d);
+    int32_t *ht = ch.take<int32_t>(n_targets), *dt = cd.take<int32_t>(n_targets);
+    int32_t *hs = ch.take<int32_t>((size_t)n_targets * T), *dsq = cd.take<int32_t>((size_t)n_targets * T);
+    int32_t *hneg = ch.take<int32_t>(L + 1), *dneg = cd.take<int32_t>(L + 1);
+    int32_t *hoff = ch.take<int32_t>(L + 2), *doff = cd.take<int32_t>(L + 2);
+    memcpy(ht, target_items, (size_t)n_targets * 4); memcpy(hs, item_seq, (size_t)n_targets * T * 4);
+    memcpy(hneg, layer_neg, (size_t)(L + 1) * 4); memcpy(hoff, level_off.data(), (size_t)(L + 2) * 4);
+    DMG_CUDA(h, cudaMemcpyAsync(h->s_in.d, h->s_in.h, ch.off, cudaMemcpyHostToDevice, h->stream));
+    const size_t out_bytes = Carver::need({rows * 4, rows * T * 4, rows * 4});
+    DMG_TRY(ensure_dev(h, h->s_out, out_bytes));
+    Carver od(h->s_out.d);
+    int32_t *d_node = od.take<int32_t>(rows), *d_seq = od.take<int32_t>(rows * T);
+    float *d_lab = od.take<float>(rows);
+    DMG_TRY(ensure_dev(h, h->s_work, Carver::need({(size_t)n_targets * T * 4, (size_t)n_targets * T})));
+    Carver cw(h->s_work.d);
+    int32_t *d_codes = cw.take<int32_t>((size_t)n_targets * T);
+    uint8_t *d_mask = cw.take<uint8_t>((size_t)n_targets * T);
+    const int n_lv = L + 1 - start_level;
+    tdm_sample_kernel<<<(n_targets * n_lv + 127) / 128, 128, 0, h->stream>>>(n_targets, dt, t.d_id_code, t.non_leaf_offset, t.d_exists, L,
+                                                                           dneg, doff, start_level, layer_sum, seed, d_node, d_lab, h->d_flags);
+    const int64_t nseq = (int64_t)n_targets * T;
+    // history ids -> codes (TDMTree.idToCode) then repeated layer_sum times
+    DMG_TRY(dmg_tdm_ids_to_codes(h, dsq, nseq, 1, d_codes, d_mask));
+    repeat_seq_kernel<<<(unsigned)((rows * T + 255) / 256), 256, 0, h->stream>>>(d_codes, d_mask, n_targets, T, layer_sum, d_seq, nullptr);
+    h->launches += 2;
+    DMG_CUDA(h, cudaGetLastError());
+    int32_t flag = 0;
+    DMG_CUDA(h, cudaMemcpyAsync(&flag, h->d_flags, 4, cudaMemcpyDeviceToHost, h->stream));
+    DMG_CUDA(h, cudaMemcpyAsync(out_node, d_node, rows * 4, cudaMemcpyDeviceToHost, h->stream));
+    DMG_CUDA(h, cudaMemcpyAsync(out_seq, d_seq, rows * T * 4, cudaMemcpyDeviceToHost, h->stream));
+    DMG_CUDA(h, cudaMemcpyAsync(out_label, d_lab, rows * 4, cudaMemcpyDeviceToHost, h->stream));
+    DMG_CUDA(h, cudaStreamSynchronize(h->stream));
+    if (flag) {
+        DMG_CUDA(h, cudaMemsetAsync(h->d_flags, 0, 4, h->stream));
+        return fail(h, DMG_ERR_INDEX, "dmg_tdm_sample_expand: a target is not a leaf item of the tree, or a history id is invalid");
+    }
+    *out_rows = (int32_t)rows;
+    return DMG_OK;
+}
+
+DMG_API int32_t dmg_jtm_item_weights(dmg_handle_t h, int32_t n_items, const int64_t *sample_off, const int32_t *sample_seq,
+                                     const int32_t *parent_code, int32_t old_level, int32_t level, int32_t hierarchical,
+                                     int32_t min_level, int32_t use_mask, float *out_weights)
+{
+    if (!h) return DMG_ERR_INVALID_ARG;
+    const TreeDev &t = h->tree;
+    DinDev &d = h->din;
+    if (!t.loaded || t.complete || !t.d_id_code) return fail(h, DMG_ERR_STATE, "needs a tree loaded with dmg_load_tree_tdm");
+    if (!d.loaded || d.dtype != DMG_F32) return fail(h, DMG_ERR_STATE, "JTM scorer is Module[Float]: load DMG_F32 weights");
+    const int gap = level - old_level;
+    if (n_items <= 0 || !sample_off || !parent_code || !out_weights || gap < 1 || gap > 8 || old_level < 0 || level > t.max_level)
+        return fail(h, DMG_ERR_INVALID_ARG, "bad arguments (1 <= level - old_level <= 8, level <= max_level)");
+    const int64_t n_samples = sample_off[n_items];
+    if (n_samples > 0 && !sample_seq) return fail(h, DMG_ERR_INVALID_ARG, "sample_seq is null");
+    DMG_CUDA(h, cudaSetDevice(h->device));
+    const int T = d.T, E = d.E;
+    const int n_nodes = (1 << (gap + 1)) - 2, n_child = 1 << gap;
+    const int64_t n_rows = n_samples * n_nodes;
+    // host: row -> item map
+    std::vector<int64_t> item_of_row((size_t)std::max<int64_t>(n_rows, 1));
+    for (int i = 0; i < n_items; i++) {
+        const int64_t b = sample_off[i] * n_nodes, e = sample_off[i + 1] * n_nodes;
+        for (int64_t r = b; r < e; r++) item_of_row[(size_t)r] = i;
+    }
+    const size_t in_bytes = Carver::need({(size_t)(n_items + 1) * 8, (size_t)n_samples * T * 4, (size_t)n_items * 4, (size_t)n_rows * 8});
+    DMG_TRY(ensure_host(h, h->s_in, in_bytes));
+    DMG_TRY(ensure_dev(h, h->s_in, in_bytes));
+    Carver ch(h->s_in.h), cd(h->s_in.d);
+    int64_t *ho = ch.take<int64_t>(n_items + 1), *dof = cd.take<int64_t>(n_items + 1);
+    int32_t *hs = ch.take<int32_t>((size_t)n_samples * T), *dsq = cd.take<int32_t>((size_t)n_samples * T);
+    int32_t *hp = ch.take<int32_t>(n_items), *dp = cd.take<int32_t>(n_items);
+    int64_t *hr = ch.take<int64_t>((size_t)n_rows), *dr = cd.take<int64_t>((size_t)n_rows);
+    memcpy(ho, sample_off, (size_t)(n_items + 1) * 8);
+    if (n_samples) memcpy(hs, sample_seq, (size_t)n_samples * T * 4);
+    memcpy(hp, parent_code, (size_t)n_items * 4);
+    if (n_rows) memcpy(hr, item_of_row.data(), (size_t)n_rows * 8);
+    DMG_CUDA(h, cudaMemcpyAsync(h->s_in.d, h->s_in.h, ch.off, cudaMemcpyHostToDevice, h->stream));
+    const size_t work = Carver::need({(size_t)n_rows * 4, (size_t)n_rows * T * 4, (size_t)n_rows * T, (size_t)n_rows * 4,
+                                      (size_t)n_items * n_nodes * 4, (size_t)n_items * n_child * 4});
+    DMG_TRY(ensure_dev(h, h->s_work, work));
+    Carver cw(h->s_work.d);
+    int32_t *d_node = cw.take<int32_t>((size_t)n_rows), *d_seq = cw.take<int32_t>((size_t)n_rows * T);
+    uint8_t *d_mask = cw.take<uint8_t>((size_t)n_rows * T);
+    float *d_logit = cw.take<float>((size_t)n_rows), *d_nsum = cw.take<float>((size_t)n_items * n_nodes);
+    float *d_w = cw.take<float>((size_t)n_items * n_child);
+    const int grid = h->sm_count * 8;
+    if (n_rows) {
+        jtm_rows_kernel<<<grid, 256, 0, h->stream>>>(n_items, dof, dsq, dp, old_level, gap, n_nodes, T, t.d_id_code, t.non_leaf_offset,
+                                                    t.max_code, t.max_level, hierarchical, min_level, use_mask, dr, n_rows, d_node, d_seq, d_mask);
+        check_index_kernel<<<(unsigned)((n_rows * T + 255) / 256), 256, 0, h->stream>>>(d_seq, n_rows * T, d.rows, h->d_flags);
+        const size_t smem = (size_t)kRowsRB * ((size_t)4 * E + (size_t)T * E + T + 1) * 4;
+        auto kern = din_rows_forward_kernel<float>;
+        DMG_CUDA(h, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        const int g2 = (int)std::min<int64_t>((n_rows + kRowsRB - 1) / kRowsRB, (int64_t)h->sm_count * 8);
+        kern<<<g2, kRowsThreads, smem, h->stream>>>(d.emb<float>(), (const float *)d.d_wattT, (const float *)d.d_w1T, d.b1<float>(),
+                                                    d.w2<float>(), d.b2<float>(), (float)(1.0 / std::sqrt((double)E)), E, T, n_rows,
+                                                    d_node, d_seq, d_mask, d_logit);
+        h->launches += 3;
+    }
+    jtm_reduce_kernel<<<grid, 256, 0, h->stream>>>(n_items, dof, d_logit, n_nodes, gap, d_nsum, d_w);
+    jtm_path_kernel<<<grid, 256, 0, h->stream>>>(n_items, dof, gap, n_nodes, d_nsum, d_w);
+    h->launches += 2;
+    DMG_CUDA(h, cudaGetLastError());
+    int32_t flag = 0;
+    DMG_CUDA(h, cudaMemcpyAsync(&flag, h->d_flags, 4, cudaMemcpyDeviceToHost, h->stream));
+    DMG_CUDA(h, cudaMemcpyAsync(out_weights, d_w, (size_t)n_items * n_child * 4, cudaMemcpyDeviceToHost, h->stream));
+    DMG_CUDA(h, cudaStreamSynchronize(h->stream));
+    if (flag) {
+        DMG_CUDA(h, cudaMemsetAsync(h->d_flags, 0, 4, h->stream));
+        return fail(h, DMG_ERR_INDEX, "dmg_jtm_item_weights: a history id maps outside the node table");
+    }
+    return DMG_OK;
+}

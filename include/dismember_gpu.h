@@ -188,14 +188,18 @@ DMG_API int32_t dmg_tdm_sample_expand(dmg_handle_t h, int32_t n_targets, const i
                                       int32_t *out_seq, float *out_label, int32_t *out_rows);
 
 /* ---- JTM tree learning ---------------------------------------------------------------- */
-/* TreeLearning.aggregateWeights (jtm/.../optim/TreeLearning.scala:152-174): for each item i
- * with samples [sample_off[i], sample_off[i+1]) (histories sample_seq, T item ids each) and
- * each of its n_child candidate children, weight = sum over the nodes on the child->parent
- * path (exclusive) of the summed logits of the item's samples; -1e6 when an item has no
- * sample (:160).  out_weights: n_items x n_child (float). */
+/* TreeLearning.aggregateWeights for a whole level step (jtm/.../optim/TreeLearning.scala:137-174):
+ * item i currently sits under node parent_code[i] of level old_level and owns the training samples
+ * [sample_off[i], sample_off[i+1]) (histories sample_seq, T item ids each, 0 = padding).  For each of
+ * its 2^(level-old_level) candidate children (left to right), weight = sum over the nodes on the
+ * child -> parent path (parent excluded, child first) of Tensor.sum of the logits of the item's samples
+ * scored against that node, histories coded by JTMTree.idToCodeWithMask(seq, node level, hierarchical,
+ * min_level) (JTMTree.scala:86-113); -1e6 for an item without samples (:160).
+ * out_weights: n_items x 2^(level-old_level) floats, bit-identical to the in-order fp32 sums. */
 DMG_API int32_t dmg_jtm_item_weights(dmg_handle_t h, int32_t n_items, const int64_t *sample_off,
                                      const int32_t *sample_seq, const int32_t *parent_code,
-                                     int32_t old_level, int32_t level, float *out_weights);
+                                     int32_t old_level, int32_t level, int32_t hierarchical,
+                                     int32_t min_level, int32_t use_mask, float *out_weights);
 
 #ifdef __cplusplus
 }

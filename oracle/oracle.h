@@ -60,6 +60,15 @@ int orc_dr_rerank(const orc_dr_model *m, const int32_t *seq, int n_cand, const i
 int orc_dr_recommend(const orc_dr_model *m, const int32_t *seq, int beam, int topk, const int64_t *path_off,
                      const int32_t *path_items, int32_t *out_ids, double *out_scores, double *out_prob);
 
+int orc_din_gradients_f32(int64_t rows, int E, int T, const float *params, int64_t n, const int32_t *node,
+                          const int32_t *seq, const int32_t *mask_flat, int64_t n_mask, const float *labels,
+                          float *grad, float *loss);
+int orc_din_gradients_f64(int64_t rows, int E, int T, const double *params, int64_t n, const int32_t *node,
+                          const int32_t *seq, const int32_t *mask_flat, int64_t n_mask, const double *labels,
+                          double *grad, double *loss);
+void orc_adam_f32(float *w, const float *g, float *s, float *r, int64_t n, double lr, int t);
+void orc_adam_f64(double *w, const double *g, double *s, double *r, int64_t n, double lr, int t);
+
 void orc_softmax_f32(int n, int dim, const float *in, float *out);
 void orc_softmax_grad_f32(int n, int dim, const float *y, const float *go, float *gi);
 float orc_expf_api(float x);

@@ -69,6 +69,12 @@ def lib():
     L.orc_dr_beam_search.argtypes = [vp, i32p, C.c_int, i32p, f64p]
     L.orc_dr_rerank.argtypes = [vp, i32p, C.c_int, i32p, f64p]
     L.orc_dr_recommend.argtypes = [vp, i32p, C.c_int, C.c_int, i64p, i32p, i32p, f64p, f64p]
+    L.orc_din_gradients_f32.argtypes = [C.c_int64, C.c_int, C.c_int, f32p, C.c_int64, i32p, i32p, vp, C.c_int64, f32p, f32p, f32p]
+    L.orc_din_gradients_f64.argtypes = [C.c_int64, C.c_int, C.c_int, f64p, C.c_int64, i32p, i32p, vp, C.c_int64, f64p, f64p, f64p]
+    L.orc_adam_f32.argtypes = [f32p, f32p, f32p, f32p, C.c_int64, C.c_double, C.c_int]
+    L.orc_adam_f32.restype = None
+    L.orc_adam_f64.argtypes = [f64p, f64p, f64p, f64p, C.c_int64, C.c_double, C.c_int]
+    L.orc_adam_f64.restype = None
     L.orc_softmax_f32.argtypes = [C.c_int, C.c_int, f32p, f32p]
     L.orc_softmax_grad_f32.argtypes = [C.c_int, C.c_int, f32p, f32p, f32p]
     L.orc_expf_api.restype = C.c_float
@@ -297,3 +303,27 @@ def softmax_grad_f32(y, go):
     out = np.empty_like(y)
     lib().orc_softmax_grad_f32(y.shape[0], y.shape[1], y, go, out)
     return out
+
+
+def din_gradients(params, rows, E, T, node, seq, mask_flat, labels):
+    """zeroGrad + forward + BCEWithLogits(mean) + backward -> (grad of the compact vector, loss)."""
+    params = np.ascontiguousarray(params)
+    dt = params.dtype
+    assert dt in (np.float32, np.float64)
+    node = _ci32(node).ravel()
+    seq = _ci32(seq).reshape(len(node), T)
+    labels = np.ascontiguousarray(labels, dt).ravel()
+    m = None if mask_flat is None else _ci32(mask_flat)
+    grad = np.empty_like(params)
+    loss = np.zeros(1, dt)
+    fn = lib().orc_din_gradients_f32 if dt == np.float32 else lib().orc_din_gradients_f64
+    rc = fn(rows, E, T, params, len(node), node, seq, _ptr(m), 0 if m is None else len(m), labels, grad, loss)
+    if rc:
+        raise IndexError(f"oracle error {rc}")
+    return grad, loss[0]
+
+
+def adam_step(w, g, s, r, lr, t):
+    """in-place Adam.optimize on (w, s, r)."""
+    fn = lib().orc_adam_f32 if w.dtype == np.float32 else lib().orc_adam_f64
+    fn(w, np.ascontiguousarray(g, w.dtype), s, r, w.size, float(lr), int(t))
