@@ -71,6 +71,7 @@ def load_library(build_if_missing: bool = True):
         "dmg_tdm_retrieve_dev": [vp, i32, vp, i32, i32, i32, vp, vp, vp],
         "dmg_otm_beam_search": [vp, i32, vp, i32, i32, vp, vp, vp],
         "dmg_otm_retrieve": [vp, i32, vp, i32, i32, i32, vp, vp, vp],
+        "dmg_otm_beam_search_levels": [vp, i32, vp, i32, i32, vp, vp, vp],
         "dmg_score_pairs": [vp, i64, vp, vp, vp, i64, vp],
         "dmg_dr_load": [vp, i32, i32, i32, i32, i32, vp, C.POINTER(vp), C.POINTER(vp), vp, vp, vp, vp, vp],
         "dmg_dr_load_paths": [vp, vp, vp],
@@ -225,6 +226,18 @@ class Engine:
         sc = np.empty((B, width), np.float64)
         counts = np.empty(B, np.int32)
         self._check(self.L.dmg_otm_beam_search(self.h, B, _p(seq), beam, int(use_mask), _p(ids), _p(sc), _p(counts)))
+        return ids, sc, counts
+
+    def otm_beam_search_levels(self, leaf_seq, beam, leaf_level, use_mask=True):
+        seq = _i32(leaf_seq).reshape(-1, self.T)
+        B = len(seq)
+        s = int(beam).bit_length() - 1
+        width = 2 * max(beam, 1 << s)
+        n_lvl = max(leaf_level - s, 0)
+        ids = np.empty((B, n_lvl, width), np.int32)
+        sc = np.empty((B, n_lvl, width), np.float64)
+        counts = np.empty((B, n_lvl), np.int32)
+        self._check(self.L.dmg_otm_beam_search_levels(self.h, B, _p(seq), beam, int(use_mask), _p(ids), _p(sc), _p(counts)))
         return ids, sc, counts
 
     def otm_retrieve(self, leaf_seq, beam, topk, use_mask=True):

@@ -45,6 +45,11 @@ template <typename real> struct BeamParams {
     int32_t *out_counts;
     int out_stride;
     int cap, capp;              // candidate capacity (>= 2*max beam) and its power of two
+    // optional: every level's scored candidates (OTMTree.beamSearchNodes), [user][level][lvl_stride]
+    int32_t *lvl_items;
+    real *lvl_scores;
+    int32_t *lvl_counts;        // [user][n_lvl]
+    int lvl_stride, n_lvl;
 };
 
 // ---- compile-time geometry ----------------------------------------------------------------
@@ -419,6 +424,17 @@ __global__ void __launch_bounds__(kThreads, 1) beam_search_kernel(const BeamPara
                     const int r1 = r0 + G::R;
                     gather_tile<real, E>(sX, p.emb, cur + r1, count - r1 < G::R ? count - r1 : G::R);
                     cp_async_commit();
+                }
+            }
+            if (p.lvl_items) {
+                const int li = level - s_level;
+                if (li < p.n_lvl) {
+                    const size_t base = ((size_t)user * p.n_lvl + li) * p.lvl_stride;
+                    for (int i = tid; i < p.lvl_stride; i += kThreads) {
+                        p.lvl_items[base + i] = i < count ? cur[i] : -1;
+                        p.lvl_scores[base + i] = i < count ? sScore[i] : (real)0;
+                    }
+                    if (tid == 0) p.lvl_counts[(size_t)user * p.n_lvl + li] = count;
                 }
             }
         }

@@ -472,7 +472,8 @@ DMG_API int32_t dmg_tdm_retrieve(dmg_handle_t h, int32_t B, const int32_t *item_
 
 // OTM: batchBeamSearch (dump) and recommend (topk) share one path.
 static int32_t otm_run(dmg_handle_t h, int32_t B, const int32_t *leaf_seq, int32_t beam, int32_t use_mask, int mode,
-                       int32_t topk, int32_t *out_ids, double *out_scores, int32_t *out_counts)
+                       int32_t topk, int32_t *out_ids, double *out_scores, int32_t *out_counts,
+                       int32_t *lvl_ids = nullptr, double *lvl_scores = nullptr, int32_t *lvl_counts = nullptr)
 {
     if (!h) return DMG_ERR_INVALID_ARG;
     if (!h->tree.loaded || !h->din.loaded) return fail(h, DMG_ERR_STATE, "tree and DIN weights must be loaded first");
@@ -520,8 +521,29 @@ static int32_t otm_run(dmg_handle_t h, int32_t B, const int32_t *leaf_seq, int32
     p.cap = std::max(((width + 7) / 8) * 8, 8);
     p.cap = std::max(p.cap, ((std::max(topk, 1) + 7) / 8) * 8);
     p.capp = pow2_ge(p.cap);
-    DMG_TRY(launch_beam<double>(h, p, d.E));
+    const int n_lvl = std::max(t.max_level - s, 0);
+    int32_t *d_li = nullptr, *d_lc = nullptr;
+    double *d_ls = nullptr;
+    if (lvl_ids && n_lvl > 0) {
+        const size_t lb = Carver::need({(size_t)B * n_lvl * width * 4, (size_t)B * n_lvl * width * 8, (size_t)B * n_lvl * 4});
+        void *blk = nullptr;
+        DMG_CUDA(h, cudaMalloc(&blk, lb));
+        Carver c2(blk);
+        d_li = c2.take<int32_t>((size_t)B * n_lvl * width);
+        d_ls = c2.take<double>((size_t)B * n_lvl * width);
+        d_lc = c2.take<int32_t>((size_t)B * n_lvl);
+        p.lvl_items = d_li; p.lvl_scores = d_ls; p.lvl_counts = d_lc; p.lvl_stride = width; p.n_lvl = n_lvl;
+    }
+    int32_t rc_launch = launch_beam<double>(h, p, d.E);
+    if (rc_launch != DMG_OK) { if (d_li) cudaFree(d_li); return rc_launch; }
     DMG_CUDA(h, cudaMemcpyAsync(h->s_out.h, h->s_out.d, od.off, cudaMemcpyDeviceToHost, h->stream));
+    if (d_li) {
+        cudaMemcpyAsync(lvl_ids, d_li, (size_t)B * n_lvl * width * 4, cudaMemcpyDeviceToHost, h->stream);
+        cudaMemcpyAsync(lvl_scores, d_ls, (size_t)B * n_lvl * width * 8, cudaMemcpyDeviceToHost, h->stream);
+        cudaMemcpyAsync(lvl_counts, d_lc, (size_t)B * n_lvl * 4, cudaMemcpyDeviceToHost, h->stream);
+        cudaStreamSynchronize(h->stream);
+        cudaFree(d_li);
+    }
     DMG_TRY(check_flag(h, "dmg_otm"));
     memcpy(out_ids, h_ids, (size_t)B * stride * 4);
     memcpy(out_scores, h_sc, (size_t)B * stride * 8);
@@ -533,6 +555,20 @@ DMG_API int32_t dmg_otm_beam_search(dmg_handle_t h, int32_t B, const int32_t *le
                                     int32_t *out_ids, double *out_scores, int32_t *out_counts)
 {
     return otm_run(h, B, leaf_seq, beam, use_mask, MODE_OTM_DUMP, 0, out_ids, out_scores, out_counts);
+}
+
+DMG_API int32_t dmg_otm_beam_search_levels(dmg_handle_t h, int32_t B, const int32_t *leaf_seq, int32_t beam, int32_t use_mask,
+                                           int32_t *out_ids, double *out_scores, int32_t *out_counts)
+{
+    if (!h) return DMG_ERR_INVALID_ARG;
+    if (!out_ids || !out_scores || !out_counts) return fail(h, DMG_ERR_INVALID_ARG, "null output");
+    if (!h->tree.loaded || beam <= 0 || B <= 0) return fail(h, DMG_ERR_INVALID_ARG, "bad arguments");
+    const int s = lower_log2(beam);
+    const int width = 2 * std::max(beam, 1 << s);
+    std::vector<int32_t> last_ids((size_t)B * width), last_cnt(B);
+    std::vector<double> last_sc((size_t)B * width);
+    return otm_run(h, B, leaf_seq, beam, use_mask, MODE_OTM_DUMP, 0, last_ids.data(), last_sc.data(), last_cnt.data(),
+                   out_ids, out_scores, out_counts);
 }
 
 DMG_API int32_t dmg_otm_retrieve(dmg_handle_t h, int32_t B, const int32_t *leaf_seq, int32_t beam, int32_t topk,

@@ -129,6 +129,13 @@ DMG_API int32_t dmg_tdm_retrieve_dev(dmg_handle_t h, int32_t B, const int32_t *d
 DMG_API int32_t dmg_otm_beam_search(dmg_handle_t h, int32_t B, const int32_t *leaf_seq,
                                     int32_t beam, int32_t use_mask, int32_t *out_ids,
                                     double *out_scores, int32_t *out_counts);
+/* OTMTree.beamSearchNodes (otm/.../tree/OTMTree.scala:67-91,174-212): the same search, returning the
+ * scored candidates of EVERY level startLevel+1..leafLevel (the rows the OTM trainer fits, one Adam
+ * step per level).  out_ids/out_scores: B x (leafLevel-startLevel) x 2*max(beam,2^s); out_counts:
+ * B x (leafLevel-startLevel). */
+DMG_API int32_t dmg_otm_beam_search_levels(dmg_handle_t h, int32_t B, const int32_t *leaf_seq,
+                                           int32_t beam, int32_t use_mask, int32_t *out_ids,
+                                           double *out_scores, int32_t *out_counts);
 /* OTM.recommend over a batch (otm/.../model/OTM.scala:14-23): leaf candidates that map back
  * to an item, stable sort desc, topk.  out_scores = raw logits (sigmoid on the host). */
 DMG_API int32_t dmg_otm_retrieve(dmg_handle_t h, int32_t B, const int32_t *leaf_seq, int32_t beam,

@@ -1,0 +1,93 @@
+"""Host mirrors of the reference drivers that sit on the GPU primitives: OTM per-level training
+(LocalOptimizer + OTMTree targets) and JTM tree learning (JTM.optimize + reBalance).  Assertions are
+the ones the Scala integration specs make (JtmSpec.scala:22-53, OtmModelTrainSpec.scala:43-79) plus
+consistency with the already-verified primitives."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+def _load_otm(engine, f):
+    n = len(f["items"])
+    leaf_level = int(np.ceil(np.log(n) / np.log(2)))
+    engine.load_tree_complete(leaf_level, f["items"], f["leaf_ids"])
+    engine.load_din_weights(f["params"], 8191, 16, 10)
+    return leaf_level
+
+
+def test_otm_beam_levels_consistent(engine, otm_fix, queries):
+    leaf_level = _load_otm(engine, otm_fix)
+    item_leaf = {int(a): int(b) for a, b in zip(otm_fix["items"], otm_fix["leaf_ids"])}
+    seqs = np.array([[item_leaf.get(int(x), -1) for x in s] for s in queries["seqs"][:16]], np.int32)
+    beam = 20
+    ids, sc, cnt = engine.otm_beam_search_levels(seqs, beam, leaf_level)
+    last_ids, last_sc, last_cnt = engine.otm_beam_search(seqs, beam)
+    s = 4
+    assert ids.shape[1] == leaf_level - s
+    assert (ids[:, -1] == last_ids).all() and (sc[:, -1].view(np.uint64) == last_sc.view(np.uint64)).all()
+    for u in range(len(seqs)):
+        for li in range(ids.shape[1]):
+            level = s + 1 + li
+            c = cnt[u, li]
+            nodes = ids[u, li, :c]
+            assert nodes.min() >= 2 ** level - 1 and nodes.max() <= 2 ** (level + 1) - 2
+            if li > 0:      # children (in order) of the stable top-beam of the previous level
+                pn, ps = ids[u, li - 1, :cnt[u, li - 1]], sc[u, li - 1, :cnt[u, li - 1]]
+                order = np.argsort(-ps, kind="stable")[:beam]
+                want = np.stack([2 * pn[order] + 1, 2 * pn[order] + 2], 1).ravel()
+                assert (nodes == want).all()
+            # scores are model.forward on (node, history)
+            fw = engine.score_pairs(nodes, np.tile(seqs[u], (c, 1)), np.flatnonzero(np.tile(seqs[u] == -1, c)).astype(np.int32))
+            assert (fw.view(np.uint64) == sc[u, li, :c].view(np.uint64)).all()
+
+
+def test_otm_training_minibatches(engine, otm_fix, queries):
+    from dismember_b200.otm_train import OTMTrainer
+    leaf_level = _load_otm(engine, otm_fix)
+    item_leaf = {int(a): int(b) for a, b in zip(otm_fix["items"], otm_fix["leaf_ids"])}
+    seqs = np.array([[item_leaf.get(int(x), -1) for x in s] for s in queries["seqs"][1:21]], np.int32)
+    targets = [[item_leaf[int(t)]] for t in queries["targets"][1:21]]
+    tr = OTMTrainer(engine, leaf_level, beam_size=20, seq_len=10)
+    pt = tr.optimal_pseudo_targets(seqs, targets)
+    assert len(pt) == leaf_level - tr.start_level
+    for li, lvl in enumerate(pt):
+        level = tr.start_level + 1 + li
+        for u, d in enumerate(lvl):
+            assert all(2 ** level - 1 <= n <= 2 ** (level + 1) - 2 and 0.0 <= z <= 1.0 for n, z in d.items())
+            anc = targets[u][0]
+            for _ in range(leaf_level - level):
+                anc = (anc - 1) >> 1
+            assert set(d) == {anc}                          # one target leaf -> its ancestor chain
+    nt = tr.normal_targets(targets)
+    assert all(set(nt[li][u]) == set(pt[li][u]) for li in range(len(pt)) for u in range(len(seqs)))
+    first = tr.train_minibatch(seqs, targets, lr=1e-3, target_mode="pseudo")
+    assert len(first) == leaf_level - tr.start_level and all(np.isfinite(first))
+    for _ in range(5):
+        last = tr.train_minibatch(seqs, targets, lr=1e-3, target_mode="pseudo")
+    assert np.mean(last) < np.mean(first)
+    # OtmModelTrainSpec: recommend still returns topk items after training
+    items, scores, counts = engine.otm_retrieve(seqs[:2], 20, 3)
+    assert (counts == 3).all()
+
+
+def test_jtm_tree_learning(engine, jtm_fix, queries):
+    from dismember_b200.jtm import JTM
+    f = jtm_fix
+    L = int(f["max_level"])
+    engine.load_tree_tdm(L, f["codes"], f["node_ids"], f["is_leaf"], f["leaf_ids"], f["leaf_codes"])
+    engine.load_din_weights(f["params"], 8191, 16, 10)
+    item_codes = {int(a): int(b) for a, b in zip(f["leaf_ids"], f["leaf_codes"])}
+    samples = {}
+    for s, t in zip(queries["seqs"][1:], queries["targets"][1:]):
+        samples.setdefault(int(t), []).append(s)
+    samples = {k: np.array(v, np.int32) for k, v in samples.items()}
+    jtm = JTM(engine, L, item_codes, samples, gap=3, seq_len=10, hierarchical=True, min_level=0)
+    proj = jtm.optimize()
+    # JtmSpec.scala:44-52
+    assert set(proj) == set(item_codes)
+    leaves = np.array(list(proj.values()))
+    assert leaves.min() >= 2 ** L - 1 and leaves.max() <= 2 ** (L + 1) - 2
+    assert len(set(leaves.tolist())) == len(leaves)         # capacity 1 at the leaf level
+    # deterministic
+    assert JTM(engine, L, item_codes, samples, gap=3, seq_len=10, hierarchical=True).optimize() == proj
