@@ -43,6 +43,9 @@ def parse():
     ap.add_argument("--seq-len", type=int, default=10)
     ap.add_argument("--cpu-sample-sec", type=float, default=12.0, help="target CPU work for the cpu_baseline leg")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--tau", type=float, default=None, help="certification band as a fraction of the worst-case bound")
+    ap.add_argument("--arith", default="fast", choices=["fast", "strict"],
+                    help="scorer arithmetic: tensor-core with certified cuts (same ids/logits) or strict fp32 SIMT")
     return ap.parse_args()
 
 
@@ -202,6 +205,9 @@ def main():
     eng = Engine(local)
     eng.load_tree_tdm(L, tf.codes, tf.node_ids, tf.is_leaf, tf.leaf_ids, tf.leaf_codes)
     eng.init_din_weights(np.float32, rows, E, T, seed=2)          # replicas: same table on every rank
+    eng.set_arithmetic(args.arith)
+    if args.tau is not None:
+        eng.set_fast_tolerance(args.tau)
     stream = torch.cuda.Stream(dev)                               # non-default: the engine launches on it
     torch.cuda.set_stream(stream)
     eng.set_stream(stream.cuda_stream)
@@ -246,6 +252,7 @@ def main():
     launches = eng.launch_count - l0
     kern_ms, kern_n = eng.kernel_time()
     eng.set_profiling(False)
+    fast_stats = eng.fast_stats() if args.arith == "fast" else None
     last_items = d_items.cpu().numpy().copy()
     last_logits = d_logits.cpu().numpy().copy()
 
@@ -306,11 +313,14 @@ def main():
                        "algorithmic_bytes_per_user": bytes_u, "node_table_gb": rows * E * 4 / 1e9,
                        "parallelism": f"replicas x{world}, users sharded, no collective",
                        "l2": "inputs larger than L2: 0.54 GB node table, fresh queries every step, no flush",
-                       "arithmetic": "strict fp32 (sequential-k fma chains, bit-identical to the CPU oracle)"},
+                       "arithmetic": ("tcgen05 bf16x3 tensor-core scorer + certified cuts, strict fp32 re-score of "
+                                      "near-cut candidates and of the topk (ids and logits bit-identical to the CPU oracle)")
+                       if args.arith == "fast" else "strict fp32 (sequential-k fma chains, bit-identical to the CPU oracle)",
+                       "fast_stats": fast_stats},
             "e2e": {"value": e2e_value, "unit": "users/s", "h2d_bytes_per_step": B * T * 4,
                     "d2h_bytes_per_step": B * args.topk * 8 + B * 4, "ms_per_step": e2e_s / K * 1e3},
             "gpu_launches": int(launches),
-            "roofline": {"bound": "hbm", "kernel": "beam_search_kernel<float,%d>" % E, "achieved": achieved, "peak": peak,
+            "roofline": {"bound": "hbm", "kernel": ("beam_search_fast_kernel" if args.arith == "fast" else "beam_search_kernel<float,%d>" % E), "achieved": achieved, "peak": peak,
                          "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
                          "kernel_ms_avg": kern_avg_ms, "kernel_launches_timed": int(kern_n),
                          "kernel_share_of_step": kern_ms / dev_ms if world == 1 else None},

@@ -61,6 +61,9 @@ def load_library(build_if_missing: bool = True):
         "dmg_set_stream": [vp, vp],
         "dmg_synchronize": [vp],
         "dmg_set_profiling": [vp, i32],
+        "dmg_set_arithmetic": [vp, i32],
+        "dmg_fast_stats": [vp, vp],
+        "dmg_set_fast_tolerance": [vp, dbl],
         "dmg_kernel_time": [vp, C.POINTER(dbl), C.POINTER(i64)],
         "dmg_load_tree_tdm": [vp, i32, i64, vp, vp, vp, i64, vp, vp],
         "dmg_load_tree_complete": [vp, i32, i64, vp, vp],
@@ -150,6 +153,20 @@ class Engine:
     @property
     def launch_count(self) -> int:
         return int(self.L.dmg_launch_count(self.h))
+
+    def set_arithmetic(self, mode: str):
+        """'strict' | 'fast' (tensor-core scorer with certified cuts; same ids and logits)."""
+        self._check(self.L.dmg_set_arithmetic(self.h, {"strict": 0, "fast": 1}[mode]))
+
+    def set_fast_tolerance(self, tau: float):
+        self._check(self.L.dmg_set_fast_tolerance(self.h, float(tau)))
+
+    def fast_stats(self):
+        out = np.zeros(5, np.uint64)
+        self._check(self.L.dmg_fast_stats(self.h, _p(out)))
+        ratio = float(np.array([int(out[4]) & 0xFFFFFFFF], np.uint32).view(np.float32)[0])
+        return {"cuts": int(out[0]), "cuts_rescored": int(out[1]), "rows_rescored": int(out[2]), "rows_fast": int(out[3]),
+                "max_err_over_bound": ratio}
 
     def set_profiling(self, on: bool):
         self._check(self.L.dmg_set_profiling(self.h, int(on)))

@@ -6,6 +6,7 @@
 #include <mutex>
 
 #include "beam_kernels.cuh"
+#include "beam_fast.cuh"
 #include "rows_kernels.cuh"
 
 using namespace dmg;
@@ -85,6 +86,7 @@ DMG_API int32_t dmg_destroy(dmg_handle_t h)
     for (Scratch *s : {&h->s_in, &h->s_out, &h->s_work}) { cudaFree(s->d); cudaFreeHost(s->h); }
     for (auto &ev : h->prof_events) { cudaEventDestroy(ev.first); cudaEventDestroy(ev.second); }
     cudaFree(h->d_flags);
+    cudaFree(h->d_fast_stats);
     cudaStreamDestroy(h->own_stream);
     delete h;
     return DMG_OK;
@@ -206,6 +208,7 @@ DMG_API int32_t dmg_load_tree_complete(dmg_handle_t h, int32_t leaf_level, int64
 }
 
 // ----------------------------------------------------------------------------------- weights
+static int32_t compute_fast_bounds(dmg_handle_t h);
 template <typename real> static int32_t make_transposes(dmg_handle_t h)
 {
     DinDev &d = h->din;
@@ -233,7 +236,7 @@ int32_t dmg_refresh_transposes(dmg_handle_t h)       // used by train.cu after a
     }
     h->launches += 2;
     DMG_CUDA(h, cudaGetLastError());
-    return DMG_OK;
+    return compute_fast_bounds(h);
 }
 
 static int32_t alloc_din(dmg_handle_t h, int32_t dtype, int64_t rows, int32_t E, int32_t T)
@@ -258,6 +261,7 @@ DMG_API int32_t dmg_load_din_weights(dmg_handle_t h, int32_t dtype, int64_t rows
     DinDev &d = h->din;
     DMG_TRY(h2d(h, d.d_params, params, (size_t)d.n_params * d.esz));
     DMG_TRY(dtype == DMG_F32 ? make_transposes<float>(h) : make_transposes<double>(h));
+    DMG_TRY(compute_fast_bounds(h));
     d.loaded = true;
     return DMG_OK;
 }
@@ -280,6 +284,7 @@ DMG_API int32_t dmg_init_din_weights(dmg_handle_t h, int32_t dtype, int64_t rows
     h->launches += 2;
     DMG_CUDA(h, cudaGetLastError());
     DMG_TRY(dtype == DMG_F32 ? make_transposes<float>(h) : make_transposes<double>(h));
+    DMG_TRY(compute_fast_bounds(h));
     d.loaded = true;
     return DMG_OK;
 }
@@ -331,6 +336,40 @@ template <typename real> static int32_t launch_beam(dmg_handle_t h, const BeamPa
         default:
             return fail(h, DMG_ERR_UNSUPPORTED, "beam search kernels are built for embed_size 16, 32 and 64 (got %d)", E);
     }
+}
+
+// eps_row = alpha*|x| + beta*|a| + gamma bounds |fast - strict| for the tensor-core scorer.
+static int32_t compute_fast_bounds(dmg_handle_t h)
+{
+    DinDev &d = h->din;
+    h->fast_ok = false;
+    if (d.dtype != DMG_F32 || d.E != 64) return DMG_OK;
+    const int E = d.E;
+    const size_t n_dense = (size_t)3 * E * E + 2 * E + 1;
+    std::vector<float> w(n_dense);
+    DMG_CUDA(h, cudaMemcpyAsync(w.data(), d.watt<float>(), n_dense * 4, cudaMemcpyDeviceToHost, h->stream));
+    DMG_CUDA(h, cudaStreamSynchronize(h->stream));
+    const float *watt = w.data(), *w1 = watt + E * E, *b1 = w1 + 2 * E * E, *w2 = b1 + E;
+    double F = 0, Sa = 0, Sb = 0, S1 = 0;
+    for (int i = 0; i < E * E; i++) F += (double)watt[i] * watt[i];
+    F = std::sqrt(F);
+    for (int o = 0; o < E; o++) {
+        double na = 0, nb = 0;
+        for (int k = 0; k < E; k++) { na += (double)w1[o * 2 * E + k] * w1[o * 2 * E + k]; nb += (double)w1[o * 2 * E + E + k] * w1[o * 2 * E + E + k]; }
+        Sa += std::fabs((double)w2[o]) * std::sqrt(na);
+        Sb += std::fabs((double)w2[o]) * std::sqrt(nb);
+        S1 += std::fabs((double)w2[o]) * std::fabs((double)b1[o]);
+    }
+    // c: bf16 hi/lo split truncation (3.03 * 2^-16) + fp32 accumulation of 3K products in the tensor core
+    const double c = std::ldexp(1.0, -13), g64 = 64 * std::ldexp(1.0, -24), g128 = 128 * std::ldexp(1.0, -24), safety = 1.05;
+    h->fast_alpha = (float)(safety * Sa * (c + g128 + 2 * g64));
+    h->fast_beta = (float)(safety * F * Sb * (c * (1 + c) + (c + g64) + (g128 + 2 * g64) * (1 + c)));
+    h->fast_gamma = (float)(safety * 2 * g64 * S1 + 1e-37);
+    h->fast_zeta = (float)(safety * F * Sb * (1 + c));                       // |da| -> |dlogit|
+    h->fast_cs = (float)(safety * c / std::sqrt((double)E));                 // score error per unit |x| |K_j| (scale = 1/sqrt(E))
+    h->fast_ca = (float)(safety * c);
+    h->fast_ok = std::isfinite(h->fast_alpha) && std::isfinite(h->fast_beta);
+    return DMG_OK;
 }
 
 template <typename real> static void fill_scorer(const DinDev &d, BeamParams<real> &p)
@@ -394,7 +433,64 @@ static int32_t tdm_enqueue(dmg_handle_t h, int32_t B, const int32_t *d_seq, int3
     p.cap = std::max(((2 * max_beam + 7) / 8) * 8, 8);
     p.cap = std::max(p.cap, ((topk + 7) / 8) * 8);
     p.capp = pow2_ge(p.cap);
+    if (h->arithmetic == DMG_ARITH_FAST && h->fast_ok && d.E == 64) {
+        const size_t smem = FastGeo::smem_bytes(p.cap, p.capp);
+        if (smem <= h->smem_optin) {
+            if (!h->d_fast_stats) {
+                DMG_CUDA(h, cudaMalloc(&h->d_fast_stats, 8 * sizeof(unsigned long long)));
+                DMG_CUDA(h, cudaMemsetAsync(h->d_fast_stats, 0, 8 * sizeof(unsigned long long), h->stream));
+            }
+            FastExtra fx;
+            fx.alpha = h->fast_alpha * h->fast_tau; fx.beta = h->fast_beta * h->fast_tau; fx.gamma = h->fast_gamma * h->fast_tau;
+            fx.zeta = h->fast_zeta * h->fast_tau; fx.cs = h->fast_cs; fx.ca = h->fast_ca;
+            fx.watt = d.watt<float>(); fx.w1 = d.w1<float>(); fx.stats = h->d_fast_stats;
+            DMG_CUDA(h, cudaFuncSetAttribute(beam_search_fast_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            const int grid = std::min(B, h->sm_count);
+            cudaEvent_t e0 = nullptr, e1 = nullptr;
+            if (h->profiling) {
+                DMG_CUDA(h, cudaEventCreate(&e0));
+                DMG_CUDA(h, cudaEventCreate(&e1));
+                DMG_CUDA(h, cudaEventRecord(e0, h->stream));
+            }
+            beam_search_fast_kernel<<<grid, kThreads, smem, h->stream>>>(p, fx);
+            h->launches += 1;
+            DMG_CUDA(h, cudaGetLastError());
+            if (h->profiling) {
+                DMG_CUDA(h, cudaEventRecord(e1, h->stream));
+                h->prof_events.emplace_back(e0, e1);
+            }
+            return DMG_OK;
+        }                                           // very wide beams: fall through to the strict kernel
+    }
     return launch_beam<float>(h, p, d.E);
+}
+
+DMG_API int32_t dmg_set_arithmetic(dmg_handle_t h, int32_t mode)
+{
+    if (!h) return DMG_ERR_INVALID_ARG;
+    if (mode != DMG_ARITH_STRICT && mode != DMG_ARITH_FAST) return fail(h, DMG_ERR_INVALID_ARG, "mode must be DMG_ARITH_STRICT or DMG_ARITH_FAST");
+    h->arithmetic = mode;
+    return DMG_OK;
+}
+
+DMG_API int32_t dmg_set_fast_tolerance(dmg_handle_t h, double tau)
+{
+    if (!h) return DMG_ERR_INVALID_ARG;
+    if (!(tau >= 0.0) || tau > 1.0) return fail(h, DMG_ERR_INVALID_ARG, "tau must be in [0, 1]");
+    h->fast_tau = (float)tau;
+    return DMG_OK;
+}
+
+DMG_API int32_t dmg_fast_stats(dmg_handle_t h, uint64_t *out4)
+{
+    if (!h || !out4) return DMG_ERR_INVALID_ARG;
+    for (int i = 0; i < 5; i++) out4[i] = 0;
+    if (!h->d_fast_stats) return DMG_OK;
+    DMG_CUDA(h, cudaSetDevice(h->device));
+    DMG_CUDA(h, cudaStreamSynchronize(h->stream));
+    DMG_CUDA(h, cudaMemcpy(out4, h->d_fast_stats, 5 * sizeof(uint64_t), cudaMemcpyDeviceToHost));
+    DMG_CUDA(h, cudaMemset(h->d_fast_stats, 0, 8 * sizeof(uint64_t)));
+    return DMG_OK;
 }
 
 static int32_t tdm_precheck(dmg_handle_t h, int32_t B, int32_t beam, int32_t topk)

@@ -53,6 +53,69 @@ template <typename K> __device__ void bitonic_sort_desc(K *keys, int n)
     }
 }
 
+// 64-bit keys, n <= 2*blockDim.x (blockDim.x = kThreads): every thread keeps its two elements (tid, tid + 256)
+// in registers; partner exchanges inside a warp (j < 32) are shuffles, j = 256 is register-local, and only
+// the j in {32, 64, 128} steps go through shared memory with a barrier: 9 block barriers pairs instead of 45
+// for 512 keys.  Result (descending) is written back to keys[0..n).
+__device__ __forceinline__ uint64_t shfl_xor_u64(uint64_t v, int m)
+{
+    uint32_t lo = __shfl_xor_sync(0xffffffffu, (uint32_t)v, m), hi = __shfl_xor_sync(0xffffffffu, (uint32_t)(v >> 32), m);
+    return ((uint64_t)hi << 32) | lo;
+}
+__device__ inline void bitonic_sort_desc(uint64_t *keys, int n)
+{
+    const int tid = threadIdx.x;
+    if (n > 2 * kThreads) {                                   // wide beams: plain shared-memory network
+        for (int k = 2; k <= n; k <<= 1)
+            for (int j = k >> 1; j > 0; j >>= 1) {
+                for (int i = tid; i < n; i += blockDim.x) {
+                    int ixj = i ^ j;
+                    if (ixj > i) {
+                        uint64_t a = keys[i], b = keys[ixj];
+                        bool sw = ((i & k) == 0) ? (a < b) : (b < a);
+                        if (sw) { keys[i] = b; keys[ixj] = a; }
+                    }
+                }
+                __syncthreads();
+            }
+        return;
+    }
+    const int i0 = tid, i1 = tid + kThreads;
+    uint64_t k0 = i0 < n ? keys[i0] : 0, k1 = i1 < n ? keys[i1] : 0;
+    __syncthreads();                                          // everyone has read its keys: smem is free for exchanges
+    for (int k = 2; k <= n; k <<= 1) {
+        for (int j = k >> 1; j > 0; j >>= 1) {
+            if (j == kThreads) {                              // partner is my other register
+                // i0 has (i & j) == 0 -> lower; descending block iff (i0 & k) == 0 (k == 2*j here -> always)
+                const bool desc = (i0 & k) == 0;
+                const uint64_t mx = k0 > k1 ? k0 : k1, mn = k0 > k1 ? k1 : k0;
+                k0 = desc ? mx : mn;
+                k1 = desc ? mn : mx;
+            } else if (j < 32) {
+                const uint64_t p0 = shfl_xor_u64(k0, j), p1 = shfl_xor_u64(k1, j);
+                const bool lower = (i0 & j) == 0;             // same for i0 and i1 (j < 256)
+                const bool tmax0 = lower == ((i0 & k) == 0), tmax1 = lower == ((i1 & k) == 0);
+                k0 = tmax0 ? (k0 > p0 ? k0 : p0) : (k0 > p0 ? p0 : k0);
+                k1 = tmax1 ? (k1 > p1 ? k1 : p1) : (k1 > p1 ? p1 : k1);
+            } else {                                          // cross-warp partner through shared memory
+                if (i0 < n) keys[i0] = k0;
+                if (i1 < n) keys[i1] = k1;
+                __syncthreads();
+                const uint64_t p0 = i0 < n ? keys[i0 ^ j] : 0;
+                const uint64_t p1 = i1 < n ? keys[i1 ^ j] : 0;
+                __syncthreads();
+                const bool lower = (i0 & j) == 0;
+                const bool tmax0 = lower == ((i0 & k) == 0), tmax1 = lower == ((i1 & k) == 0);
+                k0 = tmax0 ? (k0 > p0 ? k0 : p0) : (k0 > p0 ? p0 : k0);
+                k1 = tmax1 ? (k1 > p1 ? k1 : p1) : (k1 > p1 ? p1 : k1);
+            }
+        }
+    }
+    if (i0 < n) keys[i0] = k0;
+    if (i1 < n) keys[i1] = k1;
+    __syncthreads();
+}
+
 // ---- vector smem access -------------------------------------------------------------------
 __device__ __forceinline__ void ld4(const float *p, float (&v)[4])
 {

@@ -82,6 +82,11 @@ struct dmg_handle_s {
     dmg::DrDev dr;
     dmg::Scratch s_in, s_out, s_work;
     int32_t *d_flags = nullptr;     // [0] = index error flag, [1] = work counter
+    int arithmetic = DMG_ARITH_STRICT;
+    bool fast_ok = false;            // tensor-core scorer available for the loaded weights
+    float fast_alpha = 0, fast_beta = 0, fast_gamma = 0, fast_zeta = 0, fast_cs = 0, fast_ca = 0;
+    float fast_tau = 1.0f;           // fraction of the worst-case bound used as the certification band
+    unsigned long long *d_fast_stats = nullptr;
     bool profiling = false;
     std::vector<std::pair<cudaEvent_t, cudaEvent_t>> prof_events;
 };

@@ -320,3 +320,83 @@ def test_dr_synthetic_wide(engine, orc):
         assert (p[u, :c[u]] == op).all() and (bits(pr[u, :c[u]]) == bits(opr)).all()
         oi, os_, _ = model.recommend(seqs[u], 25, 100, off, flat)
         assert counts[u] == len(oi) and (items[u, :counts[u]] == oi).all() and (bits(scores[u, :counts[u]]) == bits(os_)).all()
+
+
+# ------------------------------------------------------------------ tensor-core scorer with certified cuts
+@pytest.mark.parametrize("n_items,beam,structured", [(20000, 200, True), (20000, 200, False), (300, 7, True), (5000, 64, True), (70000, 256, True), (70000, 333, True)])
+def test_fast_mode_matches_oracle(engine, orc, n_items, beam, structured):
+    """DMG_ARITH_FAST (tcgen05 bf16x3 + certified cuts) must return the oracle's ids AND logit bits."""
+    E = 64
+    tf = synth.tdm_tree(n_items, seed=17)
+    rows = (1 << (tf.max_level + 1)) - 1
+    params = synth.din_params(rows, E, seed=23, structured=structured)
+    engine.load_tree_tdm(tf.max_level, tf.codes, tf.node_ids, tf.is_leaf, tf.leaf_ids, tf.leaf_codes)
+    engine.load_din_weights(params, rows, E, 10)
+    seqs = synth.queries(160, 10, n_items, seed=29)
+    seqs[0] = 0
+    engine.set_arithmetic("fast")
+    try:
+        items, logits, counts = engine.tdm_retrieve(seqs, beam, 10)
+        stats = engine.fast_stats()
+    finally:
+        engine.set_arithmetic("strict")
+    tree = orc.Tree.from_treefile(tf)
+    model = orc.TdmModel(params, rows, E, 10)
+    oi, ol, oc = model.retrieve_batch(tree, seqs, beam, 10, n_threads=8)
+    assert (counts == oc).all()
+    assert (items == oi).all(), f"ids differ, stats={stats}"
+    assert (bits(logits) == bits(ol)).all()
+    if beam <= 256:                                       # wider beams do not fit the fast kernel's shared memory
+        assert stats["rows_fast"] > 0                     # and fall back to the strict kernel (same results)
+        assert stats["max_err_over_bound"] < 0.05         # observed |fast - strict| stays far inside the bound
+    print("fast stats", n_items, beam, stats)
+
+
+def test_fast_mode_ties_and_consumed(engine, orc):
+    """all-zero model (every score ties exactly) and the eval variant with consumed items, fast mode."""
+    E, n_items = 64, 3000
+    tf = synth.tdm_tree(n_items, seed=3)
+    rows = (1 << (tf.max_level + 1)) - 1
+    tree = orc.Tree.from_treefile(tf)
+    engine.load_tree_tdm(tf.max_level, tf.codes, tf.node_ids, tf.is_leaf, tf.leaf_ids, tf.leaf_codes)
+    seqs = synth.queries(20, 10, n_items, seed=31)
+    rng = np.random.default_rng(2)
+    cons_off = np.zeros(21, np.int64)
+    cons = []
+    for u in range(20):
+        c = sorted(set(rng.choice(tf.leaf_ids, int(rng.integers(0, 500)), replace=False).tolist()))
+        cons.extend(c)
+        cons_off[u + 1] = len(cons)
+    cons = np.array(cons, np.int32)
+    for params in (np.zeros(rows * E + 3 * E * E + 2 * E + 1, np.float32), synth.din_params(rows, E, seed=5)):
+        engine.load_din_weights(params, rows, E, 10)
+        model = orc.TdmModel(params, rows, E, 10)
+        engine.set_arithmetic("fast")
+        try:
+            a = engine.tdm_retrieve(seqs, 50, 10)
+            b = engine.tdm_retrieve(seqs, 40, 10, True, cons_off, cons, True)
+        finally:
+            engine.set_arithmetic("strict")
+        oa = model.retrieve_batch(tree, seqs, 50, 10)
+        ob = model.retrieve_batch(tree, seqs, 40, 10, cons_off=cons_off, cons=cons, widen_beam=True)
+        for got, want in ((a, oa), (b, ob)):
+            assert (got[2] == want[2]).all() and (got[0] == want[0]).all() and (bits(got[1]) == bits(want[1])).all()
+
+
+def test_fast_equals_strict_at_full_size(engine):
+    """BASELINE configs[1] (1M items, beam 200, 1024 users): the two arithmetic modes agree bit for bit."""
+    n_items = 1_000_000
+    tf = synth.tdm_tree(n_items, seed=1)
+    rows = (1 << (tf.max_level + 1)) - 1
+    engine.load_tree_tdm(tf.max_level, tf.codes, tf.node_ids, tf.is_leaf, tf.leaf_ids, tf.leaf_codes)
+    engine.init_din_weights(np.float32, rows, 64, 10, seed=2)
+    seqs = synth.queries(1024, 10, n_items, seed=4)
+    strict = engine.tdm_retrieve(seqs, 200, 10)
+    engine.set_arithmetic("fast")
+    try:
+        fast = engine.tdm_retrieve(seqs, 200, 10)
+        stats = engine.fast_stats()
+    finally:
+        engine.set_arithmetic("strict")
+    assert (fast[2] == strict[2]).all() and (fast[0] == strict[0]).all() and (bits(fast[1]) == bits(strict[1])).all()
+    print("fast stats at 1M:", stats)
