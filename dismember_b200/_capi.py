@@ -162,11 +162,11 @@ class Engine:
         self._check(self.L.dmg_set_fast_tolerance(self.h, float(tau)))
 
     def fast_stats(self):
-        out = np.zeros(5, np.uint64)
+        out = np.zeros(7, np.uint64)
         self._check(self.L.dmg_fast_stats(self.h, _p(out)))
         ratio = float(np.array([int(out[4]) & 0xFFFFFFFF], np.uint32).view(np.float32)[0])
         return {"cuts": int(out[0]), "cuts_rescored": int(out[1]), "rows_rescored": int(out[2]), "rows_fast": int(out[3]),
-                "max_err_over_bound": ratio}
+                "max_err_over_bound": ratio, "users_redone_strict": int(out[5]), "cuts_settled_in_place": int(out[6])}
 
     def set_profiling(self, on: bool):
         self._check(self.L.dmg_set_profiling(self.h, int(on)))

@@ -1,21 +1,34 @@
-// beam_fast.cuh -- tensor-core ("fast") variant of the persistent beam-search kernel, E = 64, fp32 model.
+// beam_fast.cuh -- tensor-core ("fast") persistent beam-search kernel, E = 64, fp32 model.
 //
-// Same search, same outputs as beam_search_kernel<float,64> (ids and scores bit-identical to the
-// strict path / CPU oracle), but the two dense contractions of the DIN scorer
-//     att = a . W_att^T   (128 x 64 x 64)          h = [x | att] . W1^T   (128 x 128 x 64)
-// run on the 5th-generation tensor cores: tcgen05.mma (kind::f16, bf16 operands staged in shared
-// memory in the canonical K-major no-swizzle layout, fp32 accumulators in TMEM, read back with
-// tcgen05.ld).  fp32 operands are split into bf16 hi + lo parts and three products are
-// accumulated (hi*hi + hi*lo + lo*hi), giving ~2^-16 relative accuracy per product.
+// Same search and the same outputs as beam_search_kernel<float,64> (ids and logits bit-identical
+// to the strict path / CPU oracle).  What changes is how the <= 2*beam candidate rows of a level
+// are scored and how the beam is cut:
 //
-// Exactness is restored by CERTIFIED CUTS: every row carries a rigorous bound eps on
-// |fast - strict| (eps_row = alpha*|x| + beta*|a| + gamma from the weight norms);
-// at a beam cut only candidates whose fast score lies within 2*eps of the cut can be on the wrong
-// side, and exactly those are re-scored with the strict sequential-fma scorer (score_tile) and
-// re-ranked with the reference's (score desc, position asc) key.  The attention contractions
-// (scores = X.K^T, a = P.K) run on the tensor cores too (N = 16 / K = 16 MMAs against per-user
-// bf16 copies of the history tile); the softmax stays in fp32 registers with the spec'd exp.
-// The final topk is always re-scored strictly, so returned logits are the oracle's bits.
+//  * the attention branch of the DIN scorer is linear after the softmax, so it is collapsed per
+//    user:   h = W1x.x + W1a.Watt.(sum_j p_j K_j) + b1 = W1x.x + sum_j p_j H_j + b1,
+//    H_j = M.K_j,  M = W1a.Watt (64x64, folded on the host in double).  Per candidate row the
+//    tensor cores then run two contractions only:
+//        S    = X . K^T                      (256 x 16 x 64)    attention scores
+//        Hacc = X . W1x^T  +  P . H          (256 x 64 x 80)    hidden layer
+//    as tcgen05.mma kind::f16 with bf16 hi/lo split operands (hi*hi + hi*lo + lo*hi, ~2^-16),
+//    operands in shared memory in the canonical K-major no-swizzle layout, fp32 accumulators in
+//    TMEM, read back with tcgen05.ld for the softmax (registers, one row per thread) and the
+//    ReLU / W2 epilogue.
+//  * candidate rows are gathered from the node table with coalesced 128-bit loads (16 lanes per
+//    256-byte row) straight into registers, split into bf16 hi/lo and stored as UMMA operands --
+//    no fp32 staging tile; the user's history rows are staged by the TMA bulk-copy engine.
+//  * the beam cut is a 4-pass radix SELECT of the beam-th largest fast score, not a sort.  With a
+//    rigorous bound eps on |fast - strict| for the level (DESIGN.md "certified cuts"), rows with
+//    fast > pivot + 2 eps are certainly inside the beam, rows with fast < pivot - 2 eps certainly
+//    outside; only rows within the band are re-scored by the strict sequential-fma scorer (one
+//    warp per row) and ranked by the reference's (score desc, position asc) key.
+//  * the order of the beam only matters for tie-breaking.  If two strictly re-scored rows tie
+//    exactly at a decision point (or the band is implausibly wide) the user is appended to a
+//    redo list and re-run by the strict kernel, which reproduces the reference's stable sorts.
+//  * the final topk is always re-scored strictly, so returned logits are the oracle's bits.
+//
+// Two CTAs of 256 threads per SM (about 110 KB of shared memory and 256 TMEM columns each): while
+// one CTA waits on a gather or selects its beam, the other one keeps the tensor/ALU pipes busy.
 #pragma once
 #include <cuda_bf16.h>
 
@@ -23,11 +36,20 @@
 
 namespace dmg {
 
-struct FastExtra {
-    // eps_row = alpha*|x| + beta*(|a| + da) + gamma + zeta*da,  da = Kmax*(2.1*cs*|x|*Kmax + ca)
-    float alpha, beta, gamma, zeta, cs, ca;
-    const float *watt, *w1;         // row-major [out][in] fp32 (converted to bf16 hi/lo per CTA)
-    unsigned long long *stats;      // [0] cuts, [1] cuts needing a strict re-score, [2] rows re-scored, [3] rows scored, [4] max |fast-strict|/eps (float bits)
+struct FastParams {
+    float b1[64], w2[64];           // read as constant-bank operands in the epilogue
+    float b2;
+    const float *mT;                // M~^T [k][o] fp32, M = W1a.Watt (host, double -> fp32)
+    const float *w1;                // W1 row-major [o][2E] fp32 (item half -> bf16 hi/lo operand)
+    const float *lvl_vx;            // [32] per tree level: max over nodes of sum_k v_k |x_k|
+    const float *lvl_nx;            // [32] per tree level: max |x|_2
+    const float *zvec;              // [64] z_k = sum_o sum_m |w2_o| |W1a_om| |Watt_mk|
+    float cA, cZ, cH, cGamma;       // bound constants: eps = tau (cA VX + cZ ZK + (cH + |dp|_1) HW + cGamma)
+    float tau;                      // fraction of the worst-case bound used as the band
+    int32_t *redo_list;             // users to re-run with the strict kernel
+    int32_t *redo_count;
+    int32_t *work_counter;          // dynamic user scheduler
+    unsigned long long *stats;      // [0] cuts [1] cuts re-scored [2] rows re-scored [3] rows scored [4] max ratio bits [5] redo users
 };
 
 // ---- tcgen05 / TMEM wrappers ------------------------------------------------------------------
@@ -69,7 +91,6 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32])
 #pragma unroll
     for (int i = 0; i < 32; i++) v[i] = __uint_as_float(r[i]);
 }
-
 __device__ __forceinline__ void tmem_ld16(uint32_t taddr, float (&v)[16])
 {
     uint32_t r[16];
@@ -96,215 +117,467 @@ __device__ __forceinline__ uint64_t umma_desc(uint32_t smem_addr, uint32_t lbo_b
     d |= (uint64_t)1 << 46;                       // version = 1 (Blackwell)
     return d;                                     // base_offset 0, lbo_mode 0, layout SWIZZLE_NONE
 }
-// instruction descriptor: D fp32, A/B bf16, both K-major, M = 128, N = 64
+// instruction descriptor: D fp32, A/B bf16, both K-major, M = 128, N = 64 / 16
 constexpr uint32_t kIdescBf16M128N64 = (1u << 4) | (1u << 7) | (1u << 10) | ((64u >> 3) << 17) | ((128u >> 4) << 24);
 constexpr uint32_t kIdescBf16M128N16 = (1u << 4) | (1u << 7) | (1u << 10) | ((16u >> 3) << 17) | ((128u >> 4) << 24);
 
-// fp32 -> bf16 hi + bf16 lo (round to nearest), packed pairs
-__device__ __forceinline__ void split_bf16(float x, __nv_bfloat16 &hi, __nv_bfloat16 &lo)
+// fp32 pair -> packed bf16 hi pair and bf16 lo pair (x = hi + lo + O(2^-18 |x|))
+__device__ __forceinline__ void split_pair(float x0, float x1, uint32_t &hi, uint32_t &lo)
 {
-    hi = __float2bfloat16_rn(x);
-    lo = __float2bfloat16_rn(__fsub_rn(x, __bfloat162float(hi)));
+    __nv_bfloat162 h = __floats2bfloat162_rn(x0, x1);
+    hi = *reinterpret_cast<uint32_t *>(&h);
+    const float h0 = __uint_as_float(hi << 16), h1 = __uint_as_float(hi & 0xffff0000u);
+    __nv_bfloat162 l = __floats2bfloat162_rn(__fsub_rn(x0, h0), __fsub_rn(x1, h1));
+    lo = *reinterpret_cast<uint32_t *>(&l);
 }
 __device__ __forceinline__ void split8(const float (&v)[8], uint4 &hi, uint4 &lo)
 {
-    __nv_bfloat16 h[8], l[8];
-#pragma unroll
-    for (int i = 0; i < 8; i++) split_bf16(v[i], h[i], l[i]);
-    hi = *reinterpret_cast<uint4 *>(h);
-    lo = *reinterpret_cast<uint4 *>(l);
+    split_pair(v[0], v[1], hi.x, lo.x);
+    split_pair(v[2], v[3], hi.y, lo.y);
+    split_pair(v[4], v[5], hi.z, lo.z);
+    split_pair(v[6], v[7], hi.w, lo.w);
+}
+__device__ __forceinline__ float4 ldg_row16(const float *p)
+{
+    float4 v;
+    asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p));
+    return v;
+}
+__device__ __forceinline__ float key_to_float(uint32_t k)
+{
+    return __uint_as_float((k & 0x80000000u) ? (k ^ 0x80000000u) : ~k);
 }
 
 struct FastGeo {
-    static constexpr int E = 64, R = 128, LD = 68, PLD = kMaxT + 1;
-    static constexpr int A_BYTES = R * E * 2;                 // one bf16 operand tile 128 x 64 = 16 KB
-    static constexpr int A_LBO = R * 16, B_LBO = E * 16, SBO = 128;
-    static constexpr int WATT_BYTES = E * E * 2, W1_BYTES = E * 2 * E * 2;
-    static constexpr int KB_BYTES = 16 * E * 2, KB_LBO = 16 * 16;      // history as B operand of the scores MMA: [16 j][64 k]
-    static constexpr int KT_BYTES = E * 16 * 2, KT_LBO = E * 16;       // transposed history, B operand of a = P.K: [64 e][16 j]
-    static constexpr int P_BYTES = R * 16 * 2;                         // probabilities as A operand: [128][16 j]
-    static size_t smem_bytes(int cap, int capp)
+    static constexpr int E = 64, R = 256, THREADS = 256, KLD = 68;
+    static constexpr int X_LBO = R * 16 + 16;                 // +16: the two rows of a warp store hit disjoint banks
+    static constexpr int X_BYTES = 8 * X_LBO;                 // one bf16 operand tile 256 x 64 (hi or lo)
+    static constexpr int P_LBO = R * 16, P_BYTES = 2 * P_LBO; // probabilities [256][16]
+    static constexpr int W_LBO = E * 16, W_BYTES = 8 * W_LBO; // W1x as B operand [64 o][64 k]
+    static constexpr int KB_LBO = 16 * 16, KB_BYTES = 8 * KB_LBO;   // history as B operand [16 j][64 k]
+    static constexpr int H_LBO = E * 16, H_BYTES = 2 * H_LBO;       // H as B operand [64 o][16 j]
+    static constexpr int SBO = 128;
+    static constexpr int MAX_UNC = 96;                        // widest band re-scored in place at a cut
+    static constexpr int MAX_FINAL = 256;                     // widest topk candidate set re-scored in place
+    static constexpr int SB = 32;                             // rows per strict re-score batch
+    static constexpr int STRICT_SCR = (16 + 3 * SB) * KLD * 4 + SB * 17 * 4;   // history, x, a|h, att, scores
+    // aliases inside the P operand region while no MMA is in flight
+    static constexpr int VCAP = 160;                          // band rows a user may defer to its end-of-search verification
+    static constexpr int OFF_HIST = 0, OFF_SEL = 1024, OFF_KEYU = 2048, OFF_UPOS = 4096, OFF_CLS = 6144,
+                         OFF_LCODE = 8192, OFF_LSTR = OFF_LCODE + (VCAP + MAX_FINAL) * 4;
+    static size_t smem_bytes(int cap)
     {
-        size_t b = 0;
-        b += 2 * (size_t)WATT_BYTES + 2 * (size_t)W1_BYTES;   // bf16 hi/lo weights
-        b += 4 * (size_t)A_BYTES;                             // X hi/lo, a|att hi/lo (aliased by the strict scratch: sA + sP)
-        b += 2 * (size_t)KB_BYTES + 2 * (size_t)KT_BYTES + 2 * (size_t)P_BYTES;
-        b += (size_t)kMaxT * E * 4;                           // history tile
-        b += 2 * (size_t)R * LD * 4;                          // fp32 row tiles (double buffer)
-        b += 2 * (size_t)E * 4 + 16;                          // b1, w2, b2
-        b += 4 * (size_t)R * 4;                               // |x|, |a|, partial logits (2)
-        b += (size_t)cap * 4 * 2;                             // fast scores, strict scores
-        b = (b + 15) & ~(size_t)15;
-        b += 2 * (size_t)capp * 8;                            // sort keys + scratch keys
-        b += (size_t)cap * 2 * 4;                             // candidate codes (ping-pong)
-        b += 64 * 4 + 64;                                     // misc ints, mbarriers, tmem address
+        size_t b = 2 * (size_t)X_BYTES + 2 * (size_t)P_BYTES + 2 * (size_t)W_BYTES + 2 * (size_t)KB_BYTES + 2 * (size_t)H_BYTES;
+        b += (size_t)cap * 4 * 3;                             // fast scores, candidate codes (ping-pong)
+        b += (size_t)VCAP * 12 + 32 * 4;                      // deferred verification list (code, fast score, meta), eps per segment
+        b += 128 * 4 + 64;                                    // misc ints, mbarriers
         return b;
     }
+    static constexpr int max_cap() { return 512; }            // OFF_CLS + 512 <= P region, 2 candidates per thread
 };
+static_assert(2 * FastGeo::P_BYTES >= FastGeo::OFF_LSTR + (FastGeo::VCAP + FastGeo::MAX_FINAL) * 4 && FastGeo::OFF_CLS + 512 <= FastGeo::OFF_LCODE,
+              "cut scratch must fit in the P operand region");
+static_assert(2 * FastGeo::X_BYTES >= FastGeo::STRICT_SCR, "strict scratch must fit in the X operand region");
 
-__global__ void __launch_bounds__(kThreads, 1) beam_search_fast_kernel(const BeamParams<float> p, const FastExtra fx)
+// ---- strict scorer on a batch of rows, whole CTA (bit-identical to score_tile / the oracle) ---------
+// scr: [history 16 x KLD (already loaded, zero rows for padding) | x SB x KLD | a,h SB x KLD | att SB x KLD | s,p SB x 17]
+// Rows with the codes sRow[base .. base+nr) -> sOut[base ..), nr <= 4*RPT.  Every dot product is one sequential-k
+// fma chain; thread (o = tid & 63, rg = tid >> 6) owns output column o of rows rg, rg+4, .. (RPT of them) and
+// keeps the 64 weights of that column in registers, loaded once per batch.
+template <int RPT>
+__device__ __forceinline__ void strict_score_rows(const float *__restrict__ emb, const int32_t *__restrict__ sRow,
+                                                  int base, int nr, float *__restrict__ sOut,
+                                                  float *__restrict__ scr, uint32_t maskbits, int T, float scale,
+                                                  const float *__restrict__ wattT, const float *__restrict__ w1T,
+                                                  const float *__restrict__ b1, const float *__restrict__ w2, float b2)
+{
+    constexpr int E = 64, LD = FastGeo::KLD, SB = FastGeo::SB, PLD = 17, NB = 4 * RPT;
+    float *sKf = scr, *sXs = sKf + 16 * LD, *sA = sXs + SB * LD, *sT = sA + SB * LD, *sPs = sT + SB * LD;
+    const int tid = threadIdx.x, o = tid & 63, rg = tid >> 6;
+    float w[E];
+#pragma unroll
+    for (int k = 0; k < E; k++) w[k] = __ldg(wattT + k * E + o);
+    for (int idx = tid; idx < NB * 16; idx += FastGeo::THREADS) {
+        const int r = idx >> 4, c = idx & 15;
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (r < nr) v = __ldg(reinterpret_cast<const float4 *>(emb + (size_t)sRow[base + r] * E) + c);
+        *reinterpret_cast<float4 *>(sXs + r * LD + c * 4) = v;
+    }
+    __syncthreads();
+    if (tid < NB * 8) {                                         // (1) scores: MatMul transB, Mask
+        const int r = tid >> 3, j0 = tid & 7, j1 = j0 + 8;
+        const float *xr = sXs + r * LD, *k0 = sKf + j0 * LD, *k1 = sKf + j1 * LD;
+        float a0 = 0.0f, a1 = 0.0f;
+#pragma unroll 8
+        for (int k = 0; k < E; k++) { const float xv = xr[k]; a0 = fma_(xv, k0[k], a0); a1 = fma_(xv, k1[k], a1); }
+        if (j0 < T) sPs[r * PLD + j0] = ((maskbits >> j0) & 1u) ? mask_value<float>::get() : mul_(a0, scale);
+        if (j1 < T) sPs[r * PLD + j1] = ((maskbits >> j1) & 1u) ? mask_value<float>::get() : mul_(a1, scale);
+    }
+    __syncthreads();
+    if (tid < NB) {                                             // (2) SoftMax
+        float *pr = sPs + tid * PLD;
+        float mx = pr[0];
+        for (int j = 1; j < T; j++) { const float v = pr[j]; mx = (v > mx || v != v) ? v : mx; }
+        float sum = 0.0f;
+        for (int j = 0; j < T; j++) { const float e = exp_(sub_(pr[j], mx)); pr[j] = e; sum = add_(sum, e); }
+        const float inv = inv_(sum);
+        for (int j = 0; j < T; j++) pr[j] = mul_(pr[j], inv);
+    }
+    __syncthreads();
+    if (tid < NB * 8) {                                         // (3) a = p . K
+        const int r = tid >> 3, kq = tid & 7;
+        float acc[8];
+#pragma unroll
+        for (int q = 0; q < 8; q++) acc[q] = 0.0f;
+        for (int j = 0; j < T; j++) {
+            const float pj = sPs[r * PLD + j];
+            float kv[8];
+            ld4(sKf + j * LD + kq * 8, *reinterpret_cast<float(*)[4]>(&kv[0]));
+            ld4(sKf + j * LD + kq * 8 + 4, *reinterpret_cast<float(*)[4]>(&kv[4]));
+#pragma unroll
+            for (int q = 0; q < 8; q++) acc[q] = fma_(pj, kv[q], acc[q]);
+        }
+        st4(sA + r * LD + kq * 8, *reinterpret_cast<float(*)[4]>(&acc[0]));
+        st4(sA + r * LD + kq * 8 + 4, *reinterpret_cast<float(*)[4]>(&acc[4]));
+    }
+    __syncthreads();
+    float acc[RPT];
+#pragma unroll
+    for (int i = 0; i < RPT; i++) acc[i] = 0.0f;
+#pragma unroll
+    for (int k = 0; k < E; k += 4) {                            // (4) att = a . Watt^T
+#pragma unroll
+        for (int i = 0; i < RPT; i++) {
+            float av[4];
+            ld4(sA + (rg + 4 * i) * LD + k, av);
+            acc[i] = fma_(av[0], w[k], acc[i]);
+            acc[i] = fma_(av[1], w[k + 1], acc[i]);
+            acc[i] = fma_(av[2], w[k + 2], acc[i]);
+            acc[i] = fma_(av[3], w[k + 3], acc[i]);
+        }
+    }
+#pragma unroll
+    for (int i = 0; i < RPT; i++) { sT[(rg + 4 * i) * LD + o] = acc[i]; acc[i] = 0.0f; }
+#pragma unroll
+    for (int k = 0; k < E; k++) w[k] = __ldg(w1T + k * E + o);
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < E; k += 4) {                            // (5) h = relu([x | att] . W1^T + b1): item half
+#pragma unroll
+        for (int i = 0; i < RPT; i++) {
+            float xv[4];
+            ld4(sXs + (rg + 4 * i) * LD + k, xv);
+            acc[i] = fma_(xv[0], w[k], acc[i]);
+            acc[i] = fma_(xv[1], w[k + 1], acc[i]);
+            acc[i] = fma_(xv[2], w[k + 2], acc[i]);
+            acc[i] = fma_(xv[3], w[k + 3], acc[i]);
+        }
+    }
+#pragma unroll
+    for (int k = 0; k < E; k++) w[k] = __ldg(w1T + (E + k) * E + o);
+#pragma unroll
+    for (int k = 0; k < E; k += 4) {                            //     attention half
+#pragma unroll
+        for (int i = 0; i < RPT; i++) {
+            float tv[4];
+            ld4(sT + (rg + 4 * i) * LD + k, tv);
+            acc[i] = fma_(tv[0], w[k], acc[i]);
+            acc[i] = fma_(tv[1], w[k + 1], acc[i]);
+            acc[i] = fma_(tv[2], w[k + 2], acc[i]);
+            acc[i] = fma_(tv[3], w[k + 3], acc[i]);
+        }
+    }
+    {
+        const float bo = __ldg(b1 + o);
+#pragma unroll
+        for (int i = 0; i < RPT; i++) sA[(rg + 4 * i) * LD + o] = relu_(add_(acc[i], bo));   // a[] was last read before the previous barrier
+    }
+    __syncthreads();
+    if (tid < nr) {                                             // (6) logit = h . W2 + b2
+        const float *hr = sA + tid * LD;
+        float l = 0.0f;
+#pragma unroll 8
+        for (int q = 0; q < E; q++) l = fma_(hr[q], __ldg(w2 + q), l);
+        sOut[base + tid] = add_(l, b2);
+    }
+    __syncthreads();
+}
+
+__device__ __noinline__ void strict_score_batch(const float *__restrict__ emb, const int32_t *__restrict__ sRow,
+                                                int n, float *__restrict__ sOut,
+                                                float *__restrict__ scr, uint32_t maskbits, int T, float scale,
+                                                const float *__restrict__ wattT, const float *__restrict__ w1T,
+                                                const float *__restrict__ b1, const float *__restrict__ w2, float b2)
+{
+    int base = 0;
+    while (base < n) {
+        const int rem = n - base;
+        if (rem > 16) {
+            strict_score_rows<8>(emb, sRow, base, rem < 32 ? rem : 32, sOut, scr, maskbits, T, scale, wattT, w1T, b1, w2, b2);
+            base += 32;
+        } else if (rem > 8) {
+            strict_score_rows<4>(emb, sRow, base, rem, sOut, scr, maskbits, T, scale, wattT, w1T, b1, w2, b2);
+            base += 16;
+        } else if (rem > 4) {
+            strict_score_rows<2>(emb, sRow, base, rem, sOut, scr, maskbits, T, scale, wattT, w1T, b1, w2, b2);
+            base += 8;
+        } else {
+            strict_score_rows<1>(emb, sRow, base, rem, sOut, scr, maskbits, T, scale, wattT, w1T, b1, w2, b2);
+            base += 4;
+        }
+    }
+}
+
+__device__ __forceinline__ bool elect_one()
+{
+    uint32_t pred;
+    asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+    return pred != 0;
+}
+
+// k-th largest (k >= 1) of keys[0..count), count <= 512: ONE warp, its keys in registers, 4 radix passes
+// over 8-bit digits with a 256-bin shared histogram -- no block barrier inside.
+__device__ __forceinline__ uint32_t warp_radix_select(const uint32_t *__restrict__ keys, int count, int k, int *sHist, int lane)
+{
+    uint32_t kv[16];
+#pragma unroll
+    for (int q = 0; q < 16; q++) { const int i = lane + 32 * q; kv[q] = i < count ? keys[i] : 0u; }
+    uint32_t prefix = 0, known = 0;
+#pragma unroll 1
+    for (int pass = 0; pass < 4; pass++) {
+        const int shift = 24 - 8 * pass;
+#pragma unroll
+        for (int q = 0; q < 8; q++) sHist[lane + 32 * q] = 0;
+        __syncwarp();
+#pragma unroll
+        for (int q = 0; q < 16; q++)
+            if (lane + 32 * q < count && (kv[q] & known) == prefix) atomicAdd(&sHist[(kv[q] >> shift) & 255u], 1);
+        __syncwarp();
+        int c[8], s = 0;
+#pragma unroll
+        for (int q = 0; q < 8; q++) { c[q] = sHist[lane * 8 + q]; s += c[q]; }
+        int suf = s;                                           // inclusive suffix sum: bins of lanes >= lane
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int t = __shfl_down_sync(0xffffffffu, suf, o);
+            if (lane + o < 32) suf += t;
+        }
+        const int above = suf - s;
+        const bool mine = above < k && k <= suf;
+        int bin = 0, kn = k;
+        if (mine) {
+            int acc = above;
+            bool found = false;
+#pragma unroll
+            for (int q = 7; q >= 0; q--) {
+                if (!found) {
+                    if (acc + c[q] >= k) { bin = lane * 8 + q; kn = k - acc; found = true; }
+                    else acc += c[q];
+                }
+            }
+        }
+        const int src = __ffs(__ballot_sync(0xffffffffu, mine)) - 1;
+        bin = __shfl_sync(0xffffffffu, bin, src);
+        k = __shfl_sync(0xffffffffu, kn, src);
+        prefix |= (uint32_t)bin << shift;
+        known |= 255u << shift;
+        __syncwarp();
+    }
+    return prefix;
+}
+
+// Phase timers (cycles of thread 0, summed over CTAs) -> stats[8 + i]; compiled in with -DDMG_FAST_TIMING.
+#ifdef DMG_FAST_TIMING
+#define DMG_TICK(i) do { if (tid == 0) { const long long t_ = clock64(); tacc[i] += t_ - tlast; tlast = t_; } } while (0)
+#else
+#define DMG_TICK(i) do { } while (0)
+#endif
+enum { TK_PROLOGUE = 0, TK_SELECT, TK_RESCORE, TK_EXPAND, TK_GATHER, TK_SOFTMAX, TK_EPILOGUE, TK_FINAL, TK_SCHED, TK_N };
+
+__global__ void __launch_bounds__(FastGeo::THREADS, 2) beam_search_fast_kernel(const BeamParams<float> p, const FastParams fp)
 {
     using G = FastGeo;
-    using KO = KeyOf<float>;
     constexpr int E = G::E;
-    extern __shared__ __align__(16) unsigned char smem_raw[];
+    extern __shared__ __align__(128) unsigned char smem_raw[];
     unsigned char *sp = smem_raw;
-    unsigned char *sWattH = sp; sp += G::WATT_BYTES;
-    unsigned char *sWattL = sp; sp += G::WATT_BYTES;
-    unsigned char *sW1H = sp; sp += G::W1_BYTES;
-    unsigned char *sW1L = sp; sp += G::W1_BYTES;
-    unsigned char *sAxH = sp; sp += G::A_BYTES;               // X hi
-    unsigned char *sAxL = sp; sp += G::A_BYTES;               // X lo
-    unsigned char *sAaH = sp; sp += G::A_BYTES;               // a, then att, hi
-    unsigned char *sAaL = sp; sp += G::A_BYTES;               // lo
-    float *sStrictA = reinterpret_cast<float *>(sAxH);        // strict scorer scratch [R][LD] aliases the operand tiles
-    float *sP = sStrictA + G::R * G::LD;                      // ... followed by its [R][PLD] score/probability scratch
-    static_assert((G::R * G::LD + G::R * G::PLD) * 4 <= 4 * G::A_BYTES, "strict scratch must fit in the operand tiles");
-    unsigned char *sKbH = sp; sp += G::KB_BYTES;
-    unsigned char *sKbL = sp; sp += G::KB_BYTES;
-    unsigned char *sKtH = sp; sp += G::KT_BYTES;
-    unsigned char *sKtL = sp; sp += G::KT_BYTES;
-    unsigned char *sPH = sp; sp += G::P_BYTES;
-    unsigned char *sPL = sp; sp += G::P_BYTES;
-    float *sK = reinterpret_cast<float *>(sp); sp += kMaxT * E * 4;
-    float *sX = reinterpret_cast<float *>(sp); sp += 2 * G::R * G::LD * 4;
-    float *sB1 = reinterpret_cast<float *>(sp); sp += E * 4;
-    float *sW2 = reinterpret_cast<float *>(sp); sp += E * 4;
-    float *sB2 = reinterpret_cast<float *>(sp); sp += 16;
-    float *sNx = reinterpret_cast<float *>(sp); sp += G::R * 4;
-    float *sNa = reinterpret_cast<float *>(sp); sp += G::R * 4;
-    float *sPart = reinterpret_cast<float *>(sp); sp += 2 * G::R * 4;
-    float *sScore = reinterpret_cast<float *>(sp); sp += p.cap * 4;
-    float *sStrict = reinterpret_cast<float *>(sp); sp += p.cap * 4;
-    sp = smem_raw + (((size_t)(sp - smem_raw) + 15) & ~(size_t)15);
-    uint64_t *sKey = reinterpret_cast<uint64_t *>(sp); sp += (size_t)p.capp * 8;
-    uint64_t *sKey2 = reinterpret_cast<uint64_t *>(sp); sp += (size_t)p.capp * 8;
-    int32_t *sCode0 = reinterpret_cast<int32_t *>(sp); sp += p.cap * 4;
-    int32_t *sCode1 = reinterpret_cast<int32_t *>(sp); sp += p.cap * 4;
-    int32_t *sMisc = reinterpret_cast<int32_t *>(sp); sp += 64 * 4;   // [0..15] hist, [16..31] mask, [32..39] scan, [40] eps bits, [41] tmem
-    uint64_t *sBar = reinterpret_cast<uint64_t *>(sp);                // [0] history TMA, [1] MMA
+    unsigned char *sXh = sp; sp += G::X_BYTES;
+    unsigned char *sXl = sp; sp += G::X_BYTES;
+    unsigned char *sPh = sp; sp += G::P_BYTES;
+    unsigned char *sPl = sp; sp += G::P_BYTES;
+    unsigned char *sWh = sp; sp += G::W_BYTES;
+    unsigned char *sWl = sp; sp += G::W_BYTES;
+    unsigned char *sKbh = sp; sp += G::KB_BYTES;
+    unsigned char *sKbl = sp; sp += G::KB_BYTES;
+    unsigned char *sHh = sp; sp += G::H_BYTES;
+    unsigned char *sHl = sp; sp += G::H_BYTES;
+    float *sScore = reinterpret_cast<float *>(sp); sp += (size_t)p.cap * 4;
+    int32_t *sCode0 = reinterpret_cast<int32_t *>(sp); sp += (size_t)p.cap * 4;
+    int32_t *sCode1 = reinterpret_cast<int32_t *>(sp); sp += (size_t)p.cap * 4;
+    int32_t *sVCode = reinterpret_cast<int32_t *>(sp); sp += G::VCAP * 4;   // deferred verification list
+    float *sVFast = reinterpret_cast<float *>(sp); sp += G::VCAP * 4;
+    uint32_t *sVMeta = reinterpret_cast<uint32_t *>(sp); sp += G::VCAP * 4;  // start | n << 8 | need << 16 | chosen << 24 | segment << 25
+    float *sSegEps = reinterpret_cast<float *>(sp); sp += 32 * 4;
+    int32_t *sMisc = reinterpret_cast<int32_t *>(sp); sp += 128 * 4;   // [0..15] hist codes, [16] mask bits, [32..39] scan, [40..] scalars
+    uint64_t *sBar = reinterpret_cast<uint64_t *>(sp);                 // [0] history TMA, [1] S MMAs, [2] all MMAs of a pass
+    // aliases (valid only while no MMA is in flight)
+    float *sKf = reinterpret_cast<float *>(sXh);                       // history fp32 [16][KLD]
+    int *sHist = reinterpret_cast<int *>(sPh + G::OFF_HIST);
+    int *sSel = reinterpret_cast<int *>(sPh + G::OFF_SEL);
+    uint32_t *sKeyU = reinterpret_cast<uint32_t *>(sPh + G::OFF_KEYU);
+    int *sUPos = reinterpret_cast<int *>(sPh + G::OFF_UPOS);
+    int32_t *sLCode = reinterpret_cast<int32_t *>(sPh + G::OFF_LCODE);  // codes handed to the strict scorer
+    float *sLStr = reinterpret_cast<float *>(sPh + G::OFF_LSTR);        // ... and their strict logits
+    uint8_t *sCls = reinterpret_cast<uint8_t *>(sPh + G::OFF_CLS);
+    float *sHmax = reinterpret_cast<float *>(sPh);                     // prologue only: [4][64] max_j |H_jo| partials
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int T = p.T;
 
-    // ---- one-time setup: weights -> bf16 hi/lo in UMMA K-major layout, TMEM allocation ----------
-    for (int i = tid; i < E * (E / 8); i += kThreads) {           // W_att: 64 outputs x 8 k-chunks
+    // ---- one-time setup: W1x -> bf16 hi/lo B operand, barriers, TMEM ------------------------------
+    for (int i = tid; i < E * (E / 8); i += G::THREADS) {         // 64 outputs x 8 k-chunks
         const int o = i % E, kc = i / E;
         float v[8];
 #pragma unroll
-        for (int q = 0; q < 8; q++) v[q] = fx.watt[o * E + kc * 8 + q];
+        for (int q = 0; q < 8; q++) v[q] = __ldg(fp.w1 + o * 2 * E + kc * 8 + q);
         uint4 hi, lo;
         split8(v, hi, lo);
-        *reinterpret_cast<uint4 *>(sWattH + kc * G::B_LBO + o * 16) = hi;
-        *reinterpret_cast<uint4 *>(sWattL + kc * G::B_LBO + o * 16) = lo;
+        *reinterpret_cast<uint4 *>(sWh + kc * G::W_LBO + o * 16) = hi;
+        *reinterpret_cast<uint4 *>(sWl + kc * G::W_LBO + o * 16) = lo;
     }
-    for (int i = tid; i < E * (2 * E / 8); i += kThreads) {       // W1: 64 outputs x 16 k-chunks
-        const int o = i % E, kc = i / E;
-        float v[8];
-#pragma unroll
-        for (int q = 0; q < 8; q++) v[q] = fx.w1[o * 2 * E + kc * 8 + q];
-        uint4 hi, lo;
-        split8(v, hi, lo);
-        *reinterpret_cast<uint4 *>(sW1H + kc * G::B_LBO + o * 16) = hi;
-        *reinterpret_cast<uint4 *>(sW1L + kc * G::B_LBO + o * 16) = lo;
-    }
-    for (int i = tid; i < E; i += kThreads) { sB1[i] = p.b1[i]; sW2[i] = p.w2[i]; }
-    if (tid == 0) { sB2[0] = p.b2[0]; mbar_init(&sBar[0], 1); mbar_init(&sBar[1], 1); }
-    if (warp == 0) tmem_alloc(reinterpret_cast<uint32_t *>(&sMisc[41]), 256);   // scores [0,16) a [64,128) att [128,192) h [192,256)
+    if (tid == 0) { mbar_init(&sBar[0], 1); mbar_init(&sBar[1], 1); mbar_init(&sBar[2], 1); }
+    if (warp == 0) tmem_alloc(reinterpret_cast<uint32_t *>(&sMisc[41]), 256);   // S tiles [0,32)  Hacc tiles [64,192)
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t *>(&sMisc[41]);
-    const float b2 = sB2[0];
-    uint32_t hist_phase = 0, mma_phase = 0;
-    unsigned long long st_cuts = 0, st_recuts = 0, st_rerows = 0, st_rows = 0;
+    const uint32_t tmem_lane = (uint32_t)((warp & 3) * 32) << 16;
+    const int tile_of_warp = warp >> 2;
+    uint32_t hist_phase = 0, s_phase = 0, h_phase = 0;
+    unsigned long long st_cuts = 0, st_recuts = 0, st_rerows = 0, st_rows = 0, st_redo = 0, st_sync = 0;
+    float st_ratio = 0.0f;
+#ifdef DMG_FAST_TIMING
+    long long tacc[TK_N] = {0}, tlast = clock64();
+#endif
 
-    // operand descriptors (constant per CTA)
-    const uint32_t aXH = smem_u32(sAxH), aXL = smem_u32(sAxL), aAH = smem_u32(sAaH), aAL = smem_u32(sAaL);
-    const uint32_t bWaH = smem_u32(sWattH), bWaL = smem_u32(sWattL), bW1H = smem_u32(sW1H), bW1L = smem_u32(sW1L);
-    const uint32_t bKbH = smem_u32(sKbH), bKbL = smem_u32(sKbL), bKtH = smem_u32(sKtH), bKtL = smem_u32(sKtL);
-    const uint32_t aPH = smem_u32(sPH), aPL = smem_u32(sPL);
-
-    // ---- strict scorer on `n` candidate positions listed in sKey2[0..n) (as positions) ----------
-    // gathers the rows again, scores them with score_tile (sequential-k fma chains, weights read
-    // through the generic path from global memory) and leaves the strict logits in sStrict[pos].
-    float st_ratio = 0.0f, eps_now = 0.0f;
-    auto strict_rescore = [&](const int32_t *codes, const int *positions_from_keys, int n, const uint64_t *keys) {
-        (void)positions_from_keys;
-        for (int base = 0; base < n; base += G::R) {
-            const int nr = n - base < G::R ? n - base : G::R;
-            for (int idx = tid; idx < nr * (E / 4); idx += kThreads) {
-                const int r = idx / (E / 4), v = idx % (E / 4);
-                const int pos = KO::pos(keys[base + r]);
-                cp_async16(sX + r * G::LD + v * 4, p.emb + (size_t)codes[pos] * E + v * 4);
-            }
-            cp_async_commit();
-            cp_async_wait<0>();
-            __syncthreads();
-            score_tile<float, 64>(sX, sStrictA, sP, sK, sMisc + 16, p.wattT, p.w1T, sB1, sW2, b2, p.scale, T, nr, sPart);
-            for (int r = tid; r < nr; r += kThreads) {
-                const int pos = KO::pos(keys[base + r]);
-                sStrict[pos] = sPart[r];
-                if (eps_now > 0.0f) {                              // observed |fast - strict| / eps (must stay < 1)
-                    const float ratio = fabsf(sPart[r] - sScore[pos]) / eps_now;
-                    if (ratio > st_ratio) st_ratio = ratio;
-                }
-            }
-            __syncthreads();
-        }
+    // operand descriptors = one live register (the CTA's shared-memory base) + compile-time offsets;
+    // a k-step / M-tile offset is added to the 16-byte start-address field
+    const uint32_t sbase16 = smem_u32(smem_raw) >> 4;
+    auto mkdesc = [&](uint32_t byte_off, uint32_t lbo) -> uint64_t {
+        return ((uint64_t)(0x4000u | (G::SBO >> 4)) << 32) | (uint64_t)((sbase16 + (byte_off >> 4)) | ((lbo >> 4) << 16));
     };
+    constexpr uint32_t OFF_XH = 0, OFF_XL = G::X_BYTES, OFF_PH = 2 * G::X_BYTES, OFF_PL = OFF_PH + G::P_BYTES,
+                       OFF_WH = OFF_PL + G::P_BYTES, OFF_WL = OFF_WH + G::W_BYTES, OFF_KH = OFF_WL + G::W_BYTES,
+                       OFF_KL = OFF_KH + G::KB_BYTES, OFF_HH = OFF_KL + G::KB_BYTES, OFF_HL = OFF_HH + G::H_BYTES;
 
-    for (int user = blockIdx.x; user < p.B; user += gridDim.x) {
-        // ---- K2: history tile through the TMA bulk-copy engine ------------------------------------
-        if (tid < kMaxT) {
-            int c = -1, m = 0;
-            if (tid < T) { c = p.hist[(size_t)user * T + tid]; m = p.hist_mask[(size_t)user * T + tid]; }
-            sMisc[tid] = c;
-            sMisc[16 + tid] = m;
-        }
-        __syncthreads();
+    // history rows (fp32) -> sKf through the TMA bulk-copy engine; padding rows are zero
+    auto load_history = [&]() {
         fence_proxy_async();
         if (tid == 0) {
             uint32_t bytes = 0;
             for (int j = 0; j < T; j++) if (sMisc[j] >= 0) bytes += E * sizeof(float);
             mbar_expect_tx(&sBar[0], bytes);
             for (int j = 0; j < T; j++)
-                if (sMisc[j] >= 0) tma_bulk_g2s(sK + j * E, p.emb + (size_t)sMisc[j] * E, E * sizeof(float), &sBar[0]);
+                if (sMisc[j] >= 0) tma_bulk_g2s(sKf + j * G::KLD, p.emb + (size_t)sMisc[j] * E, E * sizeof(float), &sBar[0]);
         }
-        for (int i = tid; i < T * E; i += kThreads)
-            if (sMisc[i / E] < 0) sK[i] = 0.0f;
+        for (int i = tid; i < kMaxT * E; i += G::THREADS) {
+            const int j = i / E;
+            if (j >= T || sMisc[j] < 0) sKf[j * G::KLD + (i % E)] = 0.0f;
+        }
         mbar_wait(&sBar[0], hist_phase);
         hist_phase ^= 1;
         __syncthreads();
-        // history tile -> bf16 hi/lo B operands (rows j >= T are zero) and Kmax = max_j |K_j|
-        if (tid < 128) {
+    };
+
+    // strict logits of the n rows whose codes sit in sLCode[0..n) -> sLStr[0..n)
+    auto strict_rescore = [&](int n) {
+        __syncthreads();
+        load_history();
+        strict_score_batch(p.emb, sLCode, n, sLStr, sKf, (uint32_t)sMisc[16], T, p.scale, p.wattT, p.w1T, p.b1, p.w2, fp.b2);
+    };
+    auto track_ratio = [&](float strict, float fast, float eps_now) {
+        if (eps_now > 0.0f && eps_now < 1e30f) {
+            const float ratio = fabsf(strict - fast) / eps_now;
+            if (ratio > st_ratio) st_ratio = ratio;
+        }
+    };
+
+    for (;;) {
+        // ---- next user (dynamic scheduler) ------------------------------------------------------
+        __syncthreads();
+        if (tid == 0) sMisc[42] = atomicAdd(fp.work_counter, 1);
+        __syncthreads();
+        const int user = sMisc[42];
+        if (user >= p.B) break;
+        DMG_TICK(TK_SCHED);
+
+        // ---- K2: history tile, its operand forms, H = K . M^T -------------------------------------
+        if (tid < kMaxT) {
+            int c = -1, m = 0;
+            if (tid < T) { c = p.hist[(size_t)user * T + tid]; m = p.hist_mask[(size_t)user * T + tid]; }
+            sMisc[tid] = c;
+            const uint32_t mb = __ballot_sync(0x0000ffffu, m != 0);
+            if (tid == 0) { sMisc[16] = (int)mb; sMisc[44] = 0; sMisc[45] = 0; }
+        }
+        __syncthreads();
+        load_history();
+        if (tid < 128) {                                        // history as B operand of S = X . K^T : [16 j][64 k]
             const int j = tid & 15, kc = tid >> 4;
             float v[8];
 #pragma unroll
-            for (int q = 0; q < 8; q++) v[q] = j < T ? sK[j * E + kc * 8 + q] : 0.0f;
+            for (int q = 0; q < 8; q++) v[q] = sKf[j * G::KLD + kc * 8 + q];
             uint4 hi, lo;
             split8(v, hi, lo);
-            *reinterpret_cast<uint4 *>(sKbH + kc * G::KB_LBO + j * 16) = hi;
-            *reinterpret_cast<uint4 *>(sKbL + kc * G::KB_LBO + j * 16) = lo;
-        } else {
-            const int t2 = tid - 128, e = t2 & 63, jc = t2 >> 6;
-            float v[8];
+            *reinterpret_cast<uint4 *>(sKbh + kc * G::KB_LBO + j * 16) = hi;
+            *reinterpret_cast<uint4 *>(sKbl + kc * G::KB_LBO + j * 16) = lo;
+        } else if (tid < 192) {                                 // ZK = sum_k z_k max_j |K_jk|  (two warp partials)
+            const int k = tid - 128;
+            float kab = 0.0f;
 #pragma unroll
-            for (int q = 0; q < 8; q++) v[q] = (jc * 8 + q) < T ? sK[(jc * 8 + q) * E + e] : 0.0f;
-            uint4 hi, lo;
-            split8(v, hi, lo);
-            *reinterpret_cast<uint4 *>(sKtH + jc * G::KT_LBO + e * 16) = hi;
-            *reinterpret_cast<uint4 *>(sKtL + jc * G::KT_LBO + e * 16) = lo;
-        }
-        if (tid == 0) sMisc[44] = 0;
-        __syncthreads();
-        if (tid < T) {
+            for (int j = 0; j < kMaxT; j++) { const float v = fabsf(sKf[j * G::KLD + k]); kab = (v > kab || v != v) ? v : kab; }   // NaN sticks
+            float zk = __ldg(fp.zvec + k) * kab;
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) zk += __shfl_xor_sync(0xffffffffu, zk, o);
+            if (lane == 0) sMisc[46 + (warp & 1)] = __float_as_int(zk);
+        } else if (tid < 192 + kMaxT) {                         // Kmax = max_j |K_j|_2
+            const int j = tid - 192;
             float n2 = 0.0f;
-            for (int k = 0; k < E; k++) n2 = fmaf(sK[tid * E + k], sK[tid * E + k], n2);
-            atomicMax(&sMisc[44], __float_as_int(sqrtf(n2) * 1.0001f));
+            for (int k = 0; k < E; k++) n2 = fmaf(sKf[j * G::KLD + k], sKf[j * G::KLD + k], n2);
+            float nj = sqrtf(n2) * 1.0001f;
+            if (!(nj == nj)) nj = __int_as_float(0x7f800000);
+            atomicMax(&sMisc[44], __float_as_int(nj));
+        }
+        {                                                       // H[j][o] = sum_k M[o][k] K[j][k], 4 j per thread
+            const int o = tid & 63, jg = tid >> 6;
+            float acc[4] = {0.0f, 0.0f, 0.0f, 0.0f};
+            const float *kr = sKf + (jg * 4) * G::KLD;
+#pragma unroll 8
+            for (int k = 0; k < E; k++) {
+                const float m = __ldg(fp.mT + k * E + o);
+#pragma unroll
+                for (int q = 0; q < 4; q++) acc[q] = fmaf(m, kr[q * G::KLD + k], acc[q]);
+            }
+            uint2 hi, lo;
+            split_pair(acc[0], acc[1], hi.x, lo.x);
+            split_pair(acc[2], acc[3], hi.y, lo.y);
+            const int off = (jg >> 1) * G::H_LBO + o * 16 + (jg & 1) * 8;
+            *reinterpret_cast<uint2 *>(sHh + off) = hi;
+            *reinterpret_cast<uint2 *>(sHl + off) = lo;
+            float hm = fmaxf(fmaxf(fabsf(acc[0]), fabsf(acc[1])), fmaxf(fabsf(acc[2]), fabsf(acc[3])));
+            if (acc[0] != acc[0] || acc[1] != acc[1] || acc[2] != acc[2] || acc[3] != acc[3]) hm = __int_as_float(0x7f800000);
+            sHmax[jg * E + o] = hm;
+        }
+        __syncthreads();
+        if (tid < E) {                                          // HW = sum_o |w2_o| max_j |H_jo|  (two warp partials)
+            float hw = fmaxf(fmaxf(sHmax[tid], sHmax[E + tid]), fmaxf(sHmax[2 * E + tid], sHmax[3 * E + tid])) * fabsf(fp.w2[tid]);
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) hw += __shfl_xor_sync(0xffffffffu, hw, o);
+            if (lane == 0) sMisc[48 + warp] = __float_as_int(hw);
         }
         __syncthreads();
         const float kmax = __int_as_float(sMisc[44]);
+        const float zk_user = (__int_as_float(sMisc[46]) + __int_as_float(sMisc[47])) * 1.0001f;
+        const float hw_user = (__int_as_float(sMisc[48]) + __int_as_float(sMisc[49])) * 1.0001f;
+        const uint32_t maskbits = (uint32_t)sMisc[16];
 
         const int beam = p.beam_user ? p.beam_user[user] : p.beam;
         const int s_level = 31 - __clz(beam);
@@ -313,399 +586,443 @@ __global__ void __launch_bounds__(kThreads, 1) beam_search_fast_kernel(const Bea
         if (s_level <= p.leaf_level) {
             const int64_t start = ((int64_t)1 << s_level) - 1;
             const int n0 = 1 << s_level;
-            for (int base = 0; base < n0; base += kThreads) {
-                int i = base + tid;
-                int e = (i < n0 && code_exists(p.exists, start + i)) ? 1 : 0;
+            for (int base = 0; base < n0; base += G::THREADS) {
+                const int i = base + tid;
+                const int e = (i < n0 && code_exists(p.exists, start + i)) ? 1 : 0;
                 int tot;
-                int o = block_exscan(e, sMisc + 32, &tot);
+                const int o = block_exscan(e, sMisc + 32, &tot);
                 if (e) cur[count + o] = (int32_t)(start + i);
                 count += tot;
             }
-            for (int i = tid; i < count; i += kThreads) sScore[i] = 0.0f;
             __syncthreads();
         }
-        float eps_level = 0.0f;                                   // max eps_row of the current candidates
+        DMG_TICK(TK_PROLOGUE);
+        float eps_level = 0.0f;                                 // bound on |fast - strict| of the scores in sScore
+        int vcount = 0, nseg = 0;                               // deferred verification list of this user
+        bool redo = false;
+        bool scored = false;
 
         for (int level = s_level; level < p.leaf_level && count > 0; level++) {
-            int nb = count;
-            if (count > beam) {
-                // ---- certified cut ---------------------------------------------------------------
-                int n2 = 2;
-                while (n2 < count) n2 <<= 1;
-                for (int i = tid; i < n2; i += kThreads) sKey[i] = i < count ? KO::make(sScore[i], i) : KO::lowest();
-                __syncthreads();
-                bitonic_sort_desc(sKey, n2);
-                nb = beam;
+            // ---- which candidates stay (certified cut), then their children, order preserved --------
+            bool cut = count > beam;
+            if (cut) {
                 st_cuts++;
-                const float pivot = sScore[KO::pos(sKey[beam - 1])];
-                const float band = 2.0f * eps_level * 1.0001f + 1e-30f;
-                // hi = last rank whose fast score >= pivot - band ; lo = first rank with score <= pivot + band
-                int hi_local = -1, lo_local = 1 << 30;
-                for (int i = tid; i < count; i += kThreads) {
-                    const float s = sScore[KO::pos(sKey[i])];
-                    if (!(s < pivot - band)) hi_local = i > hi_local ? i : hi_local;
-                    if (!(s > pivot + band)) lo_local = i < lo_local ? i : lo_local;
+                for (int i = tid; i < count; i += G::THREADS) sKeyU[i] = order_key(sScore[i]);
+                __syncthreads();
+                if (warp == 0) {
+                    const uint32_t pk = warp_radix_select(sKeyU, count, beam, sHist, lane);
+                    if (lane == 0) sSel[0] = (int)pk;
                 }
-                if (tid == 0) { sMisc[42] = -1; sMisc[43] = 1 << 30; }
                 __syncthreads();
-                atomicMax(&sMisc[42], hi_local);
-                atomicMin(&sMisc[43], lo_local);
-                __syncthreads();
-                const int hi = sMisc[42], lo = sMisc[43];
-                if (hi >= beam) {                                  // an outsider can overtake an insider: settle it strictly
+                const float pivot = key_to_float((uint32_t)sSel[0]);
+                const float band = 2.0f * eps_level * 1.0001f + 1e-30f;
+                const float up = pivot + band, dn = pivot - band;
+                int n_keep = 0, n_unc = 0;
+                for (int base = 0; base < count; base += G::THREADS) {
+                    const int i = base + tid;
+                    int cls = 0;                                 // 0 out, 1 in, 2 uncertain
+                    if (i < count) {
+                        const float f = sScore[i];
+                        cls = f > up ? 1 : (f < dn ? 0 : 2);
+                        sCls[i] = (uint8_t)cls;
+                    }
+                    n_keep += __syncthreads_count(cls != 0);
+                    n_unc += __syncthreads_count(cls == 2);
+                }
+                DMG_TICK(TK_SELECT);
+                if (n_keep != beam) {                            // some uncertain row must go
                     st_recuts++;
-                    eps_now = eps_level;
-                    const int na = hi - lo + 1;
-                    st_rerows += na;
-                    strict_rescore(cur, nullptr, na, sKey + lo);
-                    int m2 = 2;
-                    while (m2 < na) m2 <<= 1;
-                    for (int i = tid; i < m2; i += kThreads) {
-                        uint64_t k = KO::lowest();
-                        if (i < na) { const int pos = KO::pos(sKey[lo + i]); k = KO::make(sStrict[pos], pos); }
-                        sKey2[i] = k;
+                    if (n_unc > G::MAX_UNC) { redo = true; break; }
+                    if (tid == 0) sMisc[45] = 0;
+                    __syncthreads();
+                    for (int i = tid; i < count; i += G::THREADS)
+                        if (sCls[i] == 2) sUPos[atomicAdd(&sMisc[45], 1)] = i;
+                    __syncthreads();
+                    const int need = beam - (n_keep - n_unc);    // uncertain rows that still fit (1 <= need < n_unc)
+                    // rank of every band row by its FAST score, and the fast-score gap at the cut inside the band
+                    int frank = 0, ps = 0;
+                    if (tid < n_unc) {
+                        ps = sUPos[tid];
+                        const uint32_t ks = sKeyU[ps];
+                        for (int q = 0; q < n_unc; q++) {
+                            const int pq = sUPos[q];
+                            const uint32_t kq = sKeyU[pq];
+                            frank += (kq > ks || (kq == ks && pq < ps)) ? 1 : 0;
+                        }
+                        if (frank == need - 1) sSel[2] = __float_as_int(sScore[ps]);
+                        if (frank == need) sSel[3] = __float_as_int(sScore[ps]);
                     }
                     __syncthreads();
-                    bitonic_sort_desc(sKey2, m2);
-                    for (int i = tid; i < beam - lo; i += kThreads) sKey[lo + i] = sKey2[i];
-                    __syncthreads();
+                    const float gap = __int_as_float(sSel[2]) - __int_as_float(sSel[3]);
+                    // Observed |fast - strict| stays below 1 % of eps: with a gap of eps/16 or more the fast order is
+                    // taken now and PROVEN at the end of the search (one strict batch over every deferred band row);
+                    // a narrower gap is settled strictly right here.
+                    const bool defer = gap >= 0.0625f * eps_level && vcount + n_unc <= G::VCAP && nseg < 32 && eps_level < 1e30f;
+                    if (defer) {
+                        if (tid < n_unc) {
+                            const uint32_t chosen = frank < need ? 1u : 0u;
+                            sCls[ps] = (uint8_t)chosen;
+                            const int e = vcount + tid;
+                            sVCode[e] = cur[ps];
+                            sVFast[e] = sScore[ps];
+                            sVMeta[e] = (uint32_t)vcount | ((uint32_t)n_unc << 8) | ((uint32_t)need << 16) | (chosen << 24) | ((uint32_t)nseg << 25);
+                        }
+                        if (tid == 0) sSegEps[nseg] = eps_level;
+                        vcount += n_unc;
+                        nseg++;
+                        __syncthreads();
+                    } else {
+                        st_sync++;
+                        st_rerows += n_unc;
+                        if (tid < n_unc) sLCode[tid] = cur[ps];
+                        strict_rescore(n_unc);
+                        int tie = 0;
+                        if (tid < n_unc) {
+                            track_ratio(sLStr[tid], sScore[ps], eps_level);
+                            const uint32_t ks = order_key(sLStr[tid]);
+                            int rank = 0;
+                            for (int q = 0; q < n_unc; q++) {
+                                const uint32_t kq = order_key(sLStr[q]);
+                                rank += (kq > ks || (kq == ks && sUPos[q] < ps)) ? 1 : 0;
+                                tie |= (kq == ks && q != tid) ? 1 : 0;
+                            }
+                            sCls[ps] = rank < need ? 1 : 0;
+                        }
+                        if (__syncthreads_or(tie)) { redo = true; break; }
+                    }
+                    DMG_TICK(TK_RESCORE);
                 }
-                for (int i = tid; i < nb; i += kThreads) nxt[i] = cur[KO::pos(sKey[i])];
-                __syncthreads();
-                int32_t *t = cur; cur = nxt; nxt = t;
             }
-            // ---- children (order preserved) ---------------------------------------------------------
             int nc = 0;
-            if (p.exists == nullptr) {
-                for (int i = tid; i < nb; i += kThreads) { int32_t c = cur[i]; nxt[2 * i] = 2 * c + 1; nxt[2 * i + 1] = 2 * c + 2; }
-                nc = 2 * nb;
-                __syncthreads();
-            } else {
-                for (int base = 0; base < nb; base += kThreads) {
-                    int i = base + tid;
-                    int64_t c = i < nb ? cur[i] : 0;
-                    int e1 = (i < nb && code_exists(p.exists, 2 * c + 1)) ? 1 : 0;
-                    int e2 = (i < nb && code_exists(p.exists, 2 * c + 2)) ? 1 : 0;
-                    int tot;
-                    int o = block_exscan(e1 + e2, sMisc + 32, &tot);
-                    if (e1) nxt[nc + o] = (int32_t)(2 * c + 1);
-                    if (e2) nxt[nc + o + e1] = (int32_t)(2 * c + 2);
-                    nc += tot;
-                }
-                __syncthreads();
+            for (int base = 0; base < count; base += G::THREADS) {
+                const int i = base + tid;
+                const bool keep = i < count && (!cut || sCls[i] != 0);
+                const int64_t c = keep ? cur[i] : 0;
+                const int e1 = (keep && code_exists(p.exists, 2 * c + 1)) ? 1 : 0;
+                const int e2 = (keep && code_exists(p.exists, 2 * c + 2)) ? 1 : 0;
+                int tot;
+                const int o = block_exscan(e1 + e2, sMisc + 32, &tot);
+                if (e1) nxt[nc + o] = (int32_t)(2 * c + 1);
+                if (e2) nxt[nc + o + e1] = (int32_t)(2 * c + 2);
+                nc += tot;
             }
+            __syncthreads();
             { int32_t *t = cur; cur = nxt; nxt = t; }
             count = nc;
             st_rows += count;
-            if (tid == 0) sMisc[40] = 0;
-            // ---- fast scoring, tile by tile ------------------------------------------------------------
-            const int ntiles = (count + G::R - 1) / G::R;
-            if (ntiles > 0) {
-                gather_tile<float, 64>(sX, p.emb, cur, count < G::R ? count : G::R);
-                cp_async_commit();
+            scored = true;
+            DMG_TICK(TK_EXPAND);
+
+            // ---- eps of this level's scores (children sit on tree level `level + 1`) ------------------
+            {
+                const float u = 5.9604645e-8f;                   // 2^-24
+                const float vx = __ldg(fp.lvl_vx + level + 1), nx = __ldg(fp.lvl_nx + level + 1);
+                const float smax = p.scale * nx * kmax;
+                const float ds = 6.1035156e-5f * smax;           // 2^-14: |s_fast - s_strict| <= ds
+                const float dp1 = 2.1f * ds + 2.0f * (float)(T + 8) * u + 2.0f * 9.5367432e-7f * (1.0f + 2.0f * smax);
+                float eps = fp.cA * vx + fp.cZ * zk_user + (fp.cH + dp1) * hw_user * 1.05f + fp.cGamma;
+                if (!(ds < 0.04f) || !(eps < 1e30f)) eps = __int_as_float(0x7f800000);
+                eps_level = eps * fp.tau;
             }
-            for (int t = 0; t < ntiles; t++) {
-                const int r0 = t * G::R;
+
+            // ---- fast scoring, 256 rows per pass ---------------------------------------------------------
+            for (int r0 = 0; r0 < count; r0 += G::R) {
                 const int nrows = count - r0 < G::R ? count - r0 : G::R;
-                const float *buf = sX + (t & 1) * G::R * G::LD;
-                if (t + 1 < ntiles) {
-                    const int r1 = r0 + G::R;
-                    gather_tile<float, 64>(sX + ((t + 1) & 1) * G::R * G::LD, p.emb, cur + r1, count - r1 < G::R ? count - r1 : G::R);
-                    cp_async_commit();
-                    cp_async_wait<1>();
-                } else {
-                    cp_async_wait<0>();
-                }
-                __syncthreads();
-                // (1) x -> bf16 hi/lo operand tile, |x|
+                const int ntile = nrows > 128 ? 2 : 1;
+                // (A) gather rows (16 lanes x 16 B per row) -> bf16 hi/lo operand tiles
                 {
-                    const int r = tid >> 1, part = tid & 1;
-                    float nx = 0.0f;
-                    if (r < nrows) {
-                        const float *xr = buf + r * G::LD + part * 32;
+                    const int chunk = lane & 15, rsub = lane >> 4;
+                    const uint32_t st_off = (uint32_t)((chunk >> 1) * G::X_LBO + (chunk & 1) * 8);
+                    const int niter = (nrows + 15) >> 4;
 #pragma unroll
-                        for (int c = 0; c < 4; c++) {
-                            float xv[8];
-                            ld4(xr + c * 8, *reinterpret_cast<float(*)[4]>(&xv[0]));
-                            ld4(xr + c * 8 + 4, *reinterpret_cast<float(*)[4]>(&xv[4]));
+                    for (int hb = 0; hb < 2; hb++) {
+                        float4 v[8];
 #pragma unroll
-                            for (int q = 0; q < 8; q++) nx = fmaf(xv[q], xv[q], nx);
-                            uint4 hi, lo;
-                            const int off = (part * 4 + c) * G::A_LBO + r * 16;
-                            split8(xv, hi, lo);
-                            *reinterpret_cast<uint4 *>(sAxH + off) = hi;
-                            *reinterpret_cast<uint4 *>(sAxL + off) = lo;
+                        for (int q = 0; q < 8; q++) {
+                            const int it = hb * 8 + q;
+                            if (it < niter) {
+                                const int row = it * 16 + warp * 2 + rsub;
+                                const int32_t code = cur[r0 + (row < nrows ? row : 0)];
+                                v[q] = ldg_row16(p.emb + (size_t)code * E + chunk * 4);
+                            }
+                        }
+#pragma unroll
+                        for (int q = 0; q < 8; q++) {
+                            const int it = hb * 8 + q;
+                            if (it < niter) {
+                                const int row = it * 16 + warp * 2 + rsub;
+                                uint2 hi, lo;
+                                split_pair(v[q].x, v[q].y, hi.x, lo.x);
+                                split_pair(v[q].z, v[q].w, hi.y, lo.y);
+                                *reinterpret_cast<uint2 *>(sXh + st_off + row * 16) = hi;
+                                *reinterpret_cast<uint2 *>(sXl + st_off + row * 16) = lo;
+                            }
                         }
                     }
-                    nx += __shfl_xor_sync(0xffffffffu, nx, 1);
-                    if (part == 0 && r < nrows) sNx[r] = sqrtf(nx) * 1.0001f;
                 }
                 fence_proxy_async();
                 tc_fence_before();
                 __syncthreads();
-                // (2) attention scores S = X . K^T  (M 128, N 16, K 64) on the tensor cores
-                if (tid == 0) {
+                DMG_TICK(TK_GATHER);
+                // (B) S = X . K^T (N = 16), then Hacc = X . W1x^T (N = 64): 4 k-steps x (hi*hi + hi*lo + lo*hi).
+                // Warp 0 runs the descriptor arithmetic warp-uniformly; one elected lane issues.
+                if (warp == 0) {
                     tc_fence_after();
+                    const bool leader = elect_one();
+                    const uint64_t dXh = mkdesc(OFF_XH, G::X_LBO), dXl = mkdesc(OFF_XL, G::X_LBO);
+                    const uint64_t dKh = mkdesc(OFF_KH, G::KB_LBO), dKl = mkdesc(OFF_KL, G::KB_LBO);
+                    const uint64_t dWh = mkdesc(OFF_WH, G::W_LBO), dWl = mkdesc(OFF_WL, G::W_LBO);
+                    for (int t = 0; t < ntile; t++) {
+                        const uint64_t xo = (uint64_t)(t * 128);            // 128 rows x 16 B, in 16-byte descriptor units
 #pragma unroll
-                    for (int ks = 0; ks < 4; ks++) {
-                        const uint64_t ah = umma_desc(aXH + ks * 2 * G::A_LBO, G::A_LBO, G::SBO);
-                        const uint64_t al = umma_desc(aXL + ks * 2 * G::A_LBO, G::A_LBO, G::SBO);
-                        const uint64_t bh = umma_desc(bKbH + ks * 2 * G::KB_LBO, G::KB_LBO, G::SBO);
-                        const uint64_t bl = umma_desc(bKbL + ks * 2 * G::KB_LBO, G::KB_LBO, G::SBO);
-                        umma_bf16(tmem_base, ah, bh, kIdescBf16M128N16, ks > 0);
-                        umma_bf16(tmem_base, ah, bl, kIdescBf16M128N16, 1);
-                        umma_bf16(tmem_base, al, bh, kIdescBf16M128N16, 1);
+                        for (int ks = 0; ks < 4; ks++) {
+                            const uint64_t ah = dXh + xo + ks * (2 * G::X_LBO / 16), al = dXl + xo + ks * (2 * G::X_LBO / 16);
+                            const uint64_t bh = dKh + ks * (2 * G::KB_LBO / 16), bl = dKl + ks * (2 * G::KB_LBO / 16);
+                            if (leader) {
+                                umma_bf16(tmem_base + t * 16, ah, bh, kIdescBf16M128N16, ks > 0);
+                                umma_bf16(tmem_base + t * 16, ah, bl, kIdescBf16M128N16, 1);
+                                umma_bf16(tmem_base + t * 16, al, bh, kIdescBf16M128N16, 1);
+                            }
+                        }
                     }
-                    umma_commit(&sBar[1]);
+                    if (leader) umma_commit(&sBar[1]);
+                    for (int t = 0; t < ntile; t++) {
+                        const uint64_t xo = (uint64_t)(t * 128);
+#pragma unroll
+                        for (int ks = 0; ks < 4; ks++) {
+                            const uint64_t ah = dXh + xo + ks * (2 * G::X_LBO / 16), al = dXl + xo + ks * (2 * G::X_LBO / 16);
+                            const uint64_t bh = dWh + ks * (2 * G::W_LBO / 16), bl = dWl + ks * (2 * G::W_LBO / 16);
+                            if (leader) {
+                                umma_bf16(tmem_base + 64 + t * 64, ah, bh, kIdescBf16M128N64, ks > 0);
+                                umma_bf16(tmem_base + 64 + t * 64, ah, bl, kIdescBf16M128N64, 1);
+                                umma_bf16(tmem_base + 64 + t * 64, al, bh, kIdescBf16M128N64, 1);
+                            }
+                        }
+                    }
+                    __syncwarp();
                 }
-                mbar_wait(&sBar[1], mma_phase);
-                mma_phase ^= 1;
-                tc_fence_after();
-                // (3) Mask + SoftMax per row in registers (warps 0-3 own the 128 TMEM lanes), P -> bf16 hi/lo
-                if (warp < 4) {
-                    const int row = warp * 32 + lane;
+                // (C) Mask + SoftMax per row in registers, P -> bf16 hi/lo A operand [256][16]
+                if (warp * 32 < nrows) {
+                    mbar_wait(&sBar[1], s_phase);
+                    tc_fence_after();
                     float sc[16];
-                    tmem_ld16(tmem_base + ((uint32_t)(warp * 32) << 16), sc);
+                    tmem_ld16(tmem_base + tmem_lane + tile_of_warp * 16, sc);
                     float mx = -3.4028234663852886e+38f;
 #pragma unroll
                     for (int j = 0; j < 16; j++) {
-                        float v = mul_(sc[j], p.scale);
-                        if (j < T && sMisc[16 + j]) v = mask_value<float>::get();
+                        float v = sc[j] * p.scale;
+                        if ((maskbits >> j) & 1u) v = -3.4028234663852886e+38f;
                         sc[j] = v;
-                        if (j < T) mx = v > mx ? v : mx;
+                        if (j < T) mx = fmaxf(mx, v);
                     }
                     float sum = 0.0f;
 #pragma unroll
                     for (int j = 0; j < 16; j++) {
-                        const float e = j < T ? exp_(sub_(sc[j], mx)) : 0.0f;
+                        const float e = j < T ? __expf(sc[j] - mx) : 0.0f;
                         sc[j] = e;
-                        sum = add_(sum, e);
+                        sum += e;
                     }
-                    const float inv = inv_(sum);
+                    const float inv = 1.0f / sum;
 #pragma unroll
-                    for (int j = 0; j < 16; j++) sc[j] = mul_(sc[j], inv);
+                    for (int j = 0; j < 16; j++) sc[j] *= inv;
                     uint4 hi, lo;
                     split8(*reinterpret_cast<float(*)[8]>(&sc[0]), hi, lo);
-                    *reinterpret_cast<uint4 *>(sPH + row * 16) = hi;
-                    *reinterpret_cast<uint4 *>(sPL + row * 16) = lo;
+                    *reinterpret_cast<uint4 *>(sPh + tid * 16) = hi;
+                    *reinterpret_cast<uint4 *>(sPl + tid * 16) = lo;
                     split8(*reinterpret_cast<float(*)[8]>(&sc[8]), hi, lo);
-                    *reinterpret_cast<uint4 *>(sPH + G::A_LBO + row * 16) = hi;
-                    *reinterpret_cast<uint4 *>(sPL + G::A_LBO + row * 16) = lo;
+                    *reinterpret_cast<uint4 *>(sPh + G::P_LBO + tid * 16) = hi;
+                    *reinterpret_cast<uint4 *>(sPl + G::P_LBO + tid * 16) = lo;
                 }
+                s_phase ^= 1;
                 fence_proxy_async();
                 tc_fence_before();
                 __syncthreads();
-                // (3b) a = P . K  (M 128, N 64, K 16): one k-step
-                if (tid == 0) {
+                DMG_TICK(TK_SOFTMAX);
+                // (D) Hacc += P . H (one k-step of 16)
+                if (warp == 0) {
                     tc_fence_after();
-                    const uint64_t ah = umma_desc(aPH, G::A_LBO, G::SBO), al = umma_desc(aPL, G::A_LBO, G::SBO);
-                    const uint64_t bh = umma_desc(bKtH, G::KT_LBO, G::SBO), bl = umma_desc(bKtL, G::KT_LBO, G::SBO);
-                    umma_bf16(tmem_base + 64, ah, bh, kIdescBf16M128N64, 0);
-                    umma_bf16(tmem_base + 64, ah, bl, kIdescBf16M128N64, 1);
-                    umma_bf16(tmem_base + 64, al, bh, kIdescBf16M128N64, 1);
-                    umma_commit(&sBar[1]);
-                }
-                mbar_wait(&sBar[1], mma_phase);
-                mma_phase ^= 1;
-                tc_fence_after();
-                // (3c) a: TMEM -> registers -> bf16 hi/lo operand tile, |a|
-                {
-                    const int row = (warp & 3) * 32 + lane, cbase = (warp >> 2) * 32;
-                    float v[32];
-                    tmem_ld32(tmem_base + 64 + ((uint32_t)((warp & 3) * 32) << 16) + cbase, v);
-                    float na = 0.0f;
-#pragma unroll
-                    for (int c = 0; c < 4; c++) {
-                        float av[8];
-#pragma unroll
-                        for (int q = 0; q < 8; q++) { av[q] = v[c * 8 + q]; na = fmaf(av[q], av[q], na); }
-                        uint4 hi, lo;
-                        split8(av, hi, lo);
-                        const int off = ((cbase >> 3) + c) * G::A_LBO + row * 16;
-                        *reinterpret_cast<uint4 *>(sAaH + off) = hi;
-                        *reinterpret_cast<uint4 *>(sAaL + off) = lo;
+                    const bool leader = elect_one();
+                    const uint64_t dPh = mkdesc(OFF_PH, G::P_LBO), dPl = mkdesc(OFF_PL, G::P_LBO);
+                    const uint64_t dHh = mkdesc(OFF_HH, G::H_LBO), dHl = mkdesc(OFF_HL, G::H_LBO);
+                    for (int t = 0; t < ntile; t++) {
+                        const uint64_t ah = dPh + (uint64_t)(t * 128), al = dPl + (uint64_t)(t * 128);
+                        if (leader) {
+                            umma_bf16(tmem_base + 64 + t * 64, ah, dHh, kIdescBf16M128N64, 1);
+                            umma_bf16(tmem_base + 64 + t * 64, ah, dHl, kIdescBf16M128N64, 1);
+                            umma_bf16(tmem_base + 64 + t * 64, al, dHh, kIdescBf16M128N64, 1);
+                        }
                     }
-                    sPart[(warp >> 2) * G::R + row] = na;
+                    if (leader) umma_commit(&sBar[2]);
+                    __syncwarp();
                 }
-                fence_proxy_async();
+                // (E) epilogue: logit = relu(Hacc + b1) . W2 + b2, one row per thread
+                if (warp * 32 < nrows) {
+                    mbar_wait(&sBar[2], h_phase);
+                    tc_fence_after();
+                    float logit = 0.0f;
+#pragma unroll
+                    for (int hf = 0; hf < 2; hf++) {
+                        float v[32];
+                        tmem_ld32(tmem_base + tmem_lane + 64 + tile_of_warp * 64 + hf * 32, v);
+#pragma unroll
+                        for (int c = 0; c < 32; c++) {
+                            const float h = fmaxf(v[c] + fp.b1[hf * 32 + c], 0.0f);
+                            logit = fmaf(h, fp.w2[hf * 32 + c], logit);
+                        }
+                    }
+                    if (tid < nrows) sScore[r0 + tid] = logit + fp.b2;
+                }
+                h_phase ^= 1;
                 tc_fence_before();
                 __syncthreads();
-                if (tid < nrows) sNa[tid] = sqrtf(sPart[tid] + sPart[G::R + tid]) * 1.0001f;
-                // (4) att = a . Watt^T on the tensor cores: 4 k-steps x (hi*hi + hi*lo + lo*hi)
-                if (tid == 0) {
-                    tc_fence_after();
-#pragma unroll
-                    for (int ks = 0; ks < 4; ks++) {
-                        const uint64_t ah = umma_desc(aAH + ks * 2 * G::A_LBO, G::A_LBO, G::SBO);
-                        const uint64_t al = umma_desc(aAL + ks * 2 * G::A_LBO, G::A_LBO, G::SBO);
-                        const uint64_t bh = umma_desc(bWaH + ks * 2 * G::B_LBO, G::B_LBO, G::SBO);
-                        const uint64_t bl = umma_desc(bWaL + ks * 2 * G::B_LBO, G::B_LBO, G::SBO);
-                        umma_bf16(tmem_base + 128, ah, bh, kIdescBf16M128N64, ks > 0);
-                        umma_bf16(tmem_base + 128, ah, bl, kIdescBf16M128N64, 1);
-                        umma_bf16(tmem_base + 128, al, bh, kIdescBf16M128N64, 1);
-                    }
-                    umma_commit(&sBar[1]);
-                }
-                mbar_wait(&sBar[1], mma_phase);
-                mma_phase ^= 1;
-                tc_fence_after();
-                // (5) att: TMEM -> registers -> bf16 hi/lo operand tile (overwrites a)
-                {
-                    const int row = (warp & 3) * 32 + lane, cbase = (warp >> 2) * 32;
-                    float v[32];
-                    tmem_ld32(tmem_base + 128 + ((uint32_t)((warp & 3) * 32) << 16) + cbase, v);
-#pragma unroll
-                    for (int c = 0; c < 4; c++) {
-                        float av[8];
-#pragma unroll
-                        for (int q = 0; q < 8; q++) av[q] = v[c * 8 + q];
-                        uint4 hi, lo;
-                        split8(av, hi, lo);
-                        const int off = ((cbase >> 3) + c) * G::A_LBO + row * 16;
-                        *reinterpret_cast<uint4 *>(sAaH + off) = hi;
-                        *reinterpret_cast<uint4 *>(sAaL + off) = lo;
-                    }
-                }
-                fence_proxy_async();
-                tc_fence_before();
-                __syncthreads();
-                // (6) h = [x | att] . W1^T : 8 k-steps (4 on x, 4 on att)
-                if (tid == 0) {
-                    tc_fence_after();
-                    const uint32_t d2 = tmem_base + 192;
-#pragma unroll
-                    for (int ks = 0; ks < 8; ks++) {
-                        const uint32_t aH = ks < 4 ? aXH + ks * 2 * G::A_LBO : aAH + (ks - 4) * 2 * G::A_LBO;
-                        const uint32_t aL = ks < 4 ? aXL + ks * 2 * G::A_LBO : aAL + (ks - 4) * 2 * G::A_LBO;
-                        const uint64_t ah = umma_desc(aH, G::A_LBO, G::SBO);
-                        const uint64_t al = umma_desc(aL, G::A_LBO, G::SBO);
-                        const uint64_t bh = umma_desc(bW1H + ks * 2 * G::B_LBO, G::B_LBO, G::SBO);
-                        const uint64_t bl = umma_desc(bW1L + ks * 2 * G::B_LBO, G::B_LBO, G::SBO);
-                        umma_bf16(d2, ah, bh, kIdescBf16M128N64, ks > 0);
-                        umma_bf16(d2, ah, bl, kIdescBf16M128N64, 1);
-                        umma_bf16(d2, al, bh, kIdescBf16M128N64, 1);
-                    }
-                    umma_commit(&sBar[1]);
-                }
-                mbar_wait(&sBar[1], mma_phase);
-                mma_phase ^= 1;
-                tc_fence_after();
-                // (7) epilogue: h = relu(acc + b1); logit = h . W2 + b2 ; eps_row
-                {
-                    const int row = (warp & 3) * 32 + lane, cbase = (warp >> 2) * 32;
-                    float v[32];
-                    tmem_ld32(tmem_base + 192 + ((uint32_t)((warp & 3) * 32) << 16) + cbase, v);
-                    float part = 0.0f;
-#pragma unroll
-                    for (int c = 0; c < 32; c++) {
-                        float h = v[c] + sB1[cbase + c];
-                        h = h > 0.0f ? h : 0.0f;
-                        part = fmaf(h, sW2[cbase + c], part);
-                    }
-                    sPart[(warp >> 2) * G::R + row] = part;
-                }
-                tc_fence_before();
-                __syncthreads();
-                if (tid < nrows) {
-                    sScore[r0 + tid] = sPart[tid] + sPart[G::R + tid] + b2;
-                    const float ds = fx.cs * sNx[tid] * kmax;                 // bound on the attention-score error
-                    const float da = kmax * (2.1f * ds + fx.ca);              // bound on |a_fast - a_strict|
-                    float eps = fx.alpha * sNx[tid] + fx.beta * (sNa[tid] + da) + fx.gamma + fx.zeta * da;
-                    if (!(ds < 0.01f)) eps = 3.0e38f;                         // outside the linearised regime: certify nothing
-                    atomicMax(&sMisc[40], __float_as_int(eps));
-                }
-                __syncthreads();
+                DMG_TICK(TK_EPILOGUE);
             }
-            eps_level = __int_as_float(sMisc[40]);
         }
 
         // ---- K3: topk, always settled with strict scores -----------------------------------------------
-        const int64_t leaf_start = ((int64_t)1 << p.leaf_level) - 1;
-        const bool at_leaf = (s_level <= p.leaf_level);
-        {
-            int n2 = 2;
-            while (n2 < count) n2 <<= 1;
+        if (!redo) {
+            const int64_t leaf_start = ((int64_t)1 << p.leaf_level) - 1;
+            const bool at_leaf = (s_level <= p.leaf_level);
             const int64_t c0 = p.cons_off ? p.cons_off[user] : 0, c1 = p.cons_off ? p.cons_off[user + 1] : 0;
-            for (int i = tid; i < n2; i += kThreads) {
-                uint64_t k = KO::lowest();
+            int valid = 0;
+            for (int base = 0; base < count; base += G::THREADS) {
+                const int i = base + tid;
+                bool keep = false;
                 if (i < count && at_leaf) {
-                    int64_t slot = (int64_t)cur[i] - leaf_start;
-                    int32_t item = (slot >= 0 && slot < ((int64_t)1 << p.leaf_level)) ? __ldg(p.leaf_item + slot) : -1;
-                    bool keep = item >= 0;
+                    const int64_t slot = (int64_t)cur[i] - leaf_start;
+                    const int32_t item = (slot >= 0 && slot < ((int64_t)1 << p.leaf_level)) ? __ldg(p.leaf_item + slot) : -1;
+                    keep = item >= 0;
                     for (int64_t q = c0; q < c1 && keep; q++) keep = (__ldg(p.cons + q) != item);
-                    if (keep) k = KO::make(sScore[i], i);
                 }
-                sKey[i] = k;
+                if (i < count) sKeyU[i] = keep ? order_key(sScore[i]) : 0u;
+                valid += __syncthreads_count(keep);
             }
-            __syncthreads();
-            if (count > 0) bitonic_sort_desc(sKey, n2);
-            // valid = entries that survived the filters
-            int vloc = 0;
-            for (int i = tid; i < count; i += kThreads) vloc += KO::is_lowest(sKey[i]) ? 0 : 1;
-            if (tid == 0) sMisc[42] = 0;
-            __syncthreads();
-            atomicAdd(&sMisc[42], vloc);
-            __syncthreads();
-            const int valid = sMisc[42];
             const int kk = valid < p.topk ? valid : p.topk;
+            if (kk > 0 && !scored) redo = true;                  // beam >= 2^leaf_level: nothing was scored, every score ties
             int na = 0;
-            if (kk > 0) {
-                const bool scored = (s_level < p.leaf_level);         // s_level == leaf_level: all scores are the exact 0 of the start level
-                if (scored) {
-                    const float pivot = sScore[KO::pos(sKey[kk - 1])];
-                    const float band = 2.0f * eps_level * 1.0001f + 1e-30f;
-                    int hi_local = -1;
-                    for (int i = tid; i < valid; i += kThreads)
-                        if (!(sScore[KO::pos(sKey[i])] < pivot - band)) hi_local = i > hi_local ? i : hi_local;
-                    if (tid == 0) sMisc[43] = -1;
-                    __syncthreads();
-                    atomicMax(&sMisc[43], hi_local);
-                    __syncthreads();
-                    na = sMisc[43] + 1;                                // ranks [0, na) may end up in the topk
-                    st_rerows += na;
-                    eps_now = eps_level;
-                    strict_rescore(cur, nullptr, na, sKey);
-                } else {
-                    na = valid;
-                    for (int i = tid; i < na; i += kThreads) sStrict[KO::pos(sKey[i])] = sScore[KO::pos(sKey[i])];
-                    __syncthreads();
-                }
-                int m2 = 2;
-                while (m2 < na) m2 <<= 1;
-                for (int i = tid; i < m2; i += kThreads) {
-                    uint64_t k = KO::lowest();
-                    if (i < na) { const int pos = KO::pos(sKey[i]); k = KO::make(sStrict[pos], pos); }
-                    sKey2[i] = k;
+            if (kk > 0 && !redo) {
+                if (warp == 0) {
+                    const uint32_t pk = warp_radix_select(sKeyU, count, kk, sHist, lane);
+                    if (lane == 0) sSel[0] = (int)pk;
                 }
                 __syncthreads();
-                bitonic_sort_desc(sKey2, m2);
+                const float pivot = key_to_float((uint32_t)sSel[0]);
+                const float dn = pivot - (2.0f * eps_level * 1.0001f + 1e-30f);
+                if (tid == 0) sMisc[45] = 0;
+                __syncthreads();
+                for (int i = tid; i < count; i += G::THREADS)
+                    if (sKeyU[i] != 0u && !(sScore[i] < dn)) {
+                        const int slot = atomicAdd(&sMisc[45], 1);
+                        if (slot < G::MAX_FINAL) sUPos[slot] = i;
+                    }
+                __syncthreads();
+                na = sMisc[45];
+                if (na > G::MAX_FINAL) redo = true;
             }
-            for (int i = tid; i < p.topk; i += kThreads) {
-                int32_t item = -1;
-                float sc = 0.0f;
-                if (i < kk) {
-                    const int pos = KO::pos(sKey2[i]);
-                    item = __ldg(p.leaf_item + ((int64_t)cur[pos] - leaf_start));
-                    sc = sStrict[pos];
+            if (!redo && vcount + na > 0) {
+                // ONE strict batch: every band row deferred at a cut, then the topk candidates
+                for (int e = tid; e < vcount; e += G::THREADS) sLCode[e] = sVCode[e];
+                for (int q = tid; q < na; q += G::THREADS) sLCode[vcount + q] = cur[sUPos[q]];
+                st_rerows += vcount + na;
+                strict_rescore(vcount + na);
+                int bad = 0;
+                for (int e = tid; e < vcount; e += G::THREADS) {   // the deferred cuts: strict order must pick the same rows
+                    const uint32_t meta = sVMeta[e];
+                    const int st = meta & 255u, n = (meta >> 8) & 255u, need = (meta >> 16) & 255u, chosen = (meta >> 24) & 1u;
+                    track_ratio(sLStr[e], sVFast[e], sSegEps[meta >> 25]);
+                    const uint32_t ks = order_key(sLStr[e]);
+                    int rank = 0;
+                    for (int q = st; q < st + n; q++) {
+                        const uint32_t kq = order_key(sLStr[q]);
+                        rank += kq > ks ? 1 : 0;
+                        bad |= (kq == ks && q != e) ? 1 : 0;     // exact strict tie inside a band: the reference decides by position
+                    }
+                    bad |= ((rank < need ? 1 : 0) != chosen) ? 1 : 0;
                 }
-                p.out_items[(size_t)user * p.out_stride + i] = item;
-                p.out_scores[(size_t)user * p.out_stride + i] = sc;
+                if (tid < na) {
+                    const float mine = sLStr[vcount + tid];
+                    const int ps = sUPos[tid];
+                    track_ratio(mine, sScore[ps], eps_level);
+                    const uint32_t ks = order_key(mine);
+                    int rank = 0;
+                    for (int q = 0; q < na; q++) {
+                        const uint32_t kq = order_key(sLStr[vcount + q]);
+                        rank += (kq > ks || (kq == ks && sUPos[q] < ps)) ? 1 : 0;
+                        bad |= (kq == ks && q != tid) ? 1 : 0;
+                    }
+                    if (rank < kk) {
+                        p.out_items[(size_t)user * p.out_stride + rank] = __ldg(p.leaf_item + ((int64_t)cur[ps] - leaf_start));
+                        p.out_scores[(size_t)user * p.out_stride + rank] = mine;
+                    }
+                }
+                if (__syncthreads_or(bad)) redo = true;
             }
-            if (tid == 0) p.out_counts[user] = kk;
+            if (!redo) {
+                for (int i = kk + tid; i < p.topk; i += G::THREADS) {
+                    p.out_items[(size_t)user * p.out_stride + i] = -1;
+                    p.out_scores[(size_t)user * p.out_stride + i] = 0.0f;
+                }
+                if (tid == 0) p.out_counts[user] = kk;
+            }
         }
-        __syncthreads();
+        if (redo) {
+            st_redo++;
+            if (tid == 0) fp.redo_list[atomicAdd(fp.redo_count, 1)] = user;
+        }
+        DMG_TICK(TK_FINAL);
     }
-    if (fx.stats) {
+#ifdef DMG_FAST_TIMING
+    if (fp.stats && tid == 0)
+        for (int i = 0; i < TK_N; i++) atomicAdd(&fp.stats[8 + i], (unsigned long long)tacc[i]);
+#endif
+    if (fp.stats) {
         for (int o = 16; o > 0; o >>= 1) st_ratio = fmaxf(st_ratio, __shfl_xor_sync(0xffffffffu, st_ratio, o));
-        if (lane == 0) atomicMax(reinterpret_cast<unsigned int *>(&fx.stats[4]), __float_as_uint(st_ratio));
+        if (lane == 0) atomicMax(reinterpret_cast<unsigned int *>(&fp.stats[4]), __float_as_uint(st_ratio));
         if (tid == 0) {
-            atomicAdd(&fx.stats[0], st_cuts); atomicAdd(&fx.stats[1], st_recuts);
-            atomicAdd(&fx.stats[2], st_rerows); atomicAdd(&fx.stats[3], st_rows);
+            atomicAdd(&fp.stats[0], st_cuts); atomicAdd(&fp.stats[1], st_recuts);
+            atomicAdd(&fp.stats[2], st_rerows); atomicAdd(&fp.stats[3], st_rows);
+            atomicAdd(&fp.stats[5], st_redo); atomicAdd(&fp.stats[6], st_sync);
         }
     }
     tc_fence_before();
     __syncthreads();
     if (warp == 0) tmem_dealloc(tmem_base, 256);
+}
+
+// ---- per-level maxima of the node-dependent bound terms (run once per weight load) ----------------
+// lvl_vx[l] = max over nodes c of level l of sum_k v[k] |emb[c][k]|, lvl_nx[l] = max |emb[c]|_2 (both rounded up).
+static __global__ void level_bounds_kernel(const float *__restrict__ emb, int64_t rows, const float *__restrict__ v,
+                                           float *__restrict__ lvl_vx, float *__restrict__ lvl_nx)
+{
+    __shared__ int s_vx[32], s_nx[32];
+    if (threadIdx.x < 32) { s_vx[threadIdx.x] = 0; s_nx[threadIdx.x] = 0; }
+    __syncthreads();
+    const int lane16 = threadIdx.x & 15;
+    const float4 vv = *reinterpret_cast<const float4 *>(v + lane16 * 4);
+    const int64_t groups = (int64_t)gridDim.x * (blockDim.x >> 4);
+    for (int64_t r = (int64_t)blockIdx.x * (blockDim.x >> 4) + (threadIdx.x >> 4); r < rows + 15; r += groups) {
+        const bool ok = r < rows;
+        float4 x = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (ok) x = ldg_row16(emb + r * 64 + lane16 * 4);
+        float a = fmaf(vv.x, fabsf(x.x), fmaf(vv.y, fabsf(x.y), fmaf(vv.z, fabsf(x.z), vv.w * fabsf(x.w))));
+        float n = fmaf(x.x, x.x, fmaf(x.y, x.y, fmaf(x.z, x.z, x.w * x.w)));
+#pragma unroll
+        for (int o = 8; o > 0; o >>= 1) { a += __shfl_xor_sync(0xffffffffu, a, o); n += __shfl_xor_sync(0xffffffffu, n, o); }
+        if (ok && lane16 == 0) {
+            a *= 1.0001f;
+            n = sqrtf(n) * 1.0001f;
+            if (!(a == a)) a = __int_as_float(0x7f800000);
+            if (!(n == n)) n = __int_as_float(0x7f800000);
+            const int lvl = 63 - __clzll((unsigned long long)(r + 1));
+            atomicMax(&s_vx[lvl & 31], __float_as_int(a));
+            atomicMax(&s_nx[lvl & 31], __float_as_int(n));
+        }
+    }
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        atomicMax(reinterpret_cast<int *>(lvl_vx) + threadIdx.x, s_vx[threadIdx.x]);
+        atomicMax(reinterpret_cast<int *>(lvl_nx) + threadIdx.x, s_nx[threadIdx.x]);
+    }
 }
 
 }  // namespace dmg

@@ -50,6 +50,9 @@ template <typename real> struct BeamParams {
     real *lvl_scores;
     int32_t *lvl_counts;        // [user][n_lvl]
     int lvl_stride, n_lvl;
+    // optional: run only the users user_list[0 .. *user_count) (the fast kernel's redo list)
+    const int32_t *user_list;
+    const int32_t *user_count;
 };
 
 // ---- compile-time geometry ----------------------------------------------------------------
@@ -319,7 +322,9 @@ __global__ void __launch_bounds__(kThreads, 1) beam_search_kernel(const BeamPara
     const real b2 = sB2[0];
     uint32_t bar_phase = 0;
 
-    for (int user = blockIdx.x; user < p.B; user += gridDim.x) {
+    const int n_users = p.user_count ? *p.user_count : p.B;
+    for (int ui = blockIdx.x; ui < n_users; ui += gridDim.x) {
+        const int user = p.user_list ? p.user_list[ui] : ui;
         // ---- K2: history tile --------------------------------------------------------------
         if (tid < kMaxT) {
             int c = -1, m = 0;
@@ -492,9 +497,11 @@ __global__ void __launch_bounds__(kThreads, 1) beam_search_kernel(const BeamPara
 // TDMTree.idToCode (tdm/src/main/scala/com/mass/tdm/tree/TDMTree.scala:35-56).
 static __global__ void tdm_ids_to_codes_kernel(const int32_t *__restrict__ ids, int64_t n, const int32_t *__restrict__ id_code,
                                         int32_t non_leaf_offset, int32_t max_code, int64_t table_rows, int use_mask,
-                                        int32_t *__restrict__ codes, uint8_t *__restrict__ mask, int32_t *__restrict__ err_flag)
+                                        int32_t *__restrict__ codes, uint8_t *__restrict__ mask, int32_t *__restrict__ err_flag,
+                                        int32_t *__restrict__ fast_ctl)
 {
     int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i == 0 && fast_ctl) { fast_ctl[0] = 0; fast_ctl[1] = 0; }      // user scheduler + redo count of the fast kernel
     if (i >= n) return;
     const int32_t id = ids[i];
     int32_t code;

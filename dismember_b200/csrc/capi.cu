@@ -59,6 +59,7 @@ DMG_API int32_t dmg_create(int32_t device, dmg_handle_t *out)
     h->stream = h->own_stream;
     h->sm_count = prop.multiProcessorCount;
     h->smem_optin = prop.sharedMemPerBlockOptin;
+    h->smem_per_sm = prop.sharedMemPerMultiprocessor;
     *out = h;
     return DMG_OK;
 }
@@ -86,7 +87,7 @@ DMG_API int32_t dmg_destroy(dmg_handle_t h)
     for (Scratch *s : {&h->s_in, &h->s_out, &h->s_work}) { cudaFree(s->d); cudaFreeHost(s->h); }
     for (auto &ev : h->prof_events) { cudaEventDestroy(ev.first); cudaEventDestroy(ev.second); }
     cudaFree(h->d_flags);
-    cudaFree(h->d_fast_stats);
+    cudaFree(h->d_fast_stats); cudaFree(h->d_fast_tab); cudaFree(h->d_fast_ctl); cudaFree(h->d_redo_list);
     cudaStreamDestroy(h->own_stream);
     delete h;
     return DMG_OK;
@@ -236,7 +237,8 @@ int32_t dmg_refresh_transposes(dmg_handle_t h)       // used by train.cu after a
     }
     h->launches += 2;
     DMG_CUDA(h, cudaGetLastError());
-    return compute_fast_bounds(h);
+    h->fast_dirty = true;                              // bound tables are rebuilt at the next fast retrieval
+    return DMG_OK;
 }
 
 static int32_t alloc_din(dmg_handle_t h, int32_t dtype, int64_t rows, int32_t E, int32_t T)
@@ -261,7 +263,7 @@ DMG_API int32_t dmg_load_din_weights(dmg_handle_t h, int32_t dtype, int64_t rows
     DinDev &d = h->din;
     DMG_TRY(h2d(h, d.d_params, params, (size_t)d.n_params * d.esz));
     DMG_TRY(dtype == DMG_F32 ? make_transposes<float>(h) : make_transposes<double>(h));
-    DMG_TRY(compute_fast_bounds(h));
+    h->fast_dirty = true;
     d.loaded = true;
     return DMG_OK;
 }
@@ -284,7 +286,7 @@ DMG_API int32_t dmg_init_din_weights(dmg_handle_t h, int32_t dtype, int64_t rows
     h->launches += 2;
     DMG_CUDA(h, cudaGetLastError());
     DMG_TRY(dtype == DMG_F32 ? make_transposes<float>(h) : make_transposes<double>(h));
-    DMG_TRY(compute_fast_bounds(h));
+    h->fast_dirty = true;
     d.loaded = true;
     return DMG_OK;
 }
@@ -338,37 +340,61 @@ template <typename real> static int32_t launch_beam(dmg_handle_t h, const BeamPa
     }
 }
 
-// eps_row = alpha*|x| + beta*|a| + gamma bounds |fast - strict| for the tensor-core scorer.
+// Tables and constants of the certified-cut bound, rebuilt lazily after every weight change:
+//   M = W1a.Watt (double -> fp32, stored k-major), v[k] = sum_o |w2[o]| |W1x[o][k]|,
+//   per-level maxima of v.|x| and |x|_2 over the node table, and
+//   eps = tau * ( cA * max v.|x|  +  cBq * Kmax * (cCq + |dp|_1)  +  cGamma ).
 static int32_t compute_fast_bounds(dmg_handle_t h)
 {
     DinDev &d = h->din;
     h->fast_ok = false;
+    h->fast_dirty = false;
     if (d.dtype != DMG_F32 || d.E != 64) return DMG_OK;
     const int E = d.E;
     const size_t n_dense = (size_t)3 * E * E + 2 * E + 1;
     std::vector<float> w(n_dense);
     DMG_CUDA(h, cudaMemcpyAsync(w.data(), d.watt<float>(), n_dense * 4, cudaMemcpyDeviceToHost, h->stream));
     DMG_CUDA(h, cudaStreamSynchronize(h->stream));
-    const float *watt = w.data(), *w1 = watt + E * E, *b1 = w1 + 2 * E * E, *w2 = b1 + E;
-    double F = 0, Sa = 0, Sb = 0, S1 = 0;
-    for (int i = 0; i < E * E; i++) F += (double)watt[i] * watt[i];
-    F = std::sqrt(F);
+    const float *watt = w.data(), *w1 = watt + E * E, *b1 = w1 + 2 * E * E, *w2 = b1 + E, *b2 = w2 + E;
+    std::vector<float> tab(4288, 0.0f);                          // M^T | v | lvl_vx | lvl_nx | z
+    double S1 = 0;
+    std::vector<double> z(E, 0.0);
     for (int o = 0; o < E; o++) {
-        double na = 0, nb = 0;
-        for (int k = 0; k < E; k++) { na += (double)w1[o * 2 * E + k] * w1[o * 2 * E + k]; nb += (double)w1[o * 2 * E + E + k] * w1[o * 2 * E + E + k]; }
-        Sa += std::fabs((double)w2[o]) * std::sqrt(na);
-        Sb += std::fabs((double)w2[o]) * std::sqrt(nb);
         S1 += std::fabs((double)w2[o]) * std::fabs((double)b1[o]);
+        for (int k = 0; k < E; k++) {
+            double acc = 0, aabs = 0;
+            for (int m = 0; m < E; m++) {
+                acc += (double)w1[o * 2 * E + E + m] * (double)watt[m * E + k];
+                aabs += std::fabs((double)w1[o * 2 * E + E + m]) * std::fabs((double)watt[m * E + k]);
+            }
+            tab[(size_t)k * E + o] = (float)acc;                  // M^T[k][o]
+            z[k] += std::fabs((double)w2[o]) * aabs;              // z_k = sum_o sum_m |w2_o| |W1a_om| |Watt_mk|
+        }
     }
-    // c: bf16 hi/lo split truncation (3.03 * 2^-16) + fp32 accumulation of 3K products in the tensor core
-    const double c = std::ldexp(1.0, -13), g64 = 64 * std::ldexp(1.0, -24), g128 = 128 * std::ldexp(1.0, -24), safety = 1.05;
-    h->fast_alpha = (float)(safety * Sa * (c + g128 + 2 * g64));
-    h->fast_beta = (float)(safety * F * Sb * (c * (1 + c) + (c + g64) + (g128 + 2 * g64) * (1 + c)));
-    h->fast_gamma = (float)(safety * 2 * g64 * S1 + 1e-37);
-    h->fast_zeta = (float)(safety * F * Sb * (1 + c));                       // |da| -> |dlogit|
-    h->fast_cs = (float)(safety * c / std::sqrt((double)E));                 // score error per unit |x| |K_j| (scale = 1/sqrt(E))
-    h->fast_ca = (float)(safety * c);
-    h->fast_ok = std::isfinite(h->fast_alpha) && std::isfinite(h->fast_beta);
+    for (int k = 0; k < E; k++) tab[4224 + k] = (float)(z[k] * (1.0 + 1e-6));
+    for (int k = 0; k < E; k++) {
+        double vk = 0;
+        for (int o = 0; o < E; o++) vk += std::fabs((double)w2[o]) * std::fabs((double)w1[o * 2 * E + k]);
+        tab[4096 + k] = (float)(vk * (1.0 + 1e-6));
+    }
+    const double u = std::ldexp(1.0, -24), c_mma = std::ldexp(1.0, -15), safety = 1.05;
+    h->fast_cA = (float)(safety * (c_mma + 264 * u));             // main branch: MMA + 128-chain + b1 add + final dot
+    h->fast_cZ = (float)(safety * 273 * u);                       // attention branch, strict chains (208 u) + H in fp32 (65 u)
+    h->fast_cH = (float)(c_mma + 134 * u);                        // attention branch: P.H on the tensor cores + final dot
+    h->fast_cGamma = (float)(safety * (140 * u * S1 + 4 * u * std::fabs((double)b2[0])) + 1e-30);
+    h->fast_host.assign(b1, b1 + 2 * E + 1);                     // b1 | w2 | b2
+    if (!h->d_fast_tab) DMG_CUDA(h, cudaMalloc(&h->d_fast_tab, tab.size() * sizeof(float)));
+    if (!h->d_fast_ctl) {
+        DMG_CUDA(h, cudaMalloc(&h->d_fast_ctl, 8 * sizeof(int32_t)));
+        DMG_CUDA(h, cudaMemsetAsync(h->d_fast_ctl, 0, 8 * sizeof(int32_t), h->stream));
+    }
+    DMG_CUDA(h, cudaMemcpyAsync(h->d_fast_tab, tab.data(), tab.size() * sizeof(float), cudaMemcpyHostToDevice, h->stream));
+    level_bounds_kernel<<<h->sm_count * 8, 256, 0, h->stream>>>(d.emb<float>(), d.rows, h->d_fast_tab + 4096, h->d_fast_tab + 4160,
+                                                                h->d_fast_tab + 4192);
+    h->launches += 1;
+    DMG_CUDA(h, cudaGetLastError());
+    DMG_CUDA(h, cudaStreamSynchronize(h->stream));               // tab / w are stack-owned
+    h->fast_ok = std::isfinite(h->fast_cA) && std::isfinite(h->fast_cGamma);
     return DMG_OK;
 }
 
@@ -400,7 +426,7 @@ int32_t dmg_tdm_ids_to_codes(dmg_handle_t h, const int32_t *d_ids, int64_t n, in
 {
     const TreeDev &t = h->tree;
     tdm_ids_to_codes_kernel<<<(unsigned)((n + 255) / 256), 256, 0, h->stream>>>(d_ids, n, t.d_id_code, t.non_leaf_offset, t.max_code,
-                                                                              h->din.rows, use_mask, d_codes, d_mask, h->d_flags);
+                                                                              h->din.rows, use_mask, d_codes, d_mask, h->d_flags, nullptr);
     h->launches += 1;
     DMG_CUDA(h, cudaGetLastError());
     return DMG_OK;
@@ -419,8 +445,20 @@ static int32_t tdm_enqueue(dmg_handle_t h, int32_t B, const int32_t *d_seq, int3
     int32_t *d_codes = cw.take<int32_t>((size_t)B * T);
     uint8_t *d_mask = cw.take<uint8_t>((size_t)B * T);
     const int64_t n = (int64_t)B * T;
+    const int cap = std::max(std::max(((2 * max_beam + 7) / 8) * 8, 8), ((topk + 7) / 8) * 8);
+    bool use_fast = h->arithmetic == DMG_ARITH_FAST && d.dtype == DMG_F32 && d.E == 64 && cap <= FastGeo::max_cap() &&
+                    2 * (FastGeo::smem_bytes(cap) + 1024) <= (size_t)h->smem_per_sm;
+    if (use_fast && h->fast_dirty) DMG_TRY(compute_fast_bounds(h));
+    use_fast = use_fast && h->fast_ok;
+    if (use_fast && h->redo_cap < B) {
+        cudaFree(h->d_redo_list);
+        h->d_redo_list = nullptr; h->redo_cap = 0;
+        DMG_CUDA(h, cudaMalloc(&h->d_redo_list, ((size_t)B + 256) * sizeof(int32_t)));
+        h->redo_cap = (int64_t)B + 256;
+    }
     tdm_ids_to_codes_kernel<<<(unsigned)((n + 255) / 256), 256, 0, h->stream>>>(
-        d_seq, n, t.d_id_code, t.non_leaf_offset, t.max_code, d.rows, use_mask, d_codes, d_mask, h->d_flags);
+        d_seq, n, t.d_id_code, t.non_leaf_offset, t.max_code, d.rows, use_mask, d_codes, d_mask, h->d_flags,
+        use_fast ? h->d_fast_ctl : nullptr);
     h->launches += 1;
     DMG_CUDA(h, cudaGetLastError());
     BeamParams<float> p;
@@ -430,37 +468,46 @@ static int32_t tdm_enqueue(dmg_handle_t h, int32_t B, const int32_t *d_seq, int3
     p.always_sort = 0; p.exists = t.complete ? nullptr : t.d_exists; p.leaf_level = t.max_level;
     p.mode = MODE_TDM_TOPK; p.topk = topk; p.leaf_item = t.d_leaf_item; p.cons_off = d_cons_off; p.cons = d_cons;
     p.out_items = d_items; p.out_scores = d_logits; p.out_counts = d_counts; p.out_stride = topk;
-    p.cap = std::max(((2 * max_beam + 7) / 8) * 8, 8);
-    p.cap = std::max(p.cap, ((topk + 7) / 8) * 8);
+    p.cap = cap;
     p.capp = pow2_ge(p.cap);
-    if (h->arithmetic == DMG_ARITH_FAST && h->fast_ok && d.E == 64) {
-        const size_t smem = FastGeo::smem_bytes(p.cap, p.capp);
-        if (smem <= h->smem_optin) {
-            if (!h->d_fast_stats) {
-                DMG_CUDA(h, cudaMalloc(&h->d_fast_stats, 8 * sizeof(unsigned long long)));
-                DMG_CUDA(h, cudaMemsetAsync(h->d_fast_stats, 0, 8 * sizeof(unsigned long long), h->stream));
-            }
-            FastExtra fx;
-            fx.alpha = h->fast_alpha * h->fast_tau; fx.beta = h->fast_beta * h->fast_tau; fx.gamma = h->fast_gamma * h->fast_tau;
-            fx.zeta = h->fast_zeta * h->fast_tau; fx.cs = h->fast_cs; fx.ca = h->fast_ca;
-            fx.watt = d.watt<float>(); fx.w1 = d.w1<float>(); fx.stats = h->d_fast_stats;
-            DMG_CUDA(h, cudaFuncSetAttribute(beam_search_fast_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            const int grid = std::min(B, h->sm_count);
-            cudaEvent_t e0 = nullptr, e1 = nullptr;
-            if (h->profiling) {
-                DMG_CUDA(h, cudaEventCreate(&e0));
-                DMG_CUDA(h, cudaEventCreate(&e1));
-                DMG_CUDA(h, cudaEventRecord(e0, h->stream));
-            }
-            beam_search_fast_kernel<<<grid, kThreads, smem, h->stream>>>(p, fx);
-            h->launches += 1;
-            DMG_CUDA(h, cudaGetLastError());
-            if (h->profiling) {
-                DMG_CUDA(h, cudaEventRecord(e1, h->stream));
-                h->prof_events.emplace_back(e0, e1);
-            }
-            return DMG_OK;
-        }                                           // very wide beams: fall through to the strict kernel
+    if (use_fast) {
+        if (!h->d_fast_stats) {
+            DMG_CUDA(h, cudaMalloc(&h->d_fast_stats, 32 * sizeof(unsigned long long)));
+            DMG_CUDA(h, cudaMemsetAsync(h->d_fast_stats, 0, 32 * sizeof(unsigned long long), h->stream));
+        }
+        FastParams fx;
+        memcpy(fx.b1, h->fast_host.data(), 64 * sizeof(float));
+        memcpy(fx.w2, h->fast_host.data() + 64, 64 * sizeof(float));
+        fx.b2 = h->fast_host[128];
+        fx.mT = h->d_fast_tab; fx.w1 = d.w1<float>();
+        fx.lvl_vx = h->d_fast_tab + 4160; fx.lvl_nx = h->d_fast_tab + 4192;
+        fx.cA = h->fast_cA; fx.cZ = h->fast_cZ; fx.cH = h->fast_cH; fx.cGamma = h->fast_cGamma; fx.tau = h->fast_tau;
+        fx.zvec = h->d_fast_tab + 4224;
+        fx.redo_list = h->d_redo_list; fx.redo_count = h->d_fast_ctl + 1; fx.work_counter = h->d_fast_ctl;
+        fx.stats = h->d_fast_stats;
+        const size_t smem = FastGeo::smem_bytes(p.cap);
+        DMG_CUDA(h, cudaFuncSetAttribute(beam_search_fast_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        const int grid = std::min(B, 2 * h->sm_count);           // two co-resident CTAs per SM
+        cudaEvent_t e0 = nullptr, e1 = nullptr;
+        if (h->profiling) {
+            DMG_CUDA(h, cudaEventCreate(&e0));
+            DMG_CUDA(h, cudaEventCreate(&e1));
+            DMG_CUDA(h, cudaEventRecord(e0, h->stream));
+        }
+        beam_search_fast_kernel<<<grid, FastGeo::THREADS, smem, h->stream>>>(p, fx);
+        h->launches += 1;
+        DMG_CUDA(h, cudaGetLastError());
+        if (h->profiling) {
+            DMG_CUDA(h, cudaEventRecord(e1, h->stream));
+            h->prof_events.emplace_back(e0, e1);
+        }
+        // users the fast kernel could not certify (exact ties at a cut, implausibly wide band): strict kernel
+        p.user_list = h->d_redo_list; p.user_count = h->d_fast_ctl + 1;
+        const bool prof = h->profiling;
+        h->profiling = false;
+        const int32_t rc = launch_beam<float>(h, p, d.E);
+        h->profiling = prof;
+        return rc;
     }
     return launch_beam<float>(h, p, d.E);
 }
@@ -481,15 +528,25 @@ DMG_API int32_t dmg_set_fast_tolerance(dmg_handle_t h, double tau)
     return DMG_OK;
 }
 
-DMG_API int32_t dmg_fast_stats(dmg_handle_t h, uint64_t *out4)
+DMG_API int32_t dmg_fast_stats(dmg_handle_t h, uint64_t *out6)
 {
-    if (!h || !out4) return DMG_ERR_INVALID_ARG;
-    for (int i = 0; i < 5; i++) out4[i] = 0;
+    if (!h || !out6) return DMG_ERR_INVALID_ARG;
+    for (int i = 0; i < 7; i++) out6[i] = 0;
     if (!h->d_fast_stats) return DMG_OK;
     DMG_CUDA(h, cudaSetDevice(h->device));
     DMG_CUDA(h, cudaStreamSynchronize(h->stream));
-    DMG_CUDA(h, cudaMemcpy(out4, h->d_fast_stats, 5 * sizeof(uint64_t), cudaMemcpyDeviceToHost));
-    DMG_CUDA(h, cudaMemset(h->d_fast_stats, 0, 8 * sizeof(uint64_t)));
+    DMG_CUDA(h, cudaMemcpy(out6, h->d_fast_stats, 7 * sizeof(uint64_t), cudaMemcpyDeviceToHost));
+#ifdef DMG_FAST_TIMING
+    {
+        uint64_t t[24];
+        DMG_CUDA(h, cudaMemcpy(t, h->d_fast_stats + 8, sizeof(t), cudaMemcpyDeviceToHost));
+        static const char *names[] = {"prologue", "select", "rescore", "expand", "gather", "softmax", "epilogue", "final", "sched"};
+        double tot = 0;
+        for (int i = 0; i < 9; i++) tot += (double)t[i];
+        for (int i = 0; i < 9; i++) fprintf(stderr, "[fast timing] %-9s %6.2f %%  %.3e cyc\n", names[i], 100.0 * t[i] / (tot > 0 ? tot : 1), (double)t[i]);
+    }
+#endif
+    DMG_CUDA(h, cudaMemset(h->d_fast_stats, 0, 32 * sizeof(uint64_t)));
     return DMG_OK;
 }
 

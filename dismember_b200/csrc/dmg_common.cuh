@@ -74,7 +74,7 @@ struct dmg_handle_s {
     cudaStream_t own_stream = nullptr;
     cudaStream_t stream = nullptr;
     int sm_count = 0;
-    size_t smem_optin = 0;
+    size_t smem_optin = 0, smem_per_sm = 0;
     std::string err;
     int64_t launches = 0;
     dmg::TreeDev tree;
@@ -84,8 +84,14 @@ struct dmg_handle_s {
     int32_t *d_flags = nullptr;     // [0] = index error flag, [1] = work counter
     int arithmetic = DMG_ARITH_STRICT;
     bool fast_ok = false;            // tensor-core scorer available for the loaded weights
-    float fast_alpha = 0, fast_beta = 0, fast_gamma = 0, fast_zeta = 0, fast_cs = 0, fast_ca = 0;
+    bool fast_dirty = true;          // weights changed since the bound tables were computed
+    float fast_cA = 0, fast_cZ = 0, fast_cH = 0, fast_cGamma = 0;   // certified-cut bound constants
     float fast_tau = 1.0f;           // fraction of the worst-case bound used as the certification band
+    float *d_fast_tab = nullptr;     // [0,4096) M^T  [4096,4160) v  [4160,4192) lvl_vx  [4192,4224) lvl_nx  [4224,4288) z
+    std::vector<float> fast_host;    // host copy of b1 | w2 | b2 (kernel parameters of the fast kernel)
+    int32_t *d_fast_ctl = nullptr;   // [0] dynamic user counter, [1] redo count
+    int32_t *d_redo_list = nullptr;  // users the fast kernel hands to the strict kernel
+    int64_t redo_cap = 0;
     unsigned long long *d_fast_stats = nullptr;
     bool profiling = false;
     std::vector<std::pair<cudaEvent_t, cudaEvent_t>> prof_events;

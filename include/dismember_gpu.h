@@ -105,15 +105,17 @@ DMG_API int32_t dmg_download_din_weights(dmg_handle_t h, void *params, int64_t n
 
 /* Scorer arithmetic of dmg_tdm_retrieve.  Both modes return the SAME item ids and logits (the
  * CPU oracle's bits).  DMG_ARITH_STRICT scores every candidate with sequential-k fp32 fma chains;
- * DMG_ARITH_FAST (E = 64 fp32 models) runs the dense contractions on the tcgen05 tensor cores with
- * bf16 hi/lo split operands, bounds |fast - strict| per row, and re-scores in strict arithmetic only
- * the candidates whose fast score is within that bound of a beam cut (certified cuts) plus the
- * final topk.  dmg_fast_stats fills 5 values since the last call: {cuts, cuts that needed a strict
- * re-score, rows re-scored strictly, rows scored on the tensor cores, float bits of the largest
- * observed |fast - strict| / bound (must stay < 1)}. */
+ * DMG_ARITH_FAST (E = 64 fp32 models, beam <= 256) runs the dense contractions on the tcgen05 tensor
+ * cores with bf16 hi/lo split operands, bounds |fast - strict| per tree level, and re-scores in strict
+ * arithmetic only the candidates whose fast score is within that bound of a beam cut (certified cuts)
+ * plus the final topk; a user whose strictly re-scored candidates tie exactly at a decision point is
+ * re-run by the strict kernel.  dmg_fast_stats fills 7 values since the last call: {cuts, cuts that
+ * needed a strict re-score, rows re-scored strictly, rows scored on the tensor cores, float bits of
+ * the largest observed |fast - strict| / bound (must stay < 1), users re-run by the strict kernel,
+ * cuts whose band was settled strictly in place instead of being deferred to the end-of-search proof}. */
 enum { DMG_ARITH_STRICT = 0, DMG_ARITH_FAST = 1 };
 DMG_API int32_t dmg_set_arithmetic(dmg_handle_t h, int32_t mode);
-DMG_API int32_t dmg_fast_stats(dmg_handle_t h, uint64_t *out5);
+DMG_API int32_t dmg_fast_stats(dmg_handle_t h, uint64_t *out7);
 /* Certification band = tau x the worst-case bound.  tau = 1 (default) is provable: rounding errors
  * would all have to align.  Smaller tau trades the proof for a statistical margin (the largest error
  * ever observed is reported by dmg_fast_stats as a fraction of the worst-case bound). */
