@@ -337,11 +337,12 @@ __device__ __forceinline__ bool elect_one()
 
 // k-th largest (k >= 1) of keys[0..count), count <= 512: ONE warp, its keys in registers, 4 radix passes
 // over 8-bit digits with a 256-bin shared histogram -- no block barrier inside.
-__device__ __forceinline__ uint32_t warp_radix_select(const uint32_t *__restrict__ keys, int count, int k, int *sHist, int lane)
+template <typename KeyFn>
+__device__ __forceinline__ uint32_t warp_radix_select(KeyFn key_at, int count, int k, int *sHist, int lane)
 {
     uint32_t kv[16];
 #pragma unroll
-    for (int q = 0; q < 16; q++) { const int i = lane + 32 * q; kv[q] = i < count ? keys[i] : 0u; }
+    for (int q = 0; q < 16; q++) { const int i = lane + 32 * q; kv[q] = i < count ? key_at(i) : 0u; }
     uint32_t prefix = 0, known = 0;
 #pragma unroll 1
     for (int pass = 0; pass < 4; pass++) {
@@ -384,6 +385,36 @@ __device__ __forceinline__ uint32_t warp_radix_select(const uint32_t *__restrict
         __syncwarp();
     }
     return prefix;
+}
+
+// ---- (A) gather NIT x 16 rows of the pass: 16 lanes x 16 B per row, every load issued before the first use --
+// codes: candidate codes of the pass (shared), row = q*16 + rowbase; rows past nrows re-read the last valid row
+// (their operand rows are never consumed).  dst: operand base + this thread's chunk / row offset.
+template <int NIT>
+__device__ __forceinline__ void gather_convert(const float *__restrict__ emb_chunk, const int32_t *__restrict__ codes, int nrows,
+                                               int rowbase, unsigned char *__restrict__ dstH, unsigned char *__restrict__ dstL)
+{
+    float4 v[NIT];
+#pragma unroll
+    for (int q = 0; q < NIT; q++) {
+        int row = q * 16 + rowbase;
+        row = row < nrows ? row : nrows - 1;
+        v[q] = ldg_row16(emb_chunk + (size_t)codes[row] * 64);
+    }
+#pragma unroll
+    for (int q = 0; q < NIT; q++) {
+        uint2 hi, lo;
+        split_pair(v[q].x, v[q].y, hi.x, lo.x);
+        split_pair(v[q].z, v[q].w, hi.y, lo.y);
+        *reinterpret_cast<uint2 *>(dstH + q * 256) = hi;
+        *reinterpret_cast<uint2 *>(dstL + q * 256) = lo;
+    }
+}
+__device__ __forceinline__ float ex2_approx(float x)
+{
+    float y;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
 }
 
 // Phase timers (cycles of thread 0, summed over CTAs) -> stats[8 + i]; compiled in with -DDMG_FAST_TIMING.
@@ -452,6 +483,8 @@ __global__ void __launch_bounds__(FastGeo::THREADS, 2) beam_search_fast_kernel(c
     const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t *>(&sMisc[41]);
     const uint32_t tmem_lane = (uint32_t)((warp & 3) * 32) << 16;
     const int tile_of_warp = warp >> 2;
+    const float scale2 = p.scale * 1.4426950408889634f, inv_T = 1.0f / (float)T;
+    float *sAddv = reinterpret_cast<float *>(sMisc + 64);               // [16] additive softmax mask of the current user
     uint32_t hist_phase = 0, s_phase = 0, h_phase = 0;
     unsigned long long st_cuts = 0, st_recuts = 0, st_rerows = 0, st_rows = 0, st_redo = 0, st_sync = 0;
     float st_ratio = 0.0f;
@@ -517,6 +550,7 @@ __global__ void __launch_bounds__(FastGeo::THREADS, 2) beam_search_fast_kernel(c
             sMisc[tid] = c;
             const uint32_t mb = __ballot_sync(0x0000ffffu, m != 0);
             if (tid == 0) { sMisc[16] = (int)mb; sMisc[44] = 0; sMisc[45] = 0; }
+            sAddv[tid] = (tid < T && !m) ? 0.0f : -3.4028234663852886e+38f;
         }
         __syncthreads();
         load_history();
@@ -556,15 +590,16 @@ __global__ void __launch_bounds__(FastGeo::THREADS, 2) beam_search_fast_kernel(c
 #pragma unroll
                 for (int q = 0; q < 4; q++) acc[q] = fmaf(m, kr[q * G::KLD + k], acc[q]);
             }
+            float hm = fmaxf(fmaxf(fabsf(acc[0]), fabsf(acc[1])), fmaxf(fabsf(acc[2]), fabsf(acc[3])));
+            if (acc[0] != acc[0] || acc[1] != acc[1] || acc[2] != acc[2] || acc[3] != acc[3]) hm = __int_as_float(0x7f800000);
+            sHmax[jg * E + o] = hm;
+            if (jg == 3) acc[3] = fp.b1[o];                     // T <= 15: row 15 of H carries b1 (P column 15 is 1)
             uint2 hi, lo;
             split_pair(acc[0], acc[1], hi.x, lo.x);
             split_pair(acc[2], acc[3], hi.y, lo.y);
             const int off = (jg >> 1) * G::H_LBO + o * 16 + (jg & 1) * 8;
             *reinterpret_cast<uint2 *>(sHh + off) = hi;
             *reinterpret_cast<uint2 *>(sHl + off) = lo;
-            float hm = fmaxf(fmaxf(fabsf(acc[0]), fabsf(acc[1])), fmaxf(fabsf(acc[2]), fabsf(acc[3])));
-            if (acc[0] != acc[0] || acc[1] != acc[1] || acc[2] != acc[2] || acc[3] != acc[3]) hm = __int_as_float(0x7f800000);
-            sHmax[jg * E + o] = hm;
         }
         __syncthreads();
         if (tid < E) {                                          // HW = sum_o |w2_o| max_j |H_jo|  (two warp partials)
@@ -577,7 +612,7 @@ __global__ void __launch_bounds__(FastGeo::THREADS, 2) beam_search_fast_kernel(c
         const float kmax = __int_as_float(sMisc[44]);
         const float zk_user = (__int_as_float(sMisc[46]) + __int_as_float(sMisc[47])) * 1.0001f;
         const float hw_user = (__int_as_float(sMisc[48]) + __int_as_float(sMisc[49])) * 1.0001f;
-        const uint32_t maskbits = (uint32_t)sMisc[16];
+        const bool all_masked = ((uint32_t)sMisc[16] & ((1u << T) - 1u)) == ((1u << T) - 1u);
 
         const int beam = p.beam_user ? p.beam_user[user] : p.beam;
         const int s_level = 31 - __clz(beam);
@@ -604,53 +639,52 @@ __global__ void __launch_bounds__(FastGeo::THREADS, 2) beam_search_fast_kernel(c
 
         for (int level = s_level; level < p.leaf_level && count > 0; level++) {
             // ---- which candidates stay (certified cut), then their children, order preserved --------
-            bool cut = count > beam;
+            // thread t owns candidates 2t and 2t+1
+            const int i0 = 2 * tid, i1 = 2 * tid + 1;
+            const bool cut = count > beam;
+            int cls0 = i0 < count ? 1 : 0, cls1 = i1 < count ? 1 : 0;      // 0 out, 1 in, 2 uncertain
             if (cut) {
                 st_cuts++;
-                for (int i = tid; i < count; i += G::THREADS) sKeyU[i] = order_key(sScore[i]);
-                __syncthreads();
                 if (warp == 0) {
-                    const uint32_t pk = warp_radix_select(sKeyU, count, beam, sHist, lane);
-                    if (lane == 0) sSel[0] = (int)pk;
+                    const uint32_t pk = warp_radix_select([&](int i) { return order_key(sScore[i]); }, count, beam, sHist, lane);
+                    if (lane == 0) { sSel[0] = (int)pk; sSel[4] = 0; sSel[5] = 0; }
                 }
                 __syncthreads();
                 const float pivot = key_to_float((uint32_t)sSel[0]);
                 const float band = 2.0f * eps_level * 1.0001f + 1e-30f;
                 const float up = pivot + band, dn = pivot - band;
-                int n_keep = 0, n_unc = 0;
-                for (int base = 0; base < count; base += G::THREADS) {
-                    const int i = base + tid;
-                    int cls = 0;                                 // 0 out, 1 in, 2 uncertain
-                    if (i < count) {
-                        const float f = sScore[i];
-                        cls = f > up ? 1 : (f < dn ? 0 : 2);
-                        sCls[i] = (uint8_t)cls;
-                    }
-                    n_keep += __syncthreads_count(cls != 0);
-                    n_unc += __syncthreads_count(cls == 2);
+                const float f0 = i0 < count ? sScore[i0] : 0.0f, f1 = i1 < count ? sScore[i1] : 0.0f;
+                if (i0 < count) cls0 = f0 > up ? 1 : (f0 < dn ? 0 : 2);
+                if (i1 < count) cls1 = f1 > up ? 1 : (f1 < dn ? 0 : 2);
+                int slot0 = -1, slot1 = -1;
+                if (cls0 == 2) { slot0 = atomicAdd(&sSel[5], 1); if (slot0 < G::MAX_UNC) { sUPos[slot0] = i0; sKeyU[slot0] = order_key(f0); } }
+                if (cls1 == 2) { slot1 = atomicAdd(&sSel[5], 1); if (slot1 < G::MAX_UNC) { sUPos[slot1] = i1; sKeyU[slot1] = order_key(f1); } }
+                {
+                    const int mine = ((cls0 != 0) + (cls1 != 0)) | (((cls0 == 2) + (cls1 == 2)) << 16);
+                    const int wsum = __reduce_add_sync(0xffffffffu, mine);
+                    if (lane == 0 && wsum) atomicAdd(&sSel[4], wsum);
                 }
+                __syncthreads();
+                const int n_keep = sSel[4] & 0xffff, n_unc = sSel[4] >> 16;
                 DMG_TICK(TK_SELECT);
                 if (n_keep != beam) {                            // some uncertain row must go
                     st_recuts++;
                     if (n_unc > G::MAX_UNC) { redo = true; break; }
-                    if (tid == 0) sMisc[45] = 0;
-                    __syncthreads();
-                    for (int i = tid; i < count; i += G::THREADS)
-                        if (sCls[i] == 2) sUPos[atomicAdd(&sMisc[45], 1)] = i;
-                    __syncthreads();
                     const int need = beam - (n_keep - n_unc);    // uncertain rows that still fit (1 <= need < n_unc)
-                    // rank of every band row by its FAST score, and the fast-score gap at the cut inside the band
-                    int frank = 0, ps = 0;
-                    if (tid < n_unc) {
-                        ps = sUPos[tid];
-                        const uint32_t ks = sKeyU[ps];
+                    // rank of every band row by its FAST score (owner thread), and the fast-score gap at the cut
+                    int frank0 = 0, frank1 = 0;
+                    if (cls0 == 2 || cls1 == 2) {
+                        const uint32_t k0 = order_key(f0), k1 = order_key(f1);
                         for (int q = 0; q < n_unc; q++) {
+                            const uint32_t kq = sKeyU[q];
                             const int pq = sUPos[q];
-                            const uint32_t kq = sKeyU[pq];
-                            frank += (kq > ks || (kq == ks && pq < ps)) ? 1 : 0;
+                            frank0 += (kq > k0 || (kq == k0 && pq < i0)) ? 1 : 0;
+                            frank1 += (kq > k1 || (kq == k1 && pq < i1)) ? 1 : 0;
                         }
-                        if (frank == need - 1) sSel[2] = __float_as_int(sScore[ps]);
-                        if (frank == need) sSel[3] = __float_as_int(sScore[ps]);
+                        if (cls0 == 2 && frank0 == need - 1) sSel[2] = __float_as_int(f0);
+                        if (cls0 == 2 && frank0 == need) sSel[3] = __float_as_int(f0);
+                        if (cls1 == 2 && frank1 == need - 1) sSel[2] = __float_as_int(f1);
+                        if (cls1 == 2 && frank1 == need) sSel[3] = __float_as_int(f1);
                     }
                     __syncthreads();
                     const float gap = __int_as_float(sSel[2]) - __int_as_float(sSel[3]);
@@ -659,52 +693,59 @@ __global__ void __launch_bounds__(FastGeo::THREADS, 2) beam_search_fast_kernel(c
                     // a narrower gap is settled strictly right here.
                     const bool defer = gap >= 0.0625f * eps_level && vcount + n_unc <= G::VCAP && nseg < 32 && eps_level < 1e30f;
                     if (defer) {
-                        if (tid < n_unc) {
-                            const uint32_t chosen = frank < need ? 1u : 0u;
-                            sCls[ps] = (uint8_t)chosen;
-                            const int e = vcount + tid;
-                            sVCode[e] = cur[ps];
-                            sVFast[e] = sScore[ps];
-                            sVMeta[e] = (uint32_t)vcount | ((uint32_t)n_unc << 8) | ((uint32_t)need << 16) | (chosen << 24) | ((uint32_t)nseg << 25);
+                        if (cls0 == 2) {
+                            cls0 = frank0 < need ? 1 : 0;
+                            const int e = vcount + slot0;
+                            sVCode[e] = cur[i0]; sVFast[e] = f0;
+                            sVMeta[e] = (uint32_t)vcount | ((uint32_t)n_unc << 8) | ((uint32_t)need << 16) | ((uint32_t)cls0 << 24) | ((uint32_t)nseg << 25);
+                        }
+                        if (cls1 == 2) {
+                            cls1 = frank1 < need ? 1 : 0;
+                            const int e = vcount + slot1;
+                            sVCode[e] = cur[i1]; sVFast[e] = f1;
+                            sVMeta[e] = (uint32_t)vcount | ((uint32_t)n_unc << 8) | ((uint32_t)need << 16) | ((uint32_t)cls1 << 24) | ((uint32_t)nseg << 25);
                         }
                         if (tid == 0) sSegEps[nseg] = eps_level;
                         vcount += n_unc;
                         nseg++;
-                        __syncthreads();
                     } else {
                         st_sync++;
                         st_rerows += n_unc;
-                        if (tid < n_unc) sLCode[tid] = cur[ps];
+                        if (cls0 == 2) sLCode[slot0] = cur[i0];
+                        if (cls1 == 2) sLCode[slot1] = cur[i1];
                         strict_rescore(n_unc);
                         int tie = 0;
-                        if (tid < n_unc) {
-                            track_ratio(sLStr[tid], sScore[ps], eps_level);
-                            const uint32_t ks = order_key(sLStr[tid]);
-                            int rank = 0;
+                        if (cls0 == 2 || cls1 == 2) {
+                            const uint32_t k0 = cls0 == 2 ? order_key(sLStr[slot0]) : 0u, k1 = cls1 == 2 ? order_key(sLStr[slot1]) : 0u;
+                            if (cls0 == 2) track_ratio(sLStr[slot0], f0, eps_level);
+                            if (cls1 == 2) track_ratio(sLStr[slot1], f1, eps_level);
+                            int r0s = 0, r1s = 0;
                             for (int q = 0; q < n_unc; q++) {
                                 const uint32_t kq = order_key(sLStr[q]);
-                                rank += (kq > ks || (kq == ks && sUPos[q] < ps)) ? 1 : 0;
-                                tie |= (kq == ks && q != tid) ? 1 : 0;
+                                const int pq = sUPos[q];
+                                r0s += (kq > k0 || (kq == k0 && pq < i0)) ? 1 : 0;
+                                r1s += (kq > k1 || (kq == k1 && pq < i1)) ? 1 : 0;
+                                tie |= (cls0 == 2 && kq == k0 && pq != i0) ? 1 : 0;
+                                tie |= (cls1 == 2 && kq == k1 && pq != i1) ? 1 : 0;
                             }
-                            sCls[ps] = rank < need ? 1 : 0;
+                            if (cls0 == 2) cls0 = r0s < need ? 1 : 0;
+                            if (cls1 == 2) cls1 = r1s < need ? 1 : 0;
                         }
                         if (__syncthreads_or(tie)) { redo = true; break; }
                     }
                     DMG_TICK(TK_RESCORE);
                 }
             }
-            int nc = 0;
-            for (int base = 0; base < count; base += G::THREADS) {
-                const int i = base + tid;
-                const bool keep = i < count && (!cut || sCls[i] != 0);
-                const int64_t c = keep ? cur[i] : 0;
-                const int e1 = (keep && code_exists(p.exists, 2 * c + 1)) ? 1 : 0;
-                const int e2 = (keep && code_exists(p.exists, 2 * c + 2)) ? 1 : 0;
-                int tot;
-                const int o = block_exscan(e1 + e2, sMisc + 32, &tot);
-                if (e1) nxt[nc + o] = (int32_t)(2 * c + 1);
-                if (e2) nxt[nc + o + e1] = (int32_t)(2 * c + 2);
-                nc += tot;
+            int nc;
+            {
+                const int64_t c0 = cls0 ? cur[i0] : 0, c1 = cls1 ? cur[i1] : 0;
+                const int a1 = (cls0 && code_exists(p.exists, 2 * c0 + 1)) ? 1 : 0, a2 = (cls0 && code_exists(p.exists, 2 * c0 + 2)) ? 1 : 0;
+                const int b1 = (cls1 && code_exists(p.exists, 2 * c1 + 1)) ? 1 : 0, b2 = (cls1 && code_exists(p.exists, 2 * c1 + 2)) ? 1 : 0;
+                int o = block_exscan(a1 + a2 + b1 + b2, sMisc + 32, &nc);
+                if (a1) nxt[o++] = (int32_t)(2 * c0 + 1);
+                if (a2) nxt[o++] = (int32_t)(2 * c0 + 2);
+                if (b1) nxt[o++] = (int32_t)(2 * c1 + 1);
+                if (b2) nxt[o++] = (int32_t)(2 * c1 + 2);
             }
             __syncthreads();
             { int32_t *t = cur; cur = nxt; nxt = t; }
@@ -729,36 +770,12 @@ __global__ void __launch_bounds__(FastGeo::THREADS, 2) beam_search_fast_kernel(c
             for (int r0 = 0; r0 < count; r0 += G::R) {
                 const int nrows = count - r0 < G::R ? count - r0 : G::R;
                 const int ntile = nrows > 128 ? 2 : 1;
-                // (A) gather rows (16 lanes x 16 B per row) -> bf16 hi/lo operand tiles
+                // (A) gather rows -> bf16 hi/lo operand tiles
                 {
-                    const int chunk = lane & 15, rsub = lane >> 4;
-                    const uint32_t st_off = (uint32_t)((chunk >> 1) * G::X_LBO + (chunk & 1) * 8);
-                    const int niter = (nrows + 15) >> 4;
-#pragma unroll
-                    for (int hb = 0; hb < 2; hb++) {
-                        float4 v[8];
-#pragma unroll
-                        for (int q = 0; q < 8; q++) {
-                            const int it = hb * 8 + q;
-                            if (it < niter) {
-                                const int row = it * 16 + warp * 2 + rsub;
-                                const int32_t code = cur[r0 + (row < nrows ? row : 0)];
-                                v[q] = ldg_row16(p.emb + (size_t)code * E + chunk * 4);
-                            }
-                        }
-#pragma unroll
-                        for (int q = 0; q < 8; q++) {
-                            const int it = hb * 8 + q;
-                            if (it < niter) {
-                                const int row = it * 16 + warp * 2 + rsub;
-                                uint2 hi, lo;
-                                split_pair(v[q].x, v[q].y, hi.x, lo.x);
-                                split_pair(v[q].z, v[q].w, hi.y, lo.y);
-                                *reinterpret_cast<uint2 *>(sXh + st_off + row * 16) = hi;
-                                *reinterpret_cast<uint2 *>(sXl + st_off + row * 16) = lo;
-                            }
-                        }
-                    }
+                    const int chunk = lane & 15, rowbase = warp * 2 + (lane >> 4);
+                    const uint32_t st_off = (uint32_t)((chunk >> 1) * G::X_LBO + (chunk & 1) * 8 + rowbase * 16);
+                    if (ntile == 2) gather_convert<16>(p.emb + chunk * 4, cur + r0, nrows, rowbase, sXh + st_off, sXl + st_off);
+                    else gather_convert<8>(p.emb + chunk * 4, cur + r0, nrows, rowbase, sXh + st_off, sXl + st_off);
                 }
                 fence_proxy_async();
                 tc_fence_before();
@@ -801,30 +818,31 @@ __global__ void __launch_bounds__(FastGeo::THREADS, 2) beam_search_fast_kernel(c
                     }
                     __syncwarp();
                 }
-                // (C) Mask + SoftMax per row in registers, P -> bf16 hi/lo A operand [256][16]
+                // (C) Mask + SoftMax per row in registers (log2 domain: t_j = S_j * scale*log2e + addv_j, addv_j = -FLT_MAX on
+                // padded / masked slots), P -> bf16 hi/lo A operand [256][16]; column 15 = 1 multiplies the b1 row of H
                 if (warp * 32 < nrows) {
                     mbar_wait(&sBar[1], s_phase);
                     tc_fence_after();
                     float sc[16];
                     tmem_ld16(tmem_base + tmem_lane + tile_of_warp * 16, sc);
-                    float mx = -3.4028234663852886e+38f;
+                    if (all_masked) {                             // SoftMax of T equal values: exactly 1/T each
 #pragma unroll
-                    for (int j = 0; j < 16; j++) {
-                        float v = sc[j] * p.scale;
-                        if ((maskbits >> j) & 1u) v = -3.4028234663852886e+38f;
-                        sc[j] = v;
-                        if (j < T) mx = fmaxf(mx, v);
+                        for (int j = 0; j < 16; j++) sc[j] = j < T ? inv_T : 0.0f;
+                    } else {
+                        float mx = -3.4028234663852886e+38f;
+#pragma unroll
+                        for (int j = 0; j < 16; j++) {
+                            sc[j] = fmaf(sc[j], scale2, sAddv[j]);
+                            mx = fmaxf(mx, sc[j]);
+                        }
+                        float sum = 0.0f;
+#pragma unroll
+                        for (int j = 0; j < 16; j++) { sc[j] = ex2_approx(sc[j] - mx); sum += sc[j]; }
+                        const float inv = 1.0f / sum;
+#pragma unroll
+                        for (int j = 0; j < 16; j++) sc[j] *= inv;
                     }
-                    float sum = 0.0f;
-#pragma unroll
-                    for (int j = 0; j < 16; j++) {
-                        const float e = j < T ? __expf(sc[j] - mx) : 0.0f;
-                        sc[j] = e;
-                        sum += e;
-                    }
-                    const float inv = 1.0f / sum;
-#pragma unroll
-                    for (int j = 0; j < 16; j++) sc[j] *= inv;
+                    sc[15] = 1.0f;
                     uint4 hi, lo;
                     split8(*reinterpret_cast<float(*)[8]>(&sc[0]), hi, lo);
                     *reinterpret_cast<uint4 *>(sPh + tid * 16) = hi;
@@ -838,7 +856,7 @@ __global__ void __launch_bounds__(FastGeo::THREADS, 2) beam_search_fast_kernel(c
                 tc_fence_before();
                 __syncthreads();
                 DMG_TICK(TK_SOFTMAX);
-                // (D) Hacc += P . H (one k-step of 16)
+                // (D) Hacc += P . H (one k-step of 16; row 15 of H holds b1)
                 if (warp == 0) {
                     tc_fence_after();
                     const bool leader = elect_one();
@@ -855,7 +873,7 @@ __global__ void __launch_bounds__(FastGeo::THREADS, 2) beam_search_fast_kernel(c
                     if (leader) umma_commit(&sBar[2]);
                     __syncwarp();
                 }
-                // (E) epilogue: logit = relu(Hacc + b1) . W2 + b2, one row per thread
+                // (E) epilogue: logit = relu(Hacc) . W2 + b2 (b1 already inside Hacc), one row per thread
                 if (warp * 32 < nrows) {
                     mbar_wait(&sBar[2], h_phase);
                     tc_fence_after();
@@ -865,10 +883,7 @@ __global__ void __launch_bounds__(FastGeo::THREADS, 2) beam_search_fast_kernel(c
                         float v[32];
                         tmem_ld32(tmem_base + tmem_lane + 64 + tile_of_warp * 64 + hf * 32, v);
 #pragma unroll
-                        for (int c = 0; c < 32; c++) {
-                            const float h = fmaxf(v[c] + fp.b1[hf * 32 + c], 0.0f);
-                            logit = fmaf(h, fp.w2[hf * 32 + c], logit);
-                        }
+                        for (int c = 0; c < 32; c++) logit = fmaf(fmaxf(v[c], 0.0f), fp.w2[hf * 32 + c], logit);
                     }
                     if (tid < nrows) sScore[r0 + tid] = logit + fp.b2;
                 }
@@ -902,7 +917,7 @@ __global__ void __launch_bounds__(FastGeo::THREADS, 2) beam_search_fast_kernel(c
             int na = 0;
             if (kk > 0 && !redo) {
                 if (warp == 0) {
-                    const uint32_t pk = warp_radix_select(sKeyU, count, kk, sHist, lane);
+                    const uint32_t pk = warp_radix_select([&](int i) { return sKeyU[i]; }, count, kk, sHist, lane);
                     if (lane == 0) sSel[0] = (int)pk;
                 }
                 __syncthreads();

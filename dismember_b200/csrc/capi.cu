@@ -357,31 +357,38 @@ static int32_t compute_fast_bounds(dmg_handle_t h)
     DMG_CUDA(h, cudaStreamSynchronize(h->stream));
     const float *watt = w.data(), *w1 = watt + E * E, *b1 = w1 + 2 * E * E, *w2 = b1 + E, *b2 = w2 + E;
     std::vector<float> tab(4288, 0.0f);                          // M^T | v | lvl_vx | lvl_nx | z
-    double S1 = 0;
-    std::vector<double> z(E, 0.0);
+    // u = fp32 unit roundoff; c_mma = bf16 hi/lo split (3 * 2^-18 = 1.14e-5 per product) + fp32 accumulation inside
+    // the tensor core (allowance 0.86e-5 of sum |terms|).  A length-n fma chain perturbs its k-th term (0-based) by at
+    // most (n - k) roundings, so every weight below carries the position of its term in the strict chains.
+    const double u = std::ldexp(1.0, -24), c_mma = 2.0e-5, safety = 1.05;
+    double gam = 0;
+    std::vector<double> z(E, 0.0), vt(E, 0.0), fo(E);
+    for (int o = 0; o < E; o++) fo[o] = (2.0 * (E - o) + 4.0) * u;            // logit = h . W2 + b2, both paths
     for (int o = 0; o < E; o++) {
-        S1 += std::fabs((double)w2[o]) * std::fabs((double)b1[o]);
+        const double aw2 = std::fabs((double)w2[o]);
+        gam += aw2 * std::fabs((double)b1[o]) * (c_mma + 2 * u + fo[o]);
         for (int k = 0; k < E; k++) {
-            double acc = 0, aabs = 0;
+            double acc = 0;
             for (int m = 0; m < E; m++) {
-                acc += (double)w1[o * 2 * E + E + m] * (double)watt[m * E + k];
-                aabs += std::fabs((double)w1[o * 2 * E + E + m]) * std::fabs((double)watt[m * E + k]);
+                const double t = (double)w1[o * 2 * E + E + m] * (double)watt[m * E + k];
+                acc += t;
+                // strict: att term m sits at position 64+m of the h chain, a_k at position k of the att chain, a is a T-chain;
+                // fast:   H = M.K is a 64-chain over k in fp32 and M was rounded once
+                z[k] += aw2 * std::fabs(t) * ((E - m) + 2.0 * (E - k) + 18.0) * u;
             }
             tab[(size_t)k * E + o] = (float)acc;                  // M^T[k][o]
-            z[k] += std::fabs((double)w2[o]) * aabs;              // z_k = sum_o sum_m |w2_o| |W1a_om| |Watt_mk|
+            // main branch: MMA, position k of the 128-chain, the b1 add, the final dot
+            vt[k] += aw2 * std::fabs((double)w1[o * 2 * E + k]) * (c_mma + (2.0 * E - k) * u + 2 * u + fo[o]);
         }
     }
-    for (int k = 0; k < E; k++) tab[4224 + k] = (float)(z[k] * (1.0 + 1e-6));
     for (int k = 0; k < E; k++) {
-        double vk = 0;
-        for (int o = 0; o < E; o++) vk += std::fabs((double)w2[o]) * std::fabs((double)w1[o * 2 * E + k]);
-        tab[4096 + k] = (float)(vk * (1.0 + 1e-6));
+        tab[4096 + k] = (float)(vt[k] * (1.0 + 1e-6));
+        tab[4224 + k] = (float)(z[k] * (1.0 + 1e-6));
     }
-    const double u = std::ldexp(1.0, -24), c_mma = std::ldexp(1.0, -15), safety = 1.05;
-    h->fast_cA = (float)(safety * (c_mma + 264 * u));             // main branch: MMA + 128-chain + b1 add + final dot
-    h->fast_cZ = (float)(safety * 273 * u);                       // attention branch, strict chains (208 u) + H in fp32 (65 u)
-    h->fast_cH = (float)(c_mma + 134 * u);                        // attention branch: P.H on the tensor cores + final dot
-    h->fast_cGamma = (float)(safety * (140 * u * S1 + 4 * u * std::fabs((double)b2[0])) + 1e-30);
+    h->fast_cA = (float)safety;                                   // eps = tau (cA max v.|x| + cZ z.Kabs + (cH + |dp|_1) HW + cGamma)
+    h->fast_cZ = (float)safety;
+    h->fast_cH = (float)(c_mma + 134 * u);                        // attention branch on the tensor cores + final dot
+    h->fast_cGamma = (float)(safety * (gam + 4 * u * std::fabs((double)b2[0])) + 1e-30);
     h->fast_host.assign(b1, b1 + 2 * E + 1);                     // b1 | w2 | b2
     if (!h->d_fast_tab) DMG_CUDA(h, cudaMalloc(&h->d_fast_tab, tab.size() * sizeof(float)));
     if (!h->d_fast_ctl) {
@@ -446,7 +453,7 @@ static int32_t tdm_enqueue(dmg_handle_t h, int32_t B, const int32_t *d_seq, int3
     uint8_t *d_mask = cw.take<uint8_t>((size_t)B * T);
     const int64_t n = (int64_t)B * T;
     const int cap = std::max(std::max(((2 * max_beam + 7) / 8) * 8, 8), ((topk + 7) / 8) * 8);
-    bool use_fast = h->arithmetic == DMG_ARITH_FAST && d.dtype == DMG_F32 && d.E == 64 && cap <= FastGeo::max_cap() &&
+    bool use_fast = h->arithmetic == DMG_ARITH_FAST && d.dtype == DMG_F32 && d.E == 64 && d.T <= 15 && cap <= FastGeo::max_cap() &&
                     2 * (FastGeo::smem_bytes(cap) + 1024) <= (size_t)h->smem_per_sm;
     if (use_fast && h->fast_dirty) DMG_TRY(compute_fast_bounds(h));
     use_fast = use_fast && h->fast_ok;
