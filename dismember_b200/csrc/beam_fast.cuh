@@ -335,8 +335,9 @@ __device__ __forceinline__ bool elect_one()
     return pred != 0;
 }
 
-// k-th largest (k >= 1) of keys[0..count), count <= 512: ONE warp, its keys in registers, 4 radix passes
-// over 8-bit digits with a 256-bin shared histogram -- no block barrier inside.
+// Top 24 bits of the k-th largest (k >= 1) of keys[0..count), count <= 512: ONE warp, its keys in registers,
+// 3 radix passes over 8-bit digits with a 256-bin shared histogram -- no block barrier inside.  The k-th
+// largest key lies in [result, result | 0xff]; callers widen their band by that interval (2^-15 relative).
 template <typename KeyFn>
 __device__ __forceinline__ uint32_t warp_radix_select(KeyFn key_at, int count, int k, int *sHist, int lane)
 {
@@ -345,7 +346,7 @@ __device__ __forceinline__ uint32_t warp_radix_select(KeyFn key_at, int count, i
     for (int q = 0; q < 16; q++) { const int i = lane + 32 * q; kv[q] = i < count ? key_at(i) : 0u; }
     uint32_t prefix = 0, known = 0;
 #pragma unroll 1
-    for (int pass = 0; pass < 4; pass++) {
+    for (int pass = 0; pass < 3; pass++) {
         const int shift = 24 - 8 * pass;
 #pragma unroll
         for (int q = 0; q < 8; q++) sHist[lane + 32 * q] = 0;
@@ -650,9 +651,8 @@ __global__ void __launch_bounds__(FastGeo::THREADS, 2) beam_search_fast_kernel(c
                     if (lane == 0) { sSel[0] = (int)pk; sSel[4] = 0; sSel[5] = 0; }
                 }
                 __syncthreads();
-                const float pivot = key_to_float((uint32_t)sSel[0]);
                 const float band = 2.0f * eps_level * 1.0001f + 1e-30f;
-                const float up = pivot + band, dn = pivot - band;
+                const float up = key_to_float((uint32_t)sSel[0] | 0xffu) + band, dn = key_to_float((uint32_t)sSel[0]) - band;
                 const float f0 = i0 < count ? sScore[i0] : 0.0f, f1 = i1 < count ? sScore[i1] : 0.0f;
                 if (i0 < count) cls0 = f0 > up ? 1 : (f0 < dn ? 0 : 2);
                 if (i1 < count) cls1 = f1 > up ? 1 : (f1 < dn ? 0 : 2);
@@ -921,8 +921,7 @@ __global__ void __launch_bounds__(FastGeo::THREADS, 2) beam_search_fast_kernel(c
                     if (lane == 0) sSel[0] = (int)pk;
                 }
                 __syncthreads();
-                const float pivot = key_to_float((uint32_t)sSel[0]);
-                const float dn = pivot - (2.0f * eps_level * 1.0001f + 1e-30f);
+                const float dn = key_to_float((uint32_t)sSel[0]) - (2.0f * eps_level * 1.0001f + 1e-30f);
                 if (tid == 0) sMisc[45] = 0;
                 __syncthreads();
                 for (int i = tid; i < count; i += G::THREADS)

@@ -312,6 +312,7 @@ __global__ void __launch_bounds__(kThreads, 1) beam_search_kernel(const BeamPara
 
     const int tid = threadIdx.x;
     const int T = p.T;
+    if (p.user_count && (int)blockIdx.x >= *p.user_count) return;   // redo launch with nothing (left) to redo
 
     // weights -> shared, once per CTA
     for (int i = tid; i < E * E; i += kThreads) sWattT[i] = p.wattT[i];
