@@ -13,7 +13,7 @@ from typing import Optional
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libdismember_gpu.so")
+LIB_PATH = os.environ.get("DMG_LIB") or os.path.join(_HERE, "libdismember_gpu.so")   # DMG_LIB: instrumented dev builds
 HEADER_PATH = os.path.join(os.path.dirname(_HERE), "include", "dismember_gpu.h")
 
 DMG_OK, DMG_ERR_INVALID_ARG, DMG_ERR_CUDA, DMG_ERR_INDEX, DMG_ERR_STATE, DMG_ERR_UNSUPPORTED, DMG_ERR_NOMEM = 0, -1, -2, -3, -4, -5, -6

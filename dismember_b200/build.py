@@ -32,17 +32,17 @@ def stale() -> bool:
     return any(os.path.getmtime(d) > t for d in deps)
 
 
-def build(force: bool = False, verbose: bool = False) -> str:
-    if not force and not stale():
+def build(force: bool = False, verbose: bool = False, out: str = LIB) -> str:
+    if out == LIB and not force and not stale():
         return LIB
     extra = os.environ.get("DMG_NVCC_EXTRA", "").split()        # e.g. -DDMG_FAST_TIMING for the phase timers
-    cmd = [nvcc()] + NVCC_FLAGS + extra + (["-Xptxas", "-v"] if verbose else []) + ["-o", LIB] + [os.path.join(CSRC, s) for s in SOURCES]
+    cmd = [nvcc()] + NVCC_FLAGS + extra + (["-Xptxas", "-v"] if verbose else []) + ["-o", out] + [os.path.join(CSRC, s) for s in SOURCES]
     res = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
     if verbose or res.returncode:
         print(res.stdout)
     if res.returncode:
         raise RuntimeError("nvcc failed building libdismember_gpu.so")
-    return LIB
+    return out
 
 
 if __name__ == "__main__":

@@ -46,6 +46,7 @@ struct FastParams {
     const float *zvec;              // [64] z_k = sum_o sum_m |w2_o| |W1a_om| |Watt_mk|
     float cA, cZ, cH, cGamma;       // bound constants: eps = tau (cA VX + cZ ZK + (cH + |dp|_1) HW + cGamma)
     float tau;                      // fraction of the worst-case bound used as the band
+    int32_t sparse_from;            // lowest tree level with a missing code: expansion probes the bitmap only from there
     int32_t *redo_list;             // users to re-run with the strict kernel
     int32_t *redo_count;
     int32_t *work_counter;          // dynamic user scheduler
@@ -119,7 +120,7 @@ __device__ __forceinline__ uint64_t umma_desc(uint32_t smem_addr, uint32_t lbo_b
 }
 // instruction descriptor: D fp32, A/B bf16, both K-major, M = 128, N = 64 / 16
 constexpr uint32_t kIdescBf16M128N64 = (1u << 4) | (1u << 7) | (1u << 10) | ((64u >> 3) << 17) | ((128u >> 4) << 24);
-constexpr uint32_t kIdescBf16M128N16 = (1u << 4) | (1u << 7) | (1u << 10) | ((16u >> 3) << 17) | ((128u >> 4) << 24);
+constexpr uint32_t kIdescBf16M128N80 = (1u << 4) | (1u << 7) | (1u << 10) | ((80u >> 3) << 17) | ((128u >> 4) << 24);
 
 // fp32 pair -> packed bf16 hi pair and bf16 lo pair (x = hi + lo + O(2^-18 |x|))
 __device__ __forceinline__ void split_pair(float x0, float x1, uint32_t &hi, uint32_t &lo)
@@ -153,8 +154,7 @@ struct FastGeo {
     static constexpr int X_LBO = R * 16 + 16;                 // +16: the two rows of a warp store hit disjoint banks
     static constexpr int X_BYTES = 8 * X_LBO;                 // one bf16 operand tile 256 x 64 (hi or lo)
     static constexpr int P_LBO = R * 16, P_BYTES = 2 * P_LBO; // probabilities [256][16]
-    static constexpr int W_LBO = E * 16, W_BYTES = 8 * W_LBO; // W1x as B operand [64 o][64 k]
-    static constexpr int KB_LBO = 16 * 16, KB_BYTES = 8 * KB_LBO;   // history as B operand [16 j][64 k]
+    static constexpr int B_LBO = 80 * 16, B_BYTES = 8 * B_LBO; // B operand [80 n][64 k]: n < 64 W1x outputs, n >= 64 history slots
     static constexpr int H_LBO = E * 16, H_BYTES = 2 * H_LBO;       // H as B operand [64 o][16 j]
     static constexpr int SBO = 128;
     static constexpr int MAX_UNC = 96;                        // widest band re-scored in place at a cut
@@ -167,7 +167,7 @@ struct FastGeo {
                          OFF_LCODE = 8192, OFF_LSTR = OFF_LCODE + (VCAP + MAX_FINAL) * 4;
     static size_t smem_bytes(int cap)
     {
-        size_t b = 2 * (size_t)X_BYTES + 2 * (size_t)P_BYTES + 2 * (size_t)W_BYTES + 2 * (size_t)KB_BYTES + 2 * (size_t)H_BYTES;
+        size_t b = 2 * (size_t)X_BYTES + 2 * (size_t)P_BYTES + 2 * (size_t)B_BYTES + 2 * (size_t)H_BYTES;
         b += (size_t)cap * 4 * 3;                             // fast scores, candidate codes (ping-pong)
         b += (size_t)VCAP * 12 + 32 * 4;                      // deferred verification list (code, fast score, meta), eps per segment
         b += 128 * 4 + 64;                                    // misc ints, mbarriers
@@ -335,57 +335,85 @@ __device__ __forceinline__ bool elect_one()
     return pred != 0;
 }
 
-// Top 24 bits of the k-th largest (k >= 1) of keys[0..count), count <= 512: ONE warp, its keys in registers,
-// 3 radix passes over 8-bit digits with a 256-bin shared histogram -- no block barrier inside.  The k-th
-// largest key lies in [result, result | 0xff]; callers widen their band by that interval (2^-15 relative).
-template <typename KeyFn>
-__device__ __forceinline__ uint32_t warp_radix_select(KeyFn key_at, int count, int k, int *sHist, int lane)
+// ---- beam cut: block-wide selection of the k best fast scores -------------------------------------------------
+// The CTA holds <= 512 order keys two per thread (k0, k1; 0 marks an invalid slot).  block_select finds a threshold t
+// with EXACTLY k keys >= t and returns kdn = smallest key >= t (the k-th largest) and kup = largest key < t (the
+// (k+1)-th): a row of the upper group is certainly inside the strict top k iff fast > float(kup) + 2 eps, a row of
+// the lower group certainly outside iff fast < float(kdn) - 2 eps -- the pairwise condition against the extreme of
+// the other group, tighter than a band around a pivot.  With ties at the cut (no such t) it returns an interval
+// [kdn, kup] narrower than 2^8 key steps (2^-15 relative) that contains the k-th largest key; the same two
+// comparisons then give a (slightly wider) valid band.
+// Search: thresholds alternate between linear interpolation of the bracket counts and the bracket midpoint, both in
+// SCORE space (key space is logarithmic: its midpoints crawl through the exponents); per step two ballots per warp,
+// one 8-entry shared-memory exchange and one barrier (double-buffered); ~8 steps for 400 keys.  After 12 steps, or
+// with non-finite scores, plain key-space bisection guarantees termination.  All threads call it with the same
+// lo/hi/clo and return the same.
+// Measured alternatives (B200, cycles per cut): one warp with 16 keys per lane ~7 k (a lone warp issues ~0.2
+// instr/clk on dependent code); shared-memory histograms, radix or linear buckets, as long (ATOMS retires ~2 cycles
+// per lane); 7 thresholds per step: 3.6 steps but 1.8 k cycles each (register pressure at the 128-register cap).
+__device__ __forceinline__ void block_minmax(uint32_t k0, uint32_t k1, int *sRed, uint32_t &lo, uint32_t &hi, int &nvalid)
 {
-    uint32_t kv[16];
-#pragma unroll
-    for (int q = 0; q < 16; q++) { const int i = lane + 32 * q; kv[q] = i < count ? key_at(i) : 0u; }
-    uint32_t prefix = 0, known = 0;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    uint32_t mn = min(k0 ? k0 : 0xffffffffu, k1 ? k1 : 0xffffffffu), mx = max(k0, k1);
+    mn = __reduce_min_sync(0xffffffffu, mn);
+    mx = __reduce_max_sync(0xffffffffu, mx);
+    const int nv = __popc(__ballot_sync(0xffffffffu, k0 != 0u)) + __popc(__ballot_sync(0xffffffffu, k1 != 0u));
+    if (lane == 0) { sRed[warp] = (int)mn; sRed[8 + warp] = (int)mx; sRed[16 + warp] = nv; }
+    __syncthreads();
+    const uint4 a = *reinterpret_cast<const uint4 *>(sRed), b = *reinterpret_cast<const uint4 *>(sRed + 4);
+    const uint4 c = *reinterpret_cast<const uint4 *>(sRed + 8), d = *reinterpret_cast<const uint4 *>(sRed + 12);
+    const int4 e = *reinterpret_cast<const int4 *>(sRed + 16), f = *reinterpret_cast<const int4 *>(sRed + 20);
+    lo = min(min(min(a.x, a.y), min(a.z, a.w)), min(min(b.x, b.y), min(b.z, b.w)));
+    hi = max(max(max(c.x, c.y), max(c.z, c.w)), max(max(d.x, d.y), max(d.z, d.w)));
+    nvalid = (e.x + e.y) + (e.z + e.w) + (f.x + f.y) + (f.z + f.w);
+    __syncthreads();                                           // sRed is reused by the search
+}
+
+// lo <= every valid key <= hi, clo = number of valid keys >= k.  sRed: 128 ints (two 64-int count buffers).
+template <typename StepFn>
+__device__ __forceinline__ void block_select(uint32_t k0, uint32_t k1, int k, uint32_t lo, uint32_t hi, int clo, int *sRed,
+                                             uint32_t &kdn, uint32_t &kup, StepFn on_step)
+{
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    int chi = 0;                                               // clo = count(keys >= lo) >= k, chi = count(keys >= hi + 1) < k
+    int *sCnt = sRed;
+    int it = 0;
 #pragma unroll 1
-    for (int pass = 0; pass < 3; pass++) {
-        const int shift = 24 - 8 * pass;
-#pragma unroll
-        for (int q = 0; q < 8; q++) sHist[lane + 32 * q] = 0;
-        __syncwarp();
-#pragma unroll
-        for (int q = 0; q < 16; q++)
-            if (lane + 32 * q < count && (kv[q] & known) == prefix) atomicAdd(&sHist[(kv[q] >> shift) & 255u], 1);
-        __syncwarp();
-        int c[8], s = 0;
-#pragma unroll
-        for (int q = 0; q < 8; q++) { c[q] = sHist[lane * 8 + q]; s += c[q]; }
-        int suf = s;                                           // inclusive suffix sum: bins of lanes >= lane
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-            const int t = __shfl_down_sync(0xffffffffu, suf, o);
-            if (lane + o < 32) suf += t;
+    while (clo != k && hi - lo > 255u && hi > lo) {
+        uint32_t mid = lo + ((hi - lo) >> 1) + 1u;
+        if (it < 12) {
+            const float flo = key_to_float(lo), fhi = key_to_float(hi);
+            const float fr = (it & 1) ? 0.5f : ((float)(k - chi) - 0.5f) / (float)(clo - chi);
+            const float fm = fhi - (fhi - flo) * fr;
+            if (fm == fm) mid = order_key(fm);
         }
-        const int above = suf - s;
-        const bool mine = above < k && k <= suf;
-        int bin = 0, kn = k;
-        if (mine) {
-            int acc = above;
-            bool found = false;
-#pragma unroll
-            for (int q = 7; q >= 0; q--) {
-                if (!found) {
-                    if (acc + c[q] >= k) { bin = lane * 8 + q; kn = k - acc; found = true; }
-                    else acc += c[q];
-                }
-            }
-        }
-        const int src = __ffs(__ballot_sync(0xffffffffu, mine)) - 1;
-        bin = __shfl_sync(0xffffffffu, bin, src);
-        k = __shfl_sync(0xffffffffu, kn, src);
-        prefix |= (uint32_t)bin << shift;
-        known |= 255u << shift;
-        __syncwarp();
+        mid = min(max(mid, lo + 1u), hi);
+        int c = __popc(__ballot_sync(0xffffffffu, k0 >= mid)) + __popc(__ballot_sync(0xffffffffu, k1 >= mid));
+        if (lane == 0) sCnt[warp] = c;
+        __syncthreads();
+        const int4 a = *reinterpret_cast<const int4 *>(sCnt), b = *reinterpret_cast<const int4 *>(sCnt + 4);
+        c = (a.x + a.y) + (a.z + a.w) + (b.x + b.y) + (b.z + b.w);
+        sCnt = sRed + (sCnt == sRed ? 64 : 0);
+        it++;
+        if (c >= k) { lo = mid; clo = c; } else { hi = mid - 1u; chi = c; }
     }
-    return prefix;
+    on_step(it);
+    if (clo == k) {
+        // k keys >= lo: the k-th largest is the smallest of them, the (k+1)-th the largest key below lo
+        uint32_t a = min(k0 >= lo ? k0 : 0xffffffffu, k1 >= lo ? k1 : 0xffffffffu);
+        uint32_t b = max(k0 < lo ? k0 : 0u, k1 < lo ? k1 : 0u);
+        a = __reduce_min_sync(0xffffffffu, a);
+        b = __reduce_max_sync(0xffffffffu, b);
+        if (lane == 0) { sCnt[warp] = (int)a; sCnt[8 + warp] = (int)b; }
+        __syncthreads();
+        const uint4 p0 = *reinterpret_cast<const uint4 *>(sCnt), p1 = *reinterpret_cast<const uint4 *>(sCnt + 4);
+        const uint4 q0 = *reinterpret_cast<const uint4 *>(sCnt + 8), q1 = *reinterpret_cast<const uint4 *>(sCnt + 12);
+        kdn = min(min(min(p0.x, p0.y), min(p0.z, p0.w)), min(min(p1.x, p1.y), min(p1.z, p1.w)));
+        kup = max(max(max(q0.x, q0.y), max(q0.z, q0.w)), max(max(q1.x, q1.y), max(q1.z, q1.w)));
+        if (kup == 0u) kup = kdn;                              // no valid key below the cut (k == number of valid keys)
+    } else {
+        kdn = lo; kup = hi;
+    }
 }
 
 // ---- (A) gather NIT x 16 rows of the pass: 16 lanes x 16 B per row, every load issued before the first use --
@@ -424,7 +452,7 @@ __device__ __forceinline__ float ex2_approx(float x)
 #else
 #define DMG_TICK(i) do { } while (0)
 #endif
-enum { TK_PROLOGUE = 0, TK_SELECT, TK_RESCORE, TK_EXPAND, TK_GATHER, TK_SOFTMAX, TK_EPILOGUE, TK_FINAL, TK_SCHED, TK_N };
+enum { TK_PROLOGUE = 0, TK_SELECT, TK_RESCORE, TK_EXPAND, TK_GATHER, TK_SOFTMAX, TK_EPILOGUE, TK_FINAL, TK_SCHED, TK_SELWARP, TK_MMAWAIT, TK_PHWAIT, TK_FINPREP, TK_FINSTRICT, TK_SELA, TK_SELB, TK_N };
 
 __global__ void __launch_bounds__(FastGeo::THREADS, 2) beam_search_fast_kernel(const BeamParams<float> p, const FastParams fp)
 {
@@ -436,10 +464,8 @@ __global__ void __launch_bounds__(FastGeo::THREADS, 2) beam_search_fast_kernel(c
     unsigned char *sXl = sp; sp += G::X_BYTES;
     unsigned char *sPh = sp; sp += G::P_BYTES;
     unsigned char *sPl = sp; sp += G::P_BYTES;
-    unsigned char *sWh = sp; sp += G::W_BYTES;
-    unsigned char *sWl = sp; sp += G::W_BYTES;
-    unsigned char *sKbh = sp; sp += G::KB_BYTES;
-    unsigned char *sKbl = sp; sp += G::KB_BYTES;
+    unsigned char *sBh = sp; sp += G::B_BYTES;
+    unsigned char *sBl = sp; sp += G::B_BYTES;
     unsigned char *sHh = sp; sp += G::H_BYTES;
     unsigned char *sHl = sp; sp += G::H_BYTES;
     float *sScore = reinterpret_cast<float *>(sp); sp += (size_t)p.cap * 4;
@@ -453,7 +479,7 @@ __global__ void __launch_bounds__(FastGeo::THREADS, 2) beam_search_fast_kernel(c
     uint64_t *sBar = reinterpret_cast<uint64_t *>(sp);                 // [0] history TMA, [1] S MMAs, [2] all MMAs of a pass
     // aliases (valid only while no MMA is in flight)
     float *sKf = reinterpret_cast<float *>(sXh);                       // history fp32 [16][KLD]
-    int *sHist = reinterpret_cast<int *>(sPh + G::OFF_HIST);
+    int *sRed = reinterpret_cast<int *>(sPh + G::OFF_HIST);           // 256 ints: block_select exchange
     int *sSel = reinterpret_cast<int *>(sPh + G::OFF_SEL);
     uint32_t *sKeyU = reinterpret_cast<uint32_t *>(sPh + G::OFF_KEYU);
     int *sUPos = reinterpret_cast<int *>(sPh + G::OFF_UPOS);
@@ -473,11 +499,11 @@ __global__ void __launch_bounds__(FastGeo::THREADS, 2) beam_search_fast_kernel(c
         for (int q = 0; q < 8; q++) v[q] = __ldg(fp.w1 + o * 2 * E + kc * 8 + q);
         uint4 hi, lo;
         split8(v, hi, lo);
-        *reinterpret_cast<uint4 *>(sWh + kc * G::W_LBO + o * 16) = hi;
-        *reinterpret_cast<uint4 *>(sWl + kc * G::W_LBO + o * 16) = lo;
+        *reinterpret_cast<uint4 *>(sBh + kc * G::B_LBO + o * 16) = hi;
+        *reinterpret_cast<uint4 *>(sBl + kc * G::B_LBO + o * 16) = lo;
     }
     if (tid == 0) { mbar_init(&sBar[0], 1); mbar_init(&sBar[1], 1); mbar_init(&sBar[2], 1); }
-    if (warp == 0) tmem_alloc(reinterpret_cast<uint32_t *>(&sMisc[41]), 256);   // S tiles [0,32)  Hacc tiles [64,192)
+    if (warp == 0) tmem_alloc(reinterpret_cast<uint32_t *>(&sMisc[41]), 256);   // tile t: Hacc [128t, 128t+64), S [128t+64, 128t+80)
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
@@ -487,7 +513,7 @@ __global__ void __launch_bounds__(FastGeo::THREADS, 2) beam_search_fast_kernel(c
     const float scale2 = p.scale * 1.4426950408889634f, inv_T = 1.0f / (float)T;
     float *sAddv = reinterpret_cast<float *>(sMisc + 64);               // [16] additive softmax mask of the current user
     uint32_t hist_phase = 0, s_phase = 0, h_phase = 0;
-    unsigned long long st_cuts = 0, st_recuts = 0, st_rerows = 0, st_rows = 0, st_redo = 0, st_sync = 0;
+    unsigned long long st_cuts = 0, st_recuts = 0, st_rerows = 0, st_rows = 0, st_redo = 0, st_sync = 0, st_iters = 0;
     float st_ratio = 0.0f;
 #ifdef DMG_FAST_TIMING
     long long tacc[TK_N] = {0}, tlast = clock64();
@@ -500,8 +526,8 @@ __global__ void __launch_bounds__(FastGeo::THREADS, 2) beam_search_fast_kernel(c
         return ((uint64_t)(0x4000u | (G::SBO >> 4)) << 32) | (uint64_t)((sbase16 + (byte_off >> 4)) | ((lbo >> 4) << 16));
     };
     constexpr uint32_t OFF_XH = 0, OFF_XL = G::X_BYTES, OFF_PH = 2 * G::X_BYTES, OFF_PL = OFF_PH + G::P_BYTES,
-                       OFF_WH = OFF_PL + G::P_BYTES, OFF_WL = OFF_WH + G::W_BYTES, OFF_KH = OFF_WL + G::W_BYTES,
-                       OFF_KL = OFF_KH + G::KB_BYTES, OFF_HH = OFF_KL + G::KB_BYTES, OFF_HL = OFF_HH + G::H_BYTES;
+                       OFF_BH = OFF_PL + G::P_BYTES, OFF_BL = OFF_BH + G::B_BYTES, OFF_HH = OFF_BL + G::B_BYTES,
+                       OFF_HL = OFF_HH + G::H_BYTES;
 
     // history rows (fp32) -> sKf through the TMA bulk-copy engine; padding rows are zero
     auto load_history = [&]() {
@@ -562,8 +588,8 @@ __global__ void __launch_bounds__(FastGeo::THREADS, 2) beam_search_fast_kernel(c
             for (int q = 0; q < 8; q++) v[q] = sKf[j * G::KLD + kc * 8 + q];
             uint4 hi, lo;
             split8(v, hi, lo);
-            *reinterpret_cast<uint4 *>(sKbh + kc * G::KB_LBO + j * 16) = hi;
-            *reinterpret_cast<uint4 *>(sKbl + kc * G::KB_LBO + j * 16) = lo;
+            *reinterpret_cast<uint4 *>(sBh + kc * G::B_LBO + (64 + j) * 16) = hi;
+            *reinterpret_cast<uint4 *>(sBl + kc * G::B_LBO + (64 + j) * 16) = lo;
         } else if (tid < 192) {                                 // ZK = sum_k z_k max_j |K_jk|  (two warp partials)
             const int k = tid - 128;
             float kab = 0.0f;
@@ -636,6 +662,7 @@ __global__ void __launch_bounds__(FastGeo::THREADS, 2) beam_search_fast_kernel(c
         float eps_level = 0.0f;                                 // bound on |fast - strict| of the scores in sScore
         int vcount = 0, nseg = 0;                               // deferred verification list of this user
         bool redo = false;
+        int redo_why = 0;                                       // 0 wide band, 1 tie in place, 2 unscored, 3 wide final, 4 tie at the end, 5 proof failed
         bool scored = false;
 
         for (int level = s_level; level < p.leaf_level && count > 0; level++) {
@@ -646,14 +673,20 @@ __global__ void __launch_bounds__(FastGeo::THREADS, 2) beam_search_fast_kernel(c
             int cls0 = i0 < count ? 1 : 0, cls1 = i1 < count ? 1 : 0;      // 0 out, 1 in, 2 uncertain
             if (cut) {
                 st_cuts++;
-                if (warp == 0) {
-                    const uint32_t pk = warp_radix_select([&](int i) { return order_key(sScore[i]); }, count, beam, sHist, lane);
-                    if (lane == 0) { sSel[0] = (int)pk; sSel[4] = 0; sSel[5] = 0; }
-                }
-                __syncthreads();
-                const float band = 2.0f * eps_level * 1.0001f + 1e-30f;
-                const float up = key_to_float((uint32_t)sSel[0] | 0xffu) + band, dn = key_to_float((uint32_t)sSel[0]) - band;
                 const float f0 = i0 < count ? sScore[i0] : 0.0f, f1 = i1 < count ? sScore[i1] : 0.0f;
+                if (tid == 0) { sSel[4] = 0; sSel[5] = 0; }
+                uint32_t kdn, kup;
+                {
+                    const uint32_t key0 = i0 < count ? order_key(f0) : 0u, key1 = i1 < count ? order_key(f1) : 0u;
+                    uint32_t lo, hi;
+                    int nv;
+                    block_minmax(key0, key1, sRed, lo, hi, nv);
+                    DMG_TICK(TK_SELA);
+                    block_select(key0, key1, beam, lo, hi, nv, sRed, kdn, kup, [&](int n) { st_iters += n; });
+                    DMG_TICK(TK_SELB);
+                }
+                const float band = 2.0f * eps_level * 1.0001f + 1e-30f;
+                const float up = key_to_float(kup) + band, dn = key_to_float(kdn) - band;
                 if (i0 < count) cls0 = f0 > up ? 1 : (f0 < dn ? 0 : 2);
                 if (i1 < count) cls1 = f1 > up ? 1 : (f1 < dn ? 0 : 2);
                 int slot0 = -1, slot1 = -1;
@@ -669,7 +702,7 @@ __global__ void __launch_bounds__(FastGeo::THREADS, 2) beam_search_fast_kernel(c
                 DMG_TICK(TK_SELECT);
                 if (n_keep != beam) {                            // some uncertain row must go
                     st_recuts++;
-                    if (n_unc > G::MAX_UNC) { redo = true; break; }
+                    if (n_unc > G::MAX_UNC) { redo = true; redo_why = 0; break; }
                     const int need = beam - (n_keep - n_unc);    // uncertain rows that still fit (1 <= need < n_unc)
                     // rank of every band row by its FAST score (owner thread), and the fast-score gap at the cut
                     int frank0 = 0, frank1 = 0;
@@ -719,19 +752,22 @@ __global__ void __launch_bounds__(FastGeo::THREADS, 2) beam_search_fast_kernel(c
                             const uint32_t k0 = cls0 == 2 ? order_key(sLStr[slot0]) : 0u, k1 = cls1 == 2 ? order_key(sLStr[slot1]) : 0u;
                             if (cls0 == 2) track_ratio(sLStr[slot0], f0, eps_level);
                             if (cls1 == 2) track_ratio(sLStr[slot1], f1, eps_level);
-                            int r0s = 0, r1s = 0;
+                            // strict rank of a band row = rows strictly above it (+ an undetermined share of its exact ties: the
+                            // reference orders ties by candidate position, which this path does not track).  Only a tie that
+                            // STRADDLES the cut is undecidable here; ties on one side of it change nothing.
+                            int g0 = 0, g1 = 0, e0 = 0, e1 = 0;
                             for (int q = 0; q < n_unc; q++) {
                                 const uint32_t kq = order_key(sLStr[q]);
                                 const int pq = sUPos[q];
-                                r0s += (kq > k0 || (kq == k0 && pq < i0)) ? 1 : 0;
-                                r1s += (kq > k1 || (kq == k1 && pq < i1)) ? 1 : 0;
-                                tie |= (cls0 == 2 && kq == k0 && pq != i0) ? 1 : 0;
-                                tie |= (cls1 == 2 && kq == k1 && pq != i1) ? 1 : 0;
+                                g0 += kq > k0 ? 1 : 0;
+                                g1 += kq > k1 ? 1 : 0;
+                                e0 += (kq == k0 && pq != i0) ? 1 : 0;
+                                e1 += (kq == k1 && pq != i1) ? 1 : 0;
                             }
-                            if (cls0 == 2) cls0 = r0s < need ? 1 : 0;
-                            if (cls1 == 2) cls1 = r1s < need ? 1 : 0;
+                            if (cls0 == 2) { tie |= (g0 < need && g0 + e0 >= need) ? 1 : 0; cls0 = g0 + e0 < need ? 1 : 0; }
+                            if (cls1 == 2) { tie |= (g1 < need && g1 + e1 >= need) ? 1 : 0; cls1 = g1 + e1 < need ? 1 : 0; }
                         }
-                        if (__syncthreads_or(tie)) { redo = true; break; }
+                        if (__syncthreads_or(tie)) { redo = true; redo_why = 1; break; }
                     }
                     DMG_TICK(TK_RESCORE);
                 }
@@ -739,8 +775,9 @@ __global__ void __launch_bounds__(FastGeo::THREADS, 2) beam_search_fast_kernel(c
             int nc;
             {
                 const int64_t c0 = cls0 ? cur[i0] : 0, c1 = cls1 ? cur[i1] : 0;
-                const int a1 = (cls0 && code_exists(p.exists, 2 * c0 + 1)) ? 1 : 0, a2 = (cls0 && code_exists(p.exists, 2 * c0 + 2)) ? 1 : 0;
-                const int b1 = (cls1 && code_exists(p.exists, 2 * c1 + 1)) ? 1 : 0, b2 = (cls1 && code_exists(p.exists, 2 * c1 + 2)) ? 1 : 0;
+                const uint32_t *bm = (level + 1 >= fp.sparse_from) ? p.exists : nullptr;      // full levels: every child exists
+                const int a1 = (cls0 && code_exists(bm, 2 * c0 + 1)) ? 1 : 0, a2 = (cls0 && code_exists(bm, 2 * c0 + 2)) ? 1 : 0;
+                const int b1 = (cls1 && code_exists(bm, 2 * c1 + 1)) ? 1 : 0, b2 = (cls1 && code_exists(bm, 2 * c1 + 2)) ? 1 : 0;
                 int o = block_exscan(a1 + a2 + b1 + b2, sMisc + 32, &nc);
                 if (a1) nxt[o++] = (int32_t)(2 * c0 + 1);
                 if (a2) nxt[o++] = (int32_t)(2 * c0 + 2);
@@ -781,41 +818,27 @@ __global__ void __launch_bounds__(FastGeo::THREADS, 2) beam_search_fast_kernel(c
                 tc_fence_before();
                 __syncthreads();
                 DMG_TICK(TK_GATHER);
-                // (B) S = X . K^T (N = 16), then Hacc = X . W1x^T (N = 64): 4 k-steps x (hi*hi + hi*lo + lo*hi).
+                // (B) [Hacc | S] = X . [W1x | K]^T (N = 80: one pass over the A operand): 4 k-steps x (hi*hi + hi*lo + lo*hi).
                 // Warp 0 runs the descriptor arithmetic warp-uniformly; one elected lane issues.
                 if (warp == 0) {
                     tc_fence_after();
                     const bool leader = elect_one();
                     const uint64_t dXh = mkdesc(OFF_XH, G::X_LBO), dXl = mkdesc(OFF_XL, G::X_LBO);
-                    const uint64_t dKh = mkdesc(OFF_KH, G::KB_LBO), dKl = mkdesc(OFF_KL, G::KB_LBO);
-                    const uint64_t dWh = mkdesc(OFF_WH, G::W_LBO), dWl = mkdesc(OFF_WL, G::W_LBO);
+                    const uint64_t dBh = mkdesc(OFF_BH, G::B_LBO), dBl = mkdesc(OFF_BL, G::B_LBO);
                     for (int t = 0; t < ntile; t++) {
                         const uint64_t xo = (uint64_t)(t * 128);            // 128 rows x 16 B, in 16-byte descriptor units
 #pragma unroll
                         for (int ks = 0; ks < 4; ks++) {
                             const uint64_t ah = dXh + xo + ks * (2 * G::X_LBO / 16), al = dXl + xo + ks * (2 * G::X_LBO / 16);
-                            const uint64_t bh = dKh + ks * (2 * G::KB_LBO / 16), bl = dKl + ks * (2 * G::KB_LBO / 16);
+                            const uint64_t bh = dBh + ks * (2 * G::B_LBO / 16), bl = dBl + ks * (2 * G::B_LBO / 16);
                             if (leader) {
-                                umma_bf16(tmem_base + t * 16, ah, bh, kIdescBf16M128N16, ks > 0);
-                                umma_bf16(tmem_base + t * 16, ah, bl, kIdescBf16M128N16, 1);
-                                umma_bf16(tmem_base + t * 16, al, bh, kIdescBf16M128N16, 1);
+                                umma_bf16(tmem_base + t * 128, ah, bh, kIdescBf16M128N80, ks > 0);
+                                umma_bf16(tmem_base + t * 128, ah, bl, kIdescBf16M128N80, 1);
+                                umma_bf16(tmem_base + t * 128, al, bh, kIdescBf16M128N80, 1);
                             }
                         }
                     }
                     if (leader) umma_commit(&sBar[1]);
-                    for (int t = 0; t < ntile; t++) {
-                        const uint64_t xo = (uint64_t)(t * 128);
-#pragma unroll
-                        for (int ks = 0; ks < 4; ks++) {
-                            const uint64_t ah = dXh + xo + ks * (2 * G::X_LBO / 16), al = dXl + xo + ks * (2 * G::X_LBO / 16);
-                            const uint64_t bh = dWh + ks * (2 * G::W_LBO / 16), bl = dWl + ks * (2 * G::W_LBO / 16);
-                            if (leader) {
-                                umma_bf16(tmem_base + 64 + t * 64, ah, bh, kIdescBf16M128N64, ks > 0);
-                                umma_bf16(tmem_base + 64 + t * 64, ah, bl, kIdescBf16M128N64, 1);
-                                umma_bf16(tmem_base + 64 + t * 64, al, bh, kIdescBf16M128N64, 1);
-                            }
-                        }
-                    }
                     __syncwarp();
                 }
                 // (C) Mask + SoftMax per row in registers (log2 domain: t_j = S_j * scale*log2e + addv_j, addv_j = -FLT_MAX on
@@ -823,8 +846,9 @@ __global__ void __launch_bounds__(FastGeo::THREADS, 2) beam_search_fast_kernel(c
                 if (warp * 32 < nrows) {
                     mbar_wait(&sBar[1], s_phase);
                     tc_fence_after();
+                    DMG_TICK(TK_MMAWAIT);
                     float sc[16];
-                    tmem_ld16(tmem_base + tmem_lane + tile_of_warp * 16, sc);
+                    tmem_ld16(tmem_base + tmem_lane + tile_of_warp * 128 + 64, sc);
                     if (all_masked) {                             // SoftMax of T equal values: exactly 1/T each
 #pragma unroll
                         for (int j = 0; j < 16; j++) sc[j] = j < T ? inv_T : 0.0f;
@@ -865,9 +889,9 @@ __global__ void __launch_bounds__(FastGeo::THREADS, 2) beam_search_fast_kernel(c
                     for (int t = 0; t < ntile; t++) {
                         const uint64_t ah = dPh + (uint64_t)(t * 128), al = dPl + (uint64_t)(t * 128);
                         if (leader) {
-                            umma_bf16(tmem_base + 64 + t * 64, ah, dHh, kIdescBf16M128N64, 1);
-                            umma_bf16(tmem_base + 64 + t * 64, ah, dHl, kIdescBf16M128N64, 1);
-                            umma_bf16(tmem_base + 64 + t * 64, al, dHh, kIdescBf16M128N64, 1);
+                            umma_bf16(tmem_base + t * 128, ah, dHh, kIdescBf16M128N64, 1);
+                            umma_bf16(tmem_base + t * 128, ah, dHl, kIdescBf16M128N64, 1);
+                            umma_bf16(tmem_base + t * 128, al, dHh, kIdescBf16M128N64, 1);
                         }
                     }
                     if (leader) umma_commit(&sBar[2]);
@@ -877,11 +901,12 @@ __global__ void __launch_bounds__(FastGeo::THREADS, 2) beam_search_fast_kernel(c
                 if (warp * 32 < nrows) {
                     mbar_wait(&sBar[2], h_phase);
                     tc_fence_after();
+                    DMG_TICK(TK_PHWAIT);
                     float logit = 0.0f;
 #pragma unroll
                     for (int hf = 0; hf < 2; hf++) {
                         float v[32];
-                        tmem_ld32(tmem_base + tmem_lane + 64 + tile_of_warp * 64 + hf * 32, v);
+                        tmem_ld32(tmem_base + tmem_lane + tile_of_warp * 128 + hf * 32, v);
 #pragma unroll
                         for (int c = 0; c < 32; c++) logit = fmaf(fmaxf(v[c], 0.0f), fp.w2[hf * 32 + c], logit);
                     }
@@ -913,15 +938,18 @@ __global__ void __launch_bounds__(FastGeo::THREADS, 2) beam_search_fast_kernel(c
                 valid += __syncthreads_count(keep);
             }
             const int kk = valid < p.topk ? valid : p.topk;
-            if (kk > 0 && !scored) redo = true;                  // beam >= 2^leaf_level: nothing was scored, every score ties
+            if (kk > 0 && !scored) { redo = true; redo_why = 2; }                 // beam >= 2^leaf_level: nothing was scored, every score ties
             int na = 0;
             if (kk > 0 && !redo) {
-                if (warp == 0) {
-                    const uint32_t pk = warp_radix_select([&](int i) { return sKeyU[i]; }, count, kk, sHist, lane);
-                    if (lane == 0) sSel[0] = (int)pk;
+                uint32_t kdn, kup;
+                {
+                    const uint32_t key0 = 2 * tid < count ? sKeyU[2 * tid] : 0u, key1 = 2 * tid + 1 < count ? sKeyU[2 * tid + 1] : 0u;
+                    uint32_t lo, hi;
+                    int nv;
+                    block_minmax(key0, key1, sRed, lo, hi, nv);
+                    block_select(key0, key1, kk, lo, hi, nv, sRed, kdn, kup, [](int) {});
                 }
-                __syncthreads();
-                const float dn = key_to_float((uint32_t)sSel[0]) - (2.0f * eps_level * 1.0001f + 1e-30f);
+                const float dn = key_to_float(kdn) - (2.0f * eps_level * 1.0001f + 1e-30f);
                 if (tid == 0) sMisc[45] = 0;
                 __syncthreads();
                 for (int i = tid; i < count; i += G::THREADS)
@@ -931,45 +959,49 @@ __global__ void __launch_bounds__(FastGeo::THREADS, 2) beam_search_fast_kernel(c
                     }
                 __syncthreads();
                 na = sMisc[45];
-                if (na > G::MAX_FINAL) redo = true;
+                if (na > G::MAX_FINAL) { redo = true; redo_why = 3; }
             }
+            DMG_TICK(TK_FINPREP);
             if (!redo && vcount + na > 0) {
                 // ONE strict batch: every band row deferred at a cut, then the topk candidates
                 for (int e = tid; e < vcount; e += G::THREADS) sLCode[e] = sVCode[e];
                 for (int q = tid; q < na; q += G::THREADS) sLCode[vcount + q] = cur[sUPos[q]];
                 st_rerows += vcount + na;
                 strict_rescore(vcount + na);
+                DMG_TICK(TK_FINSTRICT);
                 int bad = 0;
                 for (int e = tid; e < vcount; e += G::THREADS) {   // the deferred cuts: strict order must pick the same rows
                     const uint32_t meta = sVMeta[e];
                     const int st = meta & 255u, n = (meta >> 8) & 255u, need = (meta >> 16) & 255u, chosen = (meta >> 24) & 1u;
                     track_ratio(sLStr[e], sVFast[e], sSegEps[meta >> 25]);
                     const uint32_t ks = order_key(sLStr[e]);
-                    int rank = 0;
+                    int rank = 0, ties = 0;
                     for (int q = st; q < st + n; q++) {
                         const uint32_t kq = order_key(sLStr[q]);
                         rank += kq > ks ? 1 : 0;
-                        bad |= (kq == ks && q != e) ? 1 : 0;     // exact strict tie inside a band: the reference decides by position
+                        ties += (kq == ks && q != e) ? 1 : 0;
                     }
-                    bad |= ((rank < need ? 1 : 0) != chosen) ? 1 : 0;
+                    bad |= (rank < need && rank + ties >= need) ? 1 : 0;   // exact strict tie across the cut: the reference decides by position
+                    bad |= ((rank + ties < need ? 1 : 0) != chosen) ? 2 : 0;
                 }
                 if (tid < na) {
                     const float mine = sLStr[vcount + tid];
                     const int ps = sUPos[tid];
                     track_ratio(mine, sScore[ps], eps_level);
                     const uint32_t ks = order_key(mine);
-                    int rank = 0;
+                    int rank = 0, ties = 0;
                     for (int q = 0; q < na; q++) {
                         const uint32_t kq = order_key(sLStr[vcount + q]);
-                        rank += (kq > ks || (kq == ks && sUPos[q] < ps)) ? 1 : 0;
-                        bad |= (kq == ks && q != tid) ? 1 : 0;
+                        rank += kq > ks ? 1 : 0;
+                        ties += (kq == ks && q != tid) ? 1 : 0;
                     }
+                    bad |= (ties > 0 && rank < kk) ? 1 : 0;          // a tie that reaches the output: its order is positional
                     if (rank < kk) {
                         p.out_items[(size_t)user * p.out_stride + rank] = __ldg(p.leaf_item + ((int64_t)cur[ps] - leaf_start));
                         p.out_scores[(size_t)user * p.out_stride + rank] = mine;
                     }
                 }
-                if (__syncthreads_or(bad)) redo = true;
+                if (__syncthreads_or(bad)) { redo = true; redo_why = 4 + (__syncthreads_or(bad & 2) ? 1 : 0); }
             }
             if (!redo) {
                 for (int i = kk + tid; i < p.topk; i += G::THREADS) {
@@ -981,7 +1013,7 @@ __global__ void __launch_bounds__(FastGeo::THREADS, 2) beam_search_fast_kernel(c
         }
         if (redo) {
             st_redo++;
-            if (tid == 0) fp.redo_list[atomicAdd(fp.redo_count, 1)] = user;
+            if (tid == 0) { fp.redo_list[atomicAdd(fp.redo_count, 1)] = user; if (fp.stats) atomicAdd(&fp.stats[24 + redo_why], 1ull); }
         }
         DMG_TICK(TK_FINAL);
     }
@@ -995,7 +1027,7 @@ __global__ void __launch_bounds__(FastGeo::THREADS, 2) beam_search_fast_kernel(c
         if (tid == 0) {
             atomicAdd(&fp.stats[0], st_cuts); atomicAdd(&fp.stats[1], st_recuts);
             atomicAdd(&fp.stats[2], st_rerows); atomicAdd(&fp.stats[3], st_rows);
-            atomicAdd(&fp.stats[5], st_redo); atomicAdd(&fp.stats[6], st_sync);
+            atomicAdd(&fp.stats[5], st_redo); atomicAdd(&fp.stats[6], st_sync); atomicAdd(&fp.stats[7], st_iters);
         }
     }
     tc_fence_before();

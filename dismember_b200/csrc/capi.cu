@@ -181,6 +181,16 @@ DMG_API int32_t dmg_load_tree_tdm(dmg_handle_t h, int32_t max_level, int64_t n_n
     DMG_TRY(h2d(h, t.d_id_code, id_code.data(), id_code.size() * sizeof(int32_t)));
     t.loaded = true; t.complete = false; t.max_level = max_level; t.n_codes = n_codes;
     t.non_leaf_offset = offset; t.max_code = mx_code; t.n_items = n_items;
+    t.sparse_from = max_level + 1;                                     // levels above it are full: no bitmap probe on expansion
+    for (int l = max_level; l >= 0; l--) {
+        const int64_t a = ((int64_t)1 << l) - 1, b = ((int64_t)2 << l) - 1;
+        bool full = true;
+        for (int64_t w = a; w < b && full;) {
+            if ((w & 31) == 0 && w + 32 <= b) { full = bm[(size_t)(w >> 5)] == 0xffffffffu; w += 32; }
+            else { full = (bm[(size_t)(w >> 5)] >> (w & 31)) & 1u; w++; }
+        }
+        if (!full) t.sparse_from = l;
+    }
     return DMG_OK;
 }
 
@@ -204,6 +214,7 @@ DMG_API int32_t dmg_load_tree_complete(dmg_handle_t h, int32_t leaf_level, int64
     DMG_CUDA(h, cudaMalloc(&t.d_leaf_item, leaf_item.size() * sizeof(int32_t)));
     DMG_TRY(h2d(h, t.d_leaf_item, leaf_item.data(), leaf_item.size() * sizeof(int32_t)));
     t.loaded = true; t.complete = true; t.max_level = leaf_level; t.n_codes = ((int64_t)1 << (leaf_level + 1)) - 1;
+    t.sparse_from = leaf_level + 1;
     t.n_items = n_items;
     return DMG_OK;
 }
@@ -492,6 +503,7 @@ static int32_t tdm_enqueue(dmg_handle_t h, int32_t B, const int32_t *d_seq, int3
         fx.zvec = h->d_fast_tab + 4224;
         fx.redo_list = h->d_redo_list; fx.redo_count = h->d_fast_ctl + 1; fx.work_counter = h->d_fast_ctl;
         fx.stats = h->d_fast_stats;
+        fx.sparse_from = t.sparse_from;
         const size_t smem = FastGeo::smem_bytes(p.cap);
         DMG_CUDA(h, cudaFuncSetAttribute(beam_search_fast_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         const int grid = std::min(B, 2 * h->sm_count);           // two co-resident CTAs per SM
@@ -547,10 +559,18 @@ DMG_API int32_t dmg_fast_stats(dmg_handle_t h, uint64_t *out6)
     {
         uint64_t t[24];
         DMG_CUDA(h, cudaMemcpy(t, h->d_fast_stats + 8, sizeof(t), cudaMemcpyDeviceToHost));
-        static const char *names[] = {"prologue", "select", "rescore", "expand", "gather", "softmax", "epilogue", "final", "sched"};
+        static const char *names[] = {"prologue", "select", "rescore", "expand", "gather", "softmax", "epilogue", "final", "sched",
+                                      "sel_warp", "mma_wait", "ph_wait", "fin_prep", "fin_strict", "sel_load", "sel_loop"};
         double tot = 0;
-        for (int i = 0; i < 9; i++) tot += (double)t[i];
-        for (int i = 0; i < 9; i++) fprintf(stderr, "[fast timing] %-9s %6.2f %%  %.3e cyc\n", names[i], 100.0 * t[i] / (tot > 0 ? tot : 1), (double)t[i]);
+        for (int i = 0; i < TK_N; i++) tot += (double)t[i];
+        uint64_t why[6];
+        cudaMemcpy(why, h->d_fast_stats + 24, sizeof(why), cudaMemcpyDeviceToHost);
+        fprintf(stderr, "[fast timing] redo reasons: wide band %llu, tie in place %llu, unscored %llu, wide final %llu, tie at end %llu, proof failed %llu\n",
+                (unsigned long long)why[0], (unsigned long long)why[1], (unsigned long long)why[2], (unsigned long long)why[3], (unsigned long long)why[4], (unsigned long long)why[5]);
+        uint64_t iters = 0;
+        cudaMemcpy(&iters, h->d_fast_stats + 7, 8, cudaMemcpyDeviceToHost);
+        fprintf(stderr, "[fast timing] select iterations per cut %.2f\n", (double)iters / (double)(out6[0] ? out6[0] : 1));
+        for (int i = 0; i < TK_N; i++) fprintf(stderr, "[fast timing] %-9s %6.2f %%  %.3e cyc\n", names[i], 100.0 * t[i] / (tot > 0 ? tot : 1), (double)t[i]);
     }
 #endif
     DMG_CUDA(h, cudaMemset(h->d_fast_stats, 0, 32 * sizeof(uint64_t)));

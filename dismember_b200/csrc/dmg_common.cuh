@@ -28,6 +28,7 @@ struct TreeDev {
     int32_t non_leaf_offset = 0;   // DistTree.scala:35
     int32_t max_code = -1;         // DistTree.scala:36
     int64_t n_items = 0;
+    int sparse_from = 0;           // lowest level with a missing code (max_level + 1 when every level is full)
 };
 
 struct DinDev {
