@@ -678,11 +678,9 @@ __global__ void __launch_bounds__(FastGeo::THREADS, 2) beam_search_fast_kernel(c
                 uint32_t kdn, kup;
                 {
                     const uint32_t key0 = i0 < count ? order_key(f0) : 0u, key1 = i1 < count ? order_key(f1) : 0u;
-                    uint32_t lo, hi;
-                    int nv;
-                    block_minmax(key0, key1, sRed, lo, hi, nv);
+                    const uint32_t lo = (uint32_t)sMisc[50], hi = (uint32_t)sMisc[51];     // from the epilogue of this level's passes
                     DMG_TICK(TK_SELA);
-                    block_select(key0, key1, beam, lo, hi, nv, sRed, kdn, kup, [&](int n) { st_iters += n; });
+                    block_select(key0, key1, beam, lo, hi, count, sRed, kdn, kup, [&](int n) { st_iters += n; });
                     DMG_TICK(TK_SELB);
                 }
                 const float band = 2.0f * eps_level * 1.0001f + 1e-30f;
@@ -721,10 +719,10 @@ __global__ void __launch_bounds__(FastGeo::THREADS, 2) beam_search_fast_kernel(c
                     }
                     __syncthreads();
                     const float gap = __int_as_float(sSel[2]) - __int_as_float(sSel[3]);
-                    // Observed |fast - strict| stays below 1 % of eps: with a gap of eps/16 or more the fast order is
+                    // Observed |fast - strict| stays below 1 % of eps: with a gap of eps/32 or more the fast order is
                     // taken now and PROVEN at the end of the search (one strict batch over every deferred band row);
                     // a narrower gap is settled strictly right here.
-                    const bool defer = gap >= 0.0625f * eps_level && vcount + n_unc <= G::VCAP && nseg < 32 && eps_level < 1e30f;
+                    const bool defer = gap >= 0.03125f * eps_level && vcount + n_unc <= G::VCAP && nseg < 32 && eps_level < 1e30f;
                     if (defer) {
                         if (cls0 == 2) {
                             cls0 = frank0 < need ? 1 : 0;
@@ -804,6 +802,7 @@ __global__ void __launch_bounds__(FastGeo::THREADS, 2) beam_search_fast_kernel(c
             }
 
             // ---- fast scoring, 256 rows per pass ---------------------------------------------------------
+            if (tid == 0) { sMisc[50] = -1; sMisc[51] = 0; }      // min / max order key of this level's scores (epilogue); ordered by the gather barrier
             for (int r0 = 0; r0 < count; r0 += G::R) {
                 const int nrows = count - r0 < G::R ? count - r0 : G::R;
                 const int ntile = nrows > 128 ? 2 : 1;
@@ -910,7 +909,14 @@ __global__ void __launch_bounds__(FastGeo::THREADS, 2) beam_search_fast_kernel(c
 #pragma unroll
                         for (int c = 0; c < 32; c++) logit = fmaf(fmaxf(v[c], 0.0f), fp.w2[hf * 32 + c], logit);
                     }
-                    if (tid < nrows) sScore[r0 + tid] = logit + fp.b2;
+                    const float sc_out = logit + fp.b2;
+                    if (tid < nrows) sScore[r0 + tid] = sc_out;
+                    {
+                        const uint32_t ky = order_key(sc_out);
+                        const uint32_t wmn = __reduce_min_sync(0xffffffffu, tid < nrows ? ky : 0xffffffffu);
+                        const uint32_t wmx = __reduce_max_sync(0xffffffffu, tid < nrows ? ky : 0u);
+                        if (lane == 0) { atomicMin(reinterpret_cast<unsigned int *>(&sMisc[50]), wmn); atomicMax(reinterpret_cast<unsigned int *>(&sMisc[51]), wmx); }
+                    }
                 }
                 h_phase ^= 1;
                 tc_fence_before();
