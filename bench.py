@@ -43,6 +43,9 @@ def parse():
     ap.add_argument("--seq-len", type=int, default=10)
     ap.add_argument("--cpu-sample-sec", type=float, default=12.0, help="target CPU work for the cpu_baseline leg")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--verify-strict", type=int, default=0,
+                    help="re-run the first N users of the last batch with the strict fp32 kernel and compare ids / logit bits "
+                         "(size-independent parity check for catalogues whose table is too large to ship to the CPU oracle)")
     ap.add_argument("--tau", type=float, default=None, help="certification band as a fraction of the worst-case bound")
     ap.add_argument("--arith", default="fast", choices=["fast", "strict"],
                     help="scorer arithmetic: tensor-core with certified cuts (same ids/logits) or strict fp32 SIMT")
@@ -282,6 +285,16 @@ def main():
         except Exception:
             traffic = None
 
+    strict_check = None
+    if args.verify_strict > 0 and args.arith == "fast":
+        nv = min(args.verify_strict, B)
+        fi, fl, fc = eng.tdm_retrieve(host_q[W + K - 1][:nv], args.beam, args.topk)
+        eng.set_arithmetic("strict")
+        si, sl, sc = eng.tdm_retrieve(host_q[W + K - 1][:nv], args.beam, args.topk)
+        eng.set_arithmetic("fast")
+        strict_check = {"users_checked": nv, "ids_identical": bool((fi == si).all() and (fc == sc).all()),
+                        "logits_bit_identical": bool((fl.view(np.uint32) == sl.view(np.uint32)).all())}
+
     # ---- cpu_baseline (rank 0, N=1 only): oracle on a bounded sample + parity check --------
     cpu = None
     parity = None
@@ -312,7 +325,7 @@ def main():
                                    f"topk={args.topk}, T={T}", "levels": L, "rows_scored_per_user": rows_u,
                        "algorithmic_bytes_per_user": bytes_u, "node_table_gb": rows * E * 4 / 1e9,
                        "parallelism": f"replicas x{world}, users sharded, no collective",
-                       "l2": "inputs larger than L2: 0.54 GB node table, fresh queries every step, no flush",
+                       "l2": f"inputs larger than L2: {rows * E * 4 / 1e9:.2f} GB node table, fresh queries every step, no flush",
                        "arithmetic": ("tcgen05 bf16x3 tensor-core scorer + certified cuts, strict fp32 re-score of "
                                       "near-cut candidates and of the topk (ids and logits bit-identical to the CPU oracle)")
                        if args.arith == "fast" else "strict fp32 (sequential-k fma chains, bit-identical to the CPU oracle)",
@@ -326,6 +339,7 @@ def main():
                          "kernel_share_of_step": kern_ms / dev_ms if world == 1 else None},
             "cpu_baseline": cpu,
             "parity": parity,
+            "parity_fast_vs_strict_kernel": strict_check,
             "clocks": clocks,
         }
         print(json.dumps(line), flush=True)

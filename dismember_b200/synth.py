@@ -51,8 +51,11 @@ def tdm_tree(n_items: int, seed: int = 1) -> TreeFile:
     ids, leaf_codes = ids[order], leaf_codes[order]
     anc = []
     cur = leaf_codes
-    for _ in range(max_level):
-        cur = np.unique((cur - 1) >> 1)
+    for _ in range(max_level):                    # leaf_codes is sorted, so every parent list is too: unique by diff, no sort
+        par = (cur - 1) >> 1
+        keep = np.ones(len(par), bool)
+        keep[1:] = par[1:] != par[:-1]
+        cur = par[keep]
         anc.append(cur)
     anc = np.concatenate(anc) if anc else np.zeros(0, np.int64)
     offset = int(ids.max()) + 1
