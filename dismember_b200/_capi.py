@@ -84,6 +84,12 @@ def load_library(build_if_missing: bool = True):
         "dmg_din_gradients": [vp, i64, vp, vp, vp, i64, vp, vp, vp, i64],
         "dmg_tdm_sample_expand": [vp, i32, vp, vp, vp, i32, u64, vp, vp, vp, C.POINTER(i32)],
         "dmg_jtm_item_weights": [vp, i32, vp, vp, vp, i32, i32, i32, i32, i32, vp],
+        "dmg_shard_unique_id": [vp, i32],
+        "dmg_shard_init": [vp, i32, i32, vp],
+        "dmg_shard_init_din_weights": [vp, i64, i32, i32, u64],
+        "dmg_shard_load_din_weights": [vp, i64, i32, i32, vp],
+        "dmg_shard_info": [vp, C.POINTER(i64), C.POINTER(i64), C.POINTER(i64)],
+        "dmg_shard_tdm_retrieve": [vp, i32, vp, i32, i32, i32, vp, vp, vp],
     }
     for name, args in sig.items():
         fn = getattr(L, name)
@@ -214,6 +220,49 @@ class Engine:
         out = np.empty(n, self.din_dtype)
         self._check(self.L.dmg_download_din_weights(self.h, _p(out), n))
         return out
+
+    # -- node table sharded over the GPUs of one box (csrc/shard.cu) ---------------
+    def shard_unique_id(self) -> bytes:
+        buf = np.zeros(128, np.uint8)
+        rc = self.L.dmg_shard_unique_id(_p(buf), 128)
+        if rc != DMG_OK:
+            raise DmgError(rc, "dmg_shard_unique_id failed (libnccl.so.2 not loadable?)")
+        return buf.tobytes()
+
+    def shard_init(self, world: int, rank: int, unique_id: Optional[bytes] = None):
+        uid = None if unique_id is None else np.frombuffer(unique_id, np.uint8).copy()
+        self._check(self.L.dmg_shard_init(self.h, world, rank, _p(uid)))
+        self.shard_world, self.shard_rank = world, rank
+
+    def shard_init_din_weights(self, rows_global: int, E: int, T: int, seed: int):
+        self._check(self.L.dmg_shard_init_din_weights(self.h, rows_global, E, T, seed))
+        self.din_dtype, self.E, self.T = np.dtype(np.float32), E, T
+        self.rows = self.shard_info()[0]
+
+    def shard_load_din_weights(self, params: np.ndarray, rows_global: int, E: int, T: int):
+        params = np.ascontiguousarray(params, np.float32).ravel()
+        n = rows_global * E + 3 * E * E + 2 * E + 1
+        if params.size != n:
+            raise DmgArgumentError(DMG_ERR_INVALID_ARG, f"compact DIN vector must hold {n} values, got {params.size}")
+        self._check(self.L.dmg_shard_load_din_weights(self.h, rows_global, E, T, _p(params)))
+        self.din_dtype, self.E, self.T = np.dtype(np.float32), E, T
+        self.rows = self.shard_info()[0]
+
+    def shard_info(self):
+        """-> (rows of the local table, rows of the whole table, candidates scored for other ranks so far)"""
+        a, b, c = C.c_int64(), C.c_int64(), C.c_int64()
+        self._check(self.L.dmg_shard_info(self.h, C.byref(a), C.byref(b), C.byref(c)))
+        return a.value, b.value, c.value
+
+    def shard_tdm_retrieve(self, item_seq, beam, topk, use_mask=True):
+        """Collective: every rank calls it with its own B users (same B everywhere)."""
+        seq = _i32(item_seq).reshape(-1, self.T)
+        B = len(seq)
+        items = np.empty((B, topk), np.int32)
+        logits = np.empty((B, topk), np.float32)
+        counts = np.empty(B, np.int32)
+        self._check(self.L.dmg_shard_tdm_retrieve(self.h, B, _p(seq), beam, topk, int(use_mask), _p(items), _p(logits), _p(counts)))
+        return items, logits, counts
 
     # -- retrieval --------------------------------------------------------------
     def tdm_retrieve(self, item_seq, beam, topk, use_mask=True, consumed_off=None, consumed=None, widen_beam=False):

@@ -9,11 +9,11 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libdismember_gpu.so")
-SOURCES = ["capi.cu", "dr.cu", "train.cu"]
+SOURCES = ["capi.cu", "dr.cu", "train.cu", "shard.cu"]
 NVCC_FLAGS = [
     "-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
     "-fmad=false",                      # only explicit fma intrinsics fuse (dmg_math.cuh)
-    "-Xcompiler", "-fPIC,-fvisibility=hidden", "-shared",
+    "-Xcompiler", "-fPIC,-fvisibility=hidden", "-shared", "-ldl",
 ]
 
 

@@ -75,12 +75,14 @@ static void free_din(DinDev &d)
     d = DinDev();
 }
 void dmg_free_dr(DrDev &d);     // dr.cu
+void dmg_shard_free(dmg_handle_t h);   // shard.cu
 
 DMG_API int32_t dmg_destroy(dmg_handle_t h)
 {
     if (!h) return DMG_ERR_INVALID_ARG;
     cudaSetDevice(h->device);
     cudaStreamSynchronize(h->stream);
+    dmg_shard_free(h);
     free_tree(h->tree);
     free_din(h->din);
     dmg_free_dr(h->dr);
@@ -581,6 +583,7 @@ static int32_t tdm_precheck(dmg_handle_t h, int32_t B, int32_t beam, int32_t top
 {
     if (!h) return DMG_ERR_INVALID_ARG;
     if (!h->tree.loaded || !h->din.loaded) return fail(h, DMG_ERR_STATE, "tree and DIN weights must be loaded first");
+    if (h->din.sharded) return fail(h, DMG_ERR_STATE, "the node table is sharded (dmg_shard_init): use the dmg_shard_* entry points");
     if (h->tree.complete || !h->tree.d_id_code) return fail(h, DMG_ERR_STATE, "dmg_tdm_retrieve needs a tree loaded with dmg_load_tree_tdm");
     if (h->din.dtype != DMG_F32) return fail(h, DMG_ERR_STATE, "TDM/JTM scorer is Module[Float]: load DMG_F32 weights");
     if (B <= 0 || beam <= 0 || topk <= 0) return fail(h, DMG_ERR_INVALID_ARG, "B, beam and topk must be positive");  // require(candidateNum > 0)
@@ -657,6 +660,7 @@ static int32_t otm_run(dmg_handle_t h, int32_t B, const int32_t *leaf_seq, int32
 {
     if (!h) return DMG_ERR_INVALID_ARG;
     if (!h->tree.loaded || !h->din.loaded) return fail(h, DMG_ERR_STATE, "tree and DIN weights must be loaded first");
+    if (h->din.sharded) return fail(h, DMG_ERR_STATE, "the node table is sharded (dmg_shard_init): use the dmg_shard_* entry points");
     if (!h->tree.complete) return fail(h, DMG_ERR_STATE, "OTM needs a complete tree (dmg_load_tree_complete)");
     if (h->din.dtype != DMG_F64) return fail(h, DMG_ERR_STATE, "OTM scorer is DeepModel[Double]: load DMG_F64 weights");
     if (B <= 0 || beam <= 0 || (mode == MODE_OTM_TOPK && topk <= 0) || !leaf_seq || !out_ids || !out_scores || !out_counts)
@@ -763,6 +767,7 @@ DMG_API int32_t dmg_score_pairs(dmg_handle_t h, int64_t n, const int32_t *node, 
 {
     if (!h) return DMG_ERR_INVALID_ARG;
     if (!h->din.loaded) return fail(h, DMG_ERR_STATE, "DIN weights must be loaded first");
+    if (h->din.sharded) return fail(h, DMG_ERR_STATE, "the node table is sharded (dmg_shard_init): use the dmg_shard_* entry points");
     if (n < 0 || n_mask < 0 || (n > 0 && (!node || !seq || !out)) || (n_mask > 0 && !mask_flat))
         return fail(h, DMG_ERR_INVALID_ARG, "bad arguments");
     if (n == 0) return DMG_OK;

@@ -41,6 +41,7 @@ struct DinDev {
     void *d_wattT = nullptr;       // k-major copies  WattT[k][o], W1T[k][o]
     void *d_w1T = nullptr;
     int64_t n_params = 0;
+    bool sharded = false;          // rows are this rank's slice of a table split by dmg_shard_init (shard.cu): shard entry points only
     // training state (allocated lazily)
     void *d_grad = nullptr, *d_m = nullptr, *d_v = nullptr;
     template <typename real> real *emb() const { return (real *)d_params; }
@@ -62,6 +63,8 @@ struct DrDev {
     int32_t *d_path_items = nullptr;
     std::vector<int64_t> h_path_off;                // kept for output sizing
 };
+
+struct ShardState;                  // shard.cu
 
 struct Scratch {                    // grow-only device / pinned buffers
     void *d = nullptr; size_t d_bytes = 0;
@@ -94,6 +97,7 @@ struct dmg_handle_s {
     int32_t *d_redo_list = nullptr;  // users the fast kernel hands to the strict kernel
     int64_t redo_cap = 0;
     unsigned long long *d_fast_stats = nullptr;
+    dmg::ShardState *shard = nullptr;   // node-table sharding over NCCL (shard.cu)
     bool profiling = false;
     std::vector<std::pair<cudaEvent_t, cudaEvent_t>> prof_events;
 };

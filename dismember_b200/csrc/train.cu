@@ -483,6 +483,7 @@ int32_t train_precheck(dmg_handle_t h, int64_t rows, const void *node, const voi
 {
     if (!h) return DMG_ERR_INVALID_ARG;
     if (!h->din.loaded) return fail(h, DMG_ERR_STATE, "DIN weights must be loaded first");
+    if (h->din.sharded) return fail(h, DMG_ERR_STATE, "the node table is sharded (dmg_shard_init): use the dmg_shard_* entry points");
     if (rows <= 0 || !node || !seq || !labels || !out) return fail(h, DMG_ERR_INVALID_ARG, "bad arguments");
     DMG_CUDA(h, cudaSetDevice(h->device));
     return DMG_OK;
@@ -608,6 +609,7 @@ DMG_API int32_t dmg_jtm_item_weights(dmg_handle_t h, int32_t n_items, const int6
     DinDev &d = h->din;
     if (!t.loaded || t.complete || !t.d_id_code) return fail(h, DMG_ERR_STATE, "needs a tree loaded with dmg_load_tree_tdm");
     if (!d.loaded || d.dtype != DMG_F32) return fail(h, DMG_ERR_STATE, "JTM scorer is Module[Float]: load DMG_F32 weights");
+    if (h->din.sharded) return fail(h, DMG_ERR_STATE, "the node table is sharded (dmg_shard_init): use the dmg_shard_* entry points");
     const int gap = level - old_level;
     if (n_items <= 0 || !sample_off || !parent_code || !out_weights || gap < 1 || gap > 8 || old_level < 0 || level > t.max_level)
         return fail(h, DMG_ERR_INVALID_ARG, "bad arguments (1 <= level - old_level <= 8, level <= max_level)");

@@ -226,6 +226,36 @@ DMG_API int32_t dmg_jtm_item_weights(dmg_handle_t h, int32_t n_items, const int6
                                      int32_t old_level, int32_t level, int32_t hierarchical,
                                      int32_t min_level, int32_t use_mask, float *out_weights);
 
+/* ---- node table sharded across the GPUs of one box ------------------------------------ */
+/* The reference has no multi-device path: model replicas are per-thread clones
+ * (tdm/.../optim/LocalOptimizer.scala:35-40) and users are split over threads
+ * (tdm/.../evaluation/Evaluator.scala:28-37).  These entry points are the engine's layout for
+ * a node table that does not fit one GPU (BASELINE.json configs 4-5): world = 2^g ranks, one
+ * handle per rank / device; tree levels above g replicated, every deeper level split into
+ * world contiguous code ranges (rank r owns the sub-trees under the r-th node of level g).
+ * One process per GPU: rank 0 calls dmg_shard_unique_id and hands the 128 bytes to every rank
+ * (any transport), every rank calls dmg_shard_init, loads the SAME tree with dmg_load_tree_tdm
+ * and then its slice of the weights.  NCCL (libnccl.so.2) is resolved at dmg_shard_init. */
+DMG_API int32_t dmg_shard_unique_id(void *out128, int32_t nbytes);
+DMG_API int32_t dmg_shard_init(dmg_handle_t h, int32_t world, int32_t rank, const void *unique_id128);
+/* Same values as dmg_init_din_weights on the unsharded table (counter-based generator). */
+DMG_API int32_t dmg_shard_init_din_weights(dmg_handle_t h, int64_t rows_global, int32_t E, int32_t T,
+                                           uint64_t seed);
+/* params = the FULL compact vector of Module.parameters() (Graph.scala:37); only the rows this
+ * rank owns are uploaded. fp32 (TDM/JTM scorer). */
+DMG_API int32_t dmg_shard_load_din_weights(dmg_handle_t h, int64_t rows_global, int32_t E, int32_t T,
+                                           const float *params);
+DMG_API int32_t dmg_shard_info(dmg_handle_t h, int64_t *local_rows, int64_t *global_rows,
+                                int64_t *exchanged_rows);
+/* TDM.recommend (tdm/.../model/TDM.scala:17-22, Recommender.scala:18-107) for this rank's B
+ * users; collective: every rank calls it with the same B, beam, topk.  Per level the candidate
+ * (slot, code) pairs go to the owners of the codes over NCCL send/recv, scores come back
+ * (12 bytes per remote candidate); strict fp32 arithmetic, results bit-identical to
+ * dmg_tdm_retrieve on the unsharded table. */
+DMG_API int32_t dmg_shard_tdm_retrieve(dmg_handle_t h, int32_t B, const int32_t *item_seq,
+                                       int32_t beam, int32_t topk, int32_t use_mask,
+                                       int32_t *out_items, float *out_logits, int32_t *out_counts);
+
 #ifdef __cplusplus
 }
 #endif

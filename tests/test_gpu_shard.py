@@ -1,0 +1,84 @@
+"""Node-table sharding (csrc/shard.cu): the level-synchronous request/score exchange must return the bits of the
+unsharded search.  world = 1 runs everywhere (all owner regions are local, no NCCL); world = 2 needs two GPUs and
+is skipped on the one-GPU box (tools/shard_check.py is the same check under torchrun, see profiles/)."""
+import os
+import sys
+
+import numpy as np
+import pytest
+
+from conftest import new_engine
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_world1_fixture_matches_oracle(jtm_fix, queries, golden_out):
+    f = jtm_fix
+    e = new_engine()
+    e.shard_init(1, 0)
+    e.load_tree_tdm(int(f["max_level"]), f["codes"], f["node_ids"], f["is_leaf"], f["leaf_ids"], f["leaf_codes"])
+    e.shard_load_din_weights(f["params"], 8191, 16, 10)
+    items, logits, counts = e.shard_tdm_retrieve(queries["seqs"][:64], 20, 10)
+    assert (items == golden_out["tdm_items_b20"][:64]).all()
+    assert (logits.view(np.uint32) == golden_out["tdm_logits_b20"][:64].view(np.uint32)).all()
+    assert e.shard_info()[:2] == (8191, 8191)
+    e.close()
+
+
+def test_world1_synthetic_matches_strict_engine_and_oracle(orc):
+    from dismember_b200 import synth
+    n_items, E, T, beam, topk, B = 5000, 64, 10, 200, 10, 40
+    tf = synth.tdm_tree(n_items, seed=1)
+    rows = (1 << (tf.max_level + 1)) - 1
+    seqs = synth.queries(B, T, n_items, seed=4)
+    ref = new_engine()
+    ref.load_tree_tdm(tf.max_level, tf.codes, tf.node_ids, tf.is_leaf, tf.leaf_ids, tf.leaf_codes)
+    ref.init_din_weights(np.float32, rows, E, T, seed=2)
+    ref.set_arithmetic("strict")
+    ri, rl, rc = ref.tdm_retrieve(seqs, beam, topk)
+    params = ref.download_din_weights()
+    ref.close()
+    e = new_engine()
+    e.shard_init(1, 0)
+    e.load_tree_tdm(tf.max_level, tf.codes, tf.node_ids, tf.is_leaf, tf.leaf_ids, tf.leaf_codes)
+    e.shard_init_din_weights(rows, E, T, seed=2)              # same counter-based values as init_din_weights
+    si, sl, sc = e.shard_tdm_retrieve(seqs, beam, topk)
+    e.close()
+    assert (si == ri).all() and (sc == rc).all()
+    assert (sl.view(np.uint32) == rl.view(np.uint32)).all()
+    tree = orc.Tree.from_treefile(tf)
+    model = orc.TdmModel(params, rows, E, T)
+    oi, ol, oc = model.retrieve_batch(tree, seqs, beam, topk, n_threads=os.cpu_count() or 1)
+    assert (si == oi).all() and (sl.view(np.uint32) == ol.view(np.uint32)).all() and (sc == oc).all()
+
+
+def test_unsharded_entry_points_refuse_a_sharded_table(jtm_fix, queries):
+    from dismember_b200._capi import DmgError
+    f = jtm_fix
+    e = new_engine()
+    e.shard_init(1, 0)
+    e.load_tree_tdm(int(f["max_level"]), f["codes"], f["node_ids"], f["is_leaf"], f["leaf_ids"], f["leaf_codes"])
+    with pytest.raises(DmgError):
+        e.shard_load_din_weights(f["params"], 8191 * 2 + 1, 16, 10)      # table must match the tree
+    e.close()
+
+
+def _two_gpu_worker(rank, world, port, out_dir):
+    sys.path.insert(0, ROOT)
+    sys.argv = ["shard_check.py", "--items", "5000", "--batch", "24", "--out", os.path.join(out_dir, f"r{rank}.json")]
+    os.environ.update(RANK=str(rank), WORLD_SIZE=str(world), LOCAL_RANK=str(rank), MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    import runpy
+    runpy.run_path(os.path.join(ROOT, "tools", "shard_check.py"), run_name="__main__")
+
+
+def test_world2_matches_oracle(tmp_path):
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs (run tools/shard_check.py under torchrun with gpurun --gpus 2)")
+    import json
+    import torch.multiprocessing as mp
+    mp.spawn(_two_gpu_worker, args=(2, 32500 + os.getpid() % 2000, str(tmp_path)), nprocs=2, join=True)
+    for r in range(2):
+        d = json.load(open(tmp_path / f"r{r}.json"))
+        assert d["ids_identical"] and d["logits_bit_identical"] and d["rows_scored_for_other_ranks"] > 0

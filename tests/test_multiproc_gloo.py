@@ -53,3 +53,102 @@ def test_two_rank_gloo_matches_single_process(tmp_path, golden_out):
     assert (got["items"] == golden_out["tdm_items_b20"][:101]).all()
     assert (got["logits"].view(np.uint32) == golden_out["tdm_logits_b20"][:101].view(np.uint32)).all()
     assert got["tmax"][0] == 2.0
+
+
+def _shard_worker(rank, world, port, out_dir):
+    """Table-sharded retrieval protocol (csrc/shard.cu) under gloo: requests travel to the owner of each code,
+    scores travel back; the scorer is the CPU oracle and REFUSES codes the rank does not own."""
+    sys.path.insert(0, ROOT)
+    import torch.distributed as dist
+    from dismember_b200 import shard
+    from oracle import oracle as orc
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    f = dict(np.load(os.path.join(ROOT, "tests", "golden", "jtm_fixture.npz")))
+    q = dict(np.load(os.path.join(ROOT, "tests", "golden", "queries.npz")))
+    L, T, beam, topk = int(f["max_level"]), 10, 20, 10
+    tree = orc.Tree(L, f["codes"], f["node_ids"], f["is_leaf"], f["leaf_ids"], f["leaf_codes"])
+    model = orc.TdmModel(f["params"], 8191, 16, T)
+    have = np.zeros(1 << (L + 1), bool)
+    have[f["codes"]] = True
+    exists = lambda c: have[c]
+    leaf_item = np.full(1 << L, -1, np.int64)
+    leaf_item[f["leaf_codes"] - ((1 << L) - 1)] = f["leaf_ids"]
+    B = 20
+    seqs = q["seqs"][rank * B:(rank + 1) * B]                 # users are sharded too, same B on every rank
+    hist = np.stack([tree.id_to_code(s)[0] for s in seqs]).astype(np.int32)         # [B, T] codes, -1 = masked
+    gathered = [None] * world
+    dist.all_gather_object(gathered, hist)                    # mirror of the history-tile all-reduce
+    hist_all = np.concatenate(gathered)
+    cap = 2 * beam
+    s_level = int(np.floor(np.log2(beam)))
+    start = (1 << s_level) - 1
+    first = np.arange(start, start + (1 << s_level))
+    cand = np.zeros((B, cap), np.int64)
+    counts = np.zeros(B, np.int64)
+    score = np.zeros((B, cap), np.float32)
+    beams = [first[exists(first)] for _ in range(B)]
+    scored_remote = 0
+
+    def score_owned(requester, slots, codes):
+        nonlocal scored_remote
+        lvl = shard.code_level(codes)
+        assert ((shard.owner_of(codes, world, rank) == rank) | (lvl < shard.shard_bits(world))).all(), "asked for a row this rank does not own"
+        assert (shard.local_row(codes, world) < shard.local_rows(world, L)).all()
+        gu = requester * B + slots // cap
+        sq = hist_all[gu]
+        mask = np.nonzero((sq < 0).ravel())[0].astype(np.int32)
+        if requester != rank:
+            scored_remote += len(codes)
+        return model.forward(codes.astype(np.int32), sq.astype(np.int32), mask)
+
+    for level in range(s_level, L):
+        for u in range(B):
+            nxt = shard.level_select_expand(beams[u], score[u, :len(beams[u])], beam, exists)
+            beams[u] = nxt
+            counts[u] = len(nxt)
+            cand[u, :len(nxt)] = nxt
+        score = shard.exchange_scores(cand, counts, score_owned)
+    from dismember_b200.jtm import stable_desc_order
+    items = np.full((B, topk), -1, np.int32)
+    logits = np.zeros((B, topk), np.float32)
+    for u in range(B):
+        it = leaf_item[beams[u] - ((1 << L) - 1)]
+        sc = score[u, :len(beams[u])][it >= 0]
+        it = it[it >= 0]
+        order = stable_desc_order(sc)[:topk]
+        items[u, :len(order)] = it[order]
+        logits[u, :len(order)] = sc[order]
+    out = [None] * world
+    dist.all_gather_object(out, (items, logits, scored_remote))
+    if rank == 0:
+        np.savez(os.path.join(out_dir, "sharded.npz"), items=np.concatenate([o[0] for o in out]),
+                 logits=np.concatenate([o[1] for o in out]), remote=np.array([o[2] for o in out]))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_shard_layout_roundtrip():
+    from dismember_b200 import shard
+    for world in (1, 2, 4, 8):
+        L = 9
+        seen = np.zeros((1 << (L + 1)) - 1, np.int64)
+        for rank in range(world):
+            n = shard.local_rows(world, L)
+            g = shard.global_row(np.arange(n), world, rank)
+            assert (shard.local_row(g, world) == np.arange(n)).all()
+            assert (shard.owner_of(g, world, rank) == rank).all()
+            seen[g] += 1
+        lvl = shard.code_level(np.arange(len(seen)))
+        assert (seen[lvl >= shard.shard_bits(world)] == 1).all() and (seen[lvl < shard.shard_bits(world)] == world).all()
+
+
+def test_two_rank_table_shard_protocol(tmp_path, golden_out):
+    import torch.multiprocessing as mp
+    port = 31500 + (os.getpid() % 2000)
+    mp.spawn(_shard_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
+    got = np.load(tmp_path / "sharded.npz")
+    assert (got["items"] == golden_out["tdm_items_b20"][:40]).all()
+    assert (got["logits"].view(np.uint32) == golden_out["tdm_logits_b20"][:40].view(np.uint32)).all()
+    assert (got["remote"] > 0).all()                          # both ranks really scored rows for the other one

@@ -1,0 +1,83 @@
+#!/usr/bin/env python3
+"""Table-sharded TDM retrieval across the GPUs of one box, checked against the CPU oracle.
+
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29533 \
+        tools/shard_check.py --items 1000000 --batch 256
+
+Every rank holds 1/world of the node table (csrc/shard.cu), brings its own `batch` users, and prints one JSON line:
+parity of its results with the oracle run on the full table, rows it scored for other ranks, users/s."""
+import argparse
+import json
+import os
+import sys
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--items", type=int, default=100_000)
+    ap.add_argument("--batch", type=int, default=256)
+    ap.add_argument("--beam", type=int, default=200)
+    ap.add_argument("--topk", type=int, default=10)
+    ap.add_argument("--dim", type=int, default=64)
+    ap.add_argument("--steps", type=int, default=4)
+    ap.add_argument("--oracle-users", type=int, default=64)
+    ap.add_argument("--out", default=None)
+    a = ap.parse_args()
+    import torch
+    import torch.distributed as dist
+    from dismember_b200 import shard, synth
+    from oracle import oracle as orc
+    rank, world, local = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1)), int(os.environ.get("LOCAL_RANK", 0))
+    os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+    os.environ.setdefault("MASTER_PORT", "29533")
+    dist.init_process_group("gloo", rank=rank, world_size=world)       # control plane only: the data path is NCCL inside the library
+    torch.cuda.set_device(local)
+    T = 10
+    tf = synth.tdm_tree(a.items, seed=1)
+    rows = (1 << (tf.max_level + 1)) - 1
+    eng = shard.make_sharded_engine(local)
+    eng.load_tree_tdm(tf.max_level, tf.codes, tf.node_ids, tf.is_leaf, tf.leaf_ids, tf.leaf_codes)
+    eng.shard_init_din_weights(rows, a.dim, T, seed=2)
+    seqs = synth.queries(a.batch, T, a.items, seed=100 + rank)
+    items, logits, counts = eng.shard_tdm_retrieve(seqs, a.beam, a.topk)           # warm-up + the checked result
+    dist.barrier()
+    t0 = time.perf_counter()
+    for _ in range(a.steps):
+        eng.shard_tdm_retrieve(seqs, a.beam, a.topk)
+    dist.barrier()
+    dt = time.perf_counter() - t0
+    local_rows, global_rows, exchanged = eng.shard_info()
+    # oracle on the full table (same counter-based values: an unsharded engine generates them)
+    n = min(a.oracle_users, a.batch)
+    from dismember_b200 import Engine
+    full = Engine(local)
+    full.load_tree_tdm(tf.max_level, tf.codes, tf.node_ids, tf.is_leaf, tf.leaf_ids, tf.leaf_codes)
+    full.init_din_weights(np.float32, rows, a.dim, T, seed=2)
+    params = full.download_din_weights()
+    full.close()
+    orc.build()
+    tree = orc.Tree.from_treefile(tf)
+    model = orc.TdmModel(params, rows, a.dim, T)
+    oi, ol, oc = model.retrieve_batch(tree, seqs[:n], a.beam, a.topk, n_threads=max(1, (os.cpu_count() or 2) // world))
+    line = {"rank": rank, "world": world, "items": a.items, "levels": tf.max_level, "batch_per_rank": a.batch, "beam": a.beam,
+            "table_rows_global": global_rows, "table_rows_local": local_rows,
+            "rows_scored_for_other_ranks": exchanged, "users_checked": n,
+            "ids_identical": bool((items[:n] == oi).all() and (counts[:n] == oc).all()),
+            "logits_bit_identical": bool((logits[:n].view(np.uint32) == ol.view(np.uint32)).all()),
+            "users_per_s_whole_job": world * a.batch * a.steps / dt}
+    print(json.dumps(line), flush=True)
+    if a.out:
+        json.dump(line, open(a.out, "w"))
+    eng.close()
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()
