@@ -1,0 +1,192 @@
+#!/usr/bin/env python3
+"""Secondary bench lines: every SURVEY 8(a) kernel other than the headline TDM search, each with its
+algorithmic figure against the measured B200 peak and the CPU oracle timed beside it.
+
+    python tools/bench_paths.py [--quick] > profiles/rN_paths.jsonl
+
+One JSON line per path.  Timed through the host-buffer C ABI (the call a Scala host would make), wall
+clock around synchronous calls, after warm-up.  bench.py stays the headline; these lines explain the
+other rows of DESIGN.md section 4."""
+import argparse
+import json
+import os
+import sys
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+
+def peaks():
+    try:
+        d = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        return float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def timeit(fn, warm=2, reps=5):
+    for _ in range(warm):
+        fn()
+    t0 = time.perf_counter()
+    for _ in range(reps):
+        fn()
+    return (time.perf_counter() - t0) / reps
+
+
+def emit(**kw):
+    print(json.dumps(kw), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--quick", action="store_true")
+    ap.add_argument("--train-items", type=int, default=10_000_000)
+    a = ap.parse_args()
+    from dismember_b200 import Engine, synth
+    from oracle import oracle as orc
+    orc.build()
+    hbm, hbm_src = peaks()
+    threads = os.cpu_count() or 1
+    E, T = 64, 10
+
+    # ---- 1. training step: fused DIN fwd/bwd + BCE + scatter-add, dense Adam -------------------
+    for n_items in ([100_000] if a.quick else [1_000_000, a.train_items]):
+        tf = synth.tdm_tree(n_items, seed=1)
+        L = tf.max_level
+        rows_tab = (1 << (L + 1)) - 1
+        eng = Engine(0)
+        eng.load_tree_tdm(L, tf.codes, tf.node_ids, tf.is_leaf, tf.leaf_ids, tf.leaf_codes)
+        eng.init_din_weights(np.float32, rows_tab, E, T, seed=2)
+        n_tg = 8                                               # ~8 k rows per step, the reference's batch (configs/tdm.conf)
+        rng = np.random.Generator(np.random.PCG64(7))
+        targets = rng.integers(1, n_items + 1, n_tg).astype(np.int32)
+        seqs = synth.queries(n_tg, T, n_items, seed=9)
+        layer_neg = np.array([0] + [min(2 ** l - 1, 63) for l in range(1, L + 1)], np.int32)     # 64 rows per level from level 6 on
+        node, sq, lab = eng.tdm_sample_expand(targets, seqs, layer_neg, 1, seed=11)
+        rows = len(node)
+        mask = np.nonzero((sq.ravel() < 0))[0].astype(np.int32)
+        step = [0]
+
+        def one():
+            step[0] += 1
+            eng.train_step(node, sq, mask, lab, 1e-3, step[0])
+        dt = timeit(one, warm=2, reps=5)
+        n_par = rows_tab * E + 3 * E * E + 2 * E + 1
+        dense = 7 * n_par * 4 + n_par * 4                     # Adam: read w,g,s,r + write w,s,r; grad zeroing
+        sparse = 2 * rows * (1 + T) * E * 4
+        emit(path="train_step (TDM sampler rows, DIN fwd/bwd, BCE, scatter-add, dense Adam)", items=n_items, levels=L,
+             rows_per_step=rows, ms_per_step=dt * 1e3, rows_per_s=rows / dt,
+             roofline={"bound": "hbm", "algorithmic_bytes_per_step": dense + sparse, "achieved": (dense + sparse) / dt / 1e9,
+                       "peak": hbm, "unit": "GB/s", "frac": (dense + sparse) / dt / 1e9 / hbm, "peak_source": hbm_src},
+             note="dense-Adam semantics of scalann Adam.scala:54-65: every parameter is touched every step")
+        if n_items <= 1_000_000:
+            params = eng.download_din_weights()
+            t0 = time.perf_counter()
+            g, loss = orc.din_gradients(params, rows_tab, E, T, node, sq, mask, lab)
+            s = np.zeros_like(params); r = np.zeros_like(params)
+            orc.adam_step(params, g, s, r, 1e-3, 1)
+            cdt = time.perf_counter() - t0
+            emit(path="train_step cpu_baseline", items=n_items, kind="port", cores=1, ms_per_step=cdt * 1e3, rows_per_s=rows / cdt,
+                 sample="one step of the same batch, oracle/ C restatement (single thread)")
+        eng.close()
+
+    # ---- 2. model.forward on independent rows (dmg_score_pairs) and JTM item weights (a22) ------------------------
+    n_items = 100_000 if a.quick else 1_000_000
+    tf = synth.tdm_tree(n_items, seed=1)
+    L = tf.max_level
+    rows_tab = (1 << (L + 1)) - 1
+    eng = Engine(0)
+    eng.load_tree_tdm(L, tf.codes, tf.node_ids, tf.is_leaf, tf.leaf_ids, tf.leaf_codes)
+    eng.init_din_weights(np.float32, rows_tab, E, T, seed=2)
+    rng = np.random.Generator(np.random.PCG64(5))
+    n = 200_000
+    node = rng.integers(0, rows_tab, n).astype(np.int32)
+    sq = rng.integers(0, rows_tab, (n, T)).astype(np.int32)
+    dt = timeit(lambda: eng.score_pairs(node, sq), warm=1, reps=3)
+    by = n * (1 + T) * E * 4 + n * 4
+    emit(path="score_pairs (model.forward on independent rows)", rows=n, ms=dt * 1e3, rows_per_s=n / dt,
+         roofline={"bound": "hbm", "algorithmic_bytes": by, "achieved": by / dt / 1e9, "peak": hbm, "unit": "GB/s", "frac": by / dt / 1e9 / hbm},
+         note="host buffers: H2D of the (1+T) indices per row and D2H of the logits are inside")
+    params = eng.download_din_weights()
+    model = orc.TdmModel(params, rows_tab, E, T)
+    t0 = time.perf_counter()
+    model.forward(node[:20000], sq[:20000])
+    cdt = time.perf_counter() - t0
+    emit(path="score_pairs cpu_baseline", kind="port", cores=1, rows_per_s=20000 / cdt, sample="20000 rows, oracle forward (single thread)")
+    # JTM: 2000 items x 16 samples, gap 4 (16 candidate children, 4 path nodes each)
+    n_it, n_s, gap, old = 2000, 16, 4, 8
+    off = np.arange(n_it + 1, dtype=np.int64) * n_s
+    sseq = synth.queries(n_it * n_s, T, n_items, seed=21)
+    par = rng.integers((1 << old) - 1, (2 << old) - 1, n_it).astype(np.int32)
+    dt = timeit(lambda: eng.jtm_item_weights(off, sseq, par, old, old + gap), warm=1, reps=3)
+    scored = n_it * n_s * ((2 << gap) - 2)
+    emit(path="jtm_item_weights (TreeLearning.aggregateWeights for a level step)", items=n_it, samples_per_item=n_s, gap=gap,
+         scorer_rows=scored, ms=dt * 1e3, scorer_rows_per_s=scored / dt)
+    eng.close()
+
+    # ---- 3. OTM retrieval, fp64 (a13-a14) ------------------------------------------------------------------------
+    n_items = 100_000 if a.quick else 1_000_000
+    items, leaf_ids, leaf_level = synth.otm_mapping(n_items, seed=42)
+    rows_tab = (1 << (leaf_level + 1)) - 1
+    eng = Engine(0)
+    eng.load_tree_complete(leaf_level, items, leaf_ids)
+    eng.init_din_weights(np.float64, rows_tab, E, T, seed=2)
+    B = 256
+    rng = np.random.Generator(np.random.PCG64(3))
+    lseq = leaf_ids[rng.integers(0, n_items, (B, T))].astype(np.int32)
+    lseq[:, :3] = -1
+    dt = timeit(lambda: eng.otm_retrieve(lseq, 200, 10), warm=1, reps=3)
+    rows_u = 256 + 400 * (leaf_level - 8)
+    emit(path="otm_retrieve (fp64 DIN scorer, complete tree)", items=n_items, levels=leaf_level, batch=B, ms=dt * 1e3, users_per_s=B / dt,
+         roofline={"bound": "fp64 FMA pipe", "algorithmic_flop_per_user": rows_u * 27324, "achieved_tflops": rows_u * 27324 * B / dt / 1e12},
+         note="strict fp64 chains (the reference's OTM model is Module[Double])")
+    params = eng.download_din_weights()
+    leaf_item = np.full(1 << leaf_level, -1, np.int32)
+    leaf_item[leaf_ids - ((1 << leaf_level) - 1)] = items
+    om = orc.OtmModel(params, rows_tab, E, T)
+    t0 = time.perf_counter()
+    oi, osc, oc = om.retrieve_batch(lseq[:2 * threads], leaf_level, 200, 10, leaf_item, n_threads=threads)
+    cdt = time.perf_counter() - t0
+    gi, gs, gc = eng.otm_retrieve(lseq[:2 * threads], 200, 10)
+    emit(path="otm_retrieve cpu_baseline", kind="port", cores=threads, users_per_s=2 * threads / cdt,
+         parity={"ids_identical": bool((gi == oi).all()), "scores_bit_identical": bool((gs.view(np.uint64) == osc.view(np.uint64)).all())})
+    eng.close()
+
+    # ---- 4. Deep Retrieval beam search + rerank, fp64 (a23) --------------------------------------------------------
+    n_item, K, D, J = (20_000, 100, 3, 2) if a.quick else (200_000, 1000, 3, 2)
+    Ed = 16 if a.quick else 64
+    rng = np.random.Generator(np.random.PCG64(8))
+    layer_emb = rng.normal(0, 0.05, (n_item + (D - 1) * K, Ed))
+    layer_w = [rng.normal(0, 0.05, (K, (T + d) * Ed)) for d in range(D)]
+    layer_b = [np.zeros(K) for _ in range(D)]
+    rr_emb = rng.normal(0, 0.05, (n_item, Ed)); rr_w = rng.normal(0, 0.05, (Ed, T * Ed)); rr_b = np.zeros(Ed)
+    sm_w = rng.normal(0, 0.05, (n_item, Ed)); sm_b = np.zeros(n_item)
+    from dismember_b200.dr import build_path_csr
+    paths = rng.integers(0, K, (n_item, J, D))
+    off, flat = build_path_csr(np.arange(n_item), paths, K)
+    eng = Engine(0)
+    eng.dr_load(n_item, K, D, T, Ed, layer_emb, layer_w, layer_b, rr_emb, rr_w, rr_b, sm_w, sm_b)
+    eng.dr_load_paths(off, flat)
+    B = 64
+    dseq = rng.integers(0, n_item, (B, T)).astype(np.int32)
+    dt = timeit(lambda: eng.dr_retrieve(dseq, 200, 10), warm=1, reps=3)
+    flop_u = 2 * K * T * Ed + sum(200 * 2 * K * (T + d) * Ed for d in range(1, D))
+    emit(path="dr_retrieve (Deep Retrieval beam search + rerank, fp64)", items=n_item, K=K, D=D, beam=200, batch=B, ms=dt * 1e3,
+         users_per_s=B / dt, roofline={"bound": "fp64 FMA pipe / top-k", "naive_flop_per_user": flop_u,
+                                       "achieved_tflops_naive": flop_u * B / dt / 1e12})
+    dm = orc.DrModel(n_item, K, D, T, Ed, layer_emb, layer_w, layer_b, rr_emb, rr_w, rr_b, sm_w, sm_b)
+    nchk = 4
+    t0 = time.perf_counter()
+    ref = [dm.recommend(dseq[i], 10, 200, off, flat) for i in range(nchk)]
+    cdt = time.perf_counter() - t0
+    gi, gs, gc = eng.dr_retrieve(dseq[:nchk], 200, 10)
+    ok = all((gi[i, :gc[i]] == ref[i][0]).all() and len(ref[i][0]) == gc[i] for i in range(nchk))
+    emit(path="dr_retrieve cpu_baseline", kind="port", cores=1, users_per_s=nchk / cdt, parity={"ids_identical": bool(ok)})
+    eng.close()
+
+
+if __name__ == "__main__":
+    main()
