@@ -21,7 +21,7 @@
 #include <dlfcn.h>
 #include <nccl.h>
 
-#include "device_utils.cuh"
+#include "beam_kernels.cuh"
 #include "rows_kernels.cuh"
 
 using namespace dmg;
@@ -246,9 +246,11 @@ static __global__ void __launch_bounds__(kThreads) shard_select_expand_kernel(in
 }
 
 // Requests (slot = u*cap + pos, code) appended to the region of the code's owner; n_out[o] counts them.
+// seg[o * B + u] = (first request of user u in the region of owner o, how many): one user's requests to one owner are
+// contiguous, so the owner scores them as tiles that share the user's history.
 static __global__ void __launch_bounds__(kThreads) shard_bucket_kernel(const int32_t *__restrict__ cand, const int32_t *__restrict__ count,
                                                                        int cap, ShardGeo g, int2 *__restrict__ region, int64_t region_stride,
-                                                                       int32_t *__restrict__ n_out)
+                                                                       int32_t *__restrict__ n_out, int2 *__restrict__ seg)
 {
     __shared__ int sCnt[32], sBase[32];
     const int u = blockIdx.x, tid = threadIdx.x;
@@ -265,7 +267,10 @@ static __global__ void __launch_bounds__(kThreads) shard_bucket_kernel(const int
         }
     }
     __syncthreads();
-    if (tid < g.world) sBase[tid] = sCnt[tid] ? atomicAdd(&n_out[tid], sCnt[tid]) : 0;
+    if (tid < g.world) {
+        sBase[tid] = sCnt[tid] ? atomicAdd(&n_out[tid], sCnt[tid]) : 0;
+        seg[(size_t)tid * gridDim.x + u] = make_int2(sBase[tid], sCnt[tid]);
+    }
     __syncthreads();
     for (int q = 0; q < 2; q++) {
         const int i = tid + q * kThreads;
@@ -359,6 +364,84 @@ static __global__ void __launch_bounds__(kRowsThreads) shard_score_rows_kernel(
         }
         __syncthreads();
     }
+}
+
+// Tiled owner scorer: one (requester rank p, user u) segment at a time per CTA -- the user's history tile and mask are
+// staged once, the requested rows are gathered R at a time and scored by score_tile (beam_kernels.cuh: 8x4 register
+// tiles of sequential-k fma chains, the strict kernel's scorer) => identical bits, ~10x the row rate of the
+// row-at-a-time kernel above, which stays as the fallback for embedding sizes without a tile geometry.
+struct ShardScoreArgs {
+    const float *emb, *wattT, *w1T, *b1, *w2, *b2, *tiles;
+    const uint8_t *mask;
+    const int2 *req_self, *req_peer;        // [G][stride] requests: own region (rank) / received regions
+    const int2 *seg_self, *seg_peer;        // [G][B] segment tables
+    float *out_self, *out_peer;             // [G][stride] scores: own region written straight into the reply buffer
+    int64_t stride;
+    int B, G, T, cap;
+    float scale;
+    int32_t *work;
+    ShardGeo geo;
+};
+template <int E>
+static __global__ void __launch_bounds__(kThreads, 1) shard_score_segments_kernel(const ShardScoreArgs a)
+{
+    using G = Geo<float, E>;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    float *sWattT = reinterpret_cast<float *>(smem_raw);
+    float *sW1T = sWattT + E * E;
+    float *sB1 = sW1T + 2 * E * E;
+    float *sW2 = sB1 + E;
+    float *sB2 = sW2 + E;                        // 4 floats
+    float *sK = sB2 + 4;                         // kMaxT x E
+    float *sX = sK + kMaxT * E;                  // R x LD
+    float *sA = sX + G::R * G::LD;
+    float *sP = sA + G::R * G::LD;
+    float *sOut = sP + G::R * G::PLD;            // R
+    int32_t *sMask = reinterpret_cast<int32_t *>(sOut + G::R);   // 16 + [16] next segment
+    const int tid = threadIdx.x, T = a.T;
+    for (int i = tid; i < E * E; i += kThreads) sWattT[i] = a.wattT[i];
+    for (int i = tid; i < 2 * E * E; i += kThreads) sW1T[i] = a.w1T[i];
+    for (int i = tid; i < E; i += kThreads) { sB1[i] = a.b1[i]; sW2[i] = a.w2[i]; }
+    if (tid == 0) sB2[0] = a.b2[0];
+    __syncthreads();
+    const float b2 = sB2[0];
+    const int n_seg = a.G * a.B;
+    for (;;) {
+        __syncthreads();
+        if (tid == 0) sMask[16] = atomicAdd(a.work, 1);
+        __syncthreads();
+        const int si = sMask[16];
+        if (si >= n_seg) break;
+        const int p = si / a.B;
+        const bool self = p == a.geo.rank;
+        const int2 sg = (self ? a.seg_self : a.seg_peer)[si];
+        if (sg.y == 0) continue;
+        const int2 *rq = (self ? a.req_self : a.req_peer) + (size_t)p * a.stride + sg.x;
+        float *out = (self ? a.out_self : a.out_peer) + (size_t)p * a.stride + sg.x;
+        const float *tile = a.tiles + (size_t)si * T * E;          // si = p * B + u = global user
+        for (int i = tid; i < T * E; i += kThreads) sK[i] = tile[i];
+        if (tid < kMaxT) sMask[tid] = tid < T ? a.mask[(size_t)si * T + tid] : 0;
+        for (int r0 = 0; r0 < sg.y; r0 += G::R) {
+            const int nrows = sg.y - r0 < G::R ? sg.y - r0 : G::R;
+            constexpr int VPR = E / 4;
+            __syncthreads();
+            for (int idx = tid; idx < nrows * VPR; idx += kThreads) {
+                const int r = idx / VPR, v = idx % VPR;
+                cp_async16(sX + r * G::LD + v * 4, a.emb + (size_t)shard_local_row(a.geo, rq[r0 + r].y) * E + v * 4);
+            }
+            cp_async_commit();
+            cp_async_wait<0>();
+            __syncthreads();
+            score_tile<float, E>(sX, sA, sP, sK, sMask, sWattT, sW1T, sB1, sW2, b2, a.scale, T, nrows, sOut);
+            __syncthreads();
+            for (int i = tid; i < nrows; i += kThreads) out[r0 + i] = sOut[i];
+        }
+    }
+}
+template <int E> static size_t shard_score_smem()
+{
+    using G = Geo<float, E>;
+    return ((size_t)3 * E * E + 2 * E + 4 + (size_t)kMaxT * E + 2 * (size_t)G::R * G::LD + (size_t)G::R * G::PLD + G::R) * 4 + 32 * 4;
 }
 
 // ---- requester side: results (Recommender.scala:103-106 + recommendItems :18-38) -----------------------------
@@ -563,7 +646,7 @@ DMG_API int32_t dmg_shard_tdm_retrieve(dmg_handle_t h, int32_t B, const int32_t 
     const size_t need = Carver::need({(size_t)B * T * 4, (size_t)BU * T * 4, (size_t)B * T, (size_t)BU * T, (size_t)BU * T * E * 4,
                                       (size_t)stride * 4, (size_t)stride * 4, (size_t)B * 4, (size_t)G * stride * 8, (size_t)G * stride * 8,
                                       (size_t)G * stride * 4, (size_t)G * stride * 4, (size_t)G * 4, (size_t)G * G * 4,
-                                      (size_t)B * topk * 4, (size_t)B * topk * 4, (size_t)B * 4});
+                                      (size_t)B * topk * 4, (size_t)B * topk * 4, (size_t)B * 4, (size_t)G * B * 8, (size_t)G * B * 8, 256});
     DMG_TRY(ensure_dev(h, s->buf, need));
     DMG_TRY(ensure_host(h, s->buf, (size_t)B * T * 4 + (size_t)G * G * 4 + (size_t)B * topk * 8 + (size_t)B * 4 + 1024));
     Carver cd(s->buf.d);
@@ -584,6 +667,9 @@ DMG_API int32_t dmg_shard_tdm_retrieve(dmg_handle_t h, int32_t B, const int32_t 
     int32_t *d_items = cd.take<int32_t>((size_t)B * topk);
     float *d_logits = cd.take<float>((size_t)B * topk);
     int32_t *d_cnt_out = cd.take<int32_t>((size_t)B);
+    int2 *d_seg = cd.take<int2>((size_t)G * B);               // my segments, one table per owner
+    int2 *d_rseg = cd.take<int2>((size_t)G * B);              // segments received, one table per requester
+    int32_t *d_work = cd.take<int32_t>(64);
     char *hp = (char *)s->buf.h;
     int32_t *h_seq = (int32_t *)hp; hp += (size_t)B * T * 4;
     int32_t *h_matrix = (int32_t *)hp; hp += (((size_t)G * G * 4 + 255) & ~(size_t)255);
@@ -619,6 +705,15 @@ DMG_API int32_t dmg_shard_tdm_retrieve(dmg_handle_t h, int32_t B, const int32_t 
     const size_t row_smem = (size_t)kRowsRB * ((size_t)4 * E + (size_t)T * E + T + 1) * 4;
     DMG_CUDA(h, cudaFuncSetAttribute(shard_score_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)row_smem));
     const float scale = (float)(1.0 / std::sqrt((double)E));
+    const bool tiled = E == 16 || E == 32 || E == 64;          // embedding sizes with a tile geometry that fits shared memory
+    if (tiled) {
+        switch (E) {
+        case 16: DMG_CUDA(h, cudaFuncSetAttribute(shard_score_segments_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)shard_score_smem<16>())); break;
+        case 32: DMG_CUDA(h, cudaFuncSetAttribute(shard_score_segments_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)shard_score_smem<32>())); break;
+        case 64: DMG_CUDA(h, cudaFuncSetAttribute(shard_score_segments_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)shard_score_smem<64>())); break;
+        default: break;
+        }
+    }
     bool reached = s_level <= L;
     if (reached) {
         shard_select_expand_kernel<<<B, kThreads, sel_smem, st>>>(d_cand, d_score, d_count, cap, capp, beam, s_level, 1, t.d_exists);
@@ -629,7 +724,7 @@ DMG_API int32_t dmg_shard_tdm_retrieve(dmg_handle_t h, int32_t B, const int32_t 
     for (int level = s_level; level < L; level++) {
         shard_select_expand_kernel<<<B, kThreads, sel_smem, st>>>(d_cand, d_score, d_count, cap, capp, beam, level, 0, t.d_exists);
         DMG_CUDA(h, cudaMemsetAsync(d_nreq, 0, (size_t)G * 4, st));
-        shard_bucket_kernel<<<B, kThreads, 0, st>>>(d_cand, d_count, cap, geo, d_req, stride, d_nreq);
+        shard_bucket_kernel<<<B, kThreads, 0, st>>>(d_cand, d_count, cap, geo, d_req, stride, d_nreq, d_seg);
         h->launches += 2;
         if (G > 1) DMG_NCCL(h, g_nccl.AllGather(d_nreq, d_matrix, (size_t)G, ncclInt32, s->comm, st));
         else DMG_CUDA(h, cudaMemcpyAsync(d_matrix, d_nreq, 4, cudaMemcpyDeviceToDevice, st));
@@ -643,9 +738,32 @@ DMG_API int32_t dmg_shard_tdm_retrieve(dmg_handle_t h, int32_t B, const int32_t 
                 const int ns = h_matrix[s->rank * G + p], nr = h_matrix[p * G + s->rank];
                 if (ns) DMG_NCCL(h, g_nccl.Send(d_req + (size_t)p * stride, (size_t)ns * 2, ncclInt32, p, s->comm, st));
                 if (nr) DMG_NCCL(h, g_nccl.Recv(d_rreq + (size_t)p * stride, (size_t)nr * 2, ncclInt32, p, s->comm, st));
+                if (tiled && ns) DMG_NCCL(h, g_nccl.Send(d_seg + (size_t)p * B, (size_t)B * 2, ncclInt32, p, s->comm, st));
+                if (tiled && nr) DMG_NCCL(h, g_nccl.Recv(d_rseg + (size_t)p * B, (size_t)B * 2, ncclInt32, p, s->comm, st));
             }
             DMG_NCCL(h, g_nccl.GroupEnd());
         }
+        if (tiled) {
+            for (int p = 0; p < G; p++)                          // a requester that sent nothing sent no table either
+                if (p != s->rank && h_matrix[p * G + s->rank] == 0) DMG_CUDA(h, cudaMemsetAsync(d_rseg + (size_t)p * B, 0, (size_t)B * 8, st));
+            DMG_CUDA(h, cudaMemsetAsync(d_work, 0, 4, st));
+            ShardScoreArgs sa;
+            sa.emb = d.emb<float>(); sa.wattT = (const float *)d.d_wattT; sa.w1T = (const float *)d.d_w1T;
+            sa.b1 = d.b1<float>(); sa.w2 = d.w2<float>(); sa.b2 = d.b2<float>(); sa.tiles = d_tiles; sa.mask = d_mask_all;
+            sa.req_self = d_req; sa.req_peer = d_rreq; sa.seg_self = d_seg; sa.seg_peer = d_rseg;
+            sa.out_self = d_reply; sa.out_peer = d_rsc; sa.stride = stride; sa.B = B; sa.G = G; sa.T = T; sa.cap = cap;
+            sa.scale = scale; sa.work = d_work; sa.geo = geo;
+            const int grid = std::min(G * B, h->sm_count);
+            switch (E) {
+            case 16: shard_score_segments_kernel<16><<<grid, kThreads, shard_score_smem<16>(), st>>>(sa); break;
+            case 32: shard_score_segments_kernel<32><<<grid, kThreads, shard_score_smem<32>(), st>>>(sa); break;
+            case 64: shard_score_segments_kernel<64><<<grid, kThreads, shard_score_smem<64>(), st>>>(sa); break;
+            default: break;
+            }
+            h->launches += 1;
+            for (int p = 0; p < G; p++)
+                if (p != s->rank) s->exchanged_rows += h_matrix[p * G + s->rank];
+        } else
         for (int p = 0; p < G; p++) {
             const int nr = h_matrix[p * G + s->rank];
             if (!nr) continue;

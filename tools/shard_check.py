@@ -27,6 +27,9 @@ def main():
     ap.add_argument("--dim", type=int, default=64)
     ap.add_argument("--steps", type=int, default=4)
     ap.add_argument("--oracle-users", type=int, default=64)
+    ap.add_argument("--check", default="oracle", choices=["oracle", "engine"],
+                    help="oracle: CPU oracle on the full table (needs the table on the host); engine: the unsharded strict "
+                         "CUDA engine on this rank's GPU (for catalogues too large to ship to the host)")
     ap.add_argument("--out", default=None)
     a = ap.parse_args()
     import torch
@@ -59,15 +62,20 @@ def main():
     full = Engine(local)
     full.load_tree_tdm(tf.max_level, tf.codes, tf.node_ids, tf.is_leaf, tf.leaf_ids, tf.leaf_codes)
     full.init_din_weights(np.float32, rows, a.dim, T, seed=2)
-    params = full.download_din_weights()
-    full.close()
-    orc.build()
-    tree = orc.Tree.from_treefile(tf)
-    model = orc.TdmModel(params, rows, a.dim, T)
-    oi, ol, oc = model.retrieve_batch(tree, seqs[:n], a.beam, a.topk, n_threads=max(1, (os.cpu_count() or 2) // world))
+    if a.check == "oracle":
+        params = full.download_din_weights()
+        full.close()
+        orc.build()
+        tree = orc.Tree.from_treefile(tf)
+        model = orc.TdmModel(params, rows, a.dim, T)
+        oi, ol, oc = model.retrieve_batch(tree, seqs[:n], a.beam, a.topk, n_threads=max(1, (os.cpu_count() or 2) // world))
+    else:
+        full.set_arithmetic("strict")
+        oi, ol, oc = full.tdm_retrieve(seqs[:n], a.beam, a.topk)
+        full.close()
     line = {"rank": rank, "world": world, "items": a.items, "levels": tf.max_level, "batch_per_rank": a.batch, "beam": a.beam,
             "table_rows_global": global_rows, "table_rows_local": local_rows,
-            "rows_scored_for_other_ranks": exchanged, "users_checked": n,
+            "rows_scored_for_other_ranks": exchanged, "users_checked": n, "checked_against": a.check,
             "ids_identical": bool((items[:n] == oi).all() and (counts[:n] == oc).all()),
             "logits_bit_identical": bool((logits[:n].view(np.uint32) == ol.view(np.uint32)).all()),
             "users_per_s_whole_job": world * a.batch * a.steps / dt}
