@@ -177,3 +177,41 @@ JNIEXPORT jfloat JNICALL Java_com_mass_gpu_DismemberGPU_00024_trainStepFloat(
     if (rc) throw_status(env, H(handle), rc);
     return loss;
 }
+
+/* ---- node table sharded across the GPUs of one box (dmg_shard_*) ---- */
+JNIEXPORT jbyteArray JNICALL Java_com_mass_gpu_DismemberGPU_00024_shardUniqueId(JNIEnv *env, jobject self)
+{
+    jbyte id[128];
+    if (dmg_shard_unique_id(id, 128)) { throw_status(env, NULL, DMG_ERR_UNSUPPORTED); return NULL; }
+    jbyteArray out = (*env)->NewByteArray(env, 128);
+    (*env)->SetByteArrayRegion(env, out, 0, 128, id);
+    return out;
+}
+
+JNIEXPORT void JNICALL Java_com_mass_gpu_DismemberGPU_00024_shardInit(
+    JNIEnv *env, jobject self, jlong handle, jint world, jint rank, jbyteArray uniqueId)
+{
+    void *id = PIN(uniqueId);
+    int32_t rc = dmg_shard_init(H(handle), world, rank, id);
+    UNPIN(uniqueId, id, JNI_ABORT);
+    if (rc) throw_status(env, H(handle), rc);
+}
+
+JNIEXPORT void JNICALL Java_com_mass_gpu_DismemberGPU_00024_shardLoadDinWeightsFloat(
+    JNIEnv *env, jobject self, jlong handle, jlong rowsGlobal, jint embedSize, jint seqLen, jfloatArray params)
+{
+    void *p = PIN(params);
+    int32_t rc = dmg_shard_load_din_weights(H(handle), rowsGlobal, embedSize, seqLen, p);
+    UNPIN(params, p, JNI_ABORT);
+    if (rc) throw_status(env, H(handle), rc);
+}
+
+JNIEXPORT void JNICALL Java_com_mass_gpu_DismemberGPU_00024_shardTdmRetrieve(
+    JNIEnv *env, jobject self, jlong handle, jint batch, jintArray itemSeq, jint beam, jint topk, jboolean useMask,
+    jintArray outItems, jfloatArray outLogits, jintArray outCounts)
+{
+    void *s = PIN(itemSeq), *oi = PIN(outItems), *ol = PIN(outLogits), *oc = PIN(outCounts);
+    int32_t rc = dmg_shard_tdm_retrieve(H(handle), batch, s, beam, topk, useMask ? 1 : 0, oi, ol, oc);
+    UNPIN(outCounts, oc, 0); UNPIN(outLogits, ol, 0); UNPIN(outItems, oi, 0); UNPIN(itemSeq, s, JNI_ABORT);
+    if (rc) throw_status(env, H(handle), rc);
+}
