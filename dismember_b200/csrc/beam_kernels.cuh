@@ -53,6 +53,10 @@ template <typename real> struct BeamParams {
     // optional: run only the users user_list[0 .. *user_count) (the fast kernel's redo list)
     const int32_t *user_list;
     const int32_t *user_count;
+    // > 1: the kernel is launched in clusters of `split` CTAs that run ONE user together -- every CTA keeps the whole
+    // beam state (same sorts, same expansion), scores only the tiles t % split == its cluster rank and writes those
+    // scores into every peer's shared memory (DSMEM).  Used for the redo list: a lone strict user costs 0.85 ms on one SM.
+    int split;
 };
 
 // ---- compile-time geometry ----------------------------------------------------------------
@@ -286,6 +290,25 @@ __device__ __forceinline__ void gather_tile(real *__restrict__ sXbuf, const real
     }
 }
 
+// ---- thread-block cluster helpers (split mode) ------------------------------------------------------------
+__device__ __forceinline__ uint32_t cluster_ctarank()
+{
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ void cluster_sync_all()
+{
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void st_cluster_f32(const float *local_smem, uint32_t peer, float v)
+{
+    uint32_t remote;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(remote) : "r"(smem_u32(local_smem)), "r"(peer));
+    asm volatile("st.shared::cluster.f32 [%0], %1;" ::"r"(remote), "f"(v) : "memory");
+}
+__device__ __forceinline__ void st_cluster_f32(const double *, uint32_t, double) {}   // split mode is fp32 only
+
 template <typename real, int E>
 __global__ void __launch_bounds__(kThreads, 1) beam_search_kernel(const BeamParams<real> p)
 {
@@ -312,7 +335,9 @@ __global__ void __launch_bounds__(kThreads, 1) beam_search_kernel(const BeamPara
 
     const int tid = threadIdx.x;
     const int T = p.T;
-    if (p.user_count && (int)blockIdx.x >= *p.user_count) return;   // redo launch with nothing (left) to redo
+    const int split = p.split > 1 ? p.split : 1;
+    const uint32_t crank = split > 1 ? cluster_ctarank() : 0u;
+    if (p.user_count && (int)blockIdx.x / split >= *p.user_count) return;   // redo launch with nothing (left) to redo (whole cluster)
 
     // weights -> shared, once per CTA
     for (int i = tid; i < E * E; i += kThreads) sWattT[i] = p.wattT[i];
@@ -324,7 +349,7 @@ __global__ void __launch_bounds__(kThreads, 1) beam_search_kernel(const BeamPara
     uint32_t bar_phase = 0;
 
     const int n_users = p.user_count ? *p.user_count : p.B;
-    for (int ui = blockIdx.x; ui < n_users; ui += gridDim.x) {
+    for (int ui = blockIdx.x / split; ui < n_users; ui += gridDim.x / split) {
         const int user = p.user_list ? p.user_list[ui] : ui;
         // ---- K2: history tile --------------------------------------------------------------
         if (tid < kMaxT) {
@@ -406,11 +431,36 @@ __global__ void __launch_bounds__(kThreads, 1) beam_search_kernel(const BeamPara
             count = nc;
             // score the candidates tile by tile, prefetching the next tile's rows
             const int ntiles = (count + G::R - 1) / G::R;
+            if (split > 1) {
+                // every CTA of the cluster holds the same candidates; this one scores tiles crank, crank + split, ...
+                for (int t = crank; t < ntiles; t += split) {
+                    const int r0 = t * G::R;
+                    const int nrows = count - r0 < G::R ? count - r0 : G::R;
+                    __syncthreads();
+                    gather_tile<real, E>(sX, p.emb, cur + r0, nrows);
+                    cp_async_commit();
+                    cp_async_wait<0>();
+                    __syncthreads();
+                    score_tile<real, E>(sX, sA, sP, sK, sMisc + 16, sWattT, sW1T, sB1, sW2, b2, p.scale, T, nrows, sScore + r0);
+                }
+                cluster_sync_all();                               // every peer is done reading the previous level's scores
+                for (int t = crank; t < ntiles; t += split) {
+                    const int r0 = t * G::R;
+                    const int nrows = count - r0 < G::R ? count - r0 : G::R;
+                    for (int i = threadIdx.x; i < nrows * (split - 1); i += kThreads) {
+                        const int r = i % nrows;
+                        uint32_t peer = (uint32_t)(i / nrows);
+                        peer += peer >= crank ? 1u : 0u;
+                        st_cluster_f32(sScore + r0 + r, peer, sScore[r0 + r]);
+                    }
+                }
+                cluster_sync_all();                               // all slices have landed everywhere
+            } else
             if (ntiles > 0) {
                 gather_tile<real, E>(sX, p.emb, cur, count < G::R ? count : G::R);
                 cp_async_commit();
             }
-            for (int t = 0; t < ntiles; t++) {
+            for (int t = 0; split == 1 && t < ntiles; t++) {
                 const int r0 = t * G::R;
                 const int nrows = count - r0 < G::R ? count - r0 : G::R;
                 real *buf = sX + (G::NBUF == 2 ? (t & 1) : 0) * G::R * G::LD;

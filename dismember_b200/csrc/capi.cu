@@ -325,13 +325,23 @@ static int32_t launch_beam_E(dmg_handle_t h, const BeamParams<real> &p)
         return fail(h, DMG_ERR_UNSUPPORTED, "beam too large: needs %zu B of shared memory per CTA (limit %zu)", smem, h->smem_optin);
     auto kern = beam_search_kernel<real, E>;
     DMG_CUDA(h, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    const int grid = std::min(p.B, h->sm_count);
+    const int split = p.split > 1 ? p.split : 1;
+    const int grid = split * std::min(p.B, std::max(h->sm_count / split, 1));
     cudaEvent_t e0 = nullptr, e1 = nullptr;
     if (h->profiling) {
         DMG_CUDA(h, cudaEventCreate(&e0));
         DMG_CUDA(h, cudaEventCreate(&e1));
         DMG_CUDA(h, cudaEventRecord(e0, h->stream));
     }
+    if (split > 1) {                                             // clusters of `split` CTAs share one user (beam_kernels.cuh)
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3((unsigned)grid); cfg.blockDim = dim3(kThreads); cfg.dynamicSmemBytes = smem; cfg.stream = h->stream;
+        cudaLaunchAttribute at[1];
+        at[0].id = cudaLaunchAttributeClusterDimension;
+        at[0].val.clusterDim.x = (unsigned)split; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+        cfg.attrs = at; cfg.numAttrs = 1;
+        DMG_CUDA(h, cudaLaunchKernelEx(&cfg, kern, p));
+    } else
     kern<<<grid, kThreads, smem, h->stream>>>(p);
     h->launches += 1;
     DMG_CUDA(h, cudaGetLastError());
@@ -524,6 +534,8 @@ static int32_t tdm_enqueue(dmg_handle_t h, int32_t B, const int32_t *d_seq, int3
         }
         // users the fast kernel could not certify (exact ties at a cut, implausibly wide band): strict kernel
         p.user_list = h->d_redo_list; p.user_count = h->d_fast_ctl + 1;
+        p.split = 4;                                             // a redo user runs on a cluster of 4 SMs: its <= 4 row tiles per level in parallel
+        p.B = std::min(B, 32);                                   // cluster slots launched (the kernel strides over the list)
         const bool prof = h->profiling;
         h->profiling = false;
         const int32_t rc = launch_beam<float>(h, p, d.E);
