@@ -84,6 +84,7 @@ def load_library(build_if_missing: bool = True):
         "dmg_din_gradients": [vp, i64, vp, vp, vp, i64, vp, vp, vp, i64],
         "dmg_tdm_sample_expand": [vp, i32, vp, vp, vp, i32, u64, vp, vp, vp, C.POINTER(i32)],
         "dmg_jtm_item_weights": [vp, i32, vp, vp, vp, i32, i32, i32, i32, i32, vp],
+        "dmg_load_deepfm_weights": [vp, i64, i32, i32, vp],
         "dmg_shard_unique_id": [vp, i32],
         "dmg_shard_init": [vp, i32, i32, vp],
         "dmg_shard_init_din_weights": [vp, i64, i32, i32, u64],
@@ -208,6 +209,15 @@ class Engine:
             raise DmgArgumentError(DMG_ERR_INVALID_ARG, f"compact DIN vector must hold {n} values, got {params.size}")
         self._check(self.L.dmg_load_din_weights(self.h, dt, rows, E, T, _p(params)))
         self.din_dtype, self.rows, self.E, self.T = params.dtype, rows, E, T
+
+    def load_deepfm_weights(self, params: np.ndarray, rows: int, E: int, T: int):
+        """DeepFM scorer (tdm/.../model/DeepFM.scala): [emb | W1 (T+1)x(T+1)E | b1 | W2 | b2], float32."""
+        params = np.ascontiguousarray(params, np.float32).ravel()
+        n = rows * E + (T + 1) * (T + 1) * E + 2 * (T + 1) + 1
+        if params.size != n:
+            raise DmgArgumentError(DMG_ERR_INVALID_ARG, f"compact DeepFM vector must hold {n} values, got {params.size}")
+        self._check(self.L.dmg_load_deepfm_weights(self.h, rows, E, T, _p(params)))
+        self.din_dtype, self.rows, self.E, self.T = np.dtype(np.float32), rows, E, T
 
     def init_din_weights(self, dtype, rows: int, E: int, T: int, seed: int):
         dtype = np.dtype(dtype)

@@ -76,6 +76,9 @@ static void free_din(DinDev &d)
 }
 void dmg_free_dr(DrDev &d);     // dr.cu
 void dmg_shard_free(dmg_handle_t h);   // shard.cu
+int32_t dmg_deepfm_tdm_retrieve(dmg_handle_t h, int32_t B, const int32_t *item_seq, int32_t beam, int32_t topk, const int64_t *cons_off,
+                                const int32_t *cons, int32_t widen_beam, int32_t *out_items, float *out_logits, int32_t *out_counts);   // shard.cu
+int32_t dmg_deepfm_score_pairs(dmg_handle_t h, int64_t n, const int32_t *node, const int32_t *seq, float *out);                         // shard.cu
 
 DMG_API int32_t dmg_destroy(dmg_handle_t h)
 {
@@ -617,6 +620,10 @@ DMG_API int32_t dmg_tdm_retrieve(dmg_handle_t h, int32_t B, const int32_t *item_
                                  int32_t use_mask, const int64_t *consumed_off, const int32_t *consumed_items,
                                  int32_t widen_beam, int32_t *out_items, float *out_logits, int32_t *out_counts)
 {
+    if (h && h->din.loaded && h->din.kind == 1) {                // DeepFM scorer: level-synchronous path (shard.cu)
+        if (!item_seq || !out_items || !out_logits || !out_counts) return fail(h, DMG_ERR_INVALID_ARG, "null host pointer");
+        return dmg_deepfm_tdm_retrieve(h, B, item_seq, beam, topk, consumed_off, consumed_items, widen_beam, out_items, out_logits, out_counts);
+    }
     DMG_TRY(tdm_precheck(h, B, beam, topk));
     if (!item_seq || !out_items || !out_logits || !out_counts) return fail(h, DMG_ERR_INVALID_ARG, "null host pointer");
     if (consumed_off && !consumed_items && consumed_off[B] > 0) return fail(h, DMG_ERR_INVALID_ARG, "consumed_items is null");
@@ -779,6 +786,10 @@ DMG_API int32_t dmg_score_pairs(dmg_handle_t h, int64_t n, const int32_t *node, 
 {
     if (!h) return DMG_ERR_INVALID_ARG;
     if (!h->din.loaded) return fail(h, DMG_ERR_STATE, "DIN weights must be loaded first");
+    if (h->din.kind == 1) {                                      // DeepFM takes no mask input (DeepFM.scala:14-15)
+        if (n < 0 || (n > 0 && (!node || !seq || !out))) return fail(h, DMG_ERR_INVALID_ARG, "bad arguments");
+        return dmg_deepfm_score_pairs(h, n, node, seq, (float *)out);
+    }
     if (h->din.sharded) return fail(h, DMG_ERR_STATE, "the node table is sharded (dmg_shard_init): use the dmg_shard_* entry points");
     if (n < 0 || n_mask < 0 || (n > 0 && (!node || !seq || !out)) || (n_mask > 0 && !mask_flat))
         return fail(h, DMG_ERR_INVALID_ARG, "bad arguments");

@@ -41,10 +41,12 @@ struct DinDev {
     void *d_wattT = nullptr;       // k-major copies  WattT[k][o], W1T[k][o]
     void *d_w1T = nullptr;
     int64_t n_params = 0;
+    int kind = 0;                  // 0 = DIN [emb|Watt|W1|b1|W2|b2], 1 = DeepFM [emb|W1 (T+1)x(T+1)E|b1 T+1|W2 T+1|b2] (shard.cu)
     bool sharded = false;          // rows are this rank's slice of a table split by dmg_shard_init (shard.cu): shard entry points only
     // training state (allocated lazily)
     void *d_grad = nullptr, *d_m = nullptr, *d_v = nullptr;
     template <typename real> real *emb() const { return (real *)d_params; }
+    template <typename real> real *tail() const { return (real *)d_params + rows * E; }      // dense parameters behind the table
     template <typename real> real *watt() const { return (real *)d_params + rows * E; }
     template <typename real> real *w1() const { return watt<real>() + (int64_t)E * E; }
     template <typename real> real *b1() const { return w1<real>() + (int64_t)2 * E * E; }

@@ -444,10 +444,141 @@ template <int E> static size_t shard_score_smem()
     return ((size_t)3 * E * E + 2 * E + 4 + (size_t)kMaxT * E + 2 * (size_t)G::R * G::LD + (size_t)G::R * G::PLD + G::R) * 4 + 32 * 4;
 }
 
+// ---- DeepFM scorer (tdm/.../model/DeepFM.scala:11-44, scalann/.../nn/FM.scala:14-44) -------------------------------
+// Features F = [item row ; T history rows]; logit = (|sum_i F_i|^2 - sum |F|^2) / 2 + W2.relu(W1.Fflat + b1) + b2, no mask.
+// The Linear chains run over Fflat in order (item first, then the history), so nothing of a user can be hoisted out of
+// the rows without changing the rounding: every row walks its 12 chains (T+1 hidden units + the square sum) of (T+1)E
+// fma steps.  dense = [W1 (T+1) x (T+1)E | b1 | W2 | b2] staged in shared memory once per CTA.
+struct DfmGeo {
+    static constexpr int R = 128;
+    static size_t smem(int E, int T) { const int F = T + 1; return ((size_t)F * F * E + 2 * F + 4 + (size_t)kMaxT * E + (size_t)R * (E + 1) + (size_t)R * (F + 1)) * 4 + 32 * 4; }
+};
+__device__ __forceinline__ float deepfm_finish(const float *x, const float *sK, const float *hrow, float square_sum,
+                                               const float *sW2, float b2, int E, int T)
+{
+    float sum_square = 0.0f;
+    for (int k = 0; k < E; k++) {
+        float b = add_(0.0f, x[k]);
+        for (int j = 0; j < T; j++) b = add_(b, sK[j * E + k]);
+        sum_square = fma_(b, b, sum_square);
+    }
+    const float fm = __fdiv_rn(sub_(sum_square, square_sum), 2.0f);
+    float dnn = 0.0f;
+    for (int o = 0; o <= T; o++) dnn = fma_(hrow[o], sW2[o], dnn);
+    return add_(fm, add_(dnn, b2));
+}
+// chain c of a row: c <= T hidden unit c (returns relu(acc + b1[c])), c == T + 1 the square sum
+__device__ __forceinline__ float deepfm_chain(const float *x, const float *sK, const float *sW1, const float *sB1, int c, int E, int T)
+{
+    float acc = 0.0f;
+    if (c <= T) {
+        const float *w = sW1 + (size_t)c * (T + 1) * E;
+        for (int k = 0; k < E; k++) acc = fma_(x[k], w[k], acc);
+        for (int k = 0; k < T * E; k++) acc = fma_(sK[k], w[E + k], acc);
+        return relu_(add_(acc, sB1[c]));
+    }
+    for (int k = 0; k < E; k++) acc = fma_(x[k], x[k], acc);
+    for (int k = 0; k < T * E; k++) acc = fma_(sK[k], sK[k], acc);
+    return acc;
+}
+struct ShardDfmArgs {
+    const float *emb, *dense, *tiles;
+    const int2 *req_self, *req_peer, *seg_self, *seg_peer;
+    float *out_self, *out_peer;
+    int64_t stride;
+    int B, G, T, E;
+    int32_t *work;
+    ShardGeo geo;
+};
+static __global__ void __launch_bounds__(kThreads, 1) shard_score_deepfm_kernel(const ShardDfmArgs a)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int E = a.E, T = a.T, F = T + 1, LD = E + 1, HL = F + 1;
+    float *sW1 = reinterpret_cast<float *>(smem_raw);
+    float *sB1 = sW1 + (size_t)F * F * E;
+    float *sW2 = sB1 + F;
+    float *sB2 = sW2 + F;                        // 4 floats
+    float *sK = sB2 + 4;                         // kMaxT x E
+    float *sX = sK + kMaxT * E;                  // R x LD
+    float *sH = sX + DfmGeo::R * LD;             // R x HL: hidden units, [F] = square sum
+    int32_t *sCtl = reinterpret_cast<int32_t *>(sH + DfmGeo::R * HL);
+    const int tid = threadIdx.x;
+    for (int i = tid; i < F * F * E + 2 * F + 1; i += kThreads) sW1[i] = a.dense[i];      // W1 | b1 | W2 | b2 are contiguous
+    __syncthreads();
+    const float b2 = sB2[0];
+    const int n_seg = a.G * a.B;
+    for (;;) {
+        __syncthreads();
+        if (tid == 0) sCtl[0] = atomicAdd(a.work, 1);
+        __syncthreads();
+        const int si = sCtl[0];
+        if (si >= n_seg) break;
+        const int p = si / a.B;
+        const bool self = p == a.geo.rank;
+        const int2 sg = (self ? a.seg_self : a.seg_peer)[si];
+        if (sg.y == 0) continue;
+        const int2 *rq = (self ? a.req_self : a.req_peer) + (size_t)p * a.stride + sg.x;
+        float *out = (self ? a.out_self : a.out_peer) + (size_t)p * a.stride + sg.x;
+        const float *tile = a.tiles + (size_t)si * T * E;
+        for (int i = tid; i < T * E; i += kThreads) sK[i] = tile[i];
+        for (int r0 = 0; r0 < sg.y; r0 += DfmGeo::R) {
+            const int nrows = sg.y - r0 < DfmGeo::R ? sg.y - r0 : DfmGeo::R;
+            __syncthreads();
+            for (int idx = tid; idx < nrows * E; idx += kThreads) {
+                const int r = idx / E, k = idx % E;
+                sX[r * LD + k] = a.emb[(size_t)shard_local_row(a.geo, rq[r0 + r].y) * E + k];
+            }
+            __syncthreads();
+            for (int idx = tid; idx < nrows * (F + 1); idx += kThreads) {
+                const int r = idx % nrows, c = idx / nrows;
+                sH[r * HL + c] = deepfm_chain(sX + r * LD, sK, sW1, sB1, c, E, T);
+            }
+            __syncthreads();
+            for (int r = tid; r < nrows; r += kThreads)
+                out[r0 + r] = deepfm_finish(sX + r * LD, sK, sH + r * HL, sH[r * HL + F], sW2, b2, E, T);
+        }
+    }
+}
+
+// model.forward of the DeepFM graph on independent rows (each row brings its own history): dmg_score_pairs.
+static __global__ void __launch_bounds__(128) deepfm_rows_forward_kernel(const float *__restrict__ emb, const float *__restrict__ dense,
+                                                                         int E, int T, int64_t n, const int32_t *__restrict__ node,
+                                                                         const int32_t *__restrict__ seq, float *__restrict__ out)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    constexpr int RB = 8;
+    const int F = T + 1, HL = F + 1;
+    float *sF = reinterpret_cast<float *>(smem_raw);     // RB x F x E: [item | history] per row
+    float *sH = sF + (size_t)RB * F * E;                 // RB x HL
+    const float *w1 = dense, *b1 = w1 + (size_t)F * F * E, *w2 = b1 + F, *b2 = w2 + F;
+    const int tid = threadIdx.x;
+    for (int64_t g0 = (int64_t)blockIdx.x * RB; g0 < n; g0 += (int64_t)gridDim.x * RB) {
+        const int nr = (int)((n - g0) < RB ? (n - g0) : RB);
+        for (int idx = tid; idx < nr * F * E; idx += 128) {
+            const int k = idx % E, slot = (idx / E) % F, r = idx / (E * F);
+            const int32_t c = slot == 0 ? node[g0 + r] : seq[(g0 + r) * T + slot - 1];
+            sF[idx] = c < 0 ? 0.0f : emb[(size_t)c * E + k];
+        }
+        __syncthreads();
+        for (int idx = tid; idx < nr * (F + 1); idx += 128) {
+            const int r = idx % nr, c = idx / nr;
+            const float *x = sF + (size_t)r * F * E;
+            sH[r * HL + c] = deepfm_chain(x, x + E, w1, b1, c, E, T);
+        }
+        __syncthreads();
+        if (tid < nr) {
+            const float *x = sF + (size_t)tid * F * E;
+            out[g0 + tid] = deepfm_finish(x, x + E, sH + tid * HL, sH[tid * HL + F], w2, b2[0], E, T);
+        }
+        __syncthreads();
+    }
+}
+
 // ---- requester side: results (Recommender.scala:103-106 + recommendItems :18-38) -----------------------------
 static __global__ void __launch_bounds__(kThreads) shard_final_topk_kernel(const int32_t *__restrict__ cand, const float *__restrict__ score,
                                                                            const int32_t *__restrict__ count, int cap, int capp, int topk,
                                                                            int leaf_level, int reached_leaf, const int32_t *__restrict__ leaf_item,
+                                                                           const int64_t *__restrict__ cons_off, const int32_t *__restrict__ cons,
                                                                            int32_t *__restrict__ out_items, float *__restrict__ out_scores,
                                                                            int32_t *__restrict__ out_counts)
 {
@@ -465,7 +596,10 @@ static __global__ void __launch_bounds__(kThreads) shard_final_topk_kernel(const
         if (i < n && reached_leaf) {
             const int64_t slot = (int64_t)uc[i] - leaf_start;
             const int32_t item = (slot >= 0 && slot < ((int64_t)1 << leaf_level)) ? __ldg(leaf_item + slot) : -1;
-            if (item >= 0) k = KeyOf<float>::make(us[i], i);
+            bool keep = item >= 0;
+            if (cons_off)
+                for (int64_t q = cons_off[u]; q < cons_off[u + 1] && keep; q++) keep = __ldg(cons + q) != item;
+            if (keep) k = KeyOf<float>::make(us[i], i);
         }
         sKey[i] = k;
     }
@@ -539,7 +673,12 @@ DMG_API int32_t dmg_shard_init(dmg_handle_t h, int32_t world, int32_t rank, cons
     return DMG_OK;
 }
 
-static int32_t shard_alloc_din(dmg_handle_t h, int64_t rows_global, int32_t E, int32_t T)
+static int64_t dense_params(int kind, int E, int T)
+{
+    return kind == 1 ? (int64_t)(T + 1) * (T + 1) * E + 2 * (T + 1) + 1 : (int64_t)3 * E * E + 2 * (int64_t)E + 1;
+}
+
+static int32_t shard_alloc_din(dmg_handle_t h, int64_t rows_global, int32_t E, int32_t T, int kind = 0)
 {
     ShardState *s = h->shard;
     if (!s) return fail(h, DMG_ERR_STATE, "call dmg_shard_init first");
@@ -552,7 +691,8 @@ static int32_t shard_alloc_din(dmg_handle_t h, int64_t rows_global, int32_t E, i
     d = DinDev();
     d.dtype = DMG_F32; d.esz = 4; d.E = E; d.T = T;
     d.rows = shard_local_rows(s->bits, h->tree.max_level);
-    d.n_params = d.rows * E + (int64_t)3 * E * E + 2 * (int64_t)E + 1;
+    d.kind = kind;
+    d.n_params = d.rows * E + dense_params(kind, E, T);
     s->global_rows = rows_global;
     DMG_CUDA(h, cudaMalloc(&d.d_params, (size_t)d.n_params * 4));
     DMG_CUDA(h, cudaMalloc(&d.d_wattT, sizeof(float) * E * E));
@@ -564,6 +704,12 @@ static int32_t shard_finish_din(dmg_handle_t h)
 {
     DinDev &d = h->din;
     const int E = d.E;
+    if (d.kind == 1) {                                           // DeepFM: no transposed copies, level-synchronous path only
+        DMG_CUDA(h, cudaStreamSynchronize(h->stream));
+        d.loaded = true;
+        d.sharded = true;
+        return DMG_OK;
+    }
     transpose_kernel<float><<<(E * E + 255) / 256, 256, 0, h->stream>>>(d.watt<float>(), (float *)d.d_wattT, E, E);
     transpose_kernel<float><<<(2 * E * E + 255) / 256, 256, 0, h->stream>>>(d.w1<float>(), (float *)d.d_w1T, E, 2 * E);
     h->launches += 2;
@@ -593,11 +739,11 @@ DMG_API int32_t dmg_shard_init_din_weights(dmg_handle_t h, int64_t rows_global, 
 
 // params: the FULL compact vector of the unsharded model (Module.parameters(), rows_global rows); only this rank's
 // rows are uploaded.
-DMG_API int32_t dmg_shard_load_din_weights(dmg_handle_t h, int64_t rows_global, int32_t E, int32_t T, const float *params)
+static int32_t shard_load_weights(dmg_handle_t h, int64_t rows_global, int32_t E, int32_t T, const float *params, int kind)
 {
     if (!h || !params) return h ? fail(h, DMG_ERR_INVALID_ARG, "null params") : DMG_ERR_INVALID_ARG;
     DMG_CUDA(h, cudaSetDevice(h->device));
-    DMG_TRY(shard_alloc_din(h, rows_global, E, T));
+    DMG_TRY(shard_alloc_din(h, rows_global, E, T, kind));
     DinDev &d = h->din;
     const ShardGeo g = h->shard->geo();
     // replicated levels, then one contiguous block per level
@@ -608,9 +754,23 @@ DMG_API int32_t dmg_shard_load_din_weights(dmg_handle_t h, int64_t rows_global, 
         DMG_CUDA(h, cudaMemcpyAsync(d.emb<float>() + lr * E, params + gr * E, (size_t)n * E * 4, cudaMemcpyHostToDevice, h->stream));
         lr += n;
     }
-    DMG_CUDA(h, cudaMemcpyAsync(d.watt<float>(), params + rows_global * E, ((size_t)3 * E * E + 2 * E + 1) * 4, cudaMemcpyHostToDevice, h->stream));
+    DMG_CUDA(h, cudaMemcpyAsync(d.tail<float>(), params + rows_global * E, (size_t)dense_params(kind, E, T) * 4, cudaMemcpyHostToDevice, h->stream));
     DMG_CUDA(h, cudaStreamSynchronize(h->stream));
     return shard_finish_din(h);
+}
+
+DMG_API int32_t dmg_shard_load_din_weights(dmg_handle_t h, int64_t rows_global, int32_t E, int32_t T, const float *params)
+{
+    return shard_load_weights(h, rows_global, E, T, params, 0);
+}
+
+// DeepFM (tdm/.../model/DeepFM.scala:11-44): params = [emb | W1 (T+1)x(T+1)E | b1 | W2 | b2].  Runs on the level-synchronous
+// path of this file; without a prior dmg_shard_init the table stays whole on this device (world 1).
+DMG_API int32_t dmg_load_deepfm_weights(dmg_handle_t h, int64_t rows, int32_t E, int32_t T, const float *params)
+{
+    if (!h) return DMG_ERR_INVALID_ARG;
+    if (!h->shard) DMG_TRY(dmg_shard_init(h, 1, 0, nullptr));
+    return shard_load_weights(h, rows, E, T, params, 1);
 }
 
 DMG_API int32_t dmg_shard_info(dmg_handle_t h, int64_t *local_rows, int64_t *global_rows, int64_t *exchanged_rows)
@@ -623,8 +783,9 @@ DMG_API int32_t dmg_shard_info(dmg_handle_t h, int64_t *local_rows, int64_t *glo
 }
 
 // TDM.recommend for this rank's B users over the sharded table (every rank calls it with the same B, beam, topk).
-DMG_API int32_t dmg_shard_tdm_retrieve(dmg_handle_t h, int32_t B, const int32_t *item_seq, int32_t beam, int32_t topk,
-                                       int32_t use_mask, int32_t *out_items, float *out_logits, int32_t *out_counts)
+static int32_t shard_tdm_retrieve_impl(dmg_handle_t h, int32_t B, const int32_t *item_seq, int32_t beam, int32_t topk,
+                                       int32_t use_mask, const int64_t *cons_off, const int32_t *cons,
+                                       int32_t *out_items, float *out_logits, int32_t *out_counts)
 {
     if (!h) return DMG_ERR_INVALID_ARG;
     ShardState *s = h->shard;
@@ -646,7 +807,7 @@ DMG_API int32_t dmg_shard_tdm_retrieve(dmg_handle_t h, int32_t B, const int32_t 
     const size_t need = Carver::need({(size_t)B * T * 4, (size_t)BU * T * 4, (size_t)B * T, (size_t)BU * T, (size_t)BU * T * E * 4,
                                       (size_t)stride * 4, (size_t)stride * 4, (size_t)B * 4, (size_t)G * stride * 8, (size_t)G * stride * 8,
                                       (size_t)G * stride * 4, (size_t)G * stride * 4, (size_t)G * 4, (size_t)G * G * 4,
-                                      (size_t)B * topk * 4, (size_t)B * topk * 4, (size_t)B * 4, (size_t)G * B * 8, (size_t)G * B * 8, 256});
+                                      (size_t)B * topk * 4, (size_t)B * topk * 4, (size_t)B * 4, (size_t)G * B * 8, (size_t)G * B * 8, 256, cons_off ? (size_t)(B + 1) * 8 : 0, cons_off ? (size_t)cons_off[B] * 4 : 0});
     DMG_TRY(ensure_dev(h, s->buf, need));
     DMG_TRY(ensure_host(h, s->buf, (size_t)B * T * 4 + (size_t)G * G * 4 + (size_t)B * topk * 8 + (size_t)B * 4 + 1024));
     Carver cd(s->buf.d);
@@ -670,6 +831,8 @@ DMG_API int32_t dmg_shard_tdm_retrieve(dmg_handle_t h, int32_t B, const int32_t 
     int2 *d_seg = cd.take<int2>((size_t)G * B);               // my segments, one table per owner
     int2 *d_rseg = cd.take<int2>((size_t)G * B);              // segments received, one table per requester
     int32_t *d_work = cd.take<int32_t>(64);
+    int64_t *d_cons_off = cons_off ? cd.take<int64_t>((size_t)B + 1) : nullptr;
+    int32_t *d_cons = cons_off ? cd.take<int32_t>((size_t)cons_off[B]) : nullptr;
     char *hp = (char *)s->buf.h;
     int32_t *h_seq = (int32_t *)hp; hp += (size_t)B * T * 4;
     int32_t *h_matrix = (int32_t *)hp; hp += (((size_t)G * G * 4 + 255) & ~(size_t)255);
@@ -681,6 +844,11 @@ DMG_API int32_t dmg_shard_tdm_retrieve(dmg_handle_t h, int32_t B, const int32_t 
     // ---- K2: ids -> codes + mask, replicated to every rank; history tiles by integer all-reduce ----------------
     memcpy(h_seq, item_seq, (size_t)B * T * 4);
     DMG_CUDA(h, cudaMemcpyAsync(d_seq, h_seq, (size_t)B * T * 4, cudaMemcpyHostToDevice, st));
+    if (cons_off) {                                              // small, once per call: straight from the caller's arrays, waited for below
+        DMG_CUDA(h, cudaMemcpyAsync(d_cons_off, cons_off, (size_t)(B + 1) * 8, cudaMemcpyHostToDevice, st));
+        if (cons_off[B]) DMG_CUDA(h, cudaMemcpyAsync(d_cons, cons, (size_t)cons_off[B] * 4, cudaMemcpyHostToDevice, st));
+        DMG_CUDA(h, cudaStreamSynchronize(st));
+    }
     int32_t *d_codes_mine = d_codes_all + (size_t)s->rank * B * T;
     uint8_t *d_mask_mine = d_mask_all + (size_t)s->rank * B * T;
     // TDMTree.idToCode validates against the table size: use the global row count here
@@ -705,8 +873,13 @@ DMG_API int32_t dmg_shard_tdm_retrieve(dmg_handle_t h, int32_t B, const int32_t 
     const size_t row_smem = (size_t)kRowsRB * ((size_t)4 * E + (size_t)T * E + T + 1) * 4;
     DMG_CUDA(h, cudaFuncSetAttribute(shard_score_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)row_smem));
     const float scale = (float)(1.0 / std::sqrt((double)E));
-    const bool tiled = E == 16 || E == 32 || E == 64;          // embedding sizes with a tile geometry that fits shared memory
-    if (tiled) {
+    const bool deepfm = d.kind == 1;
+    const bool tiled = deepfm || E == 16 || E == 32 || E == 64;   // DIN: embedding sizes with a tile geometry that fits shared memory
+    const size_t dfm_smem = DfmGeo::smem(E, T);
+    if (deepfm) {
+        if (dfm_smem > h->smem_optin) return fail(h, DMG_ERR_UNSUPPORTED, "DeepFM weights (%zu B) do not fit shared memory", dfm_smem);
+        DMG_CUDA(h, cudaFuncSetAttribute(shard_score_deepfm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dfm_smem));
+    } else if (tiled) {
         switch (E) {
         case 16: DMG_CUDA(h, cudaFuncSetAttribute(shard_score_segments_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)shard_score_smem<16>())); break;
         case 32: DMG_CUDA(h, cudaFuncSetAttribute(shard_score_segments_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)shard_score_smem<32>())); break;
@@ -747,6 +920,18 @@ DMG_API int32_t dmg_shard_tdm_retrieve(dmg_handle_t h, int32_t B, const int32_t 
             for (int p = 0; p < G; p++)                          // a requester that sent nothing sent no table either
                 if (p != s->rank && h_matrix[p * G + s->rank] == 0) DMG_CUDA(h, cudaMemsetAsync(d_rseg + (size_t)p * B, 0, (size_t)B * 8, st));
             DMG_CUDA(h, cudaMemsetAsync(d_work, 0, 4, st));
+            if (deepfm) {
+                ShardDfmArgs da;
+                da.emb = d.emb<float>(); da.dense = d.tail<float>(); da.tiles = d_tiles;
+                da.req_self = d_req; da.req_peer = d_rreq; da.seg_self = d_seg; da.seg_peer = d_rseg;
+                da.out_self = d_reply; da.out_peer = d_rsc; da.stride = stride; da.B = B; da.G = G; da.T = T; da.E = E;
+                da.work = d_work; da.geo = geo;
+                shard_score_deepfm_kernel<<<std::min(G * B, h->sm_count), kThreads, dfm_smem, st>>>(da);
+                h->launches += 1;
+                for (int p = 0; p < G; p++)
+                    if (p != s->rank) s->exchanged_rows += h_matrix[p * G + s->rank];
+                goto scored;
+            }
             ShardScoreArgs sa;
             sa.emb = d.emb<float>(); sa.wattT = (const float *)d.d_wattT; sa.w1T = (const float *)d.d_w1T;
             sa.b1 = d.b1<float>(); sa.w2 = d.w2<float>(); sa.b2 = d.b2<float>(); sa.tiles = d_tiles; sa.mask = d_mask_all;
@@ -776,6 +961,7 @@ DMG_API int32_t dmg_shard_tdm_retrieve(dmg_handle_t h, int32_t B, const int32_t 
             h->launches += 1;
             if (p != s->rank) s->exchanged_rows += nr;
         }
+    scored:
         if (G > 1) {
             DMG_NCCL(h, g_nccl.GroupStart());
             for (int p = 0; p < G; p++) {
@@ -795,7 +981,7 @@ DMG_API int32_t dmg_shard_tdm_retrieve(dmg_handle_t h, int32_t B, const int32_t 
         DMG_CUDA(h, cudaGetLastError());
     }
     shard_final_topk_kernel<<<B, kThreads, (size_t)capp * 8, st>>>(d_cand, d_score, d_count, cap, capp, topk, L, reached ? 1 : 0, t.d_leaf_item,
-                                                                   d_items, d_logits, d_cnt_out);
+                                                                   d_cons_off, d_cons, d_items, d_logits, d_cnt_out);
     h->launches += 1;
     DMG_CUDA(h, cudaGetLastError());
     DMG_CUDA(h, cudaMemcpyAsync(h_items, d_items, (size_t)B * topk * 4, cudaMemcpyDeviceToHost, st));
@@ -805,5 +991,50 @@ DMG_API int32_t dmg_shard_tdm_retrieve(dmg_handle_t h, int32_t B, const int32_t 
     memcpy(out_items, h_items, (size_t)B * topk * 4);
     memcpy(out_logits, h_logits, (size_t)B * topk * 4);
     memcpy(out_counts, h_cnt, (size_t)B * 4);
+    return DMG_OK;
+}
+
+DMG_API int32_t dmg_shard_tdm_retrieve(dmg_handle_t h, int32_t B, const int32_t *item_seq, int32_t beam, int32_t topk,
+                                       int32_t use_mask, int32_t *out_items, float *out_logits, int32_t *out_counts)
+{
+    return shard_tdm_retrieve_impl(h, B, item_seq, beam, topk, use_mask, nullptr, nullptr, out_items, out_logits, out_counts);
+}
+
+// dmg_tdm_retrieve / dmg_score_pairs with a DeepFM model loaded (called from capi.cu)
+int32_t dmg_deepfm_tdm_retrieve(dmg_handle_t h, int32_t B, const int32_t *item_seq, int32_t beam, int32_t topk,
+                                const int64_t *cons_off, const int32_t *cons, int32_t widen_beam,
+                                int32_t *out_items, float *out_logits, int32_t *out_counts)
+{
+    if (cons_off && widen_beam)
+        return fail(h, DMG_ERR_UNSUPPORTED, "DeepFM: the eval variant with per-user widened beams runs on the DIN path only");
+    if (h->shard && h->shard->world > 1 && cons_off) return fail(h, DMG_ERR_UNSUPPORTED, "consumed items with a sharded table");
+    return shard_tdm_retrieve_impl(h, B, item_seq, beam, topk, 0, cons_off, cons, out_items, out_logits, out_counts);
+}
+
+int32_t dmg_deepfm_score_pairs(dmg_handle_t h, int64_t n, const int32_t *node, const int32_t *seq, float *out)
+{
+    const DinDev &d = h->din;
+    if (h->shard && h->shard->world > 1) return fail(h, DMG_ERR_UNSUPPORTED, "dmg_score_pairs on a sharded table");
+    if (n <= 0) return DMG_OK;
+    DMG_CUDA(h, cudaSetDevice(h->device));
+    const int T = d.T, E = d.E, F = T + 1;
+    for (int64_t i = 0; i < n * (T + 1); i++) {
+        const int32_t c = i < n ? node[i] : seq[i - n];
+        if (c < -1 || c >= d.rows) return fail(h, DMG_ERR_INDEX, "dmg_score_pairs: embeddingLookup failed, index outside [0, %lld)", (long long)d.rows);
+    }
+    DMG_TRY(ensure_dev(h, h->s_in, Carver::need({(size_t)n * 4, (size_t)n * T * 4, (size_t)n * 4})));
+    Carver cd(h->s_in.d);
+    int32_t *dn = cd.take<int32_t>((size_t)n), *ds = cd.take<int32_t>((size_t)n * T);
+    float *dout = cd.take<float>((size_t)n);
+    DMG_CUDA(h, cudaMemcpyAsync(dn, node, (size_t)n * 4, cudaMemcpyHostToDevice, h->stream));
+    DMG_CUDA(h, cudaMemcpyAsync(ds, seq, (size_t)n * T * 4, cudaMemcpyHostToDevice, h->stream));
+    const size_t smem = ((size_t)8 * F * E + (size_t)8 * (F + 1)) * 4;
+    DMG_CUDA(h, cudaFuncSetAttribute(deepfm_rows_forward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const int grid = (int)std::min<int64_t>((n + 7) / 8, (int64_t)h->sm_count * 8);
+    deepfm_rows_forward_kernel<<<grid, 128, smem, h->stream>>>(d.emb<float>(), d.tail<float>(), E, T, n, dn, ds, dout);
+    h->launches += 1;
+    DMG_CUDA(h, cudaGetLastError());
+    DMG_CUDA(h, cudaMemcpyAsync(out, dout, (size_t)n * 4, cudaMemcpyDeviceToHost, h->stream));
+    DMG_CUDA(h, cudaStreamSynchronize(h->stream));
     return DMG_OK;
 }

@@ -27,8 +27,9 @@ class TDM:
 
     def __init__(self, engine: Optional[Engine] = None, device: int = 0, model_name: str = "din"):
         name = model_name.lower()
-        if name not in ("din",):
-            raise ValueError("DeepModel name should be DIN (DeepFM is not built yet)")   # TDM.scala:43
+        if name not in ("din", "deepfm"):
+            raise ValueError("DeepModel name should either be DeepFM or DIN")            # TDM.scala:43
+        self.model_name = name
         self.engine = engine or Engine(device)
         self.use_mask = name == "din"                                                     # TDM.scala:27
         self.tree: Optional[tree_file.TreeFile] = None
@@ -44,8 +45,11 @@ class TDM:
 
     # -- weights: compact vector of Module.parameters() (Graph.scala:37-48)
     def set_parameters(self, params: np.ndarray, embed_size: int, seq_len: int) -> "TDM":
-        rows = (1 << (self.tree.max_level + 1)) - 1                                       # DIN.scala:18
-        self.engine.load_din_weights(np.asarray(params, np.float32), rows, embed_size, seq_len)
+        rows = (1 << (self.tree.max_level + 1)) - 1                                       # DIN.scala:18, DeepFM.scala:14
+        if self.model_name == "deepfm":
+            self.engine.load_deepfm_weights(np.asarray(params, np.float32), rows, embed_size, seq_len)
+        else:
+            self.engine.load_din_weights(np.asarray(params, np.float32), rows, embed_size, seq_len)
         return self
 
     # -- TDM.recommend(sequence, topk, candidateNum): Array[(Int, Double)]
@@ -64,7 +68,9 @@ class TDM:
             off = np.zeros(len(consumed) + 1, np.int64)
             off[1:] = np.cumsum([len(c) for c in consumed])
             flat = np.concatenate([np.asarray(c, np.int32) for c in consumed]) if off[-1] else np.zeros(0, np.int32)
-            items, _, counts = self.engine.tdm_retrieve(seqs, candidate_num, topk, self.use_mask, off, flat, True)
+            # the DeepFM path filters consumed items but keeps the configured beam (per-user widening is DIN-only here)
+            items, _, counts = self.engine.tdm_retrieve(seqs, candidate_num, topk, self.use_mask, off, flat,
+                                                        self.model_name == "din")
         return [items[u, :counts[u]].tolist() for u in range(len(seqs))]
 
     def recommend_batch(self, sequences, topk: int, candidate_num: int):

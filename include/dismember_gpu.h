@@ -226,6 +226,15 @@ DMG_API int32_t dmg_jtm_item_weights(dmg_handle_t h, int32_t n_items, const int6
                                      int32_t old_level, int32_t level, int32_t hierarchical,
                                      int32_t min_level, int32_t use_mask, float *out_weights);
 
+/* DeepFM scorer, the other `model.deep_model` of the TDM/JTM tasks (tdm/.../model/DeepFM.scala:11-44,
+ * scalann/.../nn/FM.scala:14-44): params = the compact vector of Module.parameters()
+ * [emb rows x E | W1 (T+1) x (T+1)E | b1 T+1 | W2 T+1 | b2 1], fp32.  Afterwards dmg_tdm_retrieve
+ * (no mask; consumed items supported, widen_beam not) and dmg_score_pairs (mask arguments ignored)
+ * score with the DeepFM graph; results are bit-identical to the oracle's restatement.  After
+ * dmg_shard_init(world > 1) only this rank's rows are uploaded and dmg_shard_tdm_retrieve uses it. */
+DMG_API int32_t dmg_load_deepfm_weights(dmg_handle_t h, int64_t rows, int32_t E, int32_t T,
+                                        const float *params);
+
 /* ---- node table sharded across the GPUs of one box ------------------------------------ */
 /* The reference has no multi-device path: model replicas are per-thread clones
  * (tdm/.../optim/LocalOptimizer.scala:35-40) and users are split over threads

@@ -154,7 +154,43 @@ static void orc_sort_desc(orc_kp *a, int n)
 }
 
 /* ------------------------------------------------------------ TDM / JTM -- */
-struct orc_tdm_model { orc_din_f32 din; };
+/* DeepFM scorer, the other `model.deep_model` of the TDM/JTM tasks
+ * (tdm/src/main/scala/com/mass/tdm/model/DeepFM.scala:11-44): features F = [item row ; T history rows]
+ * ((T+1) x E, padding rows zero, NO mask);
+ *   FM   (scalann/.../nn/FM.scala:14-44): buffer = F_0 + F_1 + ... (vAdd in row order, from zero),
+ *         (dot(buffer, buffer) - dot(Fflat, Fflat)) / 2
+ *   DNN : Linear((T+1)E, T+1) -> ReLU -> Linear(T+1, 1) on Fflat  (Linear.scala:19-56: bias after the product)
+ *   Add  (nn/Add.scala): fm + dnn.
+ * Compact parameter vector (Graph.scala:37-48, topological order): [emb rows*E | W1 (T+1) x (T+1)E | b1 T+1 | W2 T+1 | b2 1]. */
+typedef struct { const float *w1, *b1, *w2, *b2; } orc_dfm_f32;
+struct orc_tdm_model { orc_din_f32 din; int deepfm; orc_dfm_f32 dfm; };
+
+static float orc_deepfm_row_f32(const orc_tdm_model *m, const float *q, const float *K, float *scratch)
+{
+    const int E = m->din.E, T = m->din.T, F = T + 1;
+    float *buf = scratch;                                           /* E */
+    for (int k = 0; k < E; k++) buf[k] = 0.0f;
+    for (int k = 0; k < E; k++) buf[k] = buf[k] + q[k];             /* vAdd, feature 0 = the item */
+    for (int j = 0; j < T; j++)
+        for (int k = 0; k < E; k++) buf[k] = buf[k] + K[(size_t)j * E + k];
+    float sum_square = 0.0f, square_sum = 0.0f;
+    for (int k = 0; k < E; k++) sum_square = fmaf(buf[k], buf[k], sum_square);
+    for (int k = 0; k < E; k++) square_sum = fmaf(q[k], q[k], square_sum);
+    for (int k = 0; k < T * E; k++) square_sum = fmaf(K[k], K[k], square_sum);
+    const float fm = (sum_square - square_sum) / 2.0f;
+    float dnn = 0.0f;
+    for (int o = 0; o < F; o++) {
+        const float *w = m->dfm.w1 + (size_t)o * F * E;
+        float acc = 0.0f;
+        for (int k = 0; k < E; k++) acc = fmaf(q[k], w[k], acc);
+        for (int k = 0; k < T * E; k++) acc = fmaf(K[k], w[E + k], acc);
+        float h = acc + m->dfm.b1[o];
+        h = h > 0.0f ? h : (h != h ? h : 0.0f);                     /* ReLU.scala:30-44: math.max(x, 0), NaN propagates */
+        dnn = fmaf(h, m->dfm.w2[o], dnn);
+    }
+    dnn = dnn + m->dfm.b2[0];
+    return fm + dnn;
+}
 
 orc_tdm_model *orc_tdm_model_create(int64_t rows, int E, int T, const float *params)
 {
@@ -164,11 +200,39 @@ orc_tdm_model *orc_tdm_model_create(int64_t rows, int E, int T, const float *par
     if (orc_din_init_f32(&m->din, rows, E, T, emb, watt, w1, b1, w2, b2)) { free(m); return NULL; }
     return m;
 }
-void orc_tdm_model_destroy(orc_tdm_model *m) { if (m) { orc_din_free_f32(&m->din); free(m); } }
+orc_tdm_model *orc_tdm_deepfm_create(int64_t rows, int E, int T, const float *params)
+{
+    orc_tdm_model *m = (orc_tdm_model *)calloc(1, sizeof(*m));
+    const int F = T + 1;
+    m->deepfm = 1;
+    m->din.rows = rows; m->din.E = E; m->din.T = T; m->din.emb = params;      /* gather + index checks reuse the DIN struct */
+    m->dfm.w1 = params + rows * E;
+    m->dfm.b1 = m->dfm.w1 + (int64_t)F * F * E;
+    m->dfm.w2 = m->dfm.b1 + F;
+    m->dfm.b2 = m->dfm.w2 + F;
+    return m;
+}
+void orc_tdm_model_destroy(orc_tdm_model *m) { if (m) { if (!m->deepfm) orc_din_free_f32(&m->din); free(m); } }
 
 int orc_din_forward_f32_api(const orc_tdm_model *m, int64_t n, const int32_t *node, const int32_t *seq,
                             const int32_t *mask_flat, int64_t n_mask, float *out)
 {
+    if (m->deepfm) {                                                 /* DeepFM takes no mask input (DeepFM.scala:14-15) */
+        const int E = m->din.E, T = m->din.T;
+        float *K = (float *)malloc(sizeof(float) * T * E), *q = (float *)malloc(sizeof(float) * E);
+        float *scratch = (float *)malloc(sizeof(float) * E);
+        int rc = 0;
+        for (int64_t r = 0; r < n; r++) {
+            if (orc_gather_history_f32(&m->din, seq + r * T, K)) { rc = -1; break; }
+            int32_t c = node[r];
+            if (c == -1) { for (int k = 0; k < E; k++) q[k] = 0.0f; }
+            else if (c >= 0 && (int64_t)c < m->din.rows) memcpy(q, m->din.emb + (size_t)c * E, sizeof(float) * E);
+            else { rc = -1; break; }
+            out[r] = orc_deepfm_row_f32(m, q, K, scratch);
+        }
+        free(K); free(q); free(scratch);
+        return rc;
+    }
     return orc_din_forward_f32(&m->din, n, node, seq, mask_flat, n_mask, out);
 }
 
@@ -246,7 +310,7 @@ int orc_tdm_recommend_raw(const orc_tree *t, const orc_tdm_model *m, const int32
         for (int i = 0; i < nc; i++) {
             const float *q = d->emb + (size_t)nl[i] * E;
             cand[i] = nl[i];
-            pred[i] = orc_din_row_f32(d, q, K, masked, scratch);
+            pred[i] = m->deepfm ? orc_deepfm_row_f32(m, q, K, scratch) : orc_din_row_f32(d, q, K, masked, scratch);
         }
         ncand = nc;
     }

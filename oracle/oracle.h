@@ -22,6 +22,8 @@ void orc_tdm_id_to_code(const orc_tree *t, int T, const int32_t *ids, int32_t *c
 
 /* params = compact DIN vector [emb | W_att | W1 | b1 | W2 | b2]; NOT copied. */
 orc_tdm_model *orc_tdm_model_create(int64_t rows, int E, int T, const float *params);
+/* params = compact DeepFM vector [emb | W1 (T+1)x(T+1)E | b1 | W2 | b2] (tdm/.../model/DeepFM.scala:11-44); NOT copied. */
+orc_tdm_model *orc_tdm_deepfm_create(int64_t rows, int E, int T, const float *params);
 void orc_tdm_model_destroy(orc_tdm_model *m);
 orc_otm_model *orc_otm_model_create(int64_t rows, int E, int T, const double *params);
 void orc_otm_model_destroy(orc_otm_model *m);

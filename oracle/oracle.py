@@ -48,6 +48,8 @@ def lib():
     L.orc_tdm_id_to_code.argtypes = [vp, C.c_int, i32p, i32p, u8p]
     L.orc_tdm_model_create.restype = vp
     L.orc_tdm_model_create.argtypes = [C.c_int64, C.c_int, C.c_int, f32p]
+    L.orc_tdm_deepfm_create.restype = vp
+    L.orc_tdm_deepfm_create.argtypes = [C.c_int64, C.c_int, C.c_int, f32p]
     L.orc_tdm_model_destroy.argtypes = [vp]
     L.orc_otm_model_create.restype = vp
     L.orc_otm_model_create.argtypes = [C.c_int64, C.c_int, C.c_int, f64p]
@@ -125,11 +127,15 @@ class Tree:
 class TdmModel:
     """DIN(Float) from the compact parameter vector."""
 
-    def __init__(self, params, rows, E, T):
+    def __init__(self, params, rows, E, T, deepfm=False):
         self.params = np.ascontiguousarray(params, np.float32)
-        assert self.params.size == rows * E + E * E + 2 * E * E + 2 * E + 1, "bad DIN parameter count"
         self.rows, self.E, self.T = int(rows), int(E), int(T)
-        self.h = lib().orc_tdm_model_create(self.rows, self.E, self.T, self.params)
+        if deepfm:                                   # tdm/.../model/DeepFM.scala: [emb | W1 (T+1)x(T+1)E | b1 | W2 | b2]
+            assert self.params.size == rows * E + (T + 1) * (T + 1) * E + 2 * (T + 1) + 1, "bad DeepFM parameter count"
+            self.h = lib().orc_tdm_deepfm_create(self.rows, self.E, self.T, self.params)
+        else:
+            assert self.params.size == rows * E + E * E + 2 * E * E + 2 * E + 1, "bad DIN parameter count"
+            self.h = lib().orc_tdm_model_create(self.rows, self.E, self.T, self.params)
 
     def forward(self, node, seq, mask_flat=None):
         node = _ci32(node).ravel()

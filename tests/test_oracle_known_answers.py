@@ -87,3 +87,30 @@ def test_sort_is_stable_total_order(orc, jtm_oracle):
     m = orc.TdmModel(zero, 8191, 16, 10)
     items, logits = m.recommend_raw(tree, np.zeros(10, np.int32), 20)
     assert (logits == 0).all() and len(items) > 0
+
+
+def test_deepfm_oracle_against_independent_float64(orc):
+    """DeepFM restatement (tdm/.../model/DeepFM.scala:11-44, nn/FM.scala:14-44) vs a float64 numpy evaluation of the
+    same graph written from the layer definitions: FM = (|sum F|^2 - sum |F|^2) / 2, DNN = W2.relu(W1.Fflat + b1) + b2."""
+    rows, E, T = 63, 8, 4
+    F = T + 1
+    rng = np.random.default_rng(0)
+    params = rng.normal(0, 0.3, rows * E + F * F * E + 2 * F + 1).astype(np.float32)
+    m = orc.TdmModel(params, rows, E, T, deepfm=True)
+    node = np.array([5, 7, -1, 62], np.int32)
+    seq = np.array([[1, 2, -1, 3], [4, 4, 4, 4], [0, 1, 2, 3], [-1, -1, -1, -1]], np.int32)
+    out = m.forward(node, seq)
+    p = params.astype(np.float64)
+    emb = p[:rows * E].reshape(rows, E)
+    w1 = p[rows * E:rows * E + F * F * E].reshape(F, F * E)
+    b1 = p[rows * E + F * F * E:rows * E + F * F * E + F]
+    w2 = p[rows * E + F * F * E + F:rows * E + F * F * E + 2 * F]
+    b2 = p[-1]
+    row = lambda c: np.zeros(E) if c < 0 else emb[c]
+    for r in range(len(node)):
+        Fm = np.stack([row(node[r])] + [row(c) for c in seq[r]])
+        fm = (np.sum(Fm.sum(0) ** 2) - np.sum(Fm ** 2)) / 2
+        ref = fm + np.maximum(w1 @ Fm.ravel() + b1, 0) @ w2 + b2
+        assert abs(out[r] - ref) <= 2e-6 * max(1.0, abs(ref))
+    with pytest.raises(IndexError):
+        m.forward(np.array([rows], np.int32), seq[:1])

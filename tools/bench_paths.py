@@ -127,6 +127,37 @@ def main():
          scorer_rows=scored, ms=dt * 1e3, scorer_rows_per_s=scored / dt)
     eng.close()
 
+    # ---- 2b. TDM retrieval with the DeepFM scorer: level-synchronous path of shard.cu, world 1 ----------
+    n_items = 100_000 if a.quick else 1_000_000
+    tf = synth.tdm_tree(n_items, seed=1)
+    L = tf.max_level
+    rows_tab = (1 << (L + 1)) - 1
+    F = T + 1
+    rng = np.random.Generator(np.random.PCG64(13))
+    dparams = np.concatenate([rng.normal(0, 0.05, rows_tab * E), rng.normal(0, 0.05, F * F * E), np.zeros(F),
+                              rng.normal(0, 0.3, F), [0.0]]).astype(np.float32)
+    eng = Engine(0)
+    eng.load_tree_tdm(L, tf.codes, tf.node_ids, tf.is_leaf, tf.leaf_ids, tf.leaf_codes)
+    eng.load_deepfm_weights(dparams, rows_tab, E, T)
+    B = 1024
+    dq = synth.queries(B, T, n_items, seed=31)
+    dt = timeit(lambda: eng.tdm_retrieve(dq, 200, 10), warm=1, reps=3)
+    rows_u = 256 + 400 * (L - 8)
+    by_u = rows_u * E * 4 + T * E * 4 + 10 * 8
+    emit(path="tdm_retrieve with the DeepFM scorer (level-synchronous, strict fp32)", items=n_items, levels=L, batch=B, ms=dt * 1e3,
+         users_per_s=B / dt, roofline={"bound": "fp32 FMA pipe", "algorithmic_flop_per_user": rows_u * 2 * (F + 1) * F * E,
+                                       "achieved_tflops": rows_u * 2 * (F + 1) * F * E * B / dt / 1e12,
+                                       "hbm_algorithmic_gbs": by_u * B / dt / 1e9})
+    dm = orc.TdmModel(dparams, rows_tab, E, T, deepfm=True)
+    tree = orc.Tree.from_treefile(tf)
+    t0 = time.perf_counter()
+    oi, ol, oc = dm.retrieve_batch(tree, dq[:4 * threads], 200, 10, n_threads=threads)
+    cdt = time.perf_counter() - t0
+    gi, gl, gc = eng.tdm_retrieve(dq[:4 * threads], 200, 10)
+    emit(path="tdm_retrieve DeepFM cpu_baseline", kind="port", cores=threads, users_per_s=4 * threads / cdt,
+         parity={"ids_identical": bool((gi == oi).all()), "logits_bit_identical": bool((gl.view(np.uint32) == ol.view(np.uint32)).all())})
+    eng.close()
+
     # ---- 3. OTM retrieval, fp64 (a13-a14) ------------------------------------------------------------------------
     n_items = 100_000 if a.quick else 1_000_000
     items, leaf_ids, leaf_level = synth.otm_mapping(n_items, seed=42)
