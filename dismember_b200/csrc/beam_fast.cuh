@@ -502,7 +502,7 @@ __global__ void __launch_bounds__(FastGeo::THREADS, 2) beam_search_fast_kernel(c
         *reinterpret_cast<uint4 *>(sBh + kc * G::B_LBO + o * 16) = hi;
         *reinterpret_cast<uint4 *>(sBl + kc * G::B_LBO + o * 16) = lo;
     }
-    if (tid == 0) { mbar_init(&sBar[0], 1); mbar_init(&sBar[1], 1); mbar_init(&sBar[2], 1); }
+    if (tid == 0) { for (int i = 0; i < 5; i++) mbar_init(&sBar[i], 1); }      // [0] history TMA; tile t: [1 + 2t] X.[W1x|K]^T done, [2 + 2t] P.H done
     if (warp == 0) tmem_alloc(reinterpret_cast<uint32_t *>(&sMisc[41]), 256);   // tile t: Hacc [128t, 128t+64), S [128t+64, 128t+80)
     tc_fence_before();
     __syncthreads();
@@ -512,7 +512,7 @@ __global__ void __launch_bounds__(FastGeo::THREADS, 2) beam_search_fast_kernel(c
     const int tile_of_warp = warp >> 2;
     const float scale2 = p.scale * 1.4426950408889634f, inv_T = 1.0f / (float)T;
     float *sAddv = reinterpret_cast<float *>(sMisc + 64);               // [16] additive softmax mask of the current user
-    uint32_t hist_phase = 0, s_phase = 0, h_phase = 0;
+    uint32_t hist_phase = 0, s_phase = 0;                        // s_phase: phase of this warpgroup's two MMA mbarriers
     unsigned long long st_cuts = 0, st_recuts = 0, st_rerows = 0, st_rows = 0, st_redo = 0, st_sync = 0, st_iters = 0;
     float st_ratio = 0.0f;
 #ifdef DMG_FAST_TIMING
@@ -803,122 +803,154 @@ __global__ void __launch_bounds__(FastGeo::THREADS, 2) beam_search_fast_kernel(c
 
             // ---- fast scoring, 256 rows per pass ---------------------------------------------------------
             if (tid == 0) { sMisc[50] = -1; sMisc[51] = 0; }      // min / max order key of this level's scores (epilogue); ordered by the gather barrier
+            // The two M tiles of a pass belong to the two warpgroups (TMEM lanes of warp w are 32 (w & 3) ..): after the
+            // shared gather each group runs its own chain  wait S -> softmax -> P -> MMA P.H -> wait -> epilogue  on its
+            // own mbarriers and a 128-thread named barrier, so tile 1's X.[W1x|K]^T runs under tile 0's softmax and the
+            // P.H products of one tile under the other tile's epilogue.
             for (int r0 = 0; r0 < count; r0 += G::R) {
                 const int nrows = count - r0 < G::R ? count - r0 : G::R;
                 const int ntile = nrows > 128 ? 2 : 1;
-                // (A) gather rows -> bf16 hi/lo operand tiles
-                {
-                    const int chunk = lane & 15, rowbase = warp * 2 + (lane >> 4);
-                    const uint32_t st_off = (uint32_t)((chunk >> 1) * G::X_LBO + (chunk & 1) * 8 + rowbase * 16);
-                    if (ntile == 2) gather_convert<16>(p.emb + chunk * 4, cur + r0, nrows, rowbase, sXh + st_off, sXl + st_off);
-                    else gather_convert<8>(p.emb + chunk * 4, cur + r0, nrows, rowbase, sXh + st_off, sXl + st_off);
+                const int grp = warp >> 2;
+                // (A) gather rows -> bf16 hi/lo operand tiles; every load of the pass is in flight before the first use
+                const int chunk = lane & 15, rowbase = warp * 2 + (lane >> 4);
+                unsigned char *dstH = sXh + (uint32_t)((chunk >> 1) * G::X_LBO + (chunk & 1) * 8 + rowbase * 16);
+                unsigned char *dstL = sXl + (uint32_t)((chunk >> 1) * G::X_LBO + (chunk & 1) * 8 + rowbase * 16);
+                float4 v[16];
+#pragma unroll
+                for (int q = 0; q < 16; q++) {
+                    if (q < 8 * ntile) {
+                        int row = q * 16 + rowbase;
+                        row = row < nrows ? row : nrows - 1;
+                        v[q] = ldg_row16(p.emb + chunk * 4 + (size_t)cur[r0 + row] * 64);
+                    }
+                }
+                const uint64_t dXh = mkdesc(OFF_XH, G::X_LBO), dXl = mkdesc(OFF_XL, G::X_LBO);
+                const uint64_t dBh = mkdesc(OFF_BH, G::B_LBO), dBl = mkdesc(OFF_BL, G::B_LBO);
+                // (B) [Hacc | S] = X . [W1x | K]^T of tile t (N = 80: one pass over the A operand): 4 k-steps x (hi*hi + hi*lo +
+                // lo*hi); the issuing warp runs the descriptor arithmetic warp-uniformly, one elected lane issues.
+                auto issue_xw = [&](int t) {
+                    tc_fence_after();
+                    const bool leader = elect_one();
+                    const uint64_t xo = (uint64_t)(t * 128);                // 128 rows x 16 B, in 16-byte descriptor units
+#pragma unroll
+                    for (int ks = 0; ks < 4; ks++) {
+                        const uint64_t ah = dXh + xo + ks * (2 * G::X_LBO / 16), al = dXl + xo + ks * (2 * G::X_LBO / 16);
+                        const uint64_t bh = dBh + ks * (2 * G::B_LBO / 16), bl = dBl + ks * (2 * G::B_LBO / 16);
+                        if (leader) {
+                            umma_bf16(tmem_base + t * 128, ah, bh, kIdescBf16M128N80, ks > 0);
+                            umma_bf16(tmem_base + t * 128, ah, bl, kIdescBf16M128N80, 1);
+                            umma_bf16(tmem_base + t * 128, al, bh, kIdescBf16M128N80, 1);
+                        }
+                    }
+                    if (leader) umma_commit(&sBar[1 + 2 * t]);
+                    __syncwarp();
+                };
+#pragma unroll
+                for (int q = 0; q < 8; q++) {
+                    uint2 hi, lo;
+                    split_pair(v[q].x, v[q].y, hi.x, lo.x);
+                    split_pair(v[q].z, v[q].w, hi.y, lo.y);
+                    *reinterpret_cast<uint2 *>(dstH + q * 256) = hi;
+                    *reinterpret_cast<uint2 *>(dstL + q * 256) = lo;
                 }
                 fence_proxy_async();
                 tc_fence_before();
                 __syncthreads();
                 DMG_TICK(TK_GATHER);
-                // (B) [Hacc | S] = X . [W1x | K]^T (N = 80: one pass over the A operand): 4 k-steps x (hi*hi + hi*lo + lo*hi).
-                // Warp 0 runs the descriptor arithmetic warp-uniformly; one elected lane issues.
-                if (warp == 0) {
-                    tc_fence_after();
-                    const bool leader = elect_one();
-                    const uint64_t dXh = mkdesc(OFF_XH, G::X_LBO), dXl = mkdesc(OFF_XL, G::X_LBO);
-                    const uint64_t dBh = mkdesc(OFF_BH, G::B_LBO), dBl = mkdesc(OFF_BL, G::B_LBO);
-                    for (int t = 0; t < ntile; t++) {
-                        const uint64_t xo = (uint64_t)(t * 128);            // 128 rows x 16 B, in 16-byte descriptor units
+                if (warp == 0) issue_xw(0);
+                if (ntile == 2) {
 #pragma unroll
-                        for (int ks = 0; ks < 4; ks++) {
-                            const uint64_t ah = dXh + xo + ks * (2 * G::X_LBO / 16), al = dXl + xo + ks * (2 * G::X_LBO / 16);
-                            const uint64_t bh = dBh + ks * (2 * G::B_LBO / 16), bl = dBl + ks * (2 * G::B_LBO / 16);
-                            if (leader) {
-                                umma_bf16(tmem_base + t * 128, ah, bh, kIdescBf16M128N80, ks > 0);
-                                umma_bf16(tmem_base + t * 128, ah, bl, kIdescBf16M128N80, 1);
-                                umma_bf16(tmem_base + t * 128, al, bh, kIdescBf16M128N80, 1);
+                    for (int q = 8; q < 16; q++) {
+                        uint2 hi, lo;
+                        split_pair(v[q].x, v[q].y, hi.x, lo.x);
+                        split_pair(v[q].z, v[q].w, hi.y, lo.y);
+                        *reinterpret_cast<uint2 *>(dstH + q * 256) = hi;
+                        *reinterpret_cast<uint2 *>(dstL + q * 256) = lo;
+                    }
+                    fence_proxy_async();
+                    tc_fence_before();
+                    __syncthreads();
+                    DMG_TICK(TK_GATHER);
+                    if (warp == 4) issue_xw(1);
+                }
+                if (grp < ntile) {
+                    // (C) Mask + SoftMax per row in registers (log2 domain: t_j = S_j * scale*log2e + addv_j, addv_j = -FLT_MAX on
+                    // padded / masked slots), P -> bf16 hi/lo A operand [256][16]; column 15 = 1 multiplies the b1 row of H
+                    if (warp * 32 < nrows) {
+                        mbar_wait(&sBar[1 + 2 * grp], s_phase);
+                        tc_fence_after();
+                        DMG_TICK(TK_MMAWAIT);
+                        float sc[16];
+                        tmem_ld16(tmem_base + tmem_lane + grp * 128 + 64, sc);
+                        if (all_masked) {                         // SoftMax of T equal values: exactly 1/T each
+#pragma unroll
+                            for (int j = 0; j < 16; j++) sc[j] = j < T ? inv_T : 0.0f;
+                        } else {
+                            float mx = -3.4028234663852886e+38f;
+#pragma unroll
+                            for (int j = 0; j < 16; j++) {
+                                sc[j] = fmaf(sc[j], scale2, sAddv[j]);
+                                mx = fmaxf(mx, sc[j]);
                             }
+                            float sum = 0.0f;
+#pragma unroll
+                            for (int j = 0; j < 16; j++) { sc[j] = ex2_approx(sc[j] - mx); sum += sc[j]; }
+                            const float inv = 1.0f / sum;
+#pragma unroll
+                            for (int j = 0; j < 16; j++) sc[j] *= inv;
                         }
+                        sc[15] = 1.0f;
+                        uint4 hi, lo;
+                        split8(*reinterpret_cast<float(*)[8]>(&sc[0]), hi, lo);
+                        *reinterpret_cast<uint4 *>(sPh + tid * 16) = hi;
+                        *reinterpret_cast<uint4 *>(sPl + tid * 16) = lo;
+                        split8(*reinterpret_cast<float(*)[8]>(&sc[8]), hi, lo);
+                        *reinterpret_cast<uint4 *>(sPh + G::P_LBO + tid * 16) = hi;
+                        *reinterpret_cast<uint4 *>(sPl + G::P_LBO + tid * 16) = lo;
                     }
-                    if (leader) umma_commit(&sBar[1]);
-                    __syncwarp();
-                }
-                // (C) Mask + SoftMax per row in registers (log2 domain: t_j = S_j * scale*log2e + addv_j, addv_j = -FLT_MAX on
-                // padded / masked slots), P -> bf16 hi/lo A operand [256][16]; column 15 = 1 multiplies the b1 row of H
-                if (warp * 32 < nrows) {
-                    mbar_wait(&sBar[1], s_phase);
-                    tc_fence_after();
-                    DMG_TICK(TK_MMAWAIT);
-                    float sc[16];
-                    tmem_ld16(tmem_base + tmem_lane + tile_of_warp * 128 + 64, sc);
-                    if (all_masked) {                             // SoftMax of T equal values: exactly 1/T each
-#pragma unroll
-                        for (int j = 0; j < 16; j++) sc[j] = j < T ? inv_T : 0.0f;
-                    } else {
-                        float mx = -3.4028234663852886e+38f;
-#pragma unroll
-                        for (int j = 0; j < 16; j++) {
-                            sc[j] = fmaf(sc[j], scale2, sAddv[j]);
-                            mx = fmaxf(mx, sc[j]);
-                        }
-                        float sum = 0.0f;
-#pragma unroll
-                        for (int j = 0; j < 16; j++) { sc[j] = ex2_approx(sc[j] - mx); sum += sc[j]; }
-                        const float inv = 1.0f / sum;
-#pragma unroll
-                        for (int j = 0; j < 16; j++) sc[j] *= inv;
-                    }
-                    sc[15] = 1.0f;
-                    uint4 hi, lo;
-                    split8(*reinterpret_cast<float(*)[8]>(&sc[0]), hi, lo);
-                    *reinterpret_cast<uint4 *>(sPh + tid * 16) = hi;
-                    *reinterpret_cast<uint4 *>(sPl + tid * 16) = lo;
-                    split8(*reinterpret_cast<float(*)[8]>(&sc[8]), hi, lo);
-                    *reinterpret_cast<uint4 *>(sPh + G::P_LBO + tid * 16) = hi;
-                    *reinterpret_cast<uint4 *>(sPl + G::P_LBO + tid * 16) = lo;
-                }
-                s_phase ^= 1;
-                fence_proxy_async();
-                tc_fence_before();
-                __syncthreads();
-                DMG_TICK(TK_SOFTMAX);
-                // (D) Hacc += P . H (one k-step of 16; row 15 of H holds b1)
-                if (warp == 0) {
-                    tc_fence_after();
-                    const bool leader = elect_one();
-                    const uint64_t dPh = mkdesc(OFF_PH, G::P_LBO), dPl = mkdesc(OFF_PL, G::P_LBO);
-                    const uint64_t dHh = mkdesc(OFF_HH, G::H_LBO), dHl = mkdesc(OFF_HL, G::H_LBO);
-                    for (int t = 0; t < ntile; t++) {
-                        const uint64_t ah = dPh + (uint64_t)(t * 128), al = dPl + (uint64_t)(t * 128);
+                    fence_proxy_async();
+                    tc_fence_before();
+                    if (grp == 0) asm volatile("bar.sync 1, 128;" ::: "memory");             // the group's P rows are complete
+                    else asm volatile("bar.sync 2, 128;" ::: "memory");
+                    DMG_TICK(TK_SOFTMAX);
+                    // (D) Hacc += P . H of this group's tile (one k-step of 16; row 15 of H holds b1)
+                    if ((warp & 3) == 0) {
+                        tc_fence_after();
+                        const bool leader = elect_one();
+                        const uint64_t dHh = mkdesc(OFF_HH, G::H_LBO), dHl = mkdesc(OFF_HL, G::H_LBO);
+                        const uint64_t ah = mkdesc(OFF_PH, G::P_LBO) + (uint64_t)(grp * 128), al = mkdesc(OFF_PL, G::P_LBO) + (uint64_t)(grp * 128);
                         if (leader) {
-                            umma_bf16(tmem_base + t * 128, ah, dHh, kIdescBf16M128N64, 1);
-                            umma_bf16(tmem_base + t * 128, ah, dHl, kIdescBf16M128N64, 1);
-                            umma_bf16(tmem_base + t * 128, al, dHh, kIdescBf16M128N64, 1);
+                            umma_bf16(tmem_base + grp * 128, ah, dHh, kIdescBf16M128N64, 1);
+                            umma_bf16(tmem_base + grp * 128, ah, dHl, kIdescBf16M128N64, 1);
+                            umma_bf16(tmem_base + grp * 128, al, dHh, kIdescBf16M128N64, 1);
+                            umma_commit(&sBar[2 + 2 * grp]);
+                        }
+                        __syncwarp();
+                    }
+                    // (E) epilogue: logit = relu(Hacc) . W2 + b2 (b1 already inside Hacc), one row per thread
+                    if (warp * 32 < nrows) {
+                        mbar_wait(&sBar[2 + 2 * grp], s_phase);
+                        tc_fence_after();
+                        DMG_TICK(TK_PHWAIT);
+                        float logit = 0.0f;
+#pragma unroll
+                        for (int hf = 0; hf < 2; hf++) {
+                            float hv[32];
+                            tmem_ld32(tmem_base + tmem_lane + grp * 128 + hf * 32, hv);
+#pragma unroll
+                            for (int c = 0; c < 32; c++) logit = fmaf(fmaxf(hv[c], 0.0f), fp.w2[hf * 32 + c], logit);
+                        }
+                        const float sc_out = logit + fp.b2;
+                        if (tid < nrows) sScore[r0 + tid] = sc_out;
+                        {
+                            const uint32_t ky = order_key(sc_out);
+                            const uint32_t wmn = __reduce_min_sync(0xffffffffu, tid < nrows ? ky : 0xffffffffu);
+                            const uint32_t wmx = __reduce_max_sync(0xffffffffu, tid < nrows ? ky : 0u);
+                            if (lane == 0) { atomicMin(reinterpret_cast<unsigned int *>(&sMisc[50]), wmn); atomicMax(reinterpret_cast<unsigned int *>(&sMisc[51]), wmx); }
                         }
                     }
-                    if (leader) umma_commit(&sBar[2]);
-                    __syncwarp();
+                    s_phase ^= 1;                                 // both mbarriers of the group completed one phase
                 }
-                // (E) epilogue: logit = relu(Hacc) . W2 + b2 (b1 already inside Hacc), one row per thread
-                if (warp * 32 < nrows) {
-                    mbar_wait(&sBar[2], h_phase);
-                    tc_fence_after();
-                    DMG_TICK(TK_PHWAIT);
-                    float logit = 0.0f;
-#pragma unroll
-                    for (int hf = 0; hf < 2; hf++) {
-                        float v[32];
-                        tmem_ld32(tmem_base + tmem_lane + tile_of_warp * 128 + hf * 32, v);
-#pragma unroll
-                        for (int c = 0; c < 32; c++) logit = fmaf(fmaxf(v[c], 0.0f), fp.w2[hf * 32 + c], logit);
-                    }
-                    const float sc_out = logit + fp.b2;
-                    if (tid < nrows) sScore[r0 + tid] = sc_out;
-                    {
-                        const uint32_t ky = order_key(sc_out);
-                        const uint32_t wmn = __reduce_min_sync(0xffffffffu, tid < nrows ? ky : 0xffffffffu);
-                        const uint32_t wmx = __reduce_max_sync(0xffffffffu, tid < nrows ? ky : 0u);
-                        if (lane == 0) { atomicMin(reinterpret_cast<unsigned int *>(&sMisc[50]), wmn); atomicMax(reinterpret_cast<unsigned int *>(&sMisc[51]), wmx); }
-                    }
-                }
-                h_phase ^= 1;
                 tc_fence_before();
                 __syncthreads();
                 DMG_TICK(TK_EPILOGUE);
