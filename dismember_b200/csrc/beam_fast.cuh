@@ -416,17 +416,17 @@ __device__ __forceinline__ void block_select(uint32_t k0, uint32_t k1, int k, ui
     }
 }
 
-// ---- (A) gather NIT x 16 rows of the pass: 16 lanes x 16 B per row, every load issued before the first use --
-// codes: candidate codes of the pass (shared), row = q*16 + rowbase; rows past nrows re-read the last valid row
+// ---- (A) gather NIT x RS rows of a tile: 16 lanes x 16 B per row, every load issued before the first use --
+// codes: candidate codes of the tile (shared), row = q*RS + rowbase; rows past nrows re-read the last valid row
 // (their operand rows are never consumed).  dst: operand base + this thread's chunk / row offset.
-template <int NIT>
+template <int NIT, int RS>
 __device__ __forceinline__ void gather_convert(const float *__restrict__ emb_chunk, const int32_t *__restrict__ codes, int nrows,
                                                int rowbase, unsigned char *__restrict__ dstH, unsigned char *__restrict__ dstL)
 {
     float4 v[NIT];
 #pragma unroll
     for (int q = 0; q < NIT; q++) {
-        int row = q * 16 + rowbase;
+        int row = q * RS + rowbase;
         row = row < nrows ? row : nrows - 1;
         v[q] = ldg_row16(emb_chunk + (size_t)codes[row] * 64);
     }
@@ -435,8 +435,8 @@ __device__ __forceinline__ void gather_convert(const float *__restrict__ emb_chu
         uint2 hi, lo;
         split_pair(v[q].x, v[q].y, hi.x, lo.x);
         split_pair(v[q].z, v[q].w, hi.y, lo.y);
-        *reinterpret_cast<uint2 *>(dstH + q * 256) = hi;
-        *reinterpret_cast<uint2 *>(dstL + q * 256) = lo;
+        *reinterpret_cast<uint2 *>(dstH + q * RS * 16) = hi;
+        *reinterpret_cast<uint2 *>(dstL + q * RS * 16) = lo;
     }
 }
 __device__ __forceinline__ float ex2_approx(float x)
@@ -781,6 +781,7 @@ __global__ void __launch_bounds__(FastGeo::THREADS, 2) beam_search_fast_kernel(c
                 if (a2) nxt[o++] = (int32_t)(2 * c0 + 2);
                 if (b1) nxt[o++] = (int32_t)(2 * c1 + 1);
                 if (b2) nxt[o++] = (int32_t)(2 * c1 + 2);
+                if (tid == 0) { sMisc[50] = -1; sMisc[51] = 0; }  // min / max order key of the scores of the level about to be scored (epilogue atomics)
             }
             __syncthreads();
             { int32_t *t = cur; cur = nxt; nxt = t; }
@@ -802,86 +803,67 @@ __global__ void __launch_bounds__(FastGeo::THREADS, 2) beam_search_fast_kernel(c
             }
 
             // ---- fast scoring, 256 rows per pass ---------------------------------------------------------
-            if (tid == 0) { sMisc[50] = -1; sMisc[51] = 0; }      // min / max order key of this level's scores (epilogue); ordered by the gather barrier
-            // The two M tiles of a pass belong to the two warpgroups (TMEM lanes of warp w are 32 (w & 3) ..): after the
-            // shared gather each group runs its own chain  wait S -> softmax -> P -> MMA P.H -> wait -> epilogue  on its
-            // own mbarriers and a 128-thread named barrier, so tile 1's X.[W1x|K]^T runs under tile 0's softmax and the
-            // P.H products of one tile under the other tile's epilogue.
-            for (int r0 = 0; r0 < count; r0 += G::R) {
-                const int nrows = count - r0 < G::R ? count - r0 : G::R;
-                const int ntile = nrows > 128 ? 2 : 1;
-                const int grp = warp >> 2;
-                // (A) gather rows -> bf16 hi/lo operand tiles; every load of the pass is in flight before the first use
-                const int chunk = lane & 15, rowbase = warp * 2 + (lane >> 4);
-                unsigned char *dstH = sXh + (uint32_t)((chunk >> 1) * G::X_LBO + (chunk & 1) * 8 + rowbase * 16);
-                unsigned char *dstL = sXl + (uint32_t)((chunk >> 1) * G::X_LBO + (chunk & 1) * 8 + rowbase * 16);
-                float4 v[16];
-#pragma unroll
-                for (int q = 0; q < 16; q++) {
-                    if (q < 8 * ntile) {
-                        int row = q * 16 + rowbase;
-                        row = row < nrows ? row : nrows - 1;
-                        v[q] = ldg_row16(p.emb + chunk * 4 + (size_t)cur[r0 + row] * 64);
+            // Two independent scoring chains per CTA: warpgroup g (TMEM lanes of warp w are 32 (w & 3) ..) owns M tile g --
+            // its own rows of X and P in shared memory, its own accumulators in TMEM, its own mbarriers and a 128-thread
+            // named barrier -- and runs  gather -> convert -> MMA X.[W1x|K]^T -> softmax -> MMA P.H -> epilogue  without a
+            // CTA-wide barrier; the groups meet again at the end of the level.  First up to 128 rows each, then the rest of
+            // the level split in halves (400 candidates: 128 + 72 rows per group), so both chains carry the same work.
+            {
+                const int grp = warp >> 2, gw = warp & 3, gtid = tid & 127;
+                const uint64_t xo = (uint64_t)(grp * 128);                    // this group's 128 rows x 16 B, in 16-byte descriptor units
+                const uint32_t tm = tmem_base + grp * 128;
+                for (int it = 0; it < 2; it++) {
+                    int rbeg, nr;
+                    if (it == 0) { rbeg = grp * 128; nr = count - rbeg < 128 ? count - rbeg : 128; }
+                    else {
+                        const int rem = count - 256;
+                        if (rem <= 0) break;
+                        const int h = (rem + 1) >> 1;
+                        rbeg = 256 + grp * h;
+                        nr = grp == 0 ? h : rem - h;
                     }
-                }
-                const uint64_t dXh = mkdesc(OFF_XH, G::X_LBO), dXl = mkdesc(OFF_XL, G::X_LBO);
-                const uint64_t dBh = mkdesc(OFF_BH, G::B_LBO), dBl = mkdesc(OFF_BL, G::B_LBO);
-                // (B) [Hacc | S] = X . [W1x | K]^T of tile t (N = 80: one pass over the A operand): 4 k-steps x (hi*hi + hi*lo +
-                // lo*hi); the issuing warp runs the descriptor arithmetic warp-uniformly, one elected lane issues.
-                auto issue_xw = [&](int t) {
-                    tc_fence_after();
-                    const bool leader = elect_one();
-                    const uint64_t xo = (uint64_t)(t * 128);                // 128 rows x 16 B, in 16-byte descriptor units
-#pragma unroll
-                    for (int ks = 0; ks < 4; ks++) {
-                        const uint64_t ah = dXh + xo + ks * (2 * G::X_LBO / 16), al = dXl + xo + ks * (2 * G::X_LBO / 16);
-                        const uint64_t bh = dBh + ks * (2 * G::B_LBO / 16), bl = dBl + ks * (2 * G::B_LBO / 16);
-                        if (leader) {
-                            umma_bf16(tmem_base + t * 128, ah, bh, kIdescBf16M128N80, ks > 0);
-                            umma_bf16(tmem_base + t * 128, ah, bl, kIdescBf16M128N80, 1);
-                            umma_bf16(tmem_base + t * 128, al, bh, kIdescBf16M128N80, 1);
-                        }
-                    }
-                    if (leader) umma_commit(&sBar[1 + 2 * t]);
-                    __syncwarp();
-                };
-#pragma unroll
-                for (int q = 0; q < 8; q++) {
-                    uint2 hi, lo;
-                    split_pair(v[q].x, v[q].y, hi.x, lo.x);
-                    split_pair(v[q].z, v[q].w, hi.y, lo.y);
-                    *reinterpret_cast<uint2 *>(dstH + q * 256) = hi;
-                    *reinterpret_cast<uint2 *>(dstL + q * 256) = lo;
-                }
-                fence_proxy_async();
-                tc_fence_before();
-                __syncthreads();
-                DMG_TICK(TK_GATHER);
-                if (warp == 0) issue_xw(0);
-                if (ntile == 2) {
-#pragma unroll
-                    for (int q = 8; q < 16; q++) {
-                        uint2 hi, lo;
-                        split_pair(v[q].x, v[q].y, hi.x, lo.x);
-                        split_pair(v[q].z, v[q].w, hi.y, lo.y);
-                        *reinterpret_cast<uint2 *>(dstH + q * 256) = hi;
-                        *reinterpret_cast<uint2 *>(dstL + q * 256) = lo;
+                    if (nr <= 0) continue;
+                    // (A) gather rows -> bf16 hi/lo operand tile; every load is in flight before the first use
+                    {
+                        const int chunk = lane & 15, rowbase = gw * 2 + (lane >> 4);
+                        const uint32_t st_off = (uint32_t)((chunk >> 1) * G::X_LBO + (chunk & 1) * 8 + (grp * 128 + rowbase) * 16);
+                        if (nr > 80) gather_convert<16, 8>(p.emb + chunk * 4, cur + rbeg, nr, rowbase, sXh + st_off, sXl + st_off);
+                        else if (nr > 64) gather_convert<10, 8>(p.emb + chunk * 4, cur + rbeg, nr, rowbase, sXh + st_off, sXl + st_off);
+                        else gather_convert<8, 8>(p.emb + chunk * 4, cur + rbeg, nr, rowbase, sXh + st_off, sXl + st_off);
                     }
                     fence_proxy_async();
                     tc_fence_before();
-                    __syncthreads();
+                    if (grp == 0) asm volatile("bar.sync 1, 128;" ::: "memory");
+                    else asm volatile("bar.sync 2, 128;" ::: "memory");
                     DMG_TICK(TK_GATHER);
-                    if (warp == 4) issue_xw(1);
-                }
-                if (grp < ntile) {
+                    // (B) [Hacc | S] = X . [W1x | K]^T (N = 80: one pass over the A operand): 4 k-steps x (hi*hi + hi*lo + lo*hi).
+                    // The group's first warp runs the descriptor arithmetic warp-uniformly; one elected lane issues.
+                    if (gw == 0) {
+                        tc_fence_after();
+                        const bool leader = elect_one();
+                        const uint64_t dXh = mkdesc(OFF_XH, G::X_LBO) + xo, dXl = mkdesc(OFF_XL, G::X_LBO) + xo;
+                        const uint64_t dBh = mkdesc(OFF_BH, G::B_LBO), dBl = mkdesc(OFF_BL, G::B_LBO);
+#pragma unroll
+                        for (int ks = 0; ks < 4; ks++) {
+                            const uint64_t ah = dXh + ks * (2 * G::X_LBO / 16), al = dXl + ks * (2 * G::X_LBO / 16);
+                            const uint64_t bh = dBh + ks * (2 * G::B_LBO / 16), bl = dBl + ks * (2 * G::B_LBO / 16);
+                            if (leader) {
+                                umma_bf16(tm, ah, bh, kIdescBf16M128N80, ks > 0);
+                                umma_bf16(tm, ah, bl, kIdescBf16M128N80, 1);
+                                umma_bf16(tm, al, bh, kIdescBf16M128N80, 1);
+                            }
+                        }
+                        if (leader) umma_commit(&sBar[1 + 2 * grp]);
+                        __syncwarp();
+                    }
                     // (C) Mask + SoftMax per row in registers (log2 domain: t_j = S_j * scale*log2e + addv_j, addv_j = -FLT_MAX on
                     // padded / masked slots), P -> bf16 hi/lo A operand [256][16]; column 15 = 1 multiplies the b1 row of H
-                    if (warp * 32 < nrows) {
+                    if (gw * 32 < nr) {
                         mbar_wait(&sBar[1 + 2 * grp], s_phase);
                         tc_fence_after();
                         DMG_TICK(TK_MMAWAIT);
                         float sc[16];
-                        tmem_ld16(tmem_base + tmem_lane + grp * 128 + 64, sc);
+                        tmem_ld16(tm + tmem_lane + 64, sc);
                         if (all_masked) {                         // SoftMax of T equal values: exactly 1/T each
 #pragma unroll
                             for (int j = 0; j < 16; j++) sc[j] = j < T ? inv_T : 0.0f;
@@ -914,21 +896,21 @@ __global__ void __launch_bounds__(FastGeo::THREADS, 2) beam_search_fast_kernel(c
                     else asm volatile("bar.sync 2, 128;" ::: "memory");
                     DMG_TICK(TK_SOFTMAX);
                     // (D) Hacc += P . H of this group's tile (one k-step of 16; row 15 of H holds b1)
-                    if ((warp & 3) == 0) {
+                    if (gw == 0) {
                         tc_fence_after();
                         const bool leader = elect_one();
                         const uint64_t dHh = mkdesc(OFF_HH, G::H_LBO), dHl = mkdesc(OFF_HL, G::H_LBO);
-                        const uint64_t ah = mkdesc(OFF_PH, G::P_LBO) + (uint64_t)(grp * 128), al = mkdesc(OFF_PL, G::P_LBO) + (uint64_t)(grp * 128);
+                        const uint64_t ah = mkdesc(OFF_PH, G::P_LBO) + xo, al = mkdesc(OFF_PL, G::P_LBO) + xo;
                         if (leader) {
-                            umma_bf16(tmem_base + grp * 128, ah, dHh, kIdescBf16M128N64, 1);
-                            umma_bf16(tmem_base + grp * 128, ah, dHl, kIdescBf16M128N64, 1);
-                            umma_bf16(tmem_base + grp * 128, al, dHh, kIdescBf16M128N64, 1);
+                            umma_bf16(tm, ah, dHh, kIdescBf16M128N64, 1);
+                            umma_bf16(tm, ah, dHl, kIdescBf16M128N64, 1);
+                            umma_bf16(tm, al, dHh, kIdescBf16M128N64, 1);
                             umma_commit(&sBar[2 + 2 * grp]);
                         }
                         __syncwarp();
                     }
                     // (E) epilogue: logit = relu(Hacc) . W2 + b2 (b1 already inside Hacc), one row per thread
-                    if (warp * 32 < nrows) {
+                    if (gw * 32 < nr) {
                         mbar_wait(&sBar[2 + 2 * grp], s_phase);
                         tc_fence_after();
                         DMG_TICK(TK_PHWAIT);
@@ -936,24 +918,25 @@ __global__ void __launch_bounds__(FastGeo::THREADS, 2) beam_search_fast_kernel(c
 #pragma unroll
                         for (int hf = 0; hf < 2; hf++) {
                             float hv[32];
-                            tmem_ld32(tmem_base + tmem_lane + grp * 128 + hf * 32, hv);
+                            tmem_ld32(tm + tmem_lane + hf * 32, hv);
 #pragma unroll
                             for (int c = 0; c < 32; c++) logit = fmaf(fmaxf(hv[c], 0.0f), fp.w2[hf * 32 + c], logit);
                         }
                         const float sc_out = logit + fp.b2;
-                        if (tid < nrows) sScore[r0 + tid] = sc_out;
+                        if (gtid < nr) sScore[rbeg + gtid] = sc_out;
                         {
                             const uint32_t ky = order_key(sc_out);
-                            const uint32_t wmn = __reduce_min_sync(0xffffffffu, tid < nrows ? ky : 0xffffffffu);
-                            const uint32_t wmx = __reduce_max_sync(0xffffffffu, tid < nrows ? ky : 0u);
+                            const uint32_t wmn = __reduce_min_sync(0xffffffffu, gtid < nr ? ky : 0xffffffffu);
+                            const uint32_t wmx = __reduce_max_sync(0xffffffffu, gtid < nr ? ky : 0u);
                             if (lane == 0) { atomicMin(reinterpret_cast<unsigned int *>(&sMisc[50]), wmn); atomicMax(reinterpret_cast<unsigned int *>(&sMisc[51]), wmx); }
                         }
                     }
                     s_phase ^= 1;                                 // both mbarriers of the group completed one phase
+                    tc_fence_before();                            // the next tile's MMAs overwrite the accumulators just read
+                    DMG_TICK(TK_EPILOGUE);
                 }
                 tc_fence_before();
                 __syncthreads();
-                DMG_TICK(TK_EPILOGUE);
             }
         }
 
