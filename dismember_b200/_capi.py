@@ -84,6 +84,7 @@ def load_library(build_if_missing: bool = True):
         "dmg_din_gradients": [vp, i64, vp, vp, vp, i64, vp, vp, vp, i64],
         "dmg_tdm_sample_expand": [vp, i32, vp, vp, vp, i32, u64, vp, vp, vp, C.POINTER(i32)],
         "dmg_jtm_item_weights": [vp, i32, vp, vp, vp, i32, i32, i32, i32, i32, vp],
+        "dmg_jtm_assign_level": [vp, i32, vp, vp, i32, vp, i32, vp],
         "dmg_load_deepfm_weights": [vp, i64, i32, i32, vp],
         "dmg_shard_unique_id": [vp, i32],
         "dmg_shard_init": [vp, i32, i32, vp],
@@ -112,6 +113,18 @@ def _p(a: Optional[np.ndarray]):
 
 def _i32(a):
     return np.ascontiguousarray(a, dtype=np.int32)
+
+
+def jtm_assign_level(parent_code, old_child, weights, max_assign) -> np.ndarray:
+    """dmg_jtm_assign_level without a handle: TreeLearning.reBalance is host code inside the library, no device needed."""
+    L = load_library()
+    par, old = _i32(parent_code).ravel(), _i32(old_child).ravel()
+    w = np.ascontiguousarray(weights, np.float32)
+    out = np.empty(len(par), np.int32)
+    rc = L.dmg_jtm_assign_level(None, len(par), _p(par), _p(old), w.shape[1], _p(w), int(max_assign), _p(out))
+    if rc != DMG_OK:
+        raise DmgArgumentError(rc, "dmg_jtm_assign_level: bad arguments")
+    return out
 
 
 class Engine:
@@ -229,6 +242,14 @@ class Engine:
         n = self.rows * self.E + 3 * self.E * self.E + 2 * self.E + 1
         out = np.empty(n, self.din_dtype)
         self._check(self.L.dmg_download_din_weights(self.h, _p(out), n))
+        return out
+
+    def jtm_assign_level(self, parent_code, old_child, weights, max_assign):
+        """TreeLearning.reBalance for one level step (native host code in the library) -> new node per item."""
+        par, old = _i32(parent_code).ravel(), _i32(old_child).ravel()
+        w = np.ascontiguousarray(weights, np.float32)
+        out = np.empty(len(par), np.int32)
+        self._check(self.L.dmg_jtm_assign_level(self.h, len(par), _p(par), _p(old), w.shape[1], _p(w), int(max_assign), _p(out)))
         return out
 
     # -- node table sharded over the GPUs of one box (csrc/shard.cu) ---------------

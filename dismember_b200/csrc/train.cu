@@ -688,3 +688,87 @@ DMG_API int32_t dmg_jtm_item_weights(dmg_handle_t h, int32_t n_items, const int6
     }
     return DMG_OK;
 }
+
+// ---- JTM: per-level item -> child assignment (K10), host code like the reference's ---------------------------------
+// TreeLearning.getChildrenProjection / sortNodeWeights / reBalance (jtm/.../optim/TreeLearning.scala:48-97,137-150,
+// 217-265) for ONE level step over all parents.  Sequential greedy per parent by construction (the heaviest child is
+// frozen first, its overflow moves to the next-best unfrozen child), so it runs on the host; the scorer work that feeds
+// it is dmg_jtm_item_weights.  Items of one parent are taken in array order (the reference's Map order is a JVM
+// artefact the caller fixes by the order of its arrays).
+//   parent_code[i]  node of level old_level the item sits under
+//   old_child[i]    JTMTree.getAncestorAtLevel(item, level) in the CURRENT tree (TreeLearning.scala:224-225: items already
+//                   under a child are kept there first)
+//   weights         n_items x n_child from dmg_jtm_item_weights (children left to right)
+//   out_node[i]     new node of level `level`; the parent code when every candidate child was full (the reference keeps
+//                   the old projection for such an item)
+namespace {
+inline uint32_t jtm_order_key(float w)                                  // Ordering[Float].reverse under Float.compare
+{
+    uint32_t u;
+    memcpy(&u, &w, 4);
+    if (w != w) u = 0x7fc00000u;
+    return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+}  // namespace
+
+DMG_API int32_t dmg_jtm_assign_level(dmg_handle_t h, int32_t n_items, const int32_t *parent_code, const int32_t *old_child,
+                                     int32_t n_child, const float *weights, int32_t max_assign, int32_t *out_node)
+{
+    // host-only: h may be NULL (no device is touched), errors are then reported by the status alone
+    if (n_items < 0 || n_child <= 0 || max_assign <= 0 || (n_items > 0 && (!parent_code || !old_child || !weights || !out_node)))
+        return fail(h, DMG_ERR_INVALID_ARG, "dmg_jtm_assign_level: bad arguments");
+    struct Entry { int32_t item; float w; int32_t next; };
+    // items grouped by parent, array order kept
+    std::vector<int32_t> order(n_items);
+    for (int32_t i = 0; i < n_items; i++) order[i] = i;
+    std::stable_sort(order.begin(), order.end(), [&](int32_t a, int32_t b) { return parent_code[a] < parent_code[b]; });
+    std::vector<int32_t> cand((size_t)n_child);
+    std::vector<std::vector<int32_t>> cand_of;                      // per item of the group: children by weight desc (stable)
+    for (int32_t g0 = 0; g0 < n_items;) {
+        int32_t g1 = g0;
+        while (g1 < n_items && parent_code[order[g1]] == parent_code[order[g0]]) g1++;
+        const int32_t par = parent_code[order[g0]], m = g1 - g0;
+        const int64_t first = ((int64_t)par + 1) * n_child - 1;       // getChildrenAtLevel: left to right
+        cand_of.assign((size_t)m, std::vector<int32_t>());
+        std::vector<std::vector<Entry>> res((size_t)n_child);
+        std::vector<char> processed((size_t)n_child, 0);
+        for (int32_t k = 0; k < m; k++) {
+            const int32_t it = order[g0 + k];
+            const float *w = weights + (size_t)it * n_child;
+            for (int32_t c = 0; c < n_child; c++) cand[c] = c;
+            std::stable_sort(cand.begin(), cand.end(), [&](int32_t a, int32_t b) { return jtm_order_key(w[a]) > jtm_order_key(w[b]); });
+            cand_of[k] = cand;
+            res[cand[0]].push_back({k, w[cand[0]], 1});
+            out_node[it] = par;
+        }
+        for (;;) {
+            int32_t best = -1, best_cnt = -1;
+            for (int32_t c = 0; c < n_child; c++) {                   // getMaxNode: first maximum wins
+                const int32_t cnt = (!processed[c] && !res[c].empty()) ? (int32_t)res[c].size() : -1;
+                if (cnt > best_cnt) { best_cnt = cnt; best = c; }
+            }
+            if (best_cnt <= max_assign) break;
+            processed[best] = 1;
+            std::vector<Entry> &lst = res[best];
+            // sortBy(i => (oldItemNodeMap(i.id) != node, i.weight)) under (Boolean asc, Float desc), stable
+            std::stable_sort(lst.begin(), lst.end(), [&](const Entry &a, const Entry &b) { return jtm_order_key(a.w) > jtm_order_key(b.w); });
+            std::stable_sort(lst.begin(), lst.end(), [&](const Entry &a, const Entry &b) {
+                const bool ma = old_child[order[g0 + a.item]] != first + best, mb = old_child[order[g0 + b.item]] != first + best;
+                return !ma && mb;
+            });
+            std::vector<Entry> rest(lst.begin() + max_assign, lst.end());
+            lst.resize((size_t)max_assign);
+            for (const Entry &e : rest) {
+                const float *w = weights + (size_t)order[g0 + e.item] * n_child;
+                for (int32_t k = e.next; k < n_child; k++) {
+                    const int32_t c = cand_of[e.item][k];
+                    if (!processed[c]) { res[c].push_back({e.item, w[c], k + 1}); break; }
+                }
+            }
+        }
+        for (int32_t c = 0; c < n_child; c++)
+            for (const Entry &e : res[c]) out_node[order[g0 + e.item]] = (int32_t)(first + c);
+        g0 = g1;
+    }
+    return DMG_OK;
+}

@@ -65,11 +65,13 @@ def re_balance(items: Sequence[int], cand_nodes: np.ndarray, cand_weights: np.nd
 
 class JTM:
     def __init__(self, engine: Engine, max_level: int, item_codes: Dict[int, int], item_samples: Dict[int, np.ndarray],
-                 gap: int, seq_len: int, hierarchical: bool = False, min_level: int = 0, use_mask: bool = True):
+                 gap: int, seq_len: int, hierarchical: bool = False, min_level: int = 0, use_mask: bool = True,
+                 native: bool = True):
         self.e, self.max_level, self.gap, self.T = engine, max_level, gap, seq_len
         self.item_codes = item_codes                      # current tree: item id -> leaf code
         self.item_samples = item_samples                  # itemSequenceMap: item -> [n_samples, T] item ids
         self.hier, self.min_level, self.use_mask = hierarchical, min_level, use_mask
+        self.native = native                              # reBalance through dmg_jtm_assign_level (False: the Python mirror below)
 
     def _ancestor_at_level(self, item: int, level: int) -> int:      # JTMTree.getAncestorAtLevel
         lim = (1 << (level + 1)) - 1
@@ -89,9 +91,13 @@ class JTM:
                                for i in items if i in self.item_samples] or [np.zeros((0, self.T), np.int32)])
         w = self.e.jtm_item_weights(off, seqs, parents, old_level, level, self.hier, self.min_level, self.use_mask)
         n_child = w.shape[1]
+        max_assign = 1 << (self.max_level - level)
+        old = np.array([self._ancestor_at_level(it, level) for it in items], np.int32)
+        if self.native:
+            nodes = self.e.jtm_assign_level(parents, old, w, max_assign)          # dmg_jtm_assign_level: reBalance in the library
+            return {it: int(n) for it, n in zip(items, nodes)}
         order = np.stack([stable_desc_order(w[i]) for i in range(len(items))])
         new_proj = dict(projection)
-        max_assign = 1 << (self.max_level - level)
         by_parent: Dict[int, List[int]] = {}
         for k, it in enumerate(items):
             by_parent.setdefault(int(parents[k]), []).append(k)
@@ -101,8 +107,8 @@ class JTM:
             its = [items[k] for k in rows]
             cn = first + order[rows]
             cw = np.take_along_axis(w[rows], order[rows], 1)
-            old = {it: self._ancestor_at_level(it, level) for it in its}
-            balanced = re_balance(its, cn, cw, old, children, max_assign)
+            old_map = {it: int(old[k]) for it, k in zip(its, rows)}
+            balanced = re_balance(its, cn, cw, old_map, children, max_assign)
             for node, assigned in balanced.items():
                 assert len(assigned) <= max_assign
                 for it in assigned:

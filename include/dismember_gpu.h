@@ -226,6 +226,16 @@ DMG_API int32_t dmg_jtm_item_weights(dmg_handle_t h, int32_t n_items, const int6
                                      int32_t old_level, int32_t level, int32_t hierarchical,
                                      int32_t min_level, int32_t use_mask, float *out_weights);
 
+/* TreeLearning.getChildrenProjection / reBalance for one level step (jtm/.../optim/TreeLearning.scala:48-97,
+ * 217-265): greedy, sequential per parent, host code inside the library (the scorer work is
+ * dmg_jtm_item_weights).  parent_code[i]: node of old_level the item sits under; old_child[i]:
+ * JTMTree.getAncestorAtLevel(item, level) in the current tree; weights: n_items x n_child (children left to
+ * right); out_node[i]: new node on `level` (the parent code if every candidate child was already full).
+ * Items of one parent are processed in array order. */
+DMG_API int32_t dmg_jtm_assign_level(dmg_handle_t h, int32_t n_items, const int32_t *parent_code,
+                                     const int32_t *old_child, int32_t n_child, const float *weights,
+                                     int32_t max_assign, int32_t *out_node);
+
 /* DeepFM scorer, the other `model.deep_model` of the TDM/JTM tasks (tdm/.../model/DeepFM.scala:11-44,
  * scalann/.../nn/FM.scala:14-44): params = the compact vector of Module.parameters()
  * [emb rows x E | W1 (T+1) x (T+1)E | b1 T+1 | W2 T+1 | b2 1], fp32.  Afterwards dmg_tdm_retrieve

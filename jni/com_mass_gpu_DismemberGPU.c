@@ -215,3 +215,15 @@ JNIEXPORT void JNICALL Java_com_mass_gpu_DismemberGPU_00024_shardTdmRetrieve(
     UNPIN(outCounts, oc, 0); UNPIN(outLogits, ol, 0); UNPIN(outItems, oi, 0); UNPIN(itemSeq, s, JNI_ABORT);
     if (rc) throw_status(env, H(handle), rc);
 }
+
+/* TreeLearning.reBalance for one level step (host code inside the library) */
+JNIEXPORT void JNICALL Java_com_mass_gpu_DismemberGPU_00024_jtmAssignLevel(
+    JNIEnv *env, jobject self, jlong handle, jintArray parentCode, jintArray oldChild, jint nChild, jfloatArray weights,
+    jint maxAssign, jintArray outNode)
+{
+    jsize n = (*env)->GetArrayLength(env, parentCode);
+    void *p = PIN(parentCode), *o = PIN(oldChild), *w = PIN(weights), *out = PIN(outNode);
+    int32_t rc = dmg_jtm_assign_level(H(handle), n, p, o, nChild, w, maxAssign, out);
+    UNPIN(outNode, out, 0); UNPIN(weights, w, JNI_ABORT); UNPIN(oldChild, o, JNI_ABORT); UNPIN(parentCode, p, JNI_ABORT);
+    if (rc) throw_status(env, H(handle), rc);
+}

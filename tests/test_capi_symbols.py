@@ -50,3 +50,35 @@ def test_fails_loudly_without_gpu():
     with pytest.raises(dmg.DmgError) as ei:
         dmg.Engine(0)
     assert "no CPU fallback" in str(ei.value)
+
+
+def test_jtm_assign_level_matches_the_python_mirror_of_rebalance():
+    """dmg_jtm_assign_level is host code inside the C-ABI library (TreeLearning.reBalance, jtm/.../optim/TreeLearning.scala:217-265):
+    it runs without a device and must pick exactly what the readable Python mirror picks, ties and overflow included."""
+    import numpy as np
+    from dismember_b200._capi import jtm_assign_level
+    from dismember_b200.jtm import re_balance, stable_desc_order
+    rng = np.random.default_rng(5)
+    for n_items, n_child, max_assign, n_par in [(40, 4, 10, 1), (300, 8, 13, 3), (64, 2, 32, 2), (50, 4, 5, 2)]:
+        parents = np.sort(rng.integers(3, 3 + n_par, n_items)).astype(np.int32)
+        rng.shuffle(parents)
+        w = rng.normal(0, 1, (n_items, n_child)).astype(np.float32)
+        w[rng.random((n_items, n_child)) < 0.2] = 0.5                  # plenty of exact ties
+        w[rng.random(n_items) < 0.1] = -1e6                            # items without samples (TreeLearning.scala:160)
+        first = (parents.astype(np.int64) + 1) * n_child - 1
+        old = (first + rng.integers(0, n_child, n_items)).astype(np.int32)
+        got = jtm_assign_level(parents, old, w, max_assign)
+        want = parents.copy()
+        for par in np.unique(parents):
+            rows = np.flatnonzero(parents == par)
+            f0 = (int(par) + 1) * n_child - 1
+            order = np.stack([stable_desc_order(w[i]) for i in rows])
+            cn = f0 + order
+            cw = np.take_along_axis(w[rows], order, 1)
+            its = [int(i) for i in rows]
+            balanced = re_balance(its, cn, cw, {int(i): int(old[i]) for i in rows}, [f0 + c for c in range(n_child)], max_assign)
+            for node, assigned in balanced.items():
+                assert len(assigned) <= max_assign
+                for it in assigned:
+                    want[it] = node
+        assert (got == want).all()

@@ -91,3 +91,5 @@ def test_jtm_tree_learning(engine, jtm_fix, queries):
     assert len(set(leaves.tolist())) == len(leaves)         # capacity 1 at the leaf level
     # deterministic
     assert JTM(engine, L, item_codes, samples, gap=3, seq_len=10, hierarchical=True).optimize() == proj
+    # the native reBalance (dmg_jtm_assign_level) and its Python mirror assign identically
+    assert JTM(engine, L, item_codes, samples, gap=3, seq_len=10, hierarchical=True, native=False).optimize() == proj
