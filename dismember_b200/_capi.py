@@ -92,6 +92,7 @@ def load_library(build_if_missing: bool = True):
         "dmg_shard_load_din_weights": [vp, i64, i32, i32, vp],
         "dmg_shard_info": [vp, C.POINTER(i64), C.POINTER(i64), C.POINTER(i64)],
         "dmg_shard_tdm_retrieve": [vp, i32, vp, i32, i32, i32, vp, vp, vp],
+        "dmg_shard_jtm_item_weights": [vp, i32, vp, vp, vp, i32, i32, i32, i32, i32, vp],
     }
     for name, args in sig.items():
         fn = getattr(L, name)
@@ -294,6 +295,18 @@ class Engine:
         counts = np.empty(B, np.int32)
         self._check(self.L.dmg_shard_tdm_retrieve(self.h, B, _p(seq), beam, topk, int(use_mask), _p(items), _p(logits), _p(counts)))
         return items, logits, counts
+
+    def shard_jtm_item_weights(self, sample_off, sample_seq, parent_code, old_level, level, hierarchical=False, min_level=0,
+                               use_mask=True):
+        """Collective dmg_jtm_item_weights over the sharded table; every rank passes its own items."""
+        off = np.ascontiguousarray(sample_off, np.int64)
+        n_items = len(off) - 1
+        seq = _i32(sample_seq).reshape(-1, self.T)
+        par = _i32(parent_code).ravel()
+        out = np.empty((n_items, 1 << (level - old_level)), np.float32)
+        self._check(self.L.dmg_shard_jtm_item_weights(self.h, n_items, _p(off), _p(seq), _p(par), old_level, level,
+                                                      int(hierarchical), int(min_level), int(use_mask), _p(out)))
+        return out
 
     # -- retrieval --------------------------------------------------------------
     def tdm_retrieve(self, item_seq, beam, topk, use_mask=True, consumed_off=None, consumed=None, widen_beam=False):

@@ -783,6 +783,185 @@ DMG_API int32_t dmg_shard_info(dmg_handle_t h, int64_t *local_rows, int64_t *glo
 }
 
 // TDM.recommend for this rank's B users over the sharded table (every rank calls it with the same B, beam, topk).
+// ---- the collective pieces shared by every sharded entry point ------------------------------------------------------
+// B "users" per rank (a user = one history tile + up to cap candidate codes): TDM retrieval brings one per query and
+// level, JTM one per (item sample, subtree depth).
+struct ShardWork {
+    int B = 0, cap = 0;
+    int64_t stride = 0;                                         // B * cap
+    int32_t *codes_all = nullptr; uint8_t *mask_all = nullptr; float *tiles = nullptr;      // [G*B][T], [G*B][T], [G*B][T][E]
+    int32_t *cand = nullptr; float *score = nullptr; int32_t *count = nullptr;              // [B][cap], [B][cap], [B]
+    int2 *req = nullptr, *rreq = nullptr; float *rsc = nullptr, *reply = nullptr;           // [G][stride]
+    int32_t *nreq = nullptr, *matrix = nullptr; int2 *seg = nullptr, *rseg = nullptr; int32_t *work = nullptr;
+    int32_t *h_matrix = nullptr;                                // pinned [G*G]
+    int32_t *codes_mine(int rank, int T) const { return codes_all + (size_t)rank * B * T; }
+    uint8_t *mask_mine(int rank, int T) const { return mask_all + (size_t)rank * B * T; }
+};
+static size_t shard_work_bytes(int G, int B, int cap, int T, int E)
+{
+    const size_t BU = (size_t)G * B, stride = (size_t)B * cap;
+    return Carver::need({BU * T * 4, BU * T, BU * T * E * 4, stride * 4, stride * 4, (size_t)B * 4, G * stride * 8, G * stride * 8,
+                         G * stride * 4, G * stride * 4, (size_t)G * 4, (size_t)G * G * 4, (size_t)G * B * 8, (size_t)G * B * 8, 256});
+}
+static void shard_work_carve(Carver &cd, ShardWork &w, int G, int B, int cap, int T, int E)
+{
+    const size_t BU = (size_t)G * B;
+    w.B = B; w.cap = cap; w.stride = (int64_t)B * cap;
+    w.codes_all = cd.take<int32_t>(BU * T);
+    w.mask_all = cd.take<uint8_t>(BU * T);
+    w.tiles = cd.take<float>(BU * T * E);
+    w.cand = cd.take<int32_t>((size_t)w.stride);
+    w.score = cd.take<float>((size_t)w.stride);
+    w.count = cd.take<int32_t>((size_t)B);
+    w.req = cd.take<int2>((size_t)G * w.stride);                // my requests, one region per owner
+    w.rreq = cd.take<int2>((size_t)G * w.stride);               // requests received, one region per requester
+    w.rsc = cd.take<float>((size_t)G * w.stride);               // scores I computed, per requester
+    w.reply = cd.take<float>((size_t)G * w.stride);             // scores received, per owner
+    w.nreq = cd.take<int32_t>((size_t)G);
+    w.matrix = cd.take<int32_t>((size_t)G * G);
+    w.seg = cd.take<int2>((size_t)G * B);                       // my segments, one table per owner
+    w.rseg = cd.take<int2>((size_t)G * B);                      // segments received, one table per requester
+    w.work = cd.take<int32_t>(64);
+}
+
+// codes / mask of this rank's users sit in their slice of codes_all / mask_all: replicate them and build every user's
+// history tile on every rank (integer-sum all-reduce of the rows each rank owns).
+static int32_t shard_history_tiles(dmg_handle_t h, const ShardWork &w)
+{
+    ShardState *s = h->shard;
+    const DinDev &d = h->din;
+    const int G = s->world, T = d.T, E = d.E;
+    const int64_t BU = (int64_t)G * w.B;
+    cudaStream_t st = h->stream;
+    if (G > 1) {
+        DMG_NCCL(h, g_nccl.AllGather(w.codes_mine(s->rank, T), w.codes_all, (size_t)w.B * T, ncclInt32, s->comm, st));
+        DMG_NCCL(h, g_nccl.AllGather(w.mask_mine(s->rank, T), w.mask_all, (size_t)w.B * T, ncclUint8, s->comm, st));
+    }
+    shard_fill_tiles_kernel<<<h->sm_count * 4, 256, 0, st>>>(d.emb<float>(), s->geo(), w.codes_all, BU * T, E, (uint32_t *)w.tiles);
+    h->launches += 1;
+    if (G > 1) DMG_NCCL(h, g_nccl.AllReduce(w.tiles, w.tiles, (size_t)BU * T * E, ncclUint32, ncclSum, s->comm, st));
+    DMG_CUDA(h, cudaGetLastError());
+    return DMG_OK;
+}
+
+static int32_t shard_prepare_scorers(dmg_handle_t h)
+{
+    const DinDev &d = h->din;
+    const int E = d.E, T = d.T;
+    const size_t row_smem = (size_t)kRowsRB * ((size_t)4 * E + (size_t)T * E + T + 1) * 4;
+    DMG_CUDA(h, cudaFuncSetAttribute(shard_score_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)row_smem));
+    if (d.kind == 1) {
+        const size_t dfm_smem = DfmGeo::smem(E, T);
+        if (dfm_smem > h->smem_optin) return fail(h, DMG_ERR_UNSUPPORTED, "DeepFM weights (%zu B) do not fit shared memory", dfm_smem);
+        DMG_CUDA(h, cudaFuncSetAttribute(shard_score_deepfm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dfm_smem));
+    } else {
+        switch (E) {
+        case 16: DMG_CUDA(h, cudaFuncSetAttribute(shard_score_segments_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)shard_score_smem<16>())); break;
+        case 32: DMG_CUDA(h, cudaFuncSetAttribute(shard_score_segments_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)shard_score_smem<32>())); break;
+        case 64: DMG_CUDA(h, cudaFuncSetAttribute(shard_score_segments_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)shard_score_smem<64>())); break;
+        default: break;
+        }
+    }
+    return DMG_OK;
+}
+
+// cand / count -> score: requests to the owners, scores back, scattered into candidate order.  One host synchronisation
+// (the G x G count matrix sizes the sends).
+static int32_t shard_score_level(dmg_handle_t h, const ShardWork &w)
+{
+    ShardState *s = h->shard;
+    const DinDev &d = h->din;
+    const int G = s->world, T = d.T, E = d.E, B = w.B, cap = w.cap;
+    const int64_t stride = w.stride;
+    const ShardGeo geo = s->geo();
+    cudaStream_t st = h->stream;
+    const bool deepfm = d.kind == 1;
+    const bool tiled = deepfm || E == 16 || E == 32 || E == 64;   // DIN: embedding sizes with a tile geometry that fits shared memory
+    const float scale = (float)(1.0 / std::sqrt((double)E));
+    int32_t *h_matrix = w.h_matrix;
+    DMG_CUDA(h, cudaMemsetAsync(w.nreq, 0, (size_t)G * 4, st));
+    shard_bucket_kernel<<<B, kThreads, 0, st>>>(w.cand, w.count, cap, geo, w.req, stride, w.nreq, w.seg);
+    h->launches += 1;
+    if (G > 1) DMG_NCCL(h, g_nccl.AllGather(w.nreq, w.matrix, (size_t)G, ncclInt32, s->comm, st));
+    else DMG_CUDA(h, cudaMemcpyAsync(w.matrix, w.nreq, 4, cudaMemcpyDeviceToDevice, st));
+    DMG_CUDA(h, cudaMemcpyAsync(h_matrix, w.matrix, (size_t)G * G * 4, cudaMemcpyDeviceToHost, st));
+    DMG_CUDA(h, cudaStreamSynchronize(st));
+    // h_matrix[src*G + dst] = requests src sends to dst
+    if (G > 1) {
+        DMG_NCCL(h, g_nccl.GroupStart());
+        for (int p = 0; p < G; p++) {
+            if (p == s->rank) continue;
+            const int ns = h_matrix[s->rank * G + p], nr = h_matrix[p * G + s->rank];
+            if (ns) DMG_NCCL(h, g_nccl.Send(w.req + (size_t)p * stride, (size_t)ns * 2, ncclInt32, p, s->comm, st));
+            if (nr) DMG_NCCL(h, g_nccl.Recv(w.rreq + (size_t)p * stride, (size_t)nr * 2, ncclInt32, p, s->comm, st));
+            if (tiled && ns) DMG_NCCL(h, g_nccl.Send(w.seg + (size_t)p * B, (size_t)B * 2, ncclInt32, p, s->comm, st));
+            if (tiled && nr) DMG_NCCL(h, g_nccl.Recv(w.rseg + (size_t)p * B, (size_t)B * 2, ncclInt32, p, s->comm, st));
+        }
+        DMG_NCCL(h, g_nccl.GroupEnd());
+    }
+    if (tiled) {
+        for (int p = 0; p < G; p++)                              // a requester that sent nothing sent no table either
+            if (p != s->rank && h_matrix[p * G + s->rank] == 0) DMG_CUDA(h, cudaMemsetAsync(w.rseg + (size_t)p * B, 0, (size_t)B * 8, st));
+        DMG_CUDA(h, cudaMemsetAsync(w.work, 0, 4, st));
+        const int grid = std::min(G * B, h->sm_count);
+        if (deepfm) {
+            ShardDfmArgs da;
+            da.emb = d.emb<float>(); da.dense = d.tail<float>(); da.tiles = w.tiles;
+            da.req_self = w.req; da.req_peer = w.rreq; da.seg_self = w.seg; da.seg_peer = w.rseg;
+            da.out_self = w.reply; da.out_peer = w.rsc; da.stride = stride; da.B = B; da.G = G; da.T = T; da.E = E;
+            da.work = w.work; da.geo = geo;
+            shard_score_deepfm_kernel<<<grid, kThreads, DfmGeo::smem(E, T), st>>>(da);
+        } else {
+            ShardScoreArgs sa;
+            sa.emb = d.emb<float>(); sa.wattT = (const float *)d.d_wattT; sa.w1T = (const float *)d.d_w1T;
+            sa.b1 = d.b1<float>(); sa.w2 = d.w2<float>(); sa.b2 = d.b2<float>(); sa.tiles = w.tiles; sa.mask = w.mask_all;
+            sa.req_self = w.req; sa.req_peer = w.rreq; sa.seg_self = w.seg; sa.seg_peer = w.rseg;
+            sa.out_self = w.reply; sa.out_peer = w.rsc; sa.stride = stride; sa.B = B; sa.G = G; sa.T = T; sa.cap = cap;
+            sa.scale = scale; sa.work = w.work; sa.geo = geo;
+            switch (E) {
+            case 16: shard_score_segments_kernel<16><<<grid, kThreads, shard_score_smem<16>(), st>>>(sa); break;
+            case 32: shard_score_segments_kernel<32><<<grid, kThreads, shard_score_smem<32>(), st>>>(sa); break;
+            default: shard_score_segments_kernel<64><<<grid, kThreads, shard_score_smem<64>(), st>>>(sa); break;
+            }
+        }
+        h->launches += 1;
+        for (int p = 0; p < G; p++)
+            if (p != s->rank) s->exchanged_rows += h_matrix[p * G + s->rank];
+    } else {
+        const size_t row_smem = (size_t)kRowsRB * ((size_t)4 * E + (size_t)T * E + T + 1) * 4;
+        for (int p = 0; p < G; p++) {
+            const int nr = h_matrix[p * G + s->rank];
+            if (!nr) continue;
+            const int2 *rq = p == s->rank ? w.req + (size_t)p * stride : w.rreq + (size_t)p * stride;
+            float *ro = p == s->rank ? w.reply + (size_t)p * stride : w.rsc + (size_t)p * stride;
+            const int grid = std::min((nr + kRowsRB - 1) / kRowsRB, h->sm_count * 8);
+            shard_score_rows_kernel<<<grid, kRowsThreads, row_smem, st>>>(d.emb<float>(), geo, (const float *)d.d_wattT, (const float *)d.d_w1T,
+                                                                          d.b1<float>(), d.w2<float>(), d.b2<float>(), scale, E, T, nr, rq, cap,
+                                                                          p * B, w.tiles, w.mask_all, ro);
+            h->launches += 1;
+            if (p != s->rank) s->exchanged_rows += nr;
+        }
+    }
+    if (G > 1) {
+        DMG_NCCL(h, g_nccl.GroupStart());
+        for (int p = 0; p < G; p++) {
+            if (p == s->rank) continue;
+            const int ns = h_matrix[s->rank * G + p], nr = h_matrix[p * G + s->rank];
+            if (nr) DMG_NCCL(h, g_nccl.Send(w.rsc + (size_t)p * stride, (size_t)nr, ncclFloat32, p, s->comm, st));
+            if (ns) DMG_NCCL(h, g_nccl.Recv(w.reply + (size_t)p * stride, (size_t)ns, ncclFloat32, p, s->comm, st));
+        }
+        DMG_NCCL(h, g_nccl.GroupEnd());
+    }
+    for (int p = 0; p < G; p++) {
+        const int ns = h_matrix[s->rank * G + p];
+        if (!ns) continue;
+        shard_scatter_kernel<<<(ns + 255) / 256, 256, 0, st>>>(w.req + (size_t)p * stride, w.reply + (size_t)p * stride, ns, w.score);
+        h->launches += 1;
+    }
+    DMG_CUDA(h, cudaGetLastError());
+    return DMG_OK;
+}
+
 static int32_t shard_tdm_retrieve_impl(dmg_handle_t h, int32_t B, const int32_t *item_seq, int32_t beam, int32_t topk,
                                        int32_t use_mask, const int64_t *cons_off, const int32_t *cons,
                                        int32_t *out_items, float *out_logits, int32_t *out_counts)
@@ -796,46 +975,30 @@ static int32_t shard_tdm_retrieve_impl(dmg_handle_t h, int32_t B, const int32_t 
     const DinDev &d = h->din;
     const TreeDev &t = h->tree;
     const int G = s->world, T = d.T, E = d.E, L = t.max_level;
-    const ShardGeo geo = s->geo();
     const int cap = std::max(((2 * beam + 7) / 8) * 8, ((topk + 7) / 8) * 8);
     if (cap > 2 * kThreads) return fail(h, DMG_ERR_UNSUPPORTED, "beam %d too wide for the sharded path (2*beam <= %d)", beam, 2 * kThreads);
     int capp = 2;
     while (capp < cap) capp <<= 1;
     const int s_level = (int)std::floor(std::log2((double)beam) + 1e-9);
-    const int64_t BU = (int64_t)G * B, stride = (int64_t)B * cap;
 
-    const size_t need = Carver::need({(size_t)B * T * 4, (size_t)BU * T * 4, (size_t)B * T, (size_t)BU * T, (size_t)BU * T * E * 4,
-                                      (size_t)stride * 4, (size_t)stride * 4, (size_t)B * 4, (size_t)G * stride * 8, (size_t)G * stride * 8,
-                                      (size_t)G * stride * 4, (size_t)G * stride * 4, (size_t)G * 4, (size_t)G * G * 4,
-                                      (size_t)B * topk * 4, (size_t)B * topk * 4, (size_t)B * 4, (size_t)G * B * 8, (size_t)G * B * 8, 256, cons_off ? (size_t)(B + 1) * 8 : 0, cons_off ? (size_t)cons_off[B] * 4 : 0});
+    const size_t need = shard_work_bytes(G, B, cap, T, E) +
+                        Carver::need({(size_t)B * T * 4, (size_t)B * T, (size_t)B * topk * 4, (size_t)B * topk * 4, (size_t)B * 4,
+                                      cons_off ? (size_t)(B + 1) * 8 : 0, cons_off ? (size_t)cons_off[B] * 4 : 0});
     DMG_TRY(ensure_dev(h, s->buf, need));
     DMG_TRY(ensure_host(h, s->buf, (size_t)B * T * 4 + (size_t)G * G * 4 + (size_t)B * topk * 8 + (size_t)B * 4 + 1024));
     Carver cd(s->buf.d);
+    ShardWork w;
+    shard_work_carve(cd, w, G, B, cap, T, E);
     int32_t *d_seq = cd.take<int32_t>((size_t)B * T);
-    int32_t *d_codes_all = cd.take<int32_t>((size_t)BU * T);
     uint8_t *d_mask = cd.take<uint8_t>((size_t)B * T);
-    uint8_t *d_mask_all = cd.take<uint8_t>((size_t)BU * T);
-    float *d_tiles = cd.take<float>((size_t)BU * T * E);
-    int32_t *d_cand = cd.take<int32_t>((size_t)stride);
-    float *d_score = cd.take<float>((size_t)stride);
-    int32_t *d_count = cd.take<int32_t>((size_t)B);
-    int2 *d_req = cd.take<int2>((size_t)G * stride);          // my requests, one region per owner
-    int2 *d_rreq = cd.take<int2>((size_t)G * stride);         // requests received, one region per requester
-    float *d_rsc = cd.take<float>((size_t)G * stride);        // scores I computed, per requester
-    float *d_reply = cd.take<float>((size_t)G * stride);      // scores received, per owner
-    int32_t *d_nreq = cd.take<int32_t>((size_t)G);
-    int32_t *d_matrix = cd.take<int32_t>((size_t)G * G);
     int32_t *d_items = cd.take<int32_t>((size_t)B * topk);
     float *d_logits = cd.take<float>((size_t)B * topk);
     int32_t *d_cnt_out = cd.take<int32_t>((size_t)B);
-    int2 *d_seg = cd.take<int2>((size_t)G * B);               // my segments, one table per owner
-    int2 *d_rseg = cd.take<int2>((size_t)G * B);              // segments received, one table per requester
-    int32_t *d_work = cd.take<int32_t>(64);
     int64_t *d_cons_off = cons_off ? cd.take<int64_t>((size_t)B + 1) : nullptr;
     int32_t *d_cons = cons_off ? cd.take<int32_t>((size_t)cons_off[B]) : nullptr;
     char *hp = (char *)s->buf.h;
     int32_t *h_seq = (int32_t *)hp; hp += (size_t)B * T * 4;
-    int32_t *h_matrix = (int32_t *)hp; hp += (((size_t)G * G * 4 + 255) & ~(size_t)255);
+    w.h_matrix = (int32_t *)hp; hp += (((size_t)G * G * 4 + 255) & ~(size_t)255);
     int32_t *h_items = (int32_t *)hp; hp += (size_t)B * topk * 4;
     float *h_logits = (float *)hp; hp += (size_t)B * topk * 4;
     int32_t *h_cnt = (int32_t *)hp;
@@ -849,138 +1012,33 @@ static int32_t shard_tdm_retrieve_impl(dmg_handle_t h, int32_t B, const int32_t 
         if (cons_off[B]) DMG_CUDA(h, cudaMemcpyAsync(d_cons, cons, (size_t)cons_off[B] * 4, cudaMemcpyHostToDevice, st));
         DMG_CUDA(h, cudaStreamSynchronize(st));
     }
-    int32_t *d_codes_mine = d_codes_all + (size_t)s->rank * B * T;
-    uint8_t *d_mask_mine = d_mask_all + (size_t)s->rank * B * T;
     // TDMTree.idToCode validates against the table size: use the global row count here
     {
         const int64_t local_rows = h->din.rows;
         h->din.rows = s->global_rows;
-        const int32_t rc = dmg_tdm_ids_to_codes(h, d_seq, (int64_t)B * T, use_mask, d_codes_mine, d_mask);
+        const int32_t rc = dmg_tdm_ids_to_codes(h, d_seq, (int64_t)B * T, use_mask, w.codes_mine(s->rank, T), d_mask);
         h->din.rows = local_rows;
         DMG_TRY(rc);
     }
-    DMG_CUDA(h, cudaMemcpyAsync(d_mask_mine, d_mask, (size_t)B * T, cudaMemcpyDeviceToDevice, st));
-    if (G > 1) {
-        DMG_NCCL(h, g_nccl.AllGather(d_codes_mine, d_codes_all, (size_t)B * T, ncclInt32, s->comm, st));
-        DMG_NCCL(h, g_nccl.AllGather(d_mask_mine, d_mask_all, (size_t)B * T, ncclUint8, s->comm, st));
-    }
-    shard_fill_tiles_kernel<<<h->sm_count * 4, 256, 0, st>>>(d.emb<float>(), geo, d_codes_all, BU * T, E, (uint32_t *)d_tiles);
-    h->launches += 1;
-    if (G > 1) DMG_NCCL(h, g_nccl.AllReduce(d_tiles, d_tiles, (size_t)BU * T * E, ncclUint32, ncclSum, s->comm, st));
+    DMG_CUDA(h, cudaMemcpyAsync(w.mask_mine(s->rank, T), d_mask, (size_t)B * T, cudaMemcpyDeviceToDevice, st));
+    DMG_TRY(shard_history_tiles(h, w));
 
     // ---- level loop -----------------------------------------------------------------------------------------------
     const size_t sel_smem = (size_t)capp * 8 + (size_t)cap * 8;
-    const size_t row_smem = (size_t)kRowsRB * ((size_t)4 * E + (size_t)T * E + T + 1) * 4;
-    DMG_CUDA(h, cudaFuncSetAttribute(shard_score_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)row_smem));
-    const float scale = (float)(1.0 / std::sqrt((double)E));
-    const bool deepfm = d.kind == 1;
-    const bool tiled = deepfm || E == 16 || E == 32 || E == 64;   // DIN: embedding sizes with a tile geometry that fits shared memory
-    const size_t dfm_smem = DfmGeo::smem(E, T);
-    if (deepfm) {
-        if (dfm_smem > h->smem_optin) return fail(h, DMG_ERR_UNSUPPORTED, "DeepFM weights (%zu B) do not fit shared memory", dfm_smem);
-        DMG_CUDA(h, cudaFuncSetAttribute(shard_score_deepfm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dfm_smem));
-    } else if (tiled) {
-        switch (E) {
-        case 16: DMG_CUDA(h, cudaFuncSetAttribute(shard_score_segments_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)shard_score_smem<16>())); break;
-        case 32: DMG_CUDA(h, cudaFuncSetAttribute(shard_score_segments_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)shard_score_smem<32>())); break;
-        case 64: DMG_CUDA(h, cudaFuncSetAttribute(shard_score_segments_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)shard_score_smem<64>())); break;
-        default: break;
-        }
-    }
-    bool reached = s_level <= L;
+    DMG_TRY(shard_prepare_scorers(h));
+    const bool reached = s_level <= L;
     if (reached) {
-        shard_select_expand_kernel<<<B, kThreads, sel_smem, st>>>(d_cand, d_score, d_count, cap, capp, beam, s_level, 1, t.d_exists);
+        shard_select_expand_kernel<<<B, kThreads, sel_smem, st>>>(w.cand, w.score, w.count, cap, capp, beam, s_level, 1, t.d_exists);
         h->launches += 1;
     } else {
-        DMG_CUDA(h, cudaMemsetAsync(d_count, 0, (size_t)B * 4, st));
+        DMG_CUDA(h, cudaMemsetAsync(w.count, 0, (size_t)B * 4, st));
     }
     for (int level = s_level; level < L; level++) {
-        shard_select_expand_kernel<<<B, kThreads, sel_smem, st>>>(d_cand, d_score, d_count, cap, capp, beam, level, 0, t.d_exists);
-        DMG_CUDA(h, cudaMemsetAsync(d_nreq, 0, (size_t)G * 4, st));
-        shard_bucket_kernel<<<B, kThreads, 0, st>>>(d_cand, d_count, cap, geo, d_req, stride, d_nreq, d_seg);
-        h->launches += 2;
-        if (G > 1) DMG_NCCL(h, g_nccl.AllGather(d_nreq, d_matrix, (size_t)G, ncclInt32, s->comm, st));
-        else DMG_CUDA(h, cudaMemcpyAsync(d_matrix, d_nreq, 4, cudaMemcpyDeviceToDevice, st));
-        DMG_CUDA(h, cudaMemcpyAsync(h_matrix, d_matrix, (size_t)G * G * 4, cudaMemcpyDeviceToHost, st));
-        DMG_CUDA(h, cudaStreamSynchronize(st));
-        // h_matrix[src*G + dst] = requests src sends to dst
-        if (G > 1) {
-            DMG_NCCL(h, g_nccl.GroupStart());
-            for (int p = 0; p < G; p++) {
-                if (p == s->rank) continue;
-                const int ns = h_matrix[s->rank * G + p], nr = h_matrix[p * G + s->rank];
-                if (ns) DMG_NCCL(h, g_nccl.Send(d_req + (size_t)p * stride, (size_t)ns * 2, ncclInt32, p, s->comm, st));
-                if (nr) DMG_NCCL(h, g_nccl.Recv(d_rreq + (size_t)p * stride, (size_t)nr * 2, ncclInt32, p, s->comm, st));
-                if (tiled && ns) DMG_NCCL(h, g_nccl.Send(d_seg + (size_t)p * B, (size_t)B * 2, ncclInt32, p, s->comm, st));
-                if (tiled && nr) DMG_NCCL(h, g_nccl.Recv(d_rseg + (size_t)p * B, (size_t)B * 2, ncclInt32, p, s->comm, st));
-            }
-            DMG_NCCL(h, g_nccl.GroupEnd());
-        }
-        if (tiled) {
-            for (int p = 0; p < G; p++)                          // a requester that sent nothing sent no table either
-                if (p != s->rank && h_matrix[p * G + s->rank] == 0) DMG_CUDA(h, cudaMemsetAsync(d_rseg + (size_t)p * B, 0, (size_t)B * 8, st));
-            DMG_CUDA(h, cudaMemsetAsync(d_work, 0, 4, st));
-            if (deepfm) {
-                ShardDfmArgs da;
-                da.emb = d.emb<float>(); da.dense = d.tail<float>(); da.tiles = d_tiles;
-                da.req_self = d_req; da.req_peer = d_rreq; da.seg_self = d_seg; da.seg_peer = d_rseg;
-                da.out_self = d_reply; da.out_peer = d_rsc; da.stride = stride; da.B = B; da.G = G; da.T = T; da.E = E;
-                da.work = d_work; da.geo = geo;
-                shard_score_deepfm_kernel<<<std::min(G * B, h->sm_count), kThreads, dfm_smem, st>>>(da);
-                h->launches += 1;
-                for (int p = 0; p < G; p++)
-                    if (p != s->rank) s->exchanged_rows += h_matrix[p * G + s->rank];
-                goto scored;
-            }
-            ShardScoreArgs sa;
-            sa.emb = d.emb<float>(); sa.wattT = (const float *)d.d_wattT; sa.w1T = (const float *)d.d_w1T;
-            sa.b1 = d.b1<float>(); sa.w2 = d.w2<float>(); sa.b2 = d.b2<float>(); sa.tiles = d_tiles; sa.mask = d_mask_all;
-            sa.req_self = d_req; sa.req_peer = d_rreq; sa.seg_self = d_seg; sa.seg_peer = d_rseg;
-            sa.out_self = d_reply; sa.out_peer = d_rsc; sa.stride = stride; sa.B = B; sa.G = G; sa.T = T; sa.cap = cap;
-            sa.scale = scale; sa.work = d_work; sa.geo = geo;
-            const int grid = std::min(G * B, h->sm_count);
-            switch (E) {
-            case 16: shard_score_segments_kernel<16><<<grid, kThreads, shard_score_smem<16>(), st>>>(sa); break;
-            case 32: shard_score_segments_kernel<32><<<grid, kThreads, shard_score_smem<32>(), st>>>(sa); break;
-            case 64: shard_score_segments_kernel<64><<<grid, kThreads, shard_score_smem<64>(), st>>>(sa); break;
-            default: break;
-            }
-            h->launches += 1;
-            for (int p = 0; p < G; p++)
-                if (p != s->rank) s->exchanged_rows += h_matrix[p * G + s->rank];
-        } else
-        for (int p = 0; p < G; p++) {
-            const int nr = h_matrix[p * G + s->rank];
-            if (!nr) continue;
-            const int2 *rq = p == s->rank ? d_req + (size_t)p * stride : d_rreq + (size_t)p * stride;
-            float *ro = p == s->rank ? d_reply + (size_t)p * stride : d_rsc + (size_t)p * stride;
-            const int grid = std::min((nr + kRowsRB - 1) / kRowsRB, h->sm_count * 8);
-            shard_score_rows_kernel<<<grid, kRowsThreads, row_smem, st>>>(d.emb<float>(), geo, (const float *)d.d_wattT, (const float *)d.d_w1T,
-                                                                          d.b1<float>(), d.w2<float>(), d.b2<float>(), scale, E, T, nr, rq, cap,
-                                                                          p * B, d_tiles, d_mask_all, ro);
-            h->launches += 1;
-            if (p != s->rank) s->exchanged_rows += nr;
-        }
-    scored:
-        if (G > 1) {
-            DMG_NCCL(h, g_nccl.GroupStart());
-            for (int p = 0; p < G; p++) {
-                if (p == s->rank) continue;
-                const int ns = h_matrix[s->rank * G + p], nr = h_matrix[p * G + s->rank];
-                if (nr) DMG_NCCL(h, g_nccl.Send(d_rsc + (size_t)p * stride, (size_t)nr, ncclFloat32, p, s->comm, st));
-                if (ns) DMG_NCCL(h, g_nccl.Recv(d_reply + (size_t)p * stride, (size_t)ns, ncclFloat32, p, s->comm, st));
-            }
-            DMG_NCCL(h, g_nccl.GroupEnd());
-        }
-        for (int p = 0; p < G; p++) {
-            const int ns = h_matrix[s->rank * G + p];
-            if (!ns) continue;
-            shard_scatter_kernel<<<(ns + 255) / 256, 256, 0, st>>>(d_req + (size_t)p * stride, d_reply + (size_t)p * stride, ns, d_score);
-            h->launches += 1;
-        }
-        DMG_CUDA(h, cudaGetLastError());
+        shard_select_expand_kernel<<<B, kThreads, sel_smem, st>>>(w.cand, w.score, w.count, cap, capp, beam, level, 0, t.d_exists);
+        h->launches += 1;
+        DMG_TRY(shard_score_level(h, w));
     }
-    shard_final_topk_kernel<<<B, kThreads, (size_t)capp * 8, st>>>(d_cand, d_score, d_count, cap, capp, topk, L, reached ? 1 : 0, t.d_leaf_item,
+    shard_final_topk_kernel<<<B, kThreads, (size_t)capp * 8, st>>>(w.cand, w.score, w.count, cap, capp, topk, L, reached ? 1 : 0, t.d_leaf_item,
                                                                    d_cons_off, d_cons, d_items, d_logits, d_cnt_out);
     h->launches += 1;
     DMG_CUDA(h, cudaGetLastError());
@@ -1036,5 +1094,186 @@ int32_t dmg_deepfm_score_pairs(dmg_handle_t h, int64_t n, const int32_t *node, c
     DMG_CUDA(h, cudaGetLastError());
     DMG_CUDA(h, cudaMemcpyAsync(out, dout, (size_t)n * 4, cudaMemcpyDeviceToHost, h->stream));
     DMG_CUDA(h, cudaStreamSynchronize(h->stream));
+    return DMG_OK;
+}
+
+// ---- JTM tree learning on the sharded table (BASELINE config 4) -----------------------------------------------------
+// dmg_jtm_item_weights with the node table split over the ranks: every rank brings ITS OWN items (any split of the
+// catalogue), the scorer rows travel to the owners of the nodes exactly like retrieval candidates.  A "user" of the
+// exchange is (item sample, depth d below the item's current node): its history is the sample re-coded for level
+// old_level + d (JTMTree.idToCodeWithMask, jtm/.../tree/JTMTree.scala:86-113), its candidates the 2^d descendants at that
+// depth.  Items are processed in chunks of whole items; chunk shape and count are agreed over NCCL (max over ranks).
+static __global__ void shard_jtm_users_kernel(int n_samples, int gap, int T, int cap, const int32_t *__restrict__ sample_seq,
+                                              const int32_t *__restrict__ sample_parent, int old_level,
+                                              const int32_t *__restrict__ id_code, int32_t non_leaf_offset, int32_t max_code,
+                                              int hierarchical, int min_level, int use_mask, int n_users_total,
+                                              int32_t *__restrict__ codes, uint8_t *__restrict__ mask, int32_t *__restrict__ cand,
+                                              int32_t *__restrict__ count)
+{
+    for (int u = blockIdx.x * blockDim.x + threadIdx.x; u < n_users_total; u += gridDim.x * blockDim.x) {
+        const int sl = u / gap, d = u % gap + 1;
+        if (sl >= n_samples) {                                      // padding users of a short chunk
+            count[u] = 0;
+            for (int j = 0; j < T; j++) { codes[(size_t)u * T + j] = -1; mask[(size_t)u * T + j] = 0; }
+            continue;
+        }
+        const int level = old_level + d;
+        for (int j = 0; j < T; j++) {                               // JTMTree.idToCodeWithMask :86-113
+            const int32_t id = sample_seq[(size_t)sl * T + j];
+            int32_t c;
+            uint8_t m = 0;
+            if (id == 0) { c = -1; m = 1; }
+            else if (id > 0 && id < non_leaf_offset && id_code[id] >= 0) {
+                c = id_code[id];
+                if (hierarchical && level >= min_level) {           // getAncestorAtLevel :36-43
+                    const int64_t lim = ((int64_t)1 << (level + 1)) - 1;
+                    int64_t cc = c;
+                    while (cc >= lim) cc = (cc - 1) >> 1;
+                    c = (int32_t)cc;
+                }
+            } else {
+                const int64_t tmp = (int64_t)id - non_leaf_offset;
+                c = tmp > max_code ? -1 : (int32_t)tmp;             // NB: not added to the mask (JTMTree.scala:104-107)
+            }
+            codes[(size_t)u * T + j] = c;
+            mask[(size_t)u * T + j] = use_mask ? m : 0;
+        }
+        const int64_t first = ((int64_t)sample_parent[sl] + 1) * ((int64_t)1 << d) - 1;   // leftmost descendant at depth d
+        const int n = 1 << d;
+        for (int j = 0; j < n; j++) cand[(size_t)u * cap + j] = (int32_t)(first + j);
+        count[u] = n;
+    }
+}
+
+// node sums over an item's samples in order (Tensor.sum), then per child the in-order sum along child -> parent
+// (TreeLearning.scala:163-172); -1e6 for an item without samples (:160).
+static __global__ void shard_jtm_reduce_kernel(int n_items, const int32_t *__restrict__ item_off /*samples of the chunk*/, int gap, int cap,
+                                               const float *__restrict__ score, float *__restrict__ out_weights)
+{
+    const int n_child = 1 << gap;
+    for (int g = blockIdx.x * blockDim.x + threadIdx.x; g < n_items * n_child; g += gridDim.x * blockDim.x) {
+        const int item = g / n_child, ch = g % n_child;
+        const int s0 = item_off[item], s1 = item_off[item + 1];
+        if (s1 == s0) { out_weights[g] = -1e6f; continue; }
+        int idx = n_child - 1 + ch;                                 // heap index inside the parent's subtree, root = 0
+        float w = 0.0f;
+        while (idx > 0) {
+            const int depth = 31 - __clz(idx + 1), j = idx + 1 - (1 << depth);
+            float acc = 0.0f;
+            for (int sm = s0; sm < s1; sm++) acc = __fadd_rn(acc, score[((size_t)sm * gap + depth - 1) * cap + j]);
+            w = __fadd_rn(w, acc);
+            idx = (idx - 1) >> 1;
+        }
+        out_weights[g] = w;
+    }
+}
+
+DMG_API int32_t dmg_shard_jtm_item_weights(dmg_handle_t h, int32_t n_items, const int64_t *sample_off, const int32_t *sample_seq,
+                                           const int32_t *parent_code, int32_t old_level, int32_t level, int32_t hierarchical,
+                                           int32_t min_level, int32_t use_mask, float *out_weights)
+{
+    if (!h) return DMG_ERR_INVALID_ARG;
+    ShardState *s = h->shard;
+    if (!s) return fail(h, DMG_ERR_STATE, "call dmg_shard_init first");
+    if (!h->tree.loaded || h->tree.complete || !h->din.loaded || h->din.kind != 0)
+        return fail(h, DMG_ERR_STATE, "TDM/JTM tree and sharded DIN weights must be loaded first");
+    const int gap = level - old_level;
+    if (n_items < 0 || gap < 1 || gap > 8 || old_level < 0 || level > h->tree.max_level || (n_items > 0 && (!sample_off || !parent_code || !out_weights)))
+        return fail(h, DMG_ERR_INVALID_ARG, "dmg_shard_jtm_item_weights: bad arguments (1 <= level - old_level <= 8, level <= max_level)");
+    DMG_CUDA(h, cudaSetDevice(h->device));
+    const DinDev &d = h->din;
+    const TreeDev &t = h->tree;
+    const int G = s->world, T = d.T, E = d.E, cap = 1 << gap, n_child = 1 << gap;
+    cudaStream_t st = h->stream;
+    for (int32_t i = 0; i < n_items; i++) {
+        const int64_t pc = parent_code[i];
+        if (pc < ((int64_t)1 << old_level) - 1 || pc > ((int64_t)2 << old_level) - 2)
+            return fail(h, DMG_ERR_INVALID_ARG, "parent_code[%d] = %lld is not a node of level %d", i, (long long)pc, old_level);
+    }
+    // chunk shape: whole items, at most ns_cap samples per chunk; agreed over the ranks
+    int64_t max_item = 0;
+    for (int32_t i = 0; i < n_items; i++) max_item = std::max(max_item, sample_off[i + 1] - sample_off[i]);
+    int32_t agree[2] = {(int32_t)std::max<int64_t>(max_item, std::max(1, 8192 / gap)), 0};
+    auto pack = [&](int ns_cap, std::vector<int32_t> &starts) {
+        starts.assign(1, 0);
+        int64_t used = 0, items = 0;                              // a chunk holds at most ns_cap samples and ns_cap items
+        for (int32_t i = 0; i < n_items; i++) {
+            const int64_t ns = sample_off[i + 1] - sample_off[i];
+            if ((used + ns > ns_cap && used > 0) || items >= ns_cap) { starts.push_back(i); used = 0; items = 0; }
+            used += ns;
+            items++;
+        }
+        if (starts.back() != n_items) starts.push_back(n_items);
+    };
+    std::vector<int32_t> starts;
+    int32_t *d_agree = nullptr;
+    if (G > 1) {
+        DMG_TRY(ensure_dev(h, s->buf, 256));
+        d_agree = (int32_t *)s->buf.d;
+        DMG_CUDA(h, cudaMemcpyAsync(d_agree, agree, 4, cudaMemcpyHostToDevice, st));
+        DMG_NCCL(h, g_nccl.AllReduce(d_agree, d_agree, 1, ncclInt32, ncclMax, s->comm, st));
+        DMG_CUDA(h, cudaMemcpyAsync(agree, d_agree, 4, cudaMemcpyDeviceToHost, st));
+        DMG_CUDA(h, cudaStreamSynchronize(st));
+    }
+    const int ns_cap = agree[0];
+    pack(ns_cap, starts);
+    int32_t n_chunks = (int32_t)starts.size() - 1;
+    if (G > 1) {
+        DMG_CUDA(h, cudaMemcpyAsync(d_agree, &n_chunks, 4, cudaMemcpyHostToDevice, st));
+        DMG_NCCL(h, g_nccl.AllReduce(d_agree, d_agree, 1, ncclInt32, ncclMax, s->comm, st));
+        DMG_CUDA(h, cudaMemcpyAsync(&n_chunks, d_agree, 4, cudaMemcpyDeviceToHost, st));
+        DMG_CUDA(h, cudaStreamSynchronize(st));
+    }
+    const int B = ns_cap * gap;                                   // users per rank and chunk
+    const size_t need = shard_work_bytes(G, B, cap, T, E) +
+                        Carver::need({(size_t)ns_cap * T * 4, (size_t)ns_cap * 4, ((size_t)ns_cap + 2) * 4, (size_t)ns_cap * n_child * 4});
+    DMG_TRY(ensure_dev(h, s->buf, need));
+    DMG_TRY(ensure_host(h, s->buf, (size_t)G * G * 4 + 256 + (size_t)ns_cap * T * 4 + (size_t)ns_cap * 4 + ((size_t)ns_cap + 2) * 4 + (size_t)ns_cap * n_child * 4 + 1024));
+    Carver cd(s->buf.d);
+    ShardWork w;
+    shard_work_carve(cd, w, G, B, cap, T, E);
+    int32_t *d_sseq = cd.take<int32_t>((size_t)ns_cap * T);
+    int32_t *d_spar = cd.take<int32_t>((size_t)ns_cap);
+    int32_t *d_ioff = cd.take<int32_t>((size_t)ns_cap + 2);
+    float *d_wout = cd.take<float>((size_t)ns_cap * n_child);
+    char *hp = (char *)s->buf.h;
+    w.h_matrix = (int32_t *)hp; hp += (((size_t)G * G * 4 + 255) & ~(size_t)255);
+    int32_t *h_sseq = (int32_t *)hp; hp += (((size_t)ns_cap * T * 4 + 255) & ~(size_t)255);
+    int32_t *h_spar = (int32_t *)hp; hp += (((size_t)ns_cap * 4 + 255) & ~(size_t)255);
+    int32_t *h_ioff = (int32_t *)hp; hp += ((((size_t)ns_cap + 2) * 4 + 255) & ~(size_t)255);
+    float *h_wout = (float *)hp;
+    DMG_TRY(shard_prepare_scorers(h));
+    for (int32_t c = 0; c < n_chunks; c++) {
+        const int32_t i0 = c + 1 < (int32_t)starts.size() ? starts[c] : n_items, i1 = c + 1 < (int32_t)starts.size() ? starts[c + 1] : n_items;
+        const int32_t ni = i1 - i0;
+        const int64_t sb = ni > 0 ? sample_off[i0] : 0;
+        const int32_t ns = ni > 0 ? (int32_t)(sample_off[i1] - sb) : 0;
+        if (ns > 0 && !sample_seq) return fail(h, DMG_ERR_INVALID_ARG, "sample_seq is null");
+        if (ns > 0) memcpy(h_sseq, sample_seq + sb * T, (size_t)ns * T * 4);
+        h_ioff[0] = 0;
+        for (int32_t i = 0; i < ni; i++) {
+            h_ioff[i + 1] = (int32_t)(sample_off[i0 + i + 1] - sb);
+            for (int32_t q = h_ioff[i]; q < h_ioff[i + 1]; q++) h_spar[q] = parent_code[i0 + i];
+        }
+        if (ns > 0) {
+            DMG_CUDA(h, cudaMemcpyAsync(d_sseq, h_sseq, (size_t)ns * T * 4, cudaMemcpyHostToDevice, st));
+            DMG_CUDA(h, cudaMemcpyAsync(d_spar, h_spar, (size_t)ns * 4, cudaMemcpyHostToDevice, st));
+        }
+        DMG_CUDA(h, cudaMemcpyAsync(d_ioff, h_ioff, ((size_t)ni + 1) * 4, cudaMemcpyHostToDevice, st));
+        shard_jtm_users_kernel<<<std::max(1, std::min((B + 255) / 256, h->sm_count * 8)), 256, 0, st>>>(
+            ns, gap, T, cap, d_sseq, d_spar, old_level, t.d_id_code, t.non_leaf_offset, t.max_code, hierarchical, min_level, use_mask, B,
+            w.codes_mine(s->rank, T), w.mask_mine(s->rank, T), w.cand, w.count);
+        h->launches += 1;
+        DMG_TRY(shard_history_tiles(h, w));
+        DMG_TRY(shard_score_level(h, w));
+        if (ni > 0) {
+            shard_jtm_reduce_kernel<<<std::min((ni * n_child + 255) / 256, h->sm_count * 8), 256, 0, st>>>(ni, d_ioff, gap, cap, w.score, d_wout);
+            h->launches += 1;
+            DMG_CUDA(h, cudaMemcpyAsync(h_wout, d_wout, (size_t)ni * n_child * 4, cudaMemcpyDeviceToHost, st));
+            DMG_CUDA(h, cudaStreamSynchronize(st));
+            memcpy(out_weights + (size_t)i0 * n_child, h_wout, (size_t)ni * n_child * 4);
+        }
+        DMG_CUDA(h, cudaGetLastError());
+    }
     return DMG_OK;
 }

@@ -275,6 +275,14 @@ DMG_API int32_t dmg_shard_tdm_retrieve(dmg_handle_t h, int32_t B, const int32_t 
                                        int32_t beam, int32_t topk, int32_t use_mask,
                                        int32_t *out_items, float *out_logits, int32_t *out_counts);
 
+/* dmg_jtm_item_weights over the sharded table (BASELINE config 4): collective; every rank passes ITS OWN items (any
+ * split of the catalogue) with the same old_level / level / flags; the (sample, node) scorer rows go to the owners of
+ * the nodes like retrieval candidates.  Same values as dmg_jtm_item_weights on the unsharded table. */
+DMG_API int32_t dmg_shard_jtm_item_weights(dmg_handle_t h, int32_t n_items, const int64_t *sample_off,
+                                           const int32_t *sample_seq, const int32_t *parent_code,
+                                           int32_t old_level, int32_t level, int32_t hierarchical,
+                                           int32_t min_level, int32_t use_mask, float *out_weights);
+
 #ifdef __cplusplus
 }
 #endif

@@ -64,6 +64,38 @@ def test_unsharded_entry_points_refuse_a_sharded_table(jtm_fix, queries):
     e.close()
 
 
+def test_world1_jtm_item_weights_match_the_unsharded_engine(jtm_fix, queries):
+    """dmg_shard_jtm_item_weights (scorer rows routed like retrieval candidates) vs dmg_jtm_item_weights, bit for bit;
+    hierarchical re-coding, items without samples, several chunks."""
+    f = jtm_fix
+    L = int(f["max_level"])
+    rng = np.random.default_rng(3)
+    n_it = 300
+    items = rng.choice(f["leaf_ids"], n_it, replace=False)
+    counts = rng.integers(0, 5, n_it)
+    counts[:5] = 0
+    off = np.zeros(n_it + 1, np.int64)
+    off[1:] = np.cumsum(counts)
+    seqs = rng.choice(f["leaf_ids"], (int(off[-1]), 10)).astype(np.int32)
+    seqs[:, :2] = 0
+    old_level, level = 3, 6
+    par = rng.integers((1 << old_level) - 1, (2 << old_level) - 1, n_it).astype(np.int32)
+    ref = new_engine()
+    ref.load_tree_tdm(L, f["codes"], f["node_ids"], f["is_leaf"], f["leaf_ids"], f["leaf_codes"])
+    ref.load_din_weights(f["params"], 8191, 16, 10)
+    e = new_engine()
+    e.shard_init(1, 0)
+    e.load_tree_tdm(L, f["codes"], f["node_ids"], f["is_leaf"], f["leaf_ids"], f["leaf_codes"])
+    e.shard_load_din_weights(f["params"], 8191, 16, 10)
+    for hier in (False, True):
+        want = ref.jtm_item_weights(off, seqs, par, old_level, level, hierarchical=hier, min_level=0)
+        got = e.shard_jtm_item_weights(off, seqs, par, old_level, level, hierarchical=hier, min_level=0)
+        assert (got.view(np.uint32) == want.view(np.uint32)).all()
+        assert (got[:5] == np.float32(-1e6)).all()
+    ref.close()
+    e.close()
+
+
 def _two_gpu_worker(rank, world, port, out_dir):
     sys.path.insert(0, ROOT)
     sys.argv = ["shard_check.py", "--items", "5000", "--batch", "24", "--out", os.path.join(out_dir, f"r{rank}.json")]

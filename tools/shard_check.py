@@ -30,6 +30,8 @@ def main():
     ap.add_argument("--check", default="oracle", choices=["oracle", "engine"],
                     help="oracle: CPU oracle on the full table (needs the table on the host); engine: the unsharded strict "
                          "CUDA engine on this rank's GPU (for catalogues too large to ship to the host)")
+    ap.add_argument("--jtm-items", type=int, default=0, help="also check dmg_shard_jtm_item_weights on this many items per rank")
+    ap.add_argument("--jtm-gap", type=int, default=4)
     ap.add_argument("--out", default=None)
     a = ap.parse_args()
     import torch
@@ -73,7 +75,28 @@ def main():
         full.set_arithmetic("strict")
         oi, ol, oc = full.tdm_retrieve(seqs[:n], a.beam, a.topk)
         full.close()
-    line = {"rank": rank, "world": world, "items": a.items, "levels": tf.max_level, "batch_per_rank": a.batch, "beam": a.beam,
+    # JTM item weights over the sharded table (config 4): this rank's slice of the items vs the unsharded engine
+    jtm = None
+    if a.jtm_items > 0:
+        rng = np.random.Generator(np.random.PCG64(50 + rank))
+        n_it = a.jtm_items
+        n_samples = rng.integers(0, 9, n_it)
+        off = np.zeros(n_it + 1, np.int64)
+        off[1:] = np.cumsum(n_samples)
+        sseq = synth.queries(int(off[-1]), T, a.items, seed=70 + rank)
+        old_level, level = 6, 6 + a.jtm_gap
+        par = rng.integers((1 << old_level) - 1, (2 << old_level) - 1, n_it).astype(np.int32)
+        t0 = time.perf_counter()
+        got = eng.shard_jtm_item_weights(off, sseq, par, old_level, level, hierarchical=True, min_level=0)
+        jdt = time.perf_counter() - t0
+        full = Engine(local)
+        full.load_tree_tdm(tf.max_level, tf.codes, tf.node_ids, tf.is_leaf, tf.leaf_ids, tf.leaf_codes)
+        full.init_din_weights(np.float32, rows, a.dim, T, seed=2)
+        want = full.jtm_item_weights(off, sseq, par, old_level, level, hierarchical=True, min_level=0)
+        full.close()
+        jtm = {"items": n_it, "samples": int(off[-1]), "gap": a.jtm_gap, "scorer_rows": int(off[-1]) * ((2 << a.jtm_gap) - 2),
+               "weights_bit_identical": bool((got.view(np.uint32) == want.view(np.uint32)).all()), "seconds": jdt}
+    line = {"rank": rank, "world": world, "jtm_item_weights": jtm, "items": a.items, "levels": tf.max_level, "batch_per_rank": a.batch, "beam": a.beam,
             "table_rows_global": global_rows, "table_rows_local": local_rows,
             "rows_scored_for_other_ranks": exchanged, "users_checked": n, "checked_against": a.check,
             "ids_identical": bool((items[:n] == oi).all() and (counts[:n] == oc).all()),
