@@ -85,6 +85,7 @@ def load_library(build_if_missing: bool = True):
         "dmg_tdm_sample_expand": [vp, i32, vp, vp, vp, i32, u64, vp, vp, vp, C.POINTER(i32)],
         "dmg_jtm_item_weights": [vp, i32, vp, vp, vp, i32, i32, i32, i32, i32, vp],
         "dmg_jtm_assign_level": [vp, i32, vp, vp, i32, vp, i32, vp],
+        "dmg_eval_metrics": [vp, i32, i32, vp, vp, vp, vp, vp],
         "dmg_load_deepfm_weights": [vp, i64, i32, i32, vp],
         "dmg_shard_unique_id": [vp, i32],
         "dmg_shard_init": [vp, i32, i32, vp],
@@ -243,6 +244,18 @@ class Engine:
         n = self.rows * self.E + 3 * self.E * self.E + 2 * self.E + 1
         out = np.empty(n, self.din_dtype)
         self._check(self.L.dmg_download_din_weights(self.h, _p(out), n))
+        return out
+
+    def eval_metrics(self, rec_items, rec_counts, labels):
+        """Metrics.computeMetrics per user -> [B, 3] (precision, recall, ndcg); labels: one sequence per user."""
+        rec = _i32(rec_items)
+        B, topk = rec.shape
+        cnt = _i32(rec_counts).ravel()
+        off = np.zeros(B + 1, np.int64)
+        off[1:] = np.cumsum([len(l) for l in labels])
+        flat = _i32(np.concatenate([np.asarray(l, np.int32) for l in labels])) if off[-1] else np.zeros(0, np.int32)
+        out = np.empty((B, 3), np.float64)
+        self._check(self.L.dmg_eval_metrics(self.h, B, topk, _p(rec), _p(cnt), _p(off), _p(flat), _p(out)))
         return out
 
     def jtm_assign_level(self, parent_code, old_child, weights, max_assign):

@@ -19,6 +19,8 @@
 #pragma once
 #include "dmg_common.cuh"
 #include "dmg_math.cuh"
+#include <algorithm>
+
 #include "device_utils.cuh"
 
 namespace dmg {
@@ -60,8 +62,8 @@ template <typename real> struct BeamParams {
 };
 
 // ---- compile-time geometry ----------------------------------------------------------------
-template <typename real, int E> struct Geo {
-    static constexpr int R = sizeof(real) == 4 ? 128 : 64;       // rows per tile
+template <typename real, int E, int RT = (sizeof(real) == 4 ? 128 : 64)> struct Geo {
+    static constexpr int R = RT;                                 // rows per tile (beam search: 128 fp32 / 64 fp64)
     static constexpr int NBUF = sizeof(real) == 4 ? 2 : 1;       // row-tile buffers
     static constexpr int VEC = 16 / sizeof(real);                // reals per 16 B
     static constexpr int LD = E + VEC;                           // padded row stride
@@ -91,14 +93,15 @@ template <typename real, int E> struct Geo {
 
 // ---- the DIN scorer on one tile of R candidate rows -----------------------------------------
 // sX: gathered candidate rows [R][LD]; sK: history [T][E]; results -> sScore[0..nrows).
-template <typename real, int E>
+// PER_ROW: every row brings its own history (model.forward on independent rows): sK is [R][T][E], sMask [R][T].
+template <typename real, int E, int RT = (sizeof(real) == 4 ? 128 : 64), bool PER_ROW = false>
 __device__ __forceinline__ void score_tile(const real *__restrict__ sX, real *__restrict__ sA, real *__restrict__ sP,
                                            const real *__restrict__ sK, const int32_t *__restrict__ sMask,
                                            const real *__restrict__ sWattT, const real *__restrict__ sW1T,
                                            const real *__restrict__ sB1, const real *__restrict__ sW2,
                                            real b2, real scale, int T, int nrows, real *__restrict__ sScoreOut)
 {
-    using G = Geo<real, E>;
+    using G = Geo<real, E, RT>;
     const int tid = threadIdx.x;
 
     // (1) attention scores: s[r][j] = scale * sum_k x[r][k] K[j][k]   (MatMul transB + Mask)
@@ -118,7 +121,7 @@ __device__ __forceinline__ void score_tile(const real *__restrict__ sX, real *__
                     const int j = part + jj * G::NP;
                     if (j < T) {
                         real kv[4];
-                        ld4(sK + j * E + k, kv);
+                        ld4(sK + (PER_ROW ? r * T + j : j) * E + k, kv);
                         acc[jj] = fma_(xv[0], kv[0], acc[jj]);
                         acc[jj] = fma_(xv[1], kv[1], acc[jj]);
                         acc[jj] = fma_(xv[2], kv[2], acc[jj]);
@@ -131,7 +134,7 @@ __device__ __forceinline__ void score_tile(const real *__restrict__ sX, real *__
                 const int j = part + jj * G::NP;
                 if (j < T) {
                     real s = mul_(acc[jj], scale);
-                    if (sMask[j]) s = mask_value<real>::get();
+                    if (sMask[PER_ROW ? r * T + j : j]) s = mask_value<real>::get();
                     sP[r * G::PLD + j] = s;
                 }
             }
@@ -159,7 +162,7 @@ __device__ __forceinline__ void score_tile(const real *__restrict__ sX, real *__
             const real *pr = sP + r * G::PLD;
             for (int j = 0; j < T; j++) {
                 const real pj = pr[j];
-                const real *kj = sK + j * E + part * G::KW;
+                const real *kj = sK + (PER_ROW ? r * T + j : j) * E + part * G::KW;
 #pragma unroll
                 for (int kk = 0; kk < G::KW; kk += G::VEC) {
                     if constexpr (G::VEC == 4) {
@@ -287,6 +290,106 @@ __device__ __forceinline__ void gather_tile(real *__restrict__ sXbuf, const real
     for (int idx = threadIdx.x; idx < nrows * VPR; idx += blockDim.x) {
         const int r = idx / VPR, v = idx % VPR;
         cp_async16(sXbuf + r * G::LD + v * G::VEC, emb + (size_t)codes[r] * E + v * G::VEC);
+    }
+}
+
+// ---- model.forward on independent rows, tiled (dmg_score_pairs, JTM weights) ------------------------------------------
+// Every row brings its own T history indices (Recommender.scala:94, OTMTree.scala:168,198, TreeLearning.scala:168).  RT rows
+// per CTA iteration: candidate rows and the RT x T history rows staged with cp.async, weights in shared memory once per
+// CTA, then score_tile in PER_ROW mode -- the strict kernel's register-tiled sequential-k chains, so the bits are those
+// of the beam search and of the oracle.  Replaces the row-at-a-time din_rows_forward_kernel for E in {16, 32, 64}.
+template <typename real, int E> struct RowsGeo {
+    static constexpr int RMIN = sizeof(real) == 4 ? 32 : 16;
+    static constexpr int RT = (1024 / E > RMIN) ? 1024 / E : RMIN;          // TM = RT / (kThreads / (E/4)) >= 1
+    using G = Geo<real, E, RT>;
+    static size_t smem_bytes(int T)
+    {
+        const size_t reals = (size_t)3 * E * E + 2 * E + 4 + (size_t)RT * T * E + 2 * (size_t)RT * G::LD + (size_t)RT * G::PLD + RT;
+        return ((reals * sizeof(real) + 15) & ~(size_t)15) + (size_t)RT * T * sizeof(int32_t) + 16;
+    }
+};
+template <typename real, int E>
+__global__ void __launch_bounds__(kThreads) din_rows_tiled_kernel(const real *__restrict__ emb, const real *__restrict__ wattT,
+                                                                  const real *__restrict__ w1T, const real *__restrict__ b1,
+                                                                  const real *__restrict__ w2, const real *__restrict__ b2, real scale,
+                                                                  int T, int64_t n, const int32_t *__restrict__ node,
+                                                                  const int32_t *__restrict__ seq, const uint8_t *__restrict__ mask,
+                                                                  real *__restrict__ out)
+{
+    using RG = RowsGeo<real, E>;
+    using G = typename RG::G;
+    constexpr int RT = RG::RT, VPR = E / G::VEC;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    real *sWattT = reinterpret_cast<real *>(smem_raw);
+    real *sW1T = sWattT + E * E;
+    real *sB1 = sW1T + 2 * E * E;
+    real *sW2 = sB1 + E;
+    real *sB2 = sW2 + E;                          // 4 reals
+    real *sK = sB2 + 4;                           // RT x T x E
+    real *sX = sK + (size_t)RT * T * E;           // RT x LD
+    real *sA = sX + RT * G::LD;
+    real *sP = sA + RT * G::LD;
+    real *sOut = sP + RT * G::PLD;                // RT
+    const size_t off = (((size_t)((unsigned char *)(sOut + RT) - smem_raw)) + 15) & ~(size_t)15;
+    int32_t *sMask = reinterpret_cast<int32_t *>(smem_raw + off);            // RT x T
+    const int tid = threadIdx.x;
+    for (int i = tid; i < E * E; i += kThreads) sWattT[i] = wattT[i];
+    for (int i = tid; i < 2 * E * E; i += kThreads) sW1T[i] = w1T[i];
+    for (int i = tid; i < E; i += kThreads) { sB1[i] = b1[i]; sW2[i] = w2[i]; }
+    if (tid == 0) sB2[0] = b2[0];
+    __syncthreads();
+    const real b2v = sB2[0];
+    for (int64_t g0 = (int64_t)blockIdx.x * RT; g0 < n; g0 += (int64_t)gridDim.x * RT) {
+        const int nr = (int)((n - g0) < RT ? (n - g0) : RT);
+        __syncthreads();
+        for (int idx = tid; idx < nr * (T + 1) * VPR; idx += kThreads) {
+            const int v = idx % VPR, slot = (idx / VPR) % (T + 1), r = idx / (VPR * (T + 1));
+            const int32_t c = slot == 0 ? node[g0 + r] : seq[(g0 + r) * T + slot - 1];
+            real *dst = slot == 0 ? sX + r * G::LD + v * G::VEC : sK + ((size_t)(r * T + slot - 1) * E + v * G::VEC);
+            if (c >= 0) cp_async16(dst, emb + (size_t)c * E + v * G::VEC);
+            else
+#pragma unroll
+                for (int q = 0; q < G::VEC; q++) dst[q] = (real)0;       // paddingIdx -> zero row (LookupTable.scala:33-34)
+        }
+        for (int i = tid; i < nr * T; i += kThreads) sMask[i] = mask[g0 * T + i];
+        cp_async_commit();
+        cp_async_wait<0>();
+        __syncthreads();
+        score_tile<real, E, RT, true>(sX, sA, sP, sK, sMask, sWattT, sW1T, sB1, sW2, b2v, scale, T, nr, sOut);
+        for (int i = tid; i < nr; i += kThreads) out[g0 + i] = sOut[i];
+    }
+}
+template <typename real, int E>
+static cudaError_t launch_rows_tiled(const real *emb, const real *wattT, const real *w1T, const real *b1, const real *w2, const real *b2,
+                                     real scale, int T, int64_t n, const int32_t *node, const int32_t *seq, const uint8_t *mask, real *out,
+                                     int sm_count, size_t smem_per_sm, cudaStream_t st)
+{
+    using RG = RowsGeo<real, E>;
+    const size_t smem = RG::smem_bytes(T);
+    auto kern = din_rows_tiled_kernel<real, E>;
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    const int per_sm = (int)std::max<size_t>(1, std::min<size_t>(4, smem_per_sm / (smem + 1024)));
+    const int64_t tiles = (n + RG::RT - 1) / RG::RT;
+    const int grid = (int)std::min<int64_t>(tiles, (int64_t)sm_count * per_sm);
+    kern<<<grid, kThreads, smem, st>>>(emb, wattT, w1T, b1, w2, b2, scale, T, n, node, seq, mask, out);
+    return cudaGetLastError();
+}
+// true when the tiled kernel took the rows (E with a tile geometry), false: the caller falls back to din_rows_forward_kernel
+template <typename real>
+static bool rows_forward_tiled(int E, const real *emb, const real *wattT, const real *w1T, const real *b1, const real *w2, const real *b2,
+                               real scale, int T, int64_t n, const int32_t *node, const int32_t *seq, const uint8_t *mask, real *out,
+                               int sm_count, size_t smem_per_sm, size_t smem_optin, cudaStream_t st, cudaError_t *err)
+{
+    *err = cudaSuccess;
+    switch (E) {
+    case 16: if (RowsGeo<real, 16>::smem_bytes(T) > smem_optin) return false;
+             *err = launch_rows_tiled<real, 16>(emb, wattT, w1T, b1, w2, b2, scale, T, n, node, seq, mask, out, sm_count, smem_per_sm, st); return true;
+    case 32: if (RowsGeo<real, 32>::smem_bytes(T) > smem_optin) return false;
+             *err = launch_rows_tiled<real, 32>(emb, wattT, w1T, b1, w2, b2, scale, T, n, node, seq, mask, out, sm_count, smem_per_sm, st); return true;
+    case 64: if (RowsGeo<real, 64>::smem_bytes(T) > smem_optin) return false;
+             *err = launch_rows_tiled<real, 64>(emb, wattT, w1T, b1, w2, b2, scale, T, n, node, seq, mask, out, sm_count, smem_per_sm, st); return true;
+    default: return false;
     }
 }
 

@@ -831,7 +831,17 @@ DMG_API int32_t dmg_score_pairs(dmg_handle_t h, int64_t n, const int32_t *node, 
     DMG_TRY(ensure_dev(h, h->s_out, out_bytes));
     const size_t smem = (size_t)kRowsRB * ((size_t)4 * E + (size_t)T * E + T + 1) * d.esz;
     const int grid = (int)std::min<int64_t>((n + kRowsRB - 1) / kRowsRB, (int64_t)h->sm_count * 8);
-    if (d.dtype == DMG_F32) {
+    cudaError_t terr = cudaSuccess;
+    const bool tiled = d.dtype == DMG_F32
+        ? rows_forward_tiled<float>(E, d.emb<float>(), (const float *)d.d_wattT, (const float *)d.d_w1T, d.b1<float>(), d.w2<float>(), d.b2<float>(),
+                                    (float)(1.0 / std::sqrt((double)E)), T, n, dn, ds, d_mask, (float *)h->s_out.d, h->sm_count, h->smem_per_sm,
+                                    h->smem_optin, h->stream, &terr)
+        : rows_forward_tiled<double>(E, d.emb<double>(), (const double *)d.d_wattT, (const double *)d.d_w1T, d.b1<double>(), d.w2<double>(), d.b2<double>(),
+                                     1.0 / std::sqrt((double)E), T, n, dn, ds, d_mask, (double *)h->s_out.d, h->sm_count, h->smem_per_sm,
+                                     h->smem_optin, h->stream, &terr);
+    DMG_CUDA(h, terr);
+    if (tiled) {
+    } else if (d.dtype == DMG_F32) {
         auto kern = din_rows_forward_kernel<float>;
         DMG_CUDA(h, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         kern<<<grid, kRowsThreads, smem, h->stream>>>(d.emb<float>(), (const float *)d.d_wattT, (const float *)d.d_w1T,

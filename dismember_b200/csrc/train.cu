@@ -15,7 +15,7 @@
 #include <algorithm>
 #include <cmath>
 
-#include "device_utils.cuh"
+#include "beam_kernels.cuh"
 #include "rows_kernels.cuh"
 
 using namespace dmg;
@@ -665,13 +665,19 @@ DMG_API int32_t dmg_jtm_item_weights(dmg_handle_t h, int32_t n_items, const int6
         jtm_rows_kernel<<<grid, 256, 0, h->stream>>>(n_items, dof, dsq, dp, old_level, gap, n_nodes, T, t.d_id_code, t.non_leaf_offset,
                                                     t.max_code, t.max_level, hierarchical, min_level, use_mask, dr, n_rows, d_node, d_seq, d_mask);
         check_index_kernel<<<(unsigned)((n_rows * T + 255) / 256), 256, 0, h->stream>>>(d_seq, n_rows * T, d.rows, h->d_flags);
-        const size_t smem = (size_t)kRowsRB * ((size_t)4 * E + (size_t)T * E + T + 1) * 4;
-        auto kern = din_rows_forward_kernel<float>;
-        DMG_CUDA(h, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        const int g2 = (int)std::min<int64_t>((n_rows + kRowsRB - 1) / kRowsRB, (int64_t)h->sm_count * 8);
-        kern<<<g2, kRowsThreads, smem, h->stream>>>(d.emb<float>(), (const float *)d.d_wattT, (const float *)d.d_w1T, d.b1<float>(),
-                                                    d.w2<float>(), d.b2<float>(), (float)(1.0 / std::sqrt((double)E)), E, T, n_rows,
-                                                    d_node, d_seq, d_mask, d_logit);
+        cudaError_t terr = cudaSuccess;
+        if (!rows_forward_tiled<float>(E, d.emb<float>(), (const float *)d.d_wattT, (const float *)d.d_w1T, d.b1<float>(), d.w2<float>(),
+                                       d.b2<float>(), (float)(1.0 / std::sqrt((double)E)), T, n_rows, d_node, d_seq, d_mask, d_logit,
+                                       h->sm_count, h->smem_per_sm, h->smem_optin, h->stream, &terr)) {
+            const size_t smem = (size_t)kRowsRB * ((size_t)4 * E + (size_t)T * E + T + 1) * 4;
+            auto kern = din_rows_forward_kernel<float>;
+            DMG_CUDA(h, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            const int g2 = (int)std::min<int64_t>((n_rows + kRowsRB - 1) / kRowsRB, (int64_t)h->sm_count * 8);
+            kern<<<g2, kRowsThreads, smem, h->stream>>>(d.emb<float>(), (const float *)d.d_wattT, (const float *)d.d_w1T, d.b1<float>(),
+                                                        d.w2<float>(), d.b2<float>(), (float)(1.0 / std::sqrt((double)E)), E, T, n_rows,
+                                                        d_node, d_seq, d_mask, d_logit);
+        }
+        DMG_CUDA(h, terr);
         h->launches += 3;
     }
     jtm_reduce_kernel<<<grid, 256, 0, h->stream>>>(n_items, dof, d_logit, n_nodes, gap, d_nsum, d_w);
@@ -770,5 +776,68 @@ DMG_API int32_t dmg_jtm_assign_level(dmg_handle_t h, int32_t n_items, const int3
             for (const Entry &e : res[c]) out_node[order[g0 + e.item]] = (int32_t)(first + c);
         g0 = g1;
     }
+    return DMG_OK;
+}
+
+// ---- evaluation metrics ----------------------------------------------------------------------------
+// Metrics.computeMetrics (tdm/.../evaluation/Metrics.scala:5-25) for a batch of users: precision = hits / k, recall =
+// hits / |labels|, NDCG = dcg / idcg with gains log(2) / log(rank + 2), k = number of items actually recommended;
+// (0, 0, 0) without a hit.  One thread per user; out[u] = (precision, recall, ndcg) in double, to be summed by the caller
+// in user order like EvalResult.+= (Evaluator.scala:62-66).
+namespace {
+__global__ void eval_metrics_kernel(int B, int stride, const int32_t *__restrict__ rec, const int32_t *__restrict__ rec_count,
+                                    const int64_t *__restrict__ label_off, const int32_t *__restrict__ labels, double *__restrict__ out)
+{
+    const int u = blockIdx.x * blockDim.x + threadIdx.x;
+    if (u >= B) return;
+    const int k = rec_count[u];
+    const int64_t l0 = label_off[u], l1 = label_off[u + 1];
+    int common = 0, j = 0;
+    double dcg = 0.0, idcg = 0.0;
+    const double ln2 = log(2.0);
+    for (int i = 0; i < k; i++) {
+        const int32_t it = rec[(size_t)u * stride + i];
+        bool hit = false;
+        for (int64_t q = l0; q < l1 && !hit; q++) hit = labels[q] == it;
+        if (hit) {
+            common++;
+            dcg += ln2 / log((double)(i + 2));
+            idcg += ln2 / log((double)(j + 2));
+            j++;
+        }
+    }
+    // labels.toSet: the recall denominator is labels.length (duplicates counted), Metrics.scala:20
+    out[(size_t)u * 3 + 0] = common ? (double)common / (double)k : 0.0;
+    out[(size_t)u * 3 + 1] = common ? (double)common / (double)(l1 - l0) : 0.0;
+    out[(size_t)u * 3 + 2] = common ? dcg / idcg : 0.0;
+}
+}  // namespace
+
+DMG_API int32_t dmg_eval_metrics(dmg_handle_t h, int32_t B, int32_t topk, const int32_t *rec_items, const int32_t *rec_counts,
+                                 const int64_t *label_off, const int32_t *labels, double *out_metrics)
+{
+    if (!h) return DMG_ERR_INVALID_ARG;
+    if (B <= 0 || topk <= 0 || !rec_items || !rec_counts || !label_off || !out_metrics || (label_off[B] > 0 && !labels))
+        return fail(h, DMG_ERR_INVALID_ARG, "dmg_eval_metrics: bad arguments");
+    for (int32_t u = 0; u < B; u++)
+        if (rec_counts[u] < 0 || rec_counts[u] > topk || label_off[u + 1] < label_off[u])
+            return fail(h, DMG_ERR_INVALID_ARG, "dmg_eval_metrics: bad count / offsets for user %d", u);
+    DMG_CUDA(h, cudaSetDevice(h->device));
+    const size_t nl = (size_t)label_off[B];
+    DMG_TRY(ensure_dev(h, h->s_in, Carver::need({(size_t)B * topk * 4, (size_t)B * 4, ((size_t)B + 1) * 8, nl * 4, (size_t)B * 24})));
+    Carver cd(h->s_in.d);
+    int32_t *d_rec = cd.take<int32_t>((size_t)B * topk), *d_cnt = cd.take<int32_t>((size_t)B);
+    int64_t *d_off = cd.take<int64_t>((size_t)B + 1);
+    int32_t *d_lab = cd.take<int32_t>(nl);
+    double *d_out = cd.take<double>((size_t)B * 3);
+    DMG_CUDA(h, cudaMemcpyAsync(d_rec, rec_items, (size_t)B * topk * 4, cudaMemcpyHostToDevice, h->stream));
+    DMG_CUDA(h, cudaMemcpyAsync(d_cnt, rec_counts, (size_t)B * 4, cudaMemcpyHostToDevice, h->stream));
+    DMG_CUDA(h, cudaMemcpyAsync(d_off, label_off, ((size_t)B + 1) * 8, cudaMemcpyHostToDevice, h->stream));
+    if (nl) DMG_CUDA(h, cudaMemcpyAsync(d_lab, labels, nl * 4, cudaMemcpyHostToDevice, h->stream));
+    eval_metrics_kernel<<<(B + 127) / 128, 128, 0, h->stream>>>(B, topk, d_rec, d_cnt, d_off, d_lab, d_out);
+    h->launches += 1;
+    DMG_CUDA(h, cudaGetLastError());
+    DMG_CUDA(h, cudaMemcpyAsync(out_metrics, d_out, (size_t)B * 24, cudaMemcpyDeviceToHost, h->stream));
+    DMG_CUDA(h, cudaStreamSynchronize(h->stream));
     return DMG_OK;
 }

@@ -236,6 +236,13 @@ DMG_API int32_t dmg_jtm_assign_level(dmg_handle_t h, int32_t n_items, const int3
                                      const int32_t *old_child, int32_t n_child, const float *weights,
                                      int32_t max_assign, int32_t *out_node);
 
+/* Metrics.computeMetrics (tdm/.../evaluation/Metrics.scala:5-25) for B users: rec_items B x topk (first rec_counts[u]
+ * valid = k of the reference), labels as CSR; out_metrics B x 3 doubles (precision, recall, NDCG), to be summed by the
+ * caller in user order like EvalResult (Evaluator.scala:62-66).  log() differs from java.lang.Math.log by <= 1 ulp. */
+DMG_API int32_t dmg_eval_metrics(dmg_handle_t h, int32_t B, int32_t topk, const int32_t *rec_items,
+                                 const int32_t *rec_counts, const int64_t *label_off, const int32_t *labels,
+                                 double *out_metrics);
+
 /* DeepFM scorer, the other `model.deep_model` of the TDM/JTM tasks (tdm/.../model/DeepFM.scala:11-44,
  * scalann/.../nn/FM.scala:14-44): params = the compact vector of Module.parameters()
  * [emb rows x E | W1 (T+1) x (T+1)E | b1 T+1 | W2 T+1 | b2 1], fp32.  Afterwards dmg_tdm_retrieve

@@ -93,3 +93,28 @@ def test_jtm_tree_learning(engine, jtm_fix, queries):
     assert JTM(engine, L, item_codes, samples, gap=3, seq_len=10, hierarchical=True).optimize() == proj
     # the native reBalance (dmg_jtm_assign_level) and its Python mirror assign identically
     assert JTM(engine, L, item_codes, samples, gap=3, seq_len=10, hierarchical=True, native=False).optimize() == proj
+
+
+def test_eval_metrics_match_the_reference_formula(engine):
+    """Metrics.computeMetrics (tdm/.../evaluation/Metrics.scala:5-25) restated in Python, per user."""
+    import math
+    rng = np.random.default_rng(2)
+    B, topk = 200, 10
+    rec = rng.integers(1, 60, (B, topk)).astype(np.int32)
+    cnt = rng.integers(0, topk + 1, B).astype(np.int32)
+    labels = [list(rng.integers(1, 60, rng.integers(1, 8))) for _ in range(B)]
+    labels[3] = [int(rec[3, 0])] * 3                              # duplicate labels: recall divides by labels.length
+    cnt[3] = 5
+    got = engine.eval_metrics(rec, cnt, labels)
+    for u in range(B):
+        k, ls = int(cnt[u]), set(int(x) for x in labels[u])
+        common = j = 0
+        dcg = idcg = 0.0
+        for i in range(k):
+            if int(rec[u, i]) in ls:
+                common += 1
+                dcg += math.log(2) / math.log(i + 2)
+                idcg += math.log(2) / math.log(j + 2)
+                j += 1
+        want = (common / k, common / len(labels[u]), dcg / idcg) if common else (0.0, 0.0, 0.0)
+        assert np.allclose(got[u], want, rtol=1e-13, atol=0)
