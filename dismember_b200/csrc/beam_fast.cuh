@@ -388,12 +388,7 @@ __device__ __forceinline__ void block_select(uint32_t k0, uint32_t k1, int k, ui
             if (fm == fm) mid = order_key(fm);
         }
         mid = min(max(mid, lo + 1u), hi);
-        int c = __popc(__ballot_sync(0xffffffffu, k0 >= mid)) + __popc(__ballot_sync(0xffffffffu, k1 >= mid));
-        if (lane == 0) sCnt[warp] = c;
-        __syncthreads();
-        const int4 a = *reinterpret_cast<const int4 *>(sCnt), b = *reinterpret_cast<const int4 *>(sCnt + 4);
-        c = (a.x + a.y) + (a.z + a.w) + (b.x + b.y) + (b.z + b.w);
-        sCnt = sRed + (sCnt == sRed ? 64 : 0);
+        const int c = __syncthreads_count(k0 >= mid) + __syncthreads_count(k1 >= mid);     // barrier.red.popc: no shared-memory round trip
         it++;
         if (c >= k) { lo = mid; clo = c; } else { hi = mid - 1u; chi = c; }
     }
