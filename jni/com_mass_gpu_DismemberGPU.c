@@ -227,3 +227,61 @@ JNIEXPORT void JNICALL Java_com_mass_gpu_DismemberGPU_00024_jtmAssignLevel(
     UNPIN(outNode, out, 0); UNPIN(weights, w, JNI_ABORT); UNPIN(oldChild, o, JNI_ABORT); UNPIN(parentCode, p, JNI_ABORT);
     if (rc) throw_status(env, H(handle), rc);
 }
+
+/* TreeLearning.aggregateWeights for a level step; out: nItems x 2^(level - oldLevel) */
+JNIEXPORT void JNICALL Java_com_mass_gpu_DismemberGPU_00024_jtmItemWeights(
+    JNIEnv *env, jobject self, jlong handle, jlongArray sampleOff, jintArray sampleSeq, jintArray parentCode, jint oldLevel,
+    jint level, jboolean hierarchical, jint minLevel, jboolean useMask, jfloatArray outWeights)
+{
+    jsize n = (*env)->GetArrayLength(env, parentCode);
+    void *o = PIN(sampleOff), *s = PIN(sampleSeq), *p = PIN(parentCode), *w = PIN(outWeights);
+    int32_t rc = dmg_jtm_item_weights(H(handle), n, o, s, p, oldLevel, level, hierarchical ? 1 : 0, minLevel, useMask ? 1 : 0, w);
+    UNPIN(outWeights, w, 0); UNPIN(parentCode, p, JNI_ABORT); UNPIN(sampleSeq, s, JNI_ABORT); UNPIN(sampleOff, o, JNI_ABORT);
+    if (rc) throw_status(env, H(handle), rc);
+}
+
+/* NegativeSampler.sample + MiniBatch.convert on the device; returns the number of rows written */
+JNIEXPORT jint JNICALL Java_com_mass_gpu_DismemberGPU_00024_tdmSampleExpand(
+    JNIEnv *env, jobject self, jlong handle, jintArray targets, jintArray itemSeq, jintArray layerNeg, jint startLevel, jlong seed,
+    jintArray outNode, jintArray outSeq, jfloatArray outLabel)
+{
+    jsize n = (*env)->GetArrayLength(env, targets);
+    int32_t rows = 0;
+    void *t = PIN(targets), *s = PIN(itemSeq), *l = PIN(layerNeg), *on = PIN(outNode), *os = PIN(outSeq), *ol = PIN(outLabel);
+    int32_t rc = dmg_tdm_sample_expand(H(handle), n, t, s, l, startLevel, (uint64_t)seed, on, os, ol, &rows);
+    UNPIN(outLabel, ol, 0); UNPIN(outSeq, os, 0); UNPIN(outNode, on, 0);
+    UNPIN(layerNeg, l, JNI_ABORT); UNPIN(itemSeq, s, JNI_ABORT); UNPIN(targets, t, JNI_ABORT);
+    if (rc) throw_status(env, H(handle), rc);
+    return rows;
+}
+
+/* Module.parameters() back to the JVM (Serialization.saveModel) */
+JNIEXPORT void JNICALL Java_com_mass_gpu_DismemberGPU_00024_downloadDinWeightsFloat(JNIEnv *env, jobject self, jlong handle, jfloatArray params)
+{
+    jsize n = (*env)->GetArrayLength(env, params);
+    void *p = PIN(params);
+    int32_t rc = dmg_download_din_weights(H(handle), p, n);
+    UNPIN(params, p, 0);
+    if (rc) throw_status(env, H(handle), rc);
+}
+
+/* model.deep_model = "DeepFM" (TDM.scala:43) */
+JNIEXPORT void JNICALL Java_com_mass_gpu_DismemberGPU_00024_loadDeepFmWeightsFloat(
+    JNIEnv *env, jobject self, jlong handle, jlong rows, jint embedSize, jint seqLen, jfloatArray params)
+{
+    void *p = PIN(params);
+    int32_t rc = dmg_load_deepfm_weights(H(handle), rows, embedSize, seqLen, p);
+    UNPIN(params, p, JNI_ABORT);
+    if (rc) throw_status(env, H(handle), rc);
+}
+
+/* Metrics.computeMetrics per user; out: batch x 3 (precision, recall, ndcg) */
+JNIEXPORT void JNICALL Java_com_mass_gpu_DismemberGPU_00024_evalMetrics(
+    JNIEnv *env, jobject self, jlong handle, jint batch, jint topk, jintArray recItems, jintArray recCounts, jlongArray labelOff,
+    jintArray labels, jdoubleArray out)
+{
+    void *r = PIN(recItems), *c = PIN(recCounts), *o = PIN(labelOff), *l = PIN(labels), *m = PIN(out);
+    int32_t rc = dmg_eval_metrics(H(handle), batch, topk, r, c, o, l, m);
+    UNPIN(out, m, 0); UNPIN(labels, l, JNI_ABORT); UNPIN(labelOff, o, JNI_ABORT); UNPIN(recCounts, c, JNI_ABORT); UNPIN(recItems, r, JNI_ABORT);
+    if (rc) throw_status(env, H(handle), rc);
+}
