@@ -451,7 +451,7 @@ template <int E> static size_t shard_score_smem()
 // fma steps.  dense = [W1 (T+1) x (T+1)E | b1 | W2 | b2] staged in shared memory once per CTA.
 struct DfmGeo {
     static constexpr int R = 128;
-    static size_t smem(int E, int T) { const int F = T + 1; return ((size_t)F * F * E + 2 * F + 4 + (size_t)kMaxT * E + (size_t)R * (E + 1) + (size_t)R * (F + 1)) * 4 + 32 * 4; }
+    static size_t smem(int E, int T) { const int F = T + 1; return ((size_t)F * F * E + 2 * F + 4 + (size_t)kMaxT * E + (size_t)R * (E + 4) + (size_t)R * (F + 1)) * 4 + 32 * 4 + 64; }
 };
 __device__ __forceinline__ float deepfm_finish(const float *x, const float *sK, const float *hrow, float square_sum,
                                                const float *sW2, float b2, int E, int T)
@@ -481,6 +481,44 @@ __device__ __forceinline__ float deepfm_chain(const float *x, const float *sK, c
     for (int k = 0; k < T * E; k++) acc = fma_(sK[k], sK[k], acc);
     return acc;
 }
+// NC chains of one row advanced together (independent accumulators give the FMA pipe its ILP; every chain is still its
+// own sequential-k chain, so the bits do not change).  Chains c0 .. c0+NC-1; chain T+1 is the square sum.
+template <int NC>
+__device__ __forceinline__ void deepfm_chains(const float *x, const float *sK, const float *sW1, const float *sB1, int c0, int E, int T,
+                                              float *hout)
+{
+    const int F = T + 1;
+    float acc[NC];
+    const float *w[NC];
+#pragma unroll
+    for (int i = 0; i < NC; i++) { acc[i] = 0.0f; w[i] = sW1 + (size_t)(c0 + i < F ? c0 + i : 0) * F * E; }
+    // 16-byte shared-memory loads: one of x (or of the history) and one per chain of its weights feed 4 fma steps each
+    for (int k = 0; k < E; k += 4) {
+        const float4 xv = *reinterpret_cast<const float4 *>(x + k);
+#pragma unroll
+        for (int i = 0; i < NC; i++) {
+            const float4 wv = c0 + i < F ? *reinterpret_cast<const float4 *>(w[i] + k) : xv;
+            acc[i] = fma_(xv.x, wv.x, acc[i]);
+            acc[i] = fma_(xv.y, wv.y, acc[i]);
+            acc[i] = fma_(xv.z, wv.z, acc[i]);
+            acc[i] = fma_(xv.w, wv.w, acc[i]);
+        }
+    }
+    for (int k = 0; k < T * E; k += 4) {
+        const float4 kv = *reinterpret_cast<const float4 *>(sK + k);
+#pragma unroll
+        for (int i = 0; i < NC; i++) {
+            const float4 wv = c0 + i < F ? *reinterpret_cast<const float4 *>(w[i] + E + k) : kv;
+            acc[i] = fma_(kv.x, wv.x, acc[i]);
+            acc[i] = fma_(kv.y, wv.y, acc[i]);
+            acc[i] = fma_(kv.z, wv.z, acc[i]);
+            acc[i] = fma_(kv.w, wv.w, acc[i]);
+        }
+    }
+#pragma unroll
+    for (int i = 0; i < NC; i++)
+        if (c0 + i <= F) hout[c0 + i] = c0 + i < F ? relu_(add_(acc[i], sB1[c0 + i])) : acc[i];
+}
 struct ShardDfmArgs {
     const float *emb, *dense, *tiles;
     const int2 *req_self, *req_peer, *seg_self, *seg_peer;
@@ -493,12 +531,12 @@ struct ShardDfmArgs {
 static __global__ void __launch_bounds__(kThreads, 1) shard_score_deepfm_kernel(const ShardDfmArgs a)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    const int E = a.E, T = a.T, F = T + 1, LD = E + 1, HL = F + 1;
+    const int E = a.E, T = a.T, F = T + 1, LD = E + 4, HL = F + 1;      // LD: rows 16-byte aligned, 8 rows span the 32 banks
     float *sW1 = reinterpret_cast<float *>(smem_raw);
     float *sB1 = sW1 + (size_t)F * F * E;
     float *sW2 = sB1 + F;
     float *sB2 = sW2 + F;                        // 4 floats
-    float *sK = sB2 + 4;                         // kMaxT x E
+    float *sK = sW1 + (((size_t)F * F * E + 2 * F + 4 + 3) & ~(size_t)3);      // kMaxT x E, 16-byte aligned
     float *sX = sK + kMaxT * E;                  // R x LD
     float *sH = sX + DfmGeo::R * LD;             // R x HL: hidden units, [F] = square sum
     int32_t *sCtl = reinterpret_cast<int32_t *>(sH + DfmGeo::R * HL);
@@ -529,9 +567,10 @@ static __global__ void __launch_bounds__(kThreads, 1) shard_score_deepfm_kernel(
                 sX[r * LD + k] = a.emb[(size_t)shard_local_row(a.geo, rq[r0 + r].y) * E + k];
             }
             __syncthreads();
-            for (int idx = tid; idx < nrows * (F + 1); idx += kThreads) {
-                const int r = idx % nrows, c = idx / nrows;
-                sH[r * HL + c] = deepfm_chain(sX + r * LD, sK, sW1, sB1, c, E, T);
+            // two threads per row, 6 chains each (T = 10: 11 hidden units + the square sum); longer histories loop
+            for (int idx = tid; idx < nrows * ((F + 6) / 6); idx += kThreads) {
+                const int r = idx % nrows, c0 = (idx / nrows) * 6;
+                deepfm_chains<6>(sX + r * LD, sK, sW1, sB1, c0, E, T, sH + r * HL);
             }
             __syncthreads();
             for (int r = tid; r < nrows; r += kThreads)
