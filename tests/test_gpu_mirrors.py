@@ -118,3 +118,55 @@ def test_eval_metrics_match_the_reference_formula(engine):
                 j += 1
         want = (common / k, common / len(labels[u]), dcg / idcg) if common else (0.0, 0.0, 0.0)
         assert np.allclose(got[u], want, rtol=1e-13, atol=0)
+
+
+def test_dr_mstep_path_scores_and_assignment(engine, orc, dr_fix, queries):
+    """CoordinateDescent (deep-retrieval/.../optim/CoordinateDescent.scala): per-item path scores from the GPU beam search equal
+    the ones from the oracle's beam search (same host aggregation), and the greedy assignment gives every item J distinct
+    candidate paths with consistent path sizes."""
+    from dismember_b200 import dr_mstep
+    D = int(dr_fix["D"])
+    args = (int(dr_fix["num_item"]), int(dr_fix["K"]), D, int(dr_fix["T"]), int(dr_fix["E"]), dr_fix["layer_emb"],
+            [dr_fix[f"layer_w{d}"] for d in range(D)], [dr_fix[f"layer_b{d}"] for d in range(D)],
+            dr_fix["rr_emb"], dr_fix["rr_w"], dr_fix["rr_b"], dr_fix["sm_w"], dr_fix["sm_b"])
+    model = orc.DrModel(*args)
+    engine.dr_load(*args)
+    item_id = {int(a): int(b) for a, b in zip(dr_fix["map_items"], dr_fix["map_ids"])}
+    seqs = np.array([[item_id.get(int(x), -1) for x in s] for s in queries["seqs"][:120]], np.int32)
+    rng = np.random.default_rng(4)
+    targets = rng.integers(0, 12, len(seqs))                       # few items, several samples each
+    n_cand, J = 8, 3
+
+    def oracle_bs(batch, beam):
+        paths = np.zeros((len(batch), beam, D), np.int32)
+        probs = np.zeros((len(batch), beam), np.float64)
+        counts = np.zeros(len(batch), np.int32)
+        for u, sq in enumerate(batch):
+            p_, pr = model.beam_search(sq, beam)
+            counts[u] = len(p_)
+            paths[u, :len(p_)] = p_
+            probs[u, :len(p_)] = pr
+        return paths, probs, counts
+
+    got = dr_mstep.batch_path_score(engine.dr_beam_search, seqs, targets, n_cand, batch_size=50)
+    want = dr_mstep.batch_path_score(oracle_bs, seqs, targets, n_cand, batch_size=7)
+    assert got == want                                              # paths and double sums identical
+    stream = dr_mstep.streaming_path_score(engine.dr_beam_search, seqs, targets, n_cand, 0.999, batch_size=64)
+    assert set(stream) == set(got) and all(len(v) <= n_cand for v in stream.values())
+    occ = {int(t): int((targets == t).sum()) for t in np.unique(targets)}
+    all_items = list(range(14))                                     # items 12, 13 never occur: random paths
+    m = dr_mstep.optimize(got, occ, all_items, num_iteration=3, num_path_per_item=J, num_layer=D, num_node=int(dr_fix["K"]),
+                          penalty_factor=3e-6, penalty_poly_order=4)
+    assert set(m) == set(all_items)
+    for v, paths in m.items():
+        assert len(paths) == J
+        if v in occ:
+            assert len(set(paths)) == J and all(p in dict(got[v]) for p in paths)
+    # with a huge penalty no path is shared between two items that could avoid it
+    m2 = dr_mstep.optimize(got, occ, list(occ), 1, 1, D, int(dr_fix["K"]), penalty_factor=1e6, penalty_poly_order=2)
+    used = set()
+    for v in sorted(occ):                                           # visiting order of one sweep
+        p = m2[v][0]
+        assert p not in used or all(c in used for c, _ in got[v])
+        used.add(p)
+    assert abs(dr_mstep.penalty_func(3, 4) - (4 ** 4 - 3 ** 4) / 4) < 1e-12
