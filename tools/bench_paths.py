@@ -186,6 +186,43 @@ def main():
          parity={"ids_identical": bool((gi == oi).all()), "scores_bit_identical": bool((gs.view(np.uint64) == osc.view(np.uint64)).all())})
     eng.close()
 
+    # ---- 3b. BASELINE configs[2]: OTM at 10 M items, fp64 -- one training step (LocalOptimizer per-level step: rows = users x 2 beam,
+    #          otm/.../optim/LocalOptimizer.scala:55-109) and retrieval on the same 17 GB table ---------------------------------------
+    if not a.quick:
+        n_items = a.train_items
+        items, leaf_ids, leaf_level = synth.otm_mapping(n_items, seed=42)
+        rows_tab = (1 << (leaf_level + 1)) - 1
+        eng = Engine(0)
+        eng.load_tree_complete(leaf_level, items, leaf_ids)
+        eng.init_din_weights(np.float64, rows_tab, E, T, seed=2)
+        rng = np.random.Generator(np.random.PCG64(17))
+        B = 256
+        lseq = leaf_ids[rng.integers(0, n_items, (B, T))].astype(np.int32)
+        lseq[:, :3] = -1
+        dt = timeit(lambda: eng.otm_retrieve(lseq, 200, 10), warm=1, reps=3)
+        rows_u = 256 + 400 * (leaf_level - 8)
+        emit(path="otm_retrieve (fp64, BASELINE configs[2] catalogue)", items=n_items, levels=leaf_level, batch=B, ms=dt * 1e3, users_per_s=B / dt,
+             roofline={"bound": "fp64 FMA pipe", "algorithmic_flop_per_user": rows_u * 27324, "achieved_tflops": rows_u * 27324 * B / dt / 1e12})
+        # one level's training rows: 20 users x 400 beam nodes of the leaf level (batch 8192 / (2 beam)), labels = pseudo targets
+        n_rows = 8000
+        node = rng.integers((1 << leaf_level) - 1, (2 << leaf_level) - 1, n_rows).astype(np.int32)
+        tseq = np.repeat(lseq[:20], 400, axis=0)
+        lab = (rng.random(n_rows) < 0.05).astype(np.float64)
+        mask = np.nonzero((tseq.ravel() < 0))[0].astype(np.int32)
+        step = [0]
+
+        def one64():
+            step[0] += 1
+            eng.train_step(node, tseq, mask, lab, 1e-3, step[0])
+        dt = timeit(one64, warm=2, reps=4)
+        n_par = rows_tab * E + 3 * E * E + 2 * E + 1
+        by = 8 * n_par * 8 + 2 * n_rows * (1 + T) * E * 8
+        emit(path="otm train_step (fp64 DIN fwd/bwd + BCE + scatter-add + dense Adam, BASELINE configs[2])", items=n_items, levels=leaf_level,
+             rows_per_step=n_rows, ms_per_step=dt * 1e3,
+             roofline={"bound": "hbm", "algorithmic_bytes_per_step": by, "achieved": by / dt / 1e9, "peak": hbm, "unit": "GB/s",
+                       "frac": by / dt / 1e9 / hbm, "peak_source": hbm_src})
+        eng.close()
+
     # ---- 4. Deep Retrieval beam search + rerank, fp64 (a23) --------------------------------------------------------
     n_item, K, D, J = (20_000, 100, 3, 2) if a.quick else (200_000, 1000, 3, 2)
     Ed = 16 if a.quick else 64
