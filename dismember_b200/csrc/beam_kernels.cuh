@@ -192,7 +192,7 @@ __device__ __forceinline__ void score_tile(const real *__restrict__ sX, real *__
 #pragma unroll
         for (int c = 0; c < 4; c++) acc[i][c] = (real)0;
     if (active) {
-#pragma unroll 2
+#pragma unroll 4
         for (int k = 0; k < E; k += 4) {
             real bv[4][4];
 #pragma unroll
@@ -219,7 +219,7 @@ __device__ __forceinline__ void score_tile(const real *__restrict__ sX, real *__
 #pragma unroll
         for (int c = 0; c < 4; c++) acc[i][c] = (real)0;
     if (active) {
-#pragma unroll 2
+#pragma unroll 4
         for (int k = 0; k < E; k += 4) {               // item half of the concat
             real bv[4][4];
 #pragma unroll
@@ -234,7 +234,7 @@ __device__ __forceinline__ void score_tile(const real *__restrict__ sX, real *__
                     for (int c = 0; c < 4; c++) acc[i][c] = fma_(av[kk], bv[kk][c], acc[i][c]);
             }
         }
-#pragma unroll 2
+#pragma unroll 4
         for (int k = 0; k < E; k += 4) {               // attention half
             real bv[4][4];
 #pragma unroll
