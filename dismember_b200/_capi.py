@@ -94,6 +94,8 @@ def load_library(build_if_missing: bool = True):
         "dmg_shard_info": [vp, C.POINTER(i64), C.POINTER(i64), C.POINTER(i64)],
         "dmg_shard_tdm_retrieve": [vp, i32, vp, i32, i32, i32, vp, vp, vp],
         "dmg_shard_jtm_item_weights": [vp, i32, vp, vp, vp, i32, i32, i32, i32, i32, vp],
+        "dmg_shard_dr_load": [vp, i32, i32, i32, i32, i32, vp, C.POINTER(vp), C.POINTER(vp), vp, vp, vp, vp, vp],
+        "dmg_shard_dr_retrieve": [vp, i32, vp, i32, i32, vp, vp, vp],
     }
     for name, args in sig.items():
         fn = getattr(L, name)
@@ -308,6 +310,29 @@ class Engine:
         counts = np.empty(B, np.int32)
         self._check(self.L.dmg_shard_tdm_retrieve(self.h, B, _p(seq), beam, topk, int(use_mask), _p(items), _p(logits), _p(counts)))
         return items, logits, counts
+
+    def shard_dr_load(self, num_item, K, D, T, E, layer_emb, layer_w, layer_b, rr_emb, rr_w, rr_b, sm_w, sm_b):
+        """dmg_shard_dr_load: same (whole) tables as dr_load, only this rank's item range is uploaded."""
+        c = lambda a: np.ascontiguousarray(a, np.float64)
+        layer_w = [c(w) for w in layer_w]
+        layer_b = [c(b) for b in layer_b]
+        wp = (C.c_void_p * D)(*[w.ctypes.data for w in layer_w])
+        bp = (C.c_void_p * D)(*[b.ctypes.data for b in layer_b])
+        arrs = [c(layer_emb), c(rr_emb), c(rr_w), c(rr_b), c(sm_w), c(sm_b)]
+        self._check(self.L.dmg_shard_dr_load(self.h, num_item, K, D, T, E, _p(arrs[0]), wp, bp, _p(arrs[1]), _p(arrs[2]),
+                                             _p(arrs[3]), _p(arrs[4]), _p(arrs[5])))
+        self.dr_shape = (num_item, K, D, T, E)
+
+    def shard_dr_retrieve(self, seq, beam, topk):
+        """Collective DeepRetrieval.recommend over the sharded item tables; every rank passes its own users."""
+        _, K, D, T, E = self.dr_shape
+        seq = _i32(seq).reshape(-1, T)
+        B = len(seq)
+        items = np.empty((B, topk), np.int32)
+        sc = np.empty((B, topk), np.float64)
+        counts = np.empty(B, np.int32)
+        self._check(self.L.dmg_shard_dr_retrieve(self.h, B, _p(seq), beam, topk, _p(items), _p(sc), _p(counts)))
+        return items, sc, counts
 
     def shard_jtm_item_weights(self, sample_off, sample_seq, parent_code, old_level, level, hierarchical=False, min_level=0,
                                use_mask=True):

@@ -56,6 +56,8 @@ struct DinDev {
 
 struct DrDev {
     bool loaded = false, paths_loaded = false;
+    bool sharded = false;          // item-indexed tables hold this rank's item range only (dmg_shard_dr_load)
+    int64_t local_items = 0, item_base = 0, item_chunk = 0;   // rows [item_base, item_base + local_items) of the item tables
     int num_item = 0, K = 0, D = 0, T = 0, E = 0;
     double *d_layer_emb = nullptr;
     std::vector<double *> d_layer_w, d_layer_b;     // device pointers per layer

@@ -17,6 +17,7 @@
 
 #include "device_utils.cuh"
 #include "rows_kernels.cuh"
+#include "shard_common.cuh"
 
 using namespace dmg;
 
@@ -33,6 +34,8 @@ struct DrBeamParams {
     const double *wT[kDrMaxD];     // [in][K]
     const double *b[kDrMaxD];
     const int32_t *seq;            // B x T, -1 = padding
+    const double *hist;            // nullable: B x T x E history rows already gathered (sharded item tables)
+    const double *node_emb;        // rows of the path nodes: layer_emb + num_item * E when the table is whole
     double *scratch;               // grid x (beam*K)
     int32_t *out_paths;            // B x beam x D
     double *out_probs;             // B x beam
@@ -81,7 +84,7 @@ __global__ void __launch_bounds__(kThreads) dr_beam_kernel(const DrBeamParams p)
     for (int user = blockIdx.x; user < p.B; user += gridDim.x) {
         for (int i = tid; i < T * E; i += kThreads) {
             const int32_t c = p.seq[(size_t)user * T + i / E];
-            sX0[i] = c < 0 ? 0.0 : p.layer_emb[(size_t)c * E + i % E];
+            sX0[i] = p.hist ? p.hist[(size_t)user * T * E + i] : (c < 0 ? 0.0 : p.layer_emb[(size_t)c * E + i % E]);
         }
         double *prob = sProb0, *nprob = sProb1;
         int32_t *path = sPath0, *npath = sPath1;
@@ -104,8 +107,8 @@ __global__ void __launch_bounds__(kThreads) dr_beam_kernel(const DrBeamParams p)
                 const int np = live - pb < kDrPC ? live - pb : kDrPC;
                 for (int i = tid; i < np * nk; i += kThreads) {
                     const int pp = i / nk, k = i % nk, j = k / E;
-                    const int32_t row = path[(pb + pp) * D + j] + p.num_item + j * K;   // CandidateSearcher.scala:54
-                    sXn[pp * nodeE + k] = p.layer_emb[(size_t)row * E + k % E];
+                    const int32_t row = path[(pb + pp) * D + j] + j * K;                // CandidateSearcher.scala:54 (numItem + j K + c)
+                    sXn[pp * nodeE + k] = p.node_emb[(size_t)row * E + k % E];
                 }
                 __syncthreads();
                 for (int o = tid; o < K; o += kThreads) {
@@ -182,6 +185,8 @@ struct DrRerankParams {
     const int32_t *path_counts;    // B
     const int64_t *path_off;
     const int32_t *path_items;
+    const double *pre_scores;      // nullable: candidate scores computed by the owners of the items (sharded tables) ...
+    const int32_t *cand_off;       // ... candidate idx of user u at pre_scores[cand_off[u] + idx]
     int32_t *out_items;            // B x topk
     double *out_scores;
     int32_t *out_counts;
@@ -201,13 +206,13 @@ __global__ void __launch_bounds__(kThreads) dr_rerank_kernel(const DrRerankParam
     const int tid = threadIdx.x;
 
     for (int user = blockIdx.x; user < p.B; user += gridDim.x) {
-        for (int i = tid; i < T * E; i += kThreads) {
+        for (int i = tid; i < T * E && !p.pre_scores; i += kThreads) {
             const int32_t c = p.seq[(size_t)user * T + i / E];
             sX[i] = c < 0 ? 0.0 : p.rr_emb[(size_t)c * E + i % E];
         }
         __syncthreads();
         // user vector u = W_r x + b_r (RerankModel.inferenceUserVector :54-68)
-        for (int o = tid; o < E; o += kThreads) {
+        for (int o = tid; o < E && !p.pre_scores; o += kThreads) {
             double acc = 0.0;
             for (int k = 0; k < T * E; k++) acc = fma_(__ldg(p.rr_wT + (size_t)k * E + o), sX[k], acc);
             sUv[o] = add_(acc, __ldg(p.rr_b + o));
@@ -235,11 +240,15 @@ __global__ void __launch_bounds__(kThreads) dr_rerank_kernel(const DrRerankParam
             for (int64_t idx = base + tid; idx < total && idx < base + kDrChunk; idx += kThreads) {
                 int lo = 0, hi = np;                                // last q with sStart[q] <= idx
                 while (hi - lo > 1) { int mid = (lo + hi) >> 1; if (sStart[mid] <= idx) lo = mid; else hi = mid; }
-                const int32_t item = p.path_items[sBase[lo] + (idx - sStart[lo])];
-                const double *w = p.sm_w + (size_t)item * E;
-                double acc = 0.0;
-                for (int k = 0; k < E; k++) acc = fma_(__ldg(w + k), sUv[k], acc);
-                const double sc = add_(acc, __ldg(p.sm_b + item));
+                double sc;
+                if (p.pre_scores) sc = p.pre_scores[(size_t)p.cand_off[user] + idx];
+                else {
+                    const int32_t item = p.path_items[sBase[lo] + (idx - sStart[lo])];
+                    const double *w = p.sm_w + (size_t)item * E;
+                    double acc = 0.0;
+                    for (int k = 0; k < E; k++) acc = fma_(__ldg(w + k), sUv[k], acc);
+                    sc = add_(acc, __ldg(p.sm_b + item));
+                }
                 const Key128 key = KO::make(sc, (int)idx);
                 if (key_better(key, tau)) sBuf[atomicAdd(sCount, 1)] = key;
             }
@@ -258,10 +267,13 @@ __global__ void __launch_bounds__(kThreads) dr_rerank_kernel(const DrRerankParam
                 int lo = 0, hi = np;
                 while (hi - lo > 1) { int mid = (lo + hi) >> 1; if (sStart[mid] <= idx) lo = mid; else hi = mid; }
                 item = p.path_items[sBase[lo] + (idx - sStart[lo])];
-                const double *w = p.sm_w + (size_t)item * E;
-                double acc = 0.0;
-                for (int k = 0; k < E; k++) acc = fma_(__ldg(w + k), sUv[k], acc);
-                sc = add_(acc, __ldg(p.sm_b + item));
+                if (p.pre_scores) sc = p.pre_scores[(size_t)p.cand_off[user] + idx];
+                else {
+                    const double *w = p.sm_w + (size_t)item * E;
+                    double acc = 0.0;
+                    for (int k = 0; k < E; k++) acc = fma_(__ldg(w + k), sUv[k], acc);
+                    sc = add_(acc, __ldg(p.sm_b + item));
+                }
             }
             p.out_items[(size_t)user * p.topk + i] = item;
             p.out_scores[(size_t)user * p.topk + i] = sc;
@@ -361,10 +373,12 @@ DMG_API int32_t dmg_dr_load_paths(dmg_handle_t h, const int64_t *path_off, const
 
 // shared by beam_search / retrieve: runs the beam kernel, leaves paths/probs/counts on the device
 static int32_t dr_beam_enqueue(dmg_handle_t h, int32_t B, const int32_t *seq_host, int32_t beam, bool for_rerank,
-                               int32_t **d_paths, double **d_probs, int32_t **d_counts, int32_t **d_seq_out)
+                               int32_t **d_paths, double **d_probs, int32_t **d_counts, int32_t **d_seq_out,
+                               const double *hist_tiles = nullptr)
 {
     DrDev &d = h->dr;
     if (!d.loaded) return fail(h, DMG_ERR_STATE, "dmg_dr_load first");
+    if (d.sharded && !hist_tiles) return fail(h, DMG_ERR_STATE, "the Deep Retrieval item tables are sharded: use dmg_shard_dr_retrieve");
     if (B <= 0 || beam <= 0 || !seq_host) return fail(h, DMG_ERR_INVALID_ARG, "bad arguments");
     if ((double)beam * d.K > 2.0e9) return fail(h, DMG_ERR_UNSUPPORTED, "beam*K too large");
     if (beam > kDrCap - kDrChunk) return fail(h, DMG_ERR_UNSUPPORTED, "beam must be <= %d", kDrCap - kDrChunk);
@@ -395,6 +409,8 @@ static int32_t dr_beam_enqueue(dmg_handle_t h, int32_t B, const int32_t *seq_hos
     memset(&p, 0, sizeof(p));
     p.num_item = d.num_item; p.K = K; p.D = D; p.T = T; p.E = E; p.B = B; p.beam = beam;
     p.layer_emb = d.d_layer_emb;
+    p.hist = hist_tiles;
+    p.node_emb = d.d_layer_emb + (size_t)(hist_tiles ? d.local_items : d.num_item) * E;
     for (int i = 0; i < D; i++) { p.wT[i] = d.d_layer_wT[i]; p.b[i] = d.d_layer_b[i]; }
     p.seq = d_seq; p.scratch = d_scr; p.out_paths = *d_paths; p.out_probs = *d_probs; p.out_counts = *d_counts;
     const int nodeE = std::max((D - 1) * E, 1);
@@ -472,5 +488,327 @@ DMG_API int32_t dmg_dr_retrieve(dmg_handle_t h, int32_t B, const int32_t *seq, i
     DMG_CUDA(h, cudaMemcpyAsync(out_scores, d_sc, (size_t)B * topk * 8, cudaMemcpyDeviceToHost, h->stream));
     DMG_CUDA(h, cudaMemcpyAsync(out_counts, d_cnt, (size_t)B * 4, cudaMemcpyDeviceToHost, h->stream));
     DMG_CUDA(h, cudaStreamSynchronize(h->stream));
+    return DMG_OK;
+}
+
+// ---- Deep Retrieval with the item-indexed tables sharded over the GPUs of one box (BASELINE config 5) --------
+// layer-embedding item rows, rerank embedding, softmax weights and biases are split by contiguous item-id range (rank r owns
+// items [r * chunk, (r+1) * chunk)); the (D-1) K path-node rows and every Linear are replicated.  Per batch:
+//   history rows of both embedding tables: each rank fills the rows it owns into zero [G*B, T, E] buffers, integer-sum
+//   all-reduce (ncclUint64: x + 0 keeps every bit) -> every rank holds its users' inputs;
+//   beam search over the K^D paths and the rerank user vector run locally (dr_beam_kernel with `hist`);
+//   rerank candidates (candidate index, item) go to the owner of the item (ncclSend/ncclRecv), which answers
+//   softmaxW[item].u + bias[item] (user vectors all-gathered once, E doubles per user); scores come back (8 B) and the
+//   requester picks its topk by the reference's (score desc, candidate index asc) order.
+// Same arithmetic and order as the unsharded kernels, so results are bit-identical to dmg_dr_retrieve.
+namespace {
+
+__global__ void dr_fill_tiles_kernel(const double *__restrict__ table, int64_t item_base, int64_t local_items, const int32_t *__restrict__ seq_all,
+                                     int64_t n_slots, int E, unsigned long long *__restrict__ tiles)
+{
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_slots * E; i += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t sl = i / E;
+        const int k = (int)(i % E);
+        const int64_t c = seq_all[sl];
+        unsigned long long v = 0ull;
+        if (c >= item_base && c < item_base + local_items) v = (unsigned long long)__double_as_longlong(table[(size_t)(c - item_base) * E + k]);
+        tiles[i] = v;
+    }
+}
+
+// u = W_r x + b_r (RerankModel.inferenceUserVector :54-68) from the gathered rerank-embedding tile
+__global__ void __launch_bounds__(kThreads) dr_uservec_kernel(int B, int T, int E, const double *__restrict__ hist_rr, const double *__restrict__ rr_wT,
+                                                              const double *__restrict__ rr_b, double *__restrict__ uvec)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    double *sX = reinterpret_cast<double *>(smem_raw);
+    for (int user = blockIdx.x; user < B; user += gridDim.x) {
+        __syncthreads();
+        for (int i = threadIdx.x; i < T * E; i += kThreads) sX[i] = hist_rr[(size_t)user * T * E + i];
+        __syncthreads();
+        for (int o = threadIdx.x; o < E; o += kThreads) {
+            double acc = 0.0;
+            for (int k = 0; k < T * E; k++) acc = fma_(__ldg(rr_wT + (size_t)k * E + o), sX[k], acc);
+            uvec[(size_t)user * E + o] = add_(acc, __ldg(rr_b + o));
+        }
+    }
+}
+
+__device__ __forceinline__ int64_t dr_path_key(const int32_t *path, int D, int K)
+{
+    int64_t key = 0;
+    for (int d = 0; d < D; d++) key = key * K + path[d];
+    return key;
+}
+// candidates of a user = items of each surviving path, in beam order (searchCandidate :8-20): count them ...
+__global__ void dr_cand_count_kernel(int B, int beam, int D, int K, const int32_t *__restrict__ paths, const int32_t *__restrict__ path_counts,
+                                     const int64_t *__restrict__ path_off, int32_t *__restrict__ totals)
+{
+    const int u = blockIdx.x * blockDim.x + threadIdx.x;
+    if (u >= B) return;
+    int64_t run = 0;
+    for (int q = 0; q < path_counts[u]; q++) {
+        const int64_t key = dr_path_key(paths + ((size_t)u * beam + q) * D, D, K);
+        run += path_off[key + 1] - path_off[key];
+    }
+    totals[u] = (int32_t)run;
+}
+// ... and list them: cand_item[cand_off[u] + idx]
+__global__ void __launch_bounds__(kThreads) dr_cand_fill_kernel(int B, int beam, int D, int K, const int32_t *__restrict__ paths,
+                                                                const int32_t *__restrict__ path_counts, const int64_t *__restrict__ path_off,
+                                                                const int32_t *__restrict__ path_items, const int32_t *__restrict__ cand_off,
+                                                                int32_t *__restrict__ cand_item)
+{
+    for (int u = blockIdx.x; u < B; u += gridDim.x) {
+        int64_t run = cand_off[u];
+        for (int q = 0; q < path_counts[u]; q++) {               // every thread walks the (short) path list, the items are split
+            const int64_t key = dr_path_key(paths + ((size_t)u * beam + q) * D, D, K);
+            const int64_t b0 = path_off[key], n = path_off[key + 1] - b0;
+            for (int64_t i = threadIdx.x; i < n; i += kThreads) cand_item[run + i] = path_items[b0 + i];
+            run += n;
+        }
+    }
+}
+// requests (candidate index, item) appended to the region of the item's owner, warp-aggregated
+__global__ void dr_bucket_kernel(int n, const int32_t *__restrict__ cand_item, int64_t chunk, int2 *__restrict__ region, int64_t region_stride,
+                                 int32_t *__restrict__ n_out)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    const bool ok = i < n;
+    const int item = ok ? cand_item[i] : 0;
+    const int o = ok ? (int)(item / chunk) : -1;
+    const unsigned peers = __match_any_sync(0xffffffffu, o);
+    const int lane = threadIdx.x & 31, leader = __ffs(peers) - 1;
+    int base = 0;
+    if (ok && lane == leader) base = atomicAdd(&n_out[o], __popc(peers));
+    base = __shfl_sync(0xffffffffu, base, leader);
+    if (ok) region[(size_t)o * region_stride + base + __popc(peers & ((1u << lane) - 1u))] = make_int2(i, item);
+}
+// owner: softmaxW[item].u + bias[item] (RerankModel.inference :43-52) for the requests of requester `p`
+__global__ void dr_score_cands_kernel(int n, const int2 *__restrict__ req, const int32_t *__restrict__ cand_off_p /* B + 1 of the requester */,
+                                      int B, int E, const double *__restrict__ uvec_p /* B x E of the requester */, int64_t item_base,
+                                      const double *__restrict__ sm_w, const double *__restrict__ sm_b, double *__restrict__ out)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const int gci = req[i].x;
+    int lo = 0, hi = B;                                          // user of the candidate: last u with cand_off[u] <= gci
+    while (hi - lo > 1) { const int mid = (lo + hi) >> 1; if (cand_off_p[mid] <= gci) lo = mid; else hi = mid; }
+    const int64_t li = (int64_t)req[i].y - item_base;
+    const double *w = sm_w + (size_t)li * E, *u = uvec_p + (size_t)lo * E;
+    double acc = 0.0;
+    for (int k = 0; k < E; k++) acc = fma_(__ldg(w + k), u[k], acc);
+    out[i] = add_(acc, __ldg(sm_b + li));
+}
+__global__ void dr_scatter_kernel(int n, const int2 *__restrict__ req, const double *__restrict__ reply, double *__restrict__ score)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) score[req[i].x] = reply[i];
+}
+
+}  // namespace
+
+// Item-indexed tables are passed WHOLE (layer_emb: num_item + K (D-1) rows, rr_emb / sm_w: num_item rows, sm_b: num_item);
+// only this rank's item range is uploaded.  Call after dmg_shard_init, on every rank.
+DMG_API int32_t dmg_shard_dr_load(dmg_handle_t h, int32_t num_item, int32_t K, int32_t D, int32_t T, int32_t E,
+                                  const double *layer_emb, const double *const *layer_w, const double *const *layer_b,
+                                  const double *rr_emb, const double *rr_w, const double *rr_b, const double *sm_w, const double *sm_b)
+{
+    if (!h) return DMG_ERR_INVALID_ARG;
+    ShardState *s = h->shard;
+    if (!s) return fail(h, DMG_ERR_STATE, "call dmg_shard_init first");
+    if (num_item <= 0 || K <= 0 || T <= 0 || E <= 0 || !layer_emb || !layer_w || !layer_b || !rr_emb || !rr_w || !rr_b || !sm_w || !sm_b)
+        return fail(h, DMG_ERR_INVALID_ARG, "dmg_shard_dr_load: bad arguments");
+    if (D < 2 || D > kDrMaxD) return fail(h, DMG_ERR_INVALID_ARG, "number of layers must be in [2, %d]", kDrMaxD);
+    DMG_CUDA(h, cudaSetDevice(h->device));
+    dmg_free_dr(h->dr);
+    DrDev &d = h->dr;
+    d.num_item = num_item; d.K = K; d.D = D; d.T = T; d.E = E;
+    d.item_chunk = ((int64_t)num_item + s->world - 1) / s->world;
+    d.item_base = std::min<int64_t>((int64_t)s->rank * d.item_chunk, num_item);
+    d.local_items = std::min<int64_t>(d.item_chunk, num_item - d.item_base);
+    d.sharded = true;
+    const size_t node_rows = (size_t)K * (D - 1);
+    // local layer table = [owned item rows | path-node rows]
+    DMG_CUDA(h, cudaMalloc(&d.d_layer_emb, ((size_t)d.local_items + node_rows) * E * sizeof(double)));
+    DMG_CUDA(h, cudaMemcpyAsync(d.d_layer_emb, layer_emb + (size_t)d.item_base * E, (size_t)d.local_items * E * 8, cudaMemcpyHostToDevice, h->stream));
+    DMG_CUDA(h, cudaMemcpyAsync(d.d_layer_emb + (size_t)d.local_items * E, layer_emb + (size_t)num_item * E, node_rows * E * 8,
+                                cudaMemcpyHostToDevice, h->stream));
+    DMG_CUDA(h, cudaStreamSynchronize(h->stream));
+    for (int i = 0; i < D; i++) {
+        const int in = (T + i) * E;
+        double *w = nullptr, *b = nullptr, *wT = nullptr;
+        DMG_TRY(up(h, &w, layer_w[i], (size_t)K * in));
+        DMG_TRY(up(h, &b, layer_b[i], (size_t)K));
+        DMG_CUDA(h, cudaMalloc(&wT, (size_t)K * in * sizeof(double)));
+        transpose_kernel<double><<<(K * in + 255) / 256, 256, 0, h->stream>>>(w, wT, K, in);
+        h->launches += 1;
+        d.d_layer_w.push_back(w); d.d_layer_b.push_back(b); d.d_layer_wT.push_back(wT);
+    }
+    const size_t li = (size_t)std::max<int64_t>(d.local_items, 1);
+    DMG_TRY(up(h, &d.d_rr_emb, rr_emb + (size_t)d.item_base * E, li * E));
+    double *rr_tmp = nullptr;
+    DMG_TRY(up(h, &rr_tmp, rr_w, (size_t)E * T * E));
+    DMG_CUDA(h, cudaMalloc(&d.d_rr_w, (size_t)E * T * E * sizeof(double)));                 // kept transposed [T*E][E]
+    transpose_kernel<double><<<(E * T * E + 255) / 256, 256, 0, h->stream>>>(rr_tmp, d.d_rr_w, E, T * E);
+    h->launches += 1;
+    DMG_CUDA(h, cudaGetLastError());
+    DMG_CUDA(h, cudaStreamSynchronize(h->stream));
+    cudaFree(rr_tmp);
+    DMG_TRY(up(h, &d.d_rr_b, rr_b, (size_t)E));
+    DMG_TRY(up(h, &d.d_sm_w, sm_w + (size_t)d.item_base * E, li * E));
+    DMG_TRY(up(h, &d.d_sm_b, sm_b + (size_t)d.item_base, li));
+    d.loaded = true;
+    return DMG_OK;
+}
+
+// DeepRetrieval.recommend for this rank's B users; collective (same B, beam, topk on every rank).
+DMG_API int32_t dmg_shard_dr_retrieve(dmg_handle_t h, int32_t B, const int32_t *seq, int32_t beam, int32_t topk,
+                                      int32_t *out_items, double *out_scores, int32_t *out_counts)
+{
+    if (!h) return DMG_ERR_INVALID_ARG;
+    ShardState *s = h->shard;
+    DrDev &d = h->dr;
+    if (!s || !d.loaded || !d.sharded) return fail(h, DMG_ERR_STATE, "dmg_shard_init and dmg_shard_dr_load first");
+    if (!d.paths_loaded) return fail(h, DMG_ERR_STATE, "dmg_dr_load_paths first");
+    if (B <= 0 || beam <= 0 || topk <= 0 || !seq || !out_items || !out_scores || !out_counts) return fail(h, DMG_ERR_INVALID_ARG, "bad arguments");
+    if (topk > kDrCap - kDrChunk) return fail(h, DMG_ERR_UNSUPPORTED, "topk must be <= %d", kDrCap - kDrChunk);
+    DMG_CUDA(h, cudaSetDevice(h->device));
+    const int G = s->world, T = d.T, E = d.E, D = d.D, K = d.K;
+    const int64_t BU = (int64_t)G * B;
+    cudaStream_t st = h->stream;
+    for (int64_t i = 0; i < (int64_t)B * T; i++)
+        if (seq[i] < -1 || seq[i] >= d.num_item) return fail(h, DMG_ERR_INDEX, "Deep Retrieval: history index outside [-1, num_item)");
+    // ---- histories of every rank, both embedding tiles ---------------------------------------------------------------
+    Scratch &sb = s->buf;
+    const size_t fixed = Carver::need({(size_t)BU * T * 4, (size_t)BU * T * E * 8, (size_t)BU * T * E * 8, (size_t)BU * E * 8,
+                                       (size_t)B * 4, (size_t)G * (B + 1) * 4, (size_t)G * 4, (size_t)G * G * 4});
+    DMG_TRY(ensure_dev(h, sb, fixed));
+    DMG_TRY(ensure_host(h, sb, (size_t)(B + 1) * 8 + (size_t)G * G * 4 + 1024));
+    Carver cd(sb.d);
+    int32_t *d_seq_all = cd.take<int32_t>((size_t)BU * T);
+    double *d_tile_l = cd.take<double>((size_t)BU * T * E), *d_tile_r = cd.take<double>((size_t)BU * T * E);
+    double *d_uvec = cd.take<double>((size_t)BU * E);
+    int32_t *d_totals = cd.take<int32_t>((size_t)B);
+    int32_t *d_off_all = cd.take<int32_t>((size_t)G * (B + 1));
+    int32_t *d_nreq = cd.take<int32_t>((size_t)G), *d_matrix = cd.take<int32_t>((size_t)G * G);
+    int32_t *h_off = (int32_t *)sb.h;                               // B + 1
+    int32_t *h_matrix = h_off + ((B + 1 + 63) & ~63);
+    int32_t *d_seq_mine = d_seq_all + (size_t)s->rank * B * T;
+    DMG_CUDA(h, cudaMemcpyAsync(d_seq_mine, seq, (size_t)B * T * 4, cudaMemcpyHostToDevice, st));
+    DMG_CUDA(h, cudaStreamSynchronize(st));                        // `seq` is the caller's
+    if (G > 1) DMG_NCCL(h, g_nccl.AllGather(d_seq_mine, d_seq_all, (size_t)B * T, ncclInt32, s->comm, st));
+    dr_fill_tiles_kernel<<<h->sm_count * 4, 256, 0, st>>>(d.d_layer_emb, d.item_base, d.local_items, d_seq_all, BU * T, E, (unsigned long long *)d_tile_l);
+    dr_fill_tiles_kernel<<<h->sm_count * 4, 256, 0, st>>>(d.d_rr_emb, d.item_base, d.local_items, d_seq_all, BU * T, E, (unsigned long long *)d_tile_r);
+    h->launches += 2;
+    if (G > 1) {
+        DMG_NCCL(h, g_nccl.AllReduce(d_tile_l, d_tile_l, (size_t)BU * T * E, ncclUint64, ncclSum, s->comm, st));
+        DMG_NCCL(h, g_nccl.AllReduce(d_tile_r, d_tile_r, (size_t)BU * T * E, ncclUint64, ncclSum, s->comm, st));
+    }
+    const double *hist_l = d_tile_l + (size_t)s->rank * B * T * E, *hist_r = d_tile_r + (size_t)s->rank * B * T * E;
+    // ---- beam search (local), user vectors (local, then replicated) ------------------------------------------------------
+    int32_t *d_paths, *d_counts, *d_seq_unused;
+    double *d_probs;
+    DMG_TRY(dr_beam_enqueue(h, B, seq, beam, true, &d_paths, &d_probs, &d_counts, &d_seq_unused, hist_l));
+    double *d_u_mine = d_uvec + (size_t)s->rank * B * E;
+    DMG_CUDA(h, cudaFuncSetAttribute(dr_uservec_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)((size_t)T * E * 8)));
+    dr_uservec_kernel<<<std::min(B, h->sm_count * 4), kThreads, (size_t)T * E * 8, st>>>(B, T, E, hist_r, d.d_rr_w, d.d_rr_b, d_u_mine);
+    h->launches += 1;
+    if (G > 1) DMG_NCCL(h, g_nccl.AllGather(d_u_mine, d_uvec, (size_t)B * E, ncclFloat64, s->comm, st));
+    // ---- candidates ----------------------------------------------------------------------------------------------------------
+    dr_cand_count_kernel<<<(B + 127) / 128, 128, 0, st>>>(B, beam, D, K, d_paths, d_counts, d.d_path_off, d_totals);
+    h->launches += 1;
+    DMG_CUDA(h, cudaMemcpyAsync(h_off + 1, d_totals, (size_t)B * 4, cudaMemcpyDeviceToHost, st));
+    DMG_CUDA(h, cudaStreamSynchronize(st));
+    h_off[0] = 0;
+    int64_t total64 = 0;
+    for (int u = 0; u < B; u++) { total64 += h_off[u + 1]; if (total64 > 0x7fffffff) return fail(h, DMG_ERR_UNSUPPORTED, "too many rerank candidates in one batch"); h_off[u + 1] = (int32_t)total64; }
+    const int total = (int)total64;
+    int32_t *d_off_mine = d_off_all + (size_t)s->rank * (B + 1);
+    DMG_CUDA(h, cudaMemcpyAsync(d_off_mine, h_off, (size_t)(B + 1) * 4, cudaMemcpyHostToDevice, st));
+    if (G > 1) DMG_NCCL(h, g_nccl.AllGather(d_off_mine, d_off_all, (size_t)B + 1, ncclInt32, s->comm, st));
+    // region capacity = the largest candidate count of any rank (sizes are exchanged below; buffers use a common bound)
+    int32_t cap_all = total;
+    if (G > 1) {
+        DMG_CUDA(h, cudaMemcpyAsync(d_nreq, &cap_all, 4, cudaMemcpyHostToDevice, st));
+        DMG_NCCL(h, g_nccl.AllReduce(d_nreq, d_nreq, 1, ncclInt32, ncclMax, s->comm, st));
+        DMG_CUDA(h, cudaMemcpyAsync(&cap_all, d_nreq, 4, cudaMemcpyDeviceToHost, st));
+        DMG_CUDA(h, cudaStreamSynchronize(st));
+    }
+    const int64_t stride = std::max<int64_t>(cap_all, 1);
+    Scratch &sw = h->s_out;                                          // second scratch block: candidate-sized buffers
+    const size_t cbytes = Carver::need({(size_t)stride * 4, (size_t)stride * 8, (size_t)G * stride * 8, (size_t)G * stride * 8,
+                                        (size_t)G * stride * 8, (size_t)G * stride * 8, (size_t)B * topk * 4, (size_t)B * topk * 8, (size_t)B * 4});
+    DMG_TRY(ensure_dev(h, sw, cbytes));
+    Carver cc(sw.d);
+    int32_t *d_cand_item = cc.take<int32_t>((size_t)stride);
+    double *d_cand_score = cc.take<double>((size_t)stride);
+    int2 *d_req = cc.take<int2>((size_t)G * stride), *d_rreq = cc.take<int2>((size_t)G * stride);
+    double *d_rsc = cc.take<double>((size_t)G * stride), *d_reply = cc.take<double>((size_t)G * stride);
+    int32_t *d_items = cc.take<int32_t>((size_t)B * topk);
+    double *d_sc = cc.take<double>((size_t)B * topk);
+    int32_t *d_cnt = cc.take<int32_t>((size_t)B);
+    dr_cand_fill_kernel<<<std::min(B, h->sm_count * 4), kThreads, 0, st>>>(B, beam, D, K, d_paths, d_counts, d.d_path_off, d.d_path_items, d_off_mine, d_cand_item);
+    DMG_CUDA(h, cudaMemsetAsync(d_nreq, 0, (size_t)G * 4, st));
+    if (total) dr_bucket_kernel<<<(total + 255) / 256, 256, 0, st>>>(total, d_cand_item, d.item_chunk, d_req, stride, d_nreq);
+    h->launches += 2;
+    if (G > 1) DMG_NCCL(h, g_nccl.AllGather(d_nreq, d_matrix, (size_t)G, ncclInt32, s->comm, st));
+    else DMG_CUDA(h, cudaMemcpyAsync(d_matrix, d_nreq, 4, cudaMemcpyDeviceToDevice, st));
+    DMG_CUDA(h, cudaMemcpyAsync(h_matrix, d_matrix, (size_t)G * G * 4, cudaMemcpyDeviceToHost, st));
+    DMG_CUDA(h, cudaStreamSynchronize(st));
+    if (G > 1) {
+        DMG_NCCL(h, g_nccl.GroupStart());
+        for (int p = 0; p < G; p++) {
+            if (p == s->rank) continue;
+            const int ns = h_matrix[s->rank * G + p], nr = h_matrix[p * G + s->rank];
+            if (ns) DMG_NCCL(h, g_nccl.Send(d_req + (size_t)p * stride, (size_t)ns * 2, ncclInt32, p, s->comm, st));
+            if (nr) DMG_NCCL(h, g_nccl.Recv(d_rreq + (size_t)p * stride, (size_t)nr * 2, ncclInt32, p, s->comm, st));
+        }
+        DMG_NCCL(h, g_nccl.GroupEnd());
+    }
+    for (int p = 0; p < G; p++) {
+        const int nr = h_matrix[p * G + s->rank];
+        if (!nr) continue;
+        const int2 *rq = p == s->rank ? d_req + (size_t)p * stride : d_rreq + (size_t)p * stride;
+        double *ro = p == s->rank ? d_reply + (size_t)p * stride : d_rsc + (size_t)p * stride;
+        dr_score_cands_kernel<<<(nr + 127) / 128, 128, 0, st>>>(nr, rq, d_off_all + (size_t)p * (B + 1), B, E, d_uvec + (size_t)p * B * E, d.item_base,
+                                                                 d.d_sm_w, d.d_sm_b, ro);
+        h->launches += 1;
+        if (p != s->rank) s->exchanged_rows += nr;
+    }
+    if (G > 1) {
+        DMG_NCCL(h, g_nccl.GroupStart());
+        for (int p = 0; p < G; p++) {
+            if (p == s->rank) continue;
+            const int ns = h_matrix[s->rank * G + p], nr = h_matrix[p * G + s->rank];
+            if (nr) DMG_NCCL(h, g_nccl.Send(d_rsc + (size_t)p * stride, (size_t)nr, ncclFloat64, p, s->comm, st));
+            if (ns) DMG_NCCL(h, g_nccl.Recv(d_reply + (size_t)p * stride, (size_t)ns, ncclFloat64, p, s->comm, st));
+        }
+        DMG_NCCL(h, g_nccl.GroupEnd());
+    }
+    for (int p = 0; p < G; p++) {
+        const int ns = h_matrix[s->rank * G + p];
+        if (!ns) continue;
+        dr_scatter_kernel<<<(ns + 255) / 256, 256, 0, st>>>(ns, d_req + (size_t)p * stride, d_reply + (size_t)p * stride, d_cand_score);
+        h->launches += 1;
+    }
+    // ---- topk per user by (score desc, candidate index asc) -----------------------------------------------------------------
+    DrRerankParams p;
+    memset(&p, 0, sizeof(p));
+    p.num_item = d.num_item; p.K = K; p.D = D; p.T = T; p.E = E; p.B = B; p.beam = beam; p.topk = topk;
+    p.rr_emb = d.d_rr_emb; p.rr_wT = d.d_rr_w; p.rr_b = d.d_rr_b; p.sm_w = d.d_sm_w; p.sm_b = d.d_sm_b;
+    p.seq = d_seq_mine; p.paths = d_paths; p.path_counts = d_counts; p.path_off = d.d_path_off; p.path_items = d.d_path_items;
+    p.pre_scores = d_cand_score; p.cand_off = d_off_mine;
+    p.out_items = d_items; p.out_scores = d_sc; p.out_counts = d_cnt;
+    const size_t smem = ((size_t)T * E + E + 2) * 8 + (size_t)kDrCap * 16 + ((size_t)2 * beam + 2) * 8 + 64 * 4 + 32;
+    if (smem > h->smem_optin) return fail(h, DMG_ERR_UNSUPPORTED, "rerank needs %zu B of shared memory", smem);
+    DMG_CUDA(h, cudaFuncSetAttribute(dr_rerank_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    dr_rerank_kernel<<<std::min(B, h->sm_count * 2), kThreads, smem, st>>>(p);
+    h->launches += 1;
+    DMG_CUDA(h, cudaGetLastError());
+    DMG_CUDA(h, cudaMemcpyAsync(out_items, d_items, (size_t)B * topk * 4, cudaMemcpyDeviceToHost, st));
+    DMG_CUDA(h, cudaMemcpyAsync(out_scores, d_sc, (size_t)B * topk * 8, cudaMemcpyDeviceToHost, st));
+    DMG_CUDA(h, cudaMemcpyAsync(out_counts, d_cnt, (size_t)B * 4, cudaMemcpyDeviceToHost, st));
+    DMG_CUDA(h, cudaStreamSynchronize(st));
     return DMG_OK;
 }

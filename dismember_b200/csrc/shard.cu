@@ -18,77 +18,13 @@
 // NCCL is resolved with dlopen at dmg_shard_init: the library has no link-time dependency on it.
 #include <algorithm>
 #include <cmath>
-#include <dlfcn.h>
-#include <nccl.h>
-
 #include "beam_kernels.cuh"
 #include "rows_kernels.cuh"
+#include "shard_common.cuh"
 
 using namespace dmg;
 
 namespace dmg {
-
-struct NcclApi {
-    void *lib = nullptr;
-    ncclResult_t (*GetUniqueId)(ncclUniqueId *) = nullptr;
-    ncclResult_t (*CommInitRank)(ncclComm_t *, int, ncclUniqueId, int) = nullptr;
-    ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
-    ncclResult_t (*AllGather)(const void *, void *, size_t, ncclDataType_t, ncclComm_t, cudaStream_t) = nullptr;
-    ncclResult_t (*AllReduce)(const void *, void *, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) = nullptr;
-    ncclResult_t (*Send)(const void *, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
-    ncclResult_t (*Recv)(void *, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
-    ncclResult_t (*GroupStart)() = nullptr;
-    ncclResult_t (*GroupEnd)() = nullptr;
-    const char *(*GetErrorString)(ncclResult_t) = nullptr;
-};
-
-static NcclApi g_nccl;
-
-static const char *load_nccl()
-{
-    if (g_nccl.lib) return nullptr;
-    void *lib = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
-    if (!lib) lib = dlopen("libnccl.so", RTLD_NOW | RTLD_GLOBAL);
-    if (!lib) return "libnccl.so.2 not found (dlopen)";
-#define DMG_NCCL_SYM(field, name)                                                   \
-    g_nccl.field = reinterpret_cast<decltype(g_nccl.field)>(dlsym(lib, name));      \
-    if (!g_nccl.field) return "libnccl is missing " name;
-    DMG_NCCL_SYM(GetUniqueId, "ncclGetUniqueId")
-    DMG_NCCL_SYM(CommInitRank, "ncclCommInitRank")
-    DMG_NCCL_SYM(CommDestroy, "ncclCommDestroy")
-    DMG_NCCL_SYM(AllGather, "ncclAllGather")
-    DMG_NCCL_SYM(AllReduce, "ncclAllReduce")
-    DMG_NCCL_SYM(Send, "ncclSend")
-    DMG_NCCL_SYM(Recv, "ncclRecv")
-    DMG_NCCL_SYM(GroupStart, "ncclGroupStart")
-    DMG_NCCL_SYM(GroupEnd, "ncclGroupEnd")
-    DMG_NCCL_SYM(GetErrorString, "ncclGetErrorString")
-#undef DMG_NCCL_SYM
-    g_nccl.lib = lib;
-    return nullptr;
-}
-
-#define DMG_NCCL(h, expr)                                                                              \
-    do {                                                                                               \
-        ncclResult_t r_ = (expr);                                                                      \
-        if (r_ != ncclSuccess)                                                                         \
-            return dmg::fail(h, DMG_ERR_CUDA, "%s failed: %s (%s:%d)", #expr, g_nccl.GetErrorString(r_), \
-                             __FILE__, __LINE__);                                                      \
-    } while (0)
-
-struct ShardGeo {
-    int bits, rank, world;
-    int64_t repl_rows;            // 2^bits - 1 replicated rows (levels < bits)
-};
-
-struct ShardState {
-    int world = 1, rank = 0, bits = 0;
-    ncclComm_t comm = nullptr;
-    int64_t global_rows = 0;
-    int64_t exchanged_rows = 0;   // candidates scored for another rank (statistics)
-    Scratch buf;                  // level-loop buffers
-    ShardGeo geo() const { ShardGeo g; g.bits = bits; g.rank = rank; g.world = world; g.repl_rows = ((int64_t)1 << bits) - 1; return g; }
-};
 
 __host__ __device__ __forceinline__ int code_level(int64_t c)
 {

@@ -290,6 +290,21 @@ DMG_API int32_t dmg_shard_jtm_item_weights(dmg_handle_t h, int32_t n_items, cons
                                            int32_t old_level, int32_t level, int32_t hierarchical,
                                            int32_t min_level, int32_t use_mask, float *out_weights);
 
+/* Deep Retrieval with the item-indexed tables (layer-embedding item rows, rerank embedding, softmax weights / biases)
+ * split by contiguous item-id range over the ranks of dmg_shard_init (BASELINE config 5); the K (D-1) path-node rows
+ * and every Linear are replicated.  dmg_shard_dr_load takes the WHOLE tables (same arguments as dmg_dr_load) and uploads
+ * this rank's range; dmg_dr_load_paths as usual (replicated).  dmg_shard_dr_retrieve = DeepRetrieval.recommend
+ * (deep-retrieval/.../model/DeepRetrieval.scala:26-46) for this rank's B users, collective: history rows by integer
+ * all-reduce, beam search locally, rerank candidates scored by the owners of the items (12 B out, 8 B back per
+ * candidate).  Results are bit-identical to dmg_dr_retrieve on the whole tables. */
+DMG_API int32_t dmg_shard_dr_load(dmg_handle_t h, int32_t num_item, int32_t K, int32_t D, int32_t T, int32_t E,
+                                  const double *layer_emb, const double *const *layer_w,
+                                  const double *const *layer_b, const double *rr_emb, const double *rr_w,
+                                  const double *rr_b, const double *sm_w, const double *sm_b);
+DMG_API int32_t dmg_shard_dr_retrieve(dmg_handle_t h, int32_t B, const int32_t *seq, int32_t beam,
+                                      int32_t topk, int32_t *out_items, double *out_scores,
+                                      int32_t *out_counts);
+
 #ifdef __cplusplus
 }
 #endif

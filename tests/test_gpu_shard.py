@@ -96,6 +96,34 @@ def test_world1_jtm_item_weights_match_the_unsharded_engine(jtm_fix, queries):
     e.close()
 
 
+def test_world1_deep_retrieval_matches_the_unsharded_engine(dr_fix, queries):
+    """dmg_shard_dr_retrieve (history tiles, owner-scored rerank candidates) vs dmg_dr_retrieve on the DR fixture, bit for bit."""
+    from dismember_b200.dr import build_path_csr
+    f = dr_fix
+    D = int(f["D"])
+    args = (int(f["num_item"]), int(f["K"]), D, int(f["T"]), int(f["E"]), f["layer_emb"],
+            [f[f"layer_w{d}"] for d in range(D)], [f[f"layer_b{d}"] for d in range(D)],
+            f["rr_emb"], f["rr_w"], f["rr_b"], f["sm_w"], f["sm_b"])
+    off, flat = build_path_csr(f["map_ids"], f["map_paths"], int(f["K"]))
+    item_id = {int(a): int(b) for a, b in zip(f["map_items"], f["map_ids"])}
+    seqs = np.array([[item_id.get(int(x), -1) for x in s] for s in queries["seqs"][:40]], np.int32)
+    seqs[1] = -1
+    ref = new_engine()
+    ref.dr_load(*args)
+    ref.dr_load_paths(off, flat)
+    e = new_engine()
+    e.shard_init(1, 0)
+    e.shard_dr_load(*args)
+    e.dr_load_paths(off, flat)
+    for beam, topk in [(50, 10), (300, 20), (7, 3)]:
+        ri, rs, rc = ref.dr_retrieve(seqs, beam, topk)
+        si, ss, sc = e.shard_dr_retrieve(seqs, beam, topk)
+        assert (sc == rc).all() and (si == ri).all()
+        assert (ss.view(np.uint64) == rs.view(np.uint64)).all()
+    ref.close()
+    e.close()
+
+
 def _two_gpu_worker(rank, world, port, out_dir):
     sys.path.insert(0, ROOT)
     sys.argv = ["shard_check.py", "--items", "5000", "--batch", "24", "--out", os.path.join(out_dir, f"r{rank}.json")]

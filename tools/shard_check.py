@@ -32,6 +32,9 @@ def main():
                          "CUDA engine on this rank's GPU (for catalogues too large to ship to the host)")
     ap.add_argument("--jtm-items", type=int, default=0, help="also check dmg_shard_jtm_item_weights on this many items per rank")
     ap.add_argument("--jtm-gap", type=int, default=4)
+    ap.add_argument("--dr-items", type=int, default=0, help="also check dmg_shard_dr_retrieve on a synthetic model with this many items")
+    ap.add_argument("--dr-k", type=int, default=100)
+    ap.add_argument("--dr-batch", type=int, default=64)
     ap.add_argument("--out", default=None)
     a = ap.parse_args()
     import torch
@@ -96,7 +99,38 @@ def main():
         full.close()
         jtm = {"items": n_it, "samples": int(off[-1]), "gap": a.jtm_gap, "scorer_rows": int(off[-1]) * ((2 << a.jtm_gap) - 2),
                "weights_bit_identical": bool((got.view(np.uint32) == want.view(np.uint32)).all()), "seconds": jdt}
-    line = {"rank": rank, "world": world, "jtm_item_weights": jtm, "items": a.items, "levels": tf.max_level, "batch_per_rank": a.batch, "beam": a.beam,
+    # Deep Retrieval with sharded item tables (config 5): this rank's users vs the unsharded engine on the whole tables
+    dr = None
+    if a.dr_items > 0:
+        from dismember_b200.dr import build_path_csr
+        n_item, K, D, Ed = a.dr_items, a.dr_k, 3, 32
+        rng = np.random.Generator(np.random.PCG64(8))                       # same tables on every rank
+        layer_emb = rng.normal(0, 0.05, (n_item + (D - 1) * K, Ed))
+        layer_w = [rng.normal(0, 0.05, (K, (T + d) * Ed)) for d in range(D)]
+        layer_b = [np.zeros(K) for _ in range(D)]
+        rr_emb = rng.normal(0, 0.05, (n_item, Ed)); rr_w = rng.normal(0, 0.05, (Ed, T * Ed)); rr_b = np.zeros(Ed)
+        sm_w = rng.normal(0, 0.05, (n_item, Ed)); sm_b = rng.normal(0, 0.01, n_item)
+        off, flat = build_path_csr(np.arange(n_item), rng.integers(0, K, (n_item, 2, D)), K)
+        args = (n_item, K, D, T, Ed, layer_emb, layer_w, layer_b, rr_emb, rr_w, rr_b, sm_w, sm_b)
+        dseq = np.random.Generator(np.random.PCG64(90 + rank)).integers(-1, n_item, (a.dr_batch, T)).astype(np.int32)
+        eng.shard_dr_load(*args)
+        eng.dr_load_paths(off, flat)
+        eng.shard_dr_retrieve(dseq, 200, 10)
+        dist.barrier()
+        t0 = time.perf_counter()
+        si, ss, sc = eng.shard_dr_retrieve(dseq, 200, 10)
+        dist.barrier()
+        ddt = time.perf_counter() - t0
+        full = Engine(local)
+        full.dr_load(*args)
+        full.dr_load_paths(off, flat)
+        ri, rs, rc = full.dr_retrieve(dseq, 200, 10)
+        full.close()
+        dr = {"items": n_item, "K": K, "D": D, "E": Ed, "batch_per_rank": a.dr_batch, "beam": 200,
+              "ids_identical": bool((si == ri).all() and (sc == rc).all()),
+              "scores_bit_identical": bool((ss.view(np.uint64) == rs.view(np.uint64)).all()),
+              "users_per_s_whole_job": world * a.dr_batch / ddt}
+    line = {"rank": rank, "world": world, "jtm_item_weights": jtm, "deep_retrieval": dr, "items": a.items, "levels": tf.max_level, "batch_per_rank": a.batch, "beam": a.beam,
             "table_rows_global": global_rows, "table_rows_local": local_rows,
             "rows_scored_for_other_ranks": exchanged, "users_checked": n, "checked_against": a.check,
             "ids_identical": bool((items[:n] == oi).all() and (counts[:n] == oc).all()),
