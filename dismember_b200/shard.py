@@ -113,6 +113,40 @@ def _send_recv(outgoing, incoming, group=None):
             w.wait()
 
 
+def exchange_requests(slots: np.ndarray, codes: np.ndarray, owners: np.ndarray, score_owned, dtype=np.float32, group=None) -> np.ndarray:
+    """The request / reply round every sharded path uses (TDM and JTM candidates by node owner, Deep Retrieval rerank candidates
+    by item owner): (slot, code) pairs travel to `owners`, score_owned(requester, slots, codes) answers, replies return in
+    request order.  -> scores aligned with `slots`."""
+    import torch
+    import torch.distributed as dist
+    world = dist.get_world_size(group)
+    tdt = torch.float32 if dtype == np.float32 else torch.float64
+    idx = [np.nonzero(owners == p)[0] for p in range(world)]
+    send = [np.stack([slots[i], codes[i]], 1).astype(np.int32) for i in idx]
+    n_send = torch.tensor([len(x) for x in send], dtype=torch.int64)
+    n_recv = torch.empty(world, dtype=torch.int64)
+    dist.all_to_all_single(n_recv, n_send, group=group)
+    recv = [torch.empty((int(n), 2), dtype=torch.int32) for n in n_recv]
+    _send_recv([torch.from_numpy(np.ascontiguousarray(x)) for x in send], recv, group)
+    ans = []
+    for p in range(world):
+        r = recv[p].numpy()
+        sc = score_owned(p, r[:, 0].astype(np.int64), r[:, 1].astype(np.int64)) if len(r) else np.zeros(0, dtype)
+        ans.append(torch.from_numpy(np.ascontiguousarray(sc, dtype)))
+    back = [torch.empty(len(x), dtype=tdt) for x in send]
+    _send_recv(ans, back, group)
+    out = np.zeros(len(slots), dtype)
+    for p in range(world):
+        out[idx[p]] = back[p].numpy()
+    return out
+
+
+def item_owner(items: np.ndarray, num_item: int, world: int) -> np.ndarray:
+    """Deep Retrieval item tables: contiguous ranges of ceil(num_item / world) items (csrc/dr.cu)."""
+    chunk = (num_item + world - 1) // world
+    return np.asarray(items, np.int64) // chunk
+
+
 def exchange_scores(cand: np.ndarray, counts: np.ndarray, score_owned, group=None) -> np.ndarray:
     """One level of the sharded search for this rank's users.
 

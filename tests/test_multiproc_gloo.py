@@ -152,3 +152,86 @@ def test_two_rank_table_shard_protocol(tmp_path, golden_out):
     assert (got["items"] == golden_out["tdm_items_b20"][:40]).all()
     assert (got["logits"].view(np.uint32) == golden_out["tdm_logits_b20"][:40].view(np.uint32)).all()
     assert (got["remote"] > 0).all()                          # both ranks really scored rows for the other one
+
+
+def _dr_shard_worker(rank, world, port, out_dir):
+    """Deep Retrieval with item tables sharded by item range (csrc/dr.cu) under gloo: rerank candidates travel to the owner of the
+    item, which scores them with the requester's user vector; the scorer is the oracle and refuses items outside its range."""
+    sys.path.insert(0, ROOT)
+    import torch.distributed as dist
+    from dismember_b200 import shard
+    from dismember_b200.dr import build_path_csr
+    from dismember_b200.jtm import stable_desc_order
+    from oracle import oracle as orc
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    f = dict(np.load(os.path.join(ROOT, "tests", "golden", "dr_fixture.npz")))
+    q = dict(np.load(os.path.join(ROOT, "tests", "golden", "queries.npz")))
+    D, K, N = int(f["D"]), int(f["K"]), int(f["num_item"])
+    model = orc.DrModel(N, K, D, int(f["T"]), int(f["E"]), f["layer_emb"], [f[f"layer_w{d}"] for d in range(D)],
+                        [f[f"layer_b{d}"] for d in range(D)], f["rr_emb"], f["rr_w"], f["rr_b"], f["sm_w"], f["sm_b"])
+    off, flat = build_path_csr(f["map_ids"], f["map_paths"], K)
+    item_id = {int(a): int(b) for a, b in zip(f["map_items"], f["map_ids"])}
+    B, beam, topk = 12, 50, 10
+    seqs_all = np.array([[item_id.get(int(x), -1) for x in s] for s in q["seqs"][:world * B]], np.int32)
+    seqs = seqs_all[rank * B:(rank + 1) * B]
+    # candidates of this rank's users (beam search is local once the history rows are there)
+    cand_items, cand_user = [], []
+    for u in range(B):
+        paths, _ = model.beam_search(seqs[u], beam)
+        for pth in paths:
+            key = 0
+            for c in pth:
+                key = key * K + int(c)
+            its = flat[off[key]:off[key + 1]]
+            cand_items.extend(int(i) for i in its)
+            cand_user.extend([u] * len(its))
+    cand_items, cand_user = np.array(cand_items, np.int64), np.array(cand_user, np.int64)
+    chunk = (N + world - 1) // world
+    remote = 0
+
+    def score_owned(requester, gci, items):
+        nonlocal remote
+        assert ((items >= rank * chunk) & (items < (rank + 1) * chunk)).all(), "asked for an item this rank does not own"
+        users = requester_users[requester][gci]
+        if requester != rank:
+            remote += len(items)
+        out = np.zeros(len(items), np.float64)
+        for u in np.unique(users):                               # the oracle reranks per user vector
+            m = users == u
+            out[m] = model.rerank(seqs_all[requester * B + u], items[m].astype(np.int32))
+        return out
+
+    gathered = [None] * world
+    dist.all_gather_object(gathered, cand_user)                  # mirror of the candidate-offset tables the owners use to find the user
+    requester_users = gathered
+    scores = shard.exchange_requests(np.arange(len(cand_items)), cand_items, shard.item_owner(cand_items, N, world), score_owned,
+                                     dtype=np.float64)
+    items = np.full((B, topk), -1, np.int32)
+    out_sc = np.zeros((B, topk), np.float64)
+    for u in range(B):
+        m = np.flatnonzero(cand_user == u)
+        order = np.argsort(-scores[m], kind="stable")[:topk]
+        items[u, :len(order)] = cand_items[m][order]
+        out_sc[u, :len(order)] = scores[m][order]
+    want_i = np.full((B, topk), -1, np.int32)
+    want_s = np.zeros((B, topk), np.float64)
+    for u in range(B):
+        oi, os_, _ = model.recommend(seqs[u], topk, beam, off, flat)
+        want_i[u, :len(oi)] = oi
+        want_s[u, :len(oi)] = os_
+    res = [None] * world
+    dist.all_gather_object(res, (bool((items == want_i).all()), bool((out_sc.view(np.uint64) == want_s.view(np.uint64)).all()), remote))
+    if rank == 0:
+        np.save(os.path.join(out_dir, "dr.npy"), np.array([[int(a), int(b), c] for a, b, c in res]))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_two_rank_deep_retrieval_item_shard_protocol(tmp_path):
+    import torch.multiprocessing as mp
+    port = 33500 + (os.getpid() % 2000)
+    mp.spawn(_dr_shard_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
+    r = np.load(tmp_path / "dr.npy")
+    assert (r[:, 0] == 1).all() and (r[:, 1] == 1).all() and r[:, 2].sum() > 0       # rows really crossed ranks
