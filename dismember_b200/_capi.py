@@ -96,6 +96,7 @@ def load_library(build_if_missing: bool = True):
         "dmg_shard_jtm_item_weights": [vp, i32, vp, vp, vp, i32, i32, i32, i32, i32, vp],
         "dmg_shard_dr_load": [vp, i32, i32, i32, i32, i32, vp, C.POINTER(vp), C.POINTER(vp), vp, vp, vp, vp, vp],
         "dmg_shard_dr_retrieve": [vp, i32, vp, i32, i32, vp, vp, vp],
+        "dmg_dp_train_step": [vp, i64, vp, vp, vp, i64, vp, dbl, i32, vp],
     }
     for name, args in sig.items():
         fn = getattr(L, name)
@@ -463,6 +464,17 @@ class Engine:
         loss = np.zeros(1, self.din_dtype)
         self._check(self.L.dmg_train_step(self.h, len(node), _p(node), _p(seq), _p(m), 0 if m is None else len(m),
                                           _p(labels), float(lr), int(step_t), _p(loss)))
+        return loss[0]
+
+    def dp_train_step(self, node, seq, mask_flat, labels, lr, step_t):
+        """Collective data-parallel step (dmg_dp_train_step): this rank's rows, gradients averaged over the ranks."""
+        node = _i32(node).ravel()
+        seq = _i32(seq).reshape(len(node), self.T)
+        labels = np.ascontiguousarray(labels, self.din_dtype).ravel()
+        m = None if mask_flat is None else _i32(mask_flat).ravel()
+        loss = np.zeros(1, self.din_dtype)
+        self._check(self.L.dmg_dp_train_step(self.h, len(node), _p(node), _p(seq), _p(m), 0 if m is None else len(m),
+                                             _p(labels), float(lr), int(step_t), _p(loss)))
         return loss[0]
 
     def tdm_sample_expand(self, target_items, item_seq, layer_neg, start_level, seed):

@@ -17,6 +17,7 @@
 
 #include "beam_kernels.cuh"
 #include "rows_kernels.cuh"
+#include "shard_common.cuh"
 
 using namespace dmg;
 
@@ -838,6 +839,34 @@ DMG_API int32_t dmg_eval_metrics(dmg_handle_t h, int32_t B, int32_t topk, const 
     h->launches += 1;
     DMG_CUDA(h, cudaGetLastError());
     DMG_CUDA(h, cudaMemcpyAsync(out_metrics, d_out, (size_t)B * 24, cudaMemcpyDeviceToHost, h->stream));
+    DMG_CUDA(h, cudaStreamSynchronize(h->stream));
+    return DMG_OK;
+}
+
+
+// ---- data-parallel training step over the replicas of one box ------------------------------------------------
+// LocalOptimizer.trainBatch / syncGradients (tdm/.../optim/LocalOptimizer.scala:139-187) with GPUs in the place of threads:
+// every rank holds the whole model (same weights), runs forward / BCE / backward on ITS rows of the mini-batch, the gradient
+// replicas are averaged -- one ncclAllReduce(ncclAvg) of the flat gradient over NVLink instead of the per-thread reduce --
+// and every rank applies the same dense Adam step, so the replicas stay bit-identical.  Call after dmg_shard_init (which only
+// provides the communicator here: the table is loaded whole with dmg_load_din_weights / dmg_init_din_weights).
+// out_loss: mean loss of this rank's rows.
+DMG_API int32_t dmg_dp_train_step(dmg_handle_t h, int64_t rows, const int32_t *node, const int32_t *seq, const int32_t *mask_flat,
+                                  int64_t n_mask, const void *labels, double lr, int32_t step_t, void *out_loss)
+{
+    DMG_TRY(train_precheck(h, rows, node, seq, labels, out_loss));
+    ShardState *s = h->shard;
+    if (!s) return fail(h, DMG_ERR_STATE, "call dmg_shard_init first (it provides the NCCL communicator)");
+    if (step_t < 1) return fail(h, DMG_ERR_INVALID_ARG, "step_t is the 1-based Adam timestep");
+    DinDev &d = h->din;
+    double loss = 0.0;
+    if (d.dtype == DMG_F32) DMG_TRY(grad_pass<float>(h, rows, node, seq, mask_flat, n_mask, (const float *)labels, &loss));
+    else DMG_TRY(grad_pass<double>(h, rows, node, seq, mask_flat, n_mask, (const double *)labels, &loss));
+    if (s->world > 1)
+        DMG_NCCL(h, g_nccl.AllReduce(d.d_grad, d.d_grad, (size_t)d.n_params, d.dtype == DMG_F32 ? ncclFloat32 : ncclFloat64, ncclAvg, s->comm,
+                                     h->stream));
+    if (d.dtype == DMG_F32) { DMG_TRY(adam_pass<float>(h, lr, step_t)); *(float *)out_loss = (float)loss; }
+    else { DMG_TRY(adam_pass<double>(h, lr, step_t)); *(double *)out_loss = loss; }
     DMG_CUDA(h, cudaStreamSynchronize(h->stream));
     return DMG_OK;
 }

@@ -305,6 +305,15 @@ DMG_API int32_t dmg_shard_dr_retrieve(dmg_handle_t h, int32_t B, const int32_t *
                                       int32_t topk, int32_t *out_items, double *out_scores,
                                       int32_t *out_counts);
 
+/* Data-parallel training step over the replicas of one box: LocalOptimizer.trainBatch / syncGradients
+ * (tdm/.../optim/LocalOptimizer.scala:139-187) with GPUs in the place of threads.  Every rank holds the whole model (same
+ * weights, loaded with dmg_load_din_weights / dmg_init_din_weights after dmg_shard_init, which provides the communicator),
+ * passes ITS rows of the mini-batch; gradients are averaged with one ncclAllReduce(ncclAvg) and every rank applies the same
+ * dense Adam step.  Collective.  out_loss: mean loss of this rank's rows. */
+DMG_API int32_t dmg_dp_train_step(dmg_handle_t h, int64_t rows, const int32_t *node, const int32_t *seq,
+                                  const int32_t *mask_flat, int64_t n_mask, const void *labels, double lr,
+                                  int32_t step_t, void *out_loss);
+
 #ifdef __cplusplus
 }
 #endif

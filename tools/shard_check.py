@@ -34,6 +34,7 @@ def main():
     ap.add_argument("--jtm-gap", type=int, default=4)
     ap.add_argument("--dr-items", type=int, default=0, help="also check dmg_shard_dr_retrieve on a synthetic model with this many items")
     ap.add_argument("--dr-k", type=int, default=100)
+    ap.add_argument("--train-targets", type=int, default=0, help="also check dmg_dp_train_step (rows from this many targets per rank)")
     ap.add_argument("--dr-batch", type=int, default=64)
     ap.add_argument("--out", default=None)
     a = ap.parse_args()
@@ -50,6 +51,10 @@ def main():
     tf = synth.tdm_tree(a.items, seed=1)
     rows = (1 << (tf.max_level + 1)) - 1
     eng = shard.make_sharded_engine(local)
+    box = [eng.shard_unique_id() if rank == 0 else None]           # a second communicator for the data-parallel replica check
+    if world > 1:
+        dist.broadcast_object_list(box, src=0)
+    uid_for_dp = box[0]
     eng.load_tree_tdm(tf.max_level, tf.codes, tf.node_ids, tf.is_leaf, tf.leaf_ids, tf.leaf_codes)
     eng.shard_init_din_weights(rows, a.dim, T, seed=2)
     seqs = synth.queries(a.batch, T, a.items, seed=100 + rank)
@@ -130,7 +135,41 @@ def main():
               "ids_identical": bool((si == ri).all() and (sc == rc).all()),
               "scores_bit_identical": bool((ss.view(np.uint64) == rs.view(np.uint64)).all()),
               "users_per_s_whole_job": world * a.dr_batch / ddt}
-    line = {"rank": rank, "world": world, "jtm_item_weights": jtm, "deep_retrieval": dr, "items": a.items, "levels": tf.max_level, "batch_per_rank": a.batch, "beam": a.beam,
+    # data-parallel training step over replicas (dmg_dp_train_step) vs ONE engine training on the concatenated batch
+    dp = None
+    if a.train_targets > 0:
+        n_it = min(a.items, 50_000)
+        ttf = synth.tdm_tree(n_it, seed=5)
+        trows = (1 << (ttf.max_level + 1)) - 1
+        rep = Engine(local)
+        rep.shard_init(world, rank, uid_for_dp)
+        rep.load_tree_tdm(ttf.max_level, ttf.codes, ttf.node_ids, ttf.is_leaf, ttf.leaf_ids, ttf.leaf_codes)
+        rep.init_din_weights(np.float32, trows, 16, T, seed=3)
+        rng = np.random.Generator(np.random.PCG64(200 + rank))
+        tg = rng.integers(1, n_it + 1, a.train_targets).astype(np.int32)
+        tsq = synth.queries(a.train_targets, T, n_it, seed=300 + rank)
+        neg = np.array([0] + [min(2 ** l - 1, 15) for l in range(1, ttf.max_level + 1)], np.int32)
+        node, sq, lab = rep.tdm_sample_expand(tg, tsq, neg, 1, seed=400 + rank)
+        mask = np.flatnonzero((sq == -1).ravel()).astype(np.int32)
+        losses = [float(rep.dp_train_step(node, sq, mask, lab, 1e-2, t)) for t in (1, 2)]
+        w_dp = rep.download_din_weights()
+        rep.close()
+        parts = [None] * world
+        dist.all_gather_object(parts, (node, sq, lab))
+        one = Engine(local)
+        one.load_tree_tdm(ttf.max_level, ttf.codes, ttf.node_ids, ttf.is_leaf, ttf.leaf_ids, ttf.leaf_codes)
+        one.init_din_weights(np.float32, trows, 16, T, seed=3)
+        an, asq, al = (np.concatenate([p[i] for p in parts]) for i in range(3))
+        am = np.flatnonzero((asq == -1).ravel()).astype(np.int32)
+        for t in (1, 2):
+            one.train_step(an, asq, am, al, 1e-2, t)
+        w_one = one.download_din_weights()
+        one.close()
+        moved = np.abs(w_one - np.float32(0)).max()
+        dp = {"rows_per_rank": int(len(node)), "steps": 2, "loss": losses,
+              "max_abs_weight_diff_vs_single_engine": float(np.abs(w_dp - w_one).max()),
+              "max_abs_weight": float(moved)}
+    line = {"rank": rank, "world": world, "jtm_item_weights": jtm, "deep_retrieval": dr, "dp_train_step": dp, "items": a.items, "levels": tf.max_level, "batch_per_rank": a.batch, "beam": a.beam,
             "table_rows_global": global_rows, "table_rows_local": local_rows,
             "rows_scored_for_other_ranks": exchanged, "users_checked": n, "checked_against": a.check,
             "ids_identical": bool((items[:n] == oi).all() and (counts[:n] == oc).all()),
