@@ -11,8 +11,11 @@ Default workload = BASELINE.json configs[1]: TDM synthetic 1M items, dim 64, bea
 value  : whole-job users/s with queries and result buffers resident in HBM (dmg_tdm_retrieve_dev)
 e2e    : same metric through the host-buffer C-ABI call (dmg_tdm_retrieve): pinned H2D of the
          B x T item ids and D2H of the topk ids/logits inside the timed region
-roofline: dominant kernel = beam_search_kernel; algorithmic bytes per user
-         = rows_scored*E*4 + T*E*4 + topk*8, rows_scored = 256 + 400*(L-8)
+roofline: dominant kernel = beam_search_fast_kernel (tcgen05 scorer + certified cuts; --arith strict: beam_search_kernel);
+         algorithmic bytes per user (SURVEY 8d) = rows_scored*E*4 + T*E*4 + topk*8, rows_scored = 256 + 400*(L-8);
+         kernel time = CUDA events around its launches on the engine's stream (dmg_set_profiling / dmg_kernel_time)
+Other catalogues: --items 10000000 / 100000000 (--verify-strict N checks N users against the strict kernel when the table is
+too large to ship to the CPU oracle).  Other paths: tools/bench_paths.py; sharded tables: tools/shard_check.py.
 """
 import argparse
 import json
