@@ -45,15 +45,16 @@ DMG_API int32_t dmg_create(int32_t device, dmg_handle_t *out)
     cudaDeviceProp prop;
     if ((e = cudaSetDevice(device)) != cudaSuccess || (e = cudaGetDeviceProperties(&prop, device)) != cudaSuccess ||
         (e = cudaStreamCreateWithFlags(&h->own_stream, cudaStreamNonBlocking)) != cudaSuccess ||
-        (e = cudaMalloc(&h->d_flags, 64 * sizeof(int32_t))) != cudaSuccess ||
-        (e = cudaMemset(h->d_flags, 0, 64 * sizeof(int32_t))) != cudaSuccess) {
+        (e = cudaHostAlloc((void **)&h->h_flags, 64 * sizeof(int32_t), cudaHostAllocMapped)) != cudaSuccess ||
+        (e = cudaHostGetDevicePointer((void **)&h->d_flags, h->h_flags, 0)) != cudaSuccess) {
         g_create_error = std::string("dmg_create: ") + cudaGetErrorString(e);
         delete h;
         return DMG_ERR_CUDA;
     }
+    memset(h->h_flags, 0, 64 * sizeof(int32_t));
     if (prop.major < 10) {
         g_create_error = "dmg_create: device is not sm_100 (Blackwell) -- kernels are built for sm_100a only";
-        cudaStreamDestroy(h->own_stream); cudaFree(h->d_flags); delete h;
+        cudaStreamDestroy(h->own_stream); cudaFreeHost(h->h_flags); delete h;
         return DMG_ERR_UNSUPPORTED;
     }
     h->stream = h->own_stream;
@@ -91,7 +92,7 @@ DMG_API int32_t dmg_destroy(dmg_handle_t h)
     dmg_free_dr(h->dr);
     for (Scratch *s : {&h->s_in, &h->s_out, &h->s_work}) { cudaFree(s->d); cudaFreeHost(s->h); }
     for (auto &ev : h->prof_events) { cudaEventDestroy(ev.first); cudaEventDestroy(ev.second); }
-    cudaFree(h->d_flags);
+    cudaFreeHost(h->h_flags);
     cudaFree(h->d_fast_stats); cudaFree(h->d_fast_tab); cudaFree(h->d_fast_ctl); cudaFree(h->d_redo_list);
     cudaStreamDestroy(h->own_stream);
     delete h;
@@ -444,11 +445,10 @@ static int lower_log2(int n) { int l = 0; while ((2 << l) <= n) l++; return l; }
 
 static int32_t check_flag(dmg_handle_t h, const char *what)
 {
-    int32_t flag = 0;
-    DMG_CUDA(h, cudaMemcpyAsync(&flag, h->d_flags, sizeof(int32_t), cudaMemcpyDeviceToHost, h->stream));
     DMG_CUDA(h, cudaStreamSynchronize(h->stream));
+    const int32_t flag = *(volatile int32_t *)h->h_flags;        // mapped pinned memory: nothing to copy
     if (flag) {
-        DMG_CUDA(h, cudaMemsetAsync(h->d_flags, 0, sizeof(int32_t), h->stream));
+        h->h_flags[0] = 0;
         return fail(h, DMG_ERR_INDEX, "%s: embeddingLookup failed, index outside [0, %lld)", what, (long long)h->din.rows);
     }
     return DMG_OK;

@@ -89,7 +89,8 @@ struct dmg_handle_s {
     dmg::DinDev din;
     dmg::DrDev dr;
     dmg::Scratch s_in, s_out, s_work;
-    int32_t *d_flags = nullptr;     // [0] = index error flag, [1] = work counter
+    int32_t *d_flags = nullptr;     // [0] = index error flag: device alias of h_flags (mapped pinned memory: kernels raise it with no copy back)
+    int32_t *h_flags = nullptr;
     int arithmetic = DMG_ARITH_STRICT;
     bool fast_ok = false;            // tensor-core scorer available for the loaded weights
     bool fast_dirty = true;          // weights changed since the bound tables were computed
