@@ -11,6 +11,10 @@ Default workload = BASELINE.json configs[1]: TDM synthetic 1M items, dim 64, bea
 value  : whole-job users/s with queries and result buffers resident in HBM (dmg_tdm_retrieve_dev)
 e2e    : same metric through the host-buffer C-ABI call (dmg_tdm_retrieve): pinned H2D of the
          B x T item ids and D2H of the topk ids/logits inside the timed region
+in flight: --inflight N (default 4) host threads, each with its own handle (the engine + dmg_clone handles sharing its
+         tables, the GPU form of the reference's per-thread model clones), take the steps round-robin, so the tail of one
+         batch's persistent kernel overlaps the head of the next; both value and e2e time EXACTLY K steps this way.
+         The roofline object is measured on a separate serial pass (one batch in flight, kernel timed alone).
 roofline: dominant kernel = beam_search_fast_kernel (tcgen05 scorer + certified cuts; --arith strict: beam_search_kernel);
          algorithmic bytes per user (SURVEY 8d) = rows_scored*E*4 + T*E*4 + topk*8, rows_scored = 256 + 400*(L-8);
          kernel time = CUDA events around its launches on the engine's stream (dmg_set_profiling / dmg_kernel_time)
@@ -50,6 +54,8 @@ def parse():
                     help="re-run the first N users of the last batch with the strict fp32 kernel and compare ids / logit bits "
                          "(size-independent parity check for catalogues whose table is too large to ship to the CPU oracle)")
     ap.add_argument("--tau", type=float, default=None, help="certification band as a fraction of the worst-case bound")
+    ap.add_argument("--inflight", type=int, default=4,
+                    help="host threads / handles driving the GPU, one batch each in flight (1 = strictly serial steps)")
     ap.add_argument("--arith", default="fast", choices=["fast", "strict"],
                     help="scorer arithmetic: tensor-core with certified cuts (same ids/logits) or strict fp32 SIMT")
     return ap.parse_args()
@@ -215,14 +221,18 @@ def main():
     eng.set_arithmetic(args.arith)
     if args.tau is not None:
         eng.set_fast_tolerance(args.tau)
-    stream = torch.cuda.Stream(dev)                               # non-default: the engine launches on it
+    NF = max(1, min(args.inflight, K))
+    engs = [eng] + [eng.clone() for _ in range(NF - 1)]           # one handle per host thread over ONE copy of the tables
+    streams = [torch.cuda.Stream(dev) for _ in engs]              # non-default: the engines launch on them
+    stream = streams[0]
     torch.cuda.set_stream(stream)
-    eng.set_stream(stream.cuda_stream)
+    for e, st in zip(engs, streams):
+        e.set_stream(st.cuda_stream)
     host_q = [make_queries(args, s, rank, world) for s in range(W + K)]
     dev_q = [torch.from_numpy(q).to(dev) for q in host_q]
-    d_items = torch.empty((B, args.topk), dtype=torch.int32, device=dev)
-    d_logits = torch.empty((B, args.topk), dtype=torch.float32, device=dev)
-    d_counts = torch.empty((B,), dtype=torch.int32, device=dev)
+    d_out = [(torch.empty((B, args.topk), dtype=torch.int32, device=dev), torch.empty((B, args.topk), dtype=torch.float32, device=dev),
+              torch.empty((B,), dtype=torch.int32, device=dev)) for _ in engs]
+    last_k = (K - 1) % NF                                         # the handle that runs the last timed step
 
     def barrier():
         if world > 1:
@@ -236,43 +246,89 @@ def main():
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item())
 
-    def step_dev(i):
-        eng.tdm_retrieve_dev(B, dev_q[i].data_ptr(), args.beam, args.topk, True, d_items.data_ptr(),
-                             d_logits.data_ptr(), d_counts.data_ptr())
+    def step_dev(i, k=0, serial=False):
+        o = d_out[k]
+        # several handles: the synchronous device-buffer call (its host thread has nothing else to do; the strict redo kernel is
+        # launched only for the batches that need it); one handle: the asynchronous call, steps queued back to back
+        fn = engs[k].tdm_retrieve_dev_sync if NF > 1 and not serial else engs[k].tdm_retrieve_dev
+        fn(B, dev_q[i].data_ptr(), args.beam, args.topk, True, o[0].data_ptr(), o[1].data_ptr(), o[2].data_ptr())
 
-    # ---- value: device-resident, CUDA events on the launching stream ---------------------
-    for i in range(W):
-        step_dev(i)
+    e2e_last = [None] * NF
+
+    def step_host(i, k=0):
+        e2e_last[k] = engs[k].tdm_retrieve(host_q[i], args.beam, args.topk)
+
+    def run_steps(step, lo, hi):
+        """steps lo..hi-1, round-robin over the NF handles, one host thread per handle"""
+        if NF == 1:
+            for i in range(lo, hi):
+                step(i, 0)
+            return
+        errs = []
+
+        def work(k):
+            try:
+                for i in range(lo + k, hi, NF):
+                    step(i, k)
+            except Exception as ex:                                # noqa: BLE001
+                errs.append(ex)
+        th = [threading.Thread(target=work, args=(k,)) for k in range(NF)]
+        for t in th:
+            t.start()
+        for t in th:
+            t.join()
+        if errs:
+            raise errs[0]
+
+    # ---- value: device-resident, CUDA events on the launching streams --------------------
+    run_steps(step_dev, 0, W)
     barrier()
     sampler = ClockSampler(local)
     sampler.start()
-    eng.set_profiling(True)
-    l0 = eng.launch_count
+    l0 = sum(e.launch_count for e in engs)
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
     e0.record(stream)
-    for i in range(W, W + K):
-        step_dev(i)
+    for st in streams[1:]:
+        st.wait_event(e0)                                         # nothing of the timed steps starts before e0
+    run_steps(step_dev, W, W + K)
+    for st in streams[1:]:
+        ek = torch.cuda.Event()
+        ek.record(st)
+        stream.wait_event(ek)                                     # e1 follows the last kernel of every stream
     e1.record(stream)
     barrier()
     dev_ms = max_over_ranks(e0.elapsed_time(e1))
-    launches = eng.launch_count - l0
+    launches = sum(e.launch_count for e in engs) - l0
+    last_items = d_out[last_k][0].cpu().numpy().copy()
+    last_logits = d_out[last_k][1].cpu().numpy().copy()
+
+    # ---- roofline pass: the same K steps, ONE batch in flight, the kernel timed alone ------
+    eng.set_profiling(True)
+    s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    s0.record(stream)
+    for i in range(W, W + K):
+        step_dev(i, 0, serial=True)
+    s1.record(stream)
+    barrier()
+    serial_ms = max_over_ranks(s0.elapsed_time(s1))
     kern_ms, kern_n = eng.kernel_time()
     eng.set_profiling(False)
-    fast_stats = eng.fast_stats() if args.arith == "fast" else None
-    last_items = d_items.cpu().numpy().copy()
-    last_logits = d_logits.cpu().numpy().copy()
+    fast_stats = None
+    if args.arith == "fast":
+        per = [e.fast_stats() for e in engs]
+        fast_stats = {k: (max(p[k] for p in per) if k == "max_err_over_bound" else sum(p[k] for p in per)) for k in per[0]}
 
     # ---- e2e: host buffers through the C ABI (H2D + D2H inside) ---------------------------
-    for i in range(W):
-        eng.tdm_retrieve(host_q[i], args.beam, args.topk)
+    run_steps(step_host, 0, W)
     barrier()
     t0 = time.perf_counter()
-    for i in range(W, W + K):
-        e2e_out = eng.tdm_retrieve(host_q[i], args.beam, args.topk)
+    run_steps(step_host, W, W + K)
     torch.cuda.synchronize(dev)
     e2e_s = max_over_ranks(time.perf_counter() - t0)
     clocks = sampler.stop()
+    e2e_out = e2e_last[last_k]
     assert (e2e_out[0] == last_items).all(), "host-buffer and device-buffer paths disagree"
 
     value = world * B * K / (dev_ms * 1e-3)
@@ -329,6 +385,10 @@ def main():
                                    f"topk={args.topk}, T={T}", "levels": L, "rows_scored_per_user": rows_u,
                        "algorithmic_bytes_per_user": bytes_u, "node_table_gb": rows * E * 4 / 1e9,
                        "parallelism": f"replicas x{world}, users sharded, no collective",
+                       "batches_in_flight": NF,
+                       "in_flight": (f"{NF} host threads, one handle each (dmg_clone: one copy of the tables), take the steps round-robin; "
+                                     "the roofline object is from a serial pass over the same steps") if NF > 1 else "serial steps",
+                       "serial_ms_per_step": serial_ms / K,
                        "l2": f"inputs larger than L2: {rows * E * 4 / 1e9:.2f} GB node table, fresh queries every step, no flush",
                        "arithmetic": ("tcgen05 bf16x3 tensor-core scorer + certified cuts, strict fp32 re-score of "
                                       "near-cut candidates and of the topk (ids and logits bit-identical to the CPU oracle)")
@@ -337,17 +397,21 @@ def main():
             "e2e": {"value": e2e_value, "unit": "users/s", "h2d_bytes_per_step": B * T * 4,
                     "d2h_bytes_per_step": B * args.topk * 8 + B * 4, "ms_per_step": e2e_s / K * 1e3},
             "gpu_launches": int(launches),
+            "roofline_in_flight": {"achieved": value / world * bytes_u / 1e9, "unit": "GB/s", "frac": value / world * bytes_u / 1e9 / peak,
+                                   "note": "whole step with the batches in flight (value x algorithmic bytes per user), not a kernel timed alone"},
             "roofline": {"bound": "hbm", "kernel": ("beam_search_fast_kernel" if args.arith == "fast" else "beam_search_kernel<float,%d>" % E), "achieved": achieved, "peak": peak,
                          "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
                          "kernel_ms_avg": kern_avg_ms, "kernel_launches_timed": int(kern_n),
-                         "kernel_share_of_step": kern_ms / dev_ms if world == 1 else None},
+                         "kernel_share_of_step": kern_ms / serial_ms if world == 1 else None,
+                         "measured_on": "serial pass (one batch in flight), CUDA events around each launch of the kernel"},
             "cpu_baseline": cpu,
             "parity": parity,
             "parity_fast_vs_strict_kernel": strict_check,
             "clocks": clocks,
         }
         print(json.dumps(line), flush=True)
-    eng.close()
+    for e in reversed(engs):
+        e.close()
     if world > 1:
         dist.destroy_process_group()
 

@@ -58,6 +58,7 @@ def load_library(build_if_missing: bool = True):
     sig = {
         "dmg_create": [i32, C.POINTER(vp)],
         "dmg_destroy": [vp],
+        "dmg_clone": [vp, C.POINTER(vp)],
         "dmg_set_stream": [vp, vp],
         "dmg_synchronize": [vp],
         "dmg_set_profiling": [vp, i32],
@@ -72,6 +73,7 @@ def load_library(build_if_missing: bool = True):
         "dmg_download_din_weights": [vp, vp, i64],
         "dmg_tdm_retrieve": [vp, i32, vp, i32, i32, i32, vp, vp, i32, vp, vp, vp],
         "dmg_tdm_retrieve_dev": [vp, i32, vp, i32, i32, i32, vp, vp, vp],
+        "dmg_tdm_retrieve_dev_sync": [vp, i32, vp, i32, i32, i32, vp, vp, vp],
         "dmg_otm_beam_search": [vp, i32, vp, i32, i32, vp, vp, vp],
         "dmg_otm_retrieve": [vp, i32, vp, i32, i32, i32, vp, vp, vp],
         "dmg_otm_beam_search_levels": [vp, i32, vp, i32, i32, vp, vp, vp],
@@ -158,9 +160,20 @@ class Engine:
             raise DmgArgumentError(rc, msg)
         raise DmgError(rc, msg)
 
+    def clone(self) -> "Engine":
+        """A handle that shares this engine's tree and weights read-only (own stream and scratch): one per host
+        thread, like the reference's per-thread model clones (LocalOptimizer.scala:35-40).  Close clones first."""
+        h = C.c_void_p()
+        self._check(self.L.dmg_clone(self.h, C.byref(h)))
+        e = Engine.__new__(Engine)
+        e.L, e.h, e.device = self.L, h, self.device
+        e.din_dtype, e.E, e.T, e.rows = self.din_dtype, self.E, self.T, self.rows
+        e._parent = self                                            # keeps the owner alive
+        return e
+
     def close(self):
         if getattr(self, "h", None):
-            self.L.dmg_destroy(self.h)
+            self._check(self.L.dmg_destroy(self.h))
             self.h = None
 
     def __del__(self):
@@ -365,6 +378,12 @@ class Engine:
         vp = C.c_void_p
         self._check(self.L.dmg_tdm_retrieve_dev(self.h, B, vp(d_seq_ptr), beam, topk, int(use_mask), vp(d_items_ptr),
                                                 vp(d_logits_ptr), vp(d_counts_ptr)))
+
+    def tdm_retrieve_dev_sync(self, B, d_seq_ptr, beam, topk, use_mask, d_items_ptr, d_logits_ptr, d_counts_ptr):
+        """Device-pointer form that returns with the results complete (strict redo launched only when a batch needs it)."""
+        vp = C.c_void_p
+        self._check(self.L.dmg_tdm_retrieve_dev_sync(self.h, B, vp(d_seq_ptr), beam, topk, int(use_mask), vp(d_items_ptr),
+                                                     vp(d_logits_ptr), vp(d_counts_ptr)))
 
     def otm_beam_search(self, leaf_seq, beam, use_mask=True):
         seq = _i32(leaf_seq).reshape(-1, self.T)

@@ -49,7 +49,10 @@ struct FastParams {
     int32_t sparse_from;            // lowest tree level with a missing code: expansion probes the bitmap only from there
     int32_t *redo_list;             // users to re-run with the strict kernel
     int32_t *redo_count;
-    int32_t *work_counter;          // dynamic user scheduler
+    int32_t *host_flags;            // mapped pinned memory: [1] is raised with the first redo user, so a synchronous caller launches the
+                                    // strict redo kernel only for the batches that need it
+    int32_t *work_counter;          // dynamic user scheduler: [0] users below tail_start, [2] tail users, [8 + smid] tail owner of an SM
+    int32_t tail_start;             // users >= tail_start (the last, partial round of the batch; == B when unused) run ONE per SM
     unsigned long long *stats;      // [0] cuts [1] cuts re-scored [2] rows re-scored [3] rows scored [4] max ratio bits [5] redo users
 };
 
@@ -556,10 +559,29 @@ __global__ void __launch_bounds__(FastGeo::THREADS, 2) beam_search_fast_kernel(c
         }
     };
 
+    if (tid == 0) sMisc[43] = 0;                                // tail owner flag (thread 0 only)
     for (;;) {
         // ---- next user (dynamic scheduler) ------------------------------------------------------
         __syncthreads();
-        if (tid == 0) sMisc[42] = atomicAdd(fp.work_counter, 1);
+        if (tid == 0) {
+            // The last round of a batch holds fewer users than SMs: the first CTA of an SM to run out of main-round users
+            // becomes its tail owner and runs tail users alone (a chain is ~20 % faster without a co-resident CTA), the
+            // other CTA of the SM retires.
+            int tail_owner = sMisc[43];
+            int u = tail_owner ? p.B : atomicAdd(fp.work_counter, 1);
+            if (u >= fp.tail_start) {
+                u = p.B;
+                if (fp.tail_start < p.B) {
+                    if (!tail_owner) {
+                        uint32_t smid;
+                        asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+                        sMisc[43] = tail_owner = atomicExch(fp.work_counter + 8 + (smid & 255), 1) == 0;
+                    }
+                    if (tail_owner) u = fp.tail_start + atomicAdd(fp.work_counter + 2, 1);
+                }
+            }
+            sMisc[42] = u;
+        }
         __syncthreads();
         const int user = sMisc[42];
         if (user >= p.B) break;
@@ -1029,7 +1051,11 @@ __global__ void __launch_bounds__(FastGeo::THREADS, 2) beam_search_fast_kernel(c
         }
         if (redo) {
             st_redo++;
-            if (tid == 0) { fp.redo_list[atomicAdd(fp.redo_count, 1)] = user; if (fp.stats) atomicAdd(&fp.stats[24 + redo_why], 1ull); }
+            if (tid == 0) {
+                fp.redo_list[atomicAdd(fp.redo_count, 1)] = user;
+                *reinterpret_cast<volatile int32_t *>(fp.host_flags + 1) = 1;
+                if (fp.stats) atomicAdd(&fp.stats[24 + redo_why], 1ull);
+            }
         }
         DMG_TICK(TK_FINAL);
     }

@@ -655,7 +655,8 @@ static __global__ void tdm_ids_to_codes_kernel(const int32_t *__restrict__ ids, 
                                         int32_t *__restrict__ fast_ctl)
 {
     int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i == 0 && fast_ctl) { fast_ctl[0] = 0; fast_ctl[1] = 0; }      // user scheduler + redo count of the fast kernel
+    if (blockIdx.x == 0 && fast_ctl)                                   // user scheduler + redo count + per-SM tail owners of the fast kernel
+        for (int j = threadIdx.x; j < DMG_FAST_CTL_WORDS; j += blockDim.x) fast_ctl[j] = 0;
     if (i >= n) return;
     const int32_t id = ids[i];
     int32_t code;

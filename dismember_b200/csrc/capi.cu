@@ -84,18 +84,50 @@ int32_t dmg_deepfm_score_pairs(dmg_handle_t h, int64_t n, const int32_t *node, c
 DMG_API int32_t dmg_destroy(dmg_handle_t h)
 {
     if (!h) return DMG_ERR_INVALID_ARG;
+    if (h->n_clones.load() > 0) return fail(h, DMG_ERR_STATE, "dmg_destroy: %d clone(s) still share this model", h->n_clones.load());
     cudaSetDevice(h->device);
     cudaStreamSynchronize(h->stream);
     dmg_shard_free(h);
-    free_tree(h->tree);
-    free_din(h->din);
-    dmg_free_dr(h->dr);
+    if (h->parent) h->parent->n_clones.fetch_sub(1);           // the tables are the parent's
+    else {
+        free_tree(h->tree);
+        free_din(h->din);
+        dmg_free_dr(h->dr);
+    }
     for (Scratch *s : {&h->s_in, &h->s_out, &h->s_work}) { cudaFree(s->d); cudaFreeHost(s->h); }
     for (auto &ev : h->prof_events) { cudaEventDestroy(ev.first); cudaEventDestroy(ev.second); }
     cudaFreeHost(h->h_flags);
     cudaFree(h->d_fast_stats); cudaFree(h->d_fast_tab); cudaFree(h->d_fast_ctl); cudaFree(h->d_redo_list);
     cudaStreamDestroy(h->own_stream);
     delete h;
+    return DMG_OK;
+}
+
+// A second handle on the same device that shares src's tree index and weight tables read-only: own stream, own scratch,
+// own scheduler / redo state.  The GPU counterpart of the reference's per-thread model clones, which share one weight
+// storage (tdm/.../optim/LocalOptimizer.scala:35-40; the evaluator splits the users over threads,
+// tdm/.../evaluation/Evaluator.scala:29-37): one clone per host thread keeps several batches in flight, and the tail of
+// one batch's persistent kernel overlaps the head of the next.
+DMG_API int32_t dmg_clone(dmg_handle_t src, dmg_handle_t *out)
+{
+    if (!src || !out) return DMG_ERR_INVALID_ARG;
+    *out = nullptr;
+    if (src->parent) src = src->parent;                          // clones of clones hang off the owner
+    if (src->shard) return fail(src, DMG_ERR_UNSUPPORTED, "dmg_clone: sharded / DeepFM handles own NCCL and exchange state -- create one handle per rank");
+    if (src->din.d_grad) return fail(src, DMG_ERR_STATE, "dmg_clone: this handle holds training state; clone an inference handle");
+    dmg_handle_t h = nullptr;
+    const int32_t rc = dmg_create(src->device, &h);
+    if (rc != DMG_OK) return fail(src, rc, "dmg_clone: %s", dmg_last_error(nullptr));
+    cudaStreamSynchronize(src->stream);                          // uploads of the model are complete before another stream reads it
+    h->tree = src->tree;
+    h->din = src->din;
+    h->dr = src->dr;
+    h->arithmetic = src->arithmetic;
+    h->fast_tau = src->fast_tau;
+    h->fast_dirty = true;                                        // its own bound tables, computed on first use
+    h->parent = src;
+    src->n_clones.fetch_add(1);
+    *out = h;
     return DMG_OK;
 }
 
@@ -147,6 +179,7 @@ DMG_API int32_t dmg_load_tree_tdm(dmg_handle_t h, int32_t max_level, int64_t n_n
                                   const int32_t *leaf_ids, const int32_t *leaf_codes)
 {
     if (!h) return DMG_ERR_INVALID_ARG;
+    DMG_TRY(model_is_shared(h, "dmg_load_tree_tdm"));
     if (max_level < 0 || max_level > 29 || n_nodes <= 0 || n_items <= 0 || !codes || !node_ids || !is_leaf ||
         !leaf_ids || !leaf_codes)
         return fail(h, DMG_ERR_INVALID_ARG, "dmg_load_tree_tdm: bad arguments (max_level must be in [0,29])");
@@ -204,6 +237,7 @@ DMG_API int32_t dmg_load_tree_complete(dmg_handle_t h, int32_t leaf_level, int64
                                        const int32_t *leaf_ids)
 {
     if (!h) return DMG_ERR_INVALID_ARG;
+    DMG_TRY(model_is_shared(h, "dmg_load_tree_complete"));
     if (leaf_level < 0 || leaf_level > 29 || n_items <= 0 || !item_ids || !leaf_ids)
         return fail(h, DMG_ERR_INVALID_ARG, "dmg_load_tree_complete: bad arguments");
     DMG_CUDA(h, cudaSetDevice(h->device));
@@ -260,6 +294,7 @@ int32_t dmg_refresh_transposes(dmg_handle_t h)       // used by train.cu after a
 
 static int32_t alloc_din(dmg_handle_t h, int32_t dtype, int64_t rows, int32_t E, int32_t T)
 {
+    DMG_TRY(model_is_shared(h, "loading weights"));
     if (dtype != DMG_F32 && dtype != DMG_F64) return fail(h, DMG_ERR_INVALID_ARG, "dtype must be DMG_F32 or DMG_F64");
     if (rows <= 0 || E <= 0 || T <= 0) return fail(h, DMG_ERR_INVALID_ARG, "rows, E, T must be positive");
     if (T > kMaxT) return fail(h, DMG_ERR_UNSUPPORTED, "seq_len %d > %d", T, kMaxT);
@@ -419,8 +454,8 @@ static int32_t compute_fast_bounds(dmg_handle_t h)
     h->fast_host.assign(b1, b1 + 2 * E + 1);                     // b1 | w2 | b2
     if (!h->d_fast_tab) DMG_CUDA(h, cudaMalloc(&h->d_fast_tab, tab.size() * sizeof(float)));
     if (!h->d_fast_ctl) {
-        DMG_CUDA(h, cudaMalloc(&h->d_fast_ctl, 8 * sizeof(int32_t)));
-        DMG_CUDA(h, cudaMemsetAsync(h->d_fast_ctl, 0, 8 * sizeof(int32_t), h->stream));
+        DMG_CUDA(h, cudaMalloc(&h->d_fast_ctl, DMG_FAST_CTL_WORDS * sizeof(int32_t)));
+        DMG_CUDA(h, cudaMemsetAsync(h->d_fast_ctl, 0, DMG_FAST_CTL_WORDS * sizeof(int32_t), h->stream));
     }
     DMG_CUDA(h, cudaMemcpyAsync(h->d_fast_tab, tab.data(), tab.size() * sizeof(float), cudaMemcpyHostToDevice, h->stream));
     level_bounds_kernel<<<h->sm_count * 8, 256, 0, h->stream>>>(d.emb<float>(), d.rows, h->d_fast_tab + 4096, h->d_fast_tab + 4160,
@@ -468,8 +503,12 @@ int32_t dmg_tdm_ids_to_codes(dmg_handle_t h, const int32_t *d_ids, int64_t n, in
 // Enqueue K2 + K1 for a TDM batch whose inputs already sit on the device.
 static int32_t tdm_enqueue(dmg_handle_t h, int32_t B, const int32_t *d_seq, int32_t beam, int max_beam,
                            const int32_t *d_beam_user, int32_t topk, int32_t use_mask, const int64_t *d_cons_off,
-                           const int32_t *d_cons, int32_t *d_items, float *d_logits, int32_t *d_counts)
+                           const int32_t *d_cons, int32_t *d_items, float *d_logits, int32_t *d_counts,
+                           BeamParams<float> *redo_out = nullptr)
 {
+    // redo_out: a caller that synchronises anyway takes the strict redo launch into its own hands (h_flags[1] tells it
+    // whether the batch has redo users); redo_out->B == 0 on return when there is no such launch.
+    if (redo_out) redo_out->B = 0;
     const DinDev &d = h->din;
     const TreeDev &t = h->tree;
     const int T = d.T;
@@ -517,11 +556,14 @@ static int32_t tdm_enqueue(dmg_handle_t h, int32_t B, const int32_t *d_seq, int3
         fx.cA = h->fast_cA; fx.cZ = h->fast_cZ; fx.cH = h->fast_cH; fx.cGamma = h->fast_cGamma; fx.tau = h->fast_tau;
         fx.zvec = h->d_fast_tab + 4224;
         fx.redo_list = h->d_redo_list; fx.redo_count = h->d_fast_ctl + 1; fx.work_counter = h->d_fast_ctl;
+        fx.host_flags = h->d_flags;
         fx.stats = h->d_fast_stats;
         fx.sparse_from = t.sparse_from;
         const size_t smem = FastGeo::smem_bytes(p.cap);
         DMG_CUDA(h, cudaFuncSetAttribute(beam_search_fast_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         const int grid = std::min(B, 2 * h->sm_count);           // two co-resident CTAs per SM
+        const int tail = B % grid;                               // last, partial round: one user per SM when it fits
+        fx.tail_start = (grid == 2 * h->sm_count && tail > 0 && tail <= h->sm_count && !getenv("DMG_NO_TAIL")) ? B - tail : B;
         cudaEvent_t e0 = nullptr, e1 = nullptr;
         if (h->profiling) {
             DMG_CUDA(h, cudaEventCreate(&e0));
@@ -539,6 +581,8 @@ static int32_t tdm_enqueue(dmg_handle_t h, int32_t B, const int32_t *d_seq, int3
         p.user_list = h->d_redo_list; p.user_count = h->d_fast_ctl + 1;
         p.split = 4;                                             // a redo user runs on a cluster of 4 SMs: its <= 4 row tiles per level in parallel
         p.B = std::min(B, 32);                                   // cluster slots launched (the kernel strides over the list)
+        if (redo_out) { *redo_out = p; return DMG_OK; }
+        h->h_flags[1] = 0;                                       // nobody reads it on this path
         const bool prof = h->profiling;
         h->profiling = false;
         const int32_t rc = launch_beam<float>(h, p, d.E);
@@ -616,6 +660,35 @@ DMG_API int32_t dmg_tdm_retrieve_dev(dmg_handle_t h, int32_t B, const int32_t *d
     return tdm_enqueue(h, B, d_item_seq, beam, beam, nullptr, topk, use_mask, nullptr, nullptr, d_out_items, d_out_logits, d_out_counts);
 }
 
+// The strict redo launch of a synchronous call: only when the fast kernel raised h_flags[1] (exact ties at a cut -- rare).
+static int32_t tdm_redo_if_flagged(dmg_handle_t h, const BeamParams<float> &redo, bool *ran)
+{
+    *ran = false;
+    if (redo.B <= 0 || !*(volatile int32_t *)(h->h_flags + 1)) return DMG_OK;
+    h->h_flags[1] = 0;
+    const bool prof = h->profiling;
+    h->profiling = false;
+    const int32_t rc = launch_beam<float>(h, redo, h->din.E);
+    h->profiling = prof;
+    *ran = rc == DMG_OK;
+    return rc;
+}
+
+DMG_API int32_t dmg_tdm_retrieve_dev_sync(dmg_handle_t h, int32_t B, const int32_t *d_item_seq, int32_t beam, int32_t topk,
+                                          int32_t use_mask, int32_t *d_out_items, float *d_out_logits, int32_t *d_out_counts)
+{
+    DMG_TRY(tdm_precheck(h, B, beam, topk));
+    if (!d_item_seq || !d_out_items || !d_out_logits || !d_out_counts) return fail(h, DMG_ERR_INVALID_ARG, "null device pointer");
+    DMG_CUDA(h, cudaSetDevice(h->device));
+    BeamParams<float> redo;
+    DMG_TRY(tdm_enqueue(h, B, d_item_seq, beam, beam, nullptr, topk, use_mask, nullptr, nullptr, d_out_items, d_out_logits, d_out_counts, &redo));
+    DMG_TRY(check_flag(h, "dmg_tdm_retrieve_dev_sync"));
+    bool ran = false;
+    DMG_TRY(tdm_redo_if_flagged(h, redo, &ran));
+    if (ran) DMG_CUDA(h, cudaStreamSynchronize(h->stream));
+    return DMG_OK;
+}
+
 DMG_API int32_t dmg_tdm_retrieve(dmg_handle_t h, int32_t B, const int32_t *item_seq, int32_t beam, int32_t topk,
                                  int32_t use_mask, const int64_t *consumed_off, const int32_t *consumed_items,
                                  int32_t widen_beam, int32_t *out_items, float *out_logits, int32_t *out_counts)
@@ -662,10 +735,17 @@ DMG_API int32_t dmg_tdm_retrieve(dmg_handle_t h, int32_t B, const int32_t *item_
     int32_t *h_items = oh.take<int32_t>((size_t)B * topk), *d_items = od.take<int32_t>((size_t)B * topk);
     float *h_log = oh.take<float>((size_t)B * topk), *d_log = od.take<float>((size_t)B * topk);
     int32_t *h_cnt = oh.take<int32_t>(B), *d_cnt = od.take<int32_t>(B);
+    BeamParams<float> redo;
     DMG_TRY(tdm_enqueue(h, B, ds, beam, max_beam, per_user ? db : nullptr, topk, use_mask, consumed_off ? dof : nullptr,
-                        consumed_off ? dc : nullptr, d_items, d_log, d_cnt));
+                        consumed_off ? dc : nullptr, d_items, d_log, d_cnt, &redo));
     DMG_CUDA(h, cudaMemcpyAsync(h->s_out.h, h->s_out.d, od.off, cudaMemcpyDeviceToHost, h->stream));
     DMG_TRY(check_flag(h, "dmg_tdm_retrieve"));
+    bool ran = false;
+    DMG_TRY(tdm_redo_if_flagged(h, redo, &ran));
+    if (ran) {                                                   // results again, now with the redo users
+        DMG_CUDA(h, cudaMemcpyAsync(h->s_out.h, h->s_out.d, od.off, cudaMemcpyDeviceToHost, h->stream));
+        DMG_CUDA(h, cudaStreamSynchronize(h->stream));
+    }
     memcpy(out_items, h_items, (size_t)B * topk * 4);
     memcpy(out_logits, h_log, (size_t)B * topk * 4);
     memcpy(out_counts, h_cnt, (size_t)B * 4);

@@ -4,6 +4,7 @@
 #include <cstdint>
 #include <cstdio>
 #include <cstring>
+#include <atomic>
 #include <string>
 #include <vector>
 
@@ -15,6 +16,7 @@ namespace dmg {
 
 constexpr int kMaxT = 16;          // history length supported by the fused kernels (reference: 10)
 constexpr int kThreads = 256;      // CTA size of the beam-search / scorer kernels
+#define DMG_FAST_CTL_WORDS 264     // fast kernel control words: [0] user counter, [1] redo count, [2] tail counter, [8 + smid] tail owners
 
 // ---- device-side index structures -------------------------------------------------------
 struct TreeDev {
@@ -98,13 +100,15 @@ struct dmg_handle_s {
     float fast_tau = 1.0f;           // fraction of the worst-case bound used as the certification band
     float *d_fast_tab = nullptr;     // [0,4096) M^T  [4096,4160) v  [4160,4192) lvl_vx  [4192,4224) lvl_nx  [4224,4288) z
     std::vector<float> fast_host;    // host copy of b1 | w2 | b2 (kernel parameters of the fast kernel)
-    int32_t *d_fast_ctl = nullptr;   // [0] dynamic user counter, [1] redo count
+    int32_t *d_fast_ctl = nullptr;   // [0] dynamic user counter, [1] redo count, [2] tail user counter, [8 + smid] tail owner flags
     int32_t *d_redo_list = nullptr;  // users the fast kernel hands to the strict kernel
     int64_t redo_cap = 0;
     unsigned long long *d_fast_stats = nullptr;
     dmg::ShardState *shard = nullptr;   // node-table sharding over NCCL (shard.cu)
     bool profiling = false;
     std::vector<std::pair<cudaEvent_t, cudaEvent_t>> prof_events;
+    dmg_handle_s *parent = nullptr;     // dmg_clone: tree / weight tables are the parent's (read-only here, never freed here)
+    std::atomic<int> n_clones{0};       // live clones: the model of this handle is frozen until they are destroyed
 };
 
 namespace dmg {
@@ -118,6 +122,14 @@ inline int32_t fail(dmg_handle_t h, int32_t code, const char *fmt, ...)
     va_end(ap);
     if (h) h->err = buf;
     return code;
+}
+
+// Entry points that replace or update the model refuse clones and handles with live clones (dmg_clone).
+inline int32_t model_is_shared(dmg_handle_t h, const char *what)
+{
+    if (h && h->parent) return fail(h, DMG_ERR_STATE, "%s: this handle is a clone (dmg_clone) and shares its parent's model read-only", what);
+    if (h && h->n_clones.load() > 0) return fail(h, DMG_ERR_STATE, "%s: %d clone(s) share this model -- destroy them first", what, h->n_clones.load());
+    return DMG_OK;
 }
 
 #define DMG_CUDA(h, expr)                                                                         \

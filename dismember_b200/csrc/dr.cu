@@ -310,6 +310,7 @@ DMG_API int32_t dmg_dr_load(dmg_handle_t h, int32_t num_item, int32_t K, int32_t
                             const double *sm_b)
 {
     if (!h) return DMG_ERR_INVALID_ARG;
+    DMG_TRY(model_is_shared(h, "dmg_dr_load"));
     if (num_item <= 0 || K <= 0 || T <= 0 || E <= 0 || !layer_emb || !layer_w || !layer_b || !rr_emb || !rr_w || !rr_b ||
         !sm_w || !sm_b)
         return fail(h, DMG_ERR_INVALID_ARG, "dmg_dr_load: bad arguments");
@@ -350,6 +351,7 @@ DMG_API int32_t dmg_dr_load(dmg_handle_t h, int32_t num_item, int32_t K, int32_t
 DMG_API int32_t dmg_dr_load_paths(dmg_handle_t h, const int64_t *path_off, const int32_t *path_items)
 {
     if (!h || !path_off) return DMG_ERR_INVALID_ARG;
+    DMG_TRY(model_is_shared(h, "dmg_dr_load_paths"));
     DrDev &d = h->dr;
     if (!d.loaded) return fail(h, DMG_ERR_STATE, "dmg_dr_load first");
     double nk = 1;
@@ -615,6 +617,7 @@ DMG_API int32_t dmg_shard_dr_load(dmg_handle_t h, int32_t num_item, int32_t K, i
                                   const double *rr_emb, const double *rr_w, const double *rr_b, const double *sm_w, const double *sm_b)
 {
     if (!h) return DMG_ERR_INVALID_ARG;
+    DMG_TRY(model_is_shared(h, "dmg_shard_dr_load"));
     ShardState *s = h->shard;
     if (!s) return fail(h, DMG_ERR_STATE, "call dmg_shard_init first");
     if (num_item <= 0 || K <= 0 || T <= 0 || E <= 0 || !layer_emb || !layer_w || !layer_b || !rr_emb || !rr_w || !rr_b || !sm_w || !sm_b)

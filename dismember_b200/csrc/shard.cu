@@ -628,6 +628,7 @@ DMG_API int32_t dmg_shard_unique_id(void *out, int32_t nbytes)
 DMG_API int32_t dmg_shard_init(dmg_handle_t h, int32_t world, int32_t rank, const void *unique_id)
 {
     if (!h) return DMG_ERR_INVALID_ARG;
+    DMG_TRY(model_is_shared(h, "dmg_shard_init"));
     if (world < 1 || world > 32 || (world & (world - 1)) || rank < 0 || rank >= world)
         return fail(h, DMG_ERR_INVALID_ARG, "dmg_shard_init: world must be a power of two <= 32, 0 <= rank < world");
     if (world > 1 && !unique_id) return fail(h, DMG_ERR_INVALID_ARG, "dmg_shard_init: unique id required for world > 1");
@@ -655,6 +656,7 @@ static int64_t dense_params(int kind, int E, int T)
 
 static int32_t shard_alloc_din(dmg_handle_t h, int64_t rows_global, int32_t E, int32_t T, int kind = 0)
 {
+    DMG_TRY(model_is_shared(h, "loading weights"));
     ShardState *s = h->shard;
     if (!s) return fail(h, DMG_ERR_STATE, "call dmg_shard_init first");
     if (!h->tree.loaded) return fail(h, DMG_ERR_STATE, "load the tree first (the shard layout follows its levels)");

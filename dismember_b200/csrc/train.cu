@@ -497,6 +497,7 @@ template <typename real> int32_t adam_pass(dmg_handle_t h, double lr, int step_t
 int32_t train_precheck(dmg_handle_t h, int64_t rows, const void *node, const void *seq, const void *labels, const void *out)
 {
     if (!h) return DMG_ERR_INVALID_ARG;
+    DMG_TRY(model_is_shared(h, "training"));
     if (!h->din.loaded) return fail(h, DMG_ERR_STATE, "DIN weights must be loaded first");
     if (h->din.sharded) return fail(h, DMG_ERR_STATE, "the node table is sharded (dmg_shard_init): use the dmg_shard_* entry points");
     if (rows <= 0 || !node || !seq || !labels || !out) return fail(h, DMG_ERR_INVALID_ARG, "bad arguments");

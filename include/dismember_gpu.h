@@ -55,6 +55,14 @@ enum { DMG_F32 = 0, DMG_F64 = 1 };
 /* ---- lifecycle ------------------------------------------------------------------------ */
 DMG_API int32_t dmg_create(int32_t device, dmg_handle_t *out);
 DMG_API int32_t dmg_destroy(dmg_handle_t h);
+/* A second handle on src's device that SHARES src's tree index and weight tables read-only (own
+ * stream, scratch and scheduler state): the GPU form of the reference's per-thread model clones over
+ * one weight storage (tdm/src/main/scala/com/mass/tdm/optim/LocalOptimizer.scala:35-40) that the
+ * evaluator hands its user slices to (tdm/.../evaluation/Evaluator.scala:29-37).  One clone per host
+ * thread keeps several batches in flight on one GPU: the tail of one batch's persistent kernel
+ * overlaps the head of the next.  While clones live, loaders and training entry points on src (and
+ * always on a clone) return DMG_ERR_STATE; destroy the clones before src. */
+DMG_API int32_t dmg_clone(dmg_handle_t src, dmg_handle_t *out);
 DMG_API const char *dmg_last_error(dmg_handle_t h);      /* h may be NULL: last create error   */
 DMG_API const char *dmg_version(void);
 /* Use a caller-owned cudaStream_t (e.g. the framework's current stream) instead of the
@@ -140,6 +148,14 @@ DMG_API int32_t dmg_tdm_retrieve_dev(dmg_handle_t h, int32_t B, const int32_t *d
                                      int32_t beam, int32_t topk, int32_t use_mask,
                                      int32_t *d_out_items, float *d_out_logits,
                                      int32_t *d_out_counts);
+/* Same device buffers, but returns after the results are complete (one stream synchronisation).  The
+ * strict re-run of the users the tensor-core kernel could not certify is then launched only for the
+ * batches that have such users; with one handle per host thread (dmg_clone) the next batch's kernel
+ * fills the SMs this batch's tail leaves idle. */
+DMG_API int32_t dmg_tdm_retrieve_dev_sync(dmg_handle_t h, int32_t B, const int32_t *d_item_seq,
+                                          int32_t beam, int32_t topk, int32_t use_mask,
+                                          int32_t *d_out_items, float *d_out_logits,
+                                          int32_t *d_out_counts);
 
 /* CandidateSearcher.batchBeamSearch (otm/.../model/CandidateSearcher.scala:15-56): per user
  * the 2*beam candidates of the leaf level with their Double scores, in candidate order.

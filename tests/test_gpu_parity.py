@@ -400,3 +400,64 @@ def test_fast_equals_strict_at_full_size(engine):
         engine.set_arithmetic("strict")
     assert (fast[2] == strict[2]).all() and (fast[0] == strict[0]).all() and (bits(fast[1]) == bits(strict[1])).all()
     print("fast stats at 1M:", stats)
+
+
+# ------------------------------------------------------------------ clones: one handle per host thread over one model
+def test_clones_share_the_model_across_threads(orc):
+    """dmg_clone: per-thread handles over the parent's tables (LocalOptimizer.scala:35-40, Evaluator.scala:29-37).
+    Three host threads retrieve their slices of the users at the same time; every slice equals the oracle bit for bit."""
+    import threading
+    from dismember_b200 import DmgError, Engine
+    E, n_items, beam = 64, 20000, 200
+    tf = synth.tdm_tree(n_items, seed=17)
+    rows = (1 << (tf.max_level + 1)) - 1
+    params = synth.din_params(rows, E, seed=23)
+    parent = Engine(0)
+    parent.load_tree_tdm(tf.max_level, tf.codes, tf.node_ids, tf.is_leaf, tf.leaf_ids, tf.leaf_codes)
+    parent.load_din_weights(params, rows, E, 10)
+    parent.set_arithmetic("fast")
+    clones = [parent.clone(), parent.clone()]
+    engines = [parent] + clones
+    seqs = synth.queries(900, 10, n_items, seed=41)
+    slices = [slice(0, 300), slice(300, 600), slice(600, 900)]
+    out, errs = [None] * 3, []
+
+    def work(k):
+        try:
+            for _ in range(3):                                   # several batches per thread, all in flight together
+                out[k] = engines[k].tdm_retrieve(seqs[slices[k]], beam, 10)
+        except Exception as ex:                                  # noqa: BLE001
+            errs.append(ex)
+    th = [threading.Thread(target=work, args=(k,)) for k in range(3)]
+    [t.start() for t in th]
+    [t.join() for t in th]
+    assert not errs, errs
+    tree = orc.Tree.from_treefile(tf)
+    model = orc.TdmModel(params, rows, E, 10)
+    oi, ol, oc = model.retrieve_batch(tree, seqs, beam, 10, n_threads=8)
+    for k in range(3):
+        items, logits, counts = out[k]
+        assert (counts == oc[slices[k]]).all() and (items == oi[slices[k]]).all() and (bits(logits) == bits(ol[slices[k]])).all()
+    assert clones[0].fast_stats()["rows_fast"] > 0              # the clone ran the tensor-core kernel with its own bound tables
+    # device-buffer forms on a clone: asynchronous and synchronous (host-gated strict redo) agree with the oracle too
+    import torch
+    dq = torch.from_numpy(seqs[:300]).cuda()
+    for fn in (clones[1].tdm_retrieve_dev, clones[1].tdm_retrieve_dev_sync):
+        di = torch.full((300, 10), -7, dtype=torch.int32, device="cuda")
+        dl = torch.zeros((300, 10), dtype=torch.float32, device="cuda")
+        dc = torch.zeros((300,), dtype=torch.int32, device="cuda")
+        torch.cuda.synchronize()
+        fn(300, dq.data_ptr(), beam, 10, True, di.data_ptr(), dl.data_ptr(), dc.data_ptr())
+        clones[1].synchronize()
+        assert (di.cpu().numpy() == oi[:300]).all() and (bits(dl.cpu().numpy()) == bits(ol[:300])).all() and (dc.cpu().numpy() == oc[:300]).all()
+    # the shared model is frozen while clones live
+    with pytest.raises(DmgError):
+        clones[0].load_din_weights(params, rows, E, 10)
+    with pytest.raises(DmgError):
+        parent.load_din_weights(params, rows, E, 10)
+    with pytest.raises(DmgError):
+        parent.close()
+    for c in clones:
+        c.close()
+    parent.load_din_weights(params, rows, E, 10)                 # free again
+    parent.close()
