@@ -84,7 +84,7 @@ class ClockSampler:
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
     def __init__(self, device):
-        self.device, self.rows, self.proc = device, [], None
+        self.device, self.rows, self.proc, self.first = device, [], None, 0
 
     def start(self):
         try:
@@ -99,6 +99,14 @@ class ClockSampler:
         for line in self.proc.stdout:
             self.rows.append([x.strip() for x in line.split(",")])
 
+    def wait_first(self, timeout):
+        t0 = time.perf_counter()
+        while self.proc and not self.rows and time.perf_counter() - t0 < timeout:
+            time.sleep(0.01)
+
+    def mark(self):
+        self.first = max(0, len(self.rows) - 1)                   # keep the sample that straddles the start of the timed region
+
     def stop(self):
         if not self.proc:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
@@ -109,7 +117,7 @@ class ClockSampler:
         except Exception:
             self.proc.kill()
         sm, mx, reasons = [], [], set()
-        for r in self.rows:
+        for r in self.rows[self.first:]:
             try:
                 sm.append(float(r[1])); mx.append(float(r[2]))
                 for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[5:9]):
@@ -191,6 +199,11 @@ def run_reference(args):
 
 def main():
     args = parse()
+    # stdout carries the ONE JSON line and nothing else: libraries that write to fd 1 (NCCL's version banner) go to stderr
+    sys.stdout.flush()
+    json_fd = os.dup(1)
+    os.dup2(2, 1)
+    sys.stdout = os.fdopen(json_fd, "w")
     if args.impl == "reference":
         return run_reference(args)
 
@@ -281,10 +294,12 @@ def main():
             raise errs[0]
 
     # ---- value: device-resident, CUDA events on the launching streams --------------------
+    sampler = ClockSampler(local)
+    sampler.start()                                               # before the warm-up: nvidia-smi's start-up (NVML init on every GPU of
+    sampler.wait_first(3.0)                                       # the box, once per rank) must not fall into the timed region
     run_steps(step_dev, 0, W)
     barrier()
-    sampler = ClockSampler(local)
-    sampler.start()
+    sampler.mark()                                                # clocks are reported from the samples taken after this point
     l0 = sum(e.launch_count for e in engs)
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()

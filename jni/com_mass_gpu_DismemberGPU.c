@@ -43,6 +43,23 @@ JNIEXPORT void JNICALL Java_com_mass_gpu_DismemberGPU_00024_destroy(JNIEnv *env,
     dmg_destroy(H(handle));
 }
 
+/* One handle per evaluator / serving thread over ONE copy of the tables: the GPU form of model.cloneModule() sharing the
+ * weight storage (tdm/.../optim/LocalOptimizer.scala:35-40, tdm/.../evaluation/Evaluator.scala:29-37). */
+JNIEXPORT jlong JNICALL Java_com_mass_gpu_DismemberGPU_00024_cloneHandle(JNIEnv *env, jobject self, jlong handle)
+{
+    dmg_handle_t h = NULL;
+    int32_t rc = dmg_clone(H(handle), &h);
+    if (rc) { throw_status(env, H(handle), rc); return 0; }
+    return (jlong)(intptr_t)h;
+}
+
+/* 0 = strict fp32 chains, 1 = tensor-core scorer with certified cuts (same ids and logit bits). */
+JNIEXPORT void JNICALL Java_com_mass_gpu_DismemberGPU_00024_setArithmetic(JNIEnv *env, jobject self, jlong handle, jint mode)
+{
+    int32_t rc = dmg_set_arithmetic(H(handle), mode);
+    if (rc) throw_status(env, H(handle), rc);
+}
+
 /* TDMOp.initTree: arrays built from DistTree's maps (codeNodeMap, idCodeMap). */
 JNIEXPORT void JNICALL Java_com_mass_gpu_DismemberGPU_00024_loadTreeTdm(
     JNIEnv *env, jobject self, jlong handle, jint maxLevel, jintArray codes, jintArray nodeIds, jbyteArray isLeaf,
