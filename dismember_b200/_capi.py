@@ -89,6 +89,7 @@ def load_library(build_if_missing: bool = True):
         "dmg_jtm_assign_level": [vp, i32, vp, vp, i32, vp, i32, vp],
         "dmg_eval_metrics": [vp, i32, i32, vp, vp, vp, vp, vp],
         "dmg_load_deepfm_weights": [vp, i64, i32, i32, vp],
+        "dmg_load_deepfm_weights_f64": [vp, i64, i32, i32, vp],
         "dmg_shard_unique_id": [vp, i32],
         "dmg_shard_init": [vp, i32, i32, vp],
         "dmg_shard_init_din_weights": [vp, i64, i32, i32, u64],
@@ -242,13 +243,17 @@ class Engine:
         self.din_dtype, self.rows, self.E, self.T = params.dtype, rows, E, T
 
     def load_deepfm_weights(self, params: np.ndarray, rows: int, E: int, T: int):
-        """DeepFM scorer (tdm/.../model/DeepFM.scala): [emb | W1 (T+1)x(T+1)E | b1 | W2 | b2], float32."""
-        params = np.ascontiguousarray(params, np.float32).ravel()
+        """DeepFM scorer: [emb | W1 (T+1)x(T+1)E | b1 | W2 | b2].  float32 = the TDM/JTM model (tdm/.../model/DeepFM.scala),
+        float64 = OTM's DeepModel[Double] (otm/.../model/DeepFM.scala); the dtype of `params` decides."""
+        params = np.asarray(params)
+        dtype = np.dtype(np.float64 if params.dtype == np.float64 else np.float32)
+        params = np.ascontiguousarray(params, dtype).ravel()
         n = rows * E + (T + 1) * (T + 1) * E + 2 * (T + 1) + 1
         if params.size != n:
             raise DmgArgumentError(DMG_ERR_INVALID_ARG, f"compact DeepFM vector must hold {n} values, got {params.size}")
-        self._check(self.L.dmg_load_deepfm_weights(self.h, rows, E, T, _p(params)))
-        self.din_dtype, self.rows, self.E, self.T = np.dtype(np.float32), rows, E, T
+        fn = self.L.dmg_load_deepfm_weights_f64 if dtype == np.float64 else self.L.dmg_load_deepfm_weights
+        self._check(fn(self.h, rows, E, T, _p(params)))
+        self.din_dtype, self.rows, self.E, self.T = dtype, rows, E, T
 
     def init_din_weights(self, dtype, rows: int, E: int, T: int, seed: int):
         dtype = np.dtype(dtype)

@@ -9,7 +9,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libdismember_gpu.so")
-SOURCES = ["capi.cu", "dr.cu", "train.cu", "shard.cu"]
+SOURCES = ["capi.cu", "dr.cu", "train.cu", "shard.cu", "otm_deepfm.cu"]
 NVCC_FLAGS = [
     "-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
     "-fmad=false",                      # only explicit fma intrinsics fuse (dmg_math.cuh)

@@ -80,6 +80,9 @@ void dmg_shard_free(dmg_handle_t h);   // shard.cu
 int32_t dmg_deepfm_tdm_retrieve(dmg_handle_t h, int32_t B, const int32_t *item_seq, int32_t beam, int32_t topk, const int64_t *cons_off,
                                 const int32_t *cons, int32_t widen_beam, int32_t *out_items, float *out_logits, int32_t *out_counts);   // shard.cu
 int32_t dmg_deepfm_score_pairs(dmg_handle_t h, int64_t n, const int32_t *node, const int32_t *seq, float *out);                         // shard.cu
+int32_t dmg_deepfm64_score_pairs(dmg_handle_t h, int64_t n, const int32_t *node, const int32_t *seq, double *out);                      // otm_deepfm.cu
+int32_t dmg_deepfm64_otm_run(dmg_handle_t h, int32_t B, const int32_t *leaf_seq, int32_t beam, int topk_mode, int32_t topk, int32_t *out_ids,
+                             double *out_scores, int32_t *out_counts, int32_t *lvl_ids, double *lvl_scores, int32_t *lvl_counts);       // otm_deepfm.cu
 
 DMG_API int32_t dmg_destroy(dmg_handle_t h)
 {
@@ -693,7 +696,7 @@ DMG_API int32_t dmg_tdm_retrieve(dmg_handle_t h, int32_t B, const int32_t *item_
                                  int32_t use_mask, const int64_t *consumed_off, const int32_t *consumed_items,
                                  int32_t widen_beam, int32_t *out_items, float *out_logits, int32_t *out_counts)
 {
-    if (h && h->din.loaded && h->din.kind == 1) {                // DeepFM scorer: level-synchronous path (shard.cu)
+    if (h && h->din.loaded && h->din.kind == 1 && h->din.dtype == DMG_F32) {   // DeepFM scorer: level-synchronous path (shard.cu)
         if (!item_seq || !out_items || !out_logits || !out_counts) return fail(h, DMG_ERR_INVALID_ARG, "null host pointer");
         return dmg_deepfm_tdm_retrieve(h, B, item_seq, beam, topk, consumed_off, consumed_items, widen_beam, out_items, out_logits, out_counts);
     }
@@ -759,13 +762,16 @@ static int32_t otm_run(dmg_handle_t h, int32_t B, const int32_t *leaf_seq, int32
 {
     if (!h) return DMG_ERR_INVALID_ARG;
     if (!h->tree.loaded || !h->din.loaded) return fail(h, DMG_ERR_STATE, "tree and DIN weights must be loaded first");
-    if (h->din.sharded) return fail(h, DMG_ERR_STATE, "the node table is sharded (dmg_shard_init): use the dmg_shard_* entry points");
+    const bool deepfm64 = h->din.kind == 1 && h->din.dtype == DMG_F64;      // DeepModel[Double] = DeepFM: level-synchronous path (otm_deepfm.cu)
+    if (h->din.sharded && !deepfm64) return fail(h, DMG_ERR_STATE, "the node table is sharded (dmg_shard_init): use the dmg_shard_* entry points");
     if (!h->tree.complete) return fail(h, DMG_ERR_STATE, "OTM needs a complete tree (dmg_load_tree_complete)");
     if (h->din.dtype != DMG_F64) return fail(h, DMG_ERR_STATE, "OTM scorer is DeepModel[Double]: load DMG_F64 weights");
     if (B <= 0 || beam <= 0 || (mode == MODE_OTM_TOPK && topk <= 0) || !leaf_seq || !out_ids || !out_scores || !out_counts)
         return fail(h, DMG_ERR_INVALID_ARG, "bad arguments");
     if (h->din.rows < h->tree.n_codes)
         return fail(h, DMG_ERR_INVALID_ARG, "node table has %lld rows, tree needs %lld", (long long)h->din.rows, (long long)h->tree.n_codes);
+    if (deepfm64)                                                 // no mask input (otm/.../model/DeepFM.scala:17-18)
+        return dmg_deepfm64_otm_run(h, B, leaf_seq, beam, mode == MODE_OTM_TOPK, topk, out_ids, out_scores, out_counts, lvl_ids, lvl_scores, lvl_counts);
     DMG_CUDA(h, cudaSetDevice(h->device));
     const DinDev &d = h->din;
     const TreeDev &t = h->tree;
@@ -868,6 +874,7 @@ DMG_API int32_t dmg_score_pairs(dmg_handle_t h, int64_t n, const int32_t *node, 
     if (!h->din.loaded) return fail(h, DMG_ERR_STATE, "DIN weights must be loaded first");
     if (h->din.kind == 1) {                                      // DeepFM takes no mask input (DeepFM.scala:14-15)
         if (n < 0 || (n > 0 && (!node || !seq || !out))) return fail(h, DMG_ERR_INVALID_ARG, "bad arguments");
+        if (h->din.dtype == DMG_F64) return dmg_deepfm64_score_pairs(h, n, node, seq, (double *)out);   // otm_deepfm.cu
         return dmg_deepfm_score_pairs(h, n, node, seq, (float *)out);
     }
     if (h->din.sharded) return fail(h, DMG_ERR_STATE, "the node table is sharded (dmg_shard_init): use the dmg_shard_* entry points");

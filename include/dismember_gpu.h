@@ -267,6 +267,13 @@ DMG_API int32_t dmg_eval_metrics(dmg_handle_t h, int32_t B, int32_t topk, const 
  * dmg_shard_init(world > 1) only this rank's rows are uploaded and dmg_shard_tdm_retrieve uses it. */
 DMG_API int32_t dmg_load_deepfm_weights(dmg_handle_t h, int64_t rows, int32_t E, int32_t T,
                                         const float *params);
+/* OTM's DeepModel[Double] = DeepFM (otm/src/main/scala/com/mass/otm/model/DeepFM.scala:12-48: the same
+ * graph for Double), same parameter layout as doubles.  Afterwards dmg_otm_beam_search,
+ * dmg_otm_beam_search_levels, dmg_otm_retrieve and dmg_score_pairs score with it (no mask input:
+ * use_mask / mask arguments are ignored), level-synchronously like CandidateSearcher.batchBeamSearch
+ * (otm/.../model/CandidateSearcher.scala:15-56); bit-identical to the oracle's restatement. */
+DMG_API int32_t dmg_load_deepfm_weights_f64(dmg_handle_t h, int64_t rows, int32_t E, int32_t T,
+                                            const double *params);
 
 /* ---- node table sharded across the GPUs of one box ------------------------------------ */
 /* The reference has no multi-device path: model replicas are per-thread clones

@@ -359,7 +359,51 @@ int orc_tdm_recommend(const orc_tree *t, const orc_tdm_model *m, const int32_t *
 }
 
 /* ------------------------------------------------------------------ OTM -- */
-struct orc_otm_model { orc_din_f64 din; };
+/* OTM's DeepFM (otm/src/main/scala/com/mass/otm/model/DeepFM.scala:12-48) is the TDM graph instantiated for Double:
+ * same features, FM (scalann/.../nn/FM.scala:14-44), Linear((T+1)E, T+1) -> ReLU -> Linear(T+1, 1), Add; no mask input. */
+typedef struct { const double *w1, *b1, *w2, *b2; } orc_dfm_f64;
+struct orc_otm_model { orc_din_f64 din; int deepfm; orc_dfm_f64 dfm; };
+
+static double orc_deepfm_row_f64(const orc_otm_model *m, const double *q, const double *K, double *scratch)
+{
+    const int E = m->din.E, T = m->din.T, F = T + 1;
+    double *buf = scratch;                                          /* E */
+    for (int k = 0; k < E; k++) buf[k] = 0.0;
+    for (int k = 0; k < E; k++) buf[k] = buf[k] + q[k];             /* vAdd, feature 0 = the item */
+    for (int j = 0; j < T; j++)
+        for (int k = 0; k < E; k++) buf[k] = buf[k] + K[(size_t)j * E + k];
+    double sum_square = 0.0, square_sum = 0.0;
+    for (int k = 0; k < E; k++) sum_square = fma(buf[k], buf[k], sum_square);
+    for (int k = 0; k < E; k++) square_sum = fma(q[k], q[k], square_sum);
+    for (int k = 0; k < T * E; k++) square_sum = fma(K[k], K[k], square_sum);
+    const double fm = (sum_square - square_sum) / 2.0;
+    double dnn = 0.0;
+    for (int o = 0; o < F; o++) {
+        const double *w = m->dfm.w1 + (size_t)o * F * E;
+        double acc = 0.0;
+        for (int k = 0; k < E; k++) acc = fma(q[k], w[k], acc);
+        for (int k = 0; k < T * E; k++) acc = fma(K[k], w[E + k], acc);
+        double h = acc + m->dfm.b1[o];
+        h = h > 0.0 ? h : (h != h ? h : 0.0);                       /* ReLU.scala:30-44 */
+        dnn = fma(h, m->dfm.w2[o], dnn);
+    }
+    dnn = dnn + m->dfm.b2[0];
+    return fm + dnn;
+}
+
+/* params = [emb rows*E | W1 (T+1) x (T+1)E | b1 T+1 | W2 T+1 | b2 1] (Graph.scala:37-48, topological order) */
+orc_otm_model *orc_otm_deepfm_create(int64_t rows, int E, int T, const double *params)
+{
+    orc_otm_model *m = (orc_otm_model *)calloc(1, sizeof(*m));
+    const int F = T + 1;
+    m->deepfm = 1;
+    m->din.rows = rows; m->din.E = E; m->din.T = T; m->din.emb = params;      /* gather + index checks reuse the DIN struct */
+    m->dfm.w1 = params + rows * E;
+    m->dfm.b1 = m->dfm.w1 + (int64_t)F * F * E;
+    m->dfm.w2 = m->dfm.b1 + F;
+    m->dfm.b2 = m->dfm.w2 + F;
+    return m;
+}
 
 orc_otm_model *orc_otm_model_create(int64_t rows, int E, int T, const double *params)
 {
@@ -369,11 +413,27 @@ orc_otm_model *orc_otm_model_create(int64_t rows, int E, int T, const double *pa
     if (orc_din_init_f64(&m->din, rows, E, T, emb, watt, w1, b1, w2, b2)) { free(m); return NULL; }
     return m;
 }
-void orc_otm_model_destroy(orc_otm_model *m) { if (m) { orc_din_free_f64(&m->din); free(m); } }
+void orc_otm_model_destroy(orc_otm_model *m) { if (m) { if (!m->deepfm) orc_din_free_f64(&m->din); free(m); } }
 
 int orc_din_forward_f64_api(const orc_otm_model *m, int64_t n, const int32_t *node, const int32_t *seq,
                             const int32_t *mask_flat, int64_t n_mask, double *out)
 {
+    if (m->deepfm) {                                                 /* no mask input (DeepFM.scala:17-18) */
+        const int E = m->din.E, T = m->din.T;
+        double *K = (double *)malloc(sizeof(double) * T * E), *q = (double *)malloc(sizeof(double) * E);
+        double *scratch = (double *)malloc(sizeof(double) * E);
+        int rc = 0;
+        for (int64_t r = 0; r < n; r++) {
+            if (orc_gather_history_f64(&m->din, seq + r * T, K)) { rc = -1; break; }
+            int32_t c = node[r];
+            if (c == -1) { for (int k = 0; k < E; k++) q[k] = 0.0; }
+            else if (c >= 0 && (int64_t)c < m->din.rows) memcpy(q, m->din.emb + (size_t)c * E, sizeof(double) * E);
+            else { rc = -1; break; }
+            out[r] = orc_deepfm_row_f64(m, q, K, scratch);
+        }
+        free(K); free(q); free(scratch);
+        return rc;
+    }
     return orc_din_forward_f64(&m->din, n, node, seq, mask_flat, n_mask, out);
 }
 
@@ -415,7 +475,8 @@ int orc_otm_beam_search(const orc_otm_model *m, const int32_t *seq, int leaf_lev
         for (int i = 0; i < n; i++) {
             if (nxt[i] < 0 || nxt[i] >= d->rows) { rc = -2; goto done; }
             ids[i] = nxt[i];
-            sc[i] = orc_din_row_f64(d, d->emb + (size_t)nxt[i] * E, K, masked, scratch);
+            sc[i] = m->deepfm ? orc_deepfm_row_f64(m, d->emb + (size_t)nxt[i] * E, K, scratch)
+                              : orc_din_row_f64(d, d->emb + (size_t)nxt[i] * E, K, masked, scratch);
         }
     }
     memcpy(out_ids, ids, sizeof(int32_t) * n);

@@ -26,6 +26,7 @@ orc_tdm_model *orc_tdm_model_create(int64_t rows, int E, int T, const float *par
 orc_tdm_model *orc_tdm_deepfm_create(int64_t rows, int E, int T, const float *params);
 void orc_tdm_model_destroy(orc_tdm_model *m);
 orc_otm_model *orc_otm_model_create(int64_t rows, int E, int T, const double *params);
+orc_otm_model *orc_otm_deepfm_create(int64_t rows, int E, int T, const double *params);   /* otm/.../model/DeepFM.scala:12-48 */
 void orc_otm_model_destroy(orc_otm_model *m);
 
 int orc_din_forward_f32_api(const orc_tdm_model *m, int64_t n, const int32_t *node, const int32_t *seq,

@@ -53,6 +53,8 @@ def lib():
     L.orc_tdm_model_destroy.argtypes = [vp]
     L.orc_otm_model_create.restype = vp
     L.orc_otm_model_create.argtypes = [C.c_int64, C.c_int, C.c_int, f64p]
+    L.orc_otm_deepfm_create.restype = vp
+    L.orc_otm_deepfm_create.argtypes = [C.c_int64, C.c_int, C.c_int, f64p]
     L.orc_otm_model_destroy.argtypes = [vp]
     L.orc_din_forward_f32_api.argtypes = [vp, C.c_int64, i32p, i32p, vp, C.c_int64, f32p]
     L.orc_din_forward_f64_api.argtypes = [vp, C.c_int64, i32p, i32p, vp, C.c_int64, f64p]
@@ -195,11 +197,15 @@ class TdmModel:
 class OtmModel:
     """DIN(Double) from the compact parameter vector."""
 
-    def __init__(self, params, rows, E, T):
+    def __init__(self, params, rows, E, T, deepfm=False):
         self.params = np.ascontiguousarray(params, np.float64)
-        assert self.params.size == rows * E + E * E + 2 * E * E + 2 * E + 1, "bad DIN parameter count"
         self.rows, self.E, self.T = int(rows), int(E), int(T)
-        self.h = lib().orc_otm_model_create(self.rows, self.E, self.T, self.params)
+        if deepfm:                                   # otm/.../model/DeepFM.scala: [emb | W1 (T+1)x(T+1)E | b1 | W2 | b2]
+            assert self.params.size == rows * E + (T + 1) * (T + 1) * E + 2 * (T + 1) + 1, "bad DeepFM parameter count"
+            self.h = lib().orc_otm_deepfm_create(self.rows, self.E, self.T, self.params)
+        else:
+            assert self.params.size == rows * E + E * E + 2 * E * E + 2 * E + 1, "bad DIN parameter count"
+            self.h = lib().orc_otm_model_create(self.rows, self.E, self.T, self.params)
 
     def forward(self, node, seq, mask_flat=None):
         node = _ci32(node).ravel()

@@ -66,3 +66,70 @@ def test_deepfm_score_pairs_is_model_forward(orc):
     with pytest.raises(DmgIndexError):
         e.score_pairs(np.array([rows], np.int32), seq[:1])
     e.close()
+
+
+# ------------------------------------------------------------------ OTM: DeepModel[Double] = DeepFM
+def deepfm_params64(rows, E, T, seed):
+    rng = np.random.Generator(np.random.PCG64(seed))
+    F = T + 1
+    return np.concatenate([rng.normal(0.0, 0.3, rows * E), rng.normal(0.0, 0.1, F * F * E), rng.normal(0.0, 0.05, F),
+                           rng.normal(0.0, 0.3, F), [0.02]])
+
+
+@pytest.mark.parametrize("E,leaf_level,beam", [(16, 11, 20), (64, 12, 200), (24, 9, 7), (8, 5, 50)])
+def test_otm_deepfm_matches_oracle(orc, E, leaf_level, beam):
+    """otm/.../model/DeepFM.scala:12-48 behind dmg_otm_*: batchBeamSearch dump, per-level dump and recommend, fp64 bits."""
+    T, topk, B = 10, 10, 19
+    rows = (1 << (leaf_level + 1)) - 1
+    n_leaf = 1 << leaf_level
+    rng = np.random.default_rng(4)
+    n_items = int(n_leaf * 0.8)
+    leaf_ids = np.sort(rng.choice(n_leaf, n_items, replace=False)).astype(np.int32) + (n_leaf - 1)
+    items = np.arange(1, n_items + 1, dtype=np.int32)
+    leaf_item = np.full(n_leaf, -1, np.int32)
+    leaf_item[leaf_ids - (n_leaf - 1)] = items
+    params = deepfm_params64(rows, E, T, seed=5)
+    seqs = leaf_ids[rng.integers(0, n_items, (B, T))].astype(np.int32)
+    seqs[rng.random((B, T)) < 0.3] = -1
+    seqs[0] = -1                                              # a user with an empty history
+    e = new_engine()
+    e.load_tree_complete(leaf_level, items, leaf_ids)
+    e.load_deepfm_weights(params, rows, E, T)
+    model = orc.OtmModel(params, rows, E, T, deepfm=True)
+    ids, sc, cnt = e.otm_beam_search(seqs, beam)
+    gi, gs, gc = e.otm_retrieve(seqs, beam, topk)
+    for u in range(B):
+        oi, os_ = model.beam_search(seqs[u], leaf_level, beam)
+        assert cnt[u] == len(oi) and (ids[u, :cnt[u]] == oi).all() and (sc[u, :cnt[u]].view(np.uint64) == os_.view(np.uint64)).all()
+        assert (ids[u, cnt[u]:] == -1).all()
+        ri, rs, _ = model.recommend(seqs[u], leaf_level, topk, beam, leaf_item)
+        assert gc[u] == len(ri) and (gi[u, :gc[u]] == ri).all() and (gs[u, :gc[u]].view(np.uint64) == rs.view(np.uint64)).all()
+        assert (gi[u, gc[u]:] == -1).all()
+    # per-level candidates (OTM training reads them): the last level equals the dump
+    li, ls, lc = e.otm_beam_search_levels(seqs, beam, leaf_level)
+    if li.shape[1] > 0:
+        assert (li[:, -1, :] == ids).all() and (ls[:, -1, :].view(np.uint64) == sc.view(np.uint64)).all() and (lc[:, -1] == cnt).all()
+    e.close()
+
+
+def test_otm_deepfm_score_pairs_is_model_forward(orc):
+    rows, E, T = 1023, 32, 10
+    params = deepfm_params64(rows, E, T, seed=9)
+    rng = np.random.default_rng(1)
+    n = 1000
+    node = rng.integers(-1, rows, n).astype(np.int32)
+    seq = rng.integers(-1, rows, (n, T)).astype(np.int32)
+    e = new_engine()
+    e.load_tree_complete(9, np.arange(1, 513, dtype=np.int32), np.arange(511, 1023, dtype=np.int32))
+    e.load_deepfm_weights(params, rows, E, T)
+    got = e.score_pairs(node, seq)
+    want = orc.OtmModel(params, rows, E, T, deepfm=True).forward(node, seq)
+    assert got.dtype == np.float64 and (got.view(np.uint64) == want.view(np.uint64)).all()
+    from dismember_b200._capi import DmgError, DmgIndexError
+    with pytest.raises(DmgIndexError):
+        e.score_pairs(np.array([rows], np.int32), seq[:1])
+    with pytest.raises(DmgIndexError):
+        e.otm_retrieve(np.full((1, T), rows, np.int32), 20, 10)
+    with pytest.raises(DmgError):                             # the TDM/JTM scorer is Module[Float]
+        e.tdm_retrieve(np.zeros((1, T), np.int32), 20, 10)
+    e.close()

@@ -114,3 +114,40 @@ def test_deepfm_oracle_against_independent_float64(orc):
         assert abs(out[r] - ref) <= 2e-6 * max(1.0, abs(ref))
     with pytest.raises(IndexError):
         m.forward(np.array([rows], np.int32), seq[:1])
+
+
+def test_otm_deepfm_oracle_against_independent_float64(orc):
+    """OTM's DeepFM (otm/.../model/DeepFM.scala:12-48: the same graph for Double) vs a numpy evaluation of the layer
+    definitions (different summation order: 1e-12), and its beam search against a search written with numpy sorts."""
+    leaf_level, E, T = 6, 8, 4
+    rows, F = (1 << (leaf_level + 1)) - 1, T + 1
+    rng = np.random.default_rng(3)
+    params = rng.normal(0, 0.3, rows * E + F * F * E + 2 * F + 1)
+    m = orc.OtmModel(params, rows, E, T, deepfm=True)
+    emb = params[:rows * E].reshape(rows, E)
+    w1 = params[rows * E:rows * E + F * F * E].reshape(F, F * E)
+    b1 = params[rows * E + F * F * E:rows * E + F * F * E + F]
+    w2 = params[rows * E + F * F * E + F:rows * E + F * F * E + 2 * F]
+    b2 = params[-1]
+    row = lambda c: np.zeros(E) if c < 0 else emb[c]
+
+    def ref(c, s):
+        Fm = np.stack([row(c)] + [row(x) for x in s])
+        return (np.sum(Fm.sum(0) ** 2) - np.sum(Fm ** 2)) / 2 + np.maximum(w1 @ Fm.ravel() + b1, 0) @ w2 + b2
+    node = np.array([5, 7, -1, rows - 1], np.int32)
+    seq = np.array([[70, 80, -1, 90], [64, 64, 64, 64], [100, 101, 102, 103], [-1, -1, -1, -1]], np.int32)
+    out = m.forward(node, seq)
+    for r in range(len(node)):
+        assert abs(out[r] - ref(node[r], seq[r])) <= 1e-12 * max(1.0, abs(ref(node[r], seq[r])))
+    # CandidateSearcher.beamSearch: level floor(log2 beam) whole, then stable top-beam and both children per level
+    beam, s = 5, seq[0]
+    ids, sc = m.beam_search(s, leaf_level, beam)
+    cur = list(range(3, 7))
+    scores = None
+    for level in range(2, leaf_level):
+        if scores is not None:
+            order = sorted(range(len(cur)), key=lambda i: (-scores[i], i))[:beam]
+            cur = [cur[i] for i in order]
+        cur = [c for p in cur for c in (2 * p + 1, 2 * p + 2)]
+        scores = [out_ for out_ in m.forward(np.array(cur, np.int32), np.tile(s, (len(cur), 1)))]
+    assert list(ids) == cur and (sc == np.array(scores)).all()
