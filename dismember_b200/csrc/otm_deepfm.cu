@@ -88,6 +88,104 @@ __global__ void __launch_bounds__(128) dfm64_rows_kernel(const double *__restric
     }
 }
 
+// The same rows when every group is a USER of the search: its n candidate rows share one history, so the history tile is
+// staged once per tile and only the item rows differ.  W1 sits in shared memory (row stride padded by one double: the
+// T+2 chains of a warp read T+2 different banks), thread (chain c, row group rg) advances chain c of R rows together:
+// one weight and one history load feed R independent fma chains (each still its own sequential-k chain: same bits).
+// Work item = (user, tile of NG*R rows), persistent CTAs, 2 per SM.
+template <int R>
+__global__ void __launch_bounds__(128, 2) dfm64_user_rows_kernel(const double *__restrict__ emb, const double *__restrict__ dense, int E, int T,
+                                                                 int B, int n, const int32_t *__restrict__ node, int64_t node_stride,
+                                                                 const int32_t *__restrict__ hist, double *__restrict__ out)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int F = T + 1, NC = F + 1, n_in = F * E, WS = n_in + 1;
+    const int NG = 128 / NC, TILE = NG * R;
+    double *sW = reinterpret_cast<double *>(smem_raw);   // F x WS
+    double *sB1 = sW + (size_t)F * WS;                   // F
+    double *sW2 = sB1 + F;                               // F
+    double *sK = sW2 + F;                                // T x E
+    double *sX = sK + (size_t)T * E;                     // TILE x E (item rows, then the FM buffers)
+    double *sH = sX + (size_t)TILE * E;                  // TILE x NC: hidden units, then the square sum
+    const double *w1 = dense, *b1 = w1 + (size_t)F * n_in, *w2 = b1 + F, *b2 = w2 + F;
+    const int tid = threadIdx.x;
+    for (int i = tid; i < F * n_in; i += 128) sW[(i / n_in) * WS + i % n_in] = w1[i];
+    for (int i = tid; i < F; i += 128) { sB1[i] = b1[i]; sW2[i] = w2[i]; }
+    const double b2v = __ldg(b2);
+    const int tiles = (n + TILE - 1) / TILE;
+    const int c = tid % NC, rg = tid / NC;
+    int staged_user = -1;
+    for (int64_t item = blockIdx.x; item < (int64_t)B * tiles; item += gridDim.x) {
+        const int user = (int)(item / tiles), r0 = (int)(item % tiles) * TILE;
+        const int nr = n - r0 < TILE ? n - r0 : TILE;
+        __syncthreads();                                 // the previous item's sX / sH are free (and sW is complete)
+        if (user != staged_user) {
+            for (int i = tid; i < T * E; i += 128) {
+                const int32_t hc = hist[(size_t)user * T + i / E];
+                sK[i] = hc < 0 ? 0.0 : emb[(size_t)hc * E + i % E];
+            }
+            staged_user = user;
+        }
+        for (int i = tid; i < nr * E; i += 128) {
+            const int32_t nc = node[(size_t)user * node_stride + r0 + i / E];
+            sX[i] = nc < 0 ? 0.0 : emb[(size_t)nc * E + i % E];
+        }
+        __syncthreads();
+        if (rg < NG) {
+            double acc[R];
+            const double *x[R];
+#pragma unroll
+            for (int i = 0; i < R; i++) { acc[i] = 0.0; x[i] = sX + (size_t)(rg * R + i < nr ? rg * R + i : 0) * E; }
+            if (c < F) {
+                const double *w = sW + (size_t)c * WS;
+                for (int k = 0; k < E; k++) {
+                    const double wk = w[k];
+#pragma unroll
+                    for (int i = 0; i < R; i++) acc[i] = fma_(x[i][k], wk, acc[i]);
+                }
+                for (int k = 0; k < T * E; k++) {
+                    const double wk = w[E + k], kk = sK[k];
+#pragma unroll
+                    for (int i = 0; i < R; i++) acc[i] = fma_(kk, wk, acc[i]);
+                }
+                const double bc = sB1[c];
+#pragma unroll
+                for (int i = 0; i < R; i++) acc[i] = relu_(add_(acc[i], bc));
+            } else {
+                for (int k = 0; k < E; k++) {
+#pragma unroll
+                    for (int i = 0; i < R; i++) acc[i] = fma_(x[i][k], x[i][k], acc[i]);
+                }
+                for (int k = 0; k < T * E; k++) {
+                    const double kk = sK[k];
+#pragma unroll
+                    for (int i = 0; i < R; i++) acc[i] = fma_(kk, kk, acc[i]);
+                }
+            }
+#pragma unroll
+            for (int i = 0; i < R; i++)
+                if (rg * R + i < nr) sH[(rg * R + i) * NC + c] = acc[i];
+        }
+        __syncthreads();
+        for (int i = tid; i < nr * E; i += 128) {        // FM buffer of (row, k): vAdd from zero, item first, then the history rows
+            const int k = i % E;
+            double bsum = add_(0.0, sX[i]);
+            for (int j = 0; j < T; j++) bsum = add_(bsum, sK[j * E + k]);
+            sX[i] = bsum;
+        }
+        __syncthreads();
+        if (tid < nr) {
+            const double *bb = sX + (size_t)tid * E, *hrow = sH + tid * NC;
+            double sum_square = 0.0;
+            for (int k = 0; k < E; k++) sum_square = fma_(bb[k], bb[k], sum_square);
+            const double fm = __ddiv_rn(sub_(sum_square, hrow[F]), 2.0);
+            double dnn = 0.0;
+            for (int o = 0; o < F; o++) dnn = fma_(hrow[o], sW2[o], dnn);
+            out[(size_t)user * node_stride + r0 + tid] = add_(fm, add_(dnn, b2v));
+        }
+    }
+}
+
 // OTMTree.initializeBeam: all nodes of the start level, score 0
 __global__ void otm_dfm_init_kernel(int B, int n0, int width, int32_t start, int32_t *__restrict__ ids, double *__restrict__ sc)
 {
@@ -206,6 +304,24 @@ int32_t launch_rows(dmg_handle_t h, int64_t n_rows, const int32_t *node, int64_t
     return DMG_OK;
 }
 
+// the n candidate rows of each of B users (node[user * node_stride + i], one history per user)
+int32_t launch_user_rows(dmg_handle_t h, int B, int n, const int32_t *node, int64_t node_stride, const int32_t *hist, double *out)
+{
+    const DinDev &d = h->din;
+    constexpr int R = 4;
+    const int F = d.T + 1, NC = F + 1, NG = 128 / NC, TILE = NG * R;
+    const size_t smem = ((size_t)F * (F * d.E + 1) + 2 * F + (size_t)d.T * d.E + (size_t)TILE * d.E + (size_t)TILE * NC) * sizeof(double);
+    if (NG < 1 || 2 * (smem + 1024) > h->smem_per_sm)             // large E x T: the generic kernel (weights through L1)
+        return launch_rows(h, (int64_t)B * n, node, node_stride, n, hist, out);
+    DMG_CUDA(h, cudaFuncSetAttribute(dfm64_user_rows_kernel<R>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const int64_t items = (int64_t)B * ((n + TILE - 1) / TILE);
+    const int grid = (int)std::min<int64_t>(items, (int64_t)h->sm_count * 2);      // persistent, two CTAs per SM
+    dfm64_user_rows_kernel<R><<<grid, 128, smem, h->stream>>>(d.emb<double>(), d.tail<double>(), d.E, d.T, B, n, node, node_stride, hist, out);
+    h->launches += 1;
+    DMG_CUDA(h, cudaGetLastError());
+    return DMG_OK;
+}
+
 int lower_log2(int n) { int l = 0; while ((2 << l) <= n) l++; return l; }
 
 }  // namespace
@@ -290,7 +406,7 @@ int32_t dmg_deepfm64_otm_run(dmg_handle_t h, int32_t B, const int32_t *leaf_seq,
             otm_dfm_expand_kernel<<<B, 256, (size_t)n * 8, h->stream>>>(n, nb, select, width, d_ids, d_sc, d_nxt);
             h->launches += 1;
             n = 2 * nb;
-            rc = launch_rows(h, (int64_t)B * n, d_nxt, width, n, d_seq, d_sc);
+            rc = launch_user_rows(h, B, n, d_nxt, width, d_seq, d_sc);
             std::swap(d_ids, d_nxt);
             if (rc == DMG_OK && d_li) {
                 const int64_t tw = (int64_t)B * width;

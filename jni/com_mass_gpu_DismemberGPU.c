@@ -293,6 +293,16 @@ JNIEXPORT void JNICALL Java_com_mass_gpu_DismemberGPU_00024_loadDeepFmWeightsFlo
 }
 
 /* Metrics.computeMetrics per user; out: batch x 3 (precision, recall, ndcg) */
+/* OTM with deepModel = "DeepFM": DeepModel[Double] (otm/.../model/DeepFM.scala:12-48) */
+JNIEXPORT void JNICALL Java_com_mass_gpu_DismemberGPU_00024_loadDeepFmWeightsDouble(
+    JNIEnv *env, jobject self, jlong handle, jlong rows, jint embedSize, jint seqLen, jdoubleArray params)
+{
+    jdouble *p = PIN(params);
+    int32_t rc = dmg_load_deepfm_weights_f64(H(handle), rows, embedSize, seqLen, p);
+    UNPIN(params, p, JNI_ABORT);
+    if (rc) throw_status(env, H(handle), rc);
+}
+
 JNIEXPORT void JNICALL Java_com_mass_gpu_DismemberGPU_00024_evalMetrics(
     JNIEnv *env, jobject self, jlong handle, jint batch, jint topk, jintArray recItems, jintArray recCounts, jlongArray labelOff,
     jintArray labels, jdoubleArray out)

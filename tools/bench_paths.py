@@ -40,10 +40,46 @@ def emit(**kw):
     print(json.dumps(kw), flush=True)
 
 
+def otm_deepfm_section(a, E, T, threads):
+    """3c. OTM retrieval with DeepModel[Double] = DeepFM: level-synchronous path of otm_deepfm.cu"""
+    from dismember_b200 import Engine, synth
+    from oracle import oracle as orc
+    n_items = 100_000 if a.quick else 1_000_000
+    items, leaf_ids, leaf_level = synth.otm_mapping(n_items, seed=42)
+    rows_tab = (1 << (leaf_level + 1)) - 1
+    F = T + 1
+    rng = np.random.Generator(np.random.PCG64(13))
+    dparams = np.concatenate([rng.normal(0, 0.05, rows_tab * E), rng.normal(0, 0.05, F * F * E), np.zeros(F),
+                              rng.normal(0, 0.3, F), [0.0]])
+    eng = Engine(0)
+    eng.load_tree_complete(leaf_level, items, leaf_ids)
+    eng.load_deepfm_weights(dparams, rows_tab, E, T)
+    B = 256
+    lseq = leaf_ids[rng.integers(0, n_items, (B, T))].astype(np.int32)
+    lseq[:, :3] = -1
+    dt = timeit(lambda: eng.otm_retrieve(lseq, 200, 10), warm=1, reps=3)
+    rows_u = 256 + 400 * (leaf_level - 8)
+    flop_u = rows_u * 2 * (F + 1) * F * E
+    emit(path="otm_retrieve with the DeepFM scorer (fp64, level-synchronous)", items=n_items, levels=leaf_level, batch=B, ms=dt * 1e3,
+         users_per_s=B / dt, roofline={"bound": "fp64 FMA pipe", "algorithmic_flop_per_user": flop_u,
+                                       "achieved_tflops": flop_u * B / dt / 1e12})
+    leaf_item = np.full(1 << leaf_level, -1, np.int32)
+    leaf_item[leaf_ids - ((1 << leaf_level) - 1)] = items
+    om = orc.OtmModel(dparams, rows_tab, E, T, deepfm=True)
+    t0 = time.perf_counter()
+    oi, osc, oc = om.retrieve_batch(lseq[:2 * threads], leaf_level, 200, 10, leaf_item, n_threads=threads)
+    cdt = time.perf_counter() - t0
+    gi, gs, gc = eng.otm_retrieve(lseq[:2 * threads], 200, 10)
+    emit(path="otm_retrieve DeepFM cpu_baseline", kind="port", cores=threads, users_per_s=2 * threads / cdt,
+         parity={"ids_identical": bool((gi == oi).all()), "scores_bit_identical": bool((gs.view(np.uint64) == osc.view(np.uint64)).all())})
+    eng.close()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--quick", action="store_true")
     ap.add_argument("--train-items", type=int, default=10_000_000)
+    ap.add_argument("--only", default=None, choices=[None, "otm_deepfm"], help="run one section only")
     a = ap.parse_args()
     from dismember_b200 import Engine, synth
     from oracle import oracle as orc
@@ -51,6 +87,8 @@ def main():
     hbm, hbm_src = peaks()
     threads = os.cpu_count() or 1
     E, T = 64, 10
+    if a.only == "otm_deepfm":
+        return otm_deepfm_section(a, E, T, threads)
 
     # ---- 1. training step: fused DIN fwd/bwd + BCE + scatter-add, dense Adam -------------------
     for n_items in ([100_000] if a.quick else [1_000_000, a.train_items]):
@@ -185,6 +223,8 @@ def main():
     emit(path="otm_retrieve cpu_baseline", kind="port", cores=threads, users_per_s=2 * threads / cdt,
          parity={"ids_identical": bool((gi == oi).all()), "scores_bit_identical": bool((gs.view(np.uint64) == osc.view(np.uint64)).all())})
     eng.close()
+
+    otm_deepfm_section(a, E, T, threads)
 
     # ---- 3b. BASELINE configs[2]: OTM at 10 M items, fp64 -- one training step (LocalOptimizer per-level step: rows = users x 2 beam,
     #          otm/.../optim/LocalOptimizer.scala:55-109) and retrieval on the same 17 GB table ---------------------------------------
