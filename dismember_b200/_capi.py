@@ -169,6 +169,7 @@ class Engine:
         e = Engine.__new__(Engine)
         e.L, e.h, e.device = self.L, h, self.device
         e.din_dtype, e.E, e.T, e.rows = self.din_dtype, self.E, self.T, self.rows
+        e._deepfm = getattr(self, "_deepfm", False)
         e._parent = self                                            # keeps the owner alive
         return e
 
@@ -241,6 +242,7 @@ class Engine:
             raise DmgArgumentError(DMG_ERR_INVALID_ARG, f"compact DIN vector must hold {n} values, got {params.size}")
         self._check(self.L.dmg_load_din_weights(self.h, dt, rows, E, T, _p(params)))
         self.din_dtype, self.rows, self.E, self.T = params.dtype, rows, E, T
+        self._deepfm = False
 
     def load_deepfm_weights(self, params: np.ndarray, rows: int, E: int, T: int):
         """DeepFM scorer: [emb | W1 (T+1)x(T+1)E | b1 | W2 | b2].  float32 = the TDM/JTM model (tdm/.../model/DeepFM.scala),
@@ -254,15 +256,20 @@ class Engine:
         fn = self.L.dmg_load_deepfm_weights_f64 if dtype == np.float64 else self.L.dmg_load_deepfm_weights
         self._check(fn(self.h, rows, E, T, _p(params)))
         self.din_dtype, self.rows, self.E, self.T = dtype, rows, E, T
+        self._deepfm = True
 
     def init_din_weights(self, dtype, rows: int, E: int, T: int, seed: int):
         dtype = np.dtype(dtype)
         dt = DMG_F32 if dtype == np.float32 else DMG_F64
         self._check(self.L.dmg_init_din_weights(self.h, dt, rows, E, T, seed))
         self.din_dtype, self.rows, self.E, self.T = dtype, rows, E, T
+        self._deepfm = False
 
     def download_din_weights(self) -> np.ndarray:
+        """Module.parameters() back from the device (DIN layout; a DeepFM model returns its own compact vector)."""
         n = self.rows * self.E + 3 * self.E * self.E + 2 * self.E + 1
+        if getattr(self, "_deepfm", False):
+            n = self.rows * self.E + (self.T + 1) * (self.T + 1) * self.E + 2 * (self.T + 1) + 1
         out = np.empty(n, self.din_dtype)
         self._check(self.L.dmg_download_din_weights(self.h, _p(out), n))
         return out
