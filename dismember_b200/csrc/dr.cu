@@ -397,7 +397,15 @@ static int32_t dr_beam_enqueue(dmg_handle_t h, int32_t B, const int32_t *seq_hos
     check_index_kernel<<<(unsigned)(((int64_t)B * T + 255) / 256), 256, 0, h->stream>>>(
         d_seq, (int64_t)B * T, for_rerank ? (int64_t)d.num_item : emb_rows, h->d_flags);
     h->launches += 1;
-    const int grid = std::min(B, h->sm_count);
+    const int nodeE = std::max((D - 1) * E, 1);
+    size_t smem = ((size_t)T * E + K + (size_t)kDrPC * nodeE + 3 * (size_t)beam + 2) * 8 + (size_t)kDrCap * 16 +
+                  (size_t)2 * beam * D * 4 + 64 * 4 + 32;
+    if (smem > h->smem_optin)
+        return fail(h, DMG_ERR_UNSUPPORTED, "Deep Retrieval shape needs %zu B of shared memory (limit %zu)", smem, h->smem_optin);
+    DMG_CUDA(h, cudaFuncSetAttribute(dr_beam_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int resident = 1;                                            // persistent CTAs: as many per SM as registers and shared memory allow
+    DMG_CUDA(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&resident, dr_beam_kernel, kThreads, smem));
+    const int grid = std::min(B, h->sm_count * std::max(resident, 1));
     const size_t scratch = (size_t)grid * beam * K * sizeof(double);
     const size_t work = Carver::need({scratch, (size_t)B * beam * D * 4, (size_t)B * beam * 8, (size_t)B * 4});
     DMG_TRY(ensure_dev(h, h->s_work, work));
@@ -415,12 +423,6 @@ static int32_t dr_beam_enqueue(dmg_handle_t h, int32_t B, const int32_t *seq_hos
     p.node_emb = d.d_layer_emb + (size_t)(hist_tiles ? d.local_items : d.num_item) * E;
     for (int i = 0; i < D; i++) { p.wT[i] = d.d_layer_wT[i]; p.b[i] = d.d_layer_b[i]; }
     p.seq = d_seq; p.scratch = d_scr; p.out_paths = *d_paths; p.out_probs = *d_probs; p.out_counts = *d_counts;
-    const int nodeE = std::max((D - 1) * E, 1);
-    size_t smem = ((size_t)T * E + K + (size_t)kDrPC * nodeE + 3 * (size_t)beam + 2) * 8 + (size_t)kDrCap * 16 +
-                  (size_t)2 * beam * D * 4 + 64 * 4 + 32;
-    if (smem > h->smem_optin)
-        return fail(h, DMG_ERR_UNSUPPORTED, "Deep Retrieval shape needs %zu B of shared memory (limit %zu)", smem, h->smem_optin);
-    DMG_CUDA(h, cudaFuncSetAttribute(dr_beam_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     dr_beam_kernel<<<grid, kThreads, smem, h->stream>>>(p);
     h->launches += 1;
     DMG_CUDA(h, cudaGetLastError());

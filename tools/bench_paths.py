@@ -75,11 +75,47 @@ def otm_deepfm_section(a, E, T, threads):
     eng.close()
 
 
+def dr_section(a, T):
+    """4. Deep Retrieval beam search + rerank, fp64 (a23)"""
+    from dismember_b200 import Engine
+    from oracle import oracle as orc
+    n_item, K, D, J = (20_000, 100, 3, 2) if a.quick else (200_000, 1000, 3, 2)
+    Ed = 16 if a.quick else 64
+    rng = np.random.Generator(np.random.PCG64(8))
+    layer_emb = rng.normal(0, 0.05, (n_item + (D - 1) * K, Ed))
+    layer_w = [rng.normal(0, 0.05, (K, (T + d) * Ed)) for d in range(D)]
+    layer_b = [np.zeros(K) for _ in range(D)]
+    rr_emb = rng.normal(0, 0.05, (n_item, Ed)); rr_w = rng.normal(0, 0.05, (Ed, T * Ed)); rr_b = np.zeros(Ed)
+    sm_w = rng.normal(0, 0.05, (n_item, Ed)); sm_b = np.zeros(n_item)
+    from dismember_b200.dr import build_path_csr
+    paths = rng.integers(0, K, (n_item, J, D))
+    off, flat = build_path_csr(np.arange(n_item), paths, K)
+    eng = Engine(0)
+    eng.dr_load(n_item, K, D, T, Ed, layer_emb, layer_w, layer_b, rr_emb, rr_w, rr_b, sm_w, sm_b)
+    eng.dr_load_paths(off, flat)
+    B = 64 if a.quick else 1024                                # enough users for every resident CTA of the persistent kernel
+    dseq = rng.integers(0, n_item, (B, T)).astype(np.int32)
+    dt = timeit(lambda: eng.dr_retrieve(dseq, 200, 10), warm=1, reps=3)
+    flop_u = 2 * K * T * Ed + sum(200 * 2 * K * (T + d) * Ed for d in range(1, D))
+    emit(path="dr_retrieve (Deep Retrieval beam search + rerank, fp64)", items=n_item, K=K, D=D, beam=200, batch=B, ms=dt * 1e3,
+         users_per_s=B / dt, roofline={"bound": "fp64 FMA pipe / top-k", "naive_flop_per_user": flop_u,
+                                       "achieved_tflops_naive": flop_u * B / dt / 1e12})
+    dm = orc.DrModel(n_item, K, D, T, Ed, layer_emb, layer_w, layer_b, rr_emb, rr_w, rr_b, sm_w, sm_b)
+    nchk = 4
+    t0 = time.perf_counter()
+    ref = [dm.recommend(dseq[i], 10, 200, off, flat) for i in range(nchk)]
+    cdt = time.perf_counter() - t0
+    gi, gs, gc = eng.dr_retrieve(dseq[:nchk], 200, 10)
+    ok = all((gi[i, :gc[i]] == ref[i][0]).all() and len(ref[i][0]) == gc[i] for i in range(nchk))
+    emit(path="dr_retrieve cpu_baseline", kind="port", cores=1, users_per_s=nchk / cdt, parity={"ids_identical": bool(ok)})
+    eng.close()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--quick", action="store_true")
     ap.add_argument("--train-items", type=int, default=10_000_000)
-    ap.add_argument("--only", default=None, choices=[None, "otm_deepfm"], help="run one section only")
+    ap.add_argument("--only", default=None, choices=[None, "otm_deepfm", "dr"], help="run one section only")
     a = ap.parse_args()
     from dismember_b200 import Engine, synth
     from oracle import oracle as orc
@@ -89,6 +125,8 @@ def main():
     E, T = 64, 10
     if a.only == "otm_deepfm":
         return otm_deepfm_section(a, E, T, threads)
+    if a.only == "dr":
+        return dr_section(a, T)
 
     # ---- 1. training step: fused DIN fwd/bwd + BCE + scatter-add, dense Adam -------------------
     for n_items in ([100_000] if a.quick else [1_000_000, a.train_items]):
@@ -263,37 +301,7 @@ def main():
                        "frac": by / dt / 1e9 / hbm, "peak_source": hbm_src})
         eng.close()
 
-    # ---- 4. Deep Retrieval beam search + rerank, fp64 (a23) --------------------------------------------------------
-    n_item, K, D, J = (20_000, 100, 3, 2) if a.quick else (200_000, 1000, 3, 2)
-    Ed = 16 if a.quick else 64
-    rng = np.random.Generator(np.random.PCG64(8))
-    layer_emb = rng.normal(0, 0.05, (n_item + (D - 1) * K, Ed))
-    layer_w = [rng.normal(0, 0.05, (K, (T + d) * Ed)) for d in range(D)]
-    layer_b = [np.zeros(K) for _ in range(D)]
-    rr_emb = rng.normal(0, 0.05, (n_item, Ed)); rr_w = rng.normal(0, 0.05, (Ed, T * Ed)); rr_b = np.zeros(Ed)
-    sm_w = rng.normal(0, 0.05, (n_item, Ed)); sm_b = np.zeros(n_item)
-    from dismember_b200.dr import build_path_csr
-    paths = rng.integers(0, K, (n_item, J, D))
-    off, flat = build_path_csr(np.arange(n_item), paths, K)
-    eng = Engine(0)
-    eng.dr_load(n_item, K, D, T, Ed, layer_emb, layer_w, layer_b, rr_emb, rr_w, rr_b, sm_w, sm_b)
-    eng.dr_load_paths(off, flat)
-    B = 64
-    dseq = rng.integers(0, n_item, (B, T)).astype(np.int32)
-    dt = timeit(lambda: eng.dr_retrieve(dseq, 200, 10), warm=1, reps=3)
-    flop_u = 2 * K * T * Ed + sum(200 * 2 * K * (T + d) * Ed for d in range(1, D))
-    emit(path="dr_retrieve (Deep Retrieval beam search + rerank, fp64)", items=n_item, K=K, D=D, beam=200, batch=B, ms=dt * 1e3,
-         users_per_s=B / dt, roofline={"bound": "fp64 FMA pipe / top-k", "naive_flop_per_user": flop_u,
-                                       "achieved_tflops_naive": flop_u * B / dt / 1e12})
-    dm = orc.DrModel(n_item, K, D, T, Ed, layer_emb, layer_w, layer_b, rr_emb, rr_w, rr_b, sm_w, sm_b)
-    nchk = 4
-    t0 = time.perf_counter()
-    ref = [dm.recommend(dseq[i], 10, 200, off, flat) for i in range(nchk)]
-    cdt = time.perf_counter() - t0
-    gi, gs, gc = eng.dr_retrieve(dseq[:nchk], 200, 10)
-    ok = all((gi[i, :gc[i]] == ref[i][0]).all() and len(ref[i][0]) == gc[i] for i in range(nchk))
-    emit(path="dr_retrieve cpu_baseline", kind="port", cores=1, users_per_s=nchk / cdt, parity={"ids_identical": bool(ok)})
-    eng.close()
+    dr_section(a, T)
 
 
 if __name__ == "__main__":
