@@ -170,6 +170,8 @@ class Engine:
         e.L, e.h, e.device = self.L, h, self.device
         e.din_dtype, e.E, e.T, e.rows = self.din_dtype, self.E, self.T, self.rows
         e._deepfm = getattr(self, "_deepfm", False)
+        if hasattr(self, "dr_shape"):
+            e.dr_shape = self.dr_shape
         e._parent = self                                            # keeps the owner alive
         return e
 

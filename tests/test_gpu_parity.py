@@ -461,3 +461,41 @@ def test_clones_share_the_model_across_threads(orc):
         c.close()
     parent.load_din_weights(params, rows, E, 10)                 # free again
     parent.close()
+
+
+def test_clones_run_otm_and_deep_retrieval(orc, otm_fix, otm_oracle, dr_fix, queries, golden_out):
+    """A clone shares the OTM (fp64) tables and the Deep Retrieval tables of its parent: same results as the parent's
+    golden outputs, from two threads at once."""
+    import threading
+    from dismember_b200 import Engine
+    from dismember_b200.dr import build_path_csr
+    parent = Engine(0)
+    load_otm(parent, otm_fix)
+    args, dr_model = _dr_models(orc, dr_fix)
+    parent.dr_load(*args)
+    off, flat = build_path_csr(dr_fix["map_ids"], dr_fix["map_paths"], int(dr_fix["K"]))
+    parent.dr_load_paths(off, flat)
+    twin = parent.clone()
+    _, _, _, item_leaf = otm_oracle
+    oseqs = np.array([[item_leaf.get(int(x), -1) for x in s] for s in queries["seqs"]], np.int32)
+    item_id = {int(a): int(b) for a, b in zip(dr_fix["map_items"], dr_fix["map_ids"])}
+    dseqs = np.array([[item_id.get(int(x), -1) for x in s] for s in queries["seqs"][:32]], np.int32)
+    out, errs = {}, []
+
+    def work(name, e):
+        try:
+            out[name] = (e.otm_retrieve(oseqs, 20, 10), e.dr_retrieve(dseqs, 50, 10))
+        except Exception as ex:                                  # noqa: BLE001
+            errs.append(ex)
+    th = [threading.Thread(target=work, args=(n, e)) for n, e in (("parent", parent), ("twin", twin))]
+    [t.start() for t in th]
+    [t.join() for t in th]
+    assert not errs, errs
+    for name in ("parent", "twin"):
+        (oi, osc, _), (di, dsc, dc) = out[name]
+        assert (oi == golden_out["otm_items_b20"]).all() and (bits(osc) == bits(golden_out["otm_scores_b20"])).all()
+        for u in range(len(dseqs)):
+            ri, rs, _ = dr_model.recommend(dseqs[u], 10, 50, off, flat)
+            assert dc[u] == len(ri) and (di[u, :dc[u]] == ri).all() and (bits(dsc[u, :dc[u]]) == bits(rs)).all()
+    twin.close()
+    parent.close()
