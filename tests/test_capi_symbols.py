@@ -82,3 +82,18 @@ def test_jtm_assign_level_matches_the_python_mirror_of_rebalance():
                 for it in assigned:
                     want[it] = node
         assert (got == want).all()
+
+
+def test_jni_shim_and_python_binding_call_only_declared_entry_points():
+    """jni/com_mass_gpu_DismemberGPU.c cannot be compiled in this image (no jni.h): check statically that every dmg_*
+    function it calls is declared in include/dismember_gpu.h, and that the ctypes binding gives every declared
+    int32-returning entry point an argument signature."""
+    import re
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    declared = set(dmg.declared_symbols())
+    jni = open(os.path.join(root, "jni", "com_mass_gpu_DismemberGPU.c")).read()
+    called = set(re.findall(r"\b(dmg_[a-z0-9_]+)\s*\(", jni))
+    assert called and not (called - declared), f"JNI shim calls undeclared functions: {sorted(called - declared)}"
+    L = dmg.load_library()
+    unbound = [s for s in declared if getattr(L, s).argtypes is None]
+    assert not unbound, f"declared but without a ctypes signature in _capi.py: {unbound}"
