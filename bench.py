@@ -87,6 +87,8 @@ class ClockSampler:
         self.device, self.rows, self.proc, self.first = device, [], None, 0
 
     def start(self):
+        if os.environ.get("DMG_BENCH_NO_CLOCKS"):                 # diagnostic only: is the sampler itself perturbing the run?
+            return
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
                                           "-lms", "100", "-i", str(self.device)], stdout=subprocess.PIPE, text=True)
