@@ -79,6 +79,7 @@ class _Reader:
         self.b = data
         self.p = 0
         self.handles: List[Any] = []
+        self.spans: List[tuple] = []   # (byte offset of the payload, element typecode, element count) per primitive array, stream order
 
     def u1(self):
         v = self.b[self.p]; self.p += 1; return v
@@ -210,6 +211,7 @@ class _Reader:
         et = cd.name[1]
         if et in _PRIM:
             dt, sz = _PRIM[et]
+            self.spans.append((self.p, et, n))
             raw = self.take(n * sz)
             arr = np.frombuffer(raw, dtype=dt).astype(np.dtype(dt).newbyteorder("="))
             self.handles[h] = arr
@@ -257,6 +259,44 @@ def load(data: bytes) -> List[Any]:
 def load_file(path: str) -> List[Any]:
     with open(path, "rb") as f:
         return load(f.read())
+
+
+def primitive_array_spans(data: bytes) -> List[tuple]:
+    """(byte offset of the payload, element typecode, element count) of every primitive array, in stream order."""
+    r = _Reader(data)
+    if r.unpack(">H") != 0xACED or r.unpack(">H") != 5:
+        raise JavaSerError("not a Java serialization stream")
+    while r.p < len(r.b):
+        r.content()
+    return list(r.spans)
+
+
+def inject_weights(data: bytes, params, min_len: int = 1000) -> bytes:
+    """The injector of SURVEY 8f rank 1: a copy of a Java-serialised model whose parameter storage holds `params`.
+
+    `Module.parameters()` of a saved model is ONE primitive array shared by every tensor (compact storage made by
+    `adjustParameters`, scalann/.../nn/abstractnn/AbstractModule.scala:163) -- the first `[F` / `[D` array of at least
+    `min_len` elements in the stream (tools/make_golden.py reads the weights from the same place; the array after it is
+    the gradient buffer).  Only its payload bytes change, so `Serialization.loadModel`
+    (tdm/.../utils/Serialization.scala:81-101) reads the file as before and finds the new weights."""
+    params = np.asarray(params)
+    for off, et, n in primitive_array_spans(data):
+        if et in ("F", "D") and n >= min_len:
+            if n != params.size:
+                raise JavaSerError(f"the model's parameter array holds {n} values, got {params.size}")
+            dt, sz = _PRIM[et]
+            if (et == "F") != (params.dtype == np.float32):
+                raise JavaSerError(f"the model stores {'Float' if et == 'F' else 'Double'} parameters, got {params.dtype}")
+            raw = np.ascontiguousarray(params.ravel()).astype(dt).tobytes()
+            return data[:off] + raw + data[off + n * sz:]
+    raise JavaSerError("no parameter array found")
+
+
+def inject_weights_file(src: str, dst: str, params, min_len: int = 1000) -> None:
+    with open(src, "rb") as f:
+        data = f.read()
+    with open(dst, "wb") as f:
+        f.write(inject_weights(data, params, min_len))
 
 
 def walk(obj, fn, _seen=None, _path="$"):

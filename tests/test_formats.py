@@ -1,5 +1,8 @@
 """On-disk formats: writers and readers round-trip without the reference."""
+import os
+
 import numpy as np
+import pytest
 
 from dismember_b200 import synth
 from dismember_b200.formats import javaser, pbwire, tree_file
@@ -50,3 +53,42 @@ def test_javaser_minimal_stream():
     data = b"\xac\xed\x00\x05" + b"\x75" + cd + struct.pack(">i", 3) + struct.pack(">fff", 1.0, -2.5, 3.25)
     objs = javaser.load(data)
     assert len(objs) == 1 and objs[0].dtype == np.float32 and objs[0].tolist() == [1.0, -2.5, 3.25]
+
+
+def test_javaser_inject_weights_round_trip():
+    """Weights back into a Java-serialised model: only the payload of the parameter array changes."""
+    import struct
+    cd = b"\x72" + struct.pack(">H", 2) + b"[F" + b"\x0b\x9c\x81\x89\x22\xe0\x0c\x42" + b"\x02" + struct.pack(">H", 0) + b"\x78\x70"
+    first = struct.pack(">ffff", 1.0, -2.5, 3.25, 0.5)
+    # two float[4] arrays: parameters, then the gradient buffer (second one through a class-descriptor reference)
+    data = (b"\xac\xed\x00\x05" + b"\x75" + cd + struct.pack(">i", 4) + first +
+            b"\x75" + b"\x71" + struct.pack(">i", 0x7E0000) + struct.pack(">i", 4) + struct.pack(">ffff", 9, 9, 9, 9))
+    spans = javaser.primitive_array_spans(data)
+    assert [(t, n) for _, t, n in spans] == [("F", 4), ("F", 4)]
+    new = np.array([7.0, 8.0, -1.0, 0.25], np.float32)
+    out = javaser.inject_weights(data, new, min_len=4)
+    assert len(out) == len(data)
+    objs = javaser.load(out)
+    assert objs[0].tolist() == new.tolist() and objs[1].tolist() == [9, 9, 9, 9]
+    off = spans[0][0]
+    assert out[:off] == data[:off] and out[off + 16:] == data[off + 16:]
+    with pytest.raises(javaser.JavaSerError):
+        javaser.inject_weights(data, np.zeros(3, np.float32), min_len=4)
+    with pytest.raises(javaser.JavaSerError):
+        javaser.inject_weights(data, np.zeros(4, np.float64), min_len=4)
+
+
+def test_javaser_inject_into_the_reference_model(jtm_fix):
+    """On the reference's own saved model (present in the build container only): inject, reload, compare."""
+    path = "/root/reference/data/jtm/example_model.bin"
+    if not os.path.exists(path):
+        pytest.skip("reference fixture not on this machine")
+    data = open(path, "rb").read()
+    params = jtm_fix["params"]                                  # the vector tools/make_golden.py took from this file
+    new = (params * np.float32(0.5) + np.float32(0.125)).astype(np.float32)
+    out = javaser.inject_weights(data, new)
+    assert len(out) == len(data)
+    arrs = javaser.primitive_arrays(javaser.load(out), 1000)
+    assert arrs[0][1].size == new.size and (arrs[0][1] == new).all()
+    back = javaser.inject_weights(out, params)
+    assert back == data                                          # and back again: byte-identical to the original file
