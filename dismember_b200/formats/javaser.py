@@ -271,32 +271,38 @@ def primitive_array_spans(data: bytes) -> List[tuple]:
     return list(r.spans)
 
 
-def inject_weights(data: bytes, params, min_len: int = 1000) -> bytes:
+def inject_weights(data: bytes, params, min_len: int = 1000, which: int = 0) -> bytes:
     """The injector of SURVEY 8f rank 1: a copy of a Java-serialised model whose parameter storage holds `params`.
 
     `Module.parameters()` of a saved model is ONE primitive array shared by every tensor (compact storage made by
     `adjustParameters`, scalann/.../nn/abstractnn/AbstractModule.scala:163) -- the first `[F` / `[D` array of at least
     `min_len` elements in the stream (tools/make_golden.py reads the weights from the same place; the array after it is
     the gradient buffer).  Only its payload bytes change, so `Serialization.loadModel`
-    (tdm/.../utils/Serialization.scala:81-101) reads the file as before and finds the new weights."""
+    (tdm/.../utils/Serialization.scala:81-101) reads the file as before and finds the new weights.  `which` picks a
+    later qualifying array instead (a Deep Retrieval file holds several storages: see `primitive_array_spans`)."""
     params = np.asarray(params)
+    seen = 0
     for off, et, n in primitive_array_spans(data):
-        if et in ("F", "D") and n >= min_len:
-            if n != params.size:
-                raise JavaSerError(f"the model's parameter array holds {n} values, got {params.size}")
-            dt, sz = _PRIM[et]
-            if (et == "F") != (params.dtype == np.float32):
-                raise JavaSerError(f"the model stores {'Float' if et == 'F' else 'Double'} parameters, got {params.dtype}")
-            raw = np.ascontiguousarray(params.ravel()).astype(dt).tobytes()
-            return data[:off] + raw + data[off + n * sz:]
+        if et not in ("F", "D") or n < min_len:
+            continue
+        seen += 1
+        if seen <= which:
+            continue
+        if n != params.size:
+            raise JavaSerError(f"the model's parameter array holds {n} values, got {params.size}")
+        dt, sz = _PRIM[et]
+        if (et == "F") != (params.dtype == np.float32):
+            raise JavaSerError(f"the model stores {'Float' if et == 'F' else 'Double'} parameters, got {params.dtype}")
+        raw = np.ascontiguousarray(params.ravel()).astype(dt).tobytes()
+        return data[:off] + raw + data[off + n * sz:]
     raise JavaSerError("no parameter array found")
 
 
-def inject_weights_file(src: str, dst: str, params, min_len: int = 1000) -> None:
+def inject_weights_file(src: str, dst: str, params, min_len: int = 1000, which: int = 0) -> None:
     with open(src, "rb") as f:
         data = f.read()
     with open(dst, "wb") as f:
-        f.write(inject_weights(data, params, min_len))
+        f.write(inject_weights(data, params, min_len, which))
 
 
 def walk(obj, fn, _seen=None, _path="$"):
