@@ -57,7 +57,9 @@ DMG_API int32_t dmg_create(int32_t device, dmg_handle_t *out);
 DMG_API int32_t dmg_destroy(dmg_handle_t h);
 /* A second handle on src's device that SHARES src's tree index and weight tables read-only (own
  * stream, scratch and scheduler state): the GPU form of the reference's per-thread model clones over
- * one weight storage (tdm/src/main/scala/com/mass/tdm/optim/LocalOptimizer.scala:35-40) that the
+ * one weight storage (tdm/src/main/scala/com/mass/tdm/optim/LocalOptimizer.scala:35-40;
+ * otm/src/main/scala/com/mass/otm/optim/LocalOptimizer.scala:225-230 cloneModule + putWeights, pinned by
+ * otm/src/test/scala/CloneModelSpec.scala: "cloned models share same weights storage") that the
  * evaluator hands its user slices to (tdm/.../evaluation/Evaluator.scala:29-37).  One clone per host
  * thread keeps several batches in flight on one GPU: the tail of one batch's persistent kernel
  * overlaps the head of the next.  While clones live, loaders and training entry points on src (and

@@ -404,7 +404,8 @@ def test_fast_equals_strict_at_full_size(engine):
 
 # ------------------------------------------------------------------ clones: one handle per host thread over one model
 def test_clones_share_the_model_across_threads(orc):
-    """dmg_clone: per-thread handles over the parent's tables (LocalOptimizer.scala:35-40, Evaluator.scala:29-37).
+    """dmg_clone: per-thread handles over the parent's tables (LocalOptimizer.scala:35-40, Evaluator.scala:29-37; the
+    reference pins the sharing in otm/src/test/scala/CloneModelSpec.scala: "cloned models share same weights storage").
     Three host threads retrieve their slices of the users at the same time; every slice equals the oracle bit for bit."""
     import threading
     from dismember_b200 import DmgError, Engine
