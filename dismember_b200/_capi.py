@@ -65,6 +65,7 @@ def load_library(build_if_missing: bool = True):
         "dmg_set_arithmetic": [vp, i32],
         "dmg_fast_stats": [vp, vp],
         "dmg_set_fast_tolerance": [vp, dbl],
+        "dmg_wave_probe": [vp, i32, vp, i32, i32, i32, i32, vp, vp, vp, vp],
         "dmg_kernel_time": [vp, C.POINTER(dbl), C.POINTER(i64)],
         "dmg_load_tree_tdm": [vp, i32, i64, vp, vp, vp, i64, vp, vp],
         "dmg_load_tree_complete": [vp, i32, i64, vp, vp],
@@ -202,6 +203,18 @@ class Engine:
 
     def set_fast_tolerance(self, tau: float):
         self._check(self.L.dmg_set_fast_tolerance(self.h, float(tau)))
+
+    def wave_probe(self, item_seq, beam, level, use_mask=True):
+        """Candidates of tree level `level` with their tensor-core scores and the bound eps (dmg_wave_probe)."""
+        seq = _i32(item_seq).reshape(-1, self.T)
+        B = len(seq)
+        cap = max(((2 * beam + 7) // 8) * 8, 8)
+        codes = np.empty((B, cap), np.int32)
+        scores = np.empty((B, cap), np.float32)
+        counts = np.empty(B, np.int32)
+        eps = np.empty(B, np.float32)
+        self._check(self.L.dmg_wave_probe(self.h, B, _p(seq), beam, int(use_mask), level, cap, _p(codes), _p(scores), _p(counts), _p(eps)))
+        return codes, scores, counts, eps
 
     def fast_stats(self):
         out = np.zeros(7, np.uint64)

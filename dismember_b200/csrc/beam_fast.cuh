@@ -187,20 +187,22 @@ static_assert(2 * FastGeo::X_BYTES >= FastGeo::STRICT_SCR, "strict scratch must 
 // Rows with the codes sRow[base .. base+nr) -> sOut[base ..), nr <= 4*RPT.  Every dot product is one sequential-k
 // fma chain; thread (o = tid & 63, rg = tid >> 6) owns output column o of rows rg, rg+4, .. (RPT of them) and
 // keeps the 64 weights of that column in registers, loaded once per batch.
-template <int RPT>
+// NT = threads of the CTA (a multiple of 64): NT / 64 row groups, NB = (NT / 64) * RPT rows per call.
+template <int RPT, int NT = FastGeo::THREADS>
 __device__ __forceinline__ void strict_score_rows(const float *__restrict__ emb, const int32_t *__restrict__ sRow,
                                                   int base, int nr, float *__restrict__ sOut,
                                                   float *__restrict__ scr, uint32_t maskbits, int T, float scale,
                                                   const float *__restrict__ wattT, const float *__restrict__ w1T,
                                                   const float *__restrict__ b1, const float *__restrict__ w2, float b2)
 {
-    constexpr int E = 64, LD = FastGeo::KLD, SB = FastGeo::SB, PLD = 17, NB = 4 * RPT;
+    constexpr int E = 64, LD = FastGeo::KLD, SB = FastGeo::SB, PLD = 17, GS = NT / 64, NB = GS * RPT;
+    static_assert(NB * 8 <= NT && NB <= SB, "row batch does not fit the CTA");
     float *sKf = scr, *sXs = sKf + 16 * LD, *sA = sXs + SB * LD, *sT = sA + SB * LD, *sPs = sT + SB * LD;
     const int tid = threadIdx.x, o = tid & 63, rg = tid >> 6;
     float w[E];
 #pragma unroll
     for (int k = 0; k < E; k++) w[k] = __ldg(wattT + k * E + o);
-    for (int idx = tid; idx < NB * 16; idx += FastGeo::THREADS) {
+    for (int idx = tid; idx < NB * 16; idx += NT) {
         const int r = idx >> 4, c = idx & 15;
         float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
         if (r < nr) v = __ldg(reinterpret_cast<const float4 *>(emb + (size_t)sRow[base + r] * E) + c);
@@ -252,7 +254,7 @@ __device__ __forceinline__ void strict_score_rows(const float *__restrict__ emb,
 #pragma unroll
         for (int i = 0; i < RPT; i++) {
             float av[4];
-            ld4(sA + (rg + 4 * i) * LD + k, av);
+            ld4(sA + (rg + GS * i) * LD + k, av);
             acc[i] = fma_(av[0], w[k], acc[i]);
             acc[i] = fma_(av[1], w[k + 1], acc[i]);
             acc[i] = fma_(av[2], w[k + 2], acc[i]);
@@ -260,7 +262,7 @@ __device__ __forceinline__ void strict_score_rows(const float *__restrict__ emb,
         }
     }
 #pragma unroll
-    for (int i = 0; i < RPT; i++) { sT[(rg + 4 * i) * LD + o] = acc[i]; acc[i] = 0.0f; }
+    for (int i = 0; i < RPT; i++) { sT[(rg + GS * i) * LD + o] = acc[i]; acc[i] = 0.0f; }
 #pragma unroll
     for (int k = 0; k < E; k++) w[k] = __ldg(w1T + k * E + o);
     __syncthreads();
@@ -269,7 +271,7 @@ __device__ __forceinline__ void strict_score_rows(const float *__restrict__ emb,
 #pragma unroll
         for (int i = 0; i < RPT; i++) {
             float xv[4];
-            ld4(sXs + (rg + 4 * i) * LD + k, xv);
+            ld4(sXs + (rg + GS * i) * LD + k, xv);
             acc[i] = fma_(xv[0], w[k], acc[i]);
             acc[i] = fma_(xv[1], w[k + 1], acc[i]);
             acc[i] = fma_(xv[2], w[k + 2], acc[i]);
@@ -283,7 +285,7 @@ __device__ __forceinline__ void strict_score_rows(const float *__restrict__ emb,
 #pragma unroll
         for (int i = 0; i < RPT; i++) {
             float tv[4];
-            ld4(sT + (rg + 4 * i) * LD + k, tv);
+            ld4(sT + (rg + GS * i) * LD + k, tv);
             acc[i] = fma_(tv[0], w[k], acc[i]);
             acc[i] = fma_(tv[1], w[k + 1], acc[i]);
             acc[i] = fma_(tv[2], w[k + 2], acc[i]);
@@ -293,7 +295,7 @@ __device__ __forceinline__ void strict_score_rows(const float *__restrict__ emb,
     {
         const float bo = __ldg(b1 + o);
 #pragma unroll
-        for (int i = 0; i < RPT; i++) sA[(rg + 4 * i) * LD + o] = relu_(add_(acc[i], bo));   // a[] was last read before the previous barrier
+        for (int i = 0; i < RPT; i++) sA[(rg + GS * i) * LD + o] = relu_(add_(acc[i], bo));   // a[] was last read before the previous barrier
     }
     __syncthreads();
     if (tid < nr) {                                             // (6) logit = h . W2 + b2
@@ -327,6 +329,32 @@ __device__ __noinline__ void strict_score_batch(const float *__restrict__ emb, c
         } else {
             strict_score_rows<1>(emb, sRow, base, rem, sOut, scr, maskbits, T, scale, wattT, w1T, b1, w2, b2);
             base += 4;
+        }
+    }
+}
+
+// the same for a CTA of 128 threads (wave_select_kernel): 16 / 8 / 4 / 2 rows per call
+__device__ __noinline__ void strict_score_batch128(const float *__restrict__ emb, const int32_t *__restrict__ sRow,
+                                                   int n, float *__restrict__ sOut,
+                                                   float *__restrict__ scr, uint32_t maskbits, int T, float scale,
+                                                   const float *__restrict__ wattT, const float *__restrict__ w1T,
+                                                   const float *__restrict__ b1, const float *__restrict__ w2, float b2)
+{
+    int base = 0;
+    while (base < n) {
+        const int rem = n - base;
+        if (rem > 8) {
+            strict_score_rows<8, 128>(emb, sRow, base, rem < 16 ? rem : 16, sOut, scr, maskbits, T, scale, wattT, w1T, b1, w2, b2);
+            base += 16;
+        } else if (rem > 4) {
+            strict_score_rows<4, 128>(emb, sRow, base, rem, sOut, scr, maskbits, T, scale, wattT, w1T, b1, w2, b2);
+            base += 8;
+        } else if (rem > 2) {
+            strict_score_rows<2, 128>(emb, sRow, base, rem, sOut, scr, maskbits, T, scale, wattT, w1T, b1, w2, b2);
+            base += 4;
+        } else {
+            strict_score_rows<1, 128>(emb, sRow, base, rem, sOut, scr, maskbits, T, scale, wattT, w1T, b1, w2, b2);
+            base += 2;
         }
     }
 }

@@ -1,0 +1,888 @@
+// beam_wave.cuh -- level-synchronous ("wave") tensor-core beam search, E = 64, fp32 model.
+//
+// Same search, same certified cuts and the same outputs as beam_search_fast_kernel (beam_fast.cuh): ids and logits
+// bit-identical to the strict path / CPU oracle.  What changes is the shape of the work.  The persistent kernel walks ONE
+// user per CTA through every level -- a serial chain select -> expand -> gather -> MMA -> softmax -> MMA -> epilogue whose
+// length, not the machine, bounds it.  Here the batch advances level by level, the way the
+// reference's own batched searcher does (otm/.../model/CandidateSearcher.scala:25-55; TDM: Recommender.scala:58-99 per user):
+//
+//   wave_prologue_kernel   per user, once: history rows -> K / H = M.K tensor-core operands (bf16 hi/lo, UMMA layout),
+//                          softmax mask, the user's terms of the error bound                         (K2)
+//   per level:
+//     wave_select_kernel   one WARP per user: certified cut of the previous level's scores (threshold search on 16 keys
+//                          per lane, ballots), band bookkeeping, children 2c+1 / 2c+2 in candidate order (K1 cut + expand)
+//     wave_score_kernel    persistent, warp-specialised, 3 CTAs per SM, tiles of (user, 128 candidate rows) from a dynamic
+//                          counter.  A control warp gathers the rows with the TMA (cp.async.bulk.tensor ... tile::gather4
+//                          from a bf16 hi|lo copy of the node table straight into the 128-byte-swizzled UMMA operand
+//                          tile: no register staging, no conversion instructions), issues the tcgen05.mma chains and
+//                          refills the tile while four consumer warps run softmax (tcgen05.ld of S) and the
+//                          ReLU / W2 epilogue of the previous MMAs                                    (K1 score)
+//   wave_final_kernel      per user: ONE strict batch over every band row deferred at a cut and over the topk candidates,
+//                          proofs of the deferred cuts, topk by the reference's (score desc, position asc) order  (K3)
+//
+// Beams, scores, band lists and per-user state live in global memory between the kernels (about 9 KB per user: L2
+// resident).  The hi|lo table costs the same 256 bytes per row as the fp32 table it is derived from (x = hi + lo +
+// O(2^-18 x)); the strict re-scores read the fp32 table.
+#pragma once
+#include <cuda.h>
+
+#include "beam_fast.cuh"
+
+namespace dmg {
+
+struct WaveUser {                   // per-user search state (64 B)
+    float eps;                      // bound on |fast - strict| of the scores in WaveParams::score (level being cut next)
+    float kmax, zk, hw;             // user terms of the bound (DESIGN.md "certified cuts")
+    uint32_t maskbits;              // Mask input, bit j = history slot j masked
+    int32_t vcount, nseg;           // deferred verification list
+    int32_t flags;                  // 1 redo, 2 scored, 4 every slot masked
+    int32_t redo_why;
+    int32_t pad[7];
+};
+enum { WU_REDO = 1, WU_SCORED = 2, WU_ALLMASK = 4 };
+
+struct WaveGeo {
+    static constexpr int THREADS = 160;                      // 4 consumer warps (TMEM lanes 32 w ..) + 1 control warp
+    static constexpr int XH = 0, XL = 16384;                 // [128 rows][128 B] bf16, SWIZZLE_128B (TMA gather4 destination)
+    static constexpr int W1H = 32768, W1L = 40960;           // B operand [64 o][64 k]: K-major, no swizzle, LBO 1024, SBO 128
+    static constexpr int KH = 49152, KL = 51200;             // B operand [16 j][64 k]: LBO 256, SBO 128
+    static constexpr int HH = 53248, HL = 55296;             // B operand [64 o][16 j]: LBO 1024, SBO 128
+    static constexpr int ADDV = 57344;                       // [16] additive softmax mask (tail of the H copy)
+    static constexpr int PH = 57472, PL = 61568;             // A operand [128 rows][16 j]: LBO 2048, SBO 128
+    static constexpr int BAR = 65664;                        // 8 mbarriers
+    static constexpr int INFO = BAR + 64;                    // 2 x int4 tile info
+    static constexpr int TMEMP = INFO + 32;
+    static constexpr int BYTES = TMEMP + 16;
+    static constexpr int SMEM = BYTES + 1024;                // + alignment slack (the X tiles need 1024-byte alignment)
+    static constexpr int UOP_BYTES = 8320;                   // per-user operand image [KH | KL | HH | HL | addv] (8256, padded)
+    static constexpr int VCAP = FastGeo::VCAP, MAX_UNC = FastGeo::MAX_UNC;
+};
+enum { WB_W1 = 0, WB_XFULL, WB_M1, WB_PFULL, WB_HFULL, WB_M2, WB_TFREE };
+
+struct WaveParams {
+    int B, T, cap, beam;
+    const int32_t *beam_user;
+    const float *emb;
+    const int32_t *hist;
+    const uint8_t *hist_mask;
+    const uint32_t *exists;
+    int leaf_level, sparse_from;
+    float scale;
+    int32_t *code[2];               // [B][cap] candidate codes, ping-pong by level parity
+    float *score;                   // [B][cap] fast scores of the current candidates
+    int32_t *count;                 // [B]
+    WaveUser *user;
+    unsigned char *uop;             // [B][UOP_BYTES]
+    int32_t *v_code; float *v_fast; uint32_t *v_meta; float *v_segeps;     // [B][VCAP] x3, [B][32]
+    const float *mT, *zvec, *lvl_vx, *lvl_nx, *b1;
+    float cA, cZ, cH, cGamma, tau;
+    unsigned long long *stats;
+    int32_t *redo_list, *redo_count, *host_flags;
+    const unsigned char *w1img;     // [W1x hi | W1x lo] in UMMA layout, 16 KB
+    const unsigned char *split;     // bf16 hi|lo table, 256 B per code
+};
+struct WaveW2 { float w2[64]; float b2; };
+
+// ---- bf16 hi|lo copy of the node table: row c = [64 hi | 64 lo] bf16 (256 B), i.e. a [2 rows][64] bf16 matrix ------
+static __global__ void wave_split_table_kernel(const float *__restrict__ emb, int64_t rows, unsigned char *__restrict__ out)
+{
+    const int64_t n = rows * 8;                               // 8 chunks of 8 floats per row
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t r = i >> 3;
+        const int c = (int)(i & 7);
+        const float4 a = ldg_row16(emb + r * 64 + c * 8), b = ldg_row16(emb + r * 64 + c * 8 + 4);
+        const float v[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+        uint4 hi, lo;
+        split8(v, hi, lo);
+        *reinterpret_cast<uint4 *>(out + r * 256 + c * 16) = hi;
+        *reinterpret_cast<uint4 *>(out + r * 256 + 128 + c * 16) = lo;
+    }
+}
+
+// W1 item half [o][k] -> UMMA B operand image [hi | lo], chunk kc at kc * 1024, row o at o * 16
+static __global__ void wave_w1_image_kernel(const float *__restrict__ w1, unsigned char *__restrict__ img)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= 64 * 8) return;
+    const int o = i & 63, kc = i >> 6;
+    float v[8];
+#pragma unroll
+    for (int q = 0; q < 8; q++) v[q] = __ldg(w1 + o * 128 + kc * 8 + q);
+    uint4 hi, lo;
+    split8(v, hi, lo);
+    *reinterpret_cast<uint4 *>(img + kc * 1024 + o * 16) = hi;
+    *reinterpret_cast<uint4 *>(img + 8192 + kc * 1024 + o * 16) = lo;
+}
+
+// ---- K2: per-user prologue ----------------------------------------------------------------------------------------
+static __global__ void __launch_bounds__(256) wave_prologue_kernel(const WaveParams p)
+{
+    constexpr int E = 64, LD = 68;
+    __shared__ __align__(16) float sKf[kMaxT * LD];
+    __shared__ float sHmax[4 * E];
+    __shared__ int sCode[kMaxT];
+    __shared__ int sRed[8];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, user = blockIdx.x, T = p.T;
+    unsigned char *uop = p.uop + (size_t)user * WaveGeo::UOP_BYTES;
+    if (tid < kMaxT) {
+        int c = -1, m = 0;
+        if (tid < T) { c = p.hist[(size_t)user * T + tid]; m = p.hist_mask[(size_t)user * T + tid]; }
+        sCode[tid] = c;
+        const uint32_t mb = __ballot_sync(0x0000ffffu, m != 0);
+        reinterpret_cast<float *>(uop + 8192)[tid] = (tid < T && !m) ? 0.0f : -3.4028234663852886e+38f;
+        if (tid == 0) { sRed[0] = (int)mb; sRed[1] = 0; }
+    }
+    __syncthreads();
+    {                                                         // history rows, 16 lanes x 16 B per row
+        const int j = tid >> 4, c16 = tid & 15;
+        const int c = sCode[j];
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (c >= 0) v = ldg_row16(p.emb + (size_t)c * E + c16 * 4);
+        *reinterpret_cast<float4 *>(sKf + j * LD + c16 * 4) = v;
+    }
+    __syncthreads();
+    if (tid < 128) {                                          // K as B operand of S = X . K^T: [16 j][64 k], LBO 256
+        const int j = tid & 15, kc = tid >> 4;
+        float v[8];
+#pragma unroll
+        for (int q = 0; q < 8; q++) v[q] = sKf[j * LD + kc * 8 + q];
+        uint4 hi, lo;
+        split8(v, hi, lo);
+        *reinterpret_cast<uint4 *>(uop + kc * 256 + j * 16) = hi;
+        *reinterpret_cast<uint4 *>(uop + 2048 + kc * 256 + j * 16) = lo;
+    } else if (tid < 192) {                                   // ZK = sum_k z_k max_j |K_jk|
+        const int k = tid - 128;
+        float kab = 0.0f;
+#pragma unroll
+        for (int j = 0; j < kMaxT; j++) { const float v = fabsf(sKf[j * LD + k]); kab = (v > kab || v != v) ? v : kab; }
+        float zk = __ldg(p.zvec + k) * kab;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) zk += __shfl_xor_sync(0xffffffffu, zk, o);
+        if (lane == 0) sRed[2 + (warp & 1)] = __float_as_int(zk);
+    } else if (tid < 192 + kMaxT) {                           // Kmax = max_j |K_j|_2
+        const int j = tid - 192;
+        float n2 = 0.0f;
+        for (int k = 0; k < E; k++) n2 = fmaf(sKf[j * LD + k], sKf[j * LD + k], n2);
+        float nj = sqrtf(n2) * 1.0001f;
+        if (!(nj == nj)) nj = __int_as_float(0x7f800000);
+        atomicMax(&sRed[1], __float_as_int(nj));
+    }
+    {                                                         // H[j][o] = sum_k M[o][k] K[j][k]; row 15 carries b1
+        const int o = tid & 63, jg = tid >> 6;
+        float acc[4] = {0.0f, 0.0f, 0.0f, 0.0f};
+        const float *kr = sKf + (jg * 4) * LD;
+#pragma unroll 8
+        for (int k = 0; k < E; k++) {
+            const float m = __ldg(p.mT + k * E + o);
+#pragma unroll
+            for (int q = 0; q < 4; q++) acc[q] = fmaf(m, kr[q * LD + k], acc[q]);
+        }
+        float hm = fmaxf(fmaxf(fabsf(acc[0]), fabsf(acc[1])), fmaxf(fabsf(acc[2]), fabsf(acc[3])));
+        if (acc[0] != acc[0] || acc[1] != acc[1] || acc[2] != acc[2] || acc[3] != acc[3]) hm = __int_as_float(0x7f800000);
+        sHmax[jg * E + o] = hm;
+        if (jg == 3) acc[3] = __ldg(p.b1 + o);
+        uint2 hi, lo;
+        split_pair(acc[0], acc[1], hi.x, lo.x);
+        split_pair(acc[2], acc[3], hi.y, lo.y);
+        const int off = (jg >> 1) * 1024 + o * 16 + (jg & 1) * 8;
+        *reinterpret_cast<uint2 *>(uop + 4096 + off) = hi;
+        *reinterpret_cast<uint2 *>(uop + 6144 + off) = lo;
+    }
+    __syncthreads();
+    if (tid < E) {
+        float hw = fmaxf(fmaxf(sHmax[tid], sHmax[E + tid]), fmaxf(sHmax[2 * E + tid], sHmax[3 * E + tid])) * fabsf(__ldg(p.b1 + E + tid));   // w2 follows b1
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) hw += __shfl_xor_sync(0xffffffffu, hw, o);
+        if (lane == 0) sRed[4 + warp] = __float_as_int(hw);
+    }
+    __syncthreads();
+    if (tid == 0) {
+        WaveUser st;
+        memset(&st, 0, sizeof(st));
+        st.kmax = __int_as_float(sRed[1]);
+        st.zk = (__int_as_float(sRed[2]) + __int_as_float(sRed[3])) * 1.0001f;
+        st.hw = (__int_as_float(sRed[4]) + __int_as_float(sRed[5])) * 1.0001f;
+        st.maskbits = (uint32_t)sRed[0];
+        const uint32_t full = (1u << T) - 1u;
+        st.flags = (((uint32_t)sRed[0] & full) == full) ? WU_ALLMASK : 0;
+        p.user[user] = st;
+        p.count[user] = 0;
+    }
+}
+
+// ---- K1 (cut + expand): one warp per user ---------------------------------------------------------------------------
+// Lane l owns the candidates i = 32 j + l, j < 16 (cap <= 512).  `level` is the tree level of the current candidates;
+// the children written to code[(slot ^ 1)] sit on level + 1.
+__device__ __forceinline__ void warp_select(const uint32_t (&k)[16], int kk, uint32_t lo, uint32_t hi, int clo,
+                                            uint32_t &kdn, uint32_t &kup, int &iters)
+{
+    int chi = 0, it = 0;
+#pragma unroll 1
+    while (clo != kk && hi - lo > 255u && hi > lo) {
+        uint32_t mid = lo + ((hi - lo) >> 1) + 1u;
+        if (it < 12) {
+            const float flo = key_to_float(lo), fhi = key_to_float(hi);
+            const float fr = (it & 1) ? 0.5f : ((float)(kk - chi) - 0.5f) / (float)(clo - chi);
+            const float fm = fhi - (fhi - flo) * fr;
+            if (fm == fm) mid = order_key(fm);
+        }
+        mid = min(max(mid, lo + 1u), hi);
+        int c = 0;
+#pragma unroll
+        for (int j = 0; j < 16; j++) c += k[j] >= mid ? 1 : 0;
+        c = __reduce_add_sync(0xffffffffu, c);
+        it++;
+        if (c >= kk) { lo = mid; clo = c; } else { hi = mid - 1u; chi = c; }
+    }
+    iters = it;
+    if (clo == kk) {
+        uint32_t a = 0xffffffffu, b = 0u;
+#pragma unroll
+        for (int j = 0; j < 16; j++) { a = min(a, k[j] >= lo ? k[j] : 0xffffffffu); b = max(b, k[j] < lo ? k[j] : 0u); }
+        kdn = __reduce_min_sync(0xffffffffu, a);
+        kup = __reduce_max_sync(0xffffffffu, b);
+        if (kup == 0u) kup = kdn;
+    } else {
+        kdn = lo; kup = hi;
+    }
+}
+
+// children of the surviving candidates in candidate order, the bound of the scores about to be computed, counters
+__device__ __forceinline__ void wave_expand_finish(const WaveParams &p, WaveUser *st, int user, int level, int lane, const int32_t (&code)[16],
+                                                   uint32_t keep, int count, int32_t *__restrict__ nxt, int flags,
+                                                   unsigned long long st_cut, unsigned long long st_recut, unsigned long long st_iters)
+{
+    const uint32_t lt = (1u << lane) - 1u;
+    int out = 0;
+    const uint32_t *bm = (level + 1 >= p.sparse_from) ? p.exists : nullptr;
+    const int nj = (count + 31) >> 5;
+#pragma unroll
+    for (int j = 0; j < 16; j++) {
+        if (j < nj) {
+            const bool kp = keep >> j & 1u;
+            const int64_t c = code[j];
+            const bool a1 = kp && code_exists(bm, 2 * c + 1), a2 = kp && code_exists(bm, 2 * c + 2);
+            const uint32_t m1 = __ballot_sync(0xffffffffu, a1), m2 = __ballot_sync(0xffffffffu, a2);
+            int o = out + __popc(m1 & lt) + __popc(m2 & lt);
+            if (a1) nxt[o++] = (int32_t)(2 * c + 1);
+            if (a2) nxt[o] = (int32_t)(2 * c + 2);
+            out += __popc(m1) + __popc(m2);
+        }
+    }
+    if (lane == 0) {
+        p.count[user] = out;
+        // eps of the scores about to be computed (children sit on tree level `level + 1`)
+        const float u = 5.9604645e-8f;
+        const float vx = __ldg(p.lvl_vx + level + 1), nx = __ldg(p.lvl_nx + level + 1);
+        const float smax = p.scale * nx * st->kmax;
+        const float ds = 6.1035156e-5f * smax;
+        const float dp1 = 2.1f * ds + 2.0f * (float)(p.T + 8) * u + 2.0f * 9.5367432e-7f * (1.0f + 2.0f * smax);
+        float eps = p.cA * vx + p.cZ * st->zk + (p.cH + dp1) * st->hw * 1.05f + p.cGamma;
+        if (!(ds < 0.04f) || !(eps < 1e30f)) eps = __int_as_float(0x7f800000);
+        st->eps = eps * p.tau;
+        if (out > 0) st->flags = flags | WU_SCORED;
+        if (p.stats) {
+            if (st_cut) { atomicAdd(&p.stats[0], st_cut); atomicAdd(&p.stats[7], st_iters); }
+            if (st_recut) atomicAdd(&p.stats[1], st_recut);
+            atomicAdd(&p.stats[3], (unsigned long long)out);
+        }
+    }
+}
+
+struct WaveStrictW { const float *wattT, *w1T, *b1, *w2; float b2; };
+
+// 4 users per CTA.  Phase 1: every warp cuts its user; a cut whose band cannot be deferred (fast-score gap at the cut below
+// eps / 32) is parked.  Phase 2: the whole CTA scores the band rows of its parked users strictly (sequential-k fma chains,
+// the oracle's bits).  Phase 3: the parked warps finish their cuts with the strict order.
+static __global__ void __launch_bounds__(128) wave_select_kernel(const WaveParams p, const WaveStrictW sw, int level, int slot)
+{
+    constexpr int MU = WaveGeo::MAX_UNC;
+    __shared__ __align__(16) float sScr[FastGeo::STRICT_SCR / 4];
+    __shared__ uint32_t sKeyU[4][MU];
+    __shared__ int sUPos[4][MU];
+    __shared__ int32_t sLCode[4][MU];
+    __shared__ float sLStr[4][MU];
+    __shared__ uint32_t sKeep[4][32], sUnc[4][32];
+    __shared__ int sGap[4][2];
+    __shared__ int sPark[4][2];                                   // n_unc (0 = not parked), need
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int user = blockIdx.x * 4 + warp;
+    const uint32_t lt = (1u << lane) - 1u;
+    if (lane == 0) sPark[warp][0] = 0;
+    WaveUser *st = p.user + (user < p.B ? user : 0);
+    int flags = 0, beam = 1, s_level = 0;
+    bool live = user < p.B;
+    if (live) {
+        flags = st->flags;
+        beam = p.beam_user ? __ldg(p.beam_user + user) : p.beam;
+        s_level = 31 - __clz(beam);
+        if ((flags & WU_REDO) || level < s_level || s_level >= p.leaf_level) {
+            if (lane == 0) p.count[user] = 0;
+            live = false;
+        }
+    }
+    const int32_t *cur = p.code[slot] + (size_t)(live ? user : 0) * p.cap;
+    int32_t *nxt = p.code[slot ^ 1] + (size_t)(live ? user : 0) * p.cap;
+    int32_t code[16];
+    uint32_t keep = 0;                                            // bit j: candidate 32 j + lane survives the cut
+    int count = 0;
+    unsigned long long st_cut = 0, st_recut = 0, st_iters = 0;
+    bool parked = false;
+    if (live) {
+        if (level == s_level) {                                   // initial beam: every existing code of the level, no scores yet
+            const int64_t start = ((int64_t)1 << s_level) - 1;
+            count = 1 << s_level;
+#pragma unroll
+            for (int j = 0; j < 16; j++) {
+                const int i = 32 * j + lane;
+                code[j] = (int32_t)(start + i);
+                if (i < count && code_exists(p.exists, start + i)) keep |= 1u << j;
+            }
+        } else {
+            count = p.count[user];
+            float f[16];
+            uint32_t key[16];
+            const float *sc = p.score + (size_t)user * p.cap;
+#pragma unroll
+            for (int j = 0; j < 16; j++) {
+                const int i = 32 * j + lane;
+                code[j] = i < count ? cur[i] : 0;
+                f[j] = i < count ? sc[i] : 0.0f;
+                key[j] = i < count ? order_key(f[j]) : 0u;
+                if (i < count) keep |= 1u << j;
+            }
+            if (count > beam) {
+                st_cut = 1;
+                uint32_t mn = 0xffffffffu, mx = 0u;
+#pragma unroll
+                for (int j = 0; j < 16; j++) { mn = min(mn, key[j] ? key[j] : 0xffffffffu); mx = max(mx, key[j]); }
+                mn = __reduce_min_sync(0xffffffffu, mn);
+                mx = __reduce_max_sync(0xffffffffu, mx);
+                uint32_t kdn, kup;
+                int iters;
+                warp_select(key, beam, mn, mx, count, kdn, kup, iters);
+                st_iters = iters;
+                const float eps_level = st->eps;
+                const float band = 2.0f * eps_level * 1.0001f + 1e-30f;
+                const float up = key_to_float(kup) + band, dn = key_to_float(kdn) - band;
+                uint32_t unc = 0;
+#pragma unroll
+                for (int j = 0; j < 16; j++) {
+                    if (keep >> j & 1u) {
+                        if (f[j] > up) { }
+                        else if (f[j] < dn) keep &= ~(1u << j);
+                        else unc |= 1u << j;
+                    }
+                }
+                const int n_keep = __reduce_add_sync(0xffffffffu, __popc(keep)), n_unc = __reduce_add_sync(0xffffffffu, __popc(unc));
+                if (n_keep != beam) {                             // some uncertain row must go
+                    st_recut = 1;
+                    if (n_unc > MU) {
+                        if (lane == 0) { st->flags = flags | WU_REDO; st->redo_why = 0; p.count[user] = 0; }
+                        live = false;
+                    } else {
+                        const int need = beam - (n_keep - n_unc);
+                        int base = 0, myslot[16];
+#pragma unroll
+                        for (int j = 0; j < 16; j++) {
+                            const uint32_t m = __ballot_sync(0xffffffffu, unc >> j & 1u);
+                            myslot[j] = base + __popc(m & lt);
+                            if (unc >> j & 1u) { sKeyU[warp][myslot[j]] = key[j]; sUPos[warp][myslot[j]] = 32 * j + lane; }
+                            base += __popc(m);
+                        }
+                        __syncwarp();
+                        uint32_t chosen = 0;
+#pragma unroll
+                        for (int j = 0; j < 16; j++) {
+                            if (unc >> j & 1u) {
+                                const int me = 32 * j + lane;
+                                int fr = 0;
+                                for (int q = 0; q < n_unc; q++) {
+                                    const uint32_t kq = sKeyU[warp][q];
+                                    fr += (kq > key[j] || (kq == key[j] && sUPos[warp][q] < me)) ? 1 : 0;
+                                }
+                                if (fr == need - 1) sGap[warp][0] = __float_as_int(f[j]);
+                                if (fr == need) sGap[warp][1] = __float_as_int(f[j]);
+                                if (fr < need) chosen |= 1u << j;
+                            }
+                        }
+                        __syncwarp();
+                        const float gap = __int_as_float(sGap[warp][0]) - __int_as_float(sGap[warp][1]);
+                        const int vcount = st->vcount, nseg = st->nseg;
+                        const bool defer = gap >= 0.03125f * eps_level && vcount + n_unc <= WaveGeo::VCAP && nseg < 32 && eps_level < 1e30f;
+                        if (defer) {
+#pragma unroll
+                            for (int j = 0; j < 16; j++) {
+                                if (unc >> j & 1u) {
+                                    const uint32_t ch = chosen >> j & 1u;
+                                    const size_t e = (size_t)user * WaveGeo::VCAP + vcount + myslot[j];
+                                    p.v_code[e] = code[j]; p.v_fast[e] = f[j];
+                                    p.v_meta[e] = (uint32_t)vcount | ((uint32_t)n_unc << 8) | ((uint32_t)need << 16) | (ch << 24) | ((uint32_t)nseg << 25);
+                                    if (!ch) keep &= ~(1u << j);
+                                }
+                            }
+                            __syncwarp();
+                            if (lane == 0) { p.v_segeps[(size_t)user * 32 + nseg] = eps_level; st->vcount = vcount + n_unc; st->nseg = nseg + 1; }
+                        } else {                                  // park: strict scores of the band decide (phases 2 and 3)
+#pragma unroll
+                            for (int j = 0; j < 16; j++)
+                                if (unc >> j & 1u) { sLCode[warp][myslot[j]] = code[j]; sLStr[warp][myslot[j]] = f[j]; }
+                            sKeep[warp][lane] = keep; sUnc[warp][lane] = unc;
+                            if (lane == 0) { sPark[warp][0] = n_unc; sPark[warp][1] = need; }
+                            parked = true;
+                        }
+                    }
+                }
+            }
+        }
+        if (live && !parked) wave_expand_finish(p, st, user, level, lane, code, keep, count, nxt, flags, st_cut, st_recut, st_iters);
+    }
+    __syncthreads();
+    // ---- phase 2: strict scores of the parked bands, whole CTA ----
+    bool any = false;
+#pragma unroll 1
+    for (int w = 0; w < 4; w++) {
+        const int n = sPark[w][0];
+        if (n == 0) continue;
+        any = true;
+        const int pu = blockIdx.x * 4 + w;
+        for (int i = tid; i < kMaxT * 64; i += 128) {              // history rows (fp32), zero rows for padding
+            const int j = i >> 6, k = i & 63;
+            const int c = j < p.T ? p.hist[(size_t)pu * p.T + j] : -1;
+            sScr[j * FastGeo::KLD + k] = c >= 0 ? __ldg(p.emb + (size_t)c * 64 + k) : 0.0f;
+        }
+        if (tid < n) sKeyU[w][tid] = __float_as_uint(sLStr[w][tid]);   // keep the fast scores (error statistics)
+        __syncthreads();
+        strict_score_batch128(p.emb, sLCode[w], n, sLStr[w], sScr, p.user[pu].maskbits, p.T, p.scale, sw.wattT, sw.w1T, sw.b1, sw.w2, sw.b2);
+    }
+    if (!any) return;
+    __syncthreads();
+    // ---- phase 3: the parked warps finish their cuts with the strict order ----
+    if (parked) {
+        const int n_unc = sPark[warp][0], need = sPark[warp][1];
+        const uint32_t unc = sUnc[warp][lane];
+        keep = sKeep[warp][lane];
+        const float eps_level = st->eps;
+        int base = 0, tie = 0;
+        float ratio = 0.0f;
+#pragma unroll
+        for (int j = 0; j < 16; j++) {
+            const uint32_t m = __ballot_sync(0xffffffffu, unc >> j & 1u);
+            if (unc >> j & 1u) {
+                const int me = base + __popc(m & lt);
+                const float mine = sLStr[warp][me];
+                const uint32_t ks = order_key(mine);
+                // strict rank = rows strictly above (+ an undetermined share of exact ties: the reference orders ties by candidate
+                // position, which this path does not track).  Only a tie that STRADDLES the cut is undecidable here.
+                int g = 0, e = 0;
+                for (int q = 0; q < n_unc; q++) {
+                    const uint32_t kq = order_key(sLStr[warp][q]);
+                    g += kq > ks ? 1 : 0;
+                    e += (kq == ks && q != me) ? 1 : 0;
+                }
+                tie |= (g < need && g + e >= need) ? 1 : 0;
+                if (!(g + e < need)) keep &= ~(1u << j);
+                if (eps_level > 0.0f && eps_level < 1e30f) ratio = fmaxf(ratio, fabsf(mine - __uint_as_float(sKeyU[warp][me])) / eps_level);
+            }
+            base += __popc(m);
+        }
+        tie = __any_sync(0xffffffffu, tie);
+        if (p.stats) {
+            for (int o = 16; o > 0; o >>= 1) ratio = fmaxf(ratio, __shfl_xor_sync(0xffffffffu, ratio, o));
+            if (lane == 0) {
+                if (ratio > 0.0f) atomicMax(reinterpret_cast<unsigned int *>(&p.stats[4]), __float_as_uint(ratio));
+                atomicAdd(&p.stats[2], (unsigned long long)n_unc); atomicAdd(&p.stats[6], 1ull);
+            }
+        }
+        if (tie) {
+            if (lane == 0) {
+                st->flags = flags | WU_REDO; st->redo_why = 1; p.count[user] = 0;
+                if (p.stats) { atomicAdd(&p.stats[0], st_cut); atomicAdd(&p.stats[1], st_recut); }
+            }
+        } else {
+            wave_expand_finish(p, st, user, level, lane, code, keep, count, nxt, flags, st_cut, st_recut, st_iters);
+        }
+    }
+}
+
+// ---- K1 (score): persistent warp-specialised tile scorer ------------------------------------------------------------
+__device__ __forceinline__ void mbar_arrive(uint64_t *bar)
+{
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tma_gather4(uint32_t dst, const void *tmap, uint32_t bar, int c0, int r0, int r1, int r2, int r3)
+{
+    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.tile::gather4.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6, %7}], [%2];"
+                 ::"r"(dst), "l"(tmap), "r"(bar), "r"(c0), "r"(r0), "r"(r1), "r"(r2), "r"(r3) : "memory");
+}
+constexpr uint32_t kIdescBf16M128N16 = (1u << 4) | (1u << 7) | (1u << 10) | ((16u >> 3) << 17) | ((128u >> 4) << 24);
+
+// MODE 0: rows gathered by the TMA (tile::gather4, 128-byte swizzle); MODE 1: by 16-byte cp.async with the swizzle applied
+// in the address (same operand tile; the reference path for the TMA one).
+template <int MODE>
+static __global__ void __launch_bounds__(WaveGeo::THREADS, 3)
+wave_score_kernel(const __grid_constant__ CUtensorMap tmap, const WaveParams p, const WaveW2 w, int slot, int32_t *tile_counter, int ntiles, int tpu)
+{
+    using G = WaveGeo;
+    extern __shared__ unsigned char smem_dyn[];
+    unsigned char *sm = reinterpret_cast<unsigned char *>((reinterpret_cast<uintptr_t>(smem_dyn) + 1023) & ~(uintptr_t)1023);
+    uint64_t *bar = reinterpret_cast<uint64_t *>(sm + G::BAR);
+    volatile int4 *sInfo = reinterpret_cast<volatile int4 *>(sm + G::INFO);
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const uint32_t sbase = smem_u32(sm);
+
+    if (tid == 128) {
+        mbar_init(&bar[WB_W1], 1);
+        mbar_init(&bar[WB_XFULL], MODE == 0 ? 1 : 32);
+        mbar_init(&bar[WB_M1], 1);
+        mbar_init(&bar[WB_PFULL], 4);
+        mbar_init(&bar[WB_HFULL], 1);
+        mbar_init(&bar[WB_M2], 1);
+        mbar_init(&bar[WB_TFREE], 4);
+    }
+    if (warp == 4) tmem_alloc(reinterpret_cast<uint32_t *>(sm + G::TMEMP), 128);     // Hacc [0, 64), S [64, 80)
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t *>(sm + G::TMEMP);
+
+    if (warp == 4) {
+        // ================= control warp: tile scheduler, TMA gathers, MMA issue =================
+        const bool leader = lane == 0;
+        if (leader) {
+            mbar_expect_tx(&bar[WB_W1], 16384);
+            tma_bulk_g2s(sm + G::W1H, p.w1img, 16384, &bar[WB_W1]);
+        }
+        auto grab = [&](int &u, int &row0, int &nr) -> bool {
+            for (;;) {
+                int idx = 0;
+                if (leader) idx = atomicAdd(tile_counter, 1);
+                idx = __shfl_sync(0xffffffffu, idx, 0);
+                if (idx >= ntiles) return false;
+                u = idx / tpu;
+                row0 = (idx - u * tpu) * 128;
+                const int cnt = __ldg(p.count + u);
+                nr = cnt - row0 < 128 ? cnt - row0 : 128;
+                if (nr > 0) return true;
+            }
+        };
+        auto issue_x = [&](int u, int row0, int nr) {            // candidate rows + the user's K operand -> WB_XFULL
+            const int32_t *cp = p.code[slot] + (size_t)u * p.cap + row0;
+            const unsigned char *uop = p.uop + (size_t)u * G::UOP_BYTES;
+            if (MODE == 0) {
+                const int nl = (nr + 3) >> 2;
+                if (leader) mbar_expect_tx(&bar[WB_XFULL], (uint32_t)nl * 1024u + 4096u);
+                __syncwarp();
+                if (lane < nl) {
+                    int4 c = *reinterpret_cast<const int4 *>(cp + 4 * lane);
+                    const int r = 4 * lane;
+                    if (r + 1 >= nr) c.y = c.x;
+                    if (r + 2 >= nr) c.z = c.x;
+                    if (r + 3 >= nr) c.w = c.x;
+                    tma_gather4(sbase + G::XH + lane * 512, &tmap, smem_u32(&bar[WB_XFULL]), 0, 2 * c.x, 2 * c.y, 2 * c.z, 2 * c.w);
+                    tma_gather4(sbase + G::XL + lane * 512, &tmap, smem_u32(&bar[WB_XFULL]), 0, 2 * c.x + 1, 2 * c.y + 1, 2 * c.z + 1, 2 * c.w + 1);
+                }
+                if (leader) tma_bulk_g2s(sm + G::KH, uop, 4096, &bar[WB_XFULL]);
+            } else {
+                for (int it = 0; it < 64; it++) {
+                    const int idx = it * 32 + lane, row = idx >> 4, ch = idx & 15;
+                    const int rr = row < nr ? row : 0;
+                    const int32_t c = __ldg(cp + rr);
+                    unsigned char *dst = sm + (ch < 8 ? G::XH : G::XL) + row * 128 + (((ch & 7) ^ (row & 7)) << 4);
+                    cp_async16(dst, p.split + (size_t)c * 256 + ch * 16);
+                }
+                for (int it = 0; it < 8; it++) cp_async16(sm + G::KH + (it * 32 + lane) * 16, uop + (it * 32 + lane) * 16);
+                cp_async_commit();
+                cp_async_wait<0>();
+                fence_proxy_async();
+                mbar_arrive(&bar[WB_XFULL]);
+            }
+        };
+        auto issue_h = [&](int u, int row0, int nr, int itn) {   // tile info + H operand + softmax mask -> WB_HFULL
+            if (leader) {
+                const int fl = u >= 0 ? p.user[u].flags : 0;
+                int4 inf; inf.x = u; inf.y = row0; inf.z = nr; inf.w = fl;
+                *const_cast<int4 *>(sInfo + (itn & 1)) = inf;
+                if (u >= 0) {
+                    mbar_expect_tx(&bar[WB_HFULL], 4160);
+                    tma_bulk_g2s(sm + G::HH, p.uop + (size_t)u * G::UOP_BYTES + 4096, 4160, &bar[WB_HFULL]);
+                } else {
+                    mbar_arrive(&bar[WB_HFULL]);
+                }
+            }
+            __syncwarp();
+        };
+        auto nsdesc = [&](uint32_t off, uint32_t lbo) -> uint64_t {
+            return ((uint64_t)(0x4000u | (128u >> 4)) << 32) | (uint64_t)(((sbase + off) >> 4) | ((lbo >> 4) << 16));
+        };
+        auto swdesc = [&](uint32_t off) -> uint64_t {             // K-major, SWIZZLE_128B: SBO 1024 (8 rows x 128 B), LBO unused (1)
+            return ((uint64_t)2 << 61) | ((uint64_t)(0x4000u | (1024u >> 4)) << 32) | (uint64_t)(((sbase + off) >> 4) | (1u << 16));
+        };
+        int it = 0, u, row0, nr;
+        bool have = grab(u, row0, nr);
+        if (have) { issue_x(u, row0, nr); issue_h(u, row0, nr, 0); }
+        mbar_wait(&bar[WB_W1], 0);
+        while (have) {
+            int u2 = -1, row2 = 0, nr2 = 0;
+            const bool have2 = grab(u2, row2, nr2);
+            const uint32_t par = it & 1;
+            mbar_wait(&bar[WB_XFULL], par);
+            if (it > 0) mbar_wait(&bar[WB_TFREE], par ^ 1);
+            tc_fence_after();
+            if (leader) {
+                const uint64_t dXh = swdesc(G::XH), dXl = swdesc(G::XL);
+                const uint64_t dWh = nsdesc(G::W1H, 1024), dWl = nsdesc(G::W1L, 1024);
+                const uint64_t dKh = nsdesc(G::KH, 256), dKl = nsdesc(G::KL, 256);
+#pragma unroll
+                for (int ks = 0; ks < 4; ks++) {
+                    const uint64_t ah = dXh + ks * 2, al = dXl + ks * 2;
+                    const uint64_t bh = dWh + ks * 128, bl = dWl + ks * 128;
+                    const uint64_t kh = dKh + ks * 32, kl = dKl + ks * 32;
+                    umma_bf16(tmem_base, ah, bh, kIdescBf16M128N64, ks > 0);
+                    umma_bf16(tmem_base, ah, bl, kIdescBf16M128N64, 1);
+                    umma_bf16(tmem_base, al, bh, kIdescBf16M128N64, 1);
+                    umma_bf16(tmem_base + 64, ah, kh, kIdescBf16M128N16, ks > 0);
+                    umma_bf16(tmem_base + 64, ah, kl, kIdescBf16M128N16, 1);
+                    umma_bf16(tmem_base + 64, al, kh, kIdescBf16M128N16, 1);
+                }
+                umma_commit(&bar[WB_M1]);
+            }
+            __syncwarp();
+            if (have2) {                                          // X and K are free once the MMAs above have completed
+                mbar_wait(&bar[WB_M1], par);
+                issue_x(u2, row2, nr2);
+            }
+            mbar_wait(&bar[WB_PFULL], par);
+            mbar_wait(&bar[WB_HFULL], par);
+            tc_fence_after();
+            if (leader) {
+                const uint64_t ah = nsdesc(G::PH, 2048), al = nsdesc(G::PL, 2048);
+                const uint64_t dHh = nsdesc(G::HH, 1024), dHl = nsdesc(G::HL, 1024);
+                umma_bf16(tmem_base, ah, dHh, kIdescBf16M128N64, 1);
+                umma_bf16(tmem_base, ah, dHl, kIdescBf16M128N64, 1);
+                umma_bf16(tmem_base, al, dHh, kIdescBf16M128N64, 1);
+                umma_commit(&bar[WB_M2]);
+            }
+            __syncwarp();
+            mbar_wait(&bar[WB_M2], par);                          // H, addv and P are free
+            issue_h(have2 ? u2 : -1, row2, nr2, it + 1);
+            have = have2; u = u2; row0 = row2; nr = nr2;
+            it++;
+        }
+        if (it == 0) issue_h(-1, 0, 0, 0);                       // no tile at all: release the consumers
+    } else {
+        // ================= consumer warps: softmax, epilogue =================
+        const uint32_t tmem_lane = (uint32_t)(warp * 32) << 16;
+        const float scale2 = p.scale * 1.4426950408889634f, inv_T = 1.0f / (float)p.T;
+        const float *sAddv = reinterpret_cast<const float *>(sm + G::ADDV);
+        for (int it = 0;; it++) {
+            const uint32_t par = it & 1;
+            mbar_wait(&bar[WB_HFULL], par);
+            const int4 inf = *const_cast<const int4 *>(sInfo + par);
+            if (inf.x < 0) break;
+            const int nr = inf.z;
+            const bool active = warp * 32 < nr;
+            mbar_wait(&bar[WB_M1], par);
+            tc_fence_after();
+            if (active) {
+                float sc[16];
+                tmem_ld16(tmem_base + tmem_lane + 64, sc);
+                if (inf.w & WU_ALLMASK) {
+#pragma unroll
+                    for (int j = 0; j < 16; j++) sc[j] = j < p.T ? inv_T : 0.0f;
+                } else {
+                    float mx = -3.4028234663852886e+38f;
+#pragma unroll
+                    for (int j = 0; j < 16; j++) { sc[j] = fmaf(sc[j], scale2, sAddv[j]); mx = fmaxf(mx, sc[j]); }
+                    float sum = 0.0f;
+#pragma unroll
+                    for (int j = 0; j < 16; j++) { sc[j] = ex2_approx(sc[j] - mx); sum += sc[j]; }
+                    const float inv = 1.0f / sum;
+#pragma unroll
+                    for (int j = 0; j < 16; j++) sc[j] *= inv;
+                }
+                sc[15] = 1.0f;
+                uint4 hi, lo;
+                split8(*reinterpret_cast<float(*)[8]>(&sc[0]), hi, lo);
+                *reinterpret_cast<uint4 *>(sm + G::PH + tid * 16) = hi;
+                *reinterpret_cast<uint4 *>(sm + G::PL + tid * 16) = lo;
+                split8(*reinterpret_cast<float(*)[8]>(&sc[8]), hi, lo);
+                *reinterpret_cast<uint4 *>(sm + G::PH + 2048 + tid * 16) = hi;
+                *reinterpret_cast<uint4 *>(sm + G::PL + 2048 + tid * 16) = lo;
+            }
+            fence_proxy_async();
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&bar[WB_PFULL]);
+            mbar_wait(&bar[WB_M2], par);
+            tc_fence_after();
+            float h0[32], h1[32];
+            if (active) {
+                tmem_ld32(tmem_base + tmem_lane, h0);
+                tmem_ld32(tmem_base + tmem_lane + 32, h1);
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&bar[WB_TFREE]);
+            if (active) {
+                float logit = 0.0f;
+#pragma unroll
+                for (int c = 0; c < 32; c++) logit = fmaf(fmaxf(h0[c], 0.0f), w.w2[c], logit);
+#pragma unroll
+                for (int c = 0; c < 32; c++) logit = fmaf(fmaxf(h1[c], 0.0f), w.w2[32 + c], logit);
+                if (tid < nr) p.score[(size_t)inf.x * p.cap + inf.y + tid] = logit + w.b2;
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 4) tmem_dealloc(tmem_base, 128);
+}
+
+// ---- K3: strict verification of the deferred cuts + topk, one CTA per user ---------------------------------------------
+static __global__ void __launch_bounds__(FastGeo::THREADS, 2) wave_final_kernel(const WaveParams p, const BeamParams<float> bp, int slot)
+{
+    using G = FastGeo;
+    constexpr int E = 64;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    float *sScr = reinterpret_cast<float *>(smem_raw);                                  // strict scratch; [0, 16 * KLD) = history
+    unsigned char *sp = smem_raw + G::STRICT_SCR;
+    float *sScore = reinterpret_cast<float *>(sp); sp += (size_t)p.cap * 4;
+    int32_t *sCode = reinterpret_cast<int32_t *>(sp); sp += (size_t)p.cap * 4;
+    uint32_t *sKeyU = reinterpret_cast<uint32_t *>(sp); sp += (size_t)p.cap * 4;
+    int *sUPos = reinterpret_cast<int *>(sp); sp += G::MAX_FINAL * 4;
+    int32_t *sLCode = reinterpret_cast<int32_t *>(sp); sp += (G::VCAP + G::MAX_FINAL) * 4;
+    float *sLStr = reinterpret_cast<float *>(sp); sp += (G::VCAP + G::MAX_FINAL) * 4;
+    int *sRed = reinterpret_cast<int *>(sp); sp += 256 * 4;
+    int *sMisc = reinterpret_cast<int *>(sp); sp += 32 * 4;
+    const int tid = threadIdx.x, lane = tid & 31, user = blockIdx.x, T = p.T;
+    const WaveUser st = p.user[user];
+    bool redo = (st.flags & WU_REDO) != 0;
+    int redo_why = st.redo_why;
+    float st_ratio = 0.0f;
+    unsigned long long st_rerows = 0;
+    auto track_ratio = [&](float strict, float fast, float eps_now) {
+        if (eps_now > 0.0f && eps_now < 1e30f) {
+            const float ratio = fabsf(strict - fast) / eps_now;
+            if (ratio > st_ratio) st_ratio = ratio;
+        }
+    };
+    if (!redo) {
+        const int beam = p.beam_user ? p.beam_user[user] : p.beam;
+        const int s_level = 31 - __clz(beam);
+        const int count = (s_level < p.leaf_level) ? p.count[user] : 0;
+        if (s_level == p.leaf_level) { redo = true; redo_why = 2; }   // nothing is scored (beam >= 2^leaf_level): every score ties -> strict kernel
+        const bool scored = (st.flags & WU_SCORED) != 0;
+        const float eps_level = st.eps;
+        const int vcount = st.vcount;
+        for (int i = tid; i < count; i += G::THREADS) {
+            sScore[i] = p.score[(size_t)user * p.cap + i];
+            sCode[i] = p.code[slot][(size_t)user * p.cap + i];
+        }
+        for (int i = tid; i < kMaxT * E; i += G::THREADS) {      // history rows (fp32) for the strict scorer
+            const int j = i >> 6, k = i & 63;
+            const int c = j < T ? p.hist[(size_t)user * T + j] : -1;
+            sScr[j * G::KLD + k] = c >= 0 ? __ldg(p.emb + (size_t)c * E + k) : 0.0f;
+        }
+        if (tid == 0) sMisc[0] = 0;
+        __syncthreads();
+        const int64_t leaf_start = ((int64_t)1 << p.leaf_level) - 1;
+        const int64_t c0 = bp.cons_off ? bp.cons_off[user] : 0, c1 = bp.cons_off ? bp.cons_off[user + 1] : 0;
+        int valid = 0;
+        for (int base = 0; base < count; base += G::THREADS) {
+            const int i = base + tid;
+            bool keep = false;
+            if (i < count) {
+                const int64_t sl = (int64_t)sCode[i] - leaf_start;
+                const int32_t item = (sl >= 0 && sl < ((int64_t)1 << p.leaf_level)) ? __ldg(bp.leaf_item + sl) : -1;
+                keep = item >= 0;
+                for (int64_t q = c0; q < c1 && keep; q++) keep = (__ldg(bp.cons + q) != item);
+            }
+            if (i < count) sKeyU[i] = keep ? order_key(sScore[i]) : 0u;
+            valid += __syncthreads_count(keep);
+        }
+        const int kk = valid < bp.topk ? valid : bp.topk;
+        if (kk > 0 && !scored) { redo = true; redo_why = 2; }
+        int na = 0;
+        if (kk > 0 && !redo) {
+            uint32_t kdn, kup;
+            {
+                const uint32_t key0 = 2 * tid < count ? sKeyU[2 * tid] : 0u, key1 = 2 * tid + 1 < count ? sKeyU[2 * tid + 1] : 0u;
+                uint32_t lo, hi;
+                int nv;
+                block_minmax(key0, key1, sRed, lo, hi, nv);
+                block_select(key0, key1, kk, lo, hi, nv, sRed, kdn, kup, [](int) {});
+            }
+            const float dn = key_to_float(kdn) - (2.0f * eps_level * 1.0001f + 1e-30f);
+            __syncthreads();
+            for (int i = tid; i < count; i += G::THREADS)
+                if (sKeyU[i] != 0u && !(sScore[i] < dn)) {
+                    const int sl = atomicAdd(&sMisc[0], 1);
+                    if (sl < G::MAX_FINAL) sUPos[sl] = i;
+                }
+            __syncthreads();
+            na = sMisc[0];
+            if (na > G::MAX_FINAL) { redo = true; redo_why = 3; }
+        }
+        if (!redo && vcount + na > 0) {
+            for (int e = tid; e < vcount; e += G::THREADS) sLCode[e] = p.v_code[(size_t)user * WaveGeo::VCAP + e];
+            for (int q = tid; q < na; q += G::THREADS) sLCode[vcount + q] = sCode[sUPos[q]];
+            st_rerows = vcount + na;
+            __syncthreads();
+            strict_score_batch(p.emb, sLCode, vcount + na, sLStr, sScr, st.maskbits, T, p.scale, bp.wattT, bp.w1T, bp.b1, bp.w2, __ldg(bp.b2));
+            int bad = 0;
+            for (int e = tid; e < vcount; e += G::THREADS) {       // the deferred cuts: strict order must pick the same rows
+                const uint32_t meta = p.v_meta[(size_t)user * WaveGeo::VCAP + e];
+                const int s0 = meta & 255u, n = (meta >> 8) & 255u, need = (meta >> 16) & 255u, chosen = (meta >> 24) & 1u;
+                track_ratio(sLStr[e], p.v_fast[(size_t)user * WaveGeo::VCAP + e], p.v_segeps[(size_t)user * 32 + (meta >> 25)]);
+                const uint32_t ks = order_key(sLStr[e]);
+                int rank = 0, ties = 0;
+                for (int q = s0; q < s0 + n; q++) {
+                    const uint32_t kq = order_key(sLStr[q]);
+                    rank += kq > ks ? 1 : 0;
+                    ties += (kq == ks && q != e) ? 1 : 0;
+                }
+                bad |= (rank < need && rank + ties >= need) ? 1 : 0;
+                bad |= ((rank + ties < need ? 1 : 0) != chosen) ? 2 : 0;
+            }
+            if (tid < na) {
+                const float mine = sLStr[vcount + tid];
+                const int ps = sUPos[tid];
+                track_ratio(mine, sScore[ps], eps_level);
+                const uint32_t ks = order_key(mine);
+                int rank = 0, ties = 0;
+                for (int q = 0; q < na; q++) {
+                    const uint32_t kq = order_key(sLStr[vcount + q]);
+                    rank += kq > ks ? 1 : 0;
+                    ties += (kq == ks && q != tid) ? 1 : 0;
+                }
+                bad |= (ties > 0 && rank < kk) ? 1 : 0;
+                if (rank < kk) {
+                    bp.out_items[(size_t)user * bp.out_stride + rank] = __ldg(bp.leaf_item + ((int64_t)sCode[ps] - leaf_start));
+                    bp.out_scores[(size_t)user * bp.out_stride + rank] = mine;
+                }
+            }
+            const int anybad = __syncthreads_or(bad), proof = __syncthreads_or(bad & 2);
+            if (anybad) { redo = true; redo_why = 4 + (proof ? 1 : 0); }
+        }
+        if (!redo) {
+            for (int i = kk + tid; i < bp.topk; i += G::THREADS) {
+                bp.out_items[(size_t)user * bp.out_stride + i] = -1;
+                bp.out_scores[(size_t)user * bp.out_stride + i] = 0.0f;
+            }
+            if (tid == 0) bp.out_counts[user] = kk;
+        }
+    }
+    if (redo && tid == 0) {
+        p.redo_list[atomicAdd(p.redo_count, 1)] = user;
+        *reinterpret_cast<volatile int32_t *>(p.host_flags + 1) = 1;
+        if (p.stats) { atomicAdd(&p.stats[5], 1ull); atomicAdd(&p.stats[24 + (redo_why & 7)], 1ull); }
+    }
+    if (p.stats) {
+        for (int o = 16; o > 0; o >>= 1) st_ratio = fmaxf(st_ratio, __shfl_xor_sync(0xffffffffu, st_ratio, o));
+        if (lane == 0 && st_ratio > 0.0f) atomicMax(reinterpret_cast<unsigned int *>(&p.stats[4]), __float_as_uint(st_ratio));
+        if (tid == 0 && st_rerows) atomicAdd(&p.stats[2], st_rerows);
+    }
+}
+
+}  // namespace dmg

@@ -7,6 +7,7 @@
 
 #include "beam_kernels.cuh"
 #include "beam_fast.cuh"
+#include "beam_wave.cuh"
 #include "rows_kernels.cuh"
 
 using namespace dmg;
@@ -73,8 +74,10 @@ static void free_tree(TreeDev &t)
 static void free_din(DinDev &d)
 {
     cudaFree(d.d_params); cudaFree(d.d_wattT); cudaFree(d.d_w1T); cudaFree(d.d_grad); cudaFree(d.d_m); cudaFree(d.d_v);
+    cudaFree(d.d_split); cudaFree(d.d_w1img);
     d = DinDev();
 }
+static int32_t compute_fast_bounds(dmg_handle_t h);
 void dmg_free_dr(DrDev &d);     // dr.cu
 void dmg_shard_free(dmg_handle_t h);   // shard.cu
 int32_t dmg_deepfm_tdm_retrieve(dmg_handle_t h, int32_t B, const int32_t *item_seq, int32_t beam, int32_t topk, const int64_t *cons_off,
@@ -97,7 +100,7 @@ DMG_API int32_t dmg_destroy(dmg_handle_t h)
         free_din(h->din);
         dmg_free_dr(h->dr);
     }
-    for (Scratch *s : {&h->s_in, &h->s_out, &h->s_work}) { cudaFree(s->d); cudaFreeHost(s->h); }
+    for (Scratch *s : {&h->s_in, &h->s_out, &h->s_work, &h->s_wave}) { cudaFree(s->d); cudaFreeHost(s->h); }
     for (auto &ev : h->prof_events) { cudaEventDestroy(ev.first); cudaEventDestroy(ev.second); }
     cudaFreeHost(h->h_flags);
     cudaFree(h->d_fast_stats); cudaFree(h->d_fast_tab); cudaFree(h->d_fast_ctl); cudaFree(h->d_redo_list);
@@ -121,6 +124,12 @@ DMG_API int32_t dmg_clone(dmg_handle_t src, dmg_handle_t *out)
     dmg_handle_t h = nullptr;
     const int32_t rc = dmg_create(src->device, &h);
     if (rc != DMG_OK) return fail(src, rc, "dmg_clone: %s", dmg_last_error(nullptr));
+    // the owner builds the shared tables of the tensor-core paths (bound tables, bf16 hi|lo copy of the node table) before
+    // they are copied: clones only read them
+    if (src->arithmetic == DMG_ARITH_FAST && src->fast_dirty && src->din.loaded && src->din.dtype == DMG_F32 && src->din.E == 64 && src->din.kind == 0) {
+        const int32_t rb = compute_fast_bounds(src);
+        if (rb != DMG_OK) { dmg_destroy(h); return rb; }
+    }
     cudaStreamSynchronize(src->stream);                          // uploads of the model are complete before another stream reads it
     h->tree = src->tree;
     h->din = src->din;
@@ -409,6 +418,48 @@ template <typename real> static int32_t launch_beam(dmg_handle_t h, const BeamPa
 //   M = W1a.Watt (double -> fp32, stored k-major), v[k] = sum_o |w2[o]| |W1x[o][k]|,
 //   per-level maxima of v.|x| and |x|_2 over the node table, and
 //   eps = tau * ( cA * max v.|x|  +  cBq * Kmax * (cCq + |dp|_1)  +  cGamma ).
+// Tables of the level-synchronous path (beam_wave.cuh): the bf16 hi|lo copy of the node table and the W1x operand image
+// belong to the model's owner (a clone reads its parent's, which dmg_clone has brought up to date); every handle encodes
+// its own TMA descriptor over the copy.  No room for the copy (it is as large as the table) => the persistent kernel runs.
+static int32_t wave_prepare(dmg_handle_t h)
+{
+    DinDev &d = h->din;
+    if (!h->parent) {
+        if (!d.d_split && cudaMalloc(&d.d_split, (size_t)d.rows * 256) != cudaSuccess) { cudaGetLastError(); d.d_split = nullptr; return DMG_OK; }
+        if (!d.d_w1img) DMG_CUDA(h, cudaMalloc(&d.d_w1img, 16384));
+        wave_split_table_kernel<<<h->sm_count * 16, 256, 0, h->stream>>>(d.emb<float>(), d.rows, d.d_split);
+        wave_w1_image_kernel<<<2, 256, 0, h->stream>>>(d.w1<float>(), d.d_w1img);
+        h->launches += 2;
+        DMG_CUDA(h, cudaGetLastError());
+        DMG_CUDA(h, cudaStreamSynchronize(h->stream));
+    } else {
+        if (h->parent->fast_dirty || !h->parent->din.d_split) return DMG_OK;
+        d.d_split = h->parent->din.d_split;
+        d.d_w1img = h->parent->din.d_w1img;
+    }
+    typedef CUresult (*encode_fn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
+                                  const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+    static encode_fn encode = nullptr;
+    if (!encode) {
+        void *fn = nullptr;
+        cudaDriverEntryPointQueryResult qr;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qr) != cudaSuccess || !fn) { cudaGetLastError(); return DMG_OK; }
+        encode = (encode_fn)fn;
+    }
+    const cuuint64_t gdim[2] = {64, (cuuint64_t)d.rows * 2};     // [2 rows][64] bf16: row 2c = hi(c), row 2c + 1 = lo(c)
+    const cuuint64_t gstr[1] = {128};
+    const cuuint32_t box[2] = {64, 1}, estr[2] = {1, 1};         // tile::gather4 fetches 4 such boxes per instruction
+    const CUresult cr = encode(reinterpret_cast<CUtensorMap *>(h->wave_tmap), CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, d.d_split, gdim, gstr, box, estr,
+                               CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                               CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (cr != CUDA_SUCCESS) return DMG_OK;
+    const char *m = getenv("DMG_WAVE_GATHER");
+    h->wave_mode = (m && !strcmp(m, "cpasync")) ? 1 : 0;
+    h->wave_ok = true;
+    return DMG_OK;
+}
+
 static int32_t compute_fast_bounds(dmg_handle_t h)
 {
     DinDev &d = h->din;
@@ -467,6 +518,9 @@ static int32_t compute_fast_bounds(dmg_handle_t h)
     DMG_CUDA(h, cudaGetLastError());
     DMG_CUDA(h, cudaStreamSynchronize(h->stream));               // tab / w are stack-owned
     h->fast_ok = std::isfinite(h->fast_cA) && std::isfinite(h->fast_cGamma);
+    h->wave_ok = false;
+    const char *impl = getenv("DMG_FAST_IMPL");
+    if (h->fast_ok && !(impl && !strcmp(impl, "v1"))) DMG_TRY(wave_prepare(h));
     return DMG_OK;
 }
 
@@ -503,11 +557,84 @@ int32_t dmg_tdm_ids_to_codes(dmg_handle_t h, const int32_t *d_ids, int64_t n, in
     return DMG_OK;
 }
 
+// The level-synchronous tensor-core path (beam_wave.cuh): prologue, then select + score per tree level, then the strict
+// final.  p / fx are the persistent kernel's parameter blocks (same tables, same outputs, same redo list).
+static int32_t wave_enqueue(dmg_handle_t h, const BeamParams<float> &p, const FastParams &fx, int max_beam, int stop_level = -1,
+                            WaveParams *wp_out = nullptr, int *slot_out = nullptr)
+{
+    using WG = WaveGeo;
+    const DinDev &d = h->din;
+    const int B = p.B, cap = p.cap;
+    DMG_TRY(ensure_dev(h, h->s_wave, Carver::need({(size_t)B * cap * 4, (size_t)B * cap * 4, (size_t)B * cap * 4, (size_t)B * 4,
+                                                   (size_t)B * sizeof(WaveUser), (size_t)B * WG::UOP_BYTES, (size_t)B * WG::VCAP * 4,
+                                                   (size_t)B * WG::VCAP * 4, (size_t)B * WG::VCAP * 4, (size_t)B * 32 * 4})));
+    Carver c(h->s_wave.d);
+    WaveParams wp;
+    memset(&wp, 0, sizeof(wp));
+    wp.B = B; wp.T = p.T; wp.cap = cap; wp.beam = p.beam; wp.beam_user = p.beam_user;
+    wp.emb = p.emb; wp.hist = p.hist; wp.hist_mask = p.hist_mask; wp.exists = p.exists;
+    wp.leaf_level = p.leaf_level; wp.sparse_from = fx.sparse_from; wp.scale = p.scale;
+    wp.code[0] = c.take<int32_t>((size_t)B * cap); wp.code[1] = c.take<int32_t>((size_t)B * cap);
+    wp.score = c.take<float>((size_t)B * cap);
+    wp.count = c.take<int32_t>(B);
+    wp.user = c.take<WaveUser>(B);
+    wp.uop = c.take<unsigned char>((size_t)B * WG::UOP_BYTES);
+    wp.v_code = c.take<int32_t>((size_t)B * WG::VCAP); wp.v_fast = c.take<float>((size_t)B * WG::VCAP);
+    wp.v_meta = c.take<uint32_t>((size_t)B * WG::VCAP); wp.v_segeps = c.take<float>((size_t)B * 32);
+    wp.mT = fx.mT; wp.zvec = fx.zvec; wp.lvl_vx = fx.lvl_vx; wp.lvl_nx = fx.lvl_nx; wp.b1 = p.b1;
+    wp.cA = fx.cA; wp.cZ = fx.cZ; wp.cH = fx.cH; wp.cGamma = fx.cGamma; wp.tau = fx.tau;
+    wp.stats = fx.stats; wp.redo_list = fx.redo_list; wp.redo_count = fx.redo_count; wp.host_flags = fx.host_flags;
+    wp.w1img = d.d_w1img; wp.split = d.d_split;
+    WaveW2 w2;
+    memcpy(w2.w2, fx.w2, sizeof(w2.w2));
+    w2.b2 = fx.b2;
+    WaveStrictW sw;
+    sw.wattT = p.wattT; sw.w1T = p.w1T; sw.b1 = p.b1; sw.w2 = p.w2; sw.b2 = fx.b2;
+    const CUtensorMap &tmap = *reinterpret_cast<const CUtensorMap *>(h->wave_tmap);
+    auto score_kernel = h->wave_mode == 0 ? wave_score_kernel<0> : wave_score_kernel<1>;
+    DMG_CUDA(h, cudaFuncSetAttribute(score_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, WG::SMEM));
+    DMG_CUDA(h, cudaFuncSetAttribute(score_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+    const size_t fin_smem = (size_t)FastGeo::STRICT_SCR + (size_t)cap * 12 + FastGeo::MAX_FINAL * 4 + (size_t)(FastGeo::VCAP + FastGeo::MAX_FINAL) * 8 + 256 * 4 + 32 * 4;
+    DMG_CUDA(h, cudaFuncSetAttribute(wave_final_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fin_smem));
+    cudaEvent_t e0 = nullptr, e1 = nullptr;
+    if (h->profiling) {
+        DMG_CUDA(h, cudaEventCreate(&e0));
+        DMG_CUDA(h, cudaEventCreate(&e1));
+        DMG_CUDA(h, cudaEventRecord(e0, h->stream));
+    }
+    wave_prologue_kernel<<<B, 256, 0, h->stream>>>(wp);
+    h->launches += 1;
+    const int tpu = (cap + 127) / 128, ntiles = B * tpu;
+    const int grid = std::min(ntiles, 3 * h->sm_count);
+    int slot = 0;
+    const int s_min = lower_log2(p.beam);                        // per-user beams only widen (Recommender.scala:28-31)
+    (void)max_beam;
+    const int last_level = stop_level >= 0 ? std::min(stop_level, p.leaf_level) : p.leaf_level;
+    for (int level = s_min; level < last_level; level++) {
+        wave_select_kernel<<<(B + 3) / 4, 128, 0, h->stream>>>(wp, sw, level, slot);
+        score_kernel<<<grid, WG::THREADS, WG::SMEM, h->stream>>>(tmap, wp, w2, slot ^ 1, h->d_fast_ctl + 8 + level, ntiles, tpu);
+        slot ^= 1;
+        h->launches += 2;
+    }
+    if (wp_out) { *wp_out = wp; *slot_out = slot; }
+    if (stop_level < 0) {
+        wave_final_kernel<<<B, FastGeo::THREADS, fin_smem, h->stream>>>(wp, p, slot);
+        h->launches += 1;
+    }
+    DMG_CUDA(h, cudaGetLastError());
+    if (h->profiling) {
+        DMG_CUDA(h, cudaEventRecord(e1, h->stream));
+        h->prof_events.emplace_back(e0, e1);
+    }
+    return DMG_OK;
+}
+
 // Enqueue K2 + K1 for a TDM batch whose inputs already sit on the device.
 static int32_t tdm_enqueue(dmg_handle_t h, int32_t B, const int32_t *d_seq, int32_t beam, int max_beam,
                            const int32_t *d_beam_user, int32_t topk, int32_t use_mask, const int64_t *d_cons_off,
                            const int32_t *d_cons, int32_t *d_items, float *d_logits, int32_t *d_counts,
-                           BeamParams<float> *redo_out = nullptr)
+                           BeamParams<float> *redo_out = nullptr, int probe_level = -1, WaveParams *probe_wp = nullptr,
+                           int *probe_slot = nullptr)
 {
     // redo_out: a caller that synchronises anyway takes the strict redo launch into its own hands (h_flags[1] tells it
     // whether the batch has redo users); redo_out->B == 0 on return when there is no such launch.
@@ -562,6 +689,13 @@ static int32_t tdm_enqueue(dmg_handle_t h, int32_t B, const int32_t *d_seq, int3
         fx.host_flags = h->d_flags;
         fx.stats = h->d_fast_stats;
         fx.sparse_from = t.sparse_from;
+        if (probe_level >= 0) {
+            if (!h->wave_ok) return fail(h, DMG_ERR_UNSUPPORTED, "dmg_wave_probe: the level-synchronous path is not available for this model");
+            return wave_enqueue(h, p, fx, max_beam, probe_level, probe_wp, probe_slot);
+        }
+        if (h->wave_ok) {
+            DMG_TRY(wave_enqueue(h, p, fx, max_beam));
+        } else {
         const size_t smem = FastGeo::smem_bytes(p.cap);
         DMG_CUDA(h, cudaFuncSetAttribute(beam_search_fast_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         const int grid = std::min(B, 2 * h->sm_count);           // two co-resident CTAs per SM
@@ -579,6 +713,7 @@ static int32_t tdm_enqueue(dmg_handle_t h, int32_t B, const int32_t *d_seq, int3
         if (h->profiling) {
             DMG_CUDA(h, cudaEventRecord(e1, h->stream));
             h->prof_events.emplace_back(e0, e1);
+        }
         }
         // users the fast kernel could not certify (exact ties at a cut, implausibly wide band): strict kernel
         p.user_list = h->d_redo_list; p.user_count = h->d_fast_ctl + 1;
@@ -752,6 +887,42 @@ DMG_API int32_t dmg_tdm_retrieve(dmg_handle_t h, int32_t B, const int32_t *item_
     memcpy(out_items, h_items, (size_t)B * topk * 4);
     memcpy(out_logits, h_log, (size_t)B * topk * 4);
     memcpy(out_counts, h_cnt, (size_t)B * 4);
+    return DMG_OK;
+}
+
+// Diagnostic: run the level-synchronous tensor-core search until the candidates of tree level `level` are scored and
+// return them with their FAST scores and the bound eps on |fast - strict| (tests compare with model.forward).
+DMG_API int32_t dmg_wave_probe(dmg_handle_t h, int32_t B, const int32_t *item_seq, int32_t beam, int32_t use_mask, int32_t level,
+                               int32_t cap, int32_t *out_codes, float *out_scores, int32_t *out_counts, float *out_eps)
+{
+    DMG_TRY(tdm_precheck(h, B, beam, 1));
+    if (!item_seq || !out_codes || !out_scores || !out_counts || !out_eps || level < 0) return fail(h, DMG_ERR_INVALID_ARG, "bad arguments");
+    if (h->arithmetic != DMG_ARITH_FAST) return fail(h, DMG_ERR_STATE, "dmg_wave_probe needs DMG_ARITH_FAST");
+    DMG_CUDA(h, cudaSetDevice(h->device));
+    const int T = h->din.T;
+    const size_t b_seq = (size_t)B * T * 4;
+    DMG_TRY(ensure_host(h, h->s_in, b_seq));
+    DMG_TRY(ensure_dev(h, h->s_in, b_seq));
+    memcpy(h->s_in.h, item_seq, b_seq);
+    DMG_CUDA(h, cudaMemcpyAsync(h->s_in.d, h->s_in.h, b_seq, cudaMemcpyHostToDevice, h->stream));
+    const size_t out_bytes = Carver::need({(size_t)B * 4, (size_t)B * 4, (size_t)B * 4});
+    DMG_TRY(ensure_dev(h, h->s_out, out_bytes));
+    Carver od(h->s_out.d);
+    int32_t *d_items = od.take<int32_t>(B);
+    float *d_log = od.take<float>(B);
+    int32_t *d_cnt = od.take<int32_t>(B);
+    WaveParams wp;
+    int slot = 0;
+    DMG_TRY(tdm_enqueue(h, B, (const int32_t *)h->s_in.d, beam, beam, nullptr, 1, use_mask, nullptr, nullptr, d_items, d_log, d_cnt, nullptr,
+                        level, &wp, &slot));
+    if (wp.cap != cap) return fail(h, DMG_ERR_INVALID_ARG, "dmg_wave_probe: cap must be %d for this beam", wp.cap);
+    std::vector<WaveUser> us(B);
+    DMG_CUDA(h, cudaMemcpyAsync(out_codes, wp.code[slot], (size_t)B * cap * 4, cudaMemcpyDeviceToHost, h->stream));
+    DMG_CUDA(h, cudaMemcpyAsync(out_scores, wp.score, (size_t)B * cap * 4, cudaMemcpyDeviceToHost, h->stream));
+    DMG_CUDA(h, cudaMemcpyAsync(out_counts, wp.count, (size_t)B * 4, cudaMemcpyDeviceToHost, h->stream));
+    DMG_CUDA(h, cudaMemcpyAsync(us.data(), wp.user, (size_t)B * sizeof(WaveUser), cudaMemcpyDeviceToHost, h->stream));
+    DMG_TRY(check_flag(h, "dmg_wave_probe"));
+    for (int u = 0; u < B; u++) out_eps[u] = (us[u].flags & WU_REDO) ? -1.0f : us[u].eps;
     return DMG_OK;
 }
 

@@ -47,6 +47,8 @@ struct DinDev {
     bool sharded = false;          // rows are this rank's slice of a table split by dmg_shard_init (shard.cu): shard entry points only
     // training state (allocated lazily)
     void *d_grad = nullptr, *d_m = nullptr, *d_v = nullptr;
+    // wave path (beam_wave.cuh): bf16 hi|lo copy of the table (256 B per row) and the W1x operand image; owned by the model's owner handle
+    unsigned char *d_split = nullptr, *d_w1img = nullptr;
     template <typename real> real *emb() const { return (real *)d_params; }
     template <typename real> real *tail() const { return (real *)d_params + rows * E; }      // dense parameters behind the table
     template <typename real> real *watt() const { return (real *)d_params + rows * E; }
@@ -90,7 +92,10 @@ struct dmg_handle_s {
     dmg::TreeDev tree;
     dmg::DinDev din;
     dmg::DrDev dr;
-    dmg::Scratch s_in, s_out, s_work;
+    dmg::Scratch s_in, s_out, s_work, s_wave;
+    bool wave_ok = false;            // level-synchronous tensor-core path (beam_wave.cuh) usable with the current tables
+    int wave_mode = 0;               // 0 = TMA gather4 row gather, 1 = cp.async row gather
+    alignas(64) unsigned char wave_tmap[128];   // CUtensorMap over the hi|lo table
     int32_t *d_flags = nullptr;     // [0] = index error flag: device alias of h_flags (mapped pinned memory: kernels raise it with no copy back)
     int32_t *h_flags = nullptr;
     int arithmetic = DMG_ARITH_STRICT;

@@ -130,6 +130,13 @@ DMG_API int32_t dmg_fast_stats(dmg_handle_t h, uint64_t *out7);
  * would all have to align.  Smaller tau trades the proof for a statistical margin (the largest error
  * ever observed is reported by dmg_fast_stats as a fraction of the worst-case bound). */
 DMG_API int32_t dmg_set_fast_tolerance(dmg_handle_t h, double tau);
+/* Diagnostic of the level-synchronous tensor-core search (DMG_ARITH_FAST): run Recommender._recommend's level loop
+ * (Recommender.scala:58-99) for B users until the candidates of tree level `level` are scored and return them:
+ * out_codes / out_scores [B x cap] (cap = 2*beam rounded up to 8), out_counts [B], out_eps [B] = the bound on
+ * |fast - strict| the certified cuts use for these scores (-1: the user was handed to the strict kernel). */
+DMG_API int32_t dmg_wave_probe(dmg_handle_t h, int32_t B, const int32_t *item_seq, int32_t beam, int32_t use_mask,
+                               int32_t level, int32_t cap, int32_t *out_codes, float *out_scores,
+                               int32_t *out_counts, float *out_eps);
 
 /* ---- retrieval ------------------------------------------------------------------------ */
 /* Recommender.recommendItems / TDM.recommend over a batch of users

@@ -1,0 +1,91 @@
+"""The level-synchronous tensor-core path (csrc/beam_wave.cuh) piece by piece: the tile scorer alone against
+model.forward (oracle) within the certified bound, with both row-gather engines (TMA tile::gather4, cp.async), then
+whole searches against the oracle bit for bit."""
+import os
+
+import numpy as np
+import pytest
+
+from dismember_b200 import synth
+
+pytestmark = pytest.mark.gpu
+
+
+def bits(a):
+    a = np.ascontiguousarray(a)
+    return a.view(np.uint32)
+
+
+def _setup(engine, n_items, E=64, seed=17, structured=True):
+    tf = synth.tdm_tree(n_items, seed=seed)
+    rows = (1 << (tf.max_level + 1)) - 1
+    params = synth.din_params(rows, E, seed=23, structured=structured)
+    engine.load_tree_tdm(tf.max_level, tf.codes, tf.node_ids, tf.is_leaf, tf.leaf_ids, tf.leaf_codes)
+    engine.load_din_weights(params, rows, E, 10)
+    return tf, rows, params
+
+
+@pytest.mark.parametrize("gather", ["tma", "cpasync"])
+def test_wave_scorer_within_bound_of_model_forward(engine, orc, gather):
+    """Fast scores of every candidate of a level = model.forward (Recommender.scala:93-94) within eps; the
+    candidates of the first scored level are all children of the start level in code order."""
+    os.environ["DMG_WAVE_GATHER"] = gather
+    try:
+        n_items, beam = 20000, 200
+        tf, rows, params = _setup(engine, n_items)
+        tree = orc.Tree.from_treefile(tf)
+        model = orc.TdmModel(params, rows, 64, 10)
+        seqs = synth.queries(48, 10, n_items, seed=29)
+        seqs[0] = 0
+        engine.set_arithmetic("fast")
+        try:
+            worst = 0.0
+            for level in (8, 9, tf.max_level):
+                codes, scores, counts, eps = engine.wave_probe(seqs, beam, level)
+                assert (counts[eps >= 0] > 0).all()
+                for u in range(len(seqs)):
+                    if eps[u] < 0:
+                        continue
+                    n = counts[u]
+                    node = codes[u, :n]
+                    lv = np.floor(np.log2(node.astype(np.int64) + 1)).astype(int)
+                    assert (lv == level).all()
+                    hc, hm = tree.id_to_code(seqs[u])
+                    seq = np.tile(hc, (n, 1))
+                    mask = (np.arange(n)[:, None] * 10 + np.flatnonzero(hm)[None, :]).ravel().astype(np.int32)
+                    want = model.forward(node, seq, mask)
+                    err = np.abs(scores[u, :n].astype(np.float64) - want.astype(np.float64))
+                    assert np.isfinite(scores[u, :n]).all()
+                    assert (err <= eps[u]).all(), (gather, level, u, err.max(), eps[u], scores[u, :4], want[:4])
+                    worst = max(worst, float(err.max() / eps[u]))
+            print("wave scorer", gather, "max |fast-strict|/eps =", worst)
+            assert worst < 0.05
+        finally:
+            engine.set_arithmetic("strict")
+    finally:
+        os.environ.pop("DMG_WAVE_GATHER", None)
+
+
+@pytest.mark.parametrize("gather", ["tma", "cpasync"])
+@pytest.mark.parametrize("n_items,beam,B", [(20000, 200, 160), (300, 7, 33), (70000, 256, 97), (5000, 64, 1)])
+def test_wave_search_matches_oracle(engine, orc, gather, n_items, beam, B):
+    os.environ["DMG_WAVE_GATHER"] = gather
+    try:
+        tf, rows, params = _setup(engine, n_items)
+        seqs = synth.queries(B, 10, n_items, seed=31)
+        engine.set_arithmetic("fast")
+        try:
+            items, logits, counts = engine.tdm_retrieve(seqs, beam, 10)
+            stats = engine.fast_stats()
+        finally:
+            engine.set_arithmetic("strict")
+        tree = orc.Tree.from_treefile(tf)
+        model = orc.TdmModel(params, rows, 64, 10)
+        oi, ol, oc = model.retrieve_batch(tree, seqs, beam, 10, n_threads=8)
+        assert (counts == oc).all()
+        assert (items == oi).all(), f"ids differ, stats={stats}"
+        assert (bits(logits) == bits(ol)).all()
+        assert stats["rows_fast"] > 0
+        print("wave stats", gather, n_items, beam, stats)
+    finally:
+        os.environ.pop("DMG_WAVE_GATHER", None)
