@@ -44,10 +44,11 @@ enum { WU_REDO = 1, WU_SCORED = 2, WU_ALLMASK = 4 };
 struct WaveGeo {
     static constexpr int THREADS = 160;                      // 4 consumer warps (TMEM lanes 32 w ..) + 1 control warp
     static constexpr int XH = 0, XL = 16384;                 // [128 rows][128 B] bf16, SWIZZLE_128B (TMA gather4 destination)
-    static constexpr int W1H = 32768, W1L = 40960;           // B operand [64 o][64 k]: K-major, no swizzle, LBO 1024, SBO 128
-    static constexpr int KH = 49152, KL = 51200;             // B operand [16 j][64 k]: LBO 256, SBO 128
+    static constexpr int BH = 32768, BL = 43008;             // B operand [80 n][64 k]: n < 64 W1x outputs, n >= 64 history slots;
+    static constexpr int B_LBO = 1280;                       //   K-major, no swizzle, LBO 1280 (80 rows x 16 B), SBO 128
     static constexpr int HH = 53248, HL = 55296;             // B operand [64 o][16 j]: LBO 1024, SBO 128
-    static constexpr int ADDV = 57344;                       // [16] additive softmax mask (tail of the H copy)
+    static constexpr int ADDV = 57344;                       // [16] additive softmax mask + [4] user flags (tail of the H copy)
+    static constexpr int H_COPY = 4096 + 80;
     static constexpr int PH = 57472, PL = 61568;             // A operand [128 rows][16 j]: LBO 2048, SBO 128
     static constexpr int BAR = 65664;                        // 8 mbarriers
     static constexpr int INFO = BAR + 64;                    // 2 x int4 tile info
@@ -57,7 +58,7 @@ struct WaveGeo {
     static constexpr int UOP_BYTES = 8320;                   // per-user operand image [KH | KL | HH | HL | addv] (8256, padded)
     static constexpr int VCAP = FastGeo::VCAP, MAX_UNC = FastGeo::MAX_UNC;
 };
-enum { WB_W1 = 0, WB_XFULL, WB_M1, WB_PFULL, WB_HFULL, WB_M2, WB_TFREE };
+enum { WB_W1 = 0, WB_XFULL, WB_M1, WB_PFULL, WB_HFULL, WB_M2, WB_TFREE, WB_INFO };
 
 struct WaveParams {
     int B, T, cap, beam;
@@ -78,7 +79,9 @@ struct WaveParams {
     float cA, cZ, cH, cGamma, tau;
     unsigned long long *stats;
     int32_t *redo_list, *redo_count, *host_flags;
-    const unsigned char *w1img;     // [W1x hi | W1x lo] in UMMA layout, 16 KB
+    int32_t *tile_list;             // [B * ceil(cap / 128)] tiles of the level being scored: user << 12 | first row >> 7 << 8 | rows - 1 ... see wave_tile_pack
+    int32_t *tile_count;            // per level: [0] tiles appended by the select kernel, [32] tiles taken by the scorer
+    const unsigned char *w1img;     // [W1x hi | W1x lo] as the n < 64 rows of the B operand, 2 x 10240 B
     const unsigned char *split;     // bf16 hi|lo table, 256 B per code
 };
 struct WaveW2 { float w2[64]; float b2; };
@@ -99,7 +102,7 @@ static __global__ void wave_split_table_kernel(const float *__restrict__ emb, in
     }
 }
 
-// W1 item half [o][k] -> UMMA B operand image [hi | lo], chunk kc at kc * 1024, row o at o * 16
+// W1 item half [o][k] -> rows n < 64 of the B operand image [hi | lo], chunk kc at kc * 1280, row o at o * 16
 static __global__ void wave_w1_image_kernel(const float *__restrict__ w1, unsigned char *__restrict__ img)
 {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -110,9 +113,11 @@ static __global__ void wave_w1_image_kernel(const float *__restrict__ w1, unsign
     for (int q = 0; q < 8; q++) v[q] = __ldg(w1 + o * 128 + kc * 8 + q);
     uint4 hi, lo;
     split8(v, hi, lo);
-    *reinterpret_cast<uint4 *>(img + kc * 1024 + o * 16) = hi;
-    *reinterpret_cast<uint4 *>(img + 8192 + kc * 1024 + o * 16) = lo;
+    *reinterpret_cast<uint4 *>(img + kc * 1280 + o * 16) = hi;
+    *reinterpret_cast<uint4 *>(img + 10240 + kc * 1280 + o * 16) = lo;
 }
+// a tile of the level being scored: user, first candidate row (multiple of 128), rows (1..128)
+__device__ __forceinline__ int32_t wave_tile_pack(int user, int row0, int nr) { return (user << 10) | ((row0 >> 7) << 8) | (nr - 1); }
 
 // ---- K2: per-user prologue ----------------------------------------------------------------------------------------
 static __global__ void __launch_bounds__(256) wave_prologue_kernel(const WaveParams p)
@@ -205,6 +210,7 @@ static __global__ void __launch_bounds__(256) wave_prologue_kernel(const WavePar
         st.maskbits = (uint32_t)sRed[0];
         const uint32_t full = (1u << T) - 1u;
         st.flags = (((uint32_t)sRed[0] & full) == full) ? WU_ALLMASK : 0;
+        reinterpret_cast<int32_t *>(uop + 8192 + 64)[0] = st.flags;
         p.user[user] = st;
         p.count[user] = 0;
     }
@@ -247,9 +253,9 @@ __device__ __forceinline__ void warp_select(const uint32_t (&k)[16], int kk, uin
     }
 }
 
-// children of the surviving candidates in candidate order, the bound of the scores about to be computed, counters
+// children of the surviving candidates in candidate order, the tiles and the bound of the scores about to be computed
 __device__ __forceinline__ void wave_expand_finish(const WaveParams &p, WaveUser *st, int user, int level, int lane, const int32_t (&code)[16],
-                                                   uint32_t keep, int count, int32_t *__restrict__ nxt, int flags,
+                                                   const uint32_t *sKeepW, int count, int32_t *__restrict__ nxt, int flags,
                                                    unsigned long long st_cut, unsigned long long st_recut, unsigned long long st_iters)
 {
     const uint32_t lt = (1u << lane) - 1u;
@@ -259,7 +265,7 @@ __device__ __forceinline__ void wave_expand_finish(const WaveParams &p, WaveUser
 #pragma unroll
     for (int j = 0; j < 16; j++) {
         if (j < nj) {
-            const bool kp = keep >> j & 1u;
+            const bool kp = sKeepW[j] >> lane & 1u;
             const int64_t c = code[j];
             const bool a1 = kp && code_exists(bm, 2 * c + 1), a2 = kp && code_exists(bm, 2 * c + 2);
             const uint32_t m1 = __ballot_sync(0xffffffffu, a1), m2 = __ballot_sync(0xffffffffu, a2);
@@ -268,6 +274,14 @@ __device__ __forceinline__ void wave_expand_finish(const WaveParams &p, WaveUser
             if (a2) nxt[o] = (int32_t)(2 * c + 2);
             out += __popc(m1) + __popc(m2);
         }
+    }
+    const int nt = (out + 127) >> 7;
+    if (lane < nt) {                                              // this user's tiles of the next level
+        int base = 0;
+        if (lane == 0) base = atomicAdd(p.tile_count + level + 1, nt);
+        base = __shfl_sync((1u << nt) - 1u, base, 0);
+        const int row0 = lane * 128;
+        p.tile_list[base + lane] = wave_tile_pack(user, row0, out - row0 < 128 ? out - row0 : 128);
     }
     if (lane == 0) {
         p.count[user] = out;
@@ -294,15 +308,20 @@ struct WaveStrictW { const float *wattT, *w1T, *b1, *w2; float b2; };
 // 4 users per CTA.  Phase 1: every warp cuts its user; a cut whose band cannot be deferred (fast-score gap at the cut below
 // eps / 32) is parked.  Phase 2: the whole CTA scores the band rows of its parked users strictly (sequential-k fma chains,
 // the oracle's bits).  Phase 3: the parked warps finish their cuts with the strict order.
+// Per-lane state is the 16 candidate codes / scores; the surviving set is a 16-word bitmap in shared memory (word j, bit
+// lane = candidate 32 j + lane) and the band rows are compacted into shared-memory lists that the lanes then walk in
+// parallel -- rolled loops, so that the kernel stays a few thousand instructions (it runs at low occupancy: instruction
+// fetch is what bounds a long unrolled body).
 static __global__ void __launch_bounds__(128) wave_select_kernel(const WaveParams p, const WaveStrictW sw, int level, int slot)
 {
     constexpr int MU = WaveGeo::MAX_UNC;
     __shared__ __align__(16) float sScr[FastGeo::STRICT_SCR / 4];
-    __shared__ uint32_t sKeyU[4][MU];
-    __shared__ int sUPos[4][MU];
-    __shared__ int32_t sLCode[4][MU];
-    __shared__ float sLStr[4][MU];
-    __shared__ uint32_t sKeep[4][32], sUnc[4][32];
+    __shared__ uint32_t sKeyU[4][MU];                             // band rows: order key of the fast score,
+    __shared__ int sUPos[4][MU];                                  //   candidate position,
+    __shared__ int32_t sLCode[4][MU];                             //   code,
+    __shared__ float sLStr[4][MU];                                //   fast score, then (parked cuts) the strict score
+    __shared__ int sFr[4][MU];                                    //   rank by fast score
+    __shared__ uint32_t sKeepW[4][16];
     __shared__ int sGap[4][2];
     __shared__ int sPark[4][2];                                   // n_unc (0 = not parked), need
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -324,7 +343,6 @@ static __global__ void __launch_bounds__(128) wave_select_kernel(const WaveParam
     const int32_t *cur = p.code[slot] + (size_t)(live ? user : 0) * p.cap;
     int32_t *nxt = p.code[slot ^ 1] + (size_t)(live ? user : 0) * p.cap;
     int32_t code[16];
-    uint32_t keep = 0;                                            // bit j: candidate 32 j + lane survives the cut
     int count = 0;
     unsigned long long st_cut = 0, st_recut = 0, st_iters = 0;
     bool parked = false;
@@ -336,26 +354,34 @@ static __global__ void __launch_bounds__(128) wave_select_kernel(const WaveParam
             for (int j = 0; j < 16; j++) {
                 const int i = 32 * j + lane;
                 code[j] = (int32_t)(start + i);
-                if (i < count && code_exists(p.exists, start + i)) keep |= 1u << j;
+                const uint32_t m = __ballot_sync(0xffffffffu, i < count && code_exists(p.exists, start + i));
+                if (lane == 0) sKeepW[warp][j] = m;
             }
         } else {
             count = p.count[user];
             float f[16];
-            uint32_t key[16];
             const float *sc = p.score + (size_t)user * p.cap;
 #pragma unroll
             for (int j = 0; j < 16; j++) {
                 const int i = 32 * j + lane;
                 code[j] = i < count ? cur[i] : 0;
                 f[j] = i < count ? sc[i] : 0.0f;
-                key[j] = i < count ? order_key(f[j]) : 0u;
-                if (i < count) keep |= 1u << j;
             }
-            if (count > beam) {
+            if (count <= beam) {
+#pragma unroll
+                for (int j = 0; j < 16; j++) {
+                    const uint32_t m = __ballot_sync(0xffffffffu, 32 * j + lane < count);
+                    if (lane == 0) sKeepW[warp][j] = m;
+                }
+            } else {
                 st_cut = 1;
+                uint32_t key[16];
                 uint32_t mn = 0xffffffffu, mx = 0u;
 #pragma unroll
-                for (int j = 0; j < 16; j++) { mn = min(mn, key[j] ? key[j] : 0xffffffffu); mx = max(mx, key[j]); }
+                for (int j = 0; j < 16; j++) {
+                    key[j] = 32 * j + lane < count ? order_key(f[j]) : 0u;
+                    mn = min(mn, key[j] ? key[j] : 0xffffffffu); mx = max(mx, key[j]);
+                }
                 mn = __reduce_min_sync(0xffffffffu, mn);
                 mx = __reduce_max_sync(0xffffffffu, mx);
                 uint32_t kdn, kup;
@@ -365,16 +391,20 @@ static __global__ void __launch_bounds__(128) wave_select_kernel(const WaveParam
                 const float eps_level = st->eps;
                 const float band = 2.0f * eps_level * 1.0001f + 1e-30f;
                 const float up = key_to_float(kup) + band, dn = key_to_float(kdn) - band;
-                uint32_t unc = 0;
+                int n_keep = 0, n_unc = 0;
 #pragma unroll
                 for (int j = 0; j < 16; j++) {
-                    if (keep >> j & 1u) {
-                        if (f[j] > up) { }
-                        else if (f[j] < dn) keep &= ~(1u << j);
-                        else unc |= 1u << j;
+                    const bool valid = 32 * j + lane < count;
+                    const bool isunc = valid && !(f[j] > up) && !(f[j] < dn);
+                    const uint32_t mk = __ballot_sync(0xffffffffu, valid && !(f[j] < dn)), mu = __ballot_sync(0xffffffffu, isunc);
+                    if (lane == 0) sKeepW[warp][j] = mk;
+                    if (isunc) {
+                        const int e = n_unc + __popc(mu & lt);
+                        if (e < MU) { sKeyU[warp][e] = key[j]; sUPos[warp][e] = 32 * j + lane; sLCode[warp][e] = code[j]; sLStr[warp][e] = f[j]; }
                     }
+                    n_keep += __popc(mk); n_unc += __popc(mu);
                 }
-                const int n_keep = __reduce_add_sync(0xffffffffu, __popc(keep)), n_unc = __reduce_add_sync(0xffffffffu, __popc(unc));
+                __syncwarp();
                 if (n_keep != beam) {                             // some uncertain row must go
                     st_recut = 1;
                     if (n_unc > MU) {
@@ -382,52 +412,39 @@ static __global__ void __launch_bounds__(128) wave_select_kernel(const WaveParam
                         live = false;
                     } else {
                         const int need = beam - (n_keep - n_unc);
-                        int base = 0, myslot[16];
-#pragma unroll
-                        for (int j = 0; j < 16; j++) {
-                            const uint32_t m = __ballot_sync(0xffffffffu, unc >> j & 1u);
-                            myslot[j] = base + __popc(m & lt);
-                            if (unc >> j & 1u) { sKeyU[warp][myslot[j]] = key[j]; sUPos[warp][myslot[j]] = 32 * j + lane; }
-                            base += __popc(m);
-                        }
-                        __syncwarp();
-                        uint32_t chosen = 0;
-#pragma unroll
-                        for (int j = 0; j < 16; j++) {
-                            if (unc >> j & 1u) {
-                                const int me = 32 * j + lane;
-                                int fr = 0;
-                                for (int q = 0; q < n_unc; q++) {
-                                    const uint32_t kq = sKeyU[warp][q];
-                                    fr += (kq > key[j] || (kq == key[j] && sUPos[warp][q] < me)) ? 1 : 0;
-                                }
-                                if (fr == need - 1) sGap[warp][0] = __float_as_int(f[j]);
-                                if (fr == need) sGap[warp][1] = __float_as_int(f[j]);
-                                if (fr < need) chosen |= 1u << j;
+#pragma unroll 1
+                        for (int e = lane; e < n_unc; e += 32) {  // rank of every band row by its FAST score, the gap at the cut
+                            const uint32_t ke = sKeyU[warp][e];
+                            const int pe = sUPos[warp][e];
+                            int fr = 0;
+#pragma unroll 4
+                            for (int q = 0; q < n_unc; q++) {
+                                const uint32_t kq = sKeyU[warp][q];
+                                fr += (kq > ke || (kq == ke && sUPos[warp][q] < pe)) ? 1 : 0;
                             }
+                            sFr[warp][e] = fr;
+                            if (fr == need - 1) sGap[warp][0] = __float_as_int(sLStr[warp][e]);
+                            if (fr == need) sGap[warp][1] = __float_as_int(sLStr[warp][e]);
                         }
                         __syncwarp();
                         const float gap = __int_as_float(sGap[warp][0]) - __int_as_float(sGap[warp][1]);
                         const int vcount = st->vcount, nseg = st->nseg;
+                        // Observed |fast - strict| stays below 1 % of eps: with a gap of eps/32 or more the fast order is taken
+                        // now and PROVEN by wave_final_kernel; a narrower gap is settled strictly right here.
                         const bool defer = gap >= 0.03125f * eps_level && vcount + n_unc <= WaveGeo::VCAP && nseg < 32 && eps_level < 1e30f;
                         if (defer) {
-#pragma unroll
-                            for (int j = 0; j < 16; j++) {
-                                if (unc >> j & 1u) {
-                                    const uint32_t ch = chosen >> j & 1u;
-                                    const size_t e = (size_t)user * WaveGeo::VCAP + vcount + myslot[j];
-                                    p.v_code[e] = code[j]; p.v_fast[e] = f[j];
-                                    p.v_meta[e] = (uint32_t)vcount | ((uint32_t)n_unc << 8) | ((uint32_t)need << 16) | (ch << 24) | ((uint32_t)nseg << 25);
-                                    if (!ch) keep &= ~(1u << j);
-                                }
+#pragma unroll 1
+                            for (int e = lane; e < n_unc; e += 32) {
+                                const uint32_t ch = sFr[warp][e] < need ? 1u : 0u;
+                                const size_t g = (size_t)user * WaveGeo::VCAP + vcount + e;
+                                p.v_code[g] = sLCode[warp][e]; p.v_fast[g] = sLStr[warp][e];
+                                p.v_meta[g] = (uint32_t)vcount | ((uint32_t)n_unc << 8) | ((uint32_t)need << 16) | (ch << 24) | ((uint32_t)nseg << 25);
+                                const int pe = sUPos[warp][e];
+                                if (!ch) atomicAnd(&sKeepW[warp][pe >> 5], ~(1u << (pe & 31)));
                             }
                             __syncwarp();
                             if (lane == 0) { p.v_segeps[(size_t)user * 32 + nseg] = eps_level; st->vcount = vcount + n_unc; st->nseg = nseg + 1; }
                         } else {                                  // park: strict scores of the band decide (phases 2 and 3)
-#pragma unroll
-                            for (int j = 0; j < 16; j++)
-                                if (unc >> j & 1u) { sLCode[warp][myslot[j]] = code[j]; sLStr[warp][myslot[j]] = f[j]; }
-                            sKeep[warp][lane] = keep; sUnc[warp][lane] = unc;
                             if (lane == 0) { sPark[warp][0] = n_unc; sPark[warp][1] = need; }
                             parked = true;
                         }
@@ -435,7 +452,8 @@ static __global__ void __launch_bounds__(128) wave_select_kernel(const WaveParam
                 }
             }
         }
-        if (live && !parked) wave_expand_finish(p, st, user, level, lane, code, keep, count, nxt, flags, st_cut, st_recut, st_iters);
+        __syncwarp();
+        if (live && !parked) wave_expand_finish(p, st, user, level, lane, code, sKeepW[warp], count, nxt, flags, st_cut, st_recut, st_iters);
     }
     __syncthreads();
     // ---- phase 2: strict scores of the parked bands, whole CTA ----
@@ -460,31 +478,26 @@ static __global__ void __launch_bounds__(128) wave_select_kernel(const WaveParam
     // ---- phase 3: the parked warps finish their cuts with the strict order ----
     if (parked) {
         const int n_unc = sPark[warp][0], need = sPark[warp][1];
-        const uint32_t unc = sUnc[warp][lane];
-        keep = sKeep[warp][lane];
         const float eps_level = st->eps;
-        int base = 0, tie = 0;
+        int tie = 0;
         float ratio = 0.0f;
-#pragma unroll
-        for (int j = 0; j < 16; j++) {
-            const uint32_t m = __ballot_sync(0xffffffffu, unc >> j & 1u);
-            if (unc >> j & 1u) {
-                const int me = base + __popc(m & lt);
-                const float mine = sLStr[warp][me];
-                const uint32_t ks = order_key(mine);
-                // strict rank = rows strictly above (+ an undetermined share of exact ties: the reference orders ties by candidate
-                // position, which this path does not track).  Only a tie that STRADDLES the cut is undecidable here.
-                int g = 0, e = 0;
-                for (int q = 0; q < n_unc; q++) {
-                    const uint32_t kq = order_key(sLStr[warp][q]);
-                    g += kq > ks ? 1 : 0;
-                    e += (kq == ks && q != me) ? 1 : 0;
-                }
-                tie |= (g < need && g + e >= need) ? 1 : 0;
-                if (!(g + e < need)) keep &= ~(1u << j);
-                if (eps_level > 0.0f && eps_level < 1e30f) ratio = fmaxf(ratio, fabsf(mine - __uint_as_float(sKeyU[warp][me])) / eps_level);
+#pragma unroll 1
+        for (int e = lane; e < n_unc; e += 32) {
+            const float mine = sLStr[warp][e];
+            const uint32_t ks = order_key(mine);
+            // strict rank = rows strictly above (+ an undetermined share of exact ties: the reference orders ties by candidate
+            // position, which this path does not track).  Only a tie that STRADDLES the cut is undecidable here.
+            int g = 0, t = 0;
+#pragma unroll 4
+            for (int q = 0; q < n_unc; q++) {
+                const uint32_t kq = order_key(sLStr[warp][q]);
+                g += kq > ks ? 1 : 0;
+                t += (kq == ks && q != e) ? 1 : 0;
             }
-            base += __popc(m);
+            tie |= (g < need && g + t >= need) ? 1 : 0;
+            const int pe = sUPos[warp][e];
+            if (!(g + t < need)) atomicAnd(&sKeepW[warp][pe >> 5], ~(1u << (pe & 31)));
+            if (eps_level > 0.0f && eps_level < 1e30f) ratio = fmaxf(ratio, fabsf(mine - __uint_as_float(sKeyU[warp][e])) / eps_level);
         }
         tie = __any_sync(0xffffffffu, tie);
         if (p.stats) {
@@ -494,13 +507,14 @@ static __global__ void __launch_bounds__(128) wave_select_kernel(const WaveParam
                 atomicAdd(&p.stats[2], (unsigned long long)n_unc); atomicAdd(&p.stats[6], 1ull);
             }
         }
+        __syncwarp();
         if (tie) {
             if (lane == 0) {
                 st->flags = flags | WU_REDO; st->redo_why = 1; p.count[user] = 0;
                 if (p.stats) { atomicAdd(&p.stats[0], st_cut); atomicAdd(&p.stats[1], st_recut); }
             }
         } else {
-            wave_expand_finish(p, st, user, level, lane, code, keep, count, nxt, flags, st_cut, st_recut, st_iters);
+            wave_expand_finish(p, st, user, level, lane, code, sKeepW[warp], count, nxt, flags, st_cut, st_recut, st_iters);
         }
     }
 }
@@ -510,35 +524,48 @@ __device__ __forceinline__ void mbar_arrive(uint64_t *bar)
 {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
-__device__ __forceinline__ void tma_gather4(uint32_t dst, const void *tmap, uint32_t bar, int c0, int r0, int r1, int r2, int r3)
+// rows c0..c3 of the bf16 hi|lo table -> 4 rows of the hi tile and 4 rows of the lo tile (row 2c = hi(c), 2c + 1 = lo(c))
+__device__ __forceinline__ void tma_gather4_hilo(uint32_t dst_hi, uint32_t dst_lo, const void *tmap, uint32_t bar, int c0, int c1, int c2, int c3)
 {
-    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.tile::gather4.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6, %7}], [%2];"
-                 ::"r"(dst), "l"(tmap), "r"(bar), "r"(c0), "r"(r0), "r"(r1), "r"(r2), "r"(r3) : "memory");
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.tile::gather4.mbarrier::complete_tx::bytes [%0], [%2, {%4, %5, %6, %7, %8}], [%3];\n\t"
+        "cp.async.bulk.tensor.2d.shared::cluster.global.tile::gather4.mbarrier::complete_tx::bytes [%1], [%2, {%4, %9, %10, %11, %12}], [%3];"
+        ::"r"(dst_hi), "r"(dst_lo), "l"(tmap), "r"(bar), "r"(0), "r"(2 * c0), "r"(2 * c1), "r"(2 * c2), "r"(2 * c3),
+          "r"(2 * c0 + 1), "r"(2 * c1 + 1), "r"(2 * c2 + 1), "r"(2 * c3 + 1) : "memory");
 }
-constexpr uint32_t kIdescBf16M128N16 = (1u << 4) | (1u << 7) | (1u << 10) | ((16u >> 3) << 17) | ((128u >> 4) << 24);
 
-// MODE 0: rows gathered by the TMA (tile::gather4, 128-byte swizzle); MODE 1: by 16-byte cp.async with the swizzle applied
-// in the address (same operand tile; the reference path for the TMA one).
-template <int MODE>
+// Tiles of (user, <= 128 candidate rows) come from the list the select kernel wrote, through a dynamic counter.
+//   control warp (warp 4): takes tiles two ahead, publishes them, issues the tcgen05.mma chains:
+//       [Hacc | S] = X . [W1x | K]^T   (128 x 80 x 64, bf16 hi*hi + hi*lo + lo*hi, fp32 accumulators in TMEM)
+//       Hacc += P . H                   (128 x 64 x 16; row 15 of H carries b1)
+//   consumer warps (0..3, TMEM lanes 32 w ..): as soon as the first chain of tile t has completed they refill the operand
+//   tile for t + 1 -- every warp gathers its own 32 rows with the TMA (tile::gather4, MODE 0) or cp.async (MODE 1), warp 0
+//   also copies the user's K rows into the B operand -- then run Mask + SoftMax on S (one row per thread, log2 domain),
+//   write P as an A operand, and after the second chain read Hacc, free the accumulators and finish
+//   logit = relu(Hacc) . W2 + b2 from registers.
+// DBG: ablation switches for profiling (results are wrong when != 0): 1 no row gather, 2 no softmax math, 4 no epilogue math, 8 no K copy, 16 no MMA
+template <int MODE, int DBG = 0>
 static __global__ void __launch_bounds__(WaveGeo::THREADS, 3)
-wave_score_kernel(const __grid_constant__ CUtensorMap tmap, const WaveParams p, const WaveW2 w, int slot, int32_t *tile_counter, int ntiles, int tpu)
+wave_score_kernel(const __grid_constant__ CUtensorMap tmap, const WaveParams p, const WaveW2 w, int slot, int level)
 {
     using G = WaveGeo;
+    constexpr int dbg = DBG;
     extern __shared__ unsigned char smem_dyn[];
     unsigned char *sm = reinterpret_cast<unsigned char *>((reinterpret_cast<uintptr_t>(smem_dyn) + 1023) & ~(uintptr_t)1023);
     uint64_t *bar = reinterpret_cast<uint64_t *>(sm + G::BAR);
-    volatile int4 *sInfo = reinterpret_cast<volatile int4 *>(sm + G::INFO);
+    int4 *sInfo = reinterpret_cast<int4 *>(sm + G::INFO);
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const uint32_t sbase = smem_u32(sm);
 
     if (tid == 128) {
         mbar_init(&bar[WB_W1], 1);
-        mbar_init(&bar[WB_XFULL], MODE == 0 ? 1 : 32);
+        mbar_init(&bar[WB_XFULL], 4);
         mbar_init(&bar[WB_M1], 1);
         mbar_init(&bar[WB_PFULL], 4);
         mbar_init(&bar[WB_HFULL], 1);
         mbar_init(&bar[WB_M2], 1);
         mbar_init(&bar[WB_TFREE], 4);
+        mbar_init(&bar[WB_INFO], 1);
     }
     if (warp == 4) tmem_alloc(reinterpret_cast<uint32_t *>(sm + G::TMEMP), 128);     // Hacc [0, 64), S [64, 80)
     tc_fence_before();
@@ -547,147 +574,155 @@ wave_score_kernel(const __grid_constant__ CUtensorMap tmap, const WaveParams p, 
     const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t *>(sm + G::TMEMP);
 
     if (warp == 4) {
-        // ================= control warp: tile scheduler, TMA gathers, MMA issue =================
+        // ================= control warp: tile scheduler, MMA issue =================
         const bool leader = lane == 0;
         if (leader) {
-            mbar_expect_tx(&bar[WB_W1], 16384);
-            tma_bulk_g2s(sm + G::W1H, p.w1img, 16384, &bar[WB_W1]);
+            mbar_expect_tx(&bar[WB_W1], 20480);
+            tma_bulk_g2s(sm + G::BH, p.w1img, 20480, &bar[WB_W1]);
         }
-        auto grab = [&](int &u, int &row0, int &nr) -> bool {
-            for (;;) {
-                int idx = 0;
-                if (leader) idx = atomicAdd(tile_counter, 1);
-                idx = __shfl_sync(0xffffffffu, idx, 0);
-                if (idx >= ntiles) return false;
-                u = idx / tpu;
-                row0 = (idx - u * tpu) * 128;
-                const int cnt = __ldg(p.count + u);
-                nr = cnt - row0 < 128 ? cnt - row0 : 128;
-                if (nr > 0) return true;
-            }
+        const int ntiles = __ldg(p.tile_count + level);
+        int32_t *counter = p.tile_count + 32 + level;
+        auto take = [&]() -> int {                                // the next tile (packed), -1 when the list is exhausted
+            int idx = 0;
+            if (leader) idx = atomicAdd(counter, 1);
+            idx = __shfl_sync(0xffffffffu, idx, 0);
+            return idx < ntiles ? __ldg(p.tile_list + idx) : -1;
         };
-        auto issue_x = [&](int u, int row0, int nr) {            // candidate rows + the user's K operand -> WB_XFULL
-            const int32_t *cp = p.code[slot] + (size_t)u * p.cap + row0;
-            const unsigned char *uop = p.uop + (size_t)u * G::UOP_BYTES;
-            if (MODE == 0) {
-                const int nl = (nr + 3) >> 2;
-                if (leader) mbar_expect_tx(&bar[WB_XFULL], (uint32_t)nl * 1024u + 4096u);
-                __syncwarp();
-                if (lane < nl) {
-                    int4 c = *reinterpret_cast<const int4 *>(cp + 4 * lane);
-                    const int r = 4 * lane;
-                    if (r + 1 >= nr) c.y = c.x;
-                    if (r + 2 >= nr) c.z = c.x;
-                    if (r + 3 >= nr) c.w = c.x;
-                    tma_gather4(sbase + G::XH + lane * 512, &tmap, smem_u32(&bar[WB_XFULL]), 0, 2 * c.x, 2 * c.y, 2 * c.z, 2 * c.w);
-                    tma_gather4(sbase + G::XL + lane * 512, &tmap, smem_u32(&bar[WB_XFULL]), 0, 2 * c.x + 1, 2 * c.y + 1, 2 * c.z + 1, 2 * c.w + 1);
-                }
-                if (leader) tma_bulk_g2s(sm + G::KH, uop, 4096, &bar[WB_XFULL]);
-            } else {
-                for (int it = 0; it < 64; it++) {
-                    const int idx = it * 32 + lane, row = idx >> 4, ch = idx & 15;
-                    const int rr = row < nr ? row : 0;
-                    const int32_t c = __ldg(cp + rr);
-                    unsigned char *dst = sm + (ch < 8 ? G::XH : G::XL) + row * 128 + (((ch & 7) ^ (row & 7)) << 4);
-                    cp_async16(dst, p.split + (size_t)c * 256 + ch * 16);
-                }
-                for (int it = 0; it < 8; it++) cp_async16(sm + G::KH + (it * 32 + lane) * 16, uop + (it * 32 + lane) * 16);
-                cp_async_commit();
-                cp_async_wait<0>();
-                fence_proxy_async();
-                mbar_arrive(&bar[WB_XFULL]);
-            }
-        };
-        auto issue_h = [&](int u, int row0, int nr, int itn) {   // tile info + H operand + softmax mask -> WB_HFULL
+        auto publish = [&](int itn, int tile) {
             if (leader) {
-                const int fl = u >= 0 ? p.user[u].flags : 0;
-                int4 inf; inf.x = u; inf.y = row0; inf.z = nr; inf.w = fl;
-                *const_cast<int4 *>(sInfo + (itn & 1)) = inf;
-                if (u >= 0) {
-                    mbar_expect_tx(&bar[WB_HFULL], 4160);
-                    tma_bulk_g2s(sm + G::HH, p.uop + (size_t)u * G::UOP_BYTES + 4096, 4160, &bar[WB_HFULL]);
-                } else {
-                    mbar_arrive(&bar[WB_HFULL]);
-                }
+                int4 inf;
+                inf.x = tile < 0 ? -1 : (tile >> 10); inf.y = ((tile >> 8) & 3) * 128; inf.z = (tile & 255) + 1; inf.w = 0;
+                sInfo[itn & 1] = inf;
+                mbar_arrive(&bar[WB_INFO]);
             }
             __syncwarp();
         };
+        // operand descriptors: K-major; X tiles SWIZZLE_128B (SBO 1024, LBO unused), everything else no swizzle (SBO 128)
         auto nsdesc = [&](uint32_t off, uint32_t lbo) -> uint64_t {
             return ((uint64_t)(0x4000u | (128u >> 4)) << 32) | (uint64_t)(((sbase + off) >> 4) | ((lbo >> 4) << 16));
         };
-        auto swdesc = [&](uint32_t off) -> uint64_t {             // K-major, SWIZZLE_128B: SBO 1024 (8 rows x 128 B), LBO unused (1)
+        auto swdesc = [&](uint32_t off) -> uint64_t {
             return ((uint64_t)2 << 61) | ((uint64_t)(0x4000u | (1024u >> 4)) << 32) | (uint64_t)(((sbase + off) >> 4) | (1u << 16));
         };
-        int it = 0, u, row0, nr;
-        bool have = grab(u, row0, nr);
-        if (have) { issue_x(u, row0, nr); issue_h(u, row0, nr, 0); }
+        const uint64_t dXh = swdesc(G::XH), dXl = swdesc(G::XL), dBh = nsdesc(G::BH, G::B_LBO), dBl = nsdesc(G::BL, G::B_LBO);
+        const uint64_t dPh = nsdesc(G::PH, 2048), dPl = nsdesc(G::PL, 2048), dHh = nsdesc(G::HH, 1024), dHl = nsdesc(G::HL, 1024);
+        int cur = take();
+        publish(0, cur);
+        int nxt = cur >= 0 ? take() : -1;
         mbar_wait(&bar[WB_W1], 0);
-        while (have) {
-            int u2 = -1, row2 = 0, nr2 = 0;
-            const bool have2 = grab(u2, row2, nr2);
+        for (int it = 0; cur >= 0; it++) {
             const uint32_t par = it & 1;
+            const int nn = nxt >= 0 ? take() : -1;                // two ahead: the atomic and the list read are off the critical path
             mbar_wait(&bar[WB_XFULL], par);
+            publish(it + 1, nxt);                                 // after XFULL(it): every consumer warp has read tile `it`, so WB_INFO never runs two phases ahead
             if (it > 0) mbar_wait(&bar[WB_TFREE], par ^ 1);
             tc_fence_after();
             if (leader) {
-                const uint64_t dXh = swdesc(G::XH), dXl = swdesc(G::XL);
-                const uint64_t dWh = nsdesc(G::W1H, 1024), dWl = nsdesc(G::W1L, 1024);
-                const uint64_t dKh = nsdesc(G::KH, 256), dKl = nsdesc(G::KL, 256);
 #pragma unroll
                 for (int ks = 0; ks < 4; ks++) {
+                    if (dbg & 16) break;
                     const uint64_t ah = dXh + ks * 2, al = dXl + ks * 2;
-                    const uint64_t bh = dWh + ks * 128, bl = dWl + ks * 128;
-                    const uint64_t kh = dKh + ks * 32, kl = dKl + ks * 32;
-                    umma_bf16(tmem_base, ah, bh, kIdescBf16M128N64, ks > 0);
-                    umma_bf16(tmem_base, ah, bl, kIdescBf16M128N64, 1);
-                    umma_bf16(tmem_base, al, bh, kIdescBf16M128N64, 1);
-                    umma_bf16(tmem_base + 64, ah, kh, kIdescBf16M128N16, ks > 0);
-                    umma_bf16(tmem_base + 64, ah, kl, kIdescBf16M128N16, 1);
-                    umma_bf16(tmem_base + 64, al, kh, kIdescBf16M128N16, 1);
+                    const uint64_t bh = dBh + ks * (2 * G::B_LBO / 16), bl = dBl + ks * (2 * G::B_LBO / 16);
+                    umma_bf16(tmem_base, ah, bh, kIdescBf16M128N80, ks > 0);
+                    umma_bf16(tmem_base, ah, bl, kIdescBf16M128N80, 1);
+                    umma_bf16(tmem_base, al, bh, kIdescBf16M128N80, 1);
                 }
                 umma_commit(&bar[WB_M1]);
             }
             __syncwarp();
-            if (have2) {                                          // X and K are free once the MMAs above have completed
-                mbar_wait(&bar[WB_M1], par);
-                issue_x(u2, row2, nr2);
-            }
             mbar_wait(&bar[WB_PFULL], par);
             mbar_wait(&bar[WB_HFULL], par);
             tc_fence_after();
             if (leader) {
-                const uint64_t ah = nsdesc(G::PH, 2048), al = nsdesc(G::PL, 2048);
-                const uint64_t dHh = nsdesc(G::HH, 1024), dHl = nsdesc(G::HL, 1024);
-                umma_bf16(tmem_base, ah, dHh, kIdescBf16M128N64, 1);
-                umma_bf16(tmem_base, ah, dHl, kIdescBf16M128N64, 1);
-                umma_bf16(tmem_base, al, dHh, kIdescBf16M128N64, 1);
+                if (!(dbg & 16)) {
+                umma_bf16(tmem_base, dPh, dHh, kIdescBf16M128N64, 1);
+                umma_bf16(tmem_base, dPh, dHl, kIdescBf16M128N64, 1);
+                umma_bf16(tmem_base, dPl, dHh, kIdescBf16M128N64, 1);
+                }
                 umma_commit(&bar[WB_M2]);
             }
             __syncwarp();
-            mbar_wait(&bar[WB_M2], par);                          // H, addv and P are free
-            issue_h(have2 ? u2 : -1, row2, nr2, it + 1);
-            have = have2; u = u2; row0 = row2; nr = nr2;
-            it++;
+            cur = nxt; nxt = nn;
         }
-        if (it == 0) issue_h(-1, 0, 0, 0);                       // no tile at all: release the consumers
     } else {
-        // ================= consumer warps: softmax, epilogue =================
+        // ================= consumer warps: operand refill, softmax, epilogue =================
         const uint32_t tmem_lane = (uint32_t)(warp * 32) << 16;
         const float scale2 = p.scale * 1.4426950408889634f, inv_T = 1.0f / (float)p.T;
         const float *sAddv = reinterpret_cast<const float *>(sm + G::ADDV);
-        for (int it = 0;; it++) {
+        const int *sFlags = reinterpret_cast<const int *>(sm + G::ADDV + 64);
+        // the operands of tile `inf`: this warp's 32 candidate rows, (warp 0) the user's K rows, -> WB_XFULL
+        auto refill_x = [&](const int4 &inf) {
+            const int u = inf.x, row0 = inf.y, nr = inf.z;
+            const int32_t *cp = p.code[slot] + (size_t)u * p.cap + row0 + warp * 32;
+            const int mine = nr - warp * 32 < 32 ? nr - warp * 32 : 32;          // rows of this warp (may be <= 0)
+            const int nl = mine > 0 ? (mine + 3) >> 2 : 0;
+            if (warp == 0 && !(dbg & 8)) {                      // K rows -> rows 64..79 of the B operand (generic proxy + fence)
+                const uint4 *src = reinterpret_cast<const uint4 *>(p.uop + (size_t)u * G::UOP_BYTES);
+                uint4 v[8];
+#pragma unroll
+                for (int i = 0; i < 8; i++) v[i] = __ldg(src + i * 32 + lane);
+#pragma unroll
+                for (int i = 0; i < 8; i++) {
+                    const int idx = i * 32 + lane, j = idx & 15, kc = (idx >> 4) & 7;
+                    *reinterpret_cast<uint4 *>(sm + (idx >> 7 ? G::BL : G::BH) + kc * G::B_LBO + 1024 + j * 16) = v[i];
+                }
+                fence_proxy_async();
+                __syncwarp();
+            }
+            if (dbg & 1) {
+                if (lane == 0) mbar_arrive(&bar[WB_XFULL]);
+            } else if (MODE == 0) {
+                if (lane == 0) mbar_expect_tx(&bar[WB_XFULL], (uint32_t)nl * 1024u);
+                __syncwarp();
+                if (lane < nl) {
+                    int4 c = *reinterpret_cast<const int4 *>(cp + 4 * lane);
+                    const int r = 4 * lane;
+                    if (r + 1 >= mine) c.y = c.x;
+                    if (r + 2 >= mine) c.z = c.x;
+                    if (r + 3 >= mine) c.w = c.x;
+                    const uint32_t off = (uint32_t)(warp * 32 + r) * 128u;
+                    tma_gather4_hilo(sbase + G::XH + off, sbase + G::XL + off, &tmap, smem_u32(&bar[WB_XFULL]), c.x, c.y, c.z, c.w);
+                }
+            } else {
+                for (int it = 0; it < 16; it++) {
+                    const int idx = it * 32 + lane, rw = idx >> 4, ch = idx & 15;
+                    if (rw < mine) {
+                        const int32_t c = __ldg(cp + rw);
+                        const int row = warp * 32 + rw;
+                        cp_async16(sm + (ch < 8 ? G::XH : G::XL) + row * 128 + (((ch & 7) ^ (row & 7)) << 4), p.split + (size_t)c * 256 + ch * 16);
+                    }
+                }
+                cp_async_commit();
+                cp_async_wait<0>();
+                fence_proxy_async();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&bar[WB_XFULL]);
+            }
+        };
+        auto refill_h = [&](const int4 &inf) {                  // H operand + softmax mask + user flags -> WB_HFULL
+            if (warp == 1 && lane == 0) {
+                mbar_expect_tx(&bar[WB_HFULL], G::H_COPY);
+                tma_bulk_g2s(sm + G::HH, p.uop + (size_t)inf.x * G::UOP_BYTES + 4096, G::H_COPY, &bar[WB_HFULL]);
+            }
+        };
+        mbar_wait(&bar[WB_INFO], 0);
+        int4 inf = sInfo[0];
+        if (inf.x >= 0) { refill_x(inf); refill_h(inf); }
+        for (int it = 0; inf.x >= 0; it++) {
             const uint32_t par = it & 1;
-            mbar_wait(&bar[WB_HFULL], par);
-            const int4 inf = *const_cast<const int4 *>(sInfo + par);
-            if (inf.x < 0) break;
             const int nr = inf.z;
             const bool active = warp * 32 < nr;
+            mbar_wait(&bar[WB_INFO], par ^ 1);                   // tile it + 1
+            const int4 ninf = sInfo[par ^ 1];
             mbar_wait(&bar[WB_M1], par);
             tc_fence_after();
+            if (ninf.x >= 0) refill_x(ninf);                     // X and the K rows are free: the first chain has completed
+            mbar_wait(&bar[WB_HFULL], par);
             if (active) {
                 float sc[16];
                 tmem_ld16(tmem_base + tmem_lane + 64, sc);
-                if (inf.w & WU_ALLMASK) {
+                if (dbg & 2) {
+                } else if (sFlags[0] & WU_ALLMASK) {
 #pragma unroll
                     for (int j = 0; j < 16; j++) sc[j] = j < p.T ? inv_T : 0.0f;
                 } else {
@@ -716,6 +751,7 @@ wave_score_kernel(const __grid_constant__ CUtensorMap tmap, const WaveParams p, 
             if (lane == 0) mbar_arrive(&bar[WB_PFULL]);
             mbar_wait(&bar[WB_M2], par);
             tc_fence_after();
+            if (ninf.x >= 0) refill_h(ninf);                     // H, the mask and P are free: the second chain has completed
             float h0[32], h1[32];
             if (active) {
                 tmem_ld32(tmem_base + tmem_lane, h0);
@@ -724,7 +760,7 @@ wave_score_kernel(const __grid_constant__ CUtensorMap tmap, const WaveParams p, 
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(&bar[WB_TFREE]);
-            if (active) {
+            if (active && !(dbg & 4)) {
                 float logit = 0.0f;
 #pragma unroll
                 for (int c = 0; c < 32; c++) logit = fmaf(fmaxf(h0[c], 0.0f), w.w2[c], logit);
@@ -732,6 +768,7 @@ wave_score_kernel(const __grid_constant__ CUtensorMap tmap, const WaveParams p, 
                 for (int c = 0; c < 32; c++) logit = fmaf(fmaxf(h1[c], 0.0f), w.w2[32 + c], logit);
                 if (tid < nr) p.score[(size_t)inf.x * p.cap + inf.y + tid] = logit + w.b2;
             }
+            inf = ninf;
         }
     }
     tc_fence_before();

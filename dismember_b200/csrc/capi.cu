@@ -426,7 +426,7 @@ static int32_t wave_prepare(dmg_handle_t h)
     DinDev &d = h->din;
     if (!h->parent) {
         if (!d.d_split && cudaMalloc(&d.d_split, (size_t)d.rows * 256) != cudaSuccess) { cudaGetLastError(); d.d_split = nullptr; return DMG_OK; }
-        if (!d.d_w1img) DMG_CUDA(h, cudaMalloc(&d.d_w1img, 16384));
+        if (!d.d_w1img) { DMG_CUDA(h, cudaMalloc(&d.d_w1img, 20480)); DMG_CUDA(h, cudaMemsetAsync(d.d_w1img, 0, 20480, h->stream)); }
         wave_split_table_kernel<<<h->sm_count * 16, 256, 0, h->stream>>>(d.emb<float>(), d.rows, d.d_split);
         wave_w1_image_kernel<<<2, 256, 0, h->stream>>>(d.w1<float>(), d.d_w1img);
         h->launches += 2;
@@ -567,7 +567,8 @@ static int32_t wave_enqueue(dmg_handle_t h, const BeamParams<float> &p, const Fa
     const int B = p.B, cap = p.cap;
     DMG_TRY(ensure_dev(h, h->s_wave, Carver::need({(size_t)B * cap * 4, (size_t)B * cap * 4, (size_t)B * cap * 4, (size_t)B * 4,
                                                    (size_t)B * sizeof(WaveUser), (size_t)B * WG::UOP_BYTES, (size_t)B * WG::VCAP * 4,
-                                                   (size_t)B * WG::VCAP * 4, (size_t)B * WG::VCAP * 4, (size_t)B * 32 * 4})));
+                                                   (size_t)B * WG::VCAP * 4, (size_t)B * WG::VCAP * 4, (size_t)B * 32 * 4,
+                                                   (size_t)B * ((cap + 127) / 128) * 4})));
     Carver c(h->s_wave.d);
     WaveParams wp;
     memset(&wp, 0, sizeof(wp));
@@ -581,6 +582,8 @@ static int32_t wave_enqueue(dmg_handle_t h, const BeamParams<float> &p, const Fa
     wp.uop = c.take<unsigned char>((size_t)B * WG::UOP_BYTES);
     wp.v_code = c.take<int32_t>((size_t)B * WG::VCAP); wp.v_fast = c.take<float>((size_t)B * WG::VCAP);
     wp.v_meta = c.take<uint32_t>((size_t)B * WG::VCAP); wp.v_segeps = c.take<float>((size_t)B * 32);
+    wp.tile_list = c.take<int32_t>((size_t)B * ((cap + 127) / 128));
+    wp.tile_count = h->d_fast_ctl + 8;                           // [level]: tiles listed, [32 + level]: tiles taken (zeroed by tdm_ids_to_codes_kernel)
     wp.mT = fx.mT; wp.zvec = fx.zvec; wp.lvl_vx = fx.lvl_vx; wp.lvl_nx = fx.lvl_nx; wp.b1 = p.b1;
     wp.cA = fx.cA; wp.cZ = fx.cZ; wp.cH = fx.cH; wp.cGamma = fx.cGamma; wp.tau = fx.tau;
     wp.stats = fx.stats; wp.redo_list = fx.redo_list; wp.redo_count = fx.redo_count; wp.host_flags = fx.host_flags;
@@ -612,7 +615,48 @@ static int32_t wave_enqueue(dmg_handle_t h, const BeamParams<float> &p, const Fa
     const int last_level = stop_level >= 0 ? std::min(stop_level, p.leaf_level) : p.leaf_level;
     for (int level = s_min; level < last_level; level++) {
         wave_select_kernel<<<(B + 3) / 4, 128, 0, h->stream>>>(wp, sw, level, slot);
-        score_kernel<<<grid, WG::THREADS, WG::SMEM, h->stream>>>(tmap, wp, w2, slot ^ 1, h->d_fast_ctl + 8 + level, ntiles, tpu);
+        score_kernel<<<grid, WG::THREADS, WG::SMEM, h->stream>>>(tmap, wp, w2, slot ^ 1, level + 1);
+        if (getenv("DMG_WAVE_ABLATE") && level == atoi(getenv("DMG_WAVE_ABLATE"))) {
+            // profiling aid: replay this level's scorer with parts switched off (scores go to a scratch buffer)
+            static float *dummy = nullptr;
+            {
+                cudaError_t e0 = cudaStreamSynchronize(h->stream);
+                fprintf(stderr, "[wave ablate] before replay: %s\n", cudaGetErrorString(e0));
+            }
+            if (!dummy) { cudaError_t em = cudaMalloc(&dummy, (size_t)B * cap * 4); fprintf(stderr, "[wave ablate] malloc: %s %p\n", cudaGetErrorString(em), (void *)dummy); }
+            WaveParams wq = wp;
+            wq.score = dummy;
+            cudaEvent_t a, b;
+            cudaEventCreate(&a); cudaEventCreate(&b);
+            std::vector<int> masks = {0, 0, 1, 2, 4, 8, 16, 3, 6, 7, 15, 31};
+            if (const char *ml = getenv("DMG_WAVE_MASKS")) { masks.clear(); for (const char *q = ml; *q; q++) if (*q >= '0' && *q <= '9') { masks.push_back(atoi(q)); while (q[1] >= '0' && q[1] <= '9') q++; } }
+            for (int mask : masks) {
+                float best = 1e9f;
+                for (int rep = 0; rep < 5; rep++) {
+                    cudaMemsetAsync(wp.tile_count + 32 + level + 1, 0, 4, h->stream);
+                    cudaEventRecord(a, h->stream);
+                    void (*kq)(const CUtensorMap, const WaveParams, const WaveW2, int, int) = nullptr;
+                    switch (mask) {
+                        case 0: kq = wave_score_kernel<0, 0>; break;   case 1: kq = wave_score_kernel<0, 1>; break;
+                        case 2: kq = wave_score_kernel<0, 2>; break;   case 4: kq = wave_score_kernel<0, 4>; break;
+                        case 8: kq = wave_score_kernel<0, 8>; break;   case 16: kq = wave_score_kernel<0, 16>; break;
+                        case 3: kq = wave_score_kernel<0, 3>; break;   case 6: kq = wave_score_kernel<0, 6>; break;
+                        case 7: kq = wave_score_kernel<0, 7>; break;   case 15: kq = wave_score_kernel<0, 15>; break;
+                        default: kq = wave_score_kernel<0, 31>; break;
+                    }
+                    cudaFuncSetAttribute(kq, cudaFuncAttributeMaxDynamicSharedMemorySize, WG::SMEM);
+                    kq<<<grid, WG::THREADS, WG::SMEM, h->stream>>>(tmap, wq, w2, slot ^ 1, level + 1);
+                    cudaEventRecord(b, h->stream);
+                    cudaEventSynchronize(b);
+                    float ms = 0.f;
+                    cudaError_t ee = cudaEventElapsedTime(&ms, a, b);
+                    if (ee != cudaSuccess) { fprintf(stderr, "[wave ablate] error %s\n", cudaGetErrorString(ee)); break; }
+                    best = std::min(best, ms);
+                }
+                fprintf(stderr, "[wave ablate] level %d mask %2d: %.1f us\n", level, mask, best * 1e3f);
+            }
+            cudaEventDestroy(a); cudaEventDestroy(b);
+        }
         slot ^= 1;
         h->launches += 2;
     }
