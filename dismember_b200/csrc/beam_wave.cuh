@@ -42,23 +42,21 @@ struct WaveUser {                   // per-user search state (64 B)
 enum { WU_REDO = 1, WU_SCORED = 2, WU_ALLMASK = 4 };
 
 struct WaveGeo {
-    static constexpr int THREADS = 160;                      // 4 consumer warps (TMEM lanes 32 w ..) + 1 control warp
-    static constexpr int XH = 0, XL = 16384;                 // [128 rows][128 B] bf16, SWIZZLE_128B (TMA gather4 destination)
-    static constexpr int BH = 32768, BL = 43008;             // B operand [80 n][64 k]: n < 64 W1x outputs, n >= 64 history slots;
-    static constexpr int B_LBO = 1280;                       //   K-major, no swizzle, LBO 1280 (80 rows x 16 B), SBO 128
-    static constexpr int HH = 53248, HL = 55296;             // B operand [64 o][16 j]: LBO 1024, SBO 128
-    static constexpr int ADDV = 57344;                       // [16] additive softmax mask + [4] user flags (tail of the H copy)
-    static constexpr int H_COPY = 4096 + 80;
-    static constexpr int PH = 57472, PL = 61568;             // A operand [128 rows][16 j]: LBO 2048, SBO 128
-    static constexpr int BAR = 65664;                        // 8 mbarriers
-    static constexpr int INFO = BAR + 64;                    // 2 x int4 tile info
-    static constexpr int TMEMP = INFO + 32;
-    static constexpr int BYTES = TMEMP + 16;
-    static constexpr int SMEM = BYTES + 1024;                // + alignment slack (the X tiles need 1024-byte alignment)
-    static constexpr int UOP_BYTES = 8320;                   // per-user operand image [KH | KL | HH | HL | addv] (8256, padded)
+    static constexpr int THREADS = 288;                      // 2 consumer warpgroups (warp w: TMEM lanes 32 (w & 3) ..) + 1 MMA-issue warp
+    // shared memory of the scorer, two pipeline stages s = tile & 1 (base 1024-byte aligned)
+    static constexpr int XH = 0, XL = 16384, X_STAGE = 32768; // X[s]: [128 rows][128 B] bf16 hi / lo, SWIZZLE_128B (TMA gather4 destination)
+    static constexpr int BH = 65536, BL = 77824;             // B operand [96 n][64 k]: n < 64 W1x outputs, 64 + 16 s + j = history slot j of stage s;
+    static constexpr int B_LBO = 1536;                       //   K-major, no swizzle, LBO 1536 (96 rows x 16 B), SBO 128
+    static constexpr int HH = 90112, HL = 92160, H_STAGE = 4096;  // H[s]: B operand [64 o][16 j]: LBO 1024, SBO 128
+    static constexpr int PH = 98304, PL = 102400, P_STAGE = 8192; // P[s]: A operand [128 rows][16 j]: LBO 2048, SBO 128
+    static constexpr int ADDV = 114688, ADDV_STAGE = 128;    // [tile & 3]: [16] additive softmax mask + [4] user flags (two slots per stage: a warp may
+    static constexpr int BAR = 115200;                       //   still read tile t's while warp 0 of its group writes tile t + 2's); 13 mbarriers
+    static constexpr int TMEMP = BAR + 13 * 8;
+    static constexpr int SMEM = TMEMP + 24;
+    static constexpr int UOP_BYTES = 8320;                   // per-user operand image [KH | KL | HH | HL | addv | flags] (8272, padded)
     static constexpr int VCAP = FastGeo::VCAP, MAX_UNC = FastGeo::MAX_UNC;
 };
-enum { WB_W1 = 0, WB_XFULL, WB_M1, WB_PFULL, WB_HFULL, WB_M2, WB_TFREE, WB_INFO };
+enum { WB_W1 = 0, WB_HFULL = 1, WB_XFULL = 3, WB_M1 = 5, WB_PFULL = 7, WB_M2 = 9, WB_TFREE = 11 };   // + stage
 
 struct WaveParams {
     int B, T, cap, beam;
@@ -80,8 +78,8 @@ struct WaveParams {
     unsigned long long *stats;
     int32_t *redo_list, *redo_count, *host_flags;
     int32_t *tile_list;             // [B * ceil(cap / 128)] tiles of the level being scored: user << 12 | first row >> 7 << 8 | rows - 1 ... see wave_tile_pack
-    int32_t *tile_count;            // per level: [0] tiles appended by the select kernel, [32] tiles taken by the scorer
-    const unsigned char *w1img;     // [W1x hi | W1x lo] as the n < 64 rows of the B operand, 2 x 10240 B
+    int32_t *tile_count;            // per level: tiles appended by the select kernel
+    const unsigned char *w1img;     // [W1x hi | W1x lo] as the n < 64 rows of the B operand, 2 x 12288 B
     const unsigned char *split;     // bf16 hi|lo table, 256 B per code
 };
 struct WaveW2 { float w2[64]; float b2; };
@@ -102,7 +100,7 @@ static __global__ void wave_split_table_kernel(const float *__restrict__ emb, in
     }
 }
 
-// W1 item half [o][k] -> rows n < 64 of the B operand image [hi | lo], chunk kc at kc * 1280, row o at o * 16
+// W1 item half [o][k] -> rows n < 64 of the B operand image [hi | lo], chunk kc at kc * 1536, row o at o * 16
 static __global__ void wave_w1_image_kernel(const float *__restrict__ w1, unsigned char *__restrict__ img)
 {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -113,8 +111,8 @@ static __global__ void wave_w1_image_kernel(const float *__restrict__ w1, unsign
     for (int q = 0; q < 8; q++) v[q] = __ldg(w1 + o * 128 + kc * 8 + q);
     uint4 hi, lo;
     split8(v, hi, lo);
-    *reinterpret_cast<uint4 *>(img + kc * 1280 + o * 16) = hi;
-    *reinterpret_cast<uint4 *>(img + 10240 + kc * 1280 + o * 16) = lo;
+    *reinterpret_cast<uint4 *>(img + kc * 1536 + o * 16) = hi;
+    *reinterpret_cast<uint4 *>(img + 12288 + kc * 1536 + o * 16) = lo;
 }
 // a tile of the level being scored: user, first candidate row (multiple of 128), rows (1..128)
 __device__ __forceinline__ int32_t wave_tile_pack(int user, int row0, int nr) { return (user << 10) | ((row0 >> 7) << 8) | (nr - 1); }
@@ -534,69 +532,59 @@ __device__ __forceinline__ void tma_gather4_hilo(uint32_t dst_hi, uint32_t dst_l
           "r"(2 * c0 + 1), "r"(2 * c1 + 1), "r"(2 * c2 + 1), "r"(2 * c3 + 1) : "memory");
 }
 
-// Tiles of (user, <= 128 candidate rows) come from the list the select kernel wrote, through a dynamic counter.
-//   control warp (warp 4): takes tiles two ahead, publishes them, issues the tcgen05.mma chains:
-//       [Hacc | S] = X . [W1x | K]^T   (128 x 80 x 64, bf16 hi*hi + hi*lo + lo*hi, fp32 accumulators in TMEM)
-//       Hacc += P . H                   (128 x 64 x 16; row 15 of H carries b1)
-//   consumer warps (0..3, TMEM lanes 32 w ..): as soon as the first chain of tile t has completed they refill the operand
-//   tile for t + 1 -- every warp gathers its own 32 rows with the TMA (tile::gather4, MODE 0) or cp.async (MODE 1), warp 0
-//   also copies the user's K rows into the B operand -- then run Mask + SoftMax on S (one row per thread, log2 domain),
-//   write P as an A operand, and after the second chain read Hacc, free the accumulators and finish
-//   logit = relu(Hacc) . W2 + b2 from registers.
+constexpr uint32_t kIdescBf16M128N96 = (1u << 4) | (1u << 7) | (1u << 10) | ((96u >> 3) << 17) | ((128u >> 4) << 24);
+
+// Tiles of (user, <= 128 candidate rows) come from the list the select kernel wrote; CTA b takes tiles b, b + grid, ...
+// Two pipeline stages (s = tile & 1), each with its own X, K rows, H, P, TMEM accumulators and its own consumer warpgroup;
+// 2 CTAs per SM (113 KB of shared memory and 256 TMEM columns each), i.e. four tile chains per SM:
+//   MMA warp (warp 8), per tile t:   [Hacc | S] = X . [W1x | K0 | K1]^T   (128 x 96 x 64, bf16 hi*hi + hi*lo + lo*hi, fp32 in TMEM;
+//                                       the history rows of stage s sit in rows 64 + 16 s .. of the B operand) as soon as X[s] has
+//                                       landed and the epilogue of tile t - 2 has drained the accumulators; then, for tile t - 1,
+//                                    Hacc += P . H   (128 x 64 x 16; row 15 of H carries b1)
+//   consumer warpgroup g (warps 4 g .. 4 g + 3, TMEM lanes 32 (w & 3) ..) owns the tiles t = g, g + 2, ..: wait S(t); refill X[g]
+//       with tile t + 2 (every warp gathers its own 32 rows with the TMA, tile::gather4; the group's first warp also copies the
+//       user's K rows, softmax mask and flags); Mask + SoftMax on S (one row per thread, log2 domain) -> P[g]; wait for the second
+//       chain; read Hacc, free the accumulators, logit = relu(Hacc) . W2 + b2.  While one group waits for the tensor pipe the
+//       other one computes.
 // DBG: ablation switches for profiling (results are wrong when != 0): 1 no row gather, 2 no softmax math, 4 no epilogue math, 8 no K copy, 16 no MMA
-template <int MODE, int DBG = 0>
-static __global__ void __launch_bounds__(WaveGeo::THREADS, 3)
+template <int DBG = 0>
+static __global__ void __launch_bounds__(WaveGeo::THREADS, 2)
 wave_score_kernel(const __grid_constant__ CUtensorMap tmap, const WaveParams p, const WaveW2 w, int slot, int level)
 {
     using G = WaveGeo;
     constexpr int dbg = DBG;
-    extern __shared__ unsigned char smem_dyn[];
-    unsigned char *sm = reinterpret_cast<unsigned char *>((reinterpret_cast<uintptr_t>(smem_dyn) + 1023) & ~(uintptr_t)1023);
+    extern __shared__ __align__(1024) unsigned char sm[];
     uint64_t *bar = reinterpret_cast<uint64_t *>(sm + G::BAR);
-    int4 *sInfo = reinterpret_cast<int4 *>(sm + G::INFO);
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const uint32_t sbase = smem_u32(sm);
+    if (sbase & 1023u) __trap();                                 // the swizzled X tiles need 1024-byte alignment
 
-    if (tid == 128) {
+    if (tid == 256) {
         mbar_init(&bar[WB_W1], 1);
-        mbar_init(&bar[WB_XFULL], 4);
-        mbar_init(&bar[WB_M1], 1);
-        mbar_init(&bar[WB_PFULL], 4);
-        mbar_init(&bar[WB_HFULL], 1);
-        mbar_init(&bar[WB_M2], 1);
-        mbar_init(&bar[WB_TFREE], 4);
-        mbar_init(&bar[WB_INFO], 1);
+        for (int s = 0; s < 2; s++) {
+            mbar_init(&bar[WB_HFULL + s], 1);
+            mbar_init(&bar[WB_XFULL + s], 4);
+            mbar_init(&bar[WB_M1 + s], 1);
+            mbar_init(&bar[WB_PFULL + s], 4);
+            mbar_init(&bar[WB_M2 + s], 1);
+            mbar_init(&bar[WB_TFREE + s], 4);
+        }
     }
-    if (warp == 4) tmem_alloc(reinterpret_cast<uint32_t *>(sm + G::TMEMP), 128);     // Hacc [0, 64), S [64, 80)
+    if (warp == 8) tmem_alloc(reinterpret_cast<uint32_t *>(sm + G::TMEMP), 256);     // stage s: Hacc [128 s, +64), S [128 s + 64 + 16 s, +16)
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t *>(sm + G::TMEMP);
+    const int ntiles = __ldg(p.tile_count + level);
+    const int n_my = ntiles > (int)blockIdx.x ? (ntiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
 
-    if (warp == 4) {
-        // ================= control warp: tile scheduler, MMA issue =================
+    if (warp == 8) {
+        // ================= MMA warp =================
         const bool leader = lane == 0;
         if (leader) {
-            mbar_expect_tx(&bar[WB_W1], 20480);
-            tma_bulk_g2s(sm + G::BH, p.w1img, 20480, &bar[WB_W1]);
+            mbar_expect_tx(&bar[WB_W1], 24576);
+            tma_bulk_g2s(sm + G::BH, p.w1img, 24576, &bar[WB_W1]);
         }
-        const int ntiles = __ldg(p.tile_count + level);
-        int32_t *counter = p.tile_count + 32 + level;
-        auto take = [&]() -> int {                                // the next tile (packed), -1 when the list is exhausted
-            int idx = 0;
-            if (leader) idx = atomicAdd(counter, 1);
-            idx = __shfl_sync(0xffffffffu, idx, 0);
-            return idx < ntiles ? __ldg(p.tile_list + idx) : -1;
-        };
-        auto publish = [&](int itn, int tile) {
-            if (leader) {
-                int4 inf;
-                inf.x = tile < 0 ? -1 : (tile >> 10); inf.y = ((tile >> 8) & 3) * 128; inf.z = (tile & 255) + 1; inf.w = 0;
-                sInfo[itn & 1] = inf;
-                mbar_arrive(&bar[WB_INFO]);
-            }
-            __syncwarp();
-        };
         // operand descriptors: K-major; X tiles SWIZZLE_128B (SBO 1024, LBO unused), everything else no swizzle (SBO 128)
         auto nsdesc = [&](uint32_t off, uint32_t lbo) -> uint64_t {
             return ((uint64_t)(0x4000u | (128u >> 4)) << 32) | (uint64_t)(((sbase + off) >> 4) | ((lbo >> 4) << 16));
@@ -606,123 +594,121 @@ wave_score_kernel(const __grid_constant__ CUtensorMap tmap, const WaveParams p, 
         };
         const uint64_t dXh = swdesc(G::XH), dXl = swdesc(G::XL), dBh = nsdesc(G::BH, G::B_LBO), dBl = nsdesc(G::BL, G::B_LBO);
         const uint64_t dPh = nsdesc(G::PH, 2048), dPl = nsdesc(G::PL, 2048), dHh = nsdesc(G::HH, 1024), dHl = nsdesc(G::HL, 1024);
-        int cur = take();
-        publish(0, cur);
-        int nxt = cur >= 0 ? take() : -1;
-        mbar_wait(&bar[WB_W1], 0);
-        for (int it = 0; cur >= 0; it++) {
-            const uint32_t par = it & 1;
-            const int nn = nxt >= 0 ? take() : -1;                // two ahead: the atomic and the list read are off the critical path
-            mbar_wait(&bar[WB_XFULL], par);
-            publish(it + 1, nxt);                                 // after XFULL(it): every consumer warp has read tile `it`, so WB_INFO never runs two phases ahead
-            if (it > 0) mbar_wait(&bar[WB_TFREE], par ^ 1);
-            tc_fence_after();
-            if (leader) {
+        if (n_my > 0) mbar_wait(&bar[WB_W1], 0);
+        for (int t = 0; t <= n_my; t++) {
+            const int s = t & 1;
+            if (t < n_my) {                                       // first chain of tile t
+                mbar_wait(&bar[WB_XFULL + s], (t >> 1) & 1);
+                if (t >= 2) mbar_wait(&bar[WB_TFREE + s], ((t - 2) >> 1) & 1);
+                tc_fence_after();
+                if (leader) {
+                    const uint32_t d = tmem_base + s * 128;
 #pragma unroll
-                for (int ks = 0; ks < 4; ks++) {
-                    if (dbg & 16) break;
-                    const uint64_t ah = dXh + ks * 2, al = dXl + ks * 2;
-                    const uint64_t bh = dBh + ks * (2 * G::B_LBO / 16), bl = dBl + ks * (2 * G::B_LBO / 16);
-                    umma_bf16(tmem_base, ah, bh, kIdescBf16M128N80, ks > 0);
-                    umma_bf16(tmem_base, ah, bl, kIdescBf16M128N80, 1);
-                    umma_bf16(tmem_base, al, bh, kIdescBf16M128N80, 1);
+                    for (int ks = 0; ks < 4; ks++) {
+                        if (dbg & 16) break;
+                        const uint64_t ah = dXh + s * (G::X_STAGE / 16) + ks * 2, al = dXl + s * (G::X_STAGE / 16) + ks * 2;
+                        const uint64_t bh = dBh + ks * (2 * G::B_LBO / 16), bl = dBl + ks * (2 * G::B_LBO / 16);
+                        umma_bf16(d, ah, bh, kIdescBf16M128N96, ks > 0);
+                        umma_bf16(d, ah, bl, kIdescBf16M128N96, 1);
+                        umma_bf16(d, al, bh, kIdescBf16M128N96, 1);
+                    }
+                    umma_commit(&bar[WB_M1 + s]);
                 }
-                umma_commit(&bar[WB_M1]);
+                __syncwarp();
             }
-            __syncwarp();
-            mbar_wait(&bar[WB_PFULL], par);
-            mbar_wait(&bar[WB_HFULL], par);
-            tc_fence_after();
-            if (leader) {
-                if (!(dbg & 16)) {
-                umma_bf16(tmem_base, dPh, dHh, kIdescBf16M128N64, 1);
-                umma_bf16(tmem_base, dPh, dHl, kIdescBf16M128N64, 1);
-                umma_bf16(tmem_base, dPl, dHh, kIdescBf16M128N64, 1);
+            if (t >= 1) {                                         // second chain of tile t - 1
+                const int q = s ^ 1;
+                mbar_wait(&bar[WB_PFULL + q], ((t - 1) >> 1) & 1);
+                mbar_wait(&bar[WB_HFULL + q], ((t - 1) >> 1) & 1);
+                tc_fence_after();
+                if (leader) {
+                    const uint32_t d = tmem_base + q * 128;
+                    if (!(dbg & 16)) {
+                        umma_bf16(d, dPh + q * (G::P_STAGE / 16), dHh + q * (G::H_STAGE / 16), kIdescBf16M128N64, 1);
+                        umma_bf16(d, dPh + q * (G::P_STAGE / 16), dHl + q * (G::H_STAGE / 16), kIdescBf16M128N64, 1);
+                        umma_bf16(d, dPl + q * (G::P_STAGE / 16), dHh + q * (G::H_STAGE / 16), kIdescBf16M128N64, 1);
+                    }
+                    umma_commit(&bar[WB_M2 + q]);
                 }
-                umma_commit(&bar[WB_M2]);
+                __syncwarp();
             }
-            __syncwarp();
-            cur = nxt; nxt = nn;
         }
     } else {
-        // ================= consumer warps: operand refill, softmax, epilogue =================
-        const uint32_t tmem_lane = (uint32_t)(warp * 32) << 16;
+        // ================= consumer warpgroups: operand refill, softmax, epilogue =================
+        const int g = warp >> 2, wq = warp & 3, gtid = tid & 127;         // group = pipeline stage, warp within the group, row of the tile
+        const uint32_t tmem_lane = (uint32_t)(wq * 32) << 16;
+        const uint32_t tm = tmem_base + g * 128 + tmem_lane;
         const float scale2 = p.scale * 1.4426950408889634f, inv_T = 1.0f / (float)p.T;
-        const float *sAddv = reinterpret_cast<const float *>(sm + G::ADDV);
-        const int *sFlags = reinterpret_cast<const int *>(sm + G::ADDV + 64);
-        // the operands of tile `inf`: this warp's 32 candidate rows, (warp 0) the user's K rows, -> WB_XFULL
-        auto refill_x = [&](const int4 &inf) {
-            const int u = inf.x, row0 = inf.y, nr = inf.z;
-            const int32_t *cp = p.code[slot] + (size_t)u * p.cap + row0 + warp * 32;
-            const int mine = nr - warp * 32 < 32 ? nr - warp * 32 : 32;          // rows of this warp (may be <= 0)
+        auto tile_of = [&](int t) -> int { return t < n_my ? __ldg(p.tile_list + blockIdx.x + t * gridDim.x) : -1; };
+        // the operands of tile `tile`: this warp's 32 candidate rows, (first warp of the group) the user's K rows, mask and flags -> WB_XFULL[g]
+        auto refill_x = [&](int tile, int aslot) {
+            const int u = tile >> 10, row0 = ((tile >> 8) & 3) * 128, nr = (tile & 255) + 1;
+            const int32_t *cp = p.code[slot] + (size_t)u * p.cap + row0 + wq * 32;
+            const int mine = nr - wq * 32 < 32 ? nr - wq * 32 : 32;              // rows of this warp (may be <= 0)
             const int nl = mine > 0 ? (mine + 3) >> 2 : 0;
-            if (warp == 0 && !(dbg & 8)) {                      // K rows -> rows 64..79 of the B operand (generic proxy + fence)
-                const uint4 *src = reinterpret_cast<const uint4 *>(p.uop + (size_t)u * G::UOP_BYTES);
-                uint4 v[8];
-#pragma unroll
-                for (int i = 0; i < 8; i++) v[i] = __ldg(src + i * 32 + lane);
-#pragma unroll
-                for (int i = 0; i < 8; i++) {
-                    const int idx = i * 32 + lane, j = idx & 15, kc = (idx >> 4) & 7;
-                    *reinterpret_cast<uint4 *>(sm + (idx >> 7 ? G::BL : G::BH) + kc * G::B_LBO + 1024 + j * 16) = v[i];
-                }
-                fence_proxy_async();
-                __syncwarp();
-            }
+            int4 c = make_int4(0, 0, 0, 0);
+            if (lane < nl) c = *reinterpret_cast<const int4 *>(cp + 4 * lane);
             if (dbg & 1) {
-                if (lane == 0) mbar_arrive(&bar[WB_XFULL]);
-            } else if (MODE == 0) {
-                if (lane == 0) mbar_expect_tx(&bar[WB_XFULL], (uint32_t)nl * 1024u);
-                __syncwarp();
+                if (lane == 0 && wq != 0) mbar_arrive(&bar[WB_XFULL + g]);
+            } else {
+                if (lane == 0 && wq != 0) mbar_expect_tx(&bar[WB_XFULL + g], (uint32_t)nl * 1024u);
                 if (lane < nl) {
-                    int4 c = *reinterpret_cast<const int4 *>(cp + 4 * lane);
                     const int r = 4 * lane;
                     if (r + 1 >= mine) c.y = c.x;
                     if (r + 2 >= mine) c.z = c.x;
                     if (r + 3 >= mine) c.w = c.x;
-                    const uint32_t off = (uint32_t)(warp * 32 + r) * 128u;
-                    tma_gather4_hilo(sbase + G::XH + off, sbase + G::XL + off, &tmap, smem_u32(&bar[WB_XFULL]), c.x, c.y, c.z, c.w);
+                    const uint32_t off = (uint32_t)(g * G::X_STAGE + (wq * 32 + r) * 128);
+                    // the group's first warp arms the barrier only after its K copy below: its gathers may complete first (the
+                    // transaction count of an mbarrier may run negative while an arrival is still pending)
+                    tma_gather4_hilo(sbase + G::XH + off, sbase + G::XL + off, &tmap, smem_u32(&bar[WB_XFULL + g]), c.x, c.y, c.z, c.w);
                 }
-            } else {
-                for (int it = 0; it < 16; it++) {
-                    const int idx = it * 32 + lane, rw = idx >> 4, ch = idx & 15;
-                    if (rw < mine) {
-                        const int32_t c = __ldg(cp + rw);
-                        const int row = warp * 32 + rw;
-                        cp_async16(sm + (ch < 8 ? G::XH : G::XL) + row * 128 + (((ch & 7) ^ (row & 7)) << 4), p.split + (size_t)c * 256 + ch * 16);
+            }
+            if (wq == 0) {                                      // K rows -> rows 64 + 16 g .. of the B operand, mask + flags (generic proxy + fence)
+                if (!(dbg & 8)) {
+                    const uint4 *src = reinterpret_cast<const uint4 *>(p.uop + (size_t)u * G::UOP_BYTES);
+                    uint4 v[8];
+#pragma unroll
+                    for (int i = 0; i < 8; i++) v[i] = __ldg(src + i * 32 + lane);
+                    uint4 av = make_uint4(0, 0, 0, 0);
+                    if (lane < 5) av = __ldg(src + 512 + lane);         // addv [16] + flags [4] behind the 8 KB of operands
+#pragma unroll
+                    for (int i = 0; i < 8; i++) {
+                        const int idx = i * 32 + lane, j = idx & 15, kc = (idx >> 4) & 7;
+                        *reinterpret_cast<uint4 *>(sm + (idx >> 7 ? G::BL : G::BH) + kc * G::B_LBO + (64 + 16 * g + j) * 16) = v[i];
                     }
+                    if (lane < 5) *reinterpret_cast<uint4 *>(sm + G::ADDV + aslot * G::ADDV_STAGE + lane * 16) = av;
                 }
-                cp_async_commit();
-                cp_async_wait<0>();
                 fence_proxy_async();
                 __syncwarp();
-                if (lane == 0) mbar_arrive(&bar[WB_XFULL]);
+                if (lane == 0) {
+                    if (dbg & 1) mbar_arrive(&bar[WB_XFULL + g]);
+                    else mbar_expect_tx(&bar[WB_XFULL + g], (uint32_t)nl * 1024u);
+                }
             }
         };
-        auto refill_h = [&](const int4 &inf) {                  // H operand + softmax mask + user flags -> WB_HFULL
-            if (warp == 1 && lane == 0) {
-                mbar_expect_tx(&bar[WB_HFULL], G::H_COPY);
-                tma_bulk_g2s(sm + G::HH, p.uop + (size_t)inf.x * G::UOP_BYTES + 4096, G::H_COPY, &bar[WB_HFULL]);
+        auto refill_h = [&](int tile) {                          // H operand of the tile's user -> WB_HFULL[g]
+            if (wq == 1 && lane == 0) {
+                mbar_expect_tx(&bar[WB_HFULL + g], 4096);
+                tma_bulk_g2s(sm + G::HH + g * G::H_STAGE, p.uop + (size_t)(tile >> 10) * G::UOP_BYTES + 4096, 4096, &bar[WB_HFULL + g]);
             }
         };
-        mbar_wait(&bar[WB_INFO], 0);
-        int4 inf = sInfo[0];
-        if (inf.x >= 0) { refill_x(inf); refill_h(inf); }
-        for (int it = 0; inf.x >= 0; it++) {
-            const uint32_t par = it & 1;
-            const int nr = inf.z;
-            const bool active = warp * 32 < nr;
-            mbar_wait(&bar[WB_INFO], par ^ 1);                   // tile it + 1
-            const int4 ninf = sInfo[par ^ 1];
-            mbar_wait(&bar[WB_M1], par);
+        int cur = tile_of(g);
+        if (cur >= 0) { refill_x(cur, g); refill_h(cur); }
+        for (int t = g; t < n_my; t += 2) {
+            const uint32_t par = (t >> 1) & 1;
+            const int nxt = tile_of(t + 2);
+            const int nr = (cur & 255) + 1;
+            const bool active = wq * 32 < nr;
+            mbar_wait(&bar[WB_XFULL + g], par);                  // acquire the first warp's mask / flags of this tile
+            mbar_wait(&bar[WB_M1 + g], par);
             tc_fence_after();
-            if (ninf.x >= 0) refill_x(ninf);                     // X and the K rows are free: the first chain has completed
-            mbar_wait(&bar[WB_HFULL], par);
+            if (nxt >= 0) refill_x(nxt, (t + 2) & 3);            // X[g] and K slot g are free: the first chain of tile t has completed
             if (active) {
                 float sc[16];
-                tmem_ld16(tmem_base + tmem_lane + 64, sc);
+                tmem_ld16(tm + 64 + 16 * g, sc);
+                const float *sAddv = reinterpret_cast<const float *>(sm + G::ADDV + (t & 3) * G::ADDV_STAGE);
                 if (dbg & 2) {
-                } else if (sFlags[0] & WU_ALLMASK) {
+                } else if (reinterpret_cast<const int *>(sAddv)[16] & WU_ALLMASK) {
 #pragma unroll
                     for (int j = 0; j < 16; j++) sc[j] = j < p.T ? inv_T : 0.0f;
                 } else {
@@ -737,43 +723,51 @@ wave_score_kernel(const __grid_constant__ CUtensorMap tmap, const WaveParams p, 
                     for (int j = 0; j < 16; j++) sc[j] *= inv;
                 }
                 sc[15] = 1.0f;
+                unsigned char *ph = sm + G::PH + g * G::P_STAGE + gtid * 16, *pl = sm + G::PL + g * G::P_STAGE + gtid * 16;
                 uint4 hi, lo;
                 split8(*reinterpret_cast<float(*)[8]>(&sc[0]), hi, lo);
-                *reinterpret_cast<uint4 *>(sm + G::PH + tid * 16) = hi;
-                *reinterpret_cast<uint4 *>(sm + G::PL + tid * 16) = lo;
+                *reinterpret_cast<uint4 *>(ph) = hi;
+                *reinterpret_cast<uint4 *>(pl) = lo;
                 split8(*reinterpret_cast<float(*)[8]>(&sc[8]), hi, lo);
-                *reinterpret_cast<uint4 *>(sm + G::PH + 2048 + tid * 16) = hi;
-                *reinterpret_cast<uint4 *>(sm + G::PL + 2048 + tid * 16) = lo;
+                *reinterpret_cast<uint4 *>(ph + 2048) = hi;
+                *reinterpret_cast<uint4 *>(pl + 2048) = lo;
+                fence_proxy_async();
             }
-            fence_proxy_async();
             tc_fence_before();
             __syncwarp();
-            if (lane == 0) mbar_arrive(&bar[WB_PFULL]);
-            mbar_wait(&bar[WB_M2], par);
+            if (lane == 0) mbar_arrive(&bar[WB_PFULL + g]);
+            mbar_wait(&bar[WB_M2 + g], par);
             tc_fence_after();
-            if (ninf.x >= 0) refill_h(ninf);                     // H, the mask and P are free: the second chain has completed
-            float h0[32], h1[32];
-            if (active) {
-                tmem_ld32(tmem_base + tmem_lane, h0);
-                tmem_ld32(tmem_base + tmem_lane + 32, h1);
-            }
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&bar[WB_TFREE]);
-            if (active && !(dbg & 4)) {
-                float logit = 0.0f;
+            if (nxt >= 0) refill_h(nxt);                         // H[g] is free: the second chain of tile t has completed
+            // epilogue in two halves of 32 accumulator columns; four interleaved chains: term o sees 18 - o/4 roundings, inside the
+            // (64 - o) + 2 the bound allows the fast path
+            float l0 = 0.0f, l1 = 0.0f, l2 = 0.0f, l3 = 0.0f;
 #pragma unroll
-                for (int c = 0; c < 32; c++) logit = fmaf(fmaxf(h0[c], 0.0f), w.w2[c], logit);
+            for (int hf = 0; hf < 2; hf++) {
+                float hv[32];
+                if (active) tmem_ld32(tm + hf * 32, hv);
+                if (hf == 1) {
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(&bar[WB_TFREE + g]);
+                }
+                if (active && !(dbg & 4)) {
 #pragma unroll
-                for (int c = 0; c < 32; c++) logit = fmaf(fmaxf(h1[c], 0.0f), w.w2[32 + c], logit);
-                if (tid < nr) p.score[(size_t)inf.x * p.cap + inf.y + tid] = logit + w.b2;
+                    for (int c = 0; c < 32; c += 4) {
+                        l0 = fmaf(fmaxf(hv[c], 0.0f), w.w2[hf * 32 + c], l0);
+                        l1 = fmaf(fmaxf(hv[c + 1], 0.0f), w.w2[hf * 32 + c + 1], l1);
+                        l2 = fmaf(fmaxf(hv[c + 2], 0.0f), w.w2[hf * 32 + c + 2], l2);
+                        l3 = fmaf(fmaxf(hv[c + 3], 0.0f), w.w2[hf * 32 + c + 3], l3);
+                    }
+                }
             }
-            inf = ninf;
+            if (active && !(dbg & 4) && gtid < nr) p.score[(size_t)(cur >> 10) * p.cap + ((cur >> 8) & 3) * 128 + gtid] = ((l0 + l1) + (l2 + l3)) + w.b2;
+            cur = nxt;
         }
     }
     tc_fence_before();
     __syncthreads();
-    if (warp == 4) tmem_dealloc(tmem_base, 128);
+    if (warp == 8) tmem_dealloc(tmem_base, 256);
 }
 
 // ---- K3: strict verification of the deferred cuts + topk, one CTA per user ---------------------------------------------

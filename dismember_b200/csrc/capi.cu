@@ -426,7 +426,7 @@ static int32_t wave_prepare(dmg_handle_t h)
     DinDev &d = h->din;
     if (!h->parent) {
         if (!d.d_split && cudaMalloc(&d.d_split, (size_t)d.rows * 256) != cudaSuccess) { cudaGetLastError(); d.d_split = nullptr; return DMG_OK; }
-        if (!d.d_w1img) { DMG_CUDA(h, cudaMalloc(&d.d_w1img, 20480)); DMG_CUDA(h, cudaMemsetAsync(d.d_w1img, 0, 20480, h->stream)); }
+        if (!d.d_w1img) { DMG_CUDA(h, cudaMalloc(&d.d_w1img, 24576)); DMG_CUDA(h, cudaMemsetAsync(d.d_w1img, 0, 24576, h->stream)); }
         wave_split_table_kernel<<<h->sm_count * 16, 256, 0, h->stream>>>(d.emb<float>(), d.rows, d.d_split);
         wave_w1_image_kernel<<<2, 256, 0, h->stream>>>(d.w1<float>(), d.d_w1img);
         h->launches += 2;
@@ -583,7 +583,7 @@ static int32_t wave_enqueue(dmg_handle_t h, const BeamParams<float> &p, const Fa
     wp.v_code = c.take<int32_t>((size_t)B * WG::VCAP); wp.v_fast = c.take<float>((size_t)B * WG::VCAP);
     wp.v_meta = c.take<uint32_t>((size_t)B * WG::VCAP); wp.v_segeps = c.take<float>((size_t)B * 32);
     wp.tile_list = c.take<int32_t>((size_t)B * ((cap + 127) / 128));
-    wp.tile_count = h->d_fast_ctl + 8;                           // [level]: tiles listed, [32 + level]: tiles taken (zeroed by tdm_ids_to_codes_kernel)
+    wp.tile_count = h->d_fast_ctl + 8;                           // [level]: tiles listed (zeroed by tdm_ids_to_codes_kernel)
     wp.mT = fx.mT; wp.zvec = fx.zvec; wp.lvl_vx = fx.lvl_vx; wp.lvl_nx = fx.lvl_nx; wp.b1 = p.b1;
     wp.cA = fx.cA; wp.cZ = fx.cZ; wp.cH = fx.cH; wp.cGamma = fx.cGamma; wp.tau = fx.tau;
     wp.stats = fx.stats; wp.redo_list = fx.redo_list; wp.redo_count = fx.redo_count; wp.host_flags = fx.host_flags;
@@ -594,7 +594,7 @@ static int32_t wave_enqueue(dmg_handle_t h, const BeamParams<float> &p, const Fa
     WaveStrictW sw;
     sw.wattT = p.wattT; sw.w1T = p.w1T; sw.b1 = p.b1; sw.w2 = p.w2; sw.b2 = fx.b2;
     const CUtensorMap &tmap = *reinterpret_cast<const CUtensorMap *>(h->wave_tmap);
-    auto score_kernel = h->wave_mode == 0 ? wave_score_kernel<0> : wave_score_kernel<1>;
+    auto score_kernel = wave_score_kernel<0>;
     DMG_CUDA(h, cudaFuncSetAttribute(score_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, WG::SMEM));
     DMG_CUDA(h, cudaFuncSetAttribute(score_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
     const size_t fin_smem = (size_t)FastGeo::STRICT_SCR + (size_t)cap * 12 + FastGeo::MAX_FINAL * 4 + (size_t)(FastGeo::VCAP + FastGeo::MAX_FINAL) * 8 + 256 * 4 + 32 * 4;
@@ -608,7 +608,7 @@ static int32_t wave_enqueue(dmg_handle_t h, const BeamParams<float> &p, const Fa
     wave_prologue_kernel<<<B, 256, 0, h->stream>>>(wp);
     h->launches += 1;
     const int tpu = (cap + 127) / 128, ntiles = B * tpu;
-    const int grid = std::min(ntiles, 3 * h->sm_count);
+    const int grid = std::min(ntiles, 2 * h->sm_count);
     int slot = 0;
     const int s_min = lower_log2(p.beam);                        // per-user beams only widen (Recommender.scala:28-31)
     (void)max_beam;
@@ -633,16 +633,15 @@ static int32_t wave_enqueue(dmg_handle_t h, const BeamParams<float> &p, const Fa
             for (int mask : masks) {
                 float best = 1e9f;
                 for (int rep = 0; rep < 5; rep++) {
-                    cudaMemsetAsync(wp.tile_count + 32 + level + 1, 0, 4, h->stream);
                     cudaEventRecord(a, h->stream);
                     void (*kq)(const CUtensorMap, const WaveParams, const WaveW2, int, int) = nullptr;
                     switch (mask) {
-                        case 0: kq = wave_score_kernel<0, 0>; break;   case 1: kq = wave_score_kernel<0, 1>; break;
-                        case 2: kq = wave_score_kernel<0, 2>; break;   case 4: kq = wave_score_kernel<0, 4>; break;
-                        case 8: kq = wave_score_kernel<0, 8>; break;   case 16: kq = wave_score_kernel<0, 16>; break;
-                        case 3: kq = wave_score_kernel<0, 3>; break;   case 6: kq = wave_score_kernel<0, 6>; break;
-                        case 7: kq = wave_score_kernel<0, 7>; break;   case 15: kq = wave_score_kernel<0, 15>; break;
-                        default: kq = wave_score_kernel<0, 31>; break;
+                        case 0: kq = wave_score_kernel<0>; break;   case 1: kq = wave_score_kernel<1>; break;
+                        case 2: kq = wave_score_kernel<2>; break;   case 4: kq = wave_score_kernel<4>; break;
+                        case 8: kq = wave_score_kernel<8>; break;   case 16: kq = wave_score_kernel<16>; break;
+                        case 3: kq = wave_score_kernel<3>; break;   case 6: kq = wave_score_kernel<6>; break;
+                        case 7: kq = wave_score_kernel<7>; break;   case 15: kq = wave_score_kernel<15>; break;
+                        default: kq = wave_score_kernel<31>; break;
                     }
                     cudaFuncSetAttribute(kq, cudaFuncAttributeMaxDynamicSharedMemorySize, WG::SMEM);
                     kq<<<grid, WG::THREADS, WG::SMEM, h->stream>>>(tmap, wq, w2, slot ^ 1, level + 1);

@@ -25,7 +25,7 @@ def _setup(engine, n_items, E=64, seed=17, structured=True):
     return tf, rows, params
 
 
-@pytest.mark.parametrize("gather", ["tma", "cpasync"])
+@pytest.mark.parametrize("gather", ["tma"])
 def test_wave_scorer_within_bound_of_model_forward(engine, orc, gather):
     """Fast scores of every candidate of a level = model.forward (Recommender.scala:93-94) within eps; the
     candidates of the first scored level are all children of the start level in code order."""
@@ -66,7 +66,7 @@ def test_wave_scorer_within_bound_of_model_forward(engine, orc, gather):
         os.environ.pop("DMG_WAVE_GATHER", None)
 
 
-@pytest.mark.parametrize("gather", ["tma", "cpasync"])
+@pytest.mark.parametrize("gather", ["tma"])
 @pytest.mark.parametrize("n_items,beam,B", [(20000, 200, 160), (300, 7, 33), (70000, 256, 97), (5000, 64, 1)])
 def test_wave_search_matches_oracle(engine, orc, gather, n_items, beam, B):
     os.environ["DMG_WAVE_GATHER"] = gather
