@@ -42,7 +42,7 @@ struct WaveUser {                   // per-user search state (64 B)
 enum { WU_REDO = 1, WU_SCORED = 2, WU_ALLMASK = 4 };
 
 struct WaveGeo {
-    static constexpr int THREADS = 288;                      // 2 consumer warpgroups (warp w: TMEM lanes 32 (w & 3) ..) + 1 MMA-issue warp
+    static constexpr int THREADS = 256;                      // 2 warpgroups (warp w: TMEM lanes 32 (w & 3) ..), one per pipeline stage
     // shared memory of the scorer, two pipeline stages s = tile & 1 (base 1024-byte aligned)
     static constexpr int XH = 0, XL = 16384, X_STAGE = 32768; // X[s]: [128 rows][128 B] bf16 hi / lo, SWIZZLE_128B (TMA gather4 destination)
     static constexpr int BH = 65536, BL = 77824;             // B operand [96 n][64 k]: n < 64 W1x outputs, 64 + 16 s + j = history slot j of stage s;
@@ -50,13 +50,13 @@ struct WaveGeo {
     static constexpr int HH = 90112, HL = 92160, H_STAGE = 4096;  // H[s]: B operand [64 o][16 j]: LBO 1024, SBO 128
     static constexpr int PH = 98304, PL = 102400, P_STAGE = 8192; // P[s]: A operand [128 rows][16 j]: LBO 2048, SBO 128
     static constexpr int ADDV = 114688, ADDV_STAGE = 128;    // [tile & 3]: [16] additive softmax mask + [4] user flags (two slots per stage: a warp may
-    static constexpr int BAR = 115200;                       //   still read tile t's while warp 0 of its group writes tile t + 2's); 13 mbarriers
+    static constexpr int BAR = 115200;                       //   still read tile t's while warp 0 of its group writes tile t + 2's); 9 mbarriers
     static constexpr int TMEMP = BAR + 13 * 8;
     static constexpr int SMEM = TMEMP + 24;
     static constexpr int UOP_BYTES = 8320;                   // per-user operand image [KH | KL | HH | HL | addv | flags] (8272, padded)
     static constexpr int VCAP = FastGeo::VCAP, MAX_UNC = FastGeo::MAX_UNC;
 };
-enum { WB_W1 = 0, WB_HFULL = 1, WB_XFULL = 3, WB_M1 = 5, WB_PFULL = 7, WB_M2 = 9, WB_TFREE = 11 };   // + stage
+enum { WB_W1 = 0, WB_HFULL = 1, WB_XFULL = 3, WB_M1 = 5, WB_M2 = 7 };   // + stage
 
 struct WaveParams {
     int B, T, cap, beam;
@@ -532,20 +532,26 @@ __device__ __forceinline__ void tma_gather4_hilo(uint32_t dst_hi, uint32_t dst_l
           "r"(2 * c0 + 1), "r"(2 * c1 + 1), "r"(2 * c2 + 1), "r"(2 * c3 + 1) : "memory");
 }
 
+#ifdef DMG_WAVE_TIMING
+#define WTICK(i) do { if (gtid == 0) { const long long t_ = clock64(); wacc[i] += t_ - wlast; wlast = t_; } } while (0)
+#else
+#define WTICK(i) do { } while (0)
+#endif
 constexpr uint32_t kIdescBf16M128N96 = (1u << 4) | (1u << 7) | (1u << 10) | ((96u >> 3) << 17) | ((128u >> 4) << 24);
 
 // Tiles of (user, <= 128 candidate rows) come from the list the select kernel wrote; CTA b takes tiles b, b + grid, ...
-// Two pipeline stages (s = tile & 1), each with its own X, K rows, H, P, TMEM accumulators and its own consumer warpgroup;
-// 2 CTAs per SM (113 KB of shared memory and 256 TMEM columns each), i.e. four tile chains per SM:
-//   MMA warp (warp 8), per tile t:   [Hacc | S] = X . [W1x | K0 | K1]^T   (128 x 96 x 64, bf16 hi*hi + hi*lo + lo*hi, fp32 in TMEM;
-//                                       the history rows of stage s sit in rows 64 + 16 s .. of the B operand) as soon as X[s] has
-//                                       landed and the epilogue of tile t - 2 has drained the accumulators; then, for tile t - 1,
-//                                    Hacc += P . H   (128 x 64 x 16; row 15 of H carries b1)
-//   consumer warpgroup g (warps 4 g .. 4 g + 3, TMEM lanes 32 (w & 3) ..) owns the tiles t = g, g + 2, ..: wait S(t); refill X[g]
-//       with tile t + 2 (every warp gathers its own 32 rows with the TMA, tile::gather4; the group's first warp also copies the
-//       user's K rows, softmax mask and flags); Mask + SoftMax on S (one row per thread, log2 domain) -> P[g]; wait for the second
-//       chain; read Hacc, free the accumulators, logit = relu(Hacc) . W2 + b2.  While one group waits for the tensor pipe the
-//       other one computes.
+// Two pipeline stages per CTA, each a warpgroup g (warps 4 g .. 4 g + 3, TMEM lanes 32 (w & 3) ..) with its own X, K rows, H, P
+// and TMEM accumulators, working through the tiles t = g, g + 2, ..; 2 CTAs per SM (113 KB of shared memory and 256 TMEM
+// columns each), i.e. four independent tile chains per SM -- while one waits for the tensor pipe or the TMA the others compute.
+// Per tile:
+//   [Hacc | S] = X . [W1x | K0 | K1]^T   128 x 96 x 64 tcgen05.mma, bf16 hi*hi + hi*lo + lo*hi, fp32 in TMEM (the history rows of stage
+//                                         g sit in rows 64 + 16 g .. of the B operand), issued by the group's first lane as soon as
+//                                         X[g] has landed and the group has drained the accumulators of its previous tile;
+//   refill X[g] with the group's next tile: every warp gathers its own 32 rows with the TMA (tile::gather4 from the bf16 hi|lo
+//                                         table), the first warp also copies the user's K rows, softmax mask and flags;
+//   Mask + SoftMax on S, one row per thread, log2 domain -> P[g] (A operand); group barrier;
+//   Hacc += P . H                         128 x 64 x 16 (row 15 of H carries b1), issued by the group's first lane;
+//   read Hacc; group barrier; [first lane: the next tile's first chain]; logit = relu(Hacc) . W2 + b2 from registers.
 // DBG: ablation switches for profiling (results are wrong when != 0): 1 no row gather, 2 no softmax math, 4 no epilogue math, 8 no K copy, 16 no MMA
 template <int DBG = 0>
 static __global__ void __launch_bounds__(WaveGeo::THREADS, 2)
@@ -559,18 +565,18 @@ wave_score_kernel(const __grid_constant__ CUtensorMap tmap, const WaveParams p, 
     const uint32_t sbase = smem_u32(sm);
     if (sbase & 1023u) __trap();                                 // the swizzled X tiles need 1024-byte alignment
 
-    if (tid == 256) {
+    if (tid == 0) {
         mbar_init(&bar[WB_W1], 1);
         for (int s = 0; s < 2; s++) {
             mbar_init(&bar[WB_HFULL + s], 1);
             mbar_init(&bar[WB_XFULL + s], 4);
             mbar_init(&bar[WB_M1 + s], 1);
-            mbar_init(&bar[WB_PFULL + s], 4);
             mbar_init(&bar[WB_M2 + s], 1);
-            mbar_init(&bar[WB_TFREE + s], 4);
         }
+        mbar_expect_tx(&bar[WB_W1], 24576);
+        tma_bulk_g2s(sm + G::BH, p.w1img, 24576, &bar[WB_W1]);
     }
-    if (warp == 8) tmem_alloc(reinterpret_cast<uint32_t *>(sm + G::TMEMP), 256);     // stage s: Hacc [128 s, +64), S [128 s + 64 + 16 s, +16)
+    if (warp == 0) tmem_alloc(reinterpret_cast<uint32_t *>(sm + G::TMEMP), 256);     // stage g: Hacc [128 g, +64), S [128 g + 64 + 16 g, +16)
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
@@ -578,196 +584,198 @@ wave_score_kernel(const __grid_constant__ CUtensorMap tmap, const WaveParams p, 
     const int ntiles = __ldg(p.tile_count + level);
     const int n_my = ntiles > (int)blockIdx.x ? (ntiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
 
-    if (warp == 8) {
-        // ================= MMA warp =================
-        const bool leader = lane == 0;
-        if (leader) {
-            mbar_expect_tx(&bar[WB_W1], 24576);
-            tma_bulk_g2s(sm + G::BH, p.w1img, 24576, &bar[WB_W1]);
+    const int g = warp >> 2, wq = warp & 3, gtid = tid & 127;             // group = pipeline stage, warp within the group, row of the tile
+    const bool issuer1 = wq == 1 && lane == 0, issuer2 = wq == 2 && lane == 0;    // first / second MMA chain of the group's tiles
+    const uint32_t tmem_lane = (uint32_t)(wq * 32) << 16;
+    const uint32_t td = tmem_base + g * 128, tm = td + tmem_lane;
+    const float scale2 = p.scale * 1.4426950408889634f, inv_T = 1.0f / (float)p.T;
+    // operand descriptors: K-major; X tiles SWIZZLE_128B (SBO 1024, LBO unused), everything else no swizzle (SBO 128)
+    auto nsdesc = [&](uint32_t off, uint32_t lbo) -> uint64_t {
+        return ((uint64_t)(0x4000u | (128u >> 4)) << 32) | (uint64_t)(((sbase + off) >> 4) | ((lbo >> 4) << 16));
+    };
+    auto swdesc = [&](uint32_t off) -> uint64_t {
+        return ((uint64_t)2 << 61) | ((uint64_t)(0x4000u | (1024u >> 4)) << 32) | (uint64_t)(((sbase + off) >> 4) | (1u << 16));
+    };
+    auto group_sync = [&]() {
+        if (g == 0) asm volatile("bar.sync 1, 128;" ::: "memory");
+        else asm volatile("bar.sync 2, 128;" ::: "memory");
+    };
+    auto tile_of = [&](int t) -> int { return t < n_my ? __ldg(p.tile_list + blockIdx.x + t * gridDim.x) : -1; };
+    auto codes_of = [&](int tile) -> int4 {                      // this lane's 4 candidate codes of the tile (lanes 0..7 of a warp)
+        int4 c = make_int4(0, 0, 0, 0);
+        if (tile >= 0) {
+            const int mine = (tile & 255) + 1 - wq * 32;
+            if (4 * lane < mine) c = __ldg(reinterpret_cast<const int4 *>(p.code[slot] + (size_t)(tile >> 10) * p.cap + ((tile >> 8) & 3) * 128 + wq * 32) + lane);
         }
-        // operand descriptors: K-major; X tiles SWIZZLE_128B (SBO 1024, LBO unused), everything else no swizzle (SBO 128)
-        auto nsdesc = [&](uint32_t off, uint32_t lbo) -> uint64_t {
-            return ((uint64_t)(0x4000u | (128u >> 4)) << 32) | (uint64_t)(((sbase + off) >> 4) | ((lbo >> 4) << 16));
-        };
-        auto swdesc = [&](uint32_t off) -> uint64_t {
-            return ((uint64_t)2 << 61) | ((uint64_t)(0x4000u | (1024u >> 4)) << 32) | (uint64_t)(((sbase + off) >> 4) | (1u << 16));
-        };
-        const uint64_t dXh = swdesc(G::XH), dXl = swdesc(G::XL), dBh = nsdesc(G::BH, G::B_LBO), dBl = nsdesc(G::BL, G::B_LBO);
-        const uint64_t dPh = nsdesc(G::PH, 2048), dPl = nsdesc(G::PL, 2048), dHh = nsdesc(G::HH, 1024), dHl = nsdesc(G::HL, 1024);
-        if (n_my > 0) mbar_wait(&bar[WB_W1], 0);
-        for (int t = 0; t <= n_my; t++) {
-            const int s = t & 1;
-            if (t < n_my) {                                       // first chain of tile t
-                mbar_wait(&bar[WB_XFULL + s], (t >> 1) & 1);
-                if (t >= 2) mbar_wait(&bar[WB_TFREE + s], ((t - 2) >> 1) & 1);
-                tc_fence_after();
-                if (leader) {
-                    const uint32_t d = tmem_base + s * 128;
+        return c;
+    };
+    // the operands of tile `tile` -> WB_XFULL[g]: this warp's 32 candidate rows (lanes 0..7: one tile::gather4 pair each), a quarter of
+    // the user's K rows (lanes 8..11: 256-byte bulk copies into rows 64 + 16 g .. of the B operand) and (first warp, lane 12) the
+    // softmax mask + flags.  Everything goes through the TMA: no register staging, no proxy fence.
+    auto refill_x = [&](int tile, int4 c, int aslot) {
+        const int u = tile >> 10, nr = (tile & 255) + 1;
+        const int mine = nr - wq * 32 < 32 ? nr - wq * 32 : 32;              // rows of this warp (may be <= 0)
+        const int nl = mine > 0 ? (mine + 3) >> 2 : 0;
+        const unsigned char *uop = p.uop + (size_t)u * G::UOP_BYTES;
+        const uint32_t kbytes = (dbg & 8) ? 0u : (wq == 0 ? 1024u + 80u : 1024u);
+        if (lane == 0) mbar_expect_tx(&bar[WB_XFULL + g], ((dbg & 1) ? 0u : (uint32_t)nl * 1024u) + kbytes);
+        __syncwarp();
+        if (!(dbg & 1) && lane < nl) {
+            const int r = 4 * lane;
+            if (r + 1 >= mine) c.y = c.x;
+            if (r + 2 >= mine) c.z = c.x;
+            if (r + 3 >= mine) c.w = c.x;
+            const uint32_t off = (uint32_t)(g * G::X_STAGE + (wq * 32 + r) * 128);
+            tma_gather4_hilo(sbase + G::XH + off, sbase + G::XL + off, &tmap, smem_u32(&bar[WB_XFULL + g]), c.x, c.y, c.z, c.w);
+        }
+        if (!(dbg & 8)) {
+            if (lane >= 8 && lane < 12) {
+                const int q = wq * 4 + (lane - 8), kc = q & 7;           // piece q: hi (q < 8) / lo, k-chunk kc: 16 rows x 16 B
+                tma_bulk_g2s(sm + (q >> 3 ? G::BL : G::BH) + kc * G::B_LBO + (64 + 16 * g) * 16, uop + q * 256, 256, &bar[WB_XFULL + g]);
+            }
+            if (wq == 0 && lane == 12) tma_bulk_g2s(sm + G::ADDV + aslot * G::ADDV_STAGE, uop + 8192, 80, &bar[WB_XFULL + g]);
+        }
+    };
+    auto refill_h = [&](int tile) {                              // H operand of the tile's user -> WB_HFULL[g]
+        if (wq == 3 && lane == 0) {
+            mbar_expect_tx(&bar[WB_HFULL + g], 4096);
+            tma_bulk_g2s(sm + G::HH + g * G::H_STAGE, p.uop + (size_t)(tile >> 10) * G::UOP_BYTES + 4096, 4096, &bar[WB_HFULL + g]);
+        }
+    };
+    auto issue_m1 = [&](int t) {                                 // first chain of tile t (stage g): called by one lane of the group
+        mbar_wait(&bar[WB_XFULL + g], (t >> 1) & 1);
+        tc_fence_after();
+        const uint64_t dXh = swdesc(G::XH + g * G::X_STAGE), dXl = swdesc(G::XL + g * G::X_STAGE);
+        const uint64_t dBh = nsdesc(G::BH, G::B_LBO), dBl = nsdesc(G::BL, G::B_LBO);
 #pragma unroll
-                    for (int ks = 0; ks < 4; ks++) {
-                        if (dbg & 16) break;
-                        const uint64_t ah = dXh + s * (G::X_STAGE / 16) + ks * 2, al = dXl + s * (G::X_STAGE / 16) + ks * 2;
-                        const uint64_t bh = dBh + ks * (2 * G::B_LBO / 16), bl = dBl + ks * (2 * G::B_LBO / 16);
-                        umma_bf16(d, ah, bh, kIdescBf16M128N96, ks > 0);
-                        umma_bf16(d, ah, bl, kIdescBf16M128N96, 1);
-                        umma_bf16(d, al, bh, kIdescBf16M128N96, 1);
-                    }
-                    umma_commit(&bar[WB_M1 + s]);
-                }
-                __syncwarp();
-            }
-            if (t >= 1) {                                         // second chain of tile t - 1
-                const int q = s ^ 1;
-                mbar_wait(&bar[WB_PFULL + q], ((t - 1) >> 1) & 1);
-                mbar_wait(&bar[WB_HFULL + q], ((t - 1) >> 1) & 1);
-                tc_fence_after();
-                if (leader) {
-                    const uint32_t d = tmem_base + q * 128;
-                    if (!(dbg & 16)) {
-                        umma_bf16(d, dPh + q * (G::P_STAGE / 16), dHh + q * (G::H_STAGE / 16), kIdescBf16M128N64, 1);
-                        umma_bf16(d, dPh + q * (G::P_STAGE / 16), dHl + q * (G::H_STAGE / 16), kIdescBf16M128N64, 1);
-                        umma_bf16(d, dPl + q * (G::P_STAGE / 16), dHh + q * (G::H_STAGE / 16), kIdescBf16M128N64, 1);
-                    }
-                    umma_commit(&bar[WB_M2 + q]);
-                }
-                __syncwarp();
-            }
+        for (int ks = 0; ks < 4; ks++) {
+            if (dbg & 16) break;
+            const uint64_t ah = dXh + ks * 2, al = dXl + ks * 2;
+            const uint64_t bh = dBh + ks * (2 * G::B_LBO / 16), bl = dBl + ks * (2 * G::B_LBO / 16);
+            umma_bf16(td, ah, bh, kIdescBf16M128N96, ks > 0);
+            umma_bf16(td, ah, bl, kIdescBf16M128N96, 1);
+            umma_bf16(td, al, bh, kIdescBf16M128N96, 1);
         }
-    } else {
-        // ================= consumer warpgroups: operand refill, softmax, epilogue =================
-        const int g = warp >> 2, wq = warp & 3, gtid = tid & 127;         // group = pipeline stage, warp within the group, row of the tile
-        const uint32_t tmem_lane = (uint32_t)(wq * 32) << 16;
-        const uint32_t tm = tmem_base + g * 128 + tmem_lane;
-        const float scale2 = p.scale * 1.4426950408889634f, inv_T = 1.0f / (float)p.T;
-        auto tile_of = [&](int t) -> int { return t < n_my ? __ldg(p.tile_list + blockIdx.x + t * gridDim.x) : -1; };
-        // the operands of tile `tile`: this warp's 32 candidate rows, (first warp of the group) the user's K rows, mask and flags -> WB_XFULL[g]
-        auto refill_x = [&](int tile, int aslot) {
-            const int u = tile >> 10, row0 = ((tile >> 8) & 3) * 128, nr = (tile & 255) + 1;
-            const int32_t *cp = p.code[slot] + (size_t)u * p.cap + row0 + wq * 32;
-            const int mine = nr - wq * 32 < 32 ? nr - wq * 32 : 32;              // rows of this warp (may be <= 0)
-            const int nl = mine > 0 ? (mine + 3) >> 2 : 0;
-            int4 c = make_int4(0, 0, 0, 0);
-            if (lane < nl) c = *reinterpret_cast<const int4 *>(cp + 4 * lane);
-            if (dbg & 1) {
-                if (lane == 0 && wq != 0) mbar_arrive(&bar[WB_XFULL + g]);
+        umma_commit(&bar[WB_M1 + g]);
+    };
+
+#ifdef DMG_WAVE_TIMING
+    long long wacc[12] = {0}, wlast = clock64();
+#endif
+    int cur = tile_of(g), nxt = tile_of(g + 2);
+    if (cur >= 0) {
+        refill_x(cur, codes_of(cur), g);
+        refill_h(cur);
+        if (issuer1) { mbar_wait(&bar[WB_W1], 0); issue_m1(g); }
+        __syncwarp();
+    }
+    for (int t = g; t < n_my; t += 2) {
+        const uint32_t par = (t >> 1) & 1;
+        const int nx2 = tile_of(t + 4);
+        const int4 cn = codes_of(nxt);                           // in flight while this tile's first chain completes
+        const int nr = (cur & 255) + 1;
+        const bool active = wq * 32 < nr;
+        WTICK(0);
+        mbar_wait(&bar[WB_XFULL + g], par);                      // acquire the first warp's mask / flags of this tile
+        WTICK(1);
+        mbar_wait(&bar[WB_M1 + g], par);
+        tc_fence_after();
+        WTICK(2);
+        if (nxt >= 0) refill_x(nxt, cn, (t + 2) & 3);            // X[g] and K slot g are free: the first chain of tile t has completed
+        WTICK(3);
+        if (active) {
+            float sc[16];
+            tmem_ld16(tm + 64 + 16 * g, sc);
+            const float *sAddv = reinterpret_cast<const float *>(sm + G::ADDV + (t & 3) * G::ADDV_STAGE);
+            if (dbg & 2) {
+            } else if (reinterpret_cast<const int *>(sAddv)[16] & WU_ALLMASK) {
+#pragma unroll
+                for (int j = 0; j < 16; j++) sc[j] = j < p.T ? inv_T : 0.0f;
             } else {
-                if (lane == 0 && wq != 0) mbar_expect_tx(&bar[WB_XFULL + g], (uint32_t)nl * 1024u);
-                if (lane < nl) {
-                    const int r = 4 * lane;
-                    if (r + 1 >= mine) c.y = c.x;
-                    if (r + 2 >= mine) c.z = c.x;
-                    if (r + 3 >= mine) c.w = c.x;
-                    const uint32_t off = (uint32_t)(g * G::X_STAGE + (wq * 32 + r) * 128);
-                    // the group's first warp arms the barrier only after its K copy below: its gathers may complete first (the
-                    // transaction count of an mbarrier may run negative while an arrival is still pending)
-                    tma_gather4_hilo(sbase + G::XH + off, sbase + G::XL + off, &tmap, smem_u32(&bar[WB_XFULL + g]), c.x, c.y, c.z, c.w);
-                }
-            }
-            if (wq == 0) {                                      // K rows -> rows 64 + 16 g .. of the B operand, mask + flags (generic proxy + fence)
-                if (!(dbg & 8)) {
-                    const uint4 *src = reinterpret_cast<const uint4 *>(p.uop + (size_t)u * G::UOP_BYTES);
-                    uint4 v[8];
+                float mx = -3.4028234663852886e+38f;
 #pragma unroll
-                    for (int i = 0; i < 8; i++) v[i] = __ldg(src + i * 32 + lane);
-                    uint4 av = make_uint4(0, 0, 0, 0);
-                    if (lane < 5) av = __ldg(src + 512 + lane);         // addv [16] + flags [4] behind the 8 KB of operands
+                for (int j = 0; j < 16; j++) { sc[j] = fmaf(sc[j], scale2, sAddv[j]); mx = fmaxf(mx, sc[j]); }
+                float sum = 0.0f;
 #pragma unroll
-                    for (int i = 0; i < 8; i++) {
-                        const int idx = i * 32 + lane, j = idx & 15, kc = (idx >> 4) & 7;
-                        *reinterpret_cast<uint4 *>(sm + (idx >> 7 ? G::BL : G::BH) + kc * G::B_LBO + (64 + 16 * g + j) * 16) = v[i];
-                    }
-                    if (lane < 5) *reinterpret_cast<uint4 *>(sm + G::ADDV + aslot * G::ADDV_STAGE + lane * 16) = av;
-                }
-                fence_proxy_async();
-                __syncwarp();
-                if (lane == 0) {
-                    if (dbg & 1) mbar_arrive(&bar[WB_XFULL + g]);
-                    else mbar_expect_tx(&bar[WB_XFULL + g], (uint32_t)nl * 1024u);
-                }
+                for (int j = 0; j < 16; j++) { sc[j] = ex2_approx(sc[j] - mx); sum += sc[j]; }
+                const float inv = 1.0f / sum;
+#pragma unroll
+                for (int j = 0; j < 16; j++) sc[j] *= inv;
             }
-        };
-        auto refill_h = [&](int tile) {                          // H operand of the tile's user -> WB_HFULL[g]
-            if (wq == 1 && lane == 0) {
-                mbar_expect_tx(&bar[WB_HFULL + g], 4096);
-                tma_bulk_g2s(sm + G::HH + g * G::H_STAGE, p.uop + (size_t)(tile >> 10) * G::UOP_BYTES + 4096, 4096, &bar[WB_HFULL + g]);
-            }
-        };
-        int cur = tile_of(g);
-        if (cur >= 0) { refill_x(cur, g); refill_h(cur); }
-        for (int t = g; t < n_my; t += 2) {
-            const uint32_t par = (t >> 1) & 1;
-            const int nxt = tile_of(t + 2);
-            const int nr = (cur & 255) + 1;
-            const bool active = wq * 32 < nr;
-            mbar_wait(&bar[WB_XFULL + g], par);                  // acquire the first warp's mask / flags of this tile
-            mbar_wait(&bar[WB_M1 + g], par);
+            sc[15] = 1.0f;
+            unsigned char *ph = sm + G::PH + g * G::P_STAGE + gtid * 16, *pl = sm + G::PL + g * G::P_STAGE + gtid * 16;
+            uint4 hi, lo;
+            split8(*reinterpret_cast<float(*)[8]>(&sc[0]), hi, lo);
+            *reinterpret_cast<uint4 *>(ph) = hi;
+            *reinterpret_cast<uint4 *>(pl) = lo;
+            split8(*reinterpret_cast<float(*)[8]>(&sc[8]), hi, lo);
+            *reinterpret_cast<uint4 *>(ph + 2048) = hi;
+            *reinterpret_cast<uint4 *>(pl + 2048) = lo;
+            fence_proxy_async();
+        }
+        WTICK(4);
+        tc_fence_before();
+        group_sync();                                            // the group's P rows are complete
+        WTICK(5);
+        if (issuer2) {                                           // second chain of tile t
+            mbar_wait(&bar[WB_HFULL + g], par);
             tc_fence_after();
-            if (nxt >= 0) refill_x(nxt, (t + 2) & 3);            // X[g] and K slot g are free: the first chain of tile t has completed
-            if (active) {
-                float sc[16];
-                tmem_ld16(tm + 64 + 16 * g, sc);
-                const float *sAddv = reinterpret_cast<const float *>(sm + G::ADDV + (t & 3) * G::ADDV_STAGE);
-                if (dbg & 2) {
-                } else if (reinterpret_cast<const int *>(sAddv)[16] & WU_ALLMASK) {
-#pragma unroll
-                    for (int j = 0; j < 16; j++) sc[j] = j < p.T ? inv_T : 0.0f;
-                } else {
-                    float mx = -3.4028234663852886e+38f;
-#pragma unroll
-                    for (int j = 0; j < 16; j++) { sc[j] = fmaf(sc[j], scale2, sAddv[j]); mx = fmaxf(mx, sc[j]); }
-                    float sum = 0.0f;
-#pragma unroll
-                    for (int j = 0; j < 16; j++) { sc[j] = ex2_approx(sc[j] - mx); sum += sc[j]; }
-                    const float inv = 1.0f / sum;
-#pragma unroll
-                    for (int j = 0; j < 16; j++) sc[j] *= inv;
-                }
-                sc[15] = 1.0f;
-                unsigned char *ph = sm + G::PH + g * G::P_STAGE + gtid * 16, *pl = sm + G::PL + g * G::P_STAGE + gtid * 16;
-                uint4 hi, lo;
-                split8(*reinterpret_cast<float(*)[8]>(&sc[0]), hi, lo);
-                *reinterpret_cast<uint4 *>(ph) = hi;
-                *reinterpret_cast<uint4 *>(pl) = lo;
-                split8(*reinterpret_cast<float(*)[8]>(&sc[8]), hi, lo);
-                *reinterpret_cast<uint4 *>(ph + 2048) = hi;
-                *reinterpret_cast<uint4 *>(pl + 2048) = lo;
-                fence_proxy_async();
+            if (!(dbg & 16)) {
+                const uint64_t dPh = nsdesc(G::PH + g * G::P_STAGE, 2048), dPl = nsdesc(G::PL + g * G::P_STAGE, 2048);
+                const uint64_t dHh = nsdesc(G::HH + g * G::H_STAGE, 1024), dHl = nsdesc(G::HL + g * G::H_STAGE, 1024);
+                umma_bf16(td, dPh, dHh, kIdescBf16M128N64, 1);
+                umma_bf16(td, dPh, dHl, kIdescBf16M128N64, 1);
+                umma_bf16(td, dPl, dHh, kIdescBf16M128N64, 1);
             }
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&bar[WB_PFULL + g]);
-            mbar_wait(&bar[WB_M2 + g], par);
-            tc_fence_after();
-            if (nxt >= 0) refill_h(nxt);                         // H[g] is free: the second chain of tile t has completed
-            // epilogue in two halves of 32 accumulator columns; four interleaved chains: term o sees 18 - o/4 roundings, inside the
-            // (64 - o) + 2 the bound allows the fast path
+            umma_commit(&bar[WB_M2 + g]);
+        }
+        __syncwarp();
+        WTICK(6);
+        mbar_wait(&bar[WB_M2 + g], par);
+        tc_fence_after();
+        WTICK(7);
+        if (nxt >= 0) refill_h(nxt);                             // H[g] is free: the second chain of tile t has completed
+        float h0[32], h1[32];
+        if (active) {
+            tmem_ld32(tm, h0);
+            tmem_ld32(tm + 32, h1);
+        }
+        WTICK(8);
+        tc_fence_before();
+        group_sync();                                            // the group has drained its accumulators
+        WTICK(9);
+        if (issuer1 && nxt >= 0) issue_m1(t + 2);                // the next tile's first chain runs under the epilogue below
+        __syncwarp();
+        WTICK(10);
+        if (active && !(dbg & 4)) {
+            // four interleaved chains: term o sees 18 - o/4 roundings, inside the (64 - o) + 2 the bound allows the fast path
             float l0 = 0.0f, l1 = 0.0f, l2 = 0.0f, l3 = 0.0f;
 #pragma unroll
-            for (int hf = 0; hf < 2; hf++) {
-                float hv[32];
-                if (active) tmem_ld32(tm + hf * 32, hv);
-                if (hf == 1) {
-                    tc_fence_before();
-                    __syncwarp();
-                    if (lane == 0) mbar_arrive(&bar[WB_TFREE + g]);
-                }
-                if (active && !(dbg & 4)) {
-#pragma unroll
-                    for (int c = 0; c < 32; c += 4) {
-                        l0 = fmaf(fmaxf(hv[c], 0.0f), w.w2[hf * 32 + c], l0);
-                        l1 = fmaf(fmaxf(hv[c + 1], 0.0f), w.w2[hf * 32 + c + 1], l1);
-                        l2 = fmaf(fmaxf(hv[c + 2], 0.0f), w.w2[hf * 32 + c + 2], l2);
-                        l3 = fmaf(fmaxf(hv[c + 3], 0.0f), w.w2[hf * 32 + c + 3], l3);
-                    }
-                }
+            for (int c = 0; c < 32; c += 4) {
+                l0 = fmaf(fmaxf(h0[c], 0.0f), w.w2[c], l0);
+                l1 = fmaf(fmaxf(h0[c + 1], 0.0f), w.w2[c + 1], l1);
+                l2 = fmaf(fmaxf(h0[c + 2], 0.0f), w.w2[c + 2], l2);
+                l3 = fmaf(fmaxf(h0[c + 3], 0.0f), w.w2[c + 3], l3);
             }
-            if (active && !(dbg & 4) && gtid < nr) p.score[(size_t)(cur >> 10) * p.cap + ((cur >> 8) & 3) * 128 + gtid] = ((l0 + l1) + (l2 + l3)) + w.b2;
-            cur = nxt;
+#pragma unroll
+            for (int c = 0; c < 32; c += 4) {
+                l0 = fmaf(fmaxf(h1[c], 0.0f), w.w2[32 + c], l0);
+                l1 = fmaf(fmaxf(h1[c + 1], 0.0f), w.w2[33 + c], l1);
+                l2 = fmaf(fmaxf(h1[c + 2], 0.0f), w.w2[34 + c], l2);
+                l3 = fmaf(fmaxf(h1[c + 3], 0.0f), w.w2[35 + c], l3);
+            }
+            if (gtid < nr) p.score[(size_t)(cur >> 10) * p.cap + ((cur >> 8) & 3) * 128 + gtid] = ((l0 + l1) + (l2 + l3)) + w.b2;
         }
+        cur = nxt; nxt = nx2;
+        WTICK(11);
     }
+#ifdef DMG_WAVE_TIMING
+    if (p.stats && gtid == 0 && g == 0)
+        for (int i = 0; i < 12; i++) atomicAdd(&p.stats[32 + i], (unsigned long long)wacc[i]);
+#endif
     tc_fence_before();
     __syncthreads();
-    if (warp == 8) tmem_dealloc(tmem_base, 256);
+    if (warp == 0) tmem_dealloc(tmem_base, 256);
 }
 
 // ---- K3: strict verification of the deferred cuts + topk, one CTA per user ---------------------------------------------

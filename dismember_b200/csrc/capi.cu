@@ -717,8 +717,8 @@ static int32_t tdm_enqueue(dmg_handle_t h, int32_t B, const int32_t *d_seq, int3
     p.capp = pow2_ge(p.cap);
     if (use_fast) {
         if (!h->d_fast_stats) {
-            DMG_CUDA(h, cudaMalloc(&h->d_fast_stats, 32 * sizeof(unsigned long long)));
-            DMG_CUDA(h, cudaMemsetAsync(h->d_fast_stats, 0, 32 * sizeof(unsigned long long), h->stream));
+            DMG_CUDA(h, cudaMalloc(&h->d_fast_stats, 64 * sizeof(unsigned long long)));
+            DMG_CUDA(h, cudaMemsetAsync(h->d_fast_stats, 0, 64 * sizeof(unsigned long long), h->stream));
         }
         FastParams fx;
         memcpy(fx.b1, h->fast_host.data(), 64 * sizeof(float));
@@ -815,7 +815,17 @@ DMG_API int32_t dmg_fast_stats(dmg_handle_t h, uint64_t *out6)
         for (int i = 0; i < TK_N; i++) fprintf(stderr, "[fast timing] %-9s %6.2f %%  %.3e cyc\n", names[i], 100.0 * t[i] / (tot > 0 ? tot : 1), (double)t[i]);
     }
 #endif
-    DMG_CUDA(h, cudaMemset(h->d_fast_stats, 0, 32 * sizeof(uint64_t)));
+#ifdef DMG_WAVE_TIMING
+    {
+        uint64_t t[12];
+        DMG_CUDA(h, cudaMemcpy(t, h->d_fast_stats + 32, sizeof(t), cudaMemcpyDeviceToHost));
+        static const char *names[] = {"loop top", "wait XFULL", "wait M1", "refill_x", "softmax", "group sync 1", "issue M2", "wait M2", "read Hacc", "group sync 2", "issue M1", "epilogue"};
+        double tot = 0;
+        for (int i = 0; i < 12; i++) tot += (double)t[i];
+        for (int i = 0; i < 12; i++) fprintf(stderr, "[wave timing] %-13s %6.2f %%  %.3e cyc\n", names[i], 100.0 * t[i] / (tot > 0 ? tot : 1), (double)t[i]);
+    }
+#endif
+    DMG_CUDA(h, cudaMemset(h->d_fast_stats, 0, 64 * sizeof(uint64_t)));
     return DMG_OK;
 }
 
