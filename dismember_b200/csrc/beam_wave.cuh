@@ -217,7 +217,8 @@ static __global__ void __launch_bounds__(256) wave_prologue_kernel(const WavePar
 // ---- K1 (cut + expand): one warp per user ---------------------------------------------------------------------------
 // Lane l owns the candidates i = 32 j + l, j < 16 (cap <= 512).  `level` is the tree level of the current candidates;
 // the children written to code[(slot ^ 1)] sit on level + 1.
-__device__ __forceinline__ void warp_select(const uint32_t (&k)[16], int kk, uint32_t lo, uint32_t hi, int clo,
+template <int NJ>
+__device__ __forceinline__ void warp_select(const uint32_t (&k)[NJ], int kk, uint32_t lo, uint32_t hi, int clo,
                                             uint32_t &kdn, uint32_t &kup, int &iters)
 {
     int chi = 0, it = 0;
@@ -233,7 +234,7 @@ __device__ __forceinline__ void warp_select(const uint32_t (&k)[16], int kk, uin
         mid = min(max(mid, lo + 1u), hi);
         int c = 0;
 #pragma unroll
-        for (int j = 0; j < 16; j++) c += k[j] >= mid ? 1 : 0;
+        for (int j = 0; j < NJ; j++) c += k[j] >= mid ? 1 : 0;
         c = __reduce_add_sync(0xffffffffu, c);
         it++;
         if (c >= kk) { lo = mid; clo = c; } else { hi = mid - 1u; chi = c; }
@@ -242,7 +243,7 @@ __device__ __forceinline__ void warp_select(const uint32_t (&k)[16], int kk, uin
     if (clo == kk) {
         uint32_t a = 0xffffffffu, b = 0u;
 #pragma unroll
-        for (int j = 0; j < 16; j++) { a = min(a, k[j] >= lo ? k[j] : 0xffffffffu); b = max(b, k[j] < lo ? k[j] : 0u); }
+        for (int j = 0; j < NJ; j++) { a = min(a, k[j] >= lo ? k[j] : 0xffffffffu); b = max(b, k[j] < lo ? k[j] : 0u); }
         kdn = __reduce_min_sync(0xffffffffu, a);
         kup = __reduce_max_sync(0xffffffffu, b);
         if (kup == 0u) kup = kdn;
@@ -252,7 +253,8 @@ __device__ __forceinline__ void warp_select(const uint32_t (&k)[16], int kk, uin
 }
 
 // children of the surviving candidates in candidate order, the tiles and the bound of the scores about to be computed
-__device__ __forceinline__ void wave_expand_finish(const WaveParams &p, WaveUser *st, int user, int level, int lane, const int32_t (&code)[16],
+template <int NJ>
+__device__ __forceinline__ void wave_expand_finish(const WaveParams &p, WaveUser *st, int user, int level, int lane, const int32_t (&code)[NJ],
                                                    const uint32_t *sKeepW, int count, int32_t *__restrict__ nxt, int flags,
                                                    unsigned long long st_cut, unsigned long long st_recut, unsigned long long st_iters)
 {
@@ -261,7 +263,7 @@ __device__ __forceinline__ void wave_expand_finish(const WaveParams &p, WaveUser
     const uint32_t *bm = (level + 1 >= p.sparse_from) ? p.exists : nullptr;
     const int nj = (count + 31) >> 5;
 #pragma unroll
-    for (int j = 0; j < 16; j++) {
+    for (int j = 0; j < NJ; j++) {
         if (j < nj) {
             const bool kp = sKeepW[j] >> lane & 1u;
             const int64_t c = code[j];
@@ -304,12 +306,13 @@ __device__ __forceinline__ void wave_expand_finish(const WaveParams &p, WaveUser
 struct WaveStrictW { const float *wattT, *w1T, *b1, *w2; float b2; };
 
 // 4 users per CTA.  Phase 1: every warp cuts its user; a cut whose band cannot be deferred (fast-score gap at the cut below
-// eps / 32) is parked.  Phase 2: the whole CTA scores the band rows of its parked users strictly (sequential-k fma chains,
+// eps / 128) is parked.  Phase 2: the whole CTA scores the band rows of its parked users strictly (sequential-k fma chains,
 // the oracle's bits).  Phase 3: the parked warps finish their cuts with the strict order.
 // Per-lane state is the 16 candidate codes / scores; the surviving set is a 16-word bitmap in shared memory (word j, bit
 // lane = candidate 32 j + lane) and the band rows are compacted into shared-memory lists that the lanes then walk in
 // parallel -- rolled loops, so that the kernel stays a few thousand instructions (it runs at low occupancy: instruction
 // fetch is what bounds a long unrolled body).
+template <int NJ>
 static __global__ void __launch_bounds__(128) wave_select_kernel(const WaveParams p, const WaveStrictW sw, int level, int slot)
 {
     constexpr int MU = WaveGeo::MAX_UNC;
@@ -319,7 +322,7 @@ static __global__ void __launch_bounds__(128) wave_select_kernel(const WaveParam
     __shared__ int32_t sLCode[4][MU];                             //   code,
     __shared__ float sLStr[4][MU];                                //   fast score, then (parked cuts) the strict score
     __shared__ int sFr[4][MU];                                    //   rank by fast score
-    __shared__ uint32_t sKeepW[4][16];
+    __shared__ uint32_t sKeepW[4][NJ];
     __shared__ int sGap[4][2];
     __shared__ int sPark[4][2];                                   // n_unc (0 = not parked), need
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -340,7 +343,7 @@ static __global__ void __launch_bounds__(128) wave_select_kernel(const WaveParam
     }
     const int32_t *cur = p.code[slot] + (size_t)(live ? user : 0) * p.cap;
     int32_t *nxt = p.code[slot ^ 1] + (size_t)(live ? user : 0) * p.cap;
-    int32_t code[16];
+    int32_t code[NJ];
     int count = 0;
     unsigned long long st_cut = 0, st_recut = 0, st_iters = 0;
     bool parked = false;
@@ -349,7 +352,7 @@ static __global__ void __launch_bounds__(128) wave_select_kernel(const WaveParam
             const int64_t start = ((int64_t)1 << s_level) - 1;
             count = 1 << s_level;
 #pragma unroll
-            for (int j = 0; j < 16; j++) {
+            for (int j = 0; j < NJ; j++) {
                 const int i = 32 * j + lane;
                 code[j] = (int32_t)(start + i);
                 const uint32_t m = __ballot_sync(0xffffffffu, i < count && code_exists(p.exists, start + i));
@@ -357,26 +360,26 @@ static __global__ void __launch_bounds__(128) wave_select_kernel(const WaveParam
             }
         } else {
             count = p.count[user];
-            float f[16];
+            float f[NJ];
             const float *sc = p.score + (size_t)user * p.cap;
 #pragma unroll
-            for (int j = 0; j < 16; j++) {
+            for (int j = 0; j < NJ; j++) {
                 const int i = 32 * j + lane;
                 code[j] = i < count ? cur[i] : 0;
                 f[j] = i < count ? sc[i] : 0.0f;
             }
             if (count <= beam) {
 #pragma unroll
-                for (int j = 0; j < 16; j++) {
+                for (int j = 0; j < NJ; j++) {
                     const uint32_t m = __ballot_sync(0xffffffffu, 32 * j + lane < count);
                     if (lane == 0) sKeepW[warp][j] = m;
                 }
             } else {
                 st_cut = 1;
-                uint32_t key[16];
+                uint32_t key[NJ];
                 uint32_t mn = 0xffffffffu, mx = 0u;
 #pragma unroll
-                for (int j = 0; j < 16; j++) {
+                for (int j = 0; j < NJ; j++) {
                     key[j] = 32 * j + lane < count ? order_key(f[j]) : 0u;
                     mn = min(mn, key[j] ? key[j] : 0xffffffffu); mx = max(mx, key[j]);
                 }
@@ -391,7 +394,7 @@ static __global__ void __launch_bounds__(128) wave_select_kernel(const WaveParam
                 const float up = key_to_float(kup) + band, dn = key_to_float(kdn) - band;
                 int n_keep = 0, n_unc = 0;
 #pragma unroll
-                for (int j = 0; j < 16; j++) {
+                for (int j = 0; j < NJ; j++) {
                     const bool valid = 32 * j + lane < count;
                     const bool isunc = valid && !(f[j] > up) && !(f[j] < dn);
                     const uint32_t mk = __ballot_sync(0xffffffffu, valid && !(f[j] < dn)), mu = __ballot_sync(0xffffffffu, isunc);
@@ -427,9 +430,9 @@ static __global__ void __launch_bounds__(128) wave_select_kernel(const WaveParam
                         __syncwarp();
                         const float gap = __int_as_float(sGap[warp][0]) - __int_as_float(sGap[warp][1]);
                         const int vcount = st->vcount, nseg = st->nseg;
-                        // Observed |fast - strict| stays below 1 % of eps: with a gap of eps/32 or more the fast order is taken
+                        // Observed |fast - strict| stays below 1 % of eps: with a gap of eps/128 or more the fast order is taken
                         // now and PROVEN by wave_final_kernel; a narrower gap is settled strictly right here.
-                        const bool defer = gap >= 0.03125f * eps_level && vcount + n_unc <= WaveGeo::VCAP && nseg < 32 && eps_level < 1e30f;
+                        const bool defer = gap >= 0.0078125f * eps_level && vcount + n_unc <= WaveGeo::VCAP && nseg < 32 && eps_level < 1e30f;
                         if (defer) {
 #pragma unroll 1
                             for (int e = lane; e < n_unc; e += 32) {
@@ -521,6 +524,32 @@ static __global__ void __launch_bounds__(128) wave_select_kernel(const WaveParam
 __device__ __forceinline__ void mbar_arrive(uint64_t *bar)
 {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+// two 32-column accumulator loads, one wait
+__device__ __forceinline__ void tmem_ld32x2(uint32_t taddr, float (&a)[32], float (&b)[32])
+{
+    uint32_t r[32], q[32];
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+          "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+          "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr) : "memory");
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(q[0]), "=r"(q[1]), "=r"(q[2]), "=r"(q[3]), "=r"(q[4]), "=r"(q[5]), "=r"(q[6]), "=r"(q[7]), "=r"(q[8]),
+          "=r"(q[9]), "=r"(q[10]), "=r"(q[11]), "=r"(q[12]), "=r"(q[13]), "=r"(q[14]), "=r"(q[15]), "=r"(q[16]),
+          "=r"(q[17]), "=r"(q[18]), "=r"(q[19]), "=r"(q[20]), "=r"(q[21]), "=r"(q[22]), "=r"(q[23]), "=r"(q[24]),
+          "=r"(q[25]), "=r"(q[26]), "=r"(q[27]), "=r"(q[28]), "=r"(q[29]), "=r"(q[30]), "=r"(q[31])
+        : "r"(taddr + 32) : "memory");
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+    for (int i = 0; i < 32; i++) { a[i] = __uint_as_float(r[i]); b[i] = __uint_as_float(q[i]); }
 }
 // rows c0..c3 of the bf16 hi|lo table -> 4 rows of the hi tile and 4 rows of the lo tile (row 2c = hi(c), 2c + 1 = lo(c))
 __device__ __forceinline__ void tma_gather4_hilo(uint32_t dst_hi, uint32_t dst_lo, const void *tmap, uint32_t bar, int c0, int c1, int c2, int c3)
@@ -736,10 +765,7 @@ wave_score_kernel(const __grid_constant__ CUtensorMap tmap, const WaveParams p, 
         WTICK(7);
         if (nxt >= 0) refill_h(nxt);                             // H[g] is free: the second chain of tile t has completed
         float h0[32], h1[32];
-        if (active) {
-            tmem_ld32(tm, h0);
-            tmem_ld32(tm + 32, h1);
-        }
+        if (active) tmem_ld32x2(tm, h0, h1);
         WTICK(8);
         tc_fence_before();
         group_sync();                                            // the group has drained its accumulators

@@ -595,6 +595,7 @@ static int32_t wave_enqueue(dmg_handle_t h, const BeamParams<float> &p, const Fa
     sw.wattT = p.wattT; sw.w1T = p.w1T; sw.b1 = p.b1; sw.w2 = p.w2; sw.b2 = fx.b2;
     const CUtensorMap &tmap = *reinterpret_cast<const CUtensorMap *>(h->wave_tmap);
     auto score_kernel = wave_score_kernel<0>;
+    auto select_kernel = cap <= 256 ? wave_select_kernel<8> : (cap <= 416 ? wave_select_kernel<13> : wave_select_kernel<16>);
     DMG_CUDA(h, cudaFuncSetAttribute(score_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, WG::SMEM));
     DMG_CUDA(h, cudaFuncSetAttribute(score_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
     const size_t fin_smem = (size_t)FastGeo::STRICT_SCR + (size_t)cap * 12 + FastGeo::MAX_FINAL * 4 + (size_t)(FastGeo::VCAP + FastGeo::MAX_FINAL) * 8 + 256 * 4 + 32 * 4;
@@ -614,7 +615,7 @@ static int32_t wave_enqueue(dmg_handle_t h, const BeamParams<float> &p, const Fa
     (void)max_beam;
     const int last_level = stop_level >= 0 ? std::min(stop_level, p.leaf_level) : p.leaf_level;
     for (int level = s_min; level < last_level; level++) {
-        wave_select_kernel<<<(B + 3) / 4, 128, 0, h->stream>>>(wp, sw, level, slot);
+        select_kernel<<<(B + 3) / 4, 128, 0, h->stream>>>(wp, sw, level, slot);
         score_kernel<<<grid, WG::THREADS, WG::SMEM, h->stream>>>(tmap, wp, w2, slot ^ 1, level + 1);
         if (getenv("DMG_WAVE_ABLATE") && level == atoi(getenv("DMG_WAVE_ABLATE"))) {
             // profiling aid: replay this level's scorer with parts switched off (scores go to a scratch buffer)
@@ -641,6 +642,8 @@ static int32_t wave_enqueue(dmg_handle_t h, const BeamParams<float> &p, const Fa
                         case 8: kq = wave_score_kernel<8>; break;   case 16: kq = wave_score_kernel<16>; break;
                         case 3: kq = wave_score_kernel<3>; break;   case 6: kq = wave_score_kernel<6>; break;
                         case 7: kq = wave_score_kernel<7>; break;   case 15: kq = wave_score_kernel<15>; break;
+                        case 30: kq = wave_score_kernel<30>; break;   case 14: kq = wave_score_kernel<14>; break;
+                        case 22: kq = wave_score_kernel<22>; break;
                         default: kq = wave_score_kernel<31>; break;
                     }
                     cudaFuncSetAttribute(kq, cudaFuncAttributeMaxDynamicSharedMemorySize, WG::SMEM);
