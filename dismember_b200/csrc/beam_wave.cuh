@@ -804,149 +804,214 @@ wave_score_kernel(const __grid_constant__ CUtensorMap tmap, const WaveParams p, 
     if (warp == 0) tmem_dealloc(tmem_base, 256);
 }
 
-// ---- K3: strict verification of the deferred cuts + topk, one CTA per user ---------------------------------------------
-static __global__ void __launch_bounds__(FastGeo::THREADS, 2) wave_final_kernel(const WaveParams p, const BeamParams<float> bp, int slot)
+// ---- K3: strict verification of the deferred cuts + topk, three throughput kernels ---------------------------------------
+//   wave_final_prep_kernel    one warp per user: consumed / empty-slot filter, the band of the topk-th fast score, the list of rows
+//                             that need strict scores (band rows deferred at the cuts, then the topk candidates) in 16-row chunks
+//   wave_strict_rows_kernel   one CTA per chunk: the strict scorer (sequential-k fma chains: the oracle's bits) on <= 16 rows
+//   wave_final_verify_kernel  one warp per user: proofs of the deferred cuts, topk by the reference's (score desc, position asc)
+//                             order (Recommender.scala:37, TDM.scala:21), outputs, users for the strict kernel
+struct WaveFinal {
+    int32_t *row_code; float *row_strict;       // [B][RCAP]: deferred band rows first, then the topk candidates
+    int32_t *fin_pos;                           // [B][MAX_FINAL] candidate positions of the topk candidates
+    int32_t *meta;                              // [B][4]: rows, topk candidates, kk, redo reason + 1 (0 = none)
+    int32_t *chunk_list, *chunk_count;          // user << 5 | chunk
+    static constexpr int RCAP = FastGeo::VCAP + FastGeo::MAX_FINAL;
+};
+
+template <int NJ>
+static __global__ void __launch_bounds__(128) wave_final_prep_kernel(const WaveParams p, const BeamParams<float> bp, const WaveFinal wf, int slot)
 {
-    using G = FastGeo;
-    constexpr int E = 64;
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    float *sScr = reinterpret_cast<float *>(smem_raw);                                  // strict scratch; [0, 16 * KLD) = history
-    unsigned char *sp = smem_raw + G::STRICT_SCR;
-    float *sScore = reinterpret_cast<float *>(sp); sp += (size_t)p.cap * 4;
-    int32_t *sCode = reinterpret_cast<int32_t *>(sp); sp += (size_t)p.cap * 4;
-    uint32_t *sKeyU = reinterpret_cast<uint32_t *>(sp); sp += (size_t)p.cap * 4;
-    int *sUPos = reinterpret_cast<int *>(sp); sp += G::MAX_FINAL * 4;
-    int32_t *sLCode = reinterpret_cast<int32_t *>(sp); sp += (G::VCAP + G::MAX_FINAL) * 4;
-    float *sLStr = reinterpret_cast<float *>(sp); sp += (G::VCAP + G::MAX_FINAL) * 4;
-    int *sRed = reinterpret_cast<int *>(sp); sp += 256 * 4;
-    int *sMisc = reinterpret_cast<int *>(sp); sp += 32 * 4;
-    const int tid = threadIdx.x, lane = tid & 31, user = blockIdx.x, T = p.T;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int user = blockIdx.x * 4 + warp;
+    if (user >= p.B) return;
+    const uint32_t lt = (1u << lane) - 1u;
     const WaveUser st = p.user[user];
-    bool redo = (st.flags & WU_REDO) != 0;
-    int redo_why = st.redo_why;
-    float st_ratio = 0.0f;
-    unsigned long long st_rerows = 0;
-    auto track_ratio = [&](float strict, float fast, float eps_now) {
-        if (eps_now > 0.0f && eps_now < 1e30f) {
-            const float ratio = fabsf(strict - fast) / eps_now;
-            if (ratio > st_ratio) st_ratio = ratio;
-        }
-    };
-    if (!redo) {
-        const int beam = p.beam_user ? p.beam_user[user] : p.beam;
-        const int s_level = 31 - __clz(beam);
+    int32_t *meta = wf.meta + (size_t)user * 4;
+    int why = (st.flags & WU_REDO) ? st.redo_why + 1 : 0;
+    const int beam = p.beam_user ? __ldg(p.beam_user + user) : p.beam;
+    const int s_level = 31 - __clz(beam);
+    if (!why && s_level == p.leaf_level) why = 3;                  // nothing is scored (beam >= 2^leaf_level): every score ties -> strict kernel
+    int n_rows = 0, na = 0, kk = 0;
+    if (!why) {
         const int count = (s_level < p.leaf_level) ? p.count[user] : 0;
-        if (s_level == p.leaf_level) { redo = true; redo_why = 2; }   // nothing is scored (beam >= 2^leaf_level): every score ties -> strict kernel
-        const bool scored = (st.flags & WU_SCORED) != 0;
-        const float eps_level = st.eps;
-        const int vcount = st.vcount;
-        for (int i = tid; i < count; i += G::THREADS) {
-            sScore[i] = p.score[(size_t)user * p.cap + i];
-            sCode[i] = p.code[slot][(size_t)user * p.cap + i];
-        }
-        for (int i = tid; i < kMaxT * E; i += G::THREADS) {      // history rows (fp32) for the strict scorer
-            const int j = i >> 6, k = i & 63;
-            const int c = j < T ? p.hist[(size_t)user * T + j] : -1;
-            sScr[j * G::KLD + k] = c >= 0 ? __ldg(p.emb + (size_t)c * E + k) : 0.0f;
-        }
-        if (tid == 0) sMisc[0] = 0;
-        __syncthreads();
+        const int32_t *cur = p.code[slot] + (size_t)user * p.cap;
+        const float *sc = p.score + (size_t)user * p.cap;
         const int64_t leaf_start = ((int64_t)1 << p.leaf_level) - 1;
         const int64_t c0 = bp.cons_off ? bp.cons_off[user] : 0, c1 = bp.cons_off ? bp.cons_off[user + 1] : 0;
+        float f[NJ];
+        uint32_t key[NJ];
+        int32_t code[NJ];
         int valid = 0;
-        for (int base = 0; base < count; base += G::THREADS) {
-            const int i = base + tid;
+        uint32_t mn = 0xffffffffu, mx = 0u;
+#pragma unroll
+        for (int j = 0; j < NJ; j++) {
+            const int i = 32 * j + lane;
             bool keep = false;
+            code[j] = 0; f[j] = 0.0f;
             if (i < count) {
-                const int64_t sl = (int64_t)sCode[i] - leaf_start;
+                code[j] = cur[i]; f[j] = sc[i];
+                const int64_t sl = (int64_t)code[j] - leaf_start;
                 const int32_t item = (sl >= 0 && sl < ((int64_t)1 << p.leaf_level)) ? __ldg(bp.leaf_item + sl) : -1;
                 keep = item >= 0;
                 for (int64_t q = c0; q < c1 && keep; q++) keep = (__ldg(bp.cons + q) != item);
             }
-            if (i < count) sKeyU[i] = keep ? order_key(sScore[i]) : 0u;
-            valid += __syncthreads_count(keep);
+            key[j] = keep ? order_key(f[j]) : 0u;
+            valid += __popc(__ballot_sync(0xffffffffu, keep));
+            mn = min(mn, key[j] ? key[j] : 0xffffffffu); mx = max(mx, key[j]);
         }
-        const int kk = valid < bp.topk ? valid : bp.topk;
-        if (kk > 0 && !scored) { redo = true; redo_why = 2; }
-        int na = 0;
-        if (kk > 0 && !redo) {
+        kk = valid < bp.topk ? valid : bp.topk;
+        if (kk > 0 && !(st.flags & WU_SCORED)) why = 3;
+        if (kk > 0 && !why) {
+            mn = __reduce_min_sync(0xffffffffu, mn);
+            mx = __reduce_max_sync(0xffffffffu, mx);
             uint32_t kdn, kup;
-            {
-                const uint32_t key0 = 2 * tid < count ? sKeyU[2 * tid] : 0u, key1 = 2 * tid + 1 < count ? sKeyU[2 * tid + 1] : 0u;
-                uint32_t lo, hi;
-                int nv;
-                block_minmax(key0, key1, sRed, lo, hi, nv);
-                block_select(key0, key1, kk, lo, hi, nv, sRed, kdn, kup, [](int) {});
+            int iters;
+            warp_select<NJ>(key, kk, mn, mx, valid, kdn, kup, iters);
+            const float dn = key_to_float(kdn) - (2.0f * st.eps * 1.0001f + 1e-30f);
+            int32_t *rc = wf.row_code + (size_t)user * WaveFinal::RCAP + st.vcount;
+            int32_t *fp = wf.fin_pos + (size_t)user * FastGeo::MAX_FINAL;
+#pragma unroll
+            for (int j = 0; j < NJ; j++) {
+                const bool c = key[j] != 0u && !(f[j] < dn);
+                const uint32_t m = __ballot_sync(0xffffffffu, c);
+                const int e = na + __popc(m & lt);
+                if (c && e < FastGeo::MAX_FINAL) { rc[e] = code[j]; fp[e] = 32 * j + lane; }
+                na += __popc(m);
             }
-            const float dn = key_to_float(kdn) - (2.0f * eps_level * 1.0001f + 1e-30f);
-            __syncthreads();
-            for (int i = tid; i < count; i += G::THREADS)
-                if (sKeyU[i] != 0u && !(sScore[i] < dn)) {
-                    const int sl = atomicAdd(&sMisc[0], 1);
-                    if (sl < G::MAX_FINAL) sUPos[sl] = i;
-                }
-            __syncthreads();
-            na = sMisc[0];
-            if (na > G::MAX_FINAL) { redo = true; redo_why = 3; }
+            if (na > FastGeo::MAX_FINAL) why = 4;
         }
-        if (!redo && vcount + na > 0) {
-            for (int e = tid; e < vcount; e += G::THREADS) sLCode[e] = p.v_code[(size_t)user * WaveGeo::VCAP + e];
-            for (int q = tid; q < na; q += G::THREADS) sLCode[vcount + q] = sCode[sUPos[q]];
-            st_rerows = vcount + na;
-            __syncthreads();
-            strict_score_batch(p.emb, sLCode, vcount + na, sLStr, sScr, st.maskbits, T, p.scale, bp.wattT, bp.w1T, bp.b1, bp.w2, __ldg(bp.b2));
-            int bad = 0;
-            for (int e = tid; e < vcount; e += G::THREADS) {       // the deferred cuts: strict order must pick the same rows
-                const uint32_t meta = p.v_meta[(size_t)user * WaveGeo::VCAP + e];
-                const int s0 = meta & 255u, n = (meta >> 8) & 255u, need = (meta >> 16) & 255u, chosen = (meta >> 24) & 1u;
-                track_ratio(sLStr[e], p.v_fast[(size_t)user * WaveGeo::VCAP + e], p.v_segeps[(size_t)user * 32 + (meta >> 25)]);
-                const uint32_t ks = order_key(sLStr[e]);
-                int rank = 0, ties = 0;
-                for (int q = s0; q < s0 + n; q++) {
-                    const uint32_t kq = order_key(sLStr[q]);
-                    rank += kq > ks ? 1 : 0;
-                    ties += (kq == ks && q != e) ? 1 : 0;
-                }
-                bad |= (rank < need && rank + ties >= need) ? 1 : 0;
-                bad |= ((rank + ties < need ? 1 : 0) != chosen) ? 2 : 0;
+        if (!why) {
+            for (int e = lane; e < st.vcount; e += 32) wf.row_code[(size_t)user * WaveFinal::RCAP + e] = p.v_code[(size_t)user * WaveGeo::VCAP + e];
+            n_rows = st.vcount + na;
+            const int nc = (n_rows + 15) >> 4;
+            if (lane < nc) {
+                int base = 0;
+                if (lane == 0) base = atomicAdd(wf.chunk_count, nc);
+                base = __shfl_sync(__activemask(), base, 0);
+                wf.chunk_list[base + lane] = (user << 5) | lane;
             }
-            if (tid < na) {
-                const float mine = sLStr[vcount + tid];
-                const int ps = sUPos[tid];
-                track_ratio(mine, sScore[ps], eps_level);
-                const uint32_t ks = order_key(mine);
-                int rank = 0, ties = 0;
-                for (int q = 0; q < na; q++) {
-                    const uint32_t kq = order_key(sLStr[vcount + q]);
-                    rank += kq > ks ? 1 : 0;
-                    ties += (kq == ks && q != tid) ? 1 : 0;
-                }
-                bad |= (ties > 0 && rank < kk) ? 1 : 0;
-                if (rank < kk) {
-                    bp.out_items[(size_t)user * bp.out_stride + rank] = __ldg(bp.leaf_item + ((int64_t)sCode[ps] - leaf_start));
-                    bp.out_scores[(size_t)user * bp.out_stride + rank] = mine;
-                }
-            }
-            const int anybad = __syncthreads_or(bad), proof = __syncthreads_or(bad & 2);
-            if (anybad) { redo = true; redo_why = 4 + (proof ? 1 : 0); }
         }
-        if (!redo) {
-            for (int i = kk + tid; i < bp.topk; i += G::THREADS) {
+    }
+    if (lane == 0) { meta[0] = n_rows; meta[1] = na; meta[2] = kk; meta[3] = why; }
+}
+
+// Persistent: weights in shared memory once per CTA, then user after user -- history tile, <= 64 listed rows per pass, the strict
+// kernel's tile scorer (score_tile: 4 x 4 register tiles of sequential-k fma chains, beam_kernels.cuh).
+struct WaveStrictGeo {
+    using G = Geo<float, 64, 64>;
+    static constexpr int RT = 64;
+    static size_t smem_bytes() { return (size_t)(3 * 64 * 64 + 2 * 64 + kMaxT * 64 + 2 * RT * G::LD + RT * G::PLD + RT) * 4 + kMaxT * 4 + 64; }
+};
+static __global__ void __launch_bounds__(kThreads, 2) wave_strict_rows_kernel(const WaveParams p, const WaveStrictW sw, const WaveFinal wf)
+{
+    using SG = WaveStrictGeo;
+    using G = SG::G;
+    constexpr int E = 64, RT = SG::RT;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    float *sWattT = reinterpret_cast<float *>(smem_raw), *sW1T = sWattT + E * E, *sB1 = sW1T + 2 * E * E, *sW2 = sB1 + E;
+    float *sK = sW2 + E, *sX = sK + kMaxT * E, *sA = sX + RT * G::LD, *sP = sA + RT * G::LD, *sOut = sP + RT * G::PLD;
+    int32_t *sMask = reinterpret_cast<int32_t *>(sOut + RT);
+    const int tid = threadIdx.x;
+    for (int i = tid; i < E * E; i += kThreads) sWattT[i] = __ldg(sw.wattT + i);
+    for (int i = tid; i < 2 * E * E; i += kThreads) sW1T[i] = __ldg(sw.w1T + i);
+    if (tid < E) { sB1[tid] = __ldg(sw.b1 + tid); sW2[tid] = __ldg(sw.w2 + tid); }
+    for (int user = blockIdx.x; user < p.B; user += gridDim.x) {
+        const int n_rows = wf.meta[(size_t)user * 4];
+        if (n_rows == 0) continue;
+        const uint32_t mb = p.user[user].maskbits;
+        __syncthreads();
+        for (int i = tid; i < kMaxT * 16; i += kThreads) {         // history rows (fp32), zero rows for padding
+            const int j = i >> 4, v = i & 15;
+            const int c = j < p.T ? p.hist[(size_t)user * p.T + j] : -1;
+            if (c >= 0) cp_async16(sK + j * E + v * 4, p.emb + (size_t)c * E + v * 4);
+            else *reinterpret_cast<float4 *>(sK + j * E + v * 4) = make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+        if (tid < kMaxT) sMask[tid] = (mb >> tid) & 1u;
+        const int32_t *rc = wf.row_code + (size_t)user * WaveFinal::RCAP;
+        float *rs = wf.row_strict + (size_t)user * WaveFinal::RCAP;
+        for (int r0 = 0; r0 < n_rows; r0 += RT) {
+            const int nr = n_rows - r0 < RT ? n_rows - r0 : RT;
+            if (r0) __syncthreads();
+            gather_tile<float, E>(sX, p.emb, rc + r0, nr);            // row stride G::LD does not depend on the tile height
+            cp_async_commit();
+            cp_async_wait<0>();
+            __syncthreads();
+            score_tile<float, E, RT>(sX, sA, sP, sK, sMask, sWattT, sW1T, sB1, sW2, sw.b2, p.scale, p.T, nr, sOut);
+            for (int i = tid; i < nr; i += kThreads) rs[r0 + i] = sOut[i];
+        }
+    }
+}
+
+static __global__ void __launch_bounds__(128) wave_final_verify_kernel(const WaveParams p, const BeamParams<float> bp, const WaveFinal wf, int slot)
+{
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int user = blockIdx.x * 4 + warp;
+    if (user >= p.B) return;
+    const int32_t *meta = wf.meta + (size_t)user * 4;
+    const int n_rows = meta[0], na = meta[1], kk = meta[2];
+    int why = meta[3];
+    float ratio = 0.0f;
+    if (!why) {
+        const WaveUser st = p.user[user];
+        const int vcount = st.vcount;
+        const float *rs = wf.row_strict + (size_t)user * WaveFinal::RCAP;
+        const int64_t leaf_start = ((int64_t)1 << p.leaf_level) - 1;
+        int bad = 0;
+        for (int e = lane; e < vcount; e += 32) {                  // the deferred cuts: the strict order must pick the same rows
+            const uint32_t m = p.v_meta[(size_t)user * WaveGeo::VCAP + e];
+            const int s0 = m & 255u, n = (m >> 8) & 255u, need = (m >> 16) & 255u, chosen = (m >> 24) & 1u;
+            const float eps_e = p.v_segeps[(size_t)user * 32 + (m >> 25)];
+            const float mine = rs[e];
+            if (eps_e > 0.0f && eps_e < 1e30f) ratio = fmaxf(ratio, fabsf(mine - p.v_fast[(size_t)user * WaveGeo::VCAP + e]) / eps_e);
+            const uint32_t ks = order_key(mine);
+            int rank = 0, ties = 0;
+            for (int q = s0; q < s0 + n; q++) {
+                const uint32_t kq = order_key(rs[q]);
+                rank += kq > ks ? 1 : 0;
+                ties += (kq == ks && q != e) ? 1 : 0;
+            }
+            bad |= (rank < need && rank + ties >= need) ? 1 : 0;   // exact strict tie across the cut: the reference decides by position
+            bad |= ((rank + ties < need ? 1 : 0) != chosen) ? 2 : 0;
+        }
+        const int32_t *fp = wf.fin_pos + (size_t)user * FastGeo::MAX_FINAL;
+        const int32_t *cur = p.code[slot] + (size_t)user * p.cap;
+        const float *sc = p.score + (size_t)user * p.cap;
+        for (int t = lane; t < na; t += 32) {
+            const float mine = rs[vcount + t];
+            const int ps = fp[t];
+            if (st.eps > 0.0f && st.eps < 1e30f) ratio = fmaxf(ratio, fabsf(mine - sc[ps]) / st.eps);
+            const uint32_t ks = order_key(mine);
+            int rank = 0, ties = 0;
+            for (int q = 0; q < na; q++) {
+                const uint32_t kq = order_key(rs[vcount + q]);
+                rank += kq > ks ? 1 : 0;
+                ties += (kq == ks && q != t) ? 1 : 0;
+            }
+            bad |= (ties > 0 && rank < kk) ? 1 : 0;                // a tie that reaches the output: its order is positional
+            if (rank < kk) {
+                bp.out_items[(size_t)user * bp.out_stride + rank] = __ldg(bp.leaf_item + ((int64_t)cur[ps] - leaf_start));
+                bp.out_scores[(size_t)user * bp.out_stride + rank] = mine;
+            }
+        }
+        const uint32_t anybad = __ballot_sync(0xffffffffu, bad != 0), proof = __ballot_sync(0xffffffffu, (bad & 2) != 0);
+        if (anybad) why = proof ? 6 : 5;
+        if (!why) {
+            for (int i = kk + lane; i < bp.topk; i += 32) {
                 bp.out_items[(size_t)user * bp.out_stride + i] = -1;
                 bp.out_scores[(size_t)user * bp.out_stride + i] = 0.0f;
             }
-            if (tid == 0) bp.out_counts[user] = kk;
+            if (lane == 0) bp.out_counts[user] = kk;
         }
     }
-    if (redo && tid == 0) {
+    if (why && lane == 0) {
         p.redo_list[atomicAdd(p.redo_count, 1)] = user;
         *reinterpret_cast<volatile int32_t *>(p.host_flags + 1) = 1;
-        if (p.stats) { atomicAdd(&p.stats[5], 1ull); atomicAdd(&p.stats[24 + (redo_why & 7)], 1ull); }
+        if (p.stats) { atomicAdd(&p.stats[5], 1ull); atomicAdd(&p.stats[24 + ((why - 1) & 7)], 1ull); }
     }
     if (p.stats) {
-        for (int o = 16; o > 0; o >>= 1) st_ratio = fmaxf(st_ratio, __shfl_xor_sync(0xffffffffu, st_ratio, o));
-        if (lane == 0 && st_ratio > 0.0f) atomicMax(reinterpret_cast<unsigned int *>(&p.stats[4]), __float_as_uint(st_ratio));
-        if (tid == 0 && st_rerows) atomicAdd(&p.stats[2], st_rerows);
+        for (int o = 16; o > 0; o >>= 1) ratio = fmaxf(ratio, __shfl_xor_sync(0xffffffffu, ratio, o));
+        if (lane == 0 && ratio > 0.0f) atomicMax(reinterpret_cast<unsigned int *>(&p.stats[4]), __float_as_uint(ratio));
+        if (lane == 0 && n_rows) atomicAdd(&p.stats[2], (unsigned long long)n_rows);
     }
 }
 

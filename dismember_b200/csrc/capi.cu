@@ -568,7 +568,8 @@ static int32_t wave_enqueue(dmg_handle_t h, const BeamParams<float> &p, const Fa
     DMG_TRY(ensure_dev(h, h->s_wave, Carver::need({(size_t)B * cap * 4, (size_t)B * cap * 4, (size_t)B * cap * 4, (size_t)B * 4,
                                                    (size_t)B * sizeof(WaveUser), (size_t)B * WG::UOP_BYTES, (size_t)B * WG::VCAP * 4,
                                                    (size_t)B * WG::VCAP * 4, (size_t)B * WG::VCAP * 4, (size_t)B * 32 * 4,
-                                                   (size_t)B * ((cap + 127) / 128) * 4})));
+                                                   (size_t)B * ((cap + 127) / 128) * 4, (size_t)B * WaveFinal::RCAP * 4, (size_t)B * WaveFinal::RCAP * 4,
+                                                   (size_t)B * FastGeo::MAX_FINAL * 4, (size_t)B * 4 * 4, (size_t)B * 27 * 4})));
     Carver c(h->s_wave.d);
     WaveParams wp;
     memset(&wp, 0, sizeof(wp));
@@ -583,6 +584,11 @@ static int32_t wave_enqueue(dmg_handle_t h, const BeamParams<float> &p, const Fa
     wp.v_code = c.take<int32_t>((size_t)B * WG::VCAP); wp.v_fast = c.take<float>((size_t)B * WG::VCAP);
     wp.v_meta = c.take<uint32_t>((size_t)B * WG::VCAP); wp.v_segeps = c.take<float>((size_t)B * 32);
     wp.tile_list = c.take<int32_t>((size_t)B * ((cap + 127) / 128));
+    WaveFinal wf;
+    wf.row_code = c.take<int32_t>((size_t)B * WaveFinal::RCAP); wf.row_strict = c.take<float>((size_t)B * WaveFinal::RCAP);
+    wf.fin_pos = c.take<int32_t>((size_t)B * FastGeo::MAX_FINAL); wf.meta = c.take<int32_t>((size_t)B * 4);
+    wf.chunk_list = c.take<int32_t>((size_t)B * 27);
+    wf.chunk_count = h->d_fast_ctl + 8 + 40;                     // zeroed by tdm_ids_to_codes_kernel
     wp.tile_count = h->d_fast_ctl + 8;                           // [level]: tiles listed (zeroed by tdm_ids_to_codes_kernel)
     wp.mT = fx.mT; wp.zvec = fx.zvec; wp.lvl_vx = fx.lvl_vx; wp.lvl_nx = fx.lvl_nx; wp.b1 = p.b1;
     wp.cA = fx.cA; wp.cZ = fx.cZ; wp.cH = fx.cH; wp.cGamma = fx.cGamma; wp.tau = fx.tau;
@@ -598,8 +604,7 @@ static int32_t wave_enqueue(dmg_handle_t h, const BeamParams<float> &p, const Fa
     auto select_kernel = cap <= 256 ? wave_select_kernel<8> : (cap <= 416 ? wave_select_kernel<13> : wave_select_kernel<16>);
     DMG_CUDA(h, cudaFuncSetAttribute(score_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, WG::SMEM));
     DMG_CUDA(h, cudaFuncSetAttribute(score_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
-    const size_t fin_smem = (size_t)FastGeo::STRICT_SCR + (size_t)cap * 12 + FastGeo::MAX_FINAL * 4 + (size_t)(FastGeo::VCAP + FastGeo::MAX_FINAL) * 8 + 256 * 4 + 32 * 4;
-    DMG_CUDA(h, cudaFuncSetAttribute(wave_final_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fin_smem));
+    DMG_CUDA(h, cudaFuncSetAttribute(wave_strict_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)WaveStrictGeo::smem_bytes()));
     cudaEvent_t e0 = nullptr, e1 = nullptr;
     if (h->profiling) {
         DMG_CUDA(h, cudaEventCreate(&e0));
@@ -664,8 +669,11 @@ static int32_t wave_enqueue(dmg_handle_t h, const BeamParams<float> &p, const Fa
     }
     if (wp_out) { *wp_out = wp; *slot_out = slot; }
     if (stop_level < 0) {
-        wave_final_kernel<<<B, FastGeo::THREADS, fin_smem, h->stream>>>(wp, p, slot);
-        h->launches += 1;
+        auto prep_kernel = cap <= 256 ? wave_final_prep_kernel<8> : (cap <= 416 ? wave_final_prep_kernel<13> : wave_final_prep_kernel<16>);
+        prep_kernel<<<(B + 3) / 4, 128, 0, h->stream>>>(wp, p, wf, slot);
+        wave_strict_rows_kernel<<<std::min(B, 2 * h->sm_count), kThreads, WaveStrictGeo::smem_bytes(), h->stream>>>(wp, sw, wf);
+        wave_final_verify_kernel<<<(B + 3) / 4, 128, 0, h->stream>>>(wp, p, wf, slot);
+        h->launches += 3;
     }
     DMG_CUDA(h, cudaGetLastError());
     if (h->profiling) {
