@@ -30,6 +30,12 @@
 
 namespace dmg {
 
+// Programmatic dependent launch: the kernels of a batch form one chain on the stream; each lets the next one start (launch_dependents)
+// as soon as it is resident and waits (grid_dep_wait) for its predecessor to complete before it touches anything the chain produced,
+// so that launch latency, barrier set-up, TMEM allocation and the weight image load of kernel n + 1 run under the tail of kernel n.
+__device__ __forceinline__ void grid_dep_launch() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void grid_dep_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
 struct WaveUser {                   // per-user search state (64 B)
     float eps;                      // bound on |fast - strict| of the scores in WaveParams::score (level being cut next)
     float kmax, zk, hw;             // user terms of the bound (DESIGN.md "certified cuts")
@@ -126,6 +132,8 @@ static __global__ void __launch_bounds__(256) wave_prologue_kernel(const WavePar
     __shared__ int sCode[kMaxT];
     __shared__ int sRed[8];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, user = blockIdx.x, T = p.T;
+    grid_dep_launch();
+    grid_dep_wait();
     unsigned char *uop = p.uop + (size_t)user * WaveGeo::UOP_BYTES;
     if (tid < kMaxT) {
         int c = -1, m = 0;
@@ -329,6 +337,8 @@ static __global__ void __launch_bounds__(128) wave_select_kernel(const WaveParam
     const int user = blockIdx.x * 4 + warp;
     const uint32_t lt = (1u << lane) - 1u;
     if (lane == 0) sPark[warp][0] = 0;
+    grid_dep_launch();
+    grid_dep_wait();
     WaveUser *st = p.user + (user < p.B ? user : 0);
     int flags = 0, beam = 1, s_level = 0;
     bool live = user < p.B;
@@ -593,6 +603,7 @@ wave_score_kernel(const __grid_constant__ CUtensorMap tmap, const WaveParams p, 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const uint32_t sbase = smem_u32(sm);
     if (sbase & 1023u) __trap();                                 // the swizzled X tiles need 1024-byte alignment
+    grid_dep_launch();
 
     if (tid == 0) {
         mbar_init(&bar[WB_W1], 1);
@@ -610,7 +621,8 @@ wave_score_kernel(const __grid_constant__ CUtensorMap tmap, const WaveParams p, 
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t *>(sm + G::TMEMP);
-    const int ntiles = __ldg(p.tile_count + level);
+    grid_dep_wait();                                             // everything above ran under the previous kernel's tail
+    const int ntiles = *(volatile const int32_t *)(p.tile_count + level);
     const int n_my = ntiles > (int)blockIdx.x ? (ntiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
 
     const int g = warp >> 2, wq = warp & 3, gtid = tid & 127;             // group = pipeline stage, warp within the group, row of the tile
@@ -823,6 +835,8 @@ static __global__ void __launch_bounds__(128) wave_final_prep_kernel(const WaveP
 {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int user = blockIdx.x * 4 + warp;
+    grid_dep_launch();
+    grid_dep_wait();
     if (user >= p.B) return;
     const uint32_t lt = (1u << lane) - 1u;
     const WaveUser st = p.user[user];
@@ -912,9 +926,11 @@ static __global__ void __launch_bounds__(kThreads, 2) wave_strict_rows_kernel(co
     float *sK = sW2 + E, *sX = sK + kMaxT * E, *sA = sX + RT * G::LD, *sP = sA + RT * G::LD, *sOut = sP + RT * G::PLD;
     int32_t *sMask = reinterpret_cast<int32_t *>(sOut + RT);
     const int tid = threadIdx.x;
-    for (int i = tid; i < E * E; i += kThreads) sWattT[i] = __ldg(sw.wattT + i);
+    grid_dep_launch();
+    for (int i = tid; i < E * E; i += kThreads) sWattT[i] = __ldg(sw.wattT + i);     // weights: constant for the whole chain
     for (int i = tid; i < 2 * E * E; i += kThreads) sW1T[i] = __ldg(sw.w1T + i);
     if (tid < E) { sB1[tid] = __ldg(sw.b1 + tid); sW2[tid] = __ldg(sw.w2 + tid); }
+    grid_dep_wait();
     for (int user = blockIdx.x; user < p.B; user += gridDim.x) {
         const int n_rows = wf.meta[(size_t)user * 4];
         if (n_rows == 0) continue;
@@ -946,6 +962,8 @@ static __global__ void __launch_bounds__(128) wave_final_verify_kernel(const Wav
 {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int user = blockIdx.x * 4 + warp;
+    grid_dep_launch();
+    grid_dep_wait();
     if (user >= p.B) return;
     const int32_t *meta = wf.meta + (size_t)user * 4;
     const int n_rows = meta[0], na = meta[1], kk = meta[2];

@@ -557,6 +557,19 @@ int32_t dmg_tdm_ids_to_codes(dmg_handle_t h, const int32_t *d_ids, int64_t n, in
     return DMG_OK;
 }
 
+// One kernel of a programmatic-dependent-launch chain (beam_wave.cuh: grid_dep_launch / grid_dep_wait).
+template <typename... KArgs, typename... Args>
+static cudaError_t launch_chain(void (*kern)(KArgs...), int grid, int block, size_t smem, cudaStream_t st, bool pdl, Args &&...args)
+{
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)grid); cfg.blockDim = dim3((unsigned)block); cfg.dynamicSmemBytes = smem; cfg.stream = st;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = pdl ? 1 : 0;
+    cfg.attrs = at; cfg.numAttrs = 1;
+    return cudaLaunchKernelEx(&cfg, kern, KArgs(args)...);
+}
+
 // The level-synchronous tensor-core path (beam_wave.cuh): prologue, then select + score per tree level, then the strict
 // final.  p / fx are the persistent kernel's parameter blocks (same tables, same outputs, same redo list).
 static int32_t wave_enqueue(dmg_handle_t h, const BeamParams<float> &p, const FastParams &fx, int max_beam, int stop_level = -1,
@@ -611,17 +624,19 @@ static int32_t wave_enqueue(dmg_handle_t h, const BeamParams<float> &p, const Fa
         DMG_CUDA(h, cudaEventCreate(&e1));
         DMG_CUDA(h, cudaEventRecord(e0, h->stream));
     }
-    wave_prologue_kernel<<<B, 256, 0, h->stream>>>(wp);
+    const bool pdl = !getenv("DMG_WAVE_NO_PDL");
+    DMG_CUDA(h, launch_chain(wave_prologue_kernel, B, 256, 0, h->stream, false, wp));   // first of the chain: ordinary stream order behind K2
     h->launches += 1;
     const int tpu = (cap + 127) / 128, ntiles = B * tpu;
-    const int grid = std::min(ntiles, 2 * h->sm_count);
+    const int ctas_per_sm = getenv("DMG_WAVE_SCORE_CTAS") ? atoi(getenv("DMG_WAVE_SCORE_CTAS")) : 2;
+    const int grid = std::min(ntiles, ctas_per_sm * h->sm_count);
     int slot = 0;
     const int s_min = lower_log2(p.beam);                        // per-user beams only widen (Recommender.scala:28-31)
     (void)max_beam;
     const int last_level = stop_level >= 0 ? std::min(stop_level, p.leaf_level) : p.leaf_level;
     for (int level = s_min; level < last_level; level++) {
-        select_kernel<<<(B + 3) / 4, 128, 0, h->stream>>>(wp, sw, level, slot);
-        score_kernel<<<grid, WG::THREADS, WG::SMEM, h->stream>>>(tmap, wp, w2, slot ^ 1, level + 1);
+        DMG_CUDA(h, launch_chain(select_kernel, (B + 3) / 4, 128, 0, h->stream, pdl, wp, sw, level, slot));
+        DMG_CUDA(h, launch_chain(score_kernel, grid, WG::THREADS, WG::SMEM, h->stream, pdl, tmap, wp, w2, slot ^ 1, level + 1));
         if (getenv("DMG_WAVE_ABLATE") && level == atoi(getenv("DMG_WAVE_ABLATE"))) {
             // profiling aid: replay this level's scorer with parts switched off (scores go to a scratch buffer)
             static float *dummy = nullptr;
@@ -670,9 +685,9 @@ static int32_t wave_enqueue(dmg_handle_t h, const BeamParams<float> &p, const Fa
     if (wp_out) { *wp_out = wp; *slot_out = slot; }
     if (stop_level < 0) {
         auto prep_kernel = cap <= 256 ? wave_final_prep_kernel<8> : (cap <= 416 ? wave_final_prep_kernel<13> : wave_final_prep_kernel<16>);
-        prep_kernel<<<(B + 3) / 4, 128, 0, h->stream>>>(wp, p, wf, slot);
-        wave_strict_rows_kernel<<<std::min(B, 2 * h->sm_count), kThreads, WaveStrictGeo::smem_bytes(), h->stream>>>(wp, sw, wf);
-        wave_final_verify_kernel<<<(B + 3) / 4, 128, 0, h->stream>>>(wp, p, wf, slot);
+        DMG_CUDA(h, launch_chain(prep_kernel, (B + 3) / 4, 128, 0, h->stream, pdl, wp, p, wf, slot));
+        DMG_CUDA(h, launch_chain(wave_strict_rows_kernel, std::min(B, 2 * h->sm_count), kThreads, WaveStrictGeo::smem_bytes(), h->stream, pdl, wp, sw, wf));
+        DMG_CUDA(h, launch_chain(wave_final_verify_kernel, (B + 3) / 4, 128, 0, h->stream, pdl, wp, p, wf, slot));
         h->launches += 3;
     }
     DMG_CUDA(h, cudaGetLastError());

@@ -98,7 +98,7 @@ struct dmg_handle_s {
     alignas(64) unsigned char wave_tmap[128];   // CUtensorMap over the hi|lo table
     int32_t *d_flags = nullptr;     // [0] = index error flag: device alias of h_flags (mapped pinned memory: kernels raise it with no copy back)
     int32_t *h_flags = nullptr;
-    int arithmetic = DMG_ARITH_STRICT;
+    int arithmetic = DMG_ARITH_FAST;   // same ids and logit bits as DMG_ARITH_STRICT (certified cuts); strict is the opt-out
     bool fast_ok = false;            // tensor-core scorer available for the loaded weights
     bool fast_dirty = true;          // weights changed since the bound tables were computed
     float fast_cA = 0, fast_cZ = 0, fast_cH = 0, fast_cGamma = 0;   // certified-cut bound constants
