@@ -11,15 +11,21 @@ Default workload = BASELINE.json configs[1]: TDM synthetic 1M items, dim 64, bea
 value  : whole-job users/s with queries and result buffers resident in HBM (dmg_tdm_retrieve_dev)
 e2e    : same metric through the host-buffer C-ABI call (dmg_tdm_retrieve): pinned H2D of the
          B x T item ids and D2H of the topk ids/logits inside the timed region
-in flight: --inflight N (default 4) host threads, each with its own handle (the engine + dmg_clone handles sharing its
-         tables, the GPU form of the reference's per-thread model clones), take the steps round-robin, so the tail of one
-         batch's persistent kernel overlaps the head of the next; both value and e2e time EXACTLY K steps this way.
-         The roofline object is measured on a separate serial pass (one batch in flight, kernel timed alone).
-roofline: dominant kernel = beam_search_fast_kernel (tcgen05 scorer + certified cuts; --arith strict: beam_search_kernel);
-         algorithmic bytes per user (SURVEY 8d) = rows_scored*E*4 + T*E*4 + topk*8, rows_scored = 256 + 400*(L-8);
-         kernel time = CUDA events around its launches on the engine's stream (dmg_set_profiling / dmg_kernel_time)
-Other catalogues: --items 10000000 / 100000000 (--verify-strict N checks N users against the strict kernel when the table is
-too large to ship to the CPU oracle).  Other paths: tools/bench_paths.py; sharded tables: tools/shard_check.py.
+timed region: the K steps are repeated R times (R sized so that every region lasts --target-sec, default 0.6 s; R is in
+         config.repeats) with query batches from a pool of 64 distinct ones; ms_per_step = region / (K x R).
+in flight: --inflight N (default 8) host threads, started BEFORE the timed region, each with its own handle (the engine +
+         dmg_clone handles sharing its tables, the GPU form of the reference's per-thread model clones), take the steps
+         round-robin: the kernels of different batches fill each other's gaps.
+roofline: dominant kernel = wave_score_kernel (level-synchronous tcgen05 scorer, one launch per tree level; --arith strict:
+         beam_search_kernel); algorithmic bytes per user = rows_scored*E*4 + T*E*4 + topk*8, rows_scored =
+         256 + 400*(L-8); measured on a separate serial pass (one batch in flight) with CUDA events around every launch
+         of the kernel (dmg_set_profiling / dmg_kernel_time): achieved = step bytes / summed launch durations of the step.
+         roofline.traffic = ncu dram bytes per launch for THIS catalogue from profiles/traffic.json, else null.
+structured: the same step on the structured ("trained-like") table of SURVEY 8d, where the users' beams diverge; with the
+         distinct candidate rows one batch touches (dmg_wave_probe).
+catalogues: --catalogues 10M,100M (default) repeats the measurement on the larger catalogues of the north star after the
+         headline (100 M: 68.7 GB table + as much for its bf16 hi|lo copy; checked against the strict kernel).
+Other paths: tools/bench_paths.py; sharded tables: tools/shard_check.py.
 """
 import argparse
 import json
@@ -54,7 +60,10 @@ def parse():
                     help="re-run the first N users of the last batch with the strict fp32 kernel and compare ids / logit bits "
                          "(size-independent parity check for catalogues whose table is too large to ship to the CPU oracle)")
     ap.add_argument("--tau", type=float, default=None, help="certification band as a fraction of the worst-case bound")
-    ap.add_argument("--inflight", type=int, default=4,
+    ap.add_argument("--target-sec", type=float, default=0.6, help="length of every timed region: the K steps are repeated R times")
+    ap.add_argument("--catalogues", default="10M,100M", help="extra catalogues measured after the headline ('' = none)")
+    ap.add_argument("--no-structured", action="store_true", help="skip the second workload on the structured ('trained-like') table")
+    ap.add_argument("--inflight", type=int, default=8,
                     help="host threads / handles driving the GPU, one batch each in flight (1 = strictly serial steps)")
     ap.add_argument("--arith", default="fast", choices=["fast", "strict"],
                     help="scorer arithmetic: tensor-core with certified cuts (same ids/logits) or strict fp32 SIMT")
@@ -66,6 +75,11 @@ def algorithmic_bytes_per_user(L, E, T, topk, beam):
     first = 2 * (1 << s)                       # children of the full start level
     rows = first + 2 * beam * max(L - s - 1, 0) if L > s else 0
     return rows, rows * E * 4 + T * E * 4 + topk * 8
+
+
+def workload_name(args, items):
+    return (f"TDM synthetic {items} items, dim={args.dim}, beam={args.beam}, batch={args.batch}, "
+            f"topk={args.topk}, T={args.seq_len}")
 
 
 def hbm_peak():
@@ -188,8 +202,8 @@ def run_reference(args):
         "value": value, "unit": "users/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic",
-        "config": {"workload": f"TDM synthetic {args.items} items, dim={args.dim}, beam={args.beam}, batch={args.batch} "
-                               f"(CPU arm: {sample} users per step)", "levels": L, "rows_scored_per_user": rows_u},
+        "config": {"workload": workload_name(args, args.items), "levels": L, "rows_scored_per_user": rows_u,
+                   "cpu_arm_users_per_step": sample},
         "cpu_baseline": {"value": value, "unit": "users/s", "cores": threads, "kind": "port",
                          "sample": f"{sample} users/step x {args.steps} steps, oracle/ C restatement (the Scala+MKL "
                                    f"reference cannot run: no JVM in the image)"},
@@ -197,6 +211,204 @@ def run_reference(args):
         "gpu_launches": 0,
     }
     print(json.dumps(line), flush=True)
+
+
+class Workers:
+    """NF persistent host threads, one per engine handle.  They are started at set-up and wait on a barrier, so no thread
+    creation falls into a timed region; run() releases them for the steps lo..hi-1 (round-robin) and returns when all are done."""
+
+    def __init__(self, n):
+        self.n, self.job, self.errs = n, None, []
+        self.go, self.done = threading.Barrier(n + 1), threading.Barrier(n + 1)
+        self.threads = [threading.Thread(target=self._loop, args=(k,), daemon=True) for k in range(n)]
+        for t in self.threads:
+            t.start()
+
+    def _loop(self, k):
+        while True:
+            self.go.wait()
+            job = self.job
+            if job is None:
+                return
+            step, lo, hi = job
+            try:
+                for i in range(lo + k, hi, self.n):
+                    step(i, k)
+            except Exception as ex:                                # noqa: BLE001
+                self.errs.append(ex)
+            self.done.wait()
+
+    def run(self, step, lo, hi, before_release=None):
+        self.job = (step, lo, hi)
+        if before_release:
+            before_release()
+        self.go.wait()
+        self.done.wait()
+        if self.errs:
+            raise self.errs[0]
+
+    def stop(self):
+        self.job = None
+        self.go.wait()
+
+
+def measure(args, env, items, structured=False, do_cpu=False, target_s=None, verify_strict=0, do_e2e=True, do_roofline=True):
+    """One catalogue: build index + table, then value (device-resident), roofline (serial pass, dominant kernel timed alone),
+    e2e (host buffers).  Returns a dict of results."""
+    import torch
+    from dismember_b200 import Engine, synth
+    dev, local, world, rank, barrier, max_over_ranks = env["dev"], env["local"], env["world"], env["rank"], env["barrier"], env["max_over_ranks"]
+    B, T, E, K, W = args.batch, args.seq_len, args.dim, args.steps, args.warmup
+    target_s = args.target_sec if target_s is None else target_s
+    tf = synth.tdm_tree(items, seed=1)
+    L = tf.max_level
+    rows = (1 << (L + 1)) - 1
+    eng = Engine(local)
+    eng.load_tree_tdm(L, tf.codes, tf.node_ids, tf.is_leaf, tf.leaf_ids, tf.leaf_codes)
+    params = None
+    if structured:
+        params = synth.din_params(rows, E, seed=2, structured=True)
+        eng.load_din_weights(params, rows, E, T)
+    else:
+        eng.init_din_weights(np.float32, rows, E, T, seed=2)      # replicas: same table on every rank
+    eng.set_arithmetic(args.arith)
+    if args.tau is not None:
+        eng.set_fast_tolerance(args.tau)
+    NF = max(1, args.inflight)
+    engs = [eng] + [eng.clone() for _ in range(NF - 1)]           # one handle per host thread over ONE copy of the tables
+    streams = [torch.cuda.Stream(dev) for _ in engs]              # non-default: the engines launch on them
+    stream = streams[0]
+    torch.cuda.set_stream(stream)
+    for e, st in zip(engs, streams):
+        e.set_stream(st.cuda_stream)
+    P = 64                                                        # distinct query batches, cycled (every batch walks its own part of the table)
+    host_q = [synth.queries(B, T, items, seed=4 + s * world + rank) for s in range(P)]
+    dev_q = [torch.from_numpy(q).to(dev) for q in host_q]
+    d_out = [(torch.empty((B, args.topk), dtype=torch.int32, device=dev), torch.empty((B, args.topk), dtype=torch.float32, device=dev),
+              torch.empty((B,), dtype=torch.int32, device=dev)) for _ in engs]
+    workers = Workers(NF)
+
+    def step_dev(i, k=0, serial=False):
+        o = d_out[k]
+        fn = engs[k].tdm_retrieve_dev_sync if NF > 1 and not serial else engs[k].tdm_retrieve_dev
+        fn(B, dev_q[i % P].data_ptr(), args.beam, args.topk, True, o[0].data_ptr(), o[1].data_ptr(), o[2].data_ptr())
+
+    e2e_last = [None] * NF
+
+    def step_host(i, k=0):
+        e2e_last[k] = engs[k].tdm_retrieve(host_q[i % P], args.beam, args.topk)
+
+    def timed_dev(n_steps):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        barrier()
+
+        def start():
+            e0.record(stream)
+            for st in streams[1:]:
+                st.wait_event(e0)                                 # nothing of the timed steps starts before e0
+        workers.run(step_dev, 0, n_steps, before_release=start)
+        for st in streams[1:]:
+            ek = torch.cuda.Event()
+            ek.record(st)
+            stream.wait_event(ek)                                 # e1 follows the last kernel of every stream
+        e1.record(stream)
+        barrier()
+        return max_over_ranks(e0.elapsed_time(e1))
+
+    # ---- warm-up, then size the timed region: the K steps are repeated R times (fresh batches from the pool) -----------
+    workers.run(step_dev, 0, max(W, NF))
+    barrier()
+    probe_ms = timed_dev(max(K, 2 * NF))
+    R = max(1, int(np.ceil(target_s * 1e3 / max(probe_ms * K / max(K, 2 * NF), 1e-3))))
+    l0 = sum(e.launch_count for e in engs)
+    dev_ms = timed_dev(K * R)
+    launches = sum(e.launch_count for e in engs) - l0
+    last_k = (K * R - 1) % NF
+    last_items = d_out[last_k][0].cpu().numpy().copy()
+    last_q = (K * R - 1) % P
+
+    out = {"items": items, "levels": L, "rows": rows, "R": R, "NF": NF, "value": world * B * K * R / (dev_ms * 1e-3),
+           "ms_per_step": dev_ms / (K * R), "launches": launches / max(K * R, 1), "timed_region_s": dev_ms * 1e-3}
+
+    # ---- roofline pass: ONE batch in flight on a handle of its own policy, the dominant kernel timed alone ---------------
+    if do_roofline:
+        os.environ["DMG_WAVE_SCORE_CTAS"] = "2"                   # a lone batch: two scorer CTAs per SM (the library's policy for a handle without clones)
+        eng.set_profiling(True)
+        s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        for i in range(3):
+            step_dev(i, 0, serial=True)
+        eng.kernel_time()
+        barrier()
+        s0.record(stream)
+        for i in range(K):
+            step_dev(i, 0, serial=True)
+        s1.record(stream)
+        barrier()
+        out["serial_ms_per_step"] = max_over_ranks(s0.elapsed_time(s1)) / K
+        kern_ms, kern_n = eng.kernel_time()
+        eng.set_profiling(False)
+        os.environ.pop("DMG_WAVE_SCORE_CTAS", None)
+        out["kern_ms_per_step"], out["kern_launches_per_step"] = kern_ms / K, kern_n / K
+    if args.arith == "fast":
+        per = [e.fast_stats() for e in engs]
+        out["fast_stats"] = {k: (max(p[k] for p in per) if k == "max_err_over_bound" else sum(p[k] for p in per)) for k in per[0]}
+
+    # ---- e2e: host buffers through the C ABI (pinned H2D + D2H inside every call) ----------------------------------------
+    if do_e2e:
+        workers.run(step_host, 0, max(W, NF))
+        barrier()
+        t0 = time.perf_counter()
+        workers.run(step_host, 0, K * R)
+        torch.cuda.synchronize(dev)
+        e2e_s = max_over_ranks(time.perf_counter() - t0)
+        out["e2e_value"], out["e2e_ms_per_step"], out["e2e_region_s"] = world * B * K * R / e2e_s, e2e_s / (K * R) * 1e3, e2e_s
+        assert (e2e_last[last_k][0] == last_items).all(), "host-buffer and device-buffer paths disagree"
+
+    if verify_strict > 0 and args.arith == "fast":
+        nv = min(verify_strict, B)
+        fi, fl, fc = eng.tdm_retrieve(host_q[last_q][:nv], args.beam, args.topk)
+        eng.set_arithmetic("strict")
+        si, sl, sc = eng.tdm_retrieve(host_q[last_q][:nv], args.beam, args.topk)
+        eng.set_arithmetic("fast")
+        out["strict_check"] = {"users_checked": nv, "ids_identical": bool((fi == si).all() and (fc == sc).all()),
+                               "logits_bit_identical": bool((fl.view(np.uint32) == sl.view(np.uint32)).all())}
+
+    if structured and args.arith == "fast" and rank == 0:
+        # how much of the node table one batch really touches: distinct candidate rows per level (dmg_wave_probe)
+        s_lvl = args.beam.bit_length() - 1
+        uniq, tot = 0, 0
+        for lvl in range(s_lvl + 1, L + 1):
+            codes, _, counts, _ = eng.wave_probe(host_q[0], args.beam, lvl)
+            m = np.arange(codes.shape[1])[None, :] < counts[:, None]
+            uniq += len(np.unique(codes[m]))
+            tot += int(counts.sum())
+        out["unique_rows_per_batch"], out["rows_per_batch"] = uniq, tot
+        out["unique_row_bytes_per_batch"] = uniq * E * 4
+
+    # ---- cpu_baseline (rank 0, N=1 only): oracle on a bounded sample + parity check ---------------------------------------
+    if do_cpu and rank == 0 and world == 1:
+        from oracle import oracle as orc
+        orc.build()
+        if params is None:
+            params = eng.download_din_weights()
+        threads = os.cpu_count() or 1
+        probe_v, _, _ = cpu_run(args, tf, params, rows, host_q[0][: 2 * threads], threads)
+        n = int(max(2 * threads, min(B * P, args.cpu_sample_sec * probe_v)))
+        nb = (n + B - 1) // B
+        sample_q = np.concatenate([host_q[j] for j in range(nb)])[:n]
+        v, dt, ref = cpu_run(args, tf, params, rows, sample_q, threads)
+        gpu_i, gpu_l, _ = eng.tdm_retrieve(sample_q, args.beam, args.topk)
+        out["cpu"] = {"value": v, "unit": "users/s", "cores": threads, "kind": "port",
+                      "sample": f"{n} users from {nb} of the timed batches, {dt:.1f} s, oracle/ C restatement on {threads} "
+                                f"host threads (the Scala+MKL reference cannot run here: no JVM)"}
+        out["parity"] = {"users_checked": n, "ids_identical": bool((ref[0] == gpu_i).all()),
+                         "logits_bit_identical": bool((ref[1].view(np.uint32) == gpu_l.view(np.uint32)).all())}
+    workers.stop()
+    for e in reversed(engs):
+        e.close()
+    del dev_q, d_out
+    torch.cuda.empty_cache()
+    return out
 
 
 def main():
@@ -211,7 +423,6 @@ def main():
 
     import torch
     import torch.distributed as dist
-    from dismember_b200 import Engine, synth
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -226,29 +437,6 @@ def main():
     dev = torch.device("cuda", local)
     B, T, E, K, W = args.batch, args.seq_len, args.dim, args.steps, args.warmup
 
-    # ---- setup (untimed): index, node table, queries -------------------------------------
-    tf = synth.tdm_tree(args.items, seed=1)
-    L = tf.max_level
-    rows = (1 << (L + 1)) - 1
-    eng = Engine(local)
-    eng.load_tree_tdm(L, tf.codes, tf.node_ids, tf.is_leaf, tf.leaf_ids, tf.leaf_codes)
-    eng.init_din_weights(np.float32, rows, E, T, seed=2)          # replicas: same table on every rank
-    eng.set_arithmetic(args.arith)
-    if args.tau is not None:
-        eng.set_fast_tolerance(args.tau)
-    NF = max(1, min(args.inflight, K))
-    engs = [eng] + [eng.clone() for _ in range(NF - 1)]           # one handle per host thread over ONE copy of the tables
-    streams = [torch.cuda.Stream(dev) for _ in engs]              # non-default: the engines launch on them
-    stream = streams[0]
-    torch.cuda.set_stream(stream)
-    for e, st in zip(engs, streams):
-        e.set_stream(st.cuda_stream)
-    host_q = [make_queries(args, s, rank, world) for s in range(W + K)]
-    dev_q = [torch.from_numpy(q).to(dev) for q in host_q]
-    d_out = [(torch.empty((B, args.topk), dtype=torch.int32, device=dev), torch.empty((B, args.topk), dtype=torch.float32, device=dev),
-              torch.empty((B,), dtype=torch.int32, device=dev)) for _ in engs]
-    last_k = (K - 1) % NF                                         # the handle that runs the last timed step
-
     def barrier():
         if world > 1:
             dist.barrier()
@@ -261,179 +449,119 @@ def main():
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item())
 
-    def step_dev(i, k=0, serial=False):
-        o = d_out[k]
-        # several handles: the synchronous device-buffer call (its host thread has nothing else to do; the strict redo kernel is
-        # launched only for the batches that need it); one handle: the asynchronous call, steps queued back to back
-        fn = engs[k].tdm_retrieve_dev_sync if NF > 1 and not serial else engs[k].tdm_retrieve_dev
-        fn(B, dev_q[i].data_ptr(), args.beam, args.topk, True, o[0].data_ptr(), o[1].data_ptr(), o[2].data_ptr())
-
-    e2e_last = [None] * NF
-
-    def step_host(i, k=0):
-        e2e_last[k] = engs[k].tdm_retrieve(host_q[i], args.beam, args.topk)
-
-    def run_steps(step, lo, hi):
-        """steps lo..hi-1, round-robin over the NF handles, one host thread per handle"""
-        if NF == 1:
-            for i in range(lo, hi):
-                step(i, 0)
-            return
-        errs = []
-
-        def work(k):
-            try:
-                for i in range(lo + k, hi, NF):
-                    step(i, k)
-            except Exception as ex:                                # noqa: BLE001
-                errs.append(ex)
-        th = [threading.Thread(target=work, args=(k,)) for k in range(NF)]
-        for t in th:
-            t.start()
-        for t in th:
-            t.join()
-        if errs:
-            raise errs[0]
-
-    # ---- value: device-resident, CUDA events on the launching streams --------------------
+    env = {"dev": dev, "local": local, "world": world, "rank": rank, "barrier": barrier, "max_over_ranks": max_over_ranks}
     import gc
     gc.collect()
-    gc.disable()                                                  # no collector pause inside a 45 ms timed region
+    gc.disable()                                                  # no collector pause inside a timed region
     sys.setswitchinterval(1e-4)                                   # worker threads hand the GIL over within 0.1 ms
     sampler = ClockSampler(local)
     sampler.start()                                               # before the warm-up: nvidia-smi's start-up (NVML init on every GPU of
-    sampler.wait_first(3.0)                                       # the box, once per rank) must not fall into the timed region
-    run_steps(step_dev, 0, W)
-    barrier()
-    sampler.mark()                                                # clocks are reported from the samples taken after this point
-    l0 = sum(e.launch_count for e in engs)
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    barrier()
-    e0.record(stream)
-    for st in streams[1:]:
-        st.wait_event(e0)                                         # nothing of the timed steps starts before e0
-    run_steps(step_dev, W, W + K)
-    for st in streams[1:]:
-        ek = torch.cuda.Event()
-        ek.record(st)
-        stream.wait_event(ek)                                     # e1 follows the last kernel of every stream
-    e1.record(stream)
-    barrier()
-    dev_ms = max_over_ranks(e0.elapsed_time(e1))
-    launches = sum(e.launch_count for e in engs) - l0
-    last_items = d_out[last_k][0].cpu().numpy().copy()
-    last_logits = d_out[last_k][1].cpu().numpy().copy()
-
-    # ---- roofline pass: the same K steps, ONE batch in flight, the kernel timed alone ------
-    eng.set_profiling(True)
-    s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    barrier()
-    s0.record(stream)
-    for i in range(W, W + K):
-        step_dev(i, 0, serial=True)
-    s1.record(stream)
-    barrier()
-    serial_ms = max_over_ranks(s0.elapsed_time(s1))
-    kern_ms, kern_n = eng.kernel_time()
-    eng.set_profiling(False)
-    fast_stats = None
-    if args.arith == "fast":
-        per = [e.fast_stats() for e in engs]
-        fast_stats = {k: (max(p[k] for p in per) if k == "max_err_over_bound" else sum(p[k] for p in per)) for k in per[0]}
-
-    # ---- e2e: host buffers through the C ABI (H2D + D2H inside) ---------------------------
-    run_steps(step_host, 0, W)
-    barrier()
-    t0 = time.perf_counter()
-    run_steps(step_host, W, W + K)
-    torch.cuda.synchronize(dev)
-    e2e_s = max_over_ranks(time.perf_counter() - t0)
+    sampler.wait_first(3.0)                                       # the box, once per rank) must not fall into a timed region
+    sampler.mark()
+    m = measure(args, env, args.items, do_cpu=not args.no_cpu_baseline, verify_strict=args.verify_strict)
     clocks = sampler.stop()
     gc.enable()
-    e2e_out = e2e_last[last_k]
-    assert (e2e_out[0] == last_items).all(), "host-buffer and device-buffer paths disagree"
 
-    value = world * B * K / (dev_ms * 1e-3)
-    e2e_value = world * B * K / e2e_s
+    L, rows = m["levels"], m["rows"]
     rows_u, bytes_u = algorithmic_bytes_per_user(L, E, T, args.topk, args.beam)
     peak, peak_src = hbm_peak()
-    kern_avg_ms = kern_ms / max(kern_n, 1)
-    achieved = B * bytes_u / (kern_avg_ms * 1e-3) / 1e9
+    value, e2e_value = m["value"], m["e2e_value"]
+    kern_ms = m.get("kern_ms_per_step", 0.0)
+    achieved = B * bytes_u / (kern_ms * 1e-3) / 1e9 if kern_ms else None
     traffic = None
+    kernel_name = "wave_score_kernel" if args.arith == "fast" else "beam_search_kernel<float,%d>" % E
     tp = os.path.join(ROOT, "profiles", "traffic.json")
     if os.path.exists(tp):
         try:
-            traffic = json.load(open(tp)).get("beam_search_kernel_dram_bytes_per_launch")
+            traffic = json.load(open(tp)).get(f"{kernel_name}@{args.items}")      # ncu dram bytes per launch for THIS catalogue, else null
         except Exception:
             traffic = None
 
-    strict_check = None
-    if args.verify_strict > 0 and args.arith == "fast":
-        nv = min(args.verify_strict, B)
-        fi, fl, fc = eng.tdm_retrieve(host_q[W + K - 1][:nv], args.beam, args.topk)
-        eng.set_arithmetic("strict")
-        si, sl, sc = eng.tdm_retrieve(host_q[W + K - 1][:nv], args.beam, args.topk)
-        eng.set_arithmetic("fast")
-        strict_check = {"users_checked": nv, "ids_identical": bool((fi == si).all() and (fc == sc).all()),
-                        "logits_bit_identical": bool((fl.view(np.uint32) == sl.view(np.uint32)).all())}
+    # ---- second workload: the structured ("trained-like") table, where the users' beams diverge -----------------------------
+    structured = None
+    if not args.no_structured and args.arith == "fast":
+        ms = measure(args, env, args.items, structured=True, target_s=min(args.target_sec, 0.4), do_e2e=False, do_roofline=True,
+                     verify_strict=min(256, B))
+        structured = {"workload": workload_name(args, args.items) + ", structured table (rank-8 component: sibling scores differ by far more than rounding)",
+                      "value": ms["value"], "unit": "users/s", "ms_per_step": ms["ms_per_step"], "R": ms["R"],
+                      "frac_in_flight": ms["value"] / world * bytes_u / 1e9 / peak,
+                      "kernel_frac": (B * bytes_u / (ms["kern_ms_per_step"] * 1e-3) / 1e9 / peak) if ms.get("kern_ms_per_step") else None,
+                      "unique_rows_per_batch": ms.get("unique_rows_per_batch"), "rows_per_batch": ms.get("rows_per_batch"),
+                      "unique_row_bytes_per_batch": ms.get("unique_row_bytes_per_batch"),
+                      "fast_stats": ms.get("fast_stats"), "parity_fast_vs_strict_kernel": ms.get("strict_check")}
 
-    # ---- cpu_baseline (rank 0, N=1 only): oracle on a bounded sample + parity check --------
-    cpu = None
-    parity = None
-    if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        from oracle import oracle as orc
-        orc.build()
-        params = eng.download_din_weights()
-        threads = os.cpu_count() or 1
-        probe_v, probe_dt, _ = cpu_run(args, tf, params, rows, host_q[W + K - 1][: 2 * threads], threads)
-        n = int(max(2 * threads, min(B * K, args.cpu_sample_sec * probe_v)))
-        nb = (n + B - 1) // B                                      # whole timed batches, newest first
-        sample_q = np.concatenate([host_q[W + K - 1 - j] for j in range(nb)])[:n]
-        v, dt, out = cpu_run(args, tf, params, rows, sample_q, threads)
-        gpu_i, gpu_l, _ = eng.tdm_retrieve(sample_q, args.beam, args.topk)
-        cpu = {"value": v, "unit": "users/s", "cores": threads, "kind": "port",
-               "sample": f"{n} users from the last {nb} timed batches, {dt:.1f} s, oracle/ C restatement on {threads} "
-                         f"host threads (the Scala+MKL reference cannot run here: no JVM)"}
-        parity = {"users_checked": n, "ids_identical": bool((out[0] == gpu_i).all()),
-                  "logits_bit_identical": bool((out[1].view(np.uint32) == gpu_l.view(np.uint32)).all())}
+    # ---- the larger catalogues of the north star (same step, same timing; 100 M needs ~141 GB of HBM) -------------------------
+    catalogues = {}
+    for name in [c for c in args.catalogues.split(",") if c]:
+        n_items = int(float(name.upper().replace("M", "e6").replace("K", "e3")))
+        if n_items == args.items:
+            continue
+        try:
+            import psutil
+            if n_items >= 50_000_000 and psutil.virtual_memory().available / max(world, 1) < 20e9:
+                catalogues[name] = {"skipped": "not enough host memory per rank to build the tree"}
+                continue
+            Lc = int(np.ceil(np.log2(n_items)))
+            need = ((1 << (Lc + 1)) - 1) * E * 4 * 2 + 4e9
+            free, _ = torch.cuda.mem_get_info(dev)
+            if need > free:
+                catalogues[name] = {"skipped": f"needs {need / 1e9:.0f} GB of HBM (table + bf16 hi|lo copy), {free / 1e9:.0f} GB free"}
+                continue
+            mc = measure(args, env, n_items, target_s=min(args.target_sec, 0.4), do_roofline=True,
+                         verify_strict=min(1024, B) if n_items >= 50_000_000 else 0, do_cpu=False)
+            _, bu = algorithmic_bytes_per_user(mc["levels"], E, T, args.topk, args.beam)
+            catalogues[name] = {"items": n_items, "levels": mc["levels"], "value": mc["value"], "e2e": mc["e2e_value"], "unit": "users/s",
+                                "ms_per_step": mc["ms_per_step"], "R": mc["R"], "node_table_gb": mc["rows"] * E * 4 / 1e9,
+                                "frac_in_flight": mc["value"] / world * bu / 1e9 / peak,
+                                "kernel_frac": (B * bu / (mc["kern_ms_per_step"] * 1e-3) / 1e9 / peak) if mc.get("kern_ms_per_step") else None,
+                                "parity": mc.get("strict_check"), "fast_stats": mc.get("fast_stats")}
+        except Exception as ex:                                    # noqa: BLE001
+            catalogues[name] = {"error": str(ex)[:300]}
 
     if rank == 0:
+        NF = m["NF"]
         line = {
             "metric": "users/sec beam-search retrieval (beam=200, topk=10, depth=ceil(log2 N))",
             "value": value, "unit": "users/s", "n_gpus": world, "steps": K, "warmup": W,
-            "ms_per_step": dev_ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "ms_per_step": m["ms_per_step"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic",
-            "config": {"workload": f"TDM synthetic {args.items} items, dim={E}, beam={args.beam}, batch={B}, "
-                                   f"topk={args.topk}, T={T}", "levels": L, "rows_scored_per_user": rows_u,
+            "config": {"workload": workload_name(args, args.items), "levels": L, "rows_scored_per_user": rows_u,
                        "algorithmic_bytes_per_user": bytes_u, "node_table_gb": rows * E * 4 / 1e9,
                        "parallelism": f"replicas x{world}, users sharded, no collective",
+                       "repeats": m["R"], "timed_region_s": m["timed_region_s"],
+                       "timed_region": f"the {K} steps are repeated R={m['R']} times inside every timed region (device and e2e) with "
+                                       f"query batches drawn from a pool of 64 distinct ones; ms_per_step = region / (steps x R)",
                        "batches_in_flight": NF,
-                       "in_flight": (f"{NF} host threads, one handle each (dmg_clone: one copy of the tables), take the steps round-robin; "
-                                     "the roofline object is from a serial pass over the same steps") if NF > 1 else "serial steps",
-                       "serial_ms_per_step": serial_ms / K,
-                       "l2": f"inputs larger than L2: {rows * E * 4 / 1e9:.2f} GB node table, fresh queries every step, no flush",
-                       "arithmetic": ("tcgen05 bf16x3 tensor-core scorer + certified cuts, strict fp32 re-score of "
-                                      "near-cut candidates and of the topk (ids and logits bit-identical to the CPU oracle)")
+                       "in_flight": (f"{NF} host threads started before the timed region, one handle each (dmg_clone: one copy of the tables), "
+                                     "take the steps round-robin; the roofline object is from a serial pass (one batch in flight)") if NF > 1 else "serial steps",
+                       "serial_ms_per_step": m.get("serial_ms_per_step"),
+                       "l2": f"inputs larger than L2: {rows * E * 4 / 1e9:.2f} GB node table + its bf16 hi|lo copy, 64 distinct query batches, no flush",
+                       "arithmetic": ("level-synchronous tcgen05 bf16x3 tensor-core scorer (TMA tile::gather4 from a bf16 hi|lo copy of the "
+                                      "table, 256 B per row like the fp32 rows) + certified cuts, strict fp32 re-score of near-cut candidates "
+                                      "and of the topk (ids and logits bit-identical to the CPU oracle)")
                        if args.arith == "fast" else "strict fp32 (sequential-k fma chains, bit-identical to the CPU oracle)",
-                       "fast_stats": fast_stats},
+                       "fast_stats": m.get("fast_stats")},
             "e2e": {"value": e2e_value, "unit": "users/s", "h2d_bytes_per_step": B * T * 4,
-                    "d2h_bytes_per_step": B * args.topk * 8 + B * 4, "ms_per_step": e2e_s / K * 1e3},
-            "gpu_launches": int(launches),
+                    "d2h_bytes_per_step": B * args.topk * 8 + B * 4, "ms_per_step": m["e2e_ms_per_step"], "timed_region_s": m["e2e_region_s"]},
+            "gpu_launches": int(round(m["launches"] * K)),
+            "gpu_launches_per_step": m["launches"],
             "roofline_in_flight": {"achieved": value / world * bytes_u / 1e9, "unit": "GB/s", "frac": value / world * bytes_u / 1e9 / peak,
                                    "note": "whole step with the batches in flight (value x algorithmic bytes per user), not a kernel timed alone"},
-            "roofline": {"bound": "hbm", "kernel": ("beam_search_fast_kernel" if args.arith == "fast" else "beam_search_kernel<float,%d>" % E), "achieved": achieved, "peak": peak,
-                         "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
-                         "kernel_ms_avg": kern_avg_ms, "kernel_launches_timed": int(kern_n),
-                         "kernel_share_of_step": kern_ms / serial_ms if world == 1 else None,
-                         "measured_on": "serial pass (one batch in flight), CUDA events around each launch of the kernel"},
-            "cpu_baseline": cpu,
-            "parity": parity,
-            "parity_fast_vs_strict_kernel": strict_check,
+            "roofline": {"bound": "hbm", "kernel": kernel_name, "achieved": achieved, "peak": peak,
+                         "unit": "GB/s", "frac": achieved / peak if achieved else None, "traffic": traffic, "peak_source": peak_src,
+                         "kernel_ms_per_step": kern_ms, "kernel_launches_per_step": m.get("kern_launches_per_step"),
+                         "kernel_ms_avg": kern_ms / max(m.get("kern_launches_per_step") or 1, 1),
+                         "kernel_share_of_step": kern_ms / m["serial_ms_per_step"] if m.get("serial_ms_per_step") else None,
+                         "measured_on": "serial pass (one batch in flight), CUDA events around every launch of the kernel (one per tree level); "
+                                        "achieved = the step's algorithmic bytes / the summed launch durations of the step"},
+            "cpu_baseline": m.get("cpu"),
+            "parity": m.get("parity"),
+            "parity_fast_vs_strict_kernel": m.get("strict_check"),
+            "structured": structured,
+            "catalogues": catalogues,
             "clocks": clocks,
         }
         print(json.dumps(line), flush=True)
-    for e in reversed(engs):
-        e.close()
     if world > 1:
         dist.destroy_process_group()
 

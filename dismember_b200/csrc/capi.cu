@@ -618,17 +618,14 @@ static int32_t wave_enqueue(dmg_handle_t h, const BeamParams<float> &p, const Fa
     DMG_CUDA(h, cudaFuncSetAttribute(score_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, WG::SMEM));
     DMG_CUDA(h, cudaFuncSetAttribute(score_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
     DMG_CUDA(h, cudaFuncSetAttribute(wave_strict_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)WaveStrictGeo::smem_bytes()));
-    cudaEvent_t e0 = nullptr, e1 = nullptr;
-    if (h->profiling) {
-        DMG_CUDA(h, cudaEventCreate(&e0));
-        DMG_CUDA(h, cudaEventCreate(&e1));
-        DMG_CUDA(h, cudaEventRecord(e0, h->stream));
-    }
     const bool pdl = !getenv("DMG_WAVE_NO_PDL");
     DMG_CUDA(h, launch_chain(wave_prologue_kernel, B, 256, 0, h->stream, false, wp));   // first of the chain: ordinary stream order behind K2
     h->launches += 1;
     const int tpu = (cap + 127) / 128, ntiles = B * tpu;
-    const int ctas_per_sm = getenv("DMG_WAVE_SCORE_CTAS") ? atoi(getenv("DMG_WAVE_SCORE_CTAS")) : 2;
+    // One scorer CTA per SM when several batches are in flight on this model (dmg_clone: the scorers of two batches then share
+    // every SM and one batch's select / strict kernels fill the other's gaps), two when the handle works alone (shortest batch).
+    const bool shared_model = h->parent != nullptr || h->n_clones.load() > 0;
+    const int ctas_per_sm = getenv("DMG_WAVE_SCORE_CTAS") ? std::max(1, std::min(2, atoi(getenv("DMG_WAVE_SCORE_CTAS")))) : (shared_model ? 1 : 2);
     const int grid = std::min(ntiles, ctas_per_sm * h->sm_count);
     int slot = 0;
     const int s_min = lower_log2(p.beam);                        // per-user beams only widen (Recommender.scala:28-31)
@@ -636,7 +633,17 @@ static int32_t wave_enqueue(dmg_handle_t h, const BeamParams<float> &p, const Fa
     const int last_level = stop_level >= 0 ? std::min(stop_level, p.leaf_level) : p.leaf_level;
     for (int level = s_min; level < last_level; level++) {
         DMG_CUDA(h, launch_chain(select_kernel, (B + 3) / 4, 128, 0, h->stream, pdl, wp, sw, level, slot));
-        DMG_CUDA(h, launch_chain(score_kernel, grid, WG::THREADS, WG::SMEM, h->stream, pdl, tmap, wp, w2, slot ^ 1, level + 1));
+        cudaEvent_t e0 = nullptr, e1 = nullptr;
+        if (h->profiling) {                                      // dmg_set_profiling: every launch of the dominant kernel timed alone
+            DMG_CUDA(h, cudaEventCreate(&e0));
+            DMG_CUDA(h, cudaEventCreate(&e1));
+            DMG_CUDA(h, cudaEventRecord(e0, h->stream));
+        }
+        DMG_CUDA(h, launch_chain(score_kernel, grid, WG::THREADS, WG::SMEM, h->stream, pdl && !h->profiling, tmap, wp, w2, slot ^ 1, level + 1));
+        if (h->profiling) {
+            DMG_CUDA(h, cudaEventRecord(e1, h->stream));
+            h->prof_events.emplace_back(e0, e1);
+        }
         if (getenv("DMG_WAVE_ABLATE") && level == atoi(getenv("DMG_WAVE_ABLATE"))) {
             // profiling aid: replay this level's scorer with parts switched off (scores go to a scratch buffer)
             static float *dummy = nullptr;
@@ -691,10 +698,6 @@ static int32_t wave_enqueue(dmg_handle_t h, const BeamParams<float> &p, const Fa
         h->launches += 3;
     }
     DMG_CUDA(h, cudaGetLastError());
-    if (h->profiling) {
-        DMG_CUDA(h, cudaEventRecord(e1, h->stream));
-        h->prof_events.emplace_back(e0, e1);
-    }
     return DMG_OK;
 }
 
