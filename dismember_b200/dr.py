@@ -14,14 +14,49 @@ from ._capi import Engine
 from .formats import tree_file
 
 
-def build_path_csr(ids, paths, K: int, reference_quirk: bool = False):
+def _improve(h: np.ndarray) -> np.ndarray:
+    """scala.collection.Hashing.improve on 32-bit ints (the hash every Scala 2.13 immutable.HashMap mixes keys with)."""
+    h = h.astype(np.uint32)
+    h = (h + ~(h << np.uint32(9))).astype(np.uint32)
+    h = h ^ (h >> np.uint32(14))
+    h = (h + (h << np.uint32(4))).astype(np.uint32)
+    return h ^ (h >> np.uint32(10))
+
+
+def champ_order(keys) -> np.ndarray:
+    """Int keys in the iteration order of a Scala 2.13 immutable.HashMap (the reference builds with Scala 2.13.8, build.sbt:4).
+
+    The map is a CHAMP trie over improve(key.##) (Int: the value itself), 5 bits per level from the least significant end;
+    the structure is canonical (a sub-tree with one entry is inlined into its parent), a node's iterator yields its own
+    entries in ascending slot order and then its child nodes in ascending slot order (ChampBaseIterator), depth first.
+    Hence the order is lexicographic in (continues below this level?, 5-bit digit) per level.  Known answer:
+    (1 to 10).toMap iterates 5, 10, 1, 6, 9, 2, 7, 3, 8, 4.
+    """
+    keys = np.asarray(keys, np.int64)
+    h = _improve(keys.astype(np.int32).view(np.uint32)).astype(np.uint64)
+    sortkey = np.zeros(len(keys), np.uint64)
+    alive = np.ones(len(keys), bool)
+    for lvl in range(7):
+        idx = np.flatnonzero(alive)
+        if len(idx) == 0:
+            break
+        prefix = h[idx] & np.uint64((1 << min(5 * (lvl + 1), 32)) - 1)
+        _, inv, cnt = np.unique(prefix, return_inverse=True, return_counts=True)
+        single = (cnt[inv] == 1) | (lvl == 6)                  # alone under this prefix: an entry of the node at this level
+        digit = (h[idx] >> np.uint64(5 * lvl)) & np.uint64(31)
+        sortkey[idx] |= ((~single).astype(np.uint64) * np.uint64(32) + digit) << np.uint64(6 * (6 - lvl))
+        alive[idx[single]] = False
+    return keys[np.argsort(sortkey, kind="stable")]
+
+
+def build_path_csr(ids, paths, K: int, keep_all_items: bool = False):
     """MappingOp.pathToItems as a CSR over path keys sum_d c_d K^(D-1-d).
 
-    The general form lists every item of a path in ascending item-index order.  The
-    reference builds the map with `flatMap` over a Map, which collapses duplicate paths to ONE
-    item per path (the last in hash-iteration order, MappingOp.scala:23-28); that order is a JVM
-    HashMap artefact that cannot be verified without a JVM, so `reference_quirk=True` keeps one item
-    per path (the largest item index) -- documented, not claimed bit-identical to the JVM.
+    Default = the reference: `itemPathMapping.flatMap { case (item, paths) => paths.map((_, item)) }` builds a
+    Map[Path, Int], so a path shared by several items keeps ONE of them -- the last one the flatMap visits, i.e. the last in
+    the immutable.HashMap's iteration order over the ids (MappingOp.scala:23-28; `champ_order` reproduces that order).
+    keep_all_items=True lists every item of a path in ascending id order instead (what the paper's structure means; not what
+    the reference code does).
     """
     ids = np.asarray(ids, np.int64)
     paths = np.asarray(paths, np.int64)                     # [n, J, D]
@@ -31,14 +66,19 @@ def build_path_csr(ids, paths, K: int, reference_quirk: bool = False):
         keys = keys * K + paths[:, :, d]
     flat_keys = keys.ravel()
     flat_items = np.repeat(ids, J)
-    order = np.lexsort((flat_items, flat_keys))
-    flat_keys, flat_items = flat_keys[order], flat_items[order]
-    keep = np.ones(len(flat_keys), bool)
-    keep[1:] = (flat_keys[1:] != flat_keys[:-1]) | (flat_items[1:] != flat_items[:-1])   # an item listed once per path
-    flat_keys, flat_items = flat_keys[keep], flat_items[keep]
-    if reference_quirk:
+    if keep_all_items:
+        order = np.lexsort((flat_items, flat_keys))
+        flat_keys, flat_items = flat_keys[order], flat_items[order]
+        keep = np.ones(len(flat_keys), bool)
+        keep[1:] = (flat_keys[1:] != flat_keys[:-1]) | (flat_items[1:] != flat_items[:-1])   # an item listed once per path
+        flat_keys, flat_items = flat_keys[keep], flat_items[keep]
+    else:
+        visit = np.empty(int(ids.max()) + 1 if len(ids) else 0, np.int64)
+        visit[champ_order(ids)] = np.arange(len(ids))       # position of every id in the HashMap's iteration
+        order = np.lexsort((visit[flat_items], flat_keys))
+        flat_keys, flat_items = flat_keys[order], flat_items[order]
         last = np.ones(len(flat_keys), bool)
-        last[:-1] = flat_keys[1:] != flat_keys[:-1]
+        last[:-1] = flat_keys[1:] != flat_keys[:-1]          # the last visitor of a path wins
         flat_keys, flat_items = flat_keys[last], flat_items[last]
     n_keys = K ** D
     off = np.zeros(n_keys + 1, np.int64)
@@ -58,14 +98,14 @@ class DeepRetrieval:
         self.engine.dr_load(num_item, K, D, T, E, layer_emb, layer_w, layer_b, rr_emb, rr_w, rr_b, sm_w, sm_b)
         return self
 
-    def load_mapping(self, path: str, reference_quirk: bool = False):
+    def load_mapping(self, path: str, keep_all_items: bool = False):
         items, ids, paths = tree_file.read_dr_mapping(path)
-        return self.set_mapping(items, ids, paths, reference_quirk)
+        return self.set_mapping(items, ids, paths, keep_all_items)
 
-    def set_mapping(self, items, ids, paths, reference_quirk: bool = False):
+    def set_mapping(self, items, ids, paths, keep_all_items: bool = False):
         self.item_id_mapping = {int(a): int(b) for a, b in zip(items, ids)}
         self.id_item_mapping = {v: k for k, v in self.item_id_mapping.items()}
-        off, flat = build_path_csr(ids, paths, self.shape[1], reference_quirk)
+        off, flat = build_path_csr(ids, paths, self.shape[1], keep_all_items)
         self.engine.dr_load_paths(off, flat)
         return self
 

@@ -92,3 +92,27 @@ def test_javaser_inject_into_the_reference_model(jtm_fix):
     assert arrs[0][1].size == new.size and (arrs[0][1] == new).all()
     back = javaser.inject_weights(out, params)
     assert back == data                                          # and back again: byte-identical to the original file
+
+
+def test_path_to_items_is_the_reference_map_not_a_multimap():
+    """MappingOp.pathToItems (MappingOp.scala:23-28) flatMaps a Map into (path -> item) pairs: a path shared by several
+    items keeps ONE, the last in the immutable.HashMap's iteration order over the ids (Scala 2.13.8, build.sbt:4)."""
+    import os
+    import numpy as np
+    from dismember_b200.dr import build_path_csr, champ_order
+    # known answers of Scala 2.13: (1 to 10).toMap / (0 until 20).toSet iterate in these orders
+    assert champ_order(np.arange(1, 11)).tolist() == [5, 10, 1, 6, 9, 2, 7, 3, 8, 4]
+    assert champ_order(np.arange(20)).tolist() == [0, 5, 10, 14, 1, 6, 9, 13, 2, 17, 12, 7, 3, 18, 16, 11, 8, 19, 4, 15]
+    f = np.load(os.path.join(os.path.dirname(__file__), "golden", "dr_fixture.npz"))       # data/dr/example_mapping.bin
+    ids, paths, K = f["map_ids"], f["map_paths"], int(f["K"])
+    off, flat = build_path_csr(ids, paths, K)
+    assert (np.diff(off) <= 1).all()                                  # a Map: at most one item per path
+    off_all, flat_all = build_path_csr(ids, paths, K, keep_all_items=True)
+    assert (np.diff(off_all) > 0).sum() == (np.diff(off) > 0).sum()   # the same set of paths
+    pos = np.empty(ids.max() + 1, np.int64)
+    pos[champ_order(ids)] = np.arange(len(ids))
+    shared = np.flatnonzero(np.diff(off_all) > 1)
+    assert len(shared) > 0                                            # the fixture does have shared paths
+    for k in shared[:200]:
+        items = flat_all[off_all[k]:off_all[k + 1]]
+        assert flat[off[k]] == items[np.argmax(pos[items])]           # the survivor is the last visitor

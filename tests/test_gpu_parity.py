@@ -310,7 +310,7 @@ def test_dr_synthetic_wide(engine, orc):
     engine.dr_load(*args)
     from dismember_b200.dr import build_path_csr
     paths = rng.integers(0, 4, (num_item, 3, D))            # few distinct paths -> long item lists
-    off, flat = build_path_csr(np.arange(num_item), paths, K)
+    off, flat = build_path_csr(np.arange(num_item), paths, K, keep_all_items=True)     # many items per path: long rerank lists
     engine.dr_load_paths(off, flat)
     seqs = rng.integers(-1, num_item, (20, T)).astype(np.int32)
     p, pr, c = engine.dr_beam_search(seqs, 100)

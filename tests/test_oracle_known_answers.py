@@ -151,3 +151,64 @@ def test_otm_deepfm_oracle_against_independent_float64(orc):
         cur = [c for p in cur for c in (2 * p + 1, 2 * p + 2)]
         scores = [out_ for out_ in m.forward(np.array(cur, np.int32), np.tile(s, (len(cur), 1)))]
     assert list(ids) == cur and (sc == np.array(scores)).all()
+
+
+def _bce_numpy(params, rows, E, T, node, seq, masked, labels):
+    """BCECriterionWithLogits (scalann/.../nn/BCECriterionWithLogits.scala:28-91): mean(max(x,0) - x z + log(1 + exp(-|x|)))"""
+    x = _din_numpy(params, rows, E, T, node, seq, masked)
+    return float(np.mean(np.maximum(x, 0.0) - x * labels + np.log1p(np.exp(-np.abs(x)))))
+
+
+@pytest.mark.parametrize("dtype", [np.float64, np.float32])
+def test_oracle_gradients_against_finite_differences(orc, dtype):
+    """The backward of every DIN layer + the criterion (orc_train.inc restates EmbeddingShare / LookupTable.updateEmbeddings,
+    Attention, Mask, SoftMax, MatMul, Concat, Linear, ReLU updateGradInput / accGradParameters) checked independently:
+    central differences of an independent float64 loss, for every dense parameter class and for touched / untouched table rows."""
+    rng = np.random.default_rng(5)
+    rows, E, T, n = 63, 16, 6, 24
+    params = rng.normal(0, 0.3, rows * E + 3 * E * E + 2 * E + 1)
+    node = rng.integers(0, rows, n).astype(np.int32)
+    seq = rng.integers(0, rows, (n, T)).astype(np.int32)
+    seq[rng.random((n, T)) < 0.25] = -1
+    seq[0] = -1                                      # a fully padded history
+    node[1] = seq[1, 2] = 7                          # the same row as item and as history of one sample
+    masked = seq == -1
+    mask_flat = np.flatnonzero(masked.ravel()).astype(np.int32)
+    labels = (rng.random(n) < 0.4).astype(np.float64)
+    grad, loss = orc.din_gradients(params.astype(dtype), rows, E, T, node, seq, mask_flat, labels.astype(dtype))
+    assert abs(float(loss) - _bce_numpy(params, rows, E, T, node, seq, masked, labels)) < (1e-12 if dtype == np.float64 else 2e-6)
+    o_w = rows * E
+    probe = list(rng.choice(rows * E, 60, replace=False)) + list(o_w + rng.choice(3 * E * E, 60, replace=False)) + \
+        list(range(o_w + 3 * E * E, o_w + 3 * E * E + 2 * E + 1, 3)) + [7 * E + 3, int(node[0]) * E]
+    h = 1e-6
+    worst = 0.0
+    for i in probe:
+        pp, pm = params.copy(), params.copy()
+        pp[i] += h; pm[i] -= h
+        fd = (_bce_numpy(pp, rows, E, T, node, seq, masked, labels) - _bce_numpy(pm, rows, E, T, node, seq, masked, labels)) / (2 * h)
+        worst = max(worst, abs(fd - float(grad[i])))
+    assert worst < (2e-8 if dtype == np.float64 else 3e-6), worst
+    used = np.zeros(rows, bool)
+    used[node] = True
+    used[seq[seq >= 0]] = True
+    g_emb = np.asarray(grad[:rows * E]).reshape(rows, E)
+    assert (g_emb[~used] == 0).all() and np.abs(g_emb[used]).sum() > 0          # scatter-add touches gathered rows only
+
+
+def test_oracle_adam_closed_form(orc):
+    """Adam.optimize (scalann/.../optim/Adam.scala:54-65): s = b1 s + (1-b1) g; r = b2 r + (1-b2) g^2; denom = sqrt(r) + eps;
+    w -= lr sqrt(1-b2^t)/(1-b1^t) s / denom, dense over every parameter (zero gradients still decay the moments)."""
+    rng = np.random.default_rng(9)
+    n = 1000
+    w = rng.normal(size=n); g = rng.normal(size=n); g[::7] = 0.0
+    s = rng.normal(size=n) * 0.1; r = np.abs(rng.normal(size=n)) * 0.01
+    for dtype, tol in ((np.float64, 1e-15), (np.float32, 2e-7)):
+        for t in (1, 2, 50):
+            wv, sv, rv = w.astype(dtype), s.astype(dtype), r.astype(dtype)
+            orc.adam_step(wv, g.astype(dtype), sv, rv, 1e-3, t)
+            s2 = 0.9 * s + 0.1 * g
+            r2 = 0.999 * r + 0.001 * g * g
+            w2 = w - 1e-3 * np.sqrt(1 - 0.999 ** t) / (1 - 0.9 ** t) * s2 / (np.sqrt(r2) + 1e-8)
+            assert np.abs(sv - s2).max() < tol * 10 and np.abs(rv - r2).max() < tol * 10
+            assert np.abs(wv - w2).max() < tol * 10 * max(1.0, np.abs(w2).max())
+            assert (sv[::7] == (0.9 * s.astype(dtype)[::7]).astype(dtype)).all() or dtype == np.float32   # zero gradient: pure decay
