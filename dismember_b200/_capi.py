@@ -67,11 +67,12 @@ def load_library(build_if_missing: bool = True):
         "dmg_set_fast_tolerance": [vp, dbl],
         "dmg_wave_probe": [vp, i32, vp, i32, i32, i32, i32, vp, vp, vp, vp],
         "dmg_kernel_time": [vp, C.POINTER(dbl), C.POINTER(i64)],
-        "dmg_load_tree_tdm": [vp, i32, i64, vp, vp, vp, i64, vp, vp],
+        "dmg_load_tree_tdm": [vp, i32, i64, vp, vp, vp, i64, vp, vp, vp],
         "dmg_load_tree_complete": [vp, i32, i64, vp, vp],
         "dmg_load_din_weights": [vp, i32, i64, i32, i32, vp],
         "dmg_init_din_weights": [vp, i32, i64, i32, i32, u64],
         "dmg_download_din_weights": [vp, vp, i64],
+        "dmg_din_shape": [vp, C.POINTER(i64), C.POINTER(i32), C.POINTER(i32), C.POINTER(i32)],
         "dmg_tdm_retrieve": [vp, i32, vp, i32, i32, i32, vp, vp, i32, vp, vp, vp],
         "dmg_tdm_retrieve_dev": [vp, i32, vp, i32, i32, i32, vp, vp, vp],
         "dmg_tdm_retrieve_dev_sync": [vp, i32, vp, i32, i32, i32, vp, vp, vp],
@@ -85,7 +86,7 @@ def load_library(build_if_missing: bool = True):
         "dmg_dr_retrieve": [vp, i32, vp, i32, i32, vp, vp, vp],
         "dmg_train_step": [vp, i64, vp, vp, vp, i64, vp, dbl, i32, vp],
         "dmg_din_gradients": [vp, i64, vp, vp, vp, i64, vp, vp, vp, i64],
-        "dmg_tdm_sample_expand": [vp, i32, vp, vp, vp, i32, u64, vp, vp, vp, C.POINTER(i32)],
+        "dmg_tdm_sample_expand": [vp, i32, vp, vp, vp, i32, i32, i32, u64, vp, vp, vp, C.POINTER(i32)],
         "dmg_jtm_item_weights": [vp, i32, vp, vp, vp, i32, i32, i32, i32, i32, vp],
         "dmg_jtm_assign_level": [vp, i32, vp, vp, i32, vp, i32, vp],
         "dmg_eval_metrics": [vp, i32, i32, vp, vp, vp, vp, vp],
@@ -216,6 +217,12 @@ class Engine:
         self._check(self.L.dmg_wave_probe(self.h, B, _p(seq), beam, int(use_mask), level, cap, _p(codes), _p(scores), _p(counts), _p(eps)))
         return codes, scores, counts, eps
 
+    def din_shape(self):
+        """-> (rows, embed_size, seq_len, dtype) of the loaded scorer"""
+        r, e, t, d = C.c_int64(), C.c_int32(), C.c_int32(), C.c_int32()
+        self._check(self.L.dmg_din_shape(self.h, C.byref(r), C.byref(e), C.byref(t), C.byref(d)))
+        return r.value, e.value, t.value, d.value
+
     def fast_stats(self):
         out = np.zeros(7, np.uint64)
         self._check(self.L.dmg_fast_stats(self.h, _p(out)))
@@ -233,11 +240,13 @@ class Engine:
         return ms.value, n.value
 
     # -- index structures -------------------------------------------------------
-    def load_tree_tdm(self, max_level, codes, node_ids, is_leaf, leaf_ids, leaf_codes):
+    def load_tree_tdm(self, max_level, codes, node_ids, is_leaf, leaf_ids, leaf_codes, prob=None):
         codes, node_ids, leaf_ids, leaf_codes = _i32(codes), _i32(node_ids), _i32(leaf_ids), _i32(leaf_codes)
         is_leaf = np.ascontiguousarray(is_leaf, np.uint8)
+        pr = None if prob is None else np.ascontiguousarray(prob, np.float32)
+        assert pr is None or len(pr) == len(codes)
         self._check(self.L.dmg_load_tree_tdm(self.h, int(max_level), len(codes), _p(codes), _p(node_ids), _p(is_leaf),
-                                             len(leaf_ids), _p(leaf_ids), _p(leaf_codes)))
+                                             len(leaf_ids), _p(leaf_ids), _p(leaf_codes), _p(pr)))
 
     def load_tree_complete(self, leaf_level, item_ids, leaf_ids):
         item_ids, leaf_ids = _i32(item_ids), _i32(leaf_ids)
@@ -523,7 +532,7 @@ class Engine:
                                              _p(labels), float(lr), int(step_t), _p(loss)))
         return loss[0]
 
-    def tdm_sample_expand(self, target_items, item_seq, layer_neg, start_level, seed):
+    def tdm_sample_expand(self, target_items, item_seq, layer_neg, start_level, seed, with_prob=False, tolerance=20):
         tg = _i32(target_items).ravel()
         seq = _i32(item_seq).reshape(len(tg), self.T)
         neg = _i32(layer_neg).ravel()
@@ -533,7 +542,7 @@ class Engine:
         oseq = np.empty((rows, self.T), np.int32)
         lab = np.empty(rows, np.float32)
         n = C.c_int32()
-        self._check(self.L.dmg_tdm_sample_expand(self.h, len(tg), _p(tg), _p(seq), _p(neg), start_level, seed, _p(node),
+        self._check(self.L.dmg_tdm_sample_expand(self.h, len(tg), _p(tg), _p(seq), _p(neg), start_level, int(with_prob), int(tolerance), seed, _p(node),
                                                  _p(oseq), _p(lab), C.byref(n)))
         assert n.value == rows
         return node, oseq, lab

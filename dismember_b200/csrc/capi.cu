@@ -68,7 +68,7 @@ DMG_API int32_t dmg_create(int32_t device, dmg_handle_t *out)
 
 static void free_tree(TreeDev &t)
 {
-    cudaFree(t.d_exists); cudaFree(t.d_leaf_item); cudaFree(t.d_id_code);
+    cudaFree(t.d_exists); cudaFree(t.d_leaf_item); cudaFree(t.d_id_code); cudaFree(t.d_cdf);
     t = TreeDev();
 }
 static void free_din(DinDev &d)
@@ -188,7 +188,7 @@ DMG_API int32_t dmg_kernel_time(dmg_handle_t h, double *total_ms, int64_t *n_lau
 // ------------------------------------------------------------------------------------- trees
 DMG_API int32_t dmg_load_tree_tdm(dmg_handle_t h, int32_t max_level, int64_t n_nodes, const int32_t *codes,
                                   const int32_t *node_ids, const uint8_t *is_leaf, int64_t n_items,
-                                  const int32_t *leaf_ids, const int32_t *leaf_codes)
+                                  const int32_t *leaf_ids, const int32_t *leaf_codes, const float *prob)
 {
     if (!h) return DMG_ERR_INVALID_ARG;
     DMG_TRY(model_is_shared(h, "dmg_load_tree_tdm"));
@@ -230,6 +230,19 @@ DMG_API int32_t dmg_load_tree_tdm(dmg_handle_t h, int32_t max_level, int64_t n_n
     DMG_TRY(h2d(h, t.d_exists, bm.data(), bm.size() * sizeof(uint32_t)));
     DMG_TRY(h2d(h, t.d_leaf_item, leaf_item.data(), leaf_item.size() * sizeof(int32_t)));
     DMG_TRY(h2d(h, t.d_id_code, id_code.data(), id_code.size() * sizeof(int32_t)));
+    if (prob) {                                                        // TreeNode.probality -> per-level cumulative weights (NegativeSampler.scala:59-66)
+        std::vector<double> cdf((size_t)n_codes, 0.0);
+        for (int64_t i = 0; i < n_nodes; i++) {
+            if (!(prob[i] >= 0.0f)) return fail(h, DMG_ERR_INVALID_ARG, "dmg_load_tree_tdm: node probabilities must be >= 0");
+            cdf[(size_t)codes[i]] = (double)prob[i];
+        }
+        for (int l = 0; l <= max_level; l++) {
+            const int64_t a = ((int64_t)1 << l) - 1, b = ((int64_t)2 << l) - 1;
+            for (int64_t c = a + 1; c < b; c++) cdf[(size_t)c] += cdf[(size_t)c - 1];
+        }
+        DMG_CUDA(h, cudaMalloc(&t.d_cdf, cdf.size() * sizeof(double)));
+        DMG_TRY(h2d(h, t.d_cdf, cdf.data(), cdf.size() * sizeof(double)));
+    }
     t.loaded = true; t.complete = false; t.max_level = max_level; t.n_codes = n_codes;
     t.non_leaf_offset = offset; t.max_code = mx_code; t.n_items = n_items;
     t.sparse_from = max_level + 1;                                     // levels above it are full: no bitmap probe on expansion
@@ -352,6 +365,14 @@ DMG_API int32_t dmg_init_din_weights(dmg_handle_t h, int32_t dtype, int64_t rows
     DMG_TRY(dtype == DMG_F32 ? make_transposes<float>(h) : make_transposes<double>(h));
     h->fast_dirty = true;
     d.loaded = true;
+    return DMG_OK;
+}
+
+DMG_API int32_t dmg_din_shape(dmg_handle_t h, int64_t *rows, int32_t *E, int32_t *T, int32_t *dtype)
+{
+    if (!h || !rows || !E || !T || !dtype) return DMG_ERR_INVALID_ARG;
+    if (!h->din.loaded) return fail(h, DMG_ERR_STATE, "no DIN / DeepFM weights loaded");
+    *rows = h->din.rows; *E = h->din.E; *T = h->din.T; *dtype = h->din.dtype;
     return DMG_OK;
 }
 

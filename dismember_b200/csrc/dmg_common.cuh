@@ -31,6 +31,7 @@ struct TreeDev {
     int32_t max_code = -1;         // DistTree.scala:36
     int64_t n_items = 0;
     int sparse_from = 0;           // lowest level with a missing code (max_level + 1 when every level is full)
+    double *d_cdf = nullptr;       // per-level inclusive prefix sums of Node.probality over the codes (NegativeSampler.levelProbs); null = no probabilities
 };
 
 struct DinDev {

@@ -263,7 +263,8 @@ __global__ void tdm_sample_kernel(int n_targets, const int32_t *__restrict__ tar
                                   int32_t non_leaf_offset, const uint32_t *__restrict__ exists, int max_level,
                                   const int32_t *__restrict__ layer_neg, const int32_t *__restrict__ level_off,
                                   int start_level, int layer_sum, uint64_t seed, int32_t *__restrict__ out_node,
-                                  float *__restrict__ out_label, int32_t *__restrict__ err_flag)
+                                  float *__restrict__ out_label, int32_t *__restrict__ err_flag,
+                                  const double *__restrict__ cdf, int tolerance)
 {
     const int n_lv = max_level + 1 - start_level;
     int gid = blockIdx.x * blockDim.x + threadIdx.x;
@@ -284,6 +285,41 @@ __global__ void tdm_sample_kernel(int n_targets, const int32_t *__restrict__ tar
     uint64_t ctr = 0;
     const uint64_t key = splitmix64(seed ^ splitmix64(((uint64_t)t << 8) | (uint64_t)level));
     const int max_try = 64 * (neg + 4);
+    if (cdf) {
+        // sampleFromCategoricalDistribution (NegativeSampler.scala:116-144): at most neg + tolerance draws from the level's
+        // EnumeratedIntegerDistribution over Node.probality, keeping new codes != the positive; what is still missing is drawn
+        // uniformly over the level WITHOUT excluding the positive (the reference's fallback loop only asks codeNodeMap.contains)
+        const double total = cdf[lstart + lsize - 1];
+        int tries = 0;
+        while (total > 0.0 && got < neg && tries < neg + tolerance) {
+            tries++;
+            const double u = (double)(splitmix64(key + ctr++) >> 11) * (1.0 / 9007199254740992.0) * total;
+            int64_t lo = 0, hi = lsize - 1;                              // first code of the level with cdf > u
+            while (lo < hi) { const int64_t mid = (lo + hi) >> 1; if (cdf[lstart + mid] > u) hi = mid; else lo = mid + 1; }
+            const int64_t c = lstart + lo;
+            if (c == pos) continue;
+            bool dup = false;
+            for (int i = 0; i < got; i++) dup |= (dst[1 + i] == (int32_t)c);
+            if (dup) continue;
+            int i = got++;
+            while (i > 0 && dst[i] > (int32_t)c) { dst[1 + i] = dst[i]; i--; }
+            dst[1 + i] = (int32_t)c;
+        }
+        int guard = 0;
+        while (got < neg && guard++ < max_try) {
+            const int64_t c = lstart + (int64_t)(splitmix64(key + ctr++) % (uint64_t)lsize);
+            if (!code_exists(exists, c)) continue;
+            bool dup = false;
+            for (int i = 0; i < got; i++) dup |= (dst[1 + i] == (int32_t)c);
+            if (dup) continue;
+            int i = got++;
+            while (i > 0 && dst[i] > (int32_t)c) { dst[1 + i] = dst[i]; i--; }
+            dst[1 + i] = (int32_t)c;
+        }
+        for (int i = got; i < neg; i++) dst[1 + i] = -1;                // fewer nodes than negatives: padding rows
+        for (int i = 0; i < neg; i++) lab[1 + i] = 0.0f;
+        return;
+    }
     while (got < neg && (int)ctr < max_try) {
         const int64_t c = lstart + (int64_t)(splitmix64(key + ctr++) % (uint64_t)lsize);
         if (c == pos || !code_exists(exists, c)) continue;
@@ -551,8 +587,8 @@ DMG_API int32_t dmg_train_step(dmg_handle_t h, int64_t rows, const int32_t *node
 }
 
 DMG_API int32_t dmg_tdm_sample_expand(dmg_handle_t h, int32_t n_targets, const int32_t *target_items, const int32_t *item_seq,
-                                      const int32_t *layer_neg, int32_t start_level, uint64_t seed, int32_t *out_node,
-                                      int32_t *out_seq, float *out_label, int32_t *out_rows)
+                                      const int32_t *layer_neg, int32_t start_level, int32_t with_prob, int32_t tolerance,
+                                      uint64_t seed, int32_t *out_node, int32_t *out_seq, float *out_label, int32_t *out_rows)
 {
     if (!h) return DMG_ERR_INVALID_ARG;
     const TreeDev &t = h->tree;
@@ -562,6 +598,8 @@ DMG_API int32_t dmg_tdm_sample_expand(dmg_handle_t h, int32_t n_targets, const i
         return fail(h, DMG_ERR_INVALID_ARG, "bad arguments");
     if (start_level < 1 || start_level > t.max_level)
         return fail(h, DMG_ERR_INVALID_ARG, "start sample level should be at least 1, got %d", start_level);   // NegativeSampler.scala:23
+    if (with_prob && !t.d_cdf) return fail(h, DMG_ERR_STATE, "withProb sampling needs node probabilities (dmg_load_tree_tdm prob)");
+    if (tolerance < 0) return fail(h, DMG_ERR_INVALID_ARG, "tolerance must be >= 0");
     const int L = t.max_level, T = h->din.T;
     std::vector<int32_t> level_off(L + 2, 0);
     int layer_sum = 0;
@@ -595,7 +633,8 @@ DMG_API int32_t dmg_tdm_sample_expand(dmg_handle_t h, int32_t n_targets, const i
     uint8_t *d_mask = cw.take<uint8_t>((size_t)n_targets * T);
     const int n_lv = L + 1 - start_level;
     tdm_sample_kernel<<<(n_targets * n_lv + 127) / 128, 128, 0, h->stream>>>(n_targets, dt, t.d_id_code, t.non_leaf_offset, t.d_exists, L,
-                                                                           dneg, doff, start_level, layer_sum, seed, d_node, d_lab, h->d_flags);
+                                                                           dneg, doff, start_level, layer_sum, seed, d_node, d_lab, h->d_flags,
+                                                                           with_prob ? t.d_cdf : nullptr, tolerance);
     const int64_t nseq = (int64_t)n_targets * T;
     // history ids -> codes (TDMTree.idToCode) then repeated layer_sum times
     DMG_TRY(dmg_tdm_ids_to_codes(h, dsq, nseq, 1, d_codes, d_mask));

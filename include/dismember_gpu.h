@@ -86,11 +86,13 @@ DMG_API int32_t dmg_kernel_time(dmg_handle_t h, double *total_ms, int64_t *n_lau
  * nonLeafOffset = max(leaf id)+1 and maxCode = max(leaf code) are derived as in :35-36.
  * All writers of the format put every leaf at max_level (TreeBuilder.flattenLeaves
  * TreeBuilder.scala:133-140, JTMTree.writeTree JTMTree.scala:115-182); a tree with a leaf
- * above max_level is rejected with DMG_ERR_UNSUPPORTED. */
+ * above max_level is rejected with DMG_ERR_UNSUPPORTED.  prob (nullable) = Node.probality of
+ * every stored node (tree.proto:4-9), the weights of NegativeSampler's withProb sampling. */
 DMG_API int32_t dmg_load_tree_tdm(dmg_handle_t h, int32_t max_level, int64_t n_nodes,
                                   const int32_t *codes, const int32_t *node_ids,
                                   const uint8_t *is_leaf, int64_t n_items,
-                                  const int32_t *leaf_ids, const int32_t *leaf_codes);
+                                  const int32_t *leaf_ids, const int32_t *leaf_codes,
+                                  const float *prob);
 
 /* OTM: complete binary tree; itemIdMapping item -> leaf node id
  * (otm/src/main/scala/com/mass/otm/model/OTM.scala:6-12, Serialization.loadMapping).
@@ -110,6 +112,8 @@ DMG_API int32_t dmg_load_din_weights(dmg_handle_t h, int32_t dtype, int64_t rows
  * (randn(0, 0.05), biases 0: EmbeddingShare.scala:21, Linear.scala:12-13), counter-based RNG. */
 DMG_API int32_t dmg_init_din_weights(dmg_handle_t h, int32_t dtype, int64_t rows, int32_t E,
                                      int32_t T, uint64_t seed);
+/* Shape of the loaded scorer: node-table rows, embed_size, seq_len, DMG_F32 / DMG_F64 (a binding sizes its arrays with it). */
+DMG_API int32_t dmg_din_shape(dmg_handle_t h, int64_t *rows, int32_t *E, int32_t *T, int32_t *dtype);
 /* Copy the compact vector back (Serialization.saveModel side).  n = element count. */
 DMG_API int32_t dmg_download_din_weights(dmg_handle_t h, void *params, int64_t n);
 
@@ -230,11 +234,16 @@ DMG_API int32_t dmg_din_gradients(dmg_handle_t h, int64_t rows, const int32_t *n
                                   const void *labels, void *out_loss, void *out_grad, int64_t n_grad);
 /* NegativeSampler.sample + MiniBatch.convert (tdm/.../utils/NegativeSampler.scala:76-158,
  * tdm/.../dataset/MiniBatch.scala:49-88): per target item the ancestor positives and
- * layer_neg[l] uniform negatives per level >= start_level, ascending code order per level.
- * out arrays sized n_targets * layer_sum. */
+ * layer_neg[l] negatives per level >= start_level, ascending code order per level (BitSet.toList):
+ * uniform over the level's existing codes (with_prob = 0, sampleFromUniformDistribution :146-158)
+ * or drawn from the level's Node.probality weights with at most layer_neg[l] + tolerance draws and
+ * the reference's uniform fallback (with_prob = 1, sampleFromCategoricalDistribution :116-144;
+ * `tolerance` = the conf key sample_tolerance).  The reference seeds from nanoTime, so only the
+ * distribution and the ordering are reproducible.  out arrays sized n_targets * layer_sum. */
 DMG_API int32_t dmg_tdm_sample_expand(dmg_handle_t h, int32_t n_targets, const int32_t *target_items,
                                       const int32_t *item_seq, const int32_t *layer_neg,
-                                      int32_t start_level, uint64_t seed, int32_t *out_node,
+                                      int32_t start_level, int32_t with_prob, int32_t tolerance,
+                                      uint64_t seed, int32_t *out_node,
                                       int32_t *out_seq, float *out_label, int32_t *out_rows);
 
 /* ---- JTM tree learning ---------------------------------------------------------------- */

@@ -30,6 +30,17 @@ def test_no_extra_public_symbols():
     assert exported == set(dmg.declared_symbols())
 
 
+def test_jni_shim_type_checks_against_the_header():
+    """jni/com_mass_gpu_DismemberGPU.c cannot be built here (no JDK): type-check it against include/dismember_gpu.h with a
+    stand-in jni.h, so that a signature drifting between the C ABI and the shim is caught (the shim forwards 1:1)."""
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run(["gcc", "-fsyntax-only", "-Wall", "-Werror=implicit-function-declaration", "-Werror=incompatible-pointer-types",
+                        "-I", os.path.join(root, "tests", "jni_stub"), "-I", os.path.join(root, "include"),
+                        os.path.join(root, "jni", "com_mass_gpu_DismemberGPU.c")], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+
+
 def test_product_never_imports_oracle():
     """oracle/ is test infrastructure: nothing under dismember_b200/ may import, include or dlopen it."""
     import re

@@ -217,3 +217,63 @@ def test_jtm_item_weights(engine, orc, jtm_fix):
                     lv -= 1
                 want[i, ci] = wsum
         assert (got.view(np.uint32) == want.view(np.uint32)).all(), (old_level, level)
+
+
+def test_categorical_sampler_follows_node_probabilities(engine, jtm_fix):
+    """NegativeSampler.sampleFromCategoricalDistribution (tdm/.../utils/NegativeSampler.scala:116-144): negatives of a level are
+    drawn from the level's Node.probality weights (levelProbs :59-66), new codes != the positive only, ascending order.  The
+    reference seeds a MersenneTwister from nanoTime, so parity is distributional: chi-square of the drawn codes of one level
+    against p_c / (1 - p_pos) (one negative per draw, the same target every time)."""
+    f = jtm_fix
+    L = int(f["max_level"])
+    rng = np.random.default_rng(3)
+    codes = f["codes"].astype(np.int64)
+    prob = rng.gamma(0.6, 1.0, len(codes)).astype(np.float32) + 1e-3          # skewed popularity
+    engine.load_tree_tdm(L, f["codes"], f["node_ids"], f["is_leaf"], f["leaf_ids"], f["leaf_codes"], prob=prob)
+    engine.load_din_weights(f["params"], 8191, 16, 10)
+    n = 40000
+    target = int(f["leaf_ids"][17])
+    targets = np.full(n, target, np.int32)
+    seqs = np.zeros((n, 10), np.int32)
+    layer_neg = np.ones(L + 1, np.int32)
+    layer_neg[0] = 0
+    node, _, lab = engine.tdm_sample_expand(targets, seqs, layer_neg, 1, seed=5, with_prob=True, tolerance=20)
+    layer_sum = 2 * L
+    node = node.reshape(n, layer_sum)
+    assert (lab.reshape(n, layer_sum)[:, 0::2] == 1).all() and (lab.reshape(n, layer_sum)[:, 1::2] == 0).all()
+    level = 6                                                                 # 64 codes, all present in the fixture tree
+    lo, hi = 2 ** level - 1, 2 ** (level + 1) - 1
+    pos = node[0, 2 * (level - 1)]
+    negs = node[:, 2 * (level - 1) + 1]
+    assert ((negs >= lo) & (negs < hi) & (negs != pos)).all()
+    p_of = dict(zip(codes.tolist(), prob.astype(np.float64).tolist()))
+    lv_codes = np.array([c for c in range(lo, hi) if c in p_of and c != pos])
+    w = np.array([p_of[int(c)] for c in lv_codes])
+    expect = n * w / w.sum()
+    got = np.array([(negs == c).sum() for c in lv_codes], np.float64)
+    chi2 = float(((got - expect) ** 2 / expect).sum())
+    dof = len(lv_codes) - 1
+    assert chi2 < dof + 5 * np.sqrt(2 * dof), (chi2, dof)                     # 5 sigma of a chi-square with dof degrees of freedom
+    # uniform draws on the same tree do NOT follow these weights (the test has power)
+    node_u, _, _ = engine.tdm_sample_expand(targets, seqs, layer_neg, 1, seed=5)
+    got_u = np.array([(node_u.reshape(n, layer_sum)[:, 2 * (level - 1) + 1] == c).sum() for c in lv_codes], np.float64)
+    assert float(((got_u - expect) ** 2 / expect).sum()) > 20 * dof
+    # several negatives per level: distinct, ascending, never the positive while the tolerance holds
+    layer_neg2 = np.array([0, 1, 2, 3, 4, 5, 6, 7, 8, 9, 10, 11, 12], np.int32)
+    node2, _, _ = engine.tdm_sample_expand(targets[:500], seqs[:500], layer_neg2, 1, seed=7, with_prob=True, tolerance=200)
+    ls2 = int(sum(1 + x for x in layer_neg2[1:]))
+    node2 = node2.reshape(500, ls2)
+    off = 0
+    for lvl in range(1, L + 1):
+        k = int(layer_neg2[lvl])
+        blk = node2[:, off:off + 1 + k]
+        if k > 1:
+            assert (np.diff(blk[:, 1:], axis=1) > 0).all()
+        if lvl >= 4:
+            assert (blk[:, 1:] != blk[:, :1]).all()
+        off += 1 + k
+    # without probabilities the withProb sampler is refused
+    engine.load_tree_tdm(L, f["codes"], f["node_ids"], f["is_leaf"], f["leaf_ids"], f["leaf_codes"])
+    from dismember_b200 import DmgError
+    with pytest.raises(DmgError):
+        engine.tdm_sample_expand(targets[:4], seqs[:4], layer_neg, 1, seed=5, with_prob=True)
