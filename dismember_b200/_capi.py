@@ -72,6 +72,7 @@ def load_library(build_if_missing: bool = True):
         "dmg_load_din_weights": [vp, i32, i64, i32, i32, vp],
         "dmg_init_din_weights": [vp, i32, i64, i32, i32, u64],
         "dmg_download_din_weights": [vp, vp, i64],
+        "dmg_otm_pseudo_targets": [vp, i32, vp, vp, vp, i32, i32, i32, vp, vp, vp],
         "dmg_din_shape": [vp, C.POINTER(i64), C.POINTER(i32), C.POINTER(i32), C.POINTER(i32)],
         "dmg_tdm_retrieve": [vp, i32, vp, i32, i32, i32, vp, vp, i32, vp, vp, vp],
         "dmg_tdm_retrieve_dev": [vp, i32, vp, i32, i32, i32, vp, vp, vp],
@@ -531,6 +532,20 @@ class Engine:
         self._check(self.L.dmg_dp_train_step(self.h, len(node), _p(node), _p(seq), _p(m), 0 if m is None else len(m),
                                              _p(labels), float(lr), int(step_t), _p(loss)))
         return loss[0]
+
+    def otm_pseudo_targets(self, leaf_seq, target_off, targets, leaf_level, start_level, use_mask=True, M=None):
+        """OTMTree.optimalPseudoTargets on the device -> (ids [n_lvl, B, M], vals, counts [n_lvl, B]), levels start_level + 1 .. leaf_level"""
+        seq = _i32(leaf_seq).reshape(-1, self.T)
+        B = len(seq)
+        off = np.ascontiguousarray(target_off, np.int64)
+        tg = _i32(targets).ravel()
+        M = int(M or max(1, int(np.diff(off).max())))
+        n_lvl = leaf_level - start_level
+        ids = np.empty((n_lvl, B, M), np.int32)
+        vals = np.empty((n_lvl, B, M), np.float64)
+        cnt = np.empty((n_lvl, B), np.int32)
+        self._check(self.L.dmg_otm_pseudo_targets(self.h, B, _p(seq), _p(off), _p(tg), start_level, int(use_mask), M, _p(ids), _p(vals), _p(cnt)))
+        return ids, vals, cnt
 
     def tdm_sample_expand(self, target_items, item_seq, layer_neg, start_level, seed, with_prob=False, tolerance=20):
         tg = _i32(target_items).ravel()

@@ -655,6 +655,145 @@ DMG_API int32_t dmg_tdm_sample_expand(dmg_handle_t h, int32_t n_targets, const i
     return DMG_OK;
 }
 
+// ---- K8: OTM pseudo targets, bottom up, on the device ---------------------------------------------------------------------------
+// OTMTree.optimalPseudoTargets / computeTargets / computeChildrenScores (otm/.../tree/OTMTree.scala:27-46, 104-172).  Per level:
+// otm_pt_expand_kernel lists (node, sibling, history) rows for every node of every user's list, the fp64 row scorer (model.forward)
+// scores the nodes and the siblings, otm_pt_combine_kernel turns them into the parents' clipped targets.  Lists are kept sorted by
+// node id in [B][M] slots (-1 padding): the reference's Lists come out of Maps and are only ever looked up by id.
+namespace {
+__global__ void otm_pt_expand_kernel(int B, int M, int T, const int32_t *__restrict__ ids, const int32_t *__restrict__ cnt,
+                                     const int32_t *__restrict__ seqs, int use_mask, int32_t *__restrict__ pos, int32_t *__restrict__ neg,
+                                     int32_t *__restrict__ rseq, uint8_t *__restrict__ rmask)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= B * M) return;
+    const int u = i / M, k = i % M;
+    const bool live = k < cnt[u];
+    const int32_t id = live ? ids[i] : -1;
+    pos[i] = id;
+    neg[i] = live ? ((id % 2 == 0) ? id - 1 : id + 1) : -1;          // OTMTree.scala:143
+    for (int j = 0; j < T; j++) {
+        const int32_t c = live ? seqs[(size_t)u * T + j] : -1;
+        rseq[(size_t)i * T + j] = c;
+        rmask[(size_t)i * T + j] = (use_mask && c == -1) ? 1 : 0;
+    }
+}
+__global__ void otm_pt_combine_kernel(int B, int M, const int32_t *__restrict__ cid, const double *__restrict__ cval,
+                                      const int32_t *__restrict__ ccnt, const double *__restrict__ ppos, const double *__restrict__ pneg,
+                                      int32_t *__restrict__ pid, double *__restrict__ pval, int32_t *__restrict__ pcnt)
+{
+    const int u = blockIdx.x * blockDim.x + threadIdx.x;
+    if (u >= B) return;
+    const int n = ccnt[u];
+    int c = 0;
+    for (int k = 0; k < M; k++) { pid[(size_t)u * M + k] = -1; pval[(size_t)u * M + k] = 0.0; }
+    for (int k = 0; k < n; k++) {
+        const int32_t id = cid[(size_t)u * M + k], sib = (id % 2 == 0) ? id - 1 : id + 1;
+        double neg_label = 0.0;                                   // nodes.find(_.id == nn): the sibling's score if it is listed (:146-150)
+        for (int q = 0; q < n; q++) if (cid[(size_t)u * M + q] == sib) { neg_label = cval[(size_t)u * M + q]; break; }
+        const double label = ppos[(size_t)u * M + k] >= pneg[(size_t)u * M + k] ? cval[(size_t)u * M + k] : neg_label;   // :117-118
+        const int32_t par = (id - 1) >> 1;
+        int j = 0;
+        while (j < c && pid[(size_t)u * M + j] != par) j++;
+        if (j == c) { pid[(size_t)u * M + c] = par; c++; }            // children are id-sorted, so parents arrive in ascending order
+        pval[(size_t)u * M + j] = __dadd_rn(pval[(size_t)u * M + j], label);                                             // groupMapReduce(_ + _)
+    }
+    for (int j = 0; j < c; j++) {
+        const double v = pval[(size_t)u * M + j];
+        pval[(size_t)u * M + j] = v < 0.0 ? 0.0 : (v > 1.0 ? 1.0 : v);                                                   // clipValue(_, 0, 1)
+    }
+    pcnt[u] = c;
+}
+}  // namespace
+
+DMG_API int32_t dmg_otm_pseudo_targets(dmg_handle_t h, int32_t B, const int32_t *leaf_seq, const int64_t *target_off,
+                                       const int32_t *target_leaves, int32_t start_level, int32_t use_mask, int32_t M,
+                                       int32_t *out_ids, double *out_vals, int32_t *out_counts)
+{
+    if (!h) return DMG_ERR_INVALID_ARG;
+    DinDev &d = h->din;
+    const TreeDev &t = h->tree;
+    if (!t.loaded || !t.complete || !d.loaded) return fail(h, DMG_ERR_STATE, "needs a complete tree (dmg_load_tree_complete) and DIN weights");
+    if (d.dtype != DMG_F64 || d.kind != 0) return fail(h, DMG_ERR_STATE, "OTM scorer is DeepModel[Double] DIN: load DMG_F64 DIN weights");
+    if (d.sharded) return fail(h, DMG_ERR_STATE, "the node table is sharded: not supported here");
+    const int L = t.max_level, n_lvl = L - start_level;
+    if (B <= 0 || M <= 0 || !leaf_seq || !target_off || !target_leaves || !out_ids || !out_vals || !out_counts || start_level < 0 || n_lvl <= 0)
+        return fail(h, DMG_ERR_INVALID_ARG, "bad arguments");
+    DMG_CUDA(h, cudaSetDevice(h->device));
+    const int T = d.T, E = d.E;
+    const size_t BM = (size_t)B * M;
+    // leaf lists on the host: Node(target, 1.0), sorted by id, duplicates collapsed
+    std::vector<int32_t> ids0(BM, -1), cnt0(B, 0);
+    std::vector<double> val0(BM, 0.0);
+    const int64_t leaf_start = ((int64_t)1 << L) - 1, leaf_end = ((int64_t)2 << L) - 1;
+    for (int u = 0; u < B; u++) {
+        std::vector<int32_t> v(target_leaves + target_off[u], target_leaves + target_off[u + 1]);
+        std::sort(v.begin(), v.end());
+        v.erase(std::unique(v.begin(), v.end()), v.end());
+        if ((int)v.size() > M) return fail(h, DMG_ERR_INVALID_ARG, "user %d has %d distinct targets, M = %d", u, (int)v.size(), M);
+        for (size_t k = 0; k < v.size(); k++) {
+            if (v[k] < leaf_start || v[k] >= leaf_end) return fail(h, DMG_ERR_INDEX, "target %d of user %d is not a leaf node id", v[k], u);
+            ids0[(size_t)u * M + k] = v[k]; val0[(size_t)u * M + k] = 1.0;
+        }
+        cnt0[u] = (int32_t)v.size();
+    }
+    const size_t need = Carver::need({(size_t)B * T * 4, (size_t)n_lvl * BM * 4, (size_t)n_lvl * BM * 8, (size_t)n_lvl * B * 4, BM * 4, BM * 4,
+                                      BM * T * 4, BM * T, BM * 8, BM * 8});
+    DMG_TRY(ensure_dev(h, h->s_work, need));
+    Carver cw(h->s_work.d);
+    int32_t *d_seq = cw.take<int32_t>((size_t)B * T);
+    int32_t *d_ids = cw.take<int32_t>((size_t)n_lvl * BM);
+    double *d_vals = cw.take<double>((size_t)n_lvl * BM);
+    int32_t *d_cnt = cw.take<int32_t>((size_t)n_lvl * B);
+    int32_t *d_pos = cw.take<int32_t>(BM), *d_neg = cw.take<int32_t>(BM), *d_rseq = cw.take<int32_t>(BM * T);
+    uint8_t *d_rmask = cw.take<uint8_t>(BM * T);
+    double *d_pp = cw.take<double>(BM), *d_pn = cw.take<double>(BM);
+    DMG_CUDA(h, cudaMemcpyAsync(d_seq, leaf_seq, (size_t)B * T * 4, cudaMemcpyHostToDevice, h->stream));
+    DMG_CUDA(h, cudaMemcpyAsync(d_ids + (size_t)(n_lvl - 1) * BM, ids0.data(), BM * 4, cudaMemcpyHostToDevice, h->stream));
+    DMG_CUDA(h, cudaMemcpyAsync(d_vals + (size_t)(n_lvl - 1) * BM, val0.data(), BM * 8, cudaMemcpyHostToDevice, h->stream));
+    DMG_CUDA(h, cudaMemcpyAsync(d_cnt + (size_t)(n_lvl - 1) * B, cnt0.data(), (size_t)B * 4, cudaMemcpyHostToDevice, h->stream));
+    check_index_kernel<<<(unsigned)(((size_t)B * T + 255) / 256), 256, 0, h->stream>>>(d_seq, (int64_t)B * T, d.rows, h->d_flags);
+    h->launches += 1;
+    const double scale = 1.0 / std::sqrt((double)E);
+    for (int li = n_lvl - 1; li > 0; li--) {
+        const int32_t *cid = d_ids + (size_t)li * BM, *ccnt = d_cnt + (size_t)li * B;
+        const double *cval = d_vals + (size_t)li * BM;
+        otm_pt_expand_kernel<<<(unsigned)((BM + 255) / 256), 256, 0, h->stream>>>(B, M, T, cid, ccnt, d_seq, use_mask, d_pos, d_neg, d_rseq, d_rmask);
+        for (int pass = 0; pass < 2; pass++) {
+            // QUIRK kept: without a mask input the reference scores the NEGATIVE tensor for both predictions (OTMTree.scala:157-161)
+            const int32_t *nodes = (pass == 0 && use_mask) ? d_pos : d_neg;
+            double *out = pass == 0 ? d_pp : d_pn;
+            cudaError_t terr = cudaSuccess;
+            if (!rows_forward_tiled<double>(E, d.emb<double>(), (const double *)d.d_wattT, (const double *)d.d_w1T, d.b1<double>(), d.w2<double>(),
+                                            d.b2<double>(), scale, T, (int64_t)BM, nodes, d_rseq, d_rmask, out, h->sm_count, h->smem_per_sm,
+                                            h->smem_optin, h->stream, &terr)) {
+                const size_t smem = (size_t)kRowsRB * ((size_t)4 * E + (size_t)T * E + T + 1) * 8;
+                auto kern = din_rows_forward_kernel<double>;
+                DMG_CUDA(h, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+                kern<<<(int)std::min<int64_t>(((int64_t)BM + kRowsRB - 1) / kRowsRB, (int64_t)h->sm_count * 8), kRowsThreads, smem, h->stream>>>(
+                    d.emb<double>(), (const double *)d.d_wattT, (const double *)d.d_w1T, d.b1<double>(), d.w2<double>(), d.b2<double>(), scale, E, T,
+                    (int64_t)BM, nodes, d_rseq, d_rmask, out);
+            }
+            DMG_CUDA(h, terr);
+        }
+        otm_pt_combine_kernel<<<(B + 127) / 128, 128, 0, h->stream>>>(B, M, cid, cval, ccnt, d_pp, d_pn, d_ids + (size_t)(li - 1) * BM,
+                                                                     d_vals + (size_t)(li - 1) * BM, d_cnt + (size_t)(li - 1) * B);
+        h->launches += 4;
+    }
+    DMG_CUDA(h, cudaGetLastError());
+    int32_t flag = 0;
+    DMG_CUDA(h, cudaMemcpyAsync(&flag, h->d_flags, 4, cudaMemcpyDeviceToHost, h->stream));
+    DMG_CUDA(h, cudaMemcpyAsync(out_ids, d_ids, (size_t)n_lvl * BM * 4, cudaMemcpyDeviceToHost, h->stream));
+    DMG_CUDA(h, cudaMemcpyAsync(out_vals, d_vals, (size_t)n_lvl * BM * 8, cudaMemcpyDeviceToHost, h->stream));
+    DMG_CUDA(h, cudaMemcpyAsync(out_counts, d_cnt, (size_t)n_lvl * B * 4, cudaMemcpyDeviceToHost, h->stream));
+    DMG_CUDA(h, cudaStreamSynchronize(h->stream));
+    if (flag) {
+        DMG_CUDA(h, cudaMemsetAsync(h->d_flags, 0, 4, h->stream));
+        return fail(h, DMG_ERR_INDEX, "dmg_otm_pseudo_targets: embeddingLookup failed, history id outside [-1, %lld)", (long long)d.rows);
+    }
+    return DMG_OK;
+}
+
 DMG_API int32_t dmg_jtm_item_weights(dmg_handle_t h, int32_t n_items, const int64_t *sample_off, const int32_t *sample_seq,
                                      const int32_t *parent_code, int32_t old_level, int32_t level, int32_t hierarchical,
                                      int32_t min_level, int32_t use_mask, float *out_weights)

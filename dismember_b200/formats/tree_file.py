@@ -106,21 +106,36 @@ def _node(node_id: int, prob: float, is_leaf: bool) -> bytes:
 
 
 def write_tree(path: str, leaf_ids, leaf_codes, max_level: int, leaf_prob=None,
-               non_leaf_offset: int | None = None) -> None:
-    """Emit the same record sequence as TreeBuilder.build / JTMTree.writeTree:
-    per leaf (in the given order) the leaf node then its not-yet-written
-    ancestors, then the Part_* chunks of 512 pairs, then tree_meta."""
+               non_leaf_offset: int | None = None, stat: Dict[int, int] | None = None) -> None:
+    """Emit the same record sequence as TreeBuilder.build (TreeBuilder.scala:24-96) / JTMTree.writeTree: leaves sorted by
+    code (`sortBy(_.code)`, stable), per leaf the leaf node then its not-yet-written ancestors, then the Part_* chunks of
+    512 pairs, then tree_meta.  `stat` = TreeBuilder's `stat: Option[Map[Int, Int]]` (item id -> count): a leaf's probability is
+    its count (1.0 when the id is missing), an ancestor's the Float sum of the counts below it (`computeNodeOccurrence`, only ids
+    present in `stat` contribute; an ancestor nobody contributes to gets 1.0).  Without `stat` every probability is 1.0
+    (`pstat.getOrElse(ancCode, 1.0f)` over an empty map).  `leaf_prob` is the array form of `stat` with every leaf present."""
+    if stat is not None:
+        ids_l = np.asarray(leaf_ids, np.int64).tolist()
+        leaf_prob = np.array([float(stat.get(i, 1)) for i in ids_l], np.float32)
+        in_stat = np.array([i in stat for i in ids_l], bool)
+    else:
+        in_stat = np.ones(len(leaf_ids), bool)
     leaf_ids = np.asarray(leaf_ids, np.int64)
     leaf_codes = np.asarray(leaf_codes, np.int64)
+    order = np.argsort(leaf_codes, kind="stable")
+    leaf_ids, leaf_codes = leaf_ids[order], leaf_codes[order]
+    pstat: Dict[int, float] = {}
     if leaf_prob is None:
         leaf_prob = np.ones(len(leaf_ids), np.float32)
+    else:
+        leaf_prob = np.asarray(leaf_prob, np.float32)[order]
+        for c, pr, ins in zip(leaf_codes.tolist(), leaf_prob.tolist(), in_stat[order].tolist()):
+            if not ins:
+                continue
+            a = c
+            for _ in range(max_level):
+                a = (a - 1) // 2
+                pstat[a] = float(np.float32(pstat.get(a, 0.0) + pr))
     offset = int(max(0, leaf_ids.max()) + 1) if non_leaf_offset is None else non_leaf_offset
-    pstat: Dict[int, float] = {}
-    for c, pr in zip(leaf_codes.tolist(), np.asarray(leaf_prob, np.float32).tolist()):
-        a = c
-        for _ in range(max_level):
-            a = (a - 1) // 2
-            pstat[a] = float(np.float32(pstat.get(a, 0.0) + pr))
     saved = set()
     parts: List[Tuple[str, bytes]] = []
     tmp = b""

@@ -22,10 +22,11 @@ def upper_log2(n: int) -> int:               # otm/package.scala:17
 class OTM:
     def __init__(self, engine: Optional[Engine] = None, device: int = 0, model_name: str = "din"):
         name = model_name.lower()
-        if name not in ("din",):
-            raise ValueError("DeepModel should be `DIN` (DeepFM is not built yet)")       # OTM.scala:57
+        if name not in ("din", "deepfm"):
+            raise ValueError("DeepModel should be `DIN` or `DeepFM`")                     # OTM.scala:54-58
         self.engine = engine or Engine(device)
-        self.use_mask = name == "din"
+        self.model_name = name
+        self.use_mask = name == "din"                                                     # OTM.scala:33 (DeepFM takes no mask)
         self.item_id_mapping: Dict[int, int] = {}
         self.leaf_level = 0
 
@@ -43,7 +44,10 @@ class OTM:
 
     def set_parameters(self, params: np.ndarray, embed_size: int, seq_len: int) -> "OTM":
         rows = (1 << (self.leaf_level + 1)) - 1
-        self.engine.load_din_weights(np.asarray(params, np.float64), rows, embed_size, seq_len)
+        if self.model_name == "deepfm":                                                   # otm/.../model/DeepFM.scala:12-48
+            self.engine.load_deepfm_weights(np.asarray(params, np.float64), rows, embed_size, seq_len)
+        else:
+            self.engine.load_din_weights(np.asarray(params, np.float64), rows, embed_size, seq_len)
         return self
 
     def sequence_ids(self, sequences) -> np.ndarray:

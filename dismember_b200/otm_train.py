@@ -47,8 +47,18 @@ class OTMTrainer:
 
     # ---- OTMTree.optimalPseudoTargets :27-46 + computeTargets :104-129 ----------------------------
     def optimal_pseudo_targets(self, seqs: np.ndarray, target_leaves: Sequence[Sequence[int]]):
-        """seqs: B x T leaf ids (-1 pad).  Returns per level (ascending) a list over users of
-        {node id: pseudo target}.  Insertion order of the dicts = order of first appearance."""
+        """seqs: B x T leaf ids (-1 pad).  Returns per level (ascending) a list over users of {node id: pseudo target}.
+        Computed on the device (dmg_otm_pseudo_targets: expand / model.forward / combine kernels per level)."""
+        off = np.zeros(len(target_leaves) + 1, np.int64)
+        off[1:] = np.cumsum([len(t) for t in target_leaves])
+        flat = np.concatenate([np.asarray(t, np.int32) for t in target_leaves]) if off[-1] else np.zeros(0, np.int32)
+        ids, vals, cnt = self.e.otm_pseudo_targets(seqs, off, flat, self.leaf_level, self.start_level, self.use_mask)
+        return [[{int(i): float(v) for i, v in zip(ids[li, u, :cnt[li, u]], vals[li, u, :cnt[li, u]])} for u in range(len(seqs))]
+                for li in range(ids.shape[0])]
+
+    def optimal_pseudo_targets_host(self, seqs: np.ndarray, target_leaves: Sequence[Sequence[int]]):
+        """The same with the Scala driver's List / Map bookkeeping on the host around model.forward (readable mirror, used by the
+        tests as a third restatement).  Insertion order of the dicts = order of first appearance."""
         B = len(seqs)
         level_nodes = [{int(i): 1.0 for i in t} for t in target_leaves]     # leaf level: Node(_, 1.0)
         out = [level_nodes]

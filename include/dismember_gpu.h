@@ -246,6 +246,15 @@ DMG_API int32_t dmg_tdm_sample_expand(dmg_handle_t h, int32_t n_targets, const i
                                       uint64_t seed, int32_t *out_node,
                                       int32_t *out_seq, float *out_label, int32_t *out_rows);
 
+/* OTMTree.optimalPseudoTargets (otm/.../tree/OTMTree.scala:27-46 with computeTargets :104-129 and computeChildrenScores :131-165):
+ * bottom-up pseudo targets of B users for the levels start_level + 1 .. leaf_level.  leaf_seq B x T leaf node ids (-1 = padding),
+ * target CSR of leaf node ids.  Per level and user the (node id, target) list sorted by id in M slots (-1 padding):
+ * out_ids / out_vals [leaf_level - start_level][B][M], out_counts [leaf_level - start_level][B], levels ascending.
+ * use_mask = 0 keeps the reference's quirk of scoring the sibling tensor for both predictions (:157-161). */
+DMG_API int32_t dmg_otm_pseudo_targets(dmg_handle_t h, int32_t B, const int32_t *leaf_seq, const int64_t *target_off,
+                                       const int32_t *target_leaves, int32_t start_level, int32_t use_mask,
+                                       int32_t M, int32_t *out_ids, double *out_vals, int32_t *out_counts);
+
 /* ---- JTM tree learning ---------------------------------------------------------------- */
 /* TreeLearning.aggregateWeights for a whole level step (jtm/.../optim/TreeLearning.scala:137-174):
  * item i currently sits under node parent_code[i] of level old_level and owns the training samples

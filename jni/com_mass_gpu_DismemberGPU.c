@@ -250,6 +250,27 @@ JNIEXPORT void JNICALL Java_com_mass_gpu_DismemberGPU_00024_drRetrieve(
     if (rc) throw_status(env, H(handle), rc);
 }
 
+/* OTMTree.optimalPseudoTargets for a mini-batch; outputs [leafLevel - startLevel][batch][maxLabels] */
+JNIEXPORT void JNICALL Java_com_mass_gpu_DismemberGPU_00024_otmPseudoTargets(
+    JNIEnv *env, jobject self, jlong handle, jint batch, jintArray leafSeq, jlongArray targetOff, jintArray targets, jint startLevel,
+    jint leafLevel, jboolean useMask, jint maxLabels, jintArray outIds, jdoubleArray outVals, jintArray outCounts)
+{
+    const jlong T = seq_len(H(handle)), nl = (jlong)leafLevel - startLevel;
+    jlong last = 0;
+    if (batch <= 0 || nl <= 0 || maxLabels <= 0 || !need(env, leafSeq, (jlong)batch * T, "leafSeq: batch x seq_len ints") ||
+        !need(env, targetOff, (jlong)batch + 1, "targetOff: batch + 1 longs"))
+        return;
+    (*env)->GetLongArrayRegion(env, targetOff, batch, 1, &last);
+    if (!need(env, targets, last, "targets: targetOff(batch) ints") || !need(env, outIds, nl * batch * maxLabels, "outIds: levels x batch x maxLabels ints") ||
+        !need(env, outVals, nl * batch * maxLabels, "outVals: levels x batch x maxLabels doubles") || !need(env, outCounts, nl * batch, "outCounts: levels x batch ints"))
+        return;
+    void *s = PIN_I(leafSeq), *o = PIN_L(targetOff), *t = PIN_I(targets), *oi = PIN_I(outIds), *ov = PIN_D(outVals), *oc = PIN_I(outCounts);
+    int32_t rc = dmg_otm_pseudo_targets(H(handle), batch, s, o, t, startLevel, useMask ? 1 : 0, maxLabels, oi, ov, oc);
+    UNPIN_I(outCounts, oc, 0); UNPIN_D(outVals, ov, 0); UNPIN_I(outIds, oi, 0);
+    UNPIN_I(targets, t, JNI_ABORT); UNPIN_L(targetOff, o, JNI_ABORT); UNPIN_I(leafSeq, s, JNI_ABORT);
+    if (rc) throw_status(env, H(handle), rc);
+}
+
 /* LocalOptimizer step on an expanded batch (Float model) */
 JNIEXPORT jfloat JNICALL Java_com_mass_gpu_DismemberGPU_00024_trainStepFloat(
     JNIEnv *env, jobject self, jlong handle, jintArray node, jintArray seq, jintArray mask, jfloatArray labels,

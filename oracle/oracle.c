@@ -442,6 +442,98 @@ int orc_din_forward_f64_api(const orc_otm_model *m, int64_t n, const int32_t *no
  * OTMTree.initializeBeam otm/.../tree/OTMTree.scala:16-23).  seq = leaf node
  * ids (-1 = padding, masked when use_mask).  Writes the candidates of the LAST
  * scored level (2*min(beam, ...) ids + scores); returns their count. */
+/* ---- OTM pseudo targets -------------------------------------------------------------------------------------------------
+ * OTMTree.optimalPseudoTargets (otm/src/main/scala/com/mass/otm/tree/OTMTree.scala:27-46): the leaf level holds the target
+ * items with score 1.0; every level above is computeTargets of the level below (:104-129):
+ *   computeChildrenScores (:131-165): for every node n of the user's list, its sibling s (n even -> n-1, else n+1), the model's
+ *     logits of n and of s with the user's history (mask = positions of the padding id), negLabel = score of s if s is in the
+ *     user's list else 0.  QUIRK kept: without a mask input the reference scores the NEGATIVE tensor for both (:157-161).
+ *   label(n) = score(n) if pred(n) >= pred(s) else negLabel (:117-118); the parent's target is the sum of the labels of its
+ *     children that are in the list (groupMapReduce(_ + _), :120-121), clipped to [0, 1] (:123, otm/package.scala clipValue).
+ * The lists are Maps turned into Lists, so their order is a HashMap artefact; every consumer looks nodes up by id
+ * (MiniBatch.batchTransform, otm/.../dataset/MiniBatch.scala:27-34), so the oracle keeps each user's list sorted by id. */
+int orc_otm_pseudo_targets(const orc_otm_model *m, int B, int T, const int32_t *seqs, const int64_t *target_off,
+                           const int32_t *targets, int leaf_level, int start_level, int use_mask, int M,
+                           int32_t *out_ids, double *out_vals, int32_t *out_cnt)
+{
+    const int n_lvl = leaf_level - start_level;
+    if (n_lvl <= 0) return 0;
+    int32_t *pos = (int32_t *)malloc(sizeof(int32_t) * (size_t)B * M), *neg = (int32_t *)malloc(sizeof(int32_t) * (size_t)B * M);
+    int32_t *rseq = (int32_t *)malloc(sizeof(int32_t) * (size_t)B * M * T), *mask = (int32_t *)malloc(sizeof(int32_t) * (size_t)B * M * T);
+    double *pp = (double *)malloc(sizeof(double) * (size_t)B * M), *pn = (double *)malloc(sizeof(double) * (size_t)B * M);
+    int rc = 0;
+    for (int li = 0; li < n_lvl; li++)
+        for (size_t i = 0; i < (size_t)B * M; i++) { out_ids[(size_t)li * B * M + i] = -1; out_vals[(size_t)li * B * M + i] = 0.0; }
+    /* leaf level: Node(target, 1.0); duplicates collapse (all scores are 1.0: a duplicate can only push a sum further past the clip) */
+    {
+        int32_t *ids = out_ids + (size_t)(n_lvl - 1) * B * M;
+        double *vals = out_vals + (size_t)(n_lvl - 1) * B * M;
+        for (int u = 0; u < B; u++) {
+            int c = 0;
+            for (int64_t q = target_off[u]; q < target_off[u + 1]; q++) {
+                const int32_t t = targets[q];
+                int k = 0;
+                while (k < c && ids[(size_t)u * M + k] < t) k++;
+                if (k < c && ids[(size_t)u * M + k] == t) continue;
+                if (c >= M) { rc = -1; goto done; }
+                for (int j = c; j > k; j--) ids[(size_t)u * M + j] = ids[(size_t)u * M + j - 1];
+                ids[(size_t)u * M + k] = t;
+                c++;
+            }
+            for (int k = 0; k < c; k++) vals[(size_t)u * M + k] = 1.0;
+            out_cnt[(size_t)(n_lvl - 1) * B + u] = c;
+        }
+    }
+    for (int li = n_lvl - 1; li > 0; li--) {                      /* children at list li -> parents at list li - 1 */
+        const int32_t *cid = out_ids + (size_t)li * B * M;
+        const double *cval = out_vals + (size_t)li * B * M;
+        const int32_t *ccnt = out_cnt + (size_t)li * B;
+        int64_t n = 0, nm = 0;
+        for (int u = 0; u < B; u++)
+            for (int k = 0; k < ccnt[u]; k++) {
+                const int32_t id = cid[(size_t)u * M + k];
+                pos[n] = id;
+                neg[n] = (id % 2 == 0) ? id - 1 : id + 1;
+                for (int j = 0; j < T; j++) {
+                    rseq[n * T + j] = seqs[(size_t)u * T + j];
+                    if (use_mask && seqs[(size_t)u * T + j] == -1) mask[nm++] = (int32_t)(n * T + j);
+                }
+                n++;
+            }
+        if (n > 0) {
+            rc = orc_din_forward_f64_api(m, n, use_mask ? pos : neg, rseq, use_mask ? mask : NULL, use_mask ? nm : 0, pp);
+            if (rc) goto done;
+            rc = orc_din_forward_f64_api(m, n, neg, rseq, use_mask ? mask : NULL, use_mask ? nm : 0, pn);
+            if (rc) goto done;
+        }
+        int32_t *pid = out_ids + (size_t)(li - 1) * B * M;
+        double *pval = out_vals + (size_t)(li - 1) * B * M;
+        int64_t row = 0;
+        for (int u = 0; u < B; u++) {
+            int c = 0;
+            for (int k = 0; k < ccnt[u]; k++, row++) {
+                const int32_t id = cid[(size_t)u * M + k], sib = neg[row];
+                double neg_label = 0.0;
+                for (int q = 0; q < ccnt[u]; q++) if (cid[(size_t)u * M + q] == sib) { neg_label = cval[(size_t)u * M + q]; break; }
+                const double label = pp[row] >= pn[row] ? cval[(size_t)u * M + k] : neg_label;
+                const int32_t par = (id - 1) >> 1;
+                int j = 0;
+                while (j < c && pid[(size_t)u * M + j] != par) j++;
+                if (j == c) { pid[(size_t)u * M + c] = par; pval[(size_t)u * M + c] = 0.0; c++; }   /* children are id-sorted: parents arrive ascending */
+                pval[(size_t)u * M + j] = pval[(size_t)u * M + j] + label;
+            }
+            for (int j = 0; j < c; j++) {
+                const double v = pval[(size_t)u * M + j];
+                pval[(size_t)u * M + j] = v < 0.0 ? 0.0 : (v > 1.0 ? 1.0 : v);
+            }
+            out_cnt[(size_t)(li - 1) * B + u] = c;
+        }
+    }
+done:
+    free(pos); free(neg); free(rseq); free(mask); free(pp); free(pn);
+    return rc;
+}
+
 int orc_otm_beam_search(const orc_otm_model *m, const int32_t *seq, int leaf_level, int beam, int use_mask,
                         int32_t *out_ids, double *out_scores)
 {

@@ -53,6 +53,14 @@ int orc_otm_retrieve_batch(const orc_otm_model *m, int B, const int32_t *seq_lea
                            int topk, int use_mask, const int32_t *leaf_item, int n_threads, int32_t *out_items,
                            double *out_scores, int32_t *out_counts);
 
+/* OTMTree.optimalPseudoTargets / computeTargets / computeChildrenScores (otm/.../tree/OTMTree.scala:27-46, 104-172): bottom-up pseudo
+ * targets of B users.  seqs B x T leaf ids (-1 pad), targets CSR of leaf node ids, M >= max targets per user.  Outputs for the levels
+ * start_level + 1 .. leaf_level (n_lvl = leaf_level - start_level of them, ascending): out_ids / out_vals [n_lvl][B][M], ids ascending,
+ * -1 padding, out_cnt [n_lvl][B]. */
+int orc_otm_pseudo_targets(const orc_otm_model *m, int B, int T, const int32_t *seqs, const int64_t *target_off,
+                           const int32_t *targets, int leaf_level, int start_level, int use_mask, int M,
+                           int32_t *out_ids, double *out_vals, int32_t *out_cnt);
+
 orc_dr_model *orc_dr_model_create(int num_item, int K, int D, int T, int E, const double *layer_emb,
                                   const double *const *layer_w, const double *const *layer_b,
                                   const double *rr_emb, const double *rr_w, const double *rr_b,

@@ -67,6 +67,8 @@ def lib():
     L.orc_otm_recommend.argtypes = [vp, i32p, C.c_int, C.c_int, C.c_int, C.c_int, i32p, i32p, f64p, f64p]
     L.orc_otm_retrieve_batch.argtypes = [vp, C.c_int, i32p, C.c_int, C.c_int, C.c_int, C.c_int, i32p, C.c_int,
                                          i32p, f64p, i32p]
+    L.orc_otm_pseudo_targets.argtypes = [vp, C.c_int, C.c_int, i32p, np.ctypeslib.ndpointer(np.int64, flags="C_CONTIGUOUS"), i32p, C.c_int, C.c_int,
+                                         C.c_int, C.c_int, i32p, f64p, i32p]
     L.orc_dr_model_create.restype = vp
     L.orc_dr_model_create.argtypes = [C.c_int] * 5 + [f64p, C.POINTER(vp), C.POINTER(vp), f64p, f64p, f64p, f64p, f64p]
     L.orc_dr_model_destroy.argtypes = [vp]
@@ -216,6 +218,22 @@ class OtmModel:
         if rc:
             raise IndexError("embeddingLookup failed: index out of range")
         return out
+
+    def pseudo_targets(self, seqs, target_off, targets, leaf_level, start_level, use_mask=True, M=None):
+        """OTMTree.optimalPseudoTargets -> (ids [n_lvl, B, M], vals, counts [n_lvl, B]) for the levels start_level + 1 .. leaf_level"""
+        seqs = _ci32(seqs).reshape(-1, self.T)
+        B = len(seqs)
+        off = np.ascontiguousarray(target_off, np.int64)
+        tg = _ci32(targets)
+        M = int(M or max(1, int(np.diff(off).max())))
+        n_lvl = leaf_level - start_level
+        ids = np.empty((n_lvl, B, M), np.int32)
+        vals = np.empty((n_lvl, B, M), np.float64)
+        cnt = np.zeros((n_lvl, B), np.int32)
+        rc = lib().orc_otm_pseudo_targets(self.h, B, self.T, seqs, off, tg, leaf_level, start_level, int(use_mask), M, ids, vals, cnt)
+        if rc:
+            raise IndexError(f"oracle error {rc}")
+        return ids, vals, cnt
 
     def beam_search(self, seq_leaf_ids, leaf_level, beam, use_mask=True):
         seq = _ci32(seq_leaf_ids)

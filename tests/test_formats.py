@@ -27,6 +27,33 @@ def test_tree_roundtrip(tmp_path, jtm_fix):
     assert (t.node_ids[anc] == t.codes[anc] + t.non_leaf_offset).all()
 
 
+def test_tree_writer_record_order_and_probabilities(tmp_path, jtm_fix):
+    """TreeBuilder.build (TreeBuilder.scala:24-96): leaves sortBy(_.code) whatever the caller's order, ancestors right after the
+    first leaf below them -> the record sequence of the reference's own data/jtm/example_tree.bin; without `stat` every node
+    carries 1.0; with `stat` a leaf carries its count and an ancestor the Float sum of the counts of the ids present in stat."""
+    p = str(tmp_path / "tree.bin")
+    rev = slice(None, None, -1)
+    tree_file.write_tree(p, jtm_fix["leaf_ids"][rev], jtm_fix["leaf_codes"][rev], int(jtm_fix["max_level"]))
+    t = tree_file.read_tree(p)
+    assert (t.codes == jtm_fix["codes"]).all() and (t.node_ids == jtm_fix["node_ids"]).all() and (t.is_leaf == jtm_fix["is_leaf"]).all()
+    assert (t.prob == 1.0).all()
+    ids = jtm_fix["leaf_ids"].tolist()
+    stat = {i: 1 + (i % 5) for i in ids[::2]}                      # every second item has a count
+    tree_file.write_tree(p, jtm_fix["leaf_ids"], jtm_fix["leaf_codes"], int(jtm_fix["max_level"]), stat=stat)
+    t = tree_file.read_tree(p)
+    prob = dict(zip(t.codes.tolist(), t.prob.tolist()))
+    want = {}
+    for i, c in zip(ids, jtm_fix["leaf_codes"].tolist()):
+        assert prob[c] == float(stat.get(i, 1))
+        while c > 0 and i in stat:
+            c = (c - 1) // 2
+            want[c] = want.get(c, 0) + stat[i]
+    for c, is_leaf in zip(t.codes.tolist(), t.is_leaf.tolist()):
+        if not is_leaf:
+            assert prob[c] == float(np.float32(want.get(c, 1)))    # sums stay below 2^24: exact in Float
+    assert prob[0] == float(sum(stat.values()))
+
+
 def test_synthetic_tree_shape():
     t = synth.tdm_tree(1000, seed=3)
     assert t.max_level == 10 and t.is_leaf.sum() == 1000

@@ -109,6 +109,13 @@ def test_otm_deepfm_matches_oracle(orc, E, leaf_level, beam):
     li, ls, lc = e.otm_beam_search_levels(seqs, beam, leaf_level)
     if li.shape[1] > 0:
         assert (li[:, -1, :] == ids).all() and (ls[:, -1, :].view(np.uint64) == sc.view(np.uint64)).all() and (lc[:, -1] == cnt).all()
+    # the host mirror of OTM.scala reaches the same scorer: OTM(modelName = "DeepFM"), useMask = false (OTM.scala:33)
+    from dismember_b200.otm import OTM
+    m = OTM(engine=e, model_name="DeepFM").set_mapping(items, leaf_ids).set_parameters(params, E, T)
+    assert m.use_mask is False and m.leaf_level == leaf_level
+    hist = [int(items[np.searchsorted(leaf_ids, x)]) if x >= 0 else 0 for x in seqs[3]]      # item ids (0 is not an item: padding)
+    rec = m.recommend(hist, topk, beam)
+    assert [i for i, _ in rec] == gi[3, :gc[3]].tolist()
     e.close()
 
 

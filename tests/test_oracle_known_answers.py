@@ -212,3 +212,70 @@ def test_oracle_adam_closed_form(orc):
             assert np.abs(sv - s2).max() < tol * 10 and np.abs(rv - r2).max() < tol * 10
             assert np.abs(wv - w2).max() < tol * 10 * max(1.0, np.abs(w2).max())
             assert (sv[::7] == (0.9 * s.astype(dtype)[::7]).astype(dtype)).all() or dtype == np.float32   # zero gradient: pure decay
+
+
+def _pseudo_targets_python(model, seqs, targets, leaf_level, start_level, use_mask):
+    """Independent restatement of OTMTree.optimalPseudoTargets with the Scala driver's List / Map bookkeeping (dicts)."""
+    T = seqs.shape[1]
+    out = [[{int(i): 1.0 for i in t} for t in targets]]
+    for _ in range(leaf_level - 1, start_level, -1):
+        children = out[0]
+        parents = []
+        for u, ch in enumerate(children):
+            nodes = list(ch.keys())
+            if not nodes:
+                parents.append({})
+                continue
+            pos = np.array(nodes, np.int32)
+            neg = np.where(pos % 2 == 0, pos - 1, pos + 1).astype(np.int32)
+            seq = np.tile(seqs[u], (len(nodes), 1))
+            mask = np.flatnonzero((seq == -1).ravel()).astype(np.int32) if use_mask else None
+            pp = model.forward(pos if use_mask else neg, seq, mask)
+            pn = model.forward(neg, seq, mask)
+            acc = {}
+            for k, n in enumerate(nodes):
+                label = ch[n] if pp[k] >= pn[k] else ch.get(int(neg[k]), 0.0)
+                acc[(n - 1) >> 1] = acc.get((n - 1) >> 1, 0.0) + label
+            parents.append({p: min(1.0, max(0.0, v)) for p, v in acc.items()})
+        out.insert(0, parents)
+    return out
+
+
+@pytest.mark.parametrize("use_mask", [True, False])
+def test_otm_pseudo_targets_oracle(orc, otm_fix, use_mask):
+    """orc_otm_pseudo_targets (OTMTree.scala:27-46, 104-172) against the dict-based restatement: users with several targets,
+    siblings both listed, shared ancestors (sums above 1 that must clip), padded histories, both useMask settings."""
+    f = otm_fix
+    n = len(f["items"])
+    leaf_level = int(np.ceil(np.log(n) / np.log(2)))
+    model = orc.OtmModel(f["params"], 8191, int(f["E"]), int(f["T"]))
+    rng = np.random.default_rng(11)
+    B, T, start_level = 24, int(f["T"]), 4
+    leaf_ids = f["leaf_ids"].astype(np.int32)
+    seqs = rng.choice(leaf_ids, (B, T)).astype(np.int32)
+    seqs[rng.random((B, T)) < 0.3] = -1
+    seqs[0] = -1
+    targets = []
+    for u in range(B):
+        k = int(rng.integers(1, 9))
+        t = rng.choice(leaf_ids, k, replace=False).tolist()
+        if u % 3 == 0:                                   # both children of one parent, and a cousin pair
+            base = int(t[0]) - (1 if int(t[0]) % 2 == 0 else 0)
+            t += [base, base + 1]
+        if u % 5 == 0:
+            t.append(t[0])                               # a duplicated target
+        targets.append([int(x) for x in t if (1 << leaf_level) - 1 <= x < (2 << leaf_level) - 1])
+    off = np.zeros(B + 1, np.int64)
+    off[1:] = np.cumsum([len(t) for t in targets])
+    flat = np.concatenate([np.array(t, np.int32) for t in targets])
+    ids, vals, cnt = model.pseudo_targets(seqs, off, flat, leaf_level, start_level, use_mask, M=12)
+    want = _pseudo_targets_python(model, seqs, targets, leaf_level, start_level, use_mask)
+    assert ids.shape[0] == len(want) == leaf_level - start_level
+    clipped = 0
+    for li in range(ids.shape[0]):
+        for u in range(B):
+            got = {int(i): float(v) for i, v in zip(ids[li, u, :cnt[li, u]], vals[li, u, :cnt[li, u]])}
+            assert got == want[li][u], (li, u)
+            assert (np.diff(ids[li, u, :cnt[li, u]]) > 0).all() and (ids[li, u, cnt[li, u]:] == -1).all()
+            clipped += sum(1 for v in got.values() if v == 1.0) + sum(1 for v in got.values() if v == 0.0)
+    assert clipped > 0
