@@ -85,6 +85,9 @@ def load_library(build_if_missing: bool = True):
         "dmg_dr_load_paths": [vp, vp, vp],
         "dmg_dr_beam_search": [vp, i32, vp, i32, vp, vp, vp],
         "dmg_dr_retrieve": [vp, i32, vp, i32, i32, vp, vp, vp],
+        "dmg_dr_load_item_paths": [vp, i32, vp],
+        "dmg_dr_train_step": [vp, i32, vp, vp, vp, i32, u64, dbl, i32, i32, i32, i32, vp, vp],
+        "dmg_dr_download": [vp, i32, vp, C.POINTER(vp), C.POINTER(vp), vp, vp, vp, vp, vp],
         "dmg_train_step": [vp, i64, vp, vp, vp, i64, vp, dbl, i32, vp],
         "dmg_din_gradients": [vp, i64, vp, vp, vp, i64, vp, vp, vp, i64],
         "dmg_tdm_sample_expand": [vp, i32, vp, vp, vp, i32, i32, i32, u64, vp, vp, vp, C.POINTER(i32)],
@@ -498,6 +501,41 @@ class Engine:
         counts = np.empty(B, np.int32)
         self._check(self.L.dmg_dr_retrieve(self.h, B, _p(seq), beam, topk, _p(items), _p(sc), _p(counts)))
         return items, sc, counts
+
+    def dr_load_item_paths(self, item_paths):
+        """itemPathMapping as [num_item, P, D] node indices"""
+        ip = _i32(item_paths)
+        num_item, K, D, T, E = self.dr_shape
+        ip = ip.reshape(num_item, -1, D)
+        self._check(self.L.dmg_dr_load_item_paths(self.h, ip.shape[1], _p(ip)))
+
+    def dr_train_step(self, seq, target, lr, step_t, rerank_step_t=None, sampled=None, num_sampled=0, seed=0, parallelism=1, apply=True):
+        """one mini-batch iteration of the Deep Retrieval LocalOptimizer -> (layer losses [D], rerank loss)"""
+        num_item, K, D, T, E = self.dr_shape
+        seq = _i32(seq).reshape(-1, T)
+        tg = _i32(target).ravel()
+        rerank_step_t = step_t if rerank_step_t is None else int(rerank_step_t)
+        sp = None
+        if sampled is not None:
+            sp = _i32(sampled).reshape(len(seq), -1)
+            num_sampled = sp.shape[1] - 1
+        loss = np.zeros(D, np.float64)
+        rloss = np.zeros(1, np.float64)
+        self._check(self.L.dmg_dr_train_step(self.h, len(seq), _p(seq), _p(tg), _p(sp), int(num_sampled), int(seed), float(lr), int(step_t),
+                                             rerank_step_t, int(parallelism), int(bool(apply)), _p(loss), _p(rloss)))
+        return loss, float(rloss[0])
+
+    def dr_download(self, gradients=False):
+        """-> dict(layer_emb, layer_w[D], layer_b[D], rr_emb, rr_w, rr_b, sm_w, sm_b): parameters, or the gradients of the last apply=False step"""
+        num_item, K, D, T, E = self.dr_shape
+        out = {"layer_emb": np.empty((num_item + K * (D - 1), E)), "layer_w": [np.empty((K, (T + d) * E)) for d in range(D)],
+               "layer_b": [np.empty(K) for _ in range(D)], "rr_emb": np.empty((num_item, E)), "rr_w": np.empty((E, T * E)),
+               "rr_b": np.empty(E), "sm_w": np.empty((num_item, E)), "sm_b": np.empty(num_item)}
+        wp = (C.c_void_p * D)(*[w.ctypes.data for w in out["layer_w"]])
+        bp = (C.c_void_p * D)(*[b.ctypes.data for b in out["layer_b"]])
+        self._check(self.L.dmg_dr_download(self.h, int(bool(gradients)), _p(out["layer_emb"]), wp, bp, _p(out["rr_emb"]), _p(out["rr_w"]),
+                                           _p(out["rr_b"]), _p(out["sm_w"]), _p(out["sm_b"])))
+        return out
 
     # -- training / JTM ---------------------------------------------------------------
     def din_gradients(self, node, seq, mask_flat, labels):

@@ -71,6 +71,11 @@ struct DrDev {
     int64_t *d_path_off = nullptr;
     int32_t *d_path_items = nullptr;
     std::vector<int64_t> h_path_off;                // kept for output sizing
+    // training (dr_train.cu): tensors in the order layer_emb, (layer_w[d], layer_b[d]) d < D, rr_emb, rr_w (kept [T E][E]), rr_b, sm_w, sm_b
+    std::vector<double *> tr_g, tr_s, tr_r;         // gradient, Adam first / second moment per tensor (allocated by the first training call)
+    int32_t *d_item_paths = nullptr;                // itemPathMapping [num_item][P][D]
+    int P = 0;
+    bool tr_dirty = false;                          // gradients left in place by a step with apply = 0: zero them before the next one
 };
 
 struct ShardState;                  // shard.cu

@@ -301,6 +301,10 @@ void dmg_free_dr(DrDev &d)
     for (double *p : d.d_layer_wT) cudaFree(p);
     cudaFree(d.d_rr_emb); cudaFree(d.d_rr_w); cudaFree(d.d_rr_b); cudaFree(d.d_sm_w); cudaFree(d.d_sm_b);
     cudaFree(d.d_path_off); cudaFree(d.d_path_items);
+    for (double *p : d.tr_g) cudaFree(p);
+    for (double *p : d.tr_s) cudaFree(p);
+    for (double *p : d.tr_r) cudaFree(p);
+    cudaFree(d.d_item_paths);
     d = DrDev();
 }
 

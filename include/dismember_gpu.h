@@ -218,6 +218,30 @@ DMG_API int32_t dmg_dr_retrieve(dmg_handle_t h, int32_t B, const int32_t *seq, i
                                 int32_t topk, int32_t *out_items, double *out_scores,
                                 int32_t *out_counts);
 
+/* Deep Retrieval training.  dmg_dr_load_item_paths: itemPathMapping (item index -> its P = numPathPerItem paths,
+ * [num_item][P][D] node indices in [0, K)), kept on the device.
+ * dmg_dr_train_step = the body of LocalOptimizer.optimize's mini-batch loop
+ * (deep-retrieval/.../optim/LocalOptimizer.scala:62-84): n samples (seq[n*T] item indices, -1 padding; target[n] item index).
+ *   layer model: MiniBatch.transformLayerData (dataset/MiniBatch.scala:19-50) -> LayerModel forward -> CrossEntropyLayer ->
+ *     backward -> syncGradients over `parallelism` thread chunks (:139-187; 1 = one chunk) -> Adam (eps 1e-8), step_t 1-based;
+ *   rerank model (rerank_step_t >= 1; 0 = epoch > reRankStoppingEpoch, skipped): RerankModel forward -> SampledSoftmaxLoss
+ *     (scalann/.../nn/SampledSoftmaxLoss.scala:49-153, batchMode = false; its Adam over the softmax weights / biases, eps 1e-7,
+ *     on gradients that are never zeroed: nn/mixin/ParameterOptimizer.scala:28-88) -> backward -> Adam.
+ *   sampled[n*(num_sampled+1)] = the reference's `sampledValues` (positive first); NULL = SampledSoftmaxLoss.uniformSampler on
+ *     the device (distinct uniform negatives != positive, ascending; counter-based generator seeded by `seed`).
+ *   apply = 0 leaves the parameters alone and the gradients in place for dmg_dr_download(which = 1).
+ * out_layer_loss[D], out_rerank_loss (NaN when skipped).  All Double. */
+DMG_API int32_t dmg_dr_load_item_paths(dmg_handle_t h, int32_t P, const int32_t *item_paths);
+DMG_API int32_t dmg_dr_train_step(dmg_handle_t h, int32_t n, const int32_t *seq, const int32_t *target,
+                                  const int32_t *sampled, int32_t num_sampled, uint64_t seed, double lr,
+                                  int32_t step_t, int32_t rerank_step_t, int32_t parallelism, int32_t apply,
+                                  double *out_layer_loss, double *out_rerank_loss);
+/* Parameters (which = 0) or gradients (which = 1) back to the host in dmg_dr_load's layout; any pointer may be NULL
+ * (what LayerModel / RerankModel.getParameters and DeepRetrieval.saveModel read). */
+DMG_API int32_t dmg_dr_download(dmg_handle_t h, int32_t which, double *layer_emb, double *const *layer_w,
+                                double *const *layer_b, double *rr_emb, double *rr_w, double *rr_b,
+                                double *sm_w, double *sm_b);
+
 /* ---- training ------------------------------------------------------------------------- */
 /* One step of LocalOptimizer.optimize on an already expanded batch
  * (tdm/.../optim/LocalOptimizer.scala:58-120,139-187; otm/.../optim/LocalOptimizer.scala:73-80):

@@ -250,6 +250,32 @@ JNIEXPORT void JNICALL Java_com_mass_gpu_DismemberGPU_00024_drRetrieve(
     if (rc) throw_status(env, H(handle), rc);
 }
 
+/* Deep Retrieval LocalOptimizer: itemPathMapping upload, then one mini-batch iteration (layer model + rerank model);
+ * outLosses = numLayer layer losses followed by the rerank loss (NaN when reRankStepT == 0) */
+JNIEXPORT void JNICALL Java_com_mass_gpu_DismemberGPU_00024_drLoadItemPaths(
+    JNIEnv *env, jobject self, jlong handle, jint numPathPerItem, jintArray itemPaths)
+{
+    if (numPathPerItem <= 0 || !need(env, itemPaths, numPathPerItem, "itemPaths: numItem x numPathPerItem x numLayer ints")) return;
+    void *p = PIN_I(itemPaths);
+    int32_t rc = dmg_dr_load_item_paths(H(handle), numPathPerItem, p);
+    UNPIN_I(itemPaths, p, JNI_ABORT);
+    if (rc) throw_status(env, H(handle), rc);
+}
+
+JNIEXPORT void JNICALL Java_com_mass_gpu_DismemberGPU_00024_drTrainStep(
+    JNIEnv *env, jobject self, jlong handle, jint batch, jint seqLen, jint numLayer, jintArray seq, jintArray target, jint numSampled,
+    jlong seed, jdouble lr, jint stepT, jint reRankStepT, jint parallelism, jdoubleArray outLosses)
+{
+    if (batch <= 0 || seqLen <= 0 || numLayer <= 0 || !need(env, seq, (jlong)batch * seqLen, "seq: batch x seq_len ints") ||
+        !need(env, target, batch, "target: batch ints") || !need(env, outLosses, (jlong)numLayer + 1, "outLosses: numLayer + 1 doubles"))
+        return;
+    void *s = PIN_I(seq), *t = PIN_I(target);
+    double *o = PIN_D(outLosses);
+    int32_t rc = dmg_dr_train_step(H(handle), batch, s, t, NULL, numSampled, (uint64_t)seed, lr, stepT, reRankStepT, parallelism, 1, o, o + numLayer);
+    UNPIN_D(outLosses, o, 0); UNPIN_I(target, t, JNI_ABORT); UNPIN_I(seq, s, JNI_ABORT);
+    if (rc) throw_status(env, H(handle), rc);
+}
+
 /* OTMTree.optimalPseudoTargets for a mini-batch; outputs [leafLevel - startLevel][batch][maxLabels] */
 JNIEXPORT void JNICALL Java_com_mass_gpu_DismemberGPU_00024_otmPseudoTargets(
     JNIEnv *env, jobject self, jlong handle, jint batch, jintArray leafSeq, jlongArray targetOff, jintArray targets, jint startLevel,

@@ -85,6 +85,18 @@ void orc_softmax_grad_f32(int n, int dim, const float *y, const float *go, float
 float orc_expf_api(float x);
 double orc_exp_api(double x);
 
+/* ---- Deep Retrieval training step (oracle_dr_train.c; deep-retrieval/.../optim/LocalOptimizer.scala:58-194) ---- */
+double orc_cross_entropy_f64(int64_t R, int C, const double *logits, const int32_t *target, double *grad);
+int orc_dr_layer_grad(int num_item, int K, int D, int T, int E, const double *emb, const double *const *w, const double *const *b,
+                      int n, const int32_t *seq, const int32_t *target, const int32_t *item_paths, int P, int parallelism,
+                      double *g_emb, double *const *g_w, double *const *g_b, double *loss);
+double orc_sampled_softmax_f64(int n, int E, int S, const double *u, const double *sm_w, const double *sm_b, const int32_t *sampled,
+                               double *gu, double *g_sm_w, double *g_sm_b);
+int orc_dr_rerank_grad(int num_item, int T, int E, const double *rr_emb, const double *rr_w, const double *rr_b, const double *sm_w,
+                       const double *sm_b, int n, const int32_t *seq, const int32_t *sampled, int S, double *g_rr_emb, double *g_rr_w,
+                       double *g_rr_b, double *g_sm_w, double *g_sm_b, double *loss);
+void orc_adam_eps_f64(double *w, const double *g, double *s, double *r, int64_t n, double lr, double eps, int t);
+
 #ifdef __cplusplus
 }
 #endif

@@ -81,6 +81,16 @@ def lib():
     L.orc_adam_f32.restype = None
     L.orc_adam_f64.argtypes = [f64p, f64p, f64p, f64p, C.c_int64, C.c_double, C.c_int]
     L.orc_adam_f64.restype = None
+    L.orc_cross_entropy_f64.argtypes = [C.c_int64, C.c_int, f64p, i32p, vp]
+    L.orc_cross_entropy_f64.restype = C.c_double
+    L.orc_dr_layer_grad.argtypes = [C.c_int] * 5 + [f64p, C.POINTER(vp), C.POINTER(vp), C.c_int, i32p, i32p, i32p, C.c_int, C.c_int,
+                                    f64p, C.POINTER(vp), C.POINTER(vp), f64p]
+    L.orc_sampled_softmax_f64.argtypes = [C.c_int, C.c_int, C.c_int, f64p, f64p, f64p, i32p, f64p, f64p, f64p]
+    L.orc_sampled_softmax_f64.restype = C.c_double
+    L.orc_dr_rerank_grad.argtypes = [C.c_int, C.c_int, C.c_int, f64p, f64p, f64p, f64p, f64p, C.c_int, i32p, i32p, C.c_int,
+                                     f64p, f64p, f64p, f64p, f64p, f64p]
+    L.orc_adam_eps_f64.argtypes = [f64p, f64p, f64p, f64p, C.c_int64, C.c_double, C.c_double, C.c_int]
+    L.orc_adam_eps_f64.restype = None
     L.orc_softmax_f32.argtypes = [C.c_int, C.c_int, f32p, f32p]
     L.orc_softmax_grad_f32.argtypes = [C.c_int, C.c_int, f32p, f32p, f32p]
     L.orc_expf_api.restype = C.c_float
@@ -318,6 +328,83 @@ class DrModel:
         if getattr(self, "h", None):
             lib().orc_dr_model_destroy(self.h)
             self.h = None
+
+
+def cross_entropy(logits, target, want_grad=True):
+    """CrossEntropyCriterion (sizeAverage) on [R, C] Double logits -> (loss, gradInput)"""
+    lg = np.ascontiguousarray(logits, np.float64)
+    grad = np.empty_like(lg) if want_grad else None
+    loss = lib().orc_cross_entropy_f64(lg.shape[0], lg.shape[1], lg, _ci32(target), grad.ctypes.data if want_grad else None)
+    return loss, grad
+
+
+def sampled_softmax(u, sm_w, sm_b, sampled, g_sm_w, g_sm_b):
+    """SampledSoftmaxLoss forward + backward on user vectors u[n, E] -> (loss, gradInput); g_sm_w / g_sm_b are accumulated into"""
+    u = np.ascontiguousarray(u, np.float64)
+    sampled = _ci32(sampled).reshape(len(u), -1)
+    gu = np.empty_like(u)
+    loss = lib().orc_sampled_softmax_f64(len(u), u.shape[1], sampled.shape[1] - 1, u, sm_w, sm_b, sampled, gu, g_sm_w, g_sm_b)
+    return loss, gu
+
+
+def adam_eps(w, g, s, r, lr, eps, t):
+    lib().orc_adam_eps_f64(w, g, s, r, w.size, lr, eps, t)
+
+
+class DrTrainer:
+    """One LocalOptimizer (deep-retrieval/.../optim/LocalOptimizer.scala) over a DrModel's arrays: layer Adam, rerank Adam and the
+    SampledSoftmaxLoss's own Adam state, updated in place by step()."""
+
+    def __init__(self, m: "DrModel", lr: float):
+        self.m, self.lr = m, lr
+        z = np.zeros_like
+        self.layer = [m.layer_emb] + [x for d in range(m.D) for x in (m.layer_w[d], m.layer_b[d])]
+        self.layer_s, self.layer_r = [z(x) for x in self.layer], [z(x) for x in self.layer]
+        self.rr = [m.rr_emb, m.rr_w, m.rr_b]
+        self.rr_s, self.rr_r = [z(x) for x in self.rr], [z(x) for x in self.rr]
+        self.sm = [m.sm_w, m.sm_b]
+        self.sm_g, self.sm_s, self.sm_r = [z(x) for x in self.sm], [z(x) for x in self.sm], [z(x) for x in self.sm]
+
+    def layer_grad(self, seq, target, item_paths, P, parallelism=1):
+        m = self.m
+        g = [np.zeros_like(x) for x in self.layer]
+        gw = (C.c_void_p * m.D)(*[g[1 + 2 * d].ctypes.data for d in range(m.D)])
+        gb = (C.c_void_p * m.D)(*[g[2 + 2 * d].ctypes.data for d in range(m.D)])
+        wp = (C.c_void_p * m.D)(*[w.ctypes.data for w in m.layer_w])
+        bp = (C.c_void_p * m.D)(*[b.ctypes.data for b in m.layer_b])
+        loss = np.zeros(m.D)
+        seq = _ci32(seq).reshape(-1, m.T)
+        rc = lib().orc_dr_layer_grad(m.num_item, m.K, m.D, m.T, m.E, m.layer_emb, wp, bp, len(seq), seq, _ci32(target), _ci32(item_paths), P,
+                                     parallelism, g[0], gw, gb, loss)
+        if rc:
+            raise IndexError(f"oracle error {rc}")
+        return g, loss
+
+    def rerank_grad(self, seq, sampled):
+        m = self.m
+        seq = _ci32(seq).reshape(-1, m.T)
+        sampled = _ci32(sampled).reshape(len(seq), -1)
+        g = [np.zeros_like(x) for x in self.rr]
+        loss = np.zeros(1)
+        rc = lib().orc_dr_rerank_grad(m.num_item, m.T, m.E, m.rr_emb, m.rr_w, m.rr_b, m.sm_w, m.sm_b, len(seq), seq, sampled,
+                                      sampled.shape[1] - 1, g[0], g[1], g[2], self.sm_g[0], self.sm_g[1], loss)
+        if rc:
+            raise IndexError(f"oracle error {rc}")
+        return g, float(loss[0])
+
+    def step(self, seq, target, item_paths, P, sampled, t, rerank_t=None, parallelism=1):
+        """the body of LocalOptimizer.optimize's while loop (:62-84) -> (layer losses [D], rerank loss)"""
+        g, loss = self.layer_grad(seq, target, item_paths, P, parallelism)
+        for x, gx, s, r in zip(self.layer, g, self.layer_s, self.layer_r):
+            lib().orc_adam_eps_f64(x.reshape(-1), gx.reshape(-1), s.reshape(-1), r.reshape(-1), x.size, self.lr, 1e-8, t)
+        rloss = float("nan")
+        if rerank_t:
+            gr, rloss = self.rerank_grad(seq, sampled)
+            for x, gx, s, r in zip(self.sm, self.sm_g, self.sm_s, self.sm_r):       # inside reRankCriterion.backward
+                lib().orc_adam_eps_f64(x.reshape(-1), gx.reshape(-1), s.reshape(-1), r.reshape(-1), x.size, self.lr, 1e-7, rerank_t)
+            for x, gx, s, r in zip(self.rr, gr, self.rr_s, self.rr_r):
+                lib().orc_adam_eps_f64(x.reshape(-1), gx.reshape(-1), s.reshape(-1), r.reshape(-1), x.size, self.lr, 1e-8, rerank_t)
+        return loss, rloss
 
 
 def softmax_f32(x):

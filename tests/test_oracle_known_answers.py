@@ -279,3 +279,144 @@ def test_otm_pseudo_targets_oracle(orc, otm_fix, use_mask):
             assert (np.diff(ids[li, u, :cnt[li, u]]) > 0).all() and (ids[li, u, cnt[li, u]:] == -1).all()
             clipped += sum(1 for v in got.values() if v == 1.0) + sum(1 for v in got.values() if v == 0.0)
     assert clipped > 0
+
+
+# ---- Deep Retrieval training (oracle/oracle_dr_train.c) -------------------------------------------------------------------
+def test_cross_entropy_reference_vectors(orc):
+    """scalann/src/test/scala/CrossEntropyTest.scala:26-43: CrossEntropyCriterion forward 1.3200 and backward, the Scala test's 1e-4."""
+    logits = np.array([[2.3, -10.2], [0.8, -3.1], [-2.2, 1.0]])
+    loss, grad = orc.cross_entropy(logits, [0, 1, 1])
+    assert abs(loss - 1.3200) < 1e-4
+    want = np.array([-1.2219e-06, 1.2422e-06, 3.2672e-01, -3.2672e-01, 1.3055e-02, -1.3055e-02]).reshape(3, 2)
+    assert grad.shape == logits.shape and np.abs(grad - want).max() < 1e-4
+    # float64 closed form: mean over rows of logsumexp - logit[target]; gradient (softmax - onehot) / R
+    z = logits - logits.max(1, keepdims=True)
+    p = np.exp(z) / np.exp(z).sum(1, keepdims=True)
+    oh = np.eye(2)[[0, 1, 1]]
+    assert abs(loss - (-np.log(p[np.arange(3), [0, 1, 1]]).mean())) < 1e-14
+    assert np.abs(grad - (p - oh) / 3).max() < 1e-15
+
+
+def test_sampled_softmax_reference_property(orc):
+    """scalann/src/test/scala/SampledSoftmaxLossTest.scala:8-52: with fixed sampledValues the loss decreases over 7 forward / backward
+    rounds (the criterion updates its own weights with Adam, lr 7e-3, on gradients it never zeroes), gradInput has inputVecs' shape."""
+    rng = np.random.default_rng(2022)
+    B, E, S, n_cls, lr = 6, 10, 4, 200, 7e-3
+    u = rng.uniform(-0.05, 0.05, (B, E))
+    w = rng.normal(0.0, 0.01, (n_cls, E))
+    b = np.zeros(n_cls)
+    pos = [0, 1, 3, 2, 77, 101]
+    neg = [[19, 3, 66, 190], [33, 4, 88, 111], [2, 48, 92, 129], [1, 66, 34, 167], [53, 11, 0, 123], [8, 99, 100, 12]]
+    sampled = np.array([[p] + n for p, n in zip(pos, neg)], np.int32)
+    gw, gb = np.zeros_like(w), np.zeros_like(b)
+    st = [np.zeros_like(w), np.zeros_like(w), np.zeros_like(b), np.zeros_like(b)]
+    losses = []
+    for t in range(1, 8):
+        loss, gu = orc.sampled_softmax(u, w, b, sampled, gw, gb)
+        assert gu.shape == u.shape
+        orc.adam_eps(w.reshape(-1), gw.reshape(-1), st[0].reshape(-1), st[1].reshape(-1), lr, 1e-7, t)
+        orc.adam_eps(b, gb, st[2], st[3], lr, 1e-7, t)
+        losses.append(loss)
+    assert all(a > b_ for a, b_ in zip(losses, losses[1:])), losses
+    assert abs(losses[0] - np.log(S + 1)) < 1e-3                       # near-zero logits: uniform over the 5 sampled classes
+
+
+def _dr_toy(seed, num_item=40, K=7, D=3, T=4, E=6, P=2):
+    rng = np.random.default_rng(seed)
+    mk = lambda *s: rng.normal(0.0, 0.3, s)
+    m = dict(num_item=num_item, K=K, D=D, T=T, E=E, layer_emb=mk(num_item + K * (D - 1), E), layer_w=[mk(K, (T + d) * E) for d in range(D)],
+             layer_b=[mk(K) for _ in range(D)], rr_emb=mk(num_item, E), rr_w=mk(E, T * E), rr_b=mk(E), sm_w=mk(num_item, E), sm_b=mk(num_item))
+    item_paths = rng.integers(0, K, (num_item, P, D)).astype(np.int32)
+    return m, item_paths
+
+
+def _dr_layer_loss_f64(m, seq, target, item_paths, emb=None, w=None, b=None):
+    """independent float64 numpy restatement of the layer model's mean cross entropies (sum over layers)"""
+    emb = m["layer_emb"] if emb is None else emb
+    w = m["layer_w"] if w is None else w
+    b = m["layer_b"] if b is None else b
+    tot = 0.0
+    rows = [(s, p) for s in range(len(seq)) for p in range(item_paths.shape[1])]
+    for d in range(m["D"]):
+        ls = []
+        for s, p in rows:
+            path = item_paths[target[s], p]
+            idx = list(seq[s]) + [path[i] + m["num_item"] + i * m["K"] for i in range(d)]
+            x = np.concatenate([emb[c] if c >= 0 else np.zeros(m["E"]) for c in idx])
+            z = w[d] @ x + b[d]
+            ls.append(np.log(np.exp(z - z.max()).sum()) + z.max() - z[path[d]])
+        tot += np.mean(ls)
+    return tot
+
+
+def test_dr_layer_gradients_by_finite_differences(orc):
+    """orc_dr_layer_grad (trainLayerBatch, LocalOptimizer.scala:139-168) against central differences of an independent float64
+    numpy loss: embedding rows (history and path-node rows), Linear weights and biases of every layer; padded histories."""
+    m, item_paths = _dr_toy(3)
+    rng = np.random.default_rng(5)
+    n = 9
+    seq = rng.integers(0, m["num_item"], (n, m["T"])).astype(np.int32)
+    seq[rng.random(seq.shape) < 0.25] = -1
+    target = rng.integers(0, m["num_item"], n).astype(np.int32)
+    model = orc.DrModel(**m)
+    tr = orc.DrTrainer(model, 1e-3)
+    g, loss = tr.layer_grad(seq, target, item_paths, item_paths.shape[1])
+    assert abs(loss.sum() - _dr_layer_loss_f64(m, seq, target, item_paths)) < 1e-12
+    h = 1e-6
+    checks = [("layer_emb", None, g[0])] + [("layer_w", d, g[1 + 2 * d]) for d in range(m["D"])] + [("layer_b", d, g[2 + 2 * d]) for d in range(m["D"])]
+    for name, d, grad in checks:
+        arr = m[name] if d is None else m[name][d]
+        flat = arr.reshape(-1)
+        for k in rng.choice(flat.size, min(12, flat.size), replace=False):
+            old = flat[k]
+            flat[k] = old + h
+            up = _dr_layer_loss_f64(m, seq, target, item_paths)
+            flat[k] = old - h
+            dn = _dr_layer_loss_f64(m, seq, target, item_paths)
+            flat[k] = old
+            assert abs((up - dn) / (2 * h) - grad.reshape(-1)[k]) < 1e-7, (name, d, k)
+    # thread chunks (syncGradients): equal chunk sizes -> the same mean gradient up to rounding; unequal -> mean of chunk means
+    g3, loss3 = tr.layer_grad(seq, target, item_paths, item_paths.shape[1], parallelism=3)
+    assert all(np.abs(a - b_).max() < 1e-14 for a, b_ in zip(g, g3)) and np.abs(loss - loss3).max() < 1e-14
+    g2, loss2 = tr.layer_grad(seq, target, item_paths, item_paths.shape[1], parallelism=2)       # chunks of 5 and 4 samples
+    ga, la = tr.layer_grad(seq[:5], target[:5], item_paths, item_paths.shape[1])
+    gb_, lb = tr.layer_grad(seq[5:], target[5:], item_paths, item_paths.shape[1])
+    assert all(np.abs(x - (a + b_) / 2).max() < 1e-15 for x, a, b_ in zip(g2, ga, gb_)) and np.abs(loss2 - (la + lb) / 2).max() < 1e-15
+
+
+def test_dr_rerank_gradients_by_finite_differences(orc):
+    """orc_dr_rerank_grad (trainRerank, LocalOptimizer.scala:122-137): model gradients against central differences of a float64
+    numpy sampled-softmax loss; softmax-parameter gradients accumulate across calls (ParameterOptimizer never zeroes them)."""
+    m, _ = _dr_toy(4)
+    rng = np.random.default_rng(6)
+    n, S = 8, 5
+    seq = rng.integers(0, m["num_item"], (n, m["T"])).astype(np.int32)
+    seq[rng.random(seq.shape) < 0.25] = -1
+    target = rng.integers(0, m["num_item"], n).astype(np.int32)
+    sampled = np.array([[t] + sorted(rng.choice([x for x in range(m["num_item"]) if x != t], S, replace=False).tolist()) for t in target], np.int32)
+
+    def loss_f64():
+        ls = []
+        for i in range(n):
+            x = np.concatenate([m["rr_emb"][c] if c >= 0 else np.zeros(m["E"]) for c in seq[i]])
+            u = m["rr_w"] @ x + m["rr_b"]
+            z = m["sm_w"][sampled[i]] @ u + m["sm_b"][sampled[i]]
+            ls.append(np.log(np.exp(z - z.max()).sum()) + z.max() - z[0])
+        return np.mean(ls)
+    tr = orc.DrTrainer(orc.DrModel(**m), 1e-3)
+    g, loss = tr.rerank_grad(seq, sampled)
+    assert abs(loss - loss_f64()) < 1e-13
+    h = 1e-6
+    for name, grad in [("rr_emb", g[0]), ("rr_w", g[1]), ("rr_b", g[2]), ("sm_w", tr.sm_g[0]), ("sm_b", tr.sm_g[1])]:
+        flat = m[name].reshape(-1)
+        for k in rng.choice(flat.size, min(12, flat.size), replace=False):
+            old = flat[k]
+            flat[k] = old + h
+            up = loss_f64()
+            flat[k] = old - h
+            dn = loss_f64()
+            flat[k] = old
+            assert abs((up - dn) / (2 * h) - grad.reshape(-1)[k]) < 1e-7, (name, k)
+    once = [x.copy() for x in tr.sm_g]
+    tr.rerank_grad(seq, sampled)
+    assert all(np.abs(x - 2 * o).max() < 1e-15 for x, o in zip(tr.sm_g, once))
