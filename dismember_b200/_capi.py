@@ -85,6 +85,7 @@ def load_library(build_if_missing: bool = True):
         "dmg_dr_load_paths": [vp, vp, vp],
         "dmg_dr_beam_search": [vp, i32, vp, i32, vp, vp, vp],
         "dmg_dr_retrieve": [vp, i32, vp, i32, i32, vp, vp, vp],
+        "dmg_kmeans_tree": [vp, i32, i32, vp, i32, u64, vp],
         "dmg_dr_load_item_paths": [vp, i32, vp],
         "dmg_dr_train_step": [vp, i32, vp, vp, vp, i32, u64, dbl, i32, i32, i32, i32, vp, vp],
         "dmg_dr_download": [vp, i32, vp, C.POINTER(vp), C.POINTER(vp), vp, vp, vp, vp, vp],
@@ -501,6 +502,13 @@ class Engine:
         counts = np.empty(B, np.int32)
         self._check(self.L.dmg_dr_retrieve(self.h, B, _p(seq), beam, topk, _p(items), _p(sc), _p(counts)))
         return items, sc, counts
+
+    def kmeans_tree(self, embeddings, iters, seed=0):
+        """RecursiveCluster.run (kmeans) -> node code per point"""
+        emb = np.ascontiguousarray(embeddings, np.float64)
+        codes = np.full(len(emb), -1, np.int32)
+        self._check(self.L.dmg_kmeans_tree(self.h, emb.shape[0], emb.shape[1], _p(emb), int(iters), int(seed), _p(codes)))
+        return codes
 
     def dr_load_item_paths(self, item_paths):
         """itemPathMapping as [num_item, P, D] node indices"""

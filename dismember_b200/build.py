@@ -9,7 +9,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libdismember_gpu.so")
-SOURCES = ["capi.cu", "dr.cu", "dr_train.cu", "train.cu", "shard.cu", "otm_deepfm.cu"]
+SOURCES = ["capi.cu", "dr.cu", "dr_train.cu", "train.cu", "shard.cu", "otm_deepfm.cu", "cluster.cu"]
 OBJ = os.path.join(HERE, "..", "build", "obj")
 NVCC_FLAGS = [
     "-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",

@@ -120,3 +120,39 @@ class DeepRetrieval:
         n = int(counts[0])
         prob = 1.0 / (1.0 + np.exp(-scores[0, :n]))                                       # dr/package.scala:21
         return [(self.id_item_mapping[int(i)], float(p)) for i, p in zip(items[0, :n], prob)]
+
+    def get_parameters(self):
+        """LayerModel / RerankModel.getParameters + the softmax weights, as a dict of arrays (DeepRetrieval.saveModel reads these)"""
+        return self.engine.dr_download()
+
+
+class LocalOptimizer:
+    """deep-retrieval/.../optim/LocalOptimizer.scala:18-120: the mini-batch loop of one epoch over (sequence, target) samples already
+    mapped to item indices.  Every iteration is ONE engine call (dmg_dr_train_step: layer model, then -- while epoch <=
+    reRankStoppingEpoch -- the rerank model); shuffling, epochs and evaluation stay with the caller as in the Scala class."""
+
+    def __init__(self, model: DeepRetrieval, item_paths, learning_rate: float, num_sampled: int, batch_size: int,
+                 re_rank_epoch: Optional[int] = None, num_thread: int = 1, seed: int = 0):
+        self.model, self.lr, self.num_sampled, self.batch_size = model, learning_rate, num_sampled, batch_size
+        self.re_rank_epoch, self.num_thread, self.seed = re_rank_epoch, num_thread, seed
+        self.layer_t = self.rerank_t = 0                      # Adam's trainCounter / ParameterOptimizer.timestep
+        model.engine.dr_load_item_paths(item_paths)           # dataset.itemPathMapping
+
+    def set_item_paths(self, item_paths):
+        """after an M-step (CoordinateDescent.optimize) the items' paths change"""
+        self.model.engine.dr_load_item_paths(item_paths)
+
+    def train_epoch(self, epoch: int, sequences, targets):
+        """-> list of (layer losses [D], rerank loss) per mini-batch"""
+        seqs = np.asarray(sequences, np.int32)
+        tg = np.asarray(targets, np.int32)
+        out = []
+        train_rerank = self.re_rank_epoch is None or epoch <= self.re_rank_epoch
+        for b0 in range(0, len(seqs), self.batch_size):
+            self.layer_t += 1
+            if train_rerank:
+                self.rerank_t += 1
+            out.append(self.model.engine.dr_train_step(seqs[b0:b0 + self.batch_size], tg[b0:b0 + self.batch_size], self.lr, self.layer_t,
+                                                       rerank_step_t=self.rerank_t if train_rerank else 0, num_sampled=self.num_sampled,
+                                                       seed=self.seed + self.layer_t, parallelism=self.num_thread))
+        return out

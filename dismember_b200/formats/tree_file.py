@@ -18,6 +18,8 @@ import struct
 from dataclasses import dataclass
 from typing import Dict, List, Tuple
 
+import math
+
 import numpy as np
 
 from . import pbwire as pb
@@ -166,6 +168,25 @@ def write_tree(path: str, leaf_ids, leaf_codes, max_level: int, leaf_prob=None,
             f.write(_kv(pid, body))
         meta = pb.field_varint(1, max_level) + b"".join(pb.field_bytes(2, pid.encode()) for pid, _ in parts)
         f.write(_kv("tree_meta", meta))
+
+
+def flatten_leaves(codes, min_code: int) -> np.ndarray:
+    """TreeBuilder.flattenLeaves (TreeBuilder.scala:131-139): sink every code to the leaf level (code * 2 + 1 until >= minCode)."""
+    c = np.asarray(codes, np.int64).copy()
+    while (c < min_code).any():
+        c = np.where(c < min_code, c * 2 + 1, c)
+    return c
+
+
+def build_tree(path: str, tree_ids, tree_codes, stat: Dict[int, int] | None = None) -> Tuple[np.ndarray, int]:
+    """TreeBuilder.build (TreeBuilder.scala:24-96): offset = max id + 1, maxLevel = floor(log2(max code + 1)), leaves flattened to
+    that level, records written by write_tree.  -> (leaf codes, maxLevel)"""
+    ids = np.asarray(tree_ids, np.int64)
+    codes = np.asarray(tree_codes, np.int64)
+    max_level = int(math.floor(math.log(int(codes.max()) + 1) / math.log(2)))
+    leaf_codes = flatten_leaves(codes, (1 << max_level) - 1)
+    write_tree(path, ids, leaf_codes, max_level, stat=stat)
+    return leaf_codes, max_level
 
 
 def read_otm_mapping(path: str) -> Tuple[np.ndarray, np.ndarray]:

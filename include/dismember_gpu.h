@@ -242,6 +242,14 @@ DMG_API int32_t dmg_dr_download(dmg_handle_t h, int32_t which, double *layer_emb
                                 double *const *layer_b, double *rr_emb, double *rr_w, double *rr_b,
                                 double *sm_w, double *sm_b);
 
+/* k-means tree rebuild: RecursiveCluster.run, clusterType = "kmeans"
+ * (tdm/.../cluster/RecursiveCluster.scala:34-214) without the file: recursive balanced bisection of n points (emb[n*E] Double,
+ * row-major) by 2-means (best of `iters` = clusterIterNum runs; smile-core 2.6.0 KMeans.fit restated, counter-based generator
+ * keyed by `seed`), squaredDistance to the first centroid, Utils.argPartition at the median; out_codes[n] = the node code of
+ * every point (TreeBuilder.build flattens and writes them: dismember_b200/formats/tree_file.py build_tree). */
+DMG_API int32_t dmg_kmeans_tree(dmg_handle_t h, int32_t n, int32_t E, const double *emb, int32_t iters,
+                                uint64_t seed, int32_t *out_codes);
+
 /* ---- training ------------------------------------------------------------------------- */
 /* One step of LocalOptimizer.optimize on an already expanded batch
  * (tdm/.../optim/LocalOptimizer.scala:58-120,139-187; otm/.../optim/LocalOptimizer.scala:73-80):

@@ -97,6 +97,10 @@ int orc_dr_rerank_grad(int num_item, int T, int E, const double *rr_emb, const d
                        double *g_rr_b, double *g_sm_w, double *g_sm_b, double *loss);
 void orc_adam_eps_f64(double *w, const double *g, double *s, double *r, int64_t n, double lr, double eps, int t);
 
+/* ---- k-means tree rebuild (oracle_cluster.c; tdm/.../cluster/RecursiveCluster.scala:34-214, utils/Utils.scala:130-199) ---- */
+int orc_arg_partition(double *elems, int n, int position, int32_t *indices);
+int orc_kmeans_tree(int n, int E, const double *emb, int iters, uint64_t seed, int32_t *codes);
+
 #ifdef __cplusplus
 }
 #endif

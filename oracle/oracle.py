@@ -91,6 +91,8 @@ def lib():
                                      f64p, f64p, f64p, f64p, f64p, f64p]
     L.orc_adam_eps_f64.argtypes = [f64p, f64p, f64p, f64p, C.c_int64, C.c_double, C.c_double, C.c_int]
     L.orc_adam_eps_f64.restype = None
+    L.orc_arg_partition.argtypes = [f64p, C.c_int, C.c_int, i32p]
+    L.orc_kmeans_tree.argtypes = [C.c_int, C.c_int, f64p, C.c_int, C.c_uint64, i32p]
     L.orc_softmax_f32.argtypes = [C.c_int, C.c_int, f32p, f32p]
     L.orc_softmax_grad_f32.argtypes = [C.c_int, C.c_int, f32p, f32p, f32p]
     L.orc_expf_api.restype = C.c_float
@@ -405,6 +407,26 @@ class DrTrainer:
             for x, gx, s, r in zip(self.rr, gr, self.rr_s, self.rr_r):
                 lib().orc_adam_eps_f64(x.reshape(-1), gx.reshape(-1), s.reshape(-1), r.reshape(-1), x.size, self.lr, 1e-8, rerank_t)
         return loss, rloss
+
+
+def arg_partition(dist, position):
+    """Utils.argPartition on a copy -> (partitioned values, indices)"""
+    d = np.ascontiguousarray(dist, np.float64).copy()
+    ix = np.arange(len(d), dtype=np.int32)
+    rc = lib().orc_arg_partition(d, len(d), int(position), ix)
+    if rc:
+        raise ValueError(f"oracle error {rc}")
+    return d, ix
+
+
+def kmeans_tree(emb, iters, seed):
+    """RecursiveCluster.run (kmeans) -> codes[n]"""
+    emb = np.ascontiguousarray(emb, np.float64)
+    codes = np.full(len(emb), -1, np.int32)
+    rc = lib().orc_kmeans_tree(emb.shape[0], emb.shape[1], emb, int(iters), int(seed), codes)
+    if rc:
+        raise ValueError(f"oracle error {rc}")
+    return codes
 
 
 def softmax_f32(x):

@@ -143,3 +143,18 @@ def test_path_to_items_is_the_reference_map_not_a_multimap():
     for k in shared[:200]:
         items = flat_all[off_all[k]:off_all[k + 1]]
         assert flat[off[k]] == items[np.argmax(pos[items])]           # the survivor is the last visitor
+
+
+def test_build_tree_is_treebuilder_build(tmp_path):
+    """TreeBuilder.build (TreeBuilder.scala:24-96) on cluster codes of uneven depth: leaves are sunk to the deepest level
+    (flattenLeaves), maxLevel = floor(log2(max code + 1)), ancestors carry code + offset."""
+    ids = np.array([10, 11, 12, 13, 14], np.int32)
+    codes = np.array([3, 9, 10, 5, 6], np.int64)               # depths 2, 3, 3, 2, 2
+    p = str(tmp_path / "t.bin")
+    leaf_codes, max_level = tree_file.build_tree(p, ids, codes)
+    assert max_level == 3 and leaf_codes.tolist() == [7, 9, 10, 11, 13]
+    t = tree_file.read_tree(p)
+    assert t.max_level == 3 and sorted(t.leaf_codes.tolist()) == [7, 9, 10, 11, 13]
+    assert dict(zip(t.leaf_codes.tolist(), t.leaf_ids.tolist())) == {7: 10, 9: 11, 10: 12, 11: 13, 13: 14}
+    anc = t.is_leaf == 0
+    assert (t.node_ids[anc] == t.codes[anc] + 15).all() and set(t.codes[anc].tolist()) == {0, 1, 2, 3, 4, 5, 6}

@@ -127,3 +127,28 @@ def test_dr_device_sampler_properties():
     with pytest.raises(Exception):
         e.dr_train_step(seq, bad, 1e-3, 1, num_sampled=5, seed=1)
     e.close()
+
+
+def test_dr_local_optimizer_mirror_learns():
+    """dismember_b200.dr.LocalOptimizer (the Scala class's mini-batch loop over dmg_dr_train_step): on a learnable toy set (the target's
+    paths are a function of the first history item) both losses fall; the rerank model stops after reRankEpoch."""
+    from dismember_b200.dr import DeepRetrieval, LocalOptimizer
+    shape = (60, 6, 2, 3, 8, 1)
+    num_item, K, D, T, E, P = shape
+    m, _ = _model(21, *shape)
+    for k in ("layer_emb", "rr_emb", "rr_w", "sm_w"):
+        m[k] = m[k] * 0.1
+    m["layer_w"] = [w * 0.1 for w in m["layer_w"]]
+    item_paths = np.stack([np.arange(num_item) % K, (np.arange(num_item) // K) % K], 1).reshape(num_item, 1, 2).astype(np.int32)
+    rng = np.random.default_rng(22)
+    seqs = rng.integers(0, num_item, (512, T)).astype(np.int32)
+    targets = seqs[:, 0].copy()
+    e = new_engine()
+    dr = DeepRetrieval(engine=e).set_model(**m)
+    opt = LocalOptimizer(dr, item_paths, learning_rate=2e-2, num_sampled=8, batch_size=128, re_rank_epoch=6, seed=5)
+    hist = [opt.train_epoch(ep, seqs, targets) for ep in range(1, 9)]
+    first, last = hist[0][0], hist[5][-1]
+    assert last[0].sum() < 0.7 * first[0].sum() and last[1] < 0.9 * first[1]
+    assert all(np.isnan(r) for _, r in hist[7]) and opt.layer_t == 32 and opt.rerank_t == 24
+    assert np.abs(dr.get_parameters()["layer_w"][0] - m["layer_w"][0]).max() > 1e-2
+    e.close()

@@ -420,3 +420,78 @@ def test_dr_rerank_gradients_by_finite_differences(orc):
     once = [x.copy() for x in tr.sm_g]
     tr.rerank_grad(seq, sampled)
     assert all(np.abs(x - 2 * o).max() < 1e-15 for x, o in zip(tr.sm_g, once))
+
+
+# ---- k-means tree rebuild (oracle/oracle_cluster.c) -----------------------------------------------------------------------------
+def _arg_partition_python(elems, position):
+    """line-by-line port of Utils.argPartition (tdm/.../utils/Utils.scala:130-199)"""
+    e = list(elems)
+    ix = list(range(len(e)))
+
+    def swap(a, b):
+        e[a], e[b] = e[b], e[a]
+        ix[a], ix[b] = ix[b], ix[a]
+
+    def med(p1, p2, p3):
+        if e[p1] < e[p2]:
+            return p2 if e[p2] < e[p3] else (p3 if e[p1] < e[p3] else p1)
+        return p2 if e[p2] > e[p3] else (p3 if e[p1] > e[p3] else p1)
+    left, right = 0, len(e) - 1
+    while left < right:
+        pvt = med(left, right, (left + right) // 2)
+        pv = e[pvt]
+        swap(pvt, left)
+        i, lt, gt = left, left, right
+        while i <= gt:
+            if e[i] < pv:
+                swap(lt, i); lt += 1; i += 1
+            elif e[i] > pv:
+                swap(gt, i); gt -= 1
+            else:
+                i += 1
+        if lt <= position <= gt:
+            left = right
+        elif position < lt:
+            right = lt - 1
+        else:
+            left = gt + 1
+    return e, ix
+
+
+def test_arg_partition_matches_the_scala_algorithm(orc):
+    rng = np.random.default_rng(31)
+    for n in [2, 3, 4, 5, 8, 17, 64, 257, 1000]:
+        for trial in range(4):
+            d = rng.random(n) if trial < 2 else rng.integers(0, 4, n).astype(np.float64)       # duplicates exercise the == branch
+            mid = n // 2
+            got_e, got_ix = orc.arg_partition(d, mid)
+            want_e, want_ix = _arg_partition_python(d.tolist(), mid)
+            assert got_ix.tolist() == want_ix and got_e.tolist() == want_e
+            # balanceTree's contract: the left half holds the mid smallest distances
+            assert sorted(got_ix.tolist()) == list(range(n)) and (d[got_ix] == got_e).all()
+            assert got_e[:mid].max() <= got_e[mid:].min()
+    with pytest.raises(ValueError):
+        orc.arg_partition(np.array([1.0, np.nan, 0.5, 2.0]), 2)
+
+
+def test_kmeans_tree_oracle_properties(orc):
+    """RecursiveCluster.run: every point gets its own code, the tree is balanced (sibling subtrees differ by at most one leaf, depth
+    floor/ceil(log2 n)), two well separated blobs are split at the root, the result is a function of the seed."""
+    rng = np.random.default_rng(32)
+    for n in [2, 3, 7, 100, 257, 1500]:
+        emb = rng.random((n, 6))
+        codes = orc.kmeans_tree(emb, 3, 7)
+        assert len(set(codes.tolist())) == n and (codes > 0).all()
+        level = np.floor(np.log2(codes + 1)).astype(int)
+        assert level.min() >= int(np.floor(np.log2(n))) and level.max() <= int(np.ceil(np.log2(n)))
+        anc = codes.copy()                                     # leaf counts under the two children of the root differ by <= 1
+        while (anc > 2).any():
+            anc = np.where(anc > 2, (anc - 1) // 2, anc)
+        assert abs(int((anc == 1).sum()) - int((anc == 2).sum())) <= 1
+        assert (orc.kmeans_tree(emb, 3, 7) == codes).all()
+    blobs = np.concatenate([rng.normal(0.0, 0.1, (64, 4)), rng.normal(5.0, 0.1, (64, 4))])
+    codes = orc.kmeans_tree(blobs, 2, 1)
+    anc = codes.copy()
+    while (anc > 2).any():
+        anc = np.where(anc > 2, (anc - 1) // 2, anc)
+    assert len(set(anc[:64].tolist())) == 1 and len(set(anc[64:].tolist())) == 1 and anc[0] != anc[64]
