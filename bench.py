@@ -63,6 +63,9 @@ def parse():
     ap.add_argument("--target-sec", type=float, default=0.6, help="length of every timed region: the K steps are repeated R times")
     ap.add_argument("--catalogues", default="10M,100M", help="extra catalogues measured after the headline ('' = none)")
     ap.add_argument("--no-structured", action="store_true", help="skip the second workload on the structured ('trained-like') table")
+    ap.add_argument("--no-sharded", action="store_true", help="N > 1 only: skip the table-sharded legs (BASELINE configs 4 and 5, sharded TDM)")
+    ap.add_argument("--shard-items", type=int, default=10_000_000, help="catalogue of the sharded TDM / JTM legs")
+    ap.add_argument("--shard-dr-items", type=int, default=100_000_000, help="catalogue of the sharded Deep Retrieval leg")
     ap.add_argument("--inflight", type=int, default=8,
                     help="host threads / handles driving the GPU, one batch each in flight (1 = strictly serial steps)")
     ap.add_argument("--arith", default="fast", choices=["fast", "strict"],
@@ -411,6 +414,123 @@ def measure(args, env, items, structured=False, do_cpu=False, target_s=None, ver
     return out
 
 
+def sharded_legs(args, env):
+    """N > 1: the tables SHARDED over the ranks (csrc/shard.cu, csrc/dr.cu; NCCL inside libdismember_gpu.so) at the sizes BASELINE.json
+    states -- configs[3] JTM item -> node weights on a 10 M item catalogue, configs[4] Deep Retrieval D=3 K=1000 on 100 M items -- plus
+    TDM retrieval on the sharded 10 M table.  Every leg is checked bit for bit against an UNSHARDED engine on this rank's GPU (the
+    tables are counter-based, so both hold the same values).  Returns one dict per leg (rank 0's view + whole-job rates)."""
+    import torch
+    import torch.distributed as dist
+    from dismember_b200 import Engine, shard, synth
+    world, rank, local, dev = env["world"], env["rank"], env["local"], env["dev"]
+    T, E, B = args.seq_len, args.dim, args.batch
+    out = {}
+    ctl = dist.new_group(backend="gloo")                           # the 128-byte NCCL id and python objects travel here
+
+    def sync():
+        dist.barrier(group=ctl)
+        torch.cuda.synchronize(dev)
+
+    def timed(fn, reps):
+        fn()                                                        # warm-up (buffers, NCCL channels)
+        sync()
+        t0 = time.perf_counter()
+        for _ in range(reps):
+            fn()
+        sync()
+        return env["max_over_ranks"](time.perf_counter() - t0) / reps
+
+    eng = None
+    try:
+        # ---- TDM retrieval + JTM weights on the sharded node table ---------------------------------------------------------
+        n_items = args.shard_items
+        tf = synth.tdm_tree(n_items, seed=1)
+        rows = (1 << (tf.max_level + 1)) - 1
+        eng = shard.make_sharded_engine(local, group=ctl)
+        eng.load_tree_tdm(tf.max_level, tf.codes, tf.node_ids, tf.is_leaf, tf.leaf_ids, tf.leaf_codes)
+        eng.shard_init_din_weights(rows, E, T, seed=2)
+        seqs = synth.queries(B, T, n_items, seed=100 + rank)
+        res = {}
+
+        def run_tdm():
+            res["r"] = eng.shard_tdm_retrieve(seqs, args.beam, args.topk)
+        dt = timed(run_tdm, 3)
+        local_rows, global_rows, exchanged = eng.shard_info()
+        full = Engine(local)
+        full.load_tree_tdm(tf.max_level, tf.codes, tf.node_ids, tf.is_leaf, tf.leaf_ids, tf.leaf_codes)
+        full.init_din_weights(np.float32, rows, E, T, seed=2)
+        full.set_arithmetic("strict")
+        n_chk = min(128, B)
+        oi, ol, oc = full.tdm_retrieve(seqs[:n_chk], args.beam, args.topk)
+        gi, gl, gc = res["r"]
+        ok = bool((gi[:n_chk] == oi).all() and (gc[:n_chk] == oc).all() and (gl[:n_chk].view(np.uint32) == ol.view(np.uint32)).all())
+        out["tdm_sharded"] = {"workload": f"TDM retrieval, node table of {n_items} items sharded by code range over {world} GPUs, "
+                                          f"{B} users per rank, beam={args.beam}", "value": world * B / dt, "unit": "users/s",
+                              "ms_per_step": dt * 1e3, "table_rows_global": global_rows, "table_rows_local": local_rows,
+                              "rows_scored_for_other_ranks_per_step": exchanged // 4,
+                              "parity_vs_unsharded_strict_engine": {"users_checked": n_chk, "ids_and_logit_bits_identical": ok}}
+        # BASELINE configs[3]: JTM tree re-learning (item -> node weights of one level step) on the sharded table
+        rng = np.random.Generator(np.random.PCG64(50 + rank))
+        n_it, gap, old_level = 100_000, 4, 8
+        n_samples = rng.integers(1, 9, n_it)
+        off = np.zeros(n_it + 1, np.int64)
+        off[1:] = np.cumsum(n_samples)
+        sseq = synth.queries(int(off[-1]), T, n_items, seed=70 + rank)
+        par = rng.integers((1 << old_level) - 1, (2 << old_level) - 1, n_it).astype(np.int32)
+
+        def run_jtm():
+            res["w"] = eng.shard_jtm_item_weights(off, sseq, par, old_level, old_level + gap, hierarchical=True, min_level=0)
+        dtj = timed(run_jtm, 1)
+        n_c = 4000
+        want = full.jtm_item_weights(off[:n_c + 1], sseq[:off[n_c]], par[:n_c], old_level, old_level + gap, hierarchical=True, min_level=0)
+        full.close()
+        got = res["w"][:n_c]
+        scorer_rows = int(off[-1]) * ((2 << gap) - 2)
+        out["config4_jtm"] = {"workload": f"JTM item->node weights (TreeLearning.aggregateWeights, one level step, gap {gap}) on a {n_items} item "
+                                          f"catalogue, node table sharded over {world} GPUs, {n_it} items ({int(off[-1])} samples) per rank",
+                              "value": world * n_it / dtj, "unit": "items/s", "scorer_rows_per_s": world * scorer_rows / dtj, "seconds": dtj,
+                              "parity_vs_unsharded_engine": {"items_checked": n_c, "weights_bit_identical":
+                                                             bool((got.view(np.uint32) == want.view(np.uint32)).all())}}
+        eng.close()
+        eng = None
+        torch.cuda.empty_cache()
+        # ---- BASELINE configs[4]: Deep Retrieval D=3 K=1000, item tables sharded by item range --------------------------------
+        n_dr, K, D, Ed, Bd, beam = args.shard_dr_items, 1000, 3, 32, 256, args.beam
+        eng = shard.make_sharded_engine(local, group=ctl)
+        eng.dr_init_synthetic(n_dr, K, D, T, Ed, J=2, seed=8)
+        dseq = np.random.Generator(np.random.PCG64(90 + rank)).integers(-1, n_dr, (Bd, T)).astype(np.int32)
+
+        def run_dr():
+            res["d"] = eng.shard_dr_retrieve(dseq, beam, args.topk)
+        dtd = timed(run_dr, 2)
+        free, _ = torch.cuda.mem_get_info(dev)
+        need = 3.0 * n_dr * Ed * 8 + 13.0 * K ** D + 4e9
+        chk = {"skipped": f"the unsharded copy needs {need / 1e9:.0f} GB, {free / 1e9:.0f} GB free"}
+        if need < free:
+            full = Engine(local)
+            full.dr_init_synthetic(n_dr, K, D, T, Ed, J=2, seed=8)
+            ri, rs, rc = full.dr_retrieve(dseq, beam, args.topk)
+            full.close()
+            si, ss, sc = res["d"]
+            chk = {"users_checked": Bd, "ids_identical": bool((si == ri).all() and (sc == rc).all()),
+                   "scores_bit_identical": bool((ss.view(np.uint64) == rs.view(np.uint64)).all()), "results_per_user": float(rc.mean())}
+        out["config5_deep_retrieval"] = {"workload": f"Deep Retrieval D={D} K={K}, {n_dr} items, E={Ed} (fp64), beam={beam}, item tables sharded by "
+                                                     f"item range over {world} GPUs, {Bd} users per rank",
+                                         "value": world * Bd / dtd, "unit": "users/s", "ms_per_step": dtd * 1e3,
+                                         "item_table_gb_global": 3.0 * n_dr * Ed * 8 / 1e9, "parity_vs_unsharded_engine": chk}
+    except Exception as ex:                                        # noqa: BLE001
+        out["error"] = f"{type(ex).__name__}: {str(ex)[:300]}"
+    finally:
+        if eng is not None:
+            try:
+                eng.close()
+            except Exception:                                      # noqa: BLE001
+                pass
+    out["data_plane"] = ("NCCL inside libdismember_gpu.so (dlopen libnccl.so.2): ncclSend/ncclRecv rounds per tree level, integer all-reduce of the "
+                         "history tiles; torch.distributed only carries the NCCL id and the timing barrier")
+    return out
+
+
 def main():
     args = parse()
     # stdout carries the ONE JSON line and nothing else: libraries that write to fd 1 (NCCL's version banner) go to stderr
@@ -429,7 +549,10 @@ def main():
     local = int(os.environ.get("LOCAL_RANK", "0"))
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        os.environ["NCCL_DEBUG"] = os.environ.get("DMG_NCCL_DEBUG", "WARN")   # NCCL's version banner goes to stdout: keep the JSON line alone
+        # NCCL's log lines go to fd 1, which now is stderr (above): the init lines ("... rank r nranks N ... Init COMPLETE") of torch's
+        # communicator and of the library's own (sharded legs) stay visible without touching the JSON line
+        os.environ["NCCL_DEBUG"] = os.environ.get("DMG_NCCL_DEBUG", "INFO")
+        os.environ.setdefault("NCCL_DEBUG_SUBSYS", "INIT")
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device: the engine has no CPU fallback")
@@ -518,6 +641,10 @@ def main():
         except Exception as ex:                                    # noqa: BLE001
             catalogues[name] = {"error": str(ex)[:300]}
 
+    sharded = None
+    if world > 1 and not args.no_sharded:
+        sharded = sharded_legs(args, env)
+
     if rank == 0:
         NF = m["NF"]
         line = {
@@ -559,6 +686,7 @@ def main():
             "parity_fast_vs_strict_kernel": m.get("strict_check"),
             "structured": structured,
             "catalogues": catalogues,
+            "sharded": sharded,
             "clocks": clocks,
         }
         print(json.dumps(line), flush=True)

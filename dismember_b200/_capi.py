@@ -87,6 +87,7 @@ def load_library(build_if_missing: bool = True):
         "dmg_dr_retrieve": [vp, i32, vp, i32, i32, vp, vp, vp],
         "dmg_kmeans_tree": [vp, i32, i32, vp, i32, u64, vp],
         "dmg_dr_load_item_paths": [vp, i32, vp],
+        "dmg_dr_init_synthetic": [vp, i32, i32, i32, i32, i32, i32, u64],
         "dmg_dr_train_step": [vp, i32, vp, vp, vp, i32, u64, dbl, i32, i32, i32, i32, vp, vp],
         "dmg_dr_download": [vp, i32, vp, C.POINTER(vp), C.POINTER(vp), vp, vp, vp, vp, vp],
         "dmg_train_step": [vp, i64, vp, vp, vp, i64, vp, dbl, i32, vp],
@@ -476,6 +477,11 @@ class Engine:
         arrs = [c(layer_emb), c(rr_emb), c(rr_w), c(rr_b), c(sm_w), c(sm_b)]
         self._check(self.L.dmg_dr_load(self.h, num_item, K, D, T, E, _p(arrs[0]), wp, bp, _p(arrs[1]), _p(arrs[2]),
                                        _p(arrs[3]), _p(arrs[4]), _p(arrs[5])))
+        self.dr_shape = (num_item, K, D, T, E)
+
+    def dr_init_synthetic(self, num_item, K, D, T, E, J=2, seed=0):
+        """synthetic model + path CSR generated on the device (whole tables, or this rank's item range after shard_init)"""
+        self._check(self.L.dmg_dr_init_synthetic(self.h, num_item, K, D, T, E, J, int(seed)))
         self.dr_shape = (num_item, K, D, T, E)
 
     def dr_load_paths(self, path_off, path_items):

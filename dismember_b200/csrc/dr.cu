@@ -821,3 +821,176 @@ DMG_API int32_t dmg_shard_dr_retrieve(dmg_handle_t h, int32_t B, const int32_t *
     DMG_CUDA(h, cudaStreamSynchronize(st));
     return DMG_OK;
 }
+
+// ---- synthetic Deep Retrieval model generated on the device (benchmarks / BASELINE config 5) ---------------------------------------
+// Tensor.randn at model construction (LayerModel.scala:22-39, RerankModel.scala:20-36: EmbeddingShare / Embedding / Linear init,
+// softmaxWeights randn(0, 0.05)) as counter-based values of the GLOBAL element index, so a rank of a sharded engine fills exactly
+// the slice an unsharded engine would hold; and a synthetic item -> path assignment (J hashed paths per item) turned into
+// MappingOp.pathItemMapping's shape -- ONE item per path (MappingOp.scala:23-28), here the largest item id -- as a CSR over the
+// K^D path keys, built on the device: a 100 M item catalogue never exists on the host.
+namespace {
+
+inline uint64_t splitmix_host(uint64_t x)
+{
+    x += 0x9E3779B97F4A7C15ull;
+    x = (x ^ (x >> 30)) * 0xBF58476D1CE4E5B9ull;
+    x = (x ^ (x >> 27)) * 0x94D049BB133111EBull;
+    return x ^ (x >> 31);
+}
+__global__ void dr_randn_kernel(double *__restrict__ dst, int64_t n, int64_t goff, uint64_t seed, double std)
+{
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        const uint64_t hsh = splitmix64(seed ^ splitmix64((uint64_t)(goff + i)));
+        const uint32_t a = (uint32_t)hsh, b = (uint32_t)(hsh >> 32);
+        const float u1 = ((float)(a >> 8) + 0.5f) * (1.0f / 16777216.0f), u2 = ((float)(b >> 8) + 0.5f) * (1.0f / 16777216.0f);
+        dst[i] = (double)(sqrtf(-2.0f * __logf(u1)) * __cosf(6.28318530718f * u2)) * std;
+    }
+}
+__global__ void dr_fill_i32_kernel(int32_t *__restrict__ dst, int64_t n, int32_t v)
+{
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) dst[i] = v;
+}
+// path key of (item, j): splitmix64(seed ^ splitmix64(item J + j)) mod K^D; the path keeps its largest item
+__global__ void dr_syn_winner_kernel(int64_t num_item, int J, int64_t n_keys, uint64_t seed, int32_t *__restrict__ winner)
+{
+    for (int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; q < num_item * J; q += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t key = (int64_t)(splitmix64(seed ^ splitmix64((uint64_t)q)) % (uint64_t)n_keys);
+        atomicMax(winner + key, (int32_t)(q / J));
+    }
+}
+constexpr int kScanPer = 8, kScanBlock = 1024 * kScanPer;
+__global__ void __launch_bounds__(1024) dr_syn_count_kernel(int64_t n_keys, const int32_t *__restrict__ winner, int64_t *__restrict__ blk)
+{
+    __shared__ int sW[32];
+    const int64_t base = (int64_t)blockIdx.x * kScanBlock + (int64_t)threadIdx.x * kScanPer;
+    int c = 0;
+    for (int q = 0; q < kScanPer; q++) c += (base + q < n_keys && winner[base + q] >= 0) ? 1 : 0;
+    for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
+    if ((threadIdx.x & 31) == 0) sW[threadIdx.x >> 5] = c;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        int t = 0;
+        for (int w = 0; w < 32; w++) t += sW[w];
+        blk[blockIdx.x] = t;
+    }
+}
+__global__ void __launch_bounds__(1024) dr_syn_scan_blocks_kernel(int64_t nb, int64_t *__restrict__ blk, int64_t *__restrict__ total)
+{
+    __shared__ int64_t sT[1024];
+    const int64_t per = (nb + 1023) / 1024, b0 = (int64_t)threadIdx.x * per, b1 = min(b0 + per, nb);
+    int64_t t = 0;
+    for (int64_t b = b0; b < b1; b++) t += blk[b];
+    sT[threadIdx.x] = t;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        int64_t run = 0;
+        for (int i = 0; i < 1024; i++) { const int64_t v = sT[i]; sT[i] = run; run += v; }
+        *total = run;
+    }
+    __syncthreads();
+    int64_t run = sT[threadIdx.x];
+    for (int64_t b = b0; b < b1; b++) { const int64_t v = blk[b]; blk[b] = run; run += v; }
+}
+__global__ void __launch_bounds__(1024) dr_syn_csr_kernel(int64_t n_keys, const int32_t *__restrict__ winner, const int64_t *__restrict__ blk,
+                                                          const int64_t *__restrict__ total, int64_t *__restrict__ path_off, int32_t *__restrict__ path_items)
+{
+    __shared__ int sW[32];
+    const int64_t base = (int64_t)blockIdx.x * kScanBlock + (int64_t)threadIdx.x * kScanPer;
+    int c = 0;
+    for (int q = 0; q < kScanPer; q++) c += (base + q < n_keys && winner[base + q] >= 0) ? 1 : 0;
+    int incl = c;
+    for (int o = 1; o < 32; o <<= 1) { const int v = __shfl_up_sync(0xffffffffu, incl, o); if ((int)(threadIdx.x & 31) >= o) incl += v; }
+    if ((threadIdx.x & 31) == 31) sW[threadIdx.x >> 5] = incl;
+    __syncthreads();
+    if (threadIdx.x == 0) { int run = 0; for (int w = 0; w < 32; w++) { const int v = sW[w]; sW[w] = run; run += v; } }
+    __syncthreads();
+    int64_t off = blk[blockIdx.x] + sW[threadIdx.x >> 5] + (incl - c);
+    for (int q = 0; q < kScanPer; q++)
+        if (base + q < n_keys) {
+            path_off[base + q] = off;
+            const int32_t w = winner[base + q];
+            if (w >= 0) path_items[off++] = w;
+        }
+    if (blockIdx.x == 0 && threadIdx.x == 0) path_off[n_keys] = *total;
+}
+
+}  // namespace
+
+DMG_API int32_t dmg_dr_init_synthetic(dmg_handle_t h, int32_t num_item, int32_t K, int32_t D, int32_t T, int32_t E, int32_t J, uint64_t seed)
+{
+    if (!h) return DMG_ERR_INVALID_ARG;
+    DMG_TRY(model_is_shared(h, "dmg_dr_init_synthetic"));
+    if (num_item <= 0 || K <= 0 || T <= 0 || E <= 0 || J <= 0) return fail(h, DMG_ERR_INVALID_ARG, "dmg_dr_init_synthetic: bad arguments");
+    if (D < 2 || D > kDrMaxD) return fail(h, DMG_ERR_INVALID_ARG, "number of layers must be in [2, %d]", kDrMaxD);
+    double nk = 1;
+    for (int i = 0; i < D; i++) nk *= K;
+    if (nk > 2.0e9) return fail(h, DMG_ERR_UNSUPPORTED, "K^D = %.3g path keys: dense CSR too large", nk);
+    const int64_t n_keys = (int64_t)nk;
+    DMG_CUDA(h, cudaSetDevice(h->device));
+    dmg_free_dr(h->dr);
+    DrDev &d = h->dr;
+    ShardState *s = h->shard;
+    const int world = s ? s->world : 1, rank = s ? s->rank : 0;
+    d.num_item = num_item; d.K = K; d.D = D; d.T = T; d.E = E;
+    d.sharded = s != nullptr;                                     // after dmg_shard_init: this rank's item range, served by dmg_shard_dr_retrieve
+    d.item_chunk = ((int64_t)num_item + world - 1) / world;
+    d.item_base = std::min<int64_t>((int64_t)rank * d.item_chunk, num_item);
+    d.local_items = std::min<int64_t>(d.item_chunk, num_item - d.item_base);
+    if (!d.sharded) { d.item_chunk = 0; d.item_base = 0; d.local_items = num_item; }
+    const int64_t node_rows = (int64_t)K * (D - 1), li = std::max<int64_t>(d.local_items, 1);
+    const int grid = h->sm_count * 16;
+    const double std_ = 0.05;
+    auto fill = [&](double *dst, int64_t n, int64_t goff, uint64_t sd, double sdv) {
+        if (n > 0) dr_randn_kernel<<<grid, 256, 0, h->stream>>>(dst, n, goff, seed ^ splitmix_host(sd), sdv);
+        h->launches += 1;
+    };
+    // local layer table = [owned item rows | path-node rows] (whole table when not sharded: the node rows follow the items anyway)
+    DMG_CUDA(h, cudaMalloc(&d.d_layer_emb, (size_t)(d.local_items + node_rows) * E * 8));
+    fill(d.d_layer_emb, d.local_items * E, d.item_base * E, 1, std_);
+    fill(d.d_layer_emb + d.local_items * E, node_rows * E, (int64_t)num_item * E, 1, std_);
+    for (int i = 0; i < D; i++) {
+        const int in = (T + i) * E;
+        double *w = nullptr, *b = nullptr, *wT = nullptr;
+        DMG_CUDA(h, cudaMalloc(&w, (size_t)K * in * 8));
+        DMG_CUDA(h, cudaMalloc(&b, (size_t)K * 8));
+        DMG_CUDA(h, cudaMalloc(&wT, (size_t)K * in * 8));
+        fill(w, (int64_t)K * in, 0, 10 + i, std_);
+        DMG_CUDA(h, cudaMemsetAsync(b, 0, (size_t)K * 8, h->stream));
+        transpose_kernel<double><<<(K * in + 255) / 256, 256, 0, h->stream>>>(w, wT, K, in);
+        h->launches += 1;
+        d.d_layer_w.push_back(w); d.d_layer_b.push_back(b); d.d_layer_wT.push_back(wT);
+    }
+    DMG_CUDA(h, cudaMalloc(&d.d_rr_emb, (size_t)li * E * 8));
+    fill(d.d_rr_emb, d.local_items * E, d.item_base * E, 2, std_);
+    DMG_CUDA(h, cudaMalloc(&d.d_rr_w, (size_t)E * T * E * 8));                              // kept [T E][E]: the values are defined in this layout
+    fill(d.d_rr_w, (int64_t)E * T * E, 0, 3, std_);
+    DMG_CUDA(h, cudaMalloc(&d.d_rr_b, (size_t)E * 8));
+    DMG_CUDA(h, cudaMemsetAsync(d.d_rr_b, 0, (size_t)E * 8, h->stream));
+    DMG_CUDA(h, cudaMalloc(&d.d_sm_w, (size_t)li * E * 8));
+    fill(d.d_sm_w, d.local_items * E, d.item_base * E, 4, std_);
+    DMG_CUDA(h, cudaMalloc(&d.d_sm_b, (size_t)li * 8));
+    fill(d.d_sm_b, d.local_items, d.item_base, 5, 0.01);
+    // path CSR (replicated)
+    int32_t *winner = nullptr;
+    int64_t *blk = nullptr;
+    const int64_t nb = (n_keys + kScanBlock - 1) / kScanBlock;
+    DMG_CUDA(h, cudaMalloc(&winner, (size_t)n_keys * 4));
+    DMG_CUDA(h, cudaMalloc(&blk, (size_t)(nb + 1) * 8));
+    dr_fill_i32_kernel<<<grid, 256, 0, h->stream>>>(winner, n_keys, -1);
+    dr_syn_winner_kernel<<<grid, 256, 0, h->stream>>>(num_item, J, n_keys, seed ^ splitmix_host(6), winner);
+    dr_syn_count_kernel<<<(unsigned)nb, 1024, 0, h->stream>>>(n_keys, winner, blk);
+    dr_syn_scan_blocks_kernel<<<1, 1024, 0, h->stream>>>(nb, blk, blk + nb);
+    int64_t total = 0;
+    DMG_CUDA(h, cudaMemcpyAsync(&total, blk + nb, 8, cudaMemcpyDeviceToHost, h->stream));
+    DMG_CUDA(h, cudaStreamSynchronize(h->stream));
+    DMG_CUDA(h, cudaMalloc(&d.d_path_off, (size_t)(n_keys + 1) * 8));
+    DMG_CUDA(h, cudaMalloc(&d.d_path_items, (size_t)std::max<int64_t>(total, 1) * 4));
+    dr_syn_csr_kernel<<<(unsigned)nb, 1024, 0, h->stream>>>(n_keys, winner, blk, blk + nb, d.d_path_off, d.d_path_items);
+    h->launches += 5;
+    DMG_CUDA(h, cudaGetLastError());
+    DMG_CUDA(h, cudaStreamSynchronize(h->stream));
+    cudaFree(winner); cudaFree(blk);
+    d.loaded = true;
+    d.paths_loaded = true;
+    return DMG_OK;
+}

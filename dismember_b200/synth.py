@@ -103,3 +103,26 @@ def queries(n_users: int, T: int, n_items: int, seed: int = 4, zipf_a: float = 1
     for u in range(n_users):
         out[u, T - lens[u]:] = items[u, :lens[u]]
     return out
+
+
+def _splitmix64(x: np.ndarray) -> np.ndarray:
+    x = (x + np.uint64(0x9E3779B97F4A7C15)).astype(np.uint64)
+    x = ((x ^ (x >> np.uint64(30))) * np.uint64(0xBF58476D1CE4E5B9)).astype(np.uint64)
+    x = ((x ^ (x >> np.uint64(27))) * np.uint64(0x94D049BB133111EB)).astype(np.uint64)
+    return x ^ (x >> np.uint64(31))
+
+
+def dr_synthetic_path_csr(num_item: int, K: int, D: int, J: int, seed: int):
+    """Host mirror of dmg_dr_init_synthetic's path assignment (csrc/dr.cu): key(item, j) = splitmix64(seed' ^ splitmix64(item J + j))
+    mod K^D with seed' = seed ^ splitmix64(6); a path keeps its largest item.  -> (path_off[K^D + 1], path_items)"""
+    with np.errstate(over="ignore"):
+        n_keys = K ** D
+        sd = np.uint64(seed) ^ _splitmix64(np.array([6], np.uint64))[0]
+        q = np.arange(num_item * J, dtype=np.uint64)
+        key = (_splitmix64(sd ^ _splitmix64(q)) % np.uint64(n_keys)).astype(np.int64)
+    winner = np.full(n_keys, -1, np.int64)
+    np.maximum.at(winner, key, (q // np.uint64(J)).astype(np.int64))
+    occ = winner >= 0
+    off = np.zeros(n_keys + 1, np.int64)
+    off[1:] = np.cumsum(occ)
+    return off, winner[occ].astype(np.int32)

@@ -387,6 +387,14 @@ DMG_API int32_t dmg_shard_dr_retrieve(dmg_handle_t h, int32_t B, const int32_t *
                                       int32_t topk, int32_t *out_items, double *out_scores,
                                       int32_t *out_counts);
 
+/* Synthetic Deep Retrieval model generated on the device (benchmarks, BASELINE config 5): Tensor.randn(0, 0.05) of every
+ * table as counter-based values of the GLOBAL element index, and J hashed paths per item folded into MappingOp.pathItemMapping's
+ * shape (one item per path, MappingOp.scala:23-28) as the CSR over the K^D path keys.  On a handle with dmg_shard_init the
+ * item-indexed tables hold this rank's item range (then dmg_shard_dr_retrieve), otherwise the whole tables (dmg_dr_retrieve);
+ * both hold the same values, so the two give bit-identical results. */
+DMG_API int32_t dmg_dr_init_synthetic(dmg_handle_t h, int32_t num_item, int32_t K, int32_t D, int32_t T, int32_t E,
+                                      int32_t J, uint64_t seed);
+
 /* Data-parallel training step over the replicas of one box: LocalOptimizer.trainBatch / syncGradients
  * (tdm/.../optim/LocalOptimizer.scala:139-187) with GPUs in the place of threads.  Every rank holds the whole model (same
  * weights, loaded with dmg_load_din_weights / dmg_init_din_weights after dmg_shard_init, which provides the communicator),

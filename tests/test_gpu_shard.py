@@ -142,3 +142,31 @@ def test_world2_matches_oracle(tmp_path):
     for r in range(2):
         d = json.load(open(tmp_path / f"r{r}.json"))
         assert d["ids_identical"] and d["logits_bit_identical"] and d["rows_scored_for_other_ranks"] > 0
+
+
+def test_dr_synthetic_model_unsharded_sharded_oracle(orc):
+    """dmg_dr_init_synthetic: the device-generated model retrieves the same items as the oracle fed with the downloaded tables and
+    the host mirror of the path assignment; a world-1 sharded handle (its own item range = everything) gives the same bits."""
+    from dismember_b200 import synth
+    num_item, K, D, T, E, J = 3000, 12, 3, 5, 16, 2
+    e = new_engine()
+    e.dr_init_synthetic(num_item, K, D, T, E, J, seed=77)
+    w = e.dr_download()
+    off, items = synth.dr_synthetic_path_csr(num_item, K, D, J, 77)
+    assert off[-1] == len(items) and 0 < len(items) <= K ** D and (np.diff(off) <= 1).all()
+    om = orc.DrModel(num_item, K, D, T, E, w["layer_emb"], w["layer_w"], w["layer_b"], w["rr_emb"], w["rr_w"], w["rr_b"], w["sm_w"], w["sm_b"])
+    assert abs(w["sm_w"].std() - 0.05) < 0.005 and (w["layer_b"][0] == 0).all()
+    rng = np.random.default_rng(3)
+    seq = rng.integers(-1, num_item, (9, T)).astype(np.int32)
+    gi, gs, gc = e.dr_retrieve(seq, 30, 10)
+    for u in range(len(seq)):
+        oi, os_, _ = om.recommend(seq[u], 10, 30, off, items)
+        assert gc[u] == len(oi) and (gi[u, :gc[u]] == oi).all() and (gs[u, :gc[u]].view(np.uint64) == os_.view(np.uint64)).all()
+    assert gc.sum() > 0
+    s = new_engine()
+    s.shard_init(1, 0)
+    s.dr_init_synthetic(num_item, K, D, T, E, J, seed=77)
+    si, ss, sc = s.shard_dr_retrieve(seq, 30, 10)
+    assert (sc == gc).all() and (si == gi).all() and (ss.view(np.uint64) == gs.view(np.uint64)).all()
+    s.close()
+    e.close()
