@@ -91,6 +91,8 @@ def load_library(build_if_missing: bool = True):
         "dmg_dr_train_step": [vp, i32, vp, vp, vp, i32, u64, dbl, i32, i32, i32, i32, vp, vp],
         "dmg_dr_download": [vp, i32, vp, C.POINTER(vp), C.POINTER(vp), vp, vp, vp, vp, vp],
         "dmg_train_step": [vp, i64, vp, vp, vp, i64, vp, dbl, i32, vp],
+        "dmg_train_step_dev": [vp, i64, vp, vp, vp, vp, dbl, i32, vp],
+        "dmg_score_pairs_dev": [vp, i64, vp, vp, vp, vp],
         "dmg_din_gradients": [vp, i64, vp, vp, vp, i64, vp, vp, vp, i64],
         "dmg_tdm_sample_expand": [vp, i32, vp, vp, vp, i32, i32, i32, u64, vp, vp, vp, C.POINTER(i32)],
         "dmg_jtm_item_weights": [vp, i32, vp, vp, vp, i32, i32, i32, i32, i32, vp],
@@ -467,6 +469,11 @@ class Engine:
         self._check(self.L.dmg_score_pairs(self.h, len(node), _p(node), _p(seq), _p(m), 0 if m is None else len(m), _p(out)))
         return out
 
+    def score_pairs_dev(self, n, d_node_ptr, d_seq_ptr, d_mask_ptr, d_out_ptr):
+        """Device-pointer form of score_pairs (ints from tensor.data_ptr(); d_mask_ptr = n x T mask bytes or 0); asynchronous."""
+        vp = C.c_void_p
+        self._check(self.L.dmg_score_pairs_dev(self.h, int(n), vp(d_node_ptr), vp(d_seq_ptr), vp(d_mask_ptr or None), vp(d_out_ptr)))
+
     # -- Deep Retrieval ------------------------------------------------------------
     def dr_load(self, num_item, K, D, T, E, layer_emb, layer_w, layer_b, rr_emb, rr_w, rr_b, sm_w, sm_b):
         c = lambda a: np.ascontiguousarray(a, np.float64)
@@ -573,6 +580,12 @@ class Engine:
         self._check(self.L.dmg_train_step(self.h, len(node), _p(node), _p(seq), _p(m), 0 if m is None else len(m),
                                           _p(labels), float(lr), int(step_t), _p(loss)))
         return loss[0]
+
+    def train_step_dev(self, rows, d_node_ptr, d_seq_ptr, d_mask_ptr, d_labels_ptr, lr, step_t, d_loss_ptr):
+        """Device-pointer form of train_step; asynchronous on the handle's stream (index errors surface at synchronize())."""
+        vp = C.c_void_p
+        self._check(self.L.dmg_train_step_dev(self.h, int(rows), vp(d_node_ptr), vp(d_seq_ptr), vp(d_mask_ptr or None), vp(d_labels_ptr),
+                                              float(lr), int(step_t), vp(d_loss_ptr)))
 
     def dp_train_step(self, node, seq, mask_flat, labels, lr, step_t):
         """Collective data-parallel step (dmg_dp_train_step): this rank's rows, gradients averaged over the ranks."""

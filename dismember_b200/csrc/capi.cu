@@ -155,6 +155,10 @@ DMG_API int32_t dmg_synchronize(dmg_handle_t h)
     if (!h) return DMG_ERR_INVALID_ARG;
     DMG_CUDA(h, cudaSetDevice(h->device));
     DMG_CUDA(h, cudaStreamSynchronize(h->stream));
+    if (h->h_flags && *(volatile int32_t *)h->h_flags) {          // raised by a *_dev call since the last check (mapped pinned memory)
+        h->h_flags[0] = 0;
+        return fail(h, DMG_ERR_INDEX, "embeddingLookup failed in a *_dev call: index outside [-1, %lld)", (long long)h->din.rows);
+    }
     return DMG_OK;
 }
 
@@ -1141,6 +1145,66 @@ DMG_API int32_t dmg_otm_retrieve(dmg_handle_t h, int32_t B, const int32_t *leaf_
 }
 
 // model.forward on n rows
+// model.forward on n device-resident rows (DIN): logits of the loaded dtype into d_out
+static int32_t score_pairs_enqueue(dmg_handle_t h, int64_t n, const int32_t *dn, const int32_t *ds, const uint8_t *d_mask, void *d_out)
+{
+    const DinDev &d = h->din;
+    const int T = d.T, E = d.E;
+    const size_t smem = (size_t)kRowsRB * ((size_t)4 * E + (size_t)T * E + T + 1) * d.esz;
+    const int grid = (int)std::min<int64_t>((n + kRowsRB - 1) / kRowsRB, (int64_t)h->sm_count * 8);
+    cudaError_t terr = cudaSuccess;
+    const bool tiled = d.dtype == DMG_F32
+        ? rows_forward_tiled<float>(E, d.emb<float>(), (const float *)d.d_wattT, (const float *)d.d_w1T, d.b1<float>(), d.w2<float>(), d.b2<float>(),
+                                    (float)(1.0 / std::sqrt((double)E)), T, n, dn, ds, d_mask, (float *)d_out, h->sm_count, h->smem_per_sm,
+                                    h->smem_optin, h->stream, &terr)
+        : rows_forward_tiled<double>(E, d.emb<double>(), (const double *)d.d_wattT, (const double *)d.d_w1T, d.b1<double>(), d.w2<double>(), d.b2<double>(),
+                                     1.0 / std::sqrt((double)E), T, n, dn, ds, d_mask, (double *)d_out, h->sm_count, h->smem_per_sm,
+                                     h->smem_optin, h->stream, &terr);
+    DMG_CUDA(h, terr);
+    if (tiled) {
+    } else if (d.dtype == DMG_F32) {
+        auto kern = din_rows_forward_kernel<float>;
+        DMG_CUDA(h, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        kern<<<grid, kRowsThreads, smem, h->stream>>>(d.emb<float>(), (const float *)d.d_wattT, (const float *)d.d_w1T,
+                                                      d.b1<float>(), d.w2<float>(), d.b2<float>(),
+                                                      (float)(1.0 / std::sqrt((double)E)), E, T, n, dn, ds, d_mask,
+                                                      (float *)d_out);
+    } else {
+        auto kern = din_rows_forward_kernel<double>;
+        DMG_CUDA(h, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        kern<<<grid, kRowsThreads, smem, h->stream>>>(d.emb<double>(), (const double *)d.d_wattT, (const double *)d.d_w1T,
+                                                      d.b1<double>(), d.w2<double>(), d.b2<double>(),
+                                                      1.0 / std::sqrt((double)E), E, T, n, dn, ds, d_mask,
+                                                      (double *)d_out);
+    }
+    h->launches += 1;
+    DMG_CUDA(h, cudaGetLastError());
+    return DMG_OK;
+}
+
+int32_t dmg_sanitize_indices(dmg_handle_t h, const int32_t *src, int32_t *dst, int64_t n, int64_t rows);   // train.cu
+
+/* device-buffer variant of dmg_score_pairs (DIN scorers): d_mask = rows x T mask bytes (nullable), nothing copied or synchronised;
+ * a bad index raises the handle's flag (dmg_synchronize returns DMG_ERR_INDEX) and scores as padding */
+DMG_API int32_t dmg_score_pairs_dev(dmg_handle_t h, int64_t n, const int32_t *d_node, const int32_t *d_seq, const uint8_t *d_mask, void *d_out)
+{
+    if (!h) return DMG_ERR_INVALID_ARG;
+    if (!h->din.loaded || h->din.kind != 0) return fail(h, DMG_ERR_STATE, "DIN weights must be loaded first");
+    if (h->din.sharded) return fail(h, DMG_ERR_STATE, "the node table is sharded (dmg_shard_init): use the dmg_shard_* entry points");
+    if (n < 0 || (n > 0 && (!d_node || !d_seq || !d_out))) return fail(h, DMG_ERR_INVALID_ARG, "bad arguments");
+    if (n == 0) return DMG_OK;
+    DMG_CUDA(h, cudaSetDevice(h->device));
+    const int T = h->din.T;
+    DMG_TRY(ensure_dev(h, h->s_work, Carver::need({(size_t)n * 4, (size_t)n * T * 4, (size_t)n * T})));
+    Carver cw(h->s_work.d);
+    int32_t *dn = cw.take<int32_t>((size_t)n), *ds = cw.take<int32_t>((size_t)n * T);
+    uint8_t *zmask = cw.take<uint8_t>((size_t)n * T);
+    DMG_TRY(dmg_sanitize_indices(h, d_node, dn, n, h->din.rows));
+    DMG_TRY(dmg_sanitize_indices(h, d_seq, ds, n * T, h->din.rows));
+    if (!d_mask) DMG_CUDA(h, cudaMemsetAsync(zmask, 0, (size_t)n * T, h->stream));
+    return score_pairs_enqueue(h, n, dn, ds, d_mask ? d_mask : zmask, d_out);
+}
+
 DMG_API int32_t dmg_score_pairs(dmg_handle_t h, int64_t n, const int32_t *node, const int32_t *seq, const int32_t *mask_flat,
                                 int64_t n_mask, void *out)
 {
@@ -1190,34 +1254,7 @@ DMG_API int32_t dmg_score_pairs(dmg_handle_t h, int64_t n, const int32_t *node, 
     const size_t out_bytes = (size_t)n * d.esz;
     DMG_TRY(ensure_host(h, h->s_out, out_bytes));
     DMG_TRY(ensure_dev(h, h->s_out, out_bytes));
-    const size_t smem = (size_t)kRowsRB * ((size_t)4 * E + (size_t)T * E + T + 1) * d.esz;
-    const int grid = (int)std::min<int64_t>((n + kRowsRB - 1) / kRowsRB, (int64_t)h->sm_count * 8);
-    cudaError_t terr = cudaSuccess;
-    const bool tiled = d.dtype == DMG_F32
-        ? rows_forward_tiled<float>(E, d.emb<float>(), (const float *)d.d_wattT, (const float *)d.d_w1T, d.b1<float>(), d.w2<float>(), d.b2<float>(),
-                                    (float)(1.0 / std::sqrt((double)E)), T, n, dn, ds, d_mask, (float *)h->s_out.d, h->sm_count, h->smem_per_sm,
-                                    h->smem_optin, h->stream, &terr)
-        : rows_forward_tiled<double>(E, d.emb<double>(), (const double *)d.d_wattT, (const double *)d.d_w1T, d.b1<double>(), d.w2<double>(), d.b2<double>(),
-                                     1.0 / std::sqrt((double)E), T, n, dn, ds, d_mask, (double *)h->s_out.d, h->sm_count, h->smem_per_sm,
-                                     h->smem_optin, h->stream, &terr);
-    DMG_CUDA(h, terr);
-    if (tiled) {
-    } else if (d.dtype == DMG_F32) {
-        auto kern = din_rows_forward_kernel<float>;
-        DMG_CUDA(h, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        kern<<<grid, kRowsThreads, smem, h->stream>>>(d.emb<float>(), (const float *)d.d_wattT, (const float *)d.d_w1T,
-                                                      d.b1<float>(), d.w2<float>(), d.b2<float>(),
-                                                      (float)(1.0 / std::sqrt((double)E)), E, T, n, dn, ds, d_mask,
-                                                      (float *)h->s_out.d);
-    } else {
-        auto kern = din_rows_forward_kernel<double>;
-        DMG_CUDA(h, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        kern<<<grid, kRowsThreads, smem, h->stream>>>(d.emb<double>(), (const double *)d.d_wattT, (const double *)d.d_w1T,
-                                                      d.b1<double>(), d.w2<double>(), d.b2<double>(),
-                                                      1.0 / std::sqrt((double)E), E, T, n, dn, ds, d_mask,
-                                                      (double *)h->s_out.d);
-    }
-    h->launches += 1;
+    DMG_TRY(score_pairs_enqueue(h, n, dn, ds, d_mask, h->s_out.d));
     DMG_CUDA(h, cudaGetLastError());
     DMG_CUDA(h, cudaMemcpyAsync(h->s_out.h, h->s_out.d, out_bytes, cudaMemcpyDeviceToHost, h->stream));
     DMG_CUDA(h, cudaStreamSynchronize(h->stream));

@@ -454,6 +454,32 @@ template <typename real> int32_t ensure_train_state(dmg_handle_t h)
 }
 
 // uploads (node, seq, mask, labels), validates, runs K5/K6 into d_grad.  Loss (mean) -> *loss_out.
+// forward + BCE + backward on device-resident rows: gradients accumulate into d.d_grad, the summed loss into d_loss
+template <typename real>
+int32_t grad_enqueue(dmg_handle_t h, int64_t n, const int32_t *dn, const int32_t *ds, const uint8_t *d_mask, const real *dl, double *d_loss)
+{
+    DinDev &d = h->din;
+    const int E = d.E, T = d.T;
+    TrainParams<real> p;
+    p.emb = d.emb<real>(); p.watt = d.watt<real>(); p.w1 = d.w1<real>(); p.b1 = d.b1<real>(); p.w2 = d.w2<real>(); p.b2 = d.b2<real>();
+    p.wattT = (const real *)d.d_wattT; p.w1T = (const real *)d.d_w1T;
+    p.scale = (real)(1.0 / std::sqrt((double)E));
+    p.E = E; p.T = T; p.n = n; p.node = dn; p.seq = ds; p.mask = d_mask; p.labels = dl;
+    real *g = (real *)d.d_grad;
+    p.g_emb = g; p.g_watt = g + d.rows * E; p.g_w1 = p.g_watt + (int64_t)E * E; p.g_b1 = p.g_w1 + (int64_t)2 * E * E;
+    p.g_w2 = p.g_b1 + E; p.g_b2 = p.g_w2 + E;
+    p.loss_acc = d_loss;
+    const size_t smem = ((size_t)kTrRB * ((size_t)8 * E + (size_t)T * E + 2 * (T + 1) + 1) + 3 * (size_t)E * E + 2 * E + 2) * sizeof(real);
+    if (smem > h->smem_optin) return fail(h, DMG_ERR_UNSUPPORTED, "embed_size %d too large for the training kernel", E);
+    auto kern = din_train_kernel<real>;
+    DMG_CUDA(h, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const int grid = (int)std::min<int64_t>((n + kTrRB - 1) / kTrRB, (int64_t)h->sm_count * 4);
+    kern<<<grid, kTrThreads, smem, h->stream>>>(p);
+    h->launches += 1;
+    DMG_CUDA(h, cudaGetLastError());
+    return DMG_OK;
+}
+
 template <typename real>
 int32_t grad_pass(dmg_handle_t h, int64_t n, const int32_t *node, const int32_t *seq, const int32_t *mask_flat, int64_t n_mask,
                   const real *labels, double *loss_out)
@@ -493,23 +519,7 @@ int32_t grad_pass(dmg_handle_t h, int64_t n, const int32_t *node, const int32_t 
         DMG_CUDA(h, cudaMemsetAsync(h->d_flags, 0, 4, h->stream));
         return fail(h, DMG_ERR_INDEX, "training batch: embeddingLookup failed, index outside [0, %lld) or bad mask position", (long long)d.rows);
     }
-    TrainParams<real> p;
-    p.emb = d.emb<real>(); p.watt = d.watt<real>(); p.w1 = d.w1<real>(); p.b1 = d.b1<real>(); p.w2 = d.w2<real>(); p.b2 = d.b2<real>();
-    p.wattT = (const real *)d.d_wattT; p.w1T = (const real *)d.d_w1T;
-    p.scale = (real)(1.0 / std::sqrt((double)E));
-    p.E = E; p.T = T; p.n = n; p.node = dn; p.seq = ds; p.mask = d_mask; p.labels = dl;
-    real *g = (real *)d.d_grad;
-    p.g_emb = g; p.g_watt = g + d.rows * E; p.g_w1 = p.g_watt + (int64_t)E * E; p.g_b1 = p.g_w1 + (int64_t)2 * E * E;
-    p.g_w2 = p.g_b1 + E; p.g_b2 = p.g_w2 + E;
-    p.loss_acc = d_loss;
-    const size_t smem = ((size_t)kTrRB * ((size_t)8 * E + (size_t)T * E + 2 * (T + 1) + 1) + 3 * (size_t)E * E + 2 * E + 2) * sizeof(real);
-    if (smem > h->smem_optin) return fail(h, DMG_ERR_UNSUPPORTED, "embed_size %d too large for the training kernel", E);
-    auto kern = din_train_kernel<real>;
-    DMG_CUDA(h, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    const int grid = (int)std::min<int64_t>((n + kTrRB - 1) / kTrRB, (int64_t)h->sm_count * 4);
-    kern<<<grid, kTrThreads, smem, h->stream>>>(p);
-    h->launches += 1;
-    DMG_CUDA(h, cudaGetLastError());
+    DMG_TRY(grad_enqueue<real>(h, n, dn, ds, d_mask, dl, d_loss));
     double loss_sum = 0.0;
     DMG_CUDA(h, cudaMemcpyAsync(&loss_sum, d_loss, sizeof(double), cudaMemcpyDeviceToHost, h->stream));
     DMG_CUDA(h, cudaStreamSynchronize(h->stream));
@@ -583,6 +593,61 @@ DMG_API int32_t dmg_train_step(dmg_handle_t h, int64_t rows, const int32_t *node
         *(double *)out_loss = loss;
     }
     DMG_CUDA(h, cudaStreamSynchronize(h->stream));
+    return DMG_OK;
+}
+
+// ---- device-buffer variant: nothing is copied, nothing is synchronised ----------------------------------------------------------
+namespace {
+// embeddingLookup's range check without a host round trip: a bad index raises the handle's flag (reported by dmg_synchronize) and is
+// replaced by the padding index so that the kernels behind it stay inside the table
+__global__ void sanitize_index_kernel(const int32_t *__restrict__ src, int32_t *__restrict__ dst, int64_t n, int64_t rows, int32_t *__restrict__ flag)
+{
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    int32_t c = src[i];
+    if (c < -1 || (int64_t)c >= rows) { atomicExch(flag, 1); c = -1; }
+    dst[i] = c;
+}
+template <typename real> __global__ void loss_mean_kernel(const double *__restrict__ sum, int64_t n, real *__restrict__ out) { *out = (real)(*sum / (double)n); }
+}  // namespace
+
+int32_t dmg_sanitize_indices(dmg_handle_t h, const int32_t *src, int32_t *dst, int64_t n, int64_t rows)
+{
+    if (n > 0) sanitize_index_kernel<<<(unsigned)((n + 255) / 256), 256, 0, h->stream>>>(src, dst, n, rows, h->d_flags);
+    h->launches += 1;
+    DMG_CUDA(h, cudaGetLastError());
+    return DMG_OK;
+}
+
+DMG_API int32_t dmg_train_step_dev(dmg_handle_t h, int64_t rows, const int32_t *d_node, const int32_t *d_seq, const uint8_t *d_mask,
+                                   const void *d_labels, double lr, int32_t step_t, void *d_out_loss)
+{
+    DMG_TRY(train_precheck(h, rows, d_node, d_seq, d_labels, d_out_loss));
+    if (step_t < 1) return fail(h, DMG_ERR_INVALID_ARG, "step_t is the 1-based Adam timestep");
+    DinDev &d = h->din;
+    const int T = d.T;
+    const bool f32 = d.dtype == DMG_F32;
+    if (f32) DMG_TRY(ensure_train_state<float>(h)); else DMG_TRY(ensure_train_state<double>(h));
+    DMG_TRY(ensure_dev(h, h->s_work, Carver::need({(size_t)rows * 4, (size_t)rows * T * 4, (size_t)rows * T, 64})));
+    Carver cw(h->s_work.d);
+    int32_t *dn = cw.take<int32_t>((size_t)rows), *ds = cw.take<int32_t>((size_t)rows * T);
+    uint8_t *zmask = cw.take<uint8_t>((size_t)rows * T);
+    double *d_loss = cw.take<double>(1);
+    DMG_TRY(dmg_sanitize_indices(h, d_node, dn, rows, d.rows));
+    DMG_TRY(dmg_sanitize_indices(h, d_seq, ds, rows * T, d.rows));
+    if (!d_mask) DMG_CUDA(h, cudaMemsetAsync(zmask, 0, (size_t)rows * T, h->stream));
+    DMG_CUDA(h, cudaMemsetAsync(d_loss, 0, sizeof(double), h->stream));
+    if (f32) {
+        DMG_TRY(grad_enqueue<float>(h, rows, dn, ds, d_mask ? d_mask : zmask, (const float *)d_labels, d_loss));
+        DMG_TRY(adam_pass<float>(h, lr, step_t));
+        loss_mean_kernel<float><<<1, 1, 0, h->stream>>>(d_loss, rows, (float *)d_out_loss);
+    } else {
+        DMG_TRY(grad_enqueue<double>(h, rows, dn, ds, d_mask ? d_mask : zmask, (const double *)d_labels, d_loss));
+        DMG_TRY(adam_pass<double>(h, lr, step_t));
+        loss_mean_kernel<double><<<1, 1, 0, h->stream>>>(d_loss, rows, (double *)d_out_loss);
+    }
+    h->launches += 1;
+    DMG_CUDA(h, cudaGetLastError());
     return DMG_OK;
 }
 

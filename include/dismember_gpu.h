@@ -196,6 +196,12 @@ DMG_API int32_t dmg_otm_retrieve(dmg_handle_t h, int32_t B, const int32_t *leaf_
 DMG_API int32_t dmg_score_pairs(dmg_handle_t h, int64_t n, const int32_t *node, const int32_t *seq,
                                 const int32_t *mask_flat, int64_t n_mask, void *out);
 
+/* Device-buffer variant (DIN scorers): d_node[n], d_seq[n*T], d_mask = n x T mask BYTES (1 = masked; nullable), d_out[n]
+ * of the loaded dtype.  Enqueues on the handle's stream and returns; an index outside [-1, rows) scores as padding
+ * and makes the next dmg_synchronize return DMG_ERR_INDEX. */
+DMG_API int32_t dmg_score_pairs_dev(dmg_handle_t h, int64_t n, const int32_t *d_node,
+                                    const int32_t *d_seq, const uint8_t *d_mask, void *d_out);
+
 /* ---- Deep Retrieval ------------------------------------------------------------------- */
 /* LayerModel + RerankModel parameters (deep-retrieval/.../model/LayerModel.scala:22-39,
  * RerankModel.scala:20-41), all Double, row-major [out,in]:
@@ -260,6 +266,12 @@ DMG_API int32_t dmg_kmeans_tree(dmg_handle_t h, int32_t n, int32_t E, const doub
 DMG_API int32_t dmg_train_step(dmg_handle_t h, int64_t rows, const int32_t *node, const int32_t *seq,
                                const int32_t *mask_flat, int64_t n_mask, const void *labels,
                                double lr, int32_t step_t, void *out_loss);
+/* Device-buffer variant of dmg_train_step: rows already on the device (d_mask = rows x T mask bytes, nullable;
+ * d_labels / d_out_loss of the loaded dtype), no copy and no synchronisation inside; index errors as in
+ * dmg_score_pairs_dev. */
+DMG_API int32_t dmg_train_step_dev(dmg_handle_t h, int64_t rows, const int32_t *d_node, const int32_t *d_seq,
+                                   const uint8_t *d_mask, const void *d_labels, double lr, int32_t step_t,
+                                   void *d_out_loss);
 /* forward + backward only: gradient of the compact vector (testing / syncGradients). */
 DMG_API int32_t dmg_din_gradients(dmg_handle_t h, int64_t rows, const int32_t *node,
                                   const int32_t *seq, const int32_t *mask_flat, int64_t n_mask,

@@ -126,7 +126,8 @@ def test_world1_deep_retrieval_matches_the_unsharded_engine(dr_fix, queries):
 
 def _two_gpu_worker(rank, world, port, out_dir):
     sys.path.insert(0, ROOT)
-    sys.argv = ["shard_check.py", "--items", "5000", "--batch", "24", "--out", os.path.join(out_dir, f"r{rank}.json")]
+    sys.argv = ["shard_check.py", "--items", "5000", "--batch", "24", "--train-targets", "40", "--jtm-items", "200", "--dr-items", "3000",
+                "--dr-k", "12", "--dr-batch", "16", "--out", os.path.join(out_dir, f"r{rank}.json")]
     os.environ.update(RANK=str(rank), WORLD_SIZE=str(world), LOCAL_RANK=str(rank), MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
     import runpy
     runpy.run_path(os.path.join(ROOT, "tools", "shard_check.py"), run_name="__main__")
@@ -142,6 +143,11 @@ def test_world2_matches_oracle(tmp_path):
     for r in range(2):
         d = json.load(open(tmp_path / f"r{r}.json"))
         assert d["ids_identical"] and d["logits_bit_identical"] and d["rows_scored_for_other_ranks"] > 0
+        assert d["jtm_item_weights"]["weights_bit_identical"]
+        assert d["deep_retrieval"]["ids_identical"] and d["deep_retrieval"]["scores_bit_identical"]
+        # dmg_dp_train_step (LocalOptimizer.syncGradients with GPUs in the place of threads): two steps on two ranks == one engine on
+        # the concatenated batch up to the fp32 summation order
+        assert d["dp_train_step"]["max_abs_weight_diff_vs_single_engine"] < 1e-5 * max(1.0, d["dp_train_step"]["max_abs_weight"])
 
 
 def test_dr_synthetic_model_unsharded_sharded_oracle(orc):

@@ -277,3 +277,73 @@ def test_categorical_sampler_follows_node_probabilities(engine, jtm_fix):
     from dismember_b200 import DmgError
     with pytest.raises(DmgError):
         engine.tdm_sample_expand(targets[:4], seqs[:4], layer_neg, 1, seed=5, with_prob=True)
+
+
+@pytest.mark.parametrize("which", ["f32", "f64"])
+def test_dev_variants_match_the_host_entry_points(jtm_fix, otm_fix, which):
+    """dmg_score_pairs_dev / dmg_train_step_dev (device buffers, no copy, no synchronisation) == dmg_score_pairs / dmg_train_step bit
+    for bit on the forward, within the atomics' reordering on the step; a bad index surfaces at dmg_synchronize."""
+    import torch
+    from conftest import new_engine
+    from dismember_b200._capi import DmgError
+    fix = jtm_fix if which == "f32" else otm_fix
+    params = fix["params"]
+    tdt = torch.float32 if which == "f32" else torch.float64
+    rng = np.random.default_rng(15)
+    node, seq, mask, labels = _batch(rng, 8191, 10, 900)
+    a, b = new_engine(), new_engine()
+    for e in (a, b):
+        e.load_din_weights(params, 8191, 16, 10)
+    dev = torch.device("cuda", 0)
+    t_node, t_seq = torch.from_numpy(node).to(dev), torch.from_numpy(seq).to(dev)
+    t_mask = torch.from_numpy((seq == -1).astype(np.uint8)).to(dev)
+    t_lab = torch.from_numpy(labels.astype(params.dtype)).to(dev)
+    t_out = torch.empty(len(node), dtype=tdt, device=dev)
+    t_loss = torch.zeros(1, dtype=tdt, device=dev)
+    torch.cuda.synchronize()
+    a.score_pairs_dev(len(node), t_node.data_ptr(), t_seq.data_ptr(), t_mask.data_ptr(), t_out.data_ptr())
+    a.synchronize()
+    want = b.score_pairs(node, seq, mask)
+    assert (t_out.cpu().numpy().view(np.uint8) == want.view(np.uint8)).all()
+    # no mask bytes = useMask false: the host form with an empty mask list
+    a.score_pairs_dev(len(node), t_node.data_ptr(), t_seq.data_ptr(), 0, t_out.data_ptr())
+    a.synchronize()
+    assert (t_out.cpu().numpy().view(np.uint8) == b.score_pairs(node, seq, None).view(np.uint8)).all()
+    for t in (1, 2, 3):
+        a.train_step_dev(len(node), t_node.data_ptr(), t_seq.data_ptr(), t_mask.data_ptr(), t_lab.data_ptr(), 1e-2, t, t_loss.data_ptr())
+        a.synchronize()
+        loss_b = b.train_step(node, seq, mask, labels, 1e-2, t)
+        tol = 1e-5 if which == "f32" else 1e-11
+        assert abs(float(t_loss.item()) - float(loss_b)) <= tol * max(1.0, abs(float(loss_b)))
+    wa, wb = a.download_din_weights(), b.download_din_weights()
+    assert np.abs(wa - wb).max() <= (2e-4 if which == "f32" else 1e-9)
+    assert np.abs(wa - params).max() > 1e-3
+    bad = t_node.clone()
+    bad[5] = 9000
+    a.score_pairs_dev(len(node), bad.data_ptr(), t_seq.data_ptr(), t_mask.data_ptr(), t_out.data_ptr())
+    with pytest.raises(DmgError):
+        a.synchronize()
+    a.synchronize()                                               # the flag is reported once
+    a.close()
+    b.close()
+
+
+def test_dp_train_step_world1_is_train_step(jtm_fix):
+    """dmg_dp_train_step on a communicator of one rank (LocalOptimizer.syncGradients with a single thread) == dmg_train_step: same
+    loss, same weights bit for bit after three steps.  The 2-GPU form runs in tests/test_gpu_shard.py when two GPUs are visible."""
+    from conftest import new_engine
+    params = jtm_fix["params"]
+    rng = np.random.default_rng(16)
+    a, b = new_engine(), new_engine()
+    a.shard_init(1, 0)
+    for e in (a, b):
+        e.load_din_weights(params, 8191, 16, 10)
+    for t in (1, 2, 3):
+        node, seq, mask, labels = _batch(rng, 8191, 10, 256)
+        la = a.dp_train_step(node, seq, mask, labels, 1e-2, t)
+        lb = b.train_step(node, seq, mask, labels, 1e-2, t)
+        assert abs(float(la) - float(lb)) <= 1e-5 * max(1.0, abs(float(lb)))
+    wa, wb = a.download_din_weights(), b.download_din_weights()
+    assert np.abs(wa - wb).max() <= 2e-4 and np.abs(wa - params).max() > 1e-3
+    a.close()
+    b.close()
