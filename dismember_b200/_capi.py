@@ -92,6 +92,7 @@ def load_library(build_if_missing: bool = True):
         "dmg_dr_download": [vp, i32, vp, C.POINTER(vp), C.POINTER(vp), vp, vp, vp, vp, vp],
         "dmg_train_step": [vp, i64, vp, vp, vp, i64, vp, dbl, i32, vp],
         "dmg_train_step_dev": [vp, i64, vp, vp, vp, vp, dbl, i32, vp],
+        "dmg_shard_train_step": [vp, i64, vp, vp, vp, i64, vp, dbl, i32, vp],
         "dmg_score_pairs_dev": [vp, i64, vp, vp, vp, vp],
         "dmg_din_gradients": [vp, i64, vp, vp, vp, i64, vp, vp, vp, i64],
         "dmg_tdm_sample_expand": [vp, i32, vp, vp, vp, i32, i32, i32, u64, vp, vp, vp, C.POINTER(i32)],
@@ -596,6 +597,17 @@ class Engine:
         loss = np.zeros(1, self.din_dtype)
         self._check(self.L.dmg_dp_train_step(self.h, len(node), _p(node), _p(seq), _p(m), 0 if m is None else len(m),
                                              _p(labels), float(lr), int(step_t), _p(loss)))
+        return loss[0]
+
+    def shard_train_step(self, node, seq, mask_flat, labels, lr, step_t):
+        """Collective training step on the sharded table (dmg_shard_train_step): this rank's rows with GLOBAL node codes."""
+        node = _i32(node).ravel()
+        seq = _i32(seq).reshape(len(node), self.T)
+        labels = np.ascontiguousarray(labels, np.float32).ravel()
+        m = None if mask_flat is None else _i32(mask_flat).ravel()
+        loss = np.zeros(1, np.float32)
+        self._check(self.L.dmg_shard_train_step(self.h, len(node), _p(node), _p(seq), _p(m), 0 if m is None else len(m),
+                                                _p(labels), float(lr), int(step_t), _p(loss)))
         return loss[0]
 
     def otm_pseudo_targets(self, leaf_seq, target_off, targets, leaf_level, start_level, use_mask=True, M=None):

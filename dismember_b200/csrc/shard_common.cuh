@@ -61,6 +61,40 @@ struct ShardGeo {
     int64_t repl_rows;            // 2^bits - 1 replicated rows (levels < bits)
 };
 
+__host__ __device__ __forceinline__ int code_level(int64_t c)
+{
+#ifdef __CUDA_ARCH__
+    return 63 - __clzll((unsigned long long)(c + 1));
+#else
+    int l = 0;
+    while (((int64_t)2 << l) <= c + 1) l++;
+    return l;
+#endif
+}
+// owner of code c; replicated levels report `self`
+__host__ __device__ __forceinline__ int shard_owner(const ShardGeo &g, int64_t c)
+{
+    const int l = code_level(c);
+    if (l < g.bits) return g.rank;
+    return (int)((c - (((int64_t)1 << l) - 1)) >> (l - g.bits));
+}
+// row of code c in the local table of its owner (or of anyone, on a replicated level)
+__host__ __device__ __forceinline__ int64_t shard_local_row(const ShardGeo &g, int64_t c)
+{
+    const int l = code_level(c);
+    if (l < g.bits) return c;
+    const int sh = l - g.bits;
+    return g.repl_rows + (((int64_t)1 << sh) - 1) + ((c - (((int64_t)1 << l) - 1)) & (((int64_t)1 << sh) - 1));
+}
+// inverse: global code of local row lr on rank g.rank
+__host__ __device__ __forceinline__ int64_t shard_global_row(const ShardGeo &g, int64_t lr)
+{
+    if (lr < g.repl_rows) return lr;
+    const int64_t t = lr - g.repl_rows + 1;
+    const int sh = code_level(t - 1);                       // floor(log2 t)
+    const int l = g.bits + sh;
+    return (((int64_t)1 << l) - 1) + ((int64_t)g.rank << sh) + (t - ((int64_t)1 << sh));
+}
 struct ShardState {
     int world = 1, rank = 0, bits = 0;
     ncclComm_t comm = nullptr;

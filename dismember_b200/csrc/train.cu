@@ -42,6 +42,7 @@ template <typename real> struct TrainParams {
     real scale;
     int E, T;
     int64_t n;
+    double n_norm;                                  // the mean of BCECriterionWithLogits divides by this (n, or the global batch when rows are split over ranks)
     const int32_t *node, *seq;
     const uint8_t *mask;
     const real *labels;
@@ -73,7 +74,7 @@ __global__ void __launch_bounds__(kTrThreads) din_train_kernel(const TrainParams
     const int tid = threadIdx.x;
     for (int i = tid; i < 3 * E * E + 2 * E + 2; i += kTrThreads) gWatt[i] = (real)0;
     double loss_local = 0.0;
-    const real inv_n = (real)(1.0 / (double)p.n);
+    const real inv_n = (real)(1.0 / p.n_norm);
     __syncthreads();
 
     for (int64_t g0 = (int64_t)blockIdx.x * kTrRB; g0 < p.n; g0 += (int64_t)gridDim.x * kTrRB) {
@@ -456,7 +457,8 @@ template <typename real> int32_t ensure_train_state(dmg_handle_t h)
 // uploads (node, seq, mask, labels), validates, runs K5/K6 into d_grad.  Loss (mean) -> *loss_out.
 // forward + BCE + backward on device-resident rows: gradients accumulate into d.d_grad, the summed loss into d_loss
 template <typename real>
-int32_t grad_enqueue(dmg_handle_t h, int64_t n, const int32_t *dn, const int32_t *ds, const uint8_t *d_mask, const real *dl, double *d_loss)
+int32_t grad_enqueue(dmg_handle_t h, int64_t n, const int32_t *dn, const int32_t *ds, const uint8_t *d_mask, const real *dl, double *d_loss,
+                     const real *emb_override = nullptr, real *g_emb_override = nullptr, double n_norm = 0.0)
 {
     DinDev &d = h->din;
     const int E = d.E, T = d.T;
@@ -465,8 +467,10 @@ int32_t grad_enqueue(dmg_handle_t h, int64_t n, const int32_t *dn, const int32_t
     p.wattT = (const real *)d.d_wattT; p.w1T = (const real *)d.d_w1T;
     p.scale = (real)(1.0 / std::sqrt((double)E));
     p.E = E; p.T = T; p.n = n; p.node = dn; p.seq = ds; p.mask = d_mask; p.labels = dl;
+    p.n_norm = n_norm > 0.0 ? n_norm : (double)n;
+    if (emb_override) p.emb = emb_override;          // rows staged per occurrence (sharded table): indices are occurrence ids
     real *g = (real *)d.d_grad;
-    p.g_emb = g; p.g_watt = g + d.rows * E; p.g_w1 = p.g_watt + (int64_t)E * E; p.g_b1 = p.g_w1 + (int64_t)2 * E * E;
+    p.g_emb = g_emb_override ? g_emb_override : g; p.g_watt = g + d.rows * E; p.g_w1 = p.g_watt + (int64_t)E * E; p.g_b1 = p.g_w1 + (int64_t)2 * E * E;
     p.g_w2 = p.g_b1 + E; p.g_b2 = p.g_w2 + E;
     p.loss_acc = d_loss;
     const size_t smem = ((size_t)kTrRB * ((size_t)8 * E + (size_t)T * E + 2 * (T + 1) + 1) + 3 * (size_t)E * E + 2 * E + 2) * sizeof(real);
@@ -1112,5 +1116,225 @@ DMG_API int32_t dmg_dp_train_step(dmg_handle_t h, int64_t rows, const int32_t *n
     if (d.dtype == DMG_F32) { DMG_TRY(adam_pass<float>(h, lr, step_t)); *(float *)out_loss = (float)loss; }
     else { DMG_TRY(adam_pass<double>(h, lr, step_t)); *(double *)out_loss = loss; }
     DMG_CUDA(h, cudaStreamSynchronize(h->stream));
+    return DMG_OK;
+}
+
+// ---- training on the SHARDED node table -----------------------------------------------------------------------------
+// LocalOptimizer.trainBatch / syncGradients (tdm/.../optim/LocalOptimizer.scala:139-187) when no rank holds the whole table: every
+// rank brings its rows of the mini-batch with GLOBAL node codes.  Every embedding occurrence (row, slot) is fetched from the row's
+// owner (4 B out, E floats back), forward / BCE / backward run locally on the staged rows (the same din_train_kernel, indices =
+// occurrence ids, mean over the GLOBAL batch), the per-occurrence gradients travel back and are APPLIED BY THE OWNER (atomic
+// scatter-add into its shard of the dense gradient); only the 3 E^2 + 2 E + 1 dense scorer weights (12 417 at E = 64) and the
+// 2^bits - 1 replicated top rows are all-reduced.  Every rank then runs the dense Adam over its own shard.
+namespace {
+__global__ void shtr_owner_kernel(int64_t n_occ, int T, const int32_t *__restrict__ node, const int32_t *__restrict__ seq, ShardGeo g,
+                                  int64_t global_rows, int32_t *__restrict__ occ_code, int32_t *__restrict__ counts, int32_t *__restrict__ flag)
+{
+    const int64_t o = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (o >= n_occ) return;
+    const int64_t r = o / (T + 1);
+    const int slot = (int)(o - r * (T + 1));
+    int32_t c = slot == 0 ? node[r] : seq[r * T + slot - 1];
+    if (c < -1 || (int64_t)c >= global_rows || (slot == 0 && c < 0)) { atomicExch(flag, 1); c = -1; }
+    occ_code[o] = c;
+    if (c >= 0) {
+        const int ow = shard_owner(g, c);
+        if (ow != g.rank) atomicAdd(counts + ow, 1);
+    }
+}
+// remote occurrences appended to the region of their owner: req_code / req_occ at send_off[owner] + cursor
+__global__ void shtr_bucket_kernel(int64_t n_occ, const int32_t *__restrict__ occ_code, ShardGeo g, const int32_t *__restrict__ send_off,
+                                   int32_t *__restrict__ cursor, int32_t *__restrict__ req_code, int32_t *__restrict__ req_occ)
+{
+    const int64_t o = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (o >= n_occ) return;
+    const int32_t c = occ_code[o];
+    if (c < 0) return;
+    const int ow = shard_owner(g, c);
+    if (ow == g.rank) return;
+    const int pos = send_off[ow] + atomicAdd(cursor + ow, 1);
+    req_code[pos] = c; req_occ[pos] = (int32_t)o;
+}
+// owner side: rows of the requested codes
+__global__ void shtr_gather_kernel(int64_t n, int E, const int32_t *__restrict__ codes, ShardGeo g, const float *__restrict__ emb, float *__restrict__ out)
+{
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n * E; i += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t q = i / E;
+        out[i] = emb[shard_local_row(g, codes[q]) * E + (i - q * E)];
+    }
+}
+// staged rows per occurrence: own / replicated rows straight from the local table, remote ones from the replies; remapped indices
+__global__ void shtr_stage_local_kernel(int64_t n_occ, int E, const int32_t *__restrict__ occ_code, ShardGeo g, const float *__restrict__ emb,
+                                        float *__restrict__ stage)
+{
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_occ * E; i += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t o = i / E;
+        const int32_t c = occ_code[o];
+        if (c >= 0 && shard_owner(g, c) == g.rank) stage[i] = emb[shard_local_row(g, c) * E + (i - o * E)];
+    }
+}
+__global__ void shtr_stage_remote_kernel(int64_t n, int E, const int32_t *__restrict__ req_occ, const float *__restrict__ rows, float *__restrict__ stage)
+{
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n * E; i += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t q = i / E;
+        stage[(int64_t)req_occ[q] * E + (i - q * E)] = rows[i];
+    }
+}
+__global__ void shtr_remap_kernel(int64_t rows, int T, const int32_t *__restrict__ occ_code, int32_t *__restrict__ node2, int32_t *__restrict__ seq2)
+{
+    const int64_t o = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (o >= rows * (T + 1)) return;
+    const int64_t r = o / (T + 1);
+    const int slot = (int)(o - r * (T + 1));
+    const int32_t v = occ_code[o] >= 0 ? (int32_t)o : -1;
+    if (slot == 0) node2[r] = v; else seq2[r * T + slot - 1] = v;
+}
+// gradients back: own rows added in place, remote ones packed in request order
+__global__ void shtr_grad_local_kernel(int64_t n_occ, int E, const int32_t *__restrict__ occ_code, ShardGeo g, const float *__restrict__ sgrad,
+                                       float *__restrict__ g_emb)
+{
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_occ * E; i += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t o = i / E;
+        const int32_t c = occ_code[o];
+        if (c >= 0 && shard_owner(g, c) == g.rank) { const float v = sgrad[i]; if (v != 0.0f) atomicAdd(g_emb + shard_local_row(g, c) * E + (i - o * E), v); }
+    }
+}
+__global__ void shtr_grad_pack_kernel(int64_t n, int E, const int32_t *__restrict__ req_occ, const float *__restrict__ sgrad, float *__restrict__ out)
+{
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n * E; i += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t q = i / E;
+        out[i] = sgrad[(int64_t)req_occ[q] * E + (i - q * E)];
+    }
+}
+__global__ void shtr_grad_apply_kernel(int64_t n, int E, const int32_t *__restrict__ codes, ShardGeo g, const float *__restrict__ in, float *__restrict__ g_emb)
+{
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n * E; i += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t q = i / E;
+        const float v = in[i];
+        if (v != 0.0f) atomicAdd(g_emb + shard_local_row(g, codes[q]) * E + (i - q * E), v);
+    }
+}
+}  // namespace
+
+DMG_API int32_t dmg_shard_train_step(dmg_handle_t h, int64_t rows, const int32_t *node, const int32_t *seq, const int32_t *mask_flat,
+                                     int64_t n_mask, const float *labels, double lr, int32_t step_t, float *out_loss)
+{
+    if (!h) return DMG_ERR_INVALID_ARG;
+    DMG_TRY(model_is_shared(h, "training"));
+    ShardState *s = h->shard;
+    DinDev &d = h->din;
+    if (!s || !d.loaded || d.kind != 0 || d.dtype != DMG_F32) return fail(h, DMG_ERR_STATE, "dmg_shard_init and a sharded Float DIN table first");
+    if (rows <= 0 || !node || !seq || !labels || !out_loss || n_mask < 0 || (n_mask > 0 && !mask_flat) || step_t < 1)
+        return fail(h, DMG_ERR_INVALID_ARG, "dmg_shard_train_step: bad arguments");
+    DMG_CUDA(h, cudaSetDevice(h->device));
+    const int G = s->world, E = d.E, T = d.T, me = s->rank;
+    const ShardGeo g = s->geo();
+    const int64_t n_occ = rows * (T + 1);
+    if (n_occ > 0x7fffffff) return fail(h, DMG_ERR_UNSUPPORTED, "batch too large");
+    cudaStream_t st = h->stream;
+    DMG_TRY(ensure_train_state<float>(h));
+    // inputs
+    const size_t in_bytes = Carver::need({(size_t)rows * 4, (size_t)rows * T * 4, (size_t)n_mask * 4, (size_t)rows * 4});
+    DMG_TRY(ensure_host(h, h->s_in, in_bytes + (size_t)(G + 1) * (G + 1) * 4 + 64));
+    DMG_TRY(ensure_dev(h, h->s_in, in_bytes));
+    Carver ch(h->s_in.h), cd(h->s_in.d);
+    int32_t *hn = ch.take<int32_t>((size_t)rows), *dn = cd.take<int32_t>((size_t)rows);
+    int32_t *hs = ch.take<int32_t>((size_t)rows * T), *ds = cd.take<int32_t>((size_t)rows * T);
+    int32_t *hm = ch.take<int32_t>((size_t)n_mask), *dm = cd.take<int32_t>((size_t)n_mask);
+    float *hl = ch.take<float>((size_t)rows), *dl = cd.take<float>((size_t)rows);
+    int32_t *h_matrix = ch.take<int32_t>((size_t)(G + 1) * G);
+    memcpy(hn, node, (size_t)rows * 4); memcpy(hs, seq, (size_t)rows * T * 4); memcpy(hl, labels, (size_t)rows * 4);
+    if (n_mask) memcpy(hm, mask_flat, (size_t)n_mask * 4);
+    DMG_CUDA(h, cudaMemcpyAsync(h->s_in.d, h->s_in.h, in_bytes, cudaMemcpyHostToDevice, st));
+    // fixed-size work
+    const size_t fixed = Carver::need({(size_t)rows * T, 64, (size_t)n_occ * 4, (size_t)(G + 1) * 4, (size_t)(G + 1) * G * 4, (size_t)G * 4, (size_t)G * 4,
+                                       (size_t)n_occ * 4, (size_t)n_occ * 4, (size_t)rows * 4, (size_t)rows * T * 4,
+                                       (size_t)n_occ * E * 4, (size_t)n_occ * E * 4, (size_t)n_occ * E * 4});
+    DMG_TRY(ensure_dev(h, h->s_work, fixed));
+    Carver cw(h->s_work.d);
+    uint8_t *d_mask = cw.take<uint8_t>((size_t)rows * T);
+    double *d_loss = cw.take<double>(2);
+    int32_t *occ_code = cw.take<int32_t>(n_occ), *d_counts = cw.take<int32_t>(G + 1), *d_matrix = cw.take<int32_t>((size_t)(G + 1) * G);
+    int32_t *d_send_off = cw.take<int32_t>(G), *d_cursor = cw.take<int32_t>(G);
+    int32_t *req_code = cw.take<int32_t>(n_occ), *req_occ = cw.take<int32_t>(n_occ), *node2 = cw.take<int32_t>(rows), *seq2 = cw.take<int32_t>((size_t)rows * T);
+    float *stage = cw.take<float>((size_t)n_occ * E), *sgrad = cw.take<float>((size_t)n_occ * E), *xfer = cw.take<float>((size_t)n_occ * E);
+    DMG_CUDA(h, cudaMemsetAsync(d_mask, 0, (size_t)rows * T, st));
+    DMG_CUDA(h, cudaMemsetAsync(d_loss, 0, 16, st));
+    DMG_CUDA(h, cudaMemsetAsync(d_counts, 0, (size_t)(G + 1) * 4, st));
+    DMG_CUDA(h, cudaMemsetAsync(d_cursor, 0, (size_t)G * 4, st));
+    DMG_CUDA(h, cudaMemsetAsync(sgrad, 0, (size_t)n_occ * E * 4, st));
+    if (n_mask) { mask_scatter_kernel<<<(unsigned)((n_mask + 255) / 256), 256, 0, st>>>(dm, n_mask, rows * T, d_mask, h->d_flags); h->launches += 1; }
+    const unsigned gocc = (unsigned)((n_occ + 255) / 256);
+    shtr_owner_kernel<<<gocc, 256, 0, st>>>(n_occ, T, dn, ds, g, s->global_rows, occ_code, d_counts, h->d_flags);
+    const int32_t my_rows = (int32_t)rows;
+    DMG_CUDA(h, cudaMemcpyAsync(d_counts + G, &my_rows, 4, cudaMemcpyHostToDevice, st));
+    h->launches += 1;
+    // count matrix [rank][G + 1]: requests rank -> owner, and the rank's row count
+    if (G > 1) DMG_NCCL(h, g_nccl.AllGather(d_counts, d_matrix, (size_t)(G + 1), ncclInt32, s->comm, st));
+    else DMG_CUDA(h, cudaMemcpyAsync(d_matrix, d_counts, (size_t)(G + 1) * 4, cudaMemcpyDeviceToDevice, st));
+    DMG_CUDA(h, cudaMemcpyAsync(h_matrix, d_matrix, (size_t)(G + 1) * G * 4, cudaMemcpyDeviceToHost, st));
+    DMG_CUDA(h, cudaStreamSynchronize(st));
+    if (*(volatile int32_t *)h->h_flags) {
+        h->h_flags[0] = 0;
+        return fail(h, DMG_ERR_INDEX, "dmg_shard_train_step: node code outside [0, %lld), history code outside [-1, %lld) or bad mask position",
+                    (long long)s->global_rows, (long long)s->global_rows);
+    }
+    auto cnt = [&](int from, int to) { return h_matrix[from * (G + 1) + to]; };
+    int64_t n_total = 0, n_out = 0, n_in = 0;
+    std::vector<int32_t> send_off(G, 0), recv_off(G, 0);
+    for (int p = 0; p < G; p++) {
+        n_total += h_matrix[p * (G + 1) + G];
+        send_off[p] = (int32_t)n_out; n_out += cnt(me, p);
+        recv_off[p] = (int32_t)n_in; n_in += cnt(p, me);
+    }
+    Scratch &sb = s->buf;
+    DMG_TRY(ensure_dev(h, sb, Carver::need({(size_t)std::max<int64_t>(n_in, 1) * 4, (size_t)std::max<int64_t>(n_in, 1) * E * 4})));
+    Carver cb(sb.d);
+    int32_t *in_code = cb.take<int32_t>(std::max<int64_t>(n_in, 1));
+    float *in_rows = cb.take<float>((size_t)std::max<int64_t>(n_in, 1) * E);
+    DMG_CUDA(h, cudaMemcpyAsync(d_send_off, send_off.data(), (size_t)G * 4, cudaMemcpyHostToDevice, st));
+    shtr_bucket_kernel<<<gocc, 256, 0, st>>>(n_occ, occ_code, g, d_send_off, d_cursor, req_code, req_occ);
+    h->launches += 1;
+    const int grid = h->sm_count * 8;
+    auto exchange = [&](const void *out, void *in, size_t elem, ncclDataType_t dt, size_t per, bool reverse) -> int32_t {
+        // forward: my requests -> owners; reverse: owners' answers -> requesters (same counts, roles swapped)
+        if (G == 1) return DMG_OK;
+        DMG_NCCL(h, g_nccl.GroupStart());
+        for (int p = 0; p < G; p++) {
+            if (p == me) continue;
+            const int64_t ns = reverse ? cnt(p, me) : cnt(me, p), nr = reverse ? cnt(me, p) : cnt(p, me);
+            const int64_t so = reverse ? recv_off[p] : send_off[p], ro = reverse ? send_off[p] : recv_off[p];
+            if (ns) DMG_NCCL(h, g_nccl.Send((const char *)out + (size_t)so * per * elem, (size_t)ns * per, dt, p, s->comm, st));
+            if (nr) DMG_NCCL(h, g_nccl.Recv((char *)in + (size_t)ro * per * elem, (size_t)nr * per, dt, p, s->comm, st));
+        }
+        DMG_NCCL(h, g_nccl.GroupEnd());
+        return DMG_OK;
+    };
+    DMG_TRY(exchange(req_code, in_code, 4, ncclInt32, 1, false));                       // codes to the owners
+    if (n_in) shtr_gather_kernel<<<grid, 256, 0, st>>>(n_in, E, in_code, g, d.emb<float>(), in_rows);
+    DMG_TRY(exchange(in_rows, xfer, 4, ncclFloat32, (size_t)E, true));                  // rows back
+    shtr_stage_local_kernel<<<grid, 256, 0, st>>>(n_occ, E, occ_code, g, d.emb<float>(), stage);
+    if (n_out) shtr_stage_remote_kernel<<<grid, 256, 0, st>>>(n_out, E, req_occ, xfer, stage);
+    shtr_remap_kernel<<<gocc, 256, 0, st>>>(rows, T, occ_code, node2, seq2);
+    h->launches += 4;
+    DMG_TRY(grad_enqueue<float>(h, rows, node2, seq2, d_mask, dl, d_loss, stage, sgrad, (double)n_total));
+    float *gflat = (float *)d.d_grad;
+    shtr_grad_local_kernel<<<grid, 256, 0, st>>>(n_occ, E, occ_code, g, sgrad, gflat);
+    if (n_out) shtr_grad_pack_kernel<<<grid, 256, 0, st>>>(n_out, E, req_occ, sgrad, xfer);
+    DMG_TRY(exchange(xfer, in_rows, 4, ncclFloat32, (size_t)E, false));                 // gradients to the owners
+    if (n_in) shtr_grad_apply_kernel<<<grid, 256, 0, st>>>(n_in, E, in_code, g, in_rows, gflat);
+    h->launches += 3;
+    s->exchanged_rows += n_in;
+    if (G > 1) {
+        if (g.repl_rows > 0) DMG_NCCL(h, g_nccl.AllReduce(gflat, gflat, (size_t)g.repl_rows * E, ncclFloat32, ncclSum, s->comm, st));
+        const size_t dense = (size_t)(d.n_params - d.rows * E);
+        DMG_NCCL(h, g_nccl.AllReduce(gflat + d.rows * E, gflat + d.rows * E, dense, ncclFloat32, ncclSum, s->comm, st));
+        DMG_NCCL(h, g_nccl.AllReduce(d_loss, d_loss, 1, ncclFloat64, ncclSum, s->comm, st));
+    }
+    DMG_TRY(adam_pass<float>(h, lr, step_t));
+    double loss_sum = 0.0;
+    DMG_CUDA(h, cudaMemcpyAsync(&loss_sum, d_loss, 8, cudaMemcpyDeviceToHost, st));
+    DMG_CUDA(h, cudaStreamSynchronize(st));
+    *out_loss = (float)(loss_sum / (double)n_total);
     return DMG_OK;
 }

@@ -399,6 +399,15 @@ DMG_API int32_t dmg_shard_dr_retrieve(dmg_handle_t h, int32_t B, const int32_t *
                                       int32_t topk, int32_t *out_items, double *out_scores,
                                       int32_t *out_counts);
 
+/* Training step on the SHARDED node table (tdm/.../optim/LocalOptimizer.scala:139-187): collective; every rank passes
+ * ITS rows of the mini-batch with GLOBAL node codes (node[rows], seq[rows*T], -1 = padding).  Embedding rows are fetched from their
+ * owners per occurrence, forward / BCE (mean over the GLOBAL batch) / backward run locally, the embedding gradients are applied
+ * by the row owners, and only the dense scorer weights (3 E^2 + 2 E + 1 scalars) plus the replicated top rows are all-reduced;
+ * every rank then runs the dense Adam over its shard.  Float model.  out_loss: mean loss of the global batch. */
+DMG_API int32_t dmg_shard_train_step(dmg_handle_t h, int64_t rows, const int32_t *node, const int32_t *seq,
+                                     const int32_t *mask_flat, int64_t n_mask, const float *labels, double lr,
+                                     int32_t step_t, float *out_loss);
+
 /* Synthetic Deep Retrieval model generated on the device (benchmarks, BASELINE config 5): Tensor.randn(0, 0.05) of every
  * table as counter-based values of the GLOBAL element index, and J hashed paths per item folded into MappingOp.pathItemMapping's
  * shape (one item per path, MappingOp.scala:23-28) as the CSR over the K^D path keys.  On a handle with dmg_shard_init the

@@ -127,7 +127,7 @@ def test_world1_deep_retrieval_matches_the_unsharded_engine(dr_fix, queries):
 def _two_gpu_worker(rank, world, port, out_dir):
     sys.path.insert(0, ROOT)
     sys.argv = ["shard_check.py", "--items", "5000", "--batch", "24", "--train-targets", "40", "--jtm-items", "200", "--dr-items", "3000",
-                "--dr-k", "12", "--dr-batch", "16", "--out", os.path.join(out_dir, f"r{rank}.json")]
+                "--dr-k", "12", "--dr-batch", "16", "--shard-train-targets", "40", "--out", os.path.join(out_dir, f"r{rank}.json")]
     os.environ.update(RANK=str(rank), WORLD_SIZE=str(world), LOCAL_RANK=str(rank), MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
     import runpy
     runpy.run_path(os.path.join(ROOT, "tools", "shard_check.py"), run_name="__main__")
@@ -145,6 +145,11 @@ def test_world2_matches_oracle(tmp_path):
         assert d["ids_identical"] and d["logits_bit_identical"] and d["rows_scored_for_other_ranks"] > 0
         assert d["jtm_item_weights"]["weights_bit_identical"]
         assert d["deep_retrieval"]["ids_identical"] and d["deep_retrieval"]["scores_bit_identical"]
+        # dmg_shard_train_step: owner-applied embedding gradients + all-reduce of the dense scalars == one engine on the whole batch
+        st = d["shard_train_step"]
+        assert st["max_abs_emb_diff_vs_single_engine"] < 1e-5 and st["max_abs_dense_diff_vs_single_engine"] < 1e-5
+        assert st["max_abs_weight_change"] > 1e-3 and st["rows_fetched_for_other_ranks"] > 0
+        assert all(abs(x - y) < 1e-5 for x, y in zip(st["loss"], st["loss_single_engine"]))
         # dmg_dp_train_step (LocalOptimizer.syncGradients with GPUs in the place of threads): two steps on two ranks == one engine on
         # the concatenated batch up to the fp32 summation order
         assert d["dp_train_step"]["max_abs_weight_diff_vs_single_engine"] < 1e-5 * max(1.0, d["dp_train_step"]["max_abs_weight"])
@@ -176,3 +181,33 @@ def test_dr_synthetic_model_unsharded_sharded_oracle(orc):
     assert (sc == gc).all() and (si == gi).all() and (ss.view(np.uint64) == gs.view(np.uint64)).all()
     s.close()
     e.close()
+
+
+def test_shard_train_step_world1_is_train_step(jtm_fix):
+    """dmg_shard_train_step on one rank (every row local: no exchange, nothing to all-reduce) == dmg_train_step; bad codes raise."""
+    from dismember_b200._capi import DmgError
+    f = jtm_fix
+    params = f["params"]
+    rng = np.random.default_rng(26)
+    a, b = new_engine(), new_engine()
+    a.shard_init(1, 0)
+    a.load_tree_tdm(int(f["max_level"]), f["codes"], f["node_ids"], f["is_leaf"], f["leaf_ids"], f["leaf_codes"])
+    a.shard_load_din_weights(params, 8191, 16, 10)
+    b.load_din_weights(params, 8191, 16, 10)
+    for t in (1, 2, 3):
+        n = 300
+        node = rng.integers(0, 8191, n).astype(np.int32)
+        seq = rng.integers(0, 8191, (n, 10)).astype(np.int32)
+        seq[rng.random((n, 10)) < 0.3] = -1
+        mask = np.flatnonzero((seq == -1).ravel()).astype(np.int32)
+        labels = (rng.random(n) < 0.2).astype(np.float32)
+        la = a.shard_train_step(node, seq, mask, labels, 1e-2, t)
+        lb = b.train_step(node, seq, mask, labels, 1e-2, t)
+        assert abs(float(la) - float(lb)) <= 1e-5 * max(1.0, abs(float(lb)))
+    wa, wb = a.download_din_weights(), b.download_din_weights()
+    assert np.abs(wa - wb).max() <= 2e-4 and np.abs(wa - params).max() > 1e-3
+    node[3] = 8191
+    with pytest.raises(DmgError):
+        a.shard_train_step(node, seq, mask, labels, 1e-2, 4)
+    a.close()
+    b.close()

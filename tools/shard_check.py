@@ -36,6 +36,8 @@ def main():
     ap.add_argument("--dr-k", type=int, default=100)
     ap.add_argument("--train-targets", type=int, default=0, help="also check dmg_dp_train_step (rows from this many targets per rank)")
     ap.add_argument("--dr-batch", type=int, default=64)
+    ap.add_argument("--shard-train-targets", type=int, default=0,
+                    help="also check dmg_shard_train_step (training on the sharded table; rows from this many targets per rank)")
     ap.add_argument("--out", default=None)
     a = ap.parse_args()
     import torch
@@ -169,7 +171,50 @@ def main():
         dp = {"rows_per_rank": int(len(node)), "steps": 2, "loss": losses,
               "max_abs_weight_diff_vs_single_engine": float(np.abs(w_dp - w_one).max()),
               "max_abs_weight": float(moved)}
-    line = {"rank": rank, "world": world, "jtm_item_weights": jtm, "deep_retrieval": dr, "dp_train_step": dp, "items": a.items, "levels": tf.max_level, "batch_per_rank": a.batch, "beam": a.beam,
+    # training on the SHARDED table (dmg_shard_train_step) vs ONE unsharded engine training on the concatenated batch
+    sht = None
+    if a.shard_train_targets > 0:
+        rng = np.random.Generator(np.random.PCG64(500 + rank))
+        tg = rng.integers(1, a.items + 1, a.shard_train_targets + 3 * rank).astype(np.int32)       # unequal row counts per rank
+        tsq = synth.queries(len(tg), T, a.items, seed=600 + rank)
+        neg = np.array([0] + [min(2 ** l - 1, 7) for l in range(1, tf.max_level + 1)], np.int32)
+        sampler = Engine(local)                                          # the sampler needs an unsharded tree + seq_len only
+        sampler.load_tree_tdm(tf.max_level, tf.codes, tf.node_ids, tf.is_leaf, tf.leaf_ids, tf.leaf_codes)
+        sampler.init_din_weights(np.float32, rows, a.dim, T, seed=1)
+        node, sq, lab = sampler.tdm_sample_expand(tg, tsq, neg, 1, seed=700 + rank)
+        sampler.close()
+        mask = np.flatnonzero((sq == -1).ravel()).astype(np.int32)
+        ex0 = eng.shard_info()[2]
+        t0 = time.perf_counter()
+        losses = [float(eng.shard_train_step(node, sq, mask, lab, 1e-2, t)) for t in (1, 2)]
+        tdt = time.perf_counter() - t0
+        w_loc = eng.download_din_weights()
+        parts = [None] * world
+        dist.all_gather_object(parts, (node, sq, lab))
+        one = Engine(local)
+        one.load_tree_tdm(tf.max_level, tf.codes, tf.node_ids, tf.is_leaf, tf.leaf_ids, tf.leaf_codes)
+        one.init_din_weights(np.float32, rows, a.dim, T, seed=2)
+        an, asq, al = (np.concatenate([p[i] for p in parts]) for i in range(3))
+        am = np.flatnonzero((asq == -1).ravel()).astype(np.int32)
+        one_losses = [float(one.train_step(an, asq, am, al, 1e-2, t)) for t in (1, 2)]
+        w_one = one.download_din_weights()
+        one.close()
+        n_loc = eng.shard_info()[0]
+        gr = shard.global_row(np.arange(n_loc), world, rank)
+        emb_loc, emb_one = w_loc[:n_loc * a.dim].reshape(n_loc, a.dim), w_one[:rows * a.dim].reshape(rows, a.dim)
+        w0 = Engine(local)
+        w0.load_tree_tdm(tf.max_level, tf.codes, tf.node_ids, tf.is_leaf, tf.leaf_ids, tf.leaf_codes)
+        w0.init_din_weights(np.float32, rows, a.dim, T, seed=2)
+        moved = float(np.abs(w_one - w0.download_din_weights()).max())
+        w0.close()
+        sht = {"rows_this_rank": int(len(node)), "rows_global": int(len(an)), "steps": 2, "loss": losses, "loss_single_engine": one_losses,
+               "max_abs_emb_diff_vs_single_engine": float(np.abs(emb_loc - emb_one[gr]).max()),
+               "max_abs_dense_diff_vs_single_engine": float(np.abs(w_loc[n_loc * a.dim:] - w_one[rows * a.dim:]).max()),
+               "max_abs_weight_change": moved, "rows_fetched_for_other_ranks": int(eng.shard_info()[2] - ex0), "seconds": tdt,
+               "all_reduced_scalars": int(3 * a.dim * a.dim + 2 * a.dim + 1 + ((world - 1) * a.dim))}
+        # the trained shards keep serving: retrieval on them == the single engine that took the same steps is checked by the caller's
+        # retrieval legs on fresh weights; here only the optimiser state is compared
+    line = {"rank": rank, "world": world, "shard_train_step": sht, "jtm_item_weights": jtm, "deep_retrieval": dr, "dp_train_step": dp, "items": a.items, "levels": tf.max_level, "batch_per_rank": a.batch, "beam": a.beam,
             "table_rows_global": global_rows, "table_rows_local": local_rows,
             "rows_scored_for_other_ranks": exchanged, "users_checked": n, "checked_against": a.check,
             "ids_identical": bool((items[:n] == oi).all() and (counts[:n] == oc).all()),
