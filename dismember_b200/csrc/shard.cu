@@ -91,7 +91,8 @@ static __global__ void shard_fill_tiles_kernel(const float *__restrict__ emb, Sh
 // expand the children 2c+1, 2c+2 that exist, order preserved (:88-92).
 static __global__ void __launch_bounds__(kThreads) shard_select_expand_kernel(int32_t *__restrict__ cand, const float *__restrict__ score,
                                                                               int32_t *__restrict__ count, int cap, int capp, int beam,
-                                                                              int level, int first, const uint32_t *__restrict__ exists)
+                                                                              int level, int first, const uint32_t *__restrict__ exists,
+                                                                              const int32_t *__restrict__ beam_user = nullptr, int leaf_level = 0)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     uint64_t *sKey = reinterpret_cast<uint64_t *>(smem_raw);
@@ -100,6 +101,14 @@ static __global__ void __launch_bounds__(kThreads) shard_select_expand_kernel(in
     __shared__ int sScan[8];
     const int u = blockIdx.x, tid = threadIdx.x;
     int32_t *uc = cand + (size_t)u * cap;
+    bool fill_then_expand = false;
+    if (beam_user) {                                              // per-user widened beams (Recommender.scala:27-33): user u starts at
+        beam = beam_user[u];                                      // floor(log2 beam_u) and keeps beam_u candidates per level; one launch
+        const int su = 31 - __clz(beam);                          // per level serves every user: not started / start level / running
+        if (level < su || (level == leaf_level && su != level)) return;
+        first = su == level;
+        fill_then_expand = first && level < leaf_level;
+    }
     if (first) {
         const int64_t start = ((int64_t)1 << level) - 1;
         const int n0 = 1 << level;
@@ -113,7 +122,8 @@ static __global__ void __launch_bounds__(kThreads) shard_select_expand_kernel(in
             cnt += tot;
         }
         if (tid == 0) count[u] = cnt < cap ? cnt : cap;
-        return;
+        if (!fill_then_expand) return;
+        __syncthreads();                                          // the start level holds at most beam_u codes: no cut, expand right away
     }
     const int n = count[u];
     const float *us = score + (size_t)u * cap;
@@ -521,11 +531,12 @@ static __global__ void __launch_bounds__(kThreads) shard_final_topk_kernel(const
                                                                            int leaf_level, int reached_leaf, const int32_t *__restrict__ leaf_item,
                                                                            const int64_t *__restrict__ cons_off, const int32_t *__restrict__ cons,
                                                                            int32_t *__restrict__ out_items, float *__restrict__ out_scores,
-                                                                           int32_t *__restrict__ out_counts)
+                                                                           int32_t *__restrict__ out_counts, const int32_t *__restrict__ beam_user = nullptr)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     uint64_t *sKey = reinterpret_cast<uint64_t *>(smem_raw);
     const int u = blockIdx.x, tid = threadIdx.x;
+    if (beam_user) reached_leaf = (31 - __clz(beam_user[u])) <= leaf_level ? 1 : 0;
     const int n = count[u];
     const int32_t *uc = cand + (size_t)u * cap;
     const float *us = score + (size_t)u * cap;
@@ -907,7 +918,7 @@ static int32_t shard_score_level(dmg_handle_t h, const ShardWork &w)
 
 static int32_t shard_tdm_retrieve_impl(dmg_handle_t h, int32_t B, const int32_t *item_seq, int32_t beam, int32_t topk,
                                        int32_t use_mask, const int64_t *cons_off, const int32_t *cons,
-                                       int32_t *out_items, float *out_logits, int32_t *out_counts)
+                                       int32_t *out_items, float *out_logits, int32_t *out_counts, const int32_t *beam_user = nullptr)
 {
     if (!h) return DMG_ERR_INVALID_ARG;
     ShardState *s = h->shard;
@@ -918,15 +929,21 @@ static int32_t shard_tdm_retrieve_impl(dmg_handle_t h, int32_t B, const int32_t 
     const DinDev &d = h->din;
     const TreeDev &t = h->tree;
     const int G = s->world, T = d.T, E = d.E, L = t.max_level;
-    const int cap = std::max(((2 * beam + 7) / 8) * 8, ((topk + 7) / 8) * 8);
-    if (cap > 2 * kThreads) return fail(h, DMG_ERR_UNSUPPORTED, "beam %d too wide for the sharded path (2*beam <= %d)", beam, 2 * kThreads);
+    int max_beam = beam;
+    if (beam_user)
+        for (int u = 0; u < B; u++) {
+            if (beam_user[u] < beam) return fail(h, DMG_ERR_INVALID_ARG, "per-user beams only widen the configured beam");
+            max_beam = std::max(max_beam, beam_user[u]);
+        }
+    const int cap = std::max(((2 * max_beam + 7) / 8) * 8, ((topk + 7) / 8) * 8);
+    if (cap > 2 * kThreads) return fail(h, DMG_ERR_UNSUPPORTED, "beam %d too wide for the level-synchronous path (2*beam <= %d)", max_beam, 2 * kThreads);
     int capp = 2;
     while (capp < cap) capp <<= 1;
     const int s_level = (int)std::floor(std::log2((double)beam) + 1e-9);
 
     const size_t need = shard_work_bytes(G, B, cap, T, E) +
                         Carver::need({(size_t)B * T * 4, (size_t)B * T, (size_t)B * topk * 4, (size_t)B * topk * 4, (size_t)B * 4,
-                                      cons_off ? (size_t)(B + 1) * 8 : 0, cons_off ? (size_t)cons_off[B] * 4 : 0});
+                                      cons_off ? (size_t)(B + 1) * 8 : 0, cons_off ? (size_t)cons_off[B] * 4 : 0, beam_user ? (size_t)B * 4 : 0});
     DMG_TRY(ensure_dev(h, s->buf, need));
     DMG_TRY(ensure_host(h, s->buf, (size_t)B * T * 4 + (size_t)G * G * 4 + (size_t)B * topk * 8 + (size_t)B * 4 + 1024));
     Carver cd(s->buf.d);
@@ -939,6 +956,7 @@ static int32_t shard_tdm_retrieve_impl(dmg_handle_t h, int32_t B, const int32_t 
     int32_t *d_cnt_out = cd.take<int32_t>((size_t)B);
     int64_t *d_cons_off = cons_off ? cd.take<int64_t>((size_t)B + 1) : nullptr;
     int32_t *d_cons = cons_off ? cd.take<int32_t>((size_t)cons_off[B]) : nullptr;
+    int32_t *d_beam_user = beam_user ? cd.take<int32_t>((size_t)B) : nullptr;
     char *hp = (char *)s->buf.h;
     int32_t *h_seq = (int32_t *)hp; hp += (size_t)B * T * 4;
     w.h_matrix = (int32_t *)hp; hp += (((size_t)G * G * 4 + 255) & ~(size_t)255);
@@ -953,6 +971,7 @@ static int32_t shard_tdm_retrieve_impl(dmg_handle_t h, int32_t B, const int32_t 
     if (cons_off) {                                              // small, once per call: straight from the caller's arrays, waited for below
         DMG_CUDA(h, cudaMemcpyAsync(d_cons_off, cons_off, (size_t)(B + 1) * 8, cudaMemcpyHostToDevice, st));
         if (cons_off[B]) DMG_CUDA(h, cudaMemcpyAsync(d_cons, cons, (size_t)cons_off[B] * 4, cudaMemcpyHostToDevice, st));
+        if (beam_user) DMG_CUDA(h, cudaMemcpyAsync(d_beam_user, beam_user, (size_t)B * 4, cudaMemcpyHostToDevice, st));
         DMG_CUDA(h, cudaStreamSynchronize(st));
     }
     // TDMTree.idToCode validates against the table size: use the global row count here
@@ -970,19 +989,28 @@ static int32_t shard_tdm_retrieve_impl(dmg_handle_t h, int32_t B, const int32_t 
     const size_t sel_smem = (size_t)capp * 8 + (size_t)cap * 8;
     DMG_TRY(shard_prepare_scorers(h));
     const bool reached = s_level <= L;
-    if (reached) {
-        shard_select_expand_kernel<<<B, kThreads, sel_smem, st>>>(w.cand, w.score, w.count, cap, capp, beam, s_level, 1, t.d_exists);
-        h->launches += 1;
-    } else {
+    if (d_beam_user) {                                           // every user from its own start level: one launch per level serves them all
         DMG_CUDA(h, cudaMemsetAsync(w.count, 0, (size_t)B * 4, st));
-    }
-    for (int level = s_level; level < L; level++) {
-        shard_select_expand_kernel<<<B, kThreads, sel_smem, st>>>(w.cand, w.score, w.count, cap, capp, beam, level, 0, t.d_exists);
-        h->launches += 1;
-        DMG_TRY(shard_score_level(h, w));
+        for (int level = s_level; level <= L; level++) {
+            shard_select_expand_kernel<<<B, kThreads, sel_smem, st>>>(w.cand, w.score, w.count, cap, capp, beam, level, 0, t.d_exists, d_beam_user, L);
+            h->launches += 1;
+            if (level < L) DMG_TRY(shard_score_level(h, w));
+        }
+    } else {
+        if (reached) {
+            shard_select_expand_kernel<<<B, kThreads, sel_smem, st>>>(w.cand, w.score, w.count, cap, capp, beam, s_level, 1, t.d_exists);
+            h->launches += 1;
+        } else {
+            DMG_CUDA(h, cudaMemsetAsync(w.count, 0, (size_t)B * 4, st));
+        }
+        for (int level = s_level; level < L; level++) {
+            shard_select_expand_kernel<<<B, kThreads, sel_smem, st>>>(w.cand, w.score, w.count, cap, capp, beam, level, 0, t.d_exists);
+            h->launches += 1;
+            DMG_TRY(shard_score_level(h, w));
+        }
     }
     shard_final_topk_kernel<<<B, kThreads, (size_t)capp * 8, st>>>(w.cand, w.score, w.count, cap, capp, topk, L, reached ? 1 : 0, t.d_leaf_item,
-                                                                   d_cons_off, d_cons, d_items, d_logits, d_cnt_out);
+                                                                   d_cons_off, d_cons, d_items, d_logits, d_cnt_out, d_beam_user);
     h->launches += 1;
     DMG_CUDA(h, cudaGetLastError());
     DMG_CUDA(h, cudaMemcpyAsync(h_items, d_items, (size_t)B * topk * 4, cudaMemcpyDeviceToHost, st));
@@ -1006,10 +1034,13 @@ int32_t dmg_deepfm_tdm_retrieve(dmg_handle_t h, int32_t B, const int32_t *item_s
                                 const int64_t *cons_off, const int32_t *cons, int32_t widen_beam,
                                 int32_t *out_items, float *out_logits, int32_t *out_counts)
 {
-    if (cons_off && widen_beam)
-        return fail(h, DMG_ERR_UNSUPPORTED, "DeepFM: the eval variant with per-user widened beams runs on the DIN path only");
     if (h->shard && h->shard->world > 1 && cons_off) return fail(h, DMG_ERR_UNSUPPORTED, "consumed items with a sharded table");
-    return shard_tdm_retrieve_impl(h, B, item_seq, beam, topk, 0, cons_off, cons, out_items, out_logits, out_counts);
+    std::vector<int32_t> bu;
+    if (cons_off && widen_beam) {                                // Recommender.recommendItems widens for every model (Recommender.scala:27-33)
+        bu.resize(B);
+        for (int u = 0; u < B; u++) bu[u] = std::max((int32_t)((cons_off[u + 1] - cons_off[u] + topk) / 2), beam);
+    }
+    return shard_tdm_retrieve_impl(h, B, item_seq, beam, topk, 0, cons_off, cons, out_items, out_logits, out_counts, bu.empty() ? nullptr : bu.data());
 }
 
 int32_t dmg_deepfm_score_pairs(dmg_handle_t h, int64_t n, const int32_t *node, const int32_t *seq, float *out)

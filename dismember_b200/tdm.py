@@ -68,9 +68,8 @@ class TDM:
             off = np.zeros(len(consumed) + 1, np.int64)
             off[1:] = np.cumsum([len(c) for c in consumed])
             flat = np.concatenate([np.asarray(c, np.int32) for c in consumed]) if off[-1] else np.zeros(0, np.int32)
-            # the DeepFM path filters consumed items but keeps the configured beam (per-user widening is DIN-only here)
-            items, _, counts = self.engine.tdm_retrieve(seqs, candidate_num, topk, self.use_mask, off, flat,
-                                                        self.model_name == "din")
+            # candidateNum widens per user for every model: max((|consumed| + topk) / 2, candidateNum)  (Recommender.scala:27-33)
+            items, _, counts = self.engine.tdm_retrieve(seqs, candidate_num, topk, self.use_mask, off, flat, True)
         return [items[u, :counts[u]].tolist() for u in range(len(seqs))]
 
     def recommend_batch(self, sequences, topk: int, candidate_num: int):

@@ -46,6 +46,17 @@ def test_deepfm_retrieve_matches_oracle(orc, E, n_items, beam):
     gi2, gl2, gc2 = e.tdm_retrieve(seqs, beam, topk, consumed_off=off, consumed=flat)
     oi2, ol2, oc2 = model.retrieve_batch(tree, seqs, beam, topk, cons_off=off, cons=flat, n_threads=2)
     assert (gi2 == oi2).all() and (gl2.view(np.uint32) == ol2.view(np.uint32)).all() and (gc2 == oc2).all()
+    # Recommender.recommendItems widens the beam per user for EVERY model (Recommender.scala:27-33): users with many consumed items
+    # start at a deeper level with a wider beam; users with few keep the configured one
+    rng = np.random.default_rng(E)
+    all_items = tf.leaf_ids
+    cons = [rng.choice(all_items, int(k), replace=False).tolist() for k in rng.choice([0, 3, 2 * beam + 5, min(5 * beam, 500)], B)]
+    cons[1] = cons[1] + list(oi[1, :4][oi[1, :4] >= 0])
+    off[1:] = np.cumsum([len(c) for c in cons])
+    flat = np.array([x for c in cons for x in c], np.int32)
+    gi3, gl3, gc3 = e.tdm_retrieve(seqs, beam, topk, consumed_off=off, consumed=flat, widen_beam=True)
+    oi3, ol3, oc3 = model.retrieve_batch(tree, seqs, beam, topk, cons_off=off, cons=flat, widen_beam=True, n_threads=2)
+    assert (gc3 == oc3).all() and (gi3 == oi3).all() and (gl3.view(np.uint32) == ol3.view(np.uint32)).all()
     e.close()
 
 
