@@ -50,7 +50,7 @@ def test_deepfm_retrieve_matches_oracle(orc, E, n_items, beam):
     # start at a deeper level with a wider beam; users with few keep the configured one
     rng = np.random.default_rng(E)
     all_items = tf.leaf_ids
-    cons = [rng.choice(all_items, int(k), replace=False).tolist() for k in rng.choice([0, 3, 2 * beam + 5, min(5 * beam, 500)], B)]
+    cons = [rng.choice(all_items, int(k), replace=False).tolist() for k in rng.choice([0, 3, 2 * beam + 5, min(5 * beam, 490)], B)]
     cons[1] = cons[1] + list(oi[1, :4][oi[1, :4] >= 0])
     off[1:] = np.cumsum([len(c) for c in cons])
     flat = np.array([x for c in cons for x in c], np.int32)
