@@ -111,11 +111,76 @@ def dr_section(a, T):
     eng.close()
 
 
+def dr_train_section(a, T):
+    """5. Deep Retrieval training step (f3): layer-model cross entropy + rerank sampled softmax, fp64, dense Adam"""
+    from dismember_b200 import Engine
+    from oracle import oracle as orc
+    hbm, _ = peaks()
+    n_item, K, D, Ed, P, S, n = (20_000, 100, 3, 16, 2, 20, 256) if a.quick else (1_000_000, 1000, 3, 64, 2, 100, 2048)
+    eng = Engine(0)
+    eng.dr_init_synthetic(n_item, K, D, T, Ed, J=P, seed=8)
+    rng = np.random.Generator(np.random.PCG64(9))
+    item_paths = rng.integers(0, K, (n_item, P, D)).astype(np.int32)
+    eng.dr_load_item_paths(item_paths)
+    seq = rng.integers(-1, n_item, (n, T)).astype(np.int32)
+    tg = rng.integers(0, n_item, n).astype(np.int32)
+    step = [0]
+
+    def one():
+        step[0] += 1
+        eng.dr_train_step(seq, tg, 1e-3, step[0], num_sampled=S, seed=step[0])
+    dt = timeit(one, warm=2, reps=5)
+    R = n * P
+    gemm_flop = sum(3 * 2 * R * K * (T + d) * Ed for d in range(D)) + 3 * 2 * n * Ed * T * Ed
+    n_par = (n_item + K * (D - 1)) * Ed + sum(K * (T + d) * Ed + K for d in range(D)) + n_item * Ed + Ed * T * Ed + Ed + n_item * Ed + n_item
+    adam_bytes = 7 * 8 * n_par
+    emit(path="dr_train_step (layer-model CE over n*P rows + rerank sampled softmax, fp64, dense Adam on every table)", items=n_item, K=K, D=D,
+         E=Ed, samples=n, paths_per_item=P, num_sampled=S, ms_per_step=dt * 1e3, samples_per_s=n / dt,
+         roofline={"bound": "fp64 FMA pipe (three GEMMs per Linear) + hbm (dense Adam)", "gemm_flop_per_step": gemm_flop,
+                   "adam_bytes_per_step": adam_bytes, "gemm_tflops_if_all_time": gemm_flop / dt / 1e12,
+                   "adam_gbs_if_all_time": adam_bytes / dt / 1e9, "hbm_peak": hbm})
+    # CPU port on a small slice of the same shapes (single thread)
+    if a.quick:
+        w = eng.dr_download()
+        om = orc.DrModel(n_item, K, D, T, Ed, w["layer_emb"], w["layer_w"], w["layer_b"], w["rr_emb"], w["rr_w"], w["rr_b"], w["sm_w"], w["sm_b"])
+        tr = orc.DrTrainer(om, 1e-3)
+        t0 = time.perf_counter()
+        tr.layer_grad(seq[:32], tg[:32], item_paths, P)
+        cdt = time.perf_counter() - t0
+        emit(path="dr_train_step cpu_baseline (layer gradients only)", kind="port", cores=1, samples_per_s=32 / cdt)
+    eng.close()
+
+
+def kmeans_section(a):
+    """6. k-means tree rebuild (f4): RecursiveCluster.run on item embeddings"""
+    from dismember_b200 import Engine
+    from oracle import oracle as orc
+    n, E, iters = (20_000, 16, 2) if a.quick else (1_000_000, 64, 3)
+    rng = np.random.Generator(np.random.PCG64(4))
+    emb = rng.random((n, E))
+    eng = Engine(0)
+    eng.kmeans_tree(emb[:1000], 1, 1)
+    l0 = eng.launch_count
+    t0 = time.perf_counter()
+    codes = eng.kmeans_tree(emb, iters, 7)
+    dt = time.perf_counter() - t0
+    emit(path="kmeans_tree (RecursiveCluster.run: level-synchronous balanced 2-means + host argPartition)", items=n, E=E, runs=iters,
+         seconds=dt, items_per_s=n / dt, launches=eng.launch_count - l0, distinct_codes=int(len(np.unique(codes))))
+    m = 20_000 if not a.quick else 5_000
+    t0 = time.perf_counter()
+    oc = orc.kmeans_tree(emb[:m], iters, 7)
+    cdt = time.perf_counter() - t0
+    gc = eng.kmeans_tree(emb[:m], iters, 7)
+    emit(path="kmeans_tree cpu_baseline", kind="port", cores=1, items=m, seconds=cdt, items_per_s=m / cdt,
+         parity={"codes_identical": bool((gc == oc).all())})
+    eng.close()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--quick", action="store_true")
     ap.add_argument("--train-items", type=int, default=10_000_000)
-    ap.add_argument("--only", default=None, choices=[None, "otm_deepfm", "dr"], help="run one section only")
+    ap.add_argument("--only", default=None, choices=[None, "otm_deepfm", "dr", "dr_train", "kmeans"], help="run one section only")
     a = ap.parse_args()
     from dismember_b200 import Engine, synth
     from oracle import oracle as orc
@@ -127,6 +192,10 @@ def main():
         return otm_deepfm_section(a, E, T, threads)
     if a.only == "dr":
         return dr_section(a, T)
+    if a.only == "dr_train":
+        return dr_train_section(a, T)
+    if a.only == "kmeans":
+        return kmeans_section(a)
 
     # ---- 1. training step: fused DIN fwd/bwd + BCE + scatter-add, dense Adam -------------------
     for n_items in ([100_000] if a.quick else [1_000_000, a.train_items]):
@@ -302,6 +371,8 @@ def main():
         eng.close()
 
     dr_section(a, T)
+    dr_train_section(a, T)
+    kmeans_section(a)
 
 
 if __name__ == "__main__":
