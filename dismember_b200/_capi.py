@@ -566,6 +566,8 @@ class Engine:
         labels = np.ascontiguousarray(labels, self.din_dtype).ravel()
         m = None if mask_flat is None else _i32(mask_flat).ravel()
         n = self.rows * self.E + 3 * self.E * self.E + 2 * self.E + 1
+        if getattr(self, "_deepfm", False):
+            n = self.rows * self.E + (self.T + 1) * (self.T + 1) * self.E + 2 * (self.T + 1) + 1
         grad = np.empty(n, self.din_dtype)
         loss = np.zeros(1, self.din_dtype)
         self._check(self.L.dmg_din_gradients(self.h, len(node), _p(node), _p(seq), _p(m), 0 if m is None else len(m),

@@ -227,6 +227,104 @@ __global__ void __launch_bounds__(kTrThreads) din_train_kernel(const TrainParams
     if ((tid & 31) == 0 && loss_local != 0.0) atomicAdd(p.loss_acc, loss_local);
 }
 
+// ---- DeepFM in the training loop (tdm/.../model/DeepFM.scala:11-44; FM.scala:46-72 backward) -----------------------------------
+// 8 rows per CTA iteration: features F = [item row ; T history rows] in shared memory, forward as deepfm_rows_forward_kernel (chains
+// over Fflat in order), BCE-with-logits (mean over n_norm), backward of Add / Linear(T+1, 1) / ReLU / Linear((T+1)E, T+1) / FM,
+// dense-weight gradients reduced per CTA in shared memory then atomicAdd, embedding gradients scatter-added (padding skipped).
+constexpr int kDfmRB = 8;
+__global__ void __launch_bounds__(kTrThreads) deepfm_train_kernel(const float *__restrict__ emb, const float *__restrict__ dense, int E, int T, int64_t n,
+                                                                   double n_norm, const int32_t *__restrict__ node, const int32_t *__restrict__ seq,
+                                                                   const float *__restrict__ labels, float *__restrict__ g_emb,
+                                                                   float *__restrict__ g_dense, double *__restrict__ loss_acc)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int F = T + 1, IN = F * E, tid = threadIdx.x;
+    float *sF = reinterpret_cast<float *>(smem_raw);             // RB x IN
+    float *sBuf = sF + kDfmRB * IN;                              // RB x E   sum of the feature rows (FM buffer)
+    float *sZ = sBuf + kDfmRB * E;                               // RB x F   pre-activations
+    float *sDz = sZ + kDfmRB * F;                                // RB x F
+    float *sDy = sDz + kDfmRB * F;                               // RB
+    float *gW1 = sDy + kDfmRB;                                   // F x IN | b1 F | w2 F | b2 1: this CTA's share of the dense gradient
+    const int n_dense = F * IN + 2 * F + 1;
+    const float *w1 = dense, *b1 = w1 + (size_t)F * IN, *w2 = b1 + F, *b2 = w2 + F;
+    float *gB1 = gW1 + F * IN, *gW2 = gB1 + F, *gB2 = gW2 + F;
+    for (int i = tid; i < n_dense; i += kTrThreads) gW1[i] = 0.0f;
+    const float inv_n = (float)(1.0 / n_norm);
+    double loss_local = 0.0;
+    __syncthreads();
+    for (int64_t g0 = (int64_t)blockIdx.x * kDfmRB; g0 < n; g0 += (int64_t)gridDim.x * kDfmRB) {
+        const int nr = (int)((n - g0) < kDfmRB ? (n - g0) : kDfmRB);
+        for (int idx = tid; idx < nr * IN; idx += kTrThreads) {
+            const int r = idx / IN, q = idx - r * IN, slot = q / E;
+            const int32_t c = slot == 0 ? node[g0 + r] : seq[(g0 + r) * T + slot - 1];
+            sF[idx] = c < 0 ? 0.0f : emb[(size_t)c * E + (q - slot * E)];
+        }
+        __syncthreads();
+        for (int idx = tid; idx < nr * E; idx += kTrThreads) {    // FM buffer: vAdd in row order from zero
+            const int r = idx / E, k = idx - r * E;
+            float b = 0.0f;
+            for (int s_ = 0; s_ < F; s_++) b = add_(b, sF[r * IN + s_ * E + k]);
+            sBuf[idx] = b;
+        }
+        for (int idx = tid; idx < nr * F; idx += kTrThreads) {    // Linear((T+1)E, T+1): one chain per (row, output)
+            const int r = idx % nr, o = idx / nr;
+            const float *x = sF + r * IN, *w = w1 + (size_t)o * IN;
+            float acc = 0.0f;
+            for (int k = 0; k < IN; k++) acc = fma_(x[k], __ldg(w + k), acc);
+            sZ[r * F + o] = add_(acc, b1[o]);
+        }
+        __syncthreads();
+        if (tid < nr) {
+            const int r = tid;
+            const float *x = sF + r * IN, *bf = sBuf + r * E;
+            float sum_square = 0.0f, square_sum = 0.0f;
+            for (int k = 0; k < E; k++) sum_square = fma_(bf[k], bf[k], sum_square);
+            for (int k = 0; k < IN; k++) square_sum = fma_(x[k], x[k], square_sum);
+            const float fm = div_(sub_(sum_square, square_sum), 2.0f);
+            float dnn = 0.0f;
+            for (int o = 0; o < F; o++) { const float z = sZ[r * F + o]; dnn = fma_(z > 0.0f ? z : 0.0f, w2[o], dnn); }
+            const float y = add_(fm, add_(dnn, b2[0]));
+            const float t = labels[g0 + r], ay = y < 0.0f ? -y : y;
+            loss_local += (double)add_(sub_(y > 0.0f ? y : 0.0f, mul_(y, t)), log1pexp_(exp_(-ay)));
+            sDy[r] = mul_(sub_(div_(1.0f, add_(1.0f, exp_(-y))), t), inv_n);
+        }
+        __syncthreads();
+        for (int idx = tid; idx < nr * F; idx += kTrThreads) {
+            const int r = idx / F, o = idx - r * F;
+            sDz[idx] = sZ[idx] <= 0.0f ? 0.0f : mul_(sDy[r], w2[o]);
+        }
+        __syncthreads();
+        if (tid < F) {                                            // Linear(T+1, 1) weight / bias, first Linear's bias
+            float a = gW2[tid], b = gB1[tid];
+            for (int r = 0; r < nr; r++) { const float z = sZ[r * F + tid]; a = fma_(sDy[r], z > 0.0f ? z : 0.0f, a); b = add_(b, sDz[r * F + tid]); }
+            gW2[tid] = a; gB1[tid] = b;
+        } else if (tid == F) {
+            float a = gB2[0];
+            for (int r = 0; r < nr; r++) a = add_(a, sDy[r]);
+            gB2[0] = a;
+        }
+        for (int idx = tid; idx < F * IN; idx += kTrThreads) {    // gradWeight of the first Linear: dz^T . Fflat
+            const int o = idx / IN, k = idx - o * IN;
+            float a = gW1[idx];
+            for (int r = 0; r < nr; r++) a = fma_(sDz[r * F + o], sF[r * IN + k], a);
+            gW1[idx] = a;
+        }
+        for (int idx = tid; idx < nr * IN; idx += kTrThreads) {   // gradInput: DNN branch + FM branch, scattered into the table gradient
+            const int r = idx / IN, q = idx - r * IN, slot = q / E, k = q - slot * E;
+            const int32_t c = slot == 0 ? node[g0 + r] : seq[(g0 + r) * T + slot - 1];
+            if (c < 0) continue;
+            float acc = 0.0f;
+            for (int o = 0; o < F; o++) acc = fma_(sDz[r * F + o], __ldg(w1 + (size_t)o * IN + q), acc);
+            acc = add_(acc, mul_(sub_(sBuf[r * E + k], sF[idx]), sDy[r]));
+            atomicAdd(g_emb + (size_t)c * E + k, acc);
+        }
+        __syncthreads();
+    }
+    for (int i = tid; i < n_dense; i += kTrThreads) { const float v = gW1[i]; if (v != 0.0f) atomicAdd(g_dense + i, v); }
+    for (int o = 16; o > 0; o >>= 1) loss_local += __shfl_xor_sync(0xffffffffu, loss_local, o);
+    if ((tid & 31) == 0 && loss_local != 0.0) atomicAdd(loss_acc, loss_local);
+}
+
 // K7: dense Adam, gradient zeroed in the same pass.  Pure streaming (4 reads + 4 writes per parameter, no reuse):
 // 16-byte vector loads, four vectors per thread in flight, so that ~64 KB per SM is outstanding -- what HBM3e needs
 // at ~800 ns latency; the scalar form moved 2.9 TB/s, this one is bound by the copy bandwidth.
@@ -462,6 +560,20 @@ int32_t grad_enqueue(dmg_handle_t h, int64_t n, const int32_t *dn, const int32_t
 {
     DinDev &d = h->din;
     const int E = d.E, T = d.T;
+    if (d.kind == 1) {                                            // DeepFM scorer: no mask input (DeepFM.scala:14-15)
+        if (sizeof(real) != 4 || emb_override) return fail(h, DMG_ERR_UNSUPPORTED, "DeepFM training is built for the Float model on an unsharded table");
+        const int F = T + 1, IN = F * E;
+        const size_t smem = ((size_t)kDfmRB * (IN + E + 2 * F + 1) + (size_t)F * IN + 2 * F + 1) * 4;
+        if (smem > h->smem_optin) return fail(h, DMG_ERR_UNSUPPORTED, "embed_size %d / seq_len %d too large for the DeepFM training kernel", E, T);
+        DMG_CUDA(h, cudaFuncSetAttribute(deepfm_train_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        const int grid = (int)std::min<int64_t>((n + kDfmRB - 1) / kDfmRB, (int64_t)h->sm_count * 2);
+        float *g = (float *)d.d_grad;
+        deepfm_train_kernel<<<grid, kTrThreads, smem, h->stream>>>(d.emb<float>(), d.tail<float>(), E, T, n, n_norm > 0.0 ? n_norm : (double)n, dn, ds,
+                                                                   (const float *)dl, g, g + d.rows * E, d_loss);
+        h->launches += 1;
+        DMG_CUDA(h, cudaGetLastError());
+        return DMG_OK;
+    }
     TrainParams<real> p;
     p.emb = d.emb<real>(); p.watt = d.watt<real>(); p.w1 = d.w1<real>(); p.b1 = d.b1<real>(); p.w2 = d.w2<real>(); p.b2 = d.b2<real>();
     p.wattT = (const real *)d.d_wattT; p.w1T = (const real *)d.d_w1T;
@@ -541,6 +653,7 @@ template <typename real> int32_t adam_pass(dmg_handle_t h, double lr, int step_t
         (real)beta2, (real)(1 - beta2), (real)eps, (real)(-step));
     h->launches += 1;
     DMG_CUDA(h, cudaGetLastError());
+    if (d.kind == 1) { h->fast_dirty = true; return DMG_OK; }   // DeepFM keeps no transposed copies
     return dmg_refresh_transposes(h);
 }
 

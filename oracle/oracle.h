@@ -77,6 +77,8 @@ int orc_din_gradients_f32(int64_t rows, int E, int T, const float *params, int64
 int orc_din_gradients_f64(int64_t rows, int E, int T, const double *params, int64_t n, const int32_t *node,
                           const int32_t *seq, const int32_t *mask_flat, int64_t n_mask, const double *labels,
                           double *grad, double *loss);
+int orc_deepfm_gradients_f32(int64_t rows, int E, int T, const float *params, int64_t n, const int32_t *node, const int32_t *seq,
+                             const float *labels, float *grad, float *loss_out);
 void orc_adam_f32(float *w, const float *g, float *s, float *r, int64_t n, double lr, int t);
 void orc_adam_f64(double *w, const double *g, double *s, double *r, int64_t n, double lr, int t);
 

@@ -77,6 +77,7 @@ def lib():
     L.orc_dr_recommend.argtypes = [vp, i32p, C.c_int, C.c_int, i64p, i32p, i32p, f64p, f64p]
     L.orc_din_gradients_f32.argtypes = [C.c_int64, C.c_int, C.c_int, f32p, C.c_int64, i32p, i32p, vp, C.c_int64, f32p, f32p, f32p]
     L.orc_din_gradients_f64.argtypes = [C.c_int64, C.c_int, C.c_int, f64p, C.c_int64, i32p, i32p, vp, C.c_int64, f64p, f64p, f64p]
+    L.orc_deepfm_gradients_f32.argtypes = [C.c_int64, C.c_int, C.c_int, f32p, C.c_int64, i32p, i32p, f32p, f32p, f32p]
     L.orc_adam_f32.argtypes = [f32p, f32p, f32p, f32p, C.c_int64, C.c_double, C.c_int]
     L.orc_adam_f32.restype = None
     L.orc_adam_f64.argtypes = [f64p, f64p, f64p, f64p, C.c_int64, C.c_double, C.c_int]
@@ -407,6 +408,19 @@ class DrTrainer:
             for x, gx, s, r in zip(self.rr, gr, self.rr_s, self.rr_r):
                 lib().orc_adam_eps_f64(x.reshape(-1), gx.reshape(-1), s.reshape(-1), r.reshape(-1), x.size, self.lr, 1e-8, rerank_t)
         return loss, rloss
+
+
+def deepfm_gradients(params, rows, E, T, node, seq, labels):
+    """one DeepFM training step's gradient of the compact vector [emb | W1 | b1 | W2 | b2] and the mean BCE loss (Float)"""
+    params = np.ascontiguousarray(params, np.float32)
+    node = _ci32(node).ravel()
+    seq = _ci32(seq).reshape(len(node), T)
+    grad = np.empty_like(params)
+    loss = np.zeros(1, np.float32)
+    rc = lib().orc_deepfm_gradients_f32(rows, E, T, params, len(node), node, seq, np.ascontiguousarray(labels, np.float32), grad, loss)
+    if rc:
+        raise IndexError(f"oracle error {rc}")
+    return grad, loss[0]
 
 
 def arg_partition(dist, position):

@@ -151,3 +151,35 @@ def test_otm_deepfm_score_pairs_is_model_forward(orc):
     with pytest.raises(DmgError):                             # the TDM/JTM scorer is Module[Float]
         e.tdm_retrieve(np.zeros((1, T), np.int32), 20, 10)
     e.close()
+
+
+def test_deepfm_training_matches_oracle(orc):
+    """DeepFM in the training loop (tdm/.../model/DeepFM.scala:11-44 behind LocalOptimizer.trainBatch): gradients of the compact vector
+    and three Adam steps against the oracle (atomics reorder the sums: 1e-5 relative, as for the DIN step)."""
+    rows, E, T = 4095, 16, 10
+    params = deepfm_params(rows, E, T, seed=8)
+    rng = np.random.default_rng(9)
+    n = 500
+    node = rng.integers(0, rows, n).astype(np.int32)
+    seq = rng.integers(0, rows, (n, T)).astype(np.int32)
+    seq[rng.random((n, T)) < 0.3] = -1
+    seq[0] = -1
+    labels = (rng.random(n) < 0.3).astype(np.float32)
+    e = new_engine()
+    e.load_deepfm_weights(params, rows, E, T)
+    g, loss = e.din_gradients(node, seq, None, labels)
+    og, oloss = orc.deepfm_gradients(params, rows, E, T, node, seq, labels)
+    assert abs(loss - oloss) <= 1e-5 * max(1.0, abs(oloss))
+    assert np.abs(g - og).max() <= 2e-5 * np.abs(og).max()
+    w = params.copy()
+    s, r = np.zeros_like(w), np.zeros_like(w)
+    for t in (1, 2, 3):
+        og, _ = orc.deepfm_gradients(w, rows, E, T, node, seq, labels)
+        orc.adam_step(w, og, s, r, 1e-2, t)
+        e.train_step(node, seq, None, labels, 1e-2, t)
+    got = e.download_din_weights()
+    assert np.abs(got - w).max() <= 2e-4 and np.abs(got - params).max() > 1e-3
+    # the trained scorer keeps serving: model.forward on the updated weights == the oracle on the same weights
+    want = orc.TdmModel(got, rows, E, T, deepfm=True).forward(node[:64], seq[:64])
+    assert (e.score_pairs(node[:64], seq[:64]).view(np.uint32) == want.view(np.uint32)).all()
+    e.close()

@@ -495,3 +495,44 @@ def test_kmeans_tree_oracle_properties(orc):
     while (anc > 2).any():
         anc = np.where(anc > 2, (anc - 1) // 2, anc)
     assert len(set(anc[:64].tolist())) == 1 and len(set(anc[64:].tolist())) == 1 and anc[0] != anc[64]
+
+
+def test_deepfm_gradients_by_finite_differences(orc):
+    """orc_deepfm_gradients_f32 (DeepFM.scala:11-44 + FM.scala:46-72 backward, BCE mean) against central differences of an independent
+    float64 numpy loss on every parameter group; padded history slots and a padded item row get no gradient."""
+    rng = np.random.default_rng(41)
+    rows, E, T, n = 63, 8, 4, 13
+    F, IN = T + 1, (T + 1) * E
+    params = np.concatenate([rng.normal(0, 0.4, rows * E), rng.normal(0, 0.3, F * IN), rng.normal(0, 0.2, F), rng.normal(0, 0.5, F),
+                             [0.1]]).astype(np.float32)
+    node = rng.integers(0, rows, n).astype(np.int32)
+    seq = rng.integers(0, rows, (n, T)).astype(np.int32)
+    seq[rng.random((n, T)) < 0.3] = -1
+    labels = (rng.random(n) < 0.4).astype(np.float32)
+
+    def loss64(p):
+        p = p.astype(np.float64)
+        emb, w1 = p[:rows * E].reshape(rows, E), p[rows * E:rows * E + F * IN].reshape(F, IN)
+        b1, w2, b2 = p[rows * E + F * IN:][:F], p[rows * E + F * IN + F:][:F], p[-1]
+        tot = 0.0
+        for r in range(n):
+            X = np.stack([emb[c] if c >= 0 else np.zeros(E) for c in [node[r]] + seq[r].tolist()])
+            fm = ((X.sum(0) ** 2).sum() - (X ** 2).sum()) / 2
+            y = fm + np.maximum(w1 @ X.ravel() + b1, 0) @ w2 + b2
+            tot += max(y, 0) - y * labels[r] + np.log1p(np.exp(-abs(y)))
+        return tot / n
+    g, loss = orc.deepfm_gradients(params, rows, E, T, node, seq, labels)
+    assert abs(loss - loss64(params)) < 1e-5
+    h = 1e-3
+    for lo, hi in [(0, rows * E), (rows * E, rows * E + F * IN), (rows * E + F * IN, len(params))]:
+        for k in rng.choice(np.arange(lo, hi), min(25, hi - lo), replace=False):
+            p = params.astype(np.float64)
+            p[k] += h
+            up = loss64(p)
+            p[k] -= 2 * h
+            dn = loss64(p)
+            assert abs((up - dn) / (2 * h) - g[k]) < 2e-4 * max(1.0, abs(g[k])), k
+    touched = np.zeros(rows, bool)
+    touched[node] = True
+    touched[seq[seq >= 0]] = True
+    assert not g[:rows * E].reshape(rows, E)[~touched].any()
