@@ -662,7 +662,9 @@ int32_t train_precheck(dmg_handle_t h, int64_t rows, const void *node, const voi
     if (!h) return DMG_ERR_INVALID_ARG;
     DMG_TRY(model_is_shared(h, "training"));
     if (!h->din.loaded) return fail(h, DMG_ERR_STATE, "DIN weights must be loaded first");
-    if (h->din.sharded) return fail(h, DMG_ERR_STATE, "the node table is sharded (dmg_shard_init): use the dmg_shard_* entry points");
+    // a Float DeepFM model carries the `sharded` mark as "level-synchronous path only"; its table is whole unless a communicator says otherwise
+    const bool whole_deepfm = h->din.kind == 1 && h->din.dtype == DMG_F32 && (!h->shard || h->shard->world == 1);
+    if (h->din.sharded && !whole_deepfm) return fail(h, DMG_ERR_STATE, "the node table is sharded (dmg_shard_init): use the dmg_shard_* entry points");
     if (rows <= 0 || !node || !seq || !labels || !out) return fail(h, DMG_ERR_INVALID_ARG, "bad arguments");
     DMG_CUDA(h, cudaSetDevice(h->device));
     return DMG_OK;

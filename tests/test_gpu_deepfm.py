@@ -156,7 +156,9 @@ def test_otm_deepfm_score_pairs_is_model_forward(orc):
 def test_deepfm_training_matches_oracle(orc):
     """DeepFM in the training loop (tdm/.../model/DeepFM.scala:11-44 behind LocalOptimizer.trainBatch): gradients of the compact vector
     and three Adam steps against the oracle (atomics reorder the sums: 1e-5 relative, as for the DIN step)."""
-    rows, E, T = 4095, 16, 10
+    from dismember_b200 import synth
+    tf = synth.tdm_tree(2000, seed=3)
+    rows, E, T = (1 << (tf.max_level + 1)) - 1, 16, 10
     params = deepfm_params(rows, E, T, seed=8)
     rng = np.random.default_rng(9)
     n = 500
@@ -166,6 +168,7 @@ def test_deepfm_training_matches_oracle(orc):
     seq[0] = -1
     labels = (rng.random(n) < 0.3).astype(np.float32)
     e = new_engine()
+    e.load_tree_tdm(tf.max_level, tf.codes, tf.node_ids, tf.is_leaf, tf.leaf_ids, tf.leaf_codes)
     e.load_deepfm_weights(params, rows, E, T)
     g, loss = e.din_gradients(node, seq, None, labels)
     og, oloss = orc.deepfm_gradients(params, rows, E, T, node, seq, labels)
