@@ -102,6 +102,7 @@ DMG_API int32_t dmg_destroy(dmg_handle_t h)
     }
     for (Scratch *s : {&h->s_in, &h->s_out, &h->s_work, &h->s_wave}) { cudaFree(s->d); cudaFreeHost(s->h); }
     for (auto &ev : h->prof_events) { cudaEventDestroy(ev.first); cudaEventDestroy(ev.second); }
+    for (StepGraph &g : h->graphs) if (g.exec) cudaGraphExecDestroy(g.exec);
     cudaFreeHost(h->h_flags);
     cudaFree(h->d_fast_stats); cudaFree(h->d_fast_tab); cudaFree(h->d_fast_ctl); cudaFree(h->d_redo_list);
     cudaStreamDestroy(h->own_stream);
@@ -727,12 +728,13 @@ static int32_t wave_enqueue(dmg_handle_t h, const BeamParams<float> &p, const Fa
 }
 
 // Enqueue K2 + K1 for a TDM batch whose inputs already sit on the device.
-static int32_t tdm_enqueue(dmg_handle_t h, int32_t B, const int32_t *d_seq, int32_t beam, int max_beam,
-                           const int32_t *d_beam_user, int32_t topk, int32_t use_mask, const int64_t *d_cons_off,
-                           const int32_t *d_cons, int32_t *d_items, float *d_logits, int32_t *d_counts,
-                           BeamParams<float> *redo_out = nullptr, int probe_level = -1, WaveParams *probe_wp = nullptr,
-                           int *probe_slot = nullptr)
+static int32_t tdm_enqueue_raw(dmg_handle_t h, int32_t B, const int32_t *d_seq, int32_t beam, int max_beam,
+                               const int32_t *d_beam_user, int32_t topk, int32_t use_mask, const int64_t *d_cons_off,
+                               const int32_t *d_cons, int32_t *d_items, float *d_logits, int32_t *d_counts,
+                               BeamParams<float> *redo_out = nullptr, int probe_level = -1, WaveParams *probe_wp = nullptr,
+                               int *probe_slot = nullptr)
 {
+    h->last_enqueue_wave = false;
     // redo_out: a caller that synchronises anyway takes the strict redo launch into its own hands (h_flags[1] tells it
     // whether the batch has redo users); redo_out->B == 0 on return when there is no such launch.
     if (redo_out) redo_out->B = 0;
@@ -792,6 +794,7 @@ static int32_t tdm_enqueue(dmg_handle_t h, int32_t B, const int32_t *d_seq, int3
         }
         if (h->wave_ok) {
             DMG_TRY(wave_enqueue(h, p, fx, max_beam));
+            h->last_enqueue_wave = true;
         } else {
         const size_t smem = FastGeo::smem_bytes(p.cap);
         DMG_CUDA(h, cudaFuncSetAttribute(beam_search_fast_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -825,6 +828,92 @@ static int32_t tdm_enqueue(dmg_handle_t h, int32_t B, const int32_t *d_seq, int3
         return rc;
     }
     return launch_beam<float>(h, p, d.E);
+}
+
+static void free_step_graphs(dmg_handle_t h)
+{
+    for (StepGraph &g : h->graphs) if (g.exec) cudaGraphExecDestroy(g.exec);
+    h->graphs.clear();
+}
+
+// K2 + K1 + K3 of a batch.  The level-synchronous path is ~31 kernel launches per batch; a host that drives several GPUs (or
+// several handles) spends its time in cudaLaunchKernel, so a step whose arguments repeat -- the serving loop: same batch shape,
+// same staging buffers -- is captured once (programmatic dependent launches become programmatic graph edges) and replayed with one
+// cudaGraphLaunch.  The key holds every argument and every pointer baked into the kernels' parameters; anything else (first call,
+// profiling, probes, the persistent / strict kernels, a failed capture) takes the plain launches.
+static int32_t tdm_enqueue(dmg_handle_t h, int32_t B, const int32_t *d_seq, int32_t beam, int max_beam,
+                           const int32_t *d_beam_user, int32_t topk, int32_t use_mask, const int64_t *d_cons_off,
+                           const int32_t *d_cons, int32_t *d_items, float *d_logits, int32_t *d_counts,
+                           BeamParams<float> *redo_out = nullptr, int probe_level = -1, WaveParams *probe_wp = nullptr,
+                           int *probe_slot = nullptr)
+{
+    static const bool no_graph = getenv("DMG_NO_GRAPH") != nullptr;
+    const bool eligible = !no_graph && probe_level < 0 && !h->profiling && h->arithmetic == DMG_ARITH_FAST && !h->fast_dirty && h->fast_ok &&
+                          h->wave_ok && !getenv("DMG_WAVE_ABLATE");
+    if (!eligible) {
+        if (h->fast_dirty) free_step_graphs(h);                  // the model changed: every captured pointer may be stale
+        return tdm_enqueue_raw(h, B, d_seq, beam, max_beam, d_beam_user, topk, use_mask, d_cons_off, d_cons, d_items, d_logits, d_counts,
+                               redo_out, probe_level, probe_wp, probe_slot);
+    }
+    uint64_t tau_bits = 0;
+    memcpy(&tau_bits, &h->fast_tau, sizeof(float));
+    const uint64_t key[16] = {(uint64_t)B, (uint64_t)beam, (uint64_t)max_beam, (uint64_t)topk, (uint64_t)use_mask, (uint64_t)(uintptr_t)d_seq,
+                              (uint64_t)(uintptr_t)d_beam_user, (uint64_t)(uintptr_t)d_cons_off, (uint64_t)(uintptr_t)d_cons,
+                              (uint64_t)(uintptr_t)d_items, (uint64_t)(uintptr_t)d_logits, (uint64_t)(uintptr_t)d_counts,
+                              (uint64_t)(uintptr_t)h->s_wave.d ^ ((uint64_t)(uintptr_t)h->s_work.d << 1), (uint64_t)(uintptr_t)h->din.d_params ^ tau_bits,
+                              (uint64_t)(uintptr_t)h->tree.d_exists ^ ((uint64_t)(uintptr_t)h->d_redo_list << 1),
+                              (uint64_t)(redo_out ? 1 : 0) | ((uint64_t)(uintptr_t)h->stream << 1)};
+    StepGraph *g = nullptr;
+    for (StepGraph &c : h->graphs) if (!memcmp(c.key, key, sizeof(key))) { g = &c; break; }
+    if (!g) {
+        if (h->graphs.size() >= 8) { if (h->graphs.front().exec) cudaGraphExecDestroy(h->graphs.front().exec); h->graphs.erase(h->graphs.begin()); }
+        h->graphs.emplace_back();
+        g = &h->graphs.back();
+        memcpy(g->key, key, sizeof(key));
+    }
+    static_assert(sizeof(BeamParams<float>) <= sizeof(g->redo), "StepGraph::redo too small");
+    if (g->exec) {
+        DMG_CUDA(h, cudaGraphLaunch(g->exec, h->stream));
+        h->launches += g->launches;
+        if (redo_out) { if (g->has_redo) memcpy(redo_out, g->redo, sizeof(BeamParams<float>)); else redo_out->B = 0; }
+        return DMG_OK;
+    }
+    g->seen++;
+    if (g->bad || g->seen < 2) {
+        const int32_t rc = tdm_enqueue_raw(h, B, d_seq, beam, max_beam, d_beam_user, topk, use_mask, d_cons_off, d_cons, d_items, d_logits, d_counts, redo_out);
+        if (rc == DMG_OK && !h->last_enqueue_wave) g->bad = true;   // not the level-synchronous path: nothing to capture
+        // tdm_enqueue_raw may have grown a scratch buffer: the key of the NEXT call will differ and start over
+        return rc;
+    }
+    // second call with the same key: capture it
+    const int64_t l0 = h->launches;
+    BeamParams<float> redo;
+    redo.B = 0;
+    if (cudaStreamBeginCapture(h->stream, cudaStreamCaptureModeThreadLocal) != cudaSuccess) {
+        cudaGetLastError();
+        g->bad = true;
+        return tdm_enqueue_raw(h, B, d_seq, beam, max_beam, d_beam_user, topk, use_mask, d_cons_off, d_cons, d_items, d_logits, d_counts, redo_out);
+    }
+    const int32_t rc = tdm_enqueue_raw(h, B, d_seq, beam, max_beam, d_beam_user, topk, use_mask, d_cons_off, d_cons, d_items, d_logits, d_counts,
+                                       redo_out ? &redo : nullptr);
+    cudaGraph_t graph = nullptr;
+    const cudaError_t ce = cudaStreamEndCapture(h->stream, &graph);
+    cudaGraphExec_t exec = nullptr;
+    if (rc != DMG_OK || ce != cudaSuccess || !graph || cudaGraphInstantiate(&exec, graph, 0) != cudaSuccess) {
+        cudaGetLastError();
+        if (graph) cudaGraphDestroy(graph);
+        g->bad = true;
+        h->launches = l0;
+        return tdm_enqueue_raw(h, B, d_seq, beam, max_beam, d_beam_user, topk, use_mask, d_cons_off, d_cons, d_items, d_logits, d_counts, redo_out);
+    }
+    cudaGraphDestroy(graph);
+    g->exec = exec;
+    g->launches = h->launches - l0;
+    g->has_redo = redo_out != nullptr && redo.B != 0;
+    if (g->has_redo) memcpy(g->redo, &redo, sizeof(redo));
+    DMG_CUDA(h, cudaGraphLaunch(exec, h->stream));
+    if (redo_out) { if (g->has_redo) *redo_out = redo; else redo_out->B = 0; }
+    return DMG_OK;
 }
 
 DMG_API int32_t dmg_set_arithmetic(dmg_handle_t h, int32_t mode)

@@ -80,6 +80,17 @@ struct DrDev {
 
 struct ShardState;                  // shard.cu
 
+// One captured retrieval step (capi.cu: tdm_enqueue): K2 + the whole level-synchronous chain of a batch as ONE graph launch.
+struct StepGraph {
+    uint64_t key[16];               // every argument and every pointer the captured kernels were given
+    int seen = 0;                   // calls with this key so far (the second one captures: all scratch is allocated by then)
+    bool bad = false;               // capture failed once: stay on plain launches
+    cudaGraphExec_t exec = nullptr;
+    int64_t launches = 0;           // kernels inside
+    unsigned char redo[256];        // the strict redo launch the synchronous callers decide on (BeamParams<float>)
+    bool has_redo = false;
+};
+
 struct Scratch {                    // grow-only device / pinned buffers
     void *d = nullptr; size_t d_bytes = 0;
     void *h = nullptr; size_t h_bytes = 0;
@@ -118,6 +129,8 @@ struct dmg_handle_s {
     dmg::ShardState *shard = nullptr;   // node-table sharding over NCCL (shard.cu)
     bool profiling = false;
     std::vector<std::pair<cudaEvent_t, cudaEvent_t>> prof_events;
+    std::vector<dmg::StepGraph> graphs;  // CUDA graphs of recent retrieval steps (one cudaGraphLaunch instead of ~31 kernel launches)
+    bool last_enqueue_wave = false;
     dmg_handle_s *parent = nullptr;     // dmg_clone: tree / weight tables are the parent's (read-only here, never freed here)
     std::atomic<int> n_clones{0};       // live clones: the model of this handle is frozen until they are destroyed
 };
