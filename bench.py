@@ -66,11 +66,14 @@ def parse():
     ap.add_argument("--no-sharded", action="store_true", help="N > 1 only: skip the table-sharded legs (BASELINE configs 4 and 5, sharded TDM)")
     ap.add_argument("--shard-items", type=int, default=10_000_000, help="catalogue of the sharded TDM / JTM legs")
     ap.add_argument("--shard-dr-items", type=int, default=100_000_000, help="catalogue of the sharded Deep Retrieval leg")
-    ap.add_argument("--inflight", type=int, default=8,
-                    help="host threads / handles driving the GPU, one batch each in flight (1 = strictly serial steps)")
+    ap.add_argument("--inflight", type=int, default=0,
+                    help="host threads / handles driving the GPU, one batch each in flight (1 = strictly serial steps; 0 = min(8, cores / ranks))")
     ap.add_argument("--arith", default="fast", choices=["fast", "strict"],
                     help="scorer arithmetic: tensor-core with certified cuts (same ids/logits) or strict fp32 SIMT")
-    return ap.parse_args()
+    a = ap.parse_args()
+    if a.inflight <= 0:
+        a.inflight = 8
+    return a
 
 
 def algorithmic_bytes_per_user(L, E, T, topk, beam):
@@ -275,6 +278,10 @@ def measure(args, env, items, structured=False, do_cpu=False, target_s=None, ver
     else:
         eng.init_din_weights(np.float32, rows, E, T, seed=2)      # replicas: same table on every rank
     eng.set_arithmetic(args.arith)
+    # waiting host threads spin while this rank's share of the cores covers them (lowest latency) and sleep otherwise (8 ranks x 8
+    # threads on a 32-core host): dmg_set_sync_mode; the clones inherit it
+    sync_mode = "sleep" if env["world"] * args.inflight * 1.5 > (os.cpu_count() or 1) else "spin"
+    eng.set_sync_mode(sync_mode)
     if args.tau is not None:
         eng.set_fast_tolerance(args.tau)
     NF = max(1, args.inflight)
@@ -330,7 +337,7 @@ def measure(args, env, items, structured=False, do_cpu=False, target_s=None, ver
     last_items = d_out[last_k][0].cpu().numpy().copy()
     last_q = (K * R - 1) % P
 
-    out = {"items": items, "levels": L, "rows": rows, "R": R, "NF": NF, "value": world * B * K * R / (dev_ms * 1e-3),
+    out = {"items": items, "levels": L, "rows": rows, "R": R, "NF": NF, "sync_mode": sync_mode, "value": world * B * K * R / (dev_ms * 1e-3),
            "ms_per_step": dev_ms / (K * R), "launches": launches / max(K * R, 1), "timed_region_s": dev_ms * 1e-3}
 
     # ---- roofline pass: ONE batch in flight on a handle of its own policy, the dominant kernel timed alone ---------------
@@ -658,7 +665,7 @@ def main():
                        "repeats": m["R"], "timed_region_s": m["timed_region_s"],
                        "timed_region": f"the {K} steps are repeated R={m['R']} times inside every timed region (device and e2e) with "
                                        f"query batches drawn from a pool of 64 distinct ones; ms_per_step = region / (steps x R)",
-                       "batches_in_flight": NF,
+                       "batches_in_flight": NF, "host_wait": m.get("sync_mode"),
                        "in_flight": (f"{NF} host threads started before the timed region, one handle each (dmg_clone: one copy of the tables), "
                                      "take the steps round-robin; the roofline object is from a serial pass (one batch in flight)") if NF > 1 else "serial steps",
                        "serial_ms_per_step": m.get("serial_ms_per_step"),

@@ -86,6 +86,7 @@ def load_library(build_if_missing: bool = True):
         "dmg_dr_beam_search": [vp, i32, vp, i32, vp, vp, vp],
         "dmg_dr_retrieve": [vp, i32, vp, i32, i32, vp, vp, vp],
         "dmg_kmeans_tree": [vp, i32, i32, vp, i32, u64, vp],
+        "dmg_set_sync_mode": [vp, i32],
         "dmg_dr_load_item_paths": [vp, i32, vp],
         "dmg_dr_init_synthetic": [vp, i32, i32, i32, i32, i32, i32, u64],
         "dmg_dr_train_step": [vp, i32, vp, vp, vp, i32, u64, dbl, i32, i32, i32, i32, vp, vp],
@@ -206,6 +207,10 @@ class Engine:
     @property
     def launch_count(self) -> int:
         return int(self.L.dmg_launch_count(self.h))
+
+    def set_sync_mode(self, mode: str):
+        """'spin' (default) | 'sleep': how the synchronous retrieval calls wait (dmg_set_sync_mode)."""
+        self._check(self.L.dmg_set_sync_mode(self.h, {"spin": 0, "sleep": 1}[mode]))
 
     def set_arithmetic(self, mode: str):
         """'strict' | 'fast' (tensor-core scorer with certified cuts; same ids and logits)."""

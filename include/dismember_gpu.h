@@ -71,6 +71,10 @@ DMG_API const char *dmg_version(void);
  * handle's own; pass NULL to go back.  Lets callers time with their own CUDA events. */
 DMG_API int32_t dmg_set_stream(dmg_handle_t h, void *cuda_stream);
 DMG_API int32_t dmg_synchronize(dmg_handle_t h);
+/* How the synchronous retrieval calls wait for their batch: 0 = spin (default, lowest latency), 1 = sleep on a blocking event
+ * (hosts where the waiting threads of all handles / processes outnumber the cores, e.g. 8 GPUs x 8 serving threads on 32 cores).
+ * Clones inherit the mode of their parent at dmg_clone. */
+DMG_API int32_t dmg_set_sync_mode(dmg_handle_t h, int32_t mode);
 /* number of kernels this handle has launched so far (bench.py's gpu_launches). */
 DMG_API int64_t dmg_launch_count(dmg_handle_t h);
 /* Optional per-kernel timing of the dominant (beam-search) kernel: when on, every launch is
