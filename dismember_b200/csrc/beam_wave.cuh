@@ -87,8 +87,16 @@ struct WaveParams {
     int32_t *tile_count;            // per level: tiles appended by the select kernel
     const unsigned char *w1img;     // [W1x hi | W1x lo] as the n < 64 rows of the B operand, 2 x 12288 B
     const unsigned char *split;     // bf16 hi|lo table, 256 B per code
+    int kind;                       // 0 DIN (this file), 1 DeepFM (beam_wave_dfm.cuh): the bound and the strict re-scores differ
+    const float *dfm_dense;         // DeepFM: [W1 | b1 | W2 | b2]
 };
 struct WaveW2 { float w2[64]; float b2; };
+struct DfmConsts {                      // DeepFM scorer constants (beam_wave_dfm.cuh): host-computed, passed by value
+    float w2[16], b1[16];               // T + 1 <= 16 hidden units
+    float b2;
+    float aw2[16];                      // |w2_o|
+    int F;
+};
 
 // ---- bf16 hi|lo copy of the node table: row c = [64 hi | 64 lo] bf16 (256 B), i.e. a [2 rows][64] bf16 matrix ------
 static __global__ void wave_split_table_kernel(const float *__restrict__ emb, int64_t rows, unsigned char *__restrict__ out)
@@ -301,6 +309,10 @@ __device__ __forceinline__ void wave_expand_finish(const WaveParams &p, WaveUser
         const float dp1 = 2.1f * ds + 2.0f * (float)(p.T + 8) * u + 2.0f * 9.5367432e-7f * (1.0f + 2.0f * smax);
         float eps = p.cA * vx + p.cZ * st->zk + (p.cH + dp1) * st->hw * 1.05f + p.cGamma;
         if (!(ds < 0.04f) || !(eps < 1e30f)) eps = __int_as_float(0x7f800000);
+        if (p.kind == 1) {                                        // DeepFM (beam_wave_dfm.cuh): vt . |x| + a0 + a1 nx + a2 nx^2, 25 % on top
+            eps = 1.25f * (vx + st->zk + st->kmax * nx + st->hw * nx * nx);
+            if (!(eps < 1e30f)) eps = __int_as_float(0x7f800000);
+        }
         st->eps = eps * p.tau;
         if (out > 0) st->flags = flags | WU_SCORED;
         if (p.stats) {
@@ -312,6 +324,9 @@ __device__ __forceinline__ void wave_expand_finish(const WaveParams &p, WaveUser
 }
 
 struct WaveStrictW { const float *wattT, *w1T, *b1, *w2; float b2; };
+__device__ void dfm_strict_batch128(const WaveParams &p, const DfmConsts &dc, const float *__restrict__ dense, int user,
+                                    const int32_t *__restrict__ sRow, int n, float *__restrict__ sOut, float *__restrict__ scr,
+                                    float *__restrict__ sDense, bool dense_loaded);   // beam_wave_dfm.cuh
 
 // 4 users per CTA.  Phase 1: every warp cuts its user; a cut whose band cannot be deferred (fast-score gap at the cut below
 // eps / 128) is parked.  Phase 2: the whole CTA scores the band rows of its parked users strictly (sequential-k fma chains,
@@ -321,7 +336,7 @@ struct WaveStrictW { const float *wattT, *w1T, *b1, *w2; float b2; };
 // parallel -- rolled loops, so that the kernel stays a few thousand instructions (it runs at low occupancy: instruction
 // fetch is what bounds a long unrolled body).
 template <int NJ>
-static __global__ void __launch_bounds__(128) wave_select_kernel(const WaveParams p, const WaveStrictW sw, int level, int slot)
+static __global__ void __launch_bounds__(128) wave_select_kernel(const WaveParams p, const WaveStrictW sw, int level, int slot, const DfmConsts dc)
 {
     constexpr int MU = WaveGeo::MAX_UNC;
     __shared__ __align__(16) float sScr[FastGeo::STRICT_SCR / 4];
@@ -333,6 +348,7 @@ static __global__ void __launch_bounds__(128) wave_select_kernel(const WaveParam
     __shared__ uint32_t sKeepW[4][NJ];
     __shared__ int sGap[4][2];
     __shared__ int sPark[4][2];                                   // n_unc (0 = not parked), need
+    extern __shared__ __align__(16) unsigned char sel_dyn[];      // DeepFM only: the dense weights of a parked cut's strict chains
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int user = blockIdx.x * 4 + warp;
     const uint32_t lt = (1u << lane) - 1u;
@@ -468,13 +484,20 @@ static __global__ void __launch_bounds__(128) wave_select_kernel(const WaveParam
     }
     __syncthreads();
     // ---- phase 2: strict scores of the parked bands, whole CTA ----
-    bool any = false;
+    bool any = false, dense_loaded = false;
 #pragma unroll 1
     for (int w = 0; w < 4; w++) {
         const int n = sPark[w][0];
         if (n == 0) continue;
         any = true;
         const int pu = blockIdx.x * 4 + w;
+        if (p.kind == 1) {                                         // DeepFM: the oracle-order chains of deepfm_common.cuh
+            if (tid < n) sKeyU[w][tid] = __float_as_uint(sLStr[w][tid]);
+            __syncthreads();
+            dfm_strict_batch128(p, dc, p.dfm_dense, pu, sLCode[w], n, sLStr[w], sScr, reinterpret_cast<float *>(sel_dyn), dense_loaded);
+            dense_loaded = true;
+            continue;
+        }
         for (int i = tid; i < kMaxT * 64; i += 128) {              // history rows (fp32), zero rows for padding
             const int j = i >> 6, k = i & 63;
             const int c = j < p.T ? p.hist[(size_t)pu * p.T + j] : -1;

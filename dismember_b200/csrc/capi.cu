@@ -8,6 +8,7 @@
 #include "beam_kernels.cuh"
 #include "beam_fast.cuh"
 #include "beam_wave.cuh"
+#include "beam_wave_dfm.cuh"
 #include "rows_kernels.cuh"
 
 using namespace dmg;
@@ -673,7 +674,7 @@ static int32_t wave_enqueue(dmg_handle_t h, const BeamParams<float> &p, const Fa
     (void)max_beam;
     const int last_level = stop_level >= 0 ? std::min(stop_level, p.leaf_level) : p.leaf_level;
     for (int level = s_min; level < last_level; level++) {
-        DMG_CUDA(h, launch_chain(select_kernel, (B + 3) / 4, 128, 0, h->stream, pdl, wp, sw, level, slot));
+        DMG_CUDA(h, launch_chain(select_kernel, (B + 3) / 4, 128, 0, h->stream, pdl, wp, sw, level, slot, DfmConsts()));
         cudaEvent_t e0 = nullptr, e1 = nullptr;
         if (h->profiling) {                                      // dmg_set_profiling: every launch of the dominant kernel timed alone
             DMG_CUDA(h, cudaEventCreate(&e0));
@@ -1047,12 +1048,232 @@ DMG_API int32_t dmg_tdm_retrieve_dev_sync(dmg_handle_t h, int32_t B, const int32
     return DMG_OK;
 }
 
+int dmg_shard_world(dmg_handle_t h);   // shard.cu
+
+// ---- DeepFM scorer: certified fast path (beam_wave_dfm.cuh) -----------------------------------------------------------------------------
+// Bound tables of the loaded DeepFM model: vt (per-dimension weight of |x| in the hidden-unit and final-dot error terms) and, through
+// level_bounds_kernel, the per-level maxima of vt . |x| and |x|_2; the transposed item half of W1 for the fast scorer.
+static int32_t compute_dfm_bounds(dmg_handle_t h)
+{
+    DinDev &d = h->din;
+    h->fast_ok = false;
+    h->fast_dirty = false;
+    if (d.kind != 1 || d.dtype != DMG_F32 || d.E != 64 || d.T > 10) return DMG_OK;   // T + 1 <= 11 hidden units in the fast scorer
+    const int E = d.E, T = d.T, F = T + 1, IN = F * E;
+    const size_t n_dense = (size_t)F * IN + 2 * F + 1;
+    std::vector<float> w(n_dense);
+    DMG_CUDA(h, cudaMemcpyAsync(w.data(), d.tail<float>(), n_dense * 4, cudaMemcpyDeviceToHost, h->stream));
+    DMG_CUDA(h, cudaStreamSynchronize(h->stream));
+    const float *w1 = w.data(), *b1 = w1 + (size_t)F * IN, *w2 = b1 + F, *b2 = w2 + F;
+    DfmConsts dc;
+    memset(&dc, 0, sizeof(dc));
+    dc.F = F; dc.b2 = b2[0];
+    for (int o = 0; o < F; o++) { dc.w2[o] = w2[o]; dc.b1[o] = b1[o]; dc.aw2[o] = std::fabs(w2[o]); }
+    static_assert(sizeof(DfmConsts) <= sizeof(h->dfm_consts), "dfm_consts too small");
+    memcpy(h->dfm_consts, &dc, sizeof(dc));
+    h->fast_host.assign(64 * 11, 0.0f);                          // W1x^T [k][o] for the fast scorer's parameter block
+    for (int k = 0; k < E; k++)
+        for (int o = 0; o < F && o < 11; o++) h->fast_host[(size_t)k * 11 + o] = w1[(size_t)o * IN + k];
+    std::vector<float> tab(4288, 0.0f);                          // [4096, 4160) vt | lvl_vx | lvl_nx
+    const double u = std::ldexp(1.0, -24);
+    bool finite = true;
+    for (int k = 0; k < E; k++) {
+        double vt = 0.0;
+        for (int o = 0; o < F; o++) {
+            vt += std::fabs((double)w2[o]) * std::fabs((double)w1[(size_t)o * IN + k]) * ((705.0 + 66.0 + 2.0) * u + 2.0 * (F + 3.0) * u);
+        }
+        tab[4096 + k] = (float)(vt * (1.0 + 1e-6));
+        finite = finite && std::isfinite(vt);
+    }
+    if (!h->d_fast_tab) DMG_CUDA(h, cudaMalloc(&h->d_fast_tab, tab.size() * sizeof(float)));
+    if (!h->d_fast_ctl) {
+        DMG_CUDA(h, cudaMalloc(&h->d_fast_ctl, DMG_FAST_CTL_WORDS * sizeof(int32_t)));
+        DMG_CUDA(h, cudaMemsetAsync(h->d_fast_ctl, 0, DMG_FAST_CTL_WORDS * sizeof(int32_t), h->stream));
+    }
+    DMG_CUDA(h, cudaMemcpyAsync(h->d_fast_tab, tab.data(), tab.size() * sizeof(float), cudaMemcpyHostToDevice, h->stream));
+    level_bounds_kernel<<<h->sm_count * 8, 256, 0, h->stream>>>(d.emb<float>(), d.rows, h->d_fast_tab + 4096, h->d_fast_tab + 4160, h->d_fast_tab + 4192);
+    h->launches += 1;
+    DMG_CUDA(h, cudaGetLastError());
+    DMG_CUDA(h, cudaStreamSynchronize(h->stream));
+    h->fast_ok = finite;
+    return DMG_OK;
+}
+
+int32_t dmg_deepfm_tdm_retrieve(dmg_handle_t h, int32_t B, const int32_t *item_seq, int32_t beam, int32_t topk, const int64_t *cons_off,
+                                const int32_t *cons, int32_t widen_beam, int32_t *out_items, float *out_logits, int32_t *out_counts);   // shard.cu
+
+// dmg_tdm_retrieve with a DeepFM model in FAST arithmetic: the level-synchronous chain of beam_wave.cuh with the DeepFM prologue /
+// scorer / strict re-scores; users the fast path hands back (exact ties across a decision point, failed proofs) re-run on the strict
+// level-synchronous path (shard.cu).  Returns DMG_ERR_UNSUPPORTED-free: `*handled` = false when the shape is outside the fast path.
+static int32_t dfm_fast_retrieve(dmg_handle_t h, int32_t B, const int32_t *item_seq, int32_t beam, int32_t topk, const int64_t *consumed_off,
+                                 const int32_t *consumed_items, int32_t widen_beam, int32_t *out_items, float *out_logits, int32_t *out_counts,
+                                 bool *handled)
+{
+    using WG = WaveGeo;
+    *handled = false;
+    DinDev &d = h->din;
+    const TreeDev &t = h->tree;
+    if (h->arithmetic != DMG_ARITH_FAST || d.E != 64 || d.T > 10 || dmg_shard_world(h) > 1 || !t.loaded || t.complete || !t.d_id_code ||
+        getenv("DMG_DFM_STRICT"))
+        return DMG_OK;
+    if (B <= 0 || beam <= 0 || topk <= 0) return DMG_OK;          // the strict path reports the argument errors
+    DMG_CUDA(h, cudaSetDevice(h->device));
+    if (h->fast_dirty) DMG_TRY(compute_dfm_bounds(h));
+    if (!h->fast_ok) return DMG_OK;
+    const int T = d.T;
+    const int64_t n_cons = consumed_off ? consumed_off[B] : 0;
+    const bool per_user = consumed_off && widen_beam;
+    int max_beam = beam;
+    if (per_user)
+        for (int u = 0; u < B; u++) max_beam = std::max(max_beam, (int)((consumed_off[u + 1] - consumed_off[u] + topk) / 2));
+    const int cap = std::max(std::max(((2 * max_beam + 7) / 8) * 8, 8), ((topk + 7) / 8) * 8);
+    if (cap > 512 || topk > FastGeo::MAX_FINAL / 2) return DMG_OK;
+    DfmConsts dc;
+    memcpy(&dc, h->dfm_consts, sizeof(dc));
+    // staging: [seq | cons_off | cons | beam_user]
+    const size_t in_bytes = Carver::need({(size_t)B * T * 4, consumed_off ? (size_t)(B + 1) * 8 : 0, (size_t)n_cons * 4, per_user ? (size_t)B * 4 : 0});
+    DMG_TRY(ensure_host(h, h->s_in, in_bytes));
+    DMG_TRY(ensure_dev(h, h->s_in, in_bytes));
+    Carver ch(h->s_in.h), cdv(h->s_in.d);
+    int32_t *hs = ch.take<int32_t>((size_t)B * T), *ds = cdv.take<int32_t>((size_t)B * T);
+    int64_t *ho = ch.take<int64_t>(consumed_off ? B + 1 : 0), *dof = cdv.take<int64_t>(consumed_off ? B + 1 : 0);
+    int32_t *hc = ch.take<int32_t>((size_t)n_cons), *dcs = cdv.take<int32_t>((size_t)n_cons);
+    int32_t *hb = ch.take<int32_t>(per_user ? B : 0), *db = cdv.take<int32_t>(per_user ? B : 0);
+    memcpy(hs, item_seq, (size_t)B * T * 4);
+    if (consumed_off) {
+        memcpy(ho, consumed_off, (size_t)(B + 1) * 8);
+        if (n_cons) memcpy(hc, consumed_items, (size_t)n_cons * 4);
+        if (per_user)
+            for (int u = 0; u < B; u++) hb[u] = std::max((int)((consumed_off[u + 1] - consumed_off[u] + topk) / 2), beam);   // Recommender.scala:28-31
+    }
+    DMG_CUDA(h, cudaMemcpyAsync(h->s_in.d, h->s_in.h, ch.off, cudaMemcpyHostToDevice, h->stream));
+    const size_t out_bytes = Carver::need({(size_t)B * topk * 4, (size_t)B * topk * 4, (size_t)B * 4, (size_t)B * 4, 64});
+    DMG_TRY(ensure_host(h, h->s_out, out_bytes));
+    DMG_TRY(ensure_dev(h, h->s_out, out_bytes));
+    Carver oh(h->s_out.h), od(h->s_out.d);
+    int32_t *h_items = oh.take<int32_t>((size_t)B * topk), *d_items = od.take<int32_t>((size_t)B * topk);
+    float *h_log = oh.take<float>((size_t)B * topk), *d_log = od.take<float>((size_t)B * topk);
+    int32_t *h_cnt = oh.take<int32_t>(B), *d_cnt = od.take<int32_t>(B);
+    int32_t *h_redo = oh.take<int32_t>(B), *d_redo = od.take<int32_t>(B);
+    int32_t *h_nredo = oh.take<int32_t>(1), *d_nredo = od.take<int32_t>(1);
+    (void)d_nredo;
+    // work: codes + mask of the histories, then the wave state
+    DMG_TRY(ensure_dev(h, h->s_work, Carver::need({(size_t)B * T * 4, (size_t)B * T})));
+    Carver cw(h->s_work.d);
+    int32_t *d_codes = cw.take<int32_t>((size_t)B * T);
+    uint8_t *d_mask = cw.take<uint8_t>((size_t)B * T);
+    DMG_TRY(ensure_dev(h, h->s_wave, Carver::need({(size_t)B * cap * 4, (size_t)B * cap * 4, (size_t)B * cap * 4, (size_t)B * 4,
+                                                   (size_t)B * sizeof(WaveUser), (size_t)B * WG::UOP_BYTES, (size_t)B * WG::VCAP * 4,
+                                                   (size_t)B * WG::VCAP * 4, (size_t)B * WG::VCAP * 4, (size_t)B * 32 * 4,
+                                                   (size_t)B * ((cap + 127) / 128) * 4, (size_t)B * WaveFinal::RCAP * 4, (size_t)B * WaveFinal::RCAP * 4,
+                                                   (size_t)B * FastGeo::MAX_FINAL * 4, (size_t)B * 4 * 4, (size_t)B * 27 * 4})));
+    if (!h->d_fast_stats) {
+        DMG_CUDA(h, cudaMalloc(&h->d_fast_stats, 64 * sizeof(unsigned long long)));
+        DMG_CUDA(h, cudaMemsetAsync(h->d_fast_stats, 0, 64 * sizeof(unsigned long long), h->stream));
+    }
+    Carver c(h->s_wave.d);
+    WaveParams wp;
+    memset(&wp, 0, sizeof(wp));
+    wp.kind = 1; wp.dfm_dense = d.tail<float>();
+    wp.B = B; wp.T = T; wp.cap = cap; wp.beam = beam; wp.beam_user = per_user ? db : nullptr;
+    wp.emb = d.emb<float>(); wp.hist = d_codes; wp.hist_mask = d_mask; wp.exists = t.d_exists;
+    wp.leaf_level = t.max_level; wp.sparse_from = t.sparse_from; wp.scale = 1.0f;
+    wp.code[0] = c.take<int32_t>((size_t)B * cap); wp.code[1] = c.take<int32_t>((size_t)B * cap);
+    wp.score = c.take<float>((size_t)B * cap);
+    wp.count = c.take<int32_t>(B);
+    wp.user = c.take<WaveUser>(B);
+    wp.uop = c.take<unsigned char>((size_t)B * WG::UOP_BYTES);
+    wp.v_code = c.take<int32_t>((size_t)B * WG::VCAP); wp.v_fast = c.take<float>((size_t)B * WG::VCAP);
+    wp.v_meta = c.take<uint32_t>((size_t)B * WG::VCAP); wp.v_segeps = c.take<float>((size_t)B * 32);
+    wp.tile_list = c.take<int32_t>((size_t)B * ((cap + 127) / 128));
+    WaveFinal wf;
+    wf.row_code = c.take<int32_t>((size_t)B * WaveFinal::RCAP); wf.row_strict = c.take<float>((size_t)B * WaveFinal::RCAP);
+    wf.fin_pos = c.take<int32_t>((size_t)B * FastGeo::MAX_FINAL); wf.meta = c.take<int32_t>((size_t)B * 4);
+    wf.chunk_list = c.take<int32_t>((size_t)B * 27);
+    wf.chunk_count = h->d_fast_ctl + 8 + 40;
+    wp.tile_count = h->d_fast_ctl + 8;
+    wp.lvl_vx = h->d_fast_tab + 4160; wp.lvl_nx = h->d_fast_tab + 4192;
+    wp.tau = h->fast_tau;
+    wp.stats = h->d_fast_stats; wp.redo_list = d_redo; wp.redo_count = h->d_fast_ctl + 1; wp.host_flags = h->d_flags;
+    BeamParams<float> bp;
+    memset(&bp, 0, sizeof(bp));
+    bp.B = B; bp.topk = topk; bp.leaf_item = t.d_leaf_item; bp.cons_off = consumed_off ? dof : nullptr; bp.cons = consumed_off ? dcs : nullptr;
+    bp.out_items = d_items; bp.out_scores = d_log; bp.out_counts = d_cnt; bp.out_stride = topk; bp.leaf_level = t.max_level; bp.cap = cap;
+    WaveStrictW sw;
+    memset(&sw, 0, sizeof(sw));
+    const int64_t n = (int64_t)B * T;
+    tdm_ids_to_codes_kernel<<<(unsigned)((n + 255) / 256), 256, 0, h->stream>>>(ds, n, t.d_id_code, t.non_leaf_offset, t.max_code, d.rows, 0, d_codes,
+                                                                              d_mask, h->d_flags, h->d_fast_ctl);
+    h->launches += 1;
+    const bool pdl = !getenv("DMG_WAVE_NO_PDL");
+    DMG_CUDA(h, launch_chain(wave_dfm_prologue_kernel, B, 128, 0, h->stream, false, wp, dc, (const float *)d.tail<float>()));
+    auto select_kernel = cap <= 256 ? wave_select_kernel<8> : (cap <= 416 ? wave_select_kernel<13> : wave_select_kernel<16>);
+    const size_t score_smem = (size_t)(128 * 68 + 96) * 4;
+    const int ntiles = B * ((cap + 127) / 128), grid = std::min(ntiles, 6 * h->sm_count);
+    DfmW1x wx;
+    memcpy(wx.w, h->fast_host.data(), sizeof(wx.w));
+    const size_t strict_smem = ((size_t)(T + 1) * (T + 1) * 64 + 2 * (T + 1) + 1 + 4 + 128 * (68 + 20)) * 4;
+    DMG_CUDA(h, cudaFuncSetAttribute(wave_dfm_strict_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)strict_smem));
+    int slot = 0;
+    const int s_min = lower_log2(beam);
+    const size_t sel_smem = ((size_t)(T + 1) * (T + 1) * 64 + 2 * (T + 1) + 1 + 4) * 4;     // the dense weights for parked cuts
+    DMG_CUDA(h, cudaFuncSetAttribute(select_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sel_smem));
+    for (int level = s_min; level < t.max_level; level++) {
+        DMG_CUDA(h, launch_chain(select_kernel, (B + 3) / 4, 128, sel_smem, h->stream, pdl, wp, sw, level, slot, dc));
+        DMG_CUDA(h, launch_chain(wave_dfm_score_kernel, grid, 128, score_smem, h->stream, pdl, wp, dc, wx, slot ^ 1, level + 1));
+        slot ^= 1;
+        h->launches += 2;
+    }
+    auto prep_kernel = cap <= 256 ? wave_final_prep_kernel<8> : (cap <= 416 ? wave_final_prep_kernel<13> : wave_final_prep_kernel<16>);
+    DMG_CUDA(h, launch_chain(prep_kernel, (B + 3) / 4, 128, 0, h->stream, pdl, wp, bp, wf, slot));
+    DMG_CUDA(h, launch_chain(wave_dfm_strict_rows_kernel, std::min(B, 2 * h->sm_count), 256, strict_smem, h->stream, pdl, wp, dc, (const float *)d.tail<float>(), wf));
+    DMG_CUDA(h, launch_chain(wave_final_verify_kernel, (B + 3) / 4, 128, 0, h->stream, pdl, wp, bp, wf, slot));
+    h->launches += 4;
+    DMG_CUDA(h, cudaGetLastError());
+    DMG_CUDA(h, cudaMemcpyAsync(h->s_out.h, h->s_out.d, od.off, cudaMemcpyDeviceToHost, h->stream));
+    DMG_CUDA(h, cudaMemcpyAsync(h_nredo, h->d_fast_ctl + 1, 4, cudaMemcpyDeviceToHost, h->stream));
+    DMG_TRY(check_flag(h, "dmg_tdm_retrieve"));
+    h->h_flags[1] = 0;
+    memcpy(out_items, h_items, (size_t)B * topk * 4);
+    memcpy(out_logits, h_log, (size_t)B * topk * 4);
+    memcpy(out_counts, h_cnt, (size_t)B * 4);
+    const int n_redo = *h_nredo;
+    if (n_redo > 0) {                                            // the strict level-synchronous path for the users handed back
+        std::vector<int32_t> rs((size_t)n_redo * T), ri((size_t)n_redo * topk), rcn(n_redo), rc_flat;
+        std::vector<float> rl((size_t)n_redo * topk);
+        std::vector<int64_t> ro;
+        if (consumed_off) ro.push_back(0);
+        for (int q = 0; q < n_redo; q++) {
+            const int u = h_redo[q];
+            memcpy(rs.data() + (size_t)q * T, item_seq + (size_t)u * T, (size_t)T * 4);
+            if (consumed_off) {
+                rc_flat.insert(rc_flat.end(), consumed_items + consumed_off[u], consumed_items + consumed_off[u + 1]);
+                ro.push_back((int64_t)rc_flat.size());
+            }
+        }
+        DMG_TRY(dmg_deepfm_tdm_retrieve(h, n_redo, rs.data(), beam, topk, consumed_off ? ro.data() : nullptr, consumed_off ? rc_flat.data() : nullptr,
+                                        widen_beam, ri.data(), rl.data(), rcn.data()));
+        for (int q = 0; q < n_redo; q++) {
+            const int u = h_redo[q];
+            memcpy(out_items + (size_t)u * topk, ri.data() + (size_t)q * topk, (size_t)topk * 4);
+            memcpy(out_logits + (size_t)u * topk, rl.data() + (size_t)q * topk, (size_t)topk * 4);
+            out_counts[u] = rcn[q];
+        }
+    }
+    *handled = true;
+    return DMG_OK;
+}
+
 DMG_API int32_t dmg_tdm_retrieve(dmg_handle_t h, int32_t B, const int32_t *item_seq, int32_t beam, int32_t topk,
                                  int32_t use_mask, const int64_t *consumed_off, const int32_t *consumed_items,
                                  int32_t widen_beam, int32_t *out_items, float *out_logits, int32_t *out_counts)
 {
     if (h && h->din.loaded && h->din.kind == 1 && h->din.dtype == DMG_F32) {   // DeepFM scorer: level-synchronous path (shard.cu)
         if (!item_seq || !out_items || !out_logits || !out_counts) return fail(h, DMG_ERR_INVALID_ARG, "null host pointer");
+        if (consumed_off && !consumed_items && B > 0 && consumed_off[B] > 0) return fail(h, DMG_ERR_INVALID_ARG, "consumed_items is null");
+        bool handled = false;
+        DMG_TRY(dfm_fast_retrieve(h, B, item_seq, beam, topk, consumed_off, consumed_items, widen_beam, out_items, out_logits, out_counts, &handled));
+        if (handled) return DMG_OK;
         return dmg_deepfm_tdm_retrieve(h, B, item_seq, beam, topk, consumed_off, consumed_items, widen_beam, out_items, out_logits, out_counts);
     }
     DMG_TRY(tdm_precheck(h, B, beam, topk));

@@ -132,6 +132,7 @@ struct dmg_handle_s {
     std::vector<dmg::StepGraph> graphs;  // CUDA graphs of recent retrieval steps (one cudaGraphLaunch instead of ~31 kernel launches)
     bool last_enqueue_wave = false;
     cudaEvent_t sync_ev = nullptr;       // blocking-sync event: a host thread waiting for its batch sleeps instead of spinning on a core
+    alignas(8) unsigned char dfm_consts[256];   // DfmConsts of the loaded DeepFM model (beam_wave_dfm.cuh), valid when !fast_dirty
     int sync_mode = 0;                   // dmg_set_sync_mode: 0 spin (lowest latency), 1 sleep (hosts with more waiting threads than cores)
     dmg_handle_s *parent = nullptr;     // dmg_clone: tree / weight tables are the parent's (read-only here, never freed here)
     std::atomic<int> n_clones{0};       // live clones: the model of this handle is frozen until they are destroyed
