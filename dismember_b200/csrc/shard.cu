@@ -597,6 +597,7 @@ static int32_t shard_finish_din(dmg_handle_t h)
     const int E = d.E;
     if (d.kind == 1) {                                           // DeepFM: no transposed copies, level-synchronous path only
         DMG_CUDA(h, cudaStreamSynchronize(h->stream));
+        h->fast_dirty = true;                                    // the fast path's bound tables and weight image follow the new weights
         d.loaded = true;
         d.sharded = true;
         return DMG_OK;

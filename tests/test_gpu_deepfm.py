@@ -186,3 +186,48 @@ def test_deepfm_training_matches_oracle(orc):
     want = orc.TdmModel(got, rows, E, T, deepfm=True).forward(node[:64], seq[:64])
     assert (e.score_pairs(node[:64], seq[:64]).view(np.uint32) == want.view(np.uint32)).all()
     e.close()
+
+
+def test_deepfm_fast_path_runs_and_hands_ties_back(orc):
+    """The certified fast path (csrc/beam_wave_dfm.cuh) is what serves E = 64: rows_fast > 0, ids and logits == the strict arithmetic and
+    the oracle; an all-zero model (every score ties exactly at every cut) is handed back to the strict level-synchronous path and
+    still matches; the eval variant with consumed items and widened beams goes through the same path."""
+    from dismember_b200 import synth
+    E, T, n_items, beam, topk, B = 64, 10, 20000, 200, 10, 96
+    tf = synth.tdm_tree(n_items, seed=5)
+    rows = (1 << (tf.max_level + 1)) - 1
+    params = deepfm_params(rows, E, T, seed=11)
+    seqs = synth.queries(B, T, n_items, seed=12)
+    seqs[0] = 0
+    e = new_engine()
+    e.load_tree_tdm(tf.max_level, tf.codes, tf.node_ids, tf.is_leaf, tf.leaf_ids, tf.leaf_codes)
+    e.load_deepfm_weights(params, rows, E, T)
+    e.fast_stats()                                            # resets the counters
+    fi, fl, fc = e.tdm_retrieve(seqs, beam, topk)
+    st = e.fast_stats()
+    assert st["rows_fast"] > B * 1000 and st["max_err_over_bound"] < 1.0
+    e.set_arithmetic("strict")
+    si, sl, sc = e.tdm_retrieve(seqs, beam, topk)
+    assert (fc == sc).all() and (fi == si).all() and (fl.view(np.uint32) == sl.view(np.uint32)).all()
+    tree = orc.Tree.from_treefile(tf)
+    model = orc.TdmModel(params, rows, E, T, deepfm=True)
+    oi, ol, oc = model.retrieve_batch(tree, seqs[:32], beam, topk, n_threads=os.cpu_count() or 1)
+    assert (fc[:32] == oc).all() and (fi[:32] == oi).all() and (fl[:32].view(np.uint32) == ol.view(np.uint32)).all()
+    # consumed items + widened beams
+    rng = np.random.default_rng(3)
+    cons = [rng.choice(tf.leaf_ids, int(k), replace=False).tolist() for k in rng.choice([0, 5, 420, 480], B)]
+    off = np.zeros(B + 1, np.int64)
+    off[1:] = np.cumsum([len(c) for c in cons])
+    flat = np.array([x for c in cons for x in c], np.int32)
+    s2 = e.tdm_retrieve(seqs, beam, topk, consumed_off=off, consumed=flat, widen_beam=True)
+    e.set_arithmetic("fast")
+    f2 = e.tdm_retrieve(seqs, beam, topk, consumed_off=off, consumed=flat, widen_beam=True)
+    assert (f2[2] == s2[2]).all() and (f2[0] == s2[0]).all() and (f2[1].view(np.uint32) == s2[1].view(np.uint32)).all()
+    # all-zero model: exact ties everywhere
+    zero = np.zeros_like(params)
+    e.load_deepfm_weights(zero, rows, E, T)
+    fz = e.tdm_retrieve(seqs[:24], beam, topk)
+    e.set_arithmetic("strict")
+    sz = e.tdm_retrieve(seqs[:24], beam, topk)
+    assert (fz[2] == sz[2]).all() and (fz[0] == sz[0]).all() and (fz[1].view(np.uint32) == sz[1].view(np.uint32)).all()
+    e.close()
