@@ -22,50 +22,80 @@ using namespace dmg;
 
 namespace {
 
-constexpr int kGT = 64, kGK = 16;       // C tile kGT x kGT per 256-thread CTA (4 x 4 per thread), k step kGK
+constexpr int kGT = 128, kGK = 8;       // C tile kGT x kGT per 256-thread CTA (8 x 8 per thread), k step kGK, two shared-memory stages
 
 // C(i, j) <- epilogue(sum_k A(i, k) B(k, j)),  A(i, k) = A[i sa_i + k sa_k],  B(k, j) = B[k sb_k + j sb_j]
 // mode 0: C = acc + bias[j] (Linear.updateOutput: addmm then add bias)   1: C = acc   2: C = C + acc
+// Thread (ty, tx) of the 16 x 16 grid owns rows {32 m + 2 ty, + 1 : m < 4} and the same pattern of columns: its a / b fragments are
+// four 16-byte shared-memory loads each per k, the rows of a warp broadcast and the 16 lanes of a column load read 256 contiguous
+// bytes.  Every accumulator is ONE fma chain over ascending k (the oracle's arithmetic).
 __global__ void __launch_bounds__(256) dr_gemm_kernel(int M, int N, int Kd, const double *__restrict__ A, int64_t sa_i, int64_t sa_k,
                                                        const double *__restrict__ B, int64_t sb_k, int64_t sb_j, double *__restrict__ C,
                                                        int64_t ldc, const double *__restrict__ bias, int mode)
 {
-    __shared__ double sA[kGK][kGT + 2], sB[kGK][kGT + 2];
+    __shared__ __align__(16) double sA[2][kGK][kGT], sB[2][kGK][kGT];
     const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
     const int i0 = blockIdx.y * kGT, j0 = blockIdx.x * kGT;
-    double acc[4][4];
+    double acc[8][8];
 #pragma unroll
-    for (int a = 0; a < 4; a++)
+    for (int a = 0; a < 8; a++)
 #pragma unroll
-        for (int b = 0; b < 4; b++) acc[a][b] = 0.0;
-    for (int k0 = 0; k0 < Kd; k0 += kGK) {
+        for (int b = 0; b < 8; b++) acc[a][b] = 0.0;
+    double ra[4], rb[4];
+    auto gload = [&](int k0) {                                      // 1024 elements of each tile, consecutive threads along the unit stride
 #pragma unroll
-        for (int q = 0; q < 4; q++) {                                   // 1024 elements of each tile, consecutive threads along the unit stride
+        for (int q = 0; q < 4; q++) {
             const int e = tid + 256 * q;
             int ai, ak, bk, bj;
-            if (sa_k == 1) { ak = e & 15; ai = e >> 4; } else { ai = e & 63; ak = e >> 6; }
-            if (sb_k == 1) { bk = e & 15; bj = e >> 4; } else { bj = e & 63; bk = e >> 6; }
-            sA[ak][ai] = (i0 + ai < M && k0 + ak < Kd) ? __ldg(A + (int64_t)(i0 + ai) * sa_i + (int64_t)(k0 + ak) * sa_k) : 0.0;
-            sB[bk][bj] = (j0 + bj < N && k0 + bk < Kd) ? __ldg(B + (int64_t)(k0 + bk) * sb_k + (int64_t)(j0 + bj) * sb_j) : 0.0;
+            if (sa_k == 1) { ak = e & 7; ai = e >> 3; } else { ai = e & 127; ak = e >> 7; }
+            if (sb_k == 1) { bk = e & 7; bj = e >> 3; } else { bj = e & 127; bk = e >> 7; }
+            ra[q] = (i0 + ai < M && k0 + ak < Kd) ? __ldg(A + (int64_t)(i0 + ai) * sa_i + (int64_t)(k0 + ak) * sa_k) : 0.0;
+            rb[q] = (j0 + bj < N && k0 + bk < Kd) ? __ldg(B + (int64_t)(k0 + bk) * sb_k + (int64_t)(j0 + bj) * sb_j) : 0.0;
         }
-        __syncthreads();
-        const int kn = Kd - k0 < kGK ? Kd - k0 : kGK;                   // padded k would add fma(0, 0, acc): harmless, but skip it
-        for (int k = 0; k < kn; k++) {
-            double a[4], b[4];
+    };
+    auto sstore = [&](int st) {
 #pragma unroll
-            for (int q = 0; q < 4; q++) { a[q] = sA[k][ty * 4 + q]; b[q] = sB[k][tx * 4 + q]; }
-#pragma unroll
-            for (int x = 0; x < 4; x++)
-#pragma unroll
-                for (int y = 0; y < 4; y++) acc[x][y] = __fma_rn(a[x], b[y], acc[x][y]);
+        for (int q = 0; q < 4; q++) {
+            const int e = tid + 256 * q;
+            int ai, ak, bk, bj;
+            if (sa_k == 1) { ak = e & 7; ai = e >> 3; } else { ai = e & 127; ak = e >> 7; }
+            if (sb_k == 1) { bk = e & 7; bj = e >> 3; } else { bj = e & 127; bk = e >> 7; }
+            sA[st][ak][ai] = ra[q];
+            sB[st][bk][bj] = rb[q];
         }
+    };
+    gload(0);
+    sstore(0);
+    __syncthreads();
+    int st = 0;
+    for (int k0 = 0; k0 < Kd; k0 += kGK, st ^= 1) {
+        const bool more = k0 + kGK < Kd;
+        if (more) gload(k0 + kGK);                                  // next tile in flight while this one is multiplied
+        const int kn = Kd - k0 < kGK ? Kd - k0 : kGK;
+#pragma unroll
+        for (int k = 0; k < kGK; k++) {
+            if (k < kn) {
+                double a[8], b[8];
+                const double2 a0 = *reinterpret_cast<const double2 *>(&sA[st][k][ty * 2]), a1 = *reinterpret_cast<const double2 *>(&sA[st][k][32 + ty * 2]);
+                const double2 a2 = *reinterpret_cast<const double2 *>(&sA[st][k][64 + ty * 2]), a3 = *reinterpret_cast<const double2 *>(&sA[st][k][96 + ty * 2]);
+                const double2 b0 = *reinterpret_cast<const double2 *>(&sB[st][k][tx * 2]), b1 = *reinterpret_cast<const double2 *>(&sB[st][k][32 + tx * 2]);
+                const double2 b2 = *reinterpret_cast<const double2 *>(&sB[st][k][64 + tx * 2]), b3 = *reinterpret_cast<const double2 *>(&sB[st][k][96 + tx * 2]);
+                a[0] = a0.x; a[1] = a0.y; a[2] = a1.x; a[3] = a1.y; a[4] = a2.x; a[5] = a2.y; a[6] = a3.x; a[7] = a3.y;
+                b[0] = b0.x; b[1] = b0.y; b[2] = b1.x; b[3] = b1.y; b[4] = b2.x; b[5] = b2.y; b[6] = b3.x; b[7] = b3.y;
+#pragma unroll
+                for (int x = 0; x < 8; x++)
+#pragma unroll
+                    for (int y = 0; y < 8; y++) acc[x][y] = __fma_rn(a[x], b[y], acc[x][y]);
+            }
+        }
+        if (more) sstore(st ^ 1);
         __syncthreads();
     }
 #pragma unroll
-    for (int x = 0; x < 4; x++)
+    for (int x = 0; x < 8; x++)
 #pragma unroll
-        for (int y = 0; y < 4; y++) {
-            const int i = i0 + ty * 4 + x, j = j0 + tx * 4 + y;
+        for (int y = 0; y < 8; y++) {
+            const int i = i0 + 32 * (x >> 1) + ty * 2 + (x & 1), j = j0 + 32 * (y >> 1) + tx * 2 + (y & 1);
             if (i < M && j < N) {
                 double *c = C + (int64_t)i * ldc + j;
                 *c = mode == 0 ? __dadd_rn(acc[x][y], bias[j]) : (mode == 1 ? acc[x][y] : __dadd_rn(*c, acc[x][y]));
@@ -245,15 +275,24 @@ template <bool ZERO>
 __global__ void __launch_bounds__(256) dr_adam_kernel(double *__restrict__ w, double *__restrict__ g, double *__restrict__ s, double *__restrict__ r,
                                                        int64_t n, double b1, double omb1, double b2, double omb2, double eps, double nstep)
 {
-    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
-        const double gi = g[i];
-        const double si = __dadd_rn(__dmul_rn(s[i], b1), __dmul_rn(omb1, gi));
-        const double ri = __dadd_rn(__dmul_rn(r[i], b2), __dmul_rn(omb2, __dmul_rn(gi, gi)));
+    auto one = [&](double &wi, double &gi, double &si_, double &ri_) {
+        const double si = __dadd_rn(__dmul_rn(si_, b1), __dmul_rn(omb1, gi));
+        const double ri = __dadd_rn(__dmul_rn(ri_, b2), __dmul_rn(omb2, __dmul_rn(gi, gi)));
         const double denom = __dadd_rn(__dsqrt_rn(ri), eps);
-        w[i] = __dadd_rn(w[i], __dmul_rn(nstep, __ddiv_rn(si, denom)));
-        s[i] = si; r[i] = ri;
-        if (ZERO) g[i] = 0.0;
+        wi = __dadd_rn(wi, __dmul_rn(nstep, __ddiv_rn(si, denom)));
+        si_ = si; ri_ = ri;
+        if (ZERO) gi = 0.0;
+    };
+    const int64_t nv = n / 2, stride = (int64_t)gridDim.x * blockDim.x;      // 16-byte accesses (every tensor is cudaMalloc-aligned)
+    double2 *wv = reinterpret_cast<double2 *>(w), *gv = reinterpret_cast<double2 *>(g), *sv = reinterpret_cast<double2 *>(s), *rv = reinterpret_cast<double2 *>(r);
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < nv; i += stride) {
+        double2 a = wv[i], b = gv[i], c = sv[i], d = rv[i];
+        one(a.x, b.x, c.x, d.x);
+        one(a.y, b.y, c.y, d.y);
+        wv[i] = a; sv[i] = c; rv[i] = d;
+        if (ZERO) gv[i] = b;
     }
+    for (int64_t i = nv * 2 + (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) one(w[i], g[i], s[i], r[i]);
 }
 
 struct Tensors {                        // DrDev's tensors in training order with their element counts
