@@ -9,7 +9,7 @@
 //                   softmax weights / biases (nn/mixin/ParameterOptimizer.scala:28-88) -> model backward -> Adam
 // Everything is Double.  The three GEMM shapes of a Linear (forward, gradWeight, gradInput) run on one tiled kernel whose every
 // output element is ONE fma chain over ascending k from 0 -- the arithmetic spec of the oracle (oracle/oracle_dr_train.c), so
-// logits, weight and bias gradients carry the oracle's bits; `log` (CUDA vs glibc) and the atomic scatter-adds into the embedding
+// logits and Linear weight gradients carry the oracle's bits; `log` (CUDA vs glibc), the chunked bias / loss sums and the atomic scatter-adds into the embedding
 // / softmax-parameter gradients differ in the last bits, so training parity is tolerance-based (1e-12 relative, tests/test_gpu_dr_train.py).
 #include <algorithm>
 #include <cmath>
@@ -22,44 +22,46 @@ using namespace dmg;
 
 namespace {
 
-constexpr int kGT = 128, kGK = 8;       // C tile kGT x kGT per 256-thread CTA (8 x 8 per thread), k step kGK, two shared-memory stages
+constexpr int kGK = 8;                   // k step; C tile TILE x TILE per 256-thread CTA (TILE / 16 squared per thread), two shared-memory stages
 
 // C(i, j) <- epilogue(sum_k A(i, k) B(k, j)),  A(i, k) = A[i sa_i + k sa_k],  B(k, j) = B[k sb_k + j sb_j]
 // mode 0: C = acc + bias[j] (Linear.updateOutput: addmm then add bias)   1: C = acc   2: C = C + acc
 // Thread (ty, tx) of the 16 x 16 grid owns rows {32 m + 2 ty, + 1 : m < 4} and the same pattern of columns: its a / b fragments are
 // four 16-byte shared-memory loads each per k, the rows of a warp broadcast and the 16 lanes of a column load read 256 contiguous
 // bytes.  Every accumulator is ONE fma chain over ascending k (the oracle's arithmetic).
+template <int TILE>
 __global__ void __launch_bounds__(256) dr_gemm_kernel(int M, int N, int Kd, const double *__restrict__ A, int64_t sa_i, int64_t sa_k,
                                                        const double *__restrict__ B, int64_t sb_k, int64_t sb_j, double *__restrict__ C,
                                                        int64_t ldc, const double *__restrict__ bias, int mode)
 {
-    __shared__ __align__(16) double sA[2][kGK][kGT], sB[2][kGK][kGT];
+    constexpr int R = TILE / 16, NQ = TILE * kGK / 256, LG = TILE == 128 ? 7 : 6;      // outputs per thread and dimension, loads per thread and tile
+    __shared__ __align__(16) double sA[2][kGK][TILE], sB[2][kGK][TILE];
     const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
-    const int i0 = blockIdx.y * kGT, j0 = blockIdx.x * kGT;
-    double acc[8][8];
+    const int i0 = blockIdx.y * TILE, j0 = blockIdx.x * TILE;
+    double acc[R][R];
 #pragma unroll
-    for (int a = 0; a < 8; a++)
+    for (int a = 0; a < R; a++)
 #pragma unroll
-        for (int b = 0; b < 8; b++) acc[a][b] = 0.0;
-    double ra[4], rb[4];
-    auto gload = [&](int k0) {                                      // 1024 elements of each tile, consecutive threads along the unit stride
+        for (int b = 0; b < R; b++) acc[a][b] = 0.0;
+    double ra[NQ], rb[NQ];
+    auto gload = [&](int k0) {                                      // TILE x 8 elements of each tile, consecutive threads along the unit stride
 #pragma unroll
-        for (int q = 0; q < 4; q++) {
+        for (int q = 0; q < NQ; q++) {
             const int e = tid + 256 * q;
             int ai, ak, bk, bj;
-            if (sa_k == 1) { ak = e & 7; ai = e >> 3; } else { ai = e & 127; ak = e >> 7; }
-            if (sb_k == 1) { bk = e & 7; bj = e >> 3; } else { bj = e & 127; bk = e >> 7; }
+            if (sa_k == 1) { ak = e & 7; ai = e >> 3; } else { ai = e & (TILE - 1); ak = e >> LG; }
+            if (sb_k == 1) { bk = e & 7; bj = e >> 3; } else { bj = e & (TILE - 1); bk = e >> LG; }
             ra[q] = (i0 + ai < M && k0 + ak < Kd) ? __ldg(A + (int64_t)(i0 + ai) * sa_i + (int64_t)(k0 + ak) * sa_k) : 0.0;
             rb[q] = (j0 + bj < N && k0 + bk < Kd) ? __ldg(B + (int64_t)(k0 + bk) * sb_k + (int64_t)(j0 + bj) * sb_j) : 0.0;
         }
     };
     auto sstore = [&](int st) {
 #pragma unroll
-        for (int q = 0; q < 4; q++) {
+        for (int q = 0; q < NQ; q++) {
             const int e = tid + 256 * q;
             int ai, ak, bk, bj;
-            if (sa_k == 1) { ak = e & 7; ai = e >> 3; } else { ai = e & 127; ak = e >> 7; }
-            if (sb_k == 1) { bk = e & 7; bj = e >> 3; } else { bj = e & 127; bk = e >> 7; }
+            if (sa_k == 1) { ak = e & 7; ai = e >> 3; } else { ai = e & (TILE - 1); ak = e >> LG; }
+            if (sb_k == 1) { bk = e & 7; bj = e >> 3; } else { bj = e & (TILE - 1); bk = e >> LG; }
             sA[st][ak][ai] = ra[q];
             sB[st][bk][bj] = rb[q];
         }
@@ -75,26 +77,25 @@ __global__ void __launch_bounds__(256) dr_gemm_kernel(int M, int N, int Kd, cons
 #pragma unroll
         for (int k = 0; k < kGK; k++) {
             if (k < kn) {
-                double a[8], b[8];
-                const double2 a0 = *reinterpret_cast<const double2 *>(&sA[st][k][ty * 2]), a1 = *reinterpret_cast<const double2 *>(&sA[st][k][32 + ty * 2]);
-                const double2 a2 = *reinterpret_cast<const double2 *>(&sA[st][k][64 + ty * 2]), a3 = *reinterpret_cast<const double2 *>(&sA[st][k][96 + ty * 2]);
-                const double2 b0 = *reinterpret_cast<const double2 *>(&sB[st][k][tx * 2]), b1 = *reinterpret_cast<const double2 *>(&sB[st][k][32 + tx * 2]);
-                const double2 b2 = *reinterpret_cast<const double2 *>(&sB[st][k][64 + tx * 2]), b3 = *reinterpret_cast<const double2 *>(&sB[st][k][96 + tx * 2]);
-                a[0] = a0.x; a[1] = a0.y; a[2] = a1.x; a[3] = a1.y; a[4] = a2.x; a[5] = a2.y; a[6] = a3.x; a[7] = a3.y;
-                b[0] = b0.x; b[1] = b0.y; b[2] = b1.x; b[3] = b1.y; b[4] = b2.x; b[5] = b2.y; b[6] = b3.x; b[7] = b3.y;
+                double a[R], b[R];
 #pragma unroll
-                for (int x = 0; x < 8; x++)
+                for (int m = 0; m < R / 2; m++) {
+                    const double2 av = *reinterpret_cast<const double2 *>(&sA[st][k][32 * m + ty * 2]), bv = *reinterpret_cast<const double2 *>(&sB[st][k][32 * m + tx * 2]);
+                    a[2 * m] = av.x; a[2 * m + 1] = av.y; b[2 * m] = bv.x; b[2 * m + 1] = bv.y;
+                }
 #pragma unroll
-                    for (int y = 0; y < 8; y++) acc[x][y] = __fma_rn(a[x], b[y], acc[x][y]);
+                for (int x = 0; x < R; x++)
+#pragma unroll
+                    for (int y = 0; y < R; y++) acc[x][y] = __fma_rn(a[x], b[y], acc[x][y]);
             }
         }
         if (more) sstore(st ^ 1);
         __syncthreads();
     }
 #pragma unroll
-    for (int x = 0; x < 8; x++)
+    for (int x = 0; x < R; x++)
 #pragma unroll
-        for (int y = 0; y < 8; y++) {
+        for (int y = 0; y < R; y++) {
             const int i = i0 + 32 * (x >> 1) + ty * 2 + (x & 1), j = j0 + 32 * (y >> 1) + tx * 2 + (y & 1);
             if (i < M && j < N) {
                 double *c = C + (int64_t)i * ldc + j;
@@ -104,12 +105,24 @@ __global__ void __launch_bounds__(256) dr_gemm_kernel(int M, int N, int Kd, cons
 }
 
 // out[j] (+)= sum_r M[r][j] (a chain over ascending r): gradBias of a Linear
-__global__ void dr_colsum_kernel(int64_t R, int N, const double *__restrict__ m, double *__restrict__ out, int accumulate)
+// blockIdx.y = one of kColChunks row ranges (a sequential chain each, written to part[chunk][j]); dr_colsum_finish_kernel adds the
+// chunks in order.  Deterministic; the order differs from the oracle's single chain over all rows in the last bits.
+constexpr int kColChunks = 32;
+__global__ void dr_colsum_kernel(int64_t R, int N, const double *__restrict__ m, double *__restrict__ part)
+{
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= N) return;
+    const int64_t per = (R + kColChunks - 1) / kColChunks, r0 = blockIdx.y * per, r1 = r0 + per < R ? r0 + per : R;
+    double acc = 0.0;
+    for (int64_t r = r0; r < r1; r++) acc = __dadd_rn(acc, m[r * N + j]);
+    part[(size_t)blockIdx.y * N + j] = acc;
+}
+__global__ void dr_colsum_finish_kernel(int N, const double *__restrict__ part, double *__restrict__ out, int accumulate)
 {
     const int j = blockIdx.x * blockDim.x + threadIdx.x;
     if (j >= N) return;
     double acc = 0.0;
-    for (int64_t r = 0; r < R; r++) acc = __fma_rn(m[r * N + j], 1.0, acc);
+    for (int c = 0; c < kColChunks; c++) acc = __dadd_rn(acc, part[(size_t)c * N + j]);
     out[j] = accumulate ? __dadd_rn(out[j], acc) : acc;
 }
 
@@ -182,9 +195,11 @@ __global__ void __launch_bounds__(256) dr_ce_kernel(int C, double *__restrict__ 
 // output = 0; output -= out[target] row after row; output /= R   (ClassNLLCriterion.updateOutput :44-64)
 __global__ void dr_loss_kernel(int64_t R, const double *__restrict__ row_out, double *__restrict__ loss, int accumulate)
 {
-    if (threadIdx.x || blockIdx.x) return;
+    if (blockIdx.x || threadIdx.x >= 32) return;                    // one warp: 32 interleaved chains, then a fixed shuffle tree
     double o = 0.0;
-    for (int64_t r = 0; r < R; r++) o = __dadd_rn(o, -row_out[r]);
+    for (int64_t r = threadIdx.x; r < R; r += 32) o = __dadd_rn(o, -row_out[r]);
+    for (int s_ = 16; s_ > 0; s_ >>= 1) o = __dadd_rn(o, __shfl_xor_sync(0xffffffffu, o, s_));
+    if (threadIdx.x) return;
     o = __ddiv_rn(o, (double)R);
     *loss = accumulate ? __dadd_rn(*loss, o) : o;
 }
@@ -248,25 +263,39 @@ __device__ __forceinline__ uint64_t splitmix64(uint64_t x)
     x = (x ^ (x >> 27)) * 0x94D049BB133111EBull;
     return x ^ (x >> 31);
 }
-__global__ void dr_sample_kernel(int n, int S, int num_item, const int32_t *__restrict__ target, uint64_t seed, int32_t *__restrict__ out)
+// One warp per sample, the sorted list in shared memory: membership and insert position by a parallel scan, the tail shifted 32 at a time.
+__global__ void __launch_bounds__(128) dr_sample_kernel(int n, int S, int num_item, const int32_t *__restrict__ target, uint64_t seed,
+                                                        int32_t *__restrict__ out)
 {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    extern __shared__ int32_t sList[];                              // [4][S]
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int i = blockIdx.x * 4 + warp;
     if (i >= n) return;
-    int32_t *row = out + (int64_t)i * (S + 1);
+    int32_t *row = sList + warp * S;
     const int32_t pos = target[i];
-    row[0] = pos;
     int have = 0;
     uint64_t ctr = 0;
     while (have < S) {
-        const int32_t s = (int32_t)(splitmix64(seed ^ splitmix64(((uint64_t)i << 32) | ctr++)) % (uint64_t)num_item);
+        const int32_t s = (int32_t)(splitmix64(seed ^ splitmix64(((uint64_t)i << 32) | ctr++)) % (uint64_t)num_item);   // the same draw on every lane
         if (s == pos) continue;
-        int lo = 0;
-        while (lo < have && row[1 + lo] < s) lo++;
-        if (lo < have && row[1 + lo] == s) continue;
-        for (int q = have; q > lo; q--) row[1 + q] = row[q];
-        row[1 + lo] = s;
+        int less = 0, dup = 0;
+        for (int q = lane; q < have; q += 32) { const int32_t v = row[q]; less += v < s ? 1 : 0; dup |= v == s ? 1 : 0; }
+        less = __reduce_add_sync(0xffffffffu, less);
+        if (__any_sync(0xffffffffu, dup)) continue;
+        for (int hi = have; hi > less; hi -= 32) {                  // shift row[less, have) one slot to the right, from the end
+            const int q = hi - 1 - lane;
+            const int32_t v = q >= less ? row[q] : 0;
+            __syncwarp();
+            if (q >= less) row[q + 1] = v;
+            __syncwarp();
+        }
+        if (lane == 0) row[less] = s;
+        __syncwarp();
         have++;
     }
+    int32_t *dst = out + (int64_t)i * (S + 1);
+    if (lane == 0) dst[0] = pos;
+    for (int q = lane; q < S; q += 32) dst[1 + q] = row[q];
 }
 
 // Adam.optimize / ParameterOptimizer.optimize: the same tensor operations (s = s b1 + (1 - b1) g; r = r b2 + (1 - b2) g g;
@@ -338,8 +367,15 @@ void gemm(dmg_handle_t h, int M, int N, int Kd, const double *A, int64_t sa_i, i
           double *C, int64_t ldc, const double *bias, int mode)
 {
     if (M <= 0 || N <= 0) return;
-    dim3 grid((unsigned)((N + kGT - 1) / kGT), (unsigned)((M + kGT - 1) / kGT));
-    dr_gemm_kernel<<<grid, 256, 0, h->stream>>>(M, N, Kd, A, sa_i, sa_k, B, sb_k, sb_j, C, ldc, bias, mode);
+    // 128 x 128 tiles (8 x 8 per thread: 1 shared-memory load per 8 fma) when they fill the machine twice over, else 64 x 64
+    const int64_t big = (int64_t)((N + 127) / 128) * ((M + 127) / 128);
+    if (big >= 2 * (int64_t)h->sm_count) {
+        dim3 grid((unsigned)((N + 127) / 128), (unsigned)((M + 127) / 128));
+        dr_gemm_kernel<128><<<grid, 256, 0, h->stream>>>(M, N, Kd, A, sa_i, sa_k, B, sb_k, sb_j, C, ldc, bias, mode);
+    } else {
+        dim3 grid((unsigned)((N + 63) / 64), (unsigned)((M + 63) / 64));
+        dr_gemm_kernel<64><<<grid, 256, 0, h->stream>>>(M, N, Kd, A, sa_i, sa_k, B, sb_k, sb_j, C, ldc, bias, mode);
+    }
     h->launches += 1;
 }
 
@@ -403,13 +439,14 @@ DMG_API int32_t dmg_dr_train_step(dmg_handle_t h, int32_t n, const int32_t *seq,
     const int W = T + D - 1, IN = W * E, INr = T * E;
     const int64_t R = (int64_t)n * P;
     const size_t need = Carver::need({(size_t)n * T * 4, (size_t)n * 4, (size_t)n * Cs * 4, (size_t)R * W * 4, (size_t)R * D * 4, (size_t)R * IN * 8,
-                                      (size_t)R * IN * 8, (size_t)R * K * 8, (size_t)R * 8, (size_t)(D + 1) * 8, (size_t)n * E * 8, (size_t)n * E * 8});
+                                      (size_t)R * IN * 8, (size_t)R * K * 8, (size_t)R * 8, (size_t)(D + 1) * 8, (size_t)n * E * 8, (size_t)n * E * 8, (size_t)kColChunks * std::max(K, E) * 8});
     DMG_TRY(ensure_dev(h, h->s_work, need));
     Carver cw(h->s_work.d);
     int32_t *d_seq = cw.take<int32_t>((size_t)n * T), *d_tgt_item = cw.take<int32_t>(n), *d_sampled = cw.take<int32_t>((size_t)n * Cs);
     int32_t *d_idx = cw.take<int32_t>((size_t)R * W), *d_tgt = cw.take<int32_t>((size_t)R * D);
     double *d_X = cw.take<double>((size_t)R * IN), *d_GX = cw.take<double>((size_t)R * IN), *d_lg = cw.take<double>((size_t)R * K);
     double *d_row = cw.take<double>(R), *d_loss = cw.take<double>(D + 1), *d_u = cw.take<double>((size_t)n * E), *d_gu = cw.take<double>((size_t)n * E);
+    double *d_part = cw.take<double>((size_t)kColChunks * std::max(K, E));
     DMG_CUDA(h, cudaMemcpyAsync(d_seq, seq, (size_t)n * T * 4, cudaMemcpyHostToDevice, h->stream));
     DMG_CUDA(h, cudaMemcpyAsync(d_tgt_item, target, (size_t)n * 4, cudaMemcpyHostToDevice, h->stream));
     // the rerank Embedding has numItem rows: the stricter of the two range checks applies when the rerank model trains
@@ -435,7 +472,8 @@ DMG_API int32_t dmg_dr_train_step(dmg_handle_t h, int32_t n, const int32_t *seq,
             dr_ce_kernel<<<(unsigned)Rc, 256, (size_t)K * 8, h->stream>>>(K, lg, d_tgt + (int64_t)l * R + r0, 1.0 / (double)Rc, d_row + r0);
             dr_loss_kernel<<<1, 32, 0, h->stream>>>(Rc, d_row + r0, d_loss + l, c > 0);
             gemm(h, K, in, (int)Rc, lg, 1, K, Xc, IN, 1, d.tr_g[1 + 2 * l], in, nullptr, 2);                           // gradWeight += gradOut^T . X
-            dr_colsum_kernel<<<(K + 127) / 128, 128, 0, h->stream>>>(Rc, K, lg, d.tr_g[2 + 2 * l], 1);                  // gradBias
+            dr_colsum_kernel<<<dim3((K + 127) / 128, kColChunks), 128, 0, h->stream>>>(Rc, K, lg, d_part);            // gradBias
+            dr_colsum_finish_kernel<<<(K + 127) / 128, 128, 0, h->stream>>>(K, d_part, d.tr_g[2 + 2 * l], 1);
             gemm(h, (int)Rc, in, K, lg, K, 1, d.d_layer_w[l], in, 1, d_GX + r0 * IN, IN, nullptr, 2);                   // gradInput += gradOut . W
             h->launches += 3;
         }
@@ -459,7 +497,7 @@ DMG_API int32_t dmg_dr_train_step(dmg_handle_t h, int32_t n, const int32_t *seq,
     // ---- rerank model: trainRerank + reRankOptimizer ----
     if (rerank_step_t) {
         if (sampled) DMG_CUDA(h, cudaMemcpyAsync(d_sampled, sampled, (size_t)n * Cs * 4, cudaMemcpyHostToDevice, h->stream));
-        else dr_sample_kernel<<<(n + 127) / 128, 128, 0, h->stream>>>(n, S, d.num_item, d_tgt_item, seed, d_sampled);
+        else dr_sample_kernel<<<(n + 3) / 4, 128, (size_t)4 * S * 4, h->stream>>>(n, S, d.num_item, d_tgt_item, seed, d_sampled);
         double *Xr = d_X, *GXr = d_GX;                                  // [n][T E]
         dr_rows_kernel<<<(unsigned)n, 128, 0, h->stream>>>(T, T, E, D, 0, d.num_item, K, d_seq, d_tgt_item, nullptr, d.d_rr_emb, d_idx, nullptr, Xr);
         gemm(h, n, E, INr, Xr, INr, 1, d.d_rr_w, E, 1, d_u, E, d.d_rr_b, 0);                                             // u = X . W_r^T + b_r (W_r kept [T E][E])
@@ -475,7 +513,8 @@ DMG_API int32_t dmg_dr_train_step(dmg_handle_t h, int32_t n, const int32_t *seq,
             adam<false>(h, d.d_sm_b, d.tr_g[iSM + 1], d.tr_s[iSM + 1], d.tr_r[iSM + 1], tw.n[iSM + 1], lr, 1e-7, rerank_step_t);
         }
         gemm(h, INr, E, n, Xr, 1, INr, d_gu, E, 1, d.tr_g[iRR + 1], E, nullptr, 1);                                       // gradWeight^T [T E][E] = X^T . gu
-        dr_colsum_kernel<<<(E + 127) / 128, 128, 0, h->stream>>>(n, E, d_gu, d.tr_g[iRR + 2], 0);
+        dr_colsum_kernel<<<dim3((E + 127) / 128, kColChunks), 128, 0, h->stream>>>(n, E, d_gu, d_part);
+        dr_colsum_finish_kernel<<<(E + 127) / 128, 128, 0, h->stream>>>(E, d_part, d.tr_g[iRR + 2], 0);
         gemm(h, n, INr, E, d_gu, E, 1, d.d_rr_w, 1, E, GXr, INr, nullptr, 1);                                             // gradInput = gu . W_r
         dr_scatter_kernel<<<(unsigned)n, 128, 0, h->stream>>>(T, E, d_idx, GXr, d.tr_g[iRR]);
         h->launches += 2;
