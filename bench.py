@@ -280,7 +280,7 @@ def measure(args, env, items, structured=False, do_cpu=False, target_s=None, ver
     eng.set_arithmetic(args.arith)
     # waiting host threads spin while this rank's share of the cores covers them (lowest latency) and sleep otherwise (8 ranks x 8
     # threads on a 32-core host): dmg_set_sync_mode; the clones inherit it
-    sync_mode = "sleep" if env["world"] * args.inflight * 1.5 > (os.cpu_count() or 1) else "spin"
+    sync_mode = "sleep" if env["world"] * args.inflight >= (os.cpu_count() or 1) else "spin"
     eng.set_sync_mode(sync_mode)
     if args.tau is not None:
         eng.set_fast_tolerance(args.tau)
@@ -326,7 +326,7 @@ def measure(args, env, items, structured=False, do_cpu=False, target_s=None, ver
         return max_over_ranks(e0.elapsed_time(e1))
 
     # ---- warm-up, then size the timed region: the K steps are repeated R times (fresh batches from the pool) -----------
-    workers.run(step_dev, 0, max(W, NF))
+    workers.run(step_dev, 0, max(W, 3 * NF))                      # every handle past its first calls (scratch allocated, its step captured)
     barrier()
     probe_ms = timed_dev(max(K, 2 * NF))
     R = max(1, int(np.ceil(target_s * 1e3 / max(probe_ms * K / max(K, 2 * NF), 1e-3))))

@@ -1010,12 +1010,24 @@ static int32_t tdm_precheck(dmg_handle_t h, int32_t B, int32_t beam, int32_t top
     return DMG_OK;
 }
 
+// The *_dev entry points copy the caller's ids (B x T x 4 bytes, device to device) into the handle's own staging buffer first: the
+// captured step (tdm_enqueue) then reads a pointer that does not change from call to call, whatever buffer the caller passes.
+static int32_t stage_dev_seq(dmg_handle_t h, int32_t B, const int32_t **d_seq)
+{
+    const size_t bytes = (size_t)B * h->din.T * 4;
+    DMG_TRY(ensure_dev(h, h->s_in, bytes));
+    DMG_CUDA(h, cudaMemcpyAsync(h->s_in.d, *d_seq, bytes, cudaMemcpyDeviceToDevice, h->stream));
+    *d_seq = (const int32_t *)h->s_in.d;
+    return DMG_OK;
+}
+
 DMG_API int32_t dmg_tdm_retrieve_dev(dmg_handle_t h, int32_t B, const int32_t *d_item_seq, int32_t beam, int32_t topk,
                                      int32_t use_mask, int32_t *d_out_items, float *d_out_logits, int32_t *d_out_counts)
 {
     DMG_TRY(tdm_precheck(h, B, beam, topk));
     if (!d_item_seq || !d_out_items || !d_out_logits || !d_out_counts) return fail(h, DMG_ERR_INVALID_ARG, "null device pointer");
     DMG_CUDA(h, cudaSetDevice(h->device));
+    DMG_TRY(stage_dev_seq(h, B, &d_item_seq));
     return tdm_enqueue(h, B, d_item_seq, beam, beam, nullptr, topk, use_mask, nullptr, nullptr, d_out_items, d_out_logits, d_out_counts);
 }
 
@@ -1040,6 +1052,7 @@ DMG_API int32_t dmg_tdm_retrieve_dev_sync(dmg_handle_t h, int32_t B, const int32
     if (!d_item_seq || !d_out_items || !d_out_logits || !d_out_counts) return fail(h, DMG_ERR_INVALID_ARG, "null device pointer");
     DMG_CUDA(h, cudaSetDevice(h->device));
     BeamParams<float> redo;
+    DMG_TRY(stage_dev_seq(h, B, &d_item_seq));
     DMG_TRY(tdm_enqueue(h, B, d_item_seq, beam, beam, nullptr, topk, use_mask, nullptr, nullptr, d_out_items, d_out_logits, d_out_counts, &redo));
     DMG_TRY(check_flag(h, "dmg_tdm_retrieve_dev_sync"));
     bool ran = false;
