@@ -250,6 +250,27 @@ JNIEXPORT void JNICALL Java_com_mass_gpu_DismemberGPU_00024_drRetrieve(
     if (rc) throw_status(env, H(handle), rc);
 }
 
+/* how the synchronous calls wait for their batch: 0 spin, 1 sleep (dmg_set_sync_mode) */
+JNIEXPORT void JNICALL Java_com_mass_gpu_DismemberGPU_00024_setSyncMode(JNIEnv *env, jobject self, jlong handle, jint mode)
+{
+    int32_t rc = dmg_set_sync_mode(H(handle), mode);
+    if (rc) throw_status(env, H(handle), rc);
+}
+
+/* RecursiveCluster.run (kmeans): node code per embedding row */
+JNIEXPORT void JNICALL Java_com_mass_gpu_DismemberGPU_00024_kmeansTree(
+    JNIEnv *env, jobject self, jlong handle, jint n, jint embedSize, jdoubleArray embeddings, jint clusterIterNum, jlong seed, jintArray outCodes)
+{
+    if (n <= 0 || embedSize <= 0 || !need(env, embeddings, (jlong)n * embedSize, "embeddings: n x embedSize doubles") ||
+        !need(env, outCodes, n, "outCodes: n ints"))
+        return;
+    double *e = PIN_D(embeddings);
+    void *o = PIN_I(outCodes);
+    int32_t rc = dmg_kmeans_tree(H(handle), n, embedSize, e, clusterIterNum, (uint64_t)seed, o);
+    UNPIN_I(outCodes, o, 0); UNPIN_D(embeddings, e, JNI_ABORT);
+    if (rc) throw_status(env, H(handle), rc);
+}
+
 /* Deep Retrieval LocalOptimizer: itemPathMapping upload, then one mini-batch iteration (layer model + rerank model);
  * outLosses = numLayer layer losses followed by the rerank loss (NaN when reRankStepT == 0) */
 JNIEXPORT void JNICALL Java_com_mass_gpu_DismemberGPU_00024_drLoadItemPaths(

@@ -89,3 +89,52 @@ def test_wave_search_matches_oracle(engine, orc, gather, n_items, beam, B):
         print("wave stats", gather, n_items, beam, stats)
     finally:
         os.environ.pop("DMG_WAVE_GATHER", None)
+
+
+def test_repeated_steps_replay_a_captured_graph(orc):
+    """A serving loop repeats one batch shape on one handle: from the third call on the step is ONE cudaGraphLaunch of the captured
+    level-synchronous chain (capi.cu: tdm_enqueue).  Every call -- plain launches, the capture, the replays -- returns the oracle's
+    ids and logit bits for ITS queries (host-buffer and device-buffer entry points, with a per-thread clone, with consumed items)."""
+    import torch
+    from conftest import new_engine
+    from dismember_b200 import synth
+    n_items, E, T, beam, topk, B = 30000, 64, 10, 200, 10, 64
+    tf = synth.tdm_tree(n_items, seed=2)
+    rows = (1 << (tf.max_level + 1)) - 1
+    params = synth.din_params(rows, E, seed=3, structured=True)
+    e = new_engine()
+    e.load_tree_tdm(tf.max_level, tf.codes, tf.node_ids, tf.is_leaf, tf.leaf_ids, tf.leaf_codes)
+    e.load_din_weights(params, rows, E, T)
+    twin = e.clone()
+    tree = orc.Tree.from_treefile(tf)
+    model = orc.TdmModel(params, rows, E, T)
+    dev = torch.device("cuda", 0)
+    d_items = torch.empty((B, topk), dtype=torch.int32, device=dev)
+    d_log = torch.empty((B, topk), dtype=torch.float32, device=dev)
+    d_cnt = torch.empty((B,), dtype=torch.int32, device=dev)
+    torch.cuda.synchronize()
+    l0 = e.launch_count
+    for it in range(6):
+        q = synth.queries(B, T, n_items, seed=50 + it)
+        oi, ol, oc = model.retrieve_batch(tree, q, beam, topk, n_threads=8)
+        gi, gl, gc = e.tdm_retrieve(q, beam, topk)
+        assert (gc == oc).all() and (gi == oi).all() and (gl.view(np.uint32) == ol.view(np.uint32)).all(), it
+        dq = torch.from_numpy(q).to(dev)                          # a fresh device buffer every call: the handle stages it
+        torch.cuda.synchronize()
+        twin.tdm_retrieve_dev_sync(B, dq.data_ptr(), beam, topk, True, d_items.data_ptr(), d_log.data_ptr(), d_cnt.data_ptr())
+        assert (d_cnt.cpu().numpy() == oc).all() and (d_items.cpu().numpy() == oi).all()
+        assert (d_log.cpu().numpy().view(np.uint32) == ol.view(np.uint32)).all(), it
+    assert e.launch_count - l0 > 6 * 25                           # replays count the kernels inside the graph
+    # the eval variant (consumed items, widened beams) is another key of the same cache
+    rng = np.random.default_rng(1)
+    for it in range(4):
+        q = synth.queries(B, T, n_items, seed=70 + it)
+        cons = [rng.choice(tf.leaf_ids, int(k), replace=False).tolist() for k in rng.choice([0, 4, 30], B)]
+        off = np.zeros(B + 1, np.int64)
+        off[1:] = np.cumsum([len(c) for c in cons])
+        flat = np.array([x for c in cons for x in c], np.int32)
+        ob = model.retrieve_batch(tree, q, beam, topk, cons_off=off, cons=flat, widen_beam=True, n_threads=8)
+        gb = e.tdm_retrieve(q, beam, topk, consumed_off=off, consumed=flat, widen_beam=True)
+        assert (gb[2] == ob[2]).all() and (gb[0] == ob[0]).all() and (gb[1].view(np.uint32) == ob[1].view(np.uint32)).all(), it
+    twin.close()
+    e.close()
