@@ -227,6 +227,30 @@ def main():
              roofline={"bound": "hbm", "algorithmic_bytes_per_step": dense + sparse, "achieved": (dense + sparse) / dt / 1e9,
                        "peak": hbm, "unit": "GB/s", "frac": (dense + sparse) / dt / 1e9 / hbm, "peak_source": hbm_src},
              note="dense-Adam semantics of scalann Adam.scala:54-65: every parameter is touched every step")
+        # the same step through the device-buffer entry point (no copies, no synchronisation inside): CUDA events around 20 calls
+        import torch
+        dev = torch.device("cuda", 0)
+        t_node, t_sq = torch.from_numpy(node).to(dev), torch.from_numpy(sq).to(dev)
+        t_mask = torch.from_numpy((sq < 0).astype(np.uint8)).to(dev)
+        t_lab, t_loss = torch.from_numpy(lab.astype(np.float32)).to(dev), torch.zeros(1, dtype=torch.float32, device=dev)
+        st = torch.cuda.Stream(dev)
+        eng.set_stream(st.cuda_stream)
+        torch.cuda.synchronize()
+        for _ in range(3):
+            step[0] += 1
+            eng.train_step_dev(rows, t_node.data_ptr(), t_sq.data_ptr(), t_mask.data_ptr(), t_lab.data_ptr(), 1e-3, step[0], t_loss.data_ptr())
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(st)
+        for _ in range(20):
+            step[0] += 1
+            eng.train_step_dev(rows, t_node.data_ptr(), t_sq.data_ptr(), t_mask.data_ptr(), t_lab.data_ptr(), 1e-3, step[0], t_loss.data_ptr())
+        e1.record(st)
+        eng.synchronize()
+        ddt = e0.elapsed_time(e1) / 20 * 1e-3
+        eng.set_stream(0)
+        emit(path="train_step_dev (device buffers: dmg_train_step_dev)", items=n_items, rows_per_step=rows, ms_per_step=ddt * 1e3, rows_per_s=rows / ddt,
+             roofline={"bound": "hbm", "algorithmic_bytes_per_step": dense + sparse, "achieved": (dense + sparse) / ddt / 1e9, "peak": hbm,
+                       "unit": "GB/s", "frac": (dense + sparse) / ddt / 1e9 / hbm, "peak_source": hbm_src})
         if n_items <= 1_000_000:
             params = eng.download_din_weights()
             t0 = time.perf_counter()
@@ -255,6 +279,24 @@ def main():
     emit(path="score_pairs (model.forward on independent rows)", rows=n, ms=dt * 1e3, rows_per_s=n / dt,
          roofline={"bound": "hbm", "algorithmic_bytes": by, "achieved": by / dt / 1e9, "peak": hbm, "unit": "GB/s", "frac": by / dt / 1e9 / hbm},
          note="host buffers: H2D of the (1+T) indices per row and D2H of the logits are inside")
+    import torch
+    dev = torch.device("cuda", 0)
+    t_node, t_sq, t_out = torch.from_numpy(node).to(dev), torch.from_numpy(sq).to(dev), torch.empty(n, dtype=torch.float32, device=dev)
+    st = torch.cuda.Stream(dev)
+    eng.set_stream(st.cuda_stream)
+    torch.cuda.synchronize()
+    for _ in range(2):
+        eng.score_pairs_dev(n, t_node.data_ptr(), t_sq.data_ptr(), 0, t_out.data_ptr())
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(st)
+    for _ in range(10):
+        eng.score_pairs_dev(n, t_node.data_ptr(), t_sq.data_ptr(), 0, t_out.data_ptr())
+    e1.record(st)
+    eng.synchronize()
+    ddt = e0.elapsed_time(e1) / 10 * 1e-3
+    eng.set_stream(0)
+    emit(path="score_pairs_dev (device buffers: dmg_score_pairs_dev)", rows=n, ms=ddt * 1e3, rows_per_s=n / ddt,
+         roofline={"bound": "hbm / fp32 FMA", "algorithmic_bytes": by, "achieved": by / ddt / 1e9, "peak": hbm, "unit": "GB/s", "frac": by / ddt / 1e9 / hbm})
     params = eng.download_din_weights()
     model = orc.TdmModel(params, rows_tab, E, T)
     t0 = time.perf_counter()
