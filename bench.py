@@ -599,7 +599,8 @@ def main():
     kern_ms = m.get("kern_ms_per_step", 0.0)
     achieved = B * bytes_u / (kern_ms * 1e-3) / 1e9 if kern_ms else None
     traffic = None
-    kernel_name = "wave_score_kernel" if args.arith == "fast" else "beam_search_kernel<float,%d>" % E
+    fast_path = args.arith == "fast" and E == 64 and T <= 15        # the tensor-core path is built for E = 64; other sizes run the strict kernel
+    kernel_name = "wave_score_kernel" if fast_path else "beam_search_kernel<float,%d>" % E
     tp = os.path.join(ROOT, "profiles", "traffic.json")
     if os.path.exists(tp):
         try:
@@ -673,7 +674,7 @@ def main():
                        "arithmetic": ("level-synchronous tcgen05 bf16x3 tensor-core scorer (TMA tile::gather4 from a bf16 hi|lo copy of the "
                                       "table, 256 B per row like the fp32 rows) + certified cuts, strict fp32 re-score of near-cut candidates "
                                       "and of the topk (ids and logits bit-identical to the CPU oracle)")
-                       if args.arith == "fast" else "strict fp32 (sequential-k fma chains, bit-identical to the CPU oracle)",
+                       if fast_path else "strict fp32 (sequential-k fma chains, bit-identical to the CPU oracle)",
                        "fast_stats": m.get("fast_stats")},
             "e2e": {"value": e2e_value, "unit": "users/s", "h2d_bytes_per_step": B * T * 4,
                     "d2h_bytes_per_step": B * args.topk * 8 + B * 4, "ms_per_step": m["e2e_ms_per_step"], "timed_region_s": m["e2e_region_s"]},
