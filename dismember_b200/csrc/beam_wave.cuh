@@ -269,7 +269,7 @@ __device__ __forceinline__ void warp_select(const uint32_t (&k)[NJ], int kk, uin
 }
 
 // children of the surviving candidates in candidate order, the tiles and the bound of the scores about to be computed
-template <int NJ>
+template <int NJ, int KIND>
 __device__ __forceinline__ void wave_expand_finish(const WaveParams &p, WaveUser *st, int user, int level, int lane, const int32_t (&code)[NJ],
                                                    const uint32_t *sKeepW, int count, int32_t *__restrict__ nxt, int flags,
                                                    unsigned long long st_cut, unsigned long long st_recut, unsigned long long st_iters)
@@ -309,7 +309,7 @@ __device__ __forceinline__ void wave_expand_finish(const WaveParams &p, WaveUser
         const float dp1 = 2.1f * ds + 2.0f * (float)(p.T + 8) * u + 2.0f * 9.5367432e-7f * (1.0f + 2.0f * smax);
         float eps = p.cA * vx + p.cZ * st->zk + (p.cH + dp1) * st->hw * 1.05f + p.cGamma;
         if (!(ds < 0.04f) || !(eps < 1e30f)) eps = __int_as_float(0x7f800000);
-        if (p.kind == 1) {                                        // DeepFM (beam_wave_dfm.cuh): vt . |x| + a0 + a1 nx + a2 nx^2, 25 % on top
+        if (KIND == 1) {                                          // DeepFM (beam_wave_dfm.cuh): vt . |x| + a0 + a1 nx + a2 nx^2, 25 % on top
             eps = 1.25f * (vx + st->zk + st->kmax * nx + st->hw * nx * nx);
             if (!(eps < 1e30f)) eps = __int_as_float(0x7f800000);
         }
@@ -335,7 +335,7 @@ __device__ void dfm_strict_batch128(const WaveParams &p, const DfmConsts &dc, co
 // lane = candidate 32 j + lane) and the band rows are compacted into shared-memory lists that the lanes then walk in
 // parallel -- rolled loops, so that the kernel stays a few thousand instructions (it runs at low occupancy: instruction
 // fetch is what bounds a long unrolled body).
-template <int NJ>
+template <int NJ, int KIND = 0>
 static __global__ void __launch_bounds__(128) wave_select_kernel(const WaveParams p, const WaveStrictW sw, int level, int slot, const DfmConsts dc)
 {
     constexpr int MU = WaveGeo::MAX_UNC;
@@ -480,7 +480,7 @@ static __global__ void __launch_bounds__(128) wave_select_kernel(const WaveParam
             }
         }
         __syncwarp();
-        if (live && !parked) wave_expand_finish(p, st, user, level, lane, code, sKeepW[warp], count, nxt, flags, st_cut, st_recut, st_iters);
+        if (live && !parked) wave_expand_finish<NJ, KIND>(p, st, user, level, lane, code, sKeepW[warp], count, nxt, flags, st_cut, st_recut, st_iters);
     }
     __syncthreads();
     // ---- phase 2: strict scores of the parked bands, whole CTA ----
@@ -491,7 +491,7 @@ static __global__ void __launch_bounds__(128) wave_select_kernel(const WaveParam
         if (n == 0) continue;
         any = true;
         const int pu = blockIdx.x * 4 + w;
-        if (p.kind == 1) {                                         // DeepFM: the oracle-order chains of deepfm_common.cuh
+        if (KIND == 1) {                                           // DeepFM: the oracle-order chains of deepfm_common.cuh
             if (tid < n) sKeyU[w][tid] = __float_as_uint(sLStr[w][tid]);
             __syncthreads();
             dfm_strict_batch128(p, dc, p.dfm_dense, pu, sLCode[w], n, sLStr[w], sScr, reinterpret_cast<float *>(sel_dyn), dense_loaded);
@@ -548,7 +548,7 @@ static __global__ void __launch_bounds__(128) wave_select_kernel(const WaveParam
                 if (p.stats) { atomicAdd(&p.stats[0], st_cut); atomicAdd(&p.stats[1], st_recut); }
             }
         } else {
-            wave_expand_finish(p, st, user, level, lane, code, sKeepW[warp], count, nxt, flags, st_cut, st_recut, st_iters);
+            wave_expand_finish<NJ, KIND>(p, st, user, level, lane, code, sKeepW[warp], count, nxt, flags, st_cut, st_recut, st_iters);
         }
     }
 }

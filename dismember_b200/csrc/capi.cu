@@ -1220,7 +1220,7 @@ static int32_t dfm_fast_retrieve(dmg_handle_t h, int32_t B, const int32_t *item_
     h->launches += 1;
     const bool pdl = !getenv("DMG_WAVE_NO_PDL");
     DMG_CUDA(h, launch_chain(wave_dfm_prologue_kernel, B, 128, 0, h->stream, false, wp, dc, (const float *)d.tail<float>()));
-    auto select_kernel = cap <= 256 ? wave_select_kernel<8> : (cap <= 416 ? wave_select_kernel<13> : wave_select_kernel<16>);
+    auto select_kernel = cap <= 256 ? wave_select_kernel<8, 1> : (cap <= 416 ? wave_select_kernel<13, 1> : wave_select_kernel<16, 1>);
     const size_t score_smem = (size_t)(128 * 68 + 96) * 4;
     const int ntiles = B * ((cap + 127) / 128), grid = std::min(ntiles, 6 * h->sm_count);
     DfmW1x wx;
