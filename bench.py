@@ -280,7 +280,7 @@ def measure(args, env, items, structured=False, do_cpu=False, target_s=None, ver
     eng.set_arithmetic(args.arith)
     # waiting host threads spin while this rank's share of the cores covers them (lowest latency) and sleep otherwise (8 ranks x 8
     # threads on a 32-core host): dmg_set_sync_mode; the clones inherit it
-    sync_mode = "sleep" if env["world"] * args.inflight >= (os.cpu_count() or 1) else "spin"
+    sync_mode = os.environ.get("DMG_BENCH_SYNC") or ("sleep" if env["world"] * args.inflight >= (os.cpu_count() or 1) else "spin")
     eng.set_sync_mode(sync_mode)
     if args.tau is not None:
         eng.set_fast_tolerance(args.tau)
