@@ -347,3 +347,26 @@ def test_dp_train_step_world1_is_train_step(jtm_fix):
     assert np.abs(wa - wb).max() <= 2e-4 and np.abs(wa - params).max() > 1e-3
     a.close()
     b.close()
+
+
+@pytest.mark.parametrize("which", ["f32", "f64"])
+def test_adam_kernel_is_bit_exact_given_the_gradient(engine, orc, jtm_fix, otm_fix, which):
+    """adam_dense_kernel vs Adam.optimize (scalann/.../optim/Adam.scala:19-73) with the SAME gradient: a one-row batch without repeated
+    ids has no summation-order freedom, so dmg_din_gradients and dmg_train_step see identical gradient bits and the updated weights
+    must equal the oracle's Adam applied to that gradient bit for bit, three steps in a row (moments included)."""
+    fix = jtm_fix if which == "f32" else otm_fix
+    params = fix["params"].copy()
+    engine.load_din_weights(params, 8191, 16, 10)
+    w, s, r = params.copy(), np.zeros_like(params), np.zeros_like(params)
+    rng = np.random.default_rng(31)
+    for t in (1, 2, 3):
+        ids = rng.choice(8191, 11, replace=False).astype(np.int32)
+        node, seq = ids[:1], ids[1:].reshape(1, 10).copy()
+        seq[0, 7:] = -1
+        mask = np.arange(7, 10, dtype=np.int32)
+        labels = np.array([1.0 if t % 2 else 0.0])
+        g, _ = engine.din_gradients(node, seq, mask, labels)
+        orc.adam_step(w, g, s, r, 3e-3, t)
+        engine.train_step(node, seq, mask, labels, 3e-3, t)
+        got = engine.download_din_weights()
+        assert (got.view(np.uint8) == w.view(np.uint8)).all(), t
