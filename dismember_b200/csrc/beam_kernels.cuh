@@ -31,6 +31,7 @@ template <typename real> struct BeamParams {
     const real *emb, *wattT, *w1T, *b1, *w2, *b2;
     real scale;
     int T, B;
+    int E_run;                  // embed size of the tables above when it differs from the loaded model's (zero-padded copy), else 0
     const int32_t *hist;        // B x T embedding indices, -1 = padding (zero row)
     const uint8_t *hist_mask;   // B x T, 1 = position listed in the Mask input
     int beam;

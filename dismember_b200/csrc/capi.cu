@@ -99,6 +99,7 @@ DMG_API int32_t dmg_destroy(dmg_handle_t h)
     else {
         free_tree(h->tree);
         free_din(h->din);
+        free_din(h->din_pad);
         dmg_free_dr(h->dr);
     }
     for (Scratch *s : {&h->s_in, &h->s_out, &h->s_work, &h->s_wave}) { cudaFree(s->d); cudaFreeHost(s->h); }
@@ -129,13 +130,15 @@ DMG_API int32_t dmg_clone(dmg_handle_t src, dmg_handle_t *out)
     if (rc != DMG_OK) return fail(src, rc, "dmg_clone: %s", dmg_last_error(nullptr));
     // the owner builds the shared tables of the tensor-core paths (bound tables, bf16 hi|lo copy of the node table) before
     // they are copied: clones only read them
-    if (src->arithmetic == DMG_ARITH_FAST && src->fast_dirty && src->din.loaded && src->din.dtype == DMG_F32 && src->din.E == 64 && src->din.kind == 0) {
+    if (src->arithmetic == DMG_ARITH_FAST && src->fast_dirty && src->din.loaded && src->din.dtype == DMG_F32 && src->din.kind == 0 &&
+        (src->din.E == 64 || src->din.E == 32 || src->din.E == 16)) {
         const int32_t rb = compute_fast_bounds(src);
         if (rb != DMG_OK) { dmg_destroy(h); return rb; }
     }
     cudaStreamSynchronize(src->stream);                          // uploads of the model are complete before another stream reads it
     h->tree = src->tree;
     h->din = src->din;
+    h->din_pad = src->din_pad;
     h->dr = src->dr;
     h->arithmetic = src->arithmetic;
     h->sync_mode = src->sync_mode;
@@ -452,7 +455,7 @@ template <typename real> static int32_t launch_beam(dmg_handle_t h, const BeamPa
 // its own TMA descriptor over the copy.  No room for the copy (it is as large as the table) => the persistent kernel runs.
 static int32_t wave_prepare(dmg_handle_t h)
 {
-    DinDev &d = h->din;
+    DinDev &d = h->din_pad.loaded ? h->din_pad : h->din;
     if (!h->parent) {
         if (!d.d_split && cudaMalloc(&d.d_split, (size_t)d.rows * 256) != cudaSuccess) { cudaGetLastError(); d.d_split = nullptr; return DMG_OK; }
         if (!d.d_w1img) { DMG_CUDA(h, cudaMalloc(&d.d_w1img, 24576)); DMG_CUDA(h, cudaMemsetAsync(d.d_w1img, 0, 24576, h->stream)); }
@@ -462,9 +465,10 @@ static int32_t wave_prepare(dmg_handle_t h)
         DMG_CUDA(h, cudaGetLastError());
         DMG_CUDA(h, cudaStreamSynchronize(h->stream));
     } else {
-        if (h->parent->fast_dirty || !h->parent->din.d_split) return DMG_OK;
-        d.d_split = h->parent->din.d_split;
-        d.d_w1img = h->parent->din.d_w1img;
+        const DinDev &pd = h->parent->din_pad.loaded ? h->parent->din_pad : h->parent->din;
+        if (h->parent->fast_dirty || !pd.d_split) return DMG_OK;
+        d.d_split = pd.d_split;
+        d.d_w1img = pd.d_w1img;
     }
     typedef CUresult (*encode_fn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
                                   const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
@@ -489,12 +493,80 @@ static int32_t wave_prepare(dmg_handle_t h)
     return DMG_OK;
 }
 
+// ---- E = 16 / 32 models on the E = 64 tensor-core path --------------------------------------------------------------------------------
+// Every configuration the reference ships uses embed_size 16 (configs/*.conf).  A narrower Float DIN model zero-padded to E = 64 --
+// table rows [x | 0], Watt / W1 / b1 / W2 with zero rows and columns, the item half and the attention half of W1 at columns 0 and 64
+// -- runs through the SAME sequential-k chains with exact zeros appended (fma(0, 0, acc) == acc), and relu(0 + 0) . 0 adds nothing to
+// the logit: the strict arithmetic of the padded model is the narrow model's bit for bit, PROVIDED the attention scale stays
+// 1 / sqrt(embed_size) of the original (DinDev::scale_E).  So retrieval in FAST arithmetic builds that copy once per weight load and
+// runs the E = 64 path on it: certified cuts, strict re-scores and the redo kernel included.  It costs 4x (E = 16) the table's memory
+// and gather traffic, and takes E = 16 retrieval from 0.62 M (strict SIMT kernel) to the E = 64 path's rate.
+static __global__ void pad_table_kernel(const float *__restrict__ src, int64_t rows, int E, float *__restrict__ dst)
+{
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < rows * 64; i += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t r = i >> 6;
+        const int k = (int)(i & 63);
+        dst[i] = k < E ? src[r * E + k] : 0.0f;
+    }
+}
+// dense tail [Watt E x E | W1 E x 2E | b1 | W2 | b2] -> [64 x 64 | 64 x 128 | 64 | 64 | 1]
+static __global__ void pad_dense_kernel(const float *__restrict__ src, int E, float *__restrict__ dst)
+{
+    const int n = 3 * 64 * 64 + 2 * 64 + 1;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        float v = 0.0f;
+        if (i < 64 * 64) {                                            // Watt[o][k]
+            const int o = i >> 6, k = i & 63;
+            if (o < E && k < E) v = src[o * E + k];
+        } else if (i < 3 * 64 * 64) {                                 // W1[o][c], c < 64 the item half, c >= 64 the attention half
+            const int q = i - 64 * 64, o = q >> 7, c = q & 127, half = c >> 6, k = c & 63;
+            if (o < E && k < E) v = src[E * E + o * 2 * E + half * E + k];
+        } else {
+            const int q = i - 3 * 64 * 64;                            // b1 | W2 | b2
+            if (q < 64) { if (q < E) v = src[3 * E * E + q]; }
+            else if (q < 128) { if (q - 64 < E) v = src[3 * E * E + E + (q - 64)]; }
+            else v = src[3 * E * E + 2 * E];
+        }
+        dst[i] = v;
+    }
+}
+static int32_t build_padded_model(dmg_handle_t h)
+{
+    const DinDev &d = h->din;
+    DinDev &p = h->din_pad;
+    if (h->parent) return DMG_OK;                                     // a clone reads its parent's copy (dmg_clone brought it up to date)
+    const int64_t n_params = d.rows * 64 + 3 * 64 * 64 + 2 * 64 + 1;
+    if (p.loaded && p.rows != d.rows) free_din(p);
+    if (!p.d_params) {
+        if (cudaMalloc(&p.d_params, (size_t)n_params * 4) != cudaSuccess) { cudaGetLastError(); p = DinDev(); return DMG_OK; }   // no room: strict kernel
+        DMG_CUDA(h, cudaMalloc(&p.d_wattT, sizeof(float) * 64 * 64));
+        DMG_CUDA(h, cudaMalloc(&p.d_w1T, sizeof(float) * 2 * 64 * 64));
+    }
+    p.dtype = DMG_F32; p.esz = 4; p.rows = d.rows; p.E = 64; p.T = d.T; p.scale_E = d.E; p.n_params = n_params; p.kind = 0;
+    pad_table_kernel<<<h->sm_count * 16, 256, 0, h->stream>>>(d.emb<float>(), d.rows, d.E, p.emb<float>());
+    pad_dense_kernel<<<64, 256, 0, h->stream>>>(d.tail<float>(), d.E, p.tail<float>());
+    transpose_kernel<float><<<(64 * 64 + 255) / 256, 256, 0, h->stream>>>(p.watt<float>(), (float *)p.d_wattT, 64, 64);
+    transpose_kernel<float><<<(2 * 64 * 64 + 255) / 256, 256, 0, h->stream>>>(p.w1<float>(), (float *)p.d_w1T, 64, 128);
+    h->launches += 4;
+    DMG_CUDA(h, cudaGetLastError());
+    p.loaded = true;
+    return DMG_OK;
+}
+static bool wants_padded_model(const dmg_handle_t h)
+{
+    const DinDev &d = h->din;
+    return h->arithmetic == DMG_ARITH_FAST && d.loaded && d.dtype == DMG_F32 && d.kind == 0 && !d.sharded && (d.E == 16 || d.E == 32) && d.T <= 15 &&
+           !getenv("DMG_NO_PAD");
+}
+
 static int32_t compute_fast_bounds(dmg_handle_t h)
 {
-    DinDev &d = h->din;
     h->fast_ok = false;
     h->fast_dirty = false;
-    if (d.dtype != DMG_F32 || d.E != 64) return DMG_OK;
+    if (wants_padded_model(h)) DMG_TRY(build_padded_model(h));
+    else if (!h->parent && h->din_pad.loaded) free_din(h->din_pad);
+    DinDev &d = h->din_pad.loaded ? h->din_pad : h->din;
+    if (d.dtype != DMG_F32 || d.E != 64 || d.kind != 0) return DMG_OK;
     const int E = d.E;
     const size_t n_dense = (size_t)3 * E * E + 2 * E + 1;
     std::vector<float> w(n_dense);
@@ -557,7 +629,7 @@ template <typename real> static void fill_scorer(const DinDev &d, BeamParams<rea
 {
     p.emb = d.emb<real>(); p.wattT = (const real *)d.d_wattT; p.w1T = (const real *)d.d_w1T;
     p.b1 = d.b1<real>(); p.w2 = d.w2<real>(); p.b2 = d.b2<real>();
-    p.scale = (real)(1.0 / std::sqrt((double)d.E));                      // Mask.scala:12
+    p.scale = (real)(1.0 / std::sqrt((double)(d.scale_E ? d.scale_E : d.E)));   // Mask.scala:12
     p.T = d.T;
 }
 
@@ -754,7 +826,9 @@ static int32_t tdm_enqueue_raw(dmg_handle_t h, int32_t B, const int32_t *d_seq, 
     // redo_out: a caller that synchronises anyway takes the strict redo launch into its own hands (h_flags[1] tells it
     // whether the batch has redo users); redo_out->B == 0 on return when there is no such launch.
     if (redo_out) redo_out->B = 0;
-    const DinDev &d = h->din;
+    if (h->fast_dirty && h->arithmetic == DMG_ARITH_FAST && h->din.dtype == DMG_F32 && h->din.kind == 0)
+        DMG_TRY(compute_fast_bounds(h));                         // bound tables; for an E = 16 / 32 model also its zero-padded E = 64 copy
+    const DinDev &d = (h->din_pad.loaded && h->arithmetic == DMG_ARITH_FAST && h->fast_ok && !h->fast_dirty) ? h->din_pad : h->din;
     const TreeDev &t = h->tree;
     const int T = d.T;
     DMG_TRY(ensure_dev(h, h->s_work, Carver::need({(size_t)B * T * 4, (size_t)B * T})));
@@ -781,6 +855,7 @@ static int32_t tdm_enqueue_raw(dmg_handle_t h, int32_t B, const int32_t *d_seq, 
     BeamParams<float> p;
     memset(&p, 0, sizeof(p));
     fill_scorer(d, p);
+    p.E_run = d.E != h->din.E ? d.E : 0;
     p.B = B; p.hist = d_codes; p.hist_mask = d_mask; p.beam = beam; p.beam_user = d_beam_user;
     p.always_sort = 0; p.exists = t.complete ? nullptr : t.d_exists; p.leaf_level = t.max_level;
     p.mode = MODE_TDM_TOPK; p.topk = topk; p.leaf_item = t.d_leaf_item; p.cons_off = d_cons_off; p.cons = d_cons;
@@ -1039,7 +1114,7 @@ static int32_t tdm_redo_if_flagged(dmg_handle_t h, const BeamParams<float> &redo
     h->h_flags[1] = 0;
     const bool prof = h->profiling;
     h->profiling = false;
-    const int32_t rc = launch_beam<float>(h, redo, h->din.E);
+    const int32_t rc = launch_beam<float>(h, redo, redo.E_run ? redo.E_run : h->din.E);
     h->profiling = prof;
     *ran = rc == DMG_OK;
     return rc;

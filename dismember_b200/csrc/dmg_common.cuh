@@ -39,6 +39,7 @@ struct DinDev {
     int dtype = DMG_F32;
     int64_t rows = 0;
     int E = 0, T = 0;
+    int scale_E = 0;               // != 0: the attention scale is 1 / sqrt(scale_E) (a zero-padded copy of a narrower model, capi.cu: build_padded_model)
     size_t esz = 4;
     void *d_params = nullptr;      // compact vector [emb | Watt | W1 | b1 | W2 | b2]
     void *d_wattT = nullptr;       // k-major copies  WattT[k][o], W1T[k][o]
@@ -108,6 +109,7 @@ struct dmg_handle_s {
     int64_t launches = 0;
     dmg::TreeDev tree;
     dmg::DinDev din;
+    dmg::DinDev din_pad;             // E = 16 / 32 Float DIN models: zero-padded E = 64 copy that the tensor-core retrieval path runs on
     dmg::DrDev dr;
     dmg::Scratch s_in, s_out, s_work, s_wave;
     bool wave_ok = false;            // level-synchronous tensor-core path (beam_wave.cuh) usable with the current tables

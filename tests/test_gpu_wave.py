@@ -138,3 +138,48 @@ def test_repeated_steps_replay_a_captured_graph(orc):
         assert (gb[2] == ob[2]).all() and (gb[0] == ob[0]).all() and (gb[1].view(np.uint32) == ob[1].view(np.uint32)).all(), it
     twin.close()
     e.close()
+
+
+@pytest.mark.parametrize("E", [16, 32])
+def test_narrow_models_run_the_tensor_core_path_on_a_zero_padded_copy(orc, E):
+    """embed_size 16 / 32 (every configuration the reference ships uses 16): FAST arithmetic builds a zero-padded E = 64 copy with the
+    ORIGINAL attention scale 1 / sqrt(E) and runs the tensor-core path on it.  Exact zeros appended to every sequential-k chain change
+    no bit, so ids and logits equal the strict E-wide kernel and the oracle; the fast scorer did score rows; clones and the eval
+    variant go through the same copy; score_pairs / download still see the narrow model."""
+    from conftest import new_engine
+    n_items, T, beam, topk, B = 20000, 10, 200, 10, 80
+    tf = synth.tdm_tree(n_items, seed=6)
+    rows = (1 << (tf.max_level + 1)) - 1
+    params = synth.din_params(rows, E, seed=7, structured=True)
+    seqs = synth.queries(B, T, n_items, seed=8)
+    seqs[0] = 0
+    e = new_engine()
+    e.load_tree_tdm(tf.max_level, tf.codes, tf.node_ids, tf.is_leaf, tf.leaf_ids, tf.leaf_codes)
+    e.load_din_weights(params, rows, E, T)
+    e.fast_stats()
+    fi, fl, fc = e.tdm_retrieve(seqs, beam, topk)
+    st = e.fast_stats()
+    assert st["rows_fast"] > B * 1000 and st["max_err_over_bound"] < 1.0
+    tree = orc.Tree.from_treefile(tf)
+    model = orc.TdmModel(params, rows, E, T)
+    oi, ol, oc = model.retrieve_batch(tree, seqs, beam, topk, n_threads=8)
+    assert (fc == oc).all() and (fi == oi).all() and (fl.view(np.uint32) == ol.view(np.uint32)).all()
+    twin = e.clone()
+    ti, tl, tc = twin.tdm_retrieve(seqs, beam, topk)
+    assert (tc == oc).all() and (ti == oi).all() and (tl.view(np.uint32) == ol.view(np.uint32)).all()
+    assert twin.fast_stats()["rows_fast"] > 0
+    twin.close()
+    e.set_arithmetic("strict")
+    si, sl, sc = e.tdm_retrieve(seqs, beam, topk)
+    assert (sc == oc).all() and (si == oi).all() and (sl.view(np.uint32) == ol.view(np.uint32)).all()
+    e.set_arithmetic("fast")
+    assert (e.download_din_weights() == params).all()
+    node = np.arange(100, 164, dtype=np.int32)
+    assert (e.score_pairs(node, seqs[:64] * 0 + node[:, None]).view(np.uint32) == model.forward(node, seqs[:64] * 0 + node[:, None]).view(np.uint32)).all()
+    # new weights: the copy follows
+    params2 = synth.din_params(rows, E, seed=9, structured=True)
+    e.load_din_weights(params2, rows, E, T)
+    o2 = orc.TdmModel(params2, rows, E, T).retrieve_batch(tree, seqs[:32], beam, topk, n_threads=8)
+    f2 = e.tdm_retrieve(seqs[:32], beam, topk)
+    assert (f2[2] == o2[2]).all() and (f2[0] == o2[0]).all() and (f2[1].view(np.uint32) == o2[1].view(np.uint32)).all()
+    e.close()
