@@ -599,7 +599,7 @@ def main():
     kern_ms = m.get("kern_ms_per_step", 0.0)
     achieved = B * bytes_u / (kern_ms * 1e-3) / 1e9 if kern_ms else None
     traffic = None
-    fast_path = args.arith == "fast" and E == 64 and T <= 15        # the tensor-core path is built for E = 64; other sizes run the strict kernel
+    fast_path = args.arith == "fast" and E in (16, 32, 64) and T <= 15   # E = 16 / 32 run the E = 64 tensor-core path on a zero-padded copy of the model
     kernel_name = "wave_score_kernel" if fast_path else "beam_search_kernel<float,%d>" % E
     tp = os.path.join(ROOT, "profiles", "traffic.json")
     if os.path.exists(tp):

@@ -552,6 +552,11 @@ static int32_t build_padded_model(dmg_handle_t h)
     p.loaded = true;
     return DMG_OK;
 }
+// the model the retrieval kernels read: the zero-padded copy when it is built and current, else the loaded one
+static const DinDev &retrieval_din(const dmg_handle_t h)
+{
+    return (h->din_pad.loaded && h->arithmetic == DMG_ARITH_FAST && h->fast_ok && !h->fast_dirty) ? h->din_pad : h->din;
+}
 static bool wants_padded_model(const dmg_handle_t h)
 {
     const DinDev &d = h->din;
@@ -690,7 +695,7 @@ static int32_t wave_enqueue(dmg_handle_t h, const BeamParams<float> &p, const Fa
                             WaveParams *wp_out = nullptr, int *slot_out = nullptr)
 {
     using WG = WaveGeo;
-    const DinDev &d = h->din;
+    const DinDev &d = retrieval_din(h);
     const int B = p.B, cap = p.cap;
     DMG_TRY(ensure_dev(h, h->s_wave, Carver::need({(size_t)B * cap * 4, (size_t)B * cap * 4, (size_t)B * cap * 4, (size_t)B * 4,
                                                    (size_t)B * sizeof(WaveUser), (size_t)B * WG::UOP_BYTES, (size_t)B * WG::VCAP * 4,
@@ -828,7 +833,7 @@ static int32_t tdm_enqueue_raw(dmg_handle_t h, int32_t B, const int32_t *d_seq, 
     if (redo_out) redo_out->B = 0;
     if (h->fast_dirty && h->arithmetic == DMG_ARITH_FAST && h->din.dtype == DMG_F32 && h->din.kind == 0)
         DMG_TRY(compute_fast_bounds(h));                         // bound tables; for an E = 16 / 32 model also its zero-padded E = 64 copy
-    const DinDev &d = (h->din_pad.loaded && h->arithmetic == DMG_ARITH_FAST && h->fast_ok && !h->fast_dirty) ? h->din_pad : h->din;
+    const DinDev &d = retrieval_din(h);
     const TreeDev &t = h->tree;
     const int T = d.T;
     DMG_TRY(ensure_dev(h, h->s_work, Carver::need({(size_t)B * T * 4, (size_t)B * T})));
