@@ -536,7 +536,7 @@ static int32_t build_padded_model(dmg_handle_t h)
     DinDev &p = h->din_pad;
     if (h->parent) return DMG_OK;                                     // a clone reads its parent's copy (dmg_clone brought it up to date)
     const int64_t n_params = d.rows * 64 + 3 * 64 * 64 + 2 * 64 + 1;
-    if (p.loaded && p.rows != d.rows) free_din(p);
+    if (p.loaded && (p.rows != d.rows || p.n_params != n_params || p.kind != 0)) free_din(p);
     if (!p.d_params) {
         if (cudaMalloc(&p.d_params, (size_t)n_params * 4) != cudaSuccess) { cudaGetLastError(); p = DinDev(); return DMG_OK; }   // no room: strict kernel
         DMG_CUDA(h, cudaMalloc(&p.d_wattT, sizeof(float) * 64 * 64));
@@ -1146,11 +1146,47 @@ int dmg_shard_world(dmg_handle_t h);   // shard.cu
 // ---- DeepFM scorer: certified fast path (beam_wave_dfm.cuh) -----------------------------------------------------------------------------
 // Bound tables of the loaded DeepFM model: vt (per-dimension weight of |x| in the hidden-unit and final-dot error terms) and, through
 // level_bounds_kernel, the per-level maxima of vt . |x| and |x|_2; the transposed item half of W1 for the fast scorer.
+// DeepFM with embed_size 16 / 32: the same zero-padding argument as for DIN (build_padded_model) -- features [x | 0], W1 with zero
+// columns at the padded positions of every feature row; the FM sums and the Linear chains only gain exact zeros.
+static __global__ void pad_dfm_dense_kernel(const float *__restrict__ src, int E, int F, float *__restrict__ dst)
+{
+    const int n = F * F * 64 + 2 * F + 1;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        float v;
+        if (i < F * F * 64) {
+            const int o = i / (F * 64), q = i - o * F * 64, sl = q >> 6, k = q & 63;
+            v = k < E ? src[(size_t)o * F * E + sl * E + k] : 0.0f;
+        } else {
+            v = src[(size_t)F * F * E + (i - F * F * 64)];             // b1 | W2 | b2
+        }
+        dst[i] = v;
+    }
+}
+static int32_t build_padded_dfm(dmg_handle_t h)
+{
+    const DinDev &d = h->din;
+    DinDev &p = h->din_pad;
+    const int F = d.T + 1;
+    const int64_t n_params = d.rows * 64 + (int64_t)F * F * 64 + 2 * F + 1;
+    if (p.loaded && (p.rows != d.rows || p.n_params != n_params)) free_din(p);
+    if (!p.d_params && cudaMalloc(&p.d_params, (size_t)n_params * 4) != cudaSuccess) { cudaGetLastError(); p = DinDev(); return DMG_OK; }
+    p.dtype = DMG_F32; p.esz = 4; p.rows = d.rows; p.E = 64; p.T = d.T; p.scale_E = d.E; p.n_params = n_params; p.kind = 1;
+    pad_table_kernel<<<h->sm_count * 16, 256, 0, h->stream>>>(d.emb<float>(), d.rows, d.E, p.emb<float>());
+    pad_dfm_dense_kernel<<<64, 256, 0, h->stream>>>(d.tail<float>(), d.E, F, p.tail<float>());
+    h->launches += 2;
+    DMG_CUDA(h, cudaGetLastError());
+    p.loaded = true;
+    return DMG_OK;
+}
+
 static int32_t compute_dfm_bounds(dmg_handle_t h)
 {
-    DinDev &d = h->din;
     h->fast_ok = false;
     h->fast_dirty = false;
+    if (h->din.kind == 1 && h->din.dtype == DMG_F32 && (h->din.E == 16 || h->din.E == 32) && h->din.T <= 10 && !getenv("DMG_NO_PAD"))
+        DMG_TRY(build_padded_dfm(h));
+    else if (h->din_pad.loaded) free_din(h->din_pad);
+    DinDev &d = h->din_pad.loaded ? h->din_pad : h->din;
     if (d.kind != 1 || d.dtype != DMG_F32 || d.E != 64 || d.T > 10) return DMG_OK;   // T + 1 <= 11 hidden units in the fast scorer
     const int E = d.E, T = d.T, F = T + 1, IN = F * E;
     const size_t n_dense = (size_t)F * IN + 2 * F + 1;
@@ -1204,15 +1240,15 @@ static int32_t dfm_fast_retrieve(dmg_handle_t h, int32_t B, const int32_t *item_
 {
     using WG = WaveGeo;
     *handled = false;
-    DinDev &d = h->din;
     const TreeDev &t = h->tree;
-    if (h->arithmetic != DMG_ARITH_FAST || d.E != 64 || d.T > 10 || dmg_shard_world(h) > 1 || !t.loaded || t.complete || !t.d_id_code ||
-        getenv("DMG_DFM_STRICT"))
+    if (h->arithmetic != DMG_ARITH_FAST || (h->din.E != 64 && h->din.E != 32 && h->din.E != 16) || h->din.T > 10 || dmg_shard_world(h) > 1 || !t.loaded ||
+        t.complete || !t.d_id_code || getenv("DMG_DFM_STRICT"))
         return DMG_OK;
     if (B <= 0 || beam <= 0 || topk <= 0) return DMG_OK;          // the strict path reports the argument errors
     DMG_CUDA(h, cudaSetDevice(h->device));
     if (h->fast_dirty) DMG_TRY(compute_dfm_bounds(h));
     if (!h->fast_ok) return DMG_OK;
+    DinDev &d = h->din_pad.loaded ? h->din_pad : h->din;          // the zero-padded E = 64 copy of an E = 16 / 32 model
     const int T = d.T;
     const int64_t n_cons = consumed_off ? consumed_off[B] : 0;
     const bool per_user = consumed_off && widen_beam;

@@ -231,3 +231,26 @@ def test_deepfm_fast_path_runs_and_hands_ties_back(orc):
     sz = e.tdm_retrieve(seqs[:24], beam, topk)
     assert (fz[2] == sz[2]).all() and (fz[0] == sz[0]).all() and (fz[1].view(np.uint32) == sz[1].view(np.uint32)).all()
     e.close()
+
+
+@pytest.mark.parametrize("E", [16, 32])
+def test_deepfm_narrow_models_take_the_fast_path_on_a_padded_copy(orc, E):
+    """DeepFM with embed_size 16 / 32: the certified fast path runs on a zero-padded E = 64 copy (features [x | 0], W1 with zero
+    columns): the FM sums and the Linear chains only gain exact zeros, so ids and logits are the narrow model's bits."""
+    from dismember_b200 import synth
+    T, n_items, beam, topk, B = 10, 8000, 60, 10, 48
+    tf = synth.tdm_tree(n_items, seed=4)
+    rows = (1 << (tf.max_level + 1)) - 1
+    params = deepfm_params(rows, E, T, seed=14)
+    seqs = synth.queries(B, T, n_items, seed=15)
+    e = new_engine()
+    e.load_tree_tdm(tf.max_level, tf.codes, tf.node_ids, tf.is_leaf, tf.leaf_ids, tf.leaf_codes)
+    e.load_deepfm_weights(params, rows, E, T)
+    e.fast_stats()
+    fi, fl, fc = e.tdm_retrieve(seqs, beam, topk)
+    assert e.fast_stats()["rows_fast"] > B * 200
+    tree = orc.Tree.from_treefile(tf)
+    oi, ol, oc = orc.TdmModel(params, rows, E, T, deepfm=True).retrieve_batch(tree, seqs, beam, topk, n_threads=8)
+    assert (fc == oc).all() and (fi == oi).all() and (fl.view(np.uint32) == ol.view(np.uint32)).all()
+    assert (e.download_din_weights() == params).all()
+    e.close()
