@@ -79,6 +79,8 @@ static void free_din(DinDev &d)
     d = DinDev();
 }
 static int32_t compute_fast_bounds(dmg_handle_t h);
+static int32_t compute_dfm_bounds(dmg_handle_t h);
+int dmg_shard_world(dmg_handle_t h);   // shard.cu
 void dmg_free_dr(DrDev &d);     // dr.cu
 void dmg_shard_free(dmg_handle_t h);   // shard.cu
 int32_t dmg_deepfm_tdm_retrieve(dmg_handle_t h, int32_t B, const int32_t *item_seq, int32_t beam, int32_t topk, const int64_t *cons_off,
@@ -123,7 +125,9 @@ DMG_API int32_t dmg_clone(dmg_handle_t src, dmg_handle_t *out)
     if (!src || !out) return DMG_ERR_INVALID_ARG;
     *out = nullptr;
     if (src->parent) src = src->parent;                          // clones of clones hang off the owner
-    if (src->shard) return fail(src, DMG_ERR_UNSUPPORTED, "dmg_clone: sharded / DeepFM handles own NCCL and exchange state -- create one handle per rank");
+    const bool whole_deepfm = src->shard && dmg_shard_world(src) == 1 && src->din.loaded && src->din.kind == 1 && src->din.dtype == DMG_F32;
+    if (src->shard && !whole_deepfm)
+        return fail(src, DMG_ERR_UNSUPPORTED, "dmg_clone: sharded handles own NCCL and exchange state -- create one handle per rank");
     if (src->din.d_grad) return fail(src, DMG_ERR_STATE, "dmg_clone: this handle holds training state; clone an inference handle");
     dmg_handle_t h = nullptr;
     const int32_t rc = dmg_create(src->device, &h);
@@ -134,6 +138,14 @@ DMG_API int32_t dmg_clone(dmg_handle_t src, dmg_handle_t *out)
         (src->din.E == 64 || src->din.E == 32 || src->din.E == 16)) {
         const int32_t rb = compute_fast_bounds(src);
         if (rb != DMG_OK) { dmg_destroy(h); return rb; }
+    }
+    if (whole_deepfm) {                                          // a Float DeepFM model on one GPU: the clone gets its own (world 1) exchange state
+        if (src->arithmetic == DMG_ARITH_FAST && src->fast_dirty) {
+            const int32_t rb = compute_dfm_bounds(src);
+            if (rb != DMG_OK) { dmg_destroy(h); return rb; }
+        }
+        const int32_t rs = dmg_shard_init(h, 1, 0, nullptr);
+        if (rs != DMG_OK) { dmg_destroy(h); return rs; }
     }
     cudaStreamSynchronize(src->stream);                          // uploads of the model are complete before another stream reads it
     h->tree = src->tree;
@@ -1141,8 +1153,6 @@ DMG_API int32_t dmg_tdm_retrieve_dev_sync(dmg_handle_t h, int32_t B, const int32
     return DMG_OK;
 }
 
-int dmg_shard_world(dmg_handle_t h);   // shard.cu
-
 // ---- DeepFM scorer: certified fast path (beam_wave_dfm.cuh) -----------------------------------------------------------------------------
 // Bound tables of the loaded DeepFM model: vt (per-dimension weight of |x| in the hidden-unit and final-dot error terms) and, through
 // level_bounds_kernel, the per-level maxima of vt . |x| and |x|_2; the transposed item half of W1 for the fast scorer.
@@ -1183,9 +1193,13 @@ static int32_t compute_dfm_bounds(dmg_handle_t h)
 {
     h->fast_ok = false;
     h->fast_dirty = false;
-    if (h->din.kind == 1 && h->din.dtype == DMG_F32 && (h->din.E == 16 || h->din.E == 32) && h->din.T <= 10 && !getenv("DMG_NO_PAD"))
+    if (h->parent) {
+        // a clone reads its parent's tables (and zero-padded copy), brought up to date by dmg_clone
+    } else if (h->din.kind == 1 && h->din.dtype == DMG_F32 && (h->din.E == 16 || h->din.E == 32) && h->din.T <= 10 && !getenv("DMG_NO_PAD")) {
         DMG_TRY(build_padded_dfm(h));
-    else if (h->din_pad.loaded) free_din(h->din_pad);
+    } else if (h->din_pad.loaded) {
+        free_din(h->din_pad);
+    }
     DinDev &d = h->din_pad.loaded ? h->din_pad : h->din;
     if (d.kind != 1 || d.dtype != DMG_F32 || d.E != 64 || d.T > 10) return DMG_OK;   // T + 1 <= 11 hidden units in the fast scorer
     const int E = d.E, T = d.T, F = T + 1, IN = F * E;

@@ -223,6 +223,20 @@ def test_deepfm_fast_path_runs_and_hands_ties_back(orc):
     e.set_arithmetic("fast")
     f2 = e.tdm_retrieve(seqs, beam, topk, consumed_off=off, consumed=flat, widen_beam=True)
     assert (f2[2] == s2[2]).all() and (f2[0] == s2[0]).all() and (f2[1].view(np.uint32) == s2[1].view(np.uint32)).all()
+    # one handle per host thread over one copy of the tables (dmg_clone), two batches in flight
+    import threading
+    twin = e.clone()
+    got = [None, None]
+
+    def work(k, eng, sl):
+        got[k] = eng.tdm_retrieve(seqs[sl], beam, topk)
+    th = [threading.Thread(target=work, args=(0, e, slice(0, B // 2))), threading.Thread(target=work, args=(1, twin, slice(B // 2, B)))]
+    [t_.start() for t_ in th]
+    [t_.join() for t_ in th]
+    for k, sl in enumerate((slice(0, B // 2), slice(B // 2, B))):
+        assert (got[k][0] == fi[sl]).all() and (got[k][1].view(np.uint32) == fl[sl].view(np.uint32)).all() and (got[k][2] == fc[sl]).all()
+    assert twin.fast_stats()["rows_fast"] > 0
+    twin.close()
     # all-zero model: exact ties everywhere
     zero = np.zeros_like(params)
     e.load_deepfm_weights(zero, rows, E, T)

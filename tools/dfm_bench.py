@@ -25,3 +25,20 @@ for mode in ("fast", "strict"):
     print(mode, "ms", dt * 1e3, "users/s", B / dt, eng.fast_stats() if mode == "fast" else "")
     if mode == "fast": rf = r
     else: print("fast == strict:", (rf[0] == r[0]).all(), (rf[1].view(np.uint32) == r[1].view(np.uint32)).all(), (rf[2] == r[2]).all())
+# batches in flight: one clone per host thread
+import threading
+eng.set_arithmetic("fast")
+NF = 4
+engs = [eng] + [eng.clone() for _ in range(NF - 1)]
+qs = [synth.queries(B, T, n_items, seed=40 + k) for k in range(NF)]
+for k, e_ in enumerate(engs):
+    e_.tdm_retrieve(qs[k], 200, 10)
+reps = 8
+def loop(k):
+    for _ in range(reps):
+        engs[k].tdm_retrieve(qs[k], 200, 10)
+th = [threading.Thread(target=loop, args=(k,)) for k in range(NF)]
+t0 = time.perf_counter()
+[t.start() for t in th]; [t.join() for t in th]
+dt = (time.perf_counter() - t0) / (reps * NF)
+print("fast, %d in flight: ms %.3f users/s %.0f" % (NF, dt * 1e3, B / dt))
