@@ -81,6 +81,7 @@ static void free_din(DinDev &d)
 static int32_t compute_fast_bounds(dmg_handle_t h);
 static int32_t compute_dfm_bounds(dmg_handle_t h);
 int dmg_shard_world(dmg_handle_t h);   // shard.cu
+void dmg_shard_copy_geometry(dmg_handle_t dst, dmg_handle_t src);   // shard.cu
 void dmg_free_dr(DrDev &d);     // dr.cu
 void dmg_shard_free(dmg_handle_t h);   // shard.cu
 int32_t dmg_deepfm_tdm_retrieve(dmg_handle_t h, int32_t B, const int32_t *item_seq, int32_t beam, int32_t topk, const int64_t *cons_off,
@@ -146,6 +147,7 @@ DMG_API int32_t dmg_clone(dmg_handle_t src, dmg_handle_t *out)
         }
         const int32_t rs = dmg_shard_init(h, 1, 0, nullptr);
         if (rs != DMG_OK) { dmg_destroy(h); return rs; }
+        dmg_shard_copy_geometry(h, src);
     }
     cudaStreamSynchronize(src->stream);                          // uploads of the model are complete before another stream reads it
     h->tree = src->tree;

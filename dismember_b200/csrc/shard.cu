@@ -527,6 +527,10 @@ void dmg_shard_free(dmg_handle_t h)
 }
 
 int dmg_shard_world(dmg_handle_t h) { return h && h->shard ? h->shard->world : 1; }   // for translation units that do not see ShardState
+void dmg_shard_copy_geometry(dmg_handle_t dst, dmg_handle_t src)                       // dmg_clone of a whole-table DeepFM engine
+{
+    if (dst && src && dst->shard && src->shard) dst->shard->global_rows = src->shard->global_rows;
+}
 
 DMG_API int32_t dmg_shard_unique_id(void *out, int32_t nbytes)
 {

@@ -241,9 +241,13 @@ def test_deepfm_fast_path_runs_and_hands_ties_back(orc):
     zero = np.zeros_like(params)
     e.load_deepfm_weights(zero, rows, E, T)
     fz = e.tdm_retrieve(seqs[:24], beam, topk)
+    twin = e.clone()                                          # the clone's own fall-back to the strict level-synchronous path
+    tz = twin.tdm_retrieve(seqs[:24], beam, topk)
+    twin.close()
     e.set_arithmetic("strict")
     sz = e.tdm_retrieve(seqs[:24], beam, topk)
     assert (fz[2] == sz[2]).all() and (fz[0] == sz[0]).all() and (fz[1].view(np.uint32) == sz[1].view(np.uint32)).all()
+    assert (tz[2] == sz[2]).all() and (tz[0] == sz[0]).all() and (tz[1].view(np.uint32) == sz[1].view(np.uint32)).all()
     e.close()
 
 
