@@ -777,6 +777,7 @@ static int32_t wave_enqueue(dmg_handle_t h, const BeamParams<float> &p, const Fa
             DMG_CUDA(h, cudaEventRecord(e1, h->stream));
             h->prof_events.emplace_back(e0, e1);
         }
+#ifdef DMG_WAVE_ABLATION                                         // profiling build only (DMG_NVCC_EXTRA=-DDMG_WAVE_ABLATION): the DBG instantiations stay out of the product
         if (getenv("DMG_WAVE_ABLATE") && level == atoi(getenv("DMG_WAVE_ABLATE"))) {
             // profiling aid: replay this level's scorer with parts switched off (scores go to a scratch buffer)
             static float *dummy = nullptr;
@@ -819,6 +820,7 @@ static int32_t wave_enqueue(dmg_handle_t h, const BeamParams<float> &p, const Fa
             }
             cudaEventDestroy(a); cudaEventDestroy(b);
         }
+#endif
         slot ^= 1;
         h->launches += 2;
     }
@@ -959,7 +961,7 @@ static int32_t tdm_enqueue(dmg_handle_t h, int32_t B, const int32_t *d_seq, int3
 {
     static const bool no_graph = getenv("DMG_NO_GRAPH") != nullptr;
     const bool eligible = !no_graph && probe_level < 0 && !h->profiling && h->arithmetic == DMG_ARITH_FAST && !h->fast_dirty && h->fast_ok &&
-                          h->wave_ok && !getenv("DMG_WAVE_ABLATE");
+                          h->wave_ok;
     if (!eligible) {
         if (h->fast_dirty) free_step_graphs(h);                  // the model changed: every captured pointer may be stale
         return tdm_enqueue_raw(h, B, d_seq, beam, max_beam, d_beam_user, topk, use_mask, d_cons_off, d_cons, d_items, d_logits, d_counts,

@@ -1,3 +1,5 @@
+"""DeepFM retrieval, certified fast path vs strict arithmetic on one handle, then four clones in flight (dev aid; the recorded
+line lives in tools/bench_paths.py).  python tools/dfm_bench.py [n_items]"""
 import sys, time, os, numpy as np
 sys.path.insert(0, "/root/repo")
 from dismember_b200 import Engine, synth
