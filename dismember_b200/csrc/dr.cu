@@ -69,7 +69,7 @@ __global__ void __launch_bounds__(kThreads) dr_beam_kernel(const DrBeamParams p)
     const int nodeE = (D - 1) * E;
     double *sX0 = reinterpret_cast<double *>(smem_raw);            // T*E
     double *sU = sX0 + T * E;                                      // K
-    double *sXn = sU + K;                                          // kDrPC x nodeE
+    double *sXn = reinterpret_cast<double *>((reinterpret_cast<uintptr_t>(sU + K) + 15) & ~(uintptr_t)15);   // nodeE x kDrPC, read as double2
     double *sSum = sXn + kDrPC * (nodeE > 0 ? nodeE : 1);          // beam
     double *sProb0 = sSum + beam;                                  // beam
     double *sProb1 = sProb0 + beam;                                // beam
@@ -97,7 +97,8 @@ __global__ void __launch_bounds__(kThreads) dr_beam_kernel(const DrBeamParams p)
             // (1) user part of the chain, once per user and layer
             for (int o = tid; o < K; o += kThreads) {
                 double acc = 0.0;
-                for (int k = 0; k < T * E; k++) acc = fma_(__ldg(wT + (size_t)k * K + o), sX0[k], acc);
+#pragma unroll 8
+                for (int k = 0; k < T * E; k++) acc = fma_(__ldg(wT + (size_t)k * K + o), sX0[k], acc);      // 8 weight loads in flight per thread
                 sU[o] = acc;
             }
             __syncthreads();
@@ -108,7 +109,7 @@ __global__ void __launch_bounds__(kThreads) dr_beam_kernel(const DrBeamParams p)
                 for (int i = tid; i < np * nk; i += kThreads) {
                     const int pp = i / nk, k = i % nk, j = k / E;
                     const int32_t row = path[(pb + pp) * D + j] + j * K;                // CandidateSearcher.scala:54 (numItem + j K + c)
-                    sXn[pp * nodeE + k] = p.node_emb[(size_t)row * E + k % E];
+                    sXn[k * kDrPC + pp] = p.node_emb[(size_t)row * E + k % E];          // [k][path]: the paths of one k are 8 16-byte loads
                 }
                 __syncthreads();
                 for (int o = tid; o < K; o += kThreads) {
@@ -116,25 +117,43 @@ __global__ void __launch_bounds__(kThreads) dr_beam_kernel(const DrBeamParams p)
                     const double u = sU[o];
 #pragma unroll
                     for (int pp = 0; pp < kDrPC; pp++) acc[pp] = u;
+#pragma unroll 8
                     for (int k = 0; k < nk; k++) {
                         const double w = __ldg(wT + (size_t)(T * E + k) * K + o);
 #pragma unroll
-                        for (int pp = 0; pp < kDrPC; pp++) acc[pp] = fma_(w, sXn[pp * nodeE + k], acc[pp]);
+                        for (int pp = 0; pp < kDrPC; pp += 2) {
+                            const double2 x2 = *reinterpret_cast<const double2 *>(sXn + k * kDrPC + pp);
+                            acc[pp] = fma_(w, x2.x, acc[pp]);
+                            acc[pp + 1] = fma_(w, x2.y, acc[pp + 1]);
+                        }
                     }
                     const double bo = __ldg(bias + o);
 #pragma unroll
                     for (int pp = 0; pp < kDrPC; pp++)
-                        if (pp < np) Lmat[(size_t)(pb + pp) * K + o] = add_(acc[pp], bo);
+                        if (pp < np) Lmat[(size_t)o * beam + (pb + pp)] = add_(acc[pp], bo);       // node-major: Lmat[c][path]
                 }
                 __syncthreads();
             }
             // (3) softmax per path: max, exp(x - max), left-to-right sum (dr/package.scala:23-28)
+            // (thread = path; with the node-major layout the path threads of a warp read consecutive addresses at every step)
             for (int pp = tid; pp < live; pp += kThreads) {
-                double *row = Lmat + (size_t)pp * K;
-                double mx = row[0];
-                for (int c = 1; c < K; c++) { const double v = row[c]; mx = v > mx ? v : mx; }
+                double *col = Lmat + pp;
+                double mx = col[0];
+                int c = 1;
+                for (; c + 4 <= K; c += 4) {                                   // four loads in flight per step (the max is order-free)
+                    const double v0 = col[(size_t)c * beam], v1 = col[(size_t)(c + 1) * beam], v2 = col[(size_t)(c + 2) * beam], v3 = col[(size_t)(c + 3) * beam];
+                    mx = v0 > mx ? v0 : mx; mx = v1 > mx ? v1 : mx; mx = v2 > mx ? v2 : mx; mx = v3 > mx ? v3 : mx;
+                }
+                for (; c < K; c++) { const double v = col[(size_t)c * beam]; mx = v > mx ? v : mx; }
                 double sum = 0.0;
-                for (int c = 0; c < K; c++) { const double e = exp_(sub_(row[c], mx)); row[c] = e; sum = add_(sum, e); }
+                c = 0;
+                for (; c + 4 <= K; c += 4) {                                   // loads and exps of four steps together; the sum stays left to right
+                    const double v0 = col[(size_t)c * beam], v1 = col[(size_t)(c + 1) * beam], v2 = col[(size_t)(c + 2) * beam], v3 = col[(size_t)(c + 3) * beam];
+                    const double e0 = exp_(sub_(v0, mx)), e1 = exp_(sub_(v1, mx)), e2 = exp_(sub_(v2, mx)), e3 = exp_(sub_(v3, mx));
+                    col[(size_t)c * beam] = e0; col[(size_t)(c + 1) * beam] = e1; col[(size_t)(c + 2) * beam] = e2; col[(size_t)(c + 3) * beam] = e3;
+                    sum = add_(add_(add_(add_(sum, e0), e1), e2), e3);
+                }
+                for (; c < K; c++) { const double e = exp_(sub_(col[(size_t)c * beam], mx)); col[(size_t)c * beam] = e; sum = add_(sum, e); }
                 sSum[pp] = sum;
             }
             if (tid == 0) { *sCount = 0; *sTau = KO::lowest(); }
@@ -143,11 +162,23 @@ __global__ void __launch_bounds__(kThreads) dr_beam_kernel(const DrBeamParams p)
             const int total = live * K;
             for (int base = 0; base < total; base += kDrChunk) {
                 const Key128 tau = *sTau;
-                for (int idx = base + tid; idx < total && idx < base + kDrChunk; idx += kThreads) {
-                    const int pp = idx / K;
-                    const double cp = mul_(prob[pp], __ddiv_rn(Lmat[idx], sSum[pp]));
-                    const Key128 key = KO::make(cp, idx);
-                    if (key_better(key, tau)) sBuf[atomicAdd(sCount, 1)] = key;
+                const int lim = total < base + kDrChunk ? total : base + kDrChunk;
+                for (int e0 = base + tid; e0 < lim; e0 += 4 * kThreads) {       // four candidates per thread and step: their loads go out together
+                    double lv[4];
+                    int cc[4], pq[4];
+#pragma unroll
+                    for (int q = 0; q < 4; q++) {
+                        const int e = e0 + q * kThreads;
+                        cc[q] = e < lim ? e / live : 0; pq[q] = e < lim ? e - cc[q] * live : 0;   // visit order is free: the key carries the candidate index
+                        lv[q] = Lmat[(size_t)cc[q] * beam + pq[q]];
+                    }
+#pragma unroll
+                    for (int q = 0; q < 4; q++) {
+                        if (e0 + q * kThreads >= lim) continue;
+                        const double cp = mul_(prob[pq[q]], __ddiv_rn(lv[q], sSum[pq[q]]));
+                        const Key128 key = KO::make(cp, pq[q] * K + cc[q]);
+                        if (key_better(key, tau)) sBuf[atomicAdd(sCount, 1)] = key;
+                    }
                 }
                 __syncthreads();
                 const int cnt = *sCount;
@@ -162,7 +193,7 @@ __global__ void __launch_bounds__(kThreads) dr_beam_kernel(const DrBeamParams p)
                 const int pp = pos / K, c = pos % K;
                 for (int j = 0; j < layer; j++) npath[q * D + j] = path[pp * D + j];
                 npath[q * D + layer] = c;
-                nprob[q] = mul_(prob[pp], __ddiv_rn(Lmat[pos], sSum[pp]));
+                nprob[q] = mul_(prob[pp], __ddiv_rn(Lmat[(size_t)c * beam + pp], sSum[pp]));
             }
             __syncthreads();
             { double *t = prob; prob = nprob; nprob = t; }
@@ -402,7 +433,7 @@ static int32_t dr_beam_enqueue(dmg_handle_t h, int32_t B, const int32_t *seq_hos
         d_seq, (int64_t)B * T, for_rerank ? (int64_t)d.num_item : emb_rows, h->d_flags);
     h->launches += 1;
     const int nodeE = std::max((D - 1) * E, 1);
-    size_t smem = ((size_t)T * E + K + (size_t)kDrPC * nodeE + 3 * (size_t)beam + 2) * 8 + (size_t)kDrCap * 16 +
+    size_t smem = ((size_t)T * E + K + 1 + (size_t)kDrPC * nodeE + 3 * (size_t)beam + 2) * 8 + (size_t)kDrCap * 16 +
                   (size_t)2 * beam * D * 4 + 64 * 4 + 32;
     if (smem > h->smem_optin)
         return fail(h, DMG_ERR_UNSUPPORTED, "Deep Retrieval shape needs %zu B of shared memory (limit %zu)", smem, h->smem_optin);
