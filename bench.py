@@ -167,6 +167,33 @@ def cpu_run(args, tree_file, params, rows, seqs, threads):
     return len(seqs) / dt, dt, out
 
 
+def cpu_tuned_run(args, tree_file, params, rows, seqs, threads, faithful=None, budget_s=10.0):
+    """SURVEY 8(d)'s second CPU form (oracle/oracle_tuned.c): re-associated arithmetic (node-side W1x.x precomputed, W1a.Watt collapsed,
+    polynomial exp, AVX-512/AVX2 clones), so NOT bit-equal to the reference -- a reported baseline, never the checker.  `agreement` says
+    how close it stays to the faithful port on the same users."""
+    from oracle import oracle as orc
+    tree = orc.Tree.from_treefile(tree_file)
+    model = orc.TdmModel(params, rows, args.dim, args.seq_len)
+    t0 = time.perf_counter()
+    tuned = orc.TunedTdm(tree, model, n_threads=threads)
+    prep = time.perf_counter() - t0
+    tuned.retrieve_batch(seqs[: 2 * threads], args.beam, args.topk, n_threads=threads)
+    reps, dt, out = 0, 0.0, None
+    while dt < budget_s and reps < 64:
+        t0 = time.perf_counter()
+        out = tuned.retrieve_batch(seqs, args.beam, args.topk, n_threads=threads)
+        dt += time.perf_counter() - t0
+        reps += 1
+    res = {"value": len(seqs) * reps / dt, "unit": "users/s", "cores": threads, "kind": "port-tuned",
+           "sample": f"{len(seqs)} users x {reps} passes, {dt:.1f} s; node-side precomputation {prep:.1f} s (+{rows * args.dim * 4 / 2**20:.0f} MiB), "
+                     f"not in the rate"}
+    if faithful is not None:
+        same = out[0] == faithful[0]
+        res["agreement"] = {"users_with_identical_topk": float(same.all(1).mean()),
+                            "max_abs_logit_diff_on_same_ids": float(np.abs(out[1][same] - faithful[1][same]).max()) if same.any() else None}
+    return res
+
+
 def run_reference(args):
     """--impl reference: the reference's CPU path (oracle port: the JVM reference cannot run here)
     on all host cores, same metric/config, each step a bounded sample of the workload."""
@@ -216,6 +243,10 @@ def run_reference(args):
         "e2e": {"value": value, "unit": "users/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
+    try:        # the tuned CPU form next to it (extra key; `value` above stays the faithful port, the arm the driver's ratio uses)
+        line["cpu_baseline_tuned"] = cpu_tuned_run(args, tf, params, rows, qs[-1], threads, budget_s=8.0)
+    except Exception as exc:  # noqa: BLE001 -- a baseline extra must never take the reference arm down
+        line["cpu_baseline_tuned"] = {"unavailable": repr(exc)}
     print(json.dumps(line), flush=True)
 
 
@@ -413,6 +444,7 @@ def measure(args, env, items, structured=False, do_cpu=False, target_s=None, ver
                                 f"host threads (the Scala+MKL reference cannot run here: no JVM)"}
         out["parity"] = {"users_checked": n, "ids_identical": bool((ref[0] == gpu_i).all()),
                          "logits_bit_identical": bool((ref[1].view(np.uint32) == gpu_l.view(np.uint32)).all())}
+        out["cpu_tuned"] = cpu_tuned_run(args, tf, params, rows, sample_q, threads, ref)
     workers.stop()
     for e in reversed(engs):
         e.close()
@@ -690,6 +722,7 @@ def main():
                          "measured_on": "serial pass (one batch in flight), CUDA events around every launch of the kernel (one per tree level); "
                                         "achieved = the step's algorithmic bytes / the summed launch durations of the step"},
             "cpu_baseline": m.get("cpu"),
+            "cpu_baseline_tuned": m.get("cpu_tuned"),
             "parity": m.get("parity"),
             "parity_fast_vs_strict_kernel": m.get("strict_check"),
             "structured": structured,

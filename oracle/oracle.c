@@ -212,6 +212,20 @@ orc_tdm_model *orc_tdm_deepfm_create(int64_t rows, int E, int T, const float *pa
     m->dfm.b2 = m->dfm.w2 + F;
     return m;
 }
+/* read-only views for oracle_tuned.c (the second CPU form of SURVEY 8(d)) */
+void orc_tree_view(const orc_tree *t, int *max_level, int64_t *n_codes, const uint8_t **exists, const uint8_t **is_leaf,
+                   const int32_t **node_id)
+{
+    *max_level = t->max_level; *n_codes = t->n_codes; *exists = t->exists; *is_leaf = t->is_leaf; *node_id = t->node_id;
+}
+int orc_tdm_model_view(const orc_tdm_model *m, int64_t *rows, int *E, int *T, const float **emb, const float **watt,
+                       const float **w1, const float **b1, const float **w2, const float **b2)
+{
+    if (m->deepfm) return -1;
+    *rows = m->din.rows; *E = m->din.E; *T = m->din.T; *emb = m->din.emb; *watt = m->din.watt; *w1 = m->din.w1;
+    *b1 = m->din.b1; *w2 = m->din.w2; *b2 = m->din.b2;
+    return 0;
+}
 void orc_tdm_model_destroy(orc_tdm_model *m) { if (m) { if (!m->deepfm) orc_din_free_f32(&m->din); free(m); } }
 
 int orc_din_forward_f32_api(const orc_tdm_model *m, int64_t n, const int32_t *node, const int32_t *seq,

@@ -44,6 +44,17 @@ int orc_tdm_retrieve_batch(const orc_tree *t, const orc_tdm_model *m, int B, con
                            int topk, int use_mask, const int64_t *cons_off, const int32_t *cons, int widen_beam,
                            int n_threads, int32_t *out_items, float *out_logits, int32_t *out_counts);
 
+/* oracle_tuned.c: the re-associated, batched CPU form (a reported baseline, never a checker) */
+typedef struct orc_tuned orc_tuned;
+void orc_tree_view(const orc_tree *t, int *max_level, int64_t *n_codes, const uint8_t **exists, const uint8_t **is_leaf,
+                   const int32_t **node_id);
+int orc_tdm_model_view(const orc_tdm_model *m, int64_t *rows, int *E, int *T, const float **emb, const float **watt,
+                       const float **w1, const float **b1, const float **w2, const float **b2);
+orc_tuned *orc_tuned_create(const orc_tree *t, const orc_tdm_model *model, int n_threads);
+void orc_tuned_destroy(orc_tuned *m);
+int orc_tuned_retrieve_batch(const orc_tuned *m, int B, const int32_t *seq_ids, int beam, int topk, int use_mask,
+                             int n_threads, int32_t *out_items, float *out_logits, int32_t *out_counts);
+
 int orc_otm_beam_search(const orc_otm_model *m, const int32_t *seq, int leaf_level, int beam, int use_mask,
                         int32_t *out_ids, double *out_scores);
 int orc_otm_recommend(const orc_otm_model *m, const int32_t *seq_leaf_ids, int leaf_level, int beam, int topk,

@@ -63,6 +63,10 @@ def lib():
                                     i32p, f32p, f64p]
     L.orc_tdm_retrieve_batch.argtypes = [vp, vp, C.c_int, i32p, C.c_int, C.c_int, C.c_int, vp, vp, C.c_int,
                                          C.c_int, i32p, f32p, i32p]
+    L.orc_tuned_create.restype = vp
+    L.orc_tuned_create.argtypes = [vp, vp, C.c_int]
+    L.orc_tuned_destroy.argtypes = [vp]
+    L.orc_tuned_retrieve_batch.argtypes = [vp, C.c_int, i32p, C.c_int, C.c_int, C.c_int, C.c_int, i32p, f32p, i32p]
     L.orc_otm_beam_search.argtypes = [vp, i32p, C.c_int, C.c_int, C.c_int, i32p, f64p]
     L.orc_otm_recommend.argtypes = [vp, i32p, C.c_int, C.c_int, C.c_int, C.c_int, i32p, i32p, f64p, f64p]
     L.orc_otm_retrieve_batch.argtypes = [vp, C.c_int, i32p, C.c_int, C.c_int, C.c_int, C.c_int, i32p, C.c_int,
@@ -206,6 +210,34 @@ class TdmModel:
     def __del__(self):
         if getattr(self, "h", None):
             lib().orc_tdm_model_destroy(self.h)
+            self.h = None
+
+
+class TunedTdm:
+    """oracle_tuned.c: the re-associated, batched CPU form of TDM retrieval over a DIN model (SURVEY 8(d)'s second CPU form).
+    A BASELINE for bench.py, never a checker: logits are close to the reference's, not bit-equal."""
+
+    def __init__(self, tree: Tree, model: TdmModel, n_threads=1):
+        self.tree, self.model = tree, model              # keep the borrowed arrays alive
+        self.T = model.T
+        self.h = lib().orc_tuned_create(tree.h, model.h, int(n_threads))
+        if not self.h:
+            raise ValueError("tuned form: DIN(Float) models only")
+
+    def retrieve_batch(self, seqs, beam, topk, use_mask=True, n_threads=1):
+        seqs = _ci32(seqs).reshape(-1, self.T)
+        B = len(seqs)
+        items = np.empty((B, topk), np.int32)
+        logits = np.empty((B, topk), np.float32)
+        counts = np.empty(B, np.int32)
+        rc = lib().orc_tuned_retrieve_batch(self.h, B, seqs, beam, topk, int(use_mask), n_threads, items, logits, counts)
+        if rc:
+            raise IndexError(f"oracle error {rc}")
+        return items, logits, counts
+
+    def __del__(self):
+        if getattr(self, "h", None):
+            lib().orc_tuned_destroy(self.h)
             self.h = None
 
 

@@ -536,3 +536,27 @@ def test_deepfm_gradients_by_finite_differences(orc):
     touched[node] = True
     touched[seq[seq >= 0]] = True
     assert not g[:rows * E].reshape(rows, E)[~touched].any()
+
+
+@pytest.mark.parametrize("E,use_mask", [(64, True), (16, True), (32, False)])
+def test_tuned_cpu_form_stays_close_to_the_faithful_port(E, use_mask):
+    """oracle_tuned.c (bench.py's `cpu_baseline_tuned`) re-associates the arithmetic, so it is only CLOSE to the faithful port: same
+    counts, logits within 2e-5 wherever the ids agree, and the same top-k on (nearly) every user; padded / unknown histories included."""
+    from oracle import oracle as orc
+    from dismember_b200 import synth
+    n_items, T, beam, topk, B = 6000, 10, 60, 10, 96
+    tf = synth.tdm_tree(n_items, seed=4)
+    rows = (1 << (tf.max_level + 1)) - 1
+    params = synth.din_params(rows, E, seed=5, structured=True)
+    tree = orc.Tree.from_treefile(tf)
+    model = orc.TdmModel(params, rows, E, T)
+    tuned = orc.TunedTdm(tree, model, n_threads=2)
+    q = synth.queries(B, T, n_items, seed=6)
+    q[0] = 0                                                        # all padding: every position masked
+    q[1, :5] = 0
+    fi, fl, fc = model.retrieve_batch(tree, q, beam, topk, use_mask=use_mask, n_threads=2)
+    ti, tl, tc = tuned.retrieve_batch(q, beam, topk, use_mask=use_mask, n_threads=3)
+    assert (fc == tc).all()
+    same = fi == ti
+    assert same.all(1).mean() >= 0.97
+    assert np.abs(fl[same] - tl[same]).max() < 2e-5
