@@ -623,7 +623,11 @@ wave_score_kernel(const __grid_constant__ CUtensorMap tmap, const WaveParams p, 
     constexpr int dbg = DBG;
     extern __shared__ __align__(1024) unsigned char sm[];
     uint64_t *bar = reinterpret_cast<uint64_t *>(sm + G::BAR);
-    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int tid = threadIdx.x, lane = tid & 31;
+    // warp-uniform for the compiler as well: every TMA / MMA / mbarrier operand derived from it goes to uniform registers, and the
+    // single-lane issue below (elect.sync) compiles to back-to-back UTMALDG / UTCHMMA instead of one ELECT .. R2UR.BROADCAST ..
+    // BRA.U.ANY loop per instruction (~100 cycles each: 1.7 K cycles per refill_x and 1.3 K per 12-MMA chain before this)
+    const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);
     const uint32_t sbase = smem_u32(sm);
     if (sbase & 1023u) __trap();                                 // the swizzled X tiles need 1024-byte alignment
     grid_dep_launch();
@@ -643,13 +647,13 @@ wave_score_kernel(const __grid_constant__ CUtensorMap tmap, const WaveParams p, 
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
-    const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t *>(sm + G::TMEMP);
+    const uint32_t tmem_base = __shfl_sync(0xffffffffu, *reinterpret_cast<volatile uint32_t *>(sm + G::TMEMP), 0);
     grid_dep_wait();                                             // everything above ran under the previous kernel's tail
-    const int ntiles = *(volatile const int32_t *)(p.tile_count + level);
+    const int ntiles = __shfl_sync(0xffffffffu, *(volatile const int32_t *)(p.tile_count + level), 0);
     const int n_my = ntiles > (int)blockIdx.x ? (ntiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
 
     const int g = warp >> 2, wq = warp & 3, gtid = tid & 127;             // group = pipeline stage, warp within the group, row of the tile
-    const bool issuer1 = wq == 1 && lane == 0, issuer2 = wq == 2 && lane == 0;    // first / second MMA chain of the group's tiles
+    const bool issuer1 = wq == 1, issuer2 = wq == 2;             // the WARPS issuing the first / second MMA chain of the group's tiles (one elected lane each)
     const uint32_t tmem_lane = (uint32_t)(wq * 32) << 16;
     const uint32_t td = tmem_base + g * 128, tm = td + tmem_lane;
     const float scale2 = p.scale * 1.4426950408889634f, inv_T = 1.0f / (float)p.T;
@@ -664,7 +668,7 @@ wave_score_kernel(const __grid_constant__ CUtensorMap tmap, const WaveParams p, 
         if (g == 0) asm volatile("bar.sync 1, 128;" ::: "memory");
         else asm volatile("bar.sync 2, 128;" ::: "memory");
     };
-    auto tile_of = [&](int t) -> int { return t < n_my ? __ldg(p.tile_list + blockIdx.x + t * gridDim.x) : -1; };
+    auto tile_of = [&](int t) -> int { return t < n_my ? __shfl_sync(0xffffffffu, __ldg(p.tile_list + blockIdx.x + t * gridDim.x), 0) : -1; };
     auto codes_of = [&](int tile) -> int4 {                      // this lane's 4 candidate codes of the tile (lanes 0..7 of a warp)
         int4 c = make_int4(0, 0, 0, 0);
         if (tile >= 0) {
@@ -676,51 +680,68 @@ wave_score_kernel(const __grid_constant__ CUtensorMap tmap, const WaveParams p, 
     // the operands of tile `tile` -> WB_XFULL[g]: this warp's 32 candidate rows (lanes 0..7: one tile::gather4 pair each), a quarter of
     // the user's K rows (lanes 8..11: 256-byte bulk copies into rows 64 + 16 g .. of the B operand) and (first warp, lane 12) the
     // softmax mask + flags.  Everything goes through the TMA: no register staging, no proxy fence.
-    auto refill_x = [&](int tile, int4 c, int aslot) {
+    auto refill_x = [&](int tile, int4 c, int aslot) {           // whole warp, converged; lane i < 8 holds the codes of rows 4 i .. 4 i + 3
         const int u = tile >> 10, nr = (tile & 255) + 1;
         const int mine = nr - wq * 32 < 32 ? nr - wq * 32 : 32;              // rows of this warp (may be <= 0)
         const int nl = mine > 0 ? (mine + 3) >> 2 : 0;
         const unsigned char *uop = p.uop + (size_t)u * G::UOP_BYTES;
         const uint32_t kbytes = (dbg & 8) ? 0u : (wq == 0 ? 1024u + 80u : 1024u);
-        if (lane == 0) mbar_expect_tx(&bar[WB_XFULL + g], ((dbg & 1) ? 0u : (uint32_t)nl * 1024u) + kbytes);
-        __syncwarp();
-        if (!(dbg & 1) && lane < nl) {
-            const int r = 4 * lane;
-            if (r + 1 >= mine) c.y = c.x;
-            if (r + 2 >= mine) c.z = c.x;
-            if (r + 3 >= mine) c.w = c.x;
-            const uint32_t off = (uint32_t)(g * G::X_STAGE + (wq * 32 + r) * 128);
-            tma_gather4_hilo(sbase + G::XH + off, sbase + G::XL + off, &tmap, smem_u32(&bar[WB_XFULL + g]), c.x, c.y, c.z, c.w);
+        const bool leader = elect_one();
+        if (leader) mbar_expect_tx(&bar[WB_XFULL + g], ((dbg & 1) ? 0u : (uint32_t)nl * 1024u) + kbytes);
+        if (!(dbg & 1)) {
+#pragma unroll
+            for (int i = 0; i < 8; i++) {
+                const int cx = __shfl_sync(0xffffffffu, c.x, i);
+                int cy = __shfl_sync(0xffffffffu, c.y, i), cz = __shfl_sync(0xffffffffu, c.z, i), cw = __shfl_sync(0xffffffffu, c.w, i);
+                if (i < nl) {
+                    const int r = 4 * i;
+                    if (r + 1 >= mine) cy = cx;
+                    if (r + 2 >= mine) cz = cx;
+                    if (r + 3 >= mine) cw = cx;
+                    const uint32_t off = (uint32_t)(g * G::X_STAGE + (wq * 32 + r) * 128);
+                    if (leader) tma_gather4_hilo(sbase + G::XH + off, sbase + G::XL + off, &tmap, smem_u32(&bar[WB_XFULL + g]), cx, cy, cz, cw);
+                }
+            }
         }
         if (!(dbg & 8)) {
-            if (lane >= 8 && lane < 12) {
-                const int q = wq * 4 + (lane - 8), kc = q & 7;           // piece q: hi (q < 8) / lo, k-chunk kc: 16 rows x 16 B
-                tma_bulk_g2s(sm + (q >> 3 ? G::BL : G::BH) + kc * G::B_LBO + (64 + 16 * g) * 16, uop + q * 256, 256, &bar[WB_XFULL + g]);
+            if (leader) {
+#pragma unroll
+                for (int i = 0; i < 4; i++) {
+                    const int q = wq * 4 + i, kc = q & 7;                    // piece q: hi (q < 8) / lo, k-chunk kc: 16 rows x 16 B
+                    tma_bulk_g2s(sm + (q >> 3 ? G::BL : G::BH) + kc * G::B_LBO + (64 + 16 * g) * 16, uop + q * 256, 256, &bar[WB_XFULL + g]);
+                }
+                if (wq == 0) tma_bulk_g2s(sm + G::ADDV + aslot * G::ADDV_STAGE, uop + 8192, 80, &bar[WB_XFULL + g]);
             }
-            if (wq == 0 && lane == 12) tma_bulk_g2s(sm + G::ADDV + aslot * G::ADDV_STAGE, uop + 8192, 80, &bar[WB_XFULL + g]);
         }
+        __syncwarp();
     };
     auto refill_h = [&](int tile) {                              // H operand of the tile's user -> WB_HFULL[g]
-        if (wq == 3 && lane == 0) {
-            mbar_expect_tx(&bar[WB_HFULL + g], 4096);
-            tma_bulk_g2s(sm + G::HH + g * G::H_STAGE, p.uop + (size_t)(tile >> 10) * G::UOP_BYTES + 4096, 4096, &bar[WB_HFULL + g]);
+        if (wq == 3) {
+            if (elect_one()) {
+                mbar_expect_tx(&bar[WB_HFULL + g], 4096);
+                tma_bulk_g2s(sm + G::HH + g * G::H_STAGE, p.uop + (size_t)(tile >> 10) * G::UOP_BYTES + 4096, 4096, &bar[WB_HFULL + g]);
+            }
+            __syncwarp();
         }
     };
-    auto issue_m1 = [&](int t) {                                 // first chain of tile t (stage g): called by one lane of the group
+    auto issue_m1 = [&](int t) {                                 // first chain of tile t (stage g): called by ONE WARP of the group, converged
         mbar_wait(&bar[WB_XFULL + g], (t >> 1) & 1);
         tc_fence_after();
         const uint64_t dXh = swdesc(G::XH + g * G::X_STAGE), dXl = swdesc(G::XL + g * G::X_STAGE);
         const uint64_t dBh = nsdesc(G::BH, G::B_LBO), dBl = nsdesc(G::BL, G::B_LBO);
+        if (elect_one()) {
 #pragma unroll
-        for (int ks = 0; ks < 4; ks++) {
-            if (dbg & 16) break;
-            const uint64_t ah = dXh + ks * 2, al = dXl + ks * 2;
-            const uint64_t bh = dBh + ks * (2 * G::B_LBO / 16), bl = dBl + ks * (2 * G::B_LBO / 16);
-            umma_bf16(td, ah, bh, kIdescBf16M128N96, ks > 0);
-            umma_bf16(td, ah, bl, kIdescBf16M128N96, 1);
-            umma_bf16(td, al, bh, kIdescBf16M128N96, 1);
+            for (int ks = 0; ks < 4; ks++) {
+                if (dbg & 16) break;
+                const uint64_t ah = dXh + ks * 2, al = dXl + ks * 2;
+                const uint64_t bh = dBh + ks * (2 * G::B_LBO / 16), bl = dBl + ks * (2 * G::B_LBO / 16);
+                umma_bf16(td, ah, bh, kIdescBf16M128N96, ks > 0);
+                umma_bf16(td, ah, bl, kIdescBf16M128N96, 1);
+                umma_bf16(td, al, bh, kIdescBf16M128N96, 1);
+            }
+            umma_commit(&bar[WB_M1 + g]);
         }
-        umma_commit(&bar[WB_M1 + g]);
+        __syncwarp();
     };
 
 #ifdef DMG_WAVE_TIMING
@@ -784,14 +805,16 @@ wave_score_kernel(const __grid_constant__ CUtensorMap tmap, const WaveParams p, 
         if (issuer2) {                                           // second chain of tile t
             mbar_wait(&bar[WB_HFULL + g], par);
             tc_fence_after();
-            if (!(dbg & 16)) {
-                const uint64_t dPh = nsdesc(G::PH + g * G::P_STAGE, 2048), dPl = nsdesc(G::PL + g * G::P_STAGE, 2048);
-                const uint64_t dHh = nsdesc(G::HH + g * G::H_STAGE, 1024), dHl = nsdesc(G::HL + g * G::H_STAGE, 1024);
-                umma_bf16(td, dPh, dHh, kIdescBf16M128N64, 1);
-                umma_bf16(td, dPh, dHl, kIdescBf16M128N64, 1);
-                umma_bf16(td, dPl, dHh, kIdescBf16M128N64, 1);
+            const uint64_t dPh = nsdesc(G::PH + g * G::P_STAGE, 2048), dPl = nsdesc(G::PL + g * G::P_STAGE, 2048);
+            const uint64_t dHh = nsdesc(G::HH + g * G::H_STAGE, 1024), dHl = nsdesc(G::HL + g * G::H_STAGE, 1024);
+            if (elect_one()) {
+                if (!(dbg & 16)) {
+                    umma_bf16(td, dPh, dHh, kIdescBf16M128N64, 1);
+                    umma_bf16(td, dPh, dHl, kIdescBf16M128N64, 1);
+                    umma_bf16(td, dPl, dHh, kIdescBf16M128N64, 1);
+                }
+                umma_commit(&bar[WB_M2 + g]);
             }
-            umma_commit(&bar[WB_M2 + g]);
         }
         __syncwarp();
         WTICK(6);
