@@ -584,14 +584,14 @@ __device__ __forceinline__ void tmem_ld32x2(uint32_t taddr, float (&a)[32], floa
 #pragma unroll
     for (int i = 0; i < 32; i++) { a[i] = __uint_as_float(r[i]); b[i] = __uint_as_float(q[i]); }
 }
-// rows c0..c3 of the bf16 hi|lo table -> 4 rows of the hi tile and 4 rows of the lo tile (row 2c = hi(c), 2c + 1 = lo(c))
+// rows c0..c3 of the bf16 hi|lo table (tensor map: [rows][128] bf16, row c = [64 hi | 64 lo], box 64 x 1) -> 4 rows of the hi tile
+// (columns 0..63) and 4 rows of the lo tile (columns 64..127): the same four row coordinates for both instructions
 __device__ __forceinline__ void tma_gather4_hilo(uint32_t dst_hi, uint32_t dst_lo, const void *tmap, uint32_t bar, int c0, int c1, int c2, int c3)
 {
     asm volatile(
-        "cp.async.bulk.tensor.2d.shared::cluster.global.tile::gather4.mbarrier::complete_tx::bytes [%0], [%2, {%4, %5, %6, %7, %8}], [%3];\n\t"
-        "cp.async.bulk.tensor.2d.shared::cluster.global.tile::gather4.mbarrier::complete_tx::bytes [%1], [%2, {%4, %9, %10, %11, %12}], [%3];"
-        ::"r"(dst_hi), "r"(dst_lo), "l"(tmap), "r"(bar), "r"(0), "r"(2 * c0), "r"(2 * c1), "r"(2 * c2), "r"(2 * c3),
-          "r"(2 * c0 + 1), "r"(2 * c1 + 1), "r"(2 * c2 + 1), "r"(2 * c3 + 1) : "memory");
+        "cp.async.bulk.tensor.2d.shared::cluster.global.tile::gather4.mbarrier::complete_tx::bytes [%0], [%2, {%4, %6, %7, %8, %9}], [%3];\n\t"
+        "cp.async.bulk.tensor.2d.shared::cluster.global.tile::gather4.mbarrier::complete_tx::bytes [%1], [%2, {%5, %6, %7, %8, %9}], [%3];"
+        ::"r"(dst_hi), "r"(dst_lo), "l"(tmap), "r"(bar), "r"(0), "r"(64), "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
 }
 
 #ifdef DMG_WAVE_TIMING
@@ -649,6 +649,11 @@ wave_score_kernel(const __grid_constant__ CUtensorMap tmap, const WaveParams p, 
     tc_fence_after();
     const uint32_t tmem_base = __shfl_sync(0xffffffffu, *reinterpret_cast<volatile uint32_t *>(sm + G::TMEMP), 0);
     grid_dep_wait();                                             // everything above ran under the previous kernel's tail
+    // the first two tile entries of this thread's group are fetched together with the level's tile count (one L2 round trip less on the
+    // launch ramp); entries at or past the count are ignored below
+    const int g_early = (tid >> 7) & 1, list_cap = p.B * ((p.cap + 127) >> 7);
+    const int i0 = (int)blockIdx.x + g_early * (int)gridDim.x, i2 = i0 + 2 * (int)gridDim.x;
+    const int raw0 = i0 < list_cap ? __ldg(p.tile_list + i0) : -1, raw2 = i2 < list_cap ? __ldg(p.tile_list + i2) : -1;
     const int ntiles = __shfl_sync(0xffffffffu, *(volatile const int32_t *)(p.tile_count + level), 0);
     const int n_my = ntiles > (int)blockIdx.x ? (ntiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
 
@@ -668,14 +673,16 @@ wave_score_kernel(const __grid_constant__ CUtensorMap tmap, const WaveParams p, 
         if (g == 0) asm volatile("bar.sync 1, 128;" ::: "memory");
         else asm volatile("bar.sync 2, 128;" ::: "memory");
     };
-    auto tile_of = [&](int t) -> int { return t < n_my ? __shfl_sync(0xffffffffu, __ldg(p.tile_list + blockIdx.x + t * gridDim.x), 0) : -1; };
+    // tile_raw: the load only (per lane, in flight); uni(): the same value made warp-uniform for the compiler at the point of use
+    auto tile_raw = [&](int t) -> int { return t < n_my ? __ldg(p.tile_list + blockIdx.x + t * gridDim.x) : -1; };
+    auto uni = [&](int v) -> int { return __shfl_sync(0xffffffffu, v, 0); };
     auto codes_of = [&](int tile) -> int4 {                      // this lane's 4 candidate codes of the tile (lanes 0..7 of a warp)
         int4 c = make_int4(0, 0, 0, 0);
         if (tile >= 0) {
             const int mine = (tile & 255) + 1 - wq * 32;
             if (4 * lane < mine) c = __ldg(reinterpret_cast<const int4 *>(p.code[slot] + (size_t)(tile >> 10) * p.cap + ((tile >> 8) & 3) * 128 + wq * 32) + lane);
         }
-        return c;
+        return c;                                                // still in flight: first touched in refill_x
     };
     // the operands of tile `tile` -> WB_XFULL[g]: this warp's 32 candidate rows (lanes 0..7: one tile::gather4 pair each), a quarter of
     // the user's K rows (lanes 8..11: 256-byte bulk copies into rows 64 + 16 g .. of the B operand) and (first warp, lane 12) the
@@ -688,21 +695,6 @@ wave_score_kernel(const __grid_constant__ CUtensorMap tmap, const WaveParams p, 
         const uint32_t kbytes = (dbg & 8) ? 0u : (wq == 0 ? 1024u + 80u : 1024u);
         const bool leader = elect_one();
         if (leader) mbar_expect_tx(&bar[WB_XFULL + g], ((dbg & 1) ? 0u : (uint32_t)nl * 1024u) + kbytes);
-        if (!(dbg & 1)) {
-#pragma unroll
-            for (int i = 0; i < 8; i++) {
-                const int cx = __shfl_sync(0xffffffffu, c.x, i);
-                int cy = __shfl_sync(0xffffffffu, c.y, i), cz = __shfl_sync(0xffffffffu, c.z, i), cw = __shfl_sync(0xffffffffu, c.w, i);
-                if (i < nl) {
-                    const int r = 4 * i;
-                    if (r + 1 >= mine) cy = cx;
-                    if (r + 2 >= mine) cz = cx;
-                    if (r + 3 >= mine) cw = cx;
-                    const uint32_t off = (uint32_t)(g * G::X_STAGE + (wq * 32 + r) * 128);
-                    if (leader) tma_gather4_hilo(sbase + G::XH + off, sbase + G::XL + off, &tmap, smem_u32(&bar[WB_XFULL + g]), cx, cy, cz, cw);
-                }
-            }
-        }
         if (!(dbg & 8)) {
             if (leader) {
 #pragma unroll
@@ -711,6 +703,28 @@ wave_score_kernel(const __grid_constant__ CUtensorMap tmap, const WaveParams p, 
                     tma_bulk_g2s(sm + (q >> 3 ? G::BL : G::BH) + kc * G::B_LBO + (64 + 16 * g) * 16, uop + q * 256, 256, &bar[WB_XFULL + g]);
                 }
                 if (wq == 0) tma_bulk_g2s(sm + G::ADDV + aslot * G::ADDV_STAGE, uop + 8192, 80, &bar[WB_XFULL + g]);
+            }
+        }
+        if (!(dbg & 1)) {
+            const uint32_t woff = (uint32_t)(g * G::X_STAGE + wq * 32 * 128);
+            const uint32_t xh = sbase + G::XH + woff, xl = sbase + G::XL + woff, xb = smem_u32(&bar[WB_XFULL + g]);
+            if (4 * lane + 1 >= mine) c.y = c.x;                 // rows past the tile's last one re-fetch a valid row (their scores are never read)
+            if (4 * lane + 2 >= mine) c.z = c.x;
+            if (4 * lane + 3 >= mine) c.w = c.x;
+            if (nl == 8) {                                       // a full warp quarter (every tile but a user's last): straight-line issue
+#pragma unroll
+                for (int i = 0; i < 8; i++) {
+                    const int cx = __shfl_sync(0xffffffffu, c.x, i), cy = __shfl_sync(0xffffffffu, c.y, i);
+                    const int cz = __shfl_sync(0xffffffffu, c.z, i), cw = __shfl_sync(0xffffffffu, c.w, i);
+                    if (leader) tma_gather4_hilo(xh + i * 512, xl + i * 512, &tmap, xb, cx, cy, cz, cw);
+                }
+            } else {
+#pragma unroll 1
+                for (int i = 0; i < nl; i++) {
+                    const int cx = __shfl_sync(0xffffffffu, c.x, i), cy = __shfl_sync(0xffffffffu, c.y, i);
+                    const int cz = __shfl_sync(0xffffffffu, c.z, i), cw = __shfl_sync(0xffffffffu, c.w, i);
+                    if (leader) tma_gather4_hilo(xh + i * 512, xl + i * 512, &tmap, xb, cx, cy, cz, cw);
+                }
             }
         }
         __syncwarp();
@@ -747,7 +761,7 @@ wave_score_kernel(const __grid_constant__ CUtensorMap tmap, const WaveParams p, 
 #ifdef DMG_WAVE_TIMING
     long long wacc[12] = {0}, wlast = clock64();
 #endif
-    int cur = tile_of(g), nxt = tile_of(g + 2);
+    int cur = uni(g < n_my ? raw0 : -1), nxt = uni(g + 2 < n_my ? raw2 : -1);
     if (cur >= 0) {
         refill_x(cur, codes_of(cur), g);
         refill_h(cur);
@@ -756,7 +770,7 @@ wave_score_kernel(const __grid_constant__ CUtensorMap tmap, const WaveParams p, 
     }
     for (int t = g; t < n_my; t += 2) {
         const uint32_t par = (t >> 1) & 1;
-        const int nx2 = tile_of(t + 4);
+        const int nx2 = tile_raw(t + 4);                         // consumed at the bottom of the iteration
         const int4 cn = codes_of(nxt);                           // in flight while this tile's first chain completes
         const int nr = (cur & 255) + 1;
         const bool active = wq * 32 < nr;
@@ -850,7 +864,7 @@ wave_score_kernel(const __grid_constant__ CUtensorMap tmap, const WaveParams p, 
             }
             if (gtid < nr) p.score[(size_t)(cur >> 10) * p.cap + ((cur >> 8) & 3) * 128 + gtid] = ((l0 + l1) + (l2 + l3)) + w.b2;
         }
-        cur = nxt; nxt = nx2;
+        cur = nxt; nxt = uni(nx2);
         WTICK(11);
     }
 #ifdef DMG_WAVE_TIMING

@@ -494,9 +494,9 @@ static int32_t wave_prepare(dmg_handle_t h)
         if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qr) != cudaSuccess || !fn) { cudaGetLastError(); return DMG_OK; }
         encode = (encode_fn)fn;
     }
-    const cuuint64_t gdim[2] = {64, (cuuint64_t)d.rows * 2};     // [2 rows][64] bf16: row 2c = hi(c), row 2c + 1 = lo(c)
-    const cuuint64_t gstr[1] = {128};
-    const cuuint32_t box[2] = {64, 1}, estr[2] = {1, 1};         // tile::gather4 fetches 4 such boxes per instruction
+    const cuuint64_t gdim[2] = {128, (cuuint64_t)d.rows};        // [rows][128] bf16: row c = [64 hi | 64 lo]
+    const cuuint64_t gstr[1] = {256};
+    const cuuint32_t box[2] = {64, 1}, estr[2] = {1, 1};         // tile::gather4 fetches 4 such boxes (half rows) per instruction: columns 0.. = hi, 64.. = lo
     const CUresult cr = encode(reinterpret_cast<CUtensorMap *>(h->wave_tmap), CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, d.d_split, gdim, gstr, box, estr,
                                CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                                CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
