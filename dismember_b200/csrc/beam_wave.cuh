@@ -687,24 +687,13 @@ wave_score_kernel(const __grid_constant__ CUtensorMap tmap, const WaveParams p, 
     // the operands of tile `tile` -> WB_XFULL[g]: this warp's 32 candidate rows (lanes 0..7: one tile::gather4 pair each), a quarter of
     // the user's K rows (lanes 8..11: 256-byte bulk copies into rows 64 + 16 g .. of the B operand) and (first warp, lane 12) the
     // softmax mask + flags.  Everything goes through the TMA: no register staging, no proxy fence.
-    auto refill_x = [&](int tile, int4 c, int aslot) {           // whole warp, converged; lane i < 8 holds the codes of rows 4 i .. 4 i + 3
-        const int u = tile >> 10, nr = (tile & 255) + 1;
+    auto refill_x = [&](int tile, int4 c) {           // whole warp, converged; lane i < 8 holds the codes of rows 4 i .. 4 i + 3
+        const int nr = (tile & 255) + 1;
         const int mine = nr - wq * 32 < 32 ? nr - wq * 32 : 32;              // rows of this warp (may be <= 0)
         const int nl = mine > 0 ? (mine + 3) >> 2 : 0;
-        const unsigned char *uop = p.uop + (size_t)u * G::UOP_BYTES;
         const uint32_t kbytes = (dbg & 8) ? 0u : (wq == 0 ? 1024u + 80u : 1024u);
         const bool leader = elect_one();
-        if (leader) mbar_expect_tx(&bar[WB_XFULL + g], ((dbg & 1) ? 0u : (uint32_t)nl * 1024u) + kbytes);
-        if (!(dbg & 8)) {
-            if (leader) {
-#pragma unroll
-                for (int i = 0; i < 4; i++) {
-                    const int q = wq * 4 + i, kc = q & 7;                    // piece q: hi (q < 8) / lo, k-chunk kc: 16 rows x 16 B
-                    tma_bulk_g2s(sm + (q >> 3 ? G::BL : G::BH) + kc * G::B_LBO + (64 + 16 * g) * 16, uop + q * 256, 256, &bar[WB_XFULL + g]);
-                }
-                if (wq == 0) tma_bulk_g2s(sm + G::ADDV + aslot * G::ADDV_STAGE, uop + 8192, 80, &bar[WB_XFULL + g]);
-            }
-        }
+        if (leader) mbar_expect_tx(&bar[WB_XFULL + g], ((dbg & 1) ? 0u : (uint32_t)nl * 1024u) + kbytes);   // includes refill_k's bytes
         if (!(dbg & 1)) {
             const uint32_t woff = (uint32_t)(g * G::X_STAGE + wq * 32 * 128);
             const uint32_t xh = sbase + G::XH + woff, xl = sbase + G::XL + woff, xb = smem_u32(&bar[WB_XFULL + g]);
@@ -728,6 +717,23 @@ wave_score_kernel(const __grid_constant__ CUtensorMap tmap, const WaveParams p, 
             }
         }
         __syncwarp();
+    };
+    // the small operands of the same tile (counted by refill_x's expect_tx): a quarter of the user's K rows per warp (256-byte bulk copies
+    // into rows 64 + 16 g .. of the B operand) and, first warp, the softmax mask + flags.  Issued while the second chain of the
+    // current tile runs: they land long before the gathered rows do.
+    auto refill_k = [&](int tile, int aslot) {
+        if (!(dbg & 8)) {
+            const unsigned char *uop = p.uop + (size_t)(tile >> 10) * G::UOP_BYTES;
+            if (elect_one()) {
+#pragma unroll
+                for (int i = 0; i < 4; i++) {
+                    const int q = wq * 4 + i, kc = q & 7;                    // piece q: hi (q < 8) / lo, k-chunk kc: 16 rows x 16 B
+                    tma_bulk_g2s(sm + (q >> 3 ? G::BL : G::BH) + kc * G::B_LBO + (64 + 16 * g) * 16, uop + q * 256, 256, &bar[WB_XFULL + g]);
+                }
+                if (wq == 0) tma_bulk_g2s(sm + G::ADDV + aslot * G::ADDV_STAGE, uop + 8192, 80, &bar[WB_XFULL + g]);
+            }
+            __syncwarp();
+        }
     };
     auto refill_h = [&](int tile) {                              // H operand of the tile's user -> WB_HFULL[g]
         if (wq == 3) {
@@ -763,15 +769,15 @@ wave_score_kernel(const __grid_constant__ CUtensorMap tmap, const WaveParams p, 
 #endif
     int cur = uni(g < n_my ? raw0 : -1), nxt = uni(g + 2 < n_my ? raw2 : -1);
     if (cur >= 0) {
-        refill_x(cur, codes_of(cur), g);
+        refill_x(cur, codes_of(cur));
+        refill_k(cur, g);
         refill_h(cur);
         if (issuer1) { mbar_wait(&bar[WB_W1], 0); issue_m1(g); }
         __syncwarp();
     }
+    int4 cn = codes_of(nxt);                                     // candidate codes of the NEXT tile, always one tile ahead
     for (int t = g; t < n_my; t += 2) {
         const uint32_t par = (t >> 1) & 1;
-        const int nx2 = tile_raw(t + 4);                         // consumed at the bottom of the iteration
-        const int4 cn = codes_of(nxt);                           // in flight while this tile's first chain completes
         const int nr = (cur & 255) + 1;
         const bool active = wq * 32 < nr;
         WTICK(0);
@@ -780,7 +786,7 @@ wave_score_kernel(const __grid_constant__ CUtensorMap tmap, const WaveParams p, 
         mbar_wait(&bar[WB_M1 + g], par);
         tc_fence_after();
         WTICK(2);
-        if (nxt >= 0) refill_x(nxt, cn, (t + 2) & 3);            // X[g] and K slot g are free: the first chain of tile t has completed
+        if (nxt >= 0) refill_x(nxt, cn);                         // X[g] and K slot g are free: the first chain of tile t has completed
         WTICK(3);
         if (active) {
             float sc[16];
@@ -831,10 +837,14 @@ wave_score_kernel(const __grid_constant__ CUtensorMap tmap, const WaveParams p, 
             }
         }
         __syncwarp();
+        const int nx2 = tile_raw(t + 4);                         // the list entry two tiles ahead: its L2 round trip hides under the second chain
+        if (nxt >= 0) refill_k(nxt, (t + 2) & 3);                // under the second chain
         WTICK(6);
         mbar_wait(&bar[WB_M2 + g], par);
         tc_fence_after();
         WTICK(7);
+        const int nn = uni(nx2);
+        cn = codes_of(nn);                                       // candidate codes of tile t + 4: in flight until the next iteration's refill_x
         if (nxt >= 0) refill_h(nxt);                             // H[g] is free: the second chain of tile t has completed
         float h0[32], h1[32];
         if (active) tmem_ld32x2(tm, h0, h1);
@@ -864,7 +874,7 @@ wave_score_kernel(const __grid_constant__ CUtensorMap tmap, const WaveParams p, 
             }
             if (gtid < nr) p.score[(size_t)(cur >> 10) * p.cap + ((cur >> 8) & 3) * 128 + gtid] = ((l0 + l1) + (l2 + l3)) + w.b2;
         }
-        cur = nxt; nxt = uni(nx2);
+        cur = nxt; nxt = nn;
         WTICK(11);
     }
 #ifdef DMG_WAVE_TIMING
