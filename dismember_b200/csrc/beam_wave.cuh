@@ -323,6 +323,9 @@ __device__ __forceinline__ void wave_expand_finish(const WaveParams &p, WaveUser
     }
 }
 
+#ifndef DMG_WAVE_PARK_FRAC
+#define DMG_WAVE_PARK_FRAC 0.0078125f                            // gap at the cut below eps / 128: settle the band strictly in place
+#endif
 struct WaveStrictW { const float *wattT, *w1T, *b1, *w2; float b2; };
 __device__ void dfm_strict_batch128(const WaveParams &p, const DfmConsts &dc, const float *__restrict__ dense, int user,
                                     const int32_t *__restrict__ sRow, int n, float *__restrict__ sOut, float *__restrict__ scr,
@@ -458,7 +461,7 @@ static __global__ void __launch_bounds__(128) wave_select_kernel(const WaveParam
                         const int vcount = st->vcount, nseg = st->nseg;
                         // Observed |fast - strict| stays below 1 % of eps: with a gap of eps/128 or more the fast order is taken
                         // now and PROVEN by wave_final_kernel; a narrower gap is settled strictly right here.
-                        const bool defer = gap >= 0.0078125f * eps_level && vcount + n_unc <= WaveGeo::VCAP && nseg < 32 && eps_level < 1e30f;
+                        const bool defer = gap >= DMG_WAVE_PARK_FRAC * eps_level && vcount + n_unc <= WaveGeo::VCAP && nseg < 32 && eps_level < 1e30f;
                         if (defer) {
 #pragma unroll 1
                             for (int e = lane; e < n_unc; e += 32) {
