@@ -61,6 +61,7 @@ struct WaveGeo {
     static constexpr int SMEM = TMEMP + 24;
     static constexpr int UOP_BYTES = 8320;                   // per-user operand image [KH | KL | HH | HL | addv | flags] (8272, padded)
     static constexpr int VCAP = FastGeo::VCAP, MAX_UNC = FastGeo::MAX_UNC;
+    static constexpr int NWIN = 16;                          // narrow park: at most this many band rows are settled strictly in place
 };
 enum { WB_W1 = 0, WB_HFULL = 1, WB_XFULL = 3, WB_M1 = 5, WB_M2 = 7 };   // + stage
 
@@ -350,7 +351,10 @@ static __global__ void __launch_bounds__(128) wave_select_kernel(const WaveParam
     __shared__ int sFr[4][MU];                                    //   rank by fast score
     __shared__ uint32_t sKeepW[4][NJ];
     __shared__ int sGap[4][2];
-    __shared__ int sPark[4][2];                                   // n_unc (0 = not parked), need
+    __shared__ int sPark[4][4];                                   // rows to score strictly (0 = not parked), need, narrow?, n_unc
+    __shared__ int32_t sWCode[4][WaveGeo::NWIN];                  // narrow park: the band rows within eps / 32 of the cut,
+    __shared__ float sWStr[4][WaveGeo::NWIN];                     //   their strict scores,
+    __shared__ int sWIdx[4][WaveGeo::NWIN];                       //   their index in the band lists (then: chosen?)
     extern __shared__ __align__(16) unsigned char sel_dyn[];      // DeepFM only: the dense weights of a parked cut's strict chains
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int user = blockIdx.x * 4 + warp;
@@ -474,8 +478,30 @@ static __global__ void __launch_bounds__(128) wave_select_kernel(const WaveParam
                             }
                             __syncwarp();
                             if (lane == 0) { p.v_segeps[(size_t)user * 32 + nseg] = eps_level; st->vcount = vcount + n_unc; st->nseg = nseg + 1; }
-                        } else {                                  // park: strict scores of the band decide (phases 2 and 3)
-                            if (lane == 0) { sPark[warp][0] = n_unc; sPark[warp][1] = need; }
+                        } else {
+                            // park.  Narrow form (the usual one): only the band rows within eps / 32 of the cut -- those whose fast
+                            // order cannot be trusted -- are scored strictly in place (phase 2); the rest of the band keeps its fast
+                            // order and the WHOLE band is deferred to the end-of-search proof like any other cut (phase 3), which
+                            // checks the chosen set against the strict ranks whatever way it was chosen.  Full form (no room on the
+                            // deferred list, or a crowded window): strict scores of the whole band decide, nothing to prove.
+                            const bool room = vcount + n_unc <= WaveGeo::VCAP && nseg < 32 && eps_level < 1e30f;
+                            const float mid = 0.5f * (__int_as_float(sGap[warp][0]) + __int_as_float(sGap[warp][1])), win = 0.03125f * eps_level;
+                            int n_w = 0;
+                            if (room) {
+#pragma unroll 1
+                                for (int e0 = 0; e0 < n_unc; e0 += 32) {
+                                    const int e = e0 + lane;
+                                    const bool in = e < n_unc && fabsf(sLStr[warp][e] - mid) <= win;
+                                    const uint32_t mw = __ballot_sync(0xffffffffu, in);
+                                    if (in) {
+                                        const int i = n_w + __popc(mw & lt);
+                                        if (i < WaveGeo::NWIN) { sWCode[warp][i] = sLCode[warp][e]; sWIdx[warp][i] = e; }
+                                    }
+                                    n_w += __popc(mw);
+                                }
+                            }
+                            const bool narrow = room && n_w >= 2 && n_w <= WaveGeo::NWIN;
+                            if (lane == 0) { sPark[warp][0] = narrow ? n_w : n_unc; sPark[warp][1] = need; sPark[warp][2] = narrow ? 1 : 0; sPark[warp][3] = n_unc; }
                             parked = true;
                         }
                     }
@@ -494,10 +520,13 @@ static __global__ void __launch_bounds__(128) wave_select_kernel(const WaveParam
         if (n == 0) continue;
         any = true;
         const int pu = blockIdx.x * 4 + w;
+        const bool narrow = sPark[w][2] != 0;
+        const int32_t *rows = narrow ? sWCode[w] : sLCode[w];
+        float *strict = narrow ? sWStr[w] : sLStr[w];
         if (KIND == 1) {                                           // DeepFM: the oracle-order chains of deepfm_common.cuh
-            if (tid < n) sKeyU[w][tid] = __float_as_uint(sLStr[w][tid]);
+            if (!narrow && tid < n) sKeyU[w][tid] = __float_as_uint(sLStr[w][tid]);
             __syncthreads();
-            dfm_strict_batch128(p, dc, p.dfm_dense, pu, sLCode[w], n, sLStr[w], sScr, reinterpret_cast<float *>(sel_dyn), dense_loaded);
+            dfm_strict_batch128(p, dc, p.dfm_dense, pu, rows, n, strict, sScr, reinterpret_cast<float *>(sel_dyn), dense_loaded);
             dense_loaded = true;
             continue;
         }
@@ -506,14 +535,76 @@ static __global__ void __launch_bounds__(128) wave_select_kernel(const WaveParam
             const int c = j < p.T ? p.hist[(size_t)pu * p.T + j] : -1;
             sScr[j * FastGeo::KLD + k] = c >= 0 ? __ldg(p.emb + (size_t)c * 64 + k) : 0.0f;
         }
-        if (tid < n) sKeyU[w][tid] = __float_as_uint(sLStr[w][tid]);   // keep the fast scores (error statistics)
+        if (!narrow && tid < n) sKeyU[w][tid] = __float_as_uint(sLStr[w][tid]);   // keep the fast scores (error statistics)
         __syncthreads();
-        strict_score_batch128(p.emb, sLCode[w], n, sLStr[w], sScr, p.user[pu].maskbits, p.T, p.scale, sw.wattT, sw.w1T, sw.b1, sw.w2, sw.b2);
+        strict_score_batch128(p.emb, rows, n, strict, sScr, p.user[pu].maskbits, p.T, p.scale, sw.wattT, sw.w1T, sw.b1, sw.w2, sw.b2);
     }
     if (!any) return;
     __syncthreads();
     // ---- phase 3: the parked warps finish their cuts with the strict order ----
-    if (parked) {
+    if (parked && sPark[warp][2]) {                               // narrow park: strict order inside the window, fast order outside, proof later
+        const int n_w = sPark[warp][0], need = sPark[warp][1], n_unc = sPark[warp][3];
+        const float eps_level = st->eps;
+        int above = 0;                                            // band rows with a fast rank above the cut that are NOT in the window: chosen
+#pragma unroll 1
+        for (int e0 = 0; e0 < n_unc; e0 += 32) {
+            const int e = e0 + lane;
+            above += __popc(__ballot_sync(0xffffffffu, e < n_unc && sFr[warp][e] < need));
+        }
+        int in_above = 0, tie = 0, mych = 0;
+        float ratio = 0.0f;
+        if (lane < n_w) {
+            const int e = sWIdx[warp][lane];
+            in_above = sFr[warp][e] < need ? 1 : 0;
+        }
+        above -= __popc(__ballot_sync(0xffffffffu, in_above != 0));
+        const int need_w = need - above;                          // rows the window contributes to the kept set
+        if (lane < n_w) {
+            const float mine = sWStr[warp][lane];
+            const uint32_t ks = order_key(mine);
+            int g = 0, t = 0;
+            for (int q = 0; q < n_w; q++) {
+                const uint32_t kq = order_key(sWStr[warp][q]);
+                g += kq > ks ? 1 : 0;
+                t += (kq == ks && q != lane) ? 1 : 0;
+            }
+            tie = (g < need_w && g + t >= need_w) ? 1 : 0;
+            mych = g + t < need_w ? 1 : 0;
+            if (eps_level > 0.0f && eps_level < 1e30f) ratio = fabsf(mine - sLStr[warp][sWIdx[warp][lane]]) / eps_level;
+        }
+        tie = __any_sync(0xffffffffu, tie);
+        __syncwarp();
+        if (lane < n_w) sFr[warp][sWIdx[warp][lane]] = mych ? -1 : 0x7fffffff;     // the window rows' fast ranks give way to the strict decision
+        __syncwarp();
+        if (p.stats) {
+            for (int o = 16; o > 0; o >>= 1) ratio = fmaxf(ratio, __shfl_xor_sync(0xffffffffu, ratio, o));
+            if (lane == 0) {
+                if (ratio > 0.0f) atomicMax(reinterpret_cast<unsigned int *>(&p.stats[4]), __float_as_uint(ratio));
+                atomicAdd(&p.stats[2], (unsigned long long)n_w); atomicAdd(&p.stats[6], 1ull);
+            }
+        }
+        if (tie) {
+            if (lane == 0) {
+                st->flags = flags | WU_REDO; st->redo_why = 1; p.count[user] = 0;
+                if (p.stats) { atomicAdd(&p.stats[0], st_cut); atomicAdd(&p.stats[1], st_recut); }
+            }
+        } else {
+            const int vcount = st->vcount, nseg = st->nseg;
+#pragma unroll 1
+            for (int e = lane; e < n_unc; e += 32) {
+                const uint32_t ch = sFr[warp][e] < need ? 1u : 0u;
+                const size_t g = (size_t)user * WaveGeo::VCAP + vcount + e;
+                p.v_code[g] = sLCode[warp][e]; p.v_fast[g] = sLStr[warp][e];
+                p.v_meta[g] = (uint32_t)vcount | ((uint32_t)n_unc << 8) | ((uint32_t)need << 16) | (ch << 24) | ((uint32_t)nseg << 25);
+                const int pe = sUPos[warp][e];
+                if (!ch) atomicAnd(&sKeepW[warp][pe >> 5], ~(1u << (pe & 31)));
+            }
+            __syncwarp();
+            if (lane == 0) { p.v_segeps[(size_t)user * 32 + nseg] = eps_level; st->vcount = vcount + n_unc; st->nseg = nseg + 1; }
+            __syncwarp();
+            wave_expand_finish<NJ, KIND>(p, st, user, level, lane, code, sKeepW[warp], count, nxt, flags, st_cut, st_recut, st_iters);
+        }
+    } else if (parked) {
         const int n_unc = sPark[warp][0], need = sPark[warp][1];
         const float eps_level = st->eps;
         int tie = 0;
