@@ -701,13 +701,14 @@ constexpr uint32_t kIdescBf16M128N96 = (1u << 4) | (1u << 7) | (1u << 10) | ((96
 // columns each), i.e. four independent tile chains per SM -- while one waits for the tensor pipe or the TMA the others compute.
 // Per tile:
 //   [Hacc | S] = X . [W1x | K0 | K1]^T   128 x 96 x 64 tcgen05.mma, bf16 hi*hi + hi*lo + lo*hi, fp32 in TMEM (the history rows of stage
-//                                         g sit in rows 64 + 16 g .. of the B operand), issued by the group's first lane as soon as
-//                                         X[g] has landed and the group has drained the accumulators of its previous tile;
+//                                         g sit in rows 64 + 16 g .. of the B operand), issued by one elected lane of the group's
+//                                         second warp as soon as X[g] has landed and the group has drained its accumulators;
 //   refill X[g] with the group's next tile: every warp gathers its own 32 rows with the TMA (tile::gather4 from the bf16 hi|lo
-//                                         table), the first warp also copies the user's K rows, softmax mask and flags;
+//                                         table; one elected lane issues the 16 instructions from warp-uniform coordinates);
 //   Mask + SoftMax on S, one row per thread, log2 domain -> P[g] (A operand); group barrier;
-//   Hacc += P . H                         128 x 64 x 16 (row 15 of H carries b1), issued by the group's first lane;
-//   read Hacc; group barrier; [first lane: the next tile's first chain]; logit = relu(Hacc) . W2 + b2 from registers.
+//   Hacc += P . H                         128 x 64 x 16 (row 15 of H carries b1), one elected lane of the third warp; under it every
+//                                         warp copies its quarter of the next user's K rows (the first warp also mask + flags);
+//   read Hacc; group barrier; [second warp: the next tile's first chain]; logit = relu(Hacc) . W2 + b2 from registers.
 // DBG: ablation switches for profiling (results are wrong when != 0): 1 no row gather, 2 no softmax math, 4 no epilogue math, 8 no K copy, 16 no MMA
 template <int DBG = 0>
 static __global__ void __launch_bounds__(WaveGeo::THREADS, 2)
@@ -778,10 +779,9 @@ wave_score_kernel(const __grid_constant__ CUtensorMap tmap, const WaveParams p, 
         }
         return c;                                                // still in flight: first touched in refill_x
     };
-    // the operands of tile `tile` -> WB_XFULL[g]: this warp's 32 candidate rows (lanes 0..7: one tile::gather4 pair each), a quarter of
-    // the user's K rows (lanes 8..11: 256-byte bulk copies into rows 64 + 16 g .. of the B operand) and (first warp, lane 12) the
-    // softmax mask + flags.  Everything goes through the TMA: no register staging, no proxy fence.
-    auto refill_x = [&](int tile, int4 c) {           // whole warp, converged; lane i < 8 holds the codes of rows 4 i .. 4 i + 3
+    // the gathered operand of tile `tile` -> WB_XFULL[g]: this warp's 32 candidate rows, one tile::gather4 pair (hi, lo) per 4 rows.  The
+    // barrier's expect_tx also counts the bytes refill_k sends later.  Everything goes through the TMA: no register staging, no proxy fence.
+    auto refill_x = [&](int tile, int4 c) {                      // whole warp, converged; lane i < 8 holds the codes of rows 4 i .. 4 i + 3
         const int nr = (tile & 255) + 1;
         const int mine = nr - wq * 32 < 32 ? nr - wq * 32 : 32;              // rows of this warp (may be <= 0)
         const int nl = mine > 0 ? (mine + 3) >> 2 : 0;
